@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("VLLM_LOGGING_LEVEL", "WARNING")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: needs more than one CUDA device")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        have = torch.cuda.is_available()
+        n = torch.cuda.device_count() if have else 0
+    except Exception:
+        have, n = False, 0
+    for item in items:
+        if "gpu" in item.keywords and not have:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "multigpu" in item.keywords and n < 2:
+            item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))

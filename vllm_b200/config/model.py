@@ -1,0 +1,324 @@
+"""ModelConfig: architecture description taken from a HuggingFace ``config.json``
+or from a built-in preset (there is no network in the build environment, so the
+benchmark architectures are baked in).
+
+Reference: vllm/config/model.py (``ModelConfig``), transformers_utils/config.py.
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import torch
+
+_DTYPES = {
+    "auto": None, "bfloat16": torch.bfloat16, "bf16": torch.bfloat16, "float16": torch.float16,
+    "half": torch.float16, "fp16": torch.float16, "float32": torch.float32, "float": torch.float32,
+}
+
+# HF-style config dicts for the architectures named in BASELINE.json plus tiny
+# variants used by CPU tests.
+PRESETS: dict[str, dict[str, Any]] = {
+    "opt-125m": dict(
+        architectures=["OPTForCausalLM"], model_type="opt", vocab_size=50272, hidden_size=768,
+        num_hidden_layers=12, num_attention_heads=12, ffn_dim=3072, max_position_embeddings=2048,
+        word_embed_proj_dim=768, do_layer_norm_before=True, activation_function="relu",
+        bos_token_id=2, eos_token_id=2, pad_token_id=1, torch_dtype="float16", enable_bias=True,
+        layer_norm_elementwise_affine=True, tie_word_embeddings=True),
+    "opt-tiny": dict(
+        architectures=["OPTForCausalLM"], model_type="opt", vocab_size=512, hidden_size=64,
+        num_hidden_layers=2, num_attention_heads=4, ffn_dim=256, max_position_embeddings=512,
+        word_embed_proj_dim=64, do_layer_norm_before=True, activation_function="relu",
+        bos_token_id=2, eos_token_id=2, pad_token_id=1, torch_dtype="float32", enable_bias=True,
+        layer_norm_elementwise_affine=True, tie_word_embeddings=True),
+    "llama-3-8b": dict(
+        architectures=["LlamaForCausalLM"], model_type="llama", vocab_size=128256, hidden_size=4096,
+        intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8,
+        head_dim=128, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0,
+        hidden_act="silu", bos_token_id=128000, eos_token_id=128001, torch_dtype="bfloat16",
+        tie_word_embeddings=False, attention_bias=False, mlp_bias=False),
+    "llama-3-70b": dict(
+        architectures=["LlamaForCausalLM"], model_type="llama", vocab_size=128256, hidden_size=8192,
+        intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64, num_key_value_heads=8,
+        head_dim=128, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0,
+        hidden_act="silu", bos_token_id=128000, eos_token_id=128001, torch_dtype="bfloat16",
+        tie_word_embeddings=False, attention_bias=False, mlp_bias=False),
+    "llama-tiny": dict(
+        architectures=["LlamaForCausalLM"], model_type="llama", vocab_size=512, hidden_size=128,
+        intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+        head_dim=32, max_position_embeddings=1024, rms_norm_eps=1e-5, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32",
+        tie_word_embeddings=False),
+    # GPU-test sized llama: head_dim 128 so the sm_100a attention kernels apply
+    "llama-small": dict(
+        architectures=["LlamaForCausalLM"], model_type="llama", vocab_size=4096, hidden_size=1024,
+        intermediate_size=2816, num_hidden_layers=4, num_attention_heads=8, num_key_value_heads=2,
+        head_dim=128, max_position_embeddings=4096, rms_norm_eps=1e-5, rope_theta=500000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="bfloat16",
+        tie_word_embeddings=False),
+    "qwen2.5-7b": dict(
+        architectures=["Qwen2ForCausalLM"], model_type="qwen2", vocab_size=152064, hidden_size=3584,
+        intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4,
+        max_position_embeddings=32768, rms_norm_eps=1e-6, rope_theta=1000000.0, hidden_act="silu",
+        bos_token_id=151643, eos_token_id=151645, torch_dtype="bfloat16", tie_word_embeddings=False,
+        attention_bias=True),
+    "qwen3-8b": dict(
+        architectures=["Qwen3ForCausalLM"], model_type="qwen3", vocab_size=151936, hidden_size=4096,
+        intermediate_size=12288, num_hidden_layers=36, num_attention_heads=32, num_key_value_heads=8,
+        head_dim=128, max_position_embeddings=40960, rms_norm_eps=1e-6, rope_theta=1000000.0,
+        hidden_act="silu", bos_token_id=151643, eos_token_id=151645, torch_dtype="bfloat16",
+        tie_word_embeddings=False, attention_bias=False),
+    "mistral-7b": dict(
+        architectures=["MistralForCausalLM"], model_type="mistral", vocab_size=32000, hidden_size=4096,
+        intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8,
+        max_position_embeddings=32768, rms_norm_eps=1e-5, rope_theta=10000.0, hidden_act="silu",
+        sliding_window=4096, bos_token_id=1, eos_token_id=2, torch_dtype="bfloat16",
+        tie_word_embeddings=False),
+    "gemma-2b": dict(
+        architectures=["GemmaForCausalLM"], model_type="gemma", vocab_size=256000, hidden_size=2048,
+        intermediate_size=16384, num_hidden_layers=18, num_attention_heads=8, num_key_value_heads=1,
+        head_dim=256, max_position_embeddings=8192, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="gelu_pytorch_tanh", bos_token_id=2, eos_token_id=1, torch_dtype="bfloat16",
+        tie_word_embeddings=True),
+    "gpt2": dict(
+        architectures=["GPT2LMHeadModel"], model_type="gpt2", vocab_size=50257, n_embd=768, n_layer=12,
+        n_head=12, n_positions=1024, n_inner=None, activation_function="gelu_new",
+        layer_norm_epsilon=1e-5, bos_token_id=50256, eos_token_id=50256, torch_dtype="float32",
+        tie_word_embeddings=True),
+    "gpt2-tiny": dict(
+        architectures=["GPT2LMHeadModel"], model_type="gpt2", vocab_size=512, n_embd=64, n_layer=2,
+        n_head=4, n_positions=512, n_inner=None, activation_function="gelu_new",
+        layer_norm_epsilon=1e-5, bos_token_id=1, eos_token_id=2, torch_dtype="float32",
+        tie_word_embeddings=True),
+    "mixtral-8x7b": dict(
+        architectures=["MixtralForCausalLM"], model_type="mixtral", vocab_size=32000, hidden_size=4096,
+        intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8,
+        max_position_embeddings=32768, rms_norm_eps=1e-5, rope_theta=1000000.0, hidden_act="silu",
+        num_local_experts=8, num_experts_per_tok=2, bos_token_id=1, eos_token_id=2,
+        torch_dtype="bfloat16", tie_word_embeddings=False),
+    "mixtral-tiny": dict(
+        architectures=["MixtralForCausalLM"], model_type="mixtral", vocab_size=512, hidden_size=128,
+        intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+        head_dim=32, max_position_embeddings=1024, rms_norm_eps=1e-5, rope_theta=10000.0,
+        hidden_act="silu", num_local_experts=4, num_experts_per_tok=2, bos_token_id=1, eos_token_id=2,
+        torch_dtype="float32", tie_word_embeddings=False),
+    "mixtral-small": dict(
+        architectures=["MixtralForCausalLM"], model_type="mixtral", vocab_size=4096, hidden_size=1024,
+        intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=2,
+        head_dim=128, max_position_embeddings=4096, rms_norm_eps=1e-5, rope_theta=10000.0,
+        hidden_act="silu", num_local_experts=8, num_experts_per_tok=2, bos_token_id=1, eos_token_id=2,
+        torch_dtype="bfloat16", tie_word_embeddings=False),
+    "deepseek-v3": dict(
+        architectures=["DeepseekV3ForCausalLM"], model_type="deepseek_v3", vocab_size=129280,
+        hidden_size=7168, intermediate_size=18432, moe_intermediate_size=2048, num_hidden_layers=61,
+        num_attention_heads=128, num_key_value_heads=128, q_lora_rank=1536, kv_lora_rank=512,
+        qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, n_routed_experts=256,
+        n_shared_experts=1, num_experts_per_tok=8, n_group=8, topk_group=4, routed_scaling_factor=2.5,
+        first_k_dense_replace=3, moe_layer_freq=1, norm_topk_prob=True, scoring_func="sigmoid",
+        topk_method="noaux_tc", max_position_embeddings=163840, rms_norm_eps=1e-6, rope_theta=10000.0,
+        rope_scaling=dict(type="yarn", factor=40, original_max_position_embeddings=4096,
+                          beta_fast=32, beta_slow=1, mscale=1.0, mscale_all_dim=1.0),
+        hidden_act="silu", bos_token_id=0, eos_token_id=1, torch_dtype="bfloat16",
+        tie_word_embeddings=False,
+        quantization_config=dict(quant_method="fp8", fmt="e4m3", weight_block_size=[128, 128],
+                                 activation_scheme="dynamic")),
+    "deepseek-tiny": dict(
+        architectures=["DeepseekV3ForCausalLM"], model_type="deepseek_v3", vocab_size=512,
+        hidden_size=128, intermediate_size=256, moe_intermediate_size=64, num_hidden_layers=3,
+        num_attention_heads=4, num_key_value_heads=4, q_lora_rank=48, kv_lora_rank=32,
+        qk_nope_head_dim=32, qk_rope_head_dim=16, v_head_dim=32, n_routed_experts=8,
+        n_shared_experts=1, num_experts_per_tok=2, n_group=2, topk_group=1, routed_scaling_factor=2.5,
+        first_k_dense_replace=1, moe_layer_freq=1, norm_topk_prob=True, scoring_func="sigmoid",
+        topk_method="noaux_tc", max_position_embeddings=1024, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=0, eos_token_id=1, torch_dtype="float32",
+        tie_word_embeddings=False),
+    "deepseek-small": dict(
+        architectures=["DeepseekV3ForCausalLM"], model_type="deepseek_v3", vocab_size=4096,
+        hidden_size=1024, intermediate_size=2048, moe_intermediate_size=512, num_hidden_layers=3,
+        num_attention_heads=16, num_key_value_heads=16, q_lora_rank=384, kv_lora_rank=512,
+        qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, n_routed_experts=16,
+        n_shared_experts=1, num_experts_per_tok=4, n_group=4, topk_group=2, routed_scaling_factor=2.5,
+        first_k_dense_replace=1, moe_layer_freq=1, norm_topk_prob=True, scoring_func="sigmoid",
+        topk_method="noaux_tc", max_position_embeddings=4096, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=0, eos_token_id=1, torch_dtype="bfloat16",
+        tie_word_embeddings=False),
+}
+
+_ALIASES = {
+    "facebook/opt-125m": "opt-125m",
+    "meta-llama/meta-llama-3-8b": "llama-3-8b", "meta-llama/meta-llama-3-8b-instruct": "llama-3-8b",
+    "meta-llama/llama-3.1-8b": "llama-3-8b", "meta-llama/llama-3.1-8b-instruct": "llama-3-8b",
+    "meta-llama/meta-llama-3-70b": "llama-3-70b", "meta-llama/meta-llama-3-70b-instruct": "llama-3-70b",
+    "meta-llama/llama-3.1-70b": "llama-3-70b", "meta-llama/llama-3.1-70b-instruct": "llama-3-70b",
+    "mistralai/mixtral-8x7b-v0.1": "mixtral-8x7b", "mistralai/mixtral-8x7b-instruct-v0.1": "mixtral-8x7b",
+    "deepseek-ai/deepseek-v3": "deepseek-v3", "openai-community/gpt2": "gpt2",
+    "mistralai/mistral-7b-v0.1": "mistral-7b", "qwen/qwen2.5-7b": "qwen2.5-7b", "qwen/qwen3-8b": "qwen3-8b",
+    "google/gemma-2b": "gemma-2b",
+}
+
+
+def get_preset_hf_config(name: str) -> Optional[dict[str, Any]]:
+    key = name.lower()
+    key = _ALIASES.get(key, key)
+    cfg = PRESETS.get(key)
+    return dict(cfg) if cfg is not None else None
+
+
+@dataclass
+class ModelConfig:
+    model: str = "opt-tiny"
+    tokenizer: Optional[str] = None
+    tokenizer_mode: str = "auto"
+    trust_remote_code: bool = False
+    dtype: str = "auto"
+    seed: int = 0
+    revision: Optional[str] = None
+    max_model_len: int = 0  # 0 → derive from the architecture
+    quantization: Optional[str] = None  # None|fp8|fp8_block|nvfp4|awq|gptq|...
+    enforce_eager: bool = False
+    max_logprobs: int = 20
+    served_model_name: Optional[str] = None
+    hf_overrides: dict[str, Any] = field(default_factory=dict)
+    runner: str = "generate"  # generate|pooling
+    skip_tokenizer_init: bool = False
+    generation_config: str = "auto"
+    logits_processors: Optional[list[str]] = None
+    # resolved
+    hf_config: dict[str, Any] = field(default_factory=dict)
+
+    def __post_init__(self) -> None:
+        if not self.hf_config:
+            self.hf_config = self._load_hf_config()
+        self.hf_config.update(self.hf_overrides)
+        if self.tokenizer is None:
+            self.tokenizer = self.model
+        if self.served_model_name is None:
+            self.served_model_name = self.model
+        derived = self._derive_max_len()
+        if self.max_model_len <= 0:
+            self.max_model_len = derived
+        if self.quantization is None:
+            qc = self.hf_config.get("quantization_config")
+            if qc:
+                m = qc.get("quant_method")
+                if m == "fp8" and qc.get("weight_block_size"):
+                    self.quantization = "fp8_block"
+                else:
+                    self.quantization = m
+
+    # -- loading ----------------------------------------------------------
+    def _load_hf_config(self) -> dict[str, Any]:
+        path = os.path.join(self.model, "config.json") if os.path.isdir(self.model) else None
+        if path and os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
+        cfg = get_preset_hf_config(self.model)
+        if cfg is None:
+            raise ValueError(
+                f"model {self.model!r} is neither a local directory with config.json nor a built-in "
+                f"preset ({sorted(PRESETS)})")
+        return cfg
+
+    def _derive_max_len(self) -> int:
+        c = self.hf_config
+        for k in ("max_position_embeddings", "n_positions", "max_sequence_length", "seq_length"):
+            if c.get(k):
+                return int(c[k])
+        return 2048
+
+    # -- accessors --------------------------------------------------------
+    @property
+    def architecture(self) -> str:
+        return self.hf_config.get("architectures", ["LlamaForCausalLM"])[0]
+
+    @property
+    def torch_dtype(self) -> torch.dtype:
+        d = _DTYPES.get(self.dtype, None) if self.dtype in _DTYPES else None
+        if self.dtype != "auto" and d is None:
+            raise ValueError(f"unknown dtype {self.dtype}")
+        if d is not None:
+            return d
+        hd = _DTYPES.get(str(self.hf_config.get("torch_dtype", "bfloat16")), torch.bfloat16)
+        if hd == torch.float16:
+            return torch.float16
+        return hd or torch.bfloat16
+
+    @property
+    def vocab_size(self) -> int:
+        return int(self.hf_config["vocab_size"])
+
+    @property
+    def hidden_size(self) -> int:
+        return int(self.hf_config.get("hidden_size", self.hf_config.get("n_embd", 0)))
+
+    @property
+    def num_layers(self) -> int:
+        return int(self.hf_config.get("num_hidden_layers", self.hf_config.get("n_layer", 0)))
+
+    @property
+    def num_attention_heads(self) -> int:
+        return int(self.hf_config.get("num_attention_heads", self.hf_config.get("n_head", 0)))
+
+    @property
+    def num_kv_heads(self) -> int:
+        if self.is_mla:
+            return 1
+        return int(self.hf_config.get("num_key_value_heads") or self.num_attention_heads)
+
+    @property
+    def head_dim(self) -> int:
+        if self.is_mla:
+            return int(self.hf_config["kv_lora_rank"]) + int(self.hf_config["qk_rope_head_dim"])
+        hd = self.hf_config.get("head_dim")
+        return int(hd) if hd else self.hidden_size // self.num_attention_heads
+
+    @property
+    def is_mla(self) -> bool:
+        return self.hf_config.get("kv_lora_rank") is not None
+
+    @property
+    def is_moe(self) -> bool:
+        return any(self.hf_config.get(k) for k in ("num_local_experts", "n_routed_experts", "num_experts"))
+
+    @property
+    def sliding_window(self) -> Optional[int]:
+        return self.hf_config.get("sliding_window")
+
+    @property
+    def eos_token_id(self) -> Optional[int]:
+        e = self.hf_config.get("eos_token_id")
+        if isinstance(e, list):
+            return e[0]
+        return e
+
+    def get_num_kv_heads(self, tp: int) -> int:
+        return max(1, self.num_kv_heads // tp)
+
+    def get_num_attention_heads(self, tp: int) -> int:
+        return self.num_attention_heads // tp
+
+    def get_num_layers(self, pp_rank: int = 0, pp_size: int = 1) -> int:
+        from vllm_b200.parallel.utils import get_pp_indices
+        s, e = get_pp_indices(self.num_layers, pp_rank, pp_size)
+        return e - s
+
+    def kv_bytes_per_token_per_layer(self, tp: int, kv_dtype_size: int) -> int:
+        if self.is_mla:
+            return self.head_dim * kv_dtype_size
+        return 2 * self.get_num_kv_heads(tp) * self.head_dim * kv_dtype_size
+
+    def verify_with_parallel_config(self, pc) -> None:
+        tp = pc.tensor_parallel_size
+        if self.num_attention_heads % tp != 0:
+            raise ValueError(
+                f"num_attention_heads ({self.num_attention_heads}) must be divisible by TP size ({tp})")
+        if pc.pipeline_parallel_size > self.num_layers:
+            raise ValueError("pipeline_parallel_size exceeds the number of layers")
+
+    def compute_hash(self) -> str:
+        import hashlib
+        return hashlib.sha256(json.dumps(
+            [self.model, self.dtype, self.quantization, self.hf_config], sort_keys=True, default=str
+        ).encode()).hexdigest()[:16]

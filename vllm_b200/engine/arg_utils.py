@@ -1,0 +1,190 @@
+"""EngineArgs: one flat dataclass mirrored as CLI flags and ``LLM(...)`` kwargs.
+
+Behavioural reference: vllm/engine/arg_utils.py (``EngineArgs`` →
+``create_engine_config``, argparse generated from field types; usage-context
+defaults :2586-2640).
+"""
+from __future__ import annotations
+
+import argparse
+import dataclasses
+import json
+from dataclasses import dataclass, field
+from typing import Any, Optional, Union, get_args, get_origin
+
+from vllm_b200.config import (CacheConfig, CompilationConfig, DeviceConfig, FaultToleranceConfig,
+                              KVEventsConfig, KVTransferConfig, LoadConfig, LoRAConfig, ModelConfig,
+                              ObservabilityConfig, OffloadConfig, ParallelConfig, ProfilerConfig,
+                              SchedulerConfig, SpeculativeConfig, StructuredOutputsConfig, VllmConfig)
+
+
+@dataclass
+class EngineArgs:
+    model: str = "opt-tiny"
+    tokenizer: Optional[str] = None
+    tokenizer_mode: str = "auto"
+    skip_tokenizer_init: bool = False
+    trust_remote_code: bool = False
+    dtype: str = "auto"
+    seed: int = 0
+    max_model_len: Optional[int] = None
+    quantization: Optional[str] = None
+    enforce_eager: bool = False
+    max_logprobs: int = 20
+    served_model_name: Optional[str] = None
+    hf_overrides: Optional[dict[str, Any]] = None
+    runner: str = "generate"
+    load_format: str = "auto"
+    device: str = "auto"
+    # cache
+    block_size: int = 32
+    gpu_memory_utilization: float = 0.92
+    swap_space: float = 4.0
+    kv_cache_dtype: str = "auto"
+    num_gpu_blocks_override: Optional[int] = None
+    enable_prefix_caching: bool = True
+    prefix_caching_hash_algo: str = "sha256"
+    kv_cache_memory_bytes: Optional[int] = None
+    cpu_offload_gb: float = 0.0
+    # parallel
+    tensor_parallel_size: int = 1
+    pipeline_parallel_size: int = 1
+    data_parallel_size: int = 1
+    data_parallel_rank: Optional[int] = None
+    data_parallel_size_local: Optional[int] = None
+    data_parallel_address: Optional[str] = None
+    data_parallel_rpc_port: Optional[int] = None
+    data_parallel_external_lb: bool = False
+    data_parallel_hybrid_lb: bool = False
+    enable_expert_parallel: bool = False
+    all2all_backend: str = "nvswitch_fused"
+    enable_eplb: bool = False
+    enable_dbo: bool = False
+    decode_context_parallel_size: int = 1
+    prefill_context_parallel_size: int = 1
+    dcp_comm_backend: str = "ag_rs"
+    disable_custom_all_reduce: bool = False
+    distributed_executor_backend: Optional[str] = None
+    enable_elastic_ep: bool = False
+    # scheduler
+    max_num_batched_tokens: Optional[int] = None
+    max_num_seqs: Optional[int] = None
+    enable_chunked_prefill: bool = True
+    long_prefill_token_threshold: int = 0
+    scheduling_policy: str = "fcfs"
+    async_scheduling: bool = False
+    scheduler_cls: Optional[str] = None
+    # features
+    enable_lora: bool = False
+    max_lora_rank: int = 16
+    max_loras: int = 1
+    speculative_config: Optional[dict[str, Any]] = None
+    structured_outputs_backend: str = "auto"
+    reasoning_parser: str = ""
+    kv_transfer_config: Optional[dict[str, Any]] = None
+    kv_events_config: Optional[dict[str, Any]] = None
+    kv_offload_backend: Optional[str] = None
+    kv_offload_bytes: int = 0
+    # compilation / graphs
+    cudagraph_mode: str = "FULL_DECODE_ONLY"
+    cudagraph_capture_sizes: Optional[list[int]] = None
+    max_cudagraph_capture_size: int = 512
+    # observability
+    disable_log_stats: bool = False
+    otlp_traces_endpoint: Optional[str] = None
+    profiler: Optional[str] = None
+    torch_profiler_dir: Optional[str] = None
+    enable_fault_tolerance: bool = False
+
+    def create_engine_config(self) -> VllmConfig:
+        mc = ModelConfig(
+            model=self.model, tokenizer=self.tokenizer, tokenizer_mode=self.tokenizer_mode,
+            trust_remote_code=self.trust_remote_code, dtype=self.dtype, seed=self.seed,
+            max_model_len=self.max_model_len or 0, quantization=self.quantization,
+            enforce_eager=self.enforce_eager, max_logprobs=self.max_logprobs,
+            served_model_name=self.served_model_name, hf_overrides=self.hf_overrides or {},
+            runner=self.runner, skip_tokenizer_init=self.skip_tokenizer_init)
+        cc = CacheConfig(
+            block_size=self.block_size, gpu_memory_utilization=self.gpu_memory_utilization,
+            swap_space_gb=self.swap_space, cache_dtype=self.kv_cache_dtype,
+            num_gpu_blocks_override=self.num_gpu_blocks_override,
+            enable_prefix_caching=self.enable_prefix_caching,
+            prefix_caching_hash_algo=self.prefix_caching_hash_algo,
+            kv_cache_memory_bytes=self.kv_cache_memory_bytes, cpu_offload_gb=self.cpu_offload_gb)
+        pc = ParallelConfig(
+            tensor_parallel_size=self.tensor_parallel_size, pipeline_parallel_size=self.pipeline_parallel_size,
+            data_parallel_size=self.data_parallel_size, data_parallel_rank=self.data_parallel_rank or 0,
+            data_parallel_size_local=self.data_parallel_size_local,
+            data_parallel_master_ip=self.data_parallel_address or "127.0.0.1",
+            data_parallel_master_port=self.data_parallel_rpc_port or 29550,
+            data_parallel_external_lb=self.data_parallel_external_lb,
+            data_parallel_hybrid_lb=self.data_parallel_hybrid_lb,
+            enable_expert_parallel=self.enable_expert_parallel, all2all_backend=self.all2all_backend,
+            enable_eplb=self.enable_eplb, enable_dbo=self.enable_dbo,
+            decode_context_parallel_size=self.decode_context_parallel_size,
+            prefill_context_parallel_size=self.prefill_context_parallel_size,
+            dcp_comm_backend=self.dcp_comm_backend, disable_custom_all_reduce=self.disable_custom_all_reduce,
+            distributed_executor_backend=self.distributed_executor_backend,
+            enable_elastic_ep=self.enable_elastic_ep)
+        # usage defaults sized for 180 GB HBM3e (reference picks 16384/8192 on big-HBM parts)
+        mnbt = self.max_num_batched_tokens or 16384
+        mns = self.max_num_seqs or 1024
+        mml = mc.max_model_len
+        if not self.enable_chunked_prefill:
+            mnbt = max(mnbt, mml)
+        sc = SchedulerConfig(
+            max_num_batched_tokens=mnbt, max_num_seqs=mns, max_model_len=mml,
+            enable_chunked_prefill=self.enable_chunked_prefill,
+            long_prefill_token_threshold=self.long_prefill_token_threshold, policy=self.scheduling_policy,
+            async_scheduling=self.async_scheduling, scheduler_cls=self.scheduler_cls)
+        spec = SpeculativeConfig(**self.speculative_config) if self.speculative_config else None
+        kvt = KVTransferConfig(**self.kv_transfer_config) if self.kv_transfer_config else None
+        kve = KVEventsConfig(**self.kv_events_config) if self.kv_events_config else None
+        return VllmConfig(
+            model_config=mc, cache_config=cc, parallel_config=pc, scheduler_config=sc,
+            device_config=DeviceConfig(self.device), load_config=LoadConfig(load_format=self.load_format),
+            lora_config=LoRAConfig(self.max_lora_rank, self.max_loras) if self.enable_lora else None,
+            speculative_config=spec,
+            structured_outputs_config=StructuredOutputsConfig(self.structured_outputs_backend,
+                                                              reasoning_parser=self.reasoning_parser),
+            observability_config=ObservabilityConfig(otlp_traces_endpoint=self.otlp_traces_endpoint),
+            compilation_config=CompilationConfig(self.cudagraph_mode, self.cudagraph_capture_sizes,
+                                                 self.max_cudagraph_capture_size),
+            kv_transfer_config=kvt, kv_events_config=kve,
+            profiler_config=ProfilerConfig(self.profiler, self.torch_profiler_dir),
+            fault_tolerance_config=FaultToleranceConfig(self.enable_fault_tolerance),
+            offload_config=OffloadConfig(self.kv_offload_backend, self.kv_offload_bytes))
+
+    # ------------------------------------------------------------------ CLI
+    @staticmethod
+    def add_cli_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
+        for f in dataclasses.fields(EngineArgs):
+            flag = "--" + f.name.replace("_", "-")
+            typ = f.type if not isinstance(f.type, str) else eval(f.type, globals(), {"Optional": Optional, "Any": Any, "Union": Union})
+            origin = get_origin(typ)
+            inner = typ
+            if origin is Union:
+                inner = next(a for a in get_args(typ) if a is not type(None))
+                origin = get_origin(inner)
+            default = f.default if f.default is not dataclasses.MISSING else None
+            if inner is bool:
+                parser.add_argument(flag, action=argparse.BooleanOptionalAction, default=default)
+            elif origin in (dict,) or inner is dict:
+                parser.add_argument(flag, type=json.loads, default=default)
+            elif origin in (list,):
+                parser.add_argument(flag, type=lambda s: [int(x) for x in s.split(",")], default=default)
+            else:
+                parser.add_argument(flag, type=inner, default=default)
+        # reference-compatible aliases
+        parser.add_argument("-tp", dest="tensor_parallel_size", type=int, default=argparse.SUPPRESS)
+        parser.add_argument("-pp", dest="pipeline_parallel_size", type=int, default=argparse.SUPPRESS)
+        parser.add_argument("-dp", dest="data_parallel_size", type=int, default=argparse.SUPPRESS)
+        return parser
+
+    @classmethod
+    def from_cli_args(cls, args: argparse.Namespace) -> "EngineArgs":
+        names = {f.name for f in dataclasses.fields(cls)}
+        return cls(**{k: v for k, v in vars(args).items() if k in names})
+
+
+AsyncEngineArgs = EngineArgs

@@ -1,0 +1,295 @@
+"""EngineCore: scheduler + executor loop; optionally in its own process behind ZMQ.
+
+Behavioural reference: vllm/v1/engine/core.py (``EngineCore`` :105,
+``_initialize_kv_caches`` :254, ``step`` :597, ``step_with_batch_queue`` :638,
+``EngineCoreProc`` :1021 with handshake :1143-1283, busy loop :1405, IO threads
+:1688/:1791), DP variant :2000 (waves + dummy batches).
+"""
+from __future__ import annotations
+
+import os
+import queue
+import signal
+import threading
+import time
+from collections import deque
+from concurrent.futures import Future
+from typing import Any, Callable, Optional
+
+import msgspec
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.core.kv_cache_manager import get_kv_cache_config
+from vllm_b200.core.request import (EngineCoreOutputs, EngineCoreRequest, Request, RequestStatus)
+from vllm_b200.core.scheduler import Scheduler
+from vllm_b200.executor import Executor
+from vllm_b200.logger import init_logger
+
+logger = init_logger(__name__)
+
+# wire request types
+REQ_ADD, REQ_ABORT, REQ_UTILITY, REQ_START_DP_WAVE, REQ_SHUTDOWN = b"A", b"B", b"U", b"W", b"S"
+ENGINE_CORE_DEAD = b"ENGINE_CORE_DEAD"
+
+
+class EngineCore:
+    def __init__(self, vllm_config: VllmConfig, executor_class: Optional[type[Executor]] = None,
+                 log_stats: bool = False) -> None:
+        self.vllm_config = vllm_config
+        self.log_stats = log_stats
+        executor_class = executor_class or Executor.get_class(vllm_config)
+        self.model_executor = executor_class(vllm_config)
+        kv_cfg = self._initialize_kv_caches()
+        from vllm_b200.structured_output import StructuredOutputManager
+        self.structured_output_manager = StructuredOutputManager(vllm_config)
+        connector = None
+        if vllm_config.kv_transfer_config is not None and vllm_config.kv_transfer_config.kv_connector:
+            from vllm_b200.kv_transfer import create_connector
+            connector = create_connector(vllm_config, role="scheduler")
+        sched_cls = Scheduler
+        if vllm_config.scheduler_config.scheduler_cls:
+            from vllm_b200.utils import resolve_obj_by_qualname
+            sched_cls = resolve_obj_by_qualname(vllm_config.scheduler_config.scheduler_cls)
+        self.scheduler: Scheduler = sched_cls(
+            vllm_config, kv_cfg, structured_output_manager=self.structured_output_manager,
+            kv_connector=connector, include_finished_set=vllm_config.parallel_config.data_parallel_size > 1,
+            log_stats=log_stats)
+        self.block_hasher = self.scheduler.get_block_hasher()
+        n_batches = self.model_executor.max_concurrent_batches
+        self.batch_queue: Optional[deque] = deque(maxlen=n_batches) if n_batches > 1 else None
+        self.batch_queue_size = n_batches
+        self.step_fn: Callable = self.step if self.batch_queue is None else self.step_with_batch_queue
+        self._aborts_since_step: list[str] = []
+
+    def _initialize_kv_caches(self):
+        t0 = time.perf_counter()
+        ex = self.model_executor
+        specs = ex.get_kv_cache_specs()
+        avail = ex.determine_available_memory()
+        mm = min(avail)
+        cc = self.vllm_config.cache_config
+        cfg, new_len = get_kv_cache_config(
+            specs[0], mm, self.vllm_config.scheduler_config.max_model_len, cc.num_gpu_blocks_override,
+            auto_fit_max_model_len=False)
+        # every worker must use the same number of blocks
+        cc.num_gpu_blocks = cfg.num_blocks
+        ex.initialize_from_config(cfg)
+        logger.info("KV cache: %d blocks x %d tokens (%.2f GiB available), init %.2fs", cfg.num_blocks,
+                    cc.block_size, mm / 2**30, time.perf_counter() - t0)
+        return cfg
+
+    # ----------------------------------------------------------------- API
+    def add_request(self, req: EngineCoreRequest) -> None:
+        so_req = None
+        sp = req.sampling_params
+        if sp is not None and sp.structured_outputs is not None:
+            so_req = self.structured_output_manager.make_request(req.request_id, sp.structured_outputs)
+        r = Request.from_engine_core_request(req, self.block_hasher, so_req)
+        if len(r.prompt_token_ids) >= self.vllm_config.scheduler_config.max_model_len:
+            raise ValueError(f"prompt of {len(r.prompt_token_ids)} tokens exceeds max_model_len")
+        self.scheduler.add_request(r)
+
+    def abort_requests(self, request_ids: list[str]) -> None:
+        self.scheduler.finish_requests(request_ids, RequestStatus.FINISHED_ABORTED)
+
+    def step(self) -> tuple[dict[int, EngineCoreOutputs], bool]:
+        if not self.scheduler.has_requests():
+            return {}, False
+        so = self.scheduler.schedule()
+        so.grammar_bitmask = self.scheduler.get_grammar_bitmask(so)
+        mo = self.model_executor.execute_model(so)
+        out = self.scheduler.update_from_output(so, mo)
+        return out, so.total_num_scheduled_tokens > 0
+
+    def step_with_batch_queue(self) -> tuple[Optional[dict[int, EngineCoreOutputs]], bool]:
+        """Keep up to ``batch_queue_size`` steps in flight (PP stages / async scheduling)."""
+        bq = self.batch_queue
+        assert bq is not None
+        scheduled = False
+        if len(bq) < self.batch_queue_size and self.scheduler.has_requests():
+            so = self.scheduler.schedule()
+            if so.total_num_scheduled_tokens > 0 or so.finished_req_ids:
+                so.grammar_bitmask = self.scheduler.get_grammar_bitmask(so)
+                fut = self.model_executor.execute_model(so, non_block=True)
+                bq.appendleft((fut, so))
+                scheduled = so.total_num_scheduled_tokens > 0
+                if scheduled and len(bq) < self.batch_queue_size and not bq[-1][0].done():
+                    return None, True  # try to fill the pipeline before blocking
+        if not bq:
+            return None, False
+        fut, so = bq.pop()
+        mo = fut.result()
+        return self.scheduler.update_from_output(so, mo), scheduled
+
+    # -------------------------------------------------------------- utility
+    def profile(self, is_start: bool = True) -> None:
+        self.model_executor.profile(is_start)
+
+    def reset_prefix_cache(self) -> bool:
+        return self.scheduler.reset_prefix_cache()
+
+    def sleep(self, level: int = 1) -> None:
+        self.model_executor.sleep(level)
+
+    def wake_up(self, tags=None) -> None:
+        self.model_executor.wake_up(tags)
+
+    def is_sleeping(self) -> bool:
+        return all(self.model_executor.collective_rpc("is_sleeping"))
+
+    def save_sharded_state(self, path: str) -> None:
+        self.model_executor.save_sharded_state(path)
+
+    def collective_rpc(self, method, args=(), kwargs=None):
+        return self.model_executor.collective_rpc(method, args, kwargs)
+
+    def get_request_counts(self) -> tuple[int, int]:
+        return self.scheduler.get_request_counts()
+
+    def echo(self, x: Any) -> Any:  # used by IPC tests, cf. test_engine_core_client.py in the reference
+        return x
+
+    def shutdown(self) -> None:
+        if getattr(self, "model_executor", None) is not None:
+            self.model_executor.shutdown()
+        if getattr(self, "scheduler", None) is not None:
+            self.scheduler.shutdown()
+
+
+class EngineCoreProc(EngineCore):
+    """EngineCore in a child process. Sockets: a DEALER for inputs (connects to the
+    client's ROUTER) and a PUSH for outputs. Decode/encode runs on IO threads so the
+    busy loop only touches in-process queues."""
+
+    def __init__(self, vllm_config: VllmConfig, input_addr: str, output_addr: str, engine_index: int = 0,
+                 log_stats: bool = False, executor_class=None) -> None:
+        import zmq
+        self.engine_index = engine_index
+        self.input_queue: "queue.Queue[tuple[bytes, Any]]" = queue.Queue()
+        self.output_queue: "queue.Queue[Any]" = queue.Queue()
+        self._zctx = zmq.Context(io_threads=2)
+        identity = engine_index.to_bytes(2, "little")
+        # handshake first so a slow model load does not look like a dead engine
+        self._in_sock = self._zctx.socket(zmq.DEALER)
+        self._in_sock.setsockopt(zmq.IDENTITY, identity)
+        self._in_sock.connect(input_addr)
+        self._in_sock.send(b"HELLO")
+        self._out_sock = self._zctx.socket(zmq.PUSH)
+        self._out_sock.connect(output_addr)
+        super().__init__(vllm_config, executor_class, log_stats)
+        self._in_sock.send(msgspec.msgpack.encode(
+            {"status": "READY", "num_gpu_blocks": vllm_config.cache_config.num_gpu_blocks}))
+        self._stop = False
+        self._threads = [threading.Thread(target=self._input_loop, daemon=True),
+                         threading.Thread(target=self._output_loop, daemon=True)]
+        for t in self._threads:
+            t.start()
+
+    # ---- IO threads
+    def _input_loop(self) -> None:
+        from vllm_b200.engine.serial import decode_request
+        while not self._stop:
+            try:
+                frames = self._in_sock.recv_multipart()
+            except Exception:
+                break
+            kind = frames[0]
+            if kind == REQ_ADD:
+                self.input_queue.put((kind, decode_request(frames[1])))
+            else:
+                self.input_queue.put((kind, msgspec.msgpack.decode(frames[1]) if len(frames) > 1 else None))
+
+    def _output_loop(self) -> None:
+        from vllm_b200.engine.serial import encode_outputs
+        while True:
+            item = self.output_queue.get()
+            if item is None:
+                break
+            if isinstance(item, bytes):
+                self._out_sock.send(item)
+                continue
+            self._out_sock.send(encode_outputs(item))
+
+    # ---- busy loop
+    def run_busy_loop(self) -> None:
+        idle_sleep = 0.0
+        while True:
+            # drain inputs; block when idle
+            block = not self.scheduler.has_requests() and not (self.batch_queue and len(self.batch_queue))
+            while True:
+                try:
+                    kind, payload = self.input_queue.get(block=block, timeout=None if block else 0)
+                except queue.Empty:
+                    break
+                block = False
+                if kind == REQ_SHUTDOWN:
+                    return
+                self._handle(kind, payload)
+            outs, _ = self.step_fn()
+            for ci, o in (outs or {}).items():
+                o.engine_index = self.engine_index
+                self.output_queue.put((ci, o))
+            del idle_sleep
+
+    def _handle(self, kind: bytes, payload: Any) -> None:
+        if kind == REQ_ADD:
+            try:
+                self.add_request(payload)
+            except Exception as e:  # bad request must not kill the engine
+                logger.warning("rejecting request %s: %s", payload.request_id, e)
+                from vllm_b200.core.request import EngineCoreOutput, FinishReason
+                self.output_queue.put((payload.client_index, EngineCoreOutputs(
+                    engine_index=self.engine_index,
+                    outputs=[EngineCoreOutput(request_id=payload.request_id, new_token_ids=[],
+                                              finish_reason=int(FinishReason.ABORT), stop_reason=str(e))])))
+        elif kind == REQ_ABORT:
+            self.abort_requests(payload)
+        elif kind == REQ_UTILITY:
+            client_index, call_id, method, args = payload
+            try:
+                result = getattr(self, method)(*args)
+                uo = (call_id, None, result)
+            except Exception as e:
+                logger.exception("utility %s failed", method)
+                uo = (call_id, f"{type(e).__name__}: {e}", None)
+            self.output_queue.put((client_index, EngineCoreOutputs(engine_index=self.engine_index,
+                                                                   utility_output=uo)))
+
+    def shutdown(self) -> None:
+        self._stop = True
+        self.output_queue.put(None)
+        super().shutdown()
+        try:
+            self._in_sock.close(linger=0)
+            self._out_sock.close(linger=200)
+            self._zctx.term()
+        except Exception:
+            pass
+
+    @staticmethod
+    def run_engine_core(vllm_config: VllmConfig, input_addr: str, output_addr: str, engine_index: int = 0,
+                        log_stats: bool = False, dp_rank: int = 0, parent_pid: Optional[int] = None) -> None:
+        """Process entry point."""
+        from vllm_b200.logger import set_process_prefix
+        set_process_prefix(f"(EngineCore_{engine_index}) ")
+        signal.signal(signal.SIGTERM, lambda *a: (_ for _ in ()).throw(SystemExit()))
+        core = None
+        try:
+            if vllm_config.parallel_config.data_parallel_size > 1:
+                from vllm_b200.engine.dp import DPEngineCoreProc
+                vllm_config.parallel_config.data_parallel_rank = dp_rank
+                core = DPEngineCoreProc(vllm_config, input_addr, output_addr, engine_index, log_stats)
+            else:
+                core = EngineCoreProc(vllm_config, input_addr, output_addr, engine_index, log_stats)
+            core.run_busy_loop()
+        except SystemExit:
+            pass
+        except Exception:
+            logger.exception("EngineCore failed")
+            if core is not None:
+                core.output_queue.put(ENGINE_CORE_DEAD)
+                time.sleep(0.2)
+            raise
+        finally:
+            if core is not None:
+                core.shutdown()

@@ -1,0 +1,27 @@
+"""Pooling heads for embedding / classification models (reference: vllm/model_executor/layers/pooler.py)."""
+from __future__ import annotations
+
+import torch
+
+
+def pool_hidden(hidden: torch.Tensor, params, model=None) -> torch.Tensor:
+    """hidden: [n_tokens, H] of ONE request."""
+    kind = params.pooling_type.upper()
+    h = hidden.float()
+    if kind == "LAST":
+        out = h[-1]
+    elif kind == "CLS":
+        out = h[0]
+    elif kind == "MEAN":
+        out = h.mean(dim=0)
+    elif kind == "ALL":
+        out = h
+    else:
+        raise ValueError(f"unknown pooling type {kind}")
+    if params.task == "classify" and model is not None and hasattr(model, "score"):
+        out = model.score(out.to(hidden.dtype)).float().softmax(-1)
+    if params.dimensions:
+        out = out[..., :params.dimensions]
+    if params.normalize and params.task in ("embed", "token_embed"):
+        out = torch.nn.functional.normalize(out, p=2, dim=-1)
+    return out

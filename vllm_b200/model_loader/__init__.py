@@ -1,0 +1,112 @@
+"""Model construction + weight loading.
+
+Reference: vllm/model_executor/model_loader/ (default safetensors/pt loader,
+``dummy`` loader = random uniform ±1e-3 with a per-parameter seed
+(weight_utils.py:1289-1349), sharded-state loader).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import time
+import zlib
+from typing import Iterable, Iterator, Optional
+
+import torch
+import torch.nn as nn
+
+from vllm_b200.config import VllmConfig, set_current_vllm_config
+from vllm_b200.logger import init_logger
+from vllm_b200.models.registry import resolve_model_cls
+
+logger = init_logger(__name__)
+
+
+def initialize_dummy_weights(model: nn.Module, seed: int = 1234, low: float = -1e-3, high: float = 1e-3) -> None:
+    for name, p in model.state_dict().items():
+        if not torch.is_floating_point(p):
+            continue
+        if name.endswith("cos_sin_cache"):
+            continue
+        g = torch.Generator(device=p.device)
+        g.manual_seed(seed + (zlib.crc32(name.encode()) & 0xFFFF))
+        if "norm" in name and name.endswith("weight") and p.dim() == 1:
+            # keep norms near identity so activations stay well-scaled through many layers
+            base = 0.0 if p.abs().max() == 0 else 1.0
+            p.copy_(base + torch.empty(p.shape, dtype=torch.float32, device=p.device).uniform_(-0.05, 0.05, generator=g))
+            continue
+        if "scale" in name:
+            p.fill_(1.0)
+            continue
+        if p.element_size() < 2:  # fp8: sample in fp16 then cast
+            tmp = torch.empty(p.shape, dtype=torch.float16, device=p.device).uniform_(-1.0, 1.0, generator=g)
+            p.copy_(tmp.to(p.dtype))
+        else:
+            p.uniform_(low, high, generator=g)
+
+
+def _iter_safetensors(path: str) -> Iterator[tuple[str, torch.Tensor]]:
+    from safetensors import safe_open
+    files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+    idx = os.path.join(path, "model.safetensors.index.json")
+    if os.path.exists(idx):
+        with open(idx) as f:
+            files = sorted({os.path.join(path, v) for v in json.load(f)["weight_map"].values()})
+    for fn in files:
+        with safe_open(fn, framework="pt", device="cpu") as f:
+            for k in f.keys():
+                yield k, f.get_tensor(k)
+
+
+def _iter_pt(path: str) -> Iterator[tuple[str, torch.Tensor]]:
+    for fn in sorted(glob.glob(os.path.join(path, "*.bin")) + glob.glob(os.path.join(path, "*.pt"))):
+        sd = torch.load(fn, map_location="cpu", weights_only=True)
+        yield from sd.items()
+        del sd
+
+
+def iter_weights(path: str, load_format: str = "auto") -> Iterator[tuple[str, torch.Tensor]]:
+    has_st = bool(glob.glob(os.path.join(path, "*.safetensors")))
+    if load_format == "safetensors" or (load_format == "auto" and has_st):
+        return _iter_safetensors(path)
+    return _iter_pt(path)
+
+
+def get_model(vllm_config: VllmConfig, device: torch.device,
+              weights: Optional[Iterable[tuple[str, torch.Tensor]]] = None) -> nn.Module:
+    mc, lc = vllm_config.model_config, vllm_config.load_config
+    cls = resolve_model_cls(mc.architecture)
+    t0 = time.perf_counter()
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(mc.torch_dtype)
+    try:
+        with set_current_vllm_config(vllm_config), torch.device(device):
+            model = cls(vllm_config)
+    finally:
+        torch.set_default_dtype(old)
+    fmt = lc.load_format
+    with torch.no_grad():
+        if weights is not None:
+            model.load_weights(weights)
+        elif fmt == "dummy" or (fmt == "auto" and not os.path.isdir(mc.model)):
+            initialize_dummy_weights(model, lc.dummy_seed)
+        elif fmt == "sharded_state":
+            from vllm_b200.model_loader.sharded_state import load_sharded_state
+            load_sharded_state(model, mc.model)
+        else:
+            loaded = model.load_weights(iter_weights(mc.model, fmt))
+            missing = {n for n, _ in model.named_parameters()} - set(loaded)
+            missing = {m for m in missing if "lm_head" not in m}
+            if missing:
+                logger.warning("%d parameters were not found in the checkpoint, e.g. %s", len(missing),
+                               sorted(missing)[:4])
+        for m in model.modules():
+            f = getattr(m, "process_weights_after_loading", None)
+            if f is not None and m is not model:
+                f()
+    model.eval()
+    n_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
+    logger.info("loaded %s (%s, %.2f GiB) in %.1fs", mc.architecture, fmt, n_bytes / 2**30,
+                time.perf_counter() - t0)
+    return model

@@ -1,0 +1,45 @@
+"""Architecture registry (reference: vllm/model_executor/models/registry.py).
+
+Maps HF ``architectures[0]`` to ``module:Class`` lazily so importing the package
+does not import every model file.
+"""
+from __future__ import annotations
+
+import importlib
+from typing import Type
+
+import torch.nn as nn
+
+_MODELS: dict[str, tuple[str, str]] = {
+    "LlamaForCausalLM": ("llama", "LlamaForCausalLM"),
+    "LLaMAForCausalLM": ("llama", "LlamaForCausalLM"),
+    "MistralForCausalLM": ("llama", "MistralForCausalLM"),
+    "Qwen2ForCausalLM": ("llama", "Qwen2ForCausalLM"),
+    "Qwen3ForCausalLM": ("llama", "Qwen3ForCausalLM"),
+    "GemmaForCausalLM": ("llama", "GemmaForCausalLM"),
+    "OPTForCausalLM": ("opt", "OPTForCausalLM"),
+    "GPT2LMHeadModel": ("opt", "GPT2LMHeadModel"),
+    "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
+    "Qwen2MoeForCausalLM": ("mixtral", "Qwen2MoeForCausalLM"),
+    "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
+    "DeepseekV2ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
+    "DeepseekV3ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
+}
+
+
+def register_model(arch: str, module: str, cls: str) -> None:
+    """Plugin hook: ``module`` is a fully qualified module path or a name under vllm_b200.models."""
+    _MODELS[arch] = (module, cls)
+
+
+def supported_archs() -> list[str]:
+    return sorted(_MODELS)
+
+
+def resolve_model_cls(arch: str) -> Type[nn.Module]:
+    if arch not in _MODELS:
+        raise ValueError(f"architecture {arch!r} is not supported; supported: {supported_archs()}")
+    mod, cls = _MODELS[arch]
+    if "." not in mod:
+        mod = f"vllm_b200.models.{mod}"
+    return getattr(importlib.import_module(mod), cls)

@@ -1,0 +1,155 @@
+"""Op dispatch: CUDA tensors → our sm_100a kernels (``ops/cuda.py`` → ``_C.so``),
+CPU tensors → the PyTorch reference (``ops/ref.py``).
+
+There is deliberately no multi-backend registry (the reference has
+``CustomOp`` + IR providers: model_executor/custom_op.py:103-210, vllm/ir/op.py);
+this framework targets exactly one device.  A CUDA tensor with the extension
+missing raises — it never silently falls back to eager PyTorch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from vllm_b200 import envs
+from vllm_b200.ops import ref
+
+_cuda_mod = None
+
+
+def cuda_ops():
+    global _cuda_mod
+    if _cuda_mod is None:
+        from vllm_b200.ops import cuda as _m
+        _cuda_mod = _m
+    return _cuda_mod
+
+
+def _use_cuda(x: torch.Tensor) -> bool:
+    return x.is_cuda and not envs.VLLM_B200_FORCE_REF_OPS
+
+
+def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, gemma: bool = False) -> torch.Tensor:
+    if _use_cuda(x):
+        return cuda_ops().rms_norm(x, weight, eps, gemma)
+    return ref.rms_norm(x, weight, eps, gemma)
+
+
+def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float,
+                       gemma: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """Returns (normed, new_residual). The CUDA path updates ``residual`` in place and
+    writes the normed result into ``x``'s storage."""
+    if _use_cuda(x):
+        return cuda_ops().fused_add_rms_norm(x, residual, weight, eps, gemma)
+    return ref.fused_add_rms_norm(x, residual, weight, eps, gemma)
+
+
+def layer_norm(x, weight, bias, eps):
+    if _use_cuda(x):
+        return cuda_ops().layer_norm(x, weight, bias, eps)
+    return ref.layer_norm(x, weight, bias, eps)
+
+
+def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
+    if _use_cuda(x):
+        return cuda_ops().act_and_mul(x, "silu")
+    return ref.silu_and_mul(x)
+
+
+def gelu_and_mul(x: torch.Tensor, approximate: str = "none") -> torch.Tensor:
+    if _use_cuda(x):
+        return cuda_ops().act_and_mul(x, "gelu_tanh" if approximate == "tanh" else "gelu")
+    return ref.gelu_and_mul(x, approximate)
+
+
+def activation(x: torch.Tensor, name: str) -> torch.Tensor:
+    if _use_cuda(x):
+        return cuda_ops().activation(x, name)
+    return ref.ACT_FNS[name](x)
+
+
+def rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox=True):
+    """In place on CUDA; returns (q, k)."""
+    if _use_cuda(q):
+        return cuda_ops().rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
+    return ref.rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
+
+
+def reshape_and_cache(key, value, kv_cache, slot_mapping) -> None:
+    if _use_cuda(key):
+        return cuda_ops().reshape_and_cache(key, value, kv_cache, slot_mapping)
+    return ref.reshape_and_cache(key, value, kv_cache, slot_mapping)
+
+
+def rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache, slot_mapping):
+    """Fused RoPE(q,k) + paged KV write. q/k: [T, H*D] views; returns (q, k) rotated."""
+    if _use_cuda(q):
+        return cuda_ops().rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache,
+                                         slot_mapping)
+    q, k = ref.rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
+    Hkv = kv_cache.shape[2]
+    ref.reshape_and_cache(k.reshape(k.shape[0], Hkv, head_dim), v.reshape(v.shape[0], Hkv, head_dim),
+                          kv_cache, slot_mapping)
+    return q, k
+
+
+def concat_and_cache_mla(kv_c, k_pe, kv_cache, slot_mapping) -> None:
+    if _use_cuda(kv_c):
+        return cuda_ops().concat_and_cache_mla(kv_c, k_pe, kv_cache, slot_mapping)
+    return ref.concat_and_cache_mla(kv_c, k_pe, kv_cache, slot_mapping)
+
+
+def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap=0.0, causal=True,
+                    out: Optional[torch.Tensor] = None):
+    """``md``: AttentionMetadata (see vllm_b200.forward_context)."""
+    if _use_cuda(q):
+        return cuda_ops().paged_attention(q, kv_cache, md, scale, sliding_window, logits_soft_cap, causal, out)
+    return ref.paged_attention(q, kv_cache, md.block_table, md.seq_lens_cpu, md.query_start_loc_cpu, scale,
+                               causal=causal, sliding_window=sliding_window, logits_soft_cap=logits_soft_cap)
+
+
+def mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank):
+    if _use_cuda(q_pe):
+        return cuda_ops().mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank)
+    return ref.mla_decode_attention(q_nope_abs, q_pe, kv_cache, md.block_table, md.seq_lens_cpu,
+                                    md.query_start_loc_cpu, scale, kv_lora_rank)
+
+
+def merge_attn_states(o1, lse1, o2, lse2):
+    if _use_cuda(o1):
+        return cuda_ops().merge_attn_states(o1, lse1, o2, lse2)
+    return ref.merge_attn_states(o1, lse1, o2, lse2)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ weight.T + bias. CUDA: tcgen05 GEMM for the shapes it covers, else cuBLASLt."""
+    if _use_cuda(x):
+        return cuda_ops().linear(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+def topk_softmax(gating, k, renormalize):
+    if _use_cuda(gating):
+        return cuda_ops().topk_softmax(gating, k, renormalize)
+    return ref.topk_softmax(gating, k, renormalize)
+
+
+def grouped_topk(scores, k, n_group, topk_group, renormalize, scoring="sigmoid", bias=None,
+                 routed_scaling_factor=1.0):
+    if _use_cuda(scores):
+        return cuda_ops().grouped_topk(scores, k, n_group, topk_group, renormalize, scoring, bias,
+                                       routed_scaling_factor)
+    return ref.grouped_topk(scores, k, n_group, topk_group, renormalize, scoring, bias, routed_scaling_factor)
+
+
+def fused_moe(x, w13, w2, topk_w, topk_ids, act="silu", expert_map=None):
+    if _use_cuda(x):
+        return cuda_ops().fused_moe(x, w13, w2, topk_w, topk_ids, act, expert_map)
+    return ref.fused_moe(x, w13, w2, topk_w, topk_ids, act, expert_map)
+
+
+def block_fp8_linear(x, wq, w_scale, block=128, bias=None):
+    if _use_cuda(x):
+        return cuda_ops().block_fp8_linear(x, wq, w_scale, block, bias)
+    return ref.block_fp8_linear(x, wq, w_scale, block, bias)

@@ -1,0 +1,380 @@
+"""Plain-PyTorch reference implementations of every op.
+
+They are (a) the CPU execution path (BASELINE config 1: OPT-125m greedy decode
+with no GPU) and (b) the fp32 oracles the CUDA kernels are tested against.
+Semantics follow the reference's ``forward_native`` methods (e.g.
+vllm/model_executor/layers/layernorm.py:96-116, activation.py,
+rotary_embedding/base.py) — re-derived, not copied.
+
+KV-cache layout (ours, chosen so one (page, head) K or V tile is a single
+contiguous 1-D bulk-copy): ``[num_blocks, 2, num_kv_heads, block_size, head_dim]``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------- norms
+def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, gemma: bool = False) -> torch.Tensor:
+    xf = x.float()
+    var = xf.pow(2).mean(-1, keepdim=True)
+    w = weight.float()
+    if gemma:
+        w = w + 1.0
+    return (xf * torch.rsqrt(var + eps) * w).to(x.dtype)
+
+
+def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float,
+                       gemma: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """residual_out = x + residual (rounded to dtype); out = rms_norm(residual_out)."""
+    r = (x.float() + residual.float()).to(x.dtype)
+    return rms_norm(r, weight, eps, gemma), r
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    return F.layer_norm(x.float(), (x.shape[-1],), weight.float(), None if bias is None else bias.float(),
+                        eps).to(x.dtype)
+
+
+# ----------------------------------------------------------- activations
+def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
+    d = x.shape[-1] // 2
+    return (F.silu(x[..., :d].float()) * x[..., d:].float()).to(x.dtype)
+
+
+def gelu_and_mul(x: torch.Tensor, approximate: str = "none") -> torch.Tensor:
+    d = x.shape[-1] // 2
+    return (F.gelu(x[..., :d].float(), approximate=approximate) * x[..., d:].float()).to(x.dtype)
+
+
+def gelu_new(x: torch.Tensor) -> torch.Tensor:
+    xf = x.float()
+    return (0.5 * xf * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (xf + 0.044715 * xf.pow(3))))).to(x.dtype)
+
+
+def gelu_fast(x: torch.Tensor) -> torch.Tensor:
+    xf = x.float()
+    return (0.5 * xf * (1.0 + torch.tanh(xf * 0.7978845608 * (1.0 + 0.044715 * xf * xf)))).to(x.dtype)
+
+
+def quick_gelu(x: torch.Tensor) -> torch.Tensor:
+    xf = x.float()
+    return (xf * torch.sigmoid(1.702 * xf)).to(x.dtype)
+
+
+ACT_FNS = {
+    "relu": F.relu, "gelu": F.gelu, "gelu_new": gelu_new, "gelu_fast": gelu_fast,
+    "gelu_pytorch_tanh": lambda x: F.gelu(x, approximate="tanh"), "quick_gelu": quick_gelu,
+    "silu": F.silu, "relu2": lambda x: F.relu(x).square(),
+}
+
+
+# ----------------------------------------------------------------- RoPE
+def rotary_embedding(positions: torch.Tensor, q: torch.Tensor, k: Optional[torch.Tensor],
+                     cos_sin_cache: torch.Tensor, head_dim: int, is_neox: bool = True,
+                     rot_dim: Optional[int] = None) -> tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """q: [T, Hq*D], k: [T, Hk*D]; cos_sin_cache: [max_pos, rot_dim] = cat(cos, sin) (fp32)."""
+    rot = rot_dim or cos_sin_cache.shape[-1]
+    cs = cos_sin_cache[positions.long()].float()  # [T, rot]
+    cos, sin = cs[:, :rot // 2], cs[:, rot // 2:]
+
+    def apply(x: torch.Tensor) -> torch.Tensor:
+        T = x.shape[0]
+        xv = x.view(T, -1, head_dim)
+        xr, xp = xv[..., :rot].float(), xv[..., rot:]
+        c, s = cos[:, None, :], sin[:, None, :]
+        if is_neox:
+            x1, x2 = xr[..., :rot // 2], xr[..., rot // 2:]
+            o = torch.cat((x1 * c - x2 * s, x2 * c + x1 * s), dim=-1)
+        else:
+            x1, x2 = xr[..., 0::2], xr[..., 1::2]
+            o = torch.stack((x1 * c - x2 * s, x2 * c + x1 * s), dim=-1).flatten(-2)
+        return torch.cat((o.to(x.dtype), xp), dim=-1).reshape(x.shape)
+
+    return apply(q), (apply(k) if k is not None else None)
+
+
+# -------------------------------------------------------------- KV cache
+def reshape_and_cache(key: torch.Tensor, value: torch.Tensor, kv_cache: torch.Tensor,
+                      slot_mapping: torch.Tensor) -> None:
+    """key/value: [T, Hkv, D]; kv_cache: [nb, 2, Hkv, bs, D]; slot = block*bs + off (<0 = skip)."""
+    bs = kv_cache.shape[3]
+    valid = slot_mapping >= 0
+    slots = slot_mapping[valid].long()
+    blk, off = slots // bs, slots % bs
+    kv_cache[blk, 0, :, off, :] = key[valid].to(kv_cache.dtype)
+    kv_cache[blk, 1, :, off, :] = value[valid].to(kv_cache.dtype)
+
+
+def concat_and_cache_mla(kv_c: torch.Tensor, k_pe: torch.Tensor, kv_cache: torch.Tensor,
+                         slot_mapping: torch.Tensor) -> None:
+    """kv_c: [T, R], k_pe: [T, P]; kv_cache: [nb, bs, R+P]."""
+    bs = kv_cache.shape[1]
+    valid = slot_mapping >= 0
+    slots = slot_mapping[valid].long()
+    kv_cache[slots // bs, slots % bs] = torch.cat((kv_c[valid], k_pe[valid]), -1).to(kv_cache.dtype)
+
+
+def gather_kv(kv_cache: torch.Tensor, block_table_row: torch.Tensor, seq_len: int
+              ) -> tuple[torch.Tensor, torch.Tensor]:
+    """Contiguous K, V [Hkv, seq_len, D] of one sequence."""
+    bs = kv_cache.shape[3]
+    nb = (seq_len + bs - 1) // bs
+    blocks = kv_cache[block_table_row[:nb].long()]  # [nb, 2, H, bs, D]
+    k = blocks[:, 0].permute(1, 0, 2, 3).reshape(kv_cache.shape[2], nb * bs, -1)[:, :seq_len]
+    v = blocks[:, 1].permute(1, 0, 2, 3).reshape(kv_cache.shape[2], nb * bs, -1)[:, :seq_len]
+    return k, v
+
+
+# ------------------------------------------------------------- attention
+def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.Tensor,
+                    seq_lens: torch.Tensor, query_start_loc: torch.Tensor, scale: float,
+                    causal: bool = True, sliding_window: Optional[int] = None,
+                    logits_soft_cap: float = 0.0, return_lse: bool = False,
+                    kv_scale: float = 1.0, sinks: Optional[torch.Tensor] = None):
+    """Unified varlen paged attention.
+
+    q: [T, Hq, D] (all requests' new tokens concatenated); request i owns rows
+    ``query_start_loc[i]:query_start_loc[i+1]`` whose positions are the *last*
+    q_len positions of its ``seq_lens[i]`` tokens.  KV for all positions
+    (including the new tokens) must already be in the cache.
+    """
+    T, Hq, D = q.shape
+    Hkv = kv_cache.shape[2]
+    G = Hq // Hkv
+    out = torch.empty_like(q)
+    lse = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
+    qsl = query_start_loc.tolist()
+    sls = seq_lens.tolist()
+    for i in range(len(sls)):
+        s, e = qsl[i], qsl[i + 1]
+        ql, sl = e - s, sls[i]
+        if ql == 0:
+            continue
+        k, v = gather_kv(kv_cache, block_table[i], sl)
+        k = k.float() * kv_scale
+        v = v.float() * kv_scale
+        qi = q[s:e].float().permute(1, 0, 2)  # [Hq, ql, D]
+        kk = k.repeat_interleave(G, dim=0)
+        vv = v.repeat_interleave(G, dim=0)
+        att = torch.einsum("hqd,hkd->hqk", qi, kk) * scale
+        if logits_soft_cap > 0:
+            att = logits_soft_cap * torch.tanh(att / logits_soft_cap)
+        qpos = torch.arange(sl - ql, sl, device=q.device)[:, None]
+        kpos = torch.arange(sl, device=q.device)[None, :]
+        mask = torch.ones(ql, sl, dtype=torch.bool, device=q.device)
+        if causal:
+            mask &= kpos <= qpos
+        if sliding_window:
+            mask &= kpos > qpos - sliding_window
+        att = att.masked_fill(~mask[None], float("-inf"))
+        l = torch.logsumexp(att, dim=-1)
+        p = torch.exp(att - l[..., None])
+        p = torch.nan_to_num(p)
+        out[s:e] = torch.einsum("hqk,hkd->hqd", p, vv).permute(1, 0, 2).to(q.dtype)
+        lse[s:e] = l.permute(1, 0)
+    return (out, lse) if return_lse else out
+
+
+def merge_attn_states(o1: torch.Tensor, lse1: torch.Tensor, o2: torch.Tensor, lse2: torch.Tensor
+                      ) -> tuple[torch.Tensor, torch.Tensor]:
+    """LSE-weighted merge of two partial attention results. o: [T,H,D], lse: [T,H]."""
+    m = torch.maximum(lse1, lse2)
+    m = torch.where(torch.isinf(m), torch.zeros_like(m), m)
+    w1, w2 = torch.exp(lse1 - m), torch.exp(lse2 - m)
+    den = (w1 + w2).clamp_min(1e-30)
+    o = (o1.float() * (w1 / den)[..., None] + o2.float() * (w2 / den)[..., None]).to(o1.dtype)
+    return o, m + torch.log(den)
+
+
+def mla_decode_attention(q_nope_abs: torch.Tensor, q_pe: torch.Tensor, kv_cache: torch.Tensor,
+                         block_table: torch.Tensor, seq_lens: torch.Tensor, query_start_loc: torch.Tensor,
+                         scale: float, kv_lora_rank: int) -> torch.Tensor:
+    """MLA as MQA over the latent cache. q_nope_abs: [T,H,R] (already multiplied by W_UK),
+    q_pe: [T,H,P]; kv_cache: [nb, bs, R+P]; returns latent-space output [T,H,R]."""
+    T, H, R = q_nope_abs.shape
+    bs = kv_cache.shape[1]
+    out = torch.empty(T, H, R, dtype=q_nope_abs.dtype, device=q_nope_abs.device)
+    qsl, sls = query_start_loc.tolist(), seq_lens.tolist()
+    for i in range(len(sls)):
+        s, e = qsl[i], qsl[i + 1]
+        ql, sl = e - s, sls[i]
+        if ql == 0:
+            continue
+        nb = (sl + bs - 1) // bs
+        lat = kv_cache[block_table[i, :nb].long()].reshape(nb * bs, -1)[:sl].float()
+        kc, kp = lat[:, :kv_lora_rank], lat[:, kv_lora_rank:]
+        att = (torch.einsum("qhr,kr->hqk", q_nope_abs[s:e].float(), kc)
+               + torch.einsum("qhp,kp->hqk", q_pe[s:e].float(), kp)) * scale
+        qpos = torch.arange(sl - ql, sl, device=att.device)[:, None]
+        kpos = torch.arange(sl, device=att.device)[None, :]
+        att = att.masked_fill(~(kpos <= qpos)[None], float("-inf"))
+        p = torch.softmax(att, dim=-1)
+        out[s:e] = torch.einsum("hqk,kr->qhr", p, kc).to(out.dtype)
+    return out
+
+
+# -------------------------------------------------------------- sampling
+def apply_penalties(logits: torch.Tensor, prompt_mask: torch.Tensor, output_counts: torch.Tensor,
+                    presence: torch.Tensor, frequency: torch.Tensor, repetition: torch.Tensor) -> torch.Tensor:
+    """logits [B,V] fp32; prompt_mask [B,V] bool; output_counts [B,V] int."""
+    seen = prompt_mask | (output_counts > 0)
+    rep = repetition[:, None].expand_as(logits)
+    logits = torch.where(seen & (logits > 0), logits / rep, logits)
+    logits = torch.where(seen & (logits <= 0), logits * rep, logits)
+    logits = logits - frequency[:, None] * output_counts.to(logits.dtype)
+    logits = logits - presence[:, None] * (output_counts > 0).to(logits.dtype)
+    return logits
+
+
+def apply_top_k_top_p_min_p(logits: torch.Tensor, top_k: Optional[torch.Tensor], top_p: Optional[torch.Tensor],
+                            min_p: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Mask filtered logits to -inf. top_k: int [B] (0 = off), top_p/min_p: float [B]."""
+    if top_k is not None or top_p is not None:
+        srt, idx = logits.sort(dim=-1, descending=False)
+        V = logits.shape[-1]
+        if top_k is not None:
+            k = torch.where(top_k <= 0, torch.full_like(top_k, V), top_k).clamp(max=V).long()
+            thresh = srt.gather(1, (V - k)[:, None])
+            srt = srt.masked_fill(srt < thresh, float("-inf"))
+        if top_p is not None:
+            probs = srt.softmax(dim=-1)
+            cum = probs.cumsum(dim=-1)
+            mask = cum <= (1.0 - top_p)[:, None]
+            mask[:, -1] = False
+            srt = srt.masked_fill(mask, float("-inf"))
+        logits = torch.empty_like(srt).scatter_(1, idx, srt)
+    if min_p is not None:
+        probs = logits.softmax(dim=-1)
+        thresh = probs.max(dim=-1, keepdim=True).values * min_p[:, None]
+        logits = logits.masked_fill(probs < thresh, float("-inf"))
+    return logits
+
+
+def gumbel_sample(logits: torch.Tensor, temperature: torch.Tensor, generators: Optional[dict] = None,
+                  noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """argmax(logits/T + Gumbel). temperature [B] (0 → greedy). ``noise``: optional uniform(0,1) [B,V]."""
+    greedy = temperature < 1e-5
+    t = torch.where(greedy, torch.ones_like(temperature), temperature)
+    scaled = logits / t[:, None]
+    if noise is None:
+        noise = torch.empty_like(scaled)
+        if generators:
+            noise.uniform_()
+            for i, g in generators.items():
+                noise[i].uniform_(generator=g)
+        else:
+            noise.uniform_()
+    g = -torch.log(-torch.log(noise.clamp(1e-10, 1.0 - 1e-7)))
+    sampled = (scaled + g).argmax(dim=-1)
+    return torch.where(greedy, logits.argmax(dim=-1), sampled)
+
+
+def compute_logprobs(logits: torch.Tensor, sampled: torch.Tensor, k: int
+                     ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Returns (ids [B,k+1], logprobs [B,k+1], rank [B]); column 0 is the sampled token."""
+    lp = logits.float().log_softmax(dim=-1)
+    s_lp = lp.gather(1, sampled[:, None].long())
+    rank = (lp > s_lp).sum(dim=-1) + 1
+    if k > 0:
+        tv, ti = lp.topk(k, dim=-1)
+        ids = torch.cat((sampled[:, None].long(), ti), dim=1)
+        vals = torch.cat((s_lp, tv), dim=1)
+    else:
+        ids, vals = sampled[:, None].long(), s_lp
+    return ids, vals, rank
+
+
+# ------------------------------------------------------------------- MoE
+def topk_softmax(gating: torch.Tensor, k: int, renormalize: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    p = gating.float().softmax(dim=-1)
+    w, ids = p.topk(k, dim=-1)
+    if renormalize:
+        w = w / w.sum(dim=-1, keepdim=True)
+    return w, ids.int()
+
+
+def grouped_topk(scores_in: torch.Tensor, k: int, n_group: int, topk_group: int, renormalize: bool,
+                 scoring: str = "sigmoid", bias: Optional[torch.Tensor] = None,
+                 routed_scaling_factor: float = 1.0) -> tuple[torch.Tensor, torch.Tensor]:
+    """DeepSeek group-limited routing."""
+    s = scores_in.float().sigmoid() if scoring == "sigmoid" else scores_in.float().softmax(-1)
+    T, E = s.shape
+    sel = s + bias.float()[None] if bias is not None else s
+    if n_group > 1:
+        g = sel.view(T, n_group, E // n_group)
+        gs = g.topk(2, dim=-1).values.sum(-1) if bias is not None else g.max(-1).values
+        gi = gs.topk(topk_group, dim=-1).indices
+        gm = torch.zeros_like(gs).scatter_(1, gi, 1.0)
+        mask = gm[:, :, None].expand(T, n_group, E // n_group).reshape(T, E)
+        sel = sel.masked_fill(mask == 0, float("-inf"))
+    ids = sel.topk(k, dim=-1).indices
+    w = s.gather(1, ids)
+    if renormalize:
+        w = w / (w.sum(-1, keepdim=True) + 1e-20)
+    return w * routed_scaling_factor, ids.int()
+
+
+def fused_moe(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_w: torch.Tensor,
+              topk_ids: torch.Tensor, act: str = "silu", expert_map: Optional[torch.Tensor] = None
+              ) -> torch.Tensor:
+    """x [T,H]; w13 [E,2I,H] (gate rows then up rows); w2 [E,H,I]. Returns [T,H]."""
+    T, H = x.shape
+    E = w13.shape[0]
+    out = torch.zeros(T, H, dtype=torch.float32, device=x.device)
+    ids = topk_ids.long()
+    if expert_map is not None:
+        ids = expert_map[ids].long()
+    for e in range(E):
+        tok, slot = (ids == e).nonzero(as_tuple=True)
+        if tok.numel() == 0:
+            continue
+        h = x[tok].float() @ w13[e].float().t()
+        I = h.shape[-1] // 2
+        a = F.silu(h[:, :I]) if act == "silu" else F.gelu(h[:, :I])
+        h = (a * h[:, I:]).to(x.dtype).float()
+        y = h @ w2[e].float().t()
+        out.index_add_(0, tok, y * topk_w[tok, slot].float()[:, None])
+    return out.to(x.dtype)
+
+
+# ---------------------------------------------------------- quantisation
+FP8_MAX = 448.0
+
+
+def per_token_group_quant_fp8(x: torch.Tensor, group: int = 128) -> tuple[torch.Tensor, torch.Tensor]:
+    T, K = x.shape
+    xg = x.float().view(T, K // group, group)
+    amax = xg.abs().amax(-1).clamp_min(1e-10)
+    scale = amax / FP8_MAX
+    q = (xg / scale[..., None]).clamp(-FP8_MAX, FP8_MAX).to(torch.float8_e4m3fn).view(T, K)
+    return q, scale
+
+
+def block_quant_weight_fp8(w: torch.Tensor, block: int = 128) -> tuple[torch.Tensor, torch.Tensor]:
+    N, K = w.shape
+    nb, kb = (N + block - 1) // block, (K + block - 1) // block
+    wp = torch.zeros(nb * block, kb * block, dtype=torch.float32, device=w.device)
+    wp[:N, :K] = w.float()
+    wb = wp.view(nb, block, kb, block)
+    amax = wb.abs().amax(dim=(1, 3)).clamp_min(1e-10)
+    scale = amax / FP8_MAX
+    q = (wb / scale[:, None, :, None]).clamp(-FP8_MAX, FP8_MAX).view(nb * block, kb * block)[:N, :K]
+    return q.to(torch.float8_e4m3fn).contiguous(), scale
+
+
+def block_fp8_linear(x: torch.Tensor, wq: torch.Tensor, w_scale: torch.Tensor, block: int = 128,
+                     bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Activation quantised per (token, 128-group), weight per 128x128 block; fp32 accumulate."""
+    xq, xs = per_token_group_quant_fp8(x, block)
+    N, K = wq.shape
+    xd = (xq.float().view(x.shape[0], K // block, block) * xs[..., None]).view(x.shape[0], K)
+    ws = w_scale.repeat_interleave(block, 0)[:N].repeat_interleave(block, 1)[:, :K]
+    y = xd @ (wq.float() * ws).t()
+    if bias is not None:
+        y = y + bias.float()
+    return y.to(x.dtype)

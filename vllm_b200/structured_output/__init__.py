@@ -1,0 +1,290 @@
+"""Structured (grammar-constrained) output.
+
+Behavioural reference: vllm/v1/structured_output/* — the grammar is compiled and
+advanced in the *scheduler* process, a per-request vocabulary bitmask is shipped
+with the SchedulerOutput (scheduler.py:1735) and applied to the logits in the
+worker (worker/gpu/structured_outputs.py).
+
+Back-ends: ``xgrammar`` (json schema / regex / EBNF / json_object) when it is
+importable and the tokenizer is HF-compatible; a built-in ``choice``/``regex``
+back-end that walks a character-level matcher over the tokenizer's vocabulary
+(works with the offline ByteTokenizer) otherwise.
+"""
+from __future__ import annotations
+
+import json
+import re
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Any, Optional
+
+import numpy as np
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.logger import init_logger
+from vllm_b200.sampling_params import StructuredOutputsParams
+
+logger = init_logger(__name__)
+
+
+class Grammar:
+    """Back-end interface."""
+
+    def fill_bitmask(self, bitmask: np.ndarray, row: int) -> None: raise NotImplementedError
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool: raise NotImplementedError
+    def validate_tokens(self, tokens: list[int]) -> list[int]: raise NotImplementedError
+    def rollback(self, n: int) -> None: raise NotImplementedError
+    def is_terminated(self) -> bool: raise NotImplementedError
+
+
+class ChoiceGrammar(Grammar):
+    """Finite set of allowed strings, matched over the token vocabulary by decoded text."""
+
+    def __init__(self, choices: list[str], tokenizer, vocab_size: int, eos: Optional[int]) -> None:
+        self.choices = choices
+        self.vocab_size = vocab_size
+        self.eos = eos
+        self.prefix = ""
+        self.history: list[str] = []
+        self._tok_text = _vocab_texts(tokenizer, vocab_size)
+
+    def _allowed(self) -> list[int]:
+        rem = [c[len(self.prefix):] for c in self.choices if c.startswith(self.prefix)]
+        out = []
+        if any(r == "" for r in rem) and self.eos is not None:
+            out.append(self.eos)
+        rem = [r for r in rem if r]
+        if rem:
+            for i, t in enumerate(self._tok_text):
+                if t and any(r.startswith(t) for r in rem):
+                    out.append(i)
+        return out
+
+    def fill_bitmask(self, bitmask: np.ndarray, row: int) -> None:
+        bitmask[row] = 0
+        for i in self._allowed():
+            bitmask[row, i >> 5] |= np.int32(np.uint32(1 << (i & 31)).view(np.int32)) if (i & 31) == 31 \
+                else np.int32(1 << (i & 31))
+
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool:
+        for t in tokens:
+            if t == self.eos:
+                continue
+            self.history.append(self.prefix)
+            self.prefix += self._tok_text[t]
+        return True
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        ok, p = [], self.prefix
+        for t in tokens:
+            s = self._tok_text[t] if t < len(self._tok_text) else ""
+            if not s or not any(c.startswith(p + s) for c in self.choices):
+                break
+            p += s
+            ok.append(t)
+        return ok
+
+    def rollback(self, n: int) -> None:
+        for _ in range(min(n, len(self.history))):
+            self.prefix = self.history.pop()
+
+    def is_terminated(self) -> bool:
+        return self.prefix in self.choices and not any(
+            c != self.prefix and c.startswith(self.prefix) for c in self.choices)
+
+
+class RegexGrammar(ChoiceGrammar):
+    """Regex constraint by partial matching: a token is allowed if prefix+token can still be
+    extended to a full match (checked with the ``regex`` module's partial matching)."""
+
+    def __init__(self, pattern: str, tokenizer, vocab_size: int, eos: Optional[int]) -> None:
+        import regex
+        self.rx = regex.compile(pattern)
+        self.vocab_size, self.eos = vocab_size, eos
+        self.prefix, self.history = "", []
+        self._tok_text = _vocab_texts(tokenizer, vocab_size)
+
+    def _allowed(self) -> list[int]:
+        out = []
+        if self.rx.fullmatch(self.prefix) and self.eos is not None:
+            out.append(self.eos)
+        for i, t in enumerate(self._tok_text):
+            if t and self.rx.fullmatch(self.prefix + t, partial=True):
+                out.append(i)
+        return out
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        ok, p = [], self.prefix
+        for t in tokens:
+            s = self._tok_text[t] if t < len(self._tok_text) else ""
+            if not s or not self.rx.fullmatch(p + s, partial=True):
+                break
+            p += s
+            ok.append(t)
+        return ok
+
+    def is_terminated(self) -> bool:
+        return bool(self.rx.fullmatch(self.prefix)) and not self._allowed()[1:]
+
+
+_VOCAB_CACHE: dict[int, list[str]] = {}
+
+
+def _vocab_texts(tokenizer, vocab_size: int) -> list[str]:
+    key = id(tokenizer)
+    if key not in _VOCAB_CACHE:
+        special = set(getattr(tokenizer, "all_special_ids", []) or [])
+        texts = []
+        for i in range(vocab_size):
+            if i in special:
+                texts.append("")
+                continue
+            try:
+                texts.append(tokenizer.decode([i]))
+            except Exception:
+                texts.append("")
+        _VOCAB_CACHE[key] = texts
+    return _VOCAB_CACHE[key]
+
+
+class XGrammarGrammar(Grammar):
+    def __init__(self, matcher, vocab_size: int) -> None:
+        self.m = matcher
+        self.vocab_size = vocab_size
+
+    def fill_bitmask(self, bitmask: np.ndarray, row: int) -> None:
+        import torch
+        t = torch.from_numpy(bitmask)
+        self.m.fill_next_token_bitmask(t, row)
+
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool:
+        for t in tokens:
+            if not self.m.accept_token(t):
+                logger.warning("grammar rejected token %d for %s", t, request_id)
+                return False
+        return True
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        ok = []
+        for t in tokens:
+            if self.m.accept_token(t):
+                ok.append(t)
+            else:
+                break
+        if ok:
+            self.m.rollback(len(ok))
+        return ok
+
+    def rollback(self, n: int) -> None:
+        self.m.rollback(n)
+
+    def is_terminated(self) -> bool:
+        return self.m.is_terminated()
+
+
+class StructuredOutputRequest:
+    def __init__(self, params: StructuredOutputsParams, fut: Future) -> None:
+        self.params = params
+        self._fut = fut
+        self.grammar: Optional[Grammar] = None
+
+    def is_ready(self) -> bool:
+        if self.grammar is not None:
+            return True
+        if self._fut.done():
+            self.grammar = self._fut.result()
+            return True
+        return False
+
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool:
+        return self.grammar.accept_tokens(request_id, tokens) if self.is_ready() else True
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        return self.grammar.validate_tokens(tokens) if self.is_ready() else tokens
+
+
+class StructuredOutputManager:
+    def __init__(self, vllm_config: VllmConfig) -> None:
+        self.vllm_config = vllm_config
+        self.vocab_size = vllm_config.model_config.vocab_size
+        self.backend = vllm_config.structured_outputs_config.backend
+        self._tokenizer = None
+        self._xgr_compiler = None
+        self._pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="grammar")
+        self._bitmask: Optional[np.ndarray] = None
+
+    @property
+    def tokenizer(self):
+        if self._tokenizer is None:
+            from vllm_b200.tokenizers import init_tokenizer_from_config
+            self._tokenizer = init_tokenizer_from_config(self.vllm_config.model_config)
+        return self._tokenizer
+
+    def make_request(self, request_id: str, params: StructuredOutputsParams) -> StructuredOutputRequest:
+        return StructuredOutputRequest(params, self._pool.submit(self._compile, params))
+
+    def _compile(self, p: StructuredOutputsParams) -> Grammar:
+        kind = p.kind()
+        tok = self.tokenizer
+        eos = self.vllm_config.model_config.eos_token_id
+        use_xgr = self.backend in ("auto", "xgrammar") and hasattr(tok, "backend_tokenizer")
+        if use_xgr:
+            try:
+                return self._compile_xgr(kind, p, tok)
+            except Exception as e:
+                if self.backend == "xgrammar" or p.disable_fallback:
+                    raise
+                logger.warning("xgrammar failed (%s); falling back to the built-in matcher", e)
+        if kind == "choice":
+            return ChoiceGrammar(list(p.choice), tok, self.vocab_size, eos)
+        if kind == "regex":
+            return RegexGrammar(p.regex, tok, self.vocab_size, eos)
+        if kind in ("json", "json_object"):
+            from vllm_b200.structured_output.json_regex import json_schema_to_regex
+            schema = p.json if kind == "json" else {"type": "object"}
+            if isinstance(schema, str):
+                schema = json.loads(schema)
+            return RegexGrammar(json_schema_to_regex(schema), tok, self.vocab_size, eos)
+        raise ValueError(f"structured output kind {kind!r} needs the xgrammar backend")
+
+    def _compile_xgr(self, kind: str, p: StructuredOutputsParams, tok) -> Grammar:
+        import xgrammar as xgr
+        if self._xgr_compiler is None:
+            info = xgr.TokenizerInfo.from_huggingface(tok, vocab_size=self.vocab_size)
+            self._xgr_compiler = xgr.GrammarCompiler(info, max_threads=2)
+        c = self._xgr_compiler
+        if kind == "json":
+            s = p.json if isinstance(p.json, str) else json.dumps(p.json)
+            g = c.compile_json_schema(s, any_whitespace=True)
+        elif kind == "json_object":
+            g = c.compile_json_schema('{"type": "object"}')
+        elif kind == "regex":
+            g = c.compile_regex(p.regex)
+        elif kind == "grammar":
+            g = c.compile_grammar(p.grammar)
+        elif kind == "choice":
+            alts = " | ".join(json.dumps(ch) for ch in p.choice)
+            g = c.compile_grammar(f"root ::= {alts}")
+        else:
+            raise ValueError(kind)
+        return XGrammarGrammar(xgr.GrammarMatcher(g, max_rollback_tokens=64), self.vocab_size)
+
+    def grammar_bitmask(self, requests: dict, structured_ids: list[str], spec_tokens: dict[str, list[int]]
+                        ) -> Optional[np.ndarray]:
+        if not structured_ids:
+            return None
+        W = (self.vocab_size + 31) // 32
+        n = len(structured_ids)
+        if self._bitmask is None or self._bitmask.shape[0] < n:
+            self._bitmask = np.full((max(n, 8), W), -1, dtype=np.int32)
+        bm = self._bitmask
+        for row, rid in enumerate(structured_ids):
+            req = requests.get(rid)
+            so = req.structured_output_request if req is not None else None
+            if so is None or not so.is_ready() or so.grammar.is_terminated():
+                bm[row] = -1
+                continue
+            so.grammar.fill_bitmask(bm, row)
+        return bm[:n].copy()
+
+    def shutdown(self) -> None:
+        self._pool.shutdown(wait=False)

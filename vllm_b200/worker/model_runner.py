@@ -1,0 +1,623 @@
+"""Model runner: persistent batch, input preparation, CUDA-graph decode, sampling.
+
+Behavioural reference: the reference's MRV2 runner
+(vllm/v1/worker/gpu/model_runner.py:1397 ``execute_model``, ``sample_tokens``
+:1682, ``capture_model`` :840) and V1 ``gpu_input_batch.py`` persistent batch.
+
+Design (ours):
+* request state lives in NumPy arrays indexed by a stable row; per-step inputs
+  (ids, positions, slot mapping, seq lens, block table) are produced with
+  vectorised NumPy into *pinned* staging buffers and copied with one async H2D
+  each into *static* device buffers — the same buffers CUDA graphs replay on;
+* decode-only steps replay a full-step CUDA graph per padded batch bucket
+  (forward + logits + fused sampling), everything else runs eagerly;
+* the sampled ids stay on the device in ``last_sampled`` so the next step's
+  input ids are gathered GPU-side (no D2H→H2D round trip on the critical path);
+  the D2H copy of sampled ids is issued on a side stream and only awaited when
+  the engine needs the python ints.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.core.kv_cache_manager import KVCacheConfig, KVCacheSpec
+from vllm_b200.core.sched_output import LogprobsTensors, ModelRunnerOutput, SchedulerOutput
+from vllm_b200.forward_context import AttentionMetadata, ForwardContext, set_forward_context
+from vllm_b200.layers.attention import attention_layers, clear_attention_layers
+from vllm_b200.logger import init_logger
+from vllm_b200.sample.sampler import RejectionSampler, Sampler, SamplingMetadata
+from vllm_b200.utils import cdiv
+
+logger = init_logger(__name__)
+
+
+@dataclass
+class ReqState:
+    req_id: str
+    row: int
+    sampling_params: Any
+    pooling_params: Any
+    generator: Optional[torch.Generator]
+    lora_request: Any = None
+    num_prompt_tokens: int = 0
+    output_token_ids: list[int] = field(default_factory=list)
+    mm_features: Optional[list] = None
+
+
+class ModelRunner:
+    def __init__(self, vllm_config: VllmConfig, device: torch.device) -> None:
+        self.vllm_config = vllm_config
+        self.mc = vllm_config.model_config
+        self.sc = vllm_config.scheduler_config
+        self.cc = vllm_config.cache_config
+        self.device = device
+        self.is_cuda = device.type == "cuda"
+        self.dtype = self.mc.torch_dtype
+        self.max_num_reqs = self.sc.max_num_seqs
+        self.max_num_tokens = self.sc.max_num_batched_tokens
+        self.max_model_len = self.sc.max_model_len
+        self.block_size = self.cc.block_size
+        self.max_blocks_per_req = cdiv(self.max_model_len, self.block_size) + 1
+        self.vocab_size = self.mc.vocab_size
+        self.model: Optional[torch.nn.Module] = None
+        self.sampler = Sampler()
+        self.rejection_sampler = RejectionSampler()
+        self.kv_caches: dict[str, torch.Tensor] = {}
+        self.layer_to_group: dict[str, int] = {}
+        self.num_kv_groups = 1
+        self.kv_cache_config: Optional[KVCacheConfig] = None
+        spec = vllm_config.speculative_config
+        self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
+        self.drafter = None
+        # ---- persistent batch (CPU)
+        R, L = self.max_num_reqs, self.max_model_len
+        self.req_ids: list[Optional[str]] = []
+        self.req_index: dict[str, int] = {}
+        self.states: dict[str, ReqState] = {}
+        self._parked: dict[str, ReqState] = {}
+        self.token_ids_cpu = np.zeros((R, L + self.num_spec_tokens + 1), dtype=np.int32)
+        self.num_tokens_cpu = np.zeros(R, dtype=np.int32)       # known tokens (prompt + sampled)
+        self.num_computed_cpu = np.zeros(R, dtype=np.int32)
+        self.block_tables_cpu: list[np.ndarray] = []
+        self.num_blocks_cpu: list[np.ndarray] = []
+        # ---- staging + device buffers
+        self._alloc_io_buffers()
+        self.graphs: dict[int, Any] = {}
+        self.graph_pool = None
+        self.use_cuda_graph = (self.is_cuda and not self.mc.enforce_eager
+                               and vllm_config.compilation_config.cudagraph_mode != "NONE")
+        self.capture_sizes: list[int] = []
+        self._step = 0
+        self._copy_stream = torch.cuda.Stream(device) if self.is_cuda else None
+        self.profile_forward_ms = 0.0
+
+    # ------------------------------------------------------------------ setup
+    def _pin(self, *shape, dtype):
+        t = torch.zeros(*shape, dtype=dtype)
+        if self.is_cuda:
+            t = t.pin_memory()
+        return t
+
+    def _alloc_io_buffers(self) -> None:
+        T, R = self.max_num_tokens, self.max_num_reqs
+        dev = self.device
+        self.input_ids_pin = self._pin(T, dtype=torch.int32)
+        self.positions_pin = self._pin(T, dtype=torch.int64)
+        self.slot_pin = self._pin(T, dtype=torch.int64)
+        self.qsl_pin = self._pin(R + 1, dtype=torch.int32)
+        self.seq_lens_pin = self._pin(R, dtype=torch.int32)
+        self.input_ids = torch.zeros(T, dtype=torch.int32, device=dev)
+        self.positions = torch.zeros(T, dtype=torch.int64, device=dev)
+        self.qsl = torch.zeros(R + 1, dtype=torch.int32, device=dev)
+        self.seq_lens = torch.zeros(R, dtype=torch.int32, device=dev)
+        self.slot_mappings: list[torch.Tensor] = []
+        self.block_tables: list[torch.Tensor] = []
+        self.block_tables_pin: list[torch.Tensor] = []
+
+    def load_model(self, weights=None) -> None:
+        from vllm_b200.model_loader import get_model
+        clear_attention_layers()
+        self.model = get_model(self.vllm_config, self.device, weights)
+        if self.vllm_config.speculative_config is not None:
+            from vllm_b200.spec_decode import make_drafter
+            self.drafter = make_drafter(self.vllm_config, self)
+
+    def get_kv_cache_specs(self) -> dict[str, KVCacheSpec]:
+        dsz = self._kv_dtype().itemsize
+        return {name: layer.get_kv_cache_spec(self.block_size, dsz) for name, layer in attention_layers().items()}
+
+    def _kv_dtype(self) -> torch.dtype:
+        cd = self.cc.cache_dtype
+        if cd == "auto":
+            return self.dtype
+        if cd.startswith("fp8"):
+            return torch.float8_e5m2 if cd.endswith("e5m2") else torch.float8_e4m3fn
+        return {"bfloat16": torch.bfloat16, "float16": torch.float16}[cd]
+
+    def initialize_kv_cache(self, cfg: KVCacheConfig) -> None:
+        from vllm_b200.core.kv_cache_manager import MLAAttentionSpec
+        self.kv_cache_config = cfg
+        self.num_kv_groups = max(len(cfg.kv_cache_groups), 1)
+        kvd = self._kv_dtype()
+        for gid, g in enumerate(cfg.kv_cache_groups):
+            s = g.spec
+            for name in g.layer_names:
+                self.layer_to_group[name] = gid
+                if isinstance(s, MLAAttentionSpec):
+                    shape = (cfg.num_blocks, s.block_size, s.head_size)
+                else:
+                    shape = (cfg.num_blocks, 2, s.num_kv_heads, s.block_size, s.head_size)
+                self.kv_caches[name] = torch.zeros(shape, dtype=kvd, device=self.device)
+        G, R, MB = self.num_kv_groups, self.max_num_reqs, self.max_blocks_per_req
+        self.block_tables_cpu = [np.zeros((R, MB), dtype=np.int32) for _ in range(G)]
+        self.num_blocks_cpu = [np.zeros(R, dtype=np.int32) for _ in range(G)]
+        self.block_tables = [torch.zeros(R, MB, dtype=torch.int32, device=self.device) for _ in range(G)]
+        self.block_tables_pin = [self._pin(R, MB, dtype=torch.int32) for _ in range(G)]
+        self.slot_mappings = [torch.zeros(self.max_num_tokens, dtype=torch.int64, device=self.device)
+                              for _ in range(G)]
+        self.slot_pins = [self._pin(self.max_num_tokens, dtype=torch.int64) for _ in range(G)]
+
+    # ------------------------------------------------------- batch maintenance
+    def _remove(self, req_id: str, park: bool = False) -> None:
+        row = self.req_index.pop(req_id, None)
+        st = self.states.pop(req_id, None)
+        if park and st is not None:
+            self._parked[req_id] = st
+        if row is None:
+            return
+        last = len(self.req_ids) - 1
+        if row != last:  # move the last row into the hole (keeps rows dense)
+            mv = self.req_ids[last]
+            self.req_ids[row] = mv
+            self.req_index[mv] = row
+            self.states[mv].row = row
+            n = self.num_tokens_cpu[last]
+            self.token_ids_cpu[row, :n] = self.token_ids_cpu[last, :n]
+            self.num_tokens_cpu[row] = n
+            self.num_computed_cpu[row] = self.num_computed_cpu[last]
+            for g in range(self.num_kv_groups):
+                nb = self.num_blocks_cpu[g][last]
+                self.block_tables_cpu[g][row, :nb] = self.block_tables_cpu[g][last, :nb]
+                self.num_blocks_cpu[g][row] = nb
+        self.req_ids.pop()
+
+    def _add_row(self, st: ReqState, token_ids, block_ids, num_computed: int) -> None:
+        row = len(self.req_ids)
+        self.req_ids.append(st.req_id)
+        self.req_index[st.req_id] = row
+        st.row = row
+        self.states[st.req_id] = st
+        n = len(token_ids)
+        self.token_ids_cpu[row, :n] = token_ids
+        self.num_tokens_cpu[row] = n
+        self.num_computed_cpu[row] = num_computed
+        for g in range(self.num_kv_groups):
+            ids = block_ids[g]
+            self.block_tables_cpu[g][row, :len(ids)] = ids
+            self.num_blocks_cpu[g][row] = len(ids)
+
+    def _add(self, nr) -> None:
+        sp = nr.sampling_params
+        gen = None
+        if sp is not None and sp.seed is not None:
+            gen = torch.Generator(device=self.device)
+            gen.manual_seed(sp.seed)
+        st = ReqState(nr.req_id, -1, sp, nr.pooling_params, gen, nr.lora_request, len(nr.prompt_token_ids),
+                      mm_features=nr.mm_features)
+        self._add_row(st, nr.prompt_token_ids, nr.block_ids, nr.num_computed_tokens)
+
+    def _update_states(self, so: SchedulerOutput) -> None:
+        for rid in so.finished_req_ids:
+            self._remove(rid)
+            self._parked.pop(rid, None)
+        for rid in so.preempted_req_ids:
+            self._remove(rid, park=True)
+        # requests in the batch that were not scheduled this step stay resident
+        for nr in so.scheduled_new_reqs:
+            if nr.req_id in self.req_index:
+                self._remove(nr.req_id)
+            self._add(nr)
+        c = so.scheduled_cached_reqs
+        for i, rid in enumerate(c.req_ids):
+            if c.resumed_from_preemption[i] or rid not in self.req_index:
+                # re-admit with its full token history (prompt + outputs so far)
+                st = self._parked.pop(rid, None) or self.states.get(rid)
+                assert st is not None, f"resumed request {rid} has no parked state"
+                self._remove(rid)
+                self._add_row(st, c.new_token_ids[i], c.new_block_ids[i], c.num_computed_tokens[i])
+                continue
+            row = self.req_index[rid]
+            self.num_computed_cpu[row] = c.num_computed_tokens[i]
+            toks = c.new_token_ids[i]
+            if toks:  # PP: tokens sampled on another rank
+                n0 = c.num_computed_tokens[i]
+                self.token_ids_cpu[row, n0:n0 + len(toks)] = toks
+                self.num_tokens_cpu[row] = max(self.num_tokens_cpu[row], n0 + len(toks))
+            nb = c.new_block_ids[i]
+            if nb is not None:
+                for g in range(self.num_kv_groups):
+                    ids = nb[g]
+                    if ids:
+                        s = self.num_blocks_cpu[g][row]
+                        self.block_tables_cpu[g][row, s:s + len(ids)] = ids
+                        self.num_blocks_cpu[g][row] = s + len(ids)
+
+    # ---------------------------------------------------------- input prep
+    def _prepare(self, so: SchedulerOutput):
+        B = len(self.req_ids)
+        n_sched = np.fromiter((so.num_scheduled_tokens.get(r, 0) for r in self.req_ids), dtype=np.int32, count=B)
+        active = np.nonzero(n_sched)[0]
+        rows = active.astype(np.int64)
+        ns = n_sched[active]
+        nb = len(rows)
+        T = int(ns.sum())
+        cu = np.zeros(nb + 1, dtype=np.int32)
+        np.cumsum(ns, out=cu[1:])
+        req_of_tok = np.repeat(np.arange(nb), ns)
+        offs = np.arange(T, dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), ns)
+        computed = self.num_computed_cpu[rows].astype(np.int64)
+        pos = computed[req_of_tok] + offs
+        row_of_tok = rows[req_of_tok]
+        # speculative tokens are appended after the known tokens of the row
+        for rid, drafts in so.scheduled_spec_decode_tokens.items():
+            r = self.req_index[rid]
+            n = self.num_tokens_cpu[r]
+            self.token_ids_cpu[r, n:n + len(drafts)] = drafts
+        ids = self.token_ids_cpu[row_of_tok, pos]
+        self.input_ids_pin[:T] = torch.from_numpy(ids)
+        self.positions_pin[:T] = torch.from_numpy(pos)
+        seq_lens = (computed + ns).astype(np.int32)
+        self.qsl_pin[:nb + 1] = torch.from_numpy(cu)
+        self.seq_lens_pin[:nb] = torch.from_numpy(seq_lens)
+        bs = self.block_size
+        for g in range(self.num_kv_groups):
+            bt = self.block_tables_cpu[g]
+            slots = bt[row_of_tok, pos // bs].astype(np.int64) * bs + pos % bs
+            self.slot_pins[g][:T] = torch.from_numpy(slots)
+        max_q = int(ns.max()) if nb else 0
+        max_s = int(seq_lens.max()) if nb else 0
+        return rows, ns, cu, T, max_q, max_s, seq_lens
+
+    def _h2d(self, rows, nb, T, pad_b, pad_t, max_s) -> None:
+        nbk = cdiv(max_s, self.block_size)
+        self.input_ids[:T].copy_(self.input_ids_pin[:T], non_blocking=True)
+        self.positions[:T].copy_(self.positions_pin[:T], non_blocking=True)
+        self.qsl[:nb + 1].copy_(self.qsl_pin[:nb + 1], non_blocking=True)
+        self.seq_lens[:nb].copy_(self.seq_lens_pin[:nb], non_blocking=True)
+        for g in range(self.num_kv_groups):
+            self.slot_mappings[g][:T].copy_(self.slot_pins[g][:T], non_blocking=True)
+            src = self.block_tables_cpu[g][rows, :nbk]
+            self.block_tables_pin[g][:nb, :nbk] = torch.from_numpy(src)
+            self.block_tables[g][:nb, :nbk].copy_(self.block_tables_pin[g][:nb, :nbk], non_blocking=True)
+        if pad_t > T:  # padded decode slots: write to the null block, attend over 1 token of block 0
+            self.input_ids[T:pad_t].zero_()
+            self.positions[T:pad_t].zero_()
+            for g in range(self.num_kv_groups):
+                self.slot_mappings[g][T:pad_t].fill_(-1)
+                self.block_tables[g][nb:pad_b, :1].zero_()
+            self.seq_lens[nb:pad_b].fill_(1)
+            self.qsl[nb + 1:pad_b + 1].copy_(
+                torch.arange(T + 1, T + 1 + pad_b - nb, dtype=torch.int32, device=self.device))
+
+    def _make_metadata(self, nb, T, max_q, max_s, decode_only, cpu_qsl=None, cpu_sl=None) -> dict[int, AttentionMetadata]:
+        nbk = max(cdiv(max_s, self.block_size), 1)
+        out = {}
+        for g in range(self.num_kv_groups):
+            out[g] = AttentionMetadata(
+                num_reqs=nb, num_actual_tokens=T, max_query_len=max_q, max_seq_len=max_s,
+                query_start_loc=self.qsl[:nb + 1], seq_lens=self.seq_lens[:nb],
+                block_table=self.block_tables[g][:nb] if self.is_cuda else self.block_tables[g][:nb, :nbk],
+                slot_mapping=self.slot_mappings[g][:T], query_start_loc_cpu=cpu_qsl, seq_lens_cpu=cpu_sl,
+                decode_only=decode_only)
+        return out
+
+    # ------------------------------------------------------------ forward
+    def _forward(self, T: int, md: dict[int, AttentionMetadata], intermediate=None):
+        ctx = ForwardContext(attn_metadata=md, kv_caches=self.kv_caches, layer_to_group=self.layer_to_group,
+                             num_tokens=T)
+        with set_forward_context(ctx):
+            return self.model(self.input_ids[:T], self.positions[:T], intermediate)
+
+    @torch.inference_mode()
+    def execute_model(self, so: SchedulerOutput, intermediate=None) -> ModelRunnerOutput:
+        t0 = time.perf_counter()
+        self._step += 1
+        self._update_states(so)
+        if so.total_num_scheduled_tokens == 0:
+            return ModelRunnerOutput()
+        rows, ns, cu, T, max_q, max_s, seq_lens = self._prepare(so)
+        nb = len(rows)
+        has_spec = bool(so.scheduled_spec_decode_tokens)
+        decode_only = max_q == 1 and not has_spec
+        pad_b = nb
+        graph = None
+        if decode_only and self.use_cuda_graph and self.graphs:
+            pad_b = self._bucket(nb)
+            graph = self.graphs.get(pad_b)
+            if graph is None:
+                pad_b = nb
+        pad_t = pad_b if graph is not None else T
+        self._h2d(rows, nb, T, pad_b, pad_t, max_s)
+        cpu_qsl = self.qsl_pin[:nb + 1] if not self.is_cuda else None
+        cpu_sl = self.seq_lens_pin[:nb] if not self.is_cuda else None
+        # which rows produce a token this step (prefill chunk finished / decode)
+        total_after = self.num_computed_cpu[rows] + ns
+        known = self.num_tokens_cpu[rows]
+        produces = total_after >= known  # spec rows: known excludes drafts
+        sampled_cpu: Optional[list[list[int]]] = None
+        lp_out = None
+        states = [self.states[self.req_ids[r]] for r in rows]
+        if graph is not None:
+            smd = self._sampling_metadata(states, rows, pad_b)
+            graph_ok = smd.all_greedy or (smd.top_k is None and smd.top_p is None and smd.min_p is None
+                                          and smd.no_penalties and smd.max_num_logprobs is None
+                                          and not smd.generators)
+            if graph_ok and not self._needs_logits_processors(smd) and self._graph_supports(graph, smd):
+                sampled = graph.replay(smd)[:nb]
+            else:
+                graph = None
+        if graph is None:
+            md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
+            hidden = self._forward(T, md, intermediate)
+            if isinstance(hidden, dict):  # non-last PP stage
+                return ModelRunnerOutput(kv_connector_output=hidden)
+            pool_states = [s for s in states if s.pooling_params is not None]
+            if pool_states:
+                return self._pool(hidden, states, rows, cu, produces, t0)
+            if has_spec:
+                return self._verify_spec(so, hidden, states, rows, ns, cu, t0)
+            last_idx = torch.from_numpy(cu[1:].astype(np.int64) - 1).to(self.device, non_blocking=True)
+            logits = self.model.compute_logits(hidden[last_idx])
+            smd = self._sampling_metadata(states, rows, nb)
+            bitmask = None
+            if so.grammar_bitmask is not None:
+                bitmask = self._gather_bitmask(so, states)
+            so_out = self.sampler(logits, smd, bitmask)
+            sampled = so_out.sampled_token_ids
+            if so_out.logprobs is not None:
+                keep = torch.from_numpy(np.nonzero(produces)[0]).to(self.device)
+                ids, vals, ranks = so_out.logprobs
+                lp_out = LogprobsTensors(ids[keep].cpu(), vals[keep].cpu(), ranks[keep].cpu())
+            plp = self._prompt_logprobs(hidden, states, rows, ns, cu) if any(
+                s.sampling_params is not None and s.sampling_params.prompt_logprobs is not None for s in states) else {}
+        else:
+            plp = {}
+        toks = sampled.tolist()  # D2H sync point
+        out_ids: list[list[int]] = []
+        req_ids = []
+        for j, r in enumerate(rows):
+            rid = self.req_ids[r]
+            req_ids.append(rid)
+            if produces[j]:
+                t = toks[j]
+                n = self.num_tokens_cpu[r]
+                self.token_ids_cpu[r, n] = t
+                self.num_tokens_cpu[r] = n + 1
+                states[j].output_token_ids.append(t)
+                out_ids.append([t])
+            else:
+                out_ids.append([])
+            self.num_computed_cpu[r] = total_after[j]
+        spec_ids = None
+        if self.drafter is not None:
+            spec_ids = self.drafter.propose(self, rows, [o for o in out_ids])
+        ms = (time.perf_counter() - t0) * 1e3
+        return ModelRunnerOutput(req_ids=req_ids, req_id_to_index={r: i for i, r in enumerate(req_ids)},
+                                 sampled_token_ids=out_ids, logprobs=lp_out, prompt_logprobs_dict=plp,
+                                 spec_token_ids=spec_ids, forward_ms=ms)
+
+    # ------------------------------------------------------------- helpers
+    @staticmethod
+    def _needs_logits_processors(smd: SamplingMetadata) -> bool:
+        return (smd.allowed_token_ids_mask is not None or bool(smd.min_tokens) or any(smd.logit_bias)
+                or bool(smd.bad_words_token_ids))
+
+    def _graph_supports(self, graph, smd: SamplingMetadata) -> bool:
+        return True
+
+    def _bucket(self, n: int) -> int:
+        for s in self.capture_sizes:
+            if s >= n:
+                return s
+        return -1
+
+    def _sampling_metadata(self, states: list[ReqState], rows, pad_b: int) -> SamplingMetadata:
+        B = len(states)
+        dev = self.device
+        temps = np.ones(pad_b, dtype=np.float32)
+        top_k = np.zeros(pad_b, dtype=np.int32)
+        top_p = np.ones(pad_b, dtype=np.float32)
+        min_p = np.zeros(pad_b, dtype=np.float32)
+        pres = np.zeros(pad_b, dtype=np.float32)
+        freq = np.zeros(pad_b, dtype=np.float32)
+        rep = np.ones(pad_b, dtype=np.float32)
+        seeds = np.zeros(pad_b, dtype=np.int64)
+        gens: dict[int, torch.Generator] = {}
+        logit_bias: list = [None] * B
+        bad: dict[int, list[list[int]]] = {}
+        min_toks: dict[int, tuple[int, set[int]]] = {}
+        max_lp: Optional[int] = None
+        allowed_rows = []
+        any_pen = False
+        for i, s in enumerate(states):
+            sp = s.sampling_params
+            if sp is None:
+                temps[i] = 0.0
+                continue
+            temps[i] = sp.temperature
+            top_k[i], top_p[i], min_p[i] = sp.top_k, sp.top_p, sp.min_p
+            pres[i], freq[i], rep[i] = sp.presence_penalty, sp.frequency_penalty, sp.repetition_penalty
+            any_pen |= sp.needs_penalties
+            if s.generator is not None:
+                gens[i] = s.generator
+            seeds[i] = (sp.seed if sp.seed is not None else hash(s.req_id)) & 0x7FFFFFFFFFFF
+            if sp.logit_bias:
+                logit_bias[i] = sp.logit_bias
+            if sp.bad_words_token_ids:
+                bad[i] = sp.bad_words_token_ids
+            if sp.min_tokens > 0 and len(s.output_token_ids) < sp.min_tokens:
+                min_toks[i] = (sp.min_tokens, set(sp.all_stop_token_ids))
+            if sp.logprobs is not None:
+                k = self.vocab_size if sp.logprobs == -1 else sp.logprobs
+                max_lp = k if max_lp is None else max(max_lp, k)
+            if sp.allowed_token_ids:
+                allowed_rows.append(i)
+        temps[B:] = 0.0
+        all_greedy = bool((temps < 1e-5).all())
+        all_random = bool((temps[:B] >= 1e-5).all())
+        t = torch.from_numpy(temps).to(dev, non_blocking=True)
+        md = SamplingMetadata(temperature=t, all_greedy=all_greedy, all_random=all_random, generators=gens,
+                              max_num_logprobs=max_lp, logit_bias=logit_bias if any(logit_bias) else [],
+                              bad_words_token_ids=bad, min_tokens=min_toks,
+                              output_token_ids=[s.output_token_ids for s in states], step=self._step)
+        if not all_greedy:
+            if (top_k > 0).any():
+                md.top_k = torch.from_numpy(top_k).to(dev)
+            if (top_p < 1.0).any():
+                md.top_p = torch.from_numpy(top_p).to(dev)
+            if (min_p > 0).any():
+                md.min_p = torch.from_numpy(min_p).to(dev)
+            md.seeds = torch.from_numpy(seeds).to(dev)
+        if any_pen:
+            md.no_penalties = False
+            md.presence, md.frequency = torch.from_numpy(pres[:B]).to(dev), torch.from_numpy(freq[:B]).to(dev)
+            md.repetition = torch.from_numpy(rep[:B]).to(dev)
+            V = self.vocab_size
+            pm = torch.zeros(B, V, dtype=torch.bool)
+            oc = torch.zeros(B, V, dtype=torch.int32)
+            for i, s in enumerate(states):
+                r = s.row
+                p = torch.from_numpy(self.token_ids_cpu[r, :s.num_prompt_tokens].astype(np.int64))
+                pm[i, p.clamp(max=V - 1)] = True
+                if s.output_token_ids:
+                    o = torch.tensor(s.output_token_ids, dtype=torch.int64).clamp(max=V - 1)
+                    oc[i].index_add_(0, o, torch.ones_like(o, dtype=torch.int32))
+            md.prompt_mask, md.output_counts = pm.to(dev), oc.to(dev)
+        if allowed_rows:
+            m = torch.zeros(B, self.vocab_size, dtype=torch.bool)
+            for i in allowed_rows:
+                m[i] = True
+                m[i, torch.tensor(states[i].sampling_params.allowed_token_ids)] = False
+            md.allowed_token_ids_mask = m.to(dev)
+        return md
+
+    def _gather_bitmask(self, so: SchedulerOutput, states: list[ReqState]) -> Optional[torch.Tensor]:
+        bm = so.grammar_bitmask
+        idx = {rid: i for i, rid in enumerate(so.structured_output_request_ids)}
+        W = bm.shape[1]
+        full = np.full((len(states), W), -1, dtype=np.int32)
+        for j, s in enumerate(states):
+            i = idx.get(s.req_id)
+            if i is not None:
+                full[j] = bm[i]
+        return torch.from_numpy(full).to(self.device)
+
+    def _prompt_logprobs(self, hidden, states, rows, ns, cu) -> dict[str, Optional[LogprobsTensors]]:
+        out: dict[str, Optional[LogprobsTensors]] = {}
+        for j, s in enumerate(states):
+            sp = s.sampling_params
+            if sp is None or sp.prompt_logprobs is None:
+                continue
+            r = rows[j]
+            start = int(self.num_computed_cpu[r])
+            if start >= s.num_prompt_tokens - 1:
+                continue
+            n = min(int(ns[j]), s.num_prompt_tokens - 1 - start)
+            if n <= 0:
+                continue
+            h = hidden[cu[j]:cu[j] + n]
+            logits = self.model.compute_logits(h).float()
+            tgt = torch.from_numpy(self.token_ids_cpu[r, start + 1:start + 1 + n].astype(np.int64)).to(self.device)
+            k = self.vocab_size if sp.prompt_logprobs == -1 else sp.prompt_logprobs
+            from vllm_b200.ops import ref
+            ids, vals, ranks = ref.compute_logprobs(logits, tgt, k)
+            out[s.req_id] = LogprobsTensors(ids.cpu(), vals.cpu(), ranks.cpu())
+        return out
+
+    def _pool(self, hidden, states, rows, cu, produces, t0) -> ModelRunnerOutput:
+        from vllm_b200.layers.pooler import pool_hidden
+        req_ids, pooled, out_ids = [], [], []
+        for j, s in enumerate(states):
+            r = rows[j]
+            req_ids.append(s.req_id)
+            out_ids.append([])
+            self.num_computed_cpu[r] = self.num_computed_cpu[r] + (cu[j + 1] - cu[j])
+            if produces[j] and s.pooling_params is not None:
+                pooled.append(pool_hidden(hidden[cu[j]:cu[j + 1]], s.pooling_params, self.model).cpu())
+            else:
+                pooled.append(None)
+        return ModelRunnerOutput(req_ids=req_ids, req_id_to_index={r: i for i, r in enumerate(req_ids)},
+                                 sampled_token_ids=out_ids, pooler_output=pooled,
+                                 forward_ms=(time.perf_counter() - t0) * 1e3)
+
+    def _verify_spec(self, so, hidden, states, rows, ns, cu, t0) -> ModelRunnerOutput:
+        """Target-model verification of scheduled draft tokens."""
+        idx_list, draft_lists, cu_l = [], [], [0]
+        for j, s in enumerate(states):
+            drafts = so.scheduled_spec_decode_tokens.get(s.req_id, [])
+            k = len(drafts)
+            end = int(cu[j + 1])
+            idx_list.extend(range(end - k - 1, end))
+            draft_lists.append(list(drafts))
+            cu_l.append(cu_l[-1] + k + 1)
+        idx = torch.tensor(idx_list, dtype=torch.int64, device=self.device)
+        logits = self.model.compute_logits(hidden[idx]).float()
+        smd = self._sampling_metadata(states, rows, len(states))
+        total_after = self.num_computed_cpu[rows] + ns
+        accepted = self.rejection_sampler(logits, draft_lists, smd, cu_l)
+        req_ids, out_ids = [], []
+        for j, s in enumerate(states):
+            r = rows[j]
+            req_ids.append(s.req_id)
+            k = len(draft_lists[j])
+            known = self.num_tokens_cpu[r]
+            if total_after[j] - k < known:  # still prefilling
+                out_ids.append([])
+                self.num_computed_cpu[r] = total_after[j]
+                continue
+            acc = accepted[j]
+            n = known
+            self.token_ids_cpu[r, n:n + len(acc)] = acc
+            self.num_tokens_cpu[r] = n + len(acc)
+            s.output_token_ids.extend(acc)
+            out_ids.append(acc)
+            # rejected drafts' KV slots are simply overwritten next step
+            self.num_computed_cpu[r] = total_after[j] - (k + 1 - len(acc))
+        spec_ids = self.drafter.propose(self, rows, out_ids) if self.drafter is not None else None
+        return ModelRunnerOutput(req_ids=req_ids, req_id_to_index={r: i for i, r in enumerate(req_ids)},
+                                 sampled_token_ids=out_ids, spec_token_ids=spec_ids,
+                                 forward_ms=(time.perf_counter() - t0) * 1e3)
+
+    # --------------------------------------------------------- profiling
+    @torch.inference_mode()
+    def profile_run(self) -> None:
+        """Dummy forward at ``max_num_batched_tokens`` with no KV cache (peak activation memory)."""
+        T = min(self.max_num_tokens, self.max_model_len * self.max_num_reqs)
+        self.input_ids[:T].zero_()
+        self.positions[:T].zero_()
+        hidden = self._forward(T, {})
+        if not isinstance(hidden, dict):
+            n = min(self.max_num_reqs, T)
+            logits = self.model.compute_logits(hidden[:n])
+            logits.float().argmax(-1)
+        if self.is_cuda:
+            torch.cuda.synchronize()
+
+    # -------------------------------------------------------- CUDA graphs
+    def capture_model(self) -> None:
+        if not self.use_cuda_graph:
+            return
+        from vllm_b200.worker.cudagraph import DecodeGraph
+        sizes = self.vllm_config.compilation_config.capture_sizes(self.max_num_reqs)
+        self.capture_sizes = sorted(sizes)
+        t0 = time.perf_counter()
+        for b in reversed(self.capture_sizes):
+            self.graphs[b] = DecodeGraph(self, b)
+        torch.cuda.synchronize()
+        logger.info("captured %d decode CUDA graphs in %.1fs", len(self.graphs), time.perf_counter() - t0)

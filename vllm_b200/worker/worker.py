@@ -1,0 +1,195 @@
+"""Worker: one process (or in-process object) per device.
+
+Behavioural reference: vllm/v1/worker/gpu_worker.py (``init_device`` :316,
+``load_model`` :456, ``determine_available_memory`` :481-634,
+``compile_or_warm_up_model`` :705, ``execute_model`` :1064 with PP send/recv
+:1112-1151, sleep/wake :204-260, profiler RPC :1157).
+"""
+from __future__ import annotations
+
+import gc
+import os
+from typing import Any, Optional
+
+import torch
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.core.kv_cache_manager import KVCacheConfig, KVCacheSpec
+from vllm_b200.core.sched_output import ModelRunnerOutput, SchedulerOutput
+from vllm_b200.logger import init_logger, set_process_prefix
+from vllm_b200.parallel import state as pstate
+from vllm_b200.worker.model_runner import ModelRunner
+
+logger = init_logger(__name__)
+
+
+class Worker:
+    def __init__(self, vllm_config: VllmConfig, local_rank: int = 0, rank: int = 0,
+                 distributed_init_method: Optional[str] = None, is_driver_worker: bool = True) -> None:
+        self.vllm_config = vllm_config
+        self.local_rank, self.rank = local_rank, rank
+        self.init_method = distributed_init_method
+        self.is_driver_worker = is_driver_worker
+        self.device: Optional[torch.device] = None
+        self.runner: Optional[ModelRunner] = None
+        self.profiler = None
+        self._sleep_saved: dict[str, torch.Tensor] = {}
+        self._sleeping = False
+        self.init_free_bytes = 0
+
+    # ----------------------------------------------------------------- init
+    def init_device(self) -> None:
+        pc = self.vllm_config.parallel_config
+        dev_type = self.vllm_config.device_config.resolve()
+        if dev_type == "cuda":
+            torch.cuda.set_device(self.local_rank)
+            self.device = torch.device("cuda", self.local_rank)
+            gc.collect()
+            torch.cuda.empty_cache()
+            self.init_free_bytes, self.total_bytes = torch.cuda.mem_get_info(self.device)
+        else:
+            self.device = torch.device("cpu")
+        world = pc.world_size
+        if world > 1:
+            set_process_prefix(f"(Worker rank={self.rank}) ")
+        pstate.init_distributed_environment(world, self.rank, self.local_rank, self.init_method)
+        pstate.initialize_model_parallel(pc.tensor_parallel_size, pc.pipeline_parallel_size, 1,
+                                         pc.decode_context_parallel_size, pc.prefill_context_parallel_size,
+                                         enable_device_comm=not pc.disable_custom_all_reduce)
+        torch.manual_seed(self.vllm_config.model_config.seed)
+        self.runner = ModelRunner(self.vllm_config, self.device)
+
+    def load_model(self, weights=None) -> None:
+        self.runner.load_model(weights)
+
+    def get_kv_cache_specs(self) -> dict[str, KVCacheSpec]:
+        return self.runner.get_kv_cache_specs()
+
+    def determine_available_memory(self) -> int:
+        """Bytes available for the KV cache = util * total − (weights + peak activations + other)."""
+        cc = self.vllm_config.cache_config
+        if cc.kv_cache_memory_bytes is not None:
+            return cc.kv_cache_memory_bytes
+        if self.device.type != "cuda":
+            return int(cc.swap_space_gb * (1 << 30)) or (1 << 30)
+        torch.cuda.reset_peak_memory_stats(self.device)
+        self.runner.profile_run()
+        torch.cuda.synchronize()
+        peak_torch = torch.cuda.max_memory_allocated(self.device)
+        free, total = torch.cuda.mem_get_info(self.device)
+        non_torch = max((total - free) - torch.cuda.memory_reserved(self.device), 0)
+        budget = int(total * cc.gpu_memory_utilization)
+        graph_reserve = 0 if self.vllm_config.model_config.enforce_eager else (2 << 30)
+        avail = budget - peak_torch - non_torch - graph_reserve
+        gc.collect()
+        torch.cuda.empty_cache()
+        logger.info("memory: total %.1f GiB, budget %.1f, torch peak %.1f, non-torch %.1f → KV %.1f GiB",
+                    total / 2**30, budget / 2**30, peak_torch / 2**30, non_torch / 2**30, avail / 2**30)
+        return max(avail, 0)
+
+    def initialize_from_config(self, kv_cache_config: KVCacheConfig) -> None:
+        self.runner.initialize_kv_cache(kv_cache_config)
+
+    def compile_or_warm_up_model(self) -> None:
+        if self.device.type == "cuda":
+            self.runner.capture_model()
+
+    # -------------------------------------------------------------- execute
+    @torch.inference_mode()
+    def execute_model(self, so: SchedulerOutput) -> Optional[ModelRunnerOutput]:
+        pp = pstate.get_pp_group()
+        intermediate = None
+        if pp.world_size > 1 and not pp.is_first_rank:
+            if so.total_num_scheduled_tokens > 0:
+                intermediate = pp.recv_tensor_dict(device=self.device)
+        out = self.runner.execute_model(so, intermediate)
+        if pp.world_size > 1 and not pp.is_last_rank:
+            if isinstance(out.kv_connector_output, dict):
+                pp.send_tensor_dict(out.kv_connector_output)
+            return None
+        return out
+
+    # -------------------------------------------------------- sleep / wake
+    def sleep(self, level: int = 1) -> None:
+        """Level 1: weights → pinned CPU, KV discarded. Level 2: both discarded."""
+        if self._sleeping:
+            return
+        model = self.runner.model
+        self._param_shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
+        if level == 1:
+            for n, p in model.named_parameters():
+                self._sleep_saved[n] = p.data.to("cpu", non_blocking=False).pin_memory() \
+                    if self.device.type == "cuda" else p.data.clone()
+        for p in model.parameters():
+            p.data = torch.empty(0, dtype=p.dtype, device=self.device)
+        self._kv_shapes = {k: (v.shape, v.dtype) for k, v in self.runner.kv_caches.items()}
+        for k in list(self.runner.kv_caches):
+            self.runner.kv_caches[k] = torch.empty(0, device=self.device)
+        self.runner.graphs.clear()
+        gc.collect()
+        if self.device.type == "cuda":
+            torch.cuda.empty_cache()
+        self._sleeping = True
+        self._sleep_level = level
+
+    def wake_up(self, tags: Optional[list[str]] = None) -> None:
+        if not self._sleeping:
+            return
+        model = self.runner.model
+        if self._sleep_level == 1:
+            for n, p in model.named_parameters():
+                p.data = self._sleep_saved[n].to(self.device, non_blocking=True)
+            self._sleep_saved.clear()
+        else:
+            # level 2 discarded the weights: re-materialise storage; the caller is expected to
+            # push fresh weights (update_weights / reload_weights) before serving again
+            for n, p in model.named_parameters():
+                p.data = torch.zeros(self._param_shapes[n], dtype=p.dtype, device=self.device)
+        for k, (shape, dt) in self._kv_shapes.items():
+            self.runner.kv_caches[k] = torch.zeros(shape, dtype=dt, device=self.device)
+        self._sleeping = False
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+            self.runner.capture_model()
+
+    def is_sleeping(self) -> bool:
+        return self._sleeping
+
+    # ------------------------------------------------------------- profiler
+    def profile(self, is_start: bool = True) -> None:
+        from vllm_b200.profiler import make_profiler
+        if self.profiler is None:
+            self.profiler = make_profiler(self.vllm_config.profiler_config, self.rank)
+        if is_start:
+            self.profiler.start()
+        else:
+            self.profiler.stop()
+
+    # -------------------------------------------------------------- weights
+    def save_sharded_state(self, path: str) -> str:
+        from vllm_b200.model_loader.sharded_state import save_sharded_state
+        return save_sharded_state(self.runner.model, path)
+
+    def update_weights(self, named: list[tuple[str, torch.Tensor]]) -> int:
+        """RLHF-style in-place weight update (reference: gpu_worker.py:1329)."""
+        loaded = self.runner.model.load_weights(iter(named))
+        return len(loaded)
+
+    def reload_weights(self) -> None:
+        from vllm_b200.model_loader import initialize_dummy_weights, iter_weights
+        mc = self.vllm_config.model_config
+        with torch.no_grad():
+            if os.path.isdir(mc.model):
+                self.runner.model.load_weights(iter_weights(mc.model))
+            else:
+                initialize_dummy_weights(self.runner.model, self.vllm_config.load_config.dummy_seed)
+
+    def check_health(self) -> bool:
+        return True
+
+    def get_model(self):
+        return self.runner.model
+
+    def shutdown(self) -> None:
+        self.runner = None
+        pstate.destroy_model_parallel()
