@@ -1,0 +1,211 @@
+"""sm_100a kernel numerics vs the plain-PyTorch fp32 references (run on the B200 box).
+Tolerances follow the reference's tests/kernels/allclose_default.py (bf16: atol 1e-3.., rtol 1.6e-2)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vllm_b200.ops import ref  # noqa: E402
+
+
+def cu():
+    from vllm_b200.ops import cuda_ops
+    return cuda_ops()
+
+
+def close(a, b, atol=2e-2, rtol=2e-2):
+    torch.testing.assert_close(a.float(), b.float(), atol=atol, rtol=rtol)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T,H", [(1, 128), (7, 1024), (64, 4096), (33, 8192), (5, 7168)])
+def test_rms_norm(dtype, T, H):
+    torch.manual_seed(0)
+    x = torch.randn(T, H, device="cuda", dtype=dtype)
+    r = torch.randn(T, H, device="cuda", dtype=dtype)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dtype)
+    close(cu().rms_norm(x, w, 1e-5), ref.rms_norm(x, w, 1e-5))
+    close(cu().rms_norm(x, w, 1e-6, True), ref.rms_norm(x, w, 1e-6, True))
+    eo, er = ref.fused_add_rms_norm(x, r, w, 1e-5)
+    x2, r2 = x.clone(), r.clone()
+    o, rr = cu().fused_add_rms_norm(x2, r2, w, 1e-5)
+    close(o, eo)
+    close(rr, er, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_layer_norm_and_acts(dtype):
+    torch.manual_seed(1)
+    x = torch.randn(19, 768, device="cuda", dtype=dtype)
+    w = torch.randn(768, device="cuda", dtype=dtype)
+    b = torch.randn(768, device="cuda", dtype=dtype)
+    close(cu().layer_norm(x, w, b, 1e-5), ref.layer_norm(x, w, b, 1e-5))
+    y = torch.randn(23, 2 * 1408, device="cuda", dtype=dtype)
+    close(cu().act_and_mul(y, "silu"), ref.silu_and_mul(y))
+    close(cu().act_and_mul(y, "gelu"), ref.gelu_and_mul(y))
+    close(cu().act_and_mul(y, "gelu_tanh"), ref.gelu_and_mul(y, "tanh"))
+    for name in ("relu", "gelu_new", "gelu_fast", "quick_gelu", "gelu", "silu"):
+        close(cu().activation(x, name), ref.ACT_FNS[name](x.float()))
+
+
+@pytest.mark.parametrize("neox", [True, False])
+@pytest.mark.parametrize("Hq,Hkv,D", [(32, 8, 128), (8, 1, 128), (4, 4, 64)])
+def test_rope_and_cache(neox, Hq, Hkv, D):
+    torch.manual_seed(2)
+    T, BS, NB = 37, 32, 16
+    dtype = torch.bfloat16
+    from vllm_b200.layers.rotary import RotaryEmbedding
+    rope = RotaryEmbedding(D, D, 4096, 10000.0, neox).cuda()
+    qkv = torch.randn(T, (Hq + 2 * Hkv) * D, device="cuda", dtype=dtype)
+    pos = torch.randint(0, 4096, (T,), device="cuda")
+    slots = torch.randperm(NB * BS, device="cuda")[:T].long()
+    slots[3] = -1
+    q, k, v = qkv.split([Hq * D, Hkv * D, Hkv * D], dim=-1)
+    eq, ek = ref.rotary_embedding(pos, q.clone(), k.clone(), rope.cos_sin_cache, D, neox)
+    cache_ref = torch.zeros(NB, 2, Hkv, BS, D, device="cuda", dtype=dtype)
+    ref.reshape_and_cache(ek.view(T, Hkv, D), v.reshape(T, Hkv, D), cache_ref, slots)
+    cache = torch.zeros_like(cache_ref)
+    oq, ok = cu().rope_and_cache(pos, q, k, v, rope.cos_sin_cache, D, neox, cache, slots)
+    close(oq, eq)
+    close(ok, ek)
+    close(cache, cache_ref)
+    # stand-alone variants
+    q2, k2 = qkv.clone().split([Hq * D, Hkv * D, Hkv * D], dim=-1)[:2]
+    cache2 = torch.zeros_like(cache_ref)
+    cu().reshape_and_cache(ek.view(T, Hkv, D).contiguous(), v.reshape(T, Hkv, D).contiguous(), cache2, slots)
+    close(cache2, cache_ref)
+
+
+def _mk_attn_case(B, Hq, Hkv, D, BS, seq_lens, q_lens, dtype=torch.bfloat16, seed=0):
+    from vllm_b200.forward_context import AttentionMetadata
+    torch.manual_seed(seed)
+    max_blocks = max((s + BS - 1) // BS for s in seq_lens) + 1
+    NB = B * max_blocks + 4
+    cache = (torch.randn(NB, 2, Hkv, BS, D, device="cuda") * 0.5).to(dtype)
+    perm = torch.randperm(NB - 1, device="cuda")[:B * max_blocks].int() + 1
+    bt = perm.view(B, max_blocks).contiguous()
+    T = sum(q_lens)
+    q = (torch.randn(T, Hq, D, device="cuda") * 0.5).to(dtype)
+    qsl = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    sl = torch.tensor(seq_lens, dtype=torch.int32, device="cuda")
+    md = AttentionMetadata(num_reqs=B, num_actual_tokens=T, max_query_len=max(q_lens), max_seq_len=max(seq_lens),
+                           query_start_loc=qsl, seq_lens=sl, block_table=bt, slot_mapping=torch.empty(0),
+                           query_start_loc_cpu=qsl.cpu(), seq_lens_cpu=sl.cpu(), decode_only=all(x == 1 for x in q_lens))
+    return q, cache, md
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(32, 8), (8, 1), (4, 4), (16, 8)])
+@pytest.mark.parametrize("D,BS", [(128, 32), (64, 16), (128, 16)])
+@pytest.mark.parametrize("splits", [1, 3, 8])
+def test_paged_attention_decode(Hq, Hkv, D, BS, splits):
+    seq_lens = [1, 31, 32, 33, 257, 1000, 64, 5]
+    B = len(seq_lens)
+    q, cache, md = _mk_attn_case(B, Hq, Hkv, D, BS, seq_lens, [1] * B)
+    md.num_splits = splits
+    scale = 1.0 / math.sqrt(D)
+    out = cu().paged_attention(q, cache, md, scale)
+    exp = ref.paged_attention(q, cache, md.block_table, md.seq_lens_cpu, md.query_start_loc_cpu, scale)
+    close(out, exp, atol=1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(32, 8), (8, 1), (4, 4)])
+@pytest.mark.parametrize("window", [None, 48])
+def test_paged_attention_prefill(Hq, Hkv, window):
+    D, BS = 128, 32
+    seq_lens = [17, 64, 200, 130, 1]
+    q_lens = [17, 64, 72, 1, 1]  # full prefill, full, chunk with context, decode-in-mixed-batch
+    q, cache, md = _mk_attn_case(len(seq_lens), Hq, Hkv, D, BS, seq_lens, q_lens, seed=3)
+    scale = 1.0 / math.sqrt(D)
+    out, lse = cu().paged_attention(q, cache, md, scale, sliding_window=window, return_lse=True)
+    exp, elsee = ref.paged_attention(q, cache, md.block_table, md.seq_lens_cpu, md.query_start_loc_cpu, scale,
+                                     sliding_window=window, return_lse=True)
+    close(out, exp, atol=1e-2, rtol=2e-2)
+    close(lse, elsee, atol=1e-2, rtol=1e-2)
+
+
+def test_merge_attn_states():
+    torch.manual_seed(5)
+    T, H, D = 9, 8, 128
+    o1 = torch.randn(T, H, D, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.randn(T, H, D, device="cuda", dtype=torch.bfloat16)
+    l1 = torch.randn(T, H, device="cuda")
+    l2 = torch.randn(T, H, device="cuda")
+    l2[0] = float("-inf")
+    o, l = cu().merge_attn_states(o1, l1, o2, l2)
+    eo, el = ref.merge_attn_states(o1, l1, o2, l2)
+    close(o, eo)
+    close(l, el, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_argmax_and_sampling(dtype):
+    torch.manual_seed(6)
+    B, V = 13, 128256
+    logits = torch.randn(B, V, device="cuda").to(dtype)
+    assert torch.equal(cu().argmax(logits), logits.float().argmax(-1))
+    # temperature 0 rows are greedy; sampling is reproducible per (seed, step) and differs across steps
+    temp = torch.tensor([0.0, 1.0] * 6 + [0.7], device="cuda")
+    seeds = torch.arange(B, device="cuda", dtype=torch.int64) + 1234
+    a = cu().fused_sample(logits, temp, seeds, 3)
+    b = cu().fused_sample(logits, temp, seeds, 3)
+    c = cu().fused_sample(logits, temp, seeds, 4)
+    assert torch.equal(a, b)
+    assert torch.equal(a[temp == 0], logits.float().argmax(-1)[temp == 0])
+    assert not torch.equal(a[temp > 0], c[temp > 0])
+    # distribution check on a small vocab: empirical frequencies follow softmax(logits / T)
+    small = torch.tensor([[2.0, 1.0, 0.0, -1.0] + [-30.0] * 12], device="cuda").repeat(1, 1)
+    counts = torch.zeros(16, device="cuda")
+    big = small.repeat(4096, 1).contiguous()
+    s = cu().fused_sample(big, torch.ones(4096, device="cuda"), torch.arange(4096, device="cuda"), 9)
+    counts = torch.bincount(s, minlength=16).float() / 4096
+    close(counts[:4], small[0, :4].softmax(-1), atol=3e-2, rtol=0.2)
+
+
+def test_topk_topp_mask():
+    torch.manual_seed(7)
+    B, V = 6, 5000
+    logits = torch.randn(B, V, device="cuda") * 3
+    k = torch.tensor([0, 1, 10, 50, 0, 7], dtype=torch.int32, device="cuda")
+    p = torch.tensor([1.0, 1.0, 1.0, 0.9, 0.5, 0.8], device="cuda")
+    exp = ref.apply_top_k_top_p_min_p(logits.clone(), k, p)
+    got = cu().topk_topp_mask_(logits.clone(), k, p)
+    kept_e, kept_g = ~torch.isinf(exp), ~torch.isinf(got)
+    # bisection vs sort may differ by a boundary element
+    assert (kept_e ^ kept_g).sum(dim=-1).max().item() <= 1
+    assert torch.equal(got[kept_g], logits[kept_g])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M", [1, 7, 16, 33, 64, 100, 128, 200, 256])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (1024, 14336), (256, 512), (128256, 1024)])
+def test_gemm_tc_small_m(dtype, M, N, K):
+    if N == 128256 and M not in (7, 64):
+        pytest.skip("large-N case sampled")
+    torch.manual_seed(8)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    bias = torch.randn(N, device="cuda").to(dtype) if M % 2 else None
+    y = cu().gemm_tc(x, w, bias)
+    exp = torch.nn.functional.linear(x.float(), w.float(), None if bias is None else bias.float())
+    close(y, exp, atol=3e-2, rtol=2e-2)
+    # twice more: split-K counters must self-reset
+    close(cu().gemm_tc(x, w, bias), exp, atol=3e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 256), (1024, 4096, 4096), (4097, 1024, 2048), (512, 28672, 1024)])
+def test_gemm_tc_large_m(M, N, K):
+    torch.manual_seed(9)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    y = cu().gemm_tc(x, w)
+    close(y, x.float() @ w.float().t(), atol=3e-2, rtol=2e-2)
+
+
+def test_gemm_tc_strided_input():
+    torch.manual_seed(10)
+    big = (torch.randn(64, 3 * 1024, device="cuda") * 0.5).to(torch.bfloat16)
+    x = big[:, 1024:2048]
+    w = (torch.randn(512, 1024, device="cuda") * 0.05).to(torch.bfloat16)
+    close(cu().gemm_tc(x, w), x.float() @ w.float().t(), atol=3e-2, rtol=2e-2)

@@ -1,0 +1,38 @@
+"""Shared test helpers: tiny HF models built in-memory (no downloads) and engine factories."""
+from __future__ import annotations
+
+import torch
+
+from vllm_b200.config import get_preset_hf_config
+
+
+def make_hf_model(preset: str, seed: int = 0, dtype=torch.float32):
+    """Random-init HuggingFace model with the preset's architecture."""
+    import transformers
+    cfg = get_preset_hf_config(preset)
+    arch = cfg["architectures"][0]
+    mt = cfg["model_type"]
+    kw = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type", "torch_dtype")}
+    hf_cfg = transformers.AutoConfig.for_model(mt, **kw)
+    torch.manual_seed(seed)
+    model = getattr(transformers, arch)(hf_cfg).to(dtype).eval()
+    return model
+
+
+def make_llm(preset: str, weights=None, **kw):
+    from vllm_b200 import LLM
+    defaults = dict(device="cpu", max_model_len=256, max_num_seqs=16, max_num_batched_tokens=128,
+                    kv_cache_memory_bytes=16 << 20, dtype="float32")
+    defaults.update(kw)
+    llm = LLM(preset, **defaults)
+    if weights is not None:
+        llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model.load_weights(weights)
+    return llm
+
+
+def hf_greedy(model, prompt_ids: list[int], n: int) -> list[int]:
+    ids = torch.tensor([prompt_ids])
+    with torch.no_grad():
+        out = model.generate(ids, max_new_tokens=n, do_sample=False, pad_token_id=0,
+                             eos_token_id=None)
+    return out[0, len(prompt_ids):].tolist()

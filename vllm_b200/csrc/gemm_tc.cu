@@ -1,0 +1,326 @@
+// bf16/fp16 GEMM on the 5th-gen tensor cores:  Y[M,N] = X[M,K] · W[N,K]^T (+bias)
+//
+// Hand-written tcgen05 pipeline (no CUTLASS): TMA (cp.async.bulk.tensor, 128B swizzle) →
+// shared-memory ring → tcgen05.mma issued by one elected thread, fp32 accumulators in TMEM →
+// tcgen05.ld epilogue.  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner,
+// 2..5 = epilogue (one per TMEM lane quarter).
+//
+// Two operand assignments share the kernel:
+//   SWAP=1 (decode, M <= 256): A := W tile (128 output features), B := X (all M tokens, N_mma = M
+//          padded to 16).  The accumulator is Y^T: TMEM lane = output feature, column = token.
+//          Every CTA streams a [128 x K/splits] slab of the weight exactly once — the op is
+//          weight-bandwidth bound, so the grid is (N/128) x splits CTAs sized to cover all 148 SMs,
+//          split-K partials are reduced by the last-arriving CTA of each tile (fp32 workspace that
+//          stays in the 126 MB L2, self-resetting counters → CUDA-graph replay safe).
+//   SWAP=0 (prefill, large M): A := X tile (128 tokens), B := W tile (BN features).
+//
+// The reference uses cuBLASLt for this op (layers/linear.py:210-218); our kernel exists because it is
+// the host for the fused epilogues (bias, SwiGLU, and in comm.cu the NVSwitch all-reduce + RMSNorm).
+#include "common.cuh"
+
+namespace gemm {
+
+constexpr int BK = 64;            // K elements per stage (= 128 B swizzle span)
+constexpr int TM = 128;           // UMMA M (rows of the A-operand tile)
+constexpr int NUM_THREADS = 192;  // 6 warps
+constexpr int EPI_THREADS = 128;
+
+struct Params {
+  void* y;                 // [M, N]
+  const void* bias;        // [N] or null
+  float* ws;               // split-K workspace [tiles][splits][BN_cols][128] fp32
+  unsigned* counters;      // [tiles], zero-initialised, self-resetting
+  int M, N, K;
+  int k_blocks_per_split;  // BK blocks handled by one CTA
+  int splits;
+  int act;                 // 0 none, 1 silu-mul over interleaved (gate,up) feature pairs (SWAP only)
+};
+
+template <int BN> struct SmemLayout {
+  static constexpr int A_BYTES = TM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+};
+
+template <typename T, int BN, int STAGES, bool SWAP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_base = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  int* is_last = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates: A-operand tile index (x), B-operand tile index (y), K split (z)
+  const int a_tile = blockIdx.x, b_tile = blockIdx.y, split = blockIdx.z;
+  const int kb0 = split * p.k_blocks_per_split;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int nkb = max(0, min(p.k_blocks_per_split, total_kb - kb0));
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: weights are read exactly once → evict-first; activations are re-read by every CTA → evict-last
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        unsigned char* a_dst = stage_base + s * L::STAGE_BYTES;
+        unsigned char* b_dst = a_dst + L::A_BYTES;
+        mbar_expect_tx(&full[s], L::STAGE_BYTES);
+        const int kc = (kb0 + kb) * BK;
+        tma_load_2d_hint(a_dst, &tmap_a, kc, a_tile * TM, &full[s], SWAP ? L2_EVICT_FIRST : L2_EVICT_LAST);
+        tma_load_2d_hint(b_dst, &tmap_b, kc, b_tile * BN, &full[s], SWAP ? L2_EVICT_LAST : L2_EVICT_FIRST);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint32_t idesc = umma_idesc_f16(TM, BN, DTypeOf<T>::v == DT_BF16);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full[s], (kb / STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const unsigned char* a_src = stage_base + s * L::STAGE_BYTES;
+        const uint64_t da = umma_desc_sw128(a_src), db = umma_desc_sw128(a_src + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)   // UMMA_K = 16 → advance 32 B inside the swizzle span
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);                 // frees the smem slot once these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31; columns are processed in chunks of CH
+    constexpr int CH = (BN % 32 == 0) ? 32 : 16;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // index along the A-operand tile (0..127)
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (nkb > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    auto load_chunk = [&](int c, float (&v)[CH]) {
+      if (nkb == 0) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = 0.f;
+        return;
+      }
+      if constexpr (CH == 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      } else {
+        uint32_t r[16];
+        tmem_ld_32x16(t_row + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      }
+    };
+    const int tile_id = a_tile * gridDim.y + b_tile;
+    bool do_store = true;
+    if (p.splits > 1) {
+      // partial → workspace (stays in L2); the last CTA to arrive sums the others and stores
+      float* my = p.ws + ((size_t)tile_id * p.splits + split) * (BN * TM);
+      for (int c = 0; c < BN; c += CH) {
+        float v[CH];
+        load_chunk(c, v);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) __stcg(my + (c + j) * TM + row, v[j]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      if (threadIdx.x == 64) {
+        const unsigned prev = atomicAdd(&p.counters[tile_id], 1u);
+        const int last = prev == (unsigned)(p.splits - 1);
+        if (last) p.counters[tile_id] = 0;       // self-reset for the next launch / graph replay
+        *is_last = last;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      do_store = *is_last != 0;
+      if (do_store) __threadfence();
+    }
+    if (do_store) {
+      T* y = reinterpret_cast<T*>(p.y);
+      for (int c = 0; c < BN; c += CH) {
+        float v[CH];
+        load_chunk(c, v);
+        if (p.splits > 1) {
+          for (int s2 = 0; s2 < p.splits; ++s2) {
+            if (s2 == split) continue;
+            const float* o = p.ws + ((size_t)tile_id * p.splits + s2) * (BN * TM);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] += __ldcg(o + (c + j) * TM + row);
+          }
+        }
+        if (SWAP) {
+          // accumulator is Y^T: row = output feature, column = token
+          const int n = a_tile * TM + row;
+          if (n < p.N) {
+            const float bias = p.bias ? to_f32(reinterpret_cast<const T*>(p.bias)[n]) : 0.f;
+            const int m0 = b_tile * BN + c;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (m0 + j < p.M) y[(size_t)(m0 + j) * p.N + n] = from_f32<T>(v[j] + bias);
+          }
+        } else {
+          const int m = a_tile * TM + row;
+          if (m < p.M) {
+            const int n0 = b_tile * BN + c;
+            T* yr = y + (size_t)m * p.N + n0;
+            const T* bp = p.bias ? reinterpret_cast<const T*>(p.bias) + n0 : nullptr;
+            if (n0 + CH <= p.N && (p.N % 8) == 0) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                Vec16<T> o;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o.e[e] = from_f32<T>(v[j + e] + (bp ? to_f32(bp[j + e]) : 0.f));
+                st16(yr + j, o);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (n0 + j < p.N) yr[j] = from_f32<T>(v[j] + (bp ? to_f32(bp[j]) : 0.f));
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] 16-bit matrix, box = [box_rows, 64 cols], 128B swizzle
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                     uint32_t box_rows, bool bf16) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -10;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+template <typename T, int BN, int STAGES, bool SWAP>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  const int smem = STAGES * L::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  auto k = gemm_kernel<T, BN, STAGES, SWAP>;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  k<<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gemm
+
+// Workspace requirement for vb_gemm_tc (bytes of fp32 partials, number of counters)
+EXPORT int vb_gemm_tc_plan(int M, int N, int K, int num_sms, int* swap, int* bn, int* splits, int64_t* ws_bytes,
+                           int* n_tiles) {
+  using namespace gemm;
+  const int kb = (K + BK - 1) / BK;
+  if (M <= 256) {
+    int b = ((M + 15) / 16) * 16;
+    if (b > 128 && b < 256) b = 256;   // supported N_mma: 16..128 step 16, or 256
+    const int mt = 1;
+    const int nt = (N + TM - 1) / TM;
+    int s = num_sms / (nt * mt);
+    if (s * nt * mt < num_sms - num_sms / 8 && (s + 1) * nt * mt <= num_sms + num_sms / 16) s += 1;
+    if (s > kb / 4) s = kb / 4;
+    if (s < 1) s = 1;
+    if (s > 16) s = 16;
+    *swap = 1; *bn = b; *splits = s; *n_tiles = nt * mt;
+    *ws_bytes = s > 1 ? (int64_t)nt * mt * s * b * TM * 4 : 0;
+  } else {
+    const int b = 128;
+    const int mt = (M + TM - 1) / TM, nt = (N + b - 1) / b;
+    *swap = 0; *bn = b; *splits = 1; *n_tiles = mt * nt; *ws_bytes = 0;
+  }
+  return 0;
+}
+
+EXPORT int vb_gemm_tc(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int64_t x_stride,
+                      int swap, int bn, int splits, float* ws, unsigned* counters, int dtype, cudaStream_t st) {
+  using namespace gemm;
+  if (dtype == DT_F32 || K % 8 != 0) return -1;
+  const bool bf16 = dtype == DT_BF16;
+  CUtensorMap ta, tb;
+  Params p;
+  p.y = y; p.bias = bias; p.ws = ws; p.counters = counters; p.M = M; p.N = N; p.K = K; p.splits = splits; p.act = 0;
+  const int kb = (K + BK - 1) / BK;
+  p.k_blocks_per_split = (kb + splits - 1) / splits;
+  int rc;
+  if (swap) {
+    if ((rc = make_tmap(&ta, w, N, K, K, TM, bf16))) return rc;
+    if ((rc = make_tmap(&tb, x, M, K, x_stride, bn, bf16))) return rc;
+    dim3 grid((N + TM - 1) / TM, (M + bn - 1) / bn, splits);
+#define GO(BNV, ST)                                                                      \
+    if (bf16) return launch<__nv_bfloat16, BNV, ST, true>(ta, tb, p, grid, st);          \
+    else return launch<__half, BNV, ST, true>(ta, tb, p, grid, st);
+    switch (bn) {
+      case 16: GO(16, 8)
+      case 32: GO(32, 8)
+      case 48: GO(48, 8)
+      case 64: GO(64, 8)
+      case 80: GO(80, 6)
+      case 96: GO(96, 6)
+      case 112: GO(112, 6)
+      case 128: GO(128, 6)
+      case 256: GO(256, 4)
+      default: return -2;
+    }
+#undef GO
+  } else {
+    if ((rc = make_tmap(&ta, x, M, K, x_stride, TM, bf16))) return rc;
+    if ((rc = make_tmap(&tb, w, N, K, K, bn, bf16))) return rc;
+    dim3 grid((M + TM - 1) / TM, (N + bn - 1) / bn, 1);
+    if (bn != 128) return -2;
+    if (bf16) return launch<__nv_bfloat16, 128, 6, false>(ta, tb, p, grid, st);
+    return launch<__half, 128, 6, false>(ta, tb, p, grid, st);
+  }
+}

@@ -44,8 +44,8 @@ class SamplingMetadata:
     bad_words_token_ids: dict[int, list[list[int]]] = field(default_factory=dict)
     min_tokens: dict[int, tuple[int, set[int]]] = field(default_factory=dict)  # row → (min, stop ids)
     output_token_ids: list[list[int]] = field(default_factory=list)
-    seeds: Optional[torch.Tensor] = None      # [B] int64 per-row Philox seeds (CUDA path)
-    step: int = 0
+    seeds: Optional[torch.Tensor] = None      # [B] int64 per-request noise seeds (CUDA path)
+    steps: Optional[torch.Tensor] = None      # [B] int32 per-request noise counter = #output tokens so far
 
 
 @dataclass
@@ -96,7 +96,7 @@ class Sampler:
         if logits.is_cuda and md.top_k is None and md.top_p is None and md.min_p is None \
                 and md.seeds is not None:
             from vllm_b200.ops import cuda_ops
-            return cuda_ops().fused_sample(logits, md.temperature, md.seeds, md.step)
+            return cuda_ops().fused_sample(logits, md.temperature, md.seeds, md.steps)
         filtered = logits
         if md.top_k is not None or md.top_p is not None or md.min_p is not None:
             t = torch.where(md.temperature < 1e-5, torch.ones_like(md.temperature), md.temperature)

@@ -1,0 +1,72 @@
+"""Full-step CUDA graphs for decode batches.
+
+Reference: vllm/v1/worker/gpu/cudagraph_utils.py:102 (``CudaGraphManager``), config/compilation.py:53-64
+(``CUDAGraphMode``).  One graph per padded batch bucket captures forward + LM head + fused sampling over
+the runner's static buffers; everything variable (sequence lengths, block tables, slot mapping,
+temperatures, seeds, step counter) lives in device buffers that are overwritten before replay, and the
+attention launch geometry depends only on the bucket, never on sequence lengths.
+"""
+from __future__ import annotations
+
+import torch
+
+from vllm_b200.forward_context import ForwardContext, set_forward_context
+from vllm_b200.layers.attention import attention_layers
+from vllm_b200.ops import cuda_ops
+
+
+class DecodeGraph:
+    def __init__(self, runner, b: int) -> None:
+        self.runner = runner
+        self.b = b
+        dev = runner.device
+        self.temperature = torch.zeros(b, dtype=torch.float32, device=dev)
+        self.seeds = torch.zeros(b, dtype=torch.int64, device=dev)
+        self.steps = torch.zeros(b, dtype=torch.int32, device=dev)
+        self.out = torch.zeros(b, dtype=torch.int64, device=dev)
+        # safe placeholder inputs for warm-up / capture: one token at position 0 of the null block
+        runner.input_ids[:b].zero_()
+        runner.positions[:b].zero_()
+        runner.seq_lens[:b].fill_(1)
+        runner.qsl[:b + 1].copy_(torch.arange(b + 1, dtype=torch.int32, device=dev))
+        for g in range(runner.num_kv_groups):
+            runner.slot_mappings[g][:b].fill_(-1)
+            runner.block_tables[g][:b].zero_()
+        self.md = runner._make_metadata(b, b, 1, runner.max_model_len, True)
+        layers = list(attention_layers().values())
+        hkv = max((getattr(l, "num_kv_heads", 1) for l in layers), default=1)
+        for m in self.md.values():
+            # typical context assumed for the split heuristic; the kernel itself adapts to real lengths
+            m.num_splits = cuda_ops().decode_splits(b, hkv, min(runner.max_model_len, 4096), runner.block_size)
+        self.graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if runner.graph_pool is None:
+            runner.graph_pool = torch.cuda.graph_pool_handle()
+        n0 = cuda_ops().LAUNCHES
+        with torch.cuda.graph(self.graph, pool=runner.graph_pool):
+            self._body()
+        self.num_launches = cuda_ops().LAUNCHES - n0
+
+    def _body(self) -> None:
+        r, b = self.runner, self.b
+        ctx = ForwardContext(attn_metadata=self.md, kv_caches=r.kv_caches, layer_to_group=r.layer_to_group,
+                             num_tokens=b)
+        with set_forward_context(ctx):
+            hidden = r.model(r.input_ids[:b], r.positions[:b], None)
+        logits = r.model.compute_logits(hidden)
+        cuda_ops().fused_sample(logits, self.temperature, self.seeds, self.steps, self.out)
+
+    def replay(self, smd) -> torch.Tensor:
+        self.temperature.copy_(smd.temperature, non_blocking=True)
+        if smd.seeds is not None:
+            self.seeds.copy_(smd.seeds, non_blocking=True)
+        if smd.steps is not None:
+            self.steps.copy_(smd.steps, non_blocking=True)
+        self.graph.replay()
+        return self.out

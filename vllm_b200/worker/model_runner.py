@@ -19,6 +19,7 @@ Design (ours):
 from __future__ import annotations
 
 import time
+import zlib
 from dataclasses import dataclass, field
 from typing import Any, Optional
 
@@ -96,6 +97,9 @@ class ModelRunner:
         self._step = 0
         self._copy_stream = torch.cuda.Stream(device) if self.is_cuda else None
         self.profile_forward_ms = 0.0
+        self.launch_count = 0   # our kernels launched (graph replays count their captured launches)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     # ------------------------------------------------------------------ setup
     def _pin(self, *shape, dtype):
@@ -286,6 +290,7 @@ class ModelRunner:
 
     def _h2d(self, rows, nb, T, pad_b, pad_t, max_s) -> None:
         nbk = cdiv(max_s, self.block_size)
+        self.h2d_bytes += T * (4 + 8) + (nb + 1) * 4 + nb * 4 + self.num_kv_groups * (T * 8 + nb * nbk * 4)
         self.input_ids[:T].copy_(self.input_ids_pin[:T], non_blocking=True)
         self.positions[:T].copy_(self.positions_pin[:T], non_blocking=True)
         self.qsl[:nb + 1].copy_(self.qsl_pin[:nb + 1], non_blocking=True)
@@ -356,13 +361,17 @@ class ModelRunner:
         if graph is not None:
             smd = self._sampling_metadata(states, rows, pad_b)
             graph_ok = smd.all_greedy or (smd.top_k is None and smd.top_p is None and smd.min_p is None
-                                          and smd.no_penalties and smd.max_num_logprobs is None
-                                          and not smd.generators)
+                                          and smd.no_penalties and smd.max_num_logprobs is None)
+            graph_ok = graph_ok and smd.max_num_logprobs is None and smd.no_penalties \
+                and so.grammar_bitmask is None
             if graph_ok and not self._needs_logits_processors(smd) and self._graph_supports(graph, smd):
                 sampled = graph.replay(smd)[:nb]
+                self.launch_count += graph.num_launches
+                self.h2d_bytes += pad_b * 12
             else:
                 graph = None
         if graph is None:
+            l0 = self._launches()
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
             hidden = self._forward(T, md, intermediate)
             if isinstance(hidden, dict):  # non-last PP stage
@@ -388,7 +397,10 @@ class ModelRunner:
                 s.sampling_params is not None and s.sampling_params.prompt_logprobs is not None for s in states) else {}
         else:
             plp = {}
+        if graph is None and self.is_cuda:
+            self.launch_count += self._launches() - l0
         toks = sampled.tolist()  # D2H sync point
+        self.d2h_bytes += len(toks) * 8
         out_ids: list[list[int]] = []
         req_ids = []
         for j, r in enumerate(rows):
@@ -413,6 +425,12 @@ class ModelRunner:
                                  spec_token_ids=spec_ids, forward_ms=ms)
 
     # ------------------------------------------------------------- helpers
+    def _launches(self) -> int:
+        if not self.is_cuda:
+            return 0
+        from vllm_b200.ops import cuda_ops
+        return cuda_ops().LAUNCHES
+
     @staticmethod
     def _needs_logits_processors(smd: SamplingMetadata) -> bool:
         return (smd.allowed_token_ids_mask is not None or bool(smd.min_tokens) or any(smd.logit_bias)
@@ -438,6 +456,7 @@ class ModelRunner:
         freq = np.zeros(pad_b, dtype=np.float32)
         rep = np.ones(pad_b, dtype=np.float32)
         seeds = np.zeros(pad_b, dtype=np.int64)
+        steps = np.zeros(pad_b, dtype=np.int32)
         gens: dict[int, torch.Generator] = {}
         logit_bias: list = [None] * B
         bad: dict[int, list[list[int]]] = {}
@@ -456,7 +475,10 @@ class ModelRunner:
             any_pen |= sp.needs_penalties
             if s.generator is not None:
                 gens[i] = s.generator
-            seeds[i] = (sp.seed if sp.seed is not None else hash(s.req_id)) & 0x7FFFFFFFFFFF
+            # unseeded requests get a seed that is identical on every TP rank (crc of the id + engine seed)
+            seeds[i] = (sp.seed if sp.seed is not None
+                        else zlib.crc32(s.req_id.encode()) * 2654435761 + self.mc.seed) & 0x7FFFFFFFFFFF
+            steps[i] = len(s.output_token_ids)
             if sp.logit_bias:
                 logit_bias[i] = sp.logit_bias
             if sp.bad_words_token_ids:
@@ -475,7 +497,7 @@ class ModelRunner:
         md = SamplingMetadata(temperature=t, all_greedy=all_greedy, all_random=all_random, generators=gens,
                               max_num_logprobs=max_lp, logit_bias=logit_bias if any(logit_bias) else [],
                               bad_words_token_ids=bad, min_tokens=min_toks,
-                              output_token_ids=[s.output_token_ids for s in states], step=self._step)
+                              output_token_ids=[s.output_token_ids for s in states])
         if not all_greedy:
             if (top_k > 0).any():
                 md.top_k = torch.from_numpy(top_k).to(dev)
@@ -484,6 +506,7 @@ class ModelRunner:
             if (min_p > 0).any():
                 md.min_p = torch.from_numpy(min_p).to(dev)
             md.seeds = torch.from_numpy(seeds).to(dev)
+            md.steps = torch.from_numpy(steps).to(dev)
         if any_pen:
             md.no_penalties = False
             md.presence, md.frequency = torch.from_numpy(pres[:B]).to(dev), torch.from_numpy(freq[:B]).to(dev)
