@@ -96,6 +96,7 @@ def main() -> None:
     ap.add_argument("--input-len", type=int, default=1024)
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync", action="store_true", help="disable async scheduling (host waits for every step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -121,7 +122,8 @@ def main() -> None:
                     max_model_len=max_len, max_num_seqs=max(B, 8), max_num_batched_tokens=16384,
                     enable_prefix_caching=False, enforce_eager=args.eager,
                     distributed_executor_backend="external_launcher" if world > 1 else "uni",
-                    cudagraph_capture_sizes=[B], disable_log_stats=True, gpu_memory_utilization=0.85)
+                    cudagraph_capture_sizes=[B], disable_log_stats=True, gpu_memory_utilization=0.85,
+                    async_scheduling=not args.sync)
     engine = LLMEngine.from_engine_args(ea, multiprocess_mode=False)
     runner = engine.engine_core.engine_core.model_executor.worker.runner
     vocab = engine.model_config.vocab_size

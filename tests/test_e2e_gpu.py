@@ -40,6 +40,7 @@ def test_graph_equals_eager_and_ref_logprobs():
     assert n0 > 0
     out_g_lp = llm_g.generate(PROMPTS, sp)
     llm_g.shutdown()
+    del runner
     llm_e, _ = _llm(enforce_eager=True)
     out_e = llm_e.generate(PROMPTS, SamplingParams(max_tokens=12, temperature=0.0, ignore_eos=True))
     llm_e.shutdown()

@@ -92,3 +92,21 @@ def test_stop_strings_and_detokenizer():
                                                      include_stop_str_in_output=True))[0].outputs[0]
         assert o2.text == text[:text.find(stop) + len(stop)]
     llm.shutdown()
+
+
+def test_async_scheduling_matches_sync():
+    """Async scheduling (step N+1 launched before step N's tokens reach the host) must not change outputs."""
+    hf = make_hf_model("llama-tiny")
+    sp = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True)
+    prompts = [{"prompt_token_ids": p} for p in PROMPTS]
+    a = make_llm("llama-tiny", weights=hf.state_dict().items())
+    ref = [o.outputs[0].token_ids for o in a.generate(prompts, sp)]
+    a.shutdown()
+    b = make_llm("llama-tiny", weights=hf.state_dict().items(), async_scheduling=True)
+    got = [o.outputs[0].token_ids for o in b.generate(prompts, sp)]
+    # stop conditions discovered one step late must still cut at the right place
+    eos_sp = SamplingParams(max_tokens=10, temperature=0.0, stop_token_ids=[ref[0][4]])
+    cut = b.generate(prompts[:1], eos_sp)[0].outputs[0].token_ids
+    b.shutdown()
+    assert got == ref
+    assert cut == ref[0][:ref[0].index(ref[0][4]) + 1]

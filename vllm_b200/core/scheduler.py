@@ -212,6 +212,10 @@ class Scheduler:
             if 0 < thr < n_new:
                 n_new = thr
             n_new = min(n_new, budget, self.max_model_len - 1 - req.num_computed_tokens)
+            if self.async_scheduling and req.num_output_placeholders > 0 and (
+                    req.num_output_tokens + req.num_output_placeholders >= req.max_tokens
+                    or req.num_tokens + req.num_output_placeholders >= self.max_model_len):
+                n_new = 0  # the in-flight tokens already reach the length cap: wait for them
             if n_new <= 0:
                 i += 1
                 continue

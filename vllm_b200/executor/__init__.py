@@ -105,6 +105,21 @@ def _run_method(worker, method: Union[str, Callable], args: tuple, kwargs: dict)
     return method(worker, *args, **kwargs)
 
 
+class _LazyFuture:
+    """Future-like wrapper over a launched step: ``result()`` waits for the device → host copy."""
+
+    def __init__(self, out) -> None:
+        self._out = out
+
+    def done(self) -> bool:
+        d = getattr(self._out, "done", None)
+        return d() if d is not None else True
+
+    def result(self, timeout=None):
+        g = getattr(self._out, "get", None)
+        return g() if g is not None else self._out
+
+
 class UniProcExecutor(Executor):
     """Single worker inside the engine-core process (TP=PP=1)."""
 
@@ -122,6 +137,10 @@ class UniProcExecutor(Executor):
             f.set_result(out)
             return f
         return out
+
+    def execute_model(self, so: SchedulerOutput, non_block: bool = False):
+        out = self.worker.execute_model(so, non_block=non_block)
+        return _LazyFuture(out) if non_block else out
 
     @property
     def output_rank(self) -> int:

@@ -62,11 +62,10 @@ class DecodeGraph:
         logits = r.model.compute_logits(hidden)
         cuda_ops().fused_sample(logits, self.temperature, self.seeds, self.steps, self.out)
 
-    def replay(self, smd) -> torch.Tensor:
-        self.temperature.copy_(smd.temperature, non_blocking=True)
-        if smd.seeds is not None:
-            self.seeds.copy_(smd.seeds, non_blocking=True)
-        if smd.steps is not None:
-            self.steps.copy_(smd.steps, non_blocking=True)
+    def replay_from_staging(self, stg, b: int) -> torch.Tensor:
+        """Sampling vectors come from the pinned staging set (filled from the runner's per-row arrays)."""
+        self.temperature.copy_(stg.temperature[:b], non_blocking=True)
+        self.seeds.copy_(stg.seeds[:b], non_blocking=True)
+        self.steps.copy_(stg.steps[:b], non_blocking=True)
         self.graph.replay()
         return self.out

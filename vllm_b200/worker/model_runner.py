@@ -2,19 +2,21 @@
 
 Behavioural reference: the reference's MRV2 runner
 (vllm/v1/worker/gpu/model_runner.py:1397 ``execute_model``, ``sample_tokens``
-:1682, ``capture_model`` :840) and V1 ``gpu_input_batch.py`` persistent batch.
+:1682, ``capture_model`` :840, ``AsyncOutput`` async_utils.py:115) and V1
+``gpu_input_batch.py`` persistent batch.
 
 Design (ours):
-* request state lives in NumPy arrays indexed by a stable row; per-step inputs
+* request state lives in NumPy arrays indexed by a dense row; per-step inputs
   (ids, positions, slot mapping, seq lens, block table) are produced with
-  vectorised NumPy into *pinned* staging buffers and copied with one async H2D
-  each into *static* device buffers — the same buffers CUDA graphs replay on;
+  vectorised NumPy into double-buffered *pinned* staging buffers and copied with
+  async H2D copies into *static* device buffers — the buffers CUDA graphs replay on;
 * decode-only steps replay a full-step CUDA graph per padded batch bucket
   (forward + logits + fused sampling), everything else runs eagerly;
-* the sampled ids stay on the device in ``last_sampled`` so the next step's
-  input ids are gathered GPU-side (no D2H→H2D round trip on the critical path);
-  the D2H copy of sampled ids is issued on a side stream and only awaited when
-  the engine needs the python ints.
+* sampled ids stay on the device in ``last_sampled`` (indexed by row); with async
+  scheduling the next step's input ids are patched GPU-side from it, so the host
+  never waits for step N before launching step N+1 — the D2H copy of the ids goes
+  through a pinned buffer + event and is only awaited when the engine consumes
+  the step's output (``AsyncStepOutput.get``).
 """
 from __future__ import annotations
 
@@ -49,6 +51,83 @@ class ReqState:
     num_prompt_tokens: int = 0
     output_token_ids: list[int] = field(default_factory=list)
     mm_features: Optional[list] = None
+    complex_sampling: bool = False  # needs the per-request slow path (penalties, logprobs, processors, ...)
+
+
+class _Staging:
+    """One set of pinned host buffers (inputs H2D, sampled ids D2H) + the event that guards their reuse."""
+
+    def __init__(self, T: int, R: int, MB: int, G: int, pin: bool) -> None:
+        def mk(*shape, dtype):
+            t = torch.zeros(*shape, dtype=dtype)
+            return t.pin_memory() if pin else t
+        self.input_ids = mk(T, dtype=torch.int32)
+        self.positions = mk(T, dtype=torch.int64)
+        self.qsl = mk(R + 1, dtype=torch.int32)
+        self.seq_lens = mk(R, dtype=torch.int32)
+        self.slots = [mk(T, dtype=torch.int64) for _ in range(G)]
+        self.block_tables = [mk(R, MB, dtype=torch.int32) for _ in range(G)]
+        self.sampled = mk(R, dtype=torch.int64)
+        self.temperature = mk(R, dtype=torch.float32)
+        self.seeds = mk(R, dtype=torch.int64)
+        self.steps = mk(R, dtype=torch.int32)
+        self.fix_idx = mk(R, dtype=torch.int64)
+        self.fix_rows = mk(R, dtype=torch.int64)
+        self.rows = mk(R, dtype=torch.int64)
+        self.event = torch.cuda.Event() if pin else None
+
+    def wait(self) -> None:
+        if self.event is not None:
+            self.event.synchronize()
+
+
+class AsyncStepOutput:
+    """Result of a launched step; ``get()`` waits for the D2H copy and does the host-side bookkeeping."""
+
+    def __init__(self, runner: "ModelRunner", req_ids: list[str], produces: np.ndarray, staging: _Staging,
+                 nb: int, event, t0: float, lp_out=None, plp=None) -> None:
+        self.runner, self.req_ids, self.produces = runner, req_ids, produces
+        self.staging, self.nb, self.event, self.t0 = staging, nb, event, t0
+        self.lp_out, self.plp = lp_out, plp or {}
+        self._out: Optional[ModelRunnerOutput] = None
+
+    def done(self) -> bool:
+        return self._out is not None or self.event is None or self.event.query()
+
+    def get(self) -> ModelRunnerOutput:
+        if self._out is not None:
+            return self._out
+        r = self.runner
+        if self.event is not None:
+            self.event.synchronize()
+        toks = self.staging.sampled[:self.nb].tolist()
+        r.d2h_bytes += self.nb * 8
+        out_ids: list[list[int]] = []
+        for j, rid in enumerate(self.req_ids):
+            if not self.produces[j]:
+                out_ids.append([])
+                continue
+            t = toks[j]
+            out_ids.append([t])
+            row = r.req_index.get(rid)
+            if row is None:  # aborted / finished while the step was in flight
+                continue
+            n = r.num_tokens_cpu[row]
+            r.token_ids_cpu[row, n] = t
+            r.num_tokens_cpu[row] = n + 1
+            r.states[rid].output_token_ids.append(t)
+        spec_ids = None
+        if r.drafter is not None:
+            rows = [r.req_index[rid] for rid in self.req_ids if rid in r.req_index]
+            if len(rows) == len(self.req_ids):
+                spec_ids = r.drafter.propose(r, rows, out_ids)
+        if r._pending is self:
+            r._pending = None
+        self._out = ModelRunnerOutput(
+            req_ids=self.req_ids, req_id_to_index={x: i for i, x in enumerate(self.req_ids)},
+            sampled_token_ids=out_ids, logprobs=self.lp_out, prompt_logprobs_dict=self.plp,
+            spec_token_ids=spec_ids, forward_ms=(time.perf_counter() - self.t0) * 1e3)
+        return self._out
 
 
 class ModelRunner:
@@ -76,54 +155,48 @@ class ModelRunner:
         spec = vllm_config.speculative_config
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
+        self.async_mode = bool(self.sc.async_scheduling)
         # ---- persistent batch (CPU)
         R, L = self.max_num_reqs, self.max_model_len
-        self.req_ids: list[Optional[str]] = []
+        self.req_ids: list[str] = []
         self.req_index: dict[str, int] = {}
         self.states: dict[str, ReqState] = {}
         self._parked: dict[str, ReqState] = {}
         self.token_ids_cpu = np.zeros((R, L + self.num_spec_tokens + 1), dtype=np.int32)
-        self.num_tokens_cpu = np.zeros(R, dtype=np.int32)       # known tokens (prompt + sampled)
+        self.num_tokens_cpu = np.zeros(R, dtype=np.int32)       # tokens materialised on the host
+        self.num_logical_cpu = np.zeros(R, dtype=np.int32)      # incl. tokens still in flight (async)
+        self.num_prompt_cpu = np.zeros(R, dtype=np.int32)
         self.num_computed_cpu = np.zeros(R, dtype=np.int32)
+        self.temp_cpu = np.zeros(R, dtype=np.float32)
+        self.seed_cpu = np.zeros(R, dtype=np.int64)
+        self.complex_cpu = np.zeros(R, dtype=bool)
+        self.filter_cpu = np.zeros(R, dtype=bool)                # top-k / top-p / min-p
         self.block_tables_cpu: list[np.ndarray] = []
         self.num_blocks_cpu: list[np.ndarray] = []
-        # ---- staging + device buffers
-        self._alloc_io_buffers()
+        # ---- device buffers
+        T = self.max_num_tokens
+        dev = self.device
+        self.input_ids = torch.zeros(T, dtype=torch.int32, device=dev)
+        self.positions = torch.zeros(T, dtype=torch.int64, device=dev)
+        self.qsl = torch.zeros(R + 1, dtype=torch.int32, device=dev)
+        self.seq_lens = torch.zeros(R, dtype=torch.int32, device=dev)
+        self.last_sampled = torch.zeros(R, dtype=torch.int64, device=dev)
+        self.slot_mappings: list[torch.Tensor] = []
+        self.block_tables: list[torch.Tensor] = []
+        self.staging: list[_Staging] = []
+        self._stage_i = 0
+        self._pending: Optional[AsyncStepOutput] = None
         self.graphs: dict[int, Any] = {}
         self.graph_pool = None
         self.use_cuda_graph = (self.is_cuda and not self.mc.enforce_eager
                                and vllm_config.compilation_config.cudagraph_mode != "NONE")
         self.capture_sizes: list[int] = []
         self._step = 0
-        self._copy_stream = torch.cuda.Stream(device) if self.is_cuda else None
-        self.profile_forward_ms = 0.0
         self.launch_count = 0   # our kernels launched (graph replays count their captured launches)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     # ------------------------------------------------------------------ setup
-    def _pin(self, *shape, dtype):
-        t = torch.zeros(*shape, dtype=dtype)
-        if self.is_cuda:
-            t = t.pin_memory()
-        return t
-
-    def _alloc_io_buffers(self) -> None:
-        T, R = self.max_num_tokens, self.max_num_reqs
-        dev = self.device
-        self.input_ids_pin = self._pin(T, dtype=torch.int32)
-        self.positions_pin = self._pin(T, dtype=torch.int64)
-        self.slot_pin = self._pin(T, dtype=torch.int64)
-        self.qsl_pin = self._pin(R + 1, dtype=torch.int32)
-        self.seq_lens_pin = self._pin(R, dtype=torch.int32)
-        self.input_ids = torch.zeros(T, dtype=torch.int32, device=dev)
-        self.positions = torch.zeros(T, dtype=torch.int64, device=dev)
-        self.qsl = torch.zeros(R + 1, dtype=torch.int32, device=dev)
-        self.seq_lens = torch.zeros(R, dtype=torch.int32, device=dev)
-        self.slot_mappings: list[torch.Tensor] = []
-        self.block_tables: list[torch.Tensor] = []
-        self.block_tables_pin: list[torch.Tensor] = []
-
     def load_model(self, weights=None) -> None:
         from vllm_b200.model_loader import get_model
         clear_attention_layers()
@@ -162,12 +235,25 @@ class ModelRunner:
         self.block_tables_cpu = [np.zeros((R, MB), dtype=np.int32) for _ in range(G)]
         self.num_blocks_cpu = [np.zeros(R, dtype=np.int32) for _ in range(G)]
         self.block_tables = [torch.zeros(R, MB, dtype=torch.int32, device=self.device) for _ in range(G)]
-        self.block_tables_pin = [self._pin(R, MB, dtype=torch.int32) for _ in range(G)]
         self.slot_mappings = [torch.zeros(self.max_num_tokens, dtype=torch.int64, device=self.device)
                               for _ in range(G)]
-        self.slot_pins = [self._pin(self.max_num_tokens, dtype=torch.int64) for _ in range(G)]
+        n_sets = 3 if self.is_cuda else 1
+        self.staging = [_Staging(self.max_num_tokens, R, MB, G, self.is_cuda) for _ in range(n_sets)]
 
     # ------------------------------------------------------- batch maintenance
+    def _move_row(self, src: int, dst: int) -> None:
+        n = self.num_tokens_cpu[src]
+        self.token_ids_cpu[dst, :n] = self.token_ids_cpu[src, :n]
+        for a in (self.num_tokens_cpu, self.num_logical_cpu, self.num_prompt_cpu, self.num_computed_cpu,
+                  self.temp_cpu, self.seed_cpu, self.complex_cpu, self.filter_cpu):
+            a[dst] = a[src]
+        for g in range(self.num_kv_groups):
+            nb = self.num_blocks_cpu[g][src]
+            self.block_tables_cpu[g][dst, :nb] = self.block_tables_cpu[g][src, :nb]
+            self.num_blocks_cpu[g][dst] = nb
+        if self.is_cuda:
+            self.last_sampled[dst:dst + 1].copy_(self.last_sampled[src:src + 1])
+
     def _remove(self, req_id: str, park: bool = False) -> None:
         row = self.req_index.pop(req_id, None)
         st = self.states.pop(req_id, None)
@@ -181,14 +267,7 @@ class ModelRunner:
             self.req_ids[row] = mv
             self.req_index[mv] = row
             self.states[mv].row = row
-            n = self.num_tokens_cpu[last]
-            self.token_ids_cpu[row, :n] = self.token_ids_cpu[last, :n]
-            self.num_tokens_cpu[row] = n
-            self.num_computed_cpu[row] = self.num_computed_cpu[last]
-            for g in range(self.num_kv_groups):
-                nb = self.num_blocks_cpu[g][last]
-                self.block_tables_cpu[g][row, :nb] = self.block_tables_cpu[g][last, :nb]
-                self.num_blocks_cpu[g][row] = nb
+            self._move_row(last, row)
         self.req_ids.pop()
 
     def _add_row(self, st: ReqState, token_ids, block_ids, num_computed: int) -> None:
@@ -200,7 +279,26 @@ class ModelRunner:
         n = len(token_ids)
         self.token_ids_cpu[row, :n] = token_ids
         self.num_tokens_cpu[row] = n
+        self.num_logical_cpu[row] = n
+        self.num_prompt_cpu[row] = st.num_prompt_tokens
         self.num_computed_cpu[row] = num_computed
+        sp = st.sampling_params
+        if sp is not None:
+            self.temp_cpu[row] = sp.temperature
+            # unseeded requests get a seed that is identical on every TP rank (crc of the id + engine seed)
+            self.seed_cpu[row] = (sp.seed if sp.seed is not None
+                                  else zlib.crc32(st.req_id.encode()) * 2654435761 + self.mc.seed) & 0x7FFFFFFFFFFF
+            self.filter_cpu[row] = sp.temperature >= 1e-5 and (sp.top_k > 0 or sp.top_p < 1.0 or sp.min_p > 0)
+            st.complex_sampling = bool(
+                sp.needs_penalties or sp.logprobs is not None or sp.prompt_logprobs is not None or sp.logit_bias
+                or sp.allowed_token_ids or sp.bad_words_token_ids or sp.min_tokens > 0
+                or sp.structured_outputs is not None)
+        else:
+            self.temp_cpu[row] = 0.0
+            self.seed_cpu[row] = 0
+            self.filter_cpu[row] = False
+            st.complex_sampling = True
+        self.complex_cpu[row] = st.complex_sampling
         for g in range(self.num_kv_groups):
             ids = block_ids[g]
             self.block_tables_cpu[g][row, :len(ids)] = ids
@@ -222,7 +320,6 @@ class ModelRunner:
             self._parked.pop(rid, None)
         for rid in so.preempted_req_ids:
             self._remove(rid, park=True)
-        # requests in the batch that were not scheduled this step stay resident
         for nr in so.scheduled_new_reqs:
             if nr.req_id in self.req_index:
                 self._remove(nr.req_id)
@@ -243,6 +340,7 @@ class ModelRunner:
                 n0 = c.num_computed_tokens[i]
                 self.token_ids_cpu[row, n0:n0 + len(toks)] = toks
                 self.num_tokens_cpu[row] = max(self.num_tokens_cpu[row], n0 + len(toks))
+                self.num_logical_cpu[row] = max(self.num_logical_cpu[row], self.num_tokens_cpu[row])
             nb = c.new_block_ids[i]
             if nb is not None:
                 for g in range(self.num_kv_groups):
@@ -253,20 +351,24 @@ class ModelRunner:
                         self.num_blocks_cpu[g][row] = s + len(ids)
 
     # ---------------------------------------------------------- input prep
-    def _prepare(self, so: SchedulerOutput):
+    def _prepare(self, so: SchedulerOutput, stg: _Staging):
         B = len(self.req_ids)
-        n_sched = np.fromiter((so.num_scheduled_tokens.get(r, 0) for r in self.req_ids), dtype=np.int32, count=B)
-        active = np.nonzero(n_sched)[0]
-        rows = active.astype(np.int64)
-        ns = n_sched[active]
+        get = so.num_scheduled_tokens.get
+        n_sched = np.fromiter((get(r, 0) for r in self.req_ids), dtype=np.int32, count=B)
+        rows = np.nonzero(n_sched)[0].astype(np.int64)
+        ns = n_sched[rows]
         nb = len(rows)
         T = int(ns.sum())
         cu = np.zeros(nb + 1, dtype=np.int32)
         np.cumsum(ns, out=cu[1:])
-        req_of_tok = np.repeat(np.arange(nb), ns)
-        offs = np.arange(T, dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), ns)
         computed = self.num_computed_cpu[rows].astype(np.int64)
-        pos = computed[req_of_tok] + offs
+        if T == nb:  # pure decode: one token per row
+            req_of_tok = np.arange(nb)
+            pos = computed
+        else:
+            req_of_tok = np.repeat(np.arange(nb), ns)
+            offs = np.arange(T, dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), ns)
+            pos = computed[req_of_tok] + offs
         row_of_tok = rows[req_of_tok]
         # speculative tokens are appended after the known tokens of the row
         for rid, drafts in so.scheduled_spec_decode_tokens.items():
@@ -274,32 +376,48 @@ class ModelRunner:
             n = self.num_tokens_cpu[r]
             self.token_ids_cpu[r, n:n + len(drafts)] = drafts
         ids = self.token_ids_cpu[row_of_tok, pos]
-        self.input_ids_pin[:T] = torch.from_numpy(ids)
-        self.positions_pin[:T] = torch.from_numpy(pos)
+        # tokens sampled by a step that is still in flight: patched on the device from last_sampled
+        n_spec_row = np.zeros(nb, dtype=np.int64)
+        unknown = pos >= (self.num_tokens_cpu[row_of_tok].astype(np.int64))
+        if so.scheduled_spec_decode_tokens:
+            unknown[:] = False
+        fix = np.nonzero(unknown)[0]
+        stg.input_ids[:T] = torch.from_numpy(ids)
+        stg.positions[:T] = torch.from_numpy(pos)
         seq_lens = (computed + ns).astype(np.int32)
-        self.qsl_pin[:nb + 1] = torch.from_numpy(cu)
-        self.seq_lens_pin[:nb] = torch.from_numpy(seq_lens)
+        stg.qsl[:nb + 1] = torch.from_numpy(cu)
+        stg.seq_lens[:nb] = torch.from_numpy(seq_lens)
+        stg.rows[:nb] = torch.from_numpy(rows)
         bs = self.block_size
         for g in range(self.num_kv_groups):
             bt = self.block_tables_cpu[g]
             slots = bt[row_of_tok, pos // bs].astype(np.int64) * bs + pos % bs
-            self.slot_pins[g][:T] = torch.from_numpy(slots)
+            stg.slots[g][:T] = torch.from_numpy(slots)
+        if len(fix):
+            stg.fix_idx[:len(fix)] = torch.from_numpy(fix)
+            stg.fix_rows[:len(fix)] = torch.from_numpy(row_of_tok[fix])
+        del n_spec_row
         max_q = int(ns.max()) if nb else 0
         max_s = int(seq_lens.max()) if nb else 0
-        return rows, ns, cu, T, max_q, max_s, seq_lens
+        return rows, ns, cu, T, max_q, max_s, len(fix)
 
-    def _h2d(self, rows, nb, T, pad_b, pad_t, max_s) -> None:
+    def _h2d(self, stg: _Staging, rows, nb, T, pad_b, pad_t, max_s, n_fix) -> None:
         nbk = cdiv(max_s, self.block_size)
         self.h2d_bytes += T * (4 + 8) + (nb + 1) * 4 + nb * 4 + self.num_kv_groups * (T * 8 + nb * nbk * 4)
-        self.input_ids[:T].copy_(self.input_ids_pin[:T], non_blocking=True)
-        self.positions[:T].copy_(self.positions_pin[:T], non_blocking=True)
-        self.qsl[:nb + 1].copy_(self.qsl_pin[:nb + 1], non_blocking=True)
-        self.seq_lens[:nb].copy_(self.seq_lens_pin[:nb], non_blocking=True)
+        nbc = True
+        self.input_ids[:T].copy_(stg.input_ids[:T], non_blocking=nbc)
+        self.positions[:T].copy_(stg.positions[:T], non_blocking=nbc)
+        self.qsl[:nb + 1].copy_(stg.qsl[:nb + 1], non_blocking=nbc)
+        self.seq_lens[:nb].copy_(stg.seq_lens[:nb], non_blocking=nbc)
         for g in range(self.num_kv_groups):
-            self.slot_mappings[g][:T].copy_(self.slot_pins[g][:T], non_blocking=True)
-            src = self.block_tables_cpu[g][rows, :nbk]
-            self.block_tables_pin[g][:nb, :nbk] = torch.from_numpy(src)
-            self.block_tables[g][:nb, :nbk].copy_(self.block_tables_pin[g][:nb, :nbk], non_blocking=True)
+            self.slot_mappings[g][:T].copy_(stg.slots[g][:T], non_blocking=nbc)
+            stg.block_tables[g][:nb, :nbk] = torch.from_numpy(self.block_tables_cpu[g][rows, :nbk])
+            self.block_tables[g][:nb, :nbk].copy_(stg.block_tables[g][:nb, :nbk], non_blocking=nbc)
+        if n_fix:
+            idx = stg.fix_idx[:n_fix].to(self.device, non_blocking=True)
+            src = stg.fix_rows[:n_fix].to(self.device, non_blocking=True)
+            self.input_ids[:T].index_copy_(0, idx, self.last_sampled[src].to(torch.int32))
+            self.h2d_bytes += n_fix * 16
         if pad_t > T:  # padded decode slots: write to the null block, attend over 1 token of block 0
             self.input_ids[T:pad_t].zero_()
             self.positions[T:pad_t].zero_()
@@ -329,100 +447,105 @@ class ModelRunner:
         with set_forward_context(ctx):
             return self.model(self.input_ids[:T], self.positions[:T], intermediate)
 
+    def _next_staging(self) -> _Staging:
+        self._stage_i = (self._stage_i + 1) % len(self.staging)
+        stg = self.staging[self._stage_i]
+        stg.wait()  # the copies that used this set 2-3 steps ago have long completed
+        return stg
+
+    def finalize_pending(self) -> None:
+        if self._pending is not None:
+            self._pending.get()
+
     @torch.inference_mode()
-    def execute_model(self, so: SchedulerOutput, intermediate=None) -> ModelRunnerOutput:
+    def execute_model(self, so: SchedulerOutput, intermediate=None, non_block: bool = False):
+        """Launch one step. Returns a ModelRunnerOutput, or (non_block) an AsyncStepOutput."""
         t0 = time.perf_counter()
         self._step += 1
         self._update_states(so)
         if so.total_num_scheduled_tokens == 0:
             return ModelRunnerOutput()
-        rows, ns, cu, T, max_q, max_s, seq_lens = self._prepare(so)
+        B_all = len(self.req_ids)
+        # features that need the previous step's tokens on the host force a drain of the pipeline
+        if self._pending is not None and (bool(self.complex_cpu[:B_all].any()) or so.scheduled_spec_decode_tokens
+                                          or self.drafter is not None or so.grammar_bitmask is not None):
+            self._pending.get()
+        stg = self._next_staging()
+        rows, ns, cu, T, max_q, max_s, n_fix = self._prepare(so, stg)
         nb = len(rows)
         has_spec = bool(so.scheduled_spec_decode_tokens)
         decode_only = max_q == 1 and not has_spec
         pad_b = nb
         graph = None
-        if decode_only and self.use_cuda_graph and self.graphs:
+        simple = not bool(self.complex_cpu[rows].any()) and so.grammar_bitmask is None
+        no_filter = not bool(self.filter_cpu[rows].any())
+        if decode_only and self.use_cuda_graph and self.graphs and simple and no_filter:
             pad_b = self._bucket(nb)
             graph = self.graphs.get(pad_b)
             if graph is None:
                 pad_b = nb
         pad_t = pad_b if graph is not None else T
-        self._h2d(rows, nb, T, pad_b, pad_t, max_s)
-        cpu_qsl = self.qsl_pin[:nb + 1] if not self.is_cuda else None
-        cpu_sl = self.seq_lens_pin[:nb] if not self.is_cuda else None
+        self._h2d(stg, rows, nb, T, pad_b, pad_t, max_s, n_fix)
+        cpu_qsl = stg.qsl[:nb + 1] if not self.is_cuda else None
+        cpu_sl = stg.seq_lens[:nb] if not self.is_cuda else None
         # which rows produce a token this step (prefill chunk finished / decode)
         total_after = self.num_computed_cpu[rows] + ns
-        known = self.num_tokens_cpu[rows]
-        produces = total_after >= known  # spec rows: known excludes drafts
-        sampled_cpu: Optional[list[list[int]]] = None
-        lp_out = None
-        states = [self.states[self.req_ids[r]] for r in rows]
+        produces = total_after >= self.num_logical_cpu[rows]  # spec rows: logical count excludes drafts
+        lp_out, plp = None, {}
+        req_ids = [self.req_ids[r] for r in rows]
         if graph is not None:
-            smd = self._sampling_metadata(states, rows, pad_b)
-            graph_ok = smd.all_greedy or (smd.top_k is None and smd.top_p is None and smd.min_p is None
-                                          and smd.no_penalties and smd.max_num_logprobs is None)
-            graph_ok = graph_ok and smd.max_num_logprobs is None and smd.no_penalties \
-                and so.grammar_bitmask is None
-            if graph_ok and not self._needs_logits_processors(smd) and self._graph_supports(graph, smd):
-                sampled = graph.replay(smd)[:nb]
-                self.launch_count += graph.num_launches
-                self.h2d_bytes += pad_b * 12
-            else:
-                graph = None
-        if graph is None:
+            # fast path: temperature / seed / step vectors straight from the per-row arrays
+            stg.temperature[:nb] = torch.from_numpy(self.temp_cpu[rows])
+            stg.seeds[:nb] = torch.from_numpy(self.seed_cpu[rows])
+            stg.steps[:nb] = torch.from_numpy(self.num_logical_cpu[rows] - self.num_prompt_cpu[rows])
+            if pad_b > nb:
+                stg.temperature[nb:pad_b] = 0.0
+            sampled = graph.replay_from_staging(stg, pad_b)[:nb]
+            self.launch_count += graph.num_launches
+            self.h2d_bytes += pad_b * 16
+        else:
             l0 = self._launches()
+            states = [self.states[r] for r in req_ids]
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
             hidden = self._forward(T, md, intermediate)
             if isinstance(hidden, dict):  # non-last PP stage
                 return ModelRunnerOutput(kv_connector_output=hidden)
-            pool_states = [s for s in states if s.pooling_params is not None]
-            if pool_states:
+            if any(s.pooling_params is not None for s in states):
                 return self._pool(hidden, states, rows, cu, produces, t0)
             if has_spec:
                 return self._verify_spec(so, hidden, states, rows, ns, cu, t0)
             last_idx = torch.from_numpy(cu[1:].astype(np.int64) - 1).to(self.device, non_blocking=True)
             logits = self.model.compute_logits(hidden[last_idx])
-            smd = self._sampling_metadata(states, rows, nb)
-            bitmask = None
-            if so.grammar_bitmask is not None:
-                bitmask = self._gather_bitmask(so, states)
+            smd = self._sampling_metadata(states, rows, nb, simple)
+            bitmask = self._gather_bitmask(so, states) if so.grammar_bitmask is not None else None
             so_out = self.sampler(logits, smd, bitmask)
             sampled = so_out.sampled_token_ids
             if so_out.logprobs is not None:
                 keep = torch.from_numpy(np.nonzero(produces)[0]).to(self.device)
                 ids, vals, ranks = so_out.logprobs
                 lp_out = LogprobsTensors(ids[keep].cpu(), vals[keep].cpu(), ranks[keep].cpu())
-            plp = self._prompt_logprobs(hidden, states, rows, ns, cu) if any(
-                s.sampling_params is not None and s.sampling_params.prompt_logprobs is not None for s in states) else {}
+            if not simple and any(s.sampling_params is not None and s.sampling_params.prompt_logprobs is not None
+                                  for s in states):
+                plp = self._prompt_logprobs(hidden, states, rows, ns, cu)
+            if self.is_cuda:
+                self.launch_count += self._launches() - l0
+        # publish: device-side last_sampled (for the next step's input patch) + async D2H
+        ev = None
+        if self.is_cuda:
+            rows_dev = stg.rows[:nb].to(self.device, non_blocking=True)
+            self.last_sampled.index_copy_(0, rows_dev, sampled)
+            stg.sampled[:nb].copy_(sampled, non_blocking=True)
+            stg.event.record()
+            ev = stg.event
         else:
-            plp = {}
-        if graph is None and self.is_cuda:
-            self.launch_count += self._launches() - l0
-        toks = sampled.tolist()  # D2H sync point
-        self.d2h_bytes += len(toks) * 8
-        out_ids: list[list[int]] = []
-        req_ids = []
-        for j, r in enumerate(rows):
-            rid = self.req_ids[r]
-            req_ids.append(rid)
-            if produces[j]:
-                t = toks[j]
-                n = self.num_tokens_cpu[r]
-                self.token_ids_cpu[r, n] = t
-                self.num_tokens_cpu[r] = n + 1
-                states[j].output_token_ids.append(t)
-                out_ids.append([t])
-            else:
-                out_ids.append([])
-            self.num_computed_cpu[r] = total_after[j]
-        spec_ids = None
-        if self.drafter is not None:
-            spec_ids = self.drafter.propose(self, rows, [o for o in out_ids])
-        ms = (time.perf_counter() - t0) * 1e3
-        return ModelRunnerOutput(req_ids=req_ids, req_id_to_index={r: i for i, r in enumerate(req_ids)},
-                                 sampled_token_ids=out_ids, logprobs=lp_out, prompt_logprobs_dict=plp,
-                                 spec_token_ids=spec_ids, forward_ms=ms)
+            stg.sampled[:nb] = sampled
+        self.num_logical_cpu[rows] += produces.astype(np.int32)
+        self.num_computed_cpu[rows] = total_after
+        out = AsyncStepOutput(self, req_ids, produces, stg, nb, ev, t0, lp_out, plp)
+        if non_block and self.async_mode:
+            self._pending = out
+            return out
+        return out.get()
 
     # ------------------------------------------------------------- helpers
     def _launches(self) -> int:
@@ -431,32 +554,34 @@ class ModelRunner:
         from vllm_b200.ops import cuda_ops
         return cuda_ops().LAUNCHES
 
-    @staticmethod
-    def _needs_logits_processors(smd: SamplingMetadata) -> bool:
-        return (smd.allowed_token_ids_mask is not None or bool(smd.min_tokens) or any(smd.logit_bias)
-                or bool(smd.bad_words_token_ids))
-
-    def _graph_supports(self, graph, smd: SamplingMetadata) -> bool:
-        return True
-
     def _bucket(self, n: int) -> int:
         for s in self.capture_sizes:
             if s >= n:
                 return s
         return -1
 
-    def _sampling_metadata(self, states: list[ReqState], rows, pad_b: int) -> SamplingMetadata:
+    def _sampling_metadata(self, states: list[ReqState], rows, pad_b: int, simple: bool = False) -> SamplingMetadata:
         B = len(states)
         dev = self.device
-        temps = np.ones(pad_b, dtype=np.float32)
-        top_k = np.zeros(pad_b, dtype=np.int32)
-        top_p = np.ones(pad_b, dtype=np.float32)
-        min_p = np.zeros(pad_b, dtype=np.float32)
-        pres = np.zeros(pad_b, dtype=np.float32)
-        freq = np.zeros(pad_b, dtype=np.float32)
-        rep = np.ones(pad_b, dtype=np.float32)
-        seeds = np.zeros(pad_b, dtype=np.int64)
-        steps = np.zeros(pad_b, dtype=np.int32)
+        rows = np.asarray(rows)
+        temps = self.temp_cpu[rows].copy()
+        all_greedy = bool((temps < 1e-5).all())
+        all_random = bool((temps >= 1e-5).all())
+        t = torch.from_numpy(temps).to(dev, non_blocking=True)
+        if simple and not bool(self.filter_cpu[rows].any()):
+            md = SamplingMetadata(temperature=t, all_greedy=all_greedy, all_random=all_random)
+            if not all_greedy:
+                md.seeds = torch.from_numpy(self.seed_cpu[rows]).to(dev)
+                md.steps = torch.from_numpy((self.num_logical_cpu[rows] - self.num_prompt_cpu[rows]).astype(np.int32)).to(dev)
+                if not self.is_cuda:  # the reference sampler draws from per-request torch generators
+                    md.generators = {i: s.generator for i, s in enumerate(states) if s.generator is not None}
+            return md
+        top_k = np.zeros(B, dtype=np.int32)
+        top_p = np.ones(B, dtype=np.float32)
+        min_p = np.zeros(B, dtype=np.float32)
+        pres = np.zeros(B, dtype=np.float32)
+        freq = np.zeros(B, dtype=np.float32)
+        rep = np.ones(B, dtype=np.float32)
         gens: dict[int, torch.Generator] = {}
         logit_bias: list = [None] * B
         bad: dict[int, list[list[int]]] = {}
@@ -467,18 +592,12 @@ class ModelRunner:
         for i, s in enumerate(states):
             sp = s.sampling_params
             if sp is None:
-                temps[i] = 0.0
                 continue
-            temps[i] = sp.temperature
             top_k[i], top_p[i], min_p[i] = sp.top_k, sp.top_p, sp.min_p
             pres[i], freq[i], rep[i] = sp.presence_penalty, sp.frequency_penalty, sp.repetition_penalty
             any_pen |= sp.needs_penalties
             if s.generator is not None:
                 gens[i] = s.generator
-            # unseeded requests get a seed that is identical on every TP rank (crc of the id + engine seed)
-            seeds[i] = (sp.seed if sp.seed is not None
-                        else zlib.crc32(s.req_id.encode()) * 2654435761 + self.mc.seed) & 0x7FFFFFFFFFFF
-            steps[i] = len(s.output_token_ids)
             if sp.logit_bias:
                 logit_bias[i] = sp.logit_bias
             if sp.bad_words_token_ids:
@@ -490,10 +609,6 @@ class ModelRunner:
                 max_lp = k if max_lp is None else max(max_lp, k)
             if sp.allowed_token_ids:
                 allowed_rows.append(i)
-        temps[B:] = 0.0
-        all_greedy = bool((temps < 1e-5).all())
-        all_random = bool((temps[:B] >= 1e-5).all())
-        t = torch.from_numpy(temps).to(dev, non_blocking=True)
         md = SamplingMetadata(temperature=t, all_greedy=all_greedy, all_random=all_random, generators=gens,
                               max_num_logprobs=max_lp, logit_bias=logit_bias if any(logit_bias) else [],
                               bad_words_token_ids=bad, min_tokens=min_toks,
@@ -505,12 +620,12 @@ class ModelRunner:
                 md.top_p = torch.from_numpy(top_p).to(dev)
             if (min_p > 0).any():
                 md.min_p = torch.from_numpy(min_p).to(dev)
-            md.seeds = torch.from_numpy(seeds).to(dev)
-            md.steps = torch.from_numpy(steps).to(dev)
+            md.seeds = torch.from_numpy(self.seed_cpu[rows]).to(dev)
+            md.steps = torch.from_numpy((self.num_logical_cpu[rows] - self.num_prompt_cpu[rows]).astype(np.int32)).to(dev)
         if any_pen:
             md.no_penalties = False
-            md.presence, md.frequency = torch.from_numpy(pres[:B]).to(dev), torch.from_numpy(freq[:B]).to(dev)
-            md.repetition = torch.from_numpy(rep[:B]).to(dev)
+            md.presence, md.frequency = torch.from_numpy(pres).to(dev), torch.from_numpy(freq).to(dev)
+            md.repetition = torch.from_numpy(rep).to(dev)
             V = self.vocab_size
             pm = torch.zeros(B, V, dtype=torch.bool)
             oc = torch.zeros(B, V, dtype=torch.int32)
@@ -608,6 +723,7 @@ class ModelRunner:
             n = known
             self.token_ids_cpu[r, n:n + len(acc)] = acc
             self.num_tokens_cpu[r] = n + len(acc)
+            self.num_logical_cpu[r] = n + len(acc)
             s.output_token_ids.extend(acc)
             out_ids.append(acc)
             # rejected drafts' KV slots are simply overwritten next step

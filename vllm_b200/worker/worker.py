@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import gc
 import os
+import time
 from typing import Any, Optional
 
 import torch
@@ -47,6 +48,13 @@ class Worker:
             gc.collect()
             torch.cuda.empty_cache()
             self.init_free_bytes, self.total_bytes = torch.cuda.mem_get_info(self.device)
+            # a previous process on this GPU may still be tearing down (its memory is released
+            # asynchronously): give it a moment before sizing the KV cache against free memory
+            want = self.vllm_config.cache_config.gpu_memory_utilization * self.total_bytes
+            t_end = time.time() + 20.0
+            while self.init_free_bytes < min(want, 0.9 * self.total_bytes) and time.time() < t_end:
+                time.sleep(0.5)
+                self.init_free_bytes, _ = torch.cuda.mem_get_info(self.device)
         else:
             self.device = torch.device("cpu")
         world = pc.world_size
@@ -77,8 +85,10 @@ class Worker:
         torch.cuda.synchronize()
         peak_torch = torch.cuda.max_memory_allocated(self.device)
         free, total = torch.cuda.mem_get_info(self.device)
-        non_torch = max((total - free) - torch.cuda.memory_reserved(self.device), 0)
-        budget = int(total * cc.gpu_memory_utilization)
+        # memory this process holds outside the torch allocator (CUDA context, NCCL, symmetric heap);
+        # measured against the free memory seen at start-up so other tenants are not billed to us
+        non_torch = max((self.init_free_bytes - free) - torch.cuda.memory_reserved(self.device), 0)
+        budget = min(int(total * cc.gpu_memory_utilization), self.init_free_bytes)
         graph_reserve = 0 if self.vllm_config.model_config.enforce_eager else (2 << 30)
         avail = budget - peak_torch - non_torch - graph_reserve
         gc.collect()
@@ -96,15 +106,15 @@ class Worker:
 
     # -------------------------------------------------------------- execute
     @torch.inference_mode()
-    def execute_model(self, so: SchedulerOutput) -> Optional[ModelRunnerOutput]:
+    def execute_model(self, so: SchedulerOutput, non_block: bool = False):
         pp = pstate.get_pp_group()
         intermediate = None
         if pp.world_size > 1 and not pp.is_first_rank:
             if so.total_num_scheduled_tokens > 0:
                 intermediate = pp.recv_tensor_dict(device=self.device)
-        out = self.runner.execute_model(so, intermediate)
+        out = self.runner.execute_model(so, intermediate, non_block=non_block)
         if pp.world_size > 1 and not pp.is_last_rank:
-            if isinstance(out.kv_connector_output, dict):
+            if isinstance(getattr(out, "kv_connector_output", None), dict):
                 pp.send_tensor_dict(out.kv_connector_output)
             return None
         return out
@@ -191,5 +201,16 @@ class Worker:
         return self.runner.model
 
     def shutdown(self) -> None:
+        r = self.runner
+        if r is not None:  # drop device memory even if someone still holds a reference to the runner
+            r.graphs.clear()
+            r.graph_pool = None
+            r.kv_caches.clear()
+            r.model = None
+            r.block_tables.clear()
+            r.slot_mappings.clear()
         self.runner = None
         pstate.destroy_model_parallel()
+        gc.collect()
+        if self.device is not None and self.device.type == "cuda":
+            torch.cuda.empty_cache()
