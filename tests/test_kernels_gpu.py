@@ -209,3 +209,56 @@ def test_gemm_tc_strided_input():
     x = big[:, 1024:2048]
     w = (torch.randn(512, 1024, device="cuda") * 0.05).to(torch.bfloat16)
     close(cu().gemm_tc(x, w), x.float() @ w.float().t(), atol=3e-2, rtol=2e-2)
+
+
+def _to_tc_layout(cache):
+    """Standard [nb,2,H,BS,D] cache → tensor-core layout (V pages transposed in place)."""
+    nb, _, H, BS, D = cache.shape
+    tc = cache.clone()
+    tc[:, 1] = cache[:, 1].transpose(-1, -2).contiguous().view(nb, H, BS, D)
+    return tc
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(32, 8), (8, 1), (4, 4), (64, 8)])
+@pytest.mark.parametrize("splits", [1, 3])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fmha_tc_decode(Hq, Hkv, splits, dtype):
+    D, BS = 128, 64
+    seq_lens = [1, 63, 64, 65, 127, 128, 129, 1000, 257, 5]
+    B = len(seq_lens)
+    q, cache, md = _mk_attn_case(B, Hq, Hkv, D, BS, seq_lens, [1] * B, dtype=dtype)
+    md.num_splits = splits
+    md.kv_vt = True
+    scale = 1.0 / math.sqrt(D)
+    out = cu().paged_attention(q, _to_tc_layout(cache), md, scale)
+    exp = ref.paged_attention(q, cache, md.block_table, md.seq_lens_cpu, md.query_start_loc_cpu, scale)
+    close(out, exp, atol=1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(32, 8), (8, 1), (4, 4)])
+@pytest.mark.parametrize("window", [None, 100])
+def test_fmha_tc_prefill(Hq, Hkv, window):
+    D, BS = 128, 64
+    seq_lens = [17, 64, 300, 130, 1, 513]
+    q_lens = [17, 64, 172, 1, 1, 513]
+    q, cache, md = _mk_attn_case(len(seq_lens), Hq, Hkv, D, BS, seq_lens, q_lens, seed=3)
+    md.kv_vt = True
+    scale = 1.0 / math.sqrt(D)
+    out, lse = cu().paged_attention(q, _to_tc_layout(cache), md, scale, sliding_window=window, return_lse=True)
+    exp, elsee = ref.paged_attention(q, cache, md.block_table, md.seq_lens_cpu, md.query_start_loc_cpu, scale,
+                                     sliding_window=window, return_lse=True)
+    close(out, exp, atol=1e-2, rtol=2e-2)
+    close(lse, elsee, atol=1e-2, rtol=1e-2)
+
+
+def test_cache_write_tc_layout():
+    torch.manual_seed(4)
+    T, Hkv, D, BS, NB = 50, 8, 128, 64, 8
+    k = torch.randn(T, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(T, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    slots = torch.randperm(NB * BS, device="cuda")[:T].long()
+    std = torch.zeros(NB, 2, Hkv, BS, D, device="cuda", dtype=torch.bfloat16)
+    ref.reshape_and_cache(k, v, std, slots)
+    tc = torch.zeros_like(std)
+    cu().reshape_and_cache(k, v, tc, slots, vt=True)
+    close(tc, _to_tc_layout(std), atol=0, rtol=0)

@@ -1,0 +1,41 @@
+"""Multi-GPU tests (need >= 2 GPUs on the box): symmetric-heap collectives vs NCCL, TP=2 end-to-end vs TP=1."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(n, *args, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py"), *args]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
+    return r.stdout
+
+
+def test_symm_collectives_match_nccl():
+    out = _torchrun(2, "collectives")
+    assert "collectives ok" in out
+
+
+def test_tp2_matches_tp1(tmp_path):
+    base = str(tmp_path / "e2e.json")
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29612")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py"), "e2e", base], env=env,
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    _torchrun(2, "e2e", base)
+    a, b = json.load(open(base + ".tp1")), json.load(open(base + ".tp2"))
+    agree = total = 0
+    for ta, tb, la, lb in zip(a["tokens"], b["tokens"], a["logprobs"], b["logprobs"]):
+        n = next((i for i, (x, y) in enumerate(zip(ta, tb)) if x != y), len(ta))
+        agree += n
+        total += len(ta)
+        for x, y in zip(la[:n], lb[:n]):
+            assert abs(x - y) < 0.1
+    assert agree / total > 0.7

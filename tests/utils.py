@@ -36,3 +36,32 @@ def hf_greedy(model, prompt_ids: list[int], n: int) -> list[int]:
         out = model.generate(ids, max_new_tokens=n, do_sample=False, pad_token_id=0,
                              eos_token_id=None)
     return out[0, len(prompt_ids):].tolist()
+
+
+def llama_full_weights(cfg: dict, seed: int = 0, scale: float = 0.05):
+    """Deterministic *unsharded* Llama checkpoint (HF names) so that different TP sizes load the same model."""
+    H, I, V, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"], cfg["num_hidden_layers"]
+    nh, nkv = cfg["num_attention_heads"], cfg.get("num_key_value_heads") or cfg["num_attention_heads"]
+    D = cfg.get("head_dim") or H // nh
+    g = torch.Generator().manual_seed(seed)
+
+    def rnd(*shape):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+    def norm():
+        return 1.0 + (torch.rand(H, generator=g) * 2 - 1) * 0.05
+
+    yield "model.embed_tokens.weight", rnd(V, H)
+    for i in range(L):
+        p = f"model.layers.{i}."
+        yield p + "input_layernorm.weight", norm()
+        yield p + "self_attn.q_proj.weight", rnd(nh * D, H)
+        yield p + "self_attn.k_proj.weight", rnd(nkv * D, H)
+        yield p + "self_attn.v_proj.weight", rnd(nkv * D, H)
+        yield p + "self_attn.o_proj.weight", rnd(H, nh * D)
+        yield p + "post_attention_layernorm.weight", norm()
+        yield p + "mlp.gate_proj.weight", rnd(I, H)
+        yield p + "mlp.up_proj.weight", rnd(I, H)
+        yield p + "mlp.down_proj.weight", rnd(H, I)
+    yield "model.norm.weight", norm()
+    yield "lm_head.weight", rnd(V, H)

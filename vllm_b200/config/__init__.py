@@ -40,7 +40,7 @@ class _ConfigBase:
 class CacheConfig(_ConfigBase):
     """Paged-KV configuration (reference: vllm/config/cache.py)."""
 
-    block_size: int = 32  # tokens per KV page; 32 keeps a page = one TMA box for D=128
+    block_size: int = 64  # tokens per KV page: a K page [64,128] / V^T page [128,64] is one 16 KB SW128 TMA box
     gpu_memory_utilization: float = 0.92
     swap_space_gb: float = 4.0
     cache_dtype: str = "auto"  # auto|bfloat16|fp8|fp8_e4m3|fp8_e5m2

@@ -1,0 +1,148 @@
+// Stand-alone collectives over the symmetric heap: all-reduce (+ residual add + RMSNorm), all-gather,
+// barrier.  They cover every TP collective that is not already the epilogue of a GEMM (see gemm_ar.cu).
+//
+// all-reduce with fused residual + RMSNorm (collective C1 of SURVEY §2.4 followed by the next layer's norm):
+//   phase 0  (optional) copy the local partial [T,H] into the symmetric staging region `in_off`
+//   barrier  every rank's partial is in place
+//   phase 1  rank r owns rows r*ceil(T/W)..: sum over ranks (multimem.ld_reduce in the switch, or P2P loads),
+//            += residual (residual stays SHARDED by row owner — nobody else ever reads those rows),
+//            RMSNorm, broadcast the normalised row to every rank (multimem.st / P2P stores) at `out_off`
+//   barrier  all rows have landed everywhere → kernel completion means the output is usable
+// The grid is persistent (<= #SMs CTAs looping over rows) so the intra-kernel barriers cannot deadlock.
+#include "comm.cuh"
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(1024) ar_rows_kernel(CommCtx c, const T* __restrict__ x, size_t in_off, size_t out_off,
+                                                        T* __restrict__ residual, const T* __restrict__ norm_w,
+                                                        float eps, int T_rows, int H, int gemma) {
+  __shared__ float red[32];
+  const uint32_t e0 = c.state[0];
+  const int vec_per_row = H / 8;
+  // ---- phase 0: stage the local partial
+  if (x != nullptr) {
+    const size_t total = (size_t)T_rows * vec_per_row;
+    uint4* dst = reinterpret_cast<uint4*>(c.local + in_off);
+    const uint4* src = reinterpret_cast<const uint4*>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
+  grid_rank_barrier(c, &c.state[1], &c.state[2], e0 + 1, true);
+  // ---- phase 1: my rows
+  const int per = (T_rows + c.world - 1) / c.world;
+  const int r0 = c.rank * per, r1 = min(T_rows, r0 + per);
+  for (int row = r0 + blockIdx.x; row < r1; row += gridDim.x) {
+    float acc[8];
+    float ss = 0.f;
+    const bool active = threadIdx.x < vec_per_row;
+    const size_t off = ((size_t)row * H + threadIdx.x * 8) * sizeof(T);
+    if (active) {
+      reduce8<T>(c, in_off + off, acc);
+      if (residual) {
+        Vec16<T> rv = ld16(residual + (size_t)row * H + threadIdx.x * 8), ro;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // reproduce the unfused numerics: the all-reduced value is rounded to T before the add
+          ro.e[i] = from_f32<T>(to_f32(from_f32<T>(acc[i])) + to_f32(rv.e[i]));
+          acc[i] = to_f32(ro.e[i]);
+        }
+        st16(residual + (size_t)row * H + threadIdx.x * 8, ro);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += acc[i] * acc[i];
+    }
+    uint32_t o[4];
+    if (norm_w) {
+      ss = block_sum(ss, red);
+      const float inv = rsqrtf(ss / (float)H + eps);
+      if (active) {
+        Vec16<T> wv = ld16(norm_w + threadIdx.x * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float g0 = to_f32(wv.e[2 * i]) + (gemma ? 1.f : 0.f), g1 = to_f32(wv.e[2 * i + 1]) + (gemma ? 1.f : 0.f);
+          o[i] = pack2<T>(acc[2 * i] * inv * g0, acc[2 * i + 1] * inv * g1);
+        }
+      }
+    } else if (active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = pack2<T>(acc[2 * i], acc[2 * i + 1]);
+    }
+    if (active) bcast16(c, out_off + off, o);
+  }
+  // ---- everyone's rows have been written everywhere
+  grid_rank_barrier(c, &c.state[3], &c.state[4], e0 + 2, false, true);
+}
+
+// all-gather along the last dim: out[row, rank*cols + j] = x[row, j] on every rank
+template <typename T>
+__global__ void all_gather_kernel(CommCtx c, const T* __restrict__ x, size_t out_off, int rows, int cols) {
+  const uint32_t e0 = c.state[0];
+  const int vec_per_row = cols / 8;
+  const size_t total = (size_t)rows * vec_per_row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / vec_per_row, v = i % vec_per_row;
+    const uint4 u = *reinterpret_cast<const uint4*>(x + row * cols + v * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    bcast16(c, out_off + ((row * c.world + c.rank) * cols + v * 8) * sizeof(T), w);
+  }
+  grid_rank_barrier(c, &c.state[1], &c.state[2], e0 + 1, false, true);
+}
+
+__global__ void barrier_kernel(CommCtx c) {
+  const uint32_t e0 = c.state[0];
+  grid_rank_barrier(c, &c.state[1], &c.state[2], e0 + 1, false, true);
+}
+
+}  // namespace
+
+static CommCtx make_ctx(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world) {
+  CommCtx c;
+  c.local = (unsigned char*)local;
+  for (int i = 0; i < VB_MAX_RANKS; ++i) c.peer[i] = i < world ? (unsigned char*)peers[i] : nullptr;
+  c.mc = (unsigned char*)mc;
+  c.state = state;
+  c.rank = rank;
+  c.world = world;
+  return c;
+}
+
+// x may be null when the partial already lives in the symmetric buffer at in_off (e.g. written by a GEMM epilogue)
+EXPORT int vb_comm_allreduce_rows(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
+                                  const void* x, int64_t in_off, int64_t out_off, void* residual, const void* norm_w,
+                                  float eps, int T_rows, int H, int gemma, int num_sms, int dtype, cudaStream_t st) {
+  if (T_rows == 0) return 0;
+  if (dtype == DT_F32 || H % 8 != 0 || H / 8 > 1024) return -1;
+  CommCtx c = make_ctx(local, peers, mc, state, rank, world);
+  const int per = (T_rows + world - 1) / world;
+  int grid = per < num_sms ? per : num_sms;
+  if (grid < 1) grid = 1;
+  int thr = ((H / 8 + 31) / 32) * 32;
+  DISPATCH_HALF(dtype, TT, {
+    ar_rows_kernel<TT><<<grid, thr, 0, st>>>(c, (const TT*)x, (size_t)in_off, (size_t)out_off, (TT*)residual,
+                                              (const TT*)norm_w, eps, T_rows, H, gemma);
+  });
+  return (int)cudaGetLastError();
+}
+
+EXPORT int vb_comm_all_gather(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
+                              const void* x, int64_t out_off, int rows, int cols, int num_sms, int dtype,
+                              cudaStream_t st) {
+  if (rows == 0) return 0;
+  if (dtype == DT_F32 || cols % 8 != 0) return -1;
+  CommCtx c = make_ctx(local, peers, mc, state, rank, world);
+  const size_t total = (size_t)rows * (cols / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms) grid = num_sms;
+  DISPATCH_HALF(dtype, TT, {
+    all_gather_kernel<TT><<<grid, 256, 0, st>>>(c, (const TT*)x, (size_t)out_off, rows, cols);
+  });
+  return (int)cudaGetLastError();
+}
+
+EXPORT int vb_comm_barrier(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
+                           cudaStream_t st) {
+  CommCtx c = make_ctx(local, peers, mc, state, rank, world);
+  barrier_kernel<<<1, 32, 0, st>>>(c);
+  return (int)cudaGetLastError();
+}

@@ -28,7 +28,7 @@ __global__ void rope_cache_kernel(const int64_t* __restrict__ positions, T* __re
                                   const T* __restrict__ v, const float* __restrict__ cos_sin, int rot, int Hq,
                                   int Hkv, int D, int64_t q_stride, int64_t k_stride, int64_t v_stride,
                                   void* __restrict__ kv_cache, const int64_t* __restrict__ slot_mapping, int BS,
-                                  float k_inv_scale, float v_inv_scale) {
+                                  float k_inv_scale, float v_inv_scale, int vt) {
   constexpr int N = 8;  // 16-bit dtypes only
   const int t = blockIdx.x;
   const int64_t slot = slot_mapping ? slot_mapping[t] : -1;
@@ -114,9 +114,17 @@ __global__ void rope_cache_kernel(const int64_t* __restrict__ positions, T* __re
       const int j = i - n_qk;
       const int h = j / (D / N), c = j % (D / N);
       Vec16<T> a = ld16(v + t * v_stride + (int64_t)h * D + c * N);
-      const size_t cache_off = (((size_t)blk * 2 + 1) * Hkv + h) * BS * D + (size_t)off * D + c * N;
-      if (FP8) Fp8Store<T>::store8((__nv_fp8_storage_t*)kv_cache + cache_off, a, v_inv_scale);
-      else st16((T*)kv_cache + cache_off, a);
+      if (vt) {
+        // tensor-core layout: the V page is stored transposed [D, BS] (tokens contiguous) so that it is a
+        // K-major B operand for O = P·V (see attention_tc.cu)
+        T* vc = (T*)kv_cache + (((size_t)blk * 2 + 1) * Hkv + h) * BS * D + off;
+#pragma unroll
+        for (int e = 0; e < N; ++e) vc[(size_t)(c * N + e) * BS] = a.e[e];
+      } else {
+        const size_t cache_off = (((size_t)blk * 2 + 1) * Hkv + h) * BS * D + (size_t)off * D + c * N;
+        if (FP8) Fp8Store<T>::store8((__nv_fp8_storage_t*)kv_cache + cache_off, a, v_inv_scale);
+        else st16((T*)kv_cache + cache_off, a);
+      }
     }
   }
 }
@@ -151,10 +159,12 @@ EXPORT int vb_rope_and_cache(const int64_t* positions, void* q, void* k, const v
   int thr = ((items + 31) / 32) * 32;
   thr = thr > 512 ? 512 : (thr < 64 ? 64 : thr);
   if (q == nullptr) Hq = 0;
+  const int vt = (kv_fp8 >> 1) & 1;   // bit 1 of the flags: V pages stored transposed
+  kv_fp8 &= 1;
 #define VB_ROPE_LAUNCH(NX, F8)                                                                                    \
   rope_cache_kernel<TT, NX, F8><<<T, thr, 0, st>>>(positions, (TT*)q, (TT*)k, (const TT*)v, cos_sin, rot, Hq, Hkv, \
                                                    D, q_stride, k_stride, v_stride, kv_cache, slot_mapping, BS,     \
-                                                   1.f / k_scale, 1.f / v_scale)
+                                                   1.f / k_scale, 1.f / v_scale, vt)
   DISPATCH_HALF(dtype, TT, {
     if (neox) { if (kv_fp8) VB_ROPE_LAUNCH(true, true); else VB_ROPE_LAUNCH(true, false); }
     else { if (kv_fp8) VB_ROPE_LAUNCH(false, true); else VB_ROPE_LAUNCH(false, false); }

@@ -37,7 +37,7 @@ class EngineArgs:
     load_format: str = "auto"
     device: str = "auto"
     # cache
-    block_size: int = 32
+    block_size: int = 64
     gpu_memory_utilization: float = 0.92
     swap_space: float = 4.0
     kv_cache_dtype: str = "auto"

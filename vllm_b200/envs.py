@@ -53,6 +53,7 @@ environment_variables: dict[str, Callable[[], Any]] = {
     "VLLM_B200_FORCE_REF_OPS": _bool("VLLM_B200_FORCE_REF_OPS", False),
     "VLLM_B200_GEMM": _str("VLLM_B200_GEMM", "auto"),  # auto|cublas|tcgen05
     "VLLM_B200_ATTN_SPLITS": _int("VLLM_B200_ATTN_SPLITS", 0),
+    "VLLM_B200_ATTN": _str("VLLM_B200_ATTN", "auto"),  # auto|simt (disable the tcgen05 attention kernel)
     "VLLM_B200_FUSED_AR": _bool("VLLM_B200_FUSED_AR", True),
     "VLLM_B200_AR_BACKEND": _str("VLLM_B200_AR_BACKEND", "auto"),  # auto|nvls|p2p|nccl
     "VLLM_DISABLE_CUDA_GRAPH": _bool("VLLM_DISABLE_CUDA_GRAPH", False),

@@ -27,6 +27,7 @@ class AttentionMetadata:
     query_start_loc_cpu: Optional[torch.Tensor] = None
     seq_lens_cpu: Optional[torch.Tensor] = None
     decode_only: bool = False      # every request has exactly one new token
+    kv_vt: bool = False            # tensor-core cache layout: V pages stored transposed [D, block_size]
     causal: bool = True
     # decode split-KV workspace (allocated once by the runner)
     workspace: Any = None

@@ -64,10 +64,10 @@ class Attention(nn.Module):
             return q.clone() if q.shape[-1] == self.num_heads * D else q
         if self.rope is not None and positions is not None:
             q, k = ops.rope_and_cache(positions, q, k, v, self.rope.cos_sin_cache, D,
-                                      self.rope.is_neox_style, kv_cache, md.slot_mapping)
+                                      self.rope.is_neox_style, kv_cache, md.slot_mapping, vt=md.kv_vt)
         else:
             ops.reshape_and_cache(k.view(T, self.num_kv_heads, D), v.view(T, self.num_kv_heads, D),
-                                  kv_cache, md.slot_mapping)
+                                  kv_cache, md.slot_mapping, vt=md.kv_vt)
         out = ops.paged_attention(q.view(T, self.num_heads, D), kv_cache, md, self.scale,
                                   self.sliding_window, self.logits_soft_cap, self.causal)
         return out.view(T, self.num_heads * D)

@@ -198,7 +198,8 @@ class RowParallelLinear(LinearBase):
         if self.tp_size > 1 and x.is_cuda and self.reduce_results:
             comm = get_tp_group().device_comm
             if comm is not None and self.bias is None and type(self.quant_method) is LinearMethod:
-                out = comm.gemm_allreduce_rmsnorm(x, self.weight, residual, norm.weight, norm.eps)
+                out = comm.gemm_allreduce_rmsnorm(x, self.weight, residual, norm.weight, norm.eps,
+                                                  getattr(norm, "gemma", False))
                 if out is not None:
                     return out
         y = self.forward(x)

@@ -76,17 +76,18 @@ def rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox=True):
     return ref.rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
 
 
-def reshape_and_cache(key, value, kv_cache, slot_mapping) -> None:
+def reshape_and_cache(key, value, kv_cache, slot_mapping, vt: bool = False) -> None:
     if _use_cuda(key):
-        return cuda_ops().reshape_and_cache(key, value, kv_cache, slot_mapping)
+        return cuda_ops().reshape_and_cache(key, value, kv_cache, slot_mapping, vt=vt)
     return ref.reshape_and_cache(key, value, kv_cache, slot_mapping)
 
 
-def rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache, slot_mapping):
-    """Fused RoPE(q,k) + paged KV write. q/k: [T, H*D] views; returns (q, k) rotated."""
+def rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache, slot_mapping, vt: bool = False):
+    """Fused RoPE(q,k) + paged KV write. q/k: [T, H*D] views; returns (q, k) rotated.
+    ``vt``: the cache uses the tensor-core layout (V pages transposed), CUDA only."""
     if _use_cuda(q):
         return cuda_ops().rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache,
-                                         slot_mapping)
+                                         slot_mapping, vt=vt)
     q, k = ref.rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
     Hkv = kv_cache.shape[2]
     ref.reshape_and_cache(k.reshape(k.shape[0], Hkv, head_dim), v.reshape(v.shape[0], Hkv, head_dim),

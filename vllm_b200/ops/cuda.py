@@ -48,6 +48,10 @@ _rope_and_cache = _sig("vb_rope_and_cache", _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
 _concat_mla = _sig("vb_concat_and_cache_mla", _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i, _i, _vp)
 _paged_attention = _sig("vb_paged_attention", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                         _i64, _i64, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp)
+_fmha_tc = _sig("vb_fmha_tc", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i,
+                _i, _i, _f, _i, _i, _vp)
+_fmha_tc_decode = _sig("vb_fmha_tc_decode", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i,
+                       _i, _i, _f, _i, _vp)
 _merge_states = _sig("vb_merge_attn_states", _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp)
 _argmax = _sig("vb_argmax", _vp, _i64, _i, _i, _vp, _i, _vp)
 _fused_sample = _sig("vb_fused_sample", _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp)
@@ -140,14 +144,15 @@ def _kv_fp8(kv_cache) -> int:
 
 
 def rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache, slot_mapping,
-                   k_scale: float = 1.0, v_scale: float = 1.0):
+                   k_scale: float = 1.0, v_scale: float = 1.0, vt: bool = False):
     T = q.shape[0]
     Hq, Hkv = q.shape[-1] // head_dim, k.shape[-1] // head_dim
     assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
     rot = cos_sin_cache.shape[-1]
+    flags = _kv_fp8(kv_cache) | (2 if vt else 0)
     _check(_rope_and_cache(positions.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), cos_sin_cache.data_ptr(),
                            rot, T, Hq, Hkv, head_dim, q.stride(0), k.stride(0), v.stride(0), kv_cache.data_ptr(),
-                           slot_mapping.data_ptr(), kv_cache.shape[3], int(is_neox), _kv_fp8(kv_cache), k_scale,
+                           slot_mapping.data_ptr(), kv_cache.shape[3], int(is_neox), flags, k_scale,
                            v_scale, _DT[q.dtype], _st()), "rope_and_cache")
     return q, k
 
@@ -165,11 +170,13 @@ def rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox=True):
     return q, k
 
 
-def reshape_and_cache(key, value, kv_cache, slot_mapping, k_scale: float = 1.0, v_scale: float = 1.0):
+def reshape_and_cache(key, value, kv_cache, slot_mapping, k_scale: float = 1.0, v_scale: float = 1.0,
+                      vt: bool = False):
     T, Hkv, D = key.shape
     _check(_rope_and_cache(None, None, key.data_ptr(), value.data_ptr(), None, 0, T, 0, Hkv, D, 0, key.stride(0),
                            value.stride(0), kv_cache.data_ptr(), slot_mapping.data_ptr(), kv_cache.shape[3], 1,
-                           _kv_fp8(kv_cache), k_scale, v_scale, _DT[key.dtype], _st()), "reshape_and_cache")
+                           _kv_fp8(kv_cache) | (2 if vt else 0), k_scale, v_scale, _DT[key.dtype], _st()),
+           "reshape_and_cache")
 
 
 def concat_and_cache_mla(kv_c, k_pe, kv_cache, slot_mapping):
@@ -226,6 +233,29 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
         out = torch.empty((T, Hq, D), dtype=q.dtype, device=q.device)
     lse = torch.empty((T, Hq), dtype=torch.float32, device=q.device) if return_lse else None
     bt = md.block_table
+    if md.kv_vt:
+        # tcgen05 kernel over the tensor-core cache layout
+        assert D == 128 and BS == 64 and not logits_soft_cap, "tensor-core attention: D=128, 64-token pages"
+        decode = md.decode_only
+        splits = (md.num_splits or decode_splits(md.num_reqs, Hkv, md.max_seq_len, 128)) if decode else 1
+        ws = _get_attn_ws(md.num_reqs, Hq, D, splits, q.device) if splits > 1 else None
+        G = Hq // Hkv
+        if decode and G <= 16 and (G & (G - 1)) == 0 and causal:
+            # swap-AB decode kernel: KV tokens on the MMA M axis
+            rc = _fmha_tc_decode(q.data_ptr(), kv_cache.data_ptr(), kv_cache.shape[0], bt.data_ptr(),
+                                 md.seq_lens.data_ptr(), out.data_ptr(), _p(ws.part_out) if ws else None,
+                                 _p(ws.part_lse) if ws else None, _p(lse), md.num_reqs, Hq, Hkv, q.stride(0),
+                                 out.stride(0), bt.stride(0), splits, sliding_window or 0, scale, _DT[q.dtype],
+                                 _st())
+            _check(rc, f"fmha_tc_decode(G={G})", 2 if splits > 1 else 1)
+            return (out, lse) if return_lse else out
+        rc = _fmha_tc(q.data_ptr(), kv_cache.data_ptr(), kv_cache.shape[0], bt.data_ptr(), md.seq_lens.data_ptr(),
+                      None if decode else md.query_start_loc.data_ptr(), out.data_ptr(),
+                      _p(ws.part_out) if ws else None, _p(ws.part_lse) if ws else None, _p(lse), md.num_reqs, T,
+                      md.max_query_len, Hq, Hkv, q.stride(0), out.stride(0), bt.stride(0), splits,
+                      sliding_window or 0, scale, int(causal), _DT[q.dtype], _st())
+        _check(rc, f"fmha_tc(G={Hq // Hkv})", 2 if splits > 1 else 1)
+        return (out, lse) if return_lse else out
     if md.decode_only:
         splits = md.num_splits or decode_splits(md.num_reqs, Hkv, md.max_seq_len, BS)
         ws = _get_attn_ws(md.num_reqs, Hq, D, splits, q.device) if splits > 1 else None
@@ -324,7 +354,8 @@ def _plan(M: int, N: int, K: int):
     return p
 
 
-def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Y = X W^T on our tcgen05 kernel. x: [M, K] (row stride free), w: [N, K] contiguous."""
     M, K = x.shape
     N = w.shape[0]
@@ -337,7 +368,7 @@ def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
                 raise RuntimeError("GEMM split-K workspace must be allocated before CUDA-graph capture")
             g.ws = torch.empty(max(wsb // 4, 16 << 20), dtype=torch.float32, device=x.device)
             g.counters = torch.zeros(max(tiles, 4096), dtype=torch.int32, device=x.device)
-    y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    y = out if out is not None else torch.empty((M, N), dtype=x.dtype, device=x.device)
     _check(_gemm_tc(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(), M, N, K, x.stride(0), swap, bn, splits,
                     _p(g.ws), _p(g.counters), _DT[x.dtype], _st()), f"gemm_tc(M={M},N={N},K={K})")
     return y
@@ -363,6 +394,28 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         y = gemm_tc(x2, weight, bias)
         return y.view(x.shape[:-1] + (weight.shape[0],))
     return torch.nn.functional.linear(x, weight, bias)
+
+
+# ------------------------------------------------------------------ symmetric-heap collectives
+_comm_ar_rows = _sig("vb_comm_allreduce_rows", _vp, _vp, _vp, _vp, _i, _i, _vp, _i64, _i64, _vp, _vp, _f, _i, _i, _i,
+                     _i, _i, _vp)
+_comm_ag = _sig("vb_comm_all_gather", _vp, _vp, _vp, _vp, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp)
+_comm_bar = _sig("vb_comm_barrier", _vp, _vp, _vp, _vp, _i, _i, _vp)
+
+
+def comm_allreduce_rows(c, x, in_off, out_off, residual, norm_w, eps, T, H, gemma, dtype) -> None:
+    _check(_comm_ar_rows(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, _p(x), in_off,
+                         out_off, _p(residual), _p(norm_w), eps, T, H, int(gemma), num_sms(), _DT[dtype], _st()),
+           "comm_allreduce_rows")
+
+
+def comm_all_gather(c, x, out_off, rows, cols) -> None:
+    _check(_comm_ag(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, x.data_ptr(), out_off,
+                    rows, cols, num_sms(), _DT[x.dtype], _st()), "comm_all_gather")
+
+
+def comm_barrier(c) -> None:
+    _check(_comm_bar(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, _st()), "comm_barrier")
 
 
 # ------------------------------------------------------------------ MoE / fp8 (library-backed until the grouped tcgen05 kernels land)

@@ -37,7 +37,8 @@ class DecodeGraph:
         hkv = max((getattr(l, "num_kv_heads", 1) for l in layers), default=1)
         for m in self.md.values():
             # typical context assumed for the split heuristic; the kernel itself adapts to real lengths
-            m.num_splits = cuda_ops().decode_splits(b, hkv, min(runner.max_model_len, 4096), runner.block_size)
+            m.num_splits = cuda_ops().decode_splits(b, hkv, min(runner.max_model_len, 4096),
+                                                    128 if m.kv_vt else runner.block_size)
         self.graph = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(dev)
         s.wait_stream(torch.cuda.current_stream())

@@ -152,6 +152,7 @@ class ModelRunner:
         self.layer_to_group: dict[str, int] = {}
         self.num_kv_groups = 1
         self.kv_cache_config: Optional[KVCacheConfig] = None
+        self.kv_vt: list[bool] = [False]
         spec = vllm_config.speculative_config
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
@@ -222,8 +223,16 @@ class ModelRunner:
         self.kv_cache_config = cfg
         self.num_kv_groups = max(len(cfg.kv_cache_groups), 1)
         kvd = self._kv_dtype()
+        from vllm_b200 import envs
+        self.kv_vt = []
         for gid, g in enumerate(cfg.kv_cache_groups):
             s = g.spec
+            # tensor-core cache layout (V pages transposed) whenever the tcgen05 attention kernel applies
+            self.kv_vt.append(bool(
+                self.is_cuda and not envs.VLLM_B200_FORCE_REF_OPS and envs.VLLM_B200_ATTN != "simt"
+                and not isinstance(s, MLAAttentionSpec) and getattr(s, "head_size", 0) == 128
+                and s.block_size == 64 and kvd in (torch.bfloat16, torch.float16)
+                and self.dtype in (torch.bfloat16, torch.float16)))
             for name in g.layer_names:
                 self.layer_to_group[name] = gid
                 if isinstance(s, MLAAttentionSpec):
@@ -437,7 +446,7 @@ class ModelRunner:
                 query_start_loc=self.qsl[:nb + 1], seq_lens=self.seq_lens[:nb],
                 block_table=self.block_tables[g][:nb] if self.is_cuda else self.block_tables[g][:nb, :nbk],
                 slot_mapping=self.slot_mappings[g][:T], query_start_loc_cpu=cpu_qsl, seq_lens_cpu=cpu_sl,
-                decode_only=decode_only)
+                decode_only=decode_only, kv_vt=self.kv_vt[g])
         return out
 
     # ------------------------------------------------------------ forward
