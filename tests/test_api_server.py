@@ -1,0 +1,156 @@
+"""OpenAI-compatible server tests against a real (tiny, CPU) engine running in its own process.
+Mirrors tests/entrypoints/** of the reference (RemoteOpenAIServer + dummy weights), but in-process over ASGI."""
+import asyncio
+import json
+
+import httpx
+import pytest
+
+from vllm_b200.engine.arg_utils import EngineArgs
+
+
+@pytest.fixture(scope="module")
+def server():
+    from vllm_b200.engine.async_llm import AsyncLLM
+    from vllm_b200.entrypoints.openai.api_server import ServingContext, build_app
+    ea = EngineArgs(model="llama-tiny", device="cpu", dtype="float32", max_model_len=256, max_num_seqs=8,
+                    max_num_batched_tokens=128, kv_cache_memory_bytes=8 << 20, disable_log_stats=False)
+    loop = asyncio.new_event_loop()
+    asyncio.set_event_loop(loop)
+    engine = AsyncLLM.from_engine_args(ea)
+    ctx = ServingContext(engine, "llama-tiny", 256, engine.tokenizer, tool_parser="hermes",
+                         reasoning_parser=None)
+    app = build_app(ctx)
+    client = httpx.AsyncClient(transport=httpx.ASGITransport(app=app), base_url="http://test", timeout=120)
+
+    def call(coro):
+        return loop.run_until_complete(coro)
+
+    yield client, call, engine
+    call(client.aclose())
+    engine.shutdown()
+    loop.close()
+
+
+def test_health_models_tokenize(server):
+    client, call, _ = server
+    assert call(client.get("/health")).status_code == 200
+    models = call(client.get("/v1/models")).json()
+    assert models["data"][0]["id"] == "llama-tiny"
+    tok = call(client.post("/tokenize", json={"prompt": "hello"})).json()
+    assert tok["count"] == len(tok["tokens"]) == 6
+    detok = call(client.post("/detokenize", json={"tokens": tok["tokens"][1:]})).json()
+    assert detok["prompt"] == "hello"
+
+
+def test_completion_and_logprobs(server):
+    client, call, _ = server
+    r = call(client.post("/v1/completions", json={"model": "llama-tiny", "prompt": "hello", "max_tokens": 5,
+                                                   "temperature": 0, "logprobs": 2})).json()
+    ch = r["choices"][0]
+    assert r["usage"]["completion_tokens"] == 5 and ch["finish_reason"] == "length"
+    assert len(ch["logprobs"]["tokens"]) == 5 and len(ch["logprobs"]["top_logprobs"][0]) >= 2
+    # deterministic
+    r2 = call(client.post("/v1/completions", json={"prompt": "hello", "max_tokens": 5, "temperature": 0})).json()
+    assert r2["choices"][0]["text"] == ch["text"]
+    # batch of prompts + n
+    r3 = call(client.post("/v1/completions", json={"prompt": ["a", "b"], "max_tokens": 3, "n": 2, "seed": 1})).json()
+    assert sorted(c["index"] for c in r3["choices"]) == [0, 1, 2, 3]
+    # unknown model → 404, bad params → 400
+    assert call(client.post("/v1/completions", json={"model": "nope", "prompt": "x"})).status_code == 404
+    assert call(client.post("/v1/completions", json={"prompt": "x", "temperature": -1})).status_code == 400
+    assert call(client.post("/v1/completions", json={"prompt": "x" * 1000, "max_tokens": 1})).status_code == 400
+
+
+def test_completion_streaming(server):
+    client, call, _ = server
+
+    async def run():
+        text, done, usage = "", False, None
+        async with client.stream("POST", "/v1/completions", json={
+                "prompt": "hello", "max_tokens": 6, "temperature": 0, "stream": True,
+                "stream_options": {"include_usage": True}}) as resp:
+            assert resp.status_code == 200
+            async for line in resp.aiter_lines():
+                if not line.startswith("data: "):
+                    continue
+                payload = line[6:]
+                if payload == "[DONE]":
+                    done = True
+                    break
+                obj = json.loads(payload)
+                if obj.get("usage"):
+                    usage = obj["usage"]
+                for c in obj["choices"]:
+                    text += c["text"]
+        return text, done, usage
+
+    text, done, usage = call(run())
+    full = call(client.post("/v1/completions", json={"prompt": "hello", "max_tokens": 6, "temperature": 0})).json()
+    assert done and text == full["choices"][0]["text"] and usage["completion_tokens"] == 6
+
+
+def test_chat_completion_and_stream(server):
+    client, call, _ = server
+    msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "hi"}]
+    r = call(client.post("/v1/chat/completions", json={"messages": msgs, "max_tokens": 4, "temperature": 0,
+                                                        "logprobs": True, "top_logprobs": 2})).json()
+    ch = r["choices"][0]
+    assert ch["message"]["role"] == "assistant" and r["usage"]["completion_tokens"] == 4
+    assert len(ch["logprobs"]["content"]) == 4
+
+    async def run():
+        parts, roles = [], []
+        async with client.stream("POST", "/v1/chat/completions", json={"messages": msgs, "max_tokens": 4,
+                                                                       "temperature": 0, "stream": True}) as resp:
+            async for line in resp.aiter_lines():
+                if line.startswith("data: ") and line[6:] != "[DONE]":
+                    d = json.loads(line[6:])["choices"]
+                    if d:
+                        roles.append(d[0]["delta"].get("role"))
+                        parts.append(d[0]["delta"].get("content") or "")
+        return "".join(parts), roles
+
+    text, roles = call(run())
+    assert roles[0] == "assistant" and text == (ch["message"]["content"] or "")
+
+
+def test_responses_and_anthropic_and_metrics(server):
+    client, call, _ = server
+    r = call(client.post("/v1/responses", json={"input": "hi", "max_output_tokens": 3, "temperature": 0})).json()
+    assert r["object"] == "response" and r["usage"]["output_tokens"] == 3
+    a = call(client.post("/v1/messages", json={"messages": [{"role": "user", "content": "hi"}], "max_tokens": 3})).json()
+    assert a["type"] == "message" and a["stop_reason"] == "max_tokens"
+    m = call(client.get("/metrics")).text
+    assert "vllm:generation_tokens_total" in m and "vllm:time_to_first_token_seconds" in m
+    assert call(client.post("/reset_prefix_cache")).status_code in (200, 409)
+
+
+def test_tool_and_reasoning_parsers():
+    from vllm_b200.reasoning import get_reasoning_parser
+    from vllm_b200.tool_parsers import get_tool_parser
+    p = get_tool_parser("hermes")()
+    out = p.extract('ok <tool_call>\n{"name": "f", "arguments": {"x": 1}}\n</tool_call>')
+    assert out["tool_calls"][0]["function"]["name"] == "f" and json.loads(out["tool_calls"][0]["function"]["arguments"]) == {"x": 1}
+    assert out["content"] == "ok"
+    m = get_tool_parser("mistral")().extract('[TOOL_CALLS][{"name": "g", "arguments": {"a": "b"}}]')
+    assert m["tool_calls"][0]["function"]["name"] == "g"
+    py = get_tool_parser("pythonic")().extract('[get_weather(city="Paris", days=2), f()]')
+    assert [c["function"]["name"] for c in py["tool_calls"]] == ["get_weather", "f"]
+    l3 = get_tool_parser("llama3_json")().extract('{"name": "h", "parameters": {"q": 2}}')
+    assert l3["tool_calls"][0]["function"]["name"] == "h"
+    # streaming: content passes through, the call is emitted once complete
+    sp = get_tool_parser("hermes")()
+    text, got = "", []
+    for d in ["Sure", ". <tool", "_call>{\"name\": \"f\", ", "\"arguments\": {}}", "</tool_call>"]:
+        prev, text = text, text + d
+        r = sp.extract_streaming(prev, text, d)
+        if r:
+            got.append(r)
+    assert "".join(g.get("content") or "" for g in got).strip() == "Sure."
+    assert sum(len(g.get("tool_calls", [])) for g in got) == 1
+    rp = get_reasoning_parser("deepseek_r1")()
+    assert rp.extract("<think>hmm</think>\nanswer") == ("hmm", "answer")
+    assert rp.extract("still thinking") == ("still thinking", None)
+    q = get_reasoning_parser("qwen3")()
+    assert q.extract("plain") == (None, "plain")

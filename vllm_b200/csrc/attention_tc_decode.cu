@@ -77,6 +77,8 @@ fmha_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  pdl_trigger();
+  pdl_wait();   // q, the new K/V rows and seq_lens come from the preceding kernels
   const int seq_len = p.seq_lens[b];
   const int qpos = seq_len - 1;
   const int kv_end = seq_len;
@@ -359,7 +361,7 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
   auto k = fmha_decode_kernel<T, G>;
   static bool a = false;
   if (!a) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a = true; }
-  k<<<grid, NUM_THREADS, smem, st>>>(tq, tk, tv, p);
+  vb_launch(k, grid, dim3(NUM_THREADS), (size_t)smem, st, tq, tk, tv, p);
   return (int)cudaGetLastError();
 }
 

@@ -8,6 +8,7 @@
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #define VB_HOST_DEVICE __host__ __device__ __forceinline__
 #define VB_DEVICE __device__ __forceinline__
@@ -250,6 +251,31 @@ VB_DEVICE void red_add_release_sys(uint32_t* p, uint32_t v) {
 }
 VB_DEVICE uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+// ------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel calls pdl_trigger() first (lets the next kernel in the stream begin launching: its prologue,
+// barrier init, TMEM alloc and — for GEMMs — the weight TMA stream overlap this kernel's tail) and
+// pdl_wait() before the first access to memory a predecessor may still be reading or writing.
+VB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+VB_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool vb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("VLLM_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t vb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 #define CUDA_CHECK_LAST() cudaGetLastError()

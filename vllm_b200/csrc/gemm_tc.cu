@@ -63,6 +63,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int nkb = max(0, min(p.k_blocks_per_split, total_kb - kb0));
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -80,7 +81,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer: weights are read exactly once → evict-first; activations are re-read by every CTA → evict-last
-      for (int kb = 0; kb < nkb; ++kb) {
+      // PDL: the weight operand does not depend on the preceding kernel, so the first ring of weight tiles is
+      // requested BEFORE griddepcontrol.wait — the weight stream starts while the previous kernel is still
+      // draining; only the activation operand waits for it.
+      const int pre = SWAP ? min(nkb, STAGES) : 0;
+      for (int kb = 0; kb < pre; ++kb) {
+        unsigned char* a_dst = stage_base + kb * L::STAGE_BYTES;
+        mbar_expect_tx(&full[kb], L::STAGE_BYTES);
+        tma_load_2d_hint(a_dst, &tmap_a, (kb0 + kb) * BK, a_tile * TM, &full[kb], L2_EVICT_FIRST);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) {
+        unsigned char* b_dst = stage_base + kb * L::STAGE_BYTES + L::A_BYTES;
+        tma_load_2d_hint(b_dst, &tmap_b, (kb0 + kb) * BK, b_tile * BN, &full[kb], L2_EVICT_LAST);
+      }
+      for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
         unsigned char* a_dst = stage_base + s * L::STAGE_BYTES;
@@ -115,6 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int q = warp & 3;
     const int row = q * 32 + lane;            // index along the A-operand tile (0..127)
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    pdl_wait();   // outputs / workspace may alias buffers the previous kernel is still using
     if (nkb > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -253,7 +269,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   auto k = gemm_kernel<T, BN, STAGES, SWAP>;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  k<<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  vb_launch(k, grid, dim3(NUM_THREADS), (size_t)smem, st, ta, tb, p);
   return (int)cudaGetLastError();
 }
 

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(1024) rms_norm_kernel(T* __restrict__ out, T* 
                                                          int H, float eps, int64_t x_stride) {
   constexpr int N = Vec16<T>::N;
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   T* xr = x + row * x_stride;
   T* rr = ADD ? residual + row * (int64_t)H : nullptr;
@@ -122,6 +124,8 @@ template <int ACT> VB_DEVICE float act_fn(float x) {
 template <typename T, int ACT>
 __global__ void act_and_mul_kernel(T* __restrict__ out, const T* __restrict__ x, int d, int64_t total_vec) {
   constexpr int N = Vec16<T>::N;
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = d / N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = i / vec_per_row;
@@ -166,11 +170,11 @@ EXPORT int vb_rms_norm(void* out, void* x, void* residual, const void* w, int T,
     if (H % N != 0 || H / N > 1024 * MAXV) return -1;
     const int thr = norm_threads(H, N);
     if (residual) {
-      if (gemma) rms_norm_kernel<TT, true, true><<<T, thr, 0, st>>>((TT*)x, (TT*)x, (TT*)residual, (const TT*)w, H, eps, x_stride);
-      else rms_norm_kernel<TT, true, false><<<T, thr, 0, st>>>((TT*)x, (TT*)x, (TT*)residual, (const TT*)w, H, eps, x_stride);
+      if (gemma) vb_launch(rms_norm_kernel<TT, true, true>, T, thr, 0, st, (TT*)x, (TT*)x, (TT*)residual, (const TT*)w, H, eps, x_stride);
+      else vb_launch(rms_norm_kernel<TT, true, false>, T, thr, 0, st, (TT*)x, (TT*)x, (TT*)residual, (const TT*)w, H, eps, x_stride);
     } else {
-      if (gemma) rms_norm_kernel<TT, false, true><<<T, thr, 0, st>>>((TT*)out, (TT*)x, nullptr, (const TT*)w, H, eps, x_stride);
-      else rms_norm_kernel<TT, false, false><<<T, thr, 0, st>>>((TT*)out, (TT*)x, nullptr, (const TT*)w, H, eps, x_stride);
+      if (gemma) vb_launch(rms_norm_kernel<TT, false, true>, T, thr, 0, st, (TT*)out, (TT*)x, (TT*)nullptr, (const TT*)w, H, eps, x_stride);
+      else vb_launch(rms_norm_kernel<TT, false, false>, T, thr, 0, st, (TT*)out, (TT*)x, (TT*)nullptr, (const TT*)w, H, eps, x_stride);
     }
   });
   return (int)cudaGetLastError();
@@ -206,7 +210,11 @@ EXPORT int vb_act_and_mul(void* out, const void* x, int64_t T, int d, int act, i
     if (d % N != 0) return -1;
     const int64_t total = T * (d / N);
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    ACT_SWITCH(act_and_mul_kernel, <<<blocks, 256, 0, st>>>((TT*)out, (const TT*)x, d, total));
+    switch (act) {
+      case ACT_SILU: vb_launch(act_and_mul_kernel<TT, ACT_SILU>, blocks, 256, 0, st, (TT*)out, (const TT*)x, d, total); break;
+      case ACT_GELU: vb_launch(act_and_mul_kernel<TT, ACT_GELU>, blocks, 256, 0, st, (TT*)out, (const TT*)x, d, total); break;
+      default: vb_launch(act_and_mul_kernel<TT, ACT_GELU_TANH>, blocks, 256, 0, st, (TT*)out, (const TT*)x, d, total); break;
+    }
   });
   return (int)cudaGetLastError();
 }

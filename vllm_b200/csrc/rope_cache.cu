@@ -30,6 +30,8 @@ __global__ void rope_cache_kernel(const int64_t* __restrict__ positions, T* __re
                                   void* __restrict__ kv_cache, const int64_t* __restrict__ slot_mapping, int BS,
                                   float k_inv_scale, float v_inv_scale, int vt) {
   constexpr int N = 8;  // 16-bit dtypes only
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x;
   const int64_t slot = slot_mapping ? slot_mapping[t] : -1;
   const bool do_cache = kv_cache != nullptr && slot >= 0;
@@ -162,7 +164,7 @@ EXPORT int vb_rope_and_cache(const int64_t* positions, void* q, void* k, const v
   const int vt = (kv_fp8 >> 1) & 1;   // bit 1 of the flags: V pages stored transposed
   kv_fp8 &= 1;
 #define VB_ROPE_LAUNCH(NX, F8)                                                                                    \
-  rope_cache_kernel<TT, NX, F8><<<T, thr, 0, st>>>(positions, (TT*)q, (TT*)k, (const TT*)v, cos_sin, rot, Hq, Hkv, \
+  vb_launch(rope_cache_kernel<TT, NX, F8>, T, thr, 0, st, positions, (TT*)q, (TT*)k, (const TT*)v, cos_sin, rot, Hq, Hkv, \
                                                    D, q_stride, k_stride, v_stride, kv_cache, slot_mapping, BS,     \
                                                    1.f / k_scale, 1.f / v_scale, vt)
   DISPATCH_HALF(dtype, TT, {

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logi
   constexpr int N = Vec16<T>::N;
   __shared__ float sv[32];
   __shared__ int si[32];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const T* lr = logits + (int64_t)row * row_stride;
   float temp = 0.f;
@@ -211,7 +213,7 @@ EXPORT int vb_fused_sample(const void* logits, int64_t row_stride, int B, int V,
                            const int64_t* seeds, const int* step, int64_t* out, int dtype, cudaStream_t st) {
   if (B == 0) return 0;
   DISPATCH_DTYPE(dtype, TT, {
-    sample_kernel<TT, true><<<B, 1024, 0, st>>>((const TT*)logits, row_stride, V, temperature, seeds, step, out);
+    vb_launch(sample_kernel<TT, true>, B, 1024, 0, st, (const TT*)logits, row_stride, V, temperature, seeds, step, out);
   });
   return (int)cudaGetLastError();
 }

@@ -212,7 +212,6 @@ class EngineCoreProc(EngineCore):
 
     # ---- busy loop
     def run_busy_loop(self) -> None:
-        idle_sleep = 0.0
         while True:
             # drain inputs; block when idle
             block = not self.scheduler.has_requests() and not (self.batch_queue and len(self.batch_queue))
@@ -229,7 +228,6 @@ class EngineCoreProc(EngineCore):
             for ci, o in (outs or {}).items():
                 o.engine_index = self.engine_index
                 self.output_queue.put((ci, o))
-            del idle_sleep
 
     def _handle(self, kind: bytes, payload: Any) -> None:
         if kind == REQ_ADD:

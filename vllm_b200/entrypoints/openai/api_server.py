@@ -1,0 +1,666 @@
+"""OpenAI-compatible HTTP server (FastAPI + uvicorn).
+
+Behavioural reference: vllm/entrypoints/launchers/ (``run_server`` api_server/entry.py:163, router registration
+routers.py:12, ``serve_http`` + watchdog launcher.py:50,180), openai/{completion,chat_completion}/serving.py,
+serve/ dev routes (sleep, profile, cache reset, tokenize), instrumentator/metrics.py, anthropic/, responses/.
+
+Routes: /health /ping /version /v1/models /v1/completions /v1/chat/completions /v1/embeddings /v1/responses
+/v1/messages (Anthropic) /tokenize /detokenize /score /metrics /start_profile /stop_profile /sleep /wake_up
+/is_sleeping /reset_prefix_cache /server_info /load.
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import base64
+import json
+import signal
+import struct
+import time
+from contextlib import asynccontextmanager
+from typing import Any, AsyncGenerator, Optional
+
+from fastapi import FastAPI, Request
+from fastapi.responses import JSONResponse, Response, StreamingResponse
+
+from vllm_b200.engine.arg_utils import EngineArgs
+from vllm_b200.engine.exceptions import EngineDeadError
+from vllm_b200.entrypoints.chat_utils import render_chat
+from vllm_b200.entrypoints.openai import protocol as P
+from vllm_b200.logger import init_logger
+from vllm_b200.sampling_params import PoolingParams, RequestOutputKind
+from vllm_b200.utils import random_uuid
+from vllm_b200.version import __version__
+
+logger = init_logger(__name__)
+
+
+class ServingContext:
+    """Everything the route handlers need (engine client may be a real AsyncLLM or a test fake)."""
+
+    def __init__(self, engine, model_name: str, max_model_len: int, tokenizer, api_key: Optional[str] = None,
+                 tool_parser: Optional[str] = None, reasoning_parser: Optional[str] = None,
+                 enable_auto_tools: bool = False, chat_template: Optional[str] = None) -> None:
+        self.engine = engine
+        self.model_name = model_name
+        self.max_model_len = max_model_len
+        self.tokenizer = tokenizer
+        self.api_key = api_key
+        self.tool_parser = tool_parser
+        self.reasoning_parser = reasoning_parser
+        self.enable_auto_tools = enable_auto_tools
+        self.chat_template = chat_template
+        self.inflight = 0
+        self.responses_store: dict[str, dict] = {}
+
+
+def _error(msg: str, code: int = 400, typ: str = "BadRequestError"):
+    return JSONResponse(P.ErrorResponse(error=P.ErrorInfo(message=msg, type=typ, code=code)).model_dump(),
+                        status_code=code)
+
+
+def _usage(n_prompt: int, n_out: int, cached: Optional[int] = None) -> P.UsageInfo:
+    return P.UsageInfo(prompt_tokens=n_prompt, completion_tokens=n_out, total_tokens=n_prompt + n_out,
+                       prompt_tokens_details={"cached_tokens": cached} if cached else None)
+
+
+def _completion_logprobs(ctx: ServingContext, token_ids, logprobs, k: int, offset0: int = 0) -> P.CompletionLogProbs:
+    out = P.CompletionLogProbs()
+    off = offset0
+    for tid, d in zip(token_ids, logprobs):
+        if d is None:
+            out.tokens.append(ctx.tokenizer.decode([tid]))
+            out.token_logprobs.append(None)
+            out.top_logprobs.append(None)
+            out.text_offset.append(off)
+            continue
+        tok = d[tid].decoded_token if d.get(tid) and d[tid].decoded_token is not None else ctx.tokenizer.decode([tid])
+        out.tokens.append(tok)
+        out.token_logprobs.append(max(d[tid].logprob, -9999.0) if tid in d else None)
+        out.top_logprobs.append({(v.decoded_token if v.decoded_token is not None else ctx.tokenizer.decode([t])):
+                                 max(v.logprob, -9999.0) for t, v in list(d.items())[:max(k, 1) + 1]})
+        out.text_offset.append(off)
+        off += len(tok)
+    return out
+
+
+def _chat_logprobs(ctx: ServingContext, token_ids, logprobs, k: int) -> P.ChatLogprobs:
+    content = []
+    for tid, d in zip(token_ids, logprobs):
+        def tokstr(t, v):
+            return v.decoded_token if v.decoded_token is not None else ctx.tokenizer.decode([t])
+        main = d.get(tid)
+        tok = tokstr(tid, main) if main else ctx.tokenizer.decode([tid])
+        tops = [{"token": tokstr(t, v), "logprob": max(v.logprob, -9999.0), "bytes": list(tokstr(t, v).encode())}
+                for t, v in list(d.items())[:k]] if k else []
+        content.append(P.ChatLogprob(token=tok, logprob=max(main.logprob, -9999.0) if main else -9999.0,
+                                     bytes=list(tok.encode()), top_logprobs=tops))
+    return P.ChatLogprobs(content=content)
+
+
+def build_app(ctx: ServingContext):
+    @asynccontextmanager
+    async def lifespan(app):
+        yield
+
+    app = FastAPI(lifespan=lifespan, title="vllm_b200")
+    app.state.ctx = ctx
+
+    @app.middleware("http")
+    async def auth(request: Request, call_next):
+        if ctx.api_key and request.url.path.startswith("/v1"):
+            if request.headers.get("Authorization") != f"Bearer {ctx.api_key}":
+                return JSONResponse({"error": "Unauthorized"}, status_code=401)
+        rid = request.headers.get("X-Request-Id")
+        resp = await call_next(request)
+        if rid:
+            resp.headers["X-Request-Id"] = rid
+        return resp
+
+    def check_model(name: Optional[str]):
+        if name and name != ctx.model_name:
+            return _error(f"The model `{name}` does not exist.", 404, "NotFoundError")
+        return None
+
+    # ------------------------------------------------------------- basics
+    @app.get("/health")
+    @app.get("/ping")
+    async def health():
+        try:
+            await ctx.engine.check_health()
+        except Exception:
+            return Response(status_code=503)
+        return Response(status_code=200)
+
+    @app.get("/version")
+    async def version():
+        return {"version": __version__}
+
+    @app.get("/v1/models")
+    async def models():
+        return P.ModelList(data=[P.ModelCard(id=ctx.model_name, root=ctx.model_name,
+                                             max_model_len=ctx.max_model_len)]).model_dump()
+
+    @app.get("/metrics")
+    async def metrics():
+        from vllm_b200.metrics import render_prometheus
+        body, ctype = render_prometheus()
+        return Response(content=body, media_type=ctype)
+
+    @app.get("/load")
+    async def load():
+        return {"server_load": ctx.inflight}
+
+    @app.get("/server_info")
+    async def server_info():
+        cfg = await ctx.engine.get_vllm_config()
+        return {"version": __version__, "model": ctx.model_name, "config_hash": cfg.compute_hash()}
+
+    # ------------------------------------------------------------ tokenize
+    @app.post("/tokenize")
+    async def tokenize(req: P.TokenizeRequest):
+        if req.messages is not None:
+            text = render_chat(ctx.tokenizer, req.messages, ctx.chat_template, req.add_generation_prompt)
+            ids = ctx.tokenizer.encode(text, add_special_tokens=False)
+        else:
+            ids = ctx.tokenizer.encode(req.prompt or "", add_special_tokens=req.add_special_tokens)
+        strs = ctx.tokenizer.convert_ids_to_tokens(ids) if req.return_token_strs else None
+        return P.TokenizeResponse(count=len(ids), max_model_len=ctx.max_model_len, tokens=ids, token_strs=strs)
+
+    @app.post("/detokenize")
+    async def detokenize(req: P.DetokenizeRequest):
+        return P.DetokenizeResponse(prompt=ctx.tokenizer.decode(req.tokens, skip_special_tokens=False))
+
+    # ---------------------------------------------------------- completions
+    def _prompts(prompt) -> list[Any]:
+        if isinstance(prompt, str):
+            return [prompt]
+        if isinstance(prompt, list) and prompt and isinstance(prompt[0], int):
+            return [{"prompt_token_ids": prompt}]
+        if isinstance(prompt, list) and prompt and isinstance(prompt[0], list):
+            return [{"prompt_token_ids": p} for p in prompt]
+        return list(prompt or [])
+
+    @app.post("/v1/completions")
+    async def completions(req: P.CompletionRequest, raw: Request):
+        if (e := check_model(req.model)) is not None:
+            return e
+        prompts = _prompts(req.prompt)
+        if not prompts:
+            return _error("prompt must not be empty")
+        rid_base = f"cmpl-{req.request_id or random_uuid()}"
+        try:
+            sp = req.to_sampling_params(16, req.logprobs, req.prompt_logprobs if req.prompt_logprobs is not None
+                                        else (req.logprobs if req.echo else None))
+        except (ValueError, TypeError) as ex:
+            return _error(str(ex))
+        gens = []
+        try:
+            for i, p in enumerate(prompts):
+                gens.append(ctx.engine.generate(p, sp, f"{rid_base}-{i}", priority=req.priority,
+                                                trace_headers=dict(raw.headers)))
+        except ValueError as ex:
+            return _error(str(ex))
+        created = int(time.time())
+
+        def echo_text(out) -> str:
+            return (out.prompt if out.prompt is not None else ctx.tokenizer.decode(out.prompt_token_ids)) if req.echo else ""
+
+        if req.stream:
+            async def stream() -> AsyncGenerator[str, None]:
+                ctx.inflight += 1
+                n_prompt = n_out = 0
+                try:
+                    first = {}
+                    merged = _merge(gens)
+                    async for pi, out in merged:
+                        if isinstance(out, Exception):
+                            yield f"data: {json.dumps(P.ErrorResponse(error=P.ErrorInfo(message=str(out), code=400)).model_dump())}\n\n"
+                            break
+                        for c in out.outputs:
+                            idx = pi * req.n + c.index
+                            text = c.text
+                            if req.echo and idx not in first:
+                                text = echo_text(out) + text
+                            first[idx] = True
+                            lp = _completion_logprobs(ctx, c.token_ids, c.logprobs, req.logprobs) if (
+                                req.logprobs is not None and c.logprobs) else None
+                            chunk = P.CompletionStreamResponse(id=rid_base, created=created, model=ctx.model_name, choices=[
+                                P.CompletionChoice(index=idx, text=text, logprobs=lp, finish_reason=c.finish_reason,
+                                                   stop_reason=c.stop_reason)])
+                            n_out += len(c.token_ids)
+                            yield f"data: {chunk.model_dump_json(exclude_unset=False, exclude_none=True)}\n\n"
+                        if out.finished:
+                            n_prompt += len(out.prompt_token_ids or [])
+                    if req.stream_options and req.stream_options.include_usage:
+                        final = P.CompletionStreamResponse(id=rid_base, created=created, model=ctx.model_name, choices=[],
+                                                           usage=_usage(n_prompt, n_out))
+                        yield f"data: {final.model_dump_json(exclude_none=True)}\n\n"
+                    yield "data: [DONE]\n\n"
+                finally:
+                    ctx.inflight -= 1
+            return StreamingResponse(stream(), media_type="text/event-stream")
+
+        ctx.inflight += 1
+        try:
+            finals = await asyncio.gather(*[_last(g, raw) for g in gens])
+        except ValueError as ex:
+            return _error(str(ex))
+        except EngineDeadError:
+            return _error("engine is dead", 500, "InternalServerError")
+        finally:
+            ctx.inflight -= 1
+        if any(f is None for f in finals):
+            return _error("client disconnected", 499)
+        choices, n_prompt, n_out = [], 0, 0
+        for pi, out in enumerate(finals):
+            n_prompt += len(out.prompt_token_ids or [])
+            for c in out.outputs:
+                lp = None
+                if req.logprobs is not None and c.logprobs:
+                    toks, lps = list(c.token_ids), list(c.logprobs)
+                    if req.echo and out.prompt_logprobs:
+                        toks, lps = list(out.prompt_token_ids) + toks, list(out.prompt_logprobs) + lps
+                    lp = _completion_logprobs(ctx, toks, lps, req.logprobs)
+                choices.append(P.CompletionChoice(index=pi * req.n + c.index, text=echo_text(out) + c.text, logprobs=lp,
+                                                  finish_reason=c.finish_reason, stop_reason=c.stop_reason,
+                                                  prompt_logprobs=_plp(out.prompt_logprobs) if req.prompt_logprobs is not None else None))
+                n_out += len(c.token_ids)
+        return P.CompletionResponse(id=rid_base, created=created, model=ctx.model_name, choices=choices,
+                                    usage=_usage(n_prompt, n_out, finals[0].num_cached_tokens),
+                                    kv_transfer_params=finals[0].kv_transfer_params).model_dump(exclude_none=True)
+
+    # -------------------------------------------------------------- chat
+    @app.post("/v1/chat/completions")
+    async def chat(req: P.ChatCompletionRequest, raw: Request):
+        if (e := check_model(req.model)) is not None:
+            return e
+        try:
+            prompt = render_chat(ctx.tokenizer, req.messages, req.chat_template or ctx.chat_template,
+                                 req.add_generation_prompt, req.continue_final_message, req.tools,
+                                 **(req.chat_template_kwargs or {}))
+        except Exception as ex:
+            return _error(f"chat template error: {ex}")
+        n_lp = req.top_logprobs if req.logprobs else None
+        if req.logprobs and n_lp is None:
+            n_lp = 0
+        try:
+            sp = req.to_sampling_params(ctx.max_model_len, n_lp if req.logprobs else None, req.prompt_logprobs)
+            sp.max_tokens = req.max_completion_tokens or req.max_tokens  # None → fill the context
+            if sp.max_tokens is None:
+                sp.max_tokens = None
+        except (ValueError, TypeError) as ex:
+            return _error(str(ex))
+        rid = f"chatcmpl-{req.request_id or random_uuid()}"
+        tool_parser = reasoning = None
+        if ctx.tool_parser and req.tools and req.tool_choice != "none":
+            from vllm_b200.tool_parsers import get_tool_parser
+            tool_parser = get_tool_parser(ctx.tool_parser)(ctx.tokenizer)
+        if ctx.reasoning_parser and req.include_reasoning:
+            from vllm_b200.reasoning import get_reasoning_parser
+            reasoning = get_reasoning_parser(ctx.reasoning_parser)(ctx.tokenizer)
+        try:
+            gen = ctx.engine.generate({"prompt": prompt} if isinstance(prompt, str) else prompt, sp, rid,
+                                      priority=req.priority, trace_headers=dict(raw.headers))
+        except ValueError as ex:
+            return _error(str(ex))
+        created = int(time.time())
+
+        if req.stream:
+            async def stream() -> AsyncGenerator[str, None]:
+                ctx.inflight += 1
+                try:
+                    sent_role: set[int] = set()
+                    n_prompt = n_out = 0
+                    states: dict[int, dict] = {}
+                    async for out in gen:
+                        for c in out.outputs:
+                            if c.index not in sent_role:
+                                sent_role.add(c.index)
+                                ch = P.ChatCompletionStreamResponse(id=rid, created=created, model=ctx.model_name, choices=[
+                                    P.ChatStreamChoice(index=c.index, delta=P.DeltaMessage(role="assistant", content=""))])
+                                yield f"data: {ch.model_dump_json(exclude_none=True)}\n\n"
+                            st = states.setdefault(c.index, {"text": "", "ids": []})
+                            delta = P.DeltaMessage(content=c.text)
+                            if reasoning is not None or tool_parser is not None:
+                                prev = st["text"]
+                                st["text"] += c.text
+                                st["ids"] += list(c.token_ids)
+                                dm = None
+                                if reasoning is not None and not st.get("reasoning_done"):
+                                    dm = reasoning.extract_streaming(prev, st["text"], c.text)
+                                    if dm is not None and dm.get("done"):
+                                        st["reasoning_done"] = True
+                                    if dm is not None:
+                                        delta = P.DeltaMessage(content=dm.get("content"),
+                                                               reasoning_content=dm.get("reasoning_content"))
+                                if tool_parser is not None and (reasoning is None or st.get("reasoning_done")):
+                                    tm = tool_parser.extract_streaming(prev, st["text"], c.text)
+                                    if tm is not None:
+                                        delta = P.DeltaMessage(content=tm.get("content"), tool_calls=[
+                                            P.ToolCall(**t) for t in tm.get("tool_calls", [])] or None)
+                                    elif tool_parser.in_tool_call(st["text"]):
+                                        delta = P.DeltaMessage()
+                            lp = _chat_logprobs(ctx, c.token_ids, c.logprobs, req.top_logprobs or 0) if (
+                                req.logprobs and c.logprobs) else None
+                            fr = c.finish_reason
+                            if fr is not None and tool_parser is not None and tool_parser.saw_tool_call(st["text"]):
+                                fr = "tool_calls"
+                            ch = P.ChatCompletionStreamResponse(id=rid, created=created, model=ctx.model_name, choices=[
+                                P.ChatStreamChoice(index=c.index, delta=delta, logprobs=lp, finish_reason=fr,
+                                                   stop_reason=c.stop_reason)])
+                            n_out += len(c.token_ids)
+                            yield f"data: {ch.model_dump_json(exclude_none=True)}\n\n"
+                        if out.finished:
+                            n_prompt = len(out.prompt_token_ids or [])
+                    if req.stream_options is None or req.stream_options.include_usage:
+                        if req.stream_options is not None:
+                            fin = P.ChatCompletionStreamResponse(id=rid, created=created, model=ctx.model_name,
+                                                                 choices=[], usage=_usage(n_prompt, n_out))
+                            yield f"data: {fin.model_dump_json(exclude_none=True)}\n\n"
+                    yield "data: [DONE]\n\n"
+                except ValueError as ex:
+                    yield f"data: {json.dumps(P.ErrorResponse(error=P.ErrorInfo(message=str(ex))).model_dump())}\n\n"
+                    yield "data: [DONE]\n\n"
+                finally:
+                    ctx.inflight -= 1
+            return StreamingResponse(stream(), media_type="text/event-stream")
+
+        ctx.inflight += 1
+        try:
+            out = await _last(gen, raw)
+        except ValueError as ex:
+            return _error(str(ex))
+        except EngineDeadError:
+            return _error("engine is dead", 500, "InternalServerError")
+        finally:
+            ctx.inflight -= 1
+        if out is None:
+            return _error("client disconnected", 499)
+        choices, n_out = [], 0
+        for c in out.outputs:
+            content, rc, tcs, fr = c.text, None, None, c.finish_reason
+            if reasoning is not None:
+                rc, content = reasoning.extract(content)
+            if tool_parser is not None:
+                parsed = tool_parser.extract(content or "")
+                if parsed["tool_calls"]:
+                    tcs = [P.ToolCall(**t) for t in parsed["tool_calls"]]
+                    content = parsed["content"]
+                    fr = "tool_calls"
+            lp = _chat_logprobs(ctx, c.token_ids, c.logprobs, req.top_logprobs or 0) if (req.logprobs and c.logprobs) else None
+            choices.append(P.ChatChoice(index=c.index, message=P.ChatMessage(role="assistant", content=content,
+                                                                               reasoning_content=rc, tool_calls=tcs),
+                                        logprobs=lp, finish_reason=fr, stop_reason=c.stop_reason))
+            n_out += len(c.token_ids)
+        return P.ChatCompletionResponse(id=rid, created=created, model=ctx.model_name, choices=choices,
+                                        usage=_usage(len(out.prompt_token_ids or []), n_out, out.num_cached_tokens),
+                                        prompt_logprobs=_plp(out.prompt_logprobs) if req.prompt_logprobs is not None else None,
+                                        kv_transfer_params=out.kv_transfer_params).model_dump(exclude_none=True)
+
+    # --------------------------------------------------------- embeddings
+    @app.post("/v1/embeddings")
+    async def embeddings(req: P.EmbeddingRequest):
+        if (e := check_model(req.model)) is not None:
+            return e
+        prompts = _prompts(req.input)
+        pp = PoolingParams(task="embed", dimensions=req.dimensions, normalize=req.normalize,
+                           truncate_prompt_tokens=req.truncate_prompt_tokens)
+        rid = f"embd-{random_uuid()}"
+
+        async def one(i, p):
+            async for o in ctx.engine.encode(p, pp, f"{rid}-{i}"):
+                return o
+        try:
+            outs = await asyncio.gather(*[one(i, p) for i, p in enumerate(prompts)])
+        except ValueError as ex:
+            return _error(str(ex))
+        data, n_tok = [], 0
+        for i, o in enumerate(outs):
+            vec = [float(x) for x in o.outputs.data.flatten().tolist()]
+            emb: Any = vec
+            if req.encoding_format == "base64":
+                emb = base64.b64encode(struct.pack(f"<{len(vec)}f", *vec)).decode()
+            data.append(P.EmbeddingData(index=i, embedding=emb))
+            n_tok += len(o.prompt_token_ids)
+        return P.EmbeddingResponse(id=rid, model=ctx.model_name, data=data, usage=_usage(n_tok, 0)).model_dump(exclude_none=True)
+
+    @app.post("/score")
+    @app.post("/v1/score")
+    async def score(req: P.ScoreRequest):
+        import torch
+        a = [req.text_1] if isinstance(req.text_1, str) else list(req.text_1)
+        b = [req.text_2] if isinstance(req.text_2, str) else list(req.text_2)
+        if len(a) == 1:
+            a = a * len(b)
+        pp = PoolingParams(task="embed")
+        rid = f"score-{random_uuid()}"
+
+        async def one(tag, i, p):
+            async for o in ctx.engine.encode(p, pp, f"{rid}-{tag}{i}"):
+                return o
+        ea = await asyncio.gather(*[one("a", i, p) for i, p in enumerate(a)])
+        eb = await asyncio.gather(*[one("b", i, p) for i, p in enumerate(b)])
+        data = [{"index": i, "object": "score",
+                 "score": float(torch.nn.functional.cosine_similarity(x.outputs.data.float().flatten(),
+                                                                      y.outputs.data.float().flatten(), dim=0))}
+                for i, (x, y) in enumerate(zip(ea, eb))]
+        return P.ScoreResponse(model=ctx.model_name, data=data,
+                               usage=_usage(sum(len(o.prompt_token_ids) for o in ea + eb), 0)).model_dump()
+
+    # ------------------------------------------- Responses API / Anthropic
+    @app.post("/v1/responses")
+    async def responses(req: P.ResponsesRequest, raw: Request):
+        msgs: list[dict] = []
+        if req.previous_response_id and req.previous_response_id in ctx.responses_store:
+            msgs += ctx.responses_store[req.previous_response_id]["messages"]
+        if req.instructions:
+            msgs.append({"role": "system", "content": req.instructions})
+        if isinstance(req.input, str):
+            msgs.append({"role": "user", "content": req.input})
+        else:
+            for item in req.input:
+                c = item.get("content")
+                if isinstance(c, list):
+                    c = "".join(p.get("text", "") for p in c if isinstance(p, dict))
+                msgs.append({"role": item.get("role", "user"), "content": c})
+        creq = P.ChatCompletionRequest(messages=msgs, max_tokens=req.max_output_tokens, temperature=req.temperature,
+                                       top_p=req.top_p, stream=False)
+        res = await chat(creq, raw)
+        if not isinstance(res, dict):
+            return res
+        text = res["choices"][0]["message"].get("content") or ""
+        rid = f"resp_{random_uuid()}"
+        if req.store:
+            ctx.responses_store[rid] = {"messages": msgs + [{"role": "assistant", "content": text}]}
+        u = res["usage"]
+        return {"id": rid, "object": "response", "created_at": res["created"], "status": "completed",
+                "model": ctx.model_name,
+                "output": [{"type": "message", "id": f"msg_{random_uuid()}", "role": "assistant", "status": "completed",
+                            "content": [{"type": "output_text", "text": text, "annotations": []}]}],
+                "output_text": text,
+                "usage": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"],
+                          "total_tokens": u["total_tokens"]}}
+
+    @app.post("/v1/messages")
+    async def anthropic_messages(req: P.AnthropicMessagesRequest, raw: Request):
+        msgs: list[dict] = []
+        if req.system:
+            sys_text = req.system if isinstance(req.system, str) else "".join(b.get("text", "") for b in req.system)
+            msgs.append({"role": "system", "content": sys_text})
+        for m in req.messages:
+            c = m.get("content")
+            if isinstance(c, list):
+                c = "".join(b.get("text", "") for b in c if isinstance(b, dict) and b.get("type") == "text")
+            msgs.append({"role": m["role"], "content": c})
+        creq = P.ChatCompletionRequest(messages=msgs, max_tokens=req.max_tokens, temperature=req.temperature,
+                                       top_p=req.top_p, top_k=req.top_k, stop=req.stop_sequences, stream=False)
+        res = await chat(creq, raw)
+        if not isinstance(res, dict):
+            return res
+        ch = res["choices"][0]
+        stop_map = {"stop": "end_turn", "length": "max_tokens", "tool_calls": "tool_use"}
+        return {"id": f"msg_{random_uuid()}", "type": "message", "role": "assistant", "model": ctx.model_name,
+                "content": [{"type": "text", "text": ch["message"].get("content") or ""}],
+                "stop_reason": stop_map.get(ch.get("finish_reason"), "end_turn"), "stop_sequence": None,
+                "usage": {"input_tokens": res["usage"]["prompt_tokens"],
+                          "output_tokens": res["usage"]["completion_tokens"]}}
+
+    # -------------------------------------------------------- dev routes
+    @app.post("/start_profile")
+    async def start_profile():
+        await ctx.engine.start_profile()
+        return Response(status_code=200)
+
+    @app.post("/stop_profile")
+    async def stop_profile():
+        await ctx.engine.stop_profile()
+        return Response(status_code=200)
+
+    @app.post("/sleep")
+    async def sleep(level: int = 1):
+        await ctx.engine.sleep(level)
+        return Response(status_code=200)
+
+    @app.post("/wake_up")
+    async def wake_up():
+        await ctx.engine.wake_up()
+        return Response(status_code=200)
+
+    @app.get("/is_sleeping")
+    async def is_sleeping():
+        return {"is_sleeping": await ctx.engine.is_sleeping()}
+
+    @app.post("/reset_prefix_cache")
+    async def reset_prefix_cache():
+        ok = await ctx.engine.reset_prefix_cache()
+        return Response(status_code=200 if ok else 409)
+
+    @app.post("/collective_rpc")
+    async def collective_rpc(body: dict):
+        res = await ctx.engine.collective_rpc(body["method"], tuple(body.get("args", [])), body.get("kwargs"))
+        return {"results": [r if isinstance(r, (int, float, str, bool, type(None))) else repr(r) for r in (res or [])]}
+
+    return app
+
+
+def _plp(plp):
+    if plp is None:
+        return None
+    return [None if d is None else {t: {"logprob": max(v.logprob, -9999.0), "rank": v.rank,
+                                        "decoded_token": v.decoded_token} for t, v in d.items()} for d in plp]
+
+
+async def _last(gen, raw=None):
+    """Drain a generator, aborting if the client goes away (reference: with_cancellation)."""
+    out = None
+    async for o in gen:
+        out = o
+        if raw is not None and getattr(raw, "is_disconnected", None) is not None and o is not None and not o.finished:
+            try:
+                if await raw.is_disconnected():
+                    await gen.aclose()
+                    return None
+            except Exception:
+                pass
+    return out
+
+
+async def _merge(gens):
+    """Interleave several async generators, yielding (index, item)."""
+    q: asyncio.Queue = asyncio.Queue()
+    done = object()
+
+    async def pump(i, g):
+        try:
+            async for item in g:
+                await q.put((i, item))
+        except Exception as e:  # surfaced to the consumer
+            await q.put((i, e))
+        finally:
+            await q.put((i, done))
+
+    tasks = [asyncio.create_task(pump(i, g)) for i, g in enumerate(gens)]
+    remaining = len(tasks)
+    try:
+        while remaining:
+            i, item = await q.get()
+            if item is done:
+                remaining -= 1
+                continue
+            yield i, item
+    finally:
+        for t in tasks:
+            t.cancel()
+
+
+# ---------------------------------------------------------------------------
+
+
+def make_arg_parser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser("vllm_b200 serve")
+    ap.add_argument("model_tag", nargs="?", default=None)
+    ap.add_argument("--host", default="0.0.0.0")
+    ap.add_argument("--port", type=int, default=8000)
+    ap.add_argument("--api-key", default=None)
+    ap.add_argument("--chat-template", default=None)
+    ap.add_argument("--enable-auto-tool-choice", action="store_true")
+    ap.add_argument("--tool-call-parser", default=None)
+    ap.add_argument("--uvicorn-log-level", default="warning")
+    ap.add_argument("--api-server-count", type=int, default=1)
+    ap.add_argument("--headless", action="store_true")
+    EngineArgs.add_cli_args(ap)
+    return ap
+
+
+async def run_server(args: argparse.Namespace) -> None:
+    import uvicorn
+    from vllm_b200.engine.async_llm import AsyncLLM
+    if args.model_tag:
+        args.model = args.model_tag
+    ea = EngineArgs.from_cli_args(args)
+    engine = AsyncLLM.from_engine_args(ea)
+    template = None
+    if args.chat_template:
+        with open(args.chat_template) as f:
+            template = f.read()
+    ctx = ServingContext(engine, ea.served_model_name or ea.model, engine.model_config.max_model_len, engine.tokenizer,
+                         api_key=args.api_key, tool_parser=args.tool_call_parser,
+                         reasoning_parser=ea.reasoning_parser or None, enable_auto_tools=args.enable_auto_tool_choice,
+                         chat_template=template)
+    app = build_app(ctx)
+    config = uvicorn.Config(app, host=args.host, port=args.port, log_level=args.uvicorn_log_level)
+    server = uvicorn.Server(config)
+
+    async def watchdog() -> None:  # terminate the HTTP server when the engine dies (reference launcher.py:180-203)
+        while not server.should_exit:
+            await asyncio.sleep(2)
+            if engine.errored:
+                logger.error("engine died; shutting the API server down")
+                server.should_exit = True
+
+    loop = asyncio.get_running_loop()
+    for sig in (signal.SIGINT, signal.SIGTERM):
+        try:
+            loop.add_signal_handler(sig, lambda: setattr(server, "should_exit", True))
+        except NotImplementedError:
+            pass
+    wd = asyncio.create_task(watchdog())
+    try:
+        await server.serve()
+    finally:
+        wd.cancel()
+        engine.shutdown()
+
+
+def main(argv=None) -> None:
+    args = make_arg_parser().parse_args(argv)
+    try:
+        import uvloop
+        uvloop.run(run_server(args))
+    except ImportError:
+        asyncio.run(run_server(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -106,7 +106,9 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
     """``md``: AttentionMetadata (see vllm_b200.forward_context)."""
     if _use_cuda(q):
         return cuda_ops().paged_attention(q, kv_cache, md, scale, sliding_window, logits_soft_cap, causal, out)
-    return ref.paged_attention(q, kv_cache, md.block_table, md.seq_lens_cpu, md.query_start_loc_cpu, scale,
+    sl = md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()
+    qsl = md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()
+    return ref.paged_attention(q, kv_cache, md.block_table, sl, qsl, scale,
                                causal=causal, sliding_window=sliding_window, logits_soft_cap=logits_soft_cap)
 
 

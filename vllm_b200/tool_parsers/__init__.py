@@ -1,0 +1,204 @@
+"""Tool-call parsers: model text → OpenAI ``tool_calls`` (reference: vllm/tool_parsers/*, ≈40 formats).
+
+Implemented families (each covers several reference parser names through aliases):
+``hermes`` (<tool_call>{json}</tool_call>: hermes, qwen2.5/3, nous), ``llama3_json`` ({"name":..,"parameters":..}:
+llama3.x/4 json), ``mistral`` ([TOOL_CALLS][{...}]), ``pythonic`` ([fn(a=1), ...]: llama4 pythonic, olmo3),
+``deepseek_v3`` (<｜tool▁call▁begin｜>...), ``json`` (bare JSON object/array).
+Every parser offers ``extract`` (full text) and ``extract_streaming`` (incremental deltas).
+"""
+from __future__ import annotations
+
+import ast
+import json
+import re
+import uuid
+from typing import Any, Optional
+
+
+def _call(name: str, args: Any, index: int) -> dict:
+    if not isinstance(args, str):
+        args = json.dumps(args, ensure_ascii=False)
+    return {"id": f"chatcmpl-tool-{uuid.uuid4().hex[:24]}", "type": "function", "index": index,
+            "function": {"name": name, "arguments": args}}
+
+
+class ToolParser:
+    start_markers: tuple[str, ...] = ()
+
+    def __init__(self, tokenizer=None) -> None:
+        self.tokenizer = tokenizer
+        self._sent_calls = 0
+        self._sent_content = 0
+
+    def extract(self, text: str) -> dict:
+        raise NotImplementedError
+
+    def in_tool_call(self, text: str) -> bool:
+        return any(m in text for m in self.start_markers)
+
+    def saw_tool_call(self, text: str) -> bool:
+        return bool(self.extract(text)["tool_calls"])
+
+    def extract_streaming(self, prev: str, cur: str, delta: str) -> Optional[dict]:
+        """Default streaming strategy: content before the first marker streams through; complete
+        tool calls are emitted as soon as they parse."""
+        cut = min((cur.find(m) for m in self.start_markers if m in cur), default=-1)
+        out: dict = {}
+        if cut == -1:
+            # hold back a possible partial marker at the tail
+            safe = len(cur)
+            for m in self.start_markers:
+                for k in range(1, len(m)):
+                    if cur.endswith(m[:k]):
+                        safe = min(safe, len(cur) - k)
+            if safe > self._sent_content:
+                out["content"] = cur[self._sent_content:safe]
+                self._sent_content = safe
+            return out or None
+        if cut > self._sent_content:
+            out["content"] = cur[self._sent_content:cut]
+            self._sent_content = cut
+        calls = self.extract(cur)["tool_calls"]
+        complete = calls if self._looks_complete(cur) else calls[:-1] if len(calls) > 1 else []
+        if len(complete) > self._sent_calls:
+            out["tool_calls"] = complete[self._sent_calls:]
+            self._sent_calls = len(complete)
+        return out or None
+
+    def _looks_complete(self, text: str) -> bool:
+        return True
+
+
+class HermesToolParser(ToolParser):
+    start_markers = ("<tool_call>",)
+    _rx = re.compile(r"<tool_call>\s*(.*?)\s*(?:</tool_call>|$)", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = []
+        for m in self._rx.finditer(text):
+            try:
+                obj = json.loads(m.group(1))
+                calls.append(_call(obj["name"], obj.get("arguments", obj.get("parameters", {})), len(calls)))
+            except Exception:
+                continue
+        content = text[:text.find("<tool_call>")].strip() if calls else text
+        return {"tool_calls": calls, "content": content or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith("</tool_call>")
+
+
+class Llama3JsonToolParser(ToolParser):
+    start_markers = ("<|python_tag|>", '{"name"')
+
+    def extract(self, text: str) -> dict:
+        body = text.replace("<|python_tag|>", "").strip()
+        calls = []
+        dec = json.JSONDecoder()
+        i = 0
+        while i < len(body):
+            j = body.find("{", i)
+            if j < 0:
+                break
+            try:
+                obj, end = dec.raw_decode(body[j:])
+            except ValueError:
+                i = j + 1
+                continue
+            if isinstance(obj, dict) and "name" in obj and ("parameters" in obj or "arguments" in obj):
+                calls.append(_call(obj["name"], obj.get("parameters", obj.get("arguments", {})), len(calls)))
+            i = j + end
+        return {"tool_calls": calls, "content": None if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith("}")
+
+
+class MistralToolParser(ToolParser):
+    start_markers = ("[TOOL_CALLS]",)
+
+    def extract(self, text: str) -> dict:
+        if "[TOOL_CALLS]" not in text:
+            return {"tool_calls": [], "content": text}
+        pre, _, body = text.partition("[TOOL_CALLS]")
+        calls = []
+        try:
+            arr = json.loads(body.strip())
+            for obj in arr if isinstance(arr, list) else [arr]:
+                calls.append(_call(obj["name"], obj.get("arguments", {}), len(calls)))
+        except Exception:
+            for m in re.finditer(r"(\w+)\s*(\{.*?\})(?=\s*(?:\w+\s*\{|$))", body, re.S):
+                try:
+                    calls.append(_call(m.group(1), json.loads(m.group(2)), len(calls)))
+                except Exception:
+                    pass
+        return {"tool_calls": calls, "content": pre.strip() or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        t = text.rstrip()
+        return t.endswith("]") or t.endswith("}")
+
+
+class PythonicToolParser(ToolParser):
+    start_markers = ("[",)
+
+    def extract(self, text: str) -> dict:
+        t = text.strip()
+        if not (t.startswith("[") and t.endswith("]")):
+            return {"tool_calls": [], "content": text}
+        try:
+            tree = ast.parse(t, mode="eval")
+            calls = []
+            for node in tree.body.elts:
+                if not isinstance(node, ast.Call):
+                    return {"tool_calls": [], "content": text}
+                name = ast.unparse(node.func)
+                args = {kw.arg: ast.literal_eval(kw.value) for kw in node.keywords}
+                calls.append(_call(name, args, len(calls)))
+            return {"tool_calls": calls, "content": None}
+        except Exception:
+            return {"tool_calls": [], "content": text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith("]")
+
+
+class DeepSeekV3ToolParser(ToolParser):
+    start_markers = ("<｜tool▁calls▁begin｜>",)
+    _rx = re.compile(r"<｜tool▁call▁begin｜>(?:function)?<｜tool▁sep｜>(?P<name>[^\n]+)\n```json\n(?P<args>.*?)\n```<｜tool▁call▁end｜>",
+                     re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = [_call(m.group("name").strip(), m.group("args"), i) for i, m in enumerate(self._rx.finditer(text))]
+        content = text[:text.find(self.start_markers[0])] if calls else text
+        return {"tool_calls": calls, "content": content.strip() or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        return "<｜tool▁calls▁end｜>" in text or text.rstrip().endswith("<｜tool▁call▁end｜>")
+
+
+class JsonToolParser(Llama3JsonToolParser):
+    start_markers = ("{", "[")
+
+
+_PARSERS: dict[str, type[ToolParser]] = {
+    "hermes": HermesToolParser, "qwen": HermesToolParser, "qwen3": HermesToolParser, "nous": HermesToolParser,
+    "llama3_json": Llama3JsonToolParser, "llama4_json": Llama3JsonToolParser,
+    "mistral": MistralToolParser, "pythonic": PythonicToolParser, "llama4_pythonic": PythonicToolParser,
+    "olmo3": PythonicToolParser, "deepseek_v3": DeepSeekV3ToolParser, "deepseek_v31": DeepSeekV3ToolParser,
+    "json": JsonToolParser,
+}
+
+
+def register_tool_parser(name: str, cls: type[ToolParser]) -> None:
+    _PARSERS[name] = cls
+
+
+def get_tool_parser(name: str) -> type[ToolParser]:
+    if name not in _PARSERS:
+        raise KeyError(f"unknown tool parser {name!r}; available: {sorted(_PARSERS)}")
+    return _PARSERS[name]
+
+
+def list_tool_parsers() -> list[str]:
+    return sorted(_PARSERS)
