@@ -87,6 +87,38 @@ def test_collectives():
     out = comm.gemm_allreduce_rmsnorm(xk, wk, res_mine, nw, 1e-5)
     check(out is not None, "fused path declined")
     torch.testing.assert_close(out[0].float(), e_norm.float(), atol=6e-2, rtol=3e-2)
+    # single-kernel Lamport path: varying token counts (dirty-row re-arming), both hidden sizes, many calls
+    for H, K in ((4096, 2048), (8192, 1024)):
+        gw = torch.Generator(device=dev).manual_seed(11 + rank)
+        wk = (torch.randn(H, K, device=dev, generator=gw) * 0.05).to(torch.bfloat16)
+        nw = (1 + 0.1 * torch.randn(H, device=dev, generator=torch.Generator(device=dev).manual_seed(3))).to(torch.bfloat16)
+        for it, T in enumerate((64, 7, 128, 1, 64, 33, 64, 64)):
+            xk = (torch.randn(T, K, device=dev, generator=gw) * 0.5).to(torch.bfloat16)
+            res = torch.randn(T, H, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + it)).to(torch.bfloat16)
+            y = torch.nn.functional.linear(xk, wk)
+            dist.all_reduce(y, group=tp.device_group)
+            e_norm, e_res = ref.fused_add_rms_norm(y, res, nw, 1e-5)
+            res_mine = res.clone()
+            out = comm.gemm_allreduce_rmsnorm(xk, wk, res_mine, nw, 1e-5)
+            torch.testing.assert_close(out[0].float(), e_norm.float(), atol=6e-2, rtol=3e-2)
+            torch.testing.assert_close(res_mine.float(), e_res.float(), atol=6e-2, rtol=3e-2)
+        # CUDA-graph replay of the fused kernel (device-side buffer rotation)
+        T = 64
+        xk = (torch.randn(T, K, device=dev, generator=gw) * 0.5).to(torch.bfloat16)
+        res0 = torch.randn(T, H, device=dev, generator=torch.Generator(device=dev).manual_seed(7)).to(torch.bfloat16)
+        y = torch.nn.functional.linear(xk, wk)
+        dist.all_reduce(y, group=tp.device_group)
+        e_norm, _ = ref.fused_add_rms_norm(y, res0, nw, 1e-5)
+        res_g = res0.clone()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res_g.copy_(res0)
+            og = comm.gemm_allreduce_rmsnorm(xk, wk, res_g, nw, 1e-5)[0]
+        for _ in range(7):
+            graph.replay()
+        torch.cuda.synchronize()
+        torch.testing.assert_close(og.float(), e_norm.float(), atol=6e-2, rtol=3e-2)
     if rank == 0:
         print("collectives ok (multicast=%s)" % comm.use_mc, flush=True)
 
@@ -104,9 +136,11 @@ def test_e2e_tp(expected_path):
     with torch.no_grad():
         runner.model.load_weights(llama_full_weights(llm.llm_engine.model_config.hf_config, seed=3, scale=0.05))
     prompts = [{"prompt_token_ids": [(13 * i + 7 * j) % 4000 + 5 for j in range(20 + 37 * i)]} for i in range(5)]
-    outs = llm.generate(prompts, SamplingParams(max_tokens=12, temperature=0.0, ignore_eos=True, logprobs=0))
+    outs = llm.generate(prompts, SamplingParams(max_tokens=12, temperature=0.0, ignore_eos=True, logprobs=0,
+                                                prompt_logprobs=0))
     toks = [o.outputs[0].token_ids for o in outs]
-    lps = [[list(d.values())[0].logprob for d in o.outputs[0].logprobs] for o in outs]
+    # teacher-forced quantities (no feedback): logprob of every prompt token given its prefix
+    lps = [[list(d.values())[0].logprob for d in o.prompt_logprobs[1:]] for o in outs]
     if int(os.environ.get("RANK", 0)) == 0:
         with open(expected_path + f".tp{world}", "w") as f:
             json.dump({"tokens": toks, "logprobs": lps}, f)

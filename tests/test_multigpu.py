@@ -31,11 +31,12 @@ def test_tp2_matches_tp1(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     _torchrun(2, "e2e", base)
     a, b = json.load(open(base + ".tp1")), json.load(open(base + ".tp2"))
-    agree = total = 0
+    first_agree = 0
+    diffs = []
     for ta, tb, la, lb in zip(a["tokens"], b["tokens"], a["logprobs"], b["logprobs"]):
-        n = next((i for i, (x, y) in enumerate(zip(ta, tb)) if x != y), len(ta))
-        agree += n
-        total += len(ta)
-        for x, y in zip(la[:n], lb[:n]):
-            assert abs(x - y) < 0.1
-    assert agree / total > 0.7
+        first_agree += ta[0] == tb[0]
+        assert len(la) == len(lb)
+        diffs += [abs(x - y) for x, y in zip(la, lb)]
+    # teacher-forced prompt logprobs must agree to bf16 accuracy; greedy continuations may flip near-ties later
+    assert max(diffs) < 0.15 and sum(diffs) / len(diffs) < 0.03, (max(diffs), sum(diffs) / len(diffs))
+    assert first_agree >= len(a["tokens"]) - 1

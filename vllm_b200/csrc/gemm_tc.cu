@@ -184,8 +184,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float v[CH];
         load_chunk(c, v);
         if (p.splits > 1) {
+          // deterministic: always sum the partials in split order (whichever CTA arrives last), so the
+          // result is bit-identical run to run and across TP ranks that replicate a computation
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = 0.f;
           for (int s2 = 0; s2 < p.splits; ++s2) {
-            if (s2 == split) continue;
             const float* o = p.ws + ((size_t)tile_id * p.splits + s2) * (BN * TM);
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] += __ldcg(o + (c + j) * TM + row);

@@ -81,10 +81,14 @@ class VocabParallelEmbedding(nn.Module):
     and the TP all-reduce restores the full embedding (collective C2 in SURVEY §2.4)."""
 
     def __init__(self, num_embeddings: int, embedding_dim: int, dtype=None, padding_size: int = 64,
-                 prefix: str = "") -> None:
+                 prefix: str = "", replicate: bool = False) -> None:
         super().__init__()
         g = get_tp_group()
         self.tp_rank, self.tp_size = max(g.rank_in_group, 0), g.world_size
+        if replicate:
+            # B200-first: with 180 GB per GPU the input embedding (<= a few GB) is simply replicated, which
+            # removes the embedding all-reduce (collective C2) from every step; the LM head stays sharded
+            self.tp_rank, self.tp_size = 0, 1
         self.num_embeddings = num_embeddings
         self.padded = round_up(num_embeddings, padding_size * self.tp_size)
         self.per_rank = self.padded // self.tp_size

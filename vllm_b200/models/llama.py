@@ -22,7 +22,7 @@ from vllm_b200.layers.common import (LogitsProcessor, ParallelLMHead, RMSNorm, V
                                      get_act_and_mul)
 from vllm_b200.layers.linear import MergedColumnParallelLinear, QKVParallelLinear, RowParallelLinear
 from vllm_b200.layers.rotary import get_rope
-from vllm_b200.parallel.state import get_pp_group
+from vllm_b200.parallel.state import get_pp_group, get_tp_group
 from vllm_b200.parallel.utils import get_pp_indices
 
 
@@ -117,8 +117,10 @@ class LlamaModel(nn.Module):
         self.gemma = cfg.get("model_type", "").startswith("gemma")
         self.embed_scale = cfg["hidden_size"] ** 0.5 if self.gemma else 1.0
         if self.pp_rank == 0 or (cfg.get("tie_word_embeddings") and self.pp_rank == self.pp_size - 1):
+            rep = (not cfg.get("tie_word_embeddings")
+                   and cfg["vocab_size"] * cfg["hidden_size"] * 2 <= (4 << 30))
             self.embed_tokens = VocabParallelEmbedding(cfg["vocab_size"], cfg["hidden_size"], dtype,
-                                                       prefix=f"{prefix}.embed_tokens")
+                                                       prefix=f"{prefix}.embed_tokens", replicate=rep)
         else:
             self.embed_tokens = None
         self.layers = nn.ModuleList(
@@ -148,6 +150,10 @@ class LlamaModel(nn.Module):
             hidden, residual = layer(positions, hidden, residual, nxt)
         if self.norm is None:  # not the last PP stage: ship the un-normalised pair
             return {"hidden_states": hidden, "residual": residual}
+        if get_tp_group().world_size > 1 and hidden.is_cuda:
+            # under TP the fused GEMM+all-reduce+norm returns a view of the symmetric heap, which later
+            # collectives (logits all-gather, prompt-logprob passes) recycle: detach the final states from it
+            hidden = hidden.clone()
         return hidden
 
 

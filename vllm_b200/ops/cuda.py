@@ -374,14 +374,14 @@ def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     return y
 
 
-def _tc_ok(x2: torch.Tensor, w: torch.Tensor) -> bool:
+def _tc_ok(x2: torch.Tensor, w: torch.Tensor, force: bool = False) -> bool:
     mode = envs.VLLM_B200_GEMM
-    if mode == "cublas":
+    if mode == "cublas" and not force:
         return False
     K = x2.shape[1]
     ok = (x2.dtype in (torch.bfloat16, torch.float16) and w.dtype == x2.dtype and K % 64 == 0
           and x2.stride(1) == 1 and (x2.stride(0) * 2) % 16 == 0 and x2.data_ptr() % 16 == 0 and w.is_contiguous())
-    if mode == "tcgen05":
+    if mode == "tcgen05" or force:
         return ok
     # auto: our kernel for the weight-streaming decode shapes, cuBLASLt for the rest
     return ok and x2.shape[0] <= 256
@@ -412,6 +412,44 @@ def comm_allreduce_rows(c, x, in_off, out_off, residual, norm_w, eps, T, H, gemm
 def comm_all_gather(c, x, out_off, rows, cols) -> None:
     _check(_comm_ag(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, x.data_ptr(), out_off,
                     rows, cols, num_sms(), _DT[x.dtype], _st()), "comm_all_gather")
+
+
+_gemm_ar_plan = _sig("vb_gemm_ar_plan", _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i64),
+                     ctypes.POINTER(_i))
+_gemm_ar = _sig("vb_gemm_ar", _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp,
+                _i64, _i64, _i, _f, _i, _i, _vp)
+_ar_plan_cache: dict[tuple, Optional[tuple]] = {}
+
+
+def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma) -> bool:
+    """Fused RowParallel GEMM + all-reduce + residual + RMSNorm (csrc/gemm_ar.cu). False = shape not covered."""
+    from vllm_b200.parallel.symm import LAM_T_CAP
+    M, K = x.shape
+    N = w.shape[0]
+    key = (M, N, K)
+    plan = _ar_plan_cache.get(key, 0)
+    if plan == 0:
+        bn, splits, tiles = _i(), _i(), _i()
+        wsb = _i64()
+        rc = _gemm_ar_plan(M, N, K, num_sms(), ctypes.byref(bn), ctypes.byref(splits), ctypes.byref(wsb),
+                           ctypes.byref(tiles))
+        plan = (bn.value, splits.value, wsb.value, tiles.value) if rc == 0 else None
+        _ar_plan_cache[key] = plan
+    if plan is None:
+        return False
+    bn, splits, wsb, tiles = plan
+    dev = x.device.index or 0
+    g = _gemm_ws.setdefault(dev, _GemmWorkspace())
+    if g.ws is None or g.ws.numel() * 4 < wsb or g.counters.numel() < tiles:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("GEMM split-K workspace must be allocated before CUDA-graph capture")
+        g.ws = torch.empty(max(wsb // 4, 16 << 20), dtype=torch.float32, device=x.device)
+        g.counters = torch.zeros(max(tiles, 4096), dtype=torch.int32, device=x.device)
+    _check(_gemm_ar(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, x.data_ptr(), w.data_ptr(),
+                    residual.data_ptr(), norm_w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), bn, splits,
+                    g.ws.data_ptr(), g.counters.data_ptr(), c.off_lam, c.lam_stride, LAM_T_CAP, eps, int(gemma),
+                    _DT[x.dtype], _st()), f"gemm_ar(M={M},N={N},K={K})")
+    return True
 
 
 def comm_barrier(c) -> None:

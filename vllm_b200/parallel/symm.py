@@ -29,6 +29,8 @@ from vllm_b200.logger import init_logger
 logger = init_logger(__name__)
 
 FLAGS_BYTES = 4096
+LAM_T_CAP = 128      # the fused GEMM+all-reduce kernel handles up to 128 tokens (decode / small mixed batches)
+LAM_H_MAX = 8192
 _ALIGN = 1 << 16
 
 
@@ -61,9 +63,14 @@ class SymmComm:
     # ---------------------------------------------------------------- memory
     def _alloc(self, region_bytes: int) -> None:
         region = _round(region_bytes)
-        total = FLAGS_BYTES + 3 * region
+        # Lamport receive buffers for the fused decode kernel: 3 rotating buffers x world x T_CAP rows x H_MAX
+        self.lam_stride = _round(self.world * LAM_T_CAP * LAM_H_MAX * 2)
+        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride
         self.buf = self._symm.empty(total, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
+        self.off_lam = FLAGS_BYTES + 3 * region
+        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
+        self.lam_H = 0
         torch.cuda.synchronize()
         self.hdl = self._symm.rendezvous(self.buf, self.group.device_group)
         self.region = region
@@ -152,6 +159,15 @@ class SymmComm:
         T, H = x2.shape[0], w.shape[0]
         if H % 8 or H // 8 > 1024 or not residual.is_contiguous():
             return None
+        if (T <= LAM_T_CAP and H <= LAM_H_MAX and envs.VLLM_B200_FUSED_AR and self.cu._tc_ok(x2, w, force=True)
+                and residual.dtype == x.dtype):
+            # decode: ONE kernel — tcgen05 GEMM whose epilogue multicasts the tile to every GPU (Lamport buffers),
+            # then reduces + residual + RMSNorm in place; no barrier, no NCCL
+            if H != self.lam_H:
+                self._rearm_lamport(H)
+            out = torch.empty((T, H), dtype=x.dtype, device=x.device)
+            if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, out, eps, gemma):
+                return out.view(x.shape[:-1] + (H,)), residual
         self.ensure_capacity(T * H * x.dtype.itemsize)
         part = self.staging((T, H), x.dtype)
         if self.cu._tc_ok(x2, w):
@@ -160,6 +176,18 @@ class SymmComm:
             torch.matmul(x2, w.t(), out=part)
         out = self.allreduce_rows(None, T, H, x.dtype, residual.view(T, H), norm_w, eps, gemma)
         return out.view(x.shape[:-1] + (H,)), residual
+
+    def _rearm_lamport(self, H: int) -> None:
+        """The Lamport slot layout depends on H: switching H re-arms all buffers (host side, collective)."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("Lamport buffers must be armed for this hidden size before CUDA-graph capture")
+        torch.cuda.synchronize()
+        self.group.barrier()
+        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)
+        self.state[8:13].zero_()
+        torch.cuda.synchronize()
+        self.group.barrier()
+        self.lam_H = H
 
     def embedding_allreduce(self, ids: torch.Tensor, weight: torch.Tensor, start: int) -> Optional[torch.Tensor]:
         """Vocab-sharded embedding lookup + all-reduce: the masked lookup lands in the staging region,
