@@ -23,12 +23,6 @@ struct CommCtx {
   int rank, world;
 };
 
-VB_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-VB_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // All ranks rendezvous: executed by (at least) `world` threads of ONE block per rank.
 // Rank r publishes `target` into slot r of every peer's flag array, then waits for all slots of its own.

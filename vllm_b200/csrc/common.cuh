@@ -69,6 +69,13 @@ template <> VB_DEVICE uint32_t pack2<__half>(float a, float b) {
   __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
 
+VB_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+VB_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 VB_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -136,6 +143,10 @@ VB_DEVICE void tma_load_2d_hint(void* dst_smem, const void* tmap, int c0, int c1
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
                " [%0], [%1, {%3, %4}], [%2], %5;"
                ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+// HBM → L2 only (no shared-memory slot needed): lets a CTA keep far more bytes in flight than its smem ring holds
+VB_DEVICE void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
 VB_DEVICE void tma_store_2d(const void* tmap, const void* src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -253,6 +264,21 @@ VB_DEVICE uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
+// ------------------------------------------------ thread-block clusters / distributed shared memory
+VB_DEVICE void cluster_sync() {   // every thread of every CTA in the cluster; warp-convergent
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+VB_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// shared::cluster address of `smem_addr` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+VB_DEVICE uint32_t dsmem_addr(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+VB_DEVICE float4 ld_dsmem_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // ------------------------------------------------ programmatic dependent launch (PDL)
 // Every kernel calls pdl_trigger() first (lets the next kernel in the stream begin launching: its prologue,
 // barrier init, TMEM alloc and — for GEMMs — the weight TMA stream overlap this kernel's tail) and
@@ -275,6 +301,23 @@ inline cudaError_t vb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = vb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Same, with the grid's z extent grouped into thread-block clusters of `cluster_z` CTAs (co-scheduled on one GPC,
+// distributed shared memory between them).
+template <typename... KArgs, typename... Args>
+inline cudaError_t vb_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     unsigned cluster_z, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cluster_z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vb_pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

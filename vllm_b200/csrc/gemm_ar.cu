@@ -36,6 +36,9 @@ struct Params {
   size_t lam_off;          // byte offset of the 3 Lamport buffers inside the symmetric heap
   size_t lam_stride;       // bytes per buffer (= world * t_cap * H * 2)
   int t_cap;               // rows reserved per source rank in a buffer (layout is independent of M)
+  int mode;                // 0 = one-shot Lamport push (any transport), 1 = NVLS: flags + multimem.ld_reduce + multimem.st
+  size_t part_off;         // mode 1: byte offset of this rank's partial [T,H] inside the symmetric heap
+  size_t out_off;          // mode 1: byte offset of the normalised output [T,H] (same on every rank)
   int M, N, K;             // tokens, H, local K
   int k_blocks_per_split, splits;
   float eps;
@@ -62,6 +65,25 @@ VB_DEVICE uint32_t sanitize(uint32_t w) {   // -0.0 → +0.0 in both halves
   if ((w & 0xffffu) == 0x8000u) w &= 0xffff0000u;
   if ((w >> 16) == 0x8000u) w &= 0x0000ffffu;
   return w;
+}
+
+// mode-1 flags live in the first 4 KiB of the symmetric heap (u32 slots): [64, 64+8*64) one per (source rank,
+// output tile), [576, 704) one per token row.  Values are monotonically increasing epochs (no reset, graph safe).
+constexpr int FLAG_TILE0 = 64, FLAG_ROW0 = 576, MAX_TILES = 64;
+
+VB_DEVICE void flag_publish(const CommCtx& c, int slot, uint32_t v) {
+  if (c.mc) {
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(c.mc + (size_t)slot * 4), "r"(v) : "memory");
+  } else {
+    for (int pr = 0; pr < c.world; ++pr)
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(c.peer[pr] + (size_t)slot * 4), "r"(v) : "memory");
+  }
+}
+VB_DEVICE void flag_wait(const CommCtx& c, int slot, uint32_t v) {
+  // relaxed spin; the caller issues ONE fence.acq_rel.sys after all of its flags have been observed
+  const uint32_t* f = reinterpret_cast<const uint32_t*>(c.local) + slot;
+  uint32_t x;
+  do { asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(f) : "memory"); } while ((int32_t)(x - v) < 0);
 }
 
 template <typename T, int BN, int STAGES>
@@ -120,6 +142,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_load_2d_hint(a_dst + L::A_BYTES, &tmap_b, (kb0 + kb) * BK, 0, &full[s], L2_EVICT_LAST);
       }
     }
+    if (p.splits > 1) { __syncwarp(); cluster_sync(); cluster_sync(); }   // the epilogue's two cluster barriers
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_f16(TM, BN, DTypeOf<T>::v == DT_BF16);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -137,6 +160,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       __syncwarp();
     }
+    if (p.splits > 1) { __syncwarp(); cluster_sync(); cluster_sync(); }   // the epilogue's two cluster barriers
   } else {
     // =========================== epilogue + collective ===========================
     constexpr int CH = (BN % 32 == 0) ? 32 : 16;
@@ -174,26 +198,62 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     };
     const int tile_id = a_tile;
+    const int n0 = a_tile * TM;
     bool do_push = true;
     if (p.splits > 1) {
-      float* my = p.ws + ((size_t)tile_id * p.splits + split) * (BN * TM);
+      // split-K over a thread-block cluster (grid z): every CTA parks its fp32 partial in its own shared memory
+      // (the operand ring is idle once tmem_full fired); after the cluster barrier EACH CTA reduces 1/splits of
+      // the tile out of its peers' shared memory (DSMEM, split order → deterministic) and ships that slice.
+      // No global workspace, no atomics; the fix-up and the push are spread over all SMs of the cluster.
+      do_push = false;
+      float* part_s = reinterpret_cast<float*>(stage_base);
       for (int cc = 0; cc < BN; cc += CH) {
         float v[CH];
         load_chunk(cc, v);
 #pragma unroll
-        for (int j = 0; j < CH; ++j) __stcg(my + (cc + j) * TM + row, v[j]);
+        for (int j = 0; j < CH; ++j) part_s[(cc + j) * TM + row] = v[j];
       }
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-      if (et == 0) {
-        const unsigned prev = atomicAdd(&p.counters[tile_id], 1u);
-        const int last = prev == (unsigned)(p.splits - 1);
-        if (last) p.counters[tile_id] = 0;
-        *is_last = last;
+      __syncwarp();
+      cluster_sync();
+      const int units = p.M * (TM / 8);                            // unit = 8 consecutive features of one token
+      const int per = (units + p.splits - 1) / p.splits;
+      const int u_end = min(units, (split + 1) * per);
+      const uint32_t red_s = smem_u32(stage_base);
+      T* part = reinterpret_cast<T*>(c.local + p.part_off);
+      for (int u = split * per + et; u < u_end; u += EPI_THREADS) {
+        const int t = u / (TM / 8), g = u % (TM / 8);
+        if (n0 + g * 8 >= p.N) continue;
+        const uint32_t off = red_s + (uint32_t)(t * TM + g * 8) * 4u;
+        float4 x0[8], x1[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < p.splits) {
+            const uint32_t ra = dsmem_addr(off, (uint32_t)r);
+            x0[r] = ld_dsmem_f32x4(ra); x1[r] = ld_dsmem_f32x4(ra + 16);
+          }
+        float4 a0 = x0[0], a1 = x1[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+          if (r < p.splits) {
+            a0.x += x0[r].x; a0.y += x0[r].y; a0.z += x0[r].z; a0.w += x0[r].w;
+            a1.x += x1[r].x; a1.y += x1[r].y; a1.z += x1[r].z; a1.w += x1[r].w;
+          }
+        uint32_t w[4] = {pack2<T>(a0.x, a0.y), pack2<T>(a0.z, a0.w), pack2<T>(a1.x, a1.y), pack2<T>(a1.z, a1.w)};
+        if (p.mode == 1) {
+          *reinterpret_cast<uint4*>(part + (size_t)t * p.N + n0 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = sanitize(w[e]);
+          bcast16(c, lam_cur_off + (((size_t)c.rank * p.t_cap + t) * p.N + n0 + g * 8) * sizeof(T), w);
+        }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-      do_push = *is_last != 0;
-      if (do_push) __threadfence();
+      if (p.mode == 1) __threadfence_system();   // my slice is visible system-wide before the cluster barrier
+      __syncwarp();
+      cluster_sync();                            // also: nobody's shared memory is read past this point
+      if (p.mode == 1 && split == 0 && et == 0) {
+        __threadfence_system();                  // every slice of this tile is in place (barrier = acq/rel at cluster scope)
+        flag_publish(c, FLAG_TILE0 + c.rank * MAX_TILES + a_tile, c.state[13] + 1);
+      }
     }
     // the operand ring is idle now (all MMAs of this CTA retired before tmem_full fired): reuse it as the
     // [token][feature] transposition buffer
@@ -201,24 +261,27 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (do_push) {
       for (int cc = 0; cc < BN; cc += CH) {
         float v[CH];
-        if (p.splits > 1) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = 0.f;
-          for (int s2 = 0; s2 < p.splits; ++s2) {
-            const float* o = p.ws + ((size_t)tile_id * p.splits + s2) * (BN * TM);
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] += __ldcg(o + (cc + j) * TM + row);
-          }
-        } else {
-          load_chunk(cc, v);
-        }
+        load_chunk(cc, v);
 #pragma unroll
         for (int j = 0; j < CH; ++j)
           if (cc + j < p.M) tbuf[(cc + j) * TM + row] = from_f32<T>(v[j]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      if (p.mode == 1) {
+        // NVLS mode: the tile stays in THIS rank's symmetric buffer (row-major [T][H]); peers will pull the
+        // sum of all replicas through the switch.  Publish "tile (rank, a_tile) of epoch e is complete".
+        T* part = reinterpret_cast<T*>(c.local + p.part_off);
+        for (int i = et; i < p.M * (TM / 8); i += EPI_THREADS) {
+          const int t = i / (TM / 8), g = i % (TM / 8);
+          if (n0 + g * 8 >= p.N) continue;
+          *reinterpret_cast<uint4*>(part + (size_t)t * p.N + n0 + g * 8) =
+              *reinterpret_cast<const uint4*>(tbuf + t * TM + g * 8);
+        }
+        __threadfence_system();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        if (et == 0) flag_publish(c, FLAG_TILE0 + c.rank * MAX_TILES + a_tile, c.state[13] + 1);
+      } else
       // push: item = (token, group of 8 features); wire layout [src rank][token][H]
-      const int n0 = a_tile * TM;
       for (int i = et; i < p.M * (TM / 8); i += EPI_THREADS) {
         const int t = i / (TM / 8), g = i % (TM / 8);
         if (n0 + g * 8 >= p.N) continue;
@@ -234,6 +297,69 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int cta = blockIdx.z * gridDim.x + blockIdx.x;
     const int groups = p.N / 8;                            // 16-byte groups per row
     constexpr int MAXG = 8;                                // groups per thread kept in registers (H <= 8192)
+    if (p.mode == 1) {
+      const uint32_t epoch = c.state[13] + 1;
+      const int n_tiles = gridDim.x;
+      const int per = (p.M + c.world - 1) / c.world;          // rows owned by each rank
+      const int r0 = c.rank * per, r1 = min(p.M, r0 + per);
+      const int n_mine = max(r1 - r0, 0);
+      if (cta < n_mine) {
+        const int t = r0 + cta;                               // (n_mine <= 16 << n_ctas: one row per CTA)
+        // every rank has finished every tile of this epoch?
+        for (int i = et; i < c.world * n_tiles; i += EPI_THREADS)
+          flag_wait(c, FLAG_TILE0 + (i / n_tiles) * MAX_TILES + (i % n_tiles), epoch);
+        __threadfence_system();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        float acc[MAXG][8];
+        float ss = 0.f;
+#pragma unroll
+        for (int gi = 0; gi < MAXG; ++gi) {
+          const int g = et + gi * EPI_THREADS;
+          if (g >= groups) break;
+          reduce8<T>(c, p.part_off + ((size_t)t * p.N + g * 8) * sizeof(T), acc[gi]);   // in-switch sum
+          T* rrow = reinterpret_cast<T*>(p.residual) + (size_t)t * p.N + g * 8;
+          Vec16<T> rv = ld16(rrow), ro;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ro.e[e] = from_f32<T>(to_f32(from_f32<T>(acc[gi][e])) + to_f32(rv.e[e]));
+            acc[gi][e] = to_f32(ro.e[e]);
+            ss += acc[gi][e] * acc[gi][e];
+          }
+          st16(rrow, ro);                                     // the residual stays sharded by row owner
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[q] = ss;
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        const float inv = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)p.N + p.eps);
+#pragma unroll
+        for (int gi = 0; gi < MAXG; ++gi) {
+          const int g = et + gi * EPI_THREADS;
+          if (g >= groups) break;
+          Vec16<T> wv = ld16(reinterpret_cast<const T*>(p.norm_w) + g * 8);
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float g0 = to_f32(wv.e[2 * e]) + (p.gemma ? 1.f : 0.f), g1 = to_f32(wv.e[2 * e + 1]) + (p.gemma ? 1.f : 0.f);
+            o[e] = pack2<T>(acc[gi][2 * e] * inv * g0, acc[gi][2 * e + 1] * inv * g1);
+          }
+          bcast16(c, p.out_off + ((size_t)t * p.N + g * 8) * sizeof(T), o);            // to every rank
+        }
+        __threadfence_system();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        if (et == 0) flag_publish(c, FLAG_ROW0 + t, epoch);
+      }
+      if (cta == n_ctas - 1) {
+        // the kernel may only complete once every row (from every owner) has landed in this rank's buffer
+        for (int i = et; i < p.M; i += EPI_THREADS) flag_wait(c, FLAG_ROW0 + i, epoch);
+        __threadfence_system();
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+      if (et == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&c.state[9], 1u);
+        if (prev == (unsigned)(n_ctas - 1)) { c.state[9] = 0; c.state[13] = epoch; }
+      }
+    } else {
     const int t_end = max(p.M, dirty);
     for (int t = cta; t < t_end; t += n_ctas) {
       if (t >= p.M) {   // row not used by this call but dirtied earlier: only re-arm it
@@ -311,6 +437,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         c.state[8] = call + 1;
       }
     }
+    }  // mode
   }
   tc_fence_before();
   __syncthreads();
@@ -354,7 +481,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   auto k = gemm_ar_kernel<T, BN, STAGES>;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  vb_launch(k, grid, dim3(NUM_THREADS), (size_t)smem, st, ta, tb, p, c);
+  if (grid.z > 1) vb_launch_cluster(k, grid, dim3(NUM_THREADS), (size_t)smem, st, grid.z, ta, tb, p, c);
+  else vb_launch(k, grid, dim3(NUM_THREADS), (size_t)smem, st, ta, tb, p, c);
   return (int)cudaGetLastError();
 }
 
@@ -362,26 +490,34 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 
 // Plan: number of K splits so that tiles*splits <= num_sms (all CTAs must be co-resident: reducers spin on
 // data produced by other CTAs / other GPUs).
+extern "C" int vb_gemm_max_active_clusters(int c);
+
 EXPORT int vb_gemm_ar_plan(int M, int N, int K, int num_sms, int* bn, int* splits, int64_t* ws_bytes, int* n_tiles) {
   using namespace gemm_ar;
   if (M > 128) return -1;
   const int kb = (K + BK - 1) / BK;
   const int nt = (N + TM - 1) / TM;
   if (nt > num_sms) return -2;
-  int s = num_sms / nt;
-  if (s > kb / 2) s = kb / 2;
-  if (s < 1) s = 1;
-  if (s > 16) s = 16;
+  int s = 1;                               // same policy as vb_gemm_tc_plan (cluster split-K)
+  for (int c = 8; c > 1; --c) {
+    if (c * nt > 132 || kb / c < 4) continue;
+    const int fit = vb_gemm_max_active_clusters(c);
+    if (fit > 0 && nt > fit) continue;
+    s = c;
+    break;
+  }
+  if (nt >= 56 && kb < 32) s = 1;
   const int b = ((M + 15) / 16) * 16;
   *bn = b; *splits = s; *n_tiles = nt;
-  *ws_bytes = s > 1 ? (int64_t)nt * s * b * TM * 4 : 0;
+  *ws_bytes = 0;                          // split-K partials live in (distributed) shared memory
   return 0;
 }
 
 EXPORT int vb_gemm_ar(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world, const void* x,
                       const void* w, void* residual, const void* norm_w, void* out, int M, int N, int K,
                       int64_t x_stride, int bn, int splits, float* ws, unsigned* counters, int64_t lam_off,
-                      int64_t lam_stride, int t_cap, float eps, int gemma, int dtype, cudaStream_t st) {
+                      int64_t lam_stride, int t_cap, int mode, int64_t part_off, int64_t out_off, float eps, int gemma, int dtype,
+                      cudaStream_t st) {
   using namespace gemm_ar;
   if (dtype == DT_F32 || K % 8 != 0 || N % 8 != 0 || N / 8 > 8 * EPI_THREADS) return -1;
   const bool bf16 = dtype == DT_BF16;
@@ -396,6 +532,8 @@ EXPORT int vb_gemm_ar(void* local, void* const* peers, void* mc, uint32_t* state
   const int kb = (K + BK - 1) / BK;
   p.k_blocks_per_split = (kb + splits - 1) / splits;
   p.eps = eps; p.gemma = gemma; p.t_cap = t_cap;
+  p.mode = mode; p.part_off = (size_t)part_off; p.out_off = (size_t)out_off;
+  if (mode == 1 && (N + TM - 1) / TM > MAX_TILES) return -8;
   if (M > t_cap) return -7;
   int rc;
   if ((rc = make_tmap(&ta, w, N, K, K, TM, bf16))) return rc;

@@ -10,8 +10,8 @@
 //          padded to 16).  The accumulator is Y^T: TMEM lane = output feature, column = token.
 //          Every CTA streams a [128 x K/splits] slab of the weight exactly once — the op is
 //          weight-bandwidth bound, so the grid is (N/128) x splits CTAs sized to cover all 148 SMs,
-//          split-K partials are reduced by the last-arriving CTA of each tile (fp32 workspace that
-//          stays in the 126 MB L2, self-resetting counters → CUDA-graph replay safe).
+//          the `splits` CTAs of a tile form a thread-block cluster: partials stay in shared memory and every
+//          CTA reduces + stores 1/splits of the tile through DSMEM (no workspace, no atomics, graph safe).
 //   SWAP=0 (prefill, large M): A := X tile (128 tokens), B := W tile (BN features).
 //
 // The reference uses cuBLASLt for this op (layers/linear.py:210-218); our kernel exists because it is
@@ -34,6 +34,8 @@ struct Params {
   int k_blocks_per_split;  // BK blocks handled by one CTA
   int splits;
   int act;                 // 0 none, 1 silu-mul over interleaved (gate,up) feature pairs (SWAP only)
+  int pf;                  // L2 prefetch ahead of the smem ring (SWAP)
+  long long* trace;        // debug: per-CTA clock64 stamps [cta][16] (null in production)
 };
 
 template <int BN> struct SmemLayout {
@@ -42,8 +44,10 @@ template <int BN> struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
+// STAGES <= 4 is the two-CTAs-per-SM variant (smem <= 113 KB): used when the grid has more tiles than SMs, so the
+// prologue / epilogue of one tile overlaps the weight stream of its neighbour instead of leaving the SM idle.
 template <typename T, int BN, int STAGES, bool SWAP>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, STAGES <= 4 && BN <= 128 ? 2 : 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   using L = SmemLayout<BN>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -53,7 +57,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  int* is_last = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile coordinates: A-operand tile index (x), B-operand tile index (y), K split (z)
@@ -63,6 +66,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int nkb = max(0, min(p.k_blocks_per_split, total_kb - kb0));
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 
+#define VB_TRACE(i) do { if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
+  if (threadIdx.x == 0) VB_TRACE(0);
   pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -80,6 +85,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
+      VB_TRACE(1);
       // ===== TMA producer: weights are read exactly once → evict-first; activations are re-read by every CTA → evict-last
       // PDL: the weight operand does not depend on the preceding kernel, so the first ring of weight tiles is
       // requested BEFORE griddepcontrol.wait — the weight stream starts while the previous kernel is still
@@ -90,13 +96,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_expect_tx(&full[kb], L::STAGE_BYTES);
         tma_load_2d_hint(a_dst, &tmap_a, (kb0 + kb) * BK, a_tile * TM, &full[kb], L2_EVICT_FIRST);
       }
+      // the smem ring alone (STAGES x 16 KB of weights) cannot cover the HBM latency-bandwidth product of one
+      // SM's share when few CTAs stream a lot each: run an L2 prefetch PF k-blocks ahead of the ring
+      constexpr int PF = SWAP ? 16 : 0;
+      if (SWAP && p.pf)
+        for (int kb = pre; kb < min(nkb, pre + PF); ++kb) tma_prefetch_l2_2d(&tmap_a, (kb0 + kb) * BK, a_tile * TM);
       pdl_wait();
+      VB_TRACE(2);
       for (int kb = 0; kb < pre; ++kb) {
         unsigned char* b_dst = stage_base + kb * L::STAGE_BYTES + L::A_BYTES;
         tma_load_2d_hint(b_dst, &tmap_b, (kb0 + kb) * BK, b_tile * BN, &full[kb], L2_EVICT_LAST);
       }
       for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % STAGES;
+        if (SWAP && p.pf && kb + PF < nkb) tma_prefetch_l2_2d(&tmap_a, (kb0 + kb + PF) * BK, a_tile * TM);
         mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
         unsigned char* a_dst = stage_base + s * L::STAGE_BYTES;
         unsigned char* b_dst = a_dst + L::A_BYTES;
@@ -114,13 +127,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_wait(&full[s], (kb / STAGES) & 1);
       tc_fence_after();
       if (lane == 0) {
+        if (kb == 0) VB_TRACE(3);
         const unsigned char* a_src = stage_base + s * L::STAGE_BYTES;
         const uint64_t da = umma_desc_sw128(a_src), db = umma_desc_sw128(a_src + L::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)   // UMMA_K = 16 → advance 32 B inside the swizzle span
           umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         umma_commit(&empty[s]);                 // frees the smem slot once these MMAs retire
-        if (kb == nkb - 1) umma_commit(tmem_full);
+        if (kb == nkb - 1) { umma_commit(tmem_full); VB_TRACE(4); }
       }
       __syncwarp();
     }
@@ -135,6 +149,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) VB_TRACE(5);
     auto load_chunk = [&](int c, float (&v)[CH]) {
       if (nkb == 0) {
 #pragma unroll
@@ -158,42 +173,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int tile_id = a_tile * gridDim.y + b_tile;
     bool do_store = true;
     if (p.splits > 1) {
-      // partial → workspace (stays in L2); the last CTA to arrive sums the others and stores
-      float* my = p.ws + ((size_t)tile_id * p.splits + split) * (BN * TM);
+      // split-K over a thread-block cluster: the `splits` CTAs of a tile are one cluster (grid z).  Each parks its
+      // fp32 partial in its OWN shared memory (the operand ring is idle once tmem_full fired) — part 1 of 2, the
+      // reduction itself follows the cluster barrier below.
+      float* red = reinterpret_cast<float*>(stage_base);
       for (int c = 0; c < BN; c += CH) {
         float v[CH];
         load_chunk(c, v);
 #pragma unroll
-        for (int j = 0; j < CH; ++j) __stcg(my + (c + j) * TM + row, v[j]);
+        for (int j = 0; j < CH; ++j) red[(c + j) * TM + row] = v[j];
       }
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-      if (threadIdx.x == 64) {
-        const unsigned prev = atomicAdd(&p.counters[tile_id], 1u);
-        const int last = prev == (unsigned)(p.splits - 1);
-        if (last) p.counters[tile_id] = 0;       // self-reset for the next launch / graph replay
-        *is_last = last;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-      do_store = *is_last != 0;
-      if (do_store) __threadfence();
+      if (threadIdx.x == 64) VB_TRACE(6);
+      do_store = false;
     }
     if (do_store) {
       T* y = reinterpret_cast<T*>(p.y);
       for (int c = 0; c < BN; c += CH) {
         float v[CH];
         load_chunk(c, v);
-        if (p.splits > 1) {
-          // deterministic: always sum the partials in split order (whichever CTA arrives last), so the
-          // result is bit-identical run to run and across TP ranks that replicate a computation
-#pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = 0.f;
-          for (int s2 = 0; s2 < p.splits; ++s2) {
-            const float* o = p.ws + ((size_t)tile_id * p.splits + s2) * (BN * TM);
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] += __ldcg(o + (c + j) * TM + row);
-          }
-        }
         if (SWAP) {
           // accumulator is Y^T: row = output feature, column = token
           const int n = a_tile * TM + row;
@@ -227,11 +224,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
+    if (threadIdx.x == 64) VB_TRACE(9);
     tc_fence_before();
+  }
+  if constexpr (SWAP) {
+    if (p.splits > 1) {
+      // part 2: after the cluster barrier every CTA reduces 1/splits of the tile straight out of its peers'
+      // shared memory (DSMEM) in split order (→ bit-identical run to run) and stores it.  No global workspace,
+      // no atomics, no fences; the CTAs of a cluster are co-scheduled by hardware.
+      __syncwarp();
+      cluster_sync();
+      if (warp >= 2) {
+        const int et = threadIdx.x - 64;
+        if (et == 0) VB_TRACE(7);
+        T* y = reinterpret_cast<T*>(p.y);
+        const int m_base = b_tile * BN;
+        const int cols = min(BN, p.M - m_base);                    // real tokens in this tile
+        const int units = cols * (TM / 4);                         // unit = 4 consecutive features of one token
+        const int per = (units + p.splits - 1) / p.splits;
+        const int u_end = min(units, (split + 1) * per);
+        const uint32_t red_s = smem_u32(stage_base);
+        // two units per pass: all DSMEM loads of both are in flight before the first add
+        for (int u0 = split * per + et; u0 < u_end; u0 += 2 * EPI_THREADS) {
+          float4 x[2][8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int u = u0 + h * EPI_THREADS;
+            if (u < u_end) {
+              const uint32_t off = red_s + (uint32_t)((u / (TM / 4)) * TM + (u % (TM / 4)) * 4) * 4u;
+#pragma unroll
+              for (int r = 0; r < 8; ++r)
+                if (r < p.splits) x[h][r] = ld_dsmem_f32x4(dsmem_addr(off, (uint32_t)r));
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int u = u0 + h * EPI_THREADS;
+            if (u >= u_end) break;
+            const int col = u / (TM / 4), rq = u % (TM / 4);
+            float4 acc = x[h][0];
+#pragma unroll
+            for (int r = 1; r < 8; ++r)
+              if (r < p.splits) { acc.x += x[h][r].x; acc.y += x[h][r].y; acc.z += x[h][r].z; acc.w += x[h][r].w; }
+            const int n = a_tile * TM + rq * 4;
+            T* yr = y + (size_t)(m_base + col) * p.N + n;
+            float o[4] = {acc.x, acc.y, acc.z, acc.w};
+            if (p.bias) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) o[e] += to_f32(reinterpret_cast<const T*>(p.bias)[n + e]);
+            }
+            if (n + 4 <= p.N && (p.N & 3) == 0) {
+              uint2 pk;
+              pk.x = pack2<T>(o[0], o[1]); pk.y = pack2<T>(o[2], o[3]);
+              *reinterpret_cast<uint2*>(yr) = pk;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) yr[e] = from_f32<T>(o[e]);
+            }
+          }
+        }
+        if (et == 0) VB_TRACE(8);
+      }
+      __syncwarp();
+      cluster_sync();      // nobody leaves (and frees its shared memory) while a peer may still be reading it
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) VB_TRACE(10);
+#undef VB_TRACE
 }
 
 // ------------------------------------------------------------------ host side
@@ -272,11 +334,38 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   auto k = gemm_kernel<T, BN, STAGES, SWAP>;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  vb_launch(k, grid, dim3(NUM_THREADS), (size_t)smem, st, ta, tb, p);
+  if (grid.z > 1) vb_launch_cluster(k, grid, dim3(NUM_THREADS), (size_t)smem, st, grid.z, ta, tb, p);
+  else vb_launch(k, grid, dim3(NUM_THREADS), (size_t)smem, st, ta, tb, p);
   return (int)cudaGetLastError();
 }
 
 }  // namespace gemm
+
+// how many clusters of `c` CTAs (1 CTA / SM, ~200 KB smem each) the device can hold at once
+static int max_active_clusters(int c) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < 1 || c > 8) return 0;
+  if (cache[c] == 0) {
+    using namespace gemm;
+    auto k = gemm_kernel<__nv_bfloat16, 64, 8, true>;
+    const int smem = 8 * SmemLayout<64>::STAGE_BYTES + (2 * 8 + 1) * 8 + 16 + 1024;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, c); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = c;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); n = -1; }
+    cache[c] = n > 0 ? n : -1;
+  }
+  return cache[c];
+}
+EXPORT int vb_gemm_max_active_clusters(int c) { return max_active_clusters(c); }
+
+static long long* g_trace = nullptr;
+EXPORT void vb_gemm_tc_set_trace(long long* t) { g_trace = t; }
 
 // Workspace requirement for vb_gemm_tc (bytes of fp32 partials, number of counters)
 EXPORT int vb_gemm_tc_plan(int M, int N, int K, int num_sms, int* swap, int* bn, int* splits, int64_t* ws_bytes,
@@ -288,13 +377,21 @@ EXPORT int vb_gemm_tc_plan(int M, int N, int K, int num_sms, int* swap, int* bn,
     if (b > 128 && b < 256) b = 256;   // supported N_mma: 16..128 step 16, or 256
     const int mt = 1;
     const int nt = (N + TM - 1) / TM;
-    int s = num_sms / (nt * mt);
-    if (s * nt * mt < num_sms - num_sms / 8 && (s + 1) * nt * mt <= num_sms + num_sms / 16) s += 1;
-    if (s > kb / 4) s = kb / 4;
-    if (s < 1) s = 1;
-    if (s > 16) s = 16;
+    // split-K factor = cluster size.  Measured on B200 (profiles/gemm_split_sweep.md): one CTA ingests ~57 GB/s
+    // of weights, so few-tile GEMMs want as many CTAs as fit co-resident (clusters are GPC-local: the useful
+    // ceiling is ~132 CTAs, and the occupancy query below is authoritative); a split costs ~2 us of epilogue,
+    // which short-K GEMMs that already have >= 56 tiles do not win back.
+    int s = 1;
+    for (int c = 8; c > 1; --c) {
+      if (c * nt * mt > 132 || kb / c < 4) continue;
+      const int fit = max_active_clusters(c);
+      if (fit > 0 && nt * mt > fit) continue;
+      s = c;
+      break;
+    }
+    if (nt * mt >= 56 && kb < 32) s = 1;
     *swap = 1; *bn = b; *splits = s; *n_tiles = nt * mt;
-    *ws_bytes = s > 1 ? (int64_t)nt * mt * s * b * TM * 4 : 0;
+    *ws_bytes = 0;                        // split-K partials live in (distributed) shared memory
   } else {
     const int b = 128;
     const int mt = (M + TM - 1) / TM, nt = (N + b - 1) / b;
@@ -310,6 +407,8 @@ EXPORT int vb_gemm_tc(const void* x, const void* w, const void* bias, void* y, i
   const bool bf16 = dtype == DT_BF16;
   CUtensorMap ta, tb;
   Params p;
+  p.trace = g_trace;
+  { static int pf = -1; if (pf < 0) { const char* e = std::getenv("VLLM_B200_GEMM_PF"); pf = (e && e[0] == '1') ? 1 : 0; } p.pf = pf; }
   p.y = y; p.bias = bias; p.ws = ws; p.counters = counters; p.M = M; p.N = N; p.K = K; p.splits = splits; p.act = 0;
   const int kb = (K + BK - 1) / BK;
   p.k_blocks_per_split = (kb + splits - 1) / splits;
@@ -318,19 +417,26 @@ EXPORT int vb_gemm_tc(const void* x, const void* w, const void* bias, void* y, i
     if ((rc = make_tmap(&ta, w, N, K, K, TM, bf16))) return rc;
     if ((rc = make_tmap(&tb, x, M, K, x_stride, bn, bf16))) return rc;
     dim3 grid((N + TM - 1) / TM, (M + bn - 1) / bn, splits);
-#define GO(BNV, ST)                                                                      \
+    static int n_sms = 0;
+    if (!n_sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, d); }
+    const bool two = splits == 1 && (int)(grid.x * grid.y) > n_sms && bn <= 128;   // multi-wave → 2 CTAs / SM
+#define GO(BNV, ST, ST2)                                                                 \
+    if (two) {                                                                           \
+      if (bf16) return launch<__nv_bfloat16, BNV, ST2, true>(ta, tb, p, grid, st);       \
+      else return launch<__half, BNV, ST2, true>(ta, tb, p, grid, st);                   \
+    }                                                                                    \
     if (bf16) return launch<__nv_bfloat16, BNV, ST, true>(ta, tb, p, grid, st);          \
     else return launch<__half, BNV, ST, true>(ta, tb, p, grid, st);
     switch (bn) {
-      case 16: GO(16, 8)
-      case 32: GO(32, 8)
-      case 48: GO(48, 8)
-      case 64: GO(64, 8)
-      case 80: GO(80, 6)
-      case 96: GO(96, 6)
-      case 112: GO(112, 6)
-      case 128: GO(128, 6)
-      case 256: GO(256, 4)
+      case 16: GO(16, 8, 4)
+      case 32: GO(32, 8, 4)
+      case 48: GO(48, 8, 4)
+      case 64: GO(64, 8, 4)
+      case 80: GO(80, 6, 3)
+      case 96: GO(96, 6, 3)
+      case 112: GO(112, 6, 3)
+      case 128: GO(128, 6, 3)
+      case 256: GO(256, 4, 4)
       default: return -2;
     }
 #undef GO

@@ -417,11 +417,11 @@ def comm_all_gather(c, x, out_off, rows, cols) -> None:
 _gemm_ar_plan = _sig("vb_gemm_ar_plan", _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i64),
                      ctypes.POINTER(_i))
 _gemm_ar = _sig("vb_gemm_ar", _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp,
-                _i64, _i64, _i, _f, _i, _i, _vp)
+                _i64, _i64, _i, _i, _i64, _i64, _f, _i, _i, _vp)
 _ar_plan_cache: dict[tuple, Optional[tuple]] = {}
 
 
-def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma) -> bool:
+def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma, mode=0, part_off=0, out_off=0) -> bool:
     """Fused RowParallel GEMM + all-reduce + residual + RMSNorm (csrc/gemm_ar.cu). False = shape not covered."""
     from vllm_b200.parallel.symm import LAM_T_CAP
     M, K = x.shape
@@ -446,8 +446,9 @@ def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma) -> bool:
         g.ws = torch.empty(max(wsb // 4, 16 << 20), dtype=torch.float32, device=x.device)
         g.counters = torch.zeros(max(tiles, 4096), dtype=torch.int32, device=x.device)
     _check(_gemm_ar(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, x.data_ptr(), w.data_ptr(),
-                    residual.data_ptr(), norm_w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), bn, splits,
-                    g.ws.data_ptr(), g.counters.data_ptr(), c.off_lam, c.lam_stride, LAM_T_CAP, eps, int(gemma),
+                    residual.data_ptr(), norm_w.data_ptr(), out.data_ptr() if out is not None else None, M, N, K,
+                    x.stride(0), bn, splits, g.ws.data_ptr(), g.counters.data_ptr(), c.off_lam, c.lam_stride, LAM_T_CAP, mode, part_off, out_off, eps,
+                    int(gemma),
                     _DT[x.dtype], _st()), f"gemm_ar(M={M},N={N},K={K})")
     return True
 

@@ -57,6 +57,8 @@ class SymmComm:
         self.use_mc = bool(self.mc_ptr) and envs.VLLM_B200_AR_BACKEND in ("auto", "nvls")
         if envs.VLLM_B200_AR_BACKEND == "p2p":
             self.use_mc = False
+        m = envs.VLLM_B200_FUSED_AR_MODE
+        self.fused_mode = 1 if self.use_mc and (m == "nvls" or (m == "auto" and self.world >= 4)) else 0
         logger.info("SymmComm[%s] rank %d/%d: %d MiB regions, multicast=%s", group.name, self.rank, self.world,
                     self.region >> 20, self.use_mc)
 
@@ -65,11 +67,13 @@ class SymmComm:
         region = _round(region_bytes)
         # Lamport receive buffers for the fused decode kernel: 3 rotating buffers x world x T_CAP rows x H_MAX
         self.lam_stride = _round(self.world * LAM_T_CAP * LAM_H_MAX * 2)
-        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride
+        self.fout_bytes = _round(LAM_T_CAP * LAM_H_MAX * 2)       # output rows of the NVLS-mode fused kernel
+        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride + self.fout_bytes
         self.buf = self._symm.empty(total, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
         self.off_lam = FLAGS_BYTES + 3 * region
-        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
+        self.off_fout = self.off_lam + 3 * self.lam_stride
+        self.buf[self.off_lam:self.off_fout].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
         self.lam_H = 0
         torch.cuda.synchronize()
         self.hdl = self._symm.rendezvous(self.buf, self.group.device_group)
@@ -163,11 +167,19 @@ class SymmComm:
                 and residual.dtype == x.dtype):
             # decode: ONE kernel — tcgen05 GEMM whose epilogue multicasts the tile to every GPU (Lamport buffers),
             # then reduces + residual + RMSNorm in place; no barrier, no NCCL
-            if H != self.lam_H:
-                self._rearm_lamport(H)
-            out = torch.empty((T, H), dtype=x.dtype, device=x.device)
-            if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, out, eps, gemma):
-                return out.view(x.shape[:-1] + (H,)), residual
+            if self.fused_mode == 1:
+                # W >= 4: a one-shot push receives W x the data; instead every rank keeps its tile, raises a flag,
+                # and the row owner pulls the sum through the switch (multimem.ld_reduce) and multicasts the
+                # normalised row back — same single kernel, inbound traffic independent of W
+                if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, None, eps, gemma, 1, self.off_in,
+                                   self.off_fout):
+                    return self._view(self.off_fout, x.shape[:-1] + (H,), x.dtype), residual
+            else:
+                if H != self.lam_H:
+                    self._rearm_lamport(H)
+                out = torch.empty((T, H), dtype=x.dtype, device=x.device)
+                if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, out, eps, gemma):
+                    return out.view(x.shape[:-1] + (H,)), residual
         self.ensure_capacity(T * H * x.dtype.itemsize)
         part = self.staging((T, H), x.dtype)
         if self.cu._tc_ok(x2, w):
@@ -183,7 +195,7 @@ class SymmComm:
             raise RuntimeError("Lamport buffers must be armed for this hidden size before CUDA-graph capture")
         torch.cuda.synchronize()
         self.group.barrier()
-        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)
+        self.buf[self.off_lam:self.off_fout].view(torch.int16).fill_(-32768)
         self.state[8:13].zero_()
         torch.cuda.synchronize()
         self.group.barrier()
