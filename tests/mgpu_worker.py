@@ -87,8 +87,8 @@ def test_collectives():
     out = comm.gemm_allreduce_rmsnorm(xk, wk, res_mine, nw, 1e-5)
     check(out is not None, "fused path declined")
     torch.testing.assert_close(out[0].float(), e_norm.float(), atol=6e-2, rtol=3e-2)
-    # single-kernel paths (Lamport push / NVLS flags+ld_reduce): varying token counts, both hidden sizes, many calls
-    modes = [0, 1] if comm.use_mc else [0]
+    # single-kernel paths (one-shot / two-shot Lamport): varying token counts, both hidden sizes, many calls
+    modes = [0, 1]
     for mode, (H, K) in [(m, hk) for m in modes for hk in ((4096, 2048), (8192, 1024), (4096, 14336 // world // 8 * 8))]:
         comm.fused_mode = mode
         gw = torch.Generator(device=dev).manual_seed(11 + rank)
@@ -103,7 +103,7 @@ def test_collectives():
             res_mine = res.clone()
             out = comm.gemm_allreduce_rmsnorm(xk, wk, res_mine, nw, 1e-5)
             torch.testing.assert_close(out[0].float(), e_norm.float(), atol=6e-2, rtol=3e-2)
-            per = (T + world - 1) // world if mode == 1 else T      # NVLS mode keeps the residual sharded by row owner
+            per = (T + world - 1) // world if mode == 1 else T      # two-shot keeps the residual sharded by row owner
             r0, r1 = (rank * per, min(T, rank * per + per)) if mode == 1 else (0, T)
             if r1 > r0:
                 torch.testing.assert_close(res_mine[r0:r1].float(), e_res[r0:r1].float(), atol=6e-2, rtol=3e-2)
@@ -124,7 +124,7 @@ def test_collectives():
             graph.replay()
         torch.cuda.synchronize()
         torch.testing.assert_close(og.float(), e_norm.float(), atol=6e-2, rtol=3e-2)
-    comm.fused_mode = 1 if comm.use_mc and world >= 4 else 0
+    comm.fused_mode = 1
     if rank == 0:
         print("collectives ok (multicast=%s)" % comm.use_mc, flush=True)
 

@@ -36,9 +36,10 @@ struct Params {
   size_t lam_off;          // byte offset of the 3 Lamport buffers inside the symmetric heap
   size_t lam_stride;       // bytes per buffer (= world * t_cap * H * 2)
   int t_cap;               // rows reserved per source rank in a buffer (layout is independent of M)
-  int mode;                // 0 = one-shot Lamport push (any transport), 1 = NVLS: flags + multimem.ld_reduce + multimem.st
-  size_t part_off;         // mode 1: byte offset of this rank's partial [T,H] inside the symmetric heap
-  size_t out_off;          // mode 1: byte offset of the normalised output [T,H] (same on every rank)
+  int mode;                // 0 = one-shot (every rank receives and reduces everything), 1 = two-shot (row owners
+                           //     reduce + normalise their rows, then multicast them): inbound traffic independent of W
+  size_t oring_off;        // mode 1: byte offset of the 3 rotating [t_cap][N] output buffers (sentinel-armed)
+  size_t oring_stride;
   int M, N, K;             // tokens, H, local K
   int k_blocks_per_split, splits;
   float eps;
@@ -67,23 +68,9 @@ VB_DEVICE uint32_t sanitize(uint32_t w) {   // -0.0 → +0.0 in both halves
   return w;
 }
 
-// mode-1 flags live in the first 4 KiB of the symmetric heap (u32 slots): [64, 64+8*64) one per (source rank,
-// output tile), [576, 704) one per token row.  Values are monotonically increasing epochs (no reset, graph safe).
-constexpr int FLAG_TILE0 = 64, FLAG_ROW0 = 576, MAX_TILES = 64;
-
-VB_DEVICE void flag_publish(const CommCtx& c, int slot, uint32_t v) {
-  if (c.mc) {
-    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(c.mc + (size_t)slot * 4), "r"(v) : "memory");
-  } else {
-    for (int pr = 0; pr < c.world; ++pr)
-      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(c.peer[pr] + (size_t)slot * 4), "r"(v) : "memory");
-  }
-}
-VB_DEVICE void flag_wait(const CommCtx& c, int slot, uint32_t v) {
-  // relaxed spin; the caller issues ONE fence.acq_rel.sys after all of its flags have been observed
-  const uint32_t* f = reinterpret_cast<const uint32_t*>(c.local) + slot;
-  uint32_t x;
-  do { asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(f) : "memory"); } while ((int32_t)(x - v) < 0);
+// 16-byte store into ONE peer's buffer (two-shot mode: a partial row goes only to the rank that owns the row)
+VB_DEVICE void put16(const CommCtx& c, int dst, size_t off, const uint32_t (&v)[4]) {
+  *reinterpret_cast<uint4*>(c.peer[dst] + off) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 
 template <typename T, int BN, int STAGES>
@@ -219,7 +206,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int per = (units + p.splits - 1) / p.splits;
       const int u_end = min(units, (split + 1) * per);
       const uint32_t red_s = smem_u32(stage_base);
-      T* part = reinterpret_cast<T*>(c.local + p.part_off);
+      const int own_per = (p.M + c.world - 1) / c.world;           // two-shot: rows owned by each rank
       for (int u = split * per + et; u < u_end; u += EPI_THREADS) {
         const int t = u / (TM / 8), g = u % (TM / 8);
         if (n0 + g * 8 >= p.N) continue;
@@ -239,21 +226,14 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             a1.x += x1[r].x; a1.y += x1[r].y; a1.z += x1[r].z; a1.w += x1[r].w;
           }
         uint32_t w[4] = {pack2<T>(a0.x, a0.y), pack2<T>(a0.z, a0.w), pack2<T>(a1.x, a1.y), pack2<T>(a1.z, a1.w)};
-        if (p.mode == 1) {
-          *reinterpret_cast<uint4*>(part + (size_t)t * p.N + n0 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = sanitize(w[e]);
-          bcast16(c, lam_cur_off + (((size_t)c.rank * p.t_cap + t) * p.N + n0 + g * 8) * sizeof(T), w);
-        }
+        for (int e = 0; e < 4; ++e) w[e] = sanitize(w[e]);
+        const size_t doff = lam_cur_off + (((size_t)c.rank * p.t_cap + t) * p.N + n0 + g * 8) * sizeof(T);
+        if (p.mode == 1) put16(c, t / own_per, doff, w);
+        else bcast16(c, doff, w);
       }
-      if (p.mode == 1) __threadfence_system();   // my slice is visible system-wide before the cluster barrier
       __syncwarp();
-      cluster_sync();                            // also: nobody's shared memory is read past this point
-      if (p.mode == 1 && split == 0 && et == 0) {
-        __threadfence_system();                  // every slice of this tile is in place (barrier = acq/rel at cluster scope)
-        flag_publish(c, FLAG_TILE0 + c.rank * MAX_TILES + a_tile, c.state[13] + 1);
-      }
+      cluster_sync();                            // nobody's shared memory is read past this point
     }
     // the operand ring is idle now (all MMAs of this CTA retired before tmem_full fired): reuse it as the
     // [token][feature] transposition buffer
@@ -267,20 +247,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (cc + j < p.M) tbuf[(cc + j) * TM + row] = from_f32<T>(v[j]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-      if (p.mode == 1) {
-        // NVLS mode: the tile stays in THIS rank's symmetric buffer (row-major [T][H]); peers will pull the
-        // sum of all replicas through the switch.  Publish "tile (rank, a_tile) of epoch e is complete".
-        T* part = reinterpret_cast<T*>(c.local + p.part_off);
-        for (int i = et; i < p.M * (TM / 8); i += EPI_THREADS) {
-          const int t = i / (TM / 8), g = i % (TM / 8);
-          if (n0 + g * 8 >= p.N) continue;
-          *reinterpret_cast<uint4*>(part + (size_t)t * p.N + n0 + g * 8) =
-              *reinterpret_cast<const uint4*>(tbuf + t * TM + g * 8);
-        }
-        __threadfence_system();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-        if (et == 0) flag_publish(c, FLAG_TILE0 + c.rank * MAX_TILES + a_tile, c.state[13] + 1);
-      } else
+      const int own_per = (p.M + c.world - 1) / c.world;
       // push: item = (token, group of 8 features); wire layout [src rank][token][H]
       for (int i = et; i < p.M * (TM / 8); i += EPI_THREADS) {
         const int t = i / (TM / 8), g = i % (TM / 8);
@@ -288,7 +255,8 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint4 u = *reinterpret_cast<const uint4*>(tbuf + t * TM + g * 8);
         const uint32_t w[4] = {sanitize(u.x), sanitize(u.y), sanitize(u.z), sanitize(u.w)};
         const size_t off = lam_cur_off + (((size_t)c.rank * p.t_cap + t) * p.N + n0 + g * 8) * sizeof(T);
-        bcast16(c, off, w);
+        if (p.mode == 1) put16(c, t / own_per, off, w);
+        else bcast16(c, off, w);
       }
     }
     tc_fence_before();
@@ -297,69 +265,11 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int cta = blockIdx.z * gridDim.x + blockIdx.x;
     const int groups = p.N / 8;                            // 16-byte groups per row
     constexpr int MAXG = 8;                                // groups per thread kept in registers (H <= 8192)
-    if (p.mode == 1) {
-      const uint32_t epoch = c.state[13] + 1;
-      const int n_tiles = gridDim.x;
-      const int per = (p.M + c.world - 1) / c.world;          // rows owned by each rank
-      const int r0 = c.rank * per, r1 = min(p.M, r0 + per);
-      const int n_mine = max(r1 - r0, 0);
-      if (cta < n_mine) {
-        const int t = r0 + cta;                               // (n_mine <= 16 << n_ctas: one row per CTA)
-        // every rank has finished every tile of this epoch?
-        for (int i = et; i < c.world * n_tiles; i += EPI_THREADS)
-          flag_wait(c, FLAG_TILE0 + (i / n_tiles) * MAX_TILES + (i % n_tiles), epoch);
-        __threadfence_system();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-        float acc[MAXG][8];
-        float ss = 0.f;
-#pragma unroll
-        for (int gi = 0; gi < MAXG; ++gi) {
-          const int g = et + gi * EPI_THREADS;
-          if (g >= groups) break;
-          reduce8<T>(c, p.part_off + ((size_t)t * p.N + g * 8) * sizeof(T), acc[gi]);   // in-switch sum
-          T* rrow = reinterpret_cast<T*>(p.residual) + (size_t)t * p.N + g * 8;
-          Vec16<T> rv = ld16(rrow), ro;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            ro.e[e] = from_f32<T>(to_f32(from_f32<T>(acc[gi][e])) + to_f32(rv.e[e]));
-            acc[gi][e] = to_f32(ro.e[e]);
-            ss += acc[gi][e] * acc[gi][e];
-          }
-          st16(rrow, ro);                                     // the residual stays sharded by row owner
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) red[q] = ss;
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-        const float inv = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)p.N + p.eps);
-#pragma unroll
-        for (int gi = 0; gi < MAXG; ++gi) {
-          const int g = et + gi * EPI_THREADS;
-          if (g >= groups) break;
-          Vec16<T> wv = ld16(reinterpret_cast<const T*>(p.norm_w) + g * 8);
-          uint32_t o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float g0 = to_f32(wv.e[2 * e]) + (p.gemma ? 1.f : 0.f), g1 = to_f32(wv.e[2 * e + 1]) + (p.gemma ? 1.f : 0.f);
-            o[e] = pack2<T>(acc[gi][2 * e] * inv * g0, acc[gi][2 * e + 1] * inv * g1);
-          }
-          bcast16(c, p.out_off + ((size_t)t * p.N + g * 8) * sizeof(T), o);            // to every rank
-        }
-        __threadfence_system();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-        if (et == 0) flag_publish(c, FLAG_ROW0 + t, epoch);
-      }
-      if (cta == n_ctas - 1) {
-        // the kernel may only complete once every row (from every owner) has landed in this rank's buffer
-        for (int i = et; i < p.M; i += EPI_THREADS) flag_wait(c, FLAG_ROW0 + i, epoch);
-        __threadfence_system();
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-      if (et == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(&c.state[9], 1u);
-        if (prev == (unsigned)(n_ctas - 1)) { c.state[9] = 0; c.state[13] = epoch; }
-      }
-    } else {
+    const bool two = p.mode == 1;
+    const size_t oring_cur = p.oring_off + (size_t)(call % 3) * p.oring_stride;
+    if (!two) {
+    // One-shot: this CTA reduces rows cta, cta + n_ctas, ... of ALL tokens (every rank does the same work on the
+    // same data → bit-identical rows everywhere).
     const int t_end = max(p.M, dirty);
     for (int t = cta; t < t_end; t += n_ctas) {
       if (t >= p.M) {   // row not used by this call but dirtied earlier: only re-arm it
@@ -426,6 +336,100 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         st16(reinterpret_cast<T*>(p.out) + (size_t)t * p.N + g * 8, o);
       }
     }
+    } else {
+      // Two-shot.  (A) the rows this rank owns, [r0, r1), are summed (+ residual) by ALL CTAs of the grid — one
+      // 16-byte group of one row per thread — and the new residual-stream value h goes to every rank through the
+      // output ring (NVLS multicast).  (B) every rank collects all rows of h and normalises them itself: the
+      // RMSNorm is replicated (cheap) instead of serialising a row behind one CTA, and all ranks still produce
+      // bit-identical rows because they normalise the same bf16 h.  The residual stays sharded by row owner.
+      const int own_per = (p.M + c.world - 1) / c.world;
+      const int r0 = min(p.M, c.rank * own_per), r1 = min(p.M, r0 + own_per);
+      for (int u = cta * EPI_THREADS + et; u < (r1 - r0) * groups; u += n_ctas * EPI_THREADS) {
+        const int t = r0 + u / groups, g = u % groups;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        uint32_t w[VB_MAX_RANKS][4];
+#pragma unroll
+        for (int src = 0; src < VB_MAX_RANKS; ++src)
+          if (src < c.world)
+            ld_relaxed_sys_v4(lam_cur + (((size_t)src * p.t_cap + t) * p.N + g * 8) * sizeof(T), w[src]);
+        T* rrow = reinterpret_cast<T*>(p.residual) + (size_t)t * p.N + g * 8;
+        const Vec16<T> rv = ld16(rrow);
+#pragma unroll
+        for (int src = 0; src < VB_MAX_RANKS; ++src) {
+          if (src >= c.world) break;
+          const unsigned char* ptr = lam_cur + (((size_t)src * p.t_cap + t) * p.N + g * 8) * sizeof(T);
+          while (has_sentinel(w[src])) ld_relaxed_sys_v4(ptr, w[src]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { float2 f = unpack2<T>(w[src][e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+        }
+        Vec16<T> ro;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ro.e[e] = from_f32<T>(to_f32(from_f32<T>(acc[e])) + to_f32(rv.e[e]));
+        st16(rrow, ro);
+        uint32_t o[4] = {sanitize(ro.u.x), sanitize(ro.u.y), sanitize(ro.u.z), sanitize(ro.u.w)};
+        bcast16(c, oring_cur + ((size_t)t * p.N + g * 8) * sizeof(T), o);
+      }
+      // re-arm the buffers used two calls from now: the rows this rank owned under their previous token count
+      // (input ring, all source ranks) and every row of the output ring
+      {
+        const int old_per = (dirty + c.world - 1) / c.world;
+        const int o0 = min(dirty, c.rank * old_per), o1 = min(dirty, o0 + old_per), on = o1 - o0;
+        unsigned char* oring_clear = c.local + p.oring_off + (size_t)((call + 2) % 3) * p.oring_stride;
+        const int n_in = on * c.world * groups, n_all = n_in + dirty * groups;
+        for (int u = cta * EPI_THREADS + et; u < n_all; u += n_ctas * EPI_THREADS) {
+          unsigned char* dst;
+          if (u < n_in) {
+            const int rowi = u / groups, g = u % groups;
+            dst = lam_clear + (((size_t)(rowi / on) * p.t_cap + o0 + rowi % on) * p.N + g * 8) * sizeof(T);
+          } else {
+            dst = oring_clear + (size_t)(u - n_in) * 16;
+          }
+          *reinterpret_cast<uint4*>(dst) = make_uint4(SENT32, SENT32, SENT32, SENT32);
+        }
+      }
+      // (B) collect + normalise: rows cta, cta + n_ctas, ...
+      const unsigned char* oc = c.local + oring_cur;
+      for (int t = cta; t < p.M; t += n_ctas) {
+        uint32_t w[MAXG][4];
+#pragma unroll
+        for (int gi = 0; gi < MAXG; ++gi) {
+          const int g = et + gi * EPI_THREADS;
+          if (g < groups) ld_relaxed_sys_v4(oc + ((size_t)t * p.N + g * 8) * sizeof(T), w[gi]);
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int gi = 0; gi < MAXG; ++gi) {
+          const int g = et + gi * EPI_THREADS;
+          if (g >= groups) break;
+          const unsigned char* ptr = oc + ((size_t)t * p.N + g * 8) * sizeof(T);
+          while (has_sentinel(w[gi])) ld_relaxed_sys_v4(ptr, w[gi]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { float2 f = unpack2<T>(w[gi][e]); ss += f.x * f.x + f.y * f.y; }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[q] = ss;
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        const float tot = red[0] + red[1] + red[2] + red[3];
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+        const float inv = rsqrtf(tot / (float)p.N + p.eps);
+#pragma unroll
+        for (int gi = 0; gi < MAXG; ++gi) {
+          const int g = et + gi * EPI_THREADS;
+          if (g >= groups) break;
+          Vec16<T> wv = ld16(reinterpret_cast<const T*>(p.norm_w) + g * 8);
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack2<T>(w[gi][e]);
+            const float g0 = to_f32(wv.e[2 * e]) + (p.gemma ? 1.f : 0.f), g1 = to_f32(wv.e[2 * e + 1]) + (p.gemma ? 1.f : 0.f);
+            o[e] = pack2<T>(f.x * inv * g0, f.y * inv * g1);
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + (size_t)t * p.N + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
     // ---- last CTA out advances the call counter
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     if (et == 0) {
@@ -437,7 +441,6 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         c.state[8] = call + 1;
       }
     }
-    }  // mode
   }
   tc_fence_before();
   __syncthreads();
@@ -516,7 +519,7 @@ EXPORT int vb_gemm_ar_plan(int M, int N, int K, int num_sms, int* bn, int* split
 EXPORT int vb_gemm_ar(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world, const void* x,
                       const void* w, void* residual, const void* norm_w, void* out, int M, int N, int K,
                       int64_t x_stride, int bn, int splits, float* ws, unsigned* counters, int64_t lam_off,
-                      int64_t lam_stride, int t_cap, int mode, int64_t part_off, int64_t out_off, float eps, int gemma, int dtype,
+                      int64_t lam_stride, int t_cap, int mode, int64_t oring_off, int64_t oring_stride, float eps, int gemma, int dtype,
                       cudaStream_t st) {
   using namespace gemm_ar;
   if (dtype == DT_F32 || K % 8 != 0 || N % 8 != 0 || N / 8 > 8 * EPI_THREADS) return -1;
@@ -532,8 +535,7 @@ EXPORT int vb_gemm_ar(void* local, void* const* peers, void* mc, uint32_t* state
   const int kb = (K + BK - 1) / BK;
   p.k_blocks_per_split = (kb + splits - 1) / splits;
   p.eps = eps; p.gemma = gemma; p.t_cap = t_cap;
-  p.mode = mode; p.part_off = (size_t)part_off; p.out_off = (size_t)out_off;
-  if (mode == 1 && (N + TM - 1) / TM > MAX_TILES) return -8;
+  p.mode = mode; p.oring_off = (size_t)oring_off; p.oring_stride = (size_t)oring_stride;
   if (M > t_cap) return -7;
   int rc;
   if ((rc = make_tmap(&ta, w, N, K, K, TM, bf16))) return rc;

@@ -55,7 +55,8 @@ environment_variables: dict[str, Callable[[], Any]] = {
     "VLLM_B200_ATTN_SPLITS": _int("VLLM_B200_ATTN_SPLITS", 0),
     "VLLM_B200_ATTN": _str("VLLM_B200_ATTN", "auto"),  # auto|simt (disable the tcgen05 attention kernel)
     "VLLM_B200_FUSED_AR": _bool("VLLM_B200_FUSED_AR", True),
-    # fused GEMM+all-reduce transport: lamport (one-shot push), nvls (flags + in-switch reduce), auto (nvls for world>=4)
+    # fused GEMM+all-reduce algorithm: oneshot (every rank reduces everything), twoshot (row owners reduce, then
+    # multicast; faster at every world size measured), auto = twoshot
     "VLLM_B200_FUSED_AR_MODE": lambda: os.environ.get("VLLM_B200_FUSED_AR_MODE", "auto"),
     "VLLM_B200_AR_BACKEND": _str("VLLM_B200_AR_BACKEND", "auto"),  # auto|nvls|p2p|nccl
     "VLLM_DISABLE_CUDA_GRAPH": _bool("VLLM_DISABLE_CUDA_GRAPH", False),

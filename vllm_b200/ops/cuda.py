@@ -421,7 +421,7 @@ _gemm_ar = _sig("vb_gemm_ar", _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _v
 _ar_plan_cache: dict[tuple, Optional[tuple]] = {}
 
 
-def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma, mode=0, part_off=0, out_off=0) -> bool:
+def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma, mode=0, oring_off=0, oring_stride=0) -> bool:
     """Fused RowParallel GEMM + all-reduce + residual + RMSNorm (csrc/gemm_ar.cu). False = shape not covered."""
     from vllm_b200.parallel.symm import LAM_T_CAP
     M, K = x.shape
@@ -447,7 +447,7 @@ def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma, mode=0, part_off=0, out_
         g.counters = torch.zeros(max(tiles, 4096), dtype=torch.int32, device=x.device)
     _check(_gemm_ar(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, x.data_ptr(), w.data_ptr(),
                     residual.data_ptr(), norm_w.data_ptr(), out.data_ptr() if out is not None else None, M, N, K,
-                    x.stride(0), bn, splits, g.ws.data_ptr(), g.counters.data_ptr(), c.off_lam, c.lam_stride, LAM_T_CAP, mode, part_off, out_off, eps,
+                    x.stride(0), bn, splits, g.ws.data_ptr(), g.counters.data_ptr(), c.off_lam, c.lam_stride, LAM_T_CAP, mode, oring_off, oring_stride, eps,
                     int(gemma),
                     _DT[x.dtype], _st()), f"gemm_ar(M={M},N={N},K={K})")
     return True

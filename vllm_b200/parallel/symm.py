@@ -58,7 +58,7 @@ class SymmComm:
         if envs.VLLM_B200_AR_BACKEND == "p2p":
             self.use_mc = False
         m = envs.VLLM_B200_FUSED_AR_MODE
-        self.fused_mode = 1 if self.use_mc and (m == "nvls" or (m == "auto" and self.world >= 4)) else 0
+        self.fused_mode = 0 if m == "oneshot" else 1
         logger.info("SymmComm[%s] rank %d/%d: %d MiB regions, multicast=%s", group.name, self.rank, self.world,
                     self.region >> 20, self.use_mc)
 
@@ -67,14 +67,16 @@ class SymmComm:
         region = _round(region_bytes)
         # Lamport receive buffers for the fused decode kernel: 3 rotating buffers x world x T_CAP rows x H_MAX
         self.lam_stride = _round(self.world * LAM_T_CAP * LAM_H_MAX * 2)
-        self.fout_bytes = _round(LAM_T_CAP * LAM_H_MAX * 2)       # output rows of the NVLS-mode fused kernel
-        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride + self.fout_bytes
+        # two-shot mode: 3 rotating output buffers (normalised rows multicast by their owners), sentinel-armed too
+        self.oring_stride = _round(LAM_T_CAP * LAM_H_MAX * 2)
+        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride + 3 * self.oring_stride
         self.buf = self._symm.empty(total, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
         self.off_lam = FLAGS_BYTES + 3 * region
-        self.off_fout = self.off_lam + 3 * self.lam_stride
-        self.buf[self.off_lam:self.off_fout].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
+        self.off_oring = self.off_lam + 3 * self.lam_stride
+        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
         self.lam_H = 0
+        self._armed_mode = -1
         torch.cuda.synchronize()
         self.hdl = self._symm.rendezvous(self.buf, self.group.device_group)
         self.region = region
@@ -167,19 +169,16 @@ class SymmComm:
                 and residual.dtype == x.dtype):
             # decode: ONE kernel — tcgen05 GEMM whose epilogue multicasts the tile to every GPU (Lamport buffers),
             # then reduces + residual + RMSNorm in place; no barrier, no NCCL
-            if self.fused_mode == 1:
-                # W >= 4: a one-shot push receives W x the data; instead every rank keeps its tile, raises a flag,
-                # and the row owner pulls the sum through the switch (multimem.ld_reduce) and multicasts the
-                # normalised row back — same single kernel, inbound traffic independent of W
-                if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, None, eps, gemma, 1, self.off_in,
-                                   self.off_fout):
-                    return self._view(self.off_fout, x.shape[:-1] + (H,), x.dtype), residual
-            else:
-                if H != self.lam_H:
-                    self._rearm_lamport(H)
-                out = torch.empty((T, H), dtype=x.dtype, device=x.device)
-                if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, out, eps, gemma):
-                    return out.view(x.shape[:-1] + (H,)), residual
+            # default ("two-shot"): a one-shot push makes every rank receive and reduce W x the data; instead each
+            # partial row goes only to the rank that owns the row, which reduces + normalises it and multicasts the
+            # result — still ONE kernel and no barrier, inbound traffic independent of W.  The residual then stays
+            # sharded by row owner (as in the prefill path).
+            if H != self.lam_H or self._armed_mode != self.fused_mode:
+                self._rearm_lamport(H)
+            out = torch.empty((T, H), dtype=x.dtype, device=x.device)
+            if self.cu.gemm_ar(self, x2, w, residual.view(T, H), norm_w, out, eps, gemma, self.fused_mode,
+                               self.off_oring, self.oring_stride):
+                return out.view(x.shape[:-1] + (H,)), residual
         self.ensure_capacity(T * H * x.dtype.itemsize)
         part = self.staging((T, H), x.dtype)
         if self.cu._tc_ok(x2, w):
@@ -195,11 +194,12 @@ class SymmComm:
             raise RuntimeError("Lamport buffers must be armed for this hidden size before CUDA-graph capture")
         torch.cuda.synchronize()
         self.group.barrier()
-        self.buf[self.off_lam:self.off_fout].view(torch.int16).fill_(-32768)
+        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)
         self.state[8:13].zero_()
         torch.cuda.synchronize()
         self.group.barrier()
         self.lam_H = H
+        self._armed_mode = self.fused_mode
 
     def embedding_allreduce(self, ids: torch.Tensor, weight: torch.Tensor, start: int) -> Optional[torch.Tensor]:
         """Vocab-sharded embedding lookup + all-reduce: the masked lookup lands in the staging region,
