@@ -110,6 +110,20 @@ PRESETS: dict[str, dict[str, Any]] = {
         head_dim=128, max_position_embeddings=4096, rms_norm_eps=1e-5, rope_theta=10000.0,
         hidden_act="silu", num_local_experts=8, num_experts_per_tok=2, bos_token_id=1, eos_token_id=2,
         torch_dtype="bfloat16", tie_word_embeddings=False),
+    "qwen2moe-tiny": dict(
+        architectures=["Qwen2MoeForCausalLM"], model_type="qwen2_moe", vocab_size=512, hidden_size=128,
+        intermediate_size=256, moe_intermediate_size=64, shared_expert_intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=1024,
+        rms_norm_eps=1e-6, rope_theta=10000.0, hidden_act="silu", num_experts=4, num_experts_per_tok=2,
+        norm_topk_prob=False, decoder_sparse_step=1, mlp_only_layers=[], bos_token_id=1, eos_token_id=2,
+        torch_dtype="float32", tie_word_embeddings=False),
+    "qwen3moe-tiny": dict(
+        architectures=["Qwen3MoeForCausalLM"], model_type="qwen3_moe", vocab_size=512, hidden_size=128,
+        intermediate_size=256, moe_intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, head_dim=32, max_position_embeddings=1024, rms_norm_eps=1e-6,
+        rope_theta=10000.0, hidden_act="silu", num_experts=4, num_experts_per_tok=2, norm_topk_prob=True,
+        decoder_sparse_step=1, mlp_only_layers=[], bos_token_id=1, eos_token_id=2, torch_dtype="float32",
+        tie_word_embeddings=False),
     "deepseek-v3": dict(
         architectures=["DeepseekV3ForCausalLM"], model_type="deepseek_v3", vocab_size=129280,
         hidden_size=7168, intermediate_size=18432, moe_intermediate_size=2048, num_hidden_layers=61,

@@ -202,6 +202,7 @@ class RowParallelLinear(LinearBase):
                                                   getattr(norm, "gemma", False))
                 if out is not None:
                     return out
+            return tp_reduce_residual_norm(self._local(x), residual, norm)
         y = self.forward(x)
         return norm(y, residual)
 
@@ -213,3 +214,22 @@ class RowParallelLinear(LinearBase):
         n = param.shape[in_dim]
         w = w.narrow(in_dim, self.tp_rank * n, n) if w.shape[in_dim] != n else w
         param.data.copy_(w)
+
+
+def tp_reduce_residual_norm(partial: torch.Tensor, residual: torch.Tensor, norm: nn.Module
+                            ) -> tuple[torch.Tensor, torch.Tensor]:
+    """(normed, residual) = norm(all_reduce(partial) + residual) for a per-rank partial sum that did not come
+    out of a RowParallelLinear (MoE combine, shared-expert sums ...).
+
+    On GPU under TP the residual stream is kept *sharded by row owner* by the device collectives
+    (parallel/symm.py), so every reduce+norm of one forward pass must go through them — mixing in a plain
+    all-reduce + full-residual norm would read rows this rank does not own."""
+    g = get_tp_group()
+    if g.world_size > 1 and partial.is_cuda and g.device_comm is not None:
+        out = g.device_comm.reduce_residual_norm(partial, residual, norm.weight, norm.eps,
+                                                 getattr(norm, "gemma", False))
+        if out is not None:
+            return out
+    if g.world_size > 1:
+        partial = g.all_reduce(partial)
+    return norm(partial, residual)

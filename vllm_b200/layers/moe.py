@@ -1,0 +1,110 @@
+"""Mixture-of-experts layer.
+
+Behavioural reference: vllm/model_executor/layers/fused_moe/layer.py (``FusedMoE``: expert-parallel
+expert map, ``weight_loader`` for w1/w2/w3 shards), modular_kernel.py:42-83 (router → dispatch →
+experts → combine), router/fused_topk + grouped_topk.
+
+Sharding (B200-first): with ``enable_expert_parallel`` every rank of the TP group owns E/W whole experts
+(no intra-expert sharding → every expert GEMM keeps its full K, and the only collective is the combine
+all-reduce, which under decode runs through the same fused GEMM-epilogue path as dense layers).  Without
+EP the experts are TP-sharded along the intermediate dimension exactly like a dense MLP.
+Activations are replicated across the TP group at the layer boundary (they already are after the
+attention block's all-reduce), so "dispatch" is a local selection and "combine" is one all-reduce.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from vllm_b200 import ops
+from vllm_b200.parallel.state import get_tp_group
+from vllm_b200.parallel.utils import divide
+
+
+class FusedMoE(nn.Module):
+    def __init__(self, num_experts: int, top_k: int, hidden_size: int, intermediate_size: int, dtype=None,
+                 renormalize: bool = True, use_grouped_topk: bool = False, n_group: int = 1, topk_group: int = 1,
+                 scoring_func: str = "softmax", routed_scaling_factor: float = 1.0, e_score_bias: bool = False,
+                 act: str = "silu", enable_ep: bool = False, reduce_results: bool = True, prefix: str = "") -> None:
+        super().__init__()
+        g = get_tp_group()
+        self.tp_rank, self.tp_size = max(g.rank_in_group, 0), g.world_size
+        self.num_experts, self.top_k = num_experts, top_k
+        self.renormalize = renormalize
+        self.use_grouped_topk, self.n_group, self.topk_group = use_grouped_topk, n_group, topk_group
+        self.scoring_func, self.routed_scaling_factor = scoring_func, routed_scaling_factor
+        self.act = act
+        self.reduce_results = reduce_results
+        self.ep = enable_ep and self.tp_size > 1
+        dt = dtype or torch.get_default_dtype()
+        if self.ep:
+            # contiguous expert ranges; the map turns a global expert id into a local one (or -1)
+            per = (num_experts + self.tp_size - 1) // self.tp_size
+            self.e_start = min(num_experts, self.tp_rank * per)
+            self.e_end = min(num_experts, self.e_start + per)
+            self.local_experts = self.e_end - self.e_start
+            emap = torch.full((num_experts,), -1, dtype=torch.int32)
+            emap[self.e_start:self.e_end] = torch.arange(self.local_experts, dtype=torch.int32)
+            self.register_buffer("expert_map", emap, persistent=False)
+            self.inter_per_rank = intermediate_size
+        else:
+            self.e_start, self.e_end, self.local_experts = 0, num_experts, num_experts
+            self.expert_map = None
+            self.inter_per_rank = divide(intermediate_size, self.tp_size)
+        I = self.inter_per_rank
+        self.w13_weight = nn.Parameter(torch.empty(max(self.local_experts, 1), 2 * I, hidden_size, dtype=dt),
+                                       requires_grad=False)
+        self.w2_weight = nn.Parameter(torch.empty(max(self.local_experts, 1), hidden_size, I, dtype=dt),
+                                      requires_grad=False)
+        self.e_score_correction_bias = (nn.Parameter(torch.zeros(num_experts, dtype=torch.float32),
+                                                     requires_grad=False) if e_score_bias else None)
+
+    # ------------------------------------------------------------ routing
+    def select_experts(self, router_logits: torch.Tensor):
+        if self.use_grouped_topk:
+            return ops.grouped_topk(router_logits, self.top_k, self.n_group, self.topk_group, self.renormalize,
+                                    self.scoring_func, self.e_score_correction_bias, self.routed_scaling_factor)
+        w, ids = ops.topk_softmax(router_logits, self.top_k, self.renormalize)
+        if self.routed_scaling_factor != 1.0:
+            w = w * self.routed_scaling_factor
+        return w, ids
+
+    def forward(self, x: torch.Tensor, router_logits: torch.Tensor) -> torch.Tensor:
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        w, ids = self.select_experts(router_logits.reshape(-1, router_logits.shape[-1]))
+        out = ops.fused_moe(x2, self.w13_weight, self.w2_weight, w.to(torch.float32), ids, self.act,
+                            self.expert_map)
+        if self.reduce_results and self.tp_size > 1:
+            out = get_tp_group().all_reduce(out)
+        return out.reshape(shape)
+
+    # ------------------------------------------------------------ weights
+    def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id: str, expert_id: int) -> None:
+        """shard_id: 'w1' (gate), 'w3' (up), 'w2' (down); ``w`` is the checkpoint's full tensor."""
+        if not (self.e_start <= expert_id < self.e_end):
+            return
+        le = expert_id - self.e_start
+        I = self.inter_per_rank
+        if self.ep:
+            r0 = 0
+        else:
+            r0 = self.tp_rank * I
+        if shard_id == "w2":
+            param.data[le].copy_(w[:, r0:r0 + I])
+        else:
+            off = 0 if shard_id == "w1" else I
+            param.data[le, off:off + I].copy_(w[r0:r0 + I])
+
+
+def make_expert_params_mapping(gate_name: str, down_name: str, up_name: str, num_experts: int,
+                               prefix: str = "experts") -> list[tuple[str, str, int, str]]:
+    """(param_name, checkpoint_weight_name, expert_id, shard_id) — reference: FusedMoE.make_expert_params_mapping."""
+    out = []
+    for e in range(num_experts):
+        for shard, ck in (("w1", gate_name), ("w2", down_name), ("w3", up_name)):
+            pname = f"{prefix}.w2_weight" if shard == "w2" else f"{prefix}.w13_weight"
+            out.append((pname, f"{prefix}.{e}.{ck}.weight", e, shard))
+    return out

@@ -84,10 +84,10 @@ class RotaryEmbedding(nn.Module):
             inv = inv / f * (1 - mask) + inv * mask
             max_pos = max(max_pos, int(orig * f))
             if kind == "deepseek_yarn" or "mscale_all_dim" in rs:
-                self.mscale = (yarn_mscale(f, rs.get("mscale", 1.0))
-                               / yarn_mscale(f, rs.get("mscale_all_dim", 0.0) or 1.0)
-                               * rs.get("attn_factor", 1.0)) if rs.get("mscale_all_dim") else \
-                    yarn_mscale(f, rs.get("mscale", 1.0)) * rs.get("attn_factor", 1.0)
+                # DeepSeek: cos/sin carry mscale(mscale)/mscale(mscale_all_dim); the attention layer multiplies its
+                # softmax scale by mscale(mscale_all_dim)^2 (reference: rotary_embedding/deepseek_scaling_rope.py)
+                self.mscale = (yarn_mscale(f, rs.get("mscale", 1.0)) / yarn_mscale(f, rs.get("mscale_all_dim", 0.0))
+                               * rs.get("attn_factor", 1.0))
             else:
                 self.mscale = yarn_mscale(f) * rs.get("attn_factor", 1.0)
         elif kind in ("longrope", "su"):

@@ -188,6 +188,20 @@ class SymmComm:
         out = self.allreduce_rows(None, T, H, x.dtype, residual.view(T, H), norm_w, eps, gemma)
         return out.view(x.shape[:-1] + (H,)), residual
 
+    def reduce_residual_norm(self, partial: torch.Tensor, residual: torch.Tensor, norm_w: torch.Tensor, eps: float,
+                             gemma: bool = False):
+        """Same contract as ``gemm_allreduce_rmsnorm`` for a partial sum that is already computed."""
+        H = partial.shape[-1]
+        if (partial.dtype not in (torch.bfloat16, torch.float16) or H % 8 or H // 8 > 1024
+                or not residual.is_contiguous() or residual.dtype != partial.dtype):
+            return None
+        p2 = partial.reshape(-1, H)
+        if not p2.is_contiguous():
+            p2 = p2.contiguous()
+        T = p2.shape[0]
+        out = self.allreduce_rows(p2, T, H, partial.dtype, residual.view(T, H), norm_w, eps, gemma)
+        return out.view(partial.shape), residual
+
     def _rearm_lamport(self, H: int) -> None:
         """The Lamport slot layout depends on H: switching H re-arms all buffers (host side, collective)."""
         if torch.cuda.is_current_stream_capturing():
