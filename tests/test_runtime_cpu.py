@@ -1,0 +1,69 @@
+"""Host-side runtime pieces: shm ring + native spin-wait, GIL-free file IO, multiprocess executor (gloo)."""
+import multiprocessing as mp
+import os
+
+import pytest
+
+
+def _ring_reader(handle, rank, q):
+    from vllm_b200.parallel.shm_broadcast import ShmRing
+    ring = ShmRing.attach(handle, rank)
+    tot = 0
+    for _ in range(200):
+        m = ring.get(timeout=20)
+        tot += m["i"] + len(m["pad"])
+    q.put(tot)
+    ring.close()
+
+
+def test_shm_ring_broadcast_chunked():
+    from vllm_b200.native import lib
+    from vllm_b200.parallel.shm_broadcast import ShmRing
+    assert lib() is not None, "native runtime library failed to build"
+    ctx = mp.get_context("spawn")
+    ring = ShmRing(2, slot_bytes=4096, n_slots=4)
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ring_reader, args=(ring.handle(), r, q)) for r in range(2)]
+    [p.start() for p in ps]
+    exp = 0
+    for i in range(200):
+        pad = b"x" * (i * 97 % 9000)          # messages up to 2+ slots → chunking
+        ring.put({"i": i, "pad": pad}, timeout=20)
+        exp += i + len(pad)
+    res = [q.get(timeout=30) for _ in ps]
+    [p.join(10) for p in ps]
+    ring.close()
+    assert res == [exp, exp]
+
+
+def test_native_file_io(tmp_path):
+    import ctypes
+    from vllm_b200.native import lib
+    L = lib()
+    data = os.urandom(1 << 20)
+    p = str(tmp_path / "blk.bin").encode()
+    assert L.vbn_write_file(p, data, len(data), 0, 1) == len(data)
+    assert L.vbn_file_size(p) == len(data)
+    buf = ctypes.create_string_buffer(len(data))
+    assert L.vbn_read_file(p, buf, len(data), 0, 0) == len(data)
+    assert buf.raw == data
+    assert L.vbn_read_file(str(tmp_path / "missing").encode(), buf, 16, 0, 0) < 0
+
+
+def test_multiproc_executor_tp2_matches_tp1():
+    """2 worker processes (gloo) driven through the shm ring produce the TP=1 tokens."""
+    from tests.utils import llama_full_weights, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41]}, {"prompt_token_ids": list(range(10, 40))}]
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny", weights=llama_full_weights(cfg, seed=1))
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("llama-tiny", tensor_parallel_size=2, distributed_executor_backend="mp")
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": list(llama_full_weights(cfg, seed=1))})
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    assert got == ref

@@ -22,3 +22,37 @@ def build_native(force: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"native build failed:\n{r.stderr}")
     return OUT
+
+
+_LIB = None
+
+
+def lib():
+    """ctypes handle of ``_native.so`` (built on first use; None if no compiler is available)."""
+    global _LIB
+    if _LIB is None:
+        import ctypes
+        try:
+            path = build_native()
+            if not path:
+                _LIB = False
+                return None
+            L = ctypes.CDLL(path)
+        except Exception:  # pragma: no cover - no toolchain
+            _LIB = False
+            return None
+        u64p, i64, u64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int
+        L.vbn_wait_ge_u64.argtypes = [u64p, u64, i64]; L.vbn_wait_ge_u64.restype = i32
+        L.vbn_wait_all_ge_u64.argtypes = [u64p, i32, i64, u64, i64]; L.vbn_wait_all_ge_u64.restype = i32
+        L.vbn_store_release_u64.argtypes = [u64p, u64]; L.vbn_store_release_u64.restype = None
+        L.vbn_load_acquire_u64.argtypes = [u64p]; L.vbn_load_acquire_u64.restype = u64
+        L.vbn_write_file.argtypes = [ctypes.c_char_p, ctypes.c_void_p, i64, i32, i32]; L.vbn_write_file.restype = i64
+        L.vbn_read_file.argtypes = [ctypes.c_char_p, ctypes.c_void_p, i64, i64, i32]; L.vbn_read_file.restype = i64
+        L.vbn_file_size.argtypes = [ctypes.c_char_p]; L.vbn_file_size.restype = i64
+        L.vbn_cumem_available.restype = i32
+        L.vbn_cumem_alloc.argtypes = [i32, u64, ctypes.POINTER(u64)]; L.vbn_cumem_alloc.restype = u64
+        for f in ("vbn_cumem_unmap", "vbn_cumem_remap", "vbn_cumem_free"):
+            getattr(L, f).argtypes = [u64]; getattr(L, f).restype = i32
+        L.vbn_cumem_mapped_bytes.restype = u64
+        _LIB = L
+    return _LIB or None

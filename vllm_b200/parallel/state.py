@@ -87,9 +87,9 @@ class GroupCoordinator:
             if out is not None:
                 return out
         shape = list(x.shape)
-        out = torch.empty([self.world_size] + shape, dtype=x.dtype, device=x.device)
+        out = torch.empty([self.world_size * shape[0]] + shape[1:], dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x.contiguous(), group=self.device_group)
-        out = out.movedim(0, dim)
+        out = out.view([self.world_size] + shape).movedim(0, dim)
         shape[dim] *= self.world_size
         return out.reshape(shape)
 
