@@ -67,3 +67,20 @@ def test_multiproc_executor_tp2_matches_tp1():
     got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
     llm.shutdown()
     assert got == ref
+
+
+def test_dp_coordinator_agreement():
+    import threading
+    from vllm_b200.engine.dp import DPCoordinator
+    from vllm_b200.utils import get_open_port
+    port = get_open_port()
+    res = {}
+
+    def run(rank):
+        c = DPCoordinator("127.0.0.1", port, rank, 3)
+        res[rank] = [c.any_unfinished((rank == 1 and step < 2) or (rank == 2 and step == 3)) for step in range(5)]
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert res == {r: [True, True, False, True, False] for r in range(3)}

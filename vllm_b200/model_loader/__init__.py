@@ -74,7 +74,7 @@ def iter_weights(path: str, load_format: str = "auto") -> Iterator[tuple[str, to
 
 
 def get_model(vllm_config: VllmConfig, device: torch.device,
-              weights: Optional[Iterable[tuple[str, torch.Tensor]]] = None) -> nn.Module:
+              weights: Optional[Iterable[tuple[str, torch.Tensor]]] = None, prefix: str = "") -> nn.Module:
     mc, lc = vllm_config.model_config, vllm_config.load_config
     cls = resolve_model_cls(mc.architecture)
     t0 = time.perf_counter()
@@ -82,7 +82,7 @@ def get_model(vllm_config: VllmConfig, device: torch.device,
     torch.set_default_dtype(mc.torch_dtype)
     try:
         with set_current_vllm_config(vllm_config), torch.device(device):
-            model = cls(vllm_config)
+            model = cls(vllm_config, prefix=prefix) if prefix else cls(vllm_config)
     finally:
         torch.set_default_dtype(old)
     fmt = lc.load_format

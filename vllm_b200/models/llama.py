@@ -168,7 +168,7 @@ class LlamaForCausalLM(nn.Module):
         self.cfg = cfg
         from vllm_b200.layers.quant import get_quant_config
         self.quant_config = get_quant_config(mc)
-        self.model = self.model_cls(vllm_config, "model", self.quant_config)
+        self.model = self.model_cls(vllm_config, f"{prefix}model", self.quant_config)
         self.is_last = self.model.norm is not None
         if self.is_last:
             self.lm_head = ParallelLMHead(cfg["vocab_size"], cfg["hidden_size"], dtype=mc.torch_dtype,

@@ -43,6 +43,10 @@ class Worker:
         pc = self.vllm_config.parallel_config
         dev_type = self.vllm_config.device_config.resolve()
         if dev_type == "cuda":
+            # DP rank d owns GPUs [d*world, (d+1)*world) of the node
+            ndev = torch.cuda.device_count()
+            self.local_rank = (pc.data_parallel_rank % max(pc.data_parallel_size_local or 1, 1) * pc.world_size
+                               + self.local_rank) % max(ndev, 1)
             torch.cuda.set_device(self.local_rank)
             self.device = torch.device("cuda", self.local_rank)
             gc.collect()
@@ -120,6 +124,15 @@ class Worker:
         return out
 
     # -------------------------------------------------------- sleep / wake
+    @torch.inference_mode()
+    def execute_dummy_batch(self) -> None:
+        """One token through the model with no KV cache: keeps this rank's collectives (EP all-to-all, TP
+        all-reduce) in step with peers that have real work (reference: gpu_worker.execute_dummy_batch)."""
+        r = self.runner
+        r.input_ids[:1].zero_()
+        r.positions[:1].zero_()
+        r._forward(1, {})
+
     def sleep(self, level: int = 1) -> None:
         """Level 1: weights → pinned CPU, KV discarded. Level 2: both discarded."""
         if self._sleeping:
