@@ -156,6 +156,11 @@ class ModelRunner:
         spec = vllm_config.speculative_config
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
+        self.kv_connector = None
+        ktc = vllm_config.kv_transfer_config
+        if ktc is not None and ktc.kv_connector:
+            from vllm_b200.kv_transfer import create_connector
+            self.kv_connector = create_connector(vllm_config, role="worker")
         self.async_mode = bool(self.sc.async_scheduling)
         # ---- persistent batch (CPU)
         R, L = self.max_num_reqs, self.max_model_len
@@ -488,7 +493,8 @@ class ModelRunner:
         graph = None
         simple = not bool(self.complex_cpu[rows].any()) and so.grammar_bitmask is None
         no_filter = not bool(self.filter_cpu[rows].any())
-        if decode_only and self.use_cuda_graph and self.graphs and simple and no_filter:
+        kv_meta = so.kv_connector_metadata if self.kv_connector is not None else None
+        if decode_only and self.use_cuda_graph and self.graphs and simple and no_filter and not kv_meta:
             pad_b = self._bucket(nb)
             graph = self.graphs.get(pad_b)
             if graph is None:
@@ -516,7 +522,11 @@ class ModelRunner:
             l0 = self._launches()
             states = [self.states[r] for r in req_ids]
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
+            if kv_meta:
+                self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
             hidden = self._forward(T, md, intermediate)
+            if kv_meta:
+                self.kv_connector.save_kv(kv_meta, self.kv_caches)           # freshly computed full blocks
             if isinstance(hidden, dict):  # non-last PP stage
                 return ModelRunnerOutput(kv_connector_output=hidden)
             if any(s.pooling_params is not None for s in states):
