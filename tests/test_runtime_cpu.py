@@ -84,3 +84,22 @@ def test_dp_coordinator_agreement():
     [t.start() for t in ts]
     [t.join(60) for t in ts]
     assert res == {r: [True, True, False, True, False] for r in range(3)}
+
+
+def test_multiproc_executor_pp2_matches_single():
+    """Pipeline parallelism: 2 stages in 2 worker processes, hidden states travel over the PP group."""
+    from tests.utils import llama_full_weights, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41]}, {"prompt_token_ids": list(range(10, 40))}]
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny", weights=llama_full_weights(cfg, seed=1))
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("llama-tiny", pipeline_parallel_size=2, distributed_executor_backend="mp")
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": list(llama_full_weights(cfg, seed=1))})
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    assert got == ref

@@ -68,12 +68,17 @@ class EngineCore:
         avail = ex.determine_available_memory()
         mm = min(avail)
         cc = self.vllm_config.cache_config
-        cfg, new_len = get_kv_cache_config(
-            specs[0], mm, self.vllm_config.scheduler_config.max_model_len, cc.num_gpu_blocks_override,
-            auto_fit_max_model_len=False)
-        # every worker must use the same number of blocks
+        max_len = self.vllm_config.scheduler_config.max_model_len
+        # one config per worker (pipeline stages own different layers); every worker must end up with the same
+        # number of blocks because block ids are global to the scheduler
+        cfgs = [get_kv_cache_config(sp, mm, max_len, cc.num_gpu_blocks_override, auto_fit_max_model_len=False)[0]
+                for sp in specs]
+        nblk = min(c.num_blocks for c in cfgs)
+        if any(c.num_blocks != nblk for c in cfgs):
+            cfgs = [get_kv_cache_config(sp, mm, max_len, nblk, auto_fit_max_model_len=False)[0] for sp in specs]
+        cfg = cfgs[0]
         cc.num_gpu_blocks = cfg.num_blocks
-        ex.initialize_from_config(cfg)
+        ex.initialize_from_config(cfgs if len(cfgs) > 1 else cfg)
         logger.info("KV cache: %d blocks x %d tokens (%.2f GiB available), init %.2fs", cfg.num_blocks,
                     cc.block_size, mm / 2**30, time.perf_counter() - t0)
         return cfg

@@ -80,6 +80,9 @@ def _worker_main(vllm_config: VllmConfig, rank: int, local_rank: int, init_metho
             if method == "__shutdown__":
                 break
             try:
+                if isinstance(method, tuple):
+                    import cloudpickle
+                    method = cloudpickle.loads(method[1])
                 if method == "execute_model":
                     res = worker.execute_model(*args, non_block=True)
                 else:
@@ -200,7 +203,7 @@ class MultiprocExecutor(Executor):
             raise RuntimeError("executor failed")
         if not isinstance(method, str):
             import cloudpickle
-            method = cloudpickle.loads(cloudpickle.dumps(method))
+            method = ("__callable__", cloudpickle.dumps(method))
         fut: Future = Future()
         with self._lock:      # one broadcast at a time; responses are consumed in the same order
             self.rpc.put((method, args, kwargs or {}, unique_reply_rank))

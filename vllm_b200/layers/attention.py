@@ -57,6 +57,9 @@ class Attention(nn.Module):
         D = self.head_size
         md = ctx.metadata_for(self.layer_name)
         kv_cache = ctx.kv_caches.get(self.layer_name)
+        if md is not None and kv_cache is None:
+            raise RuntimeError(f"attention layer {self.layer_name!r} has no KV cache bound (KV-cache config does not "
+                               "cover this worker's layers)")
         if md is None or kv_cache is None:
             # memory-profiling run: no cache; keep the data flow (and the GEMM shapes) intact
             if self.rope is not None and positions is not None:
@@ -98,6 +101,8 @@ class MLAAttentionCore(nn.Module):
         ctx = get_forward_context()
         md = ctx.metadata_for(self.layer_name)
         kv_cache = ctx.kv_caches.get(self.layer_name)
+        if md is not None and kv_cache is None:
+            raise RuntimeError(f"MLA layer {self.layer_name!r} has no KV cache bound")
         if md is None or kv_cache is None:
             return torch.zeros_like(q_nope_abs)
         ops.concat_and_cache_mla(kv_c, k_pe, kv_cache, md.slot_mapping)

@@ -182,6 +182,9 @@ class DeepseekV3ForCausalLM(LlamaForCausalLM):
                 if li >= self.cfg["num_hidden_layers"]:
                     continue
             if name.endswith(".mlp.gate.e_score_correction_bias"):
+                name = self._localize(name)
+                if name is None:
+                    continue
                 name = name.replace(".mlp.gate.e_score_correction_bias", ".mlp.experts.e_score_correction_bias")
                 if name in params:
                     params[name].data.copy_(w)
@@ -190,7 +193,10 @@ class DeepseekV3ForCausalLM(LlamaForCausalLM):
             if marker not in name:
                 dense.append((name, w))
                 continue
-            head, tail = name.split(marker, 1)
+            lname = self._localize(name)
+            if lname is None:
+                continue
+            head, tail = lname.split(marker, 1)
             parts = tail.split(".")
             if not parts[0].isdigit() or parts[1] not in self.expert_names:
                 continue

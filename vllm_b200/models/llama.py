@@ -190,12 +190,27 @@ class LlamaForCausalLM(nn.Module):
     stacked = [("qkv_proj", "q_proj", "q"), ("qkv_proj", "k_proj", "k"), ("qkv_proj", "v_proj", "v"),
                ("gate_up_proj", "gate_proj", 0), ("gate_up_proj", "up_proj", 1)]
 
+    def _localize(self, name: str) -> Optional[str]:
+        """Checkpoint names carry global layer indices; this PP stage holds layers [start, end) as 0..n-1."""
+        i = name.find(".layers.")
+        if i < 0:
+            return name
+        j = i + len(".layers.")
+        k = name.find(".", j)
+        g = int(name[j:k])
+        if not (self.model.start <= g < self.model.end):
+            return None
+        return name if self.model.start == 0 else f"{name[:j]}{g - self.model.start}{name[k:]}"
+
     def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
         params = dict(self.named_parameters())
         modules = dict(self.named_modules())
         loaded: set[str] = set()
         for name, w in weights:
             if "rotary_emb.inv_freq" in name:
+                continue
+            name = self._localize(name)
+            if name is None:
                 continue
             if name == "lm_head.weight" and self.cfg.get("tie_word_embeddings"):
                 continue

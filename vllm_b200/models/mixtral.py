@@ -134,7 +134,10 @@ class MixtralForCausalLM(LlamaForCausalLM):
                 dense.append((name, w))
                 continue
             # <layer>.<container>.<expert id>.<w1|w2|w3 / gate_proj|...>.weight
-            head, tail = name.split(marker, 1)
+            lname = self._localize(name)
+            if lname is None:
+                continue
+            head, tail = lname.split(marker, 1)
             parts = tail.split(".")
             if not parts[0].isdigit():
                 dense.append((name, w))

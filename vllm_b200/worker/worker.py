@@ -101,7 +101,9 @@ class Worker:
                     total / 2**30, budget / 2**30, peak_torch / 2**30, non_torch / 2**30, avail / 2**30)
         return max(avail, 0)
 
-    def initialize_from_config(self, kv_cache_config: KVCacheConfig) -> None:
+    def initialize_from_config(self, kv_cache_config) -> None:
+        if isinstance(kv_cache_config, (list, tuple)):      # one entry per worker rank
+            kv_cache_config = kv_cache_config[self.rank]
         self.runner.initialize_kv_cache(kv_cache_config)
 
     def compile_or_warm_up_model(self) -> None:
