@@ -103,3 +103,16 @@ def test_multiproc_executor_pp2_matches_single():
     got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
     llm.shutdown()
     assert got == ref
+
+
+def test_cli_bench_and_platform(capsys):
+    import json
+    from vllm_b200.entrypoints.cli import main
+    from vllm_b200 import platforms
+    assert platforms.current_platform.device_type in ("cpu", "cuda")
+    assert "vllm_b200" in platforms.collect_env()
+    main(["bench", "throughput", "--model", "llama-tiny", "--device", "cpu", "--dtype", "float32", "--num-prompts", "4",
+          "--input-len", "16", "--output-len", "4", "--max-model-len", "128", "--kv-cache-memory-bytes", str(8 << 20)])
+    out = capsys.readouterr().out
+    res = json.loads(out[out.index("{"):])
+    assert res["num_requests"] == 4 and res["total_output_tokens"] == 16

@@ -187,4 +187,9 @@ class EngineArgs:
         return cls(**{k: v for k, v in vars(args).items() if k in names})
 
 
+    def to_llm_kwargs(self) -> dict:
+        """Keyword arguments for ``LLM(**kwargs)`` equivalent to these engine args."""
+        return {f.name: getattr(self, f.name) for f in dataclasses.fields(self)}
+
+
 AsyncEngineArgs = EngineArgs

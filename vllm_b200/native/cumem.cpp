@@ -125,3 +125,25 @@ uint64_t vbn_cumem_mapped_bytes() {
 }
 
 }  // extern "C"
+
+// torch.cuda.memory.CUDAPluggableAllocator entry points: allocations made inside
+// ``CuMemAllocator.use_memory_pool`` come from the VMM arena above.
+extern "C" {
+void* vbn_torch_malloc(ssize_t size, int device, void* /*stream*/) {
+  uint64_t rounded = 0;
+  return reinterpret_cast<void*>(vbn_cumem_alloc(device, (uint64_t)size, &rounded));
+}
+void vbn_torch_free(void* ptr, ssize_t /*size*/, int /*device*/, void* /*stream*/) {
+  vbn_cumem_free(reinterpret_cast<uint64_t>(ptr));
+}
+// enumerate live blocks: fills up to `cap` (ptr, size, mapped) triples, returns the count
+int vbn_cumem_list(uint64_t* out, int cap) {
+  std::lock_guard<std::mutex> g(g_mu);
+  int n = 0;
+  for (auto& kv : g_blocks) {
+    if (n < cap) { out[3 * n] = kv.first; out[3 * n + 1] = kv.second.size; out[3 * n + 2] = kv.second.mapped ? 1 : 0; }
+    ++n;
+  }
+  return n;
+}
+}
