@@ -58,3 +58,50 @@ def test_kv_connector_prefix_reuse(tmp_path, connector, extra):
     assert wconn.num_loaded_blocks >= 9
     assert second == first
     llm.shutdown()
+
+
+def test_multi_lora_matches_merged_weights():
+    """A batch mixing base-model and two different adapters == three runs with the adapters merged into W."""
+    from vllm_b200.core.request import LoRARequest
+    cfg = get_preset_hf_config("llama-tiny")
+    base = dict(llama_full_weights(cfg, seed=5))
+    g = torch.Generator().manual_seed(0)
+    targets = ["self_attn.q_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.gate_proj", "mlp.down_proj"]
+
+    def adapter(r, scale):
+        t = {}
+        for i in range(cfg["num_hidden_layers"]):
+            for tgt in targets:
+                w = base[f"model.layers.{i}.{tgt}.weight"]
+                t[f"base_model.model.model.layers.{i}.{tgt}.lora_A.weight"] = torch.randn(r, w.shape[1], generator=g) * scale
+                t[f"base_model.model.model.layers.{i}.{tgt}.lora_B.weight"] = torch.randn(w.shape[0], r, generator=g) * scale
+        return t
+
+    ad = {1: (adapter(4, 0.3), 4, 8.0), 2: (adapter(8, 0.2), 8, 8.0)}
+
+    def merged(lid):
+        t, r, alpha = ad[lid]
+        w = dict(base)
+        for k in list(t):
+            if ".lora_A" in k:
+                name = k[len("base_model.model."):].split(".lora_A")[0] + ".weight"
+                w[name] = w[name] + (alpha / r) * t[k.replace("lora_A", "lora_B")] @ t[k]
+        return w
+
+    prompt = {"prompt_token_ids": [5, 17, 99, 3, 250, 41, 77, 8]}
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    exp = []
+    for w in (base, merged(1), merged(2)):
+        llm = make_llm("llama-tiny", weights=w.items())
+        exp.append(llm.generate([prompt], sp)[0].outputs[0].token_ids)
+        llm.shutdown()
+    assert exp[0] != exp[1] and exp[1] != exp[2]              # the adapters actually change the output
+    llm = make_llm("llama-tiny", weights=base.items(), enable_lora=True, max_loras=2, max_lora_rank=8)
+    worker = llm.llm_engine.engine_core.engine_core.model_executor.worker
+    reqs = {i: LoRARequest(f"ad{i}", i, "") for i in (1, 2)}
+    for i in (1, 2):
+        worker.add_lora(reqs[i], tensors=ad[i][0], rank=ad[i][1], alpha=ad[i][2])
+    outs = llm.generate([prompt, prompt, prompt], sp, lora_request=[None, reqs[1], reqs[2]])
+    got = [o.outputs[0].token_ids for o in outs]
+    llm.shutdown()
+    assert got == exp

@@ -61,6 +61,15 @@ class LinearBase(nn.Module):
     def process_weights_after_loading(self) -> None:
         self.quant_method.process_weights_after_loading(self)
 
+    lora_table = None   # slot → [(out_offset, out_len, A, B, scale)], attached by lora.LoRAModelManager
+
+    def _apply(self, x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+        y = self.quant_method.apply(self, x, bias)
+        if self.lora_table:
+            from vllm_b200.lora import apply_lora
+            y = apply_lora(self, x, y)
+        return y
+
 
 class ReplicatedLinear(LinearBase):
     def __init__(self, input_size, output_size, bias=False, dtype=None, quant_config=None, prefix="") -> None:
@@ -68,7 +77,7 @@ class ReplicatedLinear(LinearBase):
         self._make(input_size, output_size)
 
     def forward(self, x):
-        return self.quant_method.apply(self, x, self.bias)
+        return self._apply(x, self.bias)
 
     def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id=None) -> None:
         assert param.shape == w.shape, (self.prefix, param.shape, w.shape)
@@ -87,7 +96,7 @@ class ColumnParallelLinear(LinearBase):
         self._make(input_size, self.out_per_rank)
 
     def forward(self, x):
-        y = self.quant_method.apply(self, x, self.bias)
+        y = self._apply(x, self.bias)
         if self.gather_output and self.tp_size > 1:
             y = get_tp_group().all_gather(y, -1)
         return y
@@ -179,7 +188,7 @@ class RowParallelLinear(LinearBase):
         if not self.input_is_parallel and self.tp_size > 1:
             x = x.chunk(self.tp_size, dim=-1)[self.tp_rank].contiguous()
         # bias is added once (rank 0) so the all-reduce sums it exactly once
-        return self.quant_method.apply(self, x, self.bias if self.tp_rank == 0 else None)
+        return self._apply(x, self.bias if self.tp_rank == 0 else None)
 
     def forward(self, x):
         y = self._local(x)
@@ -197,7 +206,8 @@ class RowParallelLinear(LinearBase):
             return self.forward(x), residual
         if self.tp_size > 1 and x.is_cuda and self.reduce_results:
             comm = get_tp_group().device_comm
-            if comm is not None and self.bias is None and type(self.quant_method) is LinearMethod:
+            if (comm is not None and self.bias is None and type(self.quant_method) is LinearMethod
+                    and not self.lora_table):
                 out = comm.gemm_allreduce_rmsnorm(x, self.weight, residual, norm.weight, norm.eps,
                                                   getattr(norm, "gemma", False))
                 if out is not None:

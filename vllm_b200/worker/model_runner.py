@@ -210,6 +210,10 @@ class ModelRunner:
         if self.vllm_config.speculative_config is not None:
             from vllm_b200.spec_decode import make_drafter
             self.drafter = make_drafter(self.vllm_config, self)
+        self.lora_manager = None
+        if self.vllm_config.lora_config is not None:
+            from vllm_b200.lora import LoRAModelManager
+            self.lora_manager = LoRAModelManager(self.model, self.vllm_config.lora_config, self.device, self.dtype)
 
     def get_kv_cache_specs(self) -> dict[str, KVCacheSpec]:
         dsz = self._kv_dtype().itemsize
@@ -494,7 +498,12 @@ class ModelRunner:
         simple = not bool(self.complex_cpu[rows].any()) and so.grammar_bitmask is None
         no_filter = not bool(self.filter_cpu[rows].any())
         kv_meta = so.kv_connector_metadata if self.kv_connector is not None else None
-        if decode_only and self.use_cuda_graph and self.graphs and simple and no_filter and not kv_meta:
+        lora_batch = None
+        if getattr(self, "lora_manager", None) is not None:
+            lreqs = [self.states[self.req_ids[r]].lora_request for r in rows]
+            lora_batch = self.lora_manager.make_batch(lreqs, [int(x) for x in ns])
+        if (decode_only and self.use_cuda_graph and self.graphs and simple and no_filter and not kv_meta
+                and lora_batch is None):
             pad_b = self._bucket(nb)
             graph = self.graphs.get(pad_b)
             if graph is None:
@@ -524,7 +533,15 @@ class ModelRunner:
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
             if kv_meta:
                 self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
-            hidden = self._forward(T, md, intermediate)
+            if lora_batch is not None:
+                from vllm_b200 import lora as _lora
+                _lora.set_batch(lora_batch)
+                try:
+                    hidden = self._forward(T, md, intermediate)
+                finally:
+                    _lora.set_batch(None)
+            else:
+                hidden = self._forward(T, md, intermediate)
             if kv_meta:
                 self.kv_connector.save_kv(kv_meta, self.kv_caches)           # freshly computed full blocks
             if isinstance(hidden, dict):  # non-last PP stage

@@ -135,6 +135,25 @@ class Worker:
         r.positions[:1].zero_()
         r._forward(1, {})
 
+    # ---------------------------------------------------------------- LoRA
+    def add_lora(self, lora_request=None, tensors=None, rank: int = 0, alpha: float = 0.0) -> bool:
+        """Load an adapter from ``lora_request.lora_path`` (PEFT dir) or from in-memory tensors."""
+        from vllm_b200.lora import LoRAModel
+        mgr = self.runner.lora_manager
+        if mgr is None:
+            raise RuntimeError("LoRA is not enabled (enable_lora=True)")
+        if tensors is not None:
+            mgr.add_adapter(LoRAModel.from_tensors(lora_request.lora_int_id, dict(tensors), rank, alpha))
+        else:
+            mgr.add_adapter(LoRAModel.from_path(lora_request.lora_int_id, lora_request.lora_path))
+        return True
+
+    def remove_lora(self, lora_id: int) -> bool:
+        return self.runner.lora_manager.remove_adapter(lora_id)
+
+    def list_loras(self) -> list[int]:
+        return self.runner.lora_manager.list_adapters()
+
     def sleep(self, level: int = 1) -> None:
         """Level 1: weights → pinned CPU, KV discarded. Level 2: both discarded."""
         if self._sleeping:
