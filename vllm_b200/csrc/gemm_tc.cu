@@ -35,6 +35,10 @@ struct Params {
   int splits;
   int act;                 // 0 none, 1 silu-mul over interleaved (gate,up) feature pairs (SWAP only)
   int pf;                  // L2 prefetch ahead of the smem ring (SWAP)
+  // grouped (MoE) mode, SWAP only: grid.y = n_experts * chunks; expert e multiplies the rows
+  // [expert_offs[e], expert_offs[e+1]) of X (tokens sorted by expert) with W[e] = rows [e*N, (e+1)*N) of the weight
+  const int* expert_offs;
+  int n_experts;
   long long* trace;        // debug: per-CTA clock64 stamps [cta][16] (null in production)
 };
 
@@ -69,6 +73,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #define VB_TRACE(i) do { if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
   if (threadIdx.x == 0) VB_TRACE(0);
   pdl_trigger();
+  int a_row0 = a_tile * TM;                 // first row of the A-operand tile in its tensor map
+  int b_row0 = b_tile * BN;                 // first row of the B-operand tile
+  int m_lim = SWAP ? p.M - b_row0 : 0;      // SWAP: number of real tokens (accumulator columns) of this tile
+  if constexpr (SWAP) {
+    if (p.expert_offs) {
+      pdl_wait();                           // the offsets come from the routing kernels just before us
+      const int chunks = gridDim.y / p.n_experts;
+      const int e = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+      b_row0 = p.expert_offs[e] + chunk * BN;
+      m_lim = p.expert_offs[e + 1] - b_row0;
+      if (m_lim <= 0) return;               // no token of this chunk routed to expert e: nothing to stream
+      a_row0 += e * p.N;
+    }
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -94,29 +112,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int kb = 0; kb < pre; ++kb) {
         unsigned char* a_dst = stage_base + kb * L::STAGE_BYTES;
         mbar_expect_tx(&full[kb], L::STAGE_BYTES);
-        tma_load_2d_hint(a_dst, &tmap_a, (kb0 + kb) * BK, a_tile * TM, &full[kb], L2_EVICT_FIRST);
+        tma_load_2d_hint(a_dst, &tmap_a, (kb0 + kb) * BK, a_row0, &full[kb], L2_EVICT_FIRST);
       }
       // the smem ring alone (STAGES x 16 KB of weights) cannot cover the HBM latency-bandwidth product of one
       // SM's share when few CTAs stream a lot each: run an L2 prefetch PF k-blocks ahead of the ring
       constexpr int PF = SWAP ? 16 : 0;
       if (SWAP && p.pf)
-        for (int kb = pre; kb < min(nkb, pre + PF); ++kb) tma_prefetch_l2_2d(&tmap_a, (kb0 + kb) * BK, a_tile * TM);
+        for (int kb = pre; kb < min(nkb, pre + PF); ++kb) tma_prefetch_l2_2d(&tmap_a, (kb0 + kb) * BK, a_row0);
       pdl_wait();
       VB_TRACE(2);
       for (int kb = 0; kb < pre; ++kb) {
         unsigned char* b_dst = stage_base + kb * L::STAGE_BYTES + L::A_BYTES;
-        tma_load_2d_hint(b_dst, &tmap_b, (kb0 + kb) * BK, b_tile * BN, &full[kb], L2_EVICT_LAST);
+        tma_load_2d_hint(b_dst, &tmap_b, (kb0 + kb) * BK, b_row0, &full[kb], L2_EVICT_LAST);
       }
       for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % STAGES;
-        if (SWAP && p.pf && kb + PF < nkb) tma_prefetch_l2_2d(&tmap_a, (kb0 + kb + PF) * BK, a_tile * TM);
+        if (SWAP && p.pf && kb + PF < nkb) tma_prefetch_l2_2d(&tmap_a, (kb0 + kb + PF) * BK, a_row0);
         mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
         unsigned char* a_dst = stage_base + s * L::STAGE_BYTES;
         unsigned char* b_dst = a_dst + L::A_BYTES;
         mbar_expect_tx(&full[s], L::STAGE_BYTES);
         const int kc = (kb0 + kb) * BK;
-        tma_load_2d_hint(a_dst, &tmap_a, kc, a_tile * TM, &full[s], SWAP ? L2_EVICT_FIRST : L2_EVICT_LAST);
-        tma_load_2d_hint(b_dst, &tmap_b, kc, b_tile * BN, &full[s], SWAP ? L2_EVICT_LAST : L2_EVICT_FIRST);
+        tma_load_2d_hint(a_dst, &tmap_a, kc, a_row0, &full[s], SWAP ? L2_EVICT_FIRST : L2_EVICT_LAST);
+        tma_load_2d_hint(b_dst, &tmap_b, kc, b_row0, &full[s], SWAP ? L2_EVICT_LAST : L2_EVICT_FIRST);
       }
     }
   } else if (warp == 1) {
@@ -196,10 +214,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int n = a_tile * TM + row;
           if (n < p.N) {
             const float bias = p.bias ? to_f32(reinterpret_cast<const T*>(p.bias)[n]) : 0.f;
-            const int m0 = b_tile * BN + c;
+            const int m0 = b_row0 + c;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (m0 + j < p.M) y[(size_t)(m0 + j) * p.N + n] = from_f32<T>(v[j] + bias);
+              if (c + j < m_lim) y[(size_t)(m0 + j) * p.N + n] = from_f32<T>(v[j] + bias);
           }
         } else {
           const int m = a_tile * TM + row;
@@ -238,8 +256,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int et = threadIdx.x - 64;
         if (et == 0) VB_TRACE(7);
         T* y = reinterpret_cast<T*>(p.y);
-        const int m_base = b_tile * BN;
-        const int cols = min(BN, p.M - m_base);                    // real tokens in this tile
+        const int m_base = b_row0;
+        const int cols = min(BN, m_lim);                           // real tokens in this tile
         const int units = cols * (TM / 4);                         // unit = 4 consecutive features of one token
         const int per = (units + p.splits - 1) / p.splits;
         const int u_end = min(units, (split + 1) * per);
@@ -408,6 +426,7 @@ EXPORT int vb_gemm_tc(const void* x, const void* w, const void* bias, void* y, i
   CUtensorMap ta, tb;
   Params p;
   p.trace = g_trace;
+  p.expert_offs = nullptr; p.n_experts = 0;
   { static int pf = -1; if (pf < 0) { const char* e = std::getenv("VLLM_B200_GEMM_PF"); pf = (e && e[0] == '1') ? 1 : 0; } p.pf = pf; }
   p.y = y; p.bias = bias; p.ws = ws; p.counters = counters; p.M = M; p.N = N; p.K = K; p.splits = splits; p.act = 0;
   const int kb = (K + BK - 1) / BK;
@@ -448,4 +467,42 @@ EXPORT int vb_gemm_tc(const void* x, const void* w, const void* bias, void* y, i
     if (bf16) return launch<__nv_bfloat16, 128, 6, false>(ta, tb, p, grid, st);
     return launch<__half, 128, 6, false>(ta, tb, p, grid, st);
   }
+}
+
+
+// Grouped (MoE) GEMM: Y[r, :] = X[r, :] · W[e(r)]^T for rows sorted by expert; offs[e] .. offs[e+1] delimit expert e.
+// X: [R, K], W: [E, N, K] contiguous, Y: [R, N].  bn = token-tile width (16..128), every expert gets
+// ceil(R / bn) candidate chunks; chunks without tokens exit immediately (their weights are never read).
+EXPORT int vb_gemm_tc_grouped(const void* x, const void* w, void* y, const int* offs, int R, int N, int K, int E, int bn,
+                              int dtype, cudaStream_t st) {
+  using namespace gemm;
+  if (dtype == DT_F32 || K % 8 != 0 || bn > 128 || bn % 16) return -1;
+  const bool bf16 = dtype == DT_BF16;
+  CUtensorMap ta, tb;
+  Params p;
+  p.trace = nullptr; p.pf = 0;
+  p.y = y; p.bias = nullptr; p.ws = nullptr; p.counters = nullptr; p.M = R; p.N = N; p.K = K; p.splits = 1; p.act = 0;
+  p.expert_offs = offs; p.n_experts = E;
+  const int kb = (K + BK - 1) / BK;
+  p.k_blocks_per_split = kb;
+  int rc;
+  if ((rc = make_tmap(&ta, w, (uint64_t)E * N, K, K, TM, bf16))) return rc;
+  if ((rc = make_tmap(&tb, x, R, K, K, bn, bf16))) return rc;
+  const int chunks = (R + bn - 1) / bn;
+  dim3 grid((N + TM - 1) / TM, E * chunks, 1);
+#define GOG(BNV, ST2)                                                                    \
+    if (bf16) return launch<__nv_bfloat16, BNV, ST2, true>(ta, tb, p, grid, st);         \
+    else return launch<__half, BNV, ST2, true>(ta, tb, p, grid, st);
+  switch (bn) {
+    case 16: GOG(16, 4)
+    case 32: GOG(32, 4)
+    case 48: GOG(48, 4)
+    case 64: GOG(64, 4)
+    case 80: GOG(80, 3)
+    case 96: GOG(96, 3)
+    case 112: GOG(112, 3)
+    case 128: GOG(128, 3)
+    default: return -2;
+  }
+#undef GOG
 }

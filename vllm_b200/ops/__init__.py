@@ -115,8 +115,9 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
 def mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank):
     if _use_cuda(q_pe):
         return cuda_ops().mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank)
-    return ref.mla_decode_attention(q_nope_abs, q_pe, kv_cache, md.block_table, md.seq_lens_cpu,
-                                    md.query_start_loc_cpu, scale, kv_lora_rank)
+    sl = md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()
+    qsl = md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()
+    return ref.mla_decode_attention(q_nope_abs, q_pe, kv_cache, md.block_table, sl, qsl, scale, kv_lora_rank)
 
 
 def merge_attn_states(o1, lse1, o2, lse2):

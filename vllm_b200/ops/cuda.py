@@ -284,10 +284,24 @@ def merge_attn_states(o1, lse1, o2, lse2):
 
 
 def mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank):
-    """MLA decode/prefill as MQA over the latent cache. Until the dedicated tcgen05 MLA kernel lands this
-    runs the generic kernel over a [nb, 2, 1, bs, 576]-shaped view is not possible (K != V dims), so the
-    latent path uses batched GEMMs from torch (library) — see models/deepseek.py."""
+    """MLA as MQA over the latent cache (K = 576-d latent+rope, V = first 512 dims of the same rows).
+
+    Decode batches run as dense batched GEMMs over the gathered latent pages with a device-side length mask:
+    no host synchronisation, static shapes → CUDA-graph capturable.  Mixed / prefill batches use the
+    variable-length loop (eager only).  A dedicated tcgen05 MLA kernel (latent tile shared by all 128 heads
+    through TMEM) is the planned replacement for both."""
     from vllm_b200.ops import ref
+    if md.decode_only:
+        B, H, R = q_nope_abs.shape
+        bs = kv_cache.shape[1]
+        nbk = max((md.max_seq_len + bs - 1) // bs, 1)
+        lat = kv_cache[md.block_table[:B, :nbk].long()].reshape(B, nbk * bs, -1)        # [B, S, 576]
+        kc, kp = lat[..., :kv_lora_rank], lat[..., kv_lora_rank:]
+        att = (torch.bmm(q_nope_abs, kc.transpose(1, 2)) + torch.bmm(q_pe, kp.transpose(1, 2))).float() * scale
+        pos = torch.arange(nbk * bs, device=att.device)[None, None, :]
+        att = att.masked_fill(pos >= md.seq_lens[:B, None, None], float("-inf"))
+        p = torch.softmax(att, dim=-1).to(q_nope_abs.dtype)
+        return torch.bmm(p, kc)
     sl = md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()
     qsl = md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()
     return ref.mla_decode_attention(q_nope_abs, q_pe, kv_cache, md.block_table, sl, qsl, scale, kv_lora_rank)
@@ -457,10 +471,64 @@ def comm_barrier(c) -> None:
     _check(_comm_bar(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, _st()), "comm_barrier")
 
 
-# ------------------------------------------------------------------ MoE / fp8 (library-backed until the grouped tcgen05 kernels land)
-def topk_softmax(gating, k, renormalize):
-    from vllm_b200.ops import ref
-    return ref.topk_softmax(gating, k, renormalize)
+# ------------------------------------------------------------------ MoE (csrc/moe.cu + grouped mode of gemm_tc.cu)
+_moe_topk = _sig("vb_moe_topk_softmax", _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp)
+_moe_align = _sig("vb_moe_align", _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp)
+_moe_combine = _sig("vb_moe_combine", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp)
+_moe_gather = _sig("vb_moe_gather", _vp, _vp, _vp, _i, _i, _i, _vp)
+_gemm_grouped = _sig("vb_gemm_tc_grouped", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp)
+
+
+def topk_softmax(gating, k, renormalize, scale: float = 1.0):
+    T, E = gating.shape
+    if E > 512 or k > 32 or gating.dtype not in _DT or not gating.is_contiguous():
+        from vllm_b200.ops import ref
+        w, ids = ref.topk_softmax(gating, k, renormalize)
+        return w * scale, ids
+    w = torch.empty((T, k), dtype=torch.float32, device=gating.device)
+    ids = torch.empty((T, k), dtype=torch.int32, device=gating.device)
+    _check(_moe_topk(gating.data_ptr(), w.data_ptr(), ids.data_ptr(), T, E, k, int(renormalize), float(scale),
+                     _DT[gating.dtype], _st()), "moe_topk_softmax")
+    return w, ids
+
+
+def moe_align(topk_ids: torch.Tensor, num_local_experts: int, expert_map: Optional[torch.Tensor] = None):
+    """(sorted_tok [R], inv [R], offs [E+1]) for R = T*k (token, slot) pairs — all on the device."""
+    T, k = topk_ids.shape
+    R = T * k
+    dev = topk_ids.device
+    sorted_tok = torch.empty(R, dtype=torch.int32, device=dev)
+    inv = torch.empty(R, dtype=torch.int32, device=dev)
+    offs = torch.empty(num_local_experts + 1, dtype=torch.int32, device=dev)
+    _check(_moe_align(topk_ids.data_ptr(), _p(expert_map), sorted_tok.data_ptr(), inv.data_ptr(), offs.data_ptr(), R, k,
+                      num_local_experts, _st()), "moe_align")
+    return sorted_tok, inv, offs
+
+
+def moe_gather(x: torch.Tensor, sorted_tok: torch.Tensor) -> torch.Tensor:
+    R, H = sorted_tok.numel(), x.shape[1]
+    xs = torch.empty((R, H), dtype=x.dtype, device=x.device)
+    _check(_moe_gather(x.data_ptr(), sorted_tok.data_ptr(), xs.data_ptr(), R, H, _DT[x.dtype], _st()), "moe_gather")
+    return xs
+
+
+def moe_combine(y: torch.Tensor, inv: torch.Tensor, w: torch.Tensor, T: int) -> torch.Tensor:
+    H = y.shape[1]
+    k = inv.numel() // T
+    out = torch.empty((T, H), dtype=y.dtype, device=y.device)
+    _check(_moe_combine(y.data_ptr(), inv.data_ptr(), w.data_ptr(), out.data_ptr(), T, H, k, _DT[y.dtype], _st()),
+           "moe_combine")
+    return out
+
+
+def gemm_tc_grouped(xs: torch.Tensor, w: torch.Tensor, offs: torch.Tensor, bn: int) -> torch.Tensor:
+    """Y[r] = xs[r] · w[e(r)]^T, rows sorted by expert (``offs``). w: [E, N, K]."""
+    R, K = xs.shape
+    E, N, _ = w.shape
+    y = torch.empty((R, N), dtype=xs.dtype, device=xs.device)
+    _check(_gemm_grouped(xs.data_ptr(), w.data_ptr(), y.data_ptr(), offs.data_ptr(), R, N, K, E, bn, _DT[xs.dtype],
+                         _st()), f"gemm_tc_grouped(R={R},N={N},K={K},E={E})")
+    return y
 
 
 def grouped_topk(scores, k, n_group, topk_group, renormalize, scoring="sigmoid", bias=None, routed_scaling_factor=1.0):
