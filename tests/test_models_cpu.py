@@ -111,3 +111,18 @@ def test_async_scheduling_matches_sync():
     b.shutdown()
     assert got == ref
     assert cut == ref[0][:ref[0].index(ref[0][4]) + 1]
+
+
+def test_bert_embeddings_match_hf():
+    """Encoder-only model through the pooling runner: [CLS] embedding == HF BertModel, bidirectional attention."""
+    hf = make_hf_model("bert-tiny")
+    llm = make_llm("bert-tiny", weights=hf.state_dict().items())
+    prompts = [[3, 17, 99, 250, 41, 7], list(range(10, 45))]
+    outs = llm.embed([{"prompt_token_ids": p} for p in prompts])
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = hf(torch.tensor([p])).last_hidden_state[0, 0]
+        ref = torch.nn.functional.normalize(ref, dim=-1)
+        got = torch.as_tensor(o.outputs.data).float()
+        torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()

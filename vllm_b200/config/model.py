@@ -110,6 +110,10 @@ PRESETS: dict[str, dict[str, Any]] = {
         head_dim=128, max_position_embeddings=4096, rms_norm_eps=1e-5, rope_theta=10000.0,
         hidden_act="silu", num_local_experts=8, num_experts_per_tok=2, bos_token_id=1, eos_token_id=2,
         torch_dtype="bfloat16", tie_word_embeddings=False),
+    "bert-tiny": dict(
+        architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,
+        layer_norm_eps=1e-12, hidden_act="gelu", torch_dtype="float32", pad_token_id=0),
     "qwen2moe-tiny": dict(
         architectures=["Qwen2MoeForCausalLM"], model_type="qwen2_moe", vocab_size=512, hidden_size=128,
         intermediate_size=256, moe_intermediate_size=64, shared_expert_intermediate_size=128,
@@ -243,6 +247,11 @@ class ModelConfig:
         return 2048
 
     # -- accessors --------------------------------------------------------
+    @property
+    def is_encoder_only(self) -> bool:
+        return self.architecture in ("BertModel", "BertForMaskedLM", "BertForSequenceClassification", "RobertaModel",
+                                     "XLMRobertaModel")
+
     @property
     def architecture(self) -> str:
         return self.hf_config.get("architectures", ["LlamaForCausalLM"])[0]

@@ -130,11 +130,17 @@ class EngineArgs:
         mnbt = self.max_num_batched_tokens or 16384
         mns = self.max_num_seqs or 1024
         mml = mc.max_model_len
-        if not self.enable_chunked_prefill:
+        chunked = self.enable_chunked_prefill
+        if mc.is_encoder_only:
+            # bidirectional attention needs the whole sequence in one forward pass; nothing to reuse across requests
+            mc.runner = "pooling"
+            chunked = False
+            cc.enable_prefix_caching = False
+        if not chunked:
             mnbt = max(mnbt, mml)
         sc = SchedulerConfig(
             max_num_batched_tokens=mnbt, max_num_seqs=mns, max_model_len=mml,
-            enable_chunked_prefill=self.enable_chunked_prefill,
+            enable_chunked_prefill=chunked,
             long_prefill_token_threshold=self.long_prefill_token_threshold, policy=self.scheduling_policy,
             async_scheduling=self.async_scheduling, scheduler_cls=self.scheduler_cls)
         spec = SpeculativeConfig(**self.speculative_config) if self.speculative_config else None

@@ -6,7 +6,7 @@ import torch
 
 def pool_hidden(hidden: torch.Tensor, params, model=None) -> torch.Tensor:
     """hidden: [n_tokens, H] of ONE request."""
-    kind = params.pooling_type.upper()
+    kind = (params.pooling_type or getattr(model, "default_pooling", "LAST")).upper()
     h = hidden.float()
     if kind == "LAST":
         out = h[-1]

@@ -22,6 +22,11 @@ _MODELS: dict[str, tuple[str, str]] = {
     "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
     "Qwen2MoeForCausalLM": ("mixtral", "Qwen2MoeForCausalLM"),
     "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
+    "BertModel": ("bert", "BertEmbeddingModel"),
+    "BertForMaskedLM": ("bert", "BertEmbeddingModel"),
+    "BertForSequenceClassification": ("bert", "BertForSequenceClassification"),
+    "RobertaModel": ("bert", "RobertaModel"),
+    "XLMRobertaModel": ("bert", "RobertaModel"),
     "DeepseekV2ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
     "DeepseekV3ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
 }

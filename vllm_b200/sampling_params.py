@@ -180,7 +180,7 @@ class PoolingParams(msgspec.Struct, omit_defaults=True):
     dimensions: Optional[int] = None
     normalize: bool = True
     truncate_prompt_tokens: Optional[int] = None
-    pooling_type: str = "LAST"  # LAST|MEAN|CLS|ALL
+    pooling_type: Optional[str] = None  # LAST|MEAN|CLS|ALL; None → the model's default (LAST for decoders)
     extra_args: Optional[dict[str, Any]] = None
 
     def clone(self) -> "PoolingParams":
