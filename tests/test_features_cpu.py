@@ -105,3 +105,26 @@ def test_multi_lora_matches_merged_weights():
     got = [o.outputs[0].token_ids for o in outs]
     llm.shutdown()
     assert got == exp
+
+
+@pytest.mark.parametrize("method", ["fp8", "fp8_block"])
+def test_online_fp8_quantization_close_to_bf16(method):
+    """Online weight quantisation of an unquantised checkpoint: greedy text stays close to the full-precision run
+    (teacher-forced prompt logprobs within quantisation noise)."""
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=6, scale=0.08))
+    sp = SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True, prompt_logprobs=0)
+    prompt = [{"prompt_token_ids": [(11 * i) % 500 + 3 for i in range(40)]}]
+
+    def run(**kw):
+        llm = make_llm("llama-tiny", **kw)
+        # rebuild the model from the checkpoint so that quantisation runs on the real weights
+        llm.llm_engine.engine_core.engine_core.model_executor.collective_rpc("load_model", kwargs={"weights": list(w)})
+        o = llm.generate(prompt, sp)[0]
+        llm.shutdown()
+        return [list(d.values())[0].logprob for d in o.prompt_logprobs[1:]]
+
+    base = run()
+    q = run(quantization=method)
+    diff = max(abs(a - b) for a, b in zip(base, q))
+    assert 0 < diff < 0.25, diff
