@@ -128,3 +128,38 @@ def test_online_fp8_quantization_close_to_bf16(method):
     q = run(quantization=method)
     diff = max(abs(a - b) for a, b in zip(base, q))
     assert 0 < diff < 0.25, diff
+
+
+def test_eplb_rebalance_and_routing():
+    from vllm_b200.parallel.eplb import ExpertLoadTracker, plan_transfers, rebalance_experts, route_to_physical
+    torch.manual_seed(0)
+    L, E, ranks, P = 2, 8, 4, 12
+    tr = ExpertLoadTracker(L, E, window=16)
+    hot = torch.tensor([0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 0])            # expert 0 is hot
+    for step in range(20):
+        for l in range(L):
+            tr.record(l, hot[torch.randint(0, len(hot), (64, 2))])
+        tr.end_step()
+    load = tr.load()
+    assert load.shape == (L, E) and int(load[0].argmax()) == 0
+    pl = rebalance_experts(load, P, ranks)
+    assert pl.phy2log.shape == (L, P)
+    for l in range(L):
+        assert set(pl.phy2log[l].tolist()) == set(range(E))              # every expert is placed
+        assert int(pl.logcnt[l, 0]) >= 2                                 # the hot expert got replicas
+        per_rank = [float(sum(load[l, e] / pl.logcnt[l, e] for e in pl.phy2log[l, r * 3:(r + 1) * 3])) for r in range(ranks)]
+        assert max(per_rank) <= 1.6 * (sum(per_rank) / ranks)            # balanced within 60 % of the mean
+    ids = hot[torch.randint(0, len(hot), (32, 2))]
+    phys = route_to_physical(ids, pl, 0)
+    assert torch.equal(pl.phy2log[0][phys], ids)                          # physical slots hold the requested experts
+    moves = plan_transfers(torch.arange(P) % E, pl.phy2log[0], ranks)
+    assert all(int((torch.arange(P) % E)[s]) == int(pl.phy2log[0][d]) for s, d, _, _ in moves)
+
+
+def test_weight_transfer_buckets_roundtrip():
+    from vllm_b200.parallel.weight_transfer import pack_buckets, unpack_bucket
+    named = [(f"w{i}", torch.randn(3 + i, 5)) for i in range(7)] + [("b", torch.arange(6, dtype=torch.int32))]
+    got = {}
+    for metas, flat in pack_buckets(named, bucket_bytes=200):
+        got.update(dict(unpack_bucket(metas, flat)))
+    assert all(torch.equal(got[n], t) for n, t in named)
