@@ -126,3 +126,36 @@ def test_bert_embeddings_match_hf():
         got = torch.as_tensor(o.outputs.data).float()
         torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_llava_matches_hf_with_image():
+    """Vision tower + projector + placeholder merge + decoder == HF LlavaForConditionalGeneration (greedy)."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llava-tiny")
+    text = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type", "vision_config", "image_token_index",
+                                                        "vision_feature_layer", "vision_feature_select_strategy",
+                                                        "projector_hidden_act", "torch_dtype")}
+    hf_cfg = transformers.LlavaConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="llama", **text),
+                                      image_token_index=511, vision_feature_layer=-2,
+                                      vision_feature_select_strategy="default", projector_hidden_act="gelu")
+    torch.manual_seed(0)
+    hf = transformers.LlavaForConditionalGeneration(hf_cfg).eval()
+    llm = make_llm("llava-tiny", weights=hf.state_dict().items())
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 28, 28, generator=g)
+    ids = [5, 17, 511, 99, 3, 250]                       # one <image> placeholder → 4 patch tokens
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}},
+                        {"prompt_token_ids": [7, 8, 9, 10]}], sp)
+    got = out[0].outputs[0].token_ids
+    exp_ids = [5, 17] + [511] * 4 + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    assert got == ref
+    # the same image again: served from the encoder cache
+    runner = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner
+    llm.generate([{"prompt_token_ids": [1, 511, 2], "multi_modal_data": {"image": img}}], sp)
+    assert runner.encoder_cache.hits >= 1
+    llm.shutdown()

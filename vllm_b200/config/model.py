@@ -110,6 +110,16 @@ PRESETS: dict[str, dict[str, Any]] = {
         head_dim=128, max_position_embeddings=4096, rms_norm_eps=1e-5, rope_theta=10000.0,
         hidden_act="silu", num_local_experts=8, num_experts_per_tok=2, bos_token_id=1, eos_token_id=2,
         torch_dtype="bfloat16", tie_word_embeddings=False),
+    "llava-tiny": dict(
+        architectures=["LlavaForConditionalGeneration"], model_type="llava", image_token_index=511,
+        vision_feature_layer=-2, vision_feature_select_strategy="default", projector_hidden_act="gelu",
+        vision_config=dict(model_type="clip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=28, patch_size=14, projection_dim=32,
+                           hidden_act="quick_gelu", layer_norm_eps=1e-5),
+        # text stack (flattened text_config)
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "bert-tiny": dict(
         architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
         num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,
@@ -209,6 +219,10 @@ class ModelConfig:
     def __post_init__(self) -> None:
         if not self.hf_config:
             self.hf_config = self._load_hf_config()
+        if isinstance(self.hf_config.get("text_config"), dict):
+            # vision-language checkpoints nest the decoder's fields: lift them to the top level (top-level wins)
+            tc = self.hf_config.pop("text_config")
+            self.hf_config = {**tc, **self.hf_config}
         self.hf_config.update(self.hf_overrides)
         if self.tokenizer is None:
             self.tokenizer = self.model

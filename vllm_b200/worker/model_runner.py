@@ -156,6 +156,8 @@ class ModelRunner:
         spec = vllm_config.speculative_config
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
+        self.encoder_cache = None
+        self.has_mm = vllm_config.model_config.hf_config.get("vision_config") is not None
         self.kv_connector = None
         ktc = vllm_config.kv_transfer_config
         if ktc is not None and ktc.kv_connector:
@@ -459,11 +461,42 @@ class ModelRunner:
         return out
 
     # ------------------------------------------------------------ forward
-    def _forward(self, T: int, md: dict[int, AttentionMetadata], intermediate=None):
+    def _forward(self, T: int, md: dict[int, AttentionMetadata], intermediate=None, inputs_embeds=None):
         ctx = ForwardContext(attn_metadata=md, kv_caches=self.kv_caches, layer_to_group=self.layer_to_group,
                              num_tokens=T)
         with set_forward_context(ctx):
+            if inputs_embeds is not None:
+                return self.model(self.input_ids[:T], self.positions[:T], intermediate, inputs_embeds)
             return self.model(self.input_ids[:T], self.positions[:T], intermediate)
+
+    def _mm_inputs_embeds(self, states, rows, ns, cu, T):
+        """Token embeddings of the step with multimodal placeholder positions replaced by encoder outputs.
+        Returns None when no scheduled token range touches a multimodal item."""
+        todo = []
+        for j, s in enumerate(states):
+            if not s.mm_features:
+                continue
+            start = int(self.num_computed_cpu[rows[j]])
+            end = start + int(ns[j])
+            for f in s.mm_features:
+                lo, hi = max(start, f["offset"]), min(end, f["offset"] + f["length"])
+                if lo < hi:
+                    todo.append((j, f, lo, hi, start))
+        if not todo:
+            return None
+        if self.encoder_cache is None:
+            from vllm_b200.multimodal import EncoderCache
+            self.encoder_cache = EncoderCache()
+        emb = self.model.embed_input_ids(self.input_ids[:T]).clone()
+        for j, f, lo, hi, start in todo:
+            enc = self.encoder_cache.get(f["hash"])
+            if enc is None:
+                px = torch.as_tensor(f["data"]).to(self.device)
+                enc = self.model.embed_multimodal(px[None])[0].to(emb.dtype)
+                self.encoder_cache.put(f["hash"], enc)
+            dst0 = int(cu[j]) + (lo - start)
+            emb[dst0:dst0 + (hi - lo)] = enc[lo - f["offset"]:hi - f["offset"]]
+        return emb
 
     def _next_staging(self) -> _Staging:
         self._stage_i = (self._stage_i + 1) % len(self.staging)
@@ -533,15 +566,16 @@ class ModelRunner:
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
             if kv_meta:
                 self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
+            mm_emb = self._mm_inputs_embeds(states, rows, ns, cu, T) if self.has_mm else None
             if lora_batch is not None:
                 from vllm_b200 import lora as _lora
                 _lora.set_batch(lora_batch)
                 try:
-                    hidden = self._forward(T, md, intermediate)
+                    hidden = self._forward(T, md, intermediate, mm_emb)
                 finally:
                     _lora.set_batch(None)
             else:
-                hidden = self._forward(T, md, intermediate)
+                hidden = self._forward(T, md, intermediate, mm_emb)
             if kv_meta:
                 self.kv_connector.save_kv(kv_meta, self.kv_caches)           # freshly computed full blocks
             if isinstance(hidden, dict):  # non-last PP stage
