@@ -1,0 +1,128 @@
+"""Selective state-space (Mamba-1) mixer with a paged recurrent-state cache.
+
+Behavioural reference: vllm/model_executor/layers/mamba/mamba_mixer.py (conv state + SSM state kept per request
+in the KV-cache pool through ``MambaSpec``; causal-conv1d + selective-scan ops).
+
+State layout: one pool block per request holds ``[conv_state (d_inner x (k-1)) | ssm_state (d_inner x d_state)]``
+in fp32.  Decode batches (one token per request) are fully vectorised over the batch — gather states by block id,
+one fused update, scatter back — with no host synchronisation, so they replay inside CUDA graphs.  Prefill /
+mixed batches walk each request's segment (chunked prefill resumes from the cached state).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from vllm_b200.core.kv_cache_manager import KVCacheSpec, MambaSpec
+from vllm_b200.forward_context import get_forward_context
+from vllm_b200.layers import attention as _attn
+from vllm_b200.layers.linear import ReplicatedLinear
+
+
+class MambaMixer(nn.Module):
+    def __init__(self, hidden: int, d_inner: int, d_state: int, d_conv: int, dt_rank: int, use_bias: bool,
+                 use_conv_bias: bool, dtype, prefix: str) -> None:
+        super().__init__()
+        self.d_inner, self.d_state, self.d_conv, self.dt_rank = d_inner, d_state, d_conv, dt_rank
+        self.in_proj = ReplicatedLinear(hidden, 2 * d_inner, use_bias, dtype, None, f"{prefix}.in_proj")
+        self.conv_weight = nn.Parameter(torch.empty(d_inner, d_conv, dtype=dtype), requires_grad=False)
+        self.conv_bias = nn.Parameter(torch.zeros(d_inner, dtype=dtype), requires_grad=False) if use_conv_bias else None
+        self.x_proj = ReplicatedLinear(d_inner, dt_rank + 2 * d_state, False, dtype, None, f"{prefix}.x_proj")
+        self.dt_proj = ReplicatedLinear(dt_rank, d_inner, True, dtype, None, f"{prefix}.dt_proj")
+        self.A_log = nn.Parameter(torch.empty(d_inner, d_state, dtype=torch.float32), requires_grad=False)
+        self.D = nn.Parameter(torch.ones(d_inner, dtype=torch.float32), requires_grad=False)
+        self.out_proj = ReplicatedLinear(d_inner, hidden, use_bias, dtype, None, f"{prefix}.out_proj")
+        self.layer_name = prefix
+        self.state_elems = d_inner * (d_conv - 1) + d_inner * d_state
+        # registered next to the attention layers so the engine sizes a cache group for it
+        self.num_kv_heads, self.head_size, self.sliding_window = 1, 0, None
+        assert prefix not in _attn._LAYER_REGISTRY, f"duplicate layer name {prefix}"
+        _attn._LAYER_REGISTRY[prefix] = self
+
+    def get_kv_cache_spec(self, block_size: int, dtype_size: int) -> KVCacheSpec:
+        return MambaSpec(block_size=block_size, state_bytes=self.state_elems * 4)
+
+    # ------------------------------------------------------------------ math
+    def _ssm_params(self, x_act: torch.Tensor):
+        dbc = self.x_proj(x_act)
+        dt, B, C = dbc.split([self.dt_rank, self.d_state, self.d_state], dim=-1)
+        dt = F.softplus(self.dt_proj(dt).float())
+        return dt, B.float(), C.float()
+
+    def _split_state(self, st: torch.Tensor):
+        nconv = self.d_inner * (self.d_conv - 1)
+        return (st[..., :nconv].reshape(*st.shape[:-1], self.d_inner, self.d_conv - 1),
+                st[..., nconv:].reshape(*st.shape[:-1], self.d_inner, self.d_state))
+
+    def _segment(self, x: torch.Tensor, conv_state: torch.Tensor, h: torch.Tensor):
+        """x [q, d_inner] of ONE request → (y [q, d_inner] fp32, new conv_state, new h)."""
+        k = self.d_conv
+        xin = torch.cat([conv_state.t().to(x.dtype), x], dim=0)                 # [k-1+q, di]
+        w = self.conv_weight.float()
+        win = xin.float().unfold(0, k, 1)                                        # [q, di, k]
+        conv = (win * w[None]).sum(-1)
+        if self.conv_bias is not None:
+            conv = conv + self.conv_bias.float()
+        xa = F.silu(conv)
+        dt, B, C = self._ssm_params(xa.to(x.dtype))
+        A = -torch.exp(self.A_log)
+        ys = torch.empty_like(xa)
+        for t in range(x.shape[0]):
+            dA = torch.exp(dt[t][:, None] * A)
+            h = dA * h + (dt[t] * xa[t])[:, None] * B[t][None, :]
+            ys[t] = (h * C[t][None, :]).sum(-1)
+        ys = ys + self.D * xa
+        return ys, xin[-(k - 1):].t().float(), h
+
+    def forward(self, hidden: torch.Tensor) -> torch.Tensor:
+        ctx = get_forward_context()
+        md = ctx.metadata_for(self.layer_name)
+        cache = ctx.kv_caches.get(self.layer_name)
+        xz = self.in_proj(hidden)
+        x, z = xz.split([self.d_inner, self.d_inner], dim=-1)
+        T = x.shape[0]
+        if md is None or cache is None:          # profiling run: stateless pass over the whole buffer as one sequence
+            y, _, _ = self._segment(x, x.new_zeros(self.d_inner, self.d_conv - 1, dtype=torch.float32),
+                                    x.new_zeros(self.d_inner, self.d_state, dtype=torch.float32))
+            return self.out_proj((y * F.silu(z.float())).to(hidden.dtype))
+        cache = cache.view(cache.shape[0], -1).view(torch.float32) if cache.dtype != torch.float32 else cache
+        if md.decode_only:
+            B_ = md.num_reqs
+            slots = md.block_table[:B_, 0].long()
+            st = cache[slots]                                                     # [B, state]
+            conv_state, h = self._split_state(st)
+            xin = torch.cat([conv_state, x[:B_].float()[:, :, None]], dim=-1)      # [B, di, k]
+            conv = (xin * self.conv_weight.float()[None]).sum(-1)
+            if self.conv_bias is not None:
+                conv = conv + self.conv_bias.float()
+            xa = F.silu(conv)
+            dt, Bm, Cm = self._ssm_params(xa.to(x.dtype))
+            A = -torch.exp(self.A_log)
+            h = torch.exp(dt[:, :, None] * A[None]) * h + (dt * xa)[:, :, None] * Bm[:, None, :]
+            y = (h * Cm[:, None, :]).sum(-1) + self.D * xa
+            cache[slots] = torch.cat([xin[:, :, 1:].reshape(B_, -1), h.reshape(B_, -1)], dim=-1)
+            out = torch.zeros(T, self.d_inner, dtype=torch.float32, device=x.device)
+            out[:B_] = y
+        else:
+            qsl = (md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()).tolist()
+            sls = (md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()).tolist()
+            slots = md.block_table[:md.num_reqs, 0].tolist()
+            out = torch.zeros(T, self.d_inner, dtype=torch.float32, device=x.device)
+            for i in range(md.num_reqs):
+                s, e = qsl[i], qsl[i + 1]
+                if e <= s:
+                    continue
+                if sls[i] - (e - s) > 0:
+                    conv_state, h = self._split_state(cache[slots[i]])
+                    conv_state, h = conv_state.clone(), h.clone()
+                else:
+                    conv_state = torch.zeros(self.d_inner, self.d_conv - 1, dtype=torch.float32, device=x.device)
+                    h = torch.zeros(self.d_inner, self.d_state, dtype=torch.float32, device=x.device)
+                y, conv_state, h = self._segment(x[s:e], conv_state, h)
+                cache[slots[i]] = torch.cat([conv_state.reshape(-1), h.reshape(-1)])
+                out[s:e] = y
+        return self.out_proj((out * F.silu(z.float())).to(hidden.dtype))

@@ -230,7 +230,7 @@ class ModelRunner:
         return {"bfloat16": torch.bfloat16, "float16": torch.float16}[cd]
 
     def initialize_kv_cache(self, cfg: KVCacheConfig) -> None:
-        from vllm_b200.core.kv_cache_manager import MLAAttentionSpec
+        from vllm_b200.core.kv_cache_manager import MambaSpec, MLAAttentionSpec
         self.kv_cache_config = cfg
         self.num_kv_groups = max(len(cfg.kv_cache_groups), 1)
         kvd = self._kv_dtype()
@@ -246,6 +246,10 @@ class ModelRunner:
                 and self.dtype in (torch.bfloat16, torch.float16)))
             for name in g.layer_names:
                 self.layer_to_group[name] = gid
+                if isinstance(s, MambaSpec):
+                    self.kv_caches[name] = torch.zeros((cfg.num_blocks, s.state_bytes // 4), dtype=torch.float32,
+                                                       device=self.device)
+                    continue
                 if isinstance(s, MLAAttentionSpec):
                     shape = (cfg.num_blocks, s.block_size, s.head_size)
                 else:
