@@ -204,6 +204,17 @@ def main() -> None:
         e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d_step),
                "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / K}
     if rank == 0:
+        roof = None
+        try:   # analytical roofline of the timed steps (weights + KV bytes, FLOPs) → achieved TB/s, MBU, MFU
+            from vllm_b200.config import get_preset_hf_config
+            from vllm_b200.metrics.perf import model_step_cost, utilisation
+            hf = get_preset_hf_config(args.model)
+            if hf is not None:
+                ctx = S_in + W + K // 2
+                roof = {k: round(v, 4) for k, v in utilisation(model_step_cost(hf, B, [ctx] * B), dev_ms / K / 1e3,
+                                                                args.gpus).items()}
+        except Exception:
+            roof = None
         print(json.dumps({
             "metric": "decode output tokens/s (whole box, device-timed decode steps, max over ranks)",
             "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
@@ -213,7 +224,7 @@ def main() -> None:
             "config": {"model": args.model, "global_batch": B, "seq_len": S_in, "parallelism": f"tp{args.gpus}",
                        "cuda_graphs": not args.eager,
                        "l2": "no flush needed: every step streams >16 GB of weights+KV, far above the 126 MB L2"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "impl": "ours"}))
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "impl": "ours"}))
     engine.shutdown()
     if world > 1 and dist.is_initialized():
         dist.barrier()

@@ -196,6 +196,12 @@ class AsyncLLM:
     async def is_sleeping(self) -> bool:
         return await self.engine_core.call_utility_async("is_sleeping")
 
+    async def get_fault_status(self) -> dict:
+        return await self.engine_core.call_utility_async("get_fault_status")
+
+    async def handle_fault(self, instruction: str) -> bool:
+        return await self.engine_core.call_utility_async("handle_fault", instruction)
+
     async def collective_rpc(self, method: str, args: tuple = (), kwargs: Optional[dict] = None):
         return await self.engine_core.call_utility_async("collective_rpc", method, list(args), kwargs)
 

@@ -229,10 +229,70 @@ class EngineCoreProc(EngineCore):
                 if kind == REQ_SHUTDOWN:
                     return
                 self._handle(kind, payload)
-            outs, _ = self.step_fn()
+            try:
+                outs, _ = self.step_fn()
+            except Exception as e:
+                if not self._recover_from_fault(e):
+                    raise
+                continue
             for ci, o in (outs or {}).items():
                 o.engine_index = self.engine_index
                 self.output_queue.put((ci, o))
+
+    # ---- fault tolerance (reference: v1/fault_tolerance/engine_core_sentinel.py:24-80)
+    ft_status = "healthy"
+    _ft_instruction: Optional[str] = None
+
+    def get_fault_status(self) -> dict:
+        return {"engine_index": self.engine_index, "status": self.ft_status}
+
+    def handle_fault(self, instruction: str) -> bool:
+        """Operator instruction for a parked engine: ``retry`` (resume serving) or ``abort`` (let it die)."""
+        self._ft_instruction = instruction
+        return True
+
+    def _recover_from_fault(self, exc: Exception) -> bool:
+        """With ``--enable-fault-tolerance``: fail the in-flight requests, park the busy loop (still answering
+        utility RPCs) until an operator instruction arrives or the recovery window closes."""
+        ft = self.vllm_config.fault_tolerance_config
+        if ft is None or not ft.enable_fault_tolerance:
+            return False
+        logger.exception("engine step failed; parking for up to %.0fs (fault tolerance)", ft.engine_recovery_timeout_sec)
+        self.ft_status = "unhealthy"
+        from vllm_b200.core.request import EngineCoreOutput, FinishReason
+        per_client: dict[int, list] = {}
+        for rid, r in list(self.scheduler.requests.items()):
+            per_client.setdefault(r.client_index, []).append(EngineCoreOutput(
+                request_id=rid, new_token_ids=[], finish_reason=int(FinishReason.ABORT),
+                stop_reason=f"engine fault: {type(exc).__name__}"))
+        self.scheduler.finish_requests(list(self.scheduler.requests), RequestStatus.FINISHED_ABORTED)
+        if self.batch_queue is not None:
+            self.batch_queue.clear()
+        for ci, outs in per_client.items():
+            self.output_queue.put((ci, EngineCoreOutputs(engine_index=self.engine_index, outputs=outs)))
+        deadline = time.monotonic() + ft.engine_recovery_timeout_sec
+        self._ft_instruction = None
+        while time.monotonic() < deadline:
+            try:
+                kind, payload = self.input_queue.get(timeout=0.2)
+            except queue.Empty:
+                continue
+            if kind == REQ_SHUTDOWN:
+                return False
+            if kind == REQ_UTILITY:
+                self._handle(kind, payload)
+            if self._ft_instruction == "retry":
+                try:
+                    self.model_executor.collective_rpc("reset_after_fault")
+                except Exception:
+                    logger.exception("worker reset failed")
+                    return False
+                self.ft_status = "healthy"
+                logger.info("fault cleared by operator: resuming")
+                return True
+            if self._ft_instruction == "abort":
+                return False
+        return False
 
     def _handle(self, kind: bytes, payload: Any) -> None:
         if kind == REQ_ADD:

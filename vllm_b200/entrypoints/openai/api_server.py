@@ -52,6 +52,8 @@ class ServingContext:
         self.chat_template = chat_template
         self.inflight = 0
         self.responses_store: dict[str, dict] = {}
+        self.lora_ids: dict[str, int] = {}
+        self.lora_requests: dict[str, Any] = {}       # adapter name (usable as `model`) → LoRARequest
 
 
 def _error(msg: str, code: int = 400, typ: str = "BadRequestError"):
@@ -198,7 +200,8 @@ def build_app(ctx: ServingContext):
         try:
             for i, p in enumerate(prompts):
                 gens.append(ctx.engine.generate(p, sp, f"{rid_base}-{i}", priority=req.priority,
-                                                trace_headers=dict(raw.headers)))
+                                                trace_headers=dict(raw.headers),
+                                                lora_request=ctx.lora_requests.get(req.model)))
         except ValueError as ex:
             return _error(str(ex))
         created = int(time.time())
@@ -301,7 +304,8 @@ def build_app(ctx: ServingContext):
             reasoning = get_reasoning_parser(ctx.reasoning_parser)(ctx.tokenizer)
         try:
             gen = ctx.engine.generate({"prompt": prompt} if isinstance(prompt, str) else prompt, sp, rid,
-                                      priority=req.priority, trace_headers=dict(raw.headers))
+                                      priority=req.priority, trace_headers=dict(raw.headers),
+                                      lora_request=ctx.lora_requests.get(req.model))
         except ValueError as ex:
             return _error(str(ex))
         created = int(time.time())
@@ -535,6 +539,43 @@ def build_app(ctx: ServingContext):
     async def reset_prefix_cache():
         ok = await ctx.engine.reset_prefix_cache()
         return Response(status_code=200 if ok else 409)
+
+    # fault tolerance / LoRA management / checkpoint hooks (reference: entrypoints/serve/{fault_tolerance,lora,...})
+    @app.get("/fault_tolerance/status")
+    async def ft_status():
+        return await ctx.engine.get_fault_status()
+
+    @app.post("/fault_tolerance/apply")
+    async def ft_apply(body: dict):
+        ok = await ctx.engine.handle_fault(body.get("instruction", "retry"))
+        return {"ok": bool(ok)}
+
+    @app.post("/v1/load_lora_adapter")
+    async def load_lora(body: dict):
+        from vllm_b200.core.request import LoRARequest
+        name, path = body["lora_name"], body["lora_path"]
+        lid = ctx.lora_ids.setdefault(name, len(ctx.lora_ids) + 1)
+        ctx.lora_requests[name] = LoRARequest(name, lid, path)
+        await ctx.engine.collective_rpc("add_lora", (), {"lora_request": ctx.lora_requests[name]})
+        return {"status": "ok", "lora_int_id": lid}
+
+    @app.post("/v1/unload_lora_adapter")
+    async def unload_lora(body: dict):
+        req = ctx.lora_requests.pop(body["lora_name"], None)
+        if req is None:
+            return JSONResponse({"error": "unknown adapter"}, status_code=404)
+        await ctx.engine.collective_rpc("remove_lora", (req.lora_int_id,))
+        return {"status": "ok"}
+
+    @app.post("/checkpoint/prepare")
+    async def ckpt_prepare():
+        await ctx.engine.collective_rpc("checkpoint_prepare")
+        return Response(status_code=200)
+
+    @app.post("/checkpoint/restore")
+    async def ckpt_restore():
+        await ctx.engine.collective_rpc("checkpoint_restore")
+        return Response(status_code=200)
 
     @app.post("/collective_rpc")
     async def collective_rpc(body: dict):

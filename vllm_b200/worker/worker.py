@@ -109,6 +109,8 @@ class Worker:
     def compile_or_warm_up_model(self) -> None:
         if self.device.type == "cuda":
             self.runner.capture_model()
+        from vllm_b200.utils import gpu_sync_debug
+        gpu_sync_debug.arm()      # VLLM_GPU_SYNC_CHECK: from here on the step may not block on the device
 
     # -------------------------------------------------------------- execute
     @torch.inference_mode()
@@ -118,7 +120,9 @@ class Worker:
         if pp.world_size > 1 and not pp.is_first_rank:
             if so.total_num_scheduled_tokens > 0:
                 intermediate = pp.recv_tensor_dict(device=self.device)
-        out = self.runner.execute_model(so, intermediate, non_block=non_block)
+        from vllm_b200.utils.gpu_sync_debug import sync_guard
+        with sync_guard():
+            out = self.runner.execute_model(so, intermediate, non_block=non_block)
         if pp.world_size > 1 and not pp.is_last_rank:
             if isinstance(getattr(out, "kv_connector_output", None), dict):
                 pp.send_tensor_dict(out.kv_connector_output)
@@ -134,6 +138,44 @@ class Worker:
         r.input_ids[:1].zero_()
         r.positions[:1].zero_()
         r._forward(1, {})
+
+    def reset_after_fault(self) -> bool:
+        """Fault-tolerance retry: forget every in-flight request and pending async step, keep weights and caches
+        (reference: v1/worker/sentinel/gpu_worker_sentinel.py:30-89)."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        r = self.runner
+        r._pending = None
+        for rid in list(r.req_index):
+            r._remove(rid)
+        r._parked.clear()
+        return True
+
+    # ---------------------------------------------------------------- process checkpoint / restore
+    def checkpoint_prepare(self) -> None:
+        """Before a CRIU / cuda-checkpoint style process snapshot: drop everything that cannot be snapshotted — the
+        NVSwitch symmetric heaps (peer mappings, multicast objects) and captured CUDA graphs that reference them
+        (reference: gpu_worker.py:262-266 → parallel_state.checkpoint_prepare_distributed_state)."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        self.runner.graphs.clear()
+        for g in (pstate.get_tp_group(), pstate.get_ep_group()):
+            if g.device_comm is not None:
+                g.device_comm.close()
+                g.device_comm = None
+        self._checkpointed = True
+
+    def checkpoint_restore(self) -> None:
+        """After restore: rebuild the symmetric heaps and re-capture the decode graphs."""
+        if not getattr(self, "_checkpointed", False):
+            return
+        pc = self.vllm_config.parallel_config
+        if self.device.type == "cuda" and pc.tensor_parallel_size > 1 and not pc.disable_custom_all_reduce:
+            from vllm_b200.parallel.symm import SymmComm
+            tp = pstate.get_tp_group()
+            tp.device_comm = SymmComm(tp)
+        self.compile_or_warm_up_model()
+        self._checkpointed = False
 
     # ---------------------------------------------------------------- LoRA
     def add_lora(self, lora_request=None, tensors=None, rank: int = 0, alpha: float = 0.0) -> bool:
