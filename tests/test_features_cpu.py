@@ -163,3 +163,46 @@ def test_weight_transfer_buckets_roundtrip():
     for metas, flat in pack_buckets(named, bucket_bytes=200):
         got.update(dict(unpack_bucket(metas, flat)))
     assert all(torch.equal(got[n], t) for n, t in named)
+
+
+@pytest.mark.parametrize("method", ["awq", "gptq"])
+def test_int4_checkpoints_dequantize_on_load(method):
+    """A synthetic AWQ / GPTQ checkpoint produces exactly the model obtained from its dequantised weights."""
+    from vllm_b200.model_loader import weight_only as wo
+    torch.manual_seed(0)
+    w = torch.randn(64, 128) * 0.1
+    if method == "awq":
+        qw, qz, sc = wo.pack_awq(w, 32)
+        deq = wo.dequant_awq(qw, qz, sc, 32)
+    else:
+        qw, qz, sc, gi = wo.pack_gptq(w, 32)
+        deq = wo.dequant_gptq(qw, qz, sc, gi, 32)
+    assert deq.shape == w.shape and (deq - w).abs().max() < 0.06          # 4-bit rounding error only
+    cfg = get_preset_hf_config("llama-tiny")
+    full = dict(llama_full_weights(cfg, seed=8, scale=0.08))
+    ckpt, ref = [], {}
+    for name, t in full.items():
+        if name.endswith("proj.weight"):
+            mod = name[: -len(".weight")]
+            if method == "awq":
+                a, b, c = wo.pack_awq(t, 32)
+                ckpt += [(mod + ".qweight", a), (mod + ".qzeros", b), (mod + ".scales", c)]
+                ref[name] = wo.dequant_awq(a, b, c, 32)
+            else:
+                a, b, c, d = wo.pack_gptq(t, 32)
+                ckpt += [(mod + ".qweight", a), (mod + ".qzeros", b), (mod + ".scales", c), (mod + ".g_idx", d)]
+                ref[name] = wo.dequant_gptq(a, b, c, d, 32)
+        else:
+            ckpt.append((name, t))
+            ref[name] = t
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    prompt = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 77]}]
+    llm = make_llm("llama-tiny", weights=ref.items())
+    exp = llm.generate(prompt, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    llm = make_llm("llama-tiny", hf_overrides={"quantization_config": {"quant_method": method, "bits": 4, "group_size": 32}},
+                   quantization=method)
+    llm.llm_engine.engine_core.engine_core.model_executor.collective_rpc("load_model", kwargs={"weights": ckpt})
+    got = llm.generate(prompt, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    assert got == exp

@@ -122,7 +122,8 @@ class Fp8Config(QuantConfig):
         return Fp8LinearMethod(self.online, self.per_channel)
 
 
-QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8")
+QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8", "awq", "gptq", "awq_marlin",
+                        "gptq_marlin")
 
 
 def get_quant_config(model_config) -> Optional[QuantConfig]:
@@ -133,6 +134,8 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         online = not model_config.hf_config.get("quantization_config")
         return Fp8BlockConfig(online=online)
     hq = model_config.hf_config.get("quantization_config") or {}
+    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin"):
+        return None          # expanded to the model dtype at load time (model_loader/weight_only.py)
     if q in ("fp8", "fbgemm_fp8", "modelopt"):
         if hq.get("weight_block_size"):          # a "fp8" checkpoint with block scales (DeepSeek-V3 style)
             return Fp8BlockConfig(online=False)

@@ -86,16 +86,23 @@ def get_model(vllm_config: VllmConfig, device: torch.device,
     finally:
         torch.set_default_dtype(old)
     fmt = lc.load_format
+    hq = mc.hf_config.get("quantization_config") or {}
+    if (hq.get("quant_method") or "").lower() in ("awq", "gptq"):
+        # weight-only int4 checkpoints are expanded to the model dtype while streaming (model_loader/weight_only.py)
+        from vllm_b200.model_loader.weight_only import dequantize_stream
+        _wrap = lambda it: dequantize_stream(it, hq, mc.torch_dtype)  # noqa: E731
+    else:
+        _wrap = lambda it: it  # noqa: E731
     with torch.no_grad():
         if weights is not None:
-            model.load_weights(weights)
+            model.load_weights(_wrap(weights))
         elif fmt == "dummy" or (fmt == "auto" and not os.path.isdir(mc.model)):
             initialize_dummy_weights(model, lc.dummy_seed)
         elif fmt == "sharded_state":
             from vllm_b200.model_loader.sharded_state import load_sharded_state
             load_sharded_state(model, mc.model)
         else:
-            loaded = model.load_weights(iter_weights(mc.model, fmt))
+            loaded = model.load_weights(_wrap(iter_weights(mc.model, fmt)))
             missing = {n for n, _ in model.named_parameters()} - set(loaded)
             missing = {m for m in missing if "lm_head" not in m}
             if missing:
