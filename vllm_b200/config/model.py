@@ -125,6 +125,31 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,
         layer_norm_epsilon=1e-5, intermediate_size=128, bos_token_id=0, eos_token_id=0, pad_token_id=0,
         torch_dtype="float32", tie_word_embeddings=True, max_position_embeddings=1024),
+    "phi3-tiny": dict(
+        architectures=["Phi3ForCausalLM"], model_type="phi3", vocab_size=512, hidden_size=128, intermediate_size=256,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=1024,
+        original_max_position_embeddings=1024, rms_norm_eps=1e-5, rope_theta=10000.0, hidden_act="silu",
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "gemma2-tiny": dict(
+        architectures=["Gemma2ForCausalLM"], model_type="gemma2", vocab_size=512, hidden_size=128, intermediate_size=256,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=32, max_position_embeddings=1024,
+        rms_norm_eps=1e-6, rope_theta=10000.0, hidden_activation="gelu_pytorch_tanh", hidden_act="gelu_pytorch_tanh",
+        query_pre_attn_scalar=32, attn_logit_softcapping=50.0, final_logit_softcapping=30.0, sliding_window=16,
+        bos_token_id=2, eos_token_id=1, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "gptneox-tiny": dict(
+        architectures=["GPTNeoXForCausalLM"], model_type="gpt_neox", vocab_size=512, hidden_size=64, intermediate_size=256,
+        num_hidden_layers=2, num_attention_heads=4, max_position_embeddings=512, rotary_pct=0.25, rotary_emb_base=10000,
+        layer_norm_eps=1e-5, hidden_act="gelu", use_parallel_residual=True, bos_token_id=0, eos_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=False),
+    "starcoder2-tiny": dict(
+        architectures=["Starcoder2ForCausalLM"], model_type="starcoder2", vocab_size=512, hidden_size=64,
+        intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+        max_position_embeddings=512, rope_theta=10000.0, norm_epsilon=1e-5, hidden_act="gelu_pytorch_tanh", use_bias=True,
+        sliding_window=None, bos_token_id=0, eos_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "gptj-tiny": dict(
+        architectures=["GPTJForCausalLM"], model_type="gptj", vocab_size=512, n_embd=64, n_layer=2, n_head=4, n_inner=256,
+        n_positions=512, rotary_dim=8, layer_norm_epsilon=1e-5, activation_function="gelu_new", bos_token_id=0,
+        eos_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "bert-tiny": dict(
         architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
         num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,

@@ -254,3 +254,8 @@ class Qwen3ForCausalLM(LlamaForCausalLM):
 
 class GemmaForCausalLM(LlamaForCausalLM):
     """Gemma: (1+w) RMSNorm, sqrt(H)-scaled embeddings, GeGLU, tied head."""
+
+
+class Phi3ForCausalLM(LlamaForCausalLM):
+    """Phi-3 / Phi-3.5: Llama block with q|k|v and gate|up already fused in the checkpoint (``qkv_proj``,
+    ``gate_up_proj``) and LongRoPE scaling (reference: models/phi3.py)."""

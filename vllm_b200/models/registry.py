@@ -17,6 +17,11 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen2ForCausalLM": ("llama", "Qwen2ForCausalLM"),
     "Qwen3ForCausalLM": ("llama", "Qwen3ForCausalLM"),
     "GemmaForCausalLM": ("llama", "GemmaForCausalLM"),
+    "Phi3ForCausalLM": ("llama", "Phi3ForCausalLM"),
+    "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
+    "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
+    "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
+    "GPTJForCausalLM": ("gpt_neox", "GPTJForCausalLM"),
     "OPTForCausalLM": ("opt", "OPTForCausalLM"),
     "GPT2LMHeadModel": ("opt", "GPT2LMHeadModel"),
     "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
