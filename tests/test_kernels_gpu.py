@@ -175,6 +175,11 @@ def test_topk_topp_mask():
     # bisection vs sort may differ by a boundary element
     assert (kept_e ^ kept_g).sum(dim=-1).max().item() <= 1
     assert torch.equal(got[kept_g], logits[kept_g])
+    # pure top-k rows (no nucleus) are exact: integer-key bisection finds the k-th largest value itself
+    for r in (1, 2, 5):
+        if float(p[r]) == 1.0:
+            assert torch.equal(kept_e[r], kept_g[r])
+            assert int(kept_g[r].sum()) == int(k[r])
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])

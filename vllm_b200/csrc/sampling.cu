@@ -121,18 +121,22 @@ __global__ void __launch_bounds__(1024) topk_topp_kernel(float* __restrict__ log
   __syncthreads();
   mn = bc;
   __syncthreads();
+  // Exact selection by bisection over the order-preserving integer image of the floats (32 passes build the
+  // answer bit by bit): no sort, no scratch memory, ties at the boundary are kept like the sort-based reference.
+  auto key_of = [](float x) -> uint32_t { const uint32_t u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+  auto val_of = [](uint32_t k) -> float { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
   float cut = -INFINITY;  // keep x >= cut
   if (k > 0 && k < V) {
-    // bisection for the largest threshold t with count(x >= t) >= k
-    float lo = mn, hi = mx;
-    for (int it = 0; it < 32; ++it) {
-      const float mid = 0.5f * (lo + hi);
+    // k-th largest key = max { c : count(key >= c) >= k }
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
       float cnt = 0.f;
-      for (int i = threadIdx.x; i < V; i += blockDim.x) cnt += lr[i] >= mid ? 1.f : 0.f;
+      for (int i = threadIdx.x; i < V; i += blockDim.x) cnt += key_of(lr[i]) >= cand ? 1.f : 0.f;
       cnt = block_sum(cnt, red);
-      if (cnt >= (float)k) lo = mid; else hi = mid;
+      if (cnt >= (float)k) prefix = cand;
     }
-    cut = lo;
+    cut = val_of(prefix);
   }
   if (pth < 1.f || mp > 0.f) {
     float z = 0.f;
@@ -140,16 +144,24 @@ __global__ void __launch_bounds__(1024) topk_topp_kernel(float* __restrict__ log
     z = block_sum(z, red);
     if (mp > 0.f) cut = fmaxf(cut, mx + __logf(mp));  // p_i >= min_p * p_max
     if (pth < 1.f) {
-      // largest threshold t whose kept mass sum_{x >= t} p >= top_p
-      float lo = fmaxf(mn, cut), hi = mx;
-      for (int it = 0; it < 32; ++it) {
-        const float mid = 0.5f * (lo + hi);
+      // nucleus: an element is dropped iff the probability mass of everything <= it is <= 1 - top_p.
+      // smallest kept key = max { c : mass(key < c) <= (1 - top_p) * Z }
+      const float thr = (1.f - pth) * z;
+      const uint32_t kcut = key_of(cut);
+      uint32_t prefix = 0;
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
         float mass = 0.f;
-        for (int i = threadIdx.x; i < V; i += blockDim.x) { const float x = lr[i]; if (x >= mid) mass += __expf(x - mx); }
+        for (int i = threadIdx.x; i < V; i += blockDim.x) {
+          const float x = lr[i];
+          const uint32_t kx = key_of(x);
+          if (kx >= kcut && kx < cand) mass += __expf(x - mx);
+        }
         mass = block_sum(mass, red);
-        if (mass >= pth * z) lo = mid; else hi = mid;
+        if (mass <= thr) prefix = cand;
       }
-      cut = fmaxf(cut, lo);
+      // never drop the arg-max (mass rounding): the largest element always survives
+      cut = fmaxf(cut, fminf(val_of(prefix), mx));
     }
   }
   for (int i = threadIdx.x; i < V; i += blockDim.x)

@@ -100,6 +100,15 @@ class Sampler:
         filtered = logits
         if md.top_k is not None or md.top_p is not None or md.min_p is not None:
             t = torch.where(md.temperature < 1e-5, torch.ones_like(md.temperature), md.temperature)
+            if logits.is_cuda and md.seeds is not None and logits.dtype == torch.float32:
+                # device path: exact top-k / nucleus / min-p masking by integer-key bisection (no sort), then the
+                # fused Gumbel-max sampler (temperature already applied → 1, greedy rows stay greedy with 0)
+                from vllm_b200.ops import cuda_ops
+                cu = cuda_ops()
+                scaled = (logits / t[:, None]).contiguous()
+                cu.topk_topp_mask_(scaled, md.top_k, md.top_p, md.min_p)
+                t_eff = torch.where(md.temperature < 1e-5, md.temperature, torch.ones_like(md.temperature))
+                return cu.fused_sample(scaled, t_eff, md.seeds, md.steps)
             filtered = ref.apply_top_k_top_p_min_p(logits / t[:, None], md.top_k, md.top_p, md.min_p)
             return ref.gumbel_sample(filtered, torch.where(md.temperature < 1e-5, md.temperature,
                                                            torch.ones_like(md.temperature)), md.generators)
