@@ -452,6 +452,55 @@ def build_app(ctx: ServingContext):
         return P.ScoreResponse(model=ctx.model_name, data=data,
                                usage=_usage(sum(len(o.prompt_token_ids) for o in ea + eb), 0)).model_dump()
 
+    # ------------------------------------------- pooling family (reference: entrypoints/pooling/*)
+    async def _encode_many(inputs: list, pp: PoolingParams, tag: str):
+        rid = f"{tag}-{random_uuid()}"
+
+        async def one(i, p):
+            async for o in ctx.engine.encode({"prompt": p} if isinstance(p, str) else {"prompt_token_ids": p}, pp,
+                                              f"{rid}-{i}"):
+                return o
+        return await asyncio.gather(*[one(i, p) for i, p in enumerate(inputs)])
+
+    @app.post("/pooling")
+    async def pooling(body: dict):
+        inp = body.get("input")
+        inputs = [inp] if isinstance(inp, str) or (inp and isinstance(inp[0], int)) else list(inp)
+        pp = PoolingParams(task=body.get("task", "embed"), normalize=bool(body.get("normalize", False)),
+                           pooling_type=body.get("pooling_type"))
+        outs = await _encode_many(inputs, pp, "pool")
+        return {"id": f"pool-{random_uuid()}", "object": "list", "model": ctx.model_name,
+                "data": [{"index": i, "object": "pooling", "data": o.outputs.data.float().tolist()} for i, o in enumerate(outs)],
+                "usage": _usage(sum(len(o.prompt_token_ids) for o in outs), 0).model_dump()}
+
+    @app.post("/classify")
+    async def classify(body: dict):
+        inp = body.get("input")
+        inputs = [inp] if isinstance(inp, str) else list(inp)
+        outs = await _encode_many(inputs, PoolingParams(task="classify", normalize=False), "cls")
+        data = []
+        for i, o in enumerate(outs):
+            probs = o.outputs.data.float().flatten()
+            data.append({"index": i, "label": str(int(probs.argmax())), "probs": probs.tolist(), "num_classes": probs.numel()})
+        return {"id": f"classify-{random_uuid()}", "object": "list", "model": ctx.model_name, "data": data,
+                "usage": _usage(sum(len(o.prompt_token_ids) for o in outs), 0).model_dump()}
+
+    @app.post("/rerank")
+    @app.post("/v1/rerank")
+    @app.post("/v2/rerank")
+    async def rerank(body: dict):
+        """Jina / Cohere style: rank ``documents`` against ``query`` (bi-encoder cosine similarity)."""
+        import torch
+        docs = [d if isinstance(d, str) else d.get("text", "") for d in body["documents"]]
+        outs = await _encode_many([body["query"]] + docs, PoolingParams(task="embed"), "rerank")
+        q = outs[0].outputs.data.float().flatten()
+        scored = sorted(((float(torch.nn.functional.cosine_similarity(q, o.outputs.data.float().flatten(), dim=0)), i)
+                         for i, o in enumerate(outs[1:])), reverse=True)
+        top = scored[: int(body.get("top_n") or len(scored))]
+        return {"id": f"rerank-{random_uuid()}", "model": ctx.model_name,
+                "results": [{"index": i, "relevance_score": sc, "document": {"text": docs[i]}} for sc, i in top],
+                "usage": {"total_tokens": sum(len(o.prompt_token_ids) for o in outs)}}
+
     # ------------------------------------------- Responses API / Anthropic
     @app.post("/v1/responses")
     async def responses(req: P.ResponsesRequest, raw: Request):

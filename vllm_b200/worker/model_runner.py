@@ -20,6 +20,8 @@ Design (ours):
 """
 from __future__ import annotations
 
+import os
+
 import time
 import zlib
 from dataclasses import dataclass, field
@@ -157,6 +159,11 @@ class ModelRunner:
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
         self.encoder_cache = None
+        self.ec_connector = None
+        ecp = os.environ.get("VLLM_B200_EC_SHARED_PATH")
+        if ecp:
+            from vllm_b200.ec_transfer import ECSharedStorageConnector
+            self.ec_connector = ECSharedStorageConnector(ecp, os.environ.get("VLLM_B200_EC_ROLE", "ec_both"))
         self.has_mm = vllm_config.model_config.hf_config.get("vision_config") is not None
         self.kv_connector = None
         ktc = vllm_config.kv_transfer_config
@@ -494,10 +501,17 @@ class ModelRunner:
         emb = self.model.embed_input_ids(self.input_ids[:T]).clone()
         for j, f, lo, hi, start in todo:
             enc = self.encoder_cache.get(f["hash"])
+            if enc is None and self.ec_connector is not None:          # another instance may have encoded it
+                enc = self.ec_connector.load(f["hash"], self.device)
+                if enc is not None:
+                    enc = enc.to(emb.dtype)
+                    self.encoder_cache.put(f["hash"], enc)
             if enc is None:
                 px = torch.as_tensor(f["data"]).to(self.device)
                 enc = self.model.embed_multimodal(px[None])[0].to(emb.dtype)
                 self.encoder_cache.put(f["hash"], enc)
+                if self.ec_connector is not None:
+                    self.ec_connector.save(f["hash"], enc)
             dst0 = int(cu[j]) + (lo - start)
             emb[dst0:dst0 + (hi - lo)] = enc[lo - f["offset"]:hi - f["offset"]]
         return emb
