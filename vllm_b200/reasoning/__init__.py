@@ -29,25 +29,42 @@ class ReasoningParser:
         return (r.strip() or None), (c.lstrip("\n") or None)
 
     def extract_streaming(self, prev: str, cur: str, delta: str) -> Optional[dict]:
-        if self.end in prev:
-            return {"content": delta, "done": True}
-        if self.end in cur:
-            before, after = cur.split(self.end, 1)
-            sent = len(prev.split(self.start, 1)[-1]) if self.start in prev else len(prev)
-            body = before.split(self.start, 1)[-1]
-            out = {"done": True}
-            if len(body) > sent:
-                out["reasoning_content"] = body[sent:]
-            if after:
+        """Incremental split (one parser instance per request): reasoning text streams until the end tag, tags
+        never leak into either stream even when they are split across deltas."""
+        st = self.__dict__.setdefault("_st", {"sent_r": 0, "done": False, "sent_c": 0})
+        if st["done"]:
+            return {"content": delta, "done": True} if delta else None
+        t = cur
+        if self.start in t:
+            t = t.split(self.start, 1)[1]
+        else:
+            lead = t.lstrip()
+            if lead and self.start.startswith(lead):
+                return None                               # still inside a (possibly partial) start tag
+            if not self.start_optional:
+                st["done"] = True                         # no reasoning block at all: everything is content
+                out = cur[st["sent_c"]:]
+                st["sent_c"] = len(cur)
+                return {"content": out, "done": True} if out else None
+        if self.end in t:
+            body, after = t.split(self.end, 1)
+            st["done"] = True
+            out: dict = {"done": True}
+            if len(body) > st["sent_r"]:
+                out["reasoning_content"] = body[st["sent_r"]:]
+            if after.lstrip("\n"):
                 out["content"] = after.lstrip("\n")
             return out
-        d = delta.replace(self.start, "")
-        # hold back a partial end tag
-        for k in range(len(self.end) - 1, 0, -1):
-            if cur.endswith(self.end[:k]):
-                d = d[:-k] if len(d) >= k else ""
+        safe = len(t)
+        for k in range(len(self.end) - 1, 0, -1):        # hold back a partial end tag
+            if t.endswith(self.end[:k]):
+                safe = len(t) - k
                 break
-        return {"reasoning_content": d} if d else None
+        if safe > st["sent_r"]:
+            d = t[st["sent_r"]:safe]
+            st["sent_r"] = safe
+            return {"reasoning_content": d}
+        return None
 
 
 class Qwen3ReasoningParser(ReasoningParser):
@@ -69,11 +86,62 @@ class GraniteReasoningParser(ReasoningParser):
     start_optional = False
 
 
+def _tag_parser(start_tag: str, end_tag: str, optional_start: bool = True) -> type[ReasoningParser]:
+    return type(f"Tag_{abs(hash((start_tag, end_tag)))}", (ReasoningParser,),
+                {"start": start_tag, "end": end_tag, "start_optional": optional_start})
+
+
+class HunyuanReasoningParser(ReasoningParser):
+    """``<think>\n…\n</think>\n<answer>\n…\n</answer>``"""
+
+    def extract(self, text: str):
+        r, c = super().extract(text)
+        if c:
+            c = c.replace("<answer>", "").replace("</answer>", "").strip() or None
+        return r, c
+
+
+class GptOssReasoningParser(ReasoningParser):
+    """Harmony channels: ``<|channel|>analysis<|message|>…<|end|>`` is reasoning,
+    ``<|channel|>final<|message|>…`` is the answer."""
+    start, end = "<|channel|>analysis<|message|>", "<|end|>"
+    start_optional = False
+
+    def extract(self, text: str):
+        r, rest = None, text
+        if self.start in text:
+            body = text.split(self.start, 1)[1]
+            r, _, rest = body.partition(self.end)
+        marker = "<|channel|>final<|message|>"
+        c = rest.split(marker, 1)[1] if marker in rest else (rest if r is None else None)
+        if c:
+            c = c.replace("<|return|>", "").replace("<|end|>", "").strip() or None
+        return (r.strip() or None) if r else None, c
+
+
+class IdentityReasoningParser(ReasoningParser):
+    def extract(self, text: str):
+        return None, text
+
+    def extract_streaming(self, prev, cur, delta):
+        return {"content": delta, "done": True}
+
+
 _PARSERS = {
     "deepseek_r1": ReasoningParser, "deepseek_v3": ReasoningParser, "glm45": ReasoningParser,
     "qwen3": Qwen3ReasoningParser, "mistral": MistralReasoningParser, "granite": GraniteReasoningParser,
-    "hunyuan_a13b": ReasoningParser, "step3": ReasoningParser, "kimi_k2": ReasoningParser,
+    "hunyuan_a13b": HunyuanReasoningParser, "step3": ReasoningParser, "kimi_k2": ReasoningParser,
+    "ernie45": ReasoningParser, "minimax_m2": ReasoningParser, "olmo3": ReasoningParser, "nemotron_v3": ReasoningParser,
+    "holo2": ReasoningParser, "exaone4": Qwen3ReasoningParser, "deepseek_v32": ReasoningParser,
+    "seed_oss": _tag_parser("<seed:think>", "</seed:think>"), "kimi": _tag_parser("◁think▷", "◁/think▷"),
+    "cohere_command": _tag_parser("<|START_THINKING|>", "<|END_THINKING|>", False),
+    "gemma4": _tag_parser("<|think|>", "<|/think|>", False),
+    "gpt_oss": GptOssReasoningParser, "openai_gptoss": GptOssReasoningParser, "identity": IdentityReasoningParser,
 }
+
+
+def list_reasoning_parsers() -> list[str]:
+    return sorted(_PARSERS)
 
 
 def get_reasoning_parser(name: str) -> type[ReasoningParser]:

@@ -181,12 +181,161 @@ class JsonToolParser(Llama3JsonToolParser):
     start_markers = ("{", "[")
 
 
+def _json_calls(obj: Any) -> list[dict]:
+    """A JSON value in any of the common shapes → list of tool calls."""
+    items = obj if isinstance(obj, list) else [obj]
+    out = []
+    for it in items:
+        if not isinstance(it, dict):
+            continue
+        fn = it.get("function") if isinstance(it.get("function"), dict) else it
+        name = fn.get("name")
+        args = fn.get("arguments", fn.get("parameters", {}))
+        if name:
+            out.append(_call(name, args, len(out)))
+    return out
+
+
+class MarkerJsonToolParser(ToolParser):
+    """``<start>[{"name":…,"arguments":…}, …]<end>`` families: granite (``<|tool_call|>`` / ``<tool_call>``), jamba and
+    hunyuan (``<tool_calls>…</tool_calls>``), phi4-mini (``functools[…]``), xlam (fenced or bare JSON list),
+    internlm (``<|action_start|><|plugin|>{…}<|action_end|>``)."""
+    end_markers: tuple[str, ...] = ()
+    keep_bracket = False      # the start marker is followed directly by the JSON value
+
+    def extract(self, text: str) -> dict:
+        cut = min((text.find(m) for m in self.start_markers if m in text), default=-1)
+        if cut < 0:
+            return {"tool_calls": [], "content": text}
+        m = next(m for m in self.start_markers if text.startswith(m, cut))
+        body = text[cut + len(m):]
+        for e in self.end_markers:
+            if e in body:
+                body = body.split(e, 1)[0]
+        body = body.strip()
+        if body.startswith("```"):
+            body = body.strip("`").removeprefix("json").strip()
+        calls: list[dict] = []
+        try:
+            calls = _json_calls(json.loads(body))
+        except json.JSONDecodeError:
+            # newline-separated objects (minimax) or a truncated list: take every object that parses
+            dec = json.JSONDecoder()
+            i = 0
+            while i < len(body):
+                j = body.find("{", i)
+                if j < 0:
+                    break
+                try:
+                    obj, n = dec.raw_decode(body[j:])
+                except json.JSONDecodeError:
+                    break
+                calls.extend(_json_calls(obj))
+                i = j + n
+            for k, c in enumerate(calls):
+                c["index"] = k
+        return {"tool_calls": calls, "content": text[:cut].strip() or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        t = text.rstrip()
+        return any(t.endswith(e) for e in self.end_markers) if self.end_markers else t.endswith(("]", "}"))
+
+
+def _marker_parser(starts: tuple[str, ...], ends: tuple[str, ...] = ()) -> type[MarkerJsonToolParser]:
+    return type("MarkerJson_" + re.sub(r"\W", "", starts[0]), (MarkerJsonToolParser,),
+                {"start_markers": starts, "end_markers": ends})
+
+
+class XmlParamToolParser(ToolParser):
+    """``<tool_call><function=NAME><parameter=KEY>VALUE</parameter>…</function></tool_call>``
+    (qwen3-coder / qwen3_xml / seed_oss / step3 style; values are JSON when they parse, else strings)."""
+    start_markers = ("<tool_call>", "<function=")
+    _fn = re.compile(r"<function=([^>\s]+)>(.*?)(?:</function>|$)", re.S)
+    _par = re.compile(r"<parameter=([^>\s]+)>\s*(.*?)\s*</parameter>", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = []
+        for m in self._fn.finditer(text):
+            args = {}
+            for k, v in self._par.findall(m.group(2)):
+                try:
+                    args[k] = json.loads(v)
+                except json.JSONDecodeError:
+                    args[k] = v
+            calls.append(_call(m.group(1), args, len(calls)))
+        cut = min((text.find(x) for x in self.start_markers if x in text), default=len(text))
+        return {"tool_calls": calls, "content": (text[:cut].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("</function>", "</tool_call>"))
+
+
+class Glm4MoeToolParser(ToolParser):
+    """``<tool_call>NAME\n<arg_key>k</arg_key>\n<arg_value>v</arg_value>…</tool_call>`` (GLM-4.5 / 4.6)."""
+    start_markers = ("<tool_call>",)
+    _blk = re.compile(r"<tool_call>\s*([^\n<]+)\s*(.*?)(?:</tool_call>|$)", re.S)
+    _kv = re.compile(r"<arg_key>(.*?)</arg_key>\s*<arg_value>(.*?)</arg_value>", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = []
+        for m in self._blk.finditer(text):
+            args = {}
+            for k, v in self._kv.findall(m.group(2)):
+                try:
+                    args[k.strip()] = json.loads(v)
+                except json.JSONDecodeError:
+                    args[k.strip()] = v.strip()
+            calls.append(_call(m.group(1).strip(), args, len(calls)))
+        return {"tool_calls": calls, "content": (text[:text.find("<tool_call>")].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith("</tool_call>")
+
+
+class KimiK2ToolParser(ToolParser):
+    """``<|tool_calls_section_begin|><|tool_call_begin|>functions.NAME:IDX<|tool_call_argument_begin|>{json}<|tool_call_end|>…``"""
+    start_markers = ("<|tool_calls_section_begin|>", "<|tool_call_begin|>")
+    _rx = re.compile(r"<\|tool_call_begin\|>\s*(?:functions\.)?([\w\-.]+?)(?::\d+)?\s*<\|tool_call_argument_begin\|>\s*(.*?)\s*<\|tool_call_end\|>", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = [_call(m.group(1), m.group(2), i) for i, m in enumerate(self._rx.finditer(text))]
+        cut = min((text.find(x) for x in self.start_markers if x in text), default=len(text))
+        return {"tool_calls": calls, "content": (text[:cut].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("<|tool_call_end|>", "<|tool_calls_section_end|>"))
+
+
+class DeepSeekV31ToolParser(ToolParser):
+    """``<｜tool▁calls▁begin｜><｜tool▁call▁begin｜>NAME<｜tool▁sep｜>{json}<｜tool▁call▁end｜>…``"""
+    start_markers = ("<｜tool▁calls▁begin｜>",)
+    _rx = re.compile(r"<｜tool▁call▁begin｜>(.*?)<｜tool▁sep｜>(.*?)<｜tool▁call▁end｜>", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = [_call(m.group(1).strip(), m.group(2).strip(), i) for i, m in enumerate(self._rx.finditer(text))]
+        return {"tool_calls": calls, "content": (text[:text.find(self.start_markers[0])].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("<｜tool▁call▁end｜>", "<｜tool▁calls▁end｜>"))
+
+
 _PARSERS: dict[str, type[ToolParser]] = {
     "hermes": HermesToolParser, "qwen": HermesToolParser, "qwen3": HermesToolParser, "nous": HermesToolParser,
     "llama3_json": Llama3JsonToolParser, "llama4_json": Llama3JsonToolParser,
     "mistral": MistralToolParser, "pythonic": PythonicToolParser, "llama4_pythonic": PythonicToolParser,
-    "olmo3": PythonicToolParser, "deepseek_v3": DeepSeekV3ToolParser, "deepseek_v31": DeepSeekV3ToolParser,
+    "olmo3": PythonicToolParser, "deepseek_v3": DeepSeekV3ToolParser,
     "json": JsonToolParser,
+    "granite": _marker_parser(("<|tool_call|>", "<tool_call>")), "granite-20b-fc": _marker_parser(("<function_call>",)),
+    "jamba": _marker_parser(("<tool_calls>",), ("</tool_calls>",)),
+    "hunyuan_a13b": _marker_parser(("<tool_calls>",), ("</tool_calls>",)),
+    "minimax": _marker_parser(("<tool_calls>",), ("</tool_calls>",)),
+    "phi4_mini_json": _marker_parser(("functools",)),
+    "xlam": _marker_parser(("[TOOL_CALLS]", "```json", "[{")),
+    "internlm": _marker_parser(("<|action_start|><|plugin|>",), ("<|action_end|>",)),
+    "qwen3_coder": XmlParamToolParser, "qwen3_xml": XmlParamToolParser, "seed_oss": XmlParamToolParser,
+    "step3": XmlParamToolParser, "glm45": Glm4MoeToolParser, "glm47": Glm4MoeToolParser,
+    "kimi_k2": KimiK2ToolParser, "longcat": _marker_parser(("<longcat_tool_call>",), ("</longcat_tool_call>",)),
+    "ernie45": _marker_parser(("<tool_call>",), ("</tool_call>",)), "functiongemma": PythonicToolParser, "deepseek_v31": DeepSeekV31ToolParser, "deepseek_v32": DeepSeekV31ToolParser,
 }
 
 
