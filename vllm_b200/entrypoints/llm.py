@@ -82,7 +82,16 @@ class LLM:
             from tqdm import tqdm
             pbar = tqdm(total=self.llm_engine.get_num_unfinished_requests(), desc="Processed prompts")
         while self.llm_engine.has_unfinished_requests():
-            for o in self.llm_engine.step():
+            try:
+                step_outs = self.llm_engine.step()
+            except BaseException:
+                # leave the engine reusable: drop every request of this call (front-end state and scheduler)
+                try:
+                    self.llm_engine.abort_request(list(self.llm_engine.output_processor.request_states))
+                except Exception:
+                    pass
+                raise
+            for o in step_outs:
                 if o.finished:
                     outs.append(o)
                     if pbar:
