@@ -15,7 +15,8 @@ def _greedy(llm, n=16):
 
 
 @pytest.mark.parametrize("spec", [dict(method="ngram", num_speculative_tokens=3, prompt_lookup_max=4, prompt_lookup_min=1),
-                                  dict(method="draft_model", model="llama-tiny", num_speculative_tokens=3)])
+                                  dict(method="draft_model", model="llama-tiny", num_speculative_tokens=3),
+                                  dict(method="medusa", num_speculative_tokens=3)])
 def test_speculative_decoding_is_lossless(spec):
     """Greedy output with speculation == greedy output without (rejection sampler correctness)."""
     cfg = get_preset_hf_config("llama-tiny")

@@ -46,7 +46,10 @@ def make_drafter(vllm_config, runner) -> Optional[object]:
         return None
     if sc.method == "ngram":
         return NgramDrafter(sc.num_speculative_tokens, sc.prompt_lookup_max, sc.prompt_lookup_min)
-    if sc.method in ("eagle", "eagle3", "mtp", "draft_model", "medusa"):
+    if sc.method == "medusa":
+        from vllm_b200.spec_decode.medusa import MedusaDrafter
+        return MedusaDrafter(vllm_config, runner)
+    if sc.method in ("eagle", "eagle3", "mtp", "draft_model"):
         from vllm_b200.spec_decode.draft_model import DraftModelDrafter
         return DraftModelDrafter(vllm_config, runner)
     raise ValueError(f"unknown speculative method {sc.method!r}")

@@ -158,6 +158,7 @@ class ModelRunner:
         spec = vllm_config.speculative_config
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
+        self.spec_hidden = None
         self.encoder_cache = None
         self.ec_connector = None
         ecp = os.environ.get("VLLM_B200_EC_SHARED_PATH")
@@ -219,6 +220,10 @@ class ModelRunner:
         if self.vllm_config.speculative_config is not None:
             from vllm_b200.spec_decode import make_drafter
             self.drafter = make_drafter(self.vllm_config, self)
+        self.spec_hidden = None
+        if getattr(self.drafter, "needs_hidden", False):
+            self.spec_hidden = torch.zeros(self.max_num_reqs, self.vllm_config.model_config.hidden_size,
+                                           dtype=self.dtype, device=self.device)
         self.lora_manager = None
         if self.vllm_config.lora_config is not None:
             from vllm_b200.lora import LoRAModelManager
@@ -603,7 +608,10 @@ class ModelRunner:
             if has_spec:
                 return self._verify_spec(so, hidden, states, rows, ns, cu, t0)
             last_idx = torch.from_numpy(cu[1:].astype(np.int64) - 1).to(self.device, non_blocking=True)
-            logits = self.model.compute_logits(hidden[last_idx])
+            last_hidden = hidden[last_idx]
+            if self.spec_hidden is not None:        # hidden-state proposers (Medusa) read the newest position's state
+                self.spec_hidden.index_copy_(0, torch.from_numpy(rows.astype(np.int64)).to(self.device), last_hidden)
+            logits = self.model.compute_logits(last_hidden)
             smd = self._sampling_metadata(states, rows, nb, simple)
             bitmask = self._gather_bitmask(so, states) if so.grammar_bitmask is not None else None
             so_out = self.sampler(logits, smd, bitmask)
@@ -816,6 +824,9 @@ class ModelRunner:
             out_ids.append(acc)
             # rejected drafts' KV slots are simply overwritten next step
             self.num_computed_cpu[r] = total_after[j] - (k + 1 - len(acc))
+            if self.spec_hidden is not None and acc:
+                # state of the position that produced the last emitted token
+                self.spec_hidden[r] = hidden[int(cu[j + 1]) - k - 1 + len(acc) - 1]
         spec_ids = self.drafter.propose(self, rows, out_ids) if self.drafter is not None else None
         return ModelRunnerOutput(req_ids=req_ids, req_id_to_index={r: i for i, r in enumerate(req_ids)},
                                  sampled_token_ids=out_ids, spec_token_ids=spec_ids,
