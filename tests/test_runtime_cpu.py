@@ -116,3 +116,31 @@ def test_cli_bench_and_platform(capsys):
     out = capsys.readouterr().out
     res = json.loads(out[out.index("{"):])
     assert res["num_requests"] == 4 and res["total_output_tokens"] == 16
+
+
+@pytest.mark.parametrize("dcp", [1, 2])
+def test_deepseek_tp2_with_decode_context_parallel(dcp):
+    """MLA + MoE model on 2 worker processes; with dcp=2 the latent cache is sharded by position across the two
+    ranks (each stores every other token) and partial attention is merged by log-sum-exp — same tokens as TP=1."""
+    import torch
+    from tests.utils import make_hf_model, make_llm
+    from vllm_b200 import SamplingParams
+    hf = make_hf_model("deepseek-tiny")
+    w = [(k, v.clone()) for k, v in hf.state_dict().items()]
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 8]}, {"prompt_token_ids": list(range(10, 47))}]
+    sp = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True)
+    llm = make_llm("deepseek-tiny", weights=w)
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    # chunked prefill (16-token budget) exercises "previous context on other ranks + current chunk local"
+    llm = make_llm("deepseek-tiny", tensor_parallel_size=2, decode_context_parallel_size=dcp,
+                   distributed_executor_backend="mp", block_size=16, max_num_batched_tokens=16)
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": w})
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    if dcp > 1:
+        specs = ex.collective_rpc("get_kv_cache_specs")
+        s0 = next(iter(specs[0].values()))
+        assert s0.dcp == 2 and s0.block_size == 32 and s0.phys_block_size == 16
+    llm.shutdown()
+    assert got == ref

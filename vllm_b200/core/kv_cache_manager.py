@@ -53,10 +53,16 @@ class MLAAttentionSpec(KVCacheSpec):
     """One latent vector (kv_lora_rank + rope dims) per token, no K/V split."""
     head_size: int = 576
     dtype_size: int = 2
+    dcp: int = 1      # decode-context-parallel degree: ``block_size`` counts sequence positions, of which this
+                      # rank stores every dcp-th (block_size / dcp physical slots per block)
+
+    @property
+    def phys_block_size(self) -> int:
+        return self.block_size // self.dcp
 
     @property
     def page_size_bytes(self) -> int:
-        return self.block_size * self.head_size * self.dtype_size
+        return self.phys_block_size * self.head_size * self.dtype_size
 
 
 @dataclass(frozen=True)

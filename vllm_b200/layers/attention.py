@@ -94,7 +94,56 @@ class MLAAttentionCore(nn.Module):
         _LAYER_REGISTRY[prefix] = self  # type: ignore[assignment]
 
     def get_kv_cache_spec(self, block_size: int, dtype_size: int) -> KVCacheSpec:
-        return MLAAttentionSpec(block_size=block_size, head_size=self.head_size, dtype_size=dtype_size)
+        from vllm_b200.parallel.state import get_dcp_group
+        d = get_dcp_group().world_size
+        return MLAAttentionSpec(block_size=block_size * d, head_size=self.head_size, dtype_size=dtype_size, dcp=d)
+
+    def _forward_dcp(self, q_nope_abs, q_pe, kv_c, k_pe, md, kv_cache) -> torch.Tensor:
+        """Decode context parallelism (reference: config/parallel.py:342-388, v1/attention/ops/dcp.py): the latent
+        cache — identical on every TP rank without DCP — is sharded by position (token p lives on rank p % d), so
+        the group holds d x more context.  Queries of all ranks are gathered, every rank attends over its shard of
+        the *previous* context, partial results are merged with their log-sum-exp across the group; the tokens of
+        the current step are attended locally (their latents were just computed on every rank)."""
+        from vllm_b200.ops import ref
+        from vllm_b200.parallel.state import get_dcp_group
+        g = get_dcp_group()
+        d, r = g.world_size, g.rank_in_group
+        R = self.kv_lora_rank
+        ops.concat_and_cache_mla(kv_c, k_pe, kv_cache, md.slot_mapping)       # non-owned positions carry slot -1
+        T, h, _ = q_nope_abs.shape
+        qn_all = g.all_gather(q_nope_abs.contiguous(), dim=1)                 # [T, d*h, R]
+        qp_all = g.all_gather(q_pe.contiguous(), dim=1)
+        qsl = (md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()).tolist()
+        sls = (md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()).tolist()
+        bs = kv_cache.shape[1]
+        o_ctx = torch.zeros(T, d * h, R, dtype=torch.float32, device=q_nope_abs.device)
+        lse_ctx = torch.full((T, d * h), float("-inf"), dtype=torch.float32, device=q_nope_abs.device)
+        o_new = torch.zeros(T, h, R, dtype=torch.float32, device=q_nope_abs.device)
+        lse_new = torch.full((T, h), float("-inf"), dtype=torch.float32, device=q_nope_abs.device)
+        new_lat = torch.cat((kv_c, k_pe), dim=-1)
+        for i in range(md.num_reqs):
+            s, e = qsl[i], qsl[i + 1]
+            if e <= s:
+                continue
+            ctx = sls[i] - (e - s)                                             # positions before this step's tokens
+            n_loc = (ctx - r + d - 1) // d if ctx > r else 0                   # ... of which this rank stores n_loc
+            if n_loc > 0:
+                nb = (n_loc + bs - 1) // bs
+                lat = kv_cache[md.block_table[i, :nb].long()].reshape(nb * bs, -1)[:n_loc]
+                o_ctx[s:e], lse_ctx[s:e] = ref.mla_partial_attention(qn_all[s:e], qp_all[s:e], lat, self.scale, R)
+            o_new[s:e], lse_new[s:e] = ref.mla_partial_attention(q_nope_abs[s:e], q_pe[s:e], new_lat[s:e], self.scale, R,
+                                                                 causal_offset=0)
+        # merge the context partials of the d ranks: softmax-weighted by their lse
+        lse_all = g.all_gather(lse_ctx[..., None].contiguous(), dim=-1)       # [T, d*h, d]
+        lse_tot = torch.logsumexp(lse_all, dim=-1)
+        w = torch.exp(lse_ctx - lse_tot).nan_to_num(0.0)                      # ranks without context contribute 0
+        o_all = g.all_reduce((o_ctx * w[..., None]).contiguous())
+        o_c, lse_c = o_all[:, r * h:(r + 1) * h], lse_tot[:, r * h:(r + 1) * h]
+        # merge context and current-step parts for this rank's heads
+        m = torch.maximum(lse_c, lse_new)
+        wc, wn = torch.exp(lse_c - m).nan_to_num(0.0), torch.exp(lse_new - m)
+        out = (o_c * wc[..., None] + o_new * wn[..., None]) / (wc + wn)[..., None]
+        return out.to(q_nope_abs.dtype)
 
     def forward(self, q_nope_abs: torch.Tensor, q_pe: torch.Tensor, kv_c: torch.Tensor, k_pe: torch.Tensor
                 ) -> torch.Tensor:
@@ -105,5 +154,8 @@ class MLAAttentionCore(nn.Module):
             raise RuntimeError(f"MLA layer {self.layer_name!r} has no KV cache bound")
         if md is None or kv_cache is None:
             return torch.zeros_like(q_nope_abs)
+        from vllm_b200.parallel.state import get_dcp_group
+        if get_dcp_group().world_size > 1:
+            return self._forward_dcp(q_nope_abs, q_pe, kv_c, k_pe, md, kv_cache)
         ops.concat_and_cache_mla(kv_c, k_pe, kv_cache, md.slot_mapping)
         return ops.mla_attention(q_nope_abs, q_pe, kv_cache, md, self.scale, self.kv_lora_rank)

@@ -218,6 +218,26 @@ def mla_decode_attention(q_nope_abs: torch.Tensor, q_pe: torch.Tensor, kv_cache:
     return out
 
 
+def mla_partial_attention(q_abs: torch.Tensor, q_pe: torch.Tensor, lat: torch.Tensor, scale: float, kv_lora_rank: int,
+                          causal_offset: Optional[int] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Attention of q [q, H, R]/[q, H, P] over latent rows ``lat`` [k, R+P]; returns (out [q,H,R] fp32, lse [q,H]).
+    ``causal_offset``: query i may see keys 0..causal_offset+i (None = all keys).  k = 0 gives (0, -inf)."""
+    Q, H, R = q_abs.shape
+    if lat.shape[0] == 0:
+        return (torch.zeros(Q, H, R, dtype=torch.float32, device=q_abs.device),
+                torch.full((Q, H), float("-inf"), dtype=torch.float32, device=q_abs.device))
+    lf = lat.float()
+    kc, kp = lf[:, :kv_lora_rank], lf[:, kv_lora_rank:]
+    att = (torch.einsum("qhr,kr->qhk", q_abs.float(), kc) + torch.einsum("qhp,kp->qhk", q_pe.float(), kp)) * scale
+    if causal_offset is not None:
+        qi = torch.arange(Q, device=att.device)[:, None, None]
+        kj = torch.arange(lat.shape[0], device=att.device)[None, None, :]
+        att = att.masked_fill(kj > qi + causal_offset, float("-inf"))
+    lse = torch.logsumexp(att, dim=-1)
+    p = torch.exp(att - lse[..., None])
+    return torch.einsum("qhk,kr->qhr", p, kc), lse
+
+
 # -------------------------------------------------------------- sampling
 def apply_penalties(logits: torch.Tensor, prompt_mask: torch.Tensor, output_counts: torch.Tensor,
                     presence: torch.Tensor, frequency: torch.Tensor, repetition: torch.Tensor) -> torch.Tensor:

@@ -145,7 +145,12 @@ class ModelRunner:
         self.max_num_tokens = self.sc.max_num_batched_tokens
         self.max_model_len = self.sc.max_model_len
         self.block_size = self.cc.block_size
-        self.max_blocks_per_req = cdiv(self.max_model_len, self.block_size) + 1
+        # decode context parallelism: one block-table entry covers block_size * dcp sequence positions, of which
+        # this rank stores every dcp-th one (layers/attention.py MLAAttentionCore._forward_dcp)
+        self.dcp = max(vllm_config.parallel_config.decode_context_parallel_size, 1)
+        self.dcp_rank = 0
+        self.vblock = self.block_size * self.dcp
+        self.max_blocks_per_req = cdiv(self.max_model_len, self.vblock) + 1
         self.vocab_size = self.mc.vocab_size
         self.model: Optional[torch.nn.Module] = None
         self.sampler = Sampler()
@@ -244,6 +249,14 @@ class ModelRunner:
     def initialize_kv_cache(self, cfg: KVCacheConfig) -> None:
         from vllm_b200.core.kv_cache_manager import MambaSpec, MLAAttentionSpec
         self.kv_cache_config = cfg
+        if self.dcp > 1:
+            from vllm_b200.parallel.state import get_dcp_group
+            self.dcp_rank = max(get_dcp_group().rank_in_group, 0)
+            if not all(isinstance(g.spec, MLAAttentionSpec) for g in cfg.kv_cache_groups):
+                raise NotImplementedError("decode context parallelism is implemented for MLA (latent-cache) models")
+            if self.use_cuda_graph:
+                logger.warning("decode context parallelism runs eagerly (per-request merge on the host)")
+                self.use_cuda_graph = False
         self.num_kv_groups = max(len(cfg.kv_cache_groups), 1)
         kvd = self._kv_dtype()
         from vllm_b200 import envs
@@ -263,7 +276,7 @@ class ModelRunner:
                                                        device=self.device)
                     continue
                 if isinstance(s, MLAAttentionSpec):
-                    shape = (cfg.num_blocks, s.block_size, s.head_size)
+                    shape = (cfg.num_blocks, s.phys_block_size, s.head_size)
                 else:
                     shape = (cfg.num_blocks, 2, s.num_kv_heads, s.block_size, s.head_size)
                 self.kv_caches[name] = torch.zeros(shape, dtype=kvd, device=self.device)
@@ -427,7 +440,12 @@ class ModelRunner:
         bs = self.block_size
         for g in range(self.num_kv_groups):
             bt = self.block_tables_cpu[g]
-            slots = bt[row_of_tok, pos // bs].astype(np.int64) * bs + pos % bs
+            if self.dcp > 1:
+                d, vb = self.dcp, self.vblock
+                slots = bt[row_of_tok, pos // vb].astype(np.int64) * bs + (pos % vb) // d
+                slots = np.where(pos % d == self.dcp_rank, slots, -1)      # positions stored by another rank
+            else:
+                slots = bt[row_of_tok, pos // bs].astype(np.int64) * bs + pos % bs
             stg.slots[g][:T] = torch.from_numpy(slots)
         if len(fix):
             stg.fix_idx[:len(fix)] = torch.from_numpy(fix)
@@ -438,7 +456,7 @@ class ModelRunner:
         return rows, ns, cu, T, max_q, max_s, len(fix)
 
     def _h2d(self, stg: _Staging, rows, nb, T, pad_b, pad_t, max_s, n_fix) -> None:
-        nbk = cdiv(max_s, self.block_size)
+        nbk = cdiv(max_s, self.vblock)
         self.h2d_bytes += T * (4 + 8) + (nb + 1) * 4 + nb * 4 + self.num_kv_groups * (T * 8 + nb * nbk * 4)
         nbc = True
         self.input_ids[:T].copy_(stg.input_ids[:T], non_blocking=nbc)
@@ -465,7 +483,7 @@ class ModelRunner:
                 torch.arange(T + 1, T + 1 + pad_b - nb, dtype=torch.int32, device=self.device))
 
     def _make_metadata(self, nb, T, max_q, max_s, decode_only, cpu_qsl=None, cpu_sl=None) -> dict[int, AttentionMetadata]:
-        nbk = max(cdiv(max_s, self.block_size), 1)
+        nbk = max(cdiv(max_s, self.vblock), 1)
         out = {}
         for g in range(self.num_kv_groups):
             out[g] = AttentionMetadata(
