@@ -144,3 +144,26 @@ def test_deepseek_tp2_with_decode_context_parallel(dcp):
         assert s0.dcp == 2 and s0.block_size == 32 and s0.phys_block_size == 16
     llm.shutdown()
     assert got == ref
+
+
+def test_mixtral_expert_parallel_tp2():
+    """--enable-expert-parallel: each of the 2 ranks owns 2 whole experts (expert map), combine = all-reduce."""
+    from tests.utils import make_hf_model, make_llm
+    from vllm_b200 import SamplingParams
+    hf = make_hf_model("mixtral-tiny")
+    w = [(k, v.clone()) for k, v in hf.state_dict().items()]
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 8]}, {"prompt_token_ids": list(range(10, 40))}]
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    llm = make_llm("mixtral-tiny", weights=w)
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("mixtral-tiny", tensor_parallel_size=2, enable_expert_parallel=True, distributed_executor_backend="mp")
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": w})
+
+    def local_experts(worker):
+        return [m.local_experts for m in worker.runner.model.modules() if hasattr(m, "local_experts")][0]
+    assert ex.collective_rpc(local_experts) == [2, 2]
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    assert got == ref
