@@ -167,3 +167,36 @@ def test_mixtral_expert_parallel_tp2():
     got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
     llm.shutdown()
     assert got == ref
+
+
+def test_data_parallel_engines_load_balanced():
+    """2 engine-core processes behind the load-balancing async client: all requests finish, both engines serve."""
+    import asyncio
+    from vllm_b200 import SamplingParams
+    from vllm_b200.engine.arg_utils import EngineArgs
+    from vllm_b200.engine.async_llm import AsyncLLM
+
+    async def main():
+        ea = EngineArgs(model="llama-tiny", device="cpu", dtype="float32", max_model_len=128, max_num_seqs=8,
+                        max_num_batched_tokens=128, kv_cache_memory_bytes=8 << 20, data_parallel_size=2,
+                        disable_log_stats=True)
+        eng = AsyncLLM.from_engine_args(ea)
+        sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+        used = set()
+
+        async def one(i):
+            last = None
+            async for o in eng.generate({"prompt_token_ids": [3 + i, 9, 27, 81]}, sp, f"r{i}"):
+                last = o
+            return last
+        tasks = [asyncio.create_task(one(i)) for i in range(8)]
+        await asyncio.sleep(0)
+        outs = await asyncio.gather(*tasks)
+        used = set(eng.engine_core.engines_seen) if hasattr(eng.engine_core, "engines_seen") else set()
+        eng.shutdown()
+        return outs, used
+    outs, used = asyncio.run(main())
+    assert all(o is not None and len(o.outputs[0].token_ids) == 6 for o in outs)
+    # same prompt → same tokens regardless of which replica served it
+    assert outs[0].outputs[0].token_ids == outs[0].outputs[0].token_ids
+    assert used == {0, 1}

@@ -377,6 +377,7 @@ class DPLBAsyncMPClient(AsyncMPClient):
     def __init__(self, vllm_config: VllmConfig, log_stats: bool = False) -> None:
         super().__init__(vllm_config, log_stats)
         self.inflight: list[int] = [0] * self.num_engines
+        self.engines_seen: set[int] = set()
         self.owner: dict[str, int] = {}
         self._rr = 0
 
@@ -390,6 +391,7 @@ class DPLBAsyncMPClient(AsyncMPClient):
             self._rr += 1
         self.inflight[i] += 1
         self.owner[r.request_id] = i
+        self.engines_seen.add(i)
         return self.engine_ids[i]
 
     def _on_outputs(self, outs: EngineCoreOutputs) -> None:
