@@ -1,0 +1,74 @@
+"""Full serving stack in a subprocess (reference technique: tests/utils.py ``RemoteOpenAIServer``): ``vllm_b200 serve``
+→ uvicorn → AsyncLLM → ZMQ → EngineCore process → worker, exercised over real HTTP with the benchmark client."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import pytest
+import requests
+
+from vllm_b200.utils import get_open_port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def server():
+    port = get_open_port()
+    env = dict(os.environ, PYTHONPATH=ROOT, VLLM_LOGGING_LEVEL="WARNING")
+    cmd = [sys.executable, "-m", "vllm_b200", "serve", "llama-tiny", "--device", "cpu", "--dtype", "float32",
+           "--max-model-len", "256", "--max-num-seqs", "8", "--max-num-batched-tokens", "128",
+           "--kv-cache-memory-bytes", str(16 << 20), "--host", "127.0.0.1", "--port", str(port)]
+    proc = subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    url = f"http://127.0.0.1:{port}"
+    deadline = time.time() + 120
+    while time.time() < deadline:
+        if proc.poll() is not None:
+            pytest.fail("server exited during start-up")
+        try:
+            if requests.get(url + "/health", timeout=1).status_code == 200:
+                break
+        except requests.RequestException:
+            time.sleep(0.5)
+    else:
+        proc.terminate()
+        pytest.fail("server did not become healthy")
+    yield url
+    proc.terminate()
+    try:
+        proc.wait(timeout=20)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+
+
+def test_http_completions_chat_and_stream(server):
+    r = requests.post(server + "/v1/completions", json={"model": "llama-tiny", "prompt": [5, 6, 7, 8], "max_tokens": 5,
+                                                         "temperature": 0}, timeout=60).json()
+    assert r["usage"]["completion_tokens"] == 5
+    r = requests.post(server + "/v1/chat/completions", json={"model": "llama-tiny", "max_tokens": 4, "temperature": 0,
+                                                              "messages": [{"role": "user", "content": "hi"}]},
+                      timeout=60).json()
+    assert r["choices"][0]["message"]["role"] == "assistant" and r["usage"]["completion_tokens"] == 4
+    chunks = 0
+    with requests.post(server + "/v1/completions", json={"model": "llama-tiny", "prompt": "abc", "max_tokens": 6,
+                                                          "temperature": 0, "stream": True}, stream=True, timeout=60) as s:
+        for line in s.iter_lines():
+            if line.startswith(b"data:") and b"[DONE]" not in line:
+                chunks += 1
+    assert chunks >= 6
+    m = requests.get(server + "/metrics", timeout=10).text
+    assert "vllm:generation_tokens" in m or "generation_tokens" in m
+
+
+def test_bench_serve_against_live_server(server):
+    from vllm_b200.benchmarks import bench_serve
+    args = argparse.Namespace(base_url=server, model="llama-tiny", api_key=None, dataset_name="random", num_prompts=12,
+                              input_len=24, output_len=6, range_ratio=0.0, prefix_len=0, vocab_size=500,
+                              request_rate=float("inf"), burstiness=1.0, max_concurrency=4, seed=0)
+    res = bench_serve(args)
+    assert res["completed"] == 12 and res["failed"] == 0
+    assert res["output_throughput"] > 0 and res["ttft_ms"]["mean"] > 0
+    json.dumps(res)
