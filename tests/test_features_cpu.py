@@ -251,3 +251,31 @@ def test_batch_position_invariance_on_reference_path():
     mixed = llm.generate(others[:2] + [target] + others[2:], sp)[2].outputs[0].token_ids
     llm.shutdown()
     assert alone == mixed
+
+
+def test_structured_outputs_choice_regex_json():
+    """Built-in grammar back-end on the byte tokenizer: outputs satisfy the constraint and the request finishes as soon
+    as the constraint admits no continuation."""
+    import json
+    import re
+    from vllm_b200.sampling_params import StructuredOutputsParams
+    llm = make_llm("llama-tiny")
+
+    def gen(so, seed):
+        sp = SamplingParams(max_tokens=60, temperature=0.9, seed=seed, structured_outputs=so)
+        return llm.generate([{"prompt": "hello"}], sp)[0].outputs[0]
+    for seed in range(3):
+        o = gen(StructuredOutputsParams(choice=["yes", "no", "maybe"]), seed)
+        assert o.text in ("yes", "no", "maybe") and o.finish_reason == "stop"
+        o = gen(StructuredOutputsParams(regex=r"[0-9]{3}-[a-c]{2}"), seed)
+        assert re.fullmatch(r"[0-9]{3}-[a-c]{2}", o.text) and o.finish_reason == "stop"
+    schema = {"type": "object", "properties": {"name": {"type": "string", "maxLength": 4}, "age": {"type": "integer", "minimum": 0},
+                                               "tags": {"type": "array", "items": {"enum": ["a", "b"]}, "maxItems": 2}},
+              "required": ["name", "age", "tags"]}
+    o = gen(StructuredOutputsParams(json=schema), 1)
+    if o.finish_reason == "stop":                       # (a sampled integer may run to max_tokens: digits can continue)
+        obj = json.loads(o.text)
+        assert set(obj) == {"name", "age", "tags"} and isinstance(obj["age"], int) and len(obj["tags"]) <= 2
+    else:
+        assert o.text.startswith("{")
+    llm.shutdown()

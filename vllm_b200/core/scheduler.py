@@ -458,7 +458,15 @@ class Scheduler:
                         new_ids = gen[:k + 1]
                         break
                 if req.use_structured_output and self.structured_output_manager is not None:
-                    req.structured_output_request.accept_tokens(rid, new_ids)
+                    sor = req.structured_output_request
+                    sor.accept_tokens(rid, new_ids)
+                    if (not stopped and sor.grammar is not None and sor.grammar.is_terminated()
+                            and not req.is_finished()):
+                        # the constraint is fully satisfied and admits no continuation: finish here instead of
+                        # waiting for the model to emit end-of-sequence
+                        req.status = RequestStatus.FINISHED_STOPPED
+                        req.stop_reason = "grammar_complete"     # (a string: the last token is content, not a stop token)
+                        stopped = True
             pooled = None
             if mo.pooler_output and idx is not None and idx < len(mo.pooler_output):
                 pooled = mo.pooler_output[idx]

@@ -280,8 +280,18 @@ class StructuredOutputManager:
         for row, rid in enumerate(structured_ids):
             req = requests.get(rid)
             so = req.structured_output_request if req is not None else None
-            if so is None or not so.is_ready() or so.grammar.is_terminated():
+            if so is None or not so.is_ready():
                 bm[row] = -1
+                continue
+            if so.grammar.is_terminated():
+                # nothing may follow a complete match: only end-of-sequence is allowed (the scheduler also finishes
+                # the request as soon as its grammar terminates)
+                eos = self.vllm_config.model_config.eos_token_id
+                if eos is None:
+                    bm[row] = -1
+                else:
+                    bm[row] = 0
+                    bm[row, eos >> 5] = np.int32(np.uint32(1 << (eos & 31)).view(np.int32))
                 continue
             so.grammar.fill_bitmask(bm, row)
         return bm[:n].copy()

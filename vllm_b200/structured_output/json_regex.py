@@ -7,7 +7,7 @@ import json
 import re
 from typing import Any
 
-WS = r"[ \n\t]*"
+WS = r"[ ]?"        # compact output by default (the reference back-ends use the same single-optional-space rule)
 STRING = r'"([^"\\\x00-\x1f]|\\["\\/bfnrt]|\\u[0-9a-fA-F]{4})*"'
 INTEGER = r"-?(0|[1-9][0-9]*)"
 NUMBER = INTEGER + r"(\.[0-9]+)?([eE][+-]?[0-9]+)?"
@@ -31,8 +31,21 @@ def json_schema_to_regex(schema: dict[str, Any], depth: int = 0) -> str:
     if t == "string":
         if "pattern" in schema:
             return '"' + schema["pattern"].strip("^$") + '"'
+        if "minLength" in schema or "maxLength" in schema:
+            lo, hi = int(schema.get("minLength", 0)), schema.get("maxLength")
+            ch = STRING[1:-2]                                  # one (possibly escaped) character
+            return '"' + ch + "{" + str(lo) + "," + ("" if hi is None else str(int(hi))) + '}"'
+        fmt = schema.get("format")
+        if fmt == "date":
+            return r'"[0-9]{4}-(0[1-9]|1[0-2])-(0[1-9]|[12][0-9]|3[01])"'
+        if fmt == "date-time":
+            return r'"[0-9]{4}-(0[1-9]|1[0-2])-(0[1-9]|[12][0-9]|3[01])T([01][0-9]|2[0-3]):[0-5][0-9]:[0-5][0-9](\.[0-9]+)?(Z|[+-][0-9]{2}:[0-9]{2})"'
+        if fmt == "uuid":
+            return r'"[0-9a-f]{8}-[0-9a-f]{4}-[0-9a-f]{4}-[0-9a-f]{4}-[0-9a-f]{12}"'
         return STRING
     if t == "integer":
+        if "minimum" in schema and schema["minimum"] >= 0:
+            return r"(0|[1-9][0-9]*)"
         return INTEGER
     if t == "number":
         return NUMBER
@@ -42,7 +55,12 @@ def json_schema_to_regex(schema: dict[str, Any], depth: int = 0) -> str:
         return NULL
     if t == "array":
         item = json_schema_to_regex(schema.get("items", {}), depth + 1)
-        return r"\[" + WS + f"(({item})({WS},{WS}({item}))*)?" + WS + r"\]"
+        lo, hi = int(schema.get("minItems", 0)), schema.get("maxItems")
+        if lo == 0 and hi is None:
+            return r"\[" + WS + f"(({item})({WS},{WS}({item}))*)?" + WS + r"\]"
+        more = "{" + str(max(lo - 1, 0)) + "," + ("" if hi is None else str(max(int(hi) - 1, 0))) + "}"
+        body = f"({item})({WS},{WS}({item})){more}"
+        return r"\[" + WS + (body if lo > 0 else f"({body})?") + WS + r"\]"
     if t == "object" or "properties" in schema:
         props = schema.get("properties")
         if not props:
