@@ -72,3 +72,24 @@ def test_bench_serve_against_live_server(server):
     assert res["completed"] == 12 and res["failed"] == 0
     assert res["output_throughput"] > 0 and res["ttft_ms"]["mean"] > 0
     json.dumps(res)
+
+
+def test_token_in_token_out_and_render(server):
+    r = requests.post(server + "/inference/v1/generate", json={"token_ids": [5, 6, 7, 8], "sampling_params": {"max_tokens": 4, "temperature": 0}}, timeout=60).json()
+    assert len(r["token_ids"]) == 4 and r["finish_reason"] == "length"
+    ref = requests.post(server + "/v1/completions", json={"model": "llama-tiny", "prompt": [5, 6, 7, 8], "max_tokens": 4, "temperature": 0, "return_token_ids": True}, timeout=60).json()
+    assert ref["usage"]["completion_tokens"] == 4
+    rd = requests.post(server + "/render", json={"messages": [{"role": "user", "content": "hi"}]}, timeout=30).json()
+    assert rd["count"] == len(rd["token_ids"]) > 0 and "hi" in rd["prompt"]
+    back = requests.post(server + "/derender", json={"token_ids": rd["token_ids"]}, timeout=30).json()
+    assert "hi" in back["text"]
+
+
+def test_native_loadgen_against_live_server(server):
+    from vllm_b200.benchmarks import bench_serve
+    args = argparse.Namespace(base_url=server, model="llama-tiny", api_key=None, dataset_name="random", num_prompts=10,
+                              input_len=20, output_len=5, range_ratio=0.0, prefix_len=0, vocab_size=500,
+                              request_rate=50.0, burstiness=1.0, max_concurrency=4, seed=1, native=True)
+    res = bench_serve(args)
+    assert res["completed"] == 10 and res["failed"] == 0
+    assert res["output_throughput"] > 0 and res["ttft_ms"]["mean"] > 0 and res["e2el_ms"]["p99"] >= res["ttft_ms"]["p50"]

@@ -214,7 +214,29 @@ async def bench_serve_async(args) -> dict[str, Any]:
     return summarize(list(timings), wall)
 
 
+def bench_serve_native(args) -> dict[str, Any]:
+    """Same measurement with the C++ epoll load generator (``native/tools/loadgen.cpp``): no Python in the timing
+    path, so client-side overhead does not cap throughput at high request rates."""
+    import subprocess
+    from urllib.parse import urlparse
+    from vllm_b200.native import build_loadgen
+    u = urlparse(args.base_url)
+    cmd = [build_loadgen(), "--host", u.hostname or "127.0.0.1", "--port", str(u.port or 80), "--model", args.model,
+           "--num", str(args.num_prompts), "--input-len", str(args.input_len), "--output-len", str(args.output_len),
+           "--vocab", str(args.vocab_size), "--seed", str(args.seed),
+           "--rate", "0" if args.request_rate == float("inf") else str(args.request_rate),
+           "--concurrency", str(args.max_concurrency or 0)]
+    if args.api_key:
+        cmd += ["--api-key", args.api_key]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if not r.stdout.strip():
+        raise RuntimeError(f"loadgen failed: {r.stderr}")
+    return json.loads(r.stdout)
+
+
 def bench_serve(args) -> dict[str, Any]:
+    if getattr(args, "native", False):
+        return bench_serve_native(args)
     return asyncio.run(bench_serve_async(args))
 
 

@@ -53,6 +53,7 @@ def _bench_parser() -> argparse.ArgumentParser:
     srv.add_argument("--burstiness", type=float, default=1.0)
     srv.add_argument("--max-concurrency", type=int, default=None)
     srv.add_argument("--seed", type=int, default=0)
+    srv.add_argument("--native", action="store_true", help="drive the load with the C++ epoll client")
     srv.add_argument("--output-json", default=None)
     st = sub.add_parser("startup", **common)
     st.add_argument("--output-json", default=None)

@@ -28,7 +28,7 @@ from vllm_b200.engine.exceptions import EngineDeadError
 from vllm_b200.entrypoints.chat_utils import render_chat
 from vllm_b200.entrypoints.openai import protocol as P
 from vllm_b200.logger import init_logger
-from vllm_b200.sampling_params import PoolingParams, RequestOutputKind
+from vllm_b200.sampling_params import PoolingParams, RequestOutputKind, SamplingParams
 from vllm_b200.utils import random_uuid
 from vllm_b200.version import __version__
 
@@ -451,6 +451,60 @@ def build_app(ctx: ServingContext):
                 for i, (x, y) in enumerate(zip(ea, eb))]
         return P.ScoreResponse(model=ctx.model_name, data=data,
                                usage=_usage(sum(len(o.prompt_token_ids) for o in ea + eb), 0)).model_dump()
+
+    # ------------------------------------------- token-in / token-out and render-only fronts
+    # (reference: entrypoints/generate "/inference/v1/generate", entrypoints/scale_out render/derender split — a
+    #  tokenizer-less engine tier behind a separate rendering tier)
+    @app.post("/inference/v1/generate")
+    async def generate_tokens(body: dict, raw: Request):
+        ids = body.get("token_ids") or body.get("prompt_token_ids")
+        if not ids:
+            return _error("token_ids is required")
+        spd = dict(body.get("sampling_params") or {})
+        spd.setdefault("max_tokens", 16)
+        spd["detokenize"] = False
+        try:
+            sp = SamplingParams(**spd)
+        except (TypeError, ValueError) as ex:
+            return _error(str(ex))
+        rid = f"gen-{body.get('request_id') or random_uuid()}"
+        stream = bool(body.get("stream"))
+        gen = ctx.engine.generate({"prompt_token_ids": list(ids)}, sp, rid, priority=int(body.get("priority", 0)))
+        if stream:
+            async def sse():
+                sent = 0
+                async for o in gen:
+                    c = o.outputs[0]
+                    new = c.token_ids[sent:] if len(c.token_ids) >= sent else c.token_ids
+                    sent = len(c.token_ids)
+                    yield "data: " + json.dumps({"request_id": rid, "token_ids": list(new),
+                                                  "finish_reason": c.finish_reason}) + "\n\n"
+                yield "data: [DONE]\n\n"
+            return StreamingResponse(sse(), media_type="text/event-stream")
+        last = None
+        async for o in gen:
+            last = o
+        c = last.outputs[0]
+        return {"request_id": rid, "token_ids": list(c.token_ids), "finish_reason": c.finish_reason,
+                "num_prompt_tokens": len(ids), "num_cached_tokens": getattr(last, "num_cached_tokens", None)}
+
+    @app.post("/v1/chat/completions/render")
+    @app.post("/render")
+    async def render(body: dict):
+        """Chat messages (or a raw prompt) → the exact token ids the engine would see; no generation."""
+        from vllm_b200.entrypoints.chat_utils import render_chat
+        if body.get("messages") is not None:
+            text = render_chat(ctx.tokenizer, body["messages"], ctx.chat_template,
+                               add_generation_prompt=bool(body.get("add_generation_prompt", True)), tools=body.get("tools"))
+        else:
+            text = body.get("prompt", "")
+        ids = ctx.tokenizer.encode(text)
+        return {"prompt": text, "token_ids": list(ids), "count": len(ids), "max_model_len": ctx.max_model_len}
+
+    @app.post("/derender")
+    async def derender(body: dict):
+        return {"text": ctx.tokenizer.decode(list(body.get("token_ids", [])),
+                                             skip_special_tokens=bool(body.get("skip_special_tokens", True)))}
 
     # ------------------------------------------- pooling family (reference: entrypoints/pooling/*)
     async def _encode_many(inputs: list, pp: PoolingParams, tag: str):

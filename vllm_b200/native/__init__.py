@@ -56,3 +56,17 @@ def lib():
         L.vbn_cumem_mapped_bytes.restype = u64
         _LIB = L
     return _LIB or None
+
+
+LOADGEN = os.path.join(os.path.dirname(HERE), "_loadgen")
+
+
+def build_loadgen(force: bool = False) -> str:
+    """Compile ``native/tools/loadgen.cpp`` (epoll-based OpenAI load generator) into ``vllm_b200/_loadgen``."""
+    src = os.path.join(HERE, "tools", "loadgen.cpp")
+    if not force and os.path.exists(LOADGEN) and os.path.getmtime(LOADGEN) >= os.path.getmtime(src):
+        return LOADGEN
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", LOADGEN, src], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"loadgen build failed:\n{r.stderr}")
+    return LOADGEN
