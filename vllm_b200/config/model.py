@@ -150,6 +150,16 @@ PRESETS: dict[str, dict[str, Any]] = {
         architectures=["GPTJForCausalLM"], model_type="gptj", vocab_size=512, n_embd=64, n_layer=2, n_head=4, n_inner=256,
         n_positions=512, rotary_dim=8, layer_norm_epsilon=1e-5, activation_function="gelu_new", bos_token_id=0,
         eos_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
+        architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
+        rope_theta=10000.0, hidden_act="silu", bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
+        tie_word_embeddings=False),
+    "stablelm-tiny": dict(
+        architectures=["StableLmForCausalLM"], model_type="stablelm", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
+        partial_rotary_factor=0.25, rope_theta=10000.0, hidden_act="silu", layer_norm_eps=1e-5, use_qkv_bias=True,
+        bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "bert-tiny": dict(
         architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
         num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,

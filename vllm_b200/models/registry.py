@@ -50,6 +50,14 @@ def supported_archs() -> list[str]:
 
 def resolve_model_cls(arch: str) -> Type[nn.Module]:
     if arch not in _MODELS:
+        # the long tail: any decoder-only HF architecture runs through the Transformers back-end
+        try:
+            import transformers
+            if arch.endswith("ForCausalLM") and hasattr(transformers, arch):
+                from vllm_b200.models.transformers_backend import TransformersForCausalLM
+                return TransformersForCausalLM
+        except ImportError:
+            pass
         raise ValueError(f"architecture {arch!r} is not supported; supported: {supported_archs()}")
     mod, cls = _MODELS[arch]
     if "." not in mod:
