@@ -16,7 +16,9 @@ def _greedy(llm, n=16):
 
 @pytest.mark.parametrize("spec", [dict(method="ngram", num_speculative_tokens=3, prompt_lookup_max=4, prompt_lookup_min=1),
                                   dict(method="draft_model", model="llama-tiny", num_speculative_tokens=3),
-                                  dict(method="medusa", num_speculative_tokens=3)])
+                                  dict(method="medusa", num_speculative_tokens=3),
+                                  dict(method="eagle", num_speculative_tokens=3),
+                                  dict(method="mtp", num_speculative_tokens=2)])
 def test_speculative_decoding_is_lossless(spec):
     """Greedy output with speculation == greedy output without (rejection sampler correctness)."""
     cfg = get_preset_hf_config("llama-tiny")
@@ -29,6 +31,7 @@ def test_speculative_decoding_is_lossless(spec):
     stats = llm.llm_engine.engine_core.engine_core.scheduler
     llm.shutdown()
     assert got == ref
+    assert stats._spec_draft_tokens > 0, "the proposer never produced a draft"
 
 
 @pytest.mark.parametrize("connector,extra", [

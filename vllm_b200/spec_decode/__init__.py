@@ -49,7 +49,10 @@ def make_drafter(vllm_config, runner) -> Optional[object]:
     if sc.method == "medusa":
         from vllm_b200.spec_decode.medusa import MedusaDrafter
         return MedusaDrafter(vllm_config, runner)
-    if sc.method in ("eagle", "eagle3", "mtp", "draft_model"):
+    if sc.method in ("eagle", "eagle3", "mtp"):
+        from vllm_b200.spec_decode.eagle import EagleDrafter
+        return EagleDrafter(vllm_config, runner)
+    if sc.method == "draft_model":
         from vllm_b200.spec_decode.draft_model import DraftModelDrafter
         return DraftModelDrafter(vllm_config, runner)
     raise ValueError(f"unknown speculative method {sc.method!r}")

@@ -164,6 +164,7 @@ class ModelRunner:
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
         self.drafter = None
         self.spec_hidden = None
+        self.step_hidden = None
         self.encoder_cache = None
         self.ec_connector = None
         ecp = os.environ.get("VLLM_B200_EC_SHARED_PATH")
@@ -626,6 +627,9 @@ class ModelRunner:
             if has_spec:
                 return self._verify_spec(so, hidden, states, rows, ns, cu, t0)
             last_idx = torch.from_numpy(cu[1:].astype(np.int64) - 1).to(self.device, non_blocking=True)
+            if getattr(self.drafter, "needs_step_hidden", False):
+                # EAGLE / MTP heads consume the target hidden state of every position computed this step
+                self.step_hidden = (hidden, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
             last_hidden = hidden[last_idx]
             if self.spec_hidden is not None:        # hidden-state proposers (Medusa) read the newest position's state
                 self.spec_hidden.index_copy_(0, torch.from_numpy(rows.astype(np.int64)).to(self.device), last_hidden)
@@ -818,6 +822,8 @@ class ModelRunner:
             idx_list.extend(range(end - k - 1, end))
             draft_lists.append(list(drafts))
             cu_l.append(cu_l[-1] + k + 1)
+        if getattr(self.drafter, "needs_step_hidden", False):
+            self.step_hidden = (hidden, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
         idx = torch.tensor(idx_list, dtype=torch.int64, device=self.device)
         logits = self.model.compute_logits(hidden[idx]).float()
         smd = self._sampling_metadata(states, rows, len(states))
