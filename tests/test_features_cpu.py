@@ -282,3 +282,51 @@ def test_structured_outputs_choice_regex_json():
     else:
         assert o.text.startswith("{")
     llm.shutdown()
+
+
+def test_fp8_kv_cache_close_to_full_precision():
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=3))
+    sp = SamplingParams(max_tokens=2, temperature=0.0, ignore_eos=True, prompt_logprobs=0)
+    p = [{"prompt_token_ids": [(5 * i) % 400 + 3 for i in range(40)]}]
+    res = {}
+    for kvd in ("auto", "fp8"):
+        llm = make_llm("llama-tiny", weights=w, kv_cache_dtype=kvd, max_num_batched_tokens=16)   # chunked: reads the cache
+        o = llm.generate(p, sp)[0]
+        res[kvd] = [list(d.values())[0].logprob for d in o.prompt_logprobs[1:]]
+        if kvd == "fp8":
+            r = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner
+            assert next(iter(r.kv_caches.values())).dtype == torch.float8_e4m3fn
+        llm.shutdown()
+    assert 0 < max(abs(a - b) for a, b in zip(res["auto"], res["fp8"])) < 0.1
+
+
+def test_beam_search_and_parallel_sampling():
+    """beam search beats (or ties) greedy in cumulative log-probability; n>1 returns n distinct seeded samples."""
+    from vllm_b200.sampling_params import BeamSearchParams
+    cfg = get_preset_hf_config("llama-tiny")
+    llm = make_llm("llama-tiny", weights=list(llama_full_weights(cfg, seed=10, scale=0.1)))
+    prompt = {"prompt_token_ids": [5, 17, 99, 3, 250, 41]}
+    g = llm.generate([prompt], SamplingParams(max_tokens=5, temperature=0.0, ignore_eos=True, logprobs=0))[0].outputs[0]
+    bs = llm.beam_search([prompt], BeamSearchParams(beam_width=3, max_tokens=5, ignore_eos=True))[0]
+    best = bs.sequences[0]
+    assert len(best.tokens) == 6 + 5 and best.cum_logprob >= g.cumulative_logprob - 1e-4
+    outs = llm.generate([prompt], SamplingParams(max_tokens=6, temperature=1.0, n=4, seed=5, ignore_eos=True))[0].outputs
+    assert len(outs) == 4 and len({tuple(o.token_ids) for o in outs}) >= 3
+    again = llm.generate([prompt], SamplingParams(max_tokens=6, temperature=1.0, n=4, seed=5, ignore_eos=True))[0].outputs
+    assert [o.token_ids for o in outs] == [o.token_ids for o in again]
+    llm.shutdown()
+
+
+def test_sleep_wake_and_prefix_cache_reset():
+    llm = make_llm("llama-tiny")
+    sp = SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True)
+    p = [{"prompt_token_ids": list(range(3, 70))}]
+    a = llm.generate(p, sp)[0].outputs[0].token_ids
+    llm.sleep(level=1)
+    assert llm.llm_engine.engine_core.engine_core.model_executor.worker.is_sleeping()
+    llm.wake_up()
+    b = llm.generate(p, sp)[0].outputs[0].token_ids
+    assert a == b
+    assert llm.reset_prefix_cache()
+    llm.shutdown()
