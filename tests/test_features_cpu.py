@@ -17,6 +17,7 @@ def _greedy(llm, n=16):
 @pytest.mark.parametrize("spec", [dict(method="ngram", num_speculative_tokens=3, prompt_lookup_max=4, prompt_lookup_min=1),
                                   dict(method="draft_model", model="llama-tiny", num_speculative_tokens=3),
                                   dict(method="medusa", num_speculative_tokens=3),
+                                  dict(method="suffix", num_speculative_tokens=4, prompt_lookup_max=4, prompt_lookup_min=1),
                                   dict(method="eagle", num_speculative_tokens=3),
                                   dict(method="mtp", num_speculative_tokens=2)])
 def test_speculative_decoding_is_lossless(spec):
@@ -330,3 +331,18 @@ def test_sleep_wake_and_prefix_cache_reset():
     assert a == b
     assert llm.reset_prefix_cache()
     llm.shutdown()
+
+
+def test_prompt_embeds_equal_token_prompt():
+    """A prompt passed as embedding rows gives the same continuation as the token ids those rows came from."""
+    cfg = get_preset_hf_config("llama-tiny")
+    llm = make_llm("llama-tiny", weights=list(llama_full_weights(cfg, seed=12)), enable_prefix_caching=False)
+    ids = [5, 17, 99, 3, 250, 41, 8]
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    a = llm.generate([{"prompt_token_ids": ids}], sp)[0].outputs[0].token_ids
+    model = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    with torch.no_grad():
+        emb = model.embed_input_ids(torch.tensor(ids))
+    b = llm.generate([{"prompt_embeds": emb}], sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    assert a == b

@@ -37,6 +37,18 @@ class InputProcessor:
                        data_parallel_rank: Optional[int] = None,
                        kv_transfer_params: Optional[dict] = None) -> tuple[Optional[str], EngineCoreRequest]:
         text, ids, extras = parse_prompt(prompt)
+        embeds_feature = None
+        if ids is None and text is None and extras.get("prompt_embeds") is not None:
+            # prompt given directly as embeddings [n, hidden] (reference: ``EmbedsPrompt``): the positions carry a
+            # dummy token id and the worker splices the rows in exactly like multimodal encoder outputs
+            import torch
+            from vllm_b200.multimodal import hash_item
+            emb = torch.as_tensor(extras["prompt_embeds"])
+            if emb.dim() != 2 or emb.shape[1] != self.mc.hidden_size:
+                raise ValueError(f"prompt_embeds must be [num_tokens, {self.mc.hidden_size}]")
+            ids = [0] * emb.shape[0]
+            embeds_feature = {"modality": "embeds", "hash": hash_item(emb.float().numpy()), "offset": 0,
+                              "length": emb.shape[0], "data": emb}
         if ids is None:
             if text is None:
                 raise ValueError("prompt must contain text or token ids")
@@ -59,6 +71,8 @@ class InputProcessor:
         mm_features = None
         if extras.get("multi_modal_data") and self.mm_processor is not None:
             ids, mm_features = self.mm_processor.process(ids, extras["multi_modal_data"])
+        if embeds_feature is not None:
+            mm_features = (mm_features or []) + [embeds_feature]
         sp = pp = None
         if isinstance(params, SamplingParams):
             sp = params.clone()

@@ -40,12 +40,91 @@ class NgramDrafter:
         return out
 
 
+class SuffixDrafter:
+    """Suffix decoding (reference: v1/spec_decode/suffix_decoding.py): continuation statistics over the request's own
+    tokens AND over everything this server generated before (bounded global table), so repetitive agentic / templated
+    workloads get long accepted drafts.  A draft follows the most frequent successor chain of the longest suffix
+    (``min_n``..``max_n`` tokens) seen so far."""
+
+    def __init__(self, k: int, max_n: int, min_n: int, global_entries: int = 1 << 18) -> None:
+        from collections import Counter, OrderedDict
+        self.k, self.max_n, self.min_n = k, max(max_n, 2), max(min_n, 1)
+        self.Counter = Counter
+        self.local: dict[str, dict] = {}            # req id → {n-gram: Counter(next)}
+        self.indexed: dict[str, int] = {}           # req id → tokens already indexed
+        self.glob: "OrderedDict[tuple, Counter]" = OrderedDict()
+        self.global_entries = global_entries
+
+    def _index(self, table: dict, toks: np.ndarray, start: int) -> None:
+        L = len(toks)
+        for i in range(max(start, 1), L):
+            nxt = int(toks[i])
+            for n in range(self.min_n, min(self.max_n, i) + 1):
+                key = tuple(int(x) for x in toks[i - n:i])
+                c = table.get(key)
+                if c is None:
+                    c = table[key] = self.Counter()
+                c[nxt] += 1
+
+    def _follow(self, tables, ctx: list[int], k: int) -> list[int]:
+        out: list[int] = []
+        seq = list(ctx)
+        for _ in range(k):
+            nxt = None
+            for n in range(min(self.max_n, len(seq)), self.min_n - 1, -1):
+                key = tuple(seq[-n:])
+                for t in tables:
+                    c = t.get(key)
+                    if c:
+                        nxt = c.most_common(1)[0][0]
+                        break
+                if nxt is not None:
+                    break
+            if nxt is None:
+                break
+            out.append(nxt)
+            seq.append(nxt)
+        return out
+
+    def propose(self, runner, rows, sampled: list[list[int]]) -> list[list[int]]:
+        live = set()
+        out = []
+        for j, r in enumerate(rows):
+            rid = runner.req_ids[r]
+            live.add(rid)
+            n = int(runner.num_tokens_cpu[r])
+            toks = runner.token_ids_cpu[r, :n]
+            tab = self.local.setdefault(rid, {})
+            self._index(tab, toks, self.indexed.get(rid, 0))
+            self.indexed[rid] = n
+            room = runner.max_model_len - n - 1
+            if not sampled[j] or room <= 0:
+                out.append([])
+                continue
+            out.append(self._follow((tab, self.glob), toks[-self.max_n:].tolist(), min(self.k, room)))
+        # requests that left the batch donate their statistics to the global table
+        for rid in [x for x in self.local if x not in live and x not in runner.req_index]:
+            for key, c in self.local.pop(rid).items():
+                g = self.glob.get(key)
+                if g is None:
+                    self.glob[key] = c
+                else:
+                    g.update(c)
+                    self.glob.move_to_end(key)
+            self.indexed.pop(rid, None)
+            while len(self.glob) > self.global_entries:
+                self.glob.popitem(last=False)
+        return out
+
+
 def make_drafter(vllm_config, runner) -> Optional[object]:
     sc = vllm_config.speculative_config
     if sc is None:
         return None
     if sc.method == "ngram":
         return NgramDrafter(sc.num_speculative_tokens, sc.prompt_lookup_max, sc.prompt_lookup_min)
+    if sc.method == "suffix":
+        return SuffixDrafter(sc.num_speculative_tokens, sc.prompt_lookup_max, sc.prompt_lookup_min)
     if sc.method == "medusa":
         from vllm_b200.spec_decode.medusa import MedusaDrafter
         return MedusaDrafter(vllm_config, runner)

@@ -530,6 +530,9 @@ class ModelRunner:
                 if enc is not None:
                     enc = enc.to(emb.dtype)
                     self.encoder_cache.put(f["hash"], enc)
+            if enc is None and f.get("modality") == "embeds":            # caller-provided prompt embeddings
+                enc = torch.as_tensor(f["data"]).to(self.device, emb.dtype)
+                self.encoder_cache.put(f["hash"], enc)
             if enc is None:
                 px = torch.as_tensor(f["data"]).to(self.device)
                 enc = self.model.embed_multimodal(px[None])[0].to(emb.dtype)
@@ -608,7 +611,8 @@ class ModelRunner:
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
             if kv_meta:
                 self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
-            mm_emb = self._mm_inputs_embeds(states, rows, ns, cu, T) if self.has_mm else None
+            mm_emb = (self._mm_inputs_embeds(states, rows, ns, cu, T)
+                      if self.has_mm or any(s.mm_features for s in states) else None)
             if lora_batch is not None:
                 from vllm_b200 import lora as _lora
                 _lora.set_batch(lora_batch)
