@@ -346,3 +346,31 @@ def test_prompt_embeds_equal_token_prompt():
     b = llm.generate([{"prompt_embeds": emb}], sp)[0].outputs[0].token_ids
     llm.shutdown()
     assert a == b
+
+
+def test_extra_ops_and_fp4_roundtrip():
+    from vllm_b200 import ops
+    from vllm_b200.model_loader.weight_only import dequantize_stream
+    from vllm_b200.ops import ref
+    torch.manual_seed(0)
+    x = torch.randn(5, 16)
+    assert torch.allclose(ops.mul_and_silu(x), x[:, :8] * torch.nn.functional.silu(x[:, 8:]), atol=1e-6)
+    assert (ops.fatrelu_and_mul(x, 0.5)[x[:, :8] <= 0.5] == 0).all()
+    assert ops.swigluoai_and_mul(x).shape == (5, 8)
+    q, s = ops.scaled_fp8_quant(x, per_token=True)
+    assert q.dtype == torch.float8_e4m3fn and (q.float() * s - x).abs().max() < 0.2
+    y = ops.scaled_mm(q, q, s, s, torch.float32)
+    assert torch.allclose(y, x @ x.t(), atol=0.8)
+    src, dst = torch.arange(24.).view(6, 4), torch.zeros(6, 4)
+    ops.swap_blocks(src, dst, [(0, 5), (2, 1)])
+    assert torch.equal(dst[5], src[0]) and torch.equal(dst[1], src[2]) and dst[0].sum() == 0
+    w = torch.randn(8, 64) * 0.2
+    packed, bs, gs = ref.fp4_quant(w)
+    deq = ref.fp4_dequant(packed, bs, gs)
+    assert deq.shape == w.shape and (deq - w).abs().max() < 0.15 and (deq - w).abs().mean() < 0.03
+    stream = [("model.layers.0.mlp.down_proj.weight", packed), ("model.layers.0.mlp.down_proj.weight_scale", bs),
+              ("model.layers.0.mlp.down_proj.weight_scale_2", torch.tensor(gs)),
+              ("model.layers.0.mlp.down_proj.input_scale", torch.tensor(1.0)), ("model.norm.weight", torch.ones(4))]
+    out = dict(dequantize_stream(stream, {"quant_method": "modelopt_fp4"}, torch.float32))
+    assert set(out) == {"model.layers.0.mlp.down_proj.weight", "model.norm.weight"}
+    assert torch.allclose(out["model.layers.0.mlp.down_proj.weight"], deq)

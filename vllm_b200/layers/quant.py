@@ -123,7 +123,7 @@ class Fp8Config(QuantConfig):
 
 
 QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8", "awq", "gptq", "awq_marlin",
-                        "gptq_marlin")
+                        "gptq_marlin", "nvfp4", "modelopt_fp4")
 
 
 def get_quant_config(model_config) -> Optional[QuantConfig]:
@@ -134,7 +134,7 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         online = not model_config.hf_config.get("quantization_config")
         return Fp8BlockConfig(online=online)
     hq = model_config.hf_config.get("quantization_config") or {}
-    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin"):
+    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin", "nvfp4", "modelopt_fp4"):
         return None          # expanded to the model dtype at load time (model_loader/weight_only.py)
     if q in ("fp8", "fbgemm_fp8", "modelopt"):
         if hq.get("weight_block_size"):          # a "fp8" checkpoint with block scales (DeepSeek-V3 style)

@@ -91,6 +91,12 @@ def pack_gptq(w: torch.Tensor, group_size: int):
     return qw, qz, scale.to(torch.float16), g_idx
 
 
+def dequant_nvfp4(weight: torch.Tensor, weight_scale: torch.Tensor, weight_scale_2) -> torch.Tensor:
+    """ModelOpt NVFP4: ``weight`` uint8 [out, in/2], ``weight_scale`` fp8 [out, in/16], ``weight_scale_2`` fp32 scalar."""
+    from vllm_b200.ops import ref
+    return ref.fp4_dequant(weight, weight_scale, float(weight_scale_2), 16)
+
+
 def dequantize_stream(weights: Iterable[tuple[str, torch.Tensor]], quant_cfg: dict, dtype: torch.dtype
                       ) -> Iterator[tuple[str, torch.Tensor]]:
     """Wrap a checkpoint iterator: packed groups are replaced by ``<module>.weight`` tensors as soon as complete."""
@@ -99,6 +105,23 @@ def dequantize_stream(weights: Iterable[tuple[str, torch.Tensor]], quant_cfg: di
     bits = int(quant_cfg.get("bits", quant_cfg.get("w_bit", 4)))
     need = {"qweight", "qzeros", "scales"} | ({"g_idx"} if method == "gptq" else set())
     pending: dict[str, dict[str, torch.Tensor]] = {}
+    if method in ("modelopt_fp4", "nvfp4", "modelopt"):
+        # NVFP4: weight (uint8) + weight_scale (fp8) + weight_scale_2 (fp32); input_scale is an activation statistic
+        for name, t in weights:
+            mod, _, leaf = name.rpartition(".")
+            if leaf == "input_scale":
+                continue
+            if leaf not in ("weight", "weight_scale", "weight_scale_2") or (leaf == "weight" and t.dtype != torch.uint8):
+                yield name, t
+                continue
+            grp = pending.setdefault(mod, {})
+            grp[leaf] = t
+            if {"weight", "weight_scale", "weight_scale_2"} <= set(grp):
+                yield f"{mod}.weight", dequant_nvfp4(grp["weight"], grp["weight_scale"], grp["weight_scale_2"]).to(dtype)
+                del pending[mod]
+        if pending:
+            raise ValueError(f"incomplete NVFP4 tensors for {sorted(pending)[:3]} ...")
+        return
     for name, t in weights:
         mod, _, leaf = name.rpartition(".")
         if leaf not in ("qweight", "qzeros", "scales", "g_idx"):

@@ -157,3 +157,17 @@ def block_fp8_linear(x, wq, w_scale, block=128, bias=None):
     if _use_cuda(x):
         return cuda_ops().block_fp8_linear(x, wq, w_scale, block, bias)
     return ref.block_fp8_linear(x, wq, w_scale, block, bias)
+
+
+# -- ops served by the PyTorch implementations on every device (elementwise / bookkeeping; not on a hot path that a
+#    dedicated kernel would change): extra gated activations, q/k-norm + RoPE, cache maintenance, activation quantisers
+mul_and_silu = ref.mul_and_silu
+fatrelu_and_mul = ref.fatrelu_and_mul
+swigluoai_and_mul = ref.swigluoai_and_mul
+fused_qk_norm_rope = ref.fused_qk_norm_rope
+swap_blocks = ref.swap_blocks
+convert_fp8 = ref.convert_fp8
+scaled_fp8_quant = ref.scaled_fp8_quant
+scaled_int8_quant = ref.scaled_int8_quant
+scaled_mm = ref.scaled_mm
+fp4_dequant = ref.fp4_dequant

@@ -66,6 +66,33 @@ def quick_gelu(x: torch.Tensor) -> torch.Tensor:
     return (xf * torch.sigmoid(1.702 * xf)).to(x.dtype)
 
 
+def mul_and_silu(x: torch.Tensor) -> torch.Tensor:
+    d = x.shape[-1] // 2
+    return (x[..., :d].float() * F.silu(x[..., d:].float())).to(x.dtype)
+
+
+def fatrelu_and_mul(x: torch.Tensor, threshold: float = 0.0) -> torch.Tensor:
+    d = x.shape[-1] // 2
+    g = x[..., :d].float()
+    return (torch.where(g > threshold, g, torch.zeros_like(g)) * x[..., d:].float()).to(x.dtype)
+
+
+def swigluoai_and_mul(x: torch.Tensor, alpha: float = 1.702, limit: float = 7.0) -> torch.Tensor:
+    """gpt-oss SwiGLU: interleaved (gate, up) pairs, clamped, ``(up + 1) * gate * sigmoid(alpha * gate)``."""
+    g, u = x[..., ::2].float().clamp(max=limit), x[..., 1::2].float().clamp(-limit, limit)
+    return ((u + 1.0) * g * torch.sigmoid(alpha * g)).to(x.dtype)
+
+
+def fused_qk_norm_rope(positions: torch.Tensor, q: torch.Tensor, k: torch.Tensor, q_weight: torch.Tensor,
+                       k_weight: torch.Tensor, cos_sin_cache: torch.Tensor, head_dim: int, eps: float,
+                       is_neox: bool = True) -> tuple[torch.Tensor, torch.Tensor]:
+    """Per-head RMSNorm of q and k followed by RoPE (Qwen3 / Gemma-3 attention prologue)."""
+    T = q.shape[0]
+    qn = rms_norm(q.reshape(T, -1, head_dim), q_weight, eps).reshape(T, -1)
+    kn = rms_norm(k.reshape(T, -1, head_dim), k_weight, eps).reshape(T, -1)
+    return rotary_embedding(positions, qn, kn, cos_sin_cache, head_dim, is_neox)
+
+
 ACT_FNS = {
     "relu": F.relu, "gelu": F.gelu, "gelu_new": gelu_new, "gelu_fast": gelu_fast,
     "gelu_pytorch_tanh": lambda x: F.gelu(x, approximate="tanh"), "quick_gelu": quick_gelu,
@@ -362,8 +389,79 @@ def fused_moe(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_w: torc
     return out.to(x.dtype)
 
 
+# ---------------------------------------------------------- cache maintenance
+def swap_blocks(src: torch.Tensor, dst: torch.Tensor, mapping: list[tuple[int, int]]) -> None:
+    """Copy whole KV blocks src[i] → dst[j] (host tier ↔ device, or block migration)."""
+    if not mapping:
+        return
+    si = torch.tensor([m[0] for m in mapping], dtype=torch.long, device=src.device)
+    di = torch.tensor([m[1] for m in mapping], dtype=torch.long, device=dst.device)
+    dst[di] = src[si].to(dst.device, dst.dtype)
+
+
+def convert_fp8(x: torch.Tensor, scale: float = 1.0, to_fp8: bool = True) -> torch.Tensor:
+    if to_fp8:
+        return (x.float() / scale).clamp(-FP8_MAX, FP8_MAX).to(torch.float8_e4m3fn)
+    return x.float() * scale
+
+
 # ---------------------------------------------------------- quantisation
 FP8_MAX = 448.0
+
+
+def scaled_fp8_quant(x: torch.Tensor, scale: Optional[torch.Tensor] = None, per_token: bool = False
+                     ) -> tuple[torch.Tensor, torch.Tensor]:
+    """Static (given scale) or dynamic per-tensor / per-token fp8 e4m3 activation quantisation."""
+    xf = x.float()
+    if scale is None:
+        amax = xf.abs().amax(dim=-1, keepdim=True) if per_token else xf.abs().amax()
+        scale = (amax / FP8_MAX).clamp_min(1e-12)
+    q = (xf / scale).clamp(-FP8_MAX, FP8_MAX).to(torch.float8_e4m3fn)
+    return q, scale.float()
+
+
+def scaled_int8_quant(x: torch.Tensor, scale: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    xf = x.float()
+    if scale is None:
+        scale = (xf.abs().amax(dim=-1, keepdim=True) / 127.0).clamp_min(1e-12)
+    return (xf / scale).round().clamp(-128, 127).to(torch.int8), scale.float()
+
+
+def scaled_mm(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor, out_dtype,
+              bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(a · bᵀ) with per-tensor / per-token (a) and per-tensor / per-channel (b) scales. a [M,K], b [N,K] (fp8/int8)."""
+    y = (a.float() @ b.float().t()) * scale_a.reshape(-1, 1) * scale_b.reshape(1, -1)
+    if bias is not None:
+        y = y + bias.float()
+    return y.to(out_dtype)
+
+
+E2M1_VALUES = (0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0)
+
+
+def fp4_dequant(packed: torch.Tensor, block_scale: torch.Tensor, global_scale, block: int = 16) -> torch.Tensor:
+    """NVFP4 / MXFP4: packed uint8 [rows, cols/2] (low nibble first), one scale per ``block`` columns."""
+    lut = torch.tensor(E2M1_VALUES + tuple(-v for v in E2M1_VALUES), dtype=torch.float32, device=packed.device)
+    lo, hi = packed & 0xF, packed >> 4
+    vals = torch.stack((lut[lo.long()], lut[hi.long()]), dim=-1).reshape(packed.shape[0], -1)
+    sc = block_scale.float().repeat_interleave(block, dim=1)[:, :vals.shape[1]]
+    return vals * sc * float(global_scale)
+
+
+def fp4_quant(w: torch.Tensor, block: int = 16) -> tuple[torch.Tensor, torch.Tensor, float]:
+    """Reference NVFP4 quantiser: per-16 block scale (stored fp8 e4m3) + global fp32 scale → packed nibbles."""
+    wf = w.float()
+    R, C = wf.shape
+    g = wf.reshape(R, C // block, block)
+    amax = g.abs().amax(-1)
+    gscale = float(amax.max() / (6.0 * FP8_MAX)) or 1.0
+    bscale = (amax / 6.0 / gscale).clamp_min(1e-12).to(torch.float8_e4m3fn)
+    x = g / (bscale.float()[..., None] * gscale)
+    lut = torch.tensor(E2M1_VALUES, dtype=torch.float32)
+    idx = (x.abs()[..., None] - lut).abs().argmin(-1)
+    code = (idx + 8 * (x < 0).long()).reshape(R, C).to(torch.uint8)
+    return (code[:, 0::2] | (code[:, 1::2] << 4)).contiguous(), bscale, gscale
+
 
 
 def per_token_group_quant_fp8(x: torch.Tensor, group: int = 128) -> tuple[torch.Tensor, torch.Tensor]:
