@@ -222,6 +222,10 @@ def decode_splits(B: int, Hkv: int, max_seq_len: int, block_size: int) -> int:
     target = 2 * num_sms()
     s = max(1, min(16, (target + ctas - 1) // ctas))
     pages = max(1, (max_seq_len + block_size - 1) // block_size)
+    # a split costs ~10 us (workspace round trip + reduce kernel): measured on B200 (profiles/README.md §3) it only
+    # pays once every split still streams >= ~2k tokens — at 1k-token contexts one CTA per (sequence, kv head) wins
+    # even when that leaves SMs idle (14.5 us vs 25.8 us for 64 seqs x 1 kv head)
+    s = min(s, max(1, max_seq_len // 2048))
     return max(1, min(s, pages))
 
 
