@@ -374,3 +374,28 @@ def test_extra_ops_and_fp4_roundtrip():
     out = dict(dequantize_stream(stream, {"quant_method": "modelopt_fp4"}, torch.float32))
     assert set(out) == {"model.layers.0.mlp.down_proj.weight", "model.norm.weight"}
     assert torch.allclose(out["model.layers.0.mlp.down_proj.weight"], deq)
+
+
+def test_deepseek_fp8_block_experts_and_linears():
+    """DeepSeek-style block-scaled fp8 (online quantisation here): dense projections AND routed experts are held in
+    e4m3 with 128x128 block scales; outputs stay within quantisation noise of the unquantised model."""
+    from tests.utils import make_hf_model
+    hf = make_hf_model("deepseek-tiny")
+    w = [(k, v.clone()) for k, v in hf.state_dict().items()]
+    sp = SamplingParams(max_tokens=3, temperature=0.0, ignore_eos=True, prompt_logprobs=0)
+    prompt = [{"prompt_token_ids": [(11 * i) % 500 + 3 for i in range(30)]}]
+
+    def run(**kw):
+        llm = make_llm("deepseek-tiny", **kw)
+        ex = llm.llm_engine.engine_core.engine_core.model_executor
+        ex.collective_rpc("load_model", kwargs={"weights": list(w)})
+        model = ex.worker.runner.model
+        dts = {m.w13_weight.dtype for m in model.modules() if hasattr(m, "w13_weight")}
+        o = llm.generate(prompt, sp)[0]
+        llm.shutdown()
+        return [list(d.values())[0].logprob for d in o.prompt_logprobs[1:]], dts
+    base, d0 = run()
+    q, d1 = run(quantization="fp8_block")
+    assert d0 == {torch.float32} and d1 == {torch.float8_e4m3fn}
+    diff = max(abs(a - b) for a, b in zip(base, q))
+    assert 0 < diff < 0.3, diff

@@ -27,7 +27,8 @@ class FusedMoE(nn.Module):
     def __init__(self, num_experts: int, top_k: int, hidden_size: int, intermediate_size: int, dtype=None,
                  renormalize: bool = True, use_grouped_topk: bool = False, n_group: int = 1, topk_group: int = 1,
                  scoring_func: str = "softmax", routed_scaling_factor: float = 1.0, e_score_bias: bool = False,
-                 act: str = "silu", enable_ep: bool = False, reduce_results: bool = True, prefix: str = "") -> None:
+                 act: str = "silu", enable_ep: bool = False, reduce_results: bool = True, prefix: str = "",
+                 quant_config=None) -> None:
         super().__init__()
         g = get_tp_group()
         self.tp_rank, self.tp_size = max(g.rank_in_group, 0), g.world_size
@@ -60,6 +61,23 @@ class FusedMoE(nn.Module):
                                       requires_grad=False)
         self.e_score_correction_bias = (nn.Parameter(torch.zeros(num_experts, dtype=torch.float32),
                                                      requires_grad=False) if e_score_bias else None)
+        # block-scaled fp8 experts (DeepSeek-V3 checkpoints: ``weight`` e4m3 + ``weight_scale_inv`` per 128x128 block;
+        # or online quantisation of a bf16 checkpoint).  Only the experts a batch routes to are expanded, so decode
+        # traffic stays at the fp8 size.
+        self.fp8_block = 0
+        self.fp8_online = False
+        self.compute_dtype = dt
+        if quant_config is not None and getattr(quant_config, "name", "") == "fp8_block":
+            blk = quant_config.block
+            self.fp8_block = blk
+            self.fp8_online = bool(quant_config.online)
+            E = max(self.local_experts, 1)
+            if not self.fp8_online:
+                self.w13_weight = nn.Parameter(torch.empty(E, 2 * I, hidden_size, dtype=torch.float8_e4m3fn), requires_grad=False)
+                self.w2_weight = nn.Parameter(torch.empty(E, hidden_size, I, dtype=torch.float8_e4m3fn), requires_grad=False)
+            cb = lambda n: -(-n // blk)  # noqa: E731
+            self.w13_scale = nn.Parameter(torch.ones(E, 2 * cb(I), cb(hidden_size), dtype=torch.float32), requires_grad=False)
+            self.w2_scale = nn.Parameter(torch.ones(E, cb(hidden_size), cb(I), dtype=torch.float32), requires_grad=False)
 
     # ------------------------------------------------------------ routing
     def select_experts(self, router_logits: torch.Tensor):
@@ -75,13 +93,68 @@ class FusedMoE(nn.Module):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         w, ids = self.select_experts(router_logits.reshape(-1, router_logits.shape[-1]))
-        out = ops.fused_moe(x2, self.w13_weight, self.w2_weight, w.to(torch.float32), ids, self.act,
-                            self.expert_map)
+        if self.fp8_block and self.w13_weight.dtype == torch.float8_e4m3fn:
+            out = self._forward_fp8(x2, w.to(torch.float32), ids)
+        else:
+            out = ops.fused_moe(x2, self.w13_weight, self.w2_weight, w.to(torch.float32), ids, self.act,
+                                self.expert_map)
         if self.reduce_results and self.tp_size > 1:
             out = get_tp_group().all_reduce(out)
         return out.reshape(shape)
 
+    def _dequant(self, wq: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+        blk = self.fp8_block
+        s = scale.repeat_interleave(blk, -2)[..., :wq.shape[-2], :].repeat_interleave(blk, -1)[..., :wq.shape[-1]]
+        return (wq.float() * s).to(self.compute_dtype)
+
+    def _forward_fp8(self, x: torch.Tensor, topk_w: torch.Tensor, topk_ids: torch.Tensor) -> torch.Tensor:
+        """Expand only the routed experts to the compute dtype and run them through the regular fused path with a
+        compacted expert numbering."""
+        ids = topk_ids.long()
+        if self.expert_map is not None:
+            ids = self.expert_map[ids].long()
+        active = torch.unique(ids[ids >= 0])
+        if active.numel() == 0:
+            return torch.zeros_like(x)
+        A = active.numel()
+        remap = torch.full((max(self.local_experts, 1) + 1,), A, dtype=torch.int32, device=x.device)
+        remap[active] = torch.arange(A, dtype=torch.int32, device=x.device)
+        w13 = self._dequant(self.w13_weight[active], self.w13_scale[active])
+        w2 = self._dequant(self.w2_weight[active], self.w2_scale[active])
+        compact = remap[torch.where(ids >= 0, ids, torch.full_like(ids, remap.numel() - 1))]   # A = "not on this rank"
+        emap = torch.cat([torch.arange(A, dtype=torch.int32, device=x.device),
+                          torch.tensor([-1], dtype=torch.int32, device=x.device)])
+        return ops.fused_moe(x, w13, w2, topk_w, compact.int(), self.act, emap)
+
+    def process_weights_after_loading(self) -> None:
+        if self.fp8_block and self.fp8_online and self.w13_weight.dtype != torch.float8_e4m3fn:
+            from vllm_b200.ops import ref
+            qs13, ss13, qs2, ss2 = [], [], [], []
+            for e in range(self.w13_weight.shape[0]):
+                q, sc = ref.block_quant_weight_fp8(self.w13_weight.data[e], self.fp8_block)
+                qs13.append(q); ss13.append(sc)
+                q, sc = ref.block_quant_weight_fp8(self.w2_weight.data[e], self.fp8_block)
+                qs2.append(q); ss2.append(sc)
+            self.w13_weight = nn.Parameter(torch.stack(qs13), requires_grad=False)
+            self.w2_weight = nn.Parameter(torch.stack(qs2), requires_grad=False)
+            self.w13_scale = nn.Parameter(torch.stack(ss13).float(), requires_grad=False)
+            self.w2_scale = nn.Parameter(torch.stack(ss2).float(), requires_grad=False)
+
     # ------------------------------------------------------------ weights
+    def scale_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id: str, expert_id: int) -> None:
+        """``weight_scale_inv`` of one expert projection (block granularity; TP shards in units of blocks)."""
+        if not (self.e_start <= expert_id < self.e_end):
+            return
+        le = expert_id - self.e_start
+        blk = self.fp8_block
+        Ib = -(-self.inter_per_rank // blk)
+        r0 = 0 if self.ep else self.tp_rank * Ib
+        if shard_id == "w2":
+            param.data[le].copy_(w[:, r0:r0 + Ib])
+        else:
+            off = 0 if shard_id == "w1" else Ib
+            param.data[le, off:off + Ib].copy_(w[r0:r0 + Ib])
+
     def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id: str, expert_id: int) -> None:
         """shard_id: 'w1' (gate), 'w3' (up), 'w2' (down); ``w`` is the checkpoint's full tensor."""
         if not (self.e_start <= expert_id < self.e_end):

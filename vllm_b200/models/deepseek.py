@@ -111,7 +111,7 @@ class DeepseekMoE(nn.Module):
                                 scoring_func=cfg.get("scoring_func", "softmax"),
                                 routed_scaling_factor=cfg.get("routed_scaling_factor", 1.0), e_score_bias=noaux,
                                 act=cfg.get("hidden_act", "silu"), enable_ep=enable_ep, reduce_results=False,
-                                prefix=f"{prefix}.experts")
+                                prefix=f"{prefix}.experts", quant_config=quant_config)
         ns = cfg.get("n_shared_experts") or 0
         self.shared_experts = None
         if ns:
@@ -201,6 +201,12 @@ class DeepseekV3ForCausalLM(LlamaForCausalLM):
             if not parts[0].isdigit() or parts[1] not in self.expert_names:
                 continue
             suffix, shard = self.expert_names[parts[1]]
+            if parts[-1] == "weight_scale_inv":                  # block scales of an fp8 expert projection
+                pname = f"{head}{marker}{suffix.replace('_weight', '_scale')}"
+                if pname in params:
+                    modules[pname.rsplit(".", 1)[0]].scale_loader(params[pname], w, shard, int(parts[0]))
+                    loaded.add(pname)
+                continue
             pname = f"{head}{marker}{suffix}"
             if pname in params:
                 modules[pname.rsplit(".", 1)[0]].weight_loader(params[pname], w, shard, int(parts[0]))

@@ -465,12 +465,17 @@ def fp4_quant(w: torch.Tensor, block: int = 16) -> tuple[torch.Tensor, torch.Ten
 
 
 def per_token_group_quant_fp8(x: torch.Tensor, group: int = 128) -> tuple[torch.Tensor, torch.Tensor]:
+    """Returns (q [T, K], scale [T, ceil(K/group)]); a ragged last group is handled by zero padding."""
     T, K = x.shape
-    xg = x.float().view(T, K // group, group)
+    G = (K + group - 1) // group
+    xf = x.float()
+    if G * group != K:
+        xf = F.pad(xf, (0, G * group - K))
+    xg = xf.view(T, G, group)
     amax = xg.abs().amax(-1).clamp_min(1e-10)
     scale = amax / FP8_MAX
-    q = (xg / scale[..., None]).clamp(-FP8_MAX, FP8_MAX).to(torch.float8_e4m3fn).view(T, K)
-    return q, scale
+    q = (xg / scale[..., None]).clamp(-FP8_MAX, FP8_MAX).to(torch.float8_e4m3fn).view(T, G * group)[:, :K]
+    return q.contiguous(), scale
 
 
 def block_quant_weight_fp8(w: torch.Tensor, block: int = 128) -> tuple[torch.Tensor, torch.Tensor]:
@@ -490,7 +495,7 @@ def block_fp8_linear(x: torch.Tensor, wq: torch.Tensor, w_scale: torch.Tensor, b
     """Activation quantised per (token, 128-group), weight per 128x128 block; fp32 accumulate."""
     xq, xs = per_token_group_quant_fp8(x, block)
     N, K = wq.shape
-    xd = (xq.float().view(x.shape[0], K // block, block) * xs[..., None]).view(x.shape[0], K)
+    xd = xq.float() * xs.repeat_interleave(block, dim=1)[:, :K]
     ws = w_scale.repeat_interleave(block, 0)[:N].repeat_interleave(block, 1)[:, :K]
     y = xd @ (wq.float() * ws).t()
     if bias is not None:
