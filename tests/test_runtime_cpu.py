@@ -200,3 +200,42 @@ def test_data_parallel_engines_load_balanced():
     # same prompt → same tokens regardless of which replica served it
     assert outs[0].outputs[0].token_ids == outs[0].outputs[0].token_ids
     assert used == {0, 1}
+
+
+def test_tp2_pp2_four_processes():
+    """TP=2 x PP=2 on four worker processes (gloo): stage boundaries carry TP-sharded intermediates."""
+    from tests.utils import llama_full_weights, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41]}, {"prompt_token_ids": list(range(10, 40))}]
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny", weights=llama_full_weights(cfg, seed=1))
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("llama-tiny", tensor_parallel_size=2, pipeline_parallel_size=2, distributed_executor_backend="mp")
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": list(llama_full_weights(cfg, seed=1))})
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    assert got == ref
+
+
+def test_rlhf_weight_update_in_place():
+    """collective_rpc('update_weights'): new tensors (HF names) replace the served weights without a restart."""
+    from tests.utils import llama_full_weights, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    p = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41]}]
+    llm = make_llm("llama-tiny", weights=llama_full_weights(cfg, seed=1), enable_prefix_caching=False)
+    a = llm.generate(p, sp)[0].outputs[0].token_ids
+    n = llm.collective_rpc("update_weights", args=(list(llama_full_weights(cfg, seed=2)),))[0]
+    assert n > 0
+    b = llm.generate(p, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    llm = make_llm("llama-tiny", weights=llama_full_weights(cfg, seed=2))
+    c = llm.generate(p, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    assert b == c and a != b
