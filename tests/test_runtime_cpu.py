@@ -239,3 +239,37 @@ def test_rlhf_weight_update_in_place():
     c = llm.generate(p, sp)[0].outputs[0].token_ids
     llm.shutdown()
     assert b == c and a != b
+
+
+def test_elastic_scale_up_and_down():
+    """Start with one engine replica, grow to two under load-balancing, shrink back — requests keep being served."""
+    import asyncio
+    from vllm_b200 import SamplingParams
+    from vllm_b200.engine.arg_utils import EngineArgs
+    from vllm_b200.engine.async_llm import AsyncLLM
+
+    async def main():
+        ea = EngineArgs(model="llama-tiny", device="cpu", dtype="float32", max_model_len=128, max_num_seqs=8,
+                        max_num_batched_tokens=128, kv_cache_memory_bytes=8 << 20, enable_elastic_ep=True,
+                        disable_log_stats=True)
+        eng = AsyncLLM.from_engine_args(ea)
+        sp = SamplingParams(max_tokens=5, temperature=0.0, ignore_eos=True)
+
+        async def one(tag, i):
+            last = None
+            async for o in eng.generate({"prompt_token_ids": [3 + i, 9, 27, 81]}, sp, f"{tag}{i}"):
+                last = o
+            return last.outputs[0].token_ids
+
+        base = await asyncio.gather(*[one("a", i) for i in range(3)])
+        assert await eng.scale_elastic_ep(2) == 2
+        eng.engine_core.engines_seen.clear()
+        grown = await asyncio.gather(*[one("b", i) for i in range(6)])
+        seen = set(eng.engine_core.engines_seen)
+        assert await eng.scale_elastic_ep(1) == 1
+        shrunk = await asyncio.gather(*[one("c", i) for i in range(3)])
+        eng.shutdown()
+        return base, grown, seen, shrunk
+    base, grown, seen, shrunk = asyncio.run(main())
+    assert seen == {0, 1}
+    assert grown[:3] == base and shrunk == base

@@ -196,6 +196,12 @@ class AsyncLLM:
     async def is_sleeping(self) -> bool:
         return await self.engine_core.call_utility_async("is_sleeping")
 
+    async def scale_elastic_ep(self, new_data_parallel_size: int) -> int:
+        """Scale the number of engine replicas up or down without restarting the server."""
+        if not hasattr(self.engine_core, "scale_elastic"):
+            raise RuntimeError("elastic scaling needs --enable-elastic-ep (or data_parallel_size > 1)")
+        return await self.engine_core.scale_elastic(new_data_parallel_size)
+
     async def get_fault_status(self) -> dict:
         return await self.engine_core.call_utility_async("get_fault_status")
 

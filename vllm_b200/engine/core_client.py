@@ -36,7 +36,7 @@ class EngineCoreClient:
     def make_client(vllm_config: VllmConfig, multiprocess: bool, asyncio_mode: bool, log_stats: bool = False,
                     executor_class=None) -> "EngineCoreClient":
         if asyncio_mode:
-            if vllm_config.parallel_config.data_parallel_size > 1:
+            if vllm_config.parallel_config.data_parallel_size > 1 or vllm_config.parallel_config.enable_elastic_ep:
                 return DPLBAsyncMPClient(vllm_config, log_stats)
             return AsyncMPClient(vllm_config, log_stats)
         if multiprocess:
@@ -109,11 +109,11 @@ class _Resources:
                 p.kill()
 
 
-def _launch_engines(vllm_config: VllmConfig, input_addr: str, output_addr: str, n: int, log_stats: bool
-                    ) -> list[multiprocessing.Process]:
+def _launch_engines(vllm_config: VllmConfig, input_addr: str, output_addr: str, n: int, log_stats: bool,
+                    start: int = 0) -> list[multiprocessing.Process]:
     ctx = multiprocessing.get_context(envs.VLLM_WORKER_MULTIPROC_METHOD)
     procs = []
-    for i in range(n):
+    for i in range(start, start + n):
         p = ctx.Process(target=EngineCoreProc.run_engine_core, name=f"EngineCore_{i}",
                         kwargs=dict(vllm_config=vllm_config, input_addr=input_addr, output_addr=output_addr,
                                     engine_index=i, log_stats=log_stats, dp_rank=i, parent_pid=os.getpid()))
@@ -141,6 +141,7 @@ class MPClient(EngineCoreClient):
         self.res.sockets += [self.input_socket, self.output_socket]
         self.num_engines = vllm_config.parallel_config.data_parallel_size
         self.engine_ids = [i.to_bytes(2, "little") for i in range(self.num_engines)]
+        self.in_addr, self.out_addr, self.log_stats = in_addr, out_addr, log_stats
         self.res.procs = _launch_engines(vllm_config, in_addr, out_addr, self.num_engines, log_stats)
         self._wait_ready(in_addr)
         self.utility_results: dict[int, Any] = {}
@@ -378,6 +379,7 @@ class DPLBAsyncMPClient(AsyncMPClient):
         super().__init__(vllm_config, log_stats)
         self.inflight: list[int] = [0] * self.num_engines
         self.engines_seen: set[int] = set()
+        self.active = self.num_engines          # engines [0, active) receive new requests (elastic scale-down drains)
         self.owner: dict[str, int] = {}
         self._rr = 0
 
@@ -385,8 +387,8 @@ class DPLBAsyncMPClient(AsyncMPClient):
         if r.data_parallel_rank is not None:
             i = r.data_parallel_rank
         else:
-            m = min(self.inflight)
-            cands = [i for i, v in enumerate(self.inflight) if v == m]
+            m = min(self.inflight[:self.active])
+            cands = [i for i, v in enumerate(self.inflight[:self.active]) if v == m]
             i = cands[self._rr % len(cands)]
             self._rr += 1
         self.inflight[i] += 1
@@ -404,3 +406,47 @@ class DPLBAsyncMPClient(AsyncMPClient):
     def _engines_for(self, ids: list[str]) -> list[bytes]:
         return [self.engine_ids[i] for i in sorted({self.owner[r] for r in ids if r in self.owner})] \
             or self.engine_ids
+
+    # ---------------------------------------------------------------- elastic scaling
+    async def scale_elastic(self, new_size: int, timeout_s: float = 600.0) -> int:
+        """Grow or shrink the number of engine-core replicas at runtime (reference: ``scale_elastic_ep``,
+        async_llm.py:1051-1094 — drain → reconfigure).  Growing spawns new engine processes against the same
+        sockets and waits for their READY handshake; shrinking stops routing to the highest replicas, waits until
+        their in-flight requests finish, then shuts them down."""
+        import copy
+        if new_size < 1:
+            raise ValueError("at least one engine replica is required")
+        cur = self.num_engines
+        if new_size > cur:
+            cfg = copy.deepcopy(self.vllm_config)
+            cfg.parallel_config.data_parallel_size = new_size
+            procs = _launch_engines(cfg, self.in_addr, self.out_addr, new_size - cur, self.log_stats, start=cur)
+            self.res.procs += procs
+            ready, deadline = 0, time.time() + timeout_s
+            while ready < new_size - cur:
+                if not await self.input_socket.poll(timeout=500):
+                    if any(not p.is_alive() for p in procs):
+                        raise RuntimeError("a new engine replica died during start-up")
+                    if time.time() > deadline:
+                        raise TimeoutError("new engine replicas did not come up")
+                    continue
+                _ident, msg = await self.input_socket.recv_multipart()
+                if msg != b"HELLO" and msgspec.msgpack.decode(msg).get("status") == "READY":
+                    ready += 1
+            self.engine_ids += [i.to_bytes(2, "little") for i in range(cur, new_size)]
+            self.inflight += [0] * (new_size - cur)
+            self.num_engines = self.active = new_size
+        elif new_size < cur:
+            self.active = new_size
+            deadline = time.time() + timeout_s
+            while any(self.inflight[new_size:]) and time.time() < deadline:
+                await asyncio.sleep(0.05)
+            for eid in self.engine_ids[new_size:]:
+                await self.input_socket.send_multipart([eid, REQ_SHUTDOWN])
+            for p in self.res.procs[new_size:]:
+                p.join(timeout=10)
+                if p.is_alive():
+                    p.terminate()
+            del self.res.procs[new_size:], self.engine_ids[new_size:], self.inflight[new_size:]
+            self.num_engines = new_size
+        return self.num_engines

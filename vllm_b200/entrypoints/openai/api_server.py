@@ -670,6 +670,14 @@ def build_app(ctx: ServingContext):
         await ctx.engine.collective_rpc("remove_lora", (req.lora_int_id,))
         return {"status": "ok"}
 
+    @app.post("/scale_elastic_ep")
+    async def scale_elastic_ep(body: dict):
+        try:
+            n = await ctx.engine.scale_elastic_ep(int(body["new_data_parallel_size"]))
+        except (RuntimeError, ValueError, KeyError) as ex:
+            return _error(str(ex))
+        return {"data_parallel_size": n}
+
     @app.post("/checkpoint/prepare")
     async def ckpt_prepare():
         await ctx.engine.collective_rpc("checkpoint_prepare")
