@@ -55,3 +55,33 @@ def render_chat(tokenizer, messages: list[dict], chat_template: Optional[str] = 
 
 def extract_mm_items(messages: list[dict]) -> list[Any]:
     return _flatten_content(messages)[1]
+
+
+def load_mm_item(part: dict) -> Any:
+    """One OpenAI content part → a decoded media object (images: PIL.Image; tensors / arrays pass through).
+    ``data:`` URLs and local ``file://`` paths are supported; remote fetches need network access and are refused
+    unless ``VLLM_ALLOW_REMOTE_MEDIA=1``."""
+    import base64
+    import io
+    import os
+    t = part.get("type")
+    if t == "image" and part.get("image") is not None:
+        return part["image"]
+    if t == "image_url":
+        url = part["image_url"]["url"] if isinstance(part["image_url"], dict) else part["image_url"]
+        from PIL import Image
+        if url.startswith("data:"):
+            return Image.open(io.BytesIO(base64.b64decode(url.split(",", 1)[1]))).convert("RGB")
+        if url.startswith("file://"):
+            return Image.open(url[len("file://"):]).convert("RGB")
+        if os.environ.get("VLLM_ALLOW_REMOTE_MEDIA") == "1":
+            import requests
+            return Image.open(io.BytesIO(requests.get(url, timeout=10).content)).convert("RGB")
+        raise ValueError("remote media URLs are disabled (use a data: URL, file://, or set VLLM_ALLOW_REMOTE_MEDIA=1)")
+    raise ValueError(f"unsupported multimodal content part type {t!r}")
+
+
+def chat_multi_modal_data(messages: list[dict]) -> Optional[dict]:
+    """``{"image": [...]}`` for the image parts of a conversation, in order of appearance (None if there are none)."""
+    items = [load_mm_item(p) for p in extract_mm_items(messages) if "image" in p.get("type", "")]
+    return {"image": items} if items else None

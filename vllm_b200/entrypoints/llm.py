@@ -105,11 +105,15 @@ class LLM:
              chat_template: Optional[str] = None, add_generation_prompt: bool = True,
              continue_final_message: bool = False, tools: Optional[list[dict]] = None, lora_request=None,
              chat_template_kwargs: Optional[dict] = None) -> list[RequestOutput]:
-        from vllm_b200.entrypoints.chat_utils import render_chat
+        from vllm_b200.entrypoints.chat_utils import chat_multi_modal_data, render_chat
         convs = messages if messages and isinstance(messages[0], list) else [messages]
         tok = self.get_tokenizer()
-        prompts = [render_chat(tok, c, chat_template, add_generation_prompt, continue_final_message, tools,
-                               **(chat_template_kwargs or {})) for c in convs]
+        prompts = []
+        for c in convs:
+            text = render_chat(tok, c, chat_template, add_generation_prompt, continue_final_message, tools,
+                               **(chat_template_kwargs or {}))
+            mm = chat_multi_modal_data(c)
+            prompts.append({"prompt": text, "multi_modal_data": mm} if mm else text)
         return self.generate(prompts, sampling_params, use_tqdm, lora_request)
 
     # ----------------------------------------------------------------- pooling

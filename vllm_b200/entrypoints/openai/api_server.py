@@ -303,7 +303,11 @@ def build_app(ctx: ServingContext):
             from vllm_b200.reasoning import get_reasoning_parser
             reasoning = get_reasoning_parser(ctx.reasoning_parser)(ctx.tokenizer)
         try:
-            gen = ctx.engine.generate({"prompt": prompt} if isinstance(prompt, str) else prompt, sp, rid,
+            if isinstance(prompt, str):
+                from vllm_b200.entrypoints.chat_utils import chat_multi_modal_data
+                mm = chat_multi_modal_data(req.messages)
+                prompt = {"prompt": prompt, "multi_modal_data": mm} if mm else {"prompt": prompt}
+            gen = ctx.engine.generate(prompt, sp, rid,
                                       priority=req.priority, trace_headers=dict(raw.headers),
                                       lora_request=ctx.lora_requests.get(req.model))
         except ValueError as ex:
