@@ -37,8 +37,8 @@ def preprocess_image(img: Any, size: int, mean=CLIP_MEAN, std=CLIP_STD) -> torch
             t = torch.nn.functional.interpolate(t[None], size=(size, size), mode="bicubic", align_corners=False)[0]
         return t                                    # caller supplied normalised pixels
     if hasattr(img, "convert"):                     # PIL
-        img = np.asarray(img.convert("RGB"))
-    a = torch.as_tensor(np.asarray(img))
+        img = np.array(img.convert("RGB"))
+    a = torch.as_tensor(np.array(img))
     if a.dim() == 3 and a.shape[-1] == 3:
         a = a.permute(2, 0, 1)
     t = a.float() / (255.0 if a.dtype == torch.uint8 else 1.0)

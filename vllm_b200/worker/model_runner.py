@@ -269,7 +269,9 @@ class ModelRunner:
                 self.is_cuda and not envs.VLLM_B200_FORCE_REF_OPS and envs.VLLM_B200_ATTN != "simt"
                 and not isinstance(s, MLAAttentionSpec) and getattr(s, "head_size", 0) == 128
                 and s.block_size == 64 and kvd in (torch.bfloat16, torch.float16)
-                and self.dtype in (torch.bfloat16, torch.float16)))
+                and self.dtype in (torch.bfloat16, torch.float16)
+                # features only the generic kernel implements keep the whole group on the standard layout
+                and all(not getattr(attention_layers().get(n), "logits_soft_cap", 0.0) for n in g.layer_names)))
             for name in g.layer_names:
                 self.layer_to_group[name] = gid
                 if isinstance(s, MambaSpec):
