@@ -11,14 +11,20 @@ PROMPTS = [[5, 17, 99, 3, 250, 41], [7, 7, 7, 301, 12], list(range(10, 60))]
 
 @pytest.mark.parametrize("preset", ["llama-tiny", "opt-tiny", "gpt2-tiny", "mixtral-tiny", "qwen2moe-tiny",
                                     "qwen3moe-tiny", "deepseek-tiny", "mamba-tiny", "phi3-tiny", "gemma2-tiny", "gptneox-tiny",
-                                    "starcoder2-tiny", "gptj-tiny", "olmo-tiny", "stablelm-tiny"])
+                                    "starcoder2-tiny", "gptj-tiny", "olmo-tiny", "stablelm-tiny", "jamba-tiny"])
 def test_greedy_matches_hf(preset):
     hf = make_hf_model(preset)
     llm = make_llm(preset, weights=hf.state_dict().items())
     sp = SamplingParams(max_tokens=12, temperature=0.0, ignore_eos=True)
     outs = llm.generate([{"prompt_token_ids": p} for p in PROMPTS], sp)
     for p, o in zip(PROMPTS, outs):
-        assert o.outputs[0].token_ids == hf_greedy(hf, p, 12), preset
+        got, exp = o.outputs[0].token_ids, hf_greedy(hf, p, 12)
+        if got != exp:
+            # an exact tie in the reference logits is not a disagreement: accept a mismatch only there
+            k = next(i for i, (a, b) in enumerate(zip(got, exp)) if a != b)
+            with torch.no_grad():
+                lg = hf(torch.tensor([p + exp[:k]])).logits[0, -1]
+            assert abs(float(lg[got[k]] - lg[exp[k]])) < 1e-5, (preset, k, got, exp)
     llm.shutdown()
 
 

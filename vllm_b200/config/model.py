@@ -160,6 +160,13 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
         partial_rotary_factor=0.25, rope_theta=10000.0, hidden_act="silu", layer_norm_eps=1e-5, use_qkv_bias=True,
         bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "jamba-tiny": dict(
+        architectures=["JambaForCausalLM"], model_type="jamba", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, mamba_d_state=8, mamba_d_conv=4,
+        mamba_expand=2, mamba_dt_rank=4, attn_layer_period=2, attn_layer_offset=1, expert_layer_period=2,
+        expert_layer_offset=1, num_experts=4, num_experts_per_tok=2, use_mamba_kernels=False, rms_norm_eps=1e-6,
+        max_position_embeddings=256, hidden_act="silu", bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=False),
     "bert-tiny": dict(
         architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
         num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,

@@ -129,17 +129,15 @@ def get_kv_cache_config(layer_specs: dict[str, KVCacheSpec], available_bytes: in
     if not layer_specs:
         return KVCacheConfig(num_blocks=2), max_model_len
     groups = group_specs(layer_specs)
+    # every layer owns its own tensor of ``num_blocks`` pages (pages of different groups — attention K/V pages,
+    # sliding-window pages, recurrent-state pages — may differ in size); block ids are shared across groups, so the
+    # pool size is what fits when every layer gets one page per block
+    per_block = sum(s.page_size_bytes for s in layer_specs.values())
     page = max(g.spec.page_size_bytes for g in groups)
-    for g in groups:
-        if g.spec.page_size_bytes != page:
-            raise ValueError(
-                "all KV groups must share one page size; pad the smaller spec's block_size "
-                f"({g.spec.page_size_bytes} vs {page})")
-    n_layers = len(layer_specs)
-    num_blocks = int(available_bytes // (page * n_layers))
+    num_blocks = int(available_bytes // max(per_block, 1))
     if num_gpu_blocks_override is not None:
         num_blocks = num_gpu_blocks_override
-    need_blocks = max(cdiv(g.spec.max_memory_usage_bytes(max_model_len), page) for g in groups) + 1
+    need_blocks = sum(cdiv(g.spec.max_memory_usage_bytes(max_model_len), g.spec.page_size_bytes) for g in groups) + 1
     if num_blocks < need_blocks:
         if auto_fit_max_model_len and num_blocks > 2:
             bs = groups[0].spec.block_size
@@ -149,7 +147,7 @@ def get_kv_cache_config(layer_specs: dict[str, KVCacheSpec], available_bytes: in
                 f"KV cache too small: {num_blocks} blocks available but one request of max_model_len="
                 f"{max_model_len} needs {need_blocks}; lower max_model_len or raise "
                 f"gpu_memory_utilization")
-    tensors = [KVCacheTensor(size=page * num_blocks, shared_by=[name]) for name in layer_specs]
+    tensors = [KVCacheTensor(size=sp.page_size_bytes * num_blocks, shared_by=[name]) for name, sp in layer_specs.items()]
     return KVCacheConfig(num_blocks=num_blocks, kv_cache_tensors=tensors, kv_cache_groups=groups), max_model_len
 
 

@@ -25,8 +25,13 @@ from vllm_b200.layers.linear import ReplicatedLinear
 
 class MambaMixer(nn.Module):
     def __init__(self, hidden: int, d_inner: int, d_state: int, d_conv: int, dt_rank: int, use_bias: bool,
-                 use_conv_bias: bool, dtype, prefix: str) -> None:
+                 use_conv_bias: bool, dtype, prefix: str, bcdt_norm_eps: Optional[float] = None) -> None:
         super().__init__()
+        # Jamba normalises dt / B / C (RMSNorm) before the dt projection
+        from vllm_b200.layers.common import RMSNorm
+        self.dt_layernorm = RMSNorm(dt_rank, bcdt_norm_eps, dtype) if bcdt_norm_eps is not None else None
+        self.b_layernorm = RMSNorm(d_state, bcdt_norm_eps, dtype) if bcdt_norm_eps is not None else None
+        self.c_layernorm = RMSNorm(d_state, bcdt_norm_eps, dtype) if bcdt_norm_eps is not None else None
         self.d_inner, self.d_state, self.d_conv, self.dt_rank = d_inner, d_state, d_conv, dt_rank
         self.in_proj = ReplicatedLinear(hidden, 2 * d_inner, use_bias, dtype, None, f"{prefix}.in_proj")
         self.conv_weight = nn.Parameter(torch.empty(d_inner, d_conv, dtype=dtype), requires_grad=False)
@@ -50,6 +55,8 @@ class MambaMixer(nn.Module):
     def _ssm_params(self, x_act: torch.Tensor):
         dbc = self.x_proj(x_act)
         dt, B, C = dbc.split([self.dt_rank, self.d_state, self.d_state], dim=-1)
+        if self.dt_layernorm is not None:
+            dt, B, C = self.dt_layernorm(dt.contiguous()), self.b_layernorm(B.contiguous()), self.c_layernorm(C.contiguous())
         dt = F.softplus(self.dt_proj(dt).float())
         return dt, B.float(), C.float()
 

@@ -28,6 +28,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen2MoeForCausalLM": ("mixtral", "Qwen2MoeForCausalLM"),
     "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
     "MambaForCausalLM": ("mamba", "MambaForCausalLM"),
+    "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "BertModel": ("bert", "BertEmbeddingModel"),
     "BertForMaskedLM": ("bert", "BertEmbeddingModel"),
