@@ -166,3 +166,19 @@ def test_llava_matches_hf_with_image():
     llm.generate([{"prompt_token_ids": [1, 511, 2], "multi_modal_data": {"image": img}}], sp)
     assert runner.encoder_cache.hits >= 1
     llm.shutdown()
+
+
+def test_bart_encoder_decoder_matches_hf():
+    """Seq2seq: encoder once per request, cross-attention K/V kept per request, causal decoder over the paged cache."""
+    hf = make_hf_model("bart-tiny")
+    llm = make_llm("bart-tiny", weights=hf.state_dict().items(), enable_prefix_caching=False)
+    srcs = [[0, 17, 99, 3, 250, 41, 2], [0] + list(range(10, 40)) + [2]]
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    outs = llm.generate([{"encoder_prompt_token_ids": s} for s in srcs], sp)
+    for s, o in zip(srcs, outs):
+        with torch.no_grad():
+            ref = hf.generate(input_ids=torch.tensor([s]), max_new_tokens=8, do_sample=False, num_beams=1,
+                              decoder_start_token_id=2, eos_token_id=None, pad_token_id=1,
+                              forced_bos_token_id=None, forced_eos_token_id=None)[0, 1:].tolist()
+        assert o.outputs[0].token_ids == ref[:8], (o.outputs[0].token_ids, ref)
+    llm.shutdown()

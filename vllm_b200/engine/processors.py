@@ -38,6 +38,20 @@ class InputProcessor:
                        kv_transfer_params: Optional[dict] = None) -> tuple[Optional[str], EngineCoreRequest]:
         text, ids, extras = parse_prompt(prompt)
         embeds_feature = None
+        if extras.get("encoder_prompt_token_ids") is not None or extras.get("encoder_prompt") is not None:
+            # encoder-decoder request: the source sequence rides along as a feature record, the decoder prompt
+            # defaults to the model's decoder start token
+            from vllm_b200.multimodal import hash_item
+            import numpy as np
+            enc = extras.get("encoder_prompt_token_ids")
+            if enc is None:
+                enc = self.tokenizer.encode(extras["encoder_prompt"])
+            enc = list(enc)
+            if ids is None and text is None:
+                start = self.mc.hf_config.get("decoder_start_token_id", self.mc.hf_config.get("bos_token_id", 0))
+                ids = [start]
+            embeds_feature = {"modality": "encoder_tokens", "hash": hash_item(np.asarray(enc, dtype=np.int64)),
+                              "offset": 0, "length": 0, "data": enc}
         if ids is None and text is None and extras.get("prompt_embeds") is not None:
             # prompt given directly as embeddings [n, hidden] (reference: ``EmbedsPrompt``): the positions carry a
             # dummy token id and the worker splices the rows in exactly like multimodal encoder outputs

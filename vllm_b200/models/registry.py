@@ -29,6 +29,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
     "MambaForCausalLM": ("mamba", "MambaForCausalLM"),
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
+    "BartForConditionalGeneration": ("bart", "BartForConditionalGeneration"),
+    "BartModel": ("bart", "BartForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "BertModel": ("bert", "BertEmbeddingModel"),
     "BertForMaskedLM": ("bert", "BertEmbeddingModel"),

@@ -165,6 +165,8 @@ class ModelRunner:
         self.drafter = None
         self.spec_hidden = None
         self.step_hidden = None
+        self.cross_states: dict[str, Any] = {}       # encoder-decoder: request id → per-layer cross-attention (K, V)
+        self.is_enc_dec = bool(vllm_config.model_config.hf_config.get("is_encoder_decoder"))
         self.encoder_cache = None
         self.ec_connector = None
         ecp = os.environ.get("VLLM_B200_EC_SHARED_PATH")
@@ -311,6 +313,8 @@ class ModelRunner:
         st = self.states.pop(req_id, None)
         if park and st is not None:
             self._parked[req_id] = st
+        elif self.cross_states:
+            self.cross_states.pop(req_id, None)
         if row is None:
             return
         last = len(self.req_ids) - 1
@@ -498,9 +502,25 @@ class ModelRunner:
         return out
 
     # ------------------------------------------------------------ forward
-    def _forward(self, T: int, md: dict[int, AttentionMetadata], intermediate=None, inputs_embeds=None):
+    def _cross_context(self, states, cu):
+        """Encoder-decoder models: run the encoder for requests seen for the first time and hand the decoder the
+        per-request cross-attention K/V (kept on the device for the life of the request)."""
+        kvs = []
+        for s in states:
+            kv = self.cross_states.get(s.req_id)
+            if kv is None and s.mm_features:
+                f = next((f for f in s.mm_features if f.get("modality") == "encoder_tokens"), None)
+                if f is not None:
+                    kv = self.model.encode(torch.tensor(f["data"], dtype=torch.int64, device=self.device))
+                    self.cross_states[s.req_id] = kv
+            kvs.append(kv)
+        return [int(x) for x in cu], kvs
+
+    def _forward(self, T: int, md: dict[int, AttentionMetadata], intermediate=None, inputs_embeds=None, extra=None):
         ctx = ForwardContext(attn_metadata=md, kv_caches=self.kv_caches, layer_to_group=self.layer_to_group,
                              num_tokens=T)
+        if extra:
+            ctx.extra.update(extra)
         with set_forward_context(ctx):
             if inputs_embeds is not None:
                 return self.model(self.input_ids[:T], self.positions[:T], intermediate, inputs_embeds)
@@ -613,17 +633,22 @@ class ModelRunner:
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
             if kv_meta:
                 self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
-            mm_emb = (self._mm_inputs_embeds(states, rows, ns, cu, T)
-                      if self.has_mm or any(s.mm_features for s in states) else None)
+            extra = None
+            if self.is_enc_dec:
+                extra = {"cross": self._cross_context(states, cu)}
+                mm_emb = None
+            else:
+                mm_emb = (self._mm_inputs_embeds(states, rows, ns, cu, T)
+                          if self.has_mm or any(s.mm_features for s in states) else None)
             if lora_batch is not None:
                 from vllm_b200 import lora as _lora
                 _lora.set_batch(lora_batch)
                 try:
-                    hidden = self._forward(T, md, intermediate, mm_emb)
+                    hidden = self._forward(T, md, intermediate, mm_emb, extra)
                 finally:
                     _lora.set_batch(None)
             else:
-                hidden = self._forward(T, md, intermediate, mm_emb)
+                hidden = self._forward(T, md, intermediate, mm_emb, extra)
             if kv_meta:
                 self.kv_connector.save_kv(kv_meta, self.kv_caches)           # freshly computed full blocks
             if isinstance(hidden, dict):  # non-last PP stage
