@@ -65,6 +65,44 @@ def test_kv_connector_prefix_reuse(tmp_path, connector, extra):
     llm.shutdown()
 
 
+def test_disaggregated_prefill_decode_over_p2p_connector():
+    """Prefill instance keeps the blocks and hands out transfer params; the decode instance pulls them over the
+    network while the request waits in WAITING_FOR_REMOTE_KVS, frees the producer's blocks, and continues exactly like
+    a single instance would."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=6))
+    prompt = {"prompt_token_ids": [(11 * i) % 400 + 5 for i in range(100)]}
+    sp = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True)
+    ref_llm = make_llm("llama-tiny", weights=w, block_size=16)
+    ref = ref_llm.generate([prompt], sp)[0].outputs[0].token_ids
+    ref_llm.shutdown()
+
+    ktc = lambda role: dict(kv_connector="P2pPullConnector", kv_role=role, kv_port=port)   # noqa: E731
+    prod = make_llm("llama-tiny", weights=w, block_size=16, kv_transfer_config=ktc("kv_producer"))
+    cons = make_llm("llama-tiny", weights=w, block_size=16, kv_transfer_config=ktc("kv_consumer"))
+    pcore = prod.llm_engine.engine_core.engine_core
+    free0 = pcore.scheduler.kv_cache_manager.pool.get_num_free_blocks()
+    sp_p = SamplingParams(max_tokens=1, temperature=0.0, ignore_eos=True,
+                          extra_args={"kv_transfer_params": {"do_remote_decode": True}})
+    o = prod.generate([prompt], sp_p)[0]
+    params = o.kv_transfer_params
+    assert params and params["do_remote_prefill"] and len(params["remote_block_ids"]) == 100 // 16
+    assert o.outputs[0].token_ids == ref[:1]
+    assert pcore.scheduler.kv_cache_manager.pool.get_num_free_blocks() < free0     # held for the consumer
+
+    sp_c = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True, extra_args={"kv_transfer_params": params})
+    got = cons.generate([prompt], sp_c)[0].outputs[0].token_ids
+    assert got == ref
+    cw = cons.llm_engine.engine_core.engine_core.model_executor.worker.runner.kv_connector
+    assert cw.num_pulled_blocks == 6
+    # the consumer's "done" reaches the producer on its next step → blocks are released
+    prod.generate([{"prompt_token_ids": [1, 2, 3]}], SamplingParams(max_tokens=1))
+    assert pcore.scheduler.kv_cache_manager.pool.get_num_free_blocks() == free0
+    prod.shutdown(); cons.shutdown()
+
+
 def test_multi_lora_matches_merged_weights():
     """A batch mixing base-model and two different adapters == three runs with the adapters merged into W."""
     from vllm_b200.core.request import LoRARequest

@@ -93,3 +93,61 @@ def test_native_loadgen_against_live_server(server):
     res = bench_serve(args)
     assert res["completed"] == 10 and res["failed"] == 0
     assert res["output_throughput"] > 0 and res["ttft_ms"]["mean"] > 0 and res["e2el_ms"]["p99"] >= res["ttft_ms"]["p50"]
+
+
+def _spawn(cmd, env):
+    return subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+
+
+def _wait_healthy(procs_urls, deadline_s=180):
+    deadline = time.time() + deadline_s
+    for proc, url in procs_urls:
+        while True:
+            assert proc.poll() is None, f"{url} exited during start-up"
+            assert time.time() < deadline, f"{url} never became healthy"
+            try:
+                if requests.get(url + "/health", timeout=1).status_code == 200:
+                    break
+            except requests.RequestException:
+                time.sleep(0.5)
+
+
+def test_disaggregated_serving_through_proxy(server):
+    """prefill server + decode server + proxy == one ordinary server, token for token (greedy)."""
+    env = dict(os.environ, PYTHONPATH=ROOT, VLLM_LOGGING_LEVEL="WARNING")
+    kv_port = get_open_port()
+    base = [sys.executable, "-m", "vllm_b200", "serve", "llama-tiny", "--device", "cpu", "--dtype", "float32",
+            "--max-model-len", "256", "--max-num-seqs", "8", "--max-num-batched-tokens", "128", "--block-size", "16",
+            "--kv-cache-memory-bytes", str(16 << 20), "--host", "127.0.0.1"]
+    ports = [get_open_port() for _ in range(3)]
+    ktc = lambda role: json.dumps({"kv_connector": "P2pPullConnector", "kv_role": role, "kv_port": kv_port})  # noqa: E731
+    procs = [_spawn(base + ["--port", str(ports[0]), "--kv-transfer-config", ktc("kv_producer")], env),
+             _spawn(base + ["--port", str(ports[1]), "--kv-transfer-config", ktc("kv_consumer")], env)]
+    urls = [f"http://127.0.0.1:{p}" for p in ports]
+    try:
+        _wait_healthy(list(zip(procs, urls[:2])))
+        procs.append(_spawn([sys.executable, "-m", "vllm_b200.entrypoints.disagg_proxy", "--prefill", urls[0],
+                             "--decode", urls[1], "--host", "127.0.0.1", "--port", str(ports[2])], env))
+        _wait_healthy([(procs[2], urls[2])], 60)
+        body = {"model": "llama-tiny", "prompt": [(13 * i) % 300 + 7 for i in range(70)], "max_tokens": 12,
+                "temperature": 0}
+        want = requests.post(server + "/v1/completions", json=body, timeout=120).json()
+        got = requests.post(urls[2] + "/v1/completions", json=body, timeout=120).json()
+        assert got["choices"][0]["text"] == want["choices"][0]["text"]
+        assert got["usage"]["completion_tokens"] == 12
+        text = ""
+        with requests.post(urls[2] + "/v1/completions", json=dict(body, stream=True), stream=True, timeout=120) as s:
+            for line in s.iter_lines():
+                if line.startswith(b"data:") and b"[DONE]" not in line:
+                    text += json.loads(line[5:])["choices"][0]["text"]
+        assert text == want["choices"][0]["text"]
+        st = requests.get(urls[2] + "/proxy/stats", timeout=10).json()
+        assert st["prefill"][urls[0]] == 2 and st["decode"][urls[1]] == 2
+    finally:
+        for p in procs:
+            p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                p.kill()

@@ -524,6 +524,8 @@ class Scheduler:
         for rid in getattr(kvo, "finished_recving", None) or ():
             self.connector.mark_recv_finished(rid)
         for rid in getattr(kvo, "finished_sending", None) or ():
+            if hasattr(self.connector, "mark_send_finished"):
+                self.connector.mark_send_finished(rid)
             req = self.requests.get(rid)
             if req is not None:
                 self._free_blocks(req)

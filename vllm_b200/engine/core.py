@@ -104,6 +104,8 @@ class EngineCore:
         so.grammar_bitmask = self.scheduler.get_grammar_bitmask(so)
         mo = self.model_executor.execute_model(so)
         out = self.scheduler.update_from_output(so, mo)
+        if so.total_num_scheduled_tokens == 0 and not out:
+            time.sleep(0.001)                    # only requests waiting on remote KV: do not spin the executor
         return out, so.total_num_scheduled_tokens > 0
 
     def step_with_batch_queue(self) -> tuple[Optional[dict[int, EngineCoreOutputs]], bool]:

@@ -306,6 +306,9 @@ _REGISTRY: dict[str, tuple[str, str]] = {
     "SharedStorageConnector": ("vllm_b200.kv_transfer", "SharedStorageConnector"),
     "ExampleConnector": ("vllm_b200.kv_transfer", "SharedStorageConnector"),
     "MultiConnector": ("vllm_b200.kv_transfer", "MultiConnector"),
+    "P2pPullConnector": ("vllm_b200.kv_transfer.p2p", "P2pPullConnector"),
+    "NixlConnector": ("vllm_b200.kv_transfer.p2p", "P2pPullConnector"),
+    "P2pNcclConnector": ("vllm_b200.kv_transfer.p2p", "P2pPullConnector"),
     "OffloadingConnector": ("vllm_b200.kv_offload", "OffloadingConnector"),
     "SimpleCPUOffloadConnector": ("vllm_b200.kv_offload", "OffloadingConnector"),
 }

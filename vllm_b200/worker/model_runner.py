@@ -128,7 +128,8 @@ class AsyncStepOutput:
         self._out = ModelRunnerOutput(
             req_ids=self.req_ids, req_id_to_index={x: i for i, x in enumerate(self.req_ids)},
             sampled_token_ids=out_ids, logprobs=self.lp_out, prompt_logprobs_dict=self.plp,
-            spec_token_ids=spec_ids, forward_ms=(time.perf_counter() - self.t0) * 1e3)
+            spec_token_ids=spec_ids, forward_ms=(time.perf_counter() - self.t0) * 1e3,
+            kv_connector_output=r.kv_connector.get_finished() if r.kv_connector is not None else None)
         return self._out
 
 
@@ -285,6 +286,8 @@ class ModelRunner:
                 else:
                     shape = (cfg.num_blocks, 2, s.num_kv_heads, s.block_size, s.head_size)
                 self.kv_caches[name] = torch.zeros(shape, dtype=kvd, device=self.device)
+        if self.kv_connector is not None and hasattr(self.kv_connector, "register_kv_caches"):
+            self.kv_connector.register_kv_caches(self.kv_caches)
         G, R, MB = self.num_kv_groups, self.max_num_reqs, self.max_blocks_per_req
         self.block_tables_cpu = [np.zeros((R, MB), dtype=np.int32) for _ in range(G)]
         self.num_blocks_cpu = [np.zeros(R, dtype=np.int32) for _ in range(G)]
@@ -582,6 +585,10 @@ class ModelRunner:
         self._step += 1
         self._update_states(so)
         if so.total_num_scheduled_tokens == 0:
+            if self.kv_connector is not None:            # requests may be waiting for remote KV: drive the transfers
+                if so.kv_connector_metadata:
+                    self.kv_connector.start_load_kv(so.kv_connector_metadata, self.kv_caches)
+                return ModelRunnerOutput(kv_connector_output=self.kv_connector.get_finished())
             return ModelRunnerOutput()
         B_all = len(self.req_ids)
         # features that need the previous step's tokens on the host force a drain of the pipeline
