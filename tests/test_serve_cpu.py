@@ -151,3 +151,84 @@ def test_disaggregated_serving_through_proxy(server):
                 p.wait(timeout=20)
             except subprocess.TimeoutExpired:
                 p.kill()
+
+
+def test_native_frontend_matches_python_server(server):
+    """C++ front-end daemon (HTTP → ZMQ/msgpack → engine core) returns the same tokens as the Python API server,
+    streams SSE, detokenises incrementally and honours stop strings."""
+    env = dict(os.environ, PYTHONPATH=ROOT, VLLM_LOGGING_LEVEL="WARNING")
+    port = get_open_port()
+    proc = _spawn([sys.executable, "-m", "vllm_b200", "serve", "llama-tiny", "--device", "cpu", "--dtype", "float32",
+                   "--max-model-len", "256", "--max-num-seqs", "8", "--max-num-batched-tokens", "128",
+                   "--kv-cache-memory-bytes", str(16 << 20), "--host", "127.0.0.1", "--port", str(port),
+                   "--native-frontend"], env)
+    url = f"http://127.0.0.1:{port}"
+    try:
+        _wait_healthy([(proc, url)])
+        assert requests.get(url + "/v1/models", timeout=10).json()["data"][0]["id"] == "llama-tiny"
+        prompt = [(17 * i) % 200 + 5 for i in range(40)]
+        body = {"model": "llama-tiny", "prompt": prompt, "max_tokens": 12, "temperature": 0}
+        want = requests.post(server + "/v1/completions", json=body, timeout=120).json()
+        got = requests.post(url + "/v1/completions", json=body, timeout=120).json()
+        assert got["usage"] == {"prompt_tokens": 40, "completion_tokens": 12, "total_tokens": 52}
+        assert got["choices"][0]["finish_reason"] == "length"
+        ids = got["choices"][0]["token_ids"]
+        # same tokens as the Python stack (via its token-in/token-out route), same text as its detokeniser
+        ref = requests.post(server + "/inference/v1/generate", json={"token_ids": prompt, "sampling_params": {
+            "max_tokens": 12, "temperature": 0}}, timeout=120).json()
+        assert ids == ref["token_ids"]
+        assert got["choices"][0]["text"] == want["choices"][0]["text"]
+        tok = requests.post(url + "/inference/v1/generate", json={"token_ids": prompt, "sampling_params": {
+            "max_tokens": 12, "temperature": 0}}, timeout=120).json()
+        assert tok["token_ids"] == ids and tok["num_prompt_tokens"] == 40
+        # streaming: concatenated deltas == full text, [DONE] terminator, usage chunk on request
+        text, saw_done, usage = "", False, None
+        with requests.post(url + "/v1/completions", json=dict(body, stream=True, stream_options={"include_usage": True}),
+                           stream=True, timeout=120) as s:
+            for line in s.iter_lines():
+                if not line.startswith(b"data:"):
+                    continue
+                if b"[DONE]" in line:
+                    saw_done = True
+                    continue
+                d = json.loads(line[5:])
+                if d["choices"]:
+                    text += d["choices"][0]["text"]
+                if d.get("usage"):
+                    usage = d["usage"]
+        assert saw_done and text == got["choices"][0]["text"] and usage["completion_tokens"] == 12
+        # stop token id ends the request early with finish_reason=stop
+        r = requests.post(url + "/v1/completions", json=dict(body, stop_token_ids=[ids[3]]), timeout=120).json()
+        assert r["choices"][0]["finish_reason"] == "stop" and r["choices"][0]["token_ids"] == ids[:4]
+        # stop string: cut at the match, engine request aborted
+        full = got["choices"][0]["text"]
+        if len(full) >= 4:
+            stop = full[2:4]
+            r = requests.post(url + "/v1/completions", json=dict(body, stop=[stop]), timeout=120).json()
+            assert r["choices"][0]["finish_reason"] == "stop" and r["choices"][0]["text"] == full[:full.index(stop)]
+        # errors + misc routes
+        assert requests.post(url + "/v1/completions", json={"prompt": "text", "max_tokens": 2}, timeout=10).status_code == 400
+        assert requests.post(url + "/v1/completions", data="{bad", timeout=10).status_code == 400
+        assert requests.get(url + "/nope", timeout=10).status_code == 404
+        assert requests.post(url + "/detokenize", json={"tokens": [3 + ord("h"), 3 + ord("i")]}, timeout=10).json()["prompt"] == "hi"
+        m = requests.get(url + "/metrics", timeout=10).text
+        assert "vllm:generation_tokens_total" in m and "vllm:request_success_total" in m
+        # many concurrent keep-alive clients
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(8) as ex:
+            outs = list(ex.map(lambda _: requests.post(url + "/v1/completions", json=body, timeout=120).json()["choices"][0]["token_ids"],
+                               range(16)))
+        assert all(o == ids for o in outs)
+        # the C++ load generator (Connection: close + SSE) against the C++ front-end
+        from vllm_b200.native import build_loadgen
+        res = subprocess.run([build_loadgen(), "--host", "127.0.0.1", "--port", str(port), "--model", "llama-tiny",
+                              "--num", "24", "--input-len", "16", "--output-len", "6", "--concurrency", "8",
+                              "--vocab", "400"], capture_output=True, text=True, timeout=120)
+        lg = json.loads(res.stdout.strip().splitlines()[-1])
+        assert lg["completed"] == 24 and lg["failed"] == 0 and lg["output_throughput"] > 0
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=30)
+        except subprocess.TimeoutExpired:
+            proc.kill()

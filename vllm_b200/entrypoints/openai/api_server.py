@@ -764,7 +764,11 @@ def make_arg_parser() -> argparse.ArgumentParser:
     ap.add_argument("--tool-call-parser", default=None)
     ap.add_argument("--uvicorn-log-level", default="warning")
     ap.add_argument("--api-server-count", type=int, default=1)
-    ap.add_argument("--headless", action="store_true")
+    ap.add_argument("--headless", action="store_true", help="engine cores only; connect to a remote front-end")
+    ap.add_argument("--native-frontend", action="store_true", help="serve through the C++ front-end daemon")
+    ap.add_argument("--engine-input-addr", default=None)
+    ap.add_argument("--engine-output-addr", default=None)
+    ap.add_argument("--data-parallel-start-rank", type=int, default=None)
     EngineArgs.add_cli_args(ap)
     return ap
 
@@ -811,6 +815,12 @@ async def run_server(args: argparse.Namespace) -> None:
 
 def main(argv=None) -> None:
     args = make_arg_parser().parse_args(argv)
+    if args.headless:
+        from vllm_b200.entrypoints.native_frontend import run_headless
+        return run_headless(args)
+    if args.native_frontend:
+        from vllm_b200.entrypoints.native_frontend import run_native_server
+        return run_native_server(args)
     try:
         import uvloop
         uvloop.run(run_server(args))
