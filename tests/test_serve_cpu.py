@@ -232,3 +232,37 @@ def test_native_frontend_matches_python_server(server):
             proc.wait(timeout=30)
         except subprocess.TimeoutExpired:
             proc.kill()
+
+
+def test_multiple_api_servers_share_one_engine(server):
+    """--api-server-count 2: two HTTP processes accept on one socket and route to the same engine core by client index."""
+    env = dict(os.environ, PYTHONPATH=ROOT, VLLM_LOGGING_LEVEL="WARNING")
+    port = get_open_port()
+    proc = _spawn([sys.executable, "-m", "vllm_b200", "serve", "llama-tiny", "--device", "cpu", "--dtype", "float32",
+                   "--max-model-len", "256", "--max-num-seqs", "8", "--max-num-batched-tokens", "128",
+                   "--kv-cache-memory-bytes", str(16 << 20), "--host", "127.0.0.1", "--port", str(port),
+                   "--api-server-count", "2"], env)
+    url = f"http://127.0.0.1:{port}"
+    try:
+        _wait_healthy([(proc, url)])
+        body = {"model": "llama-tiny", "prompt": [9, 8, 7, 6, 5, 4], "max_tokens": 8, "temperature": 0}
+        want = requests.post(server + "/v1/completions", json=body, timeout=120).json()["choices"][0]["text"]
+        seen = set()
+        deadline = time.time() + 60
+        while len(seen) < 2 and time.time() < deadline:
+            info = requests.get(url + "/server_info", timeout=30).json()        # new connection each time
+            seen.add(info["api_server_index"])
+            got = requests.post(url + "/v1/completions", json=body, timeout=120).json()
+            assert got["choices"][0]["text"] == want
+        assert seen == {0, 1}
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(8) as ex:
+            outs = list(ex.map(lambda _: requests.post(url + "/v1/completions", json=body, timeout=120).json()["choices"][0]["text"],
+                               range(16)))
+        assert all(o == want for o in outs)
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=40)
+        except subprocess.TimeoutExpired:
+            proc.kill()

@@ -176,16 +176,25 @@ class EngineCoreProc(EngineCore):
         self.output_queue: "queue.Queue[Any]" = queue.Queue()
         self._zctx = zmq.Context(io_threads=2)
         identity = engine_index.to_bytes(2, "little")
+        # One (DEALER, PUSH) pair per front-end client: comma-separated address lists, position = client_index
+        # (several API-server processes in front of the same engines; reference: --api-server-count).
         # handshake first so a slow model load does not look like a dead engine
-        self._in_sock = self._zctx.socket(zmq.DEALER)
-        self._in_sock.setsockopt(zmq.IDENTITY, identity)
-        self._in_sock.connect(input_addr)
-        self._in_sock.send(b"HELLO")
-        self._out_sock = self._zctx.socket(zmq.PUSH)
-        self._out_sock.connect(output_addr)
+        self._in_socks, self._out_socks = [], []
+        for addr in input_addr.split(","):
+            s = self._zctx.socket(zmq.DEALER)
+            s.setsockopt(zmq.IDENTITY, identity)
+            s.connect(addr)
+            s.send(b"HELLO")
+            self._in_socks.append(s)
+        for addr in output_addr.split(","):
+            s = self._zctx.socket(zmq.PUSH)
+            s.connect(addr)
+            self._out_socks.append(s)
+        self._in_sock, self._out_sock = self._in_socks[0], self._out_socks[0]
         super().__init__(vllm_config, executor_class, log_stats)
-        self._in_sock.send(msgspec.msgpack.encode(
-            {"status": "READY", "num_gpu_blocks": vllm_config.cache_config.num_gpu_blocks}))
+        for s in self._in_socks:
+            s.send(msgspec.msgpack.encode(
+                {"status": "READY", "num_gpu_blocks": vllm_config.cache_config.num_gpu_blocks}))
         self._stop = False
         self._threads = [threading.Thread(target=self._input_loop, daemon=True),
                          threading.Thread(target=self._output_loop, daemon=True)]
@@ -195,16 +204,22 @@ class EngineCoreProc(EngineCore):
     # ---- IO threads
     def _input_loop(self) -> None:
         from vllm_b200.engine.serial import decode_request
+        import zmq
+        poller = zmq.Poller()
+        for s in self._in_socks:
+            poller.register(s, zmq.POLLIN)
         while not self._stop:
             try:
-                frames = self._in_sock.recv_multipart()
+                ready = poller.poll(500) if len(self._in_socks) > 1 else [(self._in_sock, zmq.POLLIN)]
+                for sock, _ in ready:
+                    frames = sock.recv_multipart()
+                    kind = frames[0]
+                    if kind == REQ_ADD:
+                        self.input_queue.put((kind, decode_request(frames[1])))
+                    else:
+                        self.input_queue.put((kind, msgspec.msgpack.decode(frames[1]) if len(frames) > 1 else None))
             except Exception:
                 break
-            kind = frames[0]
-            if kind == REQ_ADD:
-                self.input_queue.put((kind, decode_request(frames[1])))
-            else:
-                self.input_queue.put((kind, msgspec.msgpack.decode(frames[1]) if len(frames) > 1 else None))
 
     def _output_loop(self) -> None:
         from vllm_b200.engine.serial import encode_outputs
@@ -212,10 +227,12 @@ class EngineCoreProc(EngineCore):
             item = self.output_queue.get()
             if item is None:
                 break
-            if isinstance(item, bytes):
-                self._out_sock.send(item)
+            if isinstance(item, bytes):                      # ENGINE_CORE_DEAD: every front-end must hear it
+                for s in self._out_socks:
+                    s.send(item)
                 continue
-            self._out_sock.send(encode_outputs(item))
+            ci = item[0] if 0 <= item[0] < len(self._out_socks) else 0
+            self._out_socks[ci].send(encode_outputs(item))
 
     # ---- busy loop
     def run_busy_loop(self) -> None:
@@ -325,8 +342,10 @@ class EngineCoreProc(EngineCore):
         self.output_queue.put(None)
         super().shutdown()
         try:
-            self._in_sock.close(linger=0)
-            self._out_sock.close(linger=200)
+            for s in self._in_socks:
+                s.close(linger=0)
+            for s in self._out_socks:
+                s.close(linger=200)
             self._zctx.term()
         except Exception:
             pass

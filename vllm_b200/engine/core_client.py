@@ -133,7 +133,16 @@ class MPClient(EngineCoreClient):
         self._finalizer = weakref.finalize(self, self.res)
         self.ctx = zmq.asyncio.Context() if asyncio_mode else zmq.Context()
         self.res.ctx = self.ctx
-        in_addr, out_addr = get_open_zmq_ipc_path(), get_open_zmq_ipc_path()
+        # "k|in_addr|out_addr": this process is API server k of several in front of engines somebody else launched
+        # (``serve --api-server-count N``; reference: v1/utils.py APIServerProcessManager + client_index routing)
+        external = os.environ.get("VLLM_B200_EXTERNAL_ENGINE")
+        self.external_engines = bool(external)
+        if external:
+            idx, in_addr, out_addr = external.split("|")
+            self.client_index = int(idx)
+        else:
+            in_addr, out_addr = get_open_zmq_ipc_path(), get_open_zmq_ipc_path()
+            self.client_index = 0
         self.input_socket = self.ctx.socket(zmq.ROUTER)
         self.input_socket.bind(in_addr)
         self.output_socket = self.ctx.socket(zmq.PULL)
@@ -142,11 +151,11 @@ class MPClient(EngineCoreClient):
         self.num_engines = vllm_config.parallel_config.data_parallel_size
         self.engine_ids = [i.to_bytes(2, "little") for i in range(self.num_engines)]
         self.in_addr, self.out_addr, self.log_stats = in_addr, out_addr, log_stats
-        self.res.procs = _launch_engines(vllm_config, in_addr, out_addr, self.num_engines, log_stats)
+        if not external:
+            self.res.procs = _launch_engines(vllm_config, in_addr, out_addr, self.num_engines, log_stats)
         self._wait_ready(in_addr)
         self.utility_results: dict[int, Any] = {}
         self._call_id = 0
-        self.client_index = 0
 
     def _wait_ready(self, in_addr: str) -> None:
         """Startup handshake with a liveness check on the child processes."""
@@ -190,7 +199,7 @@ class MPClient(EngineCoreClient):
 
     def shutdown(self) -> None:
         try:
-            for eid in self.engine_ids:
+            for eid in ([] if self.external_engines else self.engine_ids):
                 s = self.input_socket
                 if hasattr(s, "underlying"):
                     import zmq

@@ -14,7 +14,9 @@ import argparse
 import asyncio
 import base64
 import json
+import os
 import signal
+import socket
 import struct
 import time
 from contextlib import asynccontextmanager
@@ -156,7 +158,8 @@ def build_app(ctx: ServingContext):
     @app.get("/server_info")
     async def server_info():
         cfg = await ctx.engine.get_vllm_config()
-        return {"version": __version__, "model": ctx.model_name, "config_hash": cfg.compute_hash()}
+        return {"version": __version__, "model": ctx.model_name, "config_hash": cfg.compute_hash(),
+                "api_server_index": int(os.environ.get("VLLM_B200_API_SERVER_INDEX", "0")), "pid": os.getpid()}
 
     # ------------------------------------------------------------ tokenize
     @app.post("/tokenize")
@@ -806,11 +809,68 @@ async def run_server(args: argparse.Namespace) -> None:
         except NotImplementedError:
             pass
     wd = asyncio.create_task(watchdog())
+    listen_fd = os.environ.get("VLLM_B200_LISTEN_FD")       # API server k of N: the parent owns the listening socket
+    sockets = [socket.socket(fileno=int(listen_fd))] if listen_fd else None
     try:
-        await server.serve()
+        await server.serve(sockets=sockets)
     finally:
         wd.cancel()
         engine.shutdown()
+
+
+def run_multi_api_server(args: argparse.Namespace, argv: list[str]) -> None:
+    """``--api-server-count N``: N HTTP front-end processes accept on one shared listening socket and share the
+    engine cores (each front-end is ``client_index`` k with its own ZMQ socket pair); the parent launches the
+    engines and supervises (reference: entrypoints/cli/serve.py run_multi_api_server, v1/utils.py
+    APIServerProcessManager)."""
+    import subprocess
+    import sys
+    from vllm_b200.engine.core_client import _launch_engines
+    from vllm_b200.utils import get_open_zmq_ipc_path
+    if args.model_tag:
+        args.model = args.model_tag
+    ea = EngineArgs.from_cli_args(args)
+    cfg = ea.create_engine_config()
+    n = args.api_server_count
+    addrs = [(get_open_zmq_ipc_path(), get_open_zmq_ipc_path()) for _ in range(n)]
+    lsock = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    lsock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+    lsock.bind((args.host, args.port))
+    lsock.listen(2048)
+    lsock.set_inheritable(True)
+    child_argv = [a for a in (argv if argv is not None else sys.argv[2:])]
+    servers = []
+    for k, (ia, oa) in enumerate(addrs):
+        env = dict(os.environ, VLLM_B200_EXTERNAL_ENGINE=f"{k}|{ia}|{oa}", VLLM_B200_LISTEN_FD=str(lsock.fileno()),
+                   VLLM_B200_API_SERVER_INDEX=str(k))
+        servers.append(subprocess.Popen([sys.executable, "-m", "vllm_b200", "serve", *child_argv,
+                                         "--api-server-count", "1"], env=env, pass_fds=[lsock.fileno()]))
+    engines = _launch_engines(cfg, ",".join(a for a, _ in addrs), ",".join(b for _, b in addrs),
+                              cfg.parallel_config.data_parallel_size, log_stats=not ea.disable_log_stats)
+    stop = {"v": False}
+    for sig in (signal.SIGINT, signal.SIGTERM):
+        signal.signal(sig, lambda *a: stop.__setitem__("v", True))
+    try:
+        while not stop["v"]:
+            if any(p.poll() is not None for p in servers) or any(not e.is_alive() for e in engines):
+                logger.error("a front-end or engine process exited; shutting down")
+                break
+            time.sleep(0.5)
+    finally:
+        for p in servers:
+            if p.poll() is None:
+                p.terminate()
+        for e in engines:
+            if e.is_alive():
+                e.terminate()
+        for p in servers:
+            try:
+                p.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        for e in engines:
+            e.join(timeout=20)
+        lsock.close()
 
 
 def main(argv=None) -> None:
@@ -821,6 +881,8 @@ def main(argv=None) -> None:
     if args.native_frontend:
         from vllm_b200.entrypoints.native_frontend import run_native_server
         return run_native_server(args)
+    if args.api_server_count > 1:
+        return run_multi_api_server(args, argv)
     try:
         import uvloop
         uvloop.run(run_server(args))
