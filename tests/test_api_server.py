@@ -154,3 +154,66 @@ def test_tool_and_reasoning_parsers():
     assert rp.extract("still thinking") == ("still thinking", None)
     q = get_reasoning_parser("qwen3")()
     assert q.extract("plain") == (None, "plain")
+
+
+def test_audio_transcription_api():
+    """/v1/audio/transcriptions + /translations against a tiny Whisper: WAV upload, formats, streaming, chunking."""
+    import io
+    import wave
+
+    import numpy as np
+
+    from vllm_b200.engine.async_llm import AsyncLLM
+    from vllm_b200.entrypoints.openai.api_server import ServingContext, build_app
+    ea = EngineArgs(model="whisper-tiny-test", device="cpu", dtype="float32", max_model_len=32, max_num_seqs=4,
+                    max_num_batched_tokens=64, kv_cache_memory_bytes=4 << 20, enable_prefix_caching=False)
+    loop = asyncio.new_event_loop()
+    asyncio.set_event_loop(loop)
+    engine = AsyncLLM.from_engine_args(ea)
+    app = build_app(ServingContext(engine, "whisper-tiny-test", 32, engine.tokenizer))
+    client = httpx.AsyncClient(transport=httpx.ASGITransport(app=app), base_url="http://test", timeout=300)
+    call = loop.run_until_complete
+
+    def wav_bytes(seconds: float, sr: int = 8000) -> bytes:
+        t = np.arange(int(seconds * sr)) / sr
+        pcm = (0.3 * np.sin(2 * np.pi * 330 * t) * 32767).astype("<i2")
+        buf = io.BytesIO()
+        with wave.open(buf, "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr)
+            w.writeframes(pcm.tobytes())
+        return buf.getvalue()
+    try:
+        short = wav_bytes(2.0)
+        r = call(client.post("/v1/audio/transcriptions", files={"file": ("a.wav", short, "audio/wav")},
+                             data={"model": "whisper-tiny-test"}))
+        assert r.status_code == 200, r.text
+        body = r.json()
+        assert isinstance(body["text"], str) and body["usage"]["seconds"] == 2
+        r2 = call(client.post("/v1/audio/transcriptions", files={"file": ("a.wav", short, "audio/wav")},
+                              data={"response_format": "text"}))
+        assert r2.text == body["text"]                                  # greedy → deterministic
+        # 65 s of audio → three windows, verbose_json reports one segment per window with contiguous bounds
+        r3 = call(client.post("/v1/audio/translations", files={"file": ("b.wav", wav_bytes(65.0), "audio/wav")},
+                              data={"response_format": "verbose_json"})).json()
+        assert r3["task"] == "translate" and len(r3["segments"]) == 3
+        assert r3["segments"][0]["start"] == 0 and abs(r3["segments"][-1]["end"] - 65.0) < 1e-6
+        assert all(abs(a["end"] - b["start"]) < 1e-9 for a, b in zip(r3["segments"], r3["segments"][1:]))
+        srt = call(client.post("/v1/audio/transcriptions", files={"file": ("a.wav", short, "audio/wav")},
+                               data={"response_format": "srt"})).text
+        assert srt.startswith("1\n00:00:00,000 --> 00:00:02,000")
+        # streaming: deltas concatenate to the non-streamed text
+        async def stream():
+            out = ""
+            async with client.stream("POST", "/v1/audio/transcriptions", files={"file": ("a.wav", short, "audio/wav")},
+                                     data={"stream": "true"}) as s:
+                async for line in s.aiter_lines():
+                    if line.startswith("data:") and "[DONE]" not in line:
+                        out += json.loads(line[5:])["choices"][0]["delta"]["content"]
+            return out
+        assert call(stream()).strip() == body["text"]
+        bad = call(client.post("/v1/audio/transcriptions", files={"file": ("x.wav", b"not audio", "audio/wav")}))
+        assert bad.status_code == 400
+    finally:
+        call(client.aclose())
+        engine.shutdown()
+        loop.close()

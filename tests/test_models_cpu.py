@@ -182,3 +182,36 @@ def test_bart_encoder_decoder_matches_hf():
                               forced_bos_token_id=None, forced_eos_token_id=None)[0, 1:].tolist()
         assert o.outputs[0].token_ids == ref[:8], (o.outputs[0].token_ids, ref)
     llm.shutdown()
+
+
+def test_whisper_matches_hf_and_feature_extractor():
+    """Speech path: our log-mel front-end == HF WhisperFeatureExtractor, and waveform → encoder → cross-attending
+    decoder reproduces the HF model's greedy continuation."""
+    import numpy as np
+    from transformers import WhisperFeatureExtractor
+    from vllm_b200.multimodal.audio import log_mel_spectrogram
+    rng = np.random.default_rng(0)
+    t = np.arange(16000 * 3) / 16000
+    waves = [(0.3 * np.sin(2 * np.pi * 440 * t) + 0.05 * rng.standard_normal(t.shape)).astype(np.float32),
+             (0.2 * np.sin(2 * np.pi * 220 * t[:20000]) * np.hanning(20000)).astype(np.float32)]
+    fe = WhisperFeatureExtractor(feature_size=80)
+    feats = [fe(w, sampling_rate=16000, return_tensors="pt").input_features[0] for w in waves]
+    for w, f in zip(waves, feats):
+        assert (log_mel_spectrogram(w, 80) - f).abs().max() < 1e-4
+
+    hf = make_hf_model("whisper-tiny-test")
+    llm = make_llm("whisper-tiny-test", weights=hf.state_dict().items(), enable_prefix_caching=False, max_model_len=128)
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    prompts = [{"prompt_token_ids": [1, 7, 9], "multi_modal_data": {"audio": (waves[0], 16000)}},
+               {"multi_modal_data": {"audio": (waves[1], 16000)}}]
+    outs = llm.generate(prompts, sp)
+    for p, f, o in zip(prompts, feats, outs):
+        dec = list(p.get("prompt_token_ids", [1]))
+        with torch.no_grad():
+            enc = hf.model.encoder(f[None]).last_hidden_state
+            for _ in range(8):
+                h = hf.model.decoder(input_ids=torch.tensor([dec]), encoder_hidden_states=enc).last_hidden_state
+                dec.append(int(hf.proj_out(h[0, -1]).argmax()))
+        n0 = len(p.get("prompt_token_ids", [1]))
+        assert o.outputs[0].token_ids == dec[n0:], (o.outputs[0].token_ids, dec[n0:])
+    llm.shutdown()

@@ -173,6 +173,13 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_attention_heads=4, encoder_ffn_dim=128, decoder_ffn_dim=128, max_position_embeddings=128,
         activation_function="gelu", scale_embedding=False, pad_token_id=1, bos_token_id=0, eos_token_id=2,
         decoder_start_token_id=2, torch_dtype="float32", tie_word_embeddings=True, is_encoder_decoder=True),
+    "whisper-tiny-test": dict(
+        architectures=["WhisperForConditionalGeneration"], model_type="whisper", vocab_size=512, d_model=64,
+        hidden_size=64, encoder_layers=2, decoder_layers=2, num_hidden_layers=2, encoder_attention_heads=4,
+        decoder_attention_heads=4, num_attention_heads=4, encoder_ffn_dim=128, decoder_ffn_dim=128, num_mel_bins=80,
+        max_source_positions=1500, max_target_positions=128, max_position_embeddings=128,
+        activation_function="gelu", scale_embedding=False, pad_token_id=0, bos_token_id=1, eos_token_id=2,
+        decoder_start_token_id=1, torch_dtype="float32", tie_word_embeddings=True, is_encoder_decoder=True),
     "bert-tiny": dict(
         architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
         num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,

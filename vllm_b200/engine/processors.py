@@ -52,6 +52,20 @@ class InputProcessor:
                 ids = [start]
             embeds_feature = {"modality": "encoder_tokens", "hash": hash_item(np.asarray(enc, dtype=np.int64)),
                               "offset": 0, "length": 0, "data": enc}
+        mmd = extras.get("multi_modal_data") or {}
+        if self.mc.hf_config.get("is_encoder_decoder") and mmd.get("audio") is not None:
+            # speech models: the 30-second log-mel window is the encoder input (reference: models/whisper.py
+            # WhisperMultiModalProcessor); decoder prompt = the task tokens the caller built, or the start token
+            from vllm_b200.multimodal import hash_item
+            from vllm_b200.multimodal.audio import load_audio, log_mel_spectrogram
+            audio = mmd["audio"]
+            mel = audio if (hasattr(audio, "dim") and audio.dim() == 2) else log_mel_spectrogram(
+                load_audio(audio), self.mc.hf_config.get("num_mel_bins", 80))
+            if ids is None and text is None:
+                ids = [self.mc.hf_config.get("decoder_start_token_id", self.mc.hf_config.get("bos_token_id", 0))]
+            embeds_feature = {"modality": "audio", "hash": hash_item(mel.float().numpy()), "offset": 0, "length": 0,
+                              "data": mel}
+            extras = {k: v for k, v in extras.items() if k != "multi_modal_data"}
         if ids is None and text is None and extras.get("prompt_embeds") is not None:
             # prompt given directly as embeddings [n, hidden] (reference: ``EmbedsPrompt``): the positions carry a
             # dummy token id and the worker splices the rows in exactly like multimodal encoder outputs

@@ -460,6 +460,132 @@ def build_app(ctx: ServingContext):
                                usage=_usage(sum(len(o.prompt_token_ids) for o in ea + eb), 0)).model_dump()
 
     # ------------------------------------------- token-in / token-out and render-only fronts
+    # ------------------------------------------------------------ speech to text
+    # (reference: entrypoints/speech_to_text/{api_router,serving,speech_to_text}.py — multipart upload, 30-second
+    #  chunking at quiet points, task tokens as the decoder prompt, json / text / verbose_json / srt / vtt, SSE)
+    def _stt_prompt_ids(task: str, language: Optional[str], prompt_text: Optional[str]) -> list[int]:
+        tok, cfg = ctx.tokenizer, ctx.engine.model_config.hf_config
+        start = cfg.get("decoder_start_token_id", cfg.get("bos_token_id", 0))
+        conv = getattr(tok, "convert_tokens_to_ids", None)
+        unk = getattr(tok, "unk_token_id", None)
+
+        def tid(t: str) -> Optional[int]:
+            try:
+                i = conv(t) if conv else None
+            except Exception:
+                return None
+            return i if isinstance(i, int) and i >= 0 and i != unk else None
+        sot = tid("<|startoftranscript|>")
+        if sot is None:
+            return [start]
+        ids = []
+        if prompt_text and tid("<|startofprev|>") is not None:
+            ids += [tid("<|startofprev|>")] + tok.encode(" " + prompt_text.strip(), add_special_tokens=False)
+        ids.append(sot)
+        for t in (f"<|{language or 'en'}|>", f"<|{task}|>", "<|notimestamps|>"):
+            if tid(t) is not None:
+                ids.append(tid(t))
+        return ids
+
+    def _ts(sec: float, sep: str) -> str:
+        ms = int(round(sec * 1000))
+        return f"{ms // 3600000:02d}:{ms // 60000 % 60:02d}:{ms // 1000 % 60:02d}{sep}{ms % 1000:03d}"
+
+    async def _speech_to_text(raw: Request, task: str):
+        from vllm_b200.multimodal.audio import SAMPLE_RATE, load_audio, split_chunks
+        if not ctx.engine.model_config.hf_config.get("is_encoder_decoder"):
+            return _error("the served model does not support speech-to-text", 400)
+        form = await raw.form()
+        up = form.get("file")
+        if up is None:
+            return _error("multipart field `file` is required")
+        err = check_model(form.get("model"))
+        if err:
+            return err
+        try:
+            wav = load_audio(await up.read())
+        except Exception as ex:
+            return _error(f"could not decode the audio file: {ex}")
+        fmt = form.get("response_format", "json")
+        if fmt not in ("json", "text", "verbose_json", "srt", "vtt"):
+            return _error(f"unsupported response_format {fmt!r}")
+        language = form.get("language")
+        temperature = float(form.get("temperature", 0.0) or 0.0)
+        stream = str(form.get("stream", "")).lower() in ("1", "true")
+        max_tokens = max(1, ctx.max_model_len - 8)
+        ids = _stt_prompt_ids(task, language, form.get("prompt"))
+        chunks = split_chunks(wav)
+        rid = f"{'transcribe' if task == 'transcribe' else 'translate'}-{random_uuid()}"
+        sp = SamplingParams(temperature=temperature, max_tokens=min(max_tokens, ctx.max_model_len - len(ids) - 1),
+                            seed=int(form["seed"]) if form.get("seed") else None)
+
+        async def run_chunk(i: int, chunk, on_delta=None) -> tuple[str, int]:
+            gen = ctx.engine.generate({"prompt_token_ids": list(ids), "multi_modal_data": {"audio": (chunk, SAMPLE_RATE)}},
+                                      sp, f"{rid}-{i}")
+            text, n, sent = "", 0, 0
+            async for o in gen:
+                text, n = o.outputs[0].text, len(o.outputs[0].token_ids)
+                if on_delta is not None and len(text) > sent:
+                    await on_delta(text[sent:])
+                    sent = len(text)
+            return text, n
+
+        if stream:
+            async def sse():
+                q: asyncio.Queue = asyncio.Queue()
+
+                async def push(d):
+                    await q.put(d)
+
+                async def producer():
+                    for i, c in enumerate(chunks):
+                        await run_chunk(i, c, push)
+                    await q.put(None)
+                task_ = asyncio.create_task(producer())
+                try:
+                    while True:
+                        d = await q.get()
+                        if d is None:
+                            break
+                        yield "data: " + json.dumps({"id": rid, "object": "transcription.chunk", "created": int(time.time()),
+                                                      "model": ctx.model_name,
+                                                      "choices": [{"index": 0, "delta": {"content": d}}]}) + "\n\n"
+                finally:
+                    task_.cancel()
+                yield "data: [DONE]\n\n"
+            return StreamingResponse(sse(), media_type="text/event-stream")
+
+        results = await asyncio.gather(*[run_chunk(i, c) for i, c in enumerate(chunks)])
+        text = "".join(t for t, _ in results).strip()
+        if fmt == "text":
+            return Response(content=text, media_type="text/plain")
+        bounds, pos = [], 0.0
+        for c in chunks:
+            bounds.append((pos, pos + len(c) / SAMPLE_RATE))
+            pos += len(c) / SAMPLE_RATE
+        if fmt in ("srt", "vtt"):
+            sep = "," if fmt == "srt" else "."
+            lines = ["WEBVTT", ""] if fmt == "vtt" else []
+            for i, ((a, b), (t, _)) in enumerate(zip(bounds, results)):
+                if fmt == "srt":
+                    lines.append(str(i + 1))
+                lines += [f"{_ts(a, sep)} --> {_ts(b, sep)}", t.strip(), ""]
+            return Response(content="\n".join(lines), media_type="text/plain")
+        usage = {"type": "duration", "seconds": int(round(len(wav) / SAMPLE_RATE))}
+        if fmt == "verbose_json":
+            return {"task": task, "language": language or "en", "duration": len(wav) / SAMPLE_RATE, "text": text,
+                    "segments": [{"id": i, "start": a, "end": b, "text": t.strip(), "tokens": n}
+                                 for i, ((a, b), (t, n)) in enumerate(zip(bounds, results))], "usage": usage}
+        return {"text": text, "usage": usage}
+
+    @app.post("/v1/audio/transcriptions")
+    async def transcriptions(raw: Request):
+        return await _speech_to_text(raw, "transcribe")
+
+    @app.post("/v1/audio/translations")
+    async def translations(raw: Request):
+        return await _speech_to_text(raw, "translate")
+
     # (reference: entrypoints/generate "/inference/v1/generate", entrypoints/scale_out render/derender split — a
     #  tokenizer-less engine tier behind a separate rendering tier)
     @app.post("/inference/v1/generate")

@@ -37,6 +37,6 @@ def parse_prompt(p: PromptType) -> tuple[Optional[str], Optional[list[int]], dic
             return p.get("prompt"), list(p["prompt_token_ids"]), extras
         if "prompt" in p:
             return p["prompt"], None, extras
-        if "prompt_embeds" in p or "encoder_prompt_token_ids" in p or "encoder_prompt" in p:
+        if any(k in p for k in ("prompt_embeds", "encoder_prompt_token_ids", "encoder_prompt", "multi_modal_data")):
             return None, None, extras
     raise TypeError(f"unsupported prompt type {type(p)}")

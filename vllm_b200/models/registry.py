@@ -31,6 +31,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
     "BartForConditionalGeneration": ("bart", "BartForConditionalGeneration"),
     "BartModel": ("bart", "BartForConditionalGeneration"),
+    "WhisperForConditionalGeneration": ("whisper", "WhisperForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "BertModel": ("bert", "BertEmbeddingModel"),
     "BertForMaskedLM": ("bert", "BertEmbeddingModel"),

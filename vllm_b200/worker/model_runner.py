@@ -512,9 +512,11 @@ class ModelRunner:
         for s in states:
             kv = self.cross_states.get(s.req_id)
             if kv is None and s.mm_features:
-                f = next((f for f in s.mm_features if f.get("modality") == "encoder_tokens"), None)
+                f = next((f for f in s.mm_features if f.get("modality") in ("encoder_tokens", "audio")), None)
                 if f is not None:
-                    kv = self.model.encode(torch.tensor(f["data"], dtype=torch.int64, device=self.device))
+                    src = (torch.as_tensor(f["data"]).to(self.device) if f["modality"] == "audio"
+                           else torch.tensor(f["data"], dtype=torch.int64, device=self.device))
+                    kv = self.model.encode(src)
                     self.cross_states[s.req_id] = kv
             kvs.append(kv)
         return [int(x) for x in cu], kvs
