@@ -437,3 +437,13 @@ def test_deepseek_fp8_block_experts_and_linears():
     assert d0 == {torch.float32} and d1 == {torch.float8_e4m3fn}
     diff = max(abs(a - b) for a, b in zip(base, q))
     assert 0 < diff < 0.3, diff
+
+
+def test_mxfp4_expert_dequant():
+    """e2m1 nibbles (low first) x e8m0 block exponents, the packing GPT-OSS checkpoints use."""
+    from vllm_b200.models.gpt_oss import dequant_mxfp4
+    blocks = torch.tensor([[[0x21, 0xF7] + [0] * 14]], dtype=torch.uint8)        # values: 0.5, 1.0, 6.0, -6.0, 0...
+    scales = torch.tensor([[128]], dtype=torch.uint8)                             # 2^(128-127) = 2
+    out = dequant_mxfp4(blocks, scales, torch.float32)
+    assert out.shape == (1, 32)
+    assert out[0, :4].tolist() == [1.0, 2.0, 12.0, -12.0] and out[0, 4:].abs().sum() == 0

@@ -11,7 +11,9 @@ PROMPTS = [[5, 17, 99, 3, 250, 41], [7, 7, 7, 301, 12], list(range(10, 60))]
 
 @pytest.mark.parametrize("preset", ["llama-tiny", "opt-tiny", "gpt2-tiny", "mixtral-tiny", "qwen2moe-tiny",
                                     "qwen3moe-tiny", "deepseek-tiny", "mamba-tiny", "phi3-tiny", "gemma2-tiny", "gptneox-tiny",
-                                    "starcoder2-tiny", "gptj-tiny", "olmo-tiny", "stablelm-tiny", "jamba-tiny"])
+                                    "starcoder2-tiny", "gptj-tiny", "olmo-tiny", "stablelm-tiny", "jamba-tiny",
+                                    "bloom-tiny", "mpt-tiny", "falcon-rw-tiny", "falcon-7b-tiny", "falcon-40b-tiny",
+                                    "gptoss-tiny"])
 def test_greedy_matches_hf(preset):
     hf = make_hf_model(preset)
     llm = make_llm(preset, weights=hf.state_dict().items())

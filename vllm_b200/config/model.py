@@ -150,6 +150,39 @@ PRESETS: dict[str, dict[str, Any]] = {
         architectures=["GPTJForCausalLM"], model_type="gptj", vocab_size=512, n_embd=64, n_layer=2, n_head=4, n_inner=256,
         n_positions=512, rotary_dim=8, layer_norm_epsilon=1e-5, activation_function="gelu_new", bos_token_id=0,
         eos_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "bloom-tiny": dict(
+        architectures=["BloomForCausalLM"], model_type="bloom", vocab_size=512, hidden_size=64, n_layer=2, n_head=4,
+        num_hidden_layers=2, num_attention_heads=4, layer_norm_epsilon=1e-5, bos_token_id=1, eos_token_id=2,
+        torch_dtype="float32", tie_word_embeddings=True, max_position_embeddings=512),
+    "mpt-tiny": dict(
+        architectures=["MptForCausalLM"], model_type="mpt", vocab_size=512, d_model=64, n_heads=4, n_layers=2,
+        hidden_size=64, num_hidden_layers=2, num_attention_heads=4, expansion_ratio=4, max_seq_len=512,
+        max_position_embeddings=512, no_bias=True, layer_norm_epsilon=1e-5,
+        attn_config=dict(alibi=True, alibi_bias_max=8, attn_type="multihead_attention", attn_impl="torch"),
+        torch_dtype="float32", tie_word_embeddings=True),
+    "falcon-rw-tiny": dict(
+        architectures=["FalconForCausalLM"], model_type="falcon", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_attention_heads=4, alibi=True, bias=True, multi_query=False, parallel_attn=False,
+        new_decoder_architecture=False, layer_norm_epsilon=1e-5, bos_token_id=1, eos_token_id=2,
+        max_position_embeddings=512, torch_dtype="float32", tie_word_embeddings=True),
+    "falcon-7b-tiny": dict(
+        architectures=["FalconForCausalLM"], model_type="falcon", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_attention_heads=4, alibi=False, bias=False, multi_query=True, parallel_attn=True,
+        new_decoder_architecture=False, layer_norm_epsilon=1e-5, bos_token_id=1, eos_token_id=2, rope_theta=10000.0,
+        max_position_embeddings=512, torch_dtype="float32", tie_word_embeddings=True),
+    "falcon-40b-tiny": dict(
+        architectures=["FalconForCausalLM"], model_type="falcon", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_attention_heads=4, num_kv_heads=2, alibi=False, bias=False, multi_query=True, parallel_attn=True,
+        new_decoder_architecture=True, layer_norm_epsilon=1e-5, bos_token_id=1, eos_token_id=2, rope_theta=10000.0,
+        max_position_embeddings=512, torch_dtype="float32", tie_word_embeddings=True),
+    "gptoss-tiny": dict(
+        architectures=["GptOssForCausalLM"], model_type="gpt_oss", vocab_size=512, hidden_size=64, intermediate_size=64,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, num_local_experts=4,
+        num_experts_per_tok=2, sliding_window=16, max_position_embeddings=512, rms_norm_eps=1e-5, attention_bias=True,
+        layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"],
+        rope_parameters=dict(rope_type="yarn", factor=4.0, beta_fast=32.0, beta_slow=1.0, truncate=False,
+                             original_max_position_embeddings=128, rope_theta=10000.0),
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

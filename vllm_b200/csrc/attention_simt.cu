@@ -39,6 +39,8 @@ struct AttnParams {
   float soft_cap;         // 0 = off
   float kv_scale;         // fp8 dequant scale
   int causal;
+  const float* alibi;     // optional [Hq] slopes: score += slope * (kpos - qpos)   (Bloom / MPT / Falcon-RW)
+  const float* sinks;     // optional [Hq] attention-sink logits: extra softmax mass that attends to nothing (GPT-OSS)
 };
 
 template <typename T, int D, int R, int BS, bool FP8>
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(THREADS) paged_attn_kernel(const AttnParams p)
       if (p.soft_cap > 0.f) s = p.soft_cap * tanhf(s * (p.scale_log2 * 0.6931471805599453f) / p.soft_cap) * 1.4426950408889634f;
       const int kpos = tok_base + tsel;
       const int qpos = row_pos[r];
+      if (p.alibi) s += p.alibi[h * G + (r % G)] * 1.4426950408889634f * (float)(kpos - qpos);
       bool ok = qpos >= 0 && kpos < kv_end && kpos >= kv_begin;
       if (p.causal) ok = ok && kpos <= qpos;
       if (p.window > 0) ok = ok && kpos > qpos - p.window;
@@ -244,8 +247,11 @@ __global__ void __launch_bounds__(THREADS) paged_attn_kernel(const AttnParams p)
     float m = -INFINITY;
 #pragma unroll
     for (int ww = 0; ww < WARPS; ++ww) m = fmaxf(m, merge[(ww * R + r) * (D + 2) + D]);
+    const bool has_sink = p.sinks != nullptr && split == 0;      // counted once: split 0 carries the sink mass
+    const float sink_l2 = has_sink ? p.sinks[h * G + g] * 1.4426950408889634f : -INFINITY;
+    m = fmaxf(m, sink_l2);
     const float m_use = (m == -INFINITY) ? 0.f : m;
-    float l = 0.f, o = 0.f;
+    float l = has_sink ? ex2(sink_l2 - m_use) : 0.f, o = 0.f;
 #pragma unroll
     for (int ww = 0; ww < WARPS; ++ww) {
       const float* mr = merge + (ww * R + r) * (D + 2);
@@ -348,11 +354,29 @@ int dispatch_shape(int D, int BS, int R, const AttnParams& p, dim3 grid, cudaStr
 
 // Unified entry. qsl == nullptr → decode (one query token per request, grid.x = num_splits).
 // Returns 0 on success, <0 for unsupported shapes (caller raises).
+EXPORT int vb_paged_attention_ex(const void* q, const void* kv_cache, const int* block_table, const int* seq_lens,
+                                 const int* qsl, void* out, float* part_out, float* part_lse, float* lse_out, int B,
+                                 int max_q_len, int Hq, int Hkv, int D, int BS, int64_t q_stride, int64_t out_stride,
+                                 int bt_stride, int num_splits, int window, float scale, float soft_cap, float kv_scale,
+                                 int causal, int kv_fp8, int dtype, const float* alibi, const float* sinks,
+                                 cudaStream_t st);
+
 EXPORT int vb_paged_attention(const void* q, const void* kv_cache, const int* block_table, const int* seq_lens,
                               const int* qsl, void* out, float* part_out, float* part_lse, float* lse_out, int B,
                               int max_q_len, int Hq, int Hkv, int D, int BS, int64_t q_stride, int64_t out_stride,
                               int bt_stride, int num_splits, int window, float scale, float soft_cap, float kv_scale,
                               int causal, int kv_fp8, int dtype, cudaStream_t st) {
+  return vb_paged_attention_ex(q, kv_cache, block_table, seq_lens, qsl, out, part_out, part_lse, lse_out, B, max_q_len, Hq,
+                               Hkv, D, BS, q_stride, out_stride, bt_stride, num_splits, window, scale, soft_cap, kv_scale,
+                               causal, kv_fp8, dtype, nullptr, nullptr, st);
+}
+
+EXPORT int vb_paged_attention_ex(const void* q, const void* kv_cache, const int* block_table, const int* seq_lens,
+                                 const int* qsl, void* out, float* part_out, float* part_lse, float* lse_out, int B,
+                                 int max_q_len, int Hq, int Hkv, int D, int BS, int64_t q_stride, int64_t out_stride,
+                                 int bt_stride, int num_splits, int window, float scale, float soft_cap, float kv_scale,
+                                 int causal, int kv_fp8, int dtype, const float* alibi, const float* sinks,
+                                 cudaStream_t st) {
   if (B == 0) return 0;
   if (dtype == DT_F32) return -1;
   const int G = Hq / Hkv;
@@ -361,6 +385,7 @@ EXPORT int vb_paged_attention(const void* q, const void* kv_cache, const int* bl
   p.part_out = part_out; p.part_lse = part_lse; p.lse_out = lse_out; p.q_stride = q_stride; p.out_stride = out_stride;
   p.bt_stride = bt_stride; p.Hq = Hq; p.Hkv = Hkv; p.num_splits = qsl ? 1 : num_splits; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f; p.soft_cap = soft_cap; p.kv_scale = kv_scale; p.causal = causal;
+  p.alibi = alibi; p.sinks = sinks;
   int R, TQ;
   if (G > 8 || (G & (G - 1))) return -4;     // group sizes 1,2,4,8
   if (qsl) { R = 8; TQ = 8 / G; } else { R = G; TQ = 1; }

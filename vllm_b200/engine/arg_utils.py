@@ -37,7 +37,7 @@ class EngineArgs:
     load_format: str = "auto"
     device: str = "auto"
     # cache
-    block_size: int = 64
+    block_size: Optional[int] = None      # default: 64 (tcgen05 attention page) when head_dim is 128, else 32
     gpu_memory_utilization: float = 0.92
     swap_space: float = 4.0
     kv_cache_dtype: str = "auto"
@@ -104,8 +104,15 @@ class EngineArgs:
             enforce_eager=self.enforce_eager, max_logprobs=self.max_logprobs,
             served_model_name=self.served_model_name, hf_overrides=self.hf_overrides or {},
             runner=self.runner, skip_tokenizer_init=self.skip_tokenizer_init)
+        block_size = self.block_size
+        if block_size is None:
+            # 64-token pages are the tcgen05 kernels' TMA box; models that run on the generic kernel (other head sizes,
+            # ALiBi / sinks / soft-cap) use the 32-token page it is tuned for
+            special = any(mc.hf_config.get(k) for k in ("attn_logit_softcapping", "alibi")) or \
+                mc.hf_config.get("model_type") in ("bloom", "mpt", "gpt_oss")
+            block_size = 64 if (self.device == "cpu" or mc.is_mla or (mc.head_dim == 128 and not special)) else 32
         cc = CacheConfig(
-            block_size=self.block_size, gpu_memory_utilization=self.gpu_memory_utilization,
+            block_size=block_size, gpu_memory_utilization=self.gpu_memory_utilization,
             swap_space_gb=self.swap_space, cache_dtype=self.kv_cache_dtype,
             num_gpu_blocks_override=self.num_gpu_blocks_override,
             enable_prefix_caching=self.enable_prefix_caching,

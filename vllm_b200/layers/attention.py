@@ -31,8 +31,12 @@ def clear_attention_layers() -> None:
 class Attention(nn.Module):
     def __init__(self, num_heads: int, head_size: int, scale: float, num_kv_heads: Optional[int] = None,
                  sliding_window: Optional[int] = None, logits_soft_cap: float = 0.0, prefix: str = "",
-                 causal: bool = True, rope: Optional[nn.Module] = None) -> None:
+                 causal: bool = True, rope: Optional[nn.Module] = None,
+                 alibi_slopes: Optional[torch.Tensor] = None, sinks: Optional[torch.Tensor] = None) -> None:
         super().__init__()
+        # ALiBi slopes / attention-sink logits of THIS rank's heads (buffers follow the module's device)
+        self.register_buffer("alibi_slopes", None if alibi_slopes is None else alibi_slopes.float(), persistent=False)
+        self.sinks = sinks                       # nn.Parameter owned by the model (loaded from the checkpoint) or None
         self.num_heads, self.head_size, self.scale = num_heads, head_size, scale
         self.num_kv_heads = num_kv_heads or num_heads
         self.sliding_window = sliding_window
@@ -72,7 +76,8 @@ class Attention(nn.Module):
             ops.reshape_and_cache(k.view(T, self.num_kv_heads, D), v.view(T, self.num_kv_heads, D),
                                   kv_cache, md.slot_mapping, vt=md.kv_vt)
         out = ops.paged_attention(q.view(T, self.num_heads, D), kv_cache, md, self.scale,
-                                  self.sliding_window, self.logits_soft_cap, self.causal)
+                                  self.sliding_window, self.logits_soft_cap, self.causal,
+                                  alibi_slopes=self.alibi_slopes, sinks=self.sinks)
         return out.view(T, self.num_heads * D)
 
 

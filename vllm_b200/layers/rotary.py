@@ -25,13 +25,14 @@ def _yarn_find_dim(num_rot: float, dim: int, base: float, max_pos: int) -> float
     return (dim * math.log(max_pos / (num_rot * 2 * math.pi))) / (2 * math.log(base))
 
 
-def _yarn_range(low_rot: float, high_rot: float, dim: int, base: float, max_pos: int) -> tuple[int, int]:
-    low = math.floor(_yarn_find_dim(low_rot, dim, base, max_pos))
-    high = math.ceil(_yarn_find_dim(high_rot, dim, base, max_pos))
+def _yarn_range(low_rot: float, high_rot: float, dim: int, base: float, max_pos: int, truncate: bool = True):
+    low, high = _yarn_find_dim(low_rot, dim, base, max_pos), _yarn_find_dim(high_rot, dim, base, max_pos)
+    if truncate:                                  # GPT-OSS checkpoints set ``truncate: false`` (fractional ramp ends)
+        low, high = math.floor(low), math.ceil(high)
     return max(low, 0), min(high, dim - 1)
 
 
-def _yarn_ramp(low: int, high: int, n: int) -> torch.Tensor:
+def _yarn_ramp(low: float, high: float, n: int) -> torch.Tensor:
     if low == high:
         high += 0.001
     return ((torch.arange(n, dtype=torch.float32) - low) / (high - low)).clamp(0, 1)
@@ -79,7 +80,8 @@ class RotaryEmbedding(nn.Module):
         elif kind in ("yarn", "deepseek_yarn"):
             f = rs["factor"]
             orig = rs.get("original_max_position_embeddings", max_pos)
-            lo, hi = _yarn_range(rs.get("beta_fast", 32), rs.get("beta_slow", 1), d, base, orig)
+            lo, hi = _yarn_range(rs.get("beta_fast", 32), rs.get("beta_slow", 1), d, base, orig,
+                                 bool(rs.get("truncate", True)))
             mask = (1 - _yarn_ramp(lo, hi, d // 2)) * rs.get("extrapolation_factor", 1.0)
             inv = inv / f * (1 - mask) + inv * mask
             max_pos = max(max_pos, int(orig * f))

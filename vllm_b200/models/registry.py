@@ -22,11 +22,17 @@ _MODELS: dict[str, tuple[str, str]] = {
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
     "GPTJForCausalLM": ("gpt_neox", "GPTJForCausalLM"),
+    "BloomForCausalLM": ("gpt_neox", "BloomForCausalLM"),
+    "MptForCausalLM": ("gpt_neox", "MPTForCausalLM"),
+    "MPTForCausalLM": ("gpt_neox", "MPTForCausalLM"),
+    "FalconForCausalLM": ("gpt_neox", "FalconForCausalLM"),
+    "RWForCausalLM": ("gpt_neox", "FalconForCausalLM"),
     "OPTForCausalLM": ("opt", "OPTForCausalLM"),
     "GPT2LMHeadModel": ("opt", "GPT2LMHeadModel"),
     "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
     "Qwen2MoeForCausalLM": ("mixtral", "Qwen2MoeForCausalLM"),
     "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
+    "GptOssForCausalLM": ("gpt_oss", "GptOssForCausalLM"),
     "MambaForCausalLM": ("mamba", "MambaForCausalLM"),
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
     "BartForConditionalGeneration": ("bart", "BartForConditionalGeneration"),

@@ -162,7 +162,8 @@ def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.
                     seq_lens: torch.Tensor, query_start_loc: torch.Tensor, scale: float,
                     causal: bool = True, sliding_window: Optional[int] = None,
                     logits_soft_cap: float = 0.0, return_lse: bool = False,
-                    kv_scale: float = 1.0, sinks: Optional[torch.Tensor] = None):
+                    kv_scale: float = 1.0, sinks: Optional[torch.Tensor] = None,
+                    alibi_slopes: Optional[torch.Tensor] = None):
     """Unified varlen paged attention.
 
     q: [T, Hq, D] (all requests' new tokens concatenated); request i owns rows
@@ -193,6 +194,8 @@ def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.
             att = logits_soft_cap * torch.tanh(att / logits_soft_cap)
         qpos = torch.arange(sl - ql, sl, device=q.device)[:, None]
         kpos = torch.arange(sl, device=q.device)[None, :]
+        if alibi_slopes is not None:
+            att = att + alibi_slopes.float().to(q.device)[:, None, None] * (kpos - qpos).float()[None]
         mask = torch.ones(ql, sl, dtype=torch.bool, device=q.device)
         if causal:
             mask &= kpos <= qpos
@@ -200,6 +203,8 @@ def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.
             mask &= kpos > qpos - sliding_window
         att = att.masked_fill(~mask[None], float("-inf"))
         l = torch.logsumexp(att, dim=-1)
+        if sinks is not None:            # a per-head logit that takes softmax mass but contributes no value
+            l = torch.logaddexp(l, sinks.float().to(q.device)[:, None].expand_as(l))
         p = torch.exp(att - l[..., None])
         p = torch.nan_to_num(p)
         out[s:e] = torch.einsum("hqk,hkd->hqd", p, vv).permute(1, 0, 2).to(q.dtype)

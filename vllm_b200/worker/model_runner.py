@@ -274,7 +274,9 @@ class ModelRunner:
                 and s.block_size == 64 and kvd in (torch.bfloat16, torch.float16)
                 and self.dtype in (torch.bfloat16, torch.float16)
                 # features only the generic kernel implements keep the whole group on the standard layout
-                and all(not getattr(attention_layers().get(n), "logits_soft_cap", 0.0) for n in g.layer_names)))
+                and all(not getattr(attention_layers().get(n), "logits_soft_cap", 0.0)
+                        and getattr(attention_layers().get(n), "alibi_slopes", None) is None
+                        and getattr(attention_layers().get(n), "sinks", None) is None for n in g.layer_names)))
             for name in g.layer_names:
                 self.layer_to_group[name] = gid
                 if isinstance(s, MambaSpec):
