@@ -447,3 +447,33 @@ def test_mxfp4_expert_dequant():
     out = dequant_mxfp4(blocks, scales, torch.float32)
     assert out.shape == (1, 32)
     assert out[0, :4].tolist() == [1.0, 2.0, 12.0, -12.0] and out[0, 4:].abs().sum() == 0
+
+
+def test_ssd_chunk_scan_matches_recurrence():
+    """Chunked state-space-duality scan (intra-chunk matrix form + carried state) == the token-by-token recurrence,
+    including a non-zero initial state, a ragged last chunk and grouped B/C."""
+    from vllm_b200.ops import ref
+    torch.manual_seed(0)
+    T, H, P, G, N = 37, 4, 8, 2, 6
+    x, dt = torch.randn(T, H, P), torch.rand(T, H) * 0.5 + 0.01
+    A, B, C, h0 = -torch.rand(H) - 0.1, torch.randn(T, G, N), torch.randn(T, G, N), torch.randn(H, P, N)
+    y, hT = ref.ssd_chunk_scan(x, dt, A, B, C, 16, h0)
+    h, ys = h0.clone(), []
+    for t in range(T):
+        Bh, Ch = B[t].repeat_interleave(H // G, 0), C[t].repeat_interleave(H // G, 0)
+        h = h * torch.exp(dt[t] * A)[:, None, None] + (dt[t][:, None] * x[t])[..., None] * Bh[:, None, :]
+        ys.append((h * Ch[:, None, :]).sum(-1))
+    assert (y - torch.stack(ys)).abs().max() < 1e-4 and (hT - h).abs().max() < 1e-4
+
+
+def test_recurrent_state_blocks_are_per_request():
+    """Every running request of a state-space model owns its own state block (never the shared null block)."""
+    llm = make_llm("mamba2-tiny")
+    core = llm.llm_engine.engine_core.engine_core
+    for i, p in enumerate(PROMPTS):
+        llm.llm_engine.add_request(str(i), p, SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True))
+    core.step() if hasattr(core, "step") else None
+    mgr = core.scheduler.kv_cache_manager.managers[0]
+    ids = [b.block_id for blocks in mgr.req_to_blocks.values() for b in blocks]
+    assert len(ids) == len(PROMPTS) and len(set(ids)) == len(ids) and 0 not in ids
+    llm.shutdown()

@@ -183,6 +183,19 @@ PRESETS: dict[str, dict[str, Any]] = {
         rope_parameters=dict(rope_type="yarn", factor=4.0, beta_fast=32.0, beta_slow=1.0, truncate=False,
                              original_max_position_embeddings=128, rope_theta=10000.0),
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "mamba2-tiny": dict(
+        architectures=["Mamba2ForCausalLM"], model_type="mamba2", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_heads=8, head_dim=16, expand=2, state_size=16, n_groups=2, conv_kernel=4, chunk_size=16, use_bias=False,
+        use_conv_bias=True, layer_norm_epsilon=1e-5, rms_norm=True, time_step_limit=[0.0, float("inf")],
+        bos_token_id=0, eos_token_id=0, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False,
+        num_attention_heads=8, max_position_embeddings=512),
+    "bamba-tiny": dict(
+        architectures=["BambaForCausalLM"], model_type="bamba", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, attn_layer_indices=[1, 3],
+        mamba_n_heads=8, mamba_d_head=16, mamba_expand=2, mamba_d_state=16, mamba_n_groups=2, mamba_d_conv=4,
+        mamba_chunk_size=16, mamba_conv_bias=True, mamba_proj_bias=False, rms_norm_eps=1e-5, hidden_act="silu",
+        max_position_embeddings=512, rope_theta=10000.0, partial_rotary_factor=1.0, attention_bias=False,
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

@@ -277,10 +277,10 @@ class MambaManager(SingleTypeManager):
     """One state block per request regardless of length."""
 
     def blocks_needed(self, request_id, num_tokens, new_computed) -> int:
-        return 0 if request_id in self.req_to_blocks else 1
+        return 0 if self.req_to_blocks.get(request_id) else 1
 
     def allocate_new(self, request_id, num_tokens):
-        if request_id in self.req_to_blocks:
+        if self.req_to_blocks.get(request_id):          # (an empty list is the "seen, nothing cached" marker)
             return []
         new = self.pool.get_new_blocks(1)
         self.req_to_blocks[request_id] = new

@@ -133,3 +133,122 @@ class MambaMixer(nn.Module):
                 cache[slots[i]] = torch.cat([conv_state.reshape(-1), h.reshape(-1)])
                 out[s:e] = y
         return self.out_proj((out * F.silu(z.float())).to(hidden.dtype))
+
+
+class Mamba2Mixer(nn.Module):
+    """Mamba-2 (SSD) mixer: scalar decay per head, B/C shared by head groups, gated RMSNorm before the output
+    projection.  Reference: vllm/model_executor/layers/mamba/mamba_mixer2.py (+ ops/ssd_*.py, causal_conv1d.py,
+    mamba_ssm.py ``selective_state_update``).
+
+    Cache block per request (fp32): ``[conv_state (conv_dim x (k-1)) | ssm_state (heads x head_dim x d_state)]``.
+    Decode batches are one vectorised state update (graph-capturable); prefill / mixed batches run the chunked SSD
+    scan per request and resume from the cached state (chunked prefill, prefix resume)."""
+
+    def __init__(self, hidden: int, num_heads: int, head_dim: int, d_state: int, d_conv: int, n_groups: int,
+                 use_bias: bool, use_conv_bias: bool, chunk_size: int, eps: float, dtype, prefix: str,
+                 time_step_limit: tuple[float, float] = (0.0, float("inf")), norm_before_gate: bool = False) -> None:
+        super().__init__()
+        self.nh, self.hd, self.N, self.k, self.G = num_heads, head_dim, d_state, d_conv, n_groups
+        self.d_inner = num_heads * head_dim
+        self.conv_dim = self.d_inner + 2 * n_groups * d_state
+        self.chunk = chunk_size
+        self.dt_min, self.dt_max = time_step_limit
+        self.in_proj = ReplicatedLinear(hidden, 2 * self.d_inner + 2 * n_groups * d_state + num_heads, use_bias, dtype,
+                                        None, f"{prefix}.in_proj")
+        self.conv_weight = nn.Parameter(torch.empty(self.conv_dim, d_conv, dtype=dtype), requires_grad=False)
+        self.conv_bias = nn.Parameter(torch.zeros(self.conv_dim, dtype=dtype), requires_grad=False) if use_conv_bias else None
+        self.dt_bias = nn.Parameter(torch.ones(num_heads, dtype=torch.float32), requires_grad=False)
+        self.A_log = nn.Parameter(torch.zeros(num_heads, dtype=torch.float32), requires_grad=False)
+        self.D = nn.Parameter(torch.ones(num_heads, dtype=torch.float32), requires_grad=False)
+        self.norm_weight = nn.Parameter(torch.ones(self.d_inner, dtype=dtype), requires_grad=False)
+        self.norm_eps = eps
+        self.out_proj = ReplicatedLinear(self.d_inner, hidden, use_bias, dtype, None, f"{prefix}.out_proj")
+        self.layer_name = prefix
+        self.state_elems = self.conv_dim * (d_conv - 1) + num_heads * head_dim * d_state
+        self.num_kv_heads, self.head_size, self.sliding_window = 1, 0, None
+        assert prefix not in _attn._LAYER_REGISTRY, f"duplicate layer name {prefix}"
+        _attn._LAYER_REGISTRY[prefix] = self
+
+    def get_kv_cache_spec(self, block_size: int, dtype_size: int) -> KVCacheSpec:
+        return MambaSpec(block_size=block_size, state_bytes=self.state_elems * 4)
+
+    def _split_state(self, st: torch.Tensor):
+        nconv = self.conv_dim * (self.k - 1)
+        return (st[..., :nconv].reshape(*st.shape[:-1], self.conv_dim, self.k - 1),
+                st[..., nconv:].reshape(*st.shape[:-1], self.nh, self.hd, self.N))
+
+    def _dt(self, dt: torch.Tensor) -> torch.Tensor:
+        dt = F.softplus(dt.float() + self.dt_bias)
+        return dt.clamp(self.dt_min, self.dt_max) if (self.dt_min > 0 or self.dt_max != float("inf")) else dt
+
+    def _gated_norm(self, y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        y = y.float() * F.silu(z.float())
+        y = y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + self.norm_eps)
+        return (self.norm_weight.float() * y)
+
+    def _segment(self, xbc: torch.Tensor, dt: torch.Tensor, conv_state: torch.Tensor, h: torch.Tensor):
+        """ONE request: xbc [q, conv_dim], dt [q, nh] raw → (y [q, d_inner] fp32, conv_state, h)."""
+        from vllm_b200.ops import ref
+        q = xbc.shape[0]
+        xin = torch.cat([conv_state.t().to(xbc.dtype), xbc], dim=0)                      # [k-1+q, conv_dim]
+        conv = (xin.float().unfold(0, self.k, 1) * self.conv_weight.float()[None]).sum(-1)
+        if self.conv_bias is not None:
+            conv = conv + self.conv_bias.float()
+        xa = F.silu(conv)
+        x, B, C = xa.split([self.d_inner, self.G * self.N, self.G * self.N], dim=-1)
+        y, h = ref.ssd_chunk_scan(x.view(q, self.nh, self.hd), self._dt(dt), -torch.exp(self.A_log),
+                                  B.view(q, self.G, self.N), C.view(q, self.G, self.N), self.chunk, h)
+        y = y + self.D[None, :, None] * x.view(q, self.nh, self.hd)
+        return y.reshape(q, self.d_inner), xin[-(self.k - 1):].t().float(), h
+
+    def forward(self, hidden: torch.Tensor) -> torch.Tensor:
+        ctx = get_forward_context()
+        md = ctx.metadata_for(self.layer_name)
+        cache = ctx.kv_caches.get(self.layer_name)
+        z, xbc, dt = self.in_proj(hidden).split([self.d_inner, self.conv_dim, self.nh], dim=-1)
+        T = hidden.shape[0]
+        dev = hidden.device
+        if md is None or cache is None:                      # profiling run: one stateless sequence
+            y, _, _ = self._segment(xbc, dt, torch.zeros(self.conv_dim, self.k - 1, device=dev),
+                                    torch.zeros(self.nh, self.hd, self.N, device=dev))
+            return self.out_proj(self._gated_norm(y, z).to(hidden.dtype))
+        cache = cache.view(cache.shape[0], -1).view(torch.float32) if cache.dtype != torch.float32 else cache
+        out = torch.zeros(T, self.d_inner, dtype=torch.float32, device=dev)
+        if md.decode_only:
+            Bn = md.num_reqs
+            slots = md.block_table[:Bn, 0].long()
+            conv_state, h = self._split_state(cache[slots])
+            xin = torch.cat([conv_state, xbc[:Bn].float()[:, :, None]], dim=-1)            # [B, conv_dim, k]
+            conv = (xin * self.conv_weight.float()[None]).sum(-1)
+            if self.conv_bias is not None:
+                conv = conv + self.conv_bias.float()
+            xa = F.silu(conv)
+            x, Bm, Cm = xa.split([self.d_inner, self.G * self.N, self.G * self.N], dim=-1)
+            x = x.view(Bn, self.nh, self.hd)
+            rep = self.nh // self.G
+            Bm = Bm.view(Bn, self.G, self.N).repeat_interleave(rep, dim=1)                  # [B, nh, N]
+            Cm = Cm.view(Bn, self.G, self.N).repeat_interleave(rep, dim=1)
+            dtv = self._dt(dt[:Bn])                                                         # [B, nh]
+            dA = torch.exp(dtv * (-torch.exp(self.A_log))[None])
+            h = h * dA[:, :, None, None] + (dtv[:, :, None] * x)[..., None] * Bm[:, :, None, :]
+            y = (h * Cm[:, :, None, :]).sum(-1) + self.D[None, :, None] * x
+            cache[slots] = torch.cat([xin[:, :, 1:].reshape(Bn, -1), h.reshape(Bn, -1)], dim=-1)
+            out[:Bn] = y.reshape(Bn, self.d_inner)
+        else:
+            qsl = (md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()).tolist()
+            sls = (md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()).tolist()
+            slots = md.block_table[:md.num_reqs, 0].tolist()
+            for i in range(md.num_reqs):
+                s, e = qsl[i], qsl[i + 1]
+                if e <= s:
+                    continue
+                if sls[i] - (e - s) > 0:
+                    conv_state, h = self._split_state(cache[slots[i]])
+                    conv_state, h = conv_state.clone(), h.clone()
+                else:
+                    conv_state = torch.zeros(self.conv_dim, self.k - 1, dtype=torch.float32, device=dev)
+                    h = torch.zeros(self.nh, self.hd, self.N, dtype=torch.float32, device=dev)
+                y, conv_state, h = self._segment(xbc[s:e], dt[s:e], conv_state, h)
+                cache[slots[i]] = torch.cat([conv_state.reshape(-1), h.reshape(-1)])
+                out[s:e] = y
+        return self.out_proj(self._gated_norm(out, z).to(hidden.dtype))

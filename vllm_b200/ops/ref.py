@@ -506,3 +506,49 @@ def block_fp8_linear(x: torch.Tensor, wq: torch.Tensor, w_scale: torch.Tensor, b
     if bias is not None:
         y = y + bias.float()
     return y.to(x.dtype)
+
+
+# ---------------------------------------------------------------------------
+# Mamba-2 state-space duality (reference: layers/mamba/ops/ssd_combined.py, ssd_chunk_scan.py, ssd_state_passing.py)
+def _segsum(x: torch.Tensor) -> torch.Tensor:
+    """[..., L] → [..., L, L] with out[i, j] = sum_{j < k <= i} x[k] for j <= i, -inf above the diagonal."""
+    L = x.shape[-1]
+    cs = torch.cumsum(x, dim=-1)
+    d = cs[..., :, None] - cs[..., None, :]
+    mask = torch.tril(torch.ones(L, L, dtype=torch.bool, device=x.device))
+    return d.masked_fill(~mask, float("-inf"))
+
+
+def ssd_chunk_scan(x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
+                   chunk: int, h0: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """One sequence.  x [T, H, P], dt [T, H] (post-softplus), A [H] (negative), B / C [T, G, N] (G groups of heads),
+    h0 [H, P, N] → (y [T, H, P] without the D skip, final state [H, P, N]).  Work is quadratic only inside a chunk:
+    intra-chunk outputs through the masked decay matrix, inter-chunk through the carried state."""
+    T, H, P = x.shape
+    G, N = B.shape[1], B.shape[2]
+    rep = H // G
+    x, dt, B, C = x.float(), dt.float(), B.float(), C.float()
+    pad = (-T) % chunk
+    if pad:
+        x = torch.cat([x, x.new_zeros(pad, H, P)])
+        dt = torch.cat([dt, dt.new_zeros(pad, H)])
+        B = torch.cat([B, B.new_zeros(pad, G, N)])
+        C = torch.cat([C, C.new_zeros(pad, G, N)])
+    nc = (T + pad) // chunk
+    Bh = B.repeat_interleave(rep, dim=1).view(nc, chunk, H, N)
+    Ch = C.repeat_interleave(rep, dim=1).view(nc, chunk, H, N)
+    X = (x * dt[..., None]).view(nc, chunk, H, P)
+    a = (dt * A.float()[None]).view(nc, chunk, H).permute(2, 0, 1)                # [H, nc, L] log-decay per step
+    a_cs = torch.cumsum(a, dim=-1)
+    Lm = torch.exp(_segsum(a))                                                     # [H, nc, L, L]
+    y_diag = torch.einsum("clhn,cshn,hcls,cshp->clhp", Ch, Bh, Lm, X)
+    decay_states = torch.exp(a_cs[:, :, -1:] - a_cs)                               # [H, nc, L]
+    states = torch.einsum("clhn,hcl,clhp->chpn", Bh, decay_states, X)              # state each chunk adds
+    init = h0.float()[None] if h0 is not None else states.new_zeros(1, H, P, N)
+    states = torch.cat([init, states], dim=0)                                      # [nc+1, H, P, N]
+    chunk_decay = torch.exp(_segsum(F.pad(a_cs[:, :, -1], (1, 0))))                # [H, nc+1, nc+1]
+    new_states = torch.einsum("hzc,chpn->zhpn", chunk_decay, states)
+    prev, final = new_states[:-1], new_states[-1]
+    y_off = torch.einsum("clhn,chpn,hcl->clhp", Ch, prev, torch.exp(a_cs))
+    y = (y_diag + y_off).reshape(nc * chunk, H, P)[:T]
+    return y, final
