@@ -150,7 +150,7 @@ def test_multi_lora_matches_merged_weights():
     assert got == exp
 
 
-@pytest.mark.parametrize("method", ["fp8", "fp8_block"])
+@pytest.mark.parametrize("method", ["fp8", "fp8_block", "int8"])
 def test_online_fp8_quantization_close_to_bf16(method):
     """Online weight quantisation of an unquantised checkpoint: greedy text stays close to the full-precision run
     (teacher-forced prompt logprobs within quantisation noise)."""
@@ -477,3 +477,64 @@ def test_recurrent_state_blocks_are_per_request():
     ids = [b.block_id for blocks in mgr.req_to_blocks.values() for b in blocks]
     assert len(ids) == len(PROMPTS) and len(set(ids)) == len(ids) and 0 not in ids
     llm.shutdown()
+
+
+def test_compressed_tensors_checkpoints():
+    """compressed-tensors: (a) pack-quantized W4A16 expands to exactly its dequantised weights; (b) a W8A8-int8
+    checkpoint (int8 weights + per-channel scales, dynamic per-token activations) runs through the int8 linear method
+    and stays within quantisation noise of the full-precision model."""
+    from vllm_b200.model_loader import weight_only as wo
+    cfg = get_preset_hf_config("llama-tiny")
+    full = dict(llama_full_weights(cfg, seed=9, scale=0.08))
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    prompt = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 77]}]
+    # (a) W4A16
+    ckpt, ref = [], {}
+    for name, t in full.items():
+        if name.endswith("proj.weight"):
+            mod = name[: -len(".weight")]
+            pk, sc, shp = wo.pack_compressed_tensors(t, 4, 32)
+            ckpt += [(mod + ".weight_packed", pk), (mod + ".weight_scale", sc), (mod + ".weight_shape", shp)]
+            ref[name] = wo.dequant_compressed_tensors(pk, sc, None, shp.tolist(), 4, 32, True)
+            assert (ref[name] - t).abs().max() < 0.06
+        else:
+            ckpt.append((name, t)); ref[name] = t
+    llm = make_llm("llama-tiny", weights=ref.items())
+    exp = llm.generate(prompt, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    qc = {"quant_method": "compressed-tensors", "format": "pack-quantized", "ignore": ["lm_head"],
+          "config_groups": {"group_0": {"targets": ["Linear"], "weights": {"num_bits": 4, "type": "int", "strategy": "group",
+                                                                         "group_size": 32, "symmetric": True},
+                                        "input_activations": None}}}
+    llm = make_llm("llama-tiny", hf_overrides={"quantization_config": qc})
+    llm.llm_engine.engine_core.engine_core.model_executor.collective_rpc("load_model", kwargs={"weights": ckpt})
+    got = llm.generate(prompt, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    assert got == exp
+    # (b) W8A8 int8, channel-wise weights, dynamic token activations
+    ckpt = []
+    for name, t in full.items():
+        if name.endswith("proj.weight"):
+            scale = (t.float().abs().amax(dim=1, keepdim=True) / 127.0).clamp_min(1e-12)
+            ckpt += [(name, (t.float() / scale).round().clamp(-128, 127).to(torch.int8)),
+                     (name[: -len(".weight")] + ".weight_scale", scale)]
+        else:
+            ckpt.append((name, t))
+    qc = {"quant_method": "compressed-tensors", "format": "int-quantized", "ignore": ["lm_head"],
+          "config_groups": {"group_0": {"targets": ["Linear"],
+                                        "weights": {"num_bits": 8, "type": "int", "strategy": "channel", "symmetric": True},
+                                        "input_activations": {"num_bits": 8, "type": "int", "strategy": "token",
+                                                              "dynamic": True, "symmetric": True}}}}
+    spl = SamplingParams(max_tokens=2, temperature=0.0, ignore_eos=True, prompt_logprobs=0)
+    lp = {}
+    for tag, kw, wts in (("fp", {}, list(full.items())), ("int8", {"hf_overrides": {"quantization_config": qc}}, ckpt)):
+        llm = make_llm("llama-tiny", **kw)
+        llm.llm_engine.engine_core.engine_core.model_executor.collective_rpc("load_model", kwargs={"weights": wts})
+        if tag == "int8":
+            m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+            assert m.model.layers[0].self_attn.qkv_proj.weight.dtype == torch.int8
+        o = llm.generate([{"prompt_token_ids": [(11 * i) % 500 + 3 for i in range(40)]}], spl)[0]
+        lp[tag] = [list(d.values())[0].logprob for d in o.prompt_logprobs[1:]]
+        llm.shutdown()
+    diff = max(abs(a - b) for a, b in zip(lp["fp"], lp["int8"]))
+    assert 0 < diff < 0.25, diff

@@ -71,14 +71,16 @@ class Fp8LinearMethod(LinearMethod):
     (reference: quantization/fp8.py ``Fp8LinearMethod``, kernels/linear/scaled_mm).  Checkpoints in this format
     carry ``weight`` (fp8) and ``weight_scale`` (scalar or [out]); bf16 checkpoints are quantised after loading."""
 
-    def __init__(self, online: bool, per_channel: bool = False) -> None:
-        self.online, self.per_channel = online, per_channel
+    def __init__(self, online: bool, per_channel: bool = False, static_act: bool = False) -> None:
+        self.online, self.per_channel, self.static_act = online, per_channel, static_act and not online
 
     def create_weights(self, layer, in_per_rank, out_per_rank, dtype) -> None:
         wdt = dtype if self.online else torch.float8_e4m3fn
         layer.weight = nn.Parameter(torch.empty(out_per_rank, in_per_rank, dtype=wdt), requires_grad=False)
         layer.weight_scale = nn.Parameter(torch.ones(out_per_rank if self.per_channel else 1, dtype=torch.float32),
                                           requires_grad=False)
+        if self.static_act:      # calibrated per-tensor activation scale shipped with the checkpoint
+            layer.input_scale = nn.Parameter(torch.ones(1, dtype=torch.float32), requires_grad=False)
         layer.out_dtype = dtype
 
     def process_weights_after_loading(self, layer) -> None:
@@ -94,7 +96,10 @@ class Fp8LinearMethod(LinearMethod):
     def apply(self, layer, x, bias):
         # dynamic per-token activation quantisation, fp32 accumulation, scales applied in the epilogue
         xf = x.float()
-        a_scale = (xf.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12) / ref.FP8_MAX)
+        if getattr(layer, "input_scale", None) is not None:
+            a_scale = layer.input_scale.float().max().expand(xf.shape[0], 1)
+        else:
+            a_scale = (xf.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12) / ref.FP8_MAX)
         xq = (xf / a_scale).clamp(-ref.FP8_MAX, ref.FP8_MAX).to(torch.float8_e4m3fn)
         w_scale = layer.weight_scale
         if x.is_cuda and hasattr(torch, "_scaled_mm") and x.dim() == 2 and x.shape[-1] % 16 == 0 \
@@ -113,17 +118,86 @@ class Fp8LinearMethod(LinearMethod):
 class Fp8Config(QuantConfig):
     name = "fp8"
 
-    def __init__(self, online: bool, per_channel: bool = False, ignored: tuple[str, ...] = ("lm_head", "gate.")) -> None:
-        self.online, self.per_channel, self.ignored = online, per_channel, ignored
+    def __init__(self, online: bool, per_channel: bool = False, ignored: tuple[str, ...] = ("lm_head", "gate."),
+                 static_act: bool = False) -> None:
+        self.online, self.per_channel, self.ignored, self.static_act = online, per_channel, ignored, static_act
 
     def get_linear_method(self, layer, prefix):
         if any(s in prefix for s in self.ignored):
             return None
-        return Fp8LinearMethod(self.online, self.per_channel)
+        return Fp8LinearMethod(self.online, self.per_channel, self.static_act)
+
+
+class Int8LinearMethod(LinearMethod):
+    """W8A8 int8: symmetric per-output-channel (or per-tensor) int8 weights, dynamic per-token (or static per-tensor)
+    int8 activations, int32 accumulation, scales in the epilogue (reference: quantization/compressed_tensors/schemes/
+    compressed_tensors_w8a8_int8.py, kernels/linear/scaled_mm cutlass int8 path).  bf16 checkpoints are quantised
+    after loading when ``online``."""
+
+    def __init__(self, online: bool, per_channel: bool = True, static_act: bool = False) -> None:
+        self.online, self.per_channel, self.static_act = online, per_channel, static_act and not online
+
+    def create_weights(self, layer, in_per_rank, out_per_rank, dtype) -> None:
+        layer.weight = nn.Parameter(torch.empty(out_per_rank, in_per_rank, dtype=dtype if self.online else torch.int8),
+                                    requires_grad=False)
+        layer.weight_scale = nn.Parameter(torch.ones(out_per_rank if self.per_channel else 1, 1, dtype=torch.float32),
+                                          requires_grad=False)
+        if self.static_act:
+            layer.input_scale = nn.Parameter(torch.ones(1, dtype=torch.float32), requires_grad=False)
+        layer.out_dtype = dtype
+
+    def process_weights_after_loading(self, layer) -> None:
+        if layer.weight.dtype == torch.int8:
+            return
+        w = layer.weight.data.float()
+        amax = (w.abs().amax(dim=1, keepdim=True) if self.per_channel else w.abs().amax().reshape(1, 1)).clamp_min(1e-12)
+        scale = amax / 127.0
+        layer.weight = nn.Parameter((w / scale).round().clamp(-128, 127).to(torch.int8), requires_grad=False)
+        layer.weight_scale = nn.Parameter(scale.float(), requires_grad=False)
+
+    def apply(self, layer, x, bias):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        xq, a_scale = ref.scaled_int8_quant(x2, layer.input_scale.float().max() if getattr(layer, "input_scale", None) is not None
+                                            else None)
+        if x2.is_cuda and hasattr(torch, "_int_mm") and x2.shape[0] > 16 and x2.shape[0] % 8 == 0 and x2.shape[1] % 8 == 0 \
+                and layer.weight.shape[0] % 8 == 0:
+            acc = torch._int_mm(xq, layer.weight.t()).float()                 # int8 tensor-core GEMM (library)
+        else:
+            acc = xq.float() @ layer.weight.float().t()
+        y = (acc * a_scale.reshape(-1, 1) * layer.weight_scale.reshape(1, -1)).to(layer.out_dtype)
+        y = y if bias is None else y + bias
+        return y.reshape(*shape[:-1], -1)
+
+
+class Int8Config(QuantConfig):
+    name = "int8"
+
+    def __init__(self, online: bool, per_channel: bool = True, ignored: tuple[str, ...] = ("lm_head", "gate."),
+                 static_act: bool = False) -> None:
+        self.online, self.per_channel, self.ignored, self.static_act = online, per_channel, ignored, static_act
+
+    def get_linear_method(self, layer, prefix):
+        if any(s in prefix for s in self.ignored):
+            return None
+        return Int8LinearMethod(self.online, self.per_channel, self.static_act)
+
+
+def _compressed_tensors_scheme(hq: dict) -> dict:
+    """Collapse a compressed-tensors ``quantization_config`` to the one scheme its Linear targets use
+    (reference: quantization/compressed_tensors/compressed_tensors.py ``_get_scheme_from_parts``)."""
+    groups = hq.get("config_groups") or {}
+    for g in groups.values():
+        w, a = g.get("weights") or {}, g.get("input_activations") or None
+        return dict(w_bits=int(w.get("num_bits", 8)), w_type=w.get("type", "int"), w_strategy=w.get("strategy", "tensor"),
+                    w_group=w.get("group_size"), w_symmetric=bool(w.get("symmetric", True)),
+                    a_bits=int(a["num_bits"]) if a else None, a_dynamic=bool(a.get("dynamic", False)) if a else None,
+                    fmt=g.get("format") or hq.get("format"))
+    raise ValueError("compressed-tensors config has no config_groups")
 
 
 QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8", "awq", "gptq", "awq_marlin",
-                        "gptq_marlin", "nvfp4", "modelopt_fp4")
+                        "gptq_marlin", "nvfp4", "modelopt_fp4", "int8", "w8a8", "compressed-tensors", "compressed_tensors")
 
 
 def get_quant_config(model_config) -> Optional[QuantConfig]:
@@ -140,6 +214,22 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         if hq.get("weight_block_size"):          # a "fp8" checkpoint with block scales (DeepSeek-V3 style)
             return Fp8BlockConfig(online=False)
         return Fp8Config(online=not hq, per_channel=(q == "fbgemm_fp8" or hq.get("strategy") == "channel"))
+    if q in ("int8", "w8a8"):
+        return Int8Config(online=not hq)
+    if q in ("compressed-tensors", "compressed_tensors"):
+        sc = _compressed_tensors_scheme(hq)
+        ignored = tuple(i.replace("re:", "") for i in (hq.get("ignore") or ["lm_head"])) + ("gate.",)
+        if sc["a_bits"] is None:
+            return None          # weight-only (W4A16 / W8A16 pack-quantized): expanded at load (model_loader/weight_only.py)
+        if sc["w_type"] == "float" and sc["w_bits"] == 8:
+            if sc["w_strategy"] == "block":
+                return Fp8BlockConfig(online=False)
+            return Fp8Config(online=False, per_channel=sc["w_strategy"] == "channel", ignored=ignored,
+                             static_act=not sc["a_dynamic"])
+        if sc["w_type"] == "int" and sc["w_bits"] == 8 and sc["a_bits"] == 8:
+            return Int8Config(online=False, per_channel=sc["w_strategy"] == "channel", ignored=ignored,
+                              static_act=not sc["a_dynamic"])
+        raise ValueError(f"unsupported compressed-tensors scheme {sc}")
     if q == "deepseek_v3_fp8":
         return Fp8BlockConfig(online=not hq)
     raise ValueError(f"quantization method {q!r} is not supported yet")

@@ -97,6 +97,39 @@ def dequant_nvfp4(weight: torch.Tensor, weight_scale: torch.Tensor, weight_scale
     return ref.fp4_dequant(weight, weight_scale, float(weight_scale_2), 16)
 
 
+def dequant_compressed_tensors(packed: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Tensor],
+                               shape, bits: int, group_size: Optional[int], symmetric: bool) -> torch.Tensor:
+    """compressed-tensors ``pack-quantized``: ``weight_packed`` int32 [out, in*bits/32] (value j of a word → column
+    8*i + j, stored with a +2^(bits-1) offset when symmetric), ``weight_scale`` [out, in/g] (or [out, 1]),
+    optional ``weight_zero_point`` packed along the output dim → weight [out, in]."""
+    out_f, in_f = int(shape[0]), int(shape[1])
+    q = _unpack_cols(packed, bits)[:, :in_f].float()
+    if symmetric or zero_point is None:
+        q = q - float(1 << (bits - 1))
+    else:
+        zp = _unpack_rows(zero_point, bits)[:out_f].float() if zero_point.dtype == torch.int32 else zero_point.float()
+        g = group_size or in_f
+        q = q - zp.repeat_interleave(g, dim=1)[:, :in_f]
+    sc = scale.float()
+    if sc.shape[1] != in_f:
+        sc = sc.repeat_interleave(group_size or in_f, dim=1)[:, :in_f]
+    return q * sc
+
+
+def pack_compressed_tensors(w: torch.Tensor, bits: int = 4, group_size: int = 32):
+    """Reference symmetric group quantiser + packer (tests / synthetic checkpoints)."""
+    O, I = w.shape
+    g = w.float().reshape(O, I // group_size, group_size)
+    qmax = float((1 << (bits - 1)) - 1)
+    scale = (g.abs().amax(-1) / qmax).clamp_min(1e-8)
+    q = (g / scale[..., None]).round().clamp(-qmax - 1, qmax).reshape(O, I).to(torch.int32) + (1 << (bits - 1))
+    n = 32 // bits
+    packed = torch.zeros(O, I // n, dtype=torch.int32)
+    for j in range(n):
+        packed |= (q[:, j::n] & ((1 << bits) - 1)) << (bits * j)
+    return packed, scale.to(torch.float16), torch.tensor([O, I], dtype=torch.int64)
+
+
 def dequantize_stream(weights: Iterable[tuple[str, torch.Tensor]], quant_cfg: dict, dtype: torch.dtype
                       ) -> Iterator[tuple[str, torch.Tensor]]:
     """Wrap a checkpoint iterator: packed groups are replaced by ``<module>.weight`` tensors as soon as complete."""
@@ -105,6 +138,25 @@ def dequantize_stream(weights: Iterable[tuple[str, torch.Tensor]], quant_cfg: di
     bits = int(quant_cfg.get("bits", quant_cfg.get("w_bit", 4)))
     need = {"qweight", "qzeros", "scales"} | ({"g_idx"} if method == "gptq" else set())
     pending: dict[str, dict[str, torch.Tensor]] = {}
+    if method in ("compressed-tensors", "compressed_tensors"):
+        grp0 = next(iter((quant_cfg.get("config_groups") or {}).values()))["weights"]
+        cbits, cgs, csym = int(grp0.get("num_bits", 4)), grp0.get("group_size"), bool(grp0.get("symmetric", True))
+        cneed = {"weight_packed", "weight_scale", "weight_shape"} | (set() if csym else {"weight_zero_point"})
+        for name, t in weights:
+            mod, _, leaf = name.rpartition(".")
+            if leaf not in ("weight_packed", "weight_scale", "weight_shape", "weight_zero_point", "weight_g_idx"):
+                yield name, t
+                continue
+            grp = pending.setdefault(mod, {})
+            grp[leaf] = t
+            if cneed <= set(grp):
+                w = dequant_compressed_tensors(grp["weight_packed"], grp["weight_scale"], grp.get("weight_zero_point"),
+                                               grp["weight_shape"].tolist(), cbits, cgs, csym)
+                del pending[mod]
+                yield f"{mod}.weight", w.to(dtype)
+        if pending:
+            raise ValueError(f"incomplete compressed-tensors groups for {sorted(pending)[:3]} ...")
+        return
     if method in ("modelopt_fp4", "nvfp4", "modelopt"):
         # NVFP4: weight (uint8) + weight_scale (fp8) + weight_scale_2 (fp32); input_scale is an activation statistic
         for name, t in weights:
