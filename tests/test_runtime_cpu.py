@@ -273,3 +273,48 @@ def test_elastic_scale_up_and_down():
     base, grown, seen, shrunk = asyncio.run(main())
     assert seen == {0, 1}
     assert grown[:3] == base and shrunk == base
+
+
+@pytest.mark.parametrize("backend,tp", [("allgather_reducescatter", 1), ("a2a", 1), ("a2a", 2)])
+def test_wide_expert_parallel_across_dp_replicas(backend, tp):
+    """DP=2 + --enable-expert-parallel: the experts are sharded over the two replicas (EP group = DP x TP), tokens are
+    dispatched / combined across replicas, idle replicas run dummy batches in lock-step; outputs equal a single engine."""
+    import asyncio
+    from tests.utils import make_hf_model, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.engine.arg_utils import EngineArgs
+    from vllm_b200.engine.async_llm import AsyncLLM
+    from vllm_b200.utils import get_open_port
+    hf = make_hf_model("mixtral-tiny")
+    w = [(k, v.clone()) for k, v in hf.state_dict().items()]
+    prompts = [[5, 17, 99, 3, 250, 41, 8], list(range(10, 40)), [7, 7, 7, 9], [100, 200, 300, 400, 33]]
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    llm = make_llm("mixtral-tiny", weights=w)
+    ref = [o.outputs[0].token_ids for o in llm.generate([{"prompt_token_ids": p} for p in prompts], sp)]
+    llm.shutdown()
+
+    async def main():
+        ea = EngineArgs(model="mixtral-tiny", device="cpu", dtype="float32", max_model_len=128, max_num_seqs=8,
+                        max_num_batched_tokens=128, kv_cache_memory_bytes=8 << 20, data_parallel_size=2,
+                        enable_expert_parallel=True, all2all_backend=backend, data_parallel_rpc_port=get_open_port(),
+                        tensor_parallel_size=tp, distributed_executor_backend="mp" if tp > 1 else None,
+                        disable_log_stats=True)
+        eng = AsyncLLM.from_engine_args(ea)
+        await eng.collective_rpc("load_model", kwargs={"weights": w})
+        shards = [d["local_experts"] for d in await eng.collective_rpc("describe_model")]
+
+        async def one(i, p):
+            last = None
+            async for o in eng.generate({"prompt_token_ids": p}, sp, f"r{i}"):
+                last = o
+            return last.outputs[0].token_ids
+        # first a lone request (one replica works, the other runs dummy batches), then a burst on both replicas
+        first = await one(99, prompts[0])
+        outs = await asyncio.gather(*[one(i, p) for i, p in enumerate(prompts)])
+        used = set(eng.engine_core.engines_seen)
+        eng.shutdown()
+        return first, outs, used, shards
+    first, outs, used, shards = asyncio.run(main())
+    assert shards == [4 // (2 * tp)] * tp     # 4 experts over EP = DP x TP ranks → whole experts per rank
+    assert first == ref[0] and outs == ref
+    assert used == {0, 1}

@@ -203,7 +203,7 @@ class EngineCoreProc(EngineCore):
 
     # ---- IO threads
     def _input_loop(self) -> None:
-        from vllm_b200.engine.serial import decode_request
+        from vllm_b200.engine.serial import decode_any, decode_request
         import zmq
         poller = zmq.Poller()
         for s in self._in_socks:
@@ -217,7 +217,7 @@ class EngineCoreProc(EngineCore):
                     if kind == REQ_ADD:
                         self.input_queue.put((kind, decode_request(frames[1])))
                     else:
-                        self.input_queue.put((kind, msgspec.msgpack.decode(frames[1]) if len(frames) > 1 else None))
+                        self.input_queue.put((kind, decode_any(frames[1]) if len(frames) > 1 else None))
             except Exception:
                 break
 

@@ -68,6 +68,10 @@ class DPEngineCoreProc(EngineCoreProc):
         if self.lockstep:
             self.coord = DPCoordinator(pc.data_parallel_master_ip, pc.data_parallel_master_port, self.dp_rank,
                                        self.dp_size)
+        if self.lockstep and self.batch_queue is not None:
+            # one forward pass (real or dummy) per agreement round, in the same order on every rank: no steps in flight
+            logger.info("wide expert parallelism: running the engine step synchronously (no batch queue)")
+            self.batch_queue, self.step_fn = None, self.step
         self.wave = 0
         self.steps_in_wave = 0
         logger.info("DP engine %d/%d up (lock-step=%s)", self.dp_rank, self.dp_size, self.lockstep)
@@ -77,32 +81,34 @@ class DPEngineCoreProc(EngineCoreProc):
             return super().run_busy_loop()
         running = False          # inside a wave: at least one rank has work
         while True:
-            local = self.scheduler.has_requests() or bool(self.batch_queue and len(self.batch_queue))
+            local = self.scheduler.has_requests()
             block = not local and not running
             while True:
                 try:
-                    kind, payload = self.input_queue.get(block=block, timeout=0.05 if block else 0)
+                    kind, payload = self.input_queue.get(block=block, timeout=0.005 if block else 0)
                 except queue.Empty:
                     break
                 block = False
                 if kind == REQ_SHUTDOWN:
                     return
                 self._handle(kind, payload)
-            local = self.scheduler.has_requests() or bool(self.batch_queue and len(self.batch_queue))
-            if not local and not running:
-                # idle: peers may start a wave at any time → take part in the agreement at a slow cadence
-                running = self.coord.any_unfinished(False)
-                if not running:
-                    time.sleep(0.002)
-                continue
+            local = self.scheduler.has_requests()
+            # exactly one agreement and at most one forward pass (real or dummy) per iteration on EVERY rank: the
+            # expert-parallel collectives inside the forward pass need all ranks, in the same order
             running = self.coord.any_unfinished(local)
             if local:
-                outs, _ = self.step_fn()
+                outs, executed = self.step_fn()
                 for ci, o in (outs or {}).items():
                     o.engine_index = self.engine_index
                     self.output_queue.put((ci, o))
+                if not executed:
+                    # bookkeeping-only step (e.g. the last request just finished): peers still run a forward pass
+                    self.model_executor.collective_rpc("execute_dummy_batch")
             elif running:
                 self.model_executor.collective_rpc("execute_dummy_batch")
+            else:
+                time.sleep(0.002)            # nobody has work: idle cadence of the agreement
+                continue
             self.steps_in_wave += 1
             if not running:
                 self.wave += 1

@@ -39,11 +39,25 @@ class FusedMoE(nn.Module):
         self.act = act
         self.reduce_results = reduce_results
         self.ep = enable_ep and self.tp_size > 1
+        # wide EP: the expert-parallel group also spans the data-parallel replicas (EP = DP x TP); tokens differ per
+        # replica, so the layer dispatches / combines through parallel/all2all.py instead of one TP all-reduce
+        from vllm_b200.parallel.state import get_dp_group, get_ep_group
+        epg = get_ep_group()
+        self.wide_ep = bool(enable_ep and epg.world_size > self.tp_size)
+        self.a2a = None
+        ep_rank, ep_size = self.tp_rank, self.tp_size
+        if self.wide_ep:
+            from vllm_b200.config import get_current_vllm_config
+            from vllm_b200.parallel.all2all import All2AllManager
+            self.ep = True
+            ep_rank, ep_size = max(epg.rank_in_group, 0), epg.world_size
+            backend = get_current_vllm_config().parallel_config.all2all_backend
+            self.a2a = All2AllManager(epg, get_dp_group(), g, num_experts, backend)
         dt = dtype or torch.get_default_dtype()
         if self.ep:
             # contiguous expert ranges; the map turns a global expert id into a local one (or -1)
-            per = (num_experts + self.tp_size - 1) // self.tp_size
-            self.e_start = min(num_experts, self.tp_rank * per)
+            per = (num_experts + ep_size - 1) // ep_size
+            self.e_start = min(num_experts, ep_rank * per)
             self.e_end = min(num_experts, self.e_start + per)
             self.local_experts = self.e_end - self.e_start
             emap = torch.full((num_experts,), -1, dtype=torch.int32)
@@ -93,14 +107,20 @@ class FusedMoE(nn.Module):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         w, ids = self.select_experts(router_logits.reshape(-1, router_logits.shape[-1]))
-        if self.fp8_block and self.w13_weight.dtype == torch.float8_e4m3fn:
-            out = self._forward_fp8(x2, w.to(torch.float32), ids)
-        else:
-            out = ops.fused_moe(x2, self.w13_weight, self.w2_weight, w.to(torch.float32), ids, self.act,
-                                self.expert_map)
+        if self.wide_ep:
+            out = self.a2a.dispatch_combine(x2, w.to(torch.float32), ids, self._local_experts,
+                                            reduce_tp=self.reduce_results)
+            return out.reshape(shape)
+        out = self._local_experts(x2, w.to(torch.float32), ids)
         if self.reduce_results and self.tp_size > 1:
             out = get_tp_group().all_reduce(out)
         return out.reshape(shape)
+
+    def _local_experts(self, x2: torch.Tensor, w: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """Contribution of the experts this rank owns (ids are global; the expert map drops the others)."""
+        if self.fp8_block and self.w13_weight.dtype == torch.float8_e4m3fn:
+            return self._forward_fp8(x2, w, ids)
+        return ops.fused_moe(x2, self.w13_weight, self.w2_weight, w, ids, self.act, self.expert_map)
 
     def _dequant(self, wq: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
         blk = self.fp8_block

@@ -64,8 +64,17 @@ class Worker:
         world = pc.world_size
         if world > 1:
             set_process_prefix(f"(Worker rank={self.rank}) ")
-        pstate.init_distributed_environment(world, self.rank, self.local_rank, self.init_method)
-        pstate.initialize_model_parallel(pc.tensor_parallel_size, pc.pipeline_parallel_size, 1,
+        wide_ep = (pc.enable_expert_parallel and pc.data_parallel_size > 1 and self.vllm_config.model_config.is_moe)
+        if wide_ep:
+            # experts are sharded over DP x TP: one process group across every replica's workers
+            # (rank = dp_rank * replica_world + local rank; rendezvous next to the DP coordinator's store)
+            pstate.init_distributed_environment(
+                world * pc.data_parallel_size, pc.data_parallel_rank * world + self.rank, self.local_rank,
+                f"tcp://{pc.data_parallel_master_ip}:{pc.data_parallel_master_port + 1}")
+        else:
+            pstate.init_distributed_environment(world, self.rank, self.local_rank, self.init_method)
+        pstate.initialize_model_parallel(pc.tensor_parallel_size, pc.pipeline_parallel_size,
+                                         pc.data_parallel_size if wide_ep else 1,
                                          pc.decode_context_parallel_size, pc.prefill_context_parallel_size,
                                          enable_device_comm=not pc.disable_custom_all_reduce)
         torch.manual_seed(self.vllm_config.model_config.seed)
@@ -131,6 +140,13 @@ class Worker:
 
     # -------------------------------------------------------- sleep / wake
     @torch.inference_mode()
+    def describe_model(self) -> dict:
+        """Shape of this worker's shard (debug / tests / ``collective_rpc`` from the API)."""
+        m = self.runner.model
+        experts = [int(x.local_experts) for x in m.modules() if hasattr(x, "local_experts")]
+        return {"rank": self.rank, "param_bytes": sum(p.numel() * p.element_size() for p in m.parameters()),
+                "local_experts": experts[0] if experts else 0, "class": type(m).__name__}
+
     def execute_dummy_batch(self) -> None:
         """One token through the model with no KV cache: keeps this rank's collectives (EP all-to-all, TP
         all-reduce) in step with peers that have real work (reference: gpu_worker.execute_dummy_batch)."""
