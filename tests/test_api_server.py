@@ -119,8 +119,40 @@ def test_responses_and_anthropic_and_metrics(server):
     client, call, _ = server
     r = call(client.post("/v1/responses", json={"input": "hi", "max_output_tokens": 3, "temperature": 0})).json()
     assert r["object"] == "response" and r["usage"]["output_tokens"] == 3
-    a = call(client.post("/v1/messages", json={"messages": [{"role": "user", "content": "hi"}], "max_tokens": 3})).json()
+    a = call(client.post("/v1/messages", json={"messages": [{"role": "user", "content": "hi"}], "max_tokens": 3,
+                                               "temperature": 0})).json()
     assert a["type"] == "message" and a["stop_reason"] == "max_tokens"
+    # typed streaming events: Responses API
+    async def sse(path, body):
+        evs = []
+        async with client.stream("POST", path, json=body) as s:
+            cur = None
+            async for line in s.aiter_lines():
+                if line.startswith("event:"):
+                    cur = line[6:].strip()
+                elif line.startswith("data:"):
+                    evs.append((cur, json.loads(line[5:])))
+        return evs
+    evs = call(sse("/v1/responses", {"input": "hi", "max_output_tokens": 4, "temperature": 0, "stream": True, "store": True}))
+    kinds = [k for k, _ in evs]
+    assert kinds[0] == "response.created" and kinds[-1] == "response.completed"
+    assert "response.output_text.delta" in kinds and "response.output_item.done" in kinds
+    done = evs[-1][1]["response"]
+    assert "".join(d["delta"] for k, d in evs if k == "response.output_text.delta") == done["output_text"]
+    assert done["usage"]["output_tokens"] == 4
+    assert [d["sequence_number"] for _, d in evs] == list(range(1, len(evs) + 1))
+    assert call(client.get(f"/v1/responses/{done['id']}")).json()["output_text"] == done["output_text"]
+    assert call(client.get("/v1/responses/resp_nope")).status_code == 404
+    # Anthropic streaming
+    evs = call(sse("/v1/messages", {"messages": [{"role": "user", "content": "hi"}], "max_tokens": 3, "stream": True,
+                                    "temperature": 0}))
+    kinds = [k for k, _ in evs]
+    assert kinds[:2] == ["message_start", "content_block_start"] and kinds[-2:] == ["message_delta", "message_stop"]
+    assert evs[-2][1]["delta"]["stop_reason"] == "max_tokens" and evs[-2][1]["usage"]["output_tokens"] == 3
+    assert "".join(d["delta"]["text"] for k, d in evs if k == "content_block_delta") == a["content"][0]["text"]
+    # Cohere v2 chat
+    c = call(client.post("/v2/chat", json={"messages": [{"role": "user", "content": "hi"}], "max_tokens": 3})).json()
+    assert c["finish_reason"] == "MAX_TOKENS" and c["message"]["content"][0]["type"] == "text"
     m = call(client.get("/metrics")).text
     assert "vllm:generation_tokens_total" in m and "vllm:time_to_first_token_seconds" in m
     assert call(client.post("/reset_prefix_cache")).status_code in (200, 409)

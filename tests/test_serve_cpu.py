@@ -74,6 +74,17 @@ def test_bench_serve_against_live_server(server):
     json.dumps(res)
 
 
+def test_bench_sweep_grid(server):
+    from vllm_b200.benchmarks import bench_sweep
+    from vllm_b200.entrypoints.cli import _bench_parser
+    args = _bench_parser().parse_args(["sweep", "--base-url", server, "--model", "llama-tiny", "--num-prompts", "6",
+                                       "--input-len", "16", "--output-len", "4", "--vocab-size", "500",
+                                       "--max-concurrencies", "1,4", "--slo-ttft-ms", "60000"])
+    res = bench_sweep(args)
+    assert [c["max_concurrency"] for c in res["cells"]] == [1, 4] and all(c["completed"] == 6 for c in res["cells"])
+    assert res["best_within_slo"]["max_concurrency"] in (1, 4)
+
+
 def test_token_in_token_out_and_render(server):
     r = requests.post(server + "/inference/v1/generate", json={"token_ids": [5, 6, 7, 8], "sampling_params": {"max_tokens": 4, "temperature": 0}}, timeout=60).json()
     assert len(r["token_ids"]) == 4 and r["finish_reason"] == "length"

@@ -252,3 +252,29 @@ def bench_startup(args) -> dict[str, Any]:
     t2 = time.perf_counter()
     llm.shutdown()
     return {"engine_init_s": t1 - t0, "first_token_s": t2 - t1, "total_s": t2 - t0}
+
+
+# ------------------------------------------------------------------ bench sweep
+def bench_sweep(args) -> dict[str, Any]:
+    """Grid of ``bench serve`` runs against one running server (reference: benchmarks/sweep/: serve x parameter grid
+    → table + the knee of the latency / throughput curve).  ``--request-rates`` and/or ``--max-concurrencies`` span
+    the grid; every cell reports throughput and TTFT / TPOT / ITL percentiles, the summary names the highest-throughput
+    cell that still meets the SLOs (``--slo-ttft-ms``, ``--slo-tpot-ms``)."""
+    import copy
+    rates = [float(x) for x in (args.request_rates or "inf").split(",")]
+    concs = [int(x) if x not in ("", "none", "0") else None for x in (args.max_concurrencies or "none").split(",")]
+    cells = []
+    for rate in rates:
+        for conc in concs:
+            a = copy.copy(args)
+            a.request_rate, a.max_concurrency = rate, conc
+            res = bench_serve(a)
+            cells.append({"request_rate": rate, "max_concurrency": conc, **res})
+    def ok(c):
+        return ((args.slo_ttft_ms is None or c["ttft_ms"]["p99"] <= args.slo_ttft_ms)
+                and (args.slo_tpot_ms is None or c["tpot_ms"]["p99"] <= args.slo_tpot_ms))
+    good = [c for c in cells if ok(c)]
+    best = max(good, key=lambda c: c["output_throughput"]) if good else None
+    return {"cells": cells, "best_within_slo": None if best is None else {
+        "request_rate": best["request_rate"], "max_concurrency": best["max_concurrency"],
+        "output_throughput": best["output_throughput"]}}

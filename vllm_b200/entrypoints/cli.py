@@ -55,6 +55,14 @@ def _bench_parser() -> argparse.ArgumentParser:
     srv.add_argument("--seed", type=int, default=0)
     srv.add_argument("--native", action="store_true", help="drive the load with the C++ epoll client")
     srv.add_argument("--output-json", default=None)
+    sw = sub.add_parser("sweep", **common)
+    for act in srv._actions:                       # same client options as ``bench serve`` ...
+        if act.option_strings and act.dest not in ("help", "request_rate", "max_concurrency"):
+            sw._add_action(act)
+    sw.add_argument("--request-rates", default="inf", help="comma-separated request rates (inf = closed loop)")
+    sw.add_argument("--max-concurrencies", default="none", help="comma-separated concurrency caps")
+    sw.add_argument("--slo-ttft-ms", type=float, default=None)
+    sw.add_argument("--slo-tpot-ms", type=float, default=None)
     st = sub.add_parser("startup", **common)
     st.add_argument("--output-json", default=None)
     EngineArgs.add_cli_args(st)
@@ -65,7 +73,7 @@ def _cmd_bench(argv: list[str]) -> None:
     from vllm_b200 import benchmarks as B
     args = _bench_parser().parse_args(argv)
     fn = {"latency": B.bench_latency, "throughput": B.bench_throughput, "serve": B.bench_serve,
-          "startup": B.bench_startup}[args.bench]
+          "startup": B.bench_startup, "sweep": B.bench_sweep}[args.bench]
     res = fn(args)
     print(json.dumps(res, indent=2))
     if getattr(args, "output_json", None):

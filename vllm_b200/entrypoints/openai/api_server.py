@@ -689,6 +689,44 @@ def build_app(ctx: ServingContext):
                 "usage": {"total_tokens": sum(len(o.prompt_token_ids) for o in outs)}}
 
     # ------------------------------------------- Responses API / Anthropic
+    async def _chat_deltas(creq, raw):
+        """Runs the chat handler in streaming mode and yields (delta_text, finish_reason, usage) tuples."""
+        creq.stream = True
+        creq.stream_options = P.StreamOptions(include_usage=True)
+        res = await chat(creq, raw)
+        if not isinstance(res, StreamingResponse):
+            yield res
+            return
+        async for chunk in res.body_iterator:
+            text = chunk.decode() if isinstance(chunk, (bytes, bytearray)) else chunk
+            for line in text.splitlines():
+                if not line.startswith("data:") or "[DONE]" in line:
+                    continue
+                d = json.loads(line[5:])
+                ch = d["choices"][0] if d.get("choices") else {}
+                yield (ch.get("delta", {}).get("content") or "", ch.get("finish_reason"), d.get("usage"))
+
+    def _sse_event(typ: str, payload: dict) -> str:
+        return f"event: {typ}\ndata: {json.dumps(dict(payload, type=typ))}\n\n"
+
+    @app.get("/v1/responses/{response_id}")
+    async def get_response(response_id: str):
+        st = ctx.responses_store.get(response_id)
+        if st is None or "response" not in st:
+            return _error(f"response {response_id} not found", 404, "NotFoundError")
+        return st["response"]
+
+    @app.post("/v1/responses/{response_id}/cancel")
+    async def cancel_response(response_id: str):
+        st = ctx.responses_store.get(response_id)
+        if st is None:
+            return _error(f"response {response_id} not found", 404, "NotFoundError")
+        if st.get("request_ids"):
+            await ctx.engine.abort(st["request_ids"])
+        if "response" in st:
+            st["response"]["status"] = "cancelled"
+        return st.get("response", {"id": response_id, "status": "cancelled"})
+
     @app.post("/v1/responses")
     async def responses(req: P.ResponsesRequest, raw: Request):
         msgs: list[dict] = []
@@ -706,21 +744,62 @@ def build_app(ctx: ServingContext):
                 msgs.append({"role": item.get("role", "user"), "content": c})
         creq = P.ChatCompletionRequest(messages=msgs, max_tokens=req.max_output_tokens, temperature=req.temperature,
                                        top_p=req.top_p, stream=False)
+        rid = f"resp_{random_uuid()}"
+
+        def build(text: str, usage: Optional[dict], status: str, created: int, mid: str) -> dict:
+            u = usage or {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}
+            return {"id": rid, "object": "response", "created_at": created, "status": status, "model": ctx.model_name,
+                    "output": [{"type": "message", "id": mid, "role": "assistant", "status": status,
+                                "content": [{"type": "output_text", "text": text, "annotations": []}]}],
+                    "output_text": text,
+                    "usage": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"],
+                              "total_tokens": u["total_tokens"]}}
+
+        if req.stream:
+            # typed server-sent events (reference: openai/responses/streaming_events.py)
+            async def events():
+                created, mid, seq, text, usage = int(time.time()), f"msg_{random_uuid()}", 0, "", None
+
+                def ev(typ, **kw):
+                    nonlocal seq
+                    seq += 1
+                    return _sse_event(typ, dict(kw, sequence_number=seq))
+                shell = build("", None, "in_progress", created, mid)
+                shell["output"] = []
+                yield ev("response.created", response=shell)
+                yield ev("response.in_progress", response=shell)
+                yield ev("response.output_item.added", output_index=0,
+                         item={"type": "message", "id": mid, "role": "assistant", "status": "in_progress", "content": []})
+                yield ev("response.content_part.added", item_id=mid, output_index=0, content_index=0,
+                         part={"type": "output_text", "text": "", "annotations": []})
+                async for item in _chat_deltas(creq, raw):
+                    if not isinstance(item, tuple):
+                        yield ev("error", message="generation failed")
+                        return
+                    delta, _fin, u = item
+                    usage = u or usage
+                    if delta:
+                        text += delta
+                        yield ev("response.output_text.delta", item_id=mid, output_index=0, content_index=0, delta=delta)
+                yield ev("response.output_text.done", item_id=mid, output_index=0, content_index=0, text=text)
+                yield ev("response.content_part.done", item_id=mid, output_index=0, content_index=0,
+                         part={"type": "output_text", "text": text, "annotations": []})
+                final = build(text, usage, "completed", created, mid)
+                yield ev("response.output_item.done", output_index=0, item=final["output"][0])
+                if req.store:
+                    ctx.responses_store[rid] = {"messages": msgs + [{"role": "assistant", "content": text}],
+                                                "response": final}
+                yield ev("response.completed", response=final)
+            return StreamingResponse(events(), media_type="text/event-stream")
+
         res = await chat(creq, raw)
         if not isinstance(res, dict):
             return res
         text = res["choices"][0]["message"].get("content") or ""
-        rid = f"resp_{random_uuid()}"
+        out = build(text, res["usage"], "completed", res["created"], f"msg_{random_uuid()}")
         if req.store:
-            ctx.responses_store[rid] = {"messages": msgs + [{"role": "assistant", "content": text}]}
-        u = res["usage"]
-        return {"id": rid, "object": "response", "created_at": res["created"], "status": "completed",
-                "model": ctx.model_name,
-                "output": [{"type": "message", "id": f"msg_{random_uuid()}", "role": "assistant", "status": "completed",
-                            "content": [{"type": "output_text", "text": text, "annotations": []}]}],
-                "output_text": text,
-                "usage": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"],
-                          "total_tokens": u["total_tokens"]}}
+            ctx.responses_store[rid] = {"messages": msgs + [{"role": "assistant", "content": text}], "response": out}
+        return out
 
     @app.post("/v1/messages")
     async def anthropic_messages(req: P.AnthropicMessagesRequest, raw: Request):
@@ -735,16 +814,63 @@ def build_app(ctx: ServingContext):
             msgs.append({"role": m["role"], "content": c})
         creq = P.ChatCompletionRequest(messages=msgs, max_tokens=req.max_tokens, temperature=req.temperature,
                                        top_p=req.top_p, top_k=req.top_k, stop=req.stop_sequences, stream=False)
+        stop_map = {"stop": "end_turn", "length": "max_tokens", "tool_calls": "tool_use"}
+        if getattr(req, "stream", False):
+            async def events():
+                mid = f"msg_{random_uuid()}"
+                yield _sse_event("message_start", {"message": {
+                    "id": mid, "type": "message", "role": "assistant", "model": ctx.model_name, "content": [],
+                    "stop_reason": None, "stop_sequence": None, "usage": {"input_tokens": 0, "output_tokens": 0}}})
+                yield _sse_event("content_block_start", {"index": 0, "content_block": {"type": "text", "text": ""}})
+                fin, usage = None, None
+                async for item in _chat_deltas(creq, raw):
+                    if not isinstance(item, tuple):
+                        yield _sse_event("error", {"error": {"type": "api_error", "message": "generation failed"}})
+                        return
+                    delta, f, u = item
+                    fin, usage = f or fin, u or usage
+                    if delta:
+                        yield _sse_event("content_block_delta", {"index": 0, "delta": {"type": "text_delta", "text": delta}})
+                yield _sse_event("content_block_stop", {"index": 0})
+                yield _sse_event("message_delta", {"delta": {"stop_reason": stop_map.get(fin, "end_turn"), "stop_sequence": None},
+                                                   "usage": {"input_tokens": (usage or {}).get("prompt_tokens", 0),
+                                                             "output_tokens": (usage or {}).get("completion_tokens", 0)}})
+                yield _sse_event("message_stop", {})
+            return StreamingResponse(events(), media_type="text/event-stream")
         res = await chat(creq, raw)
         if not isinstance(res, dict):
             return res
         ch = res["choices"][0]
-        stop_map = {"stop": "end_turn", "length": "max_tokens", "tool_calls": "tool_use"}
         return {"id": f"msg_{random_uuid()}", "type": "message", "role": "assistant", "model": ctx.model_name,
                 "content": [{"type": "text", "text": ch["message"].get("content") or ""}],
                 "stop_reason": stop_map.get(ch.get("finish_reason"), "end_turn"), "stop_sequence": None,
                 "usage": {"input_tokens": res["usage"]["prompt_tokens"],
                           "output_tokens": res["usage"]["completion_tokens"]}}
+
+    @app.post("/v2/chat")
+    async def cohere_chat(body: dict, raw: Request):
+        """Cohere v2 chat shape over the chat handler (reference: entrypoints/cohere/)."""
+        msgs = []
+        for m in body.get("messages") or []:
+            c = m.get("content")
+            if isinstance(c, list):
+                c = "".join(p.get("text", "") for p in c if isinstance(p, dict))
+            msgs.append({"role": m.get("role", "user"), "content": c})
+        if not msgs:
+            return _error("messages is required")
+        creq = P.ChatCompletionRequest(messages=msgs, max_tokens=body.get("max_tokens"), temperature=body.get("temperature"),
+                                       top_p=body.get("p"), top_k=body.get("k"), stop=body.get("stop_sequences"),
+                                       seed=body.get("seed"), stream=False)
+        res = await chat(creq, raw)
+        if not isinstance(res, dict):
+            return res
+        ch = res["choices"][0]
+        fin = {"stop": "COMPLETE", "length": "MAX_TOKENS", "tool_calls": "TOOL_CALL"}.get(ch.get("finish_reason"), "COMPLETE")
+        u = res["usage"]
+        return {"id": random_uuid(), "finish_reason": fin,
+                "message": {"role": "assistant", "content": [{"type": "text", "text": ch["message"].get("content") or ""}]},
+                "usage": {"billed_units": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"]},
+                          "tokens": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"]}}}
 
     # -------------------------------------------------------- dev routes
     @app.post("/start_profile")

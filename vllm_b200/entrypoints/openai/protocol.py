@@ -361,6 +361,7 @@ class ResponsesRequest(OpenAIBase):
 class AnthropicMessagesRequest(OpenAIBase):
     """Anthropic /v1/messages (reference: entrypoints/anthropic/)."""
     model: Optional[str] = None
+    stream: bool = False
     messages: list[dict[str, Any]]
     system: Optional[Union[str, list[dict[str, Any]]]] = None
     max_tokens: int = 1024
