@@ -538,3 +538,34 @@ def test_compressed_tensors_checkpoints():
         llm.shutdown()
     diff = max(abs(a - b) for a, b in zip(lp["fp"], lp["int8"]))
     assert 0 < diff < 0.25, diff
+
+
+def test_encoder_cache_connector_roundtrip_and_plugins(tmp_path, monkeypatch):
+    """Encoder-output disaggregation store (producer writes embeddings by content hash, consumer reads them) and the
+    entry-point plugin loader (allow-list through VLLM_PLUGINS, failures isolated)."""
+    from vllm_b200.ec_transfer import ECSharedStorageConnector
+    prod = ECSharedStorageConnector(str(tmp_path), "ec_producer")
+    cons = ECSharedStorageConnector(str(tmp_path), "ec_consumer")
+    emb = torch.randn(7, 32).to(torch.bfloat16)
+    prod.save("img-abc", emb)
+    got = cons.load("img-abc")
+    assert got.dtype == torch.bfloat16 and torch.equal(got, emb)
+    assert cons.load("missing") is None and prod.load("img-abc") is None      # producers do not read
+
+    import vllm_b200.plugins as pl
+    calls = []
+
+    class EP:
+        def __init__(self, name, fn):
+            self.name, self._fn = name, fn
+
+        def load(self):
+            return self._fn
+    def boom():
+        raise RuntimeError("bad plugin")
+    monkeypatch.setattr(pl, "_entry_points", lambda group: [EP("a", lambda: calls.append("a")), EP("b", boom),
+                                                            EP("c", lambda: calls.append("c"))])
+    monkeypatch.setattr(pl, "_loaded", False)
+    monkeypatch.setenv("VLLM_PLUGINS", "a,b")
+    pl.load_general_plugins()
+    assert calls == ["a"]                      # "c" filtered by the allow-list, "b" raised without taking the process down
