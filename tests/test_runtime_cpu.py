@@ -318,3 +318,42 @@ def test_wide_expert_parallel_across_dp_replicas(backend, tp):
     assert shards == [4 // (2 * tp)] * tp     # 4 experts over EP = DP x TP ranks → whole experts per rank
     assert first == ref[0] and outs == ref
     assert used == {0, 1}
+
+
+def test_pcp_plan_balances_causal_work():
+    import numpy as np
+    from vllm_b200.worker.model_runner import ModelRunner
+    ns = np.array([64, 1, 1, 7, 1])
+    cu = np.concatenate([[0], np.cumsum(ns)])
+    pieces = ModelRunner.pcp_plan(cu, ns, 2)
+    # every token exactly once
+    seen = sorted((cu[i] + t) for pc in pieces for i, a, b in pc for t in range(a, b))
+    assert seen == list(range(int(cu[-1])))
+    # the long prefill: rank 0 gets chunks 0 and 3, rank 1 chunks 1 and 2 → equal causal cost (sum of positions)
+    cost = [sum(t for i, a, b in pc if i == 0 for t in range(a, b)) for pc in pieces]
+    assert abs(cost[0] - cost[1]) <= 64
+    assert [sum(b - a for i, a, b in pc if i == 0) for pc in pieces] == [32, 32]
+
+
+@pytest.mark.parametrize("tp,pcp", [(1, 2), (2, 2)])
+def test_prefill_context_parallel_matches_single(tp, pcp):
+    """PCP ranks each run the per-token layers on a share of the step's tokens, K/V are all-gathered per layer, the
+    sampled tokens are identical to a single worker (long prefill split head+tail, decodes round-robin)."""
+    from tests.utils import llama_full_weights, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=11))
+    prompts = [{"prompt_token_ids": [(7 * i) % 400 + 3 for i in range(90)]}, {"prompt_token_ids": [5, 17, 99]},
+               {"prompt_token_ids": list(range(10, 40))}]
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny", weights=w)
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("llama-tiny", tensor_parallel_size=tp, prefill_context_parallel_size=pcp, distributed_executor_backend="mp",
+                   max_num_batched_tokens=64)          # 90-token prompt → chunked prefill across steps as well
+    llm.llm_engine.engine_core.engine_core.model_executor.collective_rpc("load_model", kwargs={"weights": w})
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    one = llm.generate(prompts[:1], sp)[0].outputs[0].token_ids          # a lone request: one rank idles on decode steps
+    llm.shutdown()
+    assert got == ref and one == ref[0]

@@ -69,7 +69,18 @@ class Attention(nn.Module):
             if self.rope is not None and positions is not None:
                 q, k = self.rope(positions, q, k)
             return q.clone() if q.shape[-1] == self.num_heads * D else q
-        if self.rope is not None and positions is not None:
+        pcp = ctx.extra.get("pcp")
+        if pcp is not None:
+            # prefill context parallelism: this rank holds a share of the step's tokens.  Rotate locally, all-gather
+            # K / V of the whole step (global token order) so that every rank's cache stays complete, attend for the
+            # local queries only (metadata describes them as the tails of shorter sequences).
+            if self.rope is not None and positions is not None:
+                q, k = self.rope(positions, q, k)
+            Tg = pcp["num_tokens"]
+            k_all, v_all = pcp["gather"](k.contiguous()), pcp["gather"](v.contiguous())
+            ops.reshape_and_cache(k_all.view(Tg, self.num_kv_heads, D), v_all.view(Tg, self.num_kv_heads, D), kv_cache,
+                                  pcp["slot_mappings"][ctx.layer_to_group.get(self.layer_name, 0)], vt=md.kv_vt)
+        elif self.rope is not None and positions is not None:
             q, k = ops.rope_and_cache(positions, q, k, v, self.rope.cos_sin_cache, D,
                                       self.rope.is_neox_style, kv_cache, md.slot_mapping, vt=md.kv_vt)
         else:

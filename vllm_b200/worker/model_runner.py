@@ -150,6 +150,12 @@ class ModelRunner:
         # this rank stores every dcp-th one (layers/attention.py MLAAttentionCore._forward_dcp)
         self.dcp = max(vllm_config.parallel_config.decode_context_parallel_size, 1)
         self.dcp_rank = 0
+        # prefill context parallelism: every rank of the PCP group runs the per-token layers on 1/P of the step's tokens
+        # (head + tail chunk of each long prefill for causal balance), K/V are all-gathered per layer so every rank's
+        # cache is complete (reference: v1/worker/gpu/pcp_manager.py DualChunkSwap, "partial query / full KV")
+        self.pcp = max(vllm_config.parallel_config.prefill_context_parallel_size, 1)
+        if self.pcp > 1 and vllm_config.parallel_config.enable_expert_parallel:
+            raise NotImplementedError("prefill context parallelism with --enable-expert-parallel")
         self.vblock = self.block_size * self.dcp
         self.max_blocks_per_req = cdiv(self.max_model_len, self.vblock) + 1
         self.vocab_size = self.mc.vocab_size
@@ -214,7 +220,7 @@ class ModelRunner:
         self.graphs: dict[int, Any] = {}
         self.graph_pool = None
         self.use_cuda_graph = (self.is_cuda and not self.mc.enforce_eager
-                               and vllm_config.compilation_config.cudagraph_mode != "NONE")
+                               and vllm_config.compilation_config.cudagraph_mode != "NONE" and self.pcp == 1)
         self.capture_sizes: list[int] = []
         self._step = 0
         self.launch_count = 0   # our kernels launched (graph replays count their captured launches)
@@ -533,6 +539,109 @@ class ModelRunner:
                 return self.model(self.input_ids[:T], self.positions[:T], intermediate, inputs_embeds)
             return self.model(self.input_ids[:T], self.positions[:T], intermediate)
 
+    # ------------------------------------------------------------ prefill context parallelism
+    @staticmethod
+    def pcp_plan(cu: np.ndarray, ns: np.ndarray, P: int):
+        """Token → rank assignment for one step.  A request with >= 2P scheduled tokens is cut into 2P chunks and rank r
+        takes chunks r and 2P-1-r (causal attention cost grows with position: head + tail balances it); shorter
+        requests (decodes) go whole to rank ``i % P``.  Returns per rank a list of (request index, a, b) pieces in
+        ascending token order, half-open and relative to the request's scheduled tokens."""
+        pieces: list[list[tuple[int, int, int]]] = [[] for _ in range(P)]
+        for i, n in enumerate(ns.tolist()):
+            if n >= 2 * P:
+                c = -(-n // (2 * P))
+                for j in range(2 * P):
+                    a, b = j * c, min((j + 1) * c, n)
+                    if a < b:
+                        pieces[j if j < P else 2 * P - 1 - j].append((i, a, b))
+            elif n > 0:
+                pieces[i % P].append((i, 0, n))
+        for r in range(P):
+            pieces[r].sort(key=lambda t: (t[0], t[1]))
+        return pieces
+
+    def _forward_pcp(self, T: int, nb: int, cu: np.ndarray, ns: np.ndarray, seq_lens: np.ndarray, intermediate=None):
+        """Runs the model on this rank's token share; returns the hidden states of every request's LAST scheduled
+        token, [nb, H] in request order, identical on every rank of the PCP group."""
+        from vllm_b200.parallel.state import get_pcp_group
+        grp = get_pcp_group()
+        P, r = self.pcp, max(grp.rank_in_group, 0)
+        pieces = self.pcp_plan(cu, ns, P)
+        sel = [np.concatenate([np.arange(cu[i] + a, cu[i] + b) for i, a, b in pc]) if pc else np.zeros(0, dtype=np.int64)
+               for pc in pieces]
+        sizes = [int(x.shape[0]) for x in sel]
+        order = np.concatenate(sel).astype(np.int64)
+        inv = torch.from_numpy(np.argsort(order, kind="stable")).to(self.device)
+        mine = pieces[r]
+        my_sel = torch.from_numpy(sel[r].astype(np.int64)).to(self.device)
+        Tl = sizes[r]
+        idle = Tl == 0
+        if idle:
+            # nothing for this rank in this step (e.g. a lone decode): run one throw-away token so that every kernel and
+            # every collective still sees a non-empty tensor; it contributes no rows to the gathers and writes no KV
+            my_sel = torch.zeros(1, dtype=torch.long, device=self.device)
+            Tl = 1
+        # metadata of my pieces: each is a pseudo-request "last (b-a) tokens of a sequence of computed+b tokens"
+        computed = seq_lens - ns
+        qlens = np.array([b - a for _, a, b in mine], dtype=np.int32)
+        sl_loc = np.array([computed[i] + b for i, _, b in mine], dtype=np.int32)
+        req_idx = torch.tensor([i for i, _, _ in mine], dtype=torch.long, device=self.device)
+        qsl_loc = np.zeros(len(mine) + 1, dtype=np.int32)
+        np.cumsum(qlens, out=qsl_loc[1:])
+        max_q = int(qlens.max()) if len(mine) else 0
+        max_s = int(sl_loc.max()) if len(mine) else 1
+        nbk = max(cdiv(max_s, self.vblock), 1)
+        qsl_t, sl_t = torch.from_numpy(qsl_loc), torch.from_numpy(sl_loc)
+        md = {}
+        if idle:
+            qsl_t, sl_t, max_q, max_s, nbk = torch.tensor([0, 1], dtype=torch.int32), torch.ones(1, dtype=torch.int32), 1, 1, 1
+        for g in range(self.num_kv_groups):
+            bt = (torch.zeros_like(self.block_tables[g][:1]) if idle            # null block
+                  else self.block_tables[g][:nb].index_select(0, req_idx))
+            slots = (torch.full((1,), -1, dtype=self.slot_mappings[g].dtype, device=self.device) if idle
+                     else self.slot_mappings[g][:T].index_select(0, my_sel))
+            md[g] = AttentionMetadata(
+                num_reqs=max(len(mine), 1), num_actual_tokens=Tl, max_query_len=max_q, max_seq_len=max_s,
+                query_start_loc=qsl_t.to(self.device), seq_lens=sl_t.to(self.device),
+                block_table=bt if self.is_cuda else bt[:, :nbk], slot_mapping=slots,
+                query_start_loc_cpu=None if self.is_cuda else qsl_t, seq_lens_cpu=None if self.is_cuda else sl_t,
+                decode_only=max_q == 1, kv_vt=self.kv_vt[g])
+
+        def gather(x: torch.Tensor) -> torch.Tensor:
+            """[Tl, ...] of every rank → [T, ...] in global token order."""
+            mx = max(max(sizes), 1)
+            pad = x.new_zeros((mx,) + tuple(x.shape[1:]))
+            pad[:sizes[r]] = x[:sizes[r]]
+            outs = [torch.empty_like(pad) for _ in range(P)]
+            torch.distributed.all_gather(outs, pad, group=grp.device_group)
+            return torch.cat([o[:n] for o, n in zip(outs, sizes)], dim=0).index_select(0, inv)
+
+        ctx = ForwardContext(attn_metadata=md, kv_caches=self.kv_caches, layer_to_group=self.layer_to_group, num_tokens=Tl)
+        ctx.extra["pcp"] = {"gather": gather, "slot_mappings": [self.slot_mappings[g][:T] for g in range(self.num_kv_groups)],
+                            "num_tokens": T}
+        with set_forward_context(ctx):
+            hidden = self.model(self.input_ids[:T].index_select(0, my_sel), self.positions[:T].index_select(0, my_sel),
+                                intermediate)
+        if isinstance(hidden, dict):
+            return hidden
+        # last scheduled token of every request: owned by exactly one rank → exchange just those rows
+        last = cu[1:].astype(np.int64) - 1
+        owner_pos = {int(t): (rr, k) for rr in range(P) for k, t in enumerate(sel[rr].tolist())}
+        mine_last = [owner_pos[int(t)][1] for t in last if owner_pos[int(t)][0] == r]
+        cnt = [sum(1 for t in last if owner_pos[int(t)][0] == rr) for rr in range(P)]
+        loc = hidden.index_select(0, torch.tensor(mine_last, dtype=torch.long, device=self.device))
+        mx = max(max(cnt), 1)
+        pad = hidden.new_zeros(mx, hidden.shape[-1])
+        pad[:loc.shape[0]] = loc
+        outs = [torch.empty_like(pad) for _ in range(P)]
+        torch.distributed.all_gather(outs, pad, group=grp.device_group)
+        rows_by_rank = [[i for i, t in enumerate(last) if owner_pos[int(t)][0] == rr] for rr in range(P)]
+        out = hidden.new_zeros(nb, hidden.shape[-1])
+        for rr in range(P):
+            if rows_by_rank[rr]:
+                out[torch.tensor(rows_by_rank[rr], dtype=torch.long, device=self.device)] = outs[rr][:cnt[rr]]
+        return out
+
     def _mm_inputs_embeds(self, states, rows, ns, cu, T):
         """Token embeddings of the step with multimodal placeholder positions replaced by encoder outputs.
         Returns None when no scheduled token range touches a multimodal item."""
@@ -651,7 +760,16 @@ class ModelRunner:
             else:
                 mm_emb = (self._mm_inputs_embeds(states, rows, ns, cu, T)
                           if self.has_mm or any(s.mm_features for s in states) else None)
-            if lora_batch is not None:
+            pcp_last = None
+            if self.pcp > 1:
+                if (lora_batch is not None or mm_emb is not None or extra or has_spec or self.drafter is not None
+                        or any(s.pooling_params is not None or (s.sampling_params is not None
+                               and s.sampling_params.prompt_logprobs is not None) for s in states)):
+                    raise NotImplementedError("prefill context parallelism serves plain text generation only "
+                                              "(no LoRA / multimodal / speculative decoding / pooling / prompt logprobs)")
+                hidden = pcp_last = self._forward_pcp(T, nb, cu, ns, (self.num_computed_cpu[rows] + ns).astype(np.int64),
+                                                      intermediate)
+            elif lora_batch is not None:
                 from vllm_b200 import lora as _lora
                 _lora.set_batch(lora_batch)
                 try:
@@ -672,7 +790,7 @@ class ModelRunner:
             if getattr(self.drafter, "needs_step_hidden", False):
                 # EAGLE / MTP heads consume the target hidden state of every position computed this step
                 self.step_hidden = (hidden, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
-            last_hidden = hidden[last_idx]
+            last_hidden = hidden[last_idx] if pcp_last is None else pcp_last
             if self.spec_hidden is not None:        # hidden-state proposers (Medusa) read the newest position's state
                 self.spec_hidden.index_copy_(0, torch.from_numpy(rows.astype(np.int64)).to(self.device), last_hidden)
             logits = self.model.compute_logits(last_hidden)
