@@ -249,3 +249,37 @@ def test_audio_transcription_api():
         call(client.aclose())
         engine.shutdown()
         loop.close()
+
+
+def test_grpc_engine_service(server):
+    """gRPC front-end next to the HTTP app: unary + server-streaming generation, health, model info, bad input."""
+    import grpc
+    from vllm_b200.entrypoints.grpc import EngineClient, start_grpc_server
+    client, call, engine = server
+
+    async def run():
+        srv, port = await start_grpc_server(engine, "llama-tiny", "127.0.0.1", 0)
+        c = EngineClient(f"127.0.0.1:{port}")
+        try:
+            h = await c.health()
+            info = await c.model_info()
+            full = [r async for r in c.generate(prompt_token_ids=[5, 6, 7, 8], max_tokens=5, temperature=0.0)]
+            chunks = [r async for r in c.generate(prompt_token_ids=[5, 6, 7, 8], max_tokens=5, temperature=0.0, stream=True)]
+            try:
+                [r async for r in c.generate(max_tokens=2)]
+                bad = None
+            except grpc.aio.AioRpcError as e:
+                bad = e.code()
+            return h, info, full, chunks, bad
+        finally:
+            await c.close()
+            await srv.stop(0)
+    h, info, full, chunks, bad = call(run())
+    assert h.healthy and info.model == "llama-tiny" and info.max_model_len == 256
+    assert len(full) == 1 and full[0].finished and len(full[0].token_ids) == 5 and full[0].finish_reason == "length"
+    assert [t for ch in chunks for t in ch.token_ids] == list(full[0].token_ids)
+    assert "".join(ch.text for ch in chunks) == full[0].text and chunks[-1].finished and not chunks[0].finished
+    assert bad == grpc.StatusCode.INVALID_ARGUMENT
+    http = call(client.post("/inference/v1/generate", json={"token_ids": [5, 6, 7, 8], "sampling_params": {
+        "max_tokens": 5, "temperature": 0}})).json()
+    assert http["token_ids"] == list(full[0].token_ids)

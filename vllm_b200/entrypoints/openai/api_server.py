@@ -1021,6 +1021,7 @@ def make_arg_parser() -> argparse.ArgumentParser:
     ap.add_argument("--api-server-count", type=int, default=1)
     ap.add_argument("--headless", action="store_true", help="engine cores only; connect to a remote front-end")
     ap.add_argument("--native-frontend", action="store_true", help="serve through the C++ front-end daemon")
+    ap.add_argument("--grpc-port", type=int, default=None, help="also serve the gRPC engine service on this port")
     ap.add_argument("--engine-input-addr", default=None)
     ap.add_argument("--engine-output-addr", default=None)
     ap.add_argument("--data-parallel-start-rank", type=int, default=None)
@@ -1060,6 +1061,10 @@ async def run_server(args: argparse.Namespace) -> None:
             loop.add_signal_handler(sig, lambda: setattr(server, "should_exit", True))
         except NotImplementedError:
             pass
+    grpc_server = None
+    if getattr(args, "grpc_port", None):
+        from vllm_b200.entrypoints.grpc import start_grpc_server
+        grpc_server, _ = await start_grpc_server(engine, ctx.model_name, args.host, args.grpc_port)
     wd = asyncio.create_task(watchdog())
     listen_fd = os.environ.get("VLLM_B200_LISTEN_FD")       # API server k of N: the parent owns the listening socket
     sockets = [socket.socket(fileno=int(listen_fd))] if listen_fd else None
@@ -1067,6 +1072,8 @@ async def run_server(args: argparse.Namespace) -> None:
         await server.serve(sockets=sockets)
     finally:
         wd.cancel()
+        if grpc_server is not None:
+            await grpc_server.stop(1)
         engine.shutdown()
 
 
