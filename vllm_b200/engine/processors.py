@@ -28,8 +28,8 @@ class InputProcessor:
         self.max_model_len = vllm_config.scheduler_config.max_model_len
         self.mm_processor = None
         if self.mc.hf_config.get("vision_config") is not None:
-            from vllm_b200.multimodal import MultiModalProcessor
-            self.mm_processor = MultiModalProcessor(self.mc)
+            from vllm_b200.multimodal import MULTIMODAL_REGISTRY
+            self.mm_processor = MULTIMODAL_REGISTRY.create_processor(self.mc)
 
     def process_inputs(self, request_id: str, prompt: PromptType,
                        params: Union[SamplingParams, PoolingParams], arrival_time: Optional[float] = None,

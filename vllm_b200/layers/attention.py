@@ -70,7 +70,14 @@ class Attention(nn.Module):
                 q, k = self.rope(positions, q, k)
             return q.clone() if q.shape[-1] == self.num_heads * D else q
         pcp = ctx.extra.get("pcp")
-        if pcp is not None:
+        mpos = ctx.extra.get("mrope_positions") if (self.rope is not None and self.rope.mrope_section) else None
+        if mpos is not None:
+            # multimodal rotary ids differ per channel section for image tokens: rotate un-fused, then the ordinary
+            # cache write (text-only steps take the fused path below with 1-D positions = index + per-request delta)
+            q, k = self.rope.forward_mrope(mpos, q, k)
+            ops.reshape_and_cache(k.view(T, self.num_kv_heads, D), v.view(T, self.num_kv_heads, D), kv_cache,
+                                  md.slot_mapping, vt=md.kv_vt)
+        elif pcp is not None:
             # prefill context parallelism: this rank holds a share of the step's tokens.  Rotate locally, all-gather
             # K / V of the whole step (global token order) so that every rank's cache stays complete, attend for the
             # local queries only (metadata describes them as the tails of shorter sequences).

@@ -105,6 +105,26 @@ class RotaryEmbedding(nn.Module):
         freqs = torch.outer(t, inv)
         return torch.cat((freqs.cos() * self.mscale, freqs.sin() * self.mscale), dim=-1).contiguous()
 
+    def forward_mrope(self, positions: torch.Tensor, q: torch.Tensor, k: torch.Tensor):
+        """positions [3, T] (temporal, height, width ids): channel section i of the rotary dims takes its angle from
+        row i % 3 (reference: rotary_embedding/mrope.py; HF ``apply_multimodal_rotary_pos_emb``)."""
+        half = self.rotary_dim // 2
+        cs = self.cos_sin_cache[positions.long()]                              # [3, T, rot]
+        cos3, sin3 = cs[..., :half], cs[..., half:]
+        sec = list(self.mrope_section)
+        idx = torch.cat([torch.full((n,), i % 3, dtype=torch.long) for i, n in enumerate(sec)]).to(q.device)[:half]
+        ar = torch.arange(half, device=q.device)
+        cos = cos3[idx, :, ar].t()                                              # [T, half]
+        sin = sin3[idx, :, ar].t()
+        T, D = positions.shape[1], self.head_size
+
+        def rot(x):
+            xh = x.view(T, -1, D).float()
+            x1, x2, rest = xh[..., :half], xh[..., half:2 * half], xh[..., 2 * half:]
+            c, s_ = cos[:, None, :], sin[:, None, :]
+            return torch.cat((x1 * c - x2 * s_, x2 * c + x1 * s_, rest), dim=-1).to(x.dtype).view(T, -1)
+        return rot(q), rot(k)
+
     def forward(self, positions: torch.Tensor, q: torch.Tensor, k: Optional[torch.Tensor]):
         if self.rotary_dim != self.head_size and q.is_cuda:
             # partial rotary handled by the generic kernel through rot_dim = cache width

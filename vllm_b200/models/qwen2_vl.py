@@ -1,0 +1,119 @@
+"""Qwen2-VL: dynamic-resolution ViT (2-D rotary, 2x2 patch merger) + Qwen2 decoder with multimodal rotary positions.
+
+Reference parity: vllm/model_executor/models/qwen2_vl.py (``Qwen2VisionTransformer``, ``Qwen2VLForConditionalGeneration``),
+layers/rotary_embedding/mrope.py.
+"""
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.models.llama import Qwen2ForCausalLM
+
+
+def _rot_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+class _VisionBlock(nn.Module):
+    def __init__(self, D: int, nh: int, mlp: int, dtype) -> None:
+        super().__init__()
+        self.nh = nh
+        self.norm1, self.norm2 = nn.LayerNorm(D, eps=1e-6, dtype=dtype), nn.LayerNorm(D, eps=1e-6, dtype=dtype)
+        self.qkv, self.proj = nn.Linear(D, 3 * D, dtype=dtype), nn.Linear(D, D, dtype=dtype)
+        self.fc1, self.fc2 = nn.Linear(D, mlp, dtype=dtype), nn.Linear(mlp, D, dtype=dtype)
+
+    def forward(self, x, cos, sin):                                # x [N, D] patches of ONE image
+        N, D = x.shape
+        q, k, v = self.qkv(self.norm1(x)).view(N, 3, self.nh, D // self.nh).unbind(1)
+        q = (q.float() * cos + _rot_half(q.float()) * sin).to(x.dtype)
+        k = (k.float() * cos + _rot_half(k.float()) * sin).to(x.dtype)
+        a = F.scaled_dot_product_attention(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1)).transpose(0, 1)
+        x = x + self.proj(a.reshape(N, D))
+        h = self.fc1(self.norm2(x))
+        return x + self.fc2(h * torch.sigmoid(1.702 * h))          # quick_gelu
+
+
+class Qwen2VisionTransformer(nn.Module):
+    def __init__(self, vc: dict, dtype) -> None:
+        super().__init__()
+        D, self.patch, self.merge = vc["embed_dim"], vc.get("patch_size", 14), vc.get("spatial_merge_size", 2)
+        self.tp = vc.get("temporal_patch_size", 2)
+        self.nh = vc["num_heads"]
+        self.patch_embed = nn.Linear(vc.get("in_channels", 3) * self.tp * self.patch ** 2, D, bias=False, dtype=dtype)
+        self.blocks = nn.ModuleList([_VisionBlock(D, self.nh, int(D * vc.get("mlp_ratio", 4)), dtype) for _ in range(vc["depth"])])
+        self.ln_q = nn.LayerNorm(D, eps=1e-6, dtype=dtype)
+        m = D * self.merge ** 2
+        self.merger_fc1, self.merger_fc2 = nn.Linear(m, m, dtype=dtype), nn.Linear(m, vc["hidden_size"], dtype=dtype)
+        hd = D // self.nh
+        self.register_buffer("inv_freq", 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float32) / (hd // 2))),
+                             persistent=False)
+
+    def _rope(self, grid):
+        t, h, w = grid
+        m = self.merge
+        hp = torch.arange(h).unsqueeze(1).expand(-1, w).reshape(h // m, m, w // m, m).permute(0, 2, 1, 3).flatten()
+        wp = torch.arange(w).unsqueeze(0).expand(h, -1).reshape(h // m, m, w // m, m).permute(0, 2, 1, 3).flatten()
+        ids = torch.stack([hp, wp], dim=-1).repeat(t, 1).to(self.inv_freq.device)
+        table = torch.outer(torch.arange(max(h, w), device=self.inv_freq.device, dtype=torch.float32), self.inv_freq)
+        f = table[ids].flatten(1)                                       # [N, hd/2]
+        emb = torch.cat((f, f), dim=-1)
+        return emb.cos()[:, None, :], emb.sin()[:, None, :]
+
+    def forward(self, patches: torch.Tensor, grid) -> torch.Tensor:
+        """patches [N, C*tp*p*p] of one image (merge-block order) → [N / merge^2, hidden] tokens for the decoder."""
+        x = self.patch_embed(patches.to(self.patch_embed.weight.dtype))
+        cos, sin = self._rope(grid)
+        for b in self.blocks:
+            x = b(x, cos, sin)
+        x = self.ln_q(x).view(-1, x.shape[-1] * self.merge ** 2)
+        return self.merger_fc2(F.gelu(self.merger_fc1(x)))
+
+
+class Qwen2VLForConditionalGeneration(Qwen2ForCausalLM):
+    uses_mrope = True
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        mc = vllm_config.model_config
+        cfg = mc.hf_config
+        tc = cfg.get("text_config") or {}
+        for k, v in tc.items():                                # the decoder reads the flat config
+            cfg.setdefault(k, v)
+        rp = cfg.get("rope_parameters") or tc.get("rope_parameters") or {}
+        sec = (cfg.get("rope_scaling") or {}).get("mrope_section") or rp.get("mrope_section") or [16, 24, 24]
+        cfg["rope_scaling"] = {"rope_type": "mrope", "mrope_section": list(sec)}
+        cfg.setdefault("rope_theta", rp.get("rope_theta", 1000000.0))
+        super().__init__(vllm_config, prefix)
+        self.visual = Qwen2VisionTransformer(cfg["vision_config"], mc.torch_dtype)
+
+    @torch.inference_mode()
+    def embed_multimodal_item(self, feature: dict) -> torch.Tensor:
+        dev = self.visual.patch_embed.weight.device
+        return self.visual(torch.as_tensor(feature["data"]).to(dev), tuple(feature["grid"]))
+
+    def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
+        vparams = dict(self.visual.named_parameters())
+        loaded: set[str] = set()
+        rest = []
+        ren = [("patch_embed.proj.", "patch_embed."), ("merger.ln_q.", "ln_q."), ("merger.mlp.0.", "merger_fc1."),
+               ("merger.mlp.2.", "merger_fc2."), (".attn.qkv.", ".qkv."), (".attn.proj.", ".proj."),
+               (".mlp.fc1.", ".fc1."), (".mlp.fc2.", ".fc2.")]
+        for name, w in weights:
+            if name.startswith("model.visual.") or name.startswith("visual."):
+                n = name.split("visual.", 1)[1]
+                for a, b in ren:
+                    n = n.replace(a, b)
+                if n in vparams:
+                    p = vparams[n]
+                    p.data.copy_(w.reshape(p.shape))               # conv3d kernel → one matrix row per output channel
+                    loaded.add("visual." + n)
+                continue
+            if name.startswith("model.language_model."):
+                name = "model." + name[len("model.language_model."):]
+            rest.append((name, w))
+        return loaded | super().load_weights(rest)

@@ -41,6 +41,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "BartForConditionalGeneration": ("bart", "BartForConditionalGeneration"),
     "BartModel": ("bart", "BartForConditionalGeneration"),
     "WhisperForConditionalGeneration": ("whisper", "WhisperForConditionalGeneration"),
+    "Qwen2VLForConditionalGeneration": ("qwen2_vl", "Qwen2VLForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "BertModel": ("bert", "BertEmbeddingModel"),
     "BertForMaskedLM": ("bert", "BertEmbeddingModel"),

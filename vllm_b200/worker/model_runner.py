@@ -181,6 +181,7 @@ class ModelRunner:
             from vllm_b200.ec_transfer import ECSharedStorageConnector
             self.ec_connector = ECSharedStorageConnector(ecp, os.environ.get("VLLM_B200_EC_ROLE", "ec_both"))
         self.has_mm = vllm_config.model_config.hf_config.get("vision_config") is not None
+        self.uses_mrope = vllm_config.model_config.hf_config.get("model_type") in ("qwen2_vl", "qwen2_5_vl")
         self.kv_connector = None
         ktc = vllm_config.kv_transfer_config
         if ktc is not None and ktc.kv_connector:
@@ -450,7 +451,13 @@ class ModelRunner:
             unknown[:] = False
         fix = np.nonzero(unknown)[0]
         stg.input_ids[:T] = torch.from_numpy(ids)
-        stg.positions[:T] = torch.from_numpy(pos)
+        rope_pos = pos
+        if self.uses_mrope:
+            # M-RoPE: image placeholders compress many tokens into few position steps, so a request's rotary position
+            # runs behind its sequence index by a per-request delta once the prompt is past
+            delta = np.array([self._mrope_delta(self.req_ids[r]) for r in rows], dtype=np.int64)
+            rope_pos = pos + delta[req_of_tok]
+        stg.positions[:T] = torch.from_numpy(rope_pos)
         seq_lens = (computed + ns).astype(np.int32)
         stg.qsl[:nb + 1] = torch.from_numpy(cu)
         stg.seq_lens[:nb] = torch.from_numpy(seq_lens)
@@ -538,6 +545,40 @@ class ModelRunner:
             if inputs_embeds is not None:
                 return self.model(self.input_ids[:T], self.positions[:T], intermediate, inputs_embeds)
             return self.model(self.input_ids[:T], self.positions[:T], intermediate)
+
+    # ------------------------------------------------------------ multimodal rotary positions
+    def _mrope_delta(self, req_id: str) -> int:
+        f = self._mrope_feature(self.states[req_id])
+        return int(f["delta"]) if f is not None else 0
+
+    @staticmethod
+    def _mrope_feature(st: "ReqState"):
+        for f in st.mm_features or ():
+            if f.get("modality") == "mrope":
+                return f
+        return None
+
+    def _mrope_positions(self, states, rows, ns, cu, T):
+        """[3, T] ids for a step that touches a stored multimodal prompt range, else None (1-D positions suffice)."""
+        need = False
+        for j, s in enumerate(states):
+            f = self._mrope_feature(s)
+            if f is not None and int(self.num_computed_cpu[rows[j]]) < f["data"].shape[1]:
+                need = True
+        if not need:
+            return None
+        out = torch.zeros(3, T, dtype=torch.long)
+        for j, s in enumerate(states):
+            start, n = int(self.num_computed_cpu[rows[j]]), int(ns[j])
+            f = self._mrope_feature(s)
+            idx = torch.arange(start, start + n)
+            if f is None:
+                col = idx[None].expand(3, -1)
+            else:
+                stored, L = torch.as_tensor(f["data"]), f["data"].shape[1]
+                col = torch.where(idx[None] < L, stored[:, idx.clamp(max=L - 1)], idx[None] + int(f["delta"]))
+            out[:, int(cu[j]):int(cu[j]) + n] = col
+        return out.to(self.device)
 
     # ------------------------------------------------------------ prefill context parallelism
     @staticmethod
@@ -672,8 +713,11 @@ class ModelRunner:
                 enc = torch.as_tensor(f["data"]).to(self.device, emb.dtype)
                 self.encoder_cache.put(f["hash"], enc)
             if enc is None:
-                px = torch.as_tensor(f["data"]).to(self.device)
-                enc = self.model.embed_multimodal(px[None])[0].to(emb.dtype)
+                if hasattr(self.model, "embed_multimodal_item"):       # towers that need more than the pixels (grids …)
+                    enc = self.model.embed_multimodal_item(f).to(emb.dtype)
+                else:
+                    px = torch.as_tensor(f["data"]).to(self.device)
+                    enc = self.model.embed_multimodal(px[None])[0].to(emb.dtype)
                 self.encoder_cache.put(f["hash"], enc)
                 if self.ec_connector is not None:
                     self.ec_connector.save(f["hash"], enc)
@@ -760,6 +804,10 @@ class ModelRunner:
             else:
                 mm_emb = (self._mm_inputs_embeds(states, rows, ns, cu, T)
                           if self.has_mm or any(s.mm_features for s in states) else None)
+                if self.uses_mrope:
+                    mpos = self._mrope_positions(states, rows, ns, cu, T)
+                    if mpos is not None:
+                        extra = {"mrope_positions": mpos}
             pcp_last = None
             if self.pcp > 1:
                 if (lora_batch is not None or mm_emb is not None or extra or has_spec or self.drafter is not None
