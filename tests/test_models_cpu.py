@@ -13,7 +13,9 @@ PROMPTS = [[5, 17, 99, 3, 250, 41], [7, 7, 7, 301, 12], list(range(10, 60))]
                                     "qwen3moe-tiny", "deepseek-tiny", "mamba-tiny", "phi3-tiny", "gemma2-tiny", "gptneox-tiny",
                                     "starcoder2-tiny", "gptj-tiny", "olmo-tiny", "stablelm-tiny", "jamba-tiny",
                                     "bloom-tiny", "mpt-tiny", "falcon-rw-tiny", "falcon-7b-tiny", "falcon-40b-tiny",
-                                    "gptoss-tiny", "mamba2-tiny", "bamba-tiny", "qwen3next-tiny"])
+                                    "gptoss-tiny", "mamba2-tiny", "bamba-tiny", "qwen3next-tiny",
+                                    "granite-tiny", "olmo2-tiny", "cohere-tiny", "phi-tiny", "glm4-tiny", "nemotron-tiny",
+                                    "gemma3-tiny"])
 def test_greedy_matches_hf(preset):
     hf = make_hf_model(preset)
     llm = make_llm(preset, weights=hf.state_dict().items())

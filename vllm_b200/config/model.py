@@ -217,6 +217,25 @@ PRESETS: dict[str, dict[str, Any]] = {
         vision_config=dict(depth=2, embed_dim=32, hidden_size=64, hidden_act="quick_gelu", mlp_ratio=2, num_heads=2,
                            in_channels=3, patch_size=14, spatial_merge_size=2, temporal_patch_size=2),
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "granite-tiny": dict(architectures=["GraniteForCausalLM"], model_type="granite", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rms_norm_eps=1e-6,
+        hidden_act="silu", embedding_multiplier=6.0, logits_scaling=4.0, residual_multiplier=0.3, attention_multiplier=0.2,
+        rope_theta=10000.0, tie_word_embeddings=True),
+    "olmo2-tiny": dict(architectures=["Olmo2ForCausalLM"], model_type="olmo2", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rms_norm_eps=1e-5, hidden_act="silu",
+        rope_theta=10000.0, tie_word_embeddings=False),
+    "cohere-tiny": dict(architectures=["CohereForCausalLM"], model_type="cohere", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", layer_norm_eps=1e-5,
+        hidden_act="silu", logit_scale=0.25, use_qk_norm=False, rope_theta=10000.0, tie_word_embeddings=True),
+    "phi-tiny": dict(architectures=["PhiForCausalLM"], model_type="phi", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", layer_norm_eps=1e-5, hidden_act="gelu_new",
+        partial_rotary_factor=0.5, qk_layernorm=False, rope_theta=10000.0, tie_word_embeddings=False),
+    "glm4-tiny": dict(architectures=["Glm4ForCausalLM"], model_type="glm4", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", head_dim=16, rms_norm_eps=1e-5,
+        hidden_act="silu", attention_bias=True, partial_rotary_factor=0.5, rope_theta=10000.0, tie_word_embeddings=False),
+    "nemotron-tiny": dict(architectures=["NemotronForCausalLM"], model_type="nemotron", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", head_dim=16, norm_eps=1e-5,
+        hidden_act="relu2", partial_rotary_factor=0.5, rope_theta=10000.0, tie_word_embeddings=False),
+    "gemma3-tiny": dict(architectures=["Gemma3ForCausalLM"], model_type="gemma3_text", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", head_dim=16, rms_norm_eps=1e-6,
+        hidden_activation="gelu_pytorch_tanh", query_pre_attn_scalar=16, sliding_window=16,
+        layer_types=["sliding_attention", "full_attention"],
+        rope_parameters=dict(sliding_attention=dict(rope_type="default", rope_theta=10000.0),
+                             full_attention=dict(rope_type="default", rope_theta=1000000.0)),
+        tie_word_embeddings=True),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

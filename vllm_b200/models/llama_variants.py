@@ -1,0 +1,264 @@
+"""Decoder families that are Llama with a twist, built from one configurable block:
+
+  Granite   — embedding / attention / residual / logit multipliers          (reference: models/granite.py)
+  OLMo-2    — no pre-norms: RMSNorm on each sub-layer OUTPUT, q/k RMSNorm over the whole projection (models/olmo2.py)
+  Cohere    — LayerNorm, attention and MLP in parallel from one norm, interleaved rotary, logit scale (models/commandr.py)
+  Phi-1/2   — LayerNorm, parallel block, plain GELU MLP with biases, partial rotary, biased LM head (models/phi.py)
+  GLM-4     — sandwich norms, fused gate_up checkpoint tensor, half-rotary interleaved           (models/glm4.py)
+  Nemotron  — LayerNorm with +1 weights, squared-ReLU plain MLP, partial rotary                  (models/nemotron.py)
+  Gemma-3   — sandwich norms, per-head (1+w) q/k norms, 5 local : 1 global layers with their own rope base
+              (models/gemma3.py; text tower)
+
+The block keeps the residual stream explicit (no fused add+norm): these families differ exactly in where the norms
+and multipliers sit, which is what the fused Llama path bakes in.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.nn as nn
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.layers.attention import Attention
+from vllm_b200.layers.common import Activation, LayerNorm, LogitsProcessor, ParallelLMHead, RMSNorm
+from vllm_b200.layers.linear import ColumnParallelLinear, QKVParallelLinear, RowParallelLinear
+from vllm_b200.layers.rotary import get_rope
+from vllm_b200.models.llama import LlamaForCausalLM, LlamaMLP, LlamaModel
+from vllm_b200.parallel.state import get_tp_group
+
+
+class _LN1P(nn.Module):
+    """LayerNorm whose stored weight is (gamma - 1) (Nemotron)."""
+
+    def __init__(self, H, eps, dtype) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(H, dtype=dtype), requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(H, dtype=dtype), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x):
+        return torch.nn.functional.layer_norm(x.float(), (x.shape[-1],), self.weight.float() + 1.0, self.bias.float(),
+                                              self.eps).to(x.dtype)
+
+
+class _Identity(nn.Module):
+    def forward(self, x, residual=None):
+        return x if residual is None else (x + residual, x + residual)
+
+
+def _norm(kind: str, H: int, eps: float, dtype) -> nn.Module:
+    if kind == "rms":
+        return RMSNorm(H, eps, dtype)
+    if kind == "rms1p":
+        return RMSNorm(H, eps, dtype, True)
+    if kind == "ln":
+        return LayerNorm(H, eps, True, dtype)
+    if kind == "ln_nobias":
+        return LayerNorm(H, eps, False, dtype)
+    if kind == "ln1p":
+        return _LN1P(H, eps, dtype)
+    if kind == "none":
+        return _Identity()
+    raise ValueError(kind)
+
+
+class _PlainMLP(nn.Module):
+    def __init__(self, H, I, act, bias, dtype, prefix) -> None:
+        super().__init__()
+        # (names differ from the gated MLP's on purpose: the Llama loader fuses ``up_proj`` into ``gate_up_proj``)
+        self.fc_in = ColumnParallelLinear(H, I, bias, dtype=dtype, prefix=f"{prefix}.fc_in")
+        self.fc_out = RowParallelLinear(I, H, bias, dtype=dtype, prefix=f"{prefix}.fc_out")
+        self.act = Activation(act) if act != "relu2" else None
+
+    def forward(self, x):
+        h = self.fc_in(x)
+        h = torch.relu(h).square() if self.act is None else self.act(h)
+        return self.fc_out(h)
+
+
+class VariantAttention(nn.Module):
+    def __init__(self, cfg, mc, dtype, prefix, layer_idx, o) -> None:
+        super().__init__()
+        H, nh = cfg["hidden_size"], cfg["num_attention_heads"]
+        nkv = cfg.get("num_key_value_heads") or nh
+        hd = cfg.get("head_dim") or H // nh
+        self.hd = hd
+        self.qkv_proj = QKVParallelLinear(H, hd, nh, nkv, o["qkv_bias"], dtype, None, f"{prefix}.qkv_proj")
+        self.o_proj = RowParallelLinear(nh * hd, H, o["o_bias"], dtype=dtype, prefix=f"{prefix}.o_proj")
+        self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
+        eps = o["eps"]
+        self.qk_norm = o["qk_norm"]                                   # None | "head" | "head1p" | "full"
+        if self.qk_norm in ("head", "head1p"):
+            self.q_norm, self.k_norm = RMSNorm(hd, eps, dtype, self.qk_norm == "head1p"), RMSNorm(hd, eps, dtype, self.qk_norm == "head1p")
+        elif self.qk_norm == "full":
+            assert get_tp_group().world_size == 1, "whole-projection q/k norms need the unsharded projection"
+            self.q_norm, self.k_norm = RMSNorm(nh * hd, eps, dtype), RMSNorm(nkv * hd, eps, dtype)
+        rp = cfg.get("rope_parameters") or {}
+        sliding = o["sliding"](layer_idx)
+        if "full_attention" in rp or "sliding_attention" in rp:             # per-layer-type rope (Gemma-3)
+            rp = rp["sliding_attention" if sliding else "full_attention"]
+        theta = rp.get("rope_theta", cfg.get("rope_theta", 10000.0))
+        scaling = cfg.get("rope_scaling") or ({k: v for k, v in rp.items() if k not in ("rope_theta", "partial_rotary_factor")}
+                                               if rp.get("rope_type", "default") != "default" else None)
+        factor = rp.get("partial_rotary_factor", cfg.get("partial_rotary_factor", 1.0))
+        max_pos = mc.max_model_len if mc.max_model_len > 0 else cfg.get("max_position_embeddings", 8192)
+        rope = get_rope(hd, int(hd * factor), max_pos, theta, o["neox"], scaling)
+        self.attn = Attention(self.qkv_proj.num_heads, hd, o["scale"] if o["scale"] is not None else hd ** -0.5,
+                              self.qkv_proj.num_kv_heads, sliding_window=cfg.get("sliding_window") if sliding else None,
+                              logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0, prefix=f"{prefix}.attn", rope=rope)
+
+    def forward(self, positions, x):
+        q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        if self.qk_norm in ("head", "head1p"):
+            T = q.shape[0]
+            q = self.q_norm(q.reshape(-1, self.hd)).view(T, -1)
+            k = self.k_norm(k.reshape(-1, self.hd)).view(T, -1)
+        elif self.qk_norm == "full":
+            q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
+        return self.o_proj(self.attn(q, k, v, positions))
+
+
+class VariantLayer(nn.Module):
+    def __init__(self, cfg, mc, dtype, quant_config, prefix, idx, o) -> None:
+        super().__init__()
+        H, eps = cfg["hidden_size"], o["eps"]
+        self.o = o
+        self.self_attn = VariantAttention(cfg, mc, dtype, f"{prefix}.self_attn", idx, o)
+        if o["gated_mlp"]:
+            self.mlp = LlamaMLP(H, cfg["intermediate_size"], o["act"], o["mlp_bias"], dtype, quant_config, f"{prefix}.mlp")
+        else:
+            self.mlp = _PlainMLP(H, cfg["intermediate_size"], o["act"], o["mlp_bias"], dtype, f"{prefix}.mlp")
+        st = o["structure"]
+        self.input_layernorm = _norm(o["norm"] if st != "post" else "none", H, eps, dtype)
+        if st in ("pre", "sandwich"):
+            self.pre_mlp_norm = _norm(o["norm"], H, eps, dtype)
+        if st in ("post", "sandwich"):
+            self.post_attn_norm, self.post_mlp_norm = _norm(o["norm"], H, eps, dtype), _norm(o["norm"], H, eps, dtype)
+        self.rm = float(o["residual_multiplier"])
+
+    def forward(self, positions, hidden, residual, next_norm: Optional[nn.Module]):
+        st, x = self.o["structure"], residual
+        if st == "parallel":
+            x = x + (self.self_attn(positions, hidden) + self.mlp(hidden)) * self.rm
+        else:
+            a = self.self_attn(positions, hidden)
+            if st in ("post", "sandwich"):
+                a = self.post_attn_norm(a)
+            x = x + a * self.rm
+            m = self.mlp(self.pre_mlp_norm(x) if st in ("pre", "sandwich") else x)
+            if st in ("post", "sandwich"):
+                m = self.post_mlp_norm(m)
+            x = x + m * self.rm
+        return (next_norm(x) if next_norm is not None else x), x
+
+
+_DEFAULTS = dict(norm="rms", structure="pre", eps=1e-6, qkv_bias=False, o_bias=False, mlp_bias=False, gated_mlp=True,
+                 act="silu", qk_norm=None, neox=True, scale=None, residual_multiplier=1.0, sliding=lambda i: False,
+                 embed_scale=1.0, logit_scale=1.0, lm_head_bias=False, final_norm_name="model.norm")
+
+
+class VariantModel(LlamaModel):
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "model", quant_config=None) -> None:
+        self._opts = vllm_config.model_config.hf_config["_variant_opts"]
+        super().__init__(vllm_config, prefix, quant_config)
+        o = self._opts
+        self.embed_scale = o["embed_scale"]
+        if self.norm is not None:
+            self.norm = _norm(o["norm"], self.cfg["hidden_size"], o["eps"], vllm_config.model_config.torch_dtype)
+
+    def _make_layer(self, cfg, mc, dtype, quant_config, prefix, idx):
+        return VariantLayer(cfg, mc, dtype, quant_config, prefix, idx, self._opts)
+
+
+class VariantForCausalLM(LlamaForCausalLM):
+    model_cls = VariantModel
+    renames: list[tuple[str, str]] = []
+
+    def options(self, cfg: dict) -> dict:
+        return {}
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        o = dict(_DEFAULTS)
+        o.update(self.options(cfg))
+        cfg["_variant_opts"] = o
+        super().__init__(vllm_config, prefix)
+        if self.is_last:
+            if o["lm_head_bias"]:
+                self.lm_head = ParallelLMHead(cfg["vocab_size"], cfg["hidden_size"], bias=True,
+                                              dtype=vllm_config.model_config.torch_dtype, prefix="lm_head")
+            self.logits_processor = LogitsProcessor(cfg["vocab_size"], scale=o["logit_scale"],
+                                                    soft_cap=cfg.get("final_logit_softcapping"))
+
+    def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
+        def mapped():
+            for name, w in weights:
+                for a, b in self.renames:
+                    if a in name:
+                        name = name.replace(a, b)
+                if name.endswith(".mlp.gate_up_proj.weight") and self.cfg["_variant_opts"]["gated_mlp"]:
+                    I = w.shape[0] // 2                     # checkpoint stores the fused tensor: feed both halves
+                    yield name.replace("gate_up_proj", "gate_proj"), w[:I]
+                    yield name.replace("gate_up_proj", "up_proj"), w[I:]
+                    continue
+                yield name, w
+        return super().load_weights(mapped())
+
+
+class GraniteForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-6), scale=float(c.get("attention_multiplier", 1.0)), qkv_bias=bool(c.get("attention_bias")),
+                    o_bias=bool(c.get("attention_bias")), mlp_bias=bool(c.get("mlp_bias")), residual_multiplier=c.get("residual_multiplier", 1.0),
+                    embed_scale=float(c.get("embedding_multiplier", 1.0)), logit_scale=1.0 / float(c.get("logits_scaling", 1.0)))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class Olmo2ForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(structure="post", eps=c.get("rms_norm_eps", 1e-5), qk_norm="full", qkv_bias=bool(c.get("attention_bias")),
+                    o_bias=bool(c.get("attention_bias")))
+    renames = [(".post_attention_layernorm.", ".post_attn_norm."), (".post_feedforward_layernorm.", ".post_mlp_norm.")]
+
+
+class CohereForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        c.setdefault("tie_word_embeddings", True)
+        return dict(norm="ln_nobias", structure="parallel", eps=c.get("layer_norm_eps", 1e-5), neox=False,
+                    qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")), logit_scale=float(c.get("logit_scale", 1.0)),
+                    qk_norm=None)
+
+
+class PhiForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(norm="ln", structure="parallel", eps=c.get("layer_norm_eps", 1e-5), qkv_bias=True, o_bias=True, mlp_bias=True,
+                    gated_mlp=False, act=c.get("hidden_act", "gelu_new"), lm_head_bias=True)
+    renames = [(".self_attn.dense.", ".self_attn.o_proj."), (".mlp.fc1.", ".mlp.fc_in."), (".mlp.fc2.", ".mlp.fc_out."),
+               ("model.final_layernorm.", "model.norm.")]
+
+
+class Glm4ForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(structure="sandwich", eps=c.get("rms_norm_eps", 1e-5), qkv_bias=bool(c.get("attention_bias", True)), neox=False)
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".post_self_attn_layernorm.", ".post_attn_norm."),
+               (".post_mlp_layernorm.", ".post_mlp_norm.")]
+
+
+class NemotronForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(norm="ln1p", eps=c.get("norm_eps", 1e-5), gated_mlp=False, act="relu2", qkv_bias=bool(c.get("attention_bias")),
+                    o_bias=bool(c.get("attention_bias")), mlp_bias=bool(c.get("mlp_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".mlp.up_proj.", ".mlp.fc_in."), (".mlp.down_proj.", ".mlp.fc_out.")]
+
+
+class Gemma3ForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        c.setdefault("tie_word_embeddings", True)
+        types = c.get("layer_types")
+        pat = c.get("sliding_window_pattern") or c.get("_sliding_window_pattern") or 6
+        return dict(norm="rms1p", structure="sandwich", eps=c.get("rms_norm_eps", 1e-6), qk_norm="head1p",
+                    act=c.get("hidden_activation", "gelu_pytorch_tanh"), scale=float(c.get("query_pre_attn_scalar", 256)) ** -0.5,
+                    embed_scale=float(c["hidden_size"]) ** 0.5, qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")),
+                    sliding=(lambda i: types[i] == "sliding_attention") if types else (lambda i: (i + 1) % pat != 0))
+    renames = [(".post_attention_layernorm.", ".post_attn_norm."), (".pre_feedforward_layernorm.", ".pre_mlp_norm."),
+               (".post_feedforward_layernorm.", ".post_mlp_norm.")]

@@ -18,6 +18,13 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3ForCausalLM": ("llama", "Qwen3ForCausalLM"),
     "GemmaForCausalLM": ("llama", "GemmaForCausalLM"),
     "Phi3ForCausalLM": ("llama", "Phi3ForCausalLM"),
+    "GraniteForCausalLM": ("llama_variants", "GraniteForCausalLM"),
+    "Olmo2ForCausalLM": ("llama_variants", "Olmo2ForCausalLM"),
+    "CohereForCausalLM": ("llama_variants", "CohereForCausalLM"),
+    "PhiForCausalLM": ("llama_variants", "PhiForCausalLM"),
+    "Glm4ForCausalLM": ("llama_variants", "Glm4ForCausalLM"),
+    "NemotronForCausalLM": ("llama_variants", "NemotronForCausalLM"),
+    "Gemma3ForCausalLM": ("llama_variants", "Gemma3ForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
