@@ -19,6 +19,7 @@ def _greedy(llm, n=16):
                                   dict(method="medusa", num_speculative_tokens=3),
                                   dict(method="suffix", num_speculative_tokens=4, prompt_lookup_max=4, prompt_lookup_min=1),
                                   dict(method="eagle", num_speculative_tokens=3),
+                                  dict(method="eagle3", num_speculative_tokens=3),
                                   dict(method="mtp", num_speculative_tokens=2)])
 def test_speculative_decoding_is_lossless(spec):
     """Greedy output with speculation == greedy output without (rejection sampler correctness)."""

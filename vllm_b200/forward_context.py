@@ -68,3 +68,7 @@ def set_forward_context(ctx: ForwardContext):
         yield ctx
     finally:
         _ctx = prev
+
+
+def get_forward_context_or_none() -> Optional[ForwardContext]:
+    return _ctx

@@ -145,9 +145,17 @@ class LlamaModel(nn.Module):
             hidden, residual = self.layers[0].input_layernorm(intermediate_tensors["hidden_states"],
                                                               intermediate_tensors["residual"])
         n = len(self.layers)
+        from vllm_b200.forward_context import get_forward_context_or_none
+        fctx = get_forward_context_or_none()
+        taps = fctx.extra.get("aux_layers") if fctx is not None else None     # EAGLE-3: residual streams of a few layers
+        aux = [] if taps else None
         for i, layer in enumerate(self.layers):
             nxt = self.layers[i + 1].input_layernorm if i + 1 < n else self.norm
             hidden, residual = layer(positions, hidden, residual, nxt)
+            if aux is not None and (self.start + i) in taps:
+                aux.append(residual)
+        if aux:
+            fctx.extra["aux_hidden"] = torch.cat(aux, dim=-1)
         if self.norm is None:  # not the last PP stage: ship the un-normalised pair
             return {"hidden_states": hidden, "residual": residual}
         if get_tp_group().world_size > 1 and hidden.is_cuda:

@@ -71,8 +71,66 @@ class EagleHead(nn.Module):
         return n
 
 
+class Eagle3Layer(nn.Module):
+    """EAGLE-3 draft layer: attention reads [norm(token embedding) ; norm(hidden)] (2H wide), the residual stream
+    carries the hidden half only (reference: model_executor/models/llama_eagle3.py)."""
+
+    def __init__(self, cfg: dict, mc, dtype, prefix: str) -> None:
+        super().__init__()
+        from vllm_b200.layers.attention import Attention
+        from vllm_b200.layers.linear import QKVParallelLinear, RowParallelLinear
+        from vllm_b200.layers.rotary import get_rope
+        from vllm_b200.models.llama import LlamaMLP
+        H, nh = cfg["hidden_size"], cfg["num_attention_heads"]
+        nkv = cfg.get("num_key_value_heads") or nh
+        hd = cfg.get("head_dim") or H // nh
+        eps = cfg.get("rms_norm_eps", 1e-6)
+        self.qkv_proj = QKVParallelLinear(2 * H, hd, nh, nkv, False, dtype, None, f"{prefix}.self_attn.qkv_proj")
+        self.o_proj = RowParallelLinear(nh * hd, H, False, dtype=dtype, prefix=f"{prefix}.self_attn.o_proj")
+        rope = get_rope(hd, hd, mc.max_model_len if mc.max_model_len > 0 else cfg.get("max_position_embeddings", 8192),
+                        cfg.get("rope_theta", 10000.0), True, cfg.get("rope_scaling"))
+        self.attn = Attention(self.qkv_proj.num_heads, hd, hd ** -0.5, self.qkv_proj.num_kv_heads,
+                              prefix=f"{prefix}.self_attn.attn", rope=rope)
+        self.mlp = LlamaMLP(H, cfg["intermediate_size"], cfg.get("hidden_act", "silu"), False, dtype, None, f"{prefix}.mlp")
+        self.input_layernorm, self.hidden_norm = RMSNorm(H, eps, dtype), RMSNorm(H, eps, dtype)
+        self.post_attention_layernorm = RMSNorm(H, eps, dtype)
+        self.sizes = [self.qkv_proj.q_size, self.qkv_proj.kv_size, self.qkv_proj.kv_size]
+
+    def forward(self, positions, emb, hidden):
+        x = torch.cat((self.input_layernorm(emb), self.hidden_norm(hidden)), dim=-1)
+        q, k, v = self.qkv_proj(x).split(self.sizes, dim=-1)
+        h = hidden + self.o_proj(self.attn(q, k, v, positions))
+        return h + self.mlp(self.post_attention_layernorm(h))
+
+
+class Eagle3Head(nn.Module):
+    """fc(3H → H) over the tapped target layers, one Eagle3Layer, its own norm; drafts are read through the target's
+    LM head (a reduced draft vocabulary + ``d2t`` table is applied when the checkpoint ships one)."""
+
+    def __init__(self, cfg: dict, mc, dtype, n_taps: int, prefix: str = "eagle3.") -> None:
+        super().__init__()
+        H = cfg["hidden_size"]
+        self.H = H
+        self.fc = nn.Linear(n_taps * H, H, bias=False, dtype=dtype)
+        self.layers = nn.ModuleList([Eagle3Layer(cfg, mc, dtype, f"{prefix}layers.0")])
+        self.norm = RMSNorm(H, cfg.get("rms_norm_eps", 1e-6), dtype)
+        self.d2t: Optional[torch.Tensor] = None
+
+    def forward(self, emb: torch.Tensor, hidden: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        if hidden.shape[-1] != self.H:               # first pass: concatenated taps; later passes feed our own state back
+            hidden = self.fc(hidden)
+        return self.layers[0](positions, emb, hidden)
+
+    def readout(self, h: torch.Tensor) -> torch.Tensor:
+        return self.norm(h)
+
+    load_weights = EagleHead.load_weights
+    stacked = EagleHead.stacked
+
+
 class EagleDrafter:
     needs_step_hidden = True
+    aux_layers: Optional[tuple] = None
 
     def __init__(self, vllm_config, runner) -> None:
         from vllm_b200.layers import attention as attn_mod
@@ -85,7 +143,12 @@ class EagleDrafter:
         torch.set_default_dtype(mc.torch_dtype)
         try:
             with torch.device(self.device):
-                self.head = EagleHead(mc.hf_config, mc, mc.torch_dtype, mtp=sc.method == "mtp")
+                if sc.method == "eagle3":
+                    L = mc.hf_config["num_hidden_layers"]
+                    self.aux_layers = tuple(sorted({min(2, L - 1), L // 2, max(L - 3, 0)}))     # low / mid / high taps
+                    self.head = Eagle3Head(mc.hf_config, mc, mc.torch_dtype, len(self.aux_layers))
+                else:
+                    self.head = EagleHead(mc.hf_config, mc, mc.torch_dtype, mtp=sc.method == "mtp")
         finally:
             torch.set_default_dtype(old)
         reg = attn_mod.attention_layers()
@@ -177,7 +240,8 @@ class EagleDrafter:
         drafts = []
         one = torch.arange(B + 1, dtype=torch.int32, device=dev)
         for step in range(self.k):
-            tok = runner.model.compute_logits(h).float().argmax(-1)
+            hn = self.head.readout(h) if hasattr(self.head, "readout") else h
+            tok = runner.model.compute_logits(hn).float().argmax(-1)
             drafts.append(tok)
             if step == self.k - 1:
                 break

@@ -172,6 +172,7 @@ class ModelRunner:
         self.drafter = None
         self.spec_hidden = None
         self.step_hidden = None
+        self._last_aux = None
         self.cross_states: dict[str, Any] = {}       # encoder-decoder: request id → per-layer cross-attention (K, V)
         self.is_enc_dec = bool(vllm_config.model_config.hf_config.get("is_encoder_decoder"))
         self.encoder_cache = None
@@ -543,8 +544,11 @@ class ModelRunner:
             ctx.extra.update(extra)
         with set_forward_context(ctx):
             if inputs_embeds is not None:
-                return self.model(self.input_ids[:T], self.positions[:T], intermediate, inputs_embeds)
-            return self.model(self.input_ids[:T], self.positions[:T], intermediate)
+                out = self.model(self.input_ids[:T], self.positions[:T], intermediate, inputs_embeds)
+            else:
+                out = self.model(self.input_ids[:T], self.positions[:T], intermediate)
+        self._last_aux = ctx.extra.get("aux_hidden")            # EAGLE-3 taps (None otherwise)
+        return out
 
     # ------------------------------------------------------------ multimodal rotary positions
     def _mrope_delta(self, req_id: str) -> int:
@@ -798,6 +802,8 @@ class ModelRunner:
             if kv_meta:
                 self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
             extra = None
+            if getattr(self.drafter, "aux_layers", None):
+                extra = {"aux_layers": self.drafter.aux_layers}
             if self.is_enc_dec:
                 extra = {"cross": self._cross_context(states, cu)}
                 mm_emb = None
@@ -807,7 +813,7 @@ class ModelRunner:
                 if self.uses_mrope:
                     mpos = self._mrope_positions(states, rows, ns, cu, T)
                     if mpos is not None:
-                        extra = {"mrope_positions": mpos}
+                        extra = dict(extra or {}, mrope_positions=mpos)
             pcp_last = None
             if self.pcp > 1:
                 if (lora_batch is not None or mm_emb is not None or extra or has_spec or self.drafter is not None
@@ -837,7 +843,8 @@ class ModelRunner:
             last_idx = torch.from_numpy(cu[1:].astype(np.int64) - 1).to(self.device, non_blocking=True)
             if getattr(self.drafter, "needs_step_hidden", False):
                 # EAGLE / MTP heads consume the target hidden state of every position computed this step
-                self.step_hidden = (hidden, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
+                src = self._last_aux if getattr(self.drafter, "aux_layers", None) else hidden
+                self.step_hidden = (src, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
             last_hidden = hidden[last_idx] if pcp_last is None else pcp_last
             if self.spec_hidden is not None:        # hidden-state proposers (Medusa) read the newest position's state
                 self.spec_hidden.index_copy_(0, torch.from_numpy(rows.astype(np.int64)).to(self.device), last_hidden)
@@ -1031,7 +1038,8 @@ class ModelRunner:
             draft_lists.append(list(drafts))
             cu_l.append(cu_l[-1] + k + 1)
         if getattr(self.drafter, "needs_step_hidden", False):
-            self.step_hidden = (hidden, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
+            src = self._last_aux if getattr(self.drafter, "aux_layers", None) else hidden
+            self.step_hidden = (src, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
         idx = torch.tensor(idx_list, dtype=torch.int64, device=self.device)
         logits = self.model.compute_logits(hidden[idx]).float()
         smd = self._sampling_metadata(states, rows, len(states))
