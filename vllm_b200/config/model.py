@@ -388,6 +388,9 @@ class ModelConfig:
 
     # -- loading ----------------------------------------------------------
     def _load_hf_config(self) -> dict[str, Any]:
+        if self.model.endswith(".gguf") and os.path.isfile(self.model):
+            from vllm_b200.model_loader.gguf import gguf_config
+            return gguf_config(self.model)
         path = os.path.join(self.model, "config.json") if os.path.isdir(self.model) else None
         if path and os.path.exists(path):
             with open(path) as f:

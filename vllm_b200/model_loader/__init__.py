@@ -99,6 +99,9 @@ def get_model(vllm_config: VllmConfig, device: torch.device,
     with torch.no_grad():
         if weights is not None:
             model.load_weights(_wrap(weights))
+        elif fmt in ("auto", "gguf") and mc.model.endswith(".gguf") and os.path.isfile(mc.model):
+            from vllm_b200.model_loader.gguf import iter_gguf_weights
+            model.load_weights(iter_gguf_weights(mc.model, mc.torch_dtype))
         elif fmt == "dummy" or (fmt == "auto" and not os.path.isdir(mc.model)):
             initialize_dummy_weights(model, lc.dummy_seed)
         elif fmt == "sharded_state":
