@@ -657,3 +657,59 @@ def test_gguf_checkpoint_roundtrip(tmp_path):
                 q4 = int((lq[l + 32] >> 4) | (((hq[l] >> 6) & 3) << 4)) - 32
                 y[o + l], y[o + l + 32], y[o + l + 64], y[o + l + 96] = d * s[i] * q1, d * s[i + 2] * q2, d * s[i + 4] * q3, d * s[i + 6] * q4
         assert np.allclose(got6[b], y, atol=1e-5)
+
+
+@pytest.mark.parametrize("backend", ["xgrammar", "guidance"])
+def test_structured_output_library_backends(backend):
+    """xgrammar / llguidance matchers behind the same bitmask interface, driven with a real (programmatically built)
+    byte-level BPE tokenizer: every token of a valid document is allowed in turn, an invalid one is masked, the
+    matcher terminates, rollback restores earlier states."""
+    import json
+    import numpy as np
+    from tokenizers import Tokenizer, decoders, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    from vllm_b200.engine.arg_utils import EngineArgs
+    from vllm_b200.sampling_params import StructuredOutputsParams
+    from vllm_b200.structured_output import StructuredOutputManager
+    vocab = {ch: i for i, ch in enumerate(sorted(pre_tokenizers.ByteLevel.alphabet()))}
+    merges = []
+    for a, b in [("t", "r"), ("tr", "u"), ("tru", "e"), ("f", "a"), ("fa", "l"), ("fal", "s"), ("fals", "e")]:
+        vocab[a + b] = len(vocab)
+        merges.append((a, b))
+    vocab["<eos>"] = len(vocab)
+    tk = Tokenizer(models.BPE(vocab=vocab, merges=merges))
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.decoder = decoders.ByteLevel()
+    hf = PreTrainedTokenizerFast(tokenizer_object=tk, eos_token="<eos>")
+    cfg = EngineArgs(model="llama-tiny", device="cpu", structured_outputs_backend=backend).create_engine_config()
+    cfg.model_config.hf_config["eos_token_id"] = hf.eos_token_id
+    mgr = StructuredOutputManager(cfg)
+    mgr._tokenizer = hf
+    schema = {"type": "object", "properties": {"ok": {"type": "boolean"}, "n": {"type": "integer"}}, "required": ["ok", "n"],
+              "additionalProperties": False}
+    req = mgr.make_request("r", StructuredOutputsParams(json=schema))
+    req._fut.result()
+    assert req.is_ready()
+    g = req.grammar
+    doc = '{"ok": true, "n": 42}'
+    ids = hf.encode(doc, add_special_tokens=False)
+    W = (mgr.vocab_size + 31) // 32
+    bm = np.zeros((1, W), dtype=np.int32)
+
+    def allowed(t):
+        g.fill_bitmask(bm, 0)
+        return bool((int(bm[0, t >> 5]) >> (t & 31)) & 1)
+    bad = hf.encode("]", add_special_tokens=False)[0]
+    assert not allowed(bad)                                   # a document cannot start with ']'
+    for i, t in enumerate(ids):
+        assert allowed(t), (i, hf.decode([t]))
+        assert g.accept_tokens("r", [t])
+    assert g.validate_tokens([bad]) == []
+    g.rollback(3)                                             # drop "42}" (three byte tokens) and replay
+    for t in ids[-3:]:
+        assert allowed(t) and g.accept_tokens("r", [t])
+    assert allowed(hf.eos_token_id) or g.is_terminated()
+    g.accept_tokens("r", [hf.eos_token_id])
+    assert g.is_terminated()
+    assert json.loads(doc)["n"] == 42
+    mgr.shutdown()

@@ -181,6 +181,43 @@ class XGrammarGrammar(Grammar):
         return self.m.is_terminated()
 
 
+class GuidanceGrammar(Grammar):
+    """llguidance matcher (reference: v1/structured_output/backend_guidance.py): JSON schema / regex / Lark grammars
+    compiled lazily by the Earley-based engine, bitmask filled straight into our int32 rows."""
+
+    def __init__(self, matcher, vocab_size: int) -> None:
+        import llguidance.numpy as lln
+        self.m, self.vocab_size, self._lln = matcher, vocab_size, lln
+        self._mask = lln.allocate_token_bitmask(1, vocab_size)
+        self.n_accepted = 0
+
+    def fill_bitmask(self, bitmask: np.ndarray, row: int) -> None:
+        self._lln.fill_next_token_bitmask(self.m, self._mask, 0)
+        w = min(bitmask.shape[1], self._mask.shape[1])
+        bitmask[row, :w] = self._mask[0, :w]
+
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool:
+        for t in tokens:
+            if self.m.is_stopped():
+                return True
+            if not self.m.consume_token(int(t)):
+                return False
+            self.n_accepted += 1
+        return True
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        n = self.m.validate_tokens([int(t) for t in tokens])
+        return list(tokens[:n])
+
+    def rollback(self, n: int) -> None:
+        if n > 0:
+            self.m.rollback(n)
+            self.n_accepted -= n
+
+    def is_terminated(self) -> bool:
+        return bool(self.m.is_stopped())
+
+
 class StructuredOutputRequest:
     def __init__(self, params: StructuredOutputsParams, fut: Future) -> None:
         self.params = params
@@ -226,6 +263,8 @@ class StructuredOutputManager:
         kind = p.kind()
         tok = self.tokenizer
         eos = self.vllm_config.model_config.eos_token_id
+        if self.backend == "guidance" and hasattr(tok, "backend_tokenizer"):
+            return self._compile_guidance(kind, p, tok)
         use_xgr = self.backend in ("auto", "xgrammar") and hasattr(tok, "backend_tokenizer")
         if use_xgr:
             try:
@@ -267,6 +306,29 @@ class StructuredOutputManager:
         else:
             raise ValueError(kind)
         return XGrammarGrammar(xgr.GrammarMatcher(g, max_rollback_tokens=64), self.vocab_size)
+
+    def _compile_guidance(self, kind: str, p: StructuredOutputsParams, tok) -> Grammar:
+        import llguidance
+        import llguidance.hf
+        if getattr(self, "_llg_tok", None) is None:
+            self._llg_tok = llguidance.hf.from_tokenizer(tok, n_vocab=self.vocab_size)
+        M = llguidance.LLMatcher
+        if kind == "json":
+            g = M.grammar_from_json_schema(p.json if isinstance(p.json, str) else json.dumps(p.json))
+        elif kind == "json_object":
+            g = M.grammar_from_json_schema('{"type": "object"}')
+        elif kind == "regex":
+            g = M.grammar_from_regex(p.regex)
+        elif kind == "grammar":
+            g = M.grammar_from_lark(p.grammar)
+        elif kind == "choice":
+            g = M.grammar_from_regex("(" + "|".join(re.escape(c) for c in p.choice) + ")")
+        else:
+            raise ValueError(kind)
+        m = M(self._llg_tok, g)
+        if m.is_error():
+            raise ValueError(f"guidance grammar error: {m.get_error()}")
+        return GuidanceGrammar(m, self.vocab_size)
 
     def grammar_bitmask(self, requests: dict, structured_ids: list[str], spec_tokens: dict[str, list[int]]
                         ) -> Optional[np.ndarray]:
