@@ -257,3 +257,38 @@ def test_qwen2_vl_matches_hf():
     llm.shutdown()
     assert outs[0].outputs[0].token_ids == ref_img, (outs[0].outputs[0].token_ids, ref_img)
     assert outs[1].outputs[0].token_ids == ref_txt
+
+
+def test_decoder_pooling_adapters_match_hf():
+    """A registered decoder as (a) sequence classifier: last-token state → score head → softmax == HF
+    LlamaForSequenceClassification; (b) embedding model loaded from a bare ``LlamaModel`` checkpoint."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    kw = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type", "torch_dtype")}
+    hf_cfg = transformers.AutoConfig.for_model("llama", **kw, num_labels=3)
+    hf_cfg.pad_token_id = 0
+    torch.manual_seed(0)
+    hf = transformers.LlamaForSequenceClassification(hf_cfg).float().eval()
+    prompts = [[5, 17, 99, 3, 250, 41], list(range(10, 45))]
+    llm = make_llm("llama-tiny", hf_overrides={"architectures": ["LlamaForSequenceClassification"], "num_labels": 3},
+                   runner="pooling")
+    runner = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner
+    assert type(runner.model).__name__ == "LlamaForSequenceClassification"
+    runner.model.load_weights(hf.state_dict().items())
+    outs = llm.classify([{"prompt_token_ids": p} for p in prompts])
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = hf(torch.tensor([p])).logits[0].softmax(-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()
+    torch.manual_seed(1)
+    base = transformers.LlamaModel(hf_cfg).float().eval()
+    llm = make_llm("llama-tiny", hf_overrides={"architectures": ["LlamaModel"]}, runner="pooling")
+    llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model.load_weights(base.state_dict().items())
+    outs = llm.embed([{"prompt_token_ids": p} for p in prompts])
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = torch.nn.functional.normalize(base(torch.tensor([p])).last_hidden_state[0, -1], dim=-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()

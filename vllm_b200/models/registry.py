@@ -69,7 +69,22 @@ def supported_archs() -> list[str]:
     return sorted(_MODELS)
 
 
+def _adapter_for(arch: str):
+    """``XForSequenceClassification`` / ``XForRewardModel`` / bare ``XModel`` of a registered ``XForCausalLM``."""
+    for suffix, kind in (("ForSequenceClassification", "cls"), ("ForRewardModel", "cls"), ("Model", "embed")):
+        if arch.endswith(suffix):
+            base = arch[: -len(suffix)] + "ForCausalLM"
+            if base in _MODELS:
+                return base, kind
+    return None
+
+
 def resolve_model_cls(arch: str) -> Type[nn.Module]:
+    if arch not in _MODELS and _adapter_for(arch):
+        from vllm_b200.models import adapters
+        base, kind = _adapter_for(arch)
+        fn = adapters.as_seq_cls_model if kind == "cls" else adapters.as_embedding_model
+        return fn(resolve_model_cls(base))
     if arch not in _MODELS:
         # the long tail: any decoder-only HF architecture runs through the Transformers back-end
         try:
