@@ -357,3 +357,29 @@ def test_prefill_context_parallel_matches_single(tp, pcp):
     one = llm.generate(prompts[:1], sp)[0].outputs[0].token_ids          # a lone request: one rank idles on decode steps
     llm.shutdown()
     assert got == ref and one == ref[0]
+
+
+def test_eplb_redundant_experts_and_runtime_rebalance():
+    """EP=2 with 2 redundant expert slots: tokens are routed to replicas, a rebalance re-places the physical experts
+    by observed load and ships the weights between the ranks — outputs stay those of the plain model throughout."""
+    from tests.utils import make_hf_model, make_llm
+    from vllm_b200 import SamplingParams
+    hf = make_hf_model("mixtral-tiny")
+    w = [(k, v.clone()) for k, v in hf.state_dict().items()]
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 8]}, {"prompt_token_ids": list(range(10, 40))}]
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    llm = make_llm("mixtral-tiny", weights=w)
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("mixtral-tiny", tensor_parallel_size=2, enable_expert_parallel=True, enable_eplb=True,
+                   num_redundant_experts=2, eplb_step_interval=5, distributed_executor_backend="mp")
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": w})
+    assert [d["local_experts"] for d in ex.collective_rpc("describe_model")] == [3, 3]      # (4 + 2) slots over 2 ranks
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]       # > 5 steps: the periodic rebalance ran
+    assert got == ref
+    info = ex.collective_rpc("eplb_rebalance")                              # and an explicit one on top
+    assert info[0]["layers"] == 2 and sum(info[0]["replicas"]) == 6 and max(info[0]["replicas"]) >= 2
+    again = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    assert again == ref

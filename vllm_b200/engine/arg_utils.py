@@ -59,6 +59,8 @@ class EngineArgs:
     enable_expert_parallel: bool = False
     all2all_backend: str = "nvswitch_fused"
     enable_eplb: bool = False
+    num_redundant_experts: int = 0
+    eplb_step_interval: int = 3000
     enable_dbo: bool = False
     decode_context_parallel_size: int = 1
     prefill_context_parallel_size: int = 1
@@ -127,7 +129,8 @@ class EngineArgs:
             data_parallel_external_lb=self.data_parallel_external_lb,
             data_parallel_hybrid_lb=self.data_parallel_hybrid_lb,
             enable_expert_parallel=self.enable_expert_parallel, all2all_backend=self.all2all_backend,
-            enable_eplb=self.enable_eplb, enable_dbo=self.enable_dbo,
+            enable_eplb=self.enable_eplb, num_redundant_experts=self.num_redundant_experts,
+            eplb_step_interval=self.eplb_step_interval, enable_dbo=self.enable_dbo,
             decode_context_parallel_size=self.decode_context_parallel_size,
             prefill_context_parallel_size=self.prefill_context_parallel_size,
             dcp_comm_backend=self.dcp_comm_backend, disable_custom_all_reduce=self.disable_custom_all_reduce,

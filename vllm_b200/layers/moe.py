@@ -54,7 +54,30 @@ class FusedMoE(nn.Module):
             backend = get_current_vllm_config().parallel_config.all2all_backend
             self.a2a = All2AllManager(epg, get_dp_group(), g, num_experts, backend)
         dt = dtype or torch.get_default_dtype()
-        if self.ep:
+        # EPLB: ``num_redundant_experts`` extra physical slots hold replicas of hot experts; the router's logical ids
+        # are mapped to physical slots per token, the slots are re-assigned (and their weights moved between ranks) by
+        # ``eplb_apply`` whenever the runner decides to rebalance (reference: distributed/eplb/eplb_state.py)
+        self.eplb = False
+        self.num_physical = num_experts
+        if self.ep and not self.wide_ep:
+            from vllm_b200.config import get_current_vllm_config_or_none
+            vc = get_current_vllm_config_or_none()
+            pc = vc.parallel_config if vc is not None else None
+            if pc is not None and pc.enable_eplb:
+                R = pc.num_redundant_experts
+                if (num_experts + R) % ep_size:
+                    raise ValueError(f"num_experts + num_redundant_experts ({num_experts}+{R}) must divide by EP size {ep_size}")
+                self.eplb, self.num_physical = True, num_experts + R
+        if self.eplb:
+            P, per = self.num_physical, self.num_physical // ep_size
+            self.ep_rank, self.ep_size = ep_rank, ep_size
+            self.e_start, self.e_end, self.local_experts = ep_rank * per, (ep_rank + 1) * per, per
+            phy2log = torch.cat([torch.arange(num_experts), torch.arange(P - num_experts) % num_experts])
+            self.register_buffer("phy2log", phy2log.long(), persistent=False)
+            self.register_buffer("eplb_load", torch.zeros(num_experts, dtype=torch.int64), persistent=False)
+            self._set_placement(phy2log)
+            self.inter_per_rank = intermediate_size
+        elif self.ep:
             # contiguous expert ranges; the map turns a global expert id into a local one (or -1)
             per = (num_experts + ep_size - 1) // ep_size
             self.e_start = min(num_experts, ep_rank * per)
@@ -111,10 +134,71 @@ class FusedMoE(nn.Module):
             out = self.a2a.dispatch_combine(x2, w.to(torch.float32), ids, self._local_experts,
                                             reduce_tp=self.reduce_results)
             return out.reshape(shape)
+        if self.eplb:
+            flat = ids.reshape(-1).long()
+            self.eplb_load += torch.bincount(flat, minlength=self.num_experts)[:self.num_experts]
+            tok = torch.arange(ids.shape[0], device=ids.device)[:, None].expand_as(ids)
+            ids = self.log2phy[ids.long(), tok % self.logcnt[ids.long()]].to(ids.dtype)       # replica by token index
         out = self._local_experts(x2, w.to(torch.float32), ids)
         if self.reduce_results and self.tp_size > 1:
             out = get_tp_group().all_reduce(out)
         return out.reshape(shape)
+
+    # ------------------------------------------------------------ EPLB
+    def _set_placement(self, phy2log: torch.Tensor) -> None:
+        """(Re)builds the routing tables IN PLACE — captured CUDA graphs keep pointing at the same buffers."""
+        E, P = self.num_experts, self.num_physical
+        phy2log = phy2log.long().cpu()
+        cnt = torch.bincount(phy2log, minlength=E)
+        l2p = torch.zeros(E, P - E + 1, dtype=torch.long)                 # a logical expert has at most R + 1 replicas
+        fill = [0] * E
+        for p_ in range(P):
+            e = int(phy2log[p_])
+            l2p[e, fill[e]] = p_
+            fill[e] += 1
+        if not hasattr(self, "log2phy"):
+            emap = torch.full((P,), -1, dtype=torch.int32)
+            emap[self.e_start:self.e_end] = torch.arange(self.local_experts, dtype=torch.int32)
+            self.register_buffer("log2phy", l2p, persistent=False)
+            self.register_buffer("logcnt", cnt, persistent=False)
+            self.register_buffer("expert_map", emap, persistent=False)
+        else:
+            self.log2phy.copy_(l2p)
+            self.logcnt.copy_(cnt)
+        self.phy2log.copy_(phy2log)
+
+    @torch.no_grad()
+    def eplb_apply(self, new_phy2log: torch.Tensor, group) -> int:
+        """Move expert weights so that physical slot p holds logical expert ``new_phy2log[p]`` (every EP rank calls this
+        with the same argument).  Slots whose content is unchanged are untouched; a needed expert is copied from a slot
+        on the same rank when one exists, otherwise received from a peer rank.  Returns the number of slots rewritten."""
+        import torch.distributed as dist
+        from vllm_b200.parallel.eplb import plan_transfers
+        moves = plan_transfers(self.phy2log.cpu(), new_phy2log.cpu(), self.ep_size)
+        per, me = self.local_experts, self.ep_rank
+        tensors = [self.w13_weight, self.w2_weight] + ([self.w13_scale, self.w2_scale] if self.fp8_block else [])
+        snap = [t.data.clone() for t in tensors]                       # reads see the OLD contents
+        ops, recv_bufs = [], []
+        for src, dst, sr, dr in moves:
+            if sr == me and dr == me:
+                for t, s0 in zip(tensors, snap):
+                    t.data[dst - me * per].copy_(s0[src - me * per])
+            elif sr == me:
+                for s0 in snap:
+                    ops.append(dist.P2POp(dist.isend, s0[src - me * per].contiguous(), group.ranks[dr], group.device_group))
+            elif dr == me:
+                for t in tensors:
+                    buf = torch.empty_like(t.data[dst - me * per])
+                    recv_bufs.append((t, dst - me * per, buf))
+                    ops.append(dist.P2POp(dist.irecv, buf, group.ranks[sr], group.device_group))
+        if ops:
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+        for t, slot, buf in recv_bufs:
+            t.data[slot].copy_(buf)
+        self._set_placement(new_phy2log)
+        self.eplb_load.zero_()
+        return len(moves)
 
     def _local_experts(self, x2: torch.Tensor, w: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
         """Contribution of the experts this rank owns (ids are global; the expert map drops the others)."""
@@ -177,6 +261,15 @@ class FusedMoE(nn.Module):
 
     def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id: str, expert_id: int) -> None:
         """shard_id: 'w1' (gate), 'w3' (up), 'w2' (down); ``w`` is the checkpoint's full tensor."""
+        if self.eplb:                                  # every local physical slot that holds this logical expert
+            I = self.inter_per_rank
+            for p_ in (self.phy2log[self.e_start:self.e_end] == expert_id).nonzero().flatten().tolist():
+                if shard_id == "w2":
+                    param.data[p_].copy_(w)
+                else:
+                    off = 0 if shard_id == "w1" else I
+                    param.data[p_, off:off + I].copy_(w)
+            return
         if not (self.e_start <= expert_id < self.e_end):
             return
         le = expert_id - self.e_start

@@ -173,6 +173,9 @@ class ModelRunner:
         self.spec_hidden = None
         self.step_hidden = None
         self._last_aux = None
+        pc_ = vllm_config.parallel_config
+        self.eplb_interval = pc_.eplb_step_interval if pc_.enable_eplb else 0
+        self.eplb_hook = None             # set by the worker (needs the process groups)
         self.cross_states: dict[str, Any] = {}       # encoder-decoder: request id → per-layer cross-attention (K, V)
         self.is_enc_dec = bool(vllm_config.model_config.hf_config.get("is_encoder_decoder"))
         self.encoder_cache = None
@@ -874,6 +877,8 @@ class ModelRunner:
             stg.sampled[:nb] = sampled
         self.num_logical_cpu[rows] += produces.astype(np.int32)
         self.num_computed_cpu[rows] = total_after
+        if self.eplb_interval and self._step % self.eplb_interval == 0 and self.eplb_hook is not None:
+            self.eplb_hook()              # every EP rank reaches the same step count: the shuffle is a collective
         out = AsyncStepOutput(self, req_ids, produces, stg, nb, ev, t0, lp_out, plp)
         if non_block and self.async_mode:
             self._pending = out

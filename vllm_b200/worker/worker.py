@@ -79,6 +79,7 @@ class Worker:
                                          enable_device_comm=not pc.disable_custom_all_reduce)
         torch.manual_seed(self.vllm_config.model_config.seed)
         self.runner = ModelRunner(self.vllm_config, self.device)
+        self.runner.eplb_hook = self.eplb_rebalance
 
     def load_model(self, weights=None) -> None:
         self.runner.load_model(weights)
@@ -140,6 +141,19 @@ class Worker:
 
     # -------------------------------------------------------- sleep / wake
     @torch.inference_mode()
+    def eplb_rebalance(self) -> dict:
+        """Re-place the physical experts of every MoE layer from the routed-token counts since the last rebalance and
+        move the weights (reference: eplb_state.py ``rearrange`` + rebalance_execute.py).  Collective over the EP group."""
+        from vllm_b200.parallel.eplb import rebalance_experts
+        layers = [m for m in self.runner.model.modules() if getattr(m, "eplb", False)]
+        if not layers:
+            return {"layers": 0, "moved": 0}
+        g = pstate.get_tp_group()
+        load = torch.stack([l.eplb_load for l in layers]).cpu()
+        pl = rebalance_experts(load, layers[0].num_physical, layers[0].ep_size)
+        moved = sum(l.eplb_apply(pl.phy2log[i], g) for i, l in enumerate(layers))
+        return {"layers": len(layers), "moved": moved, "replicas": pl.logcnt[0].tolist(), "rank": self.rank}
+
     def describe_model(self) -> dict:
         """Shape of this worker's shard (debug / tests / ``collective_rpc`` from the API)."""
         m = self.runner.model
