@@ -713,3 +713,15 @@ def test_structured_output_library_backends(backend):
     assert g.is_terminated()
     assert json.loads(doc)["n"] == 42
     mgr.shutdown()
+
+
+def test_custom_logits_processor_plugin():
+    """--logits-processors module:Class — requests opt in through extra_args, others are untouched (same batch)."""
+    llm = make_llm("llama-tiny", logits_processors=["tests.plugin_logits_processor:ForceToken"])
+    sp_plain = SamplingParams(max_tokens=5, temperature=0.0, ignore_eos=True)
+    sp_force = SamplingParams(max_tokens=5, temperature=0.0, ignore_eos=True, extra_args={"force_token": 77})
+    base = llm.generate([PROMPTS[0]], sp_plain)[0].outputs[0].token_ids
+    outs = llm.generate([PROMPTS[0], PROMPTS[0]], [sp_force, sp_plain])
+    llm.shutdown()
+    assert outs[0].outputs[0].token_ids == [77] * 5
+    assert outs[1].outputs[0].token_ids == base

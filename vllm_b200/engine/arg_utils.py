@@ -58,6 +58,7 @@ class EngineArgs:
     data_parallel_hybrid_lb: bool = False
     enable_expert_parallel: bool = False
     all2all_backend: str = "nvswitch_fused"
+    logits_processors: Optional[list[str]] = None    # "pkg.module:Class" plug-ins (comma separated on the CLI)
     enable_eplb: bool = False
     num_redundant_experts: int = 0
     eplb_step_interval: int = 3000
@@ -105,7 +106,8 @@ class EngineArgs:
             max_model_len=self.max_model_len or 0, quantization=self.quantization,
             enforce_eager=self.enforce_eager, max_logprobs=self.max_logprobs,
             served_model_name=self.served_model_name, hf_overrides=self.hf_overrides or {},
-            runner=self.runner, skip_tokenizer_init=self.skip_tokenizer_init)
+            runner=self.runner, skip_tokenizer_init=self.skip_tokenizer_init,
+            logits_processors=[str(x) for x in self.logits_processors] if self.logits_processors else None)
         block_size = self.block_size
         if block_size is None:
             # 64-token pages are the tcgen05 kernels' TMA box; models that run on the generic kernel (other head sizes,
@@ -188,7 +190,8 @@ class EngineArgs:
             elif origin in (dict,) or inner is dict:
                 parser.add_argument(flag, type=json.loads, default=default)
             elif origin in (list,):
-                parser.add_argument(flag, type=lambda s: [int(x) for x in s.split(",")], default=default)
+                elem = (get_args(inner) or (int,))[0]
+                parser.add_argument(flag, type=(lambda s, e=elem: [e(x) for x in s.split(",")]), default=default)
             else:
                 parser.add_argument(flag, type=inner, default=default)
         # reference-compatible aliases

@@ -44,6 +44,8 @@ class SamplingMetadata:
     bad_words_token_ids: dict[int, list[list[int]]] = field(default_factory=dict)
     min_tokens: dict[int, tuple[int, set[int]]] = field(default_factory=dict)  # row → (min, stop ids)
     output_token_ids: list[list[int]] = field(default_factory=list)
+    extra_args: list[Optional[dict]] = field(default_factory=list)   # per row ``SamplingParams.extra_args`` (custom processors)
+    prompt_token_ids: list[list[int]] = field(default_factory=list)
     seeds: Optional[torch.Tensor] = None      # [B] int64 per-request noise seeds (CUDA path)
     steps: Optional[torch.Tensor] = None      # [B] int32 per-request noise counter = #output tokens so far
 
@@ -54,7 +56,35 @@ class SamplerOutput:
     logprobs: Optional[tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None  # ids, vals, ranks
 
 
+class LogitsProcessor:
+    """Plug-in interface (``--logits-processors pkg.module:Class``; reference: v1/sample/logits_processor/interface.py).
+    One instance per engine; ``apply`` sees the whole batch and edits rows whose request opted in through
+    ``SamplingParams.extra_args`` (requests with extra_args take the per-request sampling path)."""
+
+    def __init__(self, vllm_config, device) -> None:
+        self.vllm_config, self.device = vllm_config, device
+
+    def is_argmax_invariant(self) -> bool:
+        """True if the processor can never change which token has the highest logit (then greedy rows skip it)."""
+        return False
+
+    def apply(self, logits: torch.Tensor, md: "SamplingMetadata") -> torch.Tensor:
+        raise NotImplementedError
+
+
+def load_logits_processors(specs, vllm_config, device) -> list[LogitsProcessor]:
+    from vllm_b200.utils import resolve_obj_by_qualname
+    out = []
+    for spec in specs or ():
+        cls = resolve_obj_by_qualname(spec.replace(":", ".")) if isinstance(spec, str) else spec
+        out.append(cls(vllm_config, device))
+    return out
+
+
 class Sampler:
+    def __init__(self, logits_processors: Optional[list] = None) -> None:
+        self.custom = list(logits_processors or [])
+
     def __call__(self, logits: torch.Tensor, md: SamplingMetadata,
                  grammar_bitmask: Optional[torch.Tensor] = None) -> SamplerOutput:
         logits = logits.float()
@@ -62,6 +92,9 @@ class Sampler:
         if grammar_bitmask is not None:
             logits = apply_bitmask(logits, grammar_bitmask)
         logits = self.apply_logits_processors(logits, md)
+        for proc in self.custom:
+            if md.extra_args and any(md.extra_args) and not (md.all_greedy and proc.is_argmax_invariant()):
+                logits = proc.apply(logits, md)
         if not md.no_penalties:
             logits = ref.apply_penalties(logits, md.prompt_mask, md.output_counts, md.presence, md.frequency,
                                          md.repetition)

@@ -160,7 +160,8 @@ class ModelRunner:
         self.max_blocks_per_req = cdiv(self.max_model_len, self.vblock) + 1
         self.vocab_size = self.mc.vocab_size
         self.model: Optional[torch.nn.Module] = None
-        self.sampler = Sampler()
+        from vllm_b200.sample.sampler import load_logits_processors
+        self.sampler = Sampler(load_logits_processors(vllm_config.model_config.logits_processors, vllm_config, device))
         self.rejection_sampler = RejectionSampler()
         self.kv_caches: dict[str, torch.Tensor] = {}
         self.layer_to_group: dict[str, int] = {}
@@ -364,7 +365,8 @@ class ModelRunner:
             st.complex_sampling = bool(
                 sp.needs_penalties or sp.logprobs is not None or sp.prompt_logprobs is not None or sp.logit_bias
                 or sp.allowed_token_ids or sp.bad_words_token_ids or sp.min_tokens > 0
-                or sp.structured_outputs is not None)
+                or sp.structured_outputs is not None
+                or (self.sampler.custom and any(k != "kv_transfer_params" for k in (sp.extra_args or {}))))
         else:
             self.temp_cpu[row] = 0.0
             self.seed_cpu[row] = 0
@@ -951,6 +953,9 @@ class ModelRunner:
                               max_num_logprobs=max_lp, logit_bias=logit_bias if any(logit_bias) else [],
                               bad_words_token_ids=bad, min_tokens=min_toks,
                               output_token_ids=[s.output_token_ids for s in states])
+        if self.sampler.custom:
+            md.extra_args = [s.sampling_params.extra_args if s.sampling_params is not None else None for s in states]
+            md.prompt_token_ids = [self.token_ids_cpu[s.row, :s.num_prompt_tokens].tolist() for s in states]
         if not all_greedy:
             if (top_k > 0).any():
                 md.top_k = torch.from_numpy(top_k).to(dev)
