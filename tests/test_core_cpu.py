@@ -181,3 +181,43 @@ def test_hybrid_groups_sliding_window_frees_old_blocks():
     assert r.is_finished()
     # while running, the sliding-window group kept only the blocks covering the last 32 tokens (+ the current one)
     assert s.kv_cache_manager.pool.get_num_free_blocks() == 63
+
+
+def test_tiktoken_tokenizer_mode(tmp_path):
+    """A rank file + tokenizer_config.json → TokenizerLike: round trip, specials, incremental detokenisation."""
+    import base64
+    import json
+    from vllm_b200.tokenizers import get_tokenizer
+    ranks = {bytes([b]): b for b in range(256)}
+    for i, tok in enumerate([b"he", b"ll", b"hell", b"hello", b" w", b" wo", b" wor", b" world"]):
+        ranks[tok] = 256 + i
+    with open(tmp_path / "model.tiktoken", "wb") as f:
+        for tok, r in ranks.items():
+            f.write(base64.b64encode(tok) + b" " + str(r).encode() + b"\n")
+    with open(tmp_path / "tokenizer_config.json", "w") as f:
+        json.dump({"added_tokens_decoder": {"264": {"content": "<|im_start|>"}, "265": {"content": "<|im_end|>"},
+                                            "266": {"content": "<|endoftext|>"}}, "eos_token": "<|endoftext|>"}, f)
+    tok = get_tokenizer(str(tmp_path), "auto")
+    assert type(tok).__name__ == "TiktokenTokenizer" and len(tok) == 267 and tok.eos_token_id == 266
+    ids = tok.encode("hello world ünï")
+    assert ids[:2] == [259, 263] and tok.decode(ids) == "hello world ünï"
+    chat = tok.apply_chat_template([{"role": "user", "content": "hello"}], tokenize=True)
+    assert chat[0] == 264 and 265 in chat and tok.decode(chat, skip_special_tokens=True).startswith("user\nhello")
+
+
+def test_mistral_tokenizer_mode(tmp_path):
+    """tokenizer_mode="mistral" over mistral-common's bundled tekken file: round trip + its own chat encoder."""
+    import os
+    import shutil
+    import mistral_common
+    src = os.path.join(os.path.dirname(mistral_common.__file__), "data", "tekken_240911.json")
+    if not os.path.exists(src):
+        pytest.skip("mistral-common ships no tekken file in this build")
+    shutil.copy(src, tmp_path / "tekken.json")
+    from vllm_b200.tokenizers import get_tokenizer
+    tok = get_tokenizer(str(tmp_path), "mistral")
+    ids = tok.encode("Hello wörld", add_special_tokens=True)
+    assert ids[0] == tok.bos_token_id and tok.decode(ids) == "Hello wörld"
+    chat = tok.apply_chat_template([{"role": "user", "content": "hi"}], tokenize=True)
+    assert chat[0] == tok.bos_token_id and "[INST]" in tok.apply_chat_template([{"role": "user", "content": "hi"}])
+    assert len(tok) > 100000

@@ -93,6 +93,15 @@ def get_tokenizer(name: Optional[str], tokenizer_mode: str = "auto", trust_remot
                   vocab_size: int = 512, eos_token_id: Optional[int] = None, **kw):
     if tokenizer_mode == "byte" or name is None or not os.path.isdir(name):
         return ByteTokenizer(vocab_size, eos_token_id)
+    import glob
+    has_hf = any(os.path.exists(os.path.join(name, f)) for f in ("tokenizer.json", "tokenizer.model", "vocab.json"))
+    if tokenizer_mode == "tiktoken" or (tokenizer_mode == "auto" and not has_hf
+                                        and (glob.glob(os.path.join(name, "*.tiktoken")) or os.path.exists(os.path.join(name, "tiktoken.model")))):
+        from vllm_b200.tokenizers.tiktoken_tok import TiktokenTokenizer
+        return TiktokenTokenizer.from_dir(name)
+    if tokenizer_mode == "mistral":
+        from vllm_b200.tokenizers.mistral_tok import MistralTokenizer
+        return MistralTokenizer.from_dir(name)
     from transformers import AutoTokenizer
     return AutoTokenizer.from_pretrained(name, trust_remote_code=trust_remote_code, **kw)
 
