@@ -66,23 +66,115 @@ def _summarise_clocks(lines: list, local_rank: int) -> dict:
             "samples": len(sm)}
 
 
+def _reference_unavailable(why: str) -> None:
+    if int(os.environ.get("RANK", 0)) == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+
+
 def run_reference(args) -> None:
-    why = None
+    """The reference arm: stock vLLM through its own public API (``vllm.LLM`` → ``llm_engine.add_request/step``), same
+    model architecture, batch, prompt length and step accounting as our arm; none of this repository's code is on
+    that path.  Source: ``baseline/_ref`` when the offline install of /root/reference succeeded; otherwise the stock
+    vLLM wheel that ships in the image (named in the output), otherwise ``unavailable``."""
+    install_note = ("pip install of /root/reference into baseline/_ref is not possible offline: the metadata step needs "
+                    "setuptools_rust (no Rust toolchain) and it pins torch==2.13 / flashinfer 0.6.17 vs torch 2.11 in "
+                    "this image; see DESIGN.md")
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref_dir, "vllm")):
-        why = ("reference not installable offline: pip metadata step needs setuptools_rust (Rust toolchain absent) "
-               "and it pins torch==2.13/flashinfer 0.6.17 vs torch 2.11 in this image; see DESIGN.md")
-    if why is None:
-        try:
-            sys.path.insert(0, ref_dir)
-            import vllm  # noqa: F401
-        except Exception as e:  # pragma: no cover
-            why = f"baseline/_ref import failed: {type(e).__name__}: {e}"
-    if why is not None:
-        if int(os.environ.get("RANK", 0)) == 0:
-            print(json.dumps({"impl": "reference", "unavailable": why}))
-        return
-    raise SystemExit("reference arm present but runner not wired")  # pragma: no cover
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]      # nothing of ours importable from here on
+    source = None
+    if os.path.isdir(os.path.join(ref_dir, "vllm")):
+        sys.path.insert(0, ref_dir)
+        source = "baseline/_ref"
+    if os.environ.get("VLLM_B200_REFERENCE_FROM_IMAGE", "1") == "0" and source is None:
+        return _reference_unavailable(install_note)
+    timeout_s = int(os.environ.get("VLLM_B200_REFERENCE_TIMEOUT", "900"))
+
+    def watchdog():
+        time.sleep(timeout_s)
+        _reference_unavailable(f"reference arm did not finish within {timeout_s}s ({install_note})")
+        os._exit(0)
+    threading.Thread(target=watchdog, daemon=True).start()
+    try:
+        os.environ.setdefault("HF_HUB_OFFLINE", "1")
+        os.environ.setdefault("VLLM_ENABLE_V1_MULTIPROCESSING", "0")       # engine core in-process: steps are timeable
+        os.environ.setdefault("VLLM_LOGGING_LEVEL", "WARNING")
+        os.environ.setdefault("VLLM_PLUGINS", "")                          # stock code path: no third-party plug-ins
+        import tempfile
+
+        import torch
+        import vllm
+        from vllm import LLM, SamplingParams
+        if source is None:
+            source = f"vllm {vllm.__version__} wheel of the image ({install_note})"
+        rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+        presets = {   # HF config.json of the benchmarked architectures (random-init weights: load_format="dummy")
+            "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                               num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0),
+            "llama-3-70b": dict(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64,
+                                num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0),
+        }
+        if args.model not in presets:
+            return _reference_unavailable(f"reference arm has no config for {args.model}")
+        cfg = dict(architectures=["LlamaForCausalLM"], model_type="llama", hidden_act="silu", rms_norm_eps=1e-5,
+                   max_position_embeddings=8192, torch_dtype="bfloat16", tie_word_embeddings=False, bos_token_id=128000,
+                   eos_token_id=128001, **presets[args.model])
+        d = tempfile.mkdtemp(prefix="ref_cfg_")
+        with open(os.path.join(d, "config.json"), "w") as f:
+            json.dump(cfg, f)
+        B, S_in, K, W = args.batch, args.input_len, args.steps, max(args.warmup, 3)
+        out_len = W + K + 2
+        llm = LLM(model=d, load_format="dummy", skip_tokenizer_init=True, dtype="bfloat16", tensor_parallel_size=args.gpus,
+                  max_model_len=S_in + 2 * out_len + 64, max_num_seqs=max(B, 8), max_num_batched_tokens=16384,
+                  enable_prefix_caching=False, gpu_memory_utilization=0.85, generation_config="vllm",
+                  distributed_executor_backend="external_launcher" if world > 1 else None, enforce_eager=args.eager)
+        eng = llm.llm_engine
+        g = torch.Generator().manual_seed(1234)
+        sp = SamplingParams(max_tokens=out_len, temperature=0.0, ignore_eos=True, detokenize=False)
+        for i in range(B):
+            ids = torch.randint(10, cfg["vocab_size"] - 10, (S_in,), generator=g).tolist()
+            eng.add_request(f"a-{i}", {"prompt_token_ids": ids}, sp)
+        seen: dict[str, int] = {}
+        while len(seen) < B:
+            for o in eng.step():
+                seen[o.request_id] = 1
+        for _ in range(W):
+            eng.step()
+        stop, lines = threading.Event(), []
+        th = threading.Thread(target=_clock_sampler, args=(stop, lines), daemon=True)
+        th.start()
+        time.sleep(0.3)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        ms = (time.perf_counter() - t0) * 1e3
+        stop.set()
+        th.join(timeout=2)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+        value = B * K / (ms / 1e3)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "decode output tokens/s (whole box, K engine decode steps, device-synchronised wall clock, max over ranks)",
+                "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic prompts (uniform random token ids), random-init weights (dummy loader)",
+                "config": {"model": args.model, "global_batch": B, "seq_len": S_in, "parallelism": f"tp{args.gpus}",
+                           "cuda_graphs": not args.eager},
+                "clocks": _summarise_clocks(lines, int(os.environ.get("LOCAL_RANK", 0))),
+                "e2e": {"value": value, "unit": "tokens/s", "ms_per_step": ms / K,
+                        "note": "the reference is timed through its public API only (engine.step), i.e. end to end"},
+                "impl": "reference", "reference_source": source}), flush=True)
+    except BaseException as e:  # noqa: BLE001 - whatever goes wrong, the arm reports instead of crashing the driver
+        _reference_unavailable(f"reference arm failed: {type(e).__name__}: {str(e)[:300]} ({install_note})")
+    os._exit(0)          # stock vLLM leaves non-daemon threads / process groups behind; the line above is the result
 
 
 def main() -> None:
