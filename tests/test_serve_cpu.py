@@ -277,3 +277,43 @@ def test_multiple_api_servers_share_one_engine(server):
             proc.wait(timeout=40)
         except subprocess.TimeoutExpired:
             proc.kill()
+
+
+def test_native_frontend_text_prompts_with_tiktoken_tokenizer(tmp_path):
+    """Text prompts on the C++ tier: the launcher exports the BPE tables of a tiktoken-style tokenizer, the daemon
+    tokenises (``/tokenize`` and ``prompt: "text"``) exactly like the Python tokenizer and detokenises the output."""
+    import base64
+    from vllm_b200.tokenizers.tiktoken_tok import TiktokenTokenizer
+    ranks = {bytes([b]): b for b in range(256)}
+    for i, t in enumerate([b"he", b"ll", b"hell", b"hello", b" w", b" wo", b" wor", b" world", b" t", b" th", b" the"]):
+        ranks[t] = 256 + i
+    with open(tmp_path / "model.tiktoken", "wb") as f:
+        for t, r in ranks.items():
+            f.write(base64.b64encode(t) + b" " + str(r).encode() + b"\n")
+    with open(tmp_path / "tokenizer_config.json", "w") as f:
+        json.dump({"added_tokens_decoder": {"267": {"content": "<|endoftext|>"}}, "eos_token": "<|endoftext|>"}, f)
+    tok = TiktokenTokenizer.from_dir(str(tmp_path))
+    env = dict(os.environ, PYTHONPATH=ROOT, VLLM_LOGGING_LEVEL="WARNING")
+    port = get_open_port()
+    proc = _spawn([sys.executable, "-m", "vllm_b200", "serve", "llama-tiny", "--tokenizer", str(tmp_path), "--device", "cpu",
+                   "--dtype", "float32", "--max-model-len", "256", "--max-num-seqs", "8", "--max-num-batched-tokens", "128",
+                   "--kv-cache-memory-bytes", str(16 << 20), "--host", "127.0.0.1", "--port", str(port), "--native-frontend"], env)
+    url = f"http://127.0.0.1:{port}"
+    try:
+        _wait_healthy([(proc, url)])
+        text = "hello world, the naïve 北京 test\n\n  1234 don't"
+        want_ids = tok.encode(text)
+        t = requests.post(url + "/tokenize", json={"prompt": text}, timeout=30).json()
+        assert t["tokens"] == want_ids and t["count"] == len(want_ids)
+        by_text = requests.post(url + "/v1/completions", json={"prompt": text, "max_tokens": 8, "temperature": 0}, timeout=120).json()
+        by_ids = requests.post(url + "/v1/completions", json={"prompt": want_ids, "max_tokens": 8, "temperature": 0}, timeout=120).json()
+        assert by_text["usage"]["prompt_tokens"] == len(want_ids)
+        assert by_text["choices"][0]["token_ids"] == by_ids["choices"][0]["token_ids"]
+        out_ids = [i for i in by_text["choices"][0]["token_ids"] if i < 267]
+        assert by_text["choices"][0]["text"] == tok.enc.decode(out_ids, errors="replace")
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=30)
+        except subprocess.TimeoutExpired:
+            proc.kill()

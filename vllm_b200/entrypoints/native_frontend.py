@@ -54,6 +54,18 @@ def token_bytes_table(tok, vocab_size: int) -> list[tuple[bytes, bool]]:
     special = set(getattr(tok, "all_special_ids", ()) or ())
     if hasattr(tok, "_tok"):                                            # built-in ByteTokenizer
         return [(tok._tok(i), i in special) for i in range(vocab_size)]
+    if type(tok).__name__ == "TiktokenTokenizer":
+        inv = {v: k for k, v in tok.special.items()}
+        out = []
+        for i in range(max(vocab_size, len(tok))):
+            if i in inv:
+                out.append((inv[i].encode(), True))
+            else:
+                try:
+                    out.append((tok.enc.decode_single_token_bytes(i), False))
+                except Exception:
+                    out.append((b"", True))
+        return out
     byte_level = False
     try:
         byte_level = "ByteLevel" in tok.backend_tokenizer.to_str()
@@ -77,6 +89,86 @@ def token_bytes_table(tok, vocab_size: int) -> list[tuple[bytes, bool]]:
     return out
 
 
+_WS = [(9, 13), (32, 32), (133, 133), (160, 160), (5760, 5760), (8192, 8202), (8232, 8233), (8239, 8239), (8287, 8287),
+       (12288, 12288)]                                      # Unicode White_Space (what \s means in the split patterns)
+_PATTERNS = {
+    0: r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+",
+    1: r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+",
+    2: r"'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+",
+}
+
+
+def _category_ranges(prefix: str) -> list[tuple[int, int]]:
+    import unicodedata
+    out, start = [], None
+    for cp in range(0x110000):
+        hit = unicodedata.category(chr(cp)).startswith(prefix)
+        if hit and start is None:
+            start = cp
+        elif not hit and start is not None:
+            out.append((start, cp - 1))
+            start = None
+    if start is not None:
+        out.append((start, 0x10FFFF))
+    return out
+
+
+def encoder_spec(tok) -> Optional[dict]:
+    """What the C++ BPE encoder needs, or None when the tokenizer is not a byte-level BPE with a known split pattern:
+    {style, add_bos, bos_id, specials {str: id}, ranks [(priority, id, bytes)]}."""
+    import json
+    norm = lambda p: p.replace("(?i:'s|'t|'re|'ve|'m|'ll|'d)", "(?i:'s|'t|'re|'ve|'m|'ll|'d)").strip()  # noqa: E731
+    if type(tok).__name__ == "TiktokenTokenizer":
+        style = next((k for k, v in _PATTERNS.items() if norm(tok.enc._pat_str) == v), None)
+        if style is None:
+            return None
+        ranks = [(r, r, b) for b, r in tok.enc._mergeable_ranks.items()]
+        return dict(style=style, add_bos=tok.bos_token_id is not None, bos_id=tok.bos_token_id if tok.bos_token_id is not None else -1,
+                    specials=dict(tok.special), ranks=ranks)
+    bt = getattr(tok, "backend_tokenizer", None)
+    if bt is None:
+        return None
+    cfg = json.loads(bt.to_str())
+    model = cfg.get("model") or {}
+    if model.get("type") != "BPE" or cfg.get("normalizer") not in (None, {}):
+        return None
+    pre = cfg.get("pre_tokenizer") or {}
+    parts = pre.get("pretokenizers") if pre.get("type") == "Sequence" else [pre]
+    style, byte_level = None, False
+    for p_ in parts or []:
+        if p_.get("type") == "ByteLevel":
+            byte_level = True
+            if p_.get("use_regex", True) and style is None:
+                style = 2
+            if p_.get("add_prefix_space"):
+                return None
+        elif p_.get("type") == "Split" and "Regex" in (p_.get("pattern") or {}):
+            style = next((k for k, v in _PATTERNS.items() if norm(p_["pattern"]["Regex"]) == v), None)
+            if style is None or p_.get("behavior") not in ("Isolated", None):
+                return None
+        else:
+            return None
+    if not byte_level or style is None:
+        return None
+    dec = _gpt2_byte_decoder()
+    vocab = model["vocab"]
+    to_b = lambda t: bytes(dec[ch] for ch in t)  # noqa: E731
+    try:
+        ranks = [(0xFFFFFFFE, i, to_b(t)) for t, i in vocab.items() if len(t) == 1]        # base alphabet: ids only
+        pairs = []
+        for rank, m in enumerate(model.get("merges") or []):
+            a, b = m.split(" ") if isinstance(m, str) else m
+            ranks.append((rank, vocab[a + b], to_b(a) + to_b(b)))
+            pairs.append((vocab[a], vocab[b], rank, vocab[a + b]))
+    except KeyError:
+        return None
+    specials = {t["content"]: t["id"] for t in cfg.get("added_tokens") or [] if t.get("special", True)}
+    probe = tok.encode("a")
+    bos = getattr(tok, "bos_token_id", None)
+    return dict(style=style, add_bos=bool(probe) and bos is not None and probe[0] == bos, bos_id=bos if bos is not None else -1,
+                specials=specials, ranks=ranks, pairs=pairs, whole_piece=bool(model.get("ignore_merges")))
+
+
 def write_vocab_table(tok, vocab_size: int, path: str) -> None:
     table = token_bytes_table(tok, vocab_size)
     with open(path, "wb") as f:
@@ -84,6 +176,26 @@ def write_vocab_table(tok, vocab_size: int, path: str) -> None:
         for b, sp in table:
             f.write(struct.pack("<BI", 1 if sp else 0, len(b)))
             f.write(b)
+        spec = encoder_spec(tok)
+        if spec is None:
+            return
+        f.write(b"ENC1")
+        f.write(struct.pack("<IIq", spec["style"], 1 if spec["add_bos"] else 0, spec["bos_id"]))
+        for ranges in (_category_ranges("L"), _category_ranges("N"), _WS):
+            f.write(struct.pack("<I", len(ranges)))
+            for lo, hi in ranges:
+                f.write(struct.pack("<II", lo, hi))
+        f.write(struct.pack("<I", len(spec["specials"])))
+        for text, tid in spec["specials"].items():
+            b = text.encode()
+            f.write(struct.pack("<II", tid, len(b)) + b)
+        f.write(struct.pack("<I", len(spec["ranks"])))
+        for pr, tid, b in spec["ranks"]:
+            f.write(struct.pack("<III", pr, tid, len(b)) + b)
+        if spec.get("pairs"):                              # HF semantics: explicit pair merges
+            f.write(struct.pack("<II", len(spec["pairs"]), 1 if spec.get("whole_piece") else 0))
+            for l, r, rank, merged in spec["pairs"]:
+                f.write(struct.pack("<IIII", l, r, rank, merged))
 
 
 def spawn_frontd(*, host: str, port: int, in_addr: str, out_addr: str, model: str, max_model_len: int,

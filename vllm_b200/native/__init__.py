@@ -77,7 +77,7 @@ FRONTD = os.path.join(os.path.dirname(HERE), "_frontd")
 
 def build_frontd(force: bool = False) -> str:
     """Compile ``native/frontend/frontd.cpp`` (C++ HTTP <-> engine-core front-end daemon) into ``vllm_b200/_frontd``."""
-    srcs = [os.path.join(HERE, "frontend", f) for f in ("frontd.cpp", "wire.hpp")]
+    srcs = [os.path.join(HERE, "frontend", f) for f in ("frontd.cpp", "wire.hpp", "tokenizer.hpp")]
     if not force and os.path.exists(FRONTD) and os.path.getmtime(FRONTD) >= max(os.path.getmtime(s) for s in srcs):
         return FRONTD
     r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", FRONTD, srcs[0], "-ldl", "-lpthread"], capture_output=True, text=True)

@@ -31,6 +31,7 @@
 #include <thread>
 #include <unordered_map>
 
+#include "tokenizer.hpp"
 #include "wire.hpp"
 
 using wire::Val;
@@ -106,9 +107,14 @@ struct Vocab {
       special[i] = fl; bytes[i].resize(len);
       if (len && fread(&bytes[i][0], 1, len, f) != len) { fclose(f); return false; }
     }
+    char magic[4];
+    if (fread(magic, 1, 4, f) == 4 && !memcmp(magic, "ENC1", 4)) {
+      if (!enc.load(f)) fprintf(stderr, "frontd: encoder section of %s is damaged; text prompts disabled\n", path.c_str());
+    }
     fclose(f);
     return true;
   }
+  tok::Encoder enc;       // optional: present when the launcher recognised the tokenizer's BPE scheme
 };
 
 // Moves every complete character of `pending` to `text`; malformed bytes become U+FFFD (what Python's
@@ -409,13 +415,19 @@ struct Server {
     std::vector<int64_t> prompt;
     const Val* p = token_api ? body.get("token_ids") : body.get("prompt");
     if (token_api && !p) p = body.get("prompt_token_ids");
-    if (p && p->t == Val::ARR && p->a.size() == 1 && p->a[0].t == Val::ARR) p = &p->a[0];
+    if (p && p->t == Val::ARR && p->a.size() == 1 && (p->a[0].t == Val::ARR || p->a[0].t == Val::STR)) p = &p->a[0];
+    if (p && p->t == Val::STR && vocab.enc.ready) {              // text prompt: native BPE encoder
+      bool bos = true;
+      if (const Val* v = body.get("add_special_tokens")) bos = v->truthy();
+      for (auto t : vocab.enc.encode(p->s, bos)) prompt.push_back(t);
+      if (prompt.empty()) { reply(c, 400, "Bad Request", error_json("the prompt is empty", "BadRequestError", 400)); return; }
+    } else
     if (!p || p->t != Val::ARR || p->a.empty() || p->a[0].t != Val::INT) {
       reply(c, 400, "Bad Request", error_json("the native front-end takes token-id prompts (a non-empty array of integers); "
                                               "send text prompts to the Python API server or tokenise client-side", "BadRequestError", 400));
       return;
     }
-    for (auto& x : p->a) prompt.push_back(x.integer());
+    if (prompt.empty()) for (auto& x : p->a) prompt.push_back(x.integer());
     if (int64_t(prompt.size()) >= cfg.max_model_len) {
       reply(c, 400, "Bad Request", error_json("prompt is longer than the model's context window", "BadRequestError", 400));
       return;
@@ -529,10 +541,21 @@ struct Server {
       }
       reply(c, 404, "Not Found", error_json("no such route", "NotFoundError", 404)); return;
     }
-    if (method == "POST" && (path == "/v1/completions" || path == "/inference/v1/generate" || path == "/detokenize")) {
+    if (method == "POST" && (path == "/v1/completions" || path == "/inference/v1/generate" || path == "/detokenize" || path == "/tokenize")) {
       Val v;
       try { wire::JsonReader jr(body); v = jr.read(); } catch (const std::exception& ex) { reply(c, 400, "Bad Request", error_json(ex.what(), "BadRequestError", 400)); return; }
       if (v.t != Val::MAP) { reply(c, 400, "Bad Request", error_json("body must be a JSON object", "BadRequestError", 400)); return; }
+      if (path == "/tokenize") {
+        const Val* pr = v.get("prompt");
+        if (!vocab.enc.ready || !pr || pr->t != Val::STR) { reply(c, 400, "Bad Request", error_json("text tokenisation is not available for this tokenizer on the native tier", "BadRequestError", 400)); return; }
+        bool bos = true;
+        if (const Val* x = v.get("add_special_tokens")) bos = x->truthy();
+        auto ids = vocab.enc.encode(pr->s, bos);
+        std::string o = "{\"count\":" + std::to_string(ids.size()) + ",\"max_model_len\":" + std::to_string(cfg.max_model_len) + ",\"tokens\":[";
+        for (size_t k = 0; k < ids.size(); k++) { if (k) o.push_back(','); o += std::to_string(ids[k]); }
+        o += "]}";
+        reply(c, 200, "OK", o); return;
+      }
       if (path == "/detokenize") {
         std::string raw, text;
         if (const Val* t = v.get("tokens")) for (auto& x : t->a) { int64_t id = x.integer(); if (id >= 0 && size_t(id) < vocab.bytes.size() && !vocab.special[id]) raw += vocab.bytes[id]; }
@@ -687,6 +710,25 @@ int main(int argc, char** argv) {
     else if (k == "--max-model-len") s.cfg.max_model_len = atoll(v.c_str());
     else if (k == "--eos-token-id") s.cfg.eos = atoll(v.c_str());
     else { fprintf(stderr, "frontd: unknown option %s\n", k.c_str()); return 2; }
+  }
+  if (argc >= 2 && std::string(argv[argc - 1]) == "--encode-stdin") {
+    // self-test / tooling: JSON array of strings on stdin → JSON array of id arrays on stdout
+    if (!s.vocab.load(s.cfg.vocab_path) || !s.vocab.enc.ready) { fprintf(stderr, "frontd: no encoder in %s\n", s.cfg.vocab_path.c_str()); return 3; }
+    std::string in; char buf[65536]; size_t n;
+    while ((n = fread(buf, 1, sizeof buf, stdin)) > 0) in.append(buf, n);
+    wire::JsonReader jr(in);
+    Val arr = jr.read();
+    std::string o = "[";
+    for (size_t k = 0; k < arr.a.size(); k++) {
+      if (k) o.push_back(',');
+      o.push_back('[');
+      auto ids = s.vocab.enc.encode(arr.a[k].s, true);
+      for (size_t j = 0; j < ids.size(); j++) { if (j) o.push_back(','); o += std::to_string(ids[j]); }
+      o.push_back(']');
+    }
+    o += "]\n";
+    fputs(o.c_str(), stdout);
+    return 0;
   }
   if (s.cfg.in_addr.empty() || s.cfg.out_addr.empty() || s.cfg.libzmq.empty()) {
     fprintf(stderr, "usage: _frontd --in-addr ADDR --out-addr ADDR --libzmq PATH [--host H --port P --model NAME --vocab FILE "
