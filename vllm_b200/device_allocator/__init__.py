@@ -43,7 +43,6 @@ class CuMemAllocator:
         self.current_tag = self.default_tag
 
     def _blocks(self) -> list[tuple[int, int, bool]]:
-        n = self.lib.vbn_cumem_list(None, 0) if False else 0
         cap = 1 << 16
         buf = (ctypes.c_uint64 * (3 * cap))()
         self.lib.vbn_cumem_list.argtypes = [ctypes.c_void_p, ctypes.c_int]

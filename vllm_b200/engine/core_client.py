@@ -160,14 +160,9 @@ class MPClient(EngineCoreClient):
     def _wait_ready(self, in_addr: str) -> None:
         """Startup handshake with a liveness check on the child processes."""
         import zmq
-        sync = zmq.Context.instance().socket(zmq.ROUTER) if False else None
-        del sync
         ready = 0
-        poller_sock = self.input_socket
-        # the handshake is done with a plain blocking zmq socket view of the same fd
-        sctx = zmq.Context.shadow(self.ctx.underlying) if hasattr(self.ctx, "underlying") else self.ctx
-        s = zmq.Socket.shadow(poller_sock.underlying) if hasattr(poller_sock, "underlying") else poller_sock
-        del sctx
+        # the handshake runs before any event loop exists: use a plain blocking view of the (possibly asyncio) socket
+        s = zmq.Socket.shadow(self.input_socket.underlying) if hasattr(self.input_socket, "underlying") else self.input_socket
         deadline = time.time() + 3600
         while ready < self.num_engines:
             if not s.poll(timeout=1000):
