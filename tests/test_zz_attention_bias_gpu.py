@@ -29,7 +29,7 @@ def _setup(B, Hq, Hkv, D, BS, lens, qlens, dtype=torch.bfloat16):
 
 
 @pytest.mark.parametrize("decode", [True, False])
-@pytest.mark.parametrize("feature", ["alibi", "sinks", "both"])
+@pytest.mark.parametrize("feature", ["alibi", "sinks", "both", "chunk"])
 def test_paged_attention_alibi_and_sinks(decode, feature):
     from vllm_b200.ops import cuda as C
     from vllm_b200.ops import ref
@@ -40,14 +40,16 @@ def test_paged_attention_alibi_and_sinks(decode, feature):
     q, kv, md, bt, sl, qsl = _setup(B, Hq, Hkv, D, BS, lens, qlens)
     slopes = torch.tensor([2.0 ** (-(i + 1)) for i in range(Hq)], device="cuda") if feature in ("alibi", "both") else None
     sinks = torch.randn(Hq, device="cuda") if feature in ("sinks", "both") else None
+    chunk = 40 if feature == "chunk" else 0
     for window in (None, 48):
-        out = C.paged_attention(q, kv, md, D ** -0.5, sliding_window=window, alibi_slopes=slopes, sinks=sinks)
+        out = C.paged_attention(q, kv, md, D ** -0.5, sliding_window=window, alibi_slopes=slopes, sinks=sinks, chunk_size=chunk)
         want = ref.paged_attention(q.float(), kv.float(), bt, sl.cpu(), qsl.cpu(), D ** -0.5, sliding_window=window,
-                                   alibi_slopes=slopes, sinks=sinks)
+                                   alibi_slopes=slopes, sinks=sinks, chunk_size=chunk)
         err = (out.float() - want).abs().max().item()
         assert err < 3e-2, (feature, decode, window, err)
     if decode:       # split-KV: the sink mass must be counted exactly once
         md.num_splits = 3
-        out = C.paged_attention(q, kv, md, D ** -0.5, alibi_slopes=slopes, sinks=sinks)
-        want = ref.paged_attention(q.float(), kv.float(), bt, sl.cpu(), qsl.cpu(), D ** -0.5, alibi_slopes=slopes, sinks=sinks)
+        out = C.paged_attention(q, kv, md, D ** -0.5, alibi_slopes=slopes, sinks=sinks, chunk_size=chunk)
+        want = ref.paged_attention(q.float(), kv.float(), bt, sl.cpu(), qsl.cpu(), D ** -0.5, alibi_slopes=slopes, sinks=sinks,
+                                   chunk_size=chunk)
         assert (out.float() - want).abs().max().item() < 3e-2

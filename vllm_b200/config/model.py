@@ -236,6 +236,20 @@ PRESETS: dict[str, dict[str, Any]] = {
         rope_parameters=dict(sliding_attention=dict(rope_type="default", rope_theta=10000.0),
                              full_attention=dict(rope_type="default", rope_theta=1000000.0)),
         tie_word_embeddings=True),
+    "glm4moe-tiny": dict(architectures=["Glm4MoeForCausalLM"], model_type="glm4_moe", vocab_size=512, hidden_size=64,
+        intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+        head_dim=16, n_routed_experts=8, n_shared_experts=1, num_experts_per_tok=2, n_group=2, topk_group=1,
+        first_k_dense_replace=1, norm_topk_prob=True, routed_scaling_factor=1.5, use_qk_norm=True, attention_bias=True,
+        partial_rotary_factor=0.5, rope_theta=10000.0, rms_norm_eps=1e-5, hidden_act="silu", max_position_embeddings=512,
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "llama4-tiny": dict(architectures=["Llama4ForCausalLM"], model_type="llama4_text", vocab_size=512, hidden_size=64,
+        intermediate_size=32, intermediate_size_mlp=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2,
+        head_dim=16, num_local_experts=4, num_experts_per_tok=1, interleave_moe_layer_step=2, moe_layers=[1, 3],
+        no_rope_layers=[1, 1, 1, 0], attention_chunk_size=16, attn_temperature_tuning=True, floor_scale=8, attn_scale=0.1,
+        use_qk_norm=True, rms_norm_eps=1e-5, hidden_act="silu", max_position_embeddings=512, attention_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0),
+        layer_types=["chunked_attention", "chunked_attention", "chunked_attention", "full_attention"],
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

@@ -41,6 +41,7 @@ struct AttnParams {
   int causal;
   const float* alibi;     // optional [Hq] slopes: score += slope * (kpos - qpos)   (Bloom / MPT / Falcon-RW)
   const float* sinks;     // optional [Hq] attention-sink logits: extra softmax mass that attends to nothing (GPT-OSS)
+  int chunk;              // chunked-local attention (Llama-4): keys of the query's own chunk only (0 = off)
 };
 
 template <typename T, int D, int R, int BS, bool FP8>
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(THREADS) paged_attn_kernel(const AttnParams p)
       bool ok = qpos >= 0 && kpos < kv_end && kpos >= kv_begin;
       if (p.causal) ok = ok && kpos <= qpos;
       if (p.window > 0) ok = ok && kpos > qpos - p.window;
+      if (p.chunk > 0) ok = ok && (kpos / p.chunk == qpos / p.chunk);
       s = ok ? s : -INFINITY;
       const float pmax = warp_max(s);
       const float m_new = fmaxf(m_run[r], pmax);
@@ -358,7 +360,7 @@ EXPORT int vb_paged_attention_ex(const void* q, const void* kv_cache, const int*
                                  const int* qsl, void* out, float* part_out, float* part_lse, float* lse_out, int B,
                                  int max_q_len, int Hq, int Hkv, int D, int BS, int64_t q_stride, int64_t out_stride,
                                  int bt_stride, int num_splits, int window, float scale, float soft_cap, float kv_scale,
-                                 int causal, int kv_fp8, int dtype, const float* alibi, const float* sinks,
+                                 int causal, int kv_fp8, int dtype, const float* alibi, const float* sinks, int chunk,
                                  cudaStream_t st);
 
 EXPORT int vb_paged_attention(const void* q, const void* kv_cache, const int* block_table, const int* seq_lens,
@@ -368,14 +370,14 @@ EXPORT int vb_paged_attention(const void* q, const void* kv_cache, const int* bl
                               int causal, int kv_fp8, int dtype, cudaStream_t st) {
   return vb_paged_attention_ex(q, kv_cache, block_table, seq_lens, qsl, out, part_out, part_lse, lse_out, B, max_q_len, Hq,
                                Hkv, D, BS, q_stride, out_stride, bt_stride, num_splits, window, scale, soft_cap, kv_scale,
-                               causal, kv_fp8, dtype, nullptr, nullptr, st);
+                               causal, kv_fp8, dtype, nullptr, nullptr, 0, st);
 }
 
 EXPORT int vb_paged_attention_ex(const void* q, const void* kv_cache, const int* block_table, const int* seq_lens,
                                  const int* qsl, void* out, float* part_out, float* part_lse, float* lse_out, int B,
                                  int max_q_len, int Hq, int Hkv, int D, int BS, int64_t q_stride, int64_t out_stride,
                                  int bt_stride, int num_splits, int window, float scale, float soft_cap, float kv_scale,
-                                 int causal, int kv_fp8, int dtype, const float* alibi, const float* sinks,
+                                 int causal, int kv_fp8, int dtype, const float* alibi, const float* sinks, int chunk,
                                  cudaStream_t st) {
   if (B == 0) return 0;
   if (dtype == DT_F32) return -1;
@@ -385,7 +387,7 @@ EXPORT int vb_paged_attention_ex(const void* q, const void* kv_cache, const int*
   p.part_out = part_out; p.part_lse = part_lse; p.lse_out = lse_out; p.q_stride = q_stride; p.out_stride = out_stride;
   p.bt_stride = bt_stride; p.Hq = Hq; p.Hkv = Hkv; p.num_splits = qsl ? 1 : num_splits; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f; p.soft_cap = soft_cap; p.kv_scale = kv_scale; p.causal = causal;
-  p.alibi = alibi; p.sinks = sinks;
+  p.alibi = alibi; p.sinks = sinks; p.chunk = chunk;
   int R, TQ;
   if (G > 8 || (G & (G - 1))) return -4;     // group sizes 1,2,4,8
   if (qsl) { R = 8; TQ = 8 / G; } else { R = G; TQ = 1; }

@@ -32,8 +32,10 @@ class Attention(nn.Module):
     def __init__(self, num_heads: int, head_size: int, scale: float, num_kv_heads: Optional[int] = None,
                  sliding_window: Optional[int] = None, logits_soft_cap: float = 0.0, prefix: str = "",
                  causal: bool = True, rope: Optional[nn.Module] = None,
-                 alibi_slopes: Optional[torch.Tensor] = None, sinks: Optional[torch.Tensor] = None) -> None:
+                 alibi_slopes: Optional[torch.Tensor] = None, sinks: Optional[torch.Tensor] = None,
+                 chunk_size: int = 0) -> None:
         super().__init__()
+        self.chunk_size = int(chunk_size or 0)        # chunked-local attention (Llama-4 rope layers)
         # ALiBi slopes / attention-sink logits of THIS rank's heads (buffers follow the module's device)
         self.register_buffer("alibi_slopes", None if alibi_slopes is None else alibi_slopes.float(), persistent=False)
         self.sinks = sinks                       # nn.Parameter owned by the model (loaded from the checkpoint) or None
@@ -95,7 +97,7 @@ class Attention(nn.Module):
                                   kv_cache, md.slot_mapping, vt=md.kv_vt)
         out = ops.paged_attention(q.view(T, self.num_heads, D), kv_cache, md, self.scale,
                                   self.sliding_window, self.logits_soft_cap, self.causal,
-                                  alibi_slopes=self.alibi_slopes, sinks=self.sinks)
+                                  alibi_slopes=self.alibi_slopes, sinks=self.sinks, chunk_size=self.chunk_size)
         return out.view(T, self.num_heads * D)
 
 

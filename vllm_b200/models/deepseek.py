@@ -232,3 +232,46 @@ class DeepseekV3ForCausalLM(LlamaForCausalLM):
                     yield f"{base}{e}.down_proj.weight", w[e]
             else:
                 yield name, w
+
+
+# ------------------------------------------------------------------------------------------------ GLM-4.5 / 4.6 (MoE)
+class Glm4MoeDecoderLayer(DeepseekDecoderLayer):
+    """DeepSeek-V3 style MoE block (sigmoid scores + correction bias, grouped top-k, shared experts, leading dense
+    layers) around ordinary GQA attention with partial rotary and optional per-head q/k norms
+    (reference: models/glm4_moe.py)."""
+
+    def __init__(self, cfg, mc, dtype, quant_config, prefix: str, layer_idx: int, enable_ep: bool) -> None:
+        nn.Module.__init__(self)
+        from vllm_b200.models.llama import LlamaAttention
+        eps = cfg.get("rms_norm_eps", 1e-5)
+        self.self_attn = LlamaAttention(cfg, mc, dtype, quant_config, f"{prefix}.self_attn", layer_idx)
+        self.input_layernorm = RMSNorm(cfg["hidden_size"], eps, dtype)
+        self.post_attention_layernorm = RMSNorm(cfg["hidden_size"], eps, dtype)
+        sparse = bool(cfg.get("n_routed_experts")) and layer_idx >= cfg.get("first_k_dense_replace", 0)
+        if sparse:
+            self.mlp = DeepseekMoE(cfg, dtype, quant_config, f"{prefix}.mlp", enable_ep)
+        else:
+            self.mlp = LlamaMLP(cfg["hidden_size"], cfg["intermediate_size"], cfg.get("hidden_act", "silu"), False,
+                                dtype, quant_config, f"{prefix}.mlp")
+        self.sparse = sparse
+
+
+class Glm4MoeModel(DeepseekModel):
+    def _make_layer(self, cfg, mc, dtype, quant_config, prefix, idx):
+        return Glm4MoeDecoderLayer(cfg, mc, dtype, quant_config, prefix, idx, self._enable_ep)
+
+
+class Glm4MoeForCausalLM(DeepseekV3ForCausalLM):
+    model_cls = Glm4MoeModel
+    stacked = [("qkv_proj", "q_proj", "q"), ("qkv_proj", "k_proj", "k"), ("qkv_proj", "v_proj", "v"),
+               ("gate_up_proj", "gate_proj", 0), ("gate_up_proj", "up_proj", 1)]
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("topk_method", "noaux_tc")
+        cfg.setdefault("scoring_func", "sigmoid")
+        cfg["qk_norm"] = bool(cfg.get("use_qk_norm", False))
+        rp = cfg.get("rope_parameters") or {}
+        cfg.setdefault("partial_rotary_factor", rp.get("partial_rotary_factor", 0.5))
+        cfg.setdefault("rope_theta", rp.get("rope_theta", 10000.0))
+        super().__init__(vllm_config, prefix)

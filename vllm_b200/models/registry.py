@@ -56,6 +56,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "RobertaModel": ("bert", "RobertaModel"),
     "XLMRobertaModel": ("bert", "RobertaModel"),
     "DeepseekV2ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
+    "Llama4ForCausalLM": ("llama4", "Llama4ForCausalLM"),
+    "Glm4MoeForCausalLM": ("deepseek", "Glm4MoeForCausalLM"),
     "DeepseekV3ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
 }
 

@@ -49,7 +49,7 @@ _concat_mla = _sig("vb_concat_and_cache_mla", _vp, _vp, _vp, _vp, _i, _i, _i, _i
 _paged_attention = _sig("vb_paged_attention", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                         _i64, _i64, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp)
 _paged_attention_ex = _sig("vb_paged_attention_ex", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
-                           _i64, _i64, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp, _vp, _vp)
+                           _i64, _i64, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp, _vp, _i, _vp)
 _fmha_tc = _sig("vb_fmha_tc", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i,
                 _i, _i, _f, _i, _i, _vp)
 _fmha_tc_decode = _sig("vb_fmha_tc_decode", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i,
@@ -232,7 +232,7 @@ def decode_splits(B: int, Hkv: int, max_seq_len: int, block_size: int) -> int:
 
 
 def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap=0.0, causal=True, out=None,
-                    kv_scale: float = 1.0, return_lse: bool = False, alibi_slopes=None, sinks=None):
+                    kv_scale: float = 1.0, return_lse: bool = False, alibi_slopes=None, sinks=None, chunk_size: int = 0):
     T, Hq, D = q.shape
     Hkv, BS = kv_cache.shape[2], kv_cache.shape[3]
     if out is None:
@@ -241,8 +241,8 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
     bt = md.block_table
     if md.kv_vt:
         # tcgen05 kernel over the tensor-core cache layout
-        assert D == 128 and BS == 64 and not logits_soft_cap and alibi_slopes is None and sinks is None, \
-            "tensor-core attention: D=128, 64-token pages, no soft-cap / ALiBi / sinks"
+        assert D == 128 and BS == 64 and not logits_soft_cap and alibi_slopes is None and sinks is None and not chunk_size, \
+            "tensor-core attention: D=128, 64-token pages, no soft-cap / ALiBi / sinks / chunked-local mask"
         decode = md.decode_only
         splits = (md.num_splits or decode_splits(md.num_reqs, Hkv, md.max_seq_len, 128)) if decode else 1
         ws = _get_attn_ws(md.num_reqs, Hq, D, splits, q.device) if splits > 1 else None
@@ -274,13 +274,13 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
                                  out.data_ptr(), _p(ws.part_out) if ws else None, _p(ws.part_lse) if ws else None,
                                  _p(lse), md.num_reqs, 1, Hq, Hkv, D, BS, q.stride(0), out.stride(0), bt.stride(0),
                                  splits, sliding_window or 0, scale, logits_soft_cap, kv_scale, int(causal),
-                                 _kv_fp8(kv_cache), _DT[q.dtype], _p(alibi_slopes), _p(sinks), _st())
+                                 _kv_fp8(kv_cache), _DT[q.dtype], _p(alibi_slopes), _p(sinks), int(chunk_size or 0), _st())
     else:
         rc = _paged_attention_ex(q.data_ptr(), kv_cache.data_ptr(), bt.data_ptr(), md.seq_lens.data_ptr(),
                                  md.query_start_loc.data_ptr(), out.data_ptr(), None, None, _p(lse), md.num_reqs,
                                  md.max_query_len, Hq, Hkv, D, BS, q.stride(0), out.stride(0), bt.stride(0), 1,
                                  sliding_window or 0, scale, logits_soft_cap, kv_scale, int(causal),
-                                 _kv_fp8(kv_cache), _DT[q.dtype], _p(alibi_slopes), _p(sinks), _st())
+                                 _kv_fp8(kv_cache), _DT[q.dtype], _p(alibi_slopes), _p(sinks), int(chunk_size or 0), _st())
     _check(rc, f"paged_attention(D={D}, BS={BS}, G={Hq // Hkv})", 2 if (md.decode_only and splits > 1) else 1)
     return (out, lse) if return_lse else out
 

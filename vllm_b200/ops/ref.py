@@ -163,7 +163,7 @@ def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.
                     causal: bool = True, sliding_window: Optional[int] = None,
                     logits_soft_cap: float = 0.0, return_lse: bool = False,
                     kv_scale: float = 1.0, sinks: Optional[torch.Tensor] = None,
-                    alibi_slopes: Optional[torch.Tensor] = None):
+                    alibi_slopes: Optional[torch.Tensor] = None, chunk_size: int = 0):
     """Unified varlen paged attention.
 
     q: [T, Hq, D] (all requests' new tokens concatenated); request i owns rows
@@ -201,6 +201,8 @@ def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.
             mask &= kpos <= qpos
         if sliding_window:
             mask &= kpos > qpos - sliding_window
+        if chunk_size:                       # chunked-local attention: keys of the query's own chunk only
+            mask &= (kpos // chunk_size) == (qpos // chunk_size)
         att = att.masked_fill(~mask[None], float("-inf"))
         l = torch.logsumexp(att, dim=-1)
         if sinks is not None:            # a per-head logit that takes softmax mass but contributes no value

@@ -288,7 +288,8 @@ class ModelRunner:
                 # features only the generic kernel implements keep the whole group on the standard layout
                 and all(not getattr(attention_layers().get(n), "logits_soft_cap", 0.0)
                         and getattr(attention_layers().get(n), "alibi_slopes", None) is None
-                        and getattr(attention_layers().get(n), "sinks", None) is None for n in g.layer_names)))
+                        and getattr(attention_layers().get(n), "sinks", None) is None
+                        and not getattr(attention_layers().get(n), "chunk_size", 0) for n in g.layer_names)))
             for name in g.layer_names:
                 self.layer_to_group[name] = gid
                 if isinstance(s, MambaSpec):
