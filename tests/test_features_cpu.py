@@ -20,6 +20,7 @@ def _greedy(llm, n=16):
                                   dict(method="suffix", num_speculative_tokens=4, prompt_lookup_max=4, prompt_lookup_min=1),
                                   dict(method="eagle", num_speculative_tokens=3),
                                   dict(method="eagle3", num_speculative_tokens=3),
+                                  dict(method="ngram", num_speculative_tokens=4, prompt_lookup_max=4, prompt_lookup_min=1, dynamic_k=True),
                                   dict(method="mtp", num_speculative_tokens=2)])
 def test_speculative_decoding_is_lossless(spec):
     """Greedy output with speculation == greedy output without (rejection sampler correctness)."""
@@ -725,3 +726,65 @@ def test_custom_logits_processor_plugin():
     llm.shutdown()
     assert outs[0].outputs[0].token_ids == [77] * 5
     assert outs[1].outputs[0].token_ids == base
+
+
+def test_bitsandbytes_nf4_checkpoint():
+    """A pre-quantised bitsandbytes NF4 checkpoint (packed codes + absmax + quant map + JSON quant state, with and
+    without double quantisation of the absmax) expands to exactly its de-quantised weights."""
+    import json
+    from vllm_b200.model_loader import weight_only as wo
+    torch.manual_seed(0)
+    w = torch.randn(64, 128) * 0.1
+    pk, am, qm = wo.pack_bnb4(w, 64)
+    deq = wo.dequant_bnb4(pk, am, qm, w.shape, 64)
+    assert (deq - w).abs().max() < 0.05 and deq.shape == w.shape
+    # double quantisation: absmax → 8-bit codes around its mean
+    off = am.mean()
+    nb = 256
+    a2 = (am - off).reshape(-1, min(nb, am.numel()))
+    nam = a2.abs().amax(1).clamp_min(1e-12)
+    nqm = torch.linspace(-1, 1, 256)
+    codes = ((a2 / nam[:, None])[..., None] - nqm).abs().argmin(-1).reshape(-1).to(torch.uint8)
+    deq2 = wo.dequant_bnb4(pk, codes, qm, w.shape, 64, nam, nqm, a2.shape[1], float(off))
+    assert (deq2 - deq).abs().max() < 0.01
+    cfg = get_preset_hf_config("llama-tiny")
+    full = dict(llama_full_weights(cfg, seed=13, scale=0.08))
+    ckpt, ref = [], {}
+    for name, t in full.items():
+        if name.endswith("proj.weight"):
+            pk, am, qm = wo.pack_bnb4(t, 64)
+            st = json.dumps({"quant_type": "nf4", "blocksize": 64, "shape": list(t.shape), "dtype": "float32"}).encode()
+            ckpt += [(name, pk), (name + ".absmax", am), (name + ".quant_map", qm),
+                     (name + ".quant_state.bitsandbytes__nf4", torch.tensor(list(st), dtype=torch.uint8))]
+            ref[name] = wo.dequant_bnb4(pk, am, qm, t.shape, 64)
+        else:
+            ckpt.append((name, t)); ref[name] = t
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    prompt = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 77]}]
+    llm = make_llm("llama-tiny", weights=ref.items())
+    exp = llm.generate(prompt, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    llm = make_llm("llama-tiny", hf_overrides={"quantization_config": {"quant_method": "bitsandbytes", "load_in_4bit": True}})
+    llm.llm_engine.engine_core.engine_core.model_executor.collective_rpc("load_model", kwargs={"weights": ckpt})
+    got = llm.generate(prompt, sp)[0].outputs[0].token_ids
+    llm.shutdown()
+    assert got == exp
+
+
+def test_numa_helpers(tmp_path):
+    from vllm_b200.utils import numa
+    assert numa.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    for n, cpus in ((0, "0-1"), (1, "2-3")):
+        d = tmp_path / f"node{n}"
+        d.mkdir()
+        (d / "cpulist").write_text(cpus + "\n")
+    nodes = numa.numa_nodes(str(tmp_path))
+    assert nodes == {0: [0, 1], 1: [2, 3]}
+    assert numa.bind_to_node(None, nodes) is None and numa.bind_to_node(7, nodes) is None
+    import os
+    have = sorted(os.sched_getaffinity(0))
+    got = numa.bind_to_node(0, {0: have[:1], 1: have[1:] or have[:1]})
+    try:
+        assert got == have[:1] and sorted(os.sched_getaffinity(0)) == have[:1]
+    finally:
+        os.sched_setaffinity(0, have)

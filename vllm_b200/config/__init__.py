@@ -199,6 +199,10 @@ class SpeculativeConfig(_ConfigBase):
     prompt_lookup_min: int = 2
     draft_tensor_parallel_size: int = 1
     disable_by_batch_size: Optional[int] = None
+    # dynamic K: per request, the number of drafts actually verified follows the acceptance rate it has seen
+    # (EMA; shrink when drafts are mostly rejected, grow back when they are accepted) between 1 and num_speculative_tokens
+    dynamic_k: bool = False
+    dynamic_k_ema: float = 0.5
 
 
 @dataclass

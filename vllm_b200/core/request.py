@@ -147,7 +147,7 @@ class Request:
         "spec_token_ids", "num_computed_tokens", "num_cached_tokens", "num_output_placeholders",
         "num_preemptions", "block_hashes", "cache_salt", "mm_features", "structured_output_request",
         "use_structured_output", "num_nans_in_logits", "trace_headers", "_hash_fn", "_block_size",
-        "current_wave", "succeeded_first_schedule_ts",
+        "current_wave", "succeeded_first_schedule_ts", "spec_accept_ema",
     )
 
     def __init__(self, request_id: str, prompt_token_ids: list[int],
@@ -184,6 +184,7 @@ class Request:
         self._output_token_ids: list[int] = []
         self._all_token_ids: list[int] = list(prompt_token_ids)
         self.spec_token_ids: list[int] = []
+        self.spec_accept_ema = 1.0        # dynamic-K speculation: running acceptance rate of this request's drafts
         self.num_computed_tokens = 0
         self.num_cached_tokens = -1
         self.num_output_placeholders = 0  # async scheduling

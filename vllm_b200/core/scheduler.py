@@ -137,6 +137,8 @@ class Scheduler:
         self.include_finished_set = include_finished_set
         spec = vllm_config.speculative_config
         self.num_spec_tokens = spec.num_speculative_tokens if spec else 0
+        self.spec_dynamic_k = bool(spec and getattr(spec, "dynamic_k", False))
+        self.spec_ema = float(getattr(spec, "dynamic_k_ema", 0.5)) if spec else 0.5
         self.use_eagle = bool(spec and spec.method in ("eagle", "eagle3", "mtp"))
         self.num_lookahead_tokens = self.num_spec_tokens if self.use_eagle else 0
         ev = vllm_config.kv_events_config
@@ -445,6 +447,9 @@ class Scheduler:
                 self._spec_drafts += 1
                 self._spec_draft_tokens += n_draft
                 self._spec_accepted += n_acc
+                if self.spec_dynamic_k:
+                    a = self.spec_ema
+                    req.spec_accept_ema = (1 - a) * getattr(req, "spec_accept_ema", 1.0) + a * (n_acc / n_draft)
             if req.num_output_placeholders > 0 and gen:
                 req.num_output_placeholders -= len(gen)
                 req.num_output_placeholders = max(req.num_output_placeholders, 0)
@@ -487,6 +492,10 @@ class Scheduler:
                 drafts = mo.spec_token_ids[idx]
                 if req.use_structured_output and self.structured_output_manager is not None:
                     drafts = req.structured_output_request.validate_tokens(drafts)
+                if self.spec_dynamic_k and drafts:
+                    # verify about as many drafts as are expected to survive (+1 to keep probing upwards)
+                    k = max(1, min(self.num_spec_tokens, int(getattr(req, "spec_accept_ema", 1.0) * self.num_spec_tokens + 1.0)))
+                    drafts = drafts[:k]
                 req.spec_token_ids = list(drafts)
             if mo.num_nans_in_logits and rid in mo.num_nans_in_logits:
                 req.num_nans_in_logits = mo.num_nans_in_logits[rid]

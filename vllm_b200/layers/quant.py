@@ -197,7 +197,8 @@ def _compressed_tensors_scheme(hq: dict) -> dict:
 
 
 QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8", "awq", "gptq", "awq_marlin",
-                        "gptq_marlin", "nvfp4", "modelopt_fp4", "int8", "w8a8", "compressed-tensors", "compressed_tensors")
+                        "gptq_marlin", "nvfp4", "modelopt_fp4", "int8", "w8a8", "compressed-tensors", "compressed_tensors",
+                        "bitsandbytes")
 
 
 def get_quant_config(model_config) -> Optional[QuantConfig]:
@@ -208,7 +209,7 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         online = not model_config.hf_config.get("quantization_config")
         return Fp8BlockConfig(online=online)
     hq = model_config.hf_config.get("quantization_config") or {}
-    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin", "nvfp4", "modelopt_fp4"):
+    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin", "nvfp4", "modelopt_fp4", "bitsandbytes"):
         return None          # expanded to the model dtype at load time (model_loader/weight_only.py)
     if q in ("fp8", "fbgemm_fp8", "modelopt"):
         if hq.get("weight_block_size"):          # a "fp8" checkpoint with block scales (DeepSeek-V3 style)

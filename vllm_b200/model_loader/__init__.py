@@ -89,7 +89,7 @@ def get_model(vllm_config: VllmConfig, device: torch.device,
     hq = mc.hf_config.get("quantization_config") or {}
     ct_weight_only = ((hq.get("quant_method") or "").lower() in ("compressed-tensors", "compressed_tensors")
                       and not next(iter((hq.get("config_groups") or {"_": {}}).values())).get("input_activations"))
-    if (ct_weight_only or (hq.get("quant_method") or "").lower() in ("awq", "gptq", "nvfp4", "modelopt_fp4")
+    if (ct_weight_only or (hq.get("quant_method") or "").lower() in ("awq", "gptq", "nvfp4", "modelopt_fp4", "bitsandbytes")
             or (hq.get("quant_method") == "modelopt" and "FP4" in str(hq.get("quant_algo", "")).upper())):
         # weight-only int4 checkpoints are expanded to the model dtype while streaming (model_loader/weight_only.py)
         from vllm_b200.model_loader.weight_only import dequantize_stream

@@ -130,6 +130,39 @@ def pack_compressed_tensors(w: torch.Tensor, bits: int = 4, group_size: int = 32
     return packed, scale.to(torch.float16), torch.tensor([O, I], dtype=torch.int64)
 
 
+NF4_TABLE = [-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635, -0.18477343022823334,
+             -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,
+             0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0]
+
+
+def dequant_bnb4(packed: torch.Tensor, absmax: torch.Tensor, quant_map: torch.Tensor, shape, blocksize: int = 64,
+                 nested_absmax: Optional[torch.Tensor] = None, nested_quant_map: Optional[torch.Tensor] = None,
+                 nested_blocksize: int = 256, offset: float = 0.0) -> torch.Tensor:
+    """bitsandbytes 4-bit (NF4 / FP4) pre-quantised weights: two codes per byte (high nibble first), one absmax per
+    ``blocksize`` values; with double quantisation the absmax vector is itself 8-bit block-quantised around ``offset``
+    (reference: quantization/bitsandbytes.py + model_loader/bitsandbytes_loader.py)."""
+    if nested_absmax is not None:
+        am = nested_quant_map.float()[absmax.long().reshape(-1)]
+        am = am * nested_absmax.float().repeat_interleave(nested_blocksize)[:am.numel()] + offset
+    else:
+        am = absmax.float().reshape(-1)
+    b = packed.reshape(-1)
+    codes = torch.stack([b >> 4, b & 0x0F], dim=-1).reshape(-1).long()
+    n = int(shape[0]) * int(shape[1])
+    vals = quant_map.float()[codes[:n]]
+    return (vals * am.repeat_interleave(blocksize)[:n]).reshape(int(shape[0]), int(shape[1]))
+
+
+def pack_bnb4(w: torch.Tensor, blocksize: int = 64, table=None):
+    """Reference NF4 quantiser (tests / synthetic checkpoints) → (packed uint8 [n/2, 1], absmax, quant_map)."""
+    qm = torch.tensor(table or NF4_TABLE, dtype=torch.float32)
+    x = w.float().reshape(-1, blocksize)
+    am = x.abs().amax(1).clamp_min(1e-12)
+    codes = ((x / am[:, None])[..., None] - qm).abs().argmin(-1).reshape(-1).to(torch.uint8)
+    packed = (codes[0::2] << 4) | codes[1::2]
+    return packed.reshape(-1, 1), am, qm
+
+
 def dequantize_stream(weights: Iterable[tuple[str, torch.Tensor]], quant_cfg: dict, dtype: torch.dtype
                       ) -> Iterator[tuple[str, torch.Tensor]]:
     """Wrap a checkpoint iterator: packed groups are replaced by ``<module>.weight`` tensors as soon as complete."""
@@ -156,6 +189,29 @@ def dequantize_stream(weights: Iterable[tuple[str, torch.Tensor]], quant_cfg: di
                 yield f"{mod}.weight", w.to(dtype)
         if pending:
             raise ValueError(f"incomplete compressed-tensors groups for {sorted(pending)[:3]} ...")
+        return
+    if method == "bitsandbytes":
+        import json as _json
+        for name, t in weights:
+            base, sep, leaf = name.partition(".weight")
+            if not sep or (leaf == "" and t.dtype != torch.uint8):
+                yield name, t
+                continue
+            grp = pending.setdefault(base, {})
+            grp[leaf or "weight"] = t
+            qs_key = next((k for k in grp if k.startswith(".quant_state.bitsandbytes__")), None)
+            if "weight" in grp and ".absmax" in grp and ".quant_map" in grp and qs_key:
+                st = _json.loads(bytes(grp[qs_key].reshape(-1).tolist()).decode())
+                nested = ".nested_absmax" in grp
+                if st.get("nested_blocksize") and not nested:
+                    continue                                  # double-quantised: wait for the nested tensors
+                w = dequant_bnb4(grp["weight"], grp[".absmax"], grp[".quant_map"], st["shape"], int(st.get("blocksize", 64)),
+                                 grp.get(".nested_absmax"), grp.get(".nested_quant_map"), int(st.get("nested_blocksize") or 256),
+                                 float(st.get("nested_offset") or 0.0))
+                del pending[base]
+                yield f"{base}.weight", w.to(dtype)
+        if pending:
+            raise ValueError(f"incomplete bitsandbytes groups for {sorted(pending)[:3]} ...")
         return
     if method in ("modelopt_fp4", "nvfp4", "modelopt"):
         # NVFP4: weight (uint8) + weight_scale (fp8) + weight_scale_2 (fp32); input_scale is an activation statistic

@@ -49,6 +49,10 @@ class Worker:
                                + self.local_rank) % max(ndev, 1)
             torch.cuda.set_device(self.local_rank)
             self.device = torch.device("cuda", self.local_rank)
+            from vllm_b200.utils.numa import bind_worker_to_gpu_node
+            cpus = bind_worker_to_gpu_node(self.local_rank)          # VLLM_B200_NUMA_BIND=1: CPUs of the GPU's NUMA node
+            if cpus:
+                logger.info("worker %d pinned to %d CPUs of its GPU's NUMA node", self.rank, len(cpus))
             gc.collect()
             torch.cuda.empty_cache()
             self.init_free_bytes, self.total_bytes = torch.cuda.mem_get_info(self.device)
