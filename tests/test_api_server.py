@@ -283,3 +283,51 @@ def test_grpc_engine_service(server):
     http = call(client.post("/inference/v1/generate", json={"token_ids": [5, 6, 7, 8], "sampling_params": {
         "max_tokens": 5, "temperature": 0}})).json()
     assert http["token_ids"] == list(full[0].token_ids)
+
+
+def test_realtime_transcription_websocket():
+    """/v1/realtime: append PCM16 chunks, commit, receive transcription deltas + the completed transcript, which
+    equals the batch endpoint's answer for the same audio."""
+    import base64
+    import io
+    import wave
+
+    import numpy as np
+    from starlette.testclient import TestClient
+
+    from vllm_b200.engine.async_llm import AsyncLLM
+    from vllm_b200.entrypoints.openai.api_server import ServingContext, build_app
+    ea = EngineArgs(model="whisper-tiny-test", device="cpu", dtype="float32", max_model_len=32, max_num_seqs=4,
+                    max_num_batched_tokens=64, kv_cache_memory_bytes=4 << 20, enable_prefix_caching=False)
+    engine = AsyncLLM.from_engine_args(ea)
+    app = build_app(ServingContext(engine, "whisper-tiny-test", 32, engine.tokenizer))
+    t = np.arange(16000 * 2) / 16000
+    pcm = (0.3 * np.sin(2 * np.pi * 330 * t) * 32767).astype("<i2")
+    buf = io.BytesIO()
+    with wave.open(buf, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(pcm.tobytes())
+    try:
+        with TestClient(app) as client:
+            want = client.post("/v1/audio/transcriptions", files={"file": ("a.wav", buf.getvalue(), "audio/wav")}).json()["text"]
+            with client.websocket_connect("/v1/realtime") as ws:
+                assert ws.receive_json()["type"] == "transcription_session.created"
+                ws.send_json({"type": "session.update", "session": {"input_audio_transcription": {"language": "en"}}})
+                assert ws.receive_json()["type"] == "transcription_session.updated"
+                raw = pcm.tobytes()
+                for i in range(0, len(raw), 16000):
+                    ws.send_json({"type": "input_audio_buffer.append", "audio": base64.b64encode(raw[i:i + 16000]).decode()})
+                ws.send_json({"type": "input_audio_buffer.commit"})
+                assert ws.receive_json()["type"] == "input_audio_buffer.committed"
+                deltas, done = "", None
+                while done is None:
+                    ev = ws.receive_json()
+                    if ev["type"].endswith(".delta"):
+                        deltas += ev["delta"]
+                    elif ev["type"].endswith(".completed"):
+                        done = ev["transcript"]
+                assert done == want and deltas.strip() == want
+                ws.send_json({"type": "input_audio_buffer.commit"})
+                assert ws.receive_json()["type"] == "error"
+    finally:
+        engine.shutdown()

@@ -22,7 +22,7 @@ import time
 from contextlib import asynccontextmanager
 from typing import Any, AsyncGenerator, Optional
 
-from fastapi import FastAPI, Request
+from fastapi import FastAPI, Request, WebSocket  # noqa: F401
 from fastapi.responses import JSONResponse, Response, StreamingResponse
 
 from vllm_b200.engine.arg_utils import EngineArgs
@@ -577,6 +577,74 @@ def build_app(ctx: ServingContext):
                     "segments": [{"id": i, "start": a, "end": b, "text": t.strip(), "tokens": n}
                                  for i, ((a, b), (t, n)) in enumerate(zip(bounds, results))], "usage": usage}
         return {"text": text, "usage": usage}
+
+    @app.websocket("/v1/realtime")
+    async def realtime(ws: WebSocket):
+        """Streaming speech recognition over a WebSocket (reference: entrypoints/speech_to_text realtime API; event names
+        follow the OpenAI Realtime transcription session): the client appends base64 PCM16 mono chunks
+        (``input_audio_buffer.append``), commits (``input_audio_buffer.commit``) and receives
+        ``conversation.item.input_audio_transcription.delta`` events followed by ``...completed``."""
+        import numpy as np
+        from vllm_b200.multimodal.audio import SAMPLE_RATE, resample, split_chunks
+        await ws.accept()
+        if not ctx.engine.model_config.hf_config.get("is_encoder_decoder"):
+            await ws.send_json({"type": "error", "error": {"message": "the served model does not support speech-to-text"}})
+            await ws.close()
+            return
+        sess = {"language": None, "prompt": None, "sample_rate": SAMPLE_RATE, "temperature": 0.0}
+        buf: list[np.ndarray] = []
+        n_items = 0
+        await ws.send_json({"type": "transcription_session.created", "session": {"model": ctx.model_name, **sess}})
+        try:
+            while True:
+                ev = await ws.receive_json()
+                typ = ev.get("type")
+                if typ in ("session.update", "transcription_session.update"):
+                    s_ = ev.get("session") or {}
+                    tr = s_.get("input_audio_transcription") or {}
+                    sess["language"] = tr.get("language", sess["language"])
+                    sess["prompt"] = tr.get("prompt", sess["prompt"])
+                    sess["sample_rate"] = int(s_.get("input_audio_sample_rate", sess["sample_rate"]))
+                    await ws.send_json({"type": "transcription_session.updated", "session": {"model": ctx.model_name, **sess}})
+                elif typ == "input_audio_buffer.append":
+                    pcm = np.frombuffer(base64.b64decode(ev.get("audio") or ""), dtype="<i2").astype(np.float32) / 32768.0
+                    buf.append(pcm)
+                elif typ == "input_audio_buffer.clear":
+                    buf.clear()
+                    await ws.send_json({"type": "input_audio_buffer.cleared"})
+                elif typ == "input_audio_buffer.commit":
+                    if not buf:
+                        await ws.send_json({"type": "error", "error": {"message": "input audio buffer is empty"}})
+                        continue
+                    wav = np.concatenate(buf)
+                    buf.clear()
+                    if sess["sample_rate"] != SAMPLE_RATE:
+                        wav = resample(wav, sess["sample_rate"], SAMPLE_RATE)
+                    n_items += 1
+                    item_id = f"item_{n_items}"
+                    await ws.send_json({"type": "input_audio_buffer.committed", "item_id": item_id})
+                    ids = _stt_prompt_ids("transcribe", sess["language"], sess["prompt"])
+                    sp = SamplingParams(temperature=float(sess["temperature"]),
+                                        max_tokens=max(1, min(ctx.max_model_len - 8, ctx.max_model_len - len(ids) - 1)))
+                    full = ""
+                    for ci, chunk in enumerate(split_chunks(wav)):
+                        sent = 0
+                        async for o in ctx.engine.generate({"prompt_token_ids": list(ids),
+                                                            "multi_modal_data": {"audio": (chunk, SAMPLE_RATE)}},
+                                                           sp, f"rt-{random_uuid()}-{ci}"):
+                            text = o.outputs[0].text
+                            if len(text) > sent:
+                                await ws.send_json({"type": "conversation.item.input_audio_transcription.delta",
+                                                    "item_id": item_id, "delta": text[sent:]})
+                                sent = len(text)
+                        full += text
+                    await ws.send_json({"type": "conversation.item.input_audio_transcription.completed", "item_id": item_id,
+                                        "transcript": full.strip()})
+                else:
+                    await ws.send_json({"type": "error", "error": {"message": f"unknown event type {typ!r}"}})
+        except Exception as ex:  # WebSocketDisconnect or malformed frames end the session
+            if type(ex).__name__ != "WebSocketDisconnect":
+                logger.warning("realtime session ended: %s", ex)
 
     @app.post("/v1/audio/transcriptions")
     async def transcriptions(raw: Request):
