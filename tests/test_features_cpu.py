@@ -788,3 +788,47 @@ def test_numa_helpers(tmp_path):
         assert got == have[:1] and sorted(os.sched_getaffinity(0)) == have[:1]
     finally:
         os.sched_setaffinity(0, have)
+
+
+def test_request_tracing_spans_and_metrics_snapshot():
+    """--otlp-traces-endpoint: one span per finished request with the gen_ai.* attributes, exported over OTLP/HTTP to a
+    collector (a local stub here) with the caller's W3C trace context as parent; the Prometheus registry exposes the
+    request / token counters the reference names."""
+    import threading
+    from http.server import BaseHTTPRequestHandler, HTTPServer
+    from vllm_b200.metrics import get_metrics_snapshot, render_prometheus
+    from vllm_b200.tracing import SpanAttributes, extract_trace_context
+    got = []
+
+    class H(BaseHTTPRequestHandler):
+        def do_POST(self):
+            got.append((self.path, self.rfile.read(int(self.headers.get("Content-Length", 0)))))
+            self.send_response(200); self.send_header("Content-Type", "application/x-protobuf"); self.end_headers()
+
+        def log_message(self, *a):
+            pass
+    srv = HTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    llm = make_llm("llama-tiny", otlp_traces_endpoint=f"http://127.0.0.1:{srv.server_address[1]}/v1/traces",
+                   disable_log_stats=False)
+    sp = SamplingParams(max_tokens=5, temperature=0.0, ignore_eos=True)
+    llm.generate(PROMPTS, sp)
+    tracer = llm.llm_engine.tracer
+    spans = list(tracer.finished)
+    flushed = tracer.flush()
+    llm.shutdown()
+    srv.shutdown()
+    assert len(spans) == len(PROMPTS)
+    s0 = spans[0]
+    assert s0[SpanAttributes.COMPLETION_TOKENS] == 5 and s0[SpanAttributes.PROMPT_TOKENS] == len(PROMPTS[0]["prompt_token_ids"])
+    assert s0[SpanAttributes.E2E] > 0 and s0[SpanAttributes.TTFT] > 0 and "length" in s0[SpanAttributes.FINISH_REASON].lower()
+    if tracer._otel is not None:                       # OpenTelemetry SDK present: the spans really left the process
+        assert flushed and got and got[0][0] == "/v1/traces" and b"llm_request" in b"".join(b for _, b in got)
+        assert b"gen_ai.usage.completion_tokens" in b"".join(b for _, b in got)
+    assert extract_trace_context({"traceparent": "00-4bf92f3577b34da6a3ce929d0e0e4736-00f067aa0ba902b7-01"}) is not None
+    body, ctype = render_prometheus()
+    text = body.decode()
+    for name in ("vllm:generation_tokens_total", "vllm:prompt_tokens_total", "vllm:request_success_total",
+                 "vllm:time_to_first_token_seconds", "vllm:num_requests_running"):
+        assert name in text, name
+    assert get_metrics_snapshot()

@@ -41,6 +41,7 @@ class RequestTracer:
     def __init__(self, endpoint: Optional[str] = None, keep: int = 1024) -> None:
         self.finished: deque[dict[str, Any]] = deque(maxlen=keep)
         self._otel = None
+        self._provider = None
         if endpoint:
             try:
                 from opentelemetry import trace
@@ -53,8 +54,8 @@ class RequestTracer:
                     from opentelemetry.exporter.otlp.proto.grpc.trace_exporter import OTLPSpanExporter
                 provider = TracerProvider(resource=Resource.create({"service.name": "vllm_b200"}))
                 provider.add_span_processor(BatchSpanProcessor(OTLPSpanExporter(endpoint=endpoint)))
-                trace.set_tracer_provider(provider)
-                self._otel = trace.get_tracer("vllm_b200.llm_engine")
+                self._provider = provider
+                self._otel = provider.get_tracer("vllm_b200.llm_engine")
             except Exception:
                 self._otel = None
 
@@ -80,6 +81,11 @@ class RequestTracer:
                                                   start_time=int(m.arrival_time * 1e9)) as span:
                 for k, v in attrs.items():
                     span.set_attribute(k, v)
+
+
+    def flush(self, timeout_ms: int = 5000) -> bool:
+        """Push pending spans to the collector now (shutdown, tests)."""
+        return bool(self._provider.force_flush(timeout_ms)) if self._provider is not None else True
 
 
 def maybe_init_tracer(obs_config) -> Optional[RequestTracer]:
