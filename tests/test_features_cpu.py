@@ -832,3 +832,64 @@ def test_request_tracing_spans_and_metrics_snapshot():
                  "vllm:time_to_first_token_seconds", "vllm:num_requests_running"):
         assert name in text, name
     assert get_metrics_snapshot()
+
+
+def test_sharded_state_checkpoint_hooks_profiler_and_crash_dump(tmp_path, monkeypatch, capfd):
+    """save_sharded_state → a fresh engine loads the per-rank file and generates the same text; checkpoint
+    prepare / restore hooks round-trip; the worker profiler honours delay / max-iterations; a failing forward pass
+    logs a dump of the scheduled step (ids and sizes, no prompts)."""
+    from vllm_b200.profiler import WorkerProfiler
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=21))
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny", weights=w)
+    exp = llm.generate(PROMPTS[:1], sp)[0].outputs[0].token_ids
+    d = str(tmp_path / "shards")
+    llm.llm_engine.engine_core.engine_core.save_sharded_state(d)
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("checkpoint_prepare")
+    ex.collective_rpc("checkpoint_restore")
+    assert llm.generate(PROMPTS[:1], sp)[0].outputs[0].token_ids == exp
+    llm.shutdown()
+    import os
+    assert any(f.endswith(".safetensors") for f in os.listdir(d))
+    llm = make_llm("llama-tiny")
+    from vllm_b200.model_loader.sharded_state import load_sharded_state
+    load_sharded_state(llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model, d)
+    assert llm.generate(PROMPTS[:1], sp)[0].outputs[0].token_ids == exp
+    # crash dump
+    core = llm.llm_engine.engine_core.engine_core
+    def boom(*a, **k):
+        raise RuntimeError("injected failure")
+    monkeypatch.setattr(core.model_executor, "execute_model", boom)
+    capfd.readouterr()
+    with pytest.raises(Exception):
+        llm.generate(PROMPTS[:1], sp)
+    llm.shutdown()
+    err = capfd.readouterr().err
+    assert "engine step failed" in err and "tokens scheduled" in err and "new requests (id, prompt tokens)" in err
+
+    events = []
+
+    class P(WorkerProfiler):
+        def _start(self): events.append("start")
+        def _stop(self): events.append("stop")
+    p = P(delay_iterations=2, max_iterations=3)
+    p.start()
+    for _ in range(8):
+        p.step()
+    assert events == ["start", "stop"] and not p.running
+
+
+def test_cli_config_file(tmp_path):
+    from vllm_b200.entrypoints.cli import expand_config_file
+    f = tmp_path / "c.yaml"
+    f.write_text("model: llama-tiny\\nmax-model-len: 256\\nenable_prefix_caching: false\\ncudagraph_capture_sizes: [1, 2]\\n"
+                 "hf_overrides: {a: 1}\\nport: 9000\\n")
+    out = expand_config_file(["serve", "--config", str(f), "--port", "9100"])
+    assert out[:2] == ["serve", "llama-tiny"] and out[-2:] == ["--port", "9100"]
+    assert "--no-enable-prefix-caching" in out and out[out.index("--cudagraph-capture-sizes") + 1] == "1,2"
+    from vllm_b200.entrypoints.openai.api_server import make_arg_parser
+    args = make_arg_parser().parse_args(out[1:])
+    assert args.model_tag == "llama-tiny" and args.port == 9100 and args.max_model_len == 256 and args.hf_overrides == {"a": 1}
+    assert args.enable_prefix_caching is False

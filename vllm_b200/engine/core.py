@@ -102,11 +102,28 @@ class EngineCore:
             return {}, False
         so = self.scheduler.schedule()
         so.grammar_bitmask = self.scheduler.get_grammar_bitmask(so)
-        mo = self.model_executor.execute_model(so)
+        try:
+            mo = self.model_executor.execute_model(so)
+        except Exception:
+            self._dump_failed_step(so)
+            raise
         out = self.scheduler.update_from_output(so, mo)
         if so.total_num_scheduled_tokens == 0 and not out:
             time.sleep(0.001)                    # only requests waiting on remote KV: do not spin the executor
         return out, so.total_num_scheduled_tokens > 0
+
+    def _dump_failed_step(self, so) -> None:
+        """Log what the failing forward pass was asked to do (reference: logging_utils/dump_input.py): request ids, token
+        counts, positions in the sequence, speculative tokens and the engine configuration — not the prompts."""
+        try:
+            new = [(r.req_id, len(r.prompt_token_ids or ())) for r in so.scheduled_new_reqs]
+            logger.error("engine step failed. config hash %s; %d tokens scheduled; new requests (id, prompt tokens): %s; "
+                         "tokens per request: %s; spec tokens: %s; finished since last step: %s; scheduler: %d running, %d waiting",
+                         self.vllm_config.compute_hash(), so.total_num_scheduled_tokens, new, dict(so.num_scheduled_tokens),
+                         {k: len(v) for k, v in so.scheduled_spec_decode_tokens.items()}, sorted(so.finished_req_ids),
+                         *self.scheduler.get_request_counts())
+        except Exception:  # pragma: no cover - the dump must never mask the original error
+            pass
 
     def step_with_batch_queue(self) -> tuple[Optional[dict[int, EngineCoreOutputs]], bool]:
         """Keep up to ``batch_queue_size`` steps in flight (PP stages / async scheduling)."""

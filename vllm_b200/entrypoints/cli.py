@@ -158,8 +158,43 @@ COMMANDS = {
 }
 
 
+def expand_config_file(argv: list[str]) -> list[str]:
+    """``--config file.yaml``: the file's keys become options placed BEFORE the explicit command-line options, so the
+    command line wins (reference: utils/argparse_utils.py FlexibleArgumentParser).  Booleans → ``--flag`` /
+    ``--no-flag``; lists → comma joined; dicts → JSON; ``model`` / ``model_tag`` → the positional model."""
+    if "--config" not in argv:
+        return argv
+    import yaml
+    i = argv.index("--config")
+    path = argv[i + 1]
+    rest = argv[:i] + argv[i + 2:]
+    with open(path) as f:
+        cfg = yaml.safe_load(f) or {}
+    opts: list[str] = []
+    positional: list[str] = []
+    for k, v in cfg.items():
+        flag = "--" + str(k).replace("_", "-")
+        if k in ("model", "model_tag") and rest and rest[0] == "serve":
+            positional.append(str(v))
+        elif isinstance(v, bool):
+            opts.append(flag if v else "--no-" + flag[2:])
+        elif isinstance(v, (list, tuple)):
+            opts += [flag, ",".join(str(x) for x in v)]
+        elif isinstance(v, dict):
+            opts += [flag, json.dumps(v)]
+        elif v is not None:
+            opts += [flag, str(v)]
+    if not rest:
+        return opts
+    # keep the sub-command first; a positional model given on the command line overrides the file's
+    head, tail = rest[:1], rest[1:]
+    if positional and (not tail or tail[0].startswith("-")):
+        head += positional
+    return head + opts + tail
+
+
 def main(argv=None) -> None:
-    argv = list(sys.argv[1:] if argv is None else argv)
+    argv = expand_config_file(list(sys.argv[1:] if argv is None else argv))
     if not argv or argv[0] in ("-h", "--help"):
         print("usage: vllm_b200 {" + ",".join(COMMANDS) + "} ...")
         return
