@@ -884,8 +884,8 @@ def test_sharded_state_checkpoint_hooks_profiler_and_crash_dump(tmp_path, monkey
 def test_cli_config_file(tmp_path):
     from vllm_b200.entrypoints.cli import expand_config_file
     f = tmp_path / "c.yaml"
-    f.write_text("model: llama-tiny\\nmax-model-len: 256\\nenable_prefix_caching: false\\ncudagraph_capture_sizes: [1, 2]\\n"
-                 "hf_overrides: {a: 1}\\nport: 9000\\n")
+    f.write_text("\n".join(["model: llama-tiny", "max-model-len: 256", "enable_prefix_caching: false",
+                            "cudagraph_capture_sizes: [1, 2]", "hf_overrides: {a: 1}", "port: 9000"]) + "\n")
     out = expand_config_file(["serve", "--config", str(f), "--port", "9100"])
     assert out[:2] == ["serve", "llama-tiny"] and out[-2:] == ["--port", "9100"]
     assert "--no-enable-prefix-caching" in out and out[out.index("--cudagraph-capture-sizes") + 1] == "1,2"
