@@ -221,3 +221,127 @@ def test_mistral_tokenizer_mode(tmp_path):
     chat = tok.apply_chat_template([{"role": "user", "content": "hi"}], tokenize=True)
     assert chat[0] == tok.bos_token_id and "[INST]" in tok.apply_chat_template([{"role": "user", "content": "hi"}])
     assert len(tok) > 100000
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# more of the reference's tests/v1/core areas: stop conditions, budgets, cache eviction order, KV events, spec accounting
+def _step_with(s: Scheduler, tokens: dict):
+    so = s.schedule()
+    ids = list(so.num_scheduled_tokens)
+    toks = [tokens.get(r, [7]) if s.requests[r].num_computed_tokens >= s.requests[r].num_tokens else [] for r in ids]
+    mo = ModelRunnerOutput(req_ids=ids, req_id_to_index={r: i for i, r in enumerate(ids)}, sampled_token_ids=toks)
+    return so, s.update_from_output(so, mo)
+
+
+def test_stop_token_eos_and_max_model_len():
+    s = create_scheduler(max_model_len=40)
+    sp = SamplingParams(max_tokens=50, temperature=0.0, stop_token_ids=[99])
+    sp.all_stop_token_ids = [99, 2]
+    r = Request("a", list(range(1, 11)), sampling_params=sp, eos_token_id=2, block_hasher=s.get_block_hasher())
+    s.add_request(r)
+    _step_with(s, {})                                     # prefill + first token (7)
+    _, out = _step_with(s, {"a": [99]})                    # a stop token id ends the request and is reported
+    o = out[0].outputs[0]
+    assert o.finish_reason is not None and o.stop_reason == 99 and "a" not in s.requests
+    r2 = Request("b", list(range(1, 11)), sampling_params=SamplingParams(max_tokens=500, temperature=0.0, ignore_eos=True),
+                 eos_token_id=2, block_hasher=s.get_block_hasher())
+    s.add_request(r2)
+    n = 0
+    while "b" in s.requests and n < 100:
+        _step_with(s, {})
+        n += 1
+    assert r2.num_tokens <= 40 and "b" not in s.requests            # the context window bounds generation
+    r3 = Request("c", list(range(1, 11)), sampling_params=SamplingParams(max_tokens=5, temperature=0.0), eos_token_id=2,
+                 block_hasher=s.get_block_hasher())
+    s.add_request(r3)
+    _step_with(s, {})
+    _, out = _step_with(s, {"c": [2]})                               # EOS
+    assert out[0].outputs[0].finish_reason is not None and out[0].outputs[0].stop_reason is None
+
+
+def test_max_num_seqs_and_token_budget_are_respected():
+    s = create_scheduler(max_num_seqs=2, max_num_batched_tokens=32, num_blocks=128)
+    for i in range(4):
+        make_request(s, f"r{i}", 20, base=100 * i)
+    so, _ = run_step(s)
+    assert sum(so.num_scheduled_tokens.values()) <= 32 and len(so.num_scheduled_tokens) <= 2
+    seen_running = set()
+    for _ in range(30):
+        so, _ = run_step(s)
+        assert sum(so.num_scheduled_tokens.values()) <= 32
+        assert len(s.running) <= 2
+        seen_running |= set(so.num_scheduled_tokens)
+        if not s.has_unfinished_requests():
+            break
+    assert seen_running == {"r0", "r1", "r2", "r3"} and not s.has_unfinished_requests()
+
+
+def test_prefix_cache_lru_eviction_and_reset():
+    s = create_scheduler(num_blocks=10, max_num_batched_tokens=128)          # 9 usable blocks (one is the null block)
+    a = make_request(s, "a", 64, max_tokens=1, base=0)                       # 4 full blocks
+    run_step(s)
+    assert "a" not in s.requests                                             # finished: blocks stay cached but evictable
+    b = make_request(s, "b", 64, max_tokens=1, base=500)
+    run_step(s)
+    pool = s.kv_cache_manager.pool
+    assert pool.get_num_free_blocks() == 9
+    c = make_request(s, "c", 64, max_tokens=1, base=0)                       # same prompt as "a": 3 cached blocks reused
+    so, _ = run_step(s)
+    assert so.num_scheduled_tokens["c"] < 64 and c.num_cached_tokens >= 48
+    d = make_request(s, "d", 96, max_tokens=1, base=900)                     # needs 6 fresh blocks → evicts the oldest cached
+    run_step(s)
+    e = make_request(s, "e", 64, max_tokens=1, base=500)                     # "b"'s blocks were the least recently used
+    so, _ = run_step(s)
+    assert so.num_scheduled_tokens["e"] == 64 and e.num_cached_tokens == 0
+    assert s.reset_prefix_cache()
+    f = make_request(s, "f", 64, max_tokens=1, base=900)
+    so, _ = run_step(s)
+    assert so.num_scheduled_tokens["f"] == 64                                # nothing survives a reset
+    del a, b, d
+
+
+def test_kv_events_stream_block_stored_and_removed():
+    s = create_scheduler(num_blocks=8)
+    pool = s.kv_cache_manager.pool
+    pool.enable_kv_cache_events = True
+    pool.block_size = BS
+    seen, orig = [], pool.take_events
+
+    def take():                      # the scheduler drains the queue every step: record what it takes
+        ev = orig()
+        seen.extend(ev)
+        return ev
+    pool.take_events = take
+    make_request(s, "a", 48, max_tokens=1)
+    run_step(s)
+    take()
+    stored = [e for e in seen if type(e).__name__ == "BlockStored"]
+    assert stored and sum(len(e.block_hashes) for e in stored) == 3 and stored[0].block_size == BS
+    assert len(stored[0].token_ids) == 48 and stored[0].parent_block_hash is None
+    make_request(s, "b", 100, max_tokens=1, base=300)                        # 7 blocks: the second chunk evicts "a"'s
+    run_step(s)
+    run_step(s)
+    take()
+    assert any(type(e).__name__ == "BlockRemoved" for e in seen)
+    pool.reset_prefix_cache()
+    take()
+    assert any(type(e).__name__ == "AllBlocksCleared" for e in seen)
+
+
+def test_speculative_tokens_accounting_and_rollback():
+    import types
+    s = create_scheduler()
+    s.num_spec_tokens = 3
+    r = make_request(s, "a", 10, max_tokens=20)
+    run_step(s)                                                              # prefill → first token
+    r.spec_token_ids = [11, 12, 13]
+    so = s.schedule()
+    assert so.scheduled_spec_decode_tokens == {"a": [11, 12, 13]} and so.num_scheduled_tokens["a"] == 4
+    computed_before = r.num_computed_tokens
+    # the verifier accepted the first draft only: 2 tokens come back (accepted draft + bonus/correction)
+    mo = ModelRunnerOutput(req_ids=["a"], req_id_to_index={"a": 0}, sampled_token_ids=[[11, 50]])
+    s.update_from_output(so, mo)
+    assert r.num_computed_tokens == computed_before - 2                      # the two rejected drafts are rolled back
+    assert list(r.output_token_ids)[-2:] == [11, 50]
+    assert s._spec_draft_tokens == 3 and s._spec_accepted == 1 and s._spec_drafts == 1
+    del types
