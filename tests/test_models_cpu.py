@@ -221,24 +221,28 @@ def test_whisper_matches_hf_and_feature_extractor():
     llm.shutdown()
 
 
-def test_qwen2_vl_matches_hf():
+@pytest.mark.parametrize("gen", ["qwen2vl-tiny", "qwen25vl-tiny"])
+def test_qwen2_vl_matches_hf(gen):
     """Dynamic-resolution ViT + M-RoPE decoder: image patches, grid, 3-D position ids and the decode position delta
     reproduce the HF model's greedy continuation for image+text and for text-only prompts in one batch."""
     import numpy as np
     import transformers
     from PIL import Image
     from vllm_b200.config import get_preset_hf_config
-    cfg = get_preset_hf_config("qwen2vl-tiny")
+    cfg = get_preset_hf_config(gen)
+    is25 = gen == "qwen25vl-tiny"
     text_keys = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
                  "num_key_value_heads", "max_position_embeddings", "rms_norm_eps", "hidden_act", "tie_word_embeddings")
     tc = {k: cfg[k] for k in text_keys}
     tc["rope_parameters"] = {"rope_type": "default", "rope_theta": cfg["rope_theta"], "mrope_section": [2, 3, 3]}
-    hf_cfg = transformers.Qwen2VLConfig(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500,
-                                        video_token_id=501, vision_start_token_id=502, vision_end_token_id=503)
+    CfgCls = transformers.Qwen2_5_VLConfig if is25 else transformers.Qwen2VLConfig
+    ModelCls = transformers.Qwen2_5_VLForConditionalGeneration if is25 else transformers.Qwen2VLForConditionalGeneration
+    hf_cfg = CfgCls(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500,
+                    video_token_id=501, vision_start_token_id=502, vision_end_token_id=503)
     torch.manual_seed(0)
-    hf = transformers.Qwen2VLForConditionalGeneration(hf_cfg).float().eval()
+    hf = ModelCls(hf_cfg).float().eval()
     rng = np.random.default_rng(0)
-    img = Image.fromarray(rng.integers(0, 255, (56, 84, 3), dtype=np.uint8))
+    img = Image.fromarray(rng.integers(0, 255, (84, 140, 3) if is25 else (56, 84, 3), dtype=np.uint8))
     ip = transformers.Qwen2VLImageProcessor()
     px = ip(images=[img], return_tensors="pt")
     n_img = int(px["image_grid_thw"][0].prod()) // 4
@@ -250,7 +254,7 @@ def test_qwen2_vl_matches_hf():
                               do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(ids_hf):].tolist()
     text_prompt = [5, 17, 99, 3, 250, 41, 5, 17, 99, 3]
     ref_txt = hf_greedy(hf, text_prompt, 8)
-    llm = make_llm("qwen2vl-tiny", weights=hf.state_dict().items(), enable_prefix_caching=False)
+    llm = make_llm(gen, weights=hf.state_dict().items(), enable_prefix_caching=False)
     sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
     outs = llm.generate([{"prompt_token_ids": pre + [500] + post, "multi_modal_data": {"image": img}},
                          {"prompt_token_ids": text_prompt}], sp)

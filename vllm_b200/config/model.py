@@ -250,6 +250,16 @@ PRESETS: dict[str, dict[str, Any]] = {
         rope_parameters=dict(rope_type="default", rope_theta=10000.0),
         layer_types=["chunked_attention", "chunked_attention", "chunked_attention", "full_attention"],
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "qwen25vl-tiny": dict(
+        architectures=["Qwen2_5_VLForConditionalGeneration"], model_type="qwen2_5_vl", vocab_size=512, hidden_size=64,
+        intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+        max_position_embeddings=512, rms_norm_eps=1e-6, hidden_act="silu", rope_theta=10000.0, attention_bias=True,
+        rope_scaling=dict(rope_type="mrope", mrope_section=[2, 3, 3]), image_token_id=500, video_token_id=501,
+        vision_start_token_id=502, vision_end_token_id=503,
+        vision_config=dict(depth=3, hidden_size=32, out_hidden_size=64, intermediate_size=48, hidden_act="silu", num_heads=2,
+                           in_channels=3, patch_size=14, spatial_merge_size=2, temporal_patch_size=2, window_size=56,
+                           fullatt_block_indexes=[1], tokens_per_second=2),
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

@@ -48,6 +48,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "BartForConditionalGeneration": ("bart", "BartForConditionalGeneration"),
     "BartModel": ("bart", "BartForConditionalGeneration"),
     "WhisperForConditionalGeneration": ("whisper", "WhisperForConditionalGeneration"),
+    "Qwen2_5_VLForConditionalGeneration": ("qwen2_vl", "Qwen2_5_VLForConditionalGeneration"),
     "Qwen2VLForConditionalGeneration": ("qwen2_vl", "Qwen2VLForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "BertModel": ("bert", "BertEmbeddingModel"),
