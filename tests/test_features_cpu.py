@@ -834,7 +834,7 @@ def test_request_tracing_spans_and_metrics_snapshot():
     assert get_metrics_snapshot()
 
 
-def test_sharded_state_checkpoint_hooks_profiler_and_crash_dump(tmp_path, monkeypatch, capfd):
+def test_sharded_state_checkpoint_hooks_profiler_and_crash_dump(tmp_path, monkeypatch):
     """save_sharded_state → a fresh engine loads the per-rank file and generates the same text; checkpoint
     prepare / restore hooks round-trip; the worker profiler honours delay / max-iterations; a failing forward pass
     logs a dump of the scheduled step (ids and sizes, no prompts)."""
@@ -862,11 +862,22 @@ def test_sharded_state_checkpoint_hooks_profiler_and_crash_dump(tmp_path, monkey
     def boom(*a, **k):
         raise RuntimeError("injected failure")
     monkeypatch.setattr(core.model_executor, "execute_model", boom)
-    capfd.readouterr()
-    with pytest.raises(Exception):
-        llm.generate(PROMPTS[:1], sp)
+    import logging
+    records = []
+
+    class Grab(logging.Handler):
+        def emit(self, record):
+            records.append(record.getMessage())
+    h = Grab(level=logging.ERROR)
+    lg = logging.getLogger("vllm_b200.engine.core")
+    lg.addHandler(h)
+    try:
+        with pytest.raises(Exception):
+            llm.generate(PROMPTS[:1], sp)
+    finally:
+        lg.removeHandler(h)
     llm.shutdown()
-    err = capfd.readouterr().err
+    err = "\n".join(records)
     assert "engine step failed" in err and "tokens scheduled" in err and "new requests (id, prompt tokens)" in err
 
     events = []
