@@ -158,6 +158,17 @@ def test_responses_and_anthropic_and_metrics(server):
     assert call(client.post("/reset_prefix_cache")).status_code in (200, 409)
 
 
+def test_orca_load_headers(server):
+    client, call, _ = server
+    r = call(client.post("/v1/completions", json={"prompt": [5, 6, 7], "max_tokens": 2, "temperature": 0},
+                         headers={"endpoint-load-metrics-format": "JSON"}))
+    rep = r.headers["endpoint-load-metrics"]
+    assert rep.startswith("JSON ") and "vllm:num_requests_running" in json.loads(rep[5:])["named_metrics"]
+    r = call(client.post("/v1/completions", json={"prompt": [5, 6, 7], "max_tokens": 2, "temperature": 0},
+                         headers={"endpoint-load-metrics-format": "TEXT"}))
+    assert r.headers["endpoint-load-metrics"].startswith("TEXT named_metrics.vllm:num_requests_running=")
+
+
 def test_tool_and_reasoning_parsers():
     from vllm_b200.reasoning import get_reasoning_parser
     from vllm_b200.tool_parsers import get_tool_parser

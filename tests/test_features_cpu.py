@@ -904,3 +904,58 @@ def test_cli_config_file(tmp_path):
     args = make_arg_parser().parse_args(out[1:])
     assert args.model_tag == "llama-tiny" and args.port == 9100 and args.max_model_len == 256 and args.hf_overrides == {"a": 1}
     assert args.enable_prefix_caching is False
+
+
+def test_decode_bench_connector_skips_prefill():
+    """The decode-benchmark connector claims every full prompt block as remotely available: the engine computes only
+    the tail of the prompt and decodes (over constant-filled KV)."""
+    llm = make_llm("llama-tiny", block_size=16, enable_prefix_caching=True,
+                   kv_transfer_config=dict(kv_connector="DecodeBenchConnector", kv_role="kv_both"))
+    core = llm.llm_engine.engine_core.engine_core
+    seen = []
+    orig = core.model_executor.execute_model
+
+    def spy(so, *a, **k):
+        seen.append(dict(so.num_scheduled_tokens))
+        return orig(so, *a, **k)
+    core.model_executor.execute_model = spy
+    prompt = [{"prompt_token_ids": [(3 * i) % 400 + 5 for i in range(100)]}]
+    out = llm.generate(prompt, SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True))[0]
+    conn = core.model_executor.worker.runner.kv_connector
+    llm.shutdown()
+    assert len(out.outputs[0].token_ids) == 4
+    assert conn.num_filled_blocks == 6 and max(seen[0].values()) == 100 - 96       # 6 blocks "loaded", 4 tokens computed
+
+
+def test_multimodal_sender_receiver_cache():
+    """Repeated multimodal items cross the front-end → engine-core channel once: the sender strips payloads the
+    receiver holds, the receiver restores them, both evict in lock-step; end to end the repeat gives the same output."""
+    from vllm_b200.multimodal.cache import ReceiverCache, SenderShadow
+    snd, rcv = SenderShadow(2), ReceiverCache(2)
+    def item(h):
+        return [{"modality": "image", "hash": h, "data": f"payload-{h}", "offset": 0, "length": 1},
+                {"modality": "mrope", "hash": "", "data": "pos", "offset": 0, "length": 0}]
+    sent = []
+    for h in ["a", "b", "a", "c", "b", "a"]:            # capacity 2: "b" is evicted by "c", "a" by the second "b"
+        f = item(h)
+        snd.strip(f)
+        sent.append(f[0]["data"] is not None)
+        rcv.restore(f)
+        assert f[0]["data"] == f"payload-{h}" and f[1]["data"] == "pos"
+    assert sent == [True, True, False, True, True, True] and snd.hits == 1
+    with pytest.raises(RuntimeError):
+        rcv.restore([{"modality": "image", "hash": "zzz", "data": None}])
+
+    import numpy as np
+    rng = np.random.default_rng(0)
+    wave = (0.2 * np.sin(2 * np.pi * 300 * np.arange(16000) / 16000) + 0.01 * rng.standard_normal(16000)).astype(np.float32)
+    llm = make_llm("whisper-tiny-test", enable_prefix_caching=False, max_model_len=64)
+    sp = SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True)
+    p = {"multi_modal_data": {"audio": (wave, 16000)}}
+    first = llm.generate([p], sp)[0].outputs[0].token_ids
+    second = llm.generate([p], sp)[0].outputs[0].token_ids
+    sender = llm.llm_engine.input_processor.mm_sender if hasattr(llm.llm_engine, "input_processor") else None
+    llm.shutdown()
+    assert first == second
+    if sender is not None:
+        assert sender.hits == 1 and sender.misses == 1

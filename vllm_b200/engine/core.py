@@ -84,7 +84,10 @@ class EngineCore:
         return cfg
 
     # ----------------------------------------------------------------- API
+    _mm_receiver = None
+
     def add_request(self, req: EngineCoreRequest) -> None:
+        self._restore_mm(req)           # first: keeps the receiver cache in step with the sender even if we reject below
         so_req = None
         sp = req.sampling_params
         if sp is not None and sp.structured_outputs is not None:
@@ -93,6 +96,13 @@ class EngineCore:
         if len(r.prompt_token_ids) >= self.vllm_config.scheduler_config.max_model_len:
             raise ValueError(f"prompt of {len(r.prompt_token_ids)} tokens exceeds max_model_len")
         self.scheduler.add_request(r)
+
+    def _restore_mm(self, req) -> None:
+        if req.mm_features:
+            if self._mm_receiver is None:
+                from vllm_b200.multimodal.cache import ReceiverCache
+                self._mm_receiver = ReceiverCache(int(os.environ.get("VLLM_B200_MM_CACHE_ITEMS", "256")))
+            self._mm_receiver.restore(req.mm_features)
 
     def abort_requests(self, request_ids: list[str]) -> None:
         self.scheduler.finish_requests(request_ids, RequestStatus.FINISHED_ABORTED)

@@ -7,6 +7,8 @@ detokenisers), logprobs.py, parallel_sampling.py (``ParentRequest`` n>1 fan-out)
 """
 from __future__ import annotations
 
+import os
+
 import asyncio
 import time
 from dataclasses import dataclass, field
@@ -27,6 +29,12 @@ class InputProcessor:
         self.tokenizer = tokenizer
         self.max_model_len = vllm_config.scheduler_config.max_model_len
         self.mm_processor = None
+        # sender half of the multimodal input cache (one engine core only: with DP the target engine is picked later)
+        self.mm_sender = None
+        if (self.mc.hf_config.get("vision_config") is not None or self.mc.hf_config.get("is_encoder_decoder")) \
+                and vllm_config.parallel_config.data_parallel_size == 1:
+            from vllm_b200.multimodal.cache import SenderShadow
+            self.mm_sender = SenderShadow(int(os.environ.get("VLLM_B200_MM_CACHE_ITEMS", "256")))
         if self.mc.hf_config.get("vision_config") is not None:
             from vllm_b200.multimodal import MULTIMODAL_REGISTRY
             self.mm_processor = MULTIMODAL_REGISTRY.create_processor(self.mc)
@@ -121,6 +129,8 @@ class InputProcessor:
                 kv_transfer_params = sp.extra_args.get("kv_transfer_params")
         else:
             pp = params.clone()
+        if self.mm_sender is not None:
+            self.mm_sender.strip(mm_features)          # last step: nothing after this point may reject the request
         req = EngineCoreRequest(
             request_id=request_id, prompt_token_ids=ids, sampling_params=sp, pooling_params=pp,
             eos_token_id=self.mc.eos_token_id, arrival_time=arrival_time or time.time(),

@@ -116,9 +116,26 @@ def build_app(ctx: ServingContext):
             if request.headers.get("Authorization") != f"Bearer {ctx.api_key}":
                 return JSONResponse({"error": "Unauthorized"}, status_code=401)
         rid = request.headers.get("X-Request-Id")
+        t0 = time.perf_counter()
         resp = await call_next(request)
         if rid:
             resp.headers["X-Request-Id"] = rid
+        if getattr(ctx, "log_requests", False) and request.method == "POST":
+            # request logger (reference: entrypoints/serve/utils/request_logger.py): who asked for what, never the payload
+            logger.info("request %s %s -> %d in %.1f ms (client %s, id %s)", request.method, request.url.path,
+                        resp.status_code, (time.perf_counter() - t0) * 1e3, request.client.host if request.client else "?", rid)
+        fmt = request.headers.get("endpoint-load-metrics-format")
+        if fmt:
+            # ORCA load report for load balancers (reference: entrypoints/serve/utils/orca_metrics.py)
+            try:
+                running, waiting = await ctx.engine.get_request_counts()
+                named = {"vllm:num_requests_running": float(running), "vllm:num_requests_waiting": float(waiting)}
+                if fmt.lower() == "json":
+                    resp.headers["endpoint-load-metrics"] = "JSON " + json.dumps({"named_metrics": named})
+                else:
+                    resp.headers["endpoint-load-metrics"] = "TEXT " + ", ".join(f"named_metrics.{k}={v}" for k, v in named.items())
+            except Exception:
+                pass
         return resp
 
     def check_model(name: Optional[str]):
@@ -1090,6 +1107,7 @@ def make_arg_parser() -> argparse.ArgumentParser:
     ap.add_argument("--headless", action="store_true", help="engine cores only; connect to a remote front-end")
     ap.add_argument("--native-frontend", action="store_true", help="serve through the C++ front-end daemon")
     ap.add_argument("--grpc-port", type=int, default=None, help="also serve the gRPC engine service on this port")
+    ap.add_argument("--enable-log-requests", action="store_true", help="log one line per API request (no payloads)")
     ap.add_argument("--engine-input-addr", default=None)
     ap.add_argument("--engine-output-addr", default=None)
     ap.add_argument("--data-parallel-start-rank", type=int, default=None)
@@ -1112,6 +1130,7 @@ async def run_server(args: argparse.Namespace) -> None:
                          api_key=args.api_key, tool_parser=args.tool_call_parser,
                          reasoning_parser=ea.reasoning_parser or None, enable_auto_tools=args.enable_auto_tool_choice,
                          chat_template=template)
+    ctx.log_requests = bool(getattr(args, "enable_log_requests", False))
     app = build_app(ctx)
     config = uvicorn.Config(app, host=args.host, port=args.port, log_level=args.uvicorn_log_level)
     server = uvicorn.Server(config)

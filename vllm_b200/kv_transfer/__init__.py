@@ -318,6 +318,42 @@ def register_connector(name: str, module: str, cls: str) -> None:
     _REGISTRY[name] = (module, cls)
 
 
+class DecodeBenchConnector(KVConnectorBase):
+    """Benchmark helper (reference: kv_connector/v1/decode_bench_connector.py): pretends every prompt's KV already
+    exists remotely, so a decode instance can be load-tested at arbitrary context lengths without running prefill —
+    the "loaded" blocks are filled with a constant instead of real keys / values."""
+
+    def __init__(self, vllm_config, role: str) -> None:
+        super().__init__(vllm_config, role)
+        self.fill = float(self.cfg.kv_connector_extra_config.get("fill_value", 0.015))
+        self._jobs: list[list[int]] = []
+        self.num_filled_blocks = 0
+
+    def get_num_new_matched_tokens(self, request, num_computed_tokens: int) -> tuple[int, bool]:
+        n = (request.num_tokens - 1) // self.block_size * self.block_size        # all full blocks but keep the last token
+        return max(n - num_computed_tokens, 0), False
+
+    def update_state_after_alloc(self, request, blocks, num_external_tokens: int) -> None:
+        if num_external_tokens > 0:
+            ids = blocks.get_block_ids()[0]
+            self._jobs.append(list(ids[: (request.num_computed_tokens + num_external_tokens) // self.block_size]))
+
+    def build_connector_meta(self, scheduler_output) -> Any:
+        jobs, self._jobs = self._jobs, []
+        return {"fill": jobs} if jobs else None
+
+    def start_load_kv(self, meta: Any, kv_caches: dict[str, torch.Tensor]) -> None:
+        for ids in (meta or {}).get("fill", ()):
+            idx = torch.tensor(ids, dtype=torch.long)
+            for t in kv_caches.values():
+                if t.dtype in (torch.float32, torch.float16, torch.bfloat16):
+                    t[idx.to(t.device)] = self.fill
+            self.num_filled_blocks += len(ids)
+
+
+_REGISTRY["DecodeBenchConnector"] = ("vllm_b200.kv_transfer", "DecodeBenchConnector")
+
+
 def create_connector(vllm_config, role: str = "worker"):
     import importlib
     name = vllm_config.kv_transfer_config.kv_connector
