@@ -959,3 +959,30 @@ def test_multimodal_sender_receiver_cache():
     assert first == second
     if sender is not None:
         assert sender.hits == 1 and sender.misses == 1
+
+
+def test_cascade_attention_shared_prefix(monkeypatch):
+    """Requests that share their leading KV blocks (prefix cache): the shared part is attended once for the batch and
+    merged with the per-request remainder by log-sum-exp — same tokens as the ordinary path."""
+    from vllm_b200.layers.attention import Attention
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=31))
+    shared = [(13 * i) % 400 + 5 for i in range(64)]
+    prompts = [{"prompt_token_ids": shared + [7 + j, 9 + 2 * j, 11 + j]} for j in range(4)]
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+
+    def run():
+        llm = make_llm("llama-tiny", weights=w, block_size=16, enable_prefix_caching=True)
+        llm.generate([{"prompt_token_ids": shared + [3]}], SamplingParams(max_tokens=1, temperature=0.0))   # fills the cache
+        before = Attention.cascade_calls
+        out = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+        used = Attention.cascade_calls - before
+        llm.shutdown()
+        return out, used
+    monkeypatch.setenv("VLLM_B200_CASCADE_MIN_REQS", "1000")
+    ref, used0 = run()
+    monkeypatch.setenv("VLLM_B200_CASCADE_MIN_REQS", "2")
+    monkeypatch.setenv("VLLM_B200_CASCADE_MIN_TOKENS", "32")
+    got, used1 = run()
+    assert used0 == 0 and used1 > 0
+    assert got == ref

@@ -32,6 +32,9 @@ class AttentionMetadata:
     # decode split-KV workspace (allocated once by the runner)
     workspace: Any = None
     num_splits: int = 0
+    # cascade attention: (metadata of the shared-prefix pass, metadata of the per-request suffix pass) when every
+    # request of the step shares its leading KV blocks (reference: v1/attention/backends use_cascade_attention)
+    cascade: Any = None
 
 
 @dataclass

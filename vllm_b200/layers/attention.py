@@ -29,6 +29,8 @@ def clear_attention_layers() -> None:
 
 
 class Attention(nn.Module):
+    cascade_calls = 0          # how many layer invocations took the cascade path (tests / debugging)
+
     def __init__(self, num_heads: int, head_size: int, scale: float, num_kv_heads: Optional[int] = None,
                  sliding_window: Optional[int] = None, logits_soft_cap: float = 0.0, prefix: str = "",
                  causal: bool = True, rope: Optional[nn.Module] = None,
@@ -95,6 +97,17 @@ class Attention(nn.Module):
         else:
             ops.reshape_and_cache(k.view(T, self.num_kv_heads, D), v.view(T, self.num_kv_heads, D),
                                   kv_cache, md.slot_mapping, vt=md.kv_vt)
+        if (md.cascade is not None and self.causal and not self.sliding_window and self.alibi_slopes is None
+                and self.sinks is None and not self.chunk_size):
+            # shared prefix: its K/V are read once for the whole batch (all queries sit after it → no causal mask),
+            # the per-request remainders are attended separately, the two partial softmaxes are merged by their LSE
+            md_p, md_s = md.cascade
+            q3 = q.view(T, self.num_heads, D)
+            o1, l1 = ops.paged_attention(q3, kv_cache, md_p, self.scale, None, self.logits_soft_cap, False, return_lse=True)
+            o2, l2 = ops.paged_attention(q3, kv_cache, md_s, self.scale, None, self.logits_soft_cap, True, return_lse=True)
+            out, _ = ops.merge_attn_states(o1, l1, o2, l2)
+            Attention.cascade_calls += 1
+            return out.view(T, self.num_heads * D)
         out = ops.paged_attention(q.view(T, self.num_heads, D), kv_cache, md, self.scale,
                                   self.sliding_window, self.logits_soft_cap, self.causal,
                                   alibi_slopes=self.alibi_slopes, sinks=self.sinks, chunk_size=self.chunk_size)

@@ -103,16 +103,17 @@ def concat_and_cache_mla(kv_c, k_pe, kv_cache, slot_mapping) -> None:
 
 def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap=0.0, causal=True,
                     out: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
-                    sinks: Optional[torch.Tensor] = None, chunk_size: int = 0):
+                    sinks: Optional[torch.Tensor] = None, chunk_size: int = 0, return_lse: bool = False):
     """``md``: AttentionMetadata (see vllm_b200.forward_context)."""
     if _use_cuda(q):
         return cuda_ops().paged_attention(q, kv_cache, md, scale, sliding_window, logits_soft_cap, causal, out,
-                                          alibi_slopes=alibi_slopes, sinks=sinks, chunk_size=chunk_size)
+                                          return_lse=return_lse, alibi_slopes=alibi_slopes, sinks=sinks,
+                                          chunk_size=chunk_size)
     sl = md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()
     qsl = md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()
     return ref.paged_attention(q, kv_cache, md.block_table, sl, qsl, scale,
                                causal=causal, sliding_window=sliding_window, logits_soft_cap=logits_soft_cap,
-                               alibi_slopes=alibi_slopes, sinks=sinks, chunk_size=chunk_size)
+                               alibi_slopes=alibi_slopes, sinks=sinks, chunk_size=chunk_size, return_lse=return_lse)
 
 
 def mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank):

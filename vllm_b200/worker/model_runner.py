@@ -174,6 +174,9 @@ class ModelRunner:
         self.spec_hidden = None
         self.step_hidden = None
         self._last_aux = None
+        import os as _os
+        self.cascade_min_tokens = int(_os.environ.get("VLLM_B200_CASCADE_MIN_TOKENS", "256"))
+        self.cascade_min_reqs = int(_os.environ.get("VLLM_B200_CASCADE_MIN_REQS", "8"))
         pc_ = vllm_config.parallel_config
         self.eplb_interval = pc_.eplb_step_interval if pc_.enable_eplb else 0
         self.eplb_hook = None             # set by the worker (needs the process groups)
@@ -556,6 +559,37 @@ class ModelRunner:
         self._last_aux = ctx.extra.get("aux_hidden")            # EAGLE-3 taps (None otherwise)
         return out
 
+    # ------------------------------------------------------------ cascade attention
+    def _add_cascade(self, md, common_blocks, rows, ns, nb, T, max_q, max_s) -> None:
+        from vllm_b200.core.kv_cache_manager import FullAttentionSpec, SlidingWindowSpec
+        computed = self.num_computed_cpu[rows]
+        for g in range(self.num_kv_groups):
+            spec = self.kv_cache_config.kv_cache_groups[g].spec
+            if type(spec) is not FullAttentionSpec or isinstance(spec, SlidingWindowSpec):
+                continue
+            nblk = int(common_blocks[g]) if g < len(common_blocks) else 0
+            P = nblk * self.block_size
+            # every query of the step must sit behind the shared prefix, and the prefix must be worth a second pass
+            if P < self.cascade_min_tokens or int(computed.min()) < P:
+                continue
+            m = md[g]
+            dev = self.device
+            qsl_p = torch.tensor([0, T], dtype=torch.int32)
+            sl_p = torch.tensor([P], dtype=torch.int32)
+            md_p = AttentionMetadata(
+                num_reqs=1, num_actual_tokens=T, max_query_len=T, max_seq_len=P, query_start_loc=qsl_p.to(dev),
+                seq_lens=sl_p.to(dev), block_table=m.block_table[:1, :nblk], slot_mapping=m.slot_mapping,
+                query_start_loc_cpu=None if self.is_cuda else qsl_p, seq_lens_cpu=None if self.is_cuda else sl_p,
+                decode_only=False, kv_vt=m.kv_vt)
+            sl_cpu = (computed + ns - P).astype(np.int32)
+            sl_s = torch.from_numpy(sl_cpu)
+            md_s = AttentionMetadata(
+                num_reqs=nb, num_actual_tokens=T, max_query_len=max_q, max_seq_len=max_s - P,
+                query_start_loc=m.query_start_loc, seq_lens=sl_s.to(dev), block_table=m.block_table[:, nblk:],
+                slot_mapping=m.slot_mapping, query_start_loc_cpu=m.query_start_loc_cpu,
+                seq_lens_cpu=None if self.is_cuda else sl_s, decode_only=m.decode_only, kv_vt=m.kv_vt)
+            m.cascade = (md_p, md_s)
+
     # ------------------------------------------------------------ multimodal rotary positions
     def _mrope_delta(self, req_id: str) -> int:
         f = self._mrope_feature(self.states[req_id])
@@ -805,6 +839,8 @@ class ModelRunner:
             l0 = self._launches()
             states = [self.states[r] for r in req_ids]
             md = self._make_metadata(nb, T, max_q, max_s, decode_only, cpu_qsl, cpu_sl)
+            if so.num_common_prefix_blocks and nb >= self.cascade_min_reqs and self.pcp == 1 and self.dcp == 1:
+                self._add_cascade(md, so.num_common_prefix_blocks, rows, ns, nb, T, max_q, max_s)
             if kv_meta:
                 self.kv_connector.start_load_kv(kv_meta, self.kv_caches)     # external prefix → our blocks
             extra = None
