@@ -260,6 +260,22 @@ PRESETS: dict[str, dict[str, Any]] = {
                            in_channels=3, patch_size=14, spatial_merge_size=2, temporal_patch_size=2, window_size=56,
                            fullatt_block_indexes=[1], tokens_per_second=2),
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "smollm3-tiny": dict(architectures=["SmolLM3ForCausalLM"], model_type="smollm3", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", rms_norm_eps=1e-6,
+        no_rope_layers=[1, 1, 1, 0], no_rope_layer_interval=4, tie_word_embeddings=True),
+    "cohere2-tiny": dict(architectures=["Cohere2ForCausalLM"], model_type="cohere2", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", head_dim=16, layer_norm_eps=1e-5,
+        logit_scale=0.25, layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"], sliding_window=16, tie_word_embeddings=True),
+    "olmo3-tiny": dict(architectures=["Olmo3ForCausalLM"], model_type="olmo3", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", rms_norm_eps=1e-5, layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"], sliding_window=16,
+        tie_word_embeddings=False),
+    "exaone4-tiny": dict(architectures=["Exaone4ForCausalLM"], model_type="exaone4", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", rms_norm_eps=1e-5, layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"], sliding_window=16,
+        sliding_window_pattern=4, tie_word_embeddings=False),
+    "seedoss-tiny": dict(architectures=["SeedOssForCausalLM"], model_type="seed_oss", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", head_dim=16, rms_norm_eps=1e-6,
+        attention_bias=True, attention_out_bias=False, tie_word_embeddings=False),
+    "arcee-tiny": dict(architectures=["ArceeForCausalLM"], model_type="arcee", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="relu2",
+        head_dim=16, rms_norm_eps=1e-5, tie_word_embeddings=False),
+    "helium-tiny": dict(architectures=["HeliumForCausalLM"], model_type="helium", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", head_dim=16, rms_norm_eps=1e-8,
+        tie_word_embeddings=False),
+    "ernie45-tiny": dict(architectures=["Ernie4_5ForCausalLM"], model_type="ernie4_5", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", head_dim=16, rms_norm_eps=1e-5,
+        use_bias=False, tie_word_embeddings=True),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

@@ -103,7 +103,7 @@ class VariantAttention(nn.Module):
                                                if rp.get("rope_type", "default") != "default" else None)
         factor = rp.get("partial_rotary_factor", cfg.get("partial_rotary_factor", 1.0))
         max_pos = mc.max_model_len if mc.max_model_len > 0 else cfg.get("max_position_embeddings", 8192)
-        rope = get_rope(hd, int(hd * factor), max_pos, theta, o["neox"], scaling)
+        rope = get_rope(hd, int(hd * factor), max_pos, theta, o["neox"], scaling) if o["use_rope"](layer_idx, sliding) else None
         self.attn = Attention(self.qkv_proj.num_heads, hd, o["scale"] if o["scale"] is not None else hd ** -0.5,
                               self.qkv_proj.num_kv_heads, sliding_window=cfg.get("sliding_window") if sliding else None,
                               logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0, prefix=f"{prefix}.attn", rope=rope)
@@ -155,7 +155,8 @@ class VariantLayer(nn.Module):
 
 _DEFAULTS = dict(norm="rms", structure="pre", eps=1e-6, qkv_bias=False, o_bias=False, mlp_bias=False, gated_mlp=True,
                  act="silu", qk_norm=None, neox=True, scale=None, residual_multiplier=1.0, sliding=lambda i: False,
-                 embed_scale=1.0, logit_scale=1.0, lm_head_bias=False, final_norm_name="model.norm")
+                 embed_scale=1.0, logit_scale=1.0, lm_head_bias=False, final_norm_name="model.norm",
+                 use_rope=lambda i, sliding: True)
 
 
 class VariantModel(LlamaModel):
@@ -262,3 +263,78 @@ class Gemma3ForCausalLM(VariantForCausalLM):
                     sliding=(lambda i: types[i] == "sliding_attention") if types else (lambda i: (i + 1) % pat != 0))
     renames = [(".post_attention_layernorm.", ".post_attn_norm."), (".pre_feedforward_layernorm.", ".pre_mlp_norm."),
                (".post_feedforward_layernorm.", ".post_mlp_norm.")]
+
+
+def _types_sliding(c):
+    types = c.get("layer_types")
+    pat = c.get("sliding_window_pattern") or 4
+    return (lambda i: types[i] == "sliding_attention") if types else (lambda i: (i + 1) % pat != 0)
+
+
+class SmolLM3ForCausalLM(VariantForCausalLM):
+    """Llama with rotary switched off on every n-th layer (reference: models/smollm3.py)."""
+    def options(self, c):
+        nope = c.get("no_rope_layers")
+        return dict(eps=c.get("rms_norm_eps", 1e-6), qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")),
+                    mlp_bias=bool(c.get("mlp_bias")),
+                    use_rope=(lambda i, sl: bool(nope[i])) if nope else (lambda i, sl: (i + 1) % (c.get("no_rope_layer_interval") or 4) != 0))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class Cohere2ForCausalLM(CohereForCausalLM):
+    """Command-R7B / Command-A: Cohere block, 3 sliding-window layers (with rope) : 1 global layer (no rope)
+    (reference: models/commandr.py Cohere2)."""
+    def options(self, c):
+        o = super().options(c)
+        sl = _types_sliding(c)
+        o.update(sliding=sl, use_rope=lambda i, sliding: sliding)
+        return o
+
+
+class Olmo3ForCausalLM(Olmo2ForCausalLM):
+    """OLMo-2 block with sliding-window layers interleaved (reference: models/olmo2.py Olmo3)."""
+    def options(self, c):
+        o = super().options(c)
+        o.update(sliding=_types_sliding(c))
+        return o
+
+
+class Exaone4ForCausalLM(VariantForCausalLM):
+    """Post-norm block, per-head q/k RMSNorm, 3 local (rope) : 1 global (no rope) when a sliding window is configured
+    (reference: models/exaone4.py)."""
+    def options(self, c):
+        hybrid = bool(c.get("sliding_window"))
+        sl = _types_sliding(c) if hybrid else (lambda i: False)
+        return dict(structure="post", eps=c.get("rms_norm_eps", 1e-5), qk_norm="head", sliding=sl,
+                    use_rope=(lambda i, sliding: sliding) if hybrid else (lambda i, sliding: True))
+    renames = [(".post_attention_layernorm.", ".post_attn_norm."), (".post_feedforward_layernorm.", ".post_mlp_norm.")]
+
+
+class SeedOssForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-6), qkv_bias=bool(c.get("attention_bias", True)),
+                    o_bias=bool(c.get("attention_out_bias", False)), mlp_bias=bool(c.get("mlp_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class ArceeForCausalLM(VariantForCausalLM):
+    """Llama block with a plain squared-ReLU MLP (reference: models/arcee.py)."""
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-5), gated_mlp=False, act="relu2", qkv_bias=bool(c.get("attention_bias")),
+                    o_bias=bool(c.get("attention_bias")), mlp_bias=bool(c.get("mlp_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".mlp.up_proj.", ".mlp.fc_in."), (".mlp.down_proj.", ".mlp.fc_out.")]
+
+
+class HeliumForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-8), neox=False, qkv_bias=bool(c.get("attention_bias")), o_bias=False,
+                    mlp_bias=bool(c.get("mlp_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class Ernie4_5ForCausalLM(VariantForCausalLM):
+    def options(self, c):
+        c.setdefault("tie_word_embeddings", True)
+        return dict(eps=c.get("rms_norm_eps", 1e-5), neox=False, qkv_bias=bool(c.get("use_bias")), o_bias=bool(c.get("use_bias")),
+                    mlp_bias=bool(c.get("use_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]

@@ -25,6 +25,14 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Glm4ForCausalLM": ("llama_variants", "Glm4ForCausalLM"),
     "NemotronForCausalLM": ("llama_variants", "NemotronForCausalLM"),
     "Gemma3ForCausalLM": ("llama_variants", "Gemma3ForCausalLM"),
+    "SmolLM3ForCausalLM": ("llama_variants", "SmolLM3ForCausalLM"),
+    "Cohere2ForCausalLM": ("llama_variants", "Cohere2ForCausalLM"),
+    "Olmo3ForCausalLM": ("llama_variants", "Olmo3ForCausalLM"),
+    "Exaone4ForCausalLM": ("llama_variants", "Exaone4ForCausalLM"),
+    "SeedOssForCausalLM": ("llama_variants", "SeedOssForCausalLM"),
+    "ArceeForCausalLM": ("llama_variants", "ArceeForCausalLM"),
+    "HeliumForCausalLM": ("llama_variants", "HeliumForCausalLM"),
+    "Ernie4_5ForCausalLM": ("llama_variants", "Ernie4_5ForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
