@@ -276,6 +276,10 @@ PRESETS: dict[str, dict[str, Any]] = {
         tie_word_embeddings=False),
     "ernie45-tiny": dict(architectures=["Ernie4_5ForCausalLM"], model_type="ernie4_5", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", head_dim=16, rms_norm_eps=1e-5,
         use_bias=False, tie_word_embeddings=True),
+    "olmoe-tiny": dict(architectures=["OlmoeForCausalLM"], model_type="olmoe", vocab_size=512, hidden_size=64,
+        intermediate_size=32, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, num_experts=4,
+        num_experts_per_tok=2, norm_topk_prob=False, max_position_embeddings=512, rms_norm_eps=1e-5, hidden_act="silu",
+        rope_theta=10000.0, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

@@ -57,7 +57,13 @@ class LlamaAttention(nn.Module):
                                         quant_config=quant_config, prefix=f"{prefix}.o_proj")
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
         self.qk_norm = bool(cfg.get("qk_norm", False))
-        if self.qk_norm:
+        self.qk_norm_full = cfg.get("qk_norm") == "full"          # OLMo-2 / OLMoE: one RMSNorm over the whole projection
+        if self.qk_norm_full:
+            assert get_tp_group().world_size == 1, "whole-projection q/k norms need the unsharded projection"
+            eps = cfg.get("rms_norm_eps", 1e-6)
+            self.q_norm = RMSNorm(self.total_heads * self.head_dim, eps, dtype)
+            self.k_norm = RMSNorm(self.total_kv * self.head_dim, eps, dtype)
+        elif self.qk_norm:
             eps = cfg.get("rms_norm_eps", 1e-6)
             self.q_norm = RMSNorm(self.head_dim, eps, dtype)
             self.k_norm = RMSNorm(self.head_dim, eps, dtype)
@@ -78,7 +84,9 @@ class LlamaAttention(nn.Module):
     def forward(self, positions, hidden):
         qkv = self.qkv_proj(hidden)
         q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
-        if self.qk_norm:
+        if self.qk_norm_full:
+            q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
+        elif self.qk_norm:
             T = q.shape[0]
             q = self.q_norm(q.reshape(T, -1, self.head_dim)).reshape(T, -1)
             k = self.k_norm(k.reshape(T, -1, self.head_dim)).reshape(T, -1)

@@ -198,3 +198,20 @@ class Qwen3MoeForCausalLM(MixtralForCausalLM):
     def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
         vllm_config.model_config.hf_config["qk_norm"] = True
         super().__init__(vllm_config, prefix)
+
+
+class OlmoeForCausalLM(MixtralForCausalLM):
+    """OLMoE: Qwen-MoE style sparse block in every layer (softmax over all experts, top-k without renormalisation)
+    behind attention with whole-projection q/k RMSNorm (reference: models/olmoe.py)."""
+    model_cls = Qwen3MoeModel
+    expert_names = Qwen2MoeForCausalLM.expert_names
+    expert_container = "mlp.experts"
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg["qk_norm"] = "full"
+        cfg.setdefault("moe_intermediate_size", cfg["intermediate_size"])
+        cfg.setdefault("norm_topk_prob", False)
+        cfg.setdefault("decoder_sparse_step", 1)
+        cfg.setdefault("mlp_only_layers", [])
+        super().__init__(vllm_config, prefix)

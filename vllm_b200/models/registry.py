@@ -46,6 +46,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "GPT2LMHeadModel": ("opt", "GPT2LMHeadModel"),
     "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
     "Qwen2MoeForCausalLM": ("mixtral", "Qwen2MoeForCausalLM"),
+    "OlmoeForCausalLM": ("mixtral", "OlmoeForCausalLM"),
     "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
     "GptOssForCausalLM": ("gpt_oss", "GptOssForCausalLM"),
     "MambaForCausalLM": ("mamba", "MambaForCausalLM"),
