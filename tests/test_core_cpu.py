@@ -345,3 +345,71 @@ def test_speculative_tokens_accounting_and_rollback():
     assert list(r.output_token_ids)[-2:] == [11, 50]
     assert s._spec_draft_tokens == 3 and s._spec_accepted == 1 and s._spec_drafts == 1
     del types
+
+
+def test_scheduler_block_accounting_invariants_under_random_load():
+    """Property test (hypothesis): any interleaving of arrivals (with shared prefixes), steps, aborts and cache resets
+    keeps the block pool consistent — reference counts match the running requests, nothing leaks, nothing is
+    double-freed, and a drained scheduler returns every block."""
+    from hypothesis import given, settings, strategies as st
+
+    ops = st.lists(st.one_of(
+        st.tuples(st.just("add"), st.integers(0, 3), st.integers(1, 70), st.integers(1, 6)),     # prefix family, length, max_tokens
+        st.tuples(st.just("step"), st.integers(1, 4)),
+        st.tuples(st.just("abort"), st.integers(0, 30)),
+        st.tuples(st.just("reset"),)), min_size=5, max_size=40)
+
+    @settings(max_examples=40, deadline=None)
+    @given(ops)
+    def run(seq):
+        s = create_scheduler(num_blocks=24, max_num_seqs=4, max_num_batched_tokens=48, max_model_len=128)
+        pool = s.kv_cache_manager.pool
+        total = pool.num_blocks - 1
+        n = 0
+        live: list[str] = []
+
+        def check():
+            held: dict[int, int] = {}
+            for m in s.kv_cache_manager.managers:
+                for blocks in m.req_to_blocks.values():
+                    for b in blocks:
+                        if not b.is_null:
+                            held[b.block_id] = held.get(b.block_id, 0) + 1
+            for b in pool.blocks:
+                if b.is_null:
+                    continue
+                assert b.ref_cnt == held.get(b.block_id, 0), (b.block_id, b.ref_cnt, held.get(b.block_id, 0))
+            assert pool.get_num_free_blocks() == total - len(held)
+            for (h, g), d in pool.cached.items():
+                assert d and all(blk.block_hash == h for blk in d.values())
+
+        for op in seq:
+            if op[0] == "add":
+                _, fam, length, mt = op
+                rid = f"r{n}"
+                n += 1
+                sp = SamplingParams(max_tokens=mt, temperature=0.0, ignore_eos=True)
+                toks = [(fam * 37 + i) % 50 + 1 for i in range(min(length, 40))] + [n % 50 + 1] * max(length - 40, 0)
+                s.add_request(Request(rid, toks, sampling_params=sp, eos_token_id=None, block_hasher=s.get_block_hasher()))
+                live.append(rid)
+            elif op[0] == "step":
+                for _ in range(op[1]):
+                    if s.has_requests():
+                        run_step(s)
+            elif op[0] == "abort" and live:
+                s.finish_requests([live[op[1] % len(live)]], RequestStatus.FINISHED_ABORTED)
+            elif op[0] == "reset":
+                s.reset_prefix_cache()
+            live = [r for r in live if r in s.requests]
+            check()
+        for _ in range(400):
+            if not s.has_unfinished_requests():
+                break
+            run_step(s)
+            check()
+        assert not s.has_unfinished_requests()
+        if s.has_requests():
+            run_step(s)
+        check()
+        assert pool.get_num_free_blocks() == total
+    run()
