@@ -298,3 +298,18 @@ def test_decoder_pooling_adapters_match_hf():
             ref = torch.nn.functional.normalize(base(torch.tensor([p])).last_hidden_state[0, -1], dim=-1)
         torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_modernbert_embeddings_match_hf():
+    """Rotary encoder with alternating global / symmetric-local attention through the pooling runner == HF."""
+    hf = make_hf_model("modernbert-tiny")
+    hf.config._attn_implementation = "eager"
+    llm = make_llm("modernbert-tiny", weights=hf.state_dict().items(), enable_prefix_caching=False)
+    prompts = [[3, 17, 99, 250, 41, 7], list(range(10, 55))]
+    outs = llm.embed([{"prompt_token_ids": p} for p in prompts])
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = hf(torch.tensor([p])).last_hidden_state[0, 0]
+        ref = torch.nn.functional.normalize(ref, dim=-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()

@@ -280,6 +280,14 @@ PRESETS: dict[str, dict[str, Any]] = {
         intermediate_size=32, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, num_experts=4,
         num_experts_per_tok=2, norm_topk_prob=False, max_position_embeddings=512, rms_norm_eps=1e-5, hidden_act="silu",
         rope_theta=10000.0, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "modernbert-tiny": dict(architectures=["ModernBertModel"], model_type="modernbert", vocab_size=512, hidden_size=64,
+        intermediate_size=96, num_hidden_layers=4, num_attention_heads=4, max_position_embeddings=512, norm_eps=1e-5,
+        norm_bias=False, attention_bias=False, mlp_bias=False, hidden_activation="gelu", local_attention=8,
+        global_attn_every_n_layers=3, layer_types=["full_attention", "sliding_attention", "sliding_attention", "full_attention"],
+        rope_parameters=dict(sliding_attention=dict(rope_type="default", rope_theta=10000.0),
+                             full_attention=dict(rope_type="default", rope_theta=160000.0)),
+        classifier_pooling="cls", pad_token_id=0, bos_token_id=1, eos_token_id=2, cls_token_id=1, sep_token_id=2,
+        torch_dtype="float32"),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

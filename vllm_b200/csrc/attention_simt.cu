@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(THREADS) paged_attn_kernel(const AttnParams p)
       if (p.alibi) s += p.alibi[h * G + (r % G)] * 1.4426950408889634f * (float)(kpos - qpos);
       bool ok = qpos >= 0 && kpos < kv_end && kpos >= kv_begin;
       if (p.causal) ok = ok && kpos <= qpos;
-      if (p.window > 0) ok = ok && kpos > qpos - p.window;
+      if (p.window > 0) ok = ok && kpos > qpos - p.window && (p.causal || kpos < qpos + p.window);
       if (p.chunk > 0) ok = ok && (kpos / p.chunk == qpos / p.chunk);
       s = ok ? s : -INFINITY;
       const float pmax = warp_max(s);

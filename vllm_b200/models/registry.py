@@ -60,6 +60,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen2_5_VLForConditionalGeneration": ("qwen2_vl", "Qwen2_5_VLForConditionalGeneration"),
     "Qwen2VLForConditionalGeneration": ("qwen2_vl", "Qwen2VLForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
+    "ModernBertModel": ("modernbert", "ModernBertModel"),
+    "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),
     "BertModel": ("bert", "BertEmbeddingModel"),
     "BertForMaskedLM": ("bert", "BertEmbeddingModel"),
     "BertForSequenceClassification": ("bert", "BertForSequenceClassification"),

@@ -201,6 +201,8 @@ def paged_attention(q: torch.Tensor, kv_cache: torch.Tensor, block_table: torch.
             mask &= kpos <= qpos
         if sliding_window:
             mask &= kpos > qpos - sliding_window
+            if not causal:                   # bidirectional local attention (ModernBERT): the window is symmetric
+                mask &= kpos < qpos + sliding_window
         if chunk_size:                       # chunked-local attention: keys of the query's own chunk only
             mask &= (kpos // chunk_size) == (qpos // chunk_size)
         att = att.masked_fill(~mask[None], float("-inf"))
