@@ -183,6 +183,72 @@ class Int8Config(QuantConfig):
         return Int8LinearMethod(self.online, self.per_channel, self.static_act)
 
 
+class BlockFloatLinearMethod(LinearMethod):
+    """Online micro-scaled weight formats: the bf16 checkpoint is quantised after loading and kept packed —
+    ``nvfp4`` (e2m1 codes, fp8 scale per 16 values + one fp32 scale per tensor) or ``mxfp8`` (e4m3 codes, power-of-two
+    e8m0 scale per 32 values).  The GEMM consumes the weights expanded per call for now; the packed layout is the one
+    the tcgen05 ``kind::mxf4nvf4`` / ``kind::mxf8f6f4`` block-scaled MMAs take directly
+    (reference: quantization/ online modes nvfp4 / mxfp8, modelopt.py, mxfp8 utils)."""
+
+    def __init__(self, fmt: str) -> None:
+        assert fmt in ("nvfp4", "mxfp8")
+        self.fmt = fmt
+
+    def create_weights(self, layer, in_per_rank, out_per_rank, dtype) -> None:
+        layer.weight = nn.Parameter(torch.empty(out_per_rank, in_per_rank, dtype=dtype), requires_grad=False)
+        layer.out_dtype = dtype
+
+    def process_weights_after_loading(self, layer) -> None:
+        if getattr(layer, "weight_packed", None) is not None:
+            return
+        w = layer.weight.data.float()
+        if self.fmt == "nvfp4":
+            K = w.shape[1]
+            pad = (-K) % 16
+            if pad:
+                w = torch.nn.functional.pad(w, (0, pad))
+            packed, bscale, gscale = ref.fp4_quant(w, 16)
+            layer.weight_packed = nn.Parameter(packed, requires_grad=False)
+            layer.weight_scale = nn.Parameter(bscale, requires_grad=False)
+            layer.weight_global_scale = float(gscale)
+        else:
+            K = w.shape[1]
+            pad = (-K) % 32
+            if pad:
+                w = torch.nn.functional.pad(w, (0, pad))
+            g = w.reshape(w.shape[0], -1, 32)
+            e = torch.ceil(torch.log2(g.abs().amax(-1).clamp_min(2.0 ** -120) / ref.FP8_MAX)).clamp(-127, 127)
+            q = (g / torch.exp2(e)[..., None]).clamp(-ref.FP8_MAX, ref.FP8_MAX).to(torch.float8_e4m3fn)
+            layer.weight_packed = nn.Parameter(q.reshape(w.shape[0], -1), requires_grad=False)
+            layer.weight_scale = nn.Parameter((e + 127).to(torch.uint8), requires_grad=False)          # e8m0
+        layer.in_features = K
+        layer.weight = nn.Parameter(torch.empty(0, dtype=layer.out_dtype), requires_grad=False)       # drop the bf16 copy
+
+    def _expand(self, layer) -> torch.Tensor:
+        if self.fmt == "nvfp4":
+            w = ref.fp4_dequant(layer.weight_packed, layer.weight_scale, layer.weight_global_scale, 16)
+        else:
+            q = layer.weight_packed.float()
+            sc = torch.exp2(layer.weight_scale.float() - 127.0).repeat_interleave(32, dim=1)
+            w = q * sc
+        return w[:, :layer.in_features].to(layer.out_dtype)
+
+    def apply(self, layer, x, bias):
+        if getattr(layer, "weight_packed", None) is None:
+            return ops.linear(x, layer.weight, bias)
+        return ops.linear(x, self._expand(layer), bias)
+
+
+class BlockFloatConfig(QuantConfig):
+    def __init__(self, fmt: str, ignored: tuple[str, ...] = ("lm_head", "gate.")) -> None:
+        self.name, self.fmt, self.ignored = fmt, fmt, ignored
+
+    def get_linear_method(self, layer, prefix):
+        if any(s in prefix for s in self.ignored):
+            return None
+        return BlockFloatLinearMethod(self.fmt)
+
+
 def _compressed_tensors_scheme(hq: dict) -> dict:
     """Collapse a compressed-tensors ``quantization_config`` to the one scheme its Linear targets use
     (reference: quantization/compressed_tensors/compressed_tensors.py ``_get_scheme_from_parts``)."""
@@ -198,7 +264,7 @@ def _compressed_tensors_scheme(hq: dict) -> dict:
 
 QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8", "awq", "gptq", "awq_marlin",
                         "gptq_marlin", "nvfp4", "modelopt_fp4", "int8", "w8a8", "compressed-tensors", "compressed_tensors",
-                        "bitsandbytes")
+                        "bitsandbytes", "mxfp8", "nvfp4_online")
 
 
 def get_quant_config(model_config) -> Optional[QuantConfig]:
@@ -209,7 +275,7 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         online = not model_config.hf_config.get("quantization_config")
         return Fp8BlockConfig(online=online)
     hq = model_config.hf_config.get("quantization_config") or {}
-    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin", "nvfp4", "modelopt_fp4", "bitsandbytes"):
+    if q in ("awq", "gptq", "awq_marlin", "gptq_marlin", "modelopt_fp4", "bitsandbytes") or (q == "nvfp4" and hq):
         return None          # expanded to the model dtype at load time (model_loader/weight_only.py)
     if q in ("fp8", "fbgemm_fp8", "modelopt"):
         if hq.get("weight_block_size"):          # a "fp8" checkpoint with block scales (DeepSeek-V3 style)
@@ -217,6 +283,8 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         return Fp8Config(online=not hq, per_channel=(q == "fbgemm_fp8" or hq.get("strategy") == "channel"))
     if q in ("int8", "w8a8"):
         return Int8Config(online=not hq)
+    if q == "mxfp8" or (q in ("nvfp4", "nvfp4_online") and not hq):
+        return BlockFloatConfig("mxfp8" if q == "mxfp8" else "nvfp4")         # online: quantise the loaded bf16 weights
     if q in ("compressed-tensors", "compressed_tensors"):
         sc = _compressed_tensors_scheme(hq)
         ignored = tuple(i.replace("re:", "") for i in (hq.get("ignore") or ["lm_head"])) + ("gate.",)
