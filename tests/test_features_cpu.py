@@ -37,7 +37,18 @@ def test_speculative_decoding_is_lossless(spec):
     assert stats._spec_draft_tokens > 0, "the proposer never produced a draft"
 
 
+def _store_extra(tmp):
+    from vllm_b200.kv_transfer.store_server import StoreServer
+    srv = StoreServer("tcp://127.0.0.1:*", 64 << 20).start()
+    _store_extra.servers.append(srv)
+    return {"store_url": srv.url}
+
+
+_store_extra.servers = []
+
+
 @pytest.mark.parametrize("connector,extra", [
+    ("RemoteStoreConnector", _store_extra),
     ("SharedStorageConnector", lambda tmp: {"shared_storage_path": str(tmp)}),
     ("OffloadingConnector", lambda tmp: {"cpu_bytes_to_use": 64 << 20, "eviction_policy": "arc"}),
 ])
@@ -54,7 +65,7 @@ def test_kv_connector_prefix_reuse(tmp_path, connector, extra):
     first = llm.generate(prompt, sp)[0].outputs[0].token_ids
     wconn = core.model_executor.worker.runner.kv_connector
     assert wconn.num_saved_blocks >= 9                      # 150 tokens / 16 = 9 full blocks
-    if connector == "SharedStorageConnector":
+    if connector in ("SharedStorageConnector", "RemoteStoreConnector"):
         llm.shutdown()                                      # a different engine instance picks the blocks up
         llm = make_llm("llama-tiny", weights=w, kv_transfer_config=ktc, block_size=16, enable_prefix_caching=True)
         core = llm.llm_engine.engine_core.engine_core
@@ -65,6 +76,10 @@ def test_kv_connector_prefix_reuse(tmp_path, connector, extra):
     assert wconn.num_loaded_blocks >= 9
     assert second == first
     llm.shutdown()
+    for srv in _store_extra.servers:
+        assert srv.stats["puts"] >= 9 and srv.stats["hits"] >= 9
+        srv.stop()
+    _store_extra.servers.clear()
 
 
 def test_disaggregated_prefill_decode_over_p2p_connector():

@@ -310,6 +310,9 @@ _REGISTRY: dict[str, tuple[str, str]] = {
     "NixlConnector": ("vllm_b200.kv_transfer.p2p", "P2pPullConnector"),
     "P2pNcclConnector": ("vllm_b200.kv_transfer.p2p", "P2pPullConnector"),
     "OffloadingConnector": ("vllm_b200.kv_offload", "OffloadingConnector"),
+    "RemoteStoreConnector": ("vllm_b200.kv_transfer.store_server", "RemoteStoreConnector"),
+    "LMCacheConnectorV1": ("vllm_b200.kv_transfer.store_server", "RemoteStoreConnector"),
+    "MooncakeStoreConnector": ("vllm_b200.kv_transfer.store_server", "RemoteStoreConnector"),
     "SimpleCPUOffloadConnector": ("vllm_b200.kv_offload", "OffloadingConnector"),
 }
 
