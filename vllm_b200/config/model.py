@@ -288,6 +288,13 @@ PRESETS: dict[str, dict[str, Any]] = {
                              full_attention=dict(rope_type="default", rope_theta=160000.0)),
         classifier_pooling="cls", pad_token_id=0, bos_token_id=1, eos_token_id=2, cls_token_id=1, sep_token_id=2,
         torch_dtype="float32"),
+    "granitemoe-tiny": dict(architectures=["GraniteMoeForCausalLM"], model_type="granitemoe", num_hidden_layers=2, vocab_size=512, hidden_size=64, intermediate_size=32, num_attention_heads=4, num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=512, rms_norm_eps=1e-6, hidden_act="silu", rope_theta=10000.0, embedding_multiplier=6.0, logits_scaling=4.0, residual_multiplier=0.3, attention_multiplier=0.2, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "granitemoeshared-tiny": dict(architectures=["GraniteMoeSharedForCausalLM"], model_type="granitemoeshared",
+        num_hidden_layers=2, shared_intermediate_size=48, vocab_size=512, hidden_size=64, intermediate_size=32, num_attention_heads=4, num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=512, rms_norm_eps=1e-6, hidden_act="silu", rope_theta=10000.0, embedding_multiplier=6.0, logits_scaling=4.0, residual_multiplier=0.3, attention_multiplier=0.2, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "granitemoehybrid-tiny": dict(architectures=["GraniteMoeHybridForCausalLM"], model_type="granitemoehybrid",
+        num_hidden_layers=4, shared_intermediate_size=48, layer_types=["mamba", "attention", "mamba", "attention"],
+        position_embedding_type="nope", mamba_n_heads=8, mamba_d_head=16, mamba_expand=2, mamba_d_state=16, mamba_n_groups=2,
+        mamba_d_conv=4, mamba_chunk_size=16, mamba_conv_bias=True, mamba_proj_bias=False, vocab_size=512, hidden_size=64, intermediate_size=32, num_attention_heads=4, num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=512, rms_norm_eps=1e-6, hidden_act="silu", rope_theta=10000.0, embedding_multiplier=6.0, logits_scaling=4.0, residual_multiplier=0.3, attention_multiplier=0.2, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

@@ -18,6 +18,9 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3ForCausalLM": ("llama", "Qwen3ForCausalLM"),
     "GemmaForCausalLM": ("llama", "GemmaForCausalLM"),
     "Phi3ForCausalLM": ("llama", "Phi3ForCausalLM"),
+    "GraniteMoeForCausalLM": ("granite_moe", "GraniteMoeForCausalLM"),
+    "GraniteMoeSharedForCausalLM": ("granite_moe", "GraniteMoeForCausalLM"),
+    "GraniteMoeHybridForCausalLM": ("granite_moe", "GraniteMoeForCausalLM"),
     "GraniteForCausalLM": ("llama_variants", "GraniteForCausalLM"),
     "Olmo2ForCausalLM": ("llama_variants", "Olmo2ForCausalLM"),
     "CohereForCausalLM": ("llama_variants", "CohereForCausalLM"),
