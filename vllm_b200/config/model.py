@@ -295,6 +295,17 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=4, shared_intermediate_size=48, layer_types=["mamba", "attention", "mamba", "attention"],
         position_embedding_type="nope", mamba_n_heads=8, mamba_d_head=16, mamba_expand=2, mamba_d_state=16, mamba_n_groups=2,
         mamba_d_conv=4, mamba_chunk_size=16, mamba_conv_bias=True, mamba_proj_bias=False, vocab_size=512, hidden_size=64, intermediate_size=32, num_attention_heads=4, num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=512, rms_norm_eps=1e-6, hidden_act="silu", rope_theta=10000.0, embedding_multiplier=6.0, logits_scaling=4.0, residual_multiplier=0.3, attention_multiplier=0.2, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "gptbigcode-tiny": dict(architectures=["GPTBigCodeForCausalLM"], model_type="gpt_bigcode", vocab_size=512, n_embd=64,
+        n_layer=2, n_head=4, n_inner=128, n_positions=512, multi_query=True, activation_function="gelu_pytorch_tanh",
+        layer_norm_epsilon=1e-5, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, max_position_embeddings=512,
+        bos_token_id=0, eos_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "dots1-tiny": dict(architectures=["Dots1ForCausalLM"], model_type="dots1", vocab_size=512, hidden_size=64,
+        intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+        head_dim=16, n_routed_experts=8, n_shared_experts=1, num_experts_per_tok=2, n_group=2, topk_group=1,
+        first_k_dense_replace=1, norm_topk_prob=True, routed_scaling_factor=1.5, attention_bias=False, rope_theta=10000.0,
+        rms_norm_eps=1e-5, hidden_act="silu", max_position_embeddings=512, sliding_window=None,
+        layer_types=["full_attention", "full_attention", "full_attention"],
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,

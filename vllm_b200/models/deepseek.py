@@ -275,3 +275,14 @@ class Glm4MoeForCausalLM(DeepseekV3ForCausalLM):
         cfg.setdefault("partial_rotary_factor", rp.get("partial_rotary_factor", 0.5))
         cfg.setdefault("rope_theta", rp.get("rope_theta", 10000.0))
         super().__init__(vllm_config, prefix)
+
+
+class Dots1ForCausalLM(Glm4MoeForCausalLM):
+    """dots.llm1: the same composition (GQA attention with per-head q/k norms + DeepSeek-V3 style MoE), full rotary
+    (reference: models/dots1.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("use_qk_norm", True)
+        cfg.setdefault("partial_rotary_factor", 1.0)
+        super().__init__(vllm_config, prefix)

@@ -123,7 +123,8 @@ class GPT2Block(nn.Module):
         eps = cfg.get("layer_norm_epsilon", 1e-5)
         self.head_dim = H // nh
         self.ln_1 = LayerNorm(H, eps, True, dtype)
-        self.c_attn = QKVParallelLinear(H, self.head_dim, nh, nh, True, dtype, prefix=f"{prefix}.attn.c_attn")
+        nkv = 1 if cfg.get("multi_query") else nh          # GPT-BigCode (StarCoder): one shared K/V head
+        self.c_attn = QKVParallelLinear(H, self.head_dim, nh, nkv, True, dtype, prefix=f"{prefix}.attn.c_attn")
         self.c_proj = RowParallelLinear(H, H, True, dtype=dtype, prefix=f"{prefix}.attn.c_proj")
         self.attn = Attention(self.c_attn.num_heads, self.head_dim, self.head_dim ** -0.5,
                               self.c_attn.num_kv_heads, prefix=f"{prefix}.attn.attn")
@@ -189,3 +190,17 @@ class GPT2LMHeadModel(nn.Module):
                 params[name].data.copy_(w)
             loaded.add(name)
         return loaded
+
+
+class GPTBigCodeForCausalLM(GPT2LMHeadModel):
+    """StarCoder / SantaCoder: GPT-2 skeleton with multi-query attention and ordinary ``nn.Linear`` weight layout
+    (reference: models/gpt_bigcode.py)."""
+
+    def load_weights(self, weights) -> set[str]:
+        def fix():
+            for name, w in weights:
+                # undo the transpose the GPT-2 loader applies to Conv1D weights: these checkpoints store [out, in]
+                if any(s in name for s in ("c_attn", "c_proj", "c_fc")) and name.endswith(".weight"):
+                    w = w.t()
+                yield name, w
+        return super().load_weights(fix())

@@ -47,6 +47,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "RWForCausalLM": ("gpt_neox", "FalconForCausalLM"),
     "OPTForCausalLM": ("opt", "OPTForCausalLM"),
     "GPT2LMHeadModel": ("opt", "GPT2LMHeadModel"),
+    "GPTBigCodeForCausalLM": ("opt", "GPTBigCodeForCausalLM"),
     "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
     "Qwen2MoeForCausalLM": ("mixtral", "Qwen2MoeForCausalLM"),
     "OlmoeForCausalLM": ("mixtral", "OlmoeForCausalLM"),
@@ -72,6 +73,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "XLMRobertaModel": ("bert", "RobertaModel"),
     "DeepseekV2ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
     "Llama4ForCausalLM": ("llama4", "Llama4ForCausalLM"),
+    "Dots1ForCausalLM": ("deepseek", "Dots1ForCausalLM"),
     "Glm4MoeForCausalLM": ("deepseek", "Glm4MoeForCausalLM"),
     "DeepseekV3ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
 }
