@@ -275,8 +275,9 @@ def test_elastic_scale_up_and_down():
     assert grown[:3] == base and shrunk == base
 
 
-@pytest.mark.parametrize("backend,tp", [("allgather_reducescatter", 1), ("a2a", 1), ("a2a", 2)])
-def test_wide_expert_parallel_across_dp_replicas(backend, tp):
+@pytest.mark.parametrize("backend,tp,dbo", [("allgather_reducescatter", 1, False), ("a2a", 1, False), ("a2a", 2, False),
+                                            ("a2a", 1, True)])
+def test_wide_expert_parallel_across_dp_replicas(backend, tp, dbo):
     """DP=2 + --enable-expert-parallel: the experts are sharded over the two replicas (EP group = DP x TP), tokens are
     dispatched / combined across replicas, idle replicas run dummy batches in lock-step; outputs equal a single engine."""
     import asyncio
@@ -298,7 +299,7 @@ def test_wide_expert_parallel_across_dp_replicas(backend, tp):
                         max_num_batched_tokens=128, kv_cache_memory_bytes=8 << 20, data_parallel_size=2,
                         enable_expert_parallel=True, all2all_backend=backend, data_parallel_rpc_port=get_open_port(),
                         tensor_parallel_size=tp, distributed_executor_backend="mp" if tp > 1 else None,
-                        disable_log_stats=True)
+                        disable_log_stats=True, enable_dbo=dbo)
         eng = AsyncLLM.from_engine_args(ea)
         await eng.collective_rpc("load_model", kwargs={"weights": w})
         shards = [d["local_experts"] for d in await eng.collective_rpc("describe_model")]

@@ -51,8 +51,8 @@ class FusedMoE(nn.Module):
             from vllm_b200.parallel.all2all import All2AllManager
             self.ep = True
             ep_rank, ep_size = max(epg.rank_in_group, 0), epg.world_size
-            backend = get_current_vllm_config().parallel_config.all2all_backend
-            self.a2a = All2AllManager(epg, get_dp_group(), g, num_experts, backend)
+            pcfg = get_current_vllm_config().parallel_config
+            self.a2a = All2AllManager(epg, get_dp_group(), g, num_experts, pcfg.all2all_backend, pcfg.enable_dbo)
         dt = dtype or torch.get_default_dtype()
         # EPLB: ``num_redundant_experts`` extra physical slots hold replicas of hot experts; the router's logical ids
         # are mapped to physical slots per token, the slots are re-assigned (and their weights moved between ranks) by
