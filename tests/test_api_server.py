@@ -342,3 +342,137 @@ def test_realtime_transcription_websocket():
                 assert ws.receive_json()["type"] == "error"
     finally:
         engine.shutdown()
+
+
+@pytest.fixture()
+def mcp_server():
+    """A tiny MCP server (streamable HTTP transport): ``add`` answers as JSON, ``tools/list`` as an event stream."""
+    import threading
+    from aiohttp import web
+    from vllm_b200.utils import get_open_port
+    seen = []
+
+    async def handle(request):
+        msg = await request.json()
+        seen.append((msg.get("method"), request.headers.get("Mcp-Session-Id")))
+        m = msg.get("method")
+        if "id" not in msg:
+            return web.Response(status=202)
+        if m == "initialize":
+            res = {"protocolVersion": "2025-03-26", "capabilities": {"tools": {}}, "serverInfo": {"name": "calc", "version": "1"}}
+            return web.json_response({"jsonrpc": "2.0", "id": msg["id"], "result": res}, headers={"Mcp-Session-Id": "s-1"})
+        if m == "tools/list":
+            res = {"tools": [{"name": "add", "description": "add two ints", "inputSchema": {
+                "type": "object", "properties": {"a": {"type": "integer"}, "b": {"type": "integer"}}, "required": ["a", "b"]}},
+                {"name": "boom", "description": "always fails", "inputSchema": {"type": "object", "properties": {}}}]}
+            body = "event: message\ndata: " + json.dumps({"jsonrpc": "2.0", "id": msg["id"], "result": res}) + "\n\n"
+            return web.Response(text=body, content_type="text/event-stream")
+        if m == "tools/call":
+            p = msg["params"]
+            if p["name"] == "add":
+                res = {"content": [{"type": "text", "text": str(p["arguments"]["a"] + p["arguments"]["b"])}]}
+            else:
+                res = {"content": [{"type": "text", "text": "kaput"}], "isError": True}
+            return web.json_response({"jsonrpc": "2.0", "id": msg["id"], "result": res})
+        return web.json_response({"jsonrpc": "2.0", "id": msg["id"], "error": {"code": -32601, "message": "no such method"}})
+
+    port = get_open_port()
+    loop = asyncio.new_event_loop()
+    started = threading.Event()
+    runner_box = []
+
+    def run():
+        asyncio.set_event_loop(loop)
+        app = web.Application()
+        app.router.add_post("/mcp", handle)
+        runner = web.AppRunner(app)
+        loop.run_until_complete(runner.setup())
+        loop.run_until_complete(web.TCPSite(runner, "127.0.0.1", port).start())
+        runner_box.append(runner)
+        started.set()
+        loop.run_forever()
+    th = threading.Thread(target=run, daemon=True)
+    th.start()
+    assert started.wait(10)
+    yield f"http://127.0.0.1:{port}/mcp", seen
+    asyncio.run_coroutine_threadsafe(runner_box[0].cleanup(), loop).result(10)
+    loop.call_soon_threadsafe(loop.stop)
+    th.join(5)
+
+
+def test_mcp_client_and_tool_loop(mcp_server):
+    from vllm_b200.entrypoints.tool_server import MCPClient, MCPError, ToolServer, input_items_to_messages, run_tool_loop
+    url, seen = mcp_server
+
+    async def main():
+        c = MCPClient(url, "calc")
+        tools = await c.list_tools()
+        assert [t["name"] for t in tools] == ["add", "boom"] and c.server_info["name"] == "calc"
+        assert await c.call_tool("add", {"a": 2, "b": 40}) == "42"
+        with pytest.raises(MCPError, match="kaput"):
+            await c.call_tool("boom", {})
+        with pytest.raises(MCPError, match="no such method"):
+            await c.request("resources/list")
+        # the session id handed out by initialize is echoed afterwards
+        assert seen[0] == ("initialize", None) and all(sid == "s-1" for _, sid in seen[1:])
+
+        ts = ToolServer()
+        fns, route, items = await ts.resolve([
+            {"type": "mcp", "server_url": url, "server_label": "calc", "allowed_tools": ["add"]},
+            {"type": "function", "name": "get_weather", "parameters": {"type": "object", "properties": {}}}])
+        assert [f["function"]["name"] for f in fns] == ["add", "get_weather"] and list(route) == ["add"]
+        assert items == [{"type": "mcp_list_tools", "server_label": "calc", "tools": [
+            {"name": "add", "description": "add two ints", "input_schema": tools[0]["inputSchema"]}]}]
+
+        # a scripted model: asks for add(20, 22), then answers with the tool result
+        turns = []
+
+        async def chat(messages, tools):
+            turns.append([m["role"] for m in messages])
+            if messages[-1]["role"] != "tool":
+                return {"message": {"content": "", "tool_calls": [{"id": "c1", "type": "function", "function": {
+                    "name": "add", "arguments": json.dumps({"a": 20, "b": 22})}}]},
+                    "usage": {"prompt_tokens": 5, "completion_tokens": 3, "total_tokens": 8}}
+            return {"message": {"content": f"the sum is {messages[-1]['content']}"},
+                    "usage": {"prompt_tokens": 9, "completion_tokens": 4, "total_tokens": 13}}
+        msg, calls, usage = await run_tool_loop(chat, [{"role": "user", "content": "20+22?"}], fns, route)
+        assert msg["content"] == "the sum is 42" and usage["total_tokens"] == 21
+        assert turns == [["user"], ["user", "assistant", "tool"]]
+        assert [(c["type"], c["name"], c["output"], c["error"]) for c in calls] == [("mcp_call", "add", "42", None)]
+
+        # a call to a client-side function ends the loop with the call left for the client
+        async def chat2(messages, tools):
+            return {"message": {"content": "", "tool_calls": [{"id": "c2", "type": "function", "function": {
+                "name": "get_weather", "arguments": "{}"}}]}, "usage": None}
+        msg, calls, _ = await run_tool_loop(chat2, [{"role": "user", "content": "weather?"}], fns, route)
+        assert calls == [] and msg["tool_calls"][0]["function"]["name"] == "get_weather"
+    asyncio.run(main())
+    msgs = input_items_to_messages([
+        {"role": "user", "content": [{"type": "input_text", "text": "weather?"}]},
+        {"type": "function_call", "call_id": "c2", "name": "get_weather", "arguments": "{}"},
+        {"type": "function_call_output", "call_id": "c2", "output": "sunny"}])
+    assert [m["role"] for m in msgs] == ["user", "assistant", "tool"]
+    assert msgs[1]["tool_calls"][0]["id"] == "c2" and msgs[2] == {"role": "tool", "tool_call_id": "c2", "content": "sunny"}
+
+
+def test_responses_api_with_mcp_tools(server, mcp_server):
+    client, call, _ = server
+    url, seen = mcp_server
+    body = {"model": "llama-tiny", "input": "add 1 and 2", "max_output_tokens": 8, "temperature": 0.0, "store": True,
+            "tools": [{"type": "mcp", "server_url": url, "server_label": "calc"}]}
+    r = call(client.post("/v1/responses", json=body))
+    assert r.status_code == 200, r.text
+    d = r.json()
+    kinds = [o["type"] for o in d["output"]]
+    assert kinds[0] == "mcp_list_tools" and kinds[-1] == "message" and d["status"] == "completed"
+    assert [t["name"] for t in d["output"][0]["tools"]] == ["add", "boom"]
+    assert d["usage"]["output_tokens"] == 8 and ("tools/list", "s-1") in seen
+    assert call(client.get(f"/v1/responses/{d['id']}")).json()["id"] == d["id"]
+    # streaming variant: typed events, one added/done pair per output item
+    r = call(client.post("/v1/responses", json=dict(body, stream=True)))
+    evs = [l.split(": ", 1)[1] for l in r.text.splitlines() if l.startswith("event: ")]
+    assert evs[0] == "response.created" and evs[-1] == "response.completed"
+    assert evs.count("response.output_item.added") == evs.count("response.output_item.done") == 2
+    # an unreachable tool server is a dependency failure, not a 500
+    bad = dict(body, tools=[{"type": "mcp", "server_url": "http://127.0.0.1:9/mcp", "server_label": "x"}])
+    assert call(client.post("/v1/responses", json=bad)).status_code == 424

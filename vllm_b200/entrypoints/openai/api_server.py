@@ -54,6 +54,7 @@ class ServingContext:
         self.chat_template = chat_template
         self.inflight = 0
         self.responses_store: dict[str, dict] = {}
+        self.tool_server = None                       # entrypoints/tool_server.ToolServer (``--tool-server``)
         self.lora_ids: dict[str, int] = {}
         self.lora_requests: dict[str, Any] = {}       # adapter name (usable as `model`) → LoRARequest
 
@@ -812,6 +813,78 @@ def build_app(ctx: ServingContext):
             st["response"]["status"] = "cancelled"
         return st.get("response", {"id": response_id, "status": "cancelled"})
 
+    async def _responses_with_tools(req, raw, msgs, rid):
+        """Function tools are handed to the model and its calls returned as ``function_call`` items for the client to
+        run; MCP tools (request ``{"type": "mcp"}`` entries and ``--tool-server``) are run here, their results fed
+        back, until the model answers (reference: openai/responses/serving.py tool loop)."""
+        from vllm_b200.entrypoints.tool_server import MCPError, ToolServer, run_tool_loop
+        ts = ctx.tool_server or ToolServer()
+        try:
+            fns, route, items = await ts.resolve(req.tools)
+        except (MCPError, OSError, KeyError) as e:
+            return _error(f"tool server: {e}", 424, "FailedDependencyError")
+        failure = []
+
+        async def chat_once(messages, tools):
+            c = P.ChatCompletionRequest(messages=messages, max_tokens=req.max_output_tokens, temperature=req.temperature,
+                                        top_p=req.top_p, stream=False, tools=tools or None,
+                                        tool_choice=(req.tool_choice or "auto") if tools else "none")
+            res = await chat(c, raw)
+            if not isinstance(res, dict):
+                failure.append(res)
+                return {"message": {"content": ""}, "usage": None}
+            return {"message": res["choices"][0]["message"], "usage": res["usage"]}
+        created = int(time.time())
+        msg, calls, u = await run_tool_loop(chat_once, msgs, fns, route, max_turns=req.max_tool_calls or 8)
+        if failure:
+            return failure[0]
+        output = items + calls
+        for c in msg.get("tool_calls") or []:
+            output.append({"type": "function_call", "id": f"fc_{random_uuid()}", "call_id": c["id"], "status": "completed",
+                           "name": c["function"]["name"], "arguments": c["function"].get("arguments") or "{}"})
+        text = msg.get("content") or ""
+        if msg.get("reasoning_content"):
+            output.append({"type": "reasoning", "id": f"rs_{random_uuid()}", "summary": [],
+                           "content": [{"type": "reasoning_text", "text": msg["reasoning_content"]}]})
+        if text or not msg.get("tool_calls"):
+            output.append({"type": "message", "id": f"msg_{random_uuid()}", "role": "assistant", "status": "completed",
+                           "content": [{"type": "output_text", "text": text, "annotations": []}]})
+        out = {"id": rid, "object": "response", "created_at": created, "status": "completed", "model": ctx.model_name,
+               "output": output, "output_text": text, "tools": req.tools or [],
+               "usage": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"],
+                         "total_tokens": u["total_tokens"]}}
+        if req.store:
+            hist = msgs + [{"role": "assistant", "content": text, **({"tool_calls": msg["tool_calls"]}
+                                                                       if msg.get("tool_calls") else {})}]
+            ctx.responses_store[rid] = {"messages": hist, "response": out}
+        if not req.stream:
+            return out
+
+        async def events():
+            seq = 0
+
+            def ev(typ, **kw):
+                nonlocal seq
+                seq += 1
+                return _sse_event(typ, dict(kw, sequence_number=seq))
+            shell = dict(out, status="in_progress", output=[], output_text="")
+            yield ev("response.created", response=shell)
+            yield ev("response.in_progress", response=shell)
+            for i, item in enumerate(output):
+                yield ev("response.output_item.added", output_index=i, item=item)
+                if item["type"] == "mcp_call":
+                    yield ev("response.mcp_call.completed" if not item["error"] else "response.mcp_call.failed",
+                             output_index=i, item_id=item["id"])
+                elif item["type"] == "function_call":
+                    yield ev("response.function_call_arguments.done", output_index=i, item_id=item["id"],
+                             arguments=item["arguments"])
+                elif item["type"] == "message":
+                    yield ev("response.output_text.delta", item_id=item["id"], output_index=i, content_index=0, delta=text)
+                    yield ev("response.output_text.done", item_id=item["id"], output_index=i, content_index=0, text=text)
+                yield ev("response.output_item.done", output_index=i, item=item)
+            yield ev("response.completed", response=out)
+        return StreamingResponse(events(), media_type="text/event-stream")
+
     @app.post("/v1/responses")
     async def responses(req: P.ResponsesRequest, raw: Request):
         msgs: list[dict] = []
@@ -822,14 +895,13 @@ def build_app(ctx: ServingContext):
         if isinstance(req.input, str):
             msgs.append({"role": "user", "content": req.input})
         else:
-            for item in req.input:
-                c = item.get("content")
-                if isinstance(c, list):
-                    c = "".join(p.get("text", "") for p in c if isinstance(p, dict))
-                msgs.append({"role": item.get("role", "user"), "content": c})
+            from vllm_b200.entrypoints.tool_server import input_items_to_messages
+            msgs += input_items_to_messages(req.input)
         creq = P.ChatCompletionRequest(messages=msgs, max_tokens=req.max_output_tokens, temperature=req.temperature,
                                        top_p=req.top_p, stream=False)
         rid = f"resp_{random_uuid()}"
+        if req.tools or ctx.tool_server is not None:
+            return await _responses_with_tools(req, raw, msgs, rid)
 
         def build(text: str, usage: Optional[dict], status: str, created: int, mid: str) -> dict:
             u = usage or {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}
@@ -1102,6 +1174,8 @@ def make_arg_parser() -> argparse.ArgumentParser:
     ap.add_argument("--chat-template", default=None)
     ap.add_argument("--enable-auto-tool-choice", action="store_true")
     ap.add_argument("--tool-call-parser", default=None)
+    ap.add_argument("--tool-server", default=None,
+                    help="comma-separated MCP server URLs whose tools every Responses-API request may use")
     ap.add_argument("--uvicorn-log-level", default="warning")
     ap.add_argument("--api-server-count", type=int, default=1)
     ap.add_argument("--headless", action="store_true", help="engine cores only; connect to a remote front-end")
@@ -1131,6 +1205,9 @@ async def run_server(args: argparse.Namespace) -> None:
                          reasoning_parser=ea.reasoning_parser or None, enable_auto_tools=args.enable_auto_tool_choice,
                          chat_template=template)
     ctx.log_requests = bool(getattr(args, "enable_log_requests", False))
+    if getattr(args, "tool_server", None):
+        from vllm_b200.entrypoints.tool_server import ToolServer
+        ctx.tool_server = ToolServer([u for u in args.tool_server.split(",") if u])
     app = build_app(ctx)
     config = uvicorn.Config(app, host=args.host, port=args.port, log_level=args.uvicorn_log_level)
     server = uvicorn.Server(config)

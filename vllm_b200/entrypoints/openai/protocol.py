@@ -354,6 +354,8 @@ class ResponsesRequest(OpenAIBase):
     top_p: Optional[float] = None
     stream: bool = False
     tools: Optional[list[dict[str, Any]]] = None
+    tool_choice: Optional[Union[str, dict[str, Any]]] = None
+    max_tool_calls: Optional[int] = None
     previous_response_id: Optional[str] = None
     store: bool = False
 
