@@ -1001,3 +1001,37 @@ def test_cascade_attention_shared_prefix(monkeypatch):
     got, used1 = run()
     assert used0 == 0 and used1 > 0
     assert got == ref
+
+
+def test_video_content_parts_decode(tmp_path):
+    """video_url parts: a base64 JPEG frame list, an OpenCV-decoded container, and an .npy frame array."""
+    import base64
+    import io
+    import numpy as np
+    from PIL import Image
+    from vllm_b200.entrypoints.chat_utils import chat_multi_modal_data, load_video, sample_frame_indices
+    assert sample_frame_indices(10, 4) == [0, 3, 6, 9] and sample_frame_indices(3, 8) == [0, 1, 2]
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 255, (6, 32, 48, 3), dtype=np.uint8)
+    enc = []
+    for f in frames:
+        b = io.BytesIO()
+        Image.fromarray(f).save(b, format="PNG")
+        enc.append(base64.b64encode(b.getvalue()).decode())
+    v = load_video("data:video/png;base64," + ",".join(enc), num_frames=3)
+    assert v.shape == (3, 32, 48, 3) and (v[0] == frames[0]).all() and (v[-1] == frames[5]).all()
+    np.save(tmp_path / "clip.npy", frames)
+    assert (load_video(f"file://{tmp_path}/clip.npy", 32) == frames).all()
+    cv2 = pytest.importorskip("cv2")
+    path = str(tmp_path / "clip.avi")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 4.0, (48, 32))
+    if w.isOpened():
+        for f in frames:
+            w.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+        w.release()
+        got = load_video("file://" + path, num_frames=4)
+        assert got.shape == (4, 32, 48, 3)
+    mm = chat_multi_modal_data([{"role": "user", "content": [
+        {"type": "text", "text": "what happens?"},
+        {"type": "video_url", "video_url": {"url": "data:video/png;base64," + ",".join(enc)}, "num_frames": 2}]}])
+    assert list(mm) == ["video"] and mm["video"][0].shape == (2, 32, 48, 3)

@@ -266,6 +266,46 @@ def test_qwen2_vl_matches_hf(gen):
     assert outs[1].outputs[0].token_ids == ref_txt
 
 
+@pytest.mark.parametrize("gen", ["qwen2vl-tiny", "qwen25vl-tiny"])
+def test_qwen2_vl_video_matches_hf(gen):
+    """Video input: frames are grouped into temporal patches, each temporal patch attends within itself in the ViT, and
+    the placeholders get (t, h, w) M-RoPE ids (Qwen2.5-VL: t stretched by seconds-per-patch x tokens_per_second)."""
+    import numpy as np
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config(gen)
+    is25 = gen == "qwen25vl-tiny"
+    text_keys = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                 "num_key_value_heads", "max_position_embeddings", "rms_norm_eps", "hidden_act", "tie_word_embeddings")
+    tc = {k: cfg[k] for k in text_keys}
+    tc["rope_parameters"] = {"rope_type": "default", "rope_theta": cfg["rope_theta"], "mrope_section": [2, 3, 3]}
+    CfgCls = transformers.Qwen2_5_VLConfig if is25 else transformers.Qwen2VLConfig
+    ModelCls = transformers.Qwen2_5_VLForConditionalGeneration if is25 else transformers.Qwen2VLForConditionalGeneration
+    hf_cfg = CfgCls(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500,
+                    video_token_id=501, vision_start_token_id=502, vision_end_token_id=503)
+    torch.manual_seed(0)
+    hf = ModelCls(hf_cfg).float().eval()
+    rng = np.random.default_rng(1)
+    vid = rng.integers(0, 255, (6, 84, 112, 3) if is25 else (4, 56, 84, 3), dtype=np.uint8)
+    vp = transformers.Qwen2VLVideoProcessor(size={"shortest_edge": 56 * 56, "longest_edge": 28 * 28 * 1280})
+    px = vp(videos=[torch.from_numpy(vid).permute(0, 3, 1, 2)], return_tensors="pt", do_sample_frames=False)
+    n_vid = int(px["video_grid_thw"][0].prod()) // 4
+    pre, post = [5, 17, 99, 502], [503, 3, 250, 41, 7]
+    ids_hf = pre + [501] * n_vid + post
+    kw = {"second_per_grid_ts": torch.tensor([0.5])} if is25 else {}
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([ids_hf]), attention_mask=torch.ones(1, len(ids_hf), dtype=torch.long),
+                          pixel_values_videos=px["pixel_values_videos"], video_grid_thw=px["video_grid_thw"],
+                          max_new_tokens=8, do_sample=False, pad_token_id=0, eos_token_id=None, **kw)[0, len(ids_hf):].tolist()
+    llm = make_llm(gen, weights=hf.state_dict().items(), enable_prefix_caching=False,
+                   hf_overrides={"video_token_id": 501})
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    mm = {"video": vid, "fps": 4.0} if is25 else {"video": [f for f in vid]}      # 2 frames / 4 fps = 0.5 s per patch
+    outs = llm.generate([{"prompt_token_ids": pre + [501] + post, "multi_modal_data": mm}], sp)
+    llm.shutdown()
+    assert outs[0].outputs[0].token_ids == ref, (outs[0].outputs[0].token_ids, ref)
+
+
 def test_decoder_pooling_adapters_match_hf():
     """A registered decoder as (a) sequence classifier: last-token state → score head → softmax == HF
     LlamaForSequenceClassification; (b) embedding model loaded from a bare ``LlamaModel`` checkpoint."""

@@ -19,7 +19,7 @@ def _flatten_content(messages: list[dict]) -> tuple[list[dict], list[Any]]:
                 t = part.get("type")
                 if t == "text":
                     texts.append(part.get("text", ""))
-                elif t in ("image_url", "image", "audio_url", "video_url", "input_audio"):
+                elif t in ("image_url", "image", "audio_url", "video_url", "video", "input_audio"):
                     mm.append(part)
                     texts.append("<image>" if "image" in t else f"<{t.split('_')[0]}>")
             m = {**m, "content": "\n".join(texts)}
@@ -78,10 +78,86 @@ def load_mm_item(part: dict) -> Any:
             import requests
             return Image.open(io.BytesIO(requests.get(url, timeout=10).content)).convert("RGB")
         raise ValueError("remote media URLs are disabled (use a data: URL, file://, or set VLLM_ALLOW_REMOTE_MEDIA=1)")
+    if t == "video" and part.get("video") is not None:
+        return part["video"]
+    if t == "video_url":
+        url = part["video_url"]["url"] if isinstance(part["video_url"], dict) else part["video_url"]
+        return load_video(url, int(part.get("num_frames") or os.environ.get("VLLM_B200_VIDEO_FRAMES", 32)))
     raise ValueError(f"unsupported multimodal content part type {t!r}")
 
 
+def sample_frame_indices(total: int, num_frames: int) -> list[int]:
+    """Uniformly spaced frame indices (reference: multimodal/video.py ``OpenCVVideoBackend`` sampling)."""
+    if num_frames <= 0 or total <= num_frames:
+        return list(range(total))
+    import numpy as np
+    return np.linspace(0, total - 1, num_frames).round().astype(int).tolist()
+
+
+def load_video(url: str, num_frames: int = 32):
+    """→ uint8 array [T, H, W, 3].  Accepted: ``data:video/jpeg;base64,<frame>,<frame>,...`` (a list of encoded
+    frames), ``data:video/<container>;base64,...`` / ``file://`` containers decoded with OpenCV, ``.npy`` frame arrays."""
+    import base64
+    import io
+    import os
+    import tempfile
+    import numpy as np
+    if url.startswith("data:video/jpeg") or url.startswith("data:video/png"):
+        from PIL import Image
+        frames = [np.asarray(Image.open(io.BytesIO(base64.b64decode(f))).convert("RGB"))
+                  for f in url.split(",")[1:] if f]
+        idx = sample_frame_indices(len(frames), num_frames)
+        return np.stack([frames[i] for i in idx])
+    tmp = None
+    if url.startswith("data:"):
+        tmp = tempfile.NamedTemporaryFile(suffix="." + url[5:url.index(";")].split("/")[-1], delete=False)
+        tmp.write(base64.b64decode(url.split(",", 1)[1]))
+        tmp.close()
+        path = tmp.name
+    elif url.startswith("file://"):
+        path = url[len("file://"):]
+    else:
+        raise ValueError("remote video URLs are disabled (use a data: URL or file://)")
+    try:
+        if path.endswith(".npy"):
+            arr = np.load(path)
+            return arr[sample_frame_indices(arr.shape[0], num_frames)]
+        import cv2
+        cap = cv2.VideoCapture(path)
+        if not cap.isOpened():
+            raise ValueError(f"cannot decode video {path!r}")
+        total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        want = set(sample_frame_indices(total, num_frames)) if total > 0 else None
+        frames, i = [], 0
+        while True:
+            ok = cap.grab()
+            if not ok:
+                break
+            if want is None or i in want:
+                ok, fr = cap.retrieve()
+                if ok:
+                    frames.append(cv2.cvtColor(fr, cv2.COLOR_BGR2RGB))
+            i += 1
+        cap.release()
+        if not frames:
+            raise ValueError(f"video {path!r} has no decodable frames")
+        if want is None:
+            frames = [frames[j] for j in sample_frame_indices(len(frames), num_frames)]
+        return np.stack(frames)
+    finally:
+        if tmp is not None:
+            os.unlink(tmp.name)
+
+
 def chat_multi_modal_data(messages: list[dict]) -> Optional[dict]:
-    """``{"image": [...]}`` for the image parts of a conversation, in order of appearance (None if there are none)."""
-    items = [load_mm_item(p) for p in extract_mm_items(messages) if "image" in p.get("type", "")]
-    return {"image": items} if items else None
+    """``{"image": [...], "video": [...]}`` for the media parts of a conversation, in order of appearance (None if
+    there are none)."""
+    parts = extract_mm_items(messages)
+    out: dict[str, list] = {}
+    for p in parts:
+        t = p.get("type", "")
+        if "image" in t:
+            out.setdefault("image", []).append(load_mm_item(p))
+        elif "video" in t:
+            out.setdefault("video", []).append(load_mm_item(p))
+    return out or None

@@ -28,12 +28,14 @@ class _VisionBlock(nn.Module):
         self.qkv, self.proj = nn.Linear(D, 3 * D, dtype=dtype), nn.Linear(D, D, dtype=dtype)
         self.fc1, self.fc2 = nn.Linear(D, mlp, dtype=dtype), nn.Linear(mlp, D, dtype=dtype)
 
-    def forward(self, x, cos, sin):                                # x [N, D] patches of ONE image
+    def forward(self, x, cos, sin, frames: int = 1):               # x [N, D] patches of ONE image / video
         N, D = x.shape
         q, k, v = self.qkv(self.norm1(x)).view(N, 3, self.nh, D // self.nh).unbind(1)
         q = (q.float() * cos + _rot_half(q.float()) * sin).to(x.dtype)
         k = (k.float() * cos + _rot_half(k.float()) * sin).to(x.dtype)
-        a = F.scaled_dot_product_attention(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1)).transpose(0, 1)
+        # every temporal patch attends within itself: [frames, heads, N/frames, hd]
+        q, k, v = (t.reshape(frames, N // frames, self.nh, -1).transpose(1, 2) for t in (q, k, v))
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2)
         x = x + self.proj(a.reshape(N, D))
         h = self.fc1(self.norm2(x))
         return x + self.fc2(h * torch.sigmoid(1.702 * h))          # quick_gelu
@@ -70,7 +72,7 @@ class Qwen2VisionTransformer(nn.Module):
         x = self.patch_embed(patches.to(self.patch_embed.weight.dtype))
         cos, sin = self._rope(grid)
         for b in self.blocks:
-            x = b(x, cos, sin)
+            x = b(x, cos, sin, grid[0])
         x = self.ln_q(x).view(-1, x.shape[-1] * self.merge ** 2)
         return self.merger_fc2(F.gelu(self.merger_fc1(x)))
 
@@ -189,12 +191,13 @@ class Qwen2_5_VisionTransformer(nn.Module):
         N, unit = x.shape[0], self.merge ** 2
         order, wbounds = self._windows(grid)
         order = order.to(x.device)
+        fbounds = [f * (N // grid[0]) for f in range(grid[0] + 1)]          # "full" attention is per temporal patch
         # the patch sequence is already in merge-block order: reorder whole 2x2 units by window
         x = x.view(N // unit, unit, -1)[order].reshape(N, -1)
         cos = cos.view(N // unit, unit, *cos.shape[1:])[order].reshape(N, *cos.shape[1:])
         sin = sin.view(N // unit, unit, *sin.shape[1:])[order].reshape(N, *sin.shape[1:])
         for i, b in enumerate(self.blocks):
-            x = b(x, cos, sin, [0, N] if i in self.full_blocks else wbounds)
+            x = b(x, cos, sin, fbounds if i in self.full_blocks else wbounds)
         x = self.ln_q(x).view(-1, x.shape[-1] * unit)
         x = self.merger_fc2(F.gelu(self.merger_fc1(x)))
         return x[torch.argsort(order)]
