@@ -384,3 +384,33 @@ def test_eplb_redundant_experts_and_runtime_rebalance():
     again = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
     llm.shutdown()
     assert again == ref
+
+
+def test_ray_executor_with_stub_cluster():
+    """The ray executor drives Worker actors through placement-group scheduling; with an in-process stand-in for the
+    ray API the whole engine runs through it and matches the in-process executor."""
+    from tests import fake_ray
+    from tests.utils import make_llm
+    from vllm_b200 import SamplingParams
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 8]}, {"prompt_token_ids": list(range(10, 30))}]
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny")
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    names = fake_ray.install()
+    try:
+        llm = make_llm("llama-tiny", distributed_executor_backend="ray")
+        ex = llm.llm_engine.engine_core.engine_core.model_executor
+        assert type(ex).__name__ == "RayExecutor" and ex.node_ips == ["127.0.0.1"]
+        pg = fake_ray.STATE["pgs"][0]
+        assert pg.strategy == "PACK" and pg.bundles == [{"CPU": 1.0}]
+        assert fake_ray.STATE["actors"][0][1]["scheduling_strategy"].index == 0
+        got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+        assert ex.collective_rpc("check_health") == [True]
+        llm.shutdown()
+        assert got == ref and fake_ray.STATE["killed"] == 1
+    finally:
+        fake_ray.uninstall(names)
+    # without ray installed the backend fails with an actionable message
+    with pytest.raises(ImportError, match="ray executor needs"):
+        make_llm("llama-tiny", distributed_executor_backend="ray")

@@ -38,6 +38,9 @@ class Executor:
             return MultiprocExecutor
         if b == "external_launcher":
             return ExternalLauncherExecutor
+        if b == "ray":
+            from vllm_b200.executor.ray_executor import RayExecutor
+            return RayExecutor
         raise ValueError(f"unknown distributed_executor_backend {b!r}")
 
     def _init_executor(self) -> None:
