@@ -17,6 +17,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+os.environ.setdefault("VLLM_B200_NO_USAGE_STATS", "1")
 import statistics
 import subprocess
 import sys

@@ -1035,3 +1035,82 @@ def test_video_content_parts_decode(tmp_path):
         {"type": "text", "text": "what happens?"},
         {"type": "video_url", "video_url": {"url": "data:video/png;base64," + ",".join(enc)}, "num_frames": 2}]}])
     assert list(mm) == ["video"] and mm["video"][0].shape == (2, 32, 48, 3)
+
+
+def test_streaming_safetensors_loader(tmp_path):
+    """--load-format streamer: concurrent positional reads with a bounded in-flight window return exactly the tensors
+    of the checkpoint (all dtypes, multi-chunk tensors, several files) and load a model identically."""
+    from safetensors.torch import save_file
+    from tests.utils import make_hf_model, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.model_loader import streamer
+    torch.manual_seed(0)
+    a = {"w.big": torch.randn(700, 1000), "w.bf16": torch.randn(33, 7).bfloat16(), "w.i64": torch.arange(11),
+         "w.fp8": torch.randn(16, 16).to(torch.float8_e4m3fn), "w.empty": torch.zeros(0, 4), "w.bool": torch.tensor([True, False])}
+    b = {"v.x": torch.randn(5, 5).half()}
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    save_file(a, str(d / "model-00001-of-00002.safetensors"))
+    save_file(b, str(d / "model-00002-of-00002.safetensors"))
+    old = streamer._CHUNK
+    streamer._CHUNK = 64 << 10                     # force the big tensor through many chunked reads
+    try:
+        stats = {}
+        got = dict(streamer.stream_safetensors(str(d), concurrency=8, memory_limit=1 << 20, stats=stats))
+    finally:
+        streamer._CHUNK = old
+    ref = {**a, **b}
+    assert set(got) == set(ref) and stats["tensors"] == len(ref)
+    for k, v in ref.items():
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape
+        assert torch.equal(got[k].view(torch.uint8) if v.dtype == torch.float8_e4m3fn else got[k],
+                           v.view(torch.uint8) if v.dtype == torch.float8_e4m3fn else v)
+    assert stats["max_in_flight"] <= max(1 << 20, a["w.big"].numel() * 4)
+    # end to end: a saved HF checkpoint served through the streaming loader
+    hf = make_hf_model("llama-tiny")
+    m = tmp_path / "llama"
+    hf.save_pretrained(str(m), safe_serialization=True)
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    p = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41]}]
+    outs = {}
+    for fmt in ("safetensors", "streamer"):
+        llm = make_llm(str(m), load_format=fmt, model_loader_extra_config={"concurrency": 4} if fmt == "streamer" else None)
+        outs[fmt] = llm.generate(p, sp)[0].outputs[0].token_ids
+        llm.shutdown()
+    assert outs["streamer"] == outs["safetensors"]
+
+
+def test_usage_stats_record_and_opt_out(tmp_path, monkeypatch):
+    import json
+    import os
+    from tests.utils import make_llm
+    from vllm_b200 import usage
+    monkeypatch.setenv("VLLM_B200_CONFIG_ROOT", str(tmp_path))
+    monkeypatch.setenv("VLLM_B200_NO_USAGE_STATS", "1")
+    assert not usage.is_usage_stats_enabled()
+    monkeypatch.setenv("VLLM_B200_NO_USAGE_STATS", "0")
+    assert usage.is_usage_stats_enabled()
+    (tmp_path / "do_not_track").write_text("")
+    assert not usage.is_usage_stats_enabled()
+    (tmp_path / "do_not_track").unlink()
+    monkeypatch.setenv("DO_NOT_TRACK", "1")
+    assert not usage.is_usage_stats_enabled()
+    monkeypatch.delenv("DO_NOT_TRACK")
+    llm = make_llm("llama-tiny")
+    msg = usage.UsageMessage()
+    usage.set_runtime_usage_data("api", "completions")
+    assert msg.report_usage(llm.llm_engine.vllm_config, "LLM_CLASS", heartbeat_s=0.05)
+    import time
+    deadline = time.time() + 5
+    while time.time() < deadline and (not os.path.exists(msg.path) or open(msg.path).read().count(msg.uuid) < 2):
+        time.sleep(0.02)
+    msg.stop()
+    llm.shutdown()
+    every = [json.loads(l) for l in open(msg.path).read().splitlines()]
+    assert any(r["uuid"] != msg.uuid and r.get("context") == "LLM_CLASS" for r in every)     # the engine's own record
+    lines = [r for r in every if r["uuid"] == msg.uuid]
+    first = lines[0]
+    assert first["model_architecture"] == "LlamaForCausalLM" and first["context"] == "LLM_CLASS"
+    assert first["tensor_parallel_size"] == 1 and first["gpu_count"] == 0 and first["uuid"] == msg.uuid
+    assert lines[1]["api"] == "completions" and lines[1]["uuid"] == msg.uuid
+    assert "prompt" not in json.dumps(first)            # configuration facts only, never request content

@@ -172,7 +172,8 @@ class DeviceConfig(_ConfigBase):
 class LoadConfig(_ConfigBase):
     """Reference: model_executor/model_loader (dummy loader: weight_utils.py:1289-1349)."""
 
-    load_format: str = "auto"  # auto|safetensors|pt|dummy|sharded_state
+    load_format: str = "auto"  # auto|safetensors|pt|dummy|sharded_state|gguf|streamer (runai_streamer)
+    model_loader_extra_config: Optional[dict] = None       # streamer: {"concurrency": 16, "memory_limit": bytes}
     download_dir: Optional[str] = None
     dummy_seed: int = 1234
     ignore_patterns: list[str] = field(default_factory=list)

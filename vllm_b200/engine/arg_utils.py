@@ -35,6 +35,7 @@ class EngineArgs:
     hf_overrides: Optional[dict[str, Any]] = None
     runner: str = "generate"
     load_format: str = "auto"
+    model_loader_extra_config: Optional[dict[str, Any]] = None
     device: str = "auto"
     # cache
     block_size: Optional[int] = None      # default: 64 (tcgen05 attention page) when head_dim is 128, else 32
@@ -160,7 +161,8 @@ class EngineArgs:
         kve = KVEventsConfig(**self.kv_events_config) if self.kv_events_config else None
         return VllmConfig(
             model_config=mc, cache_config=cc, parallel_config=pc, scheduler_config=sc,
-            device_config=DeviceConfig(self.device), load_config=LoadConfig(load_format=self.load_format),
+            device_config=DeviceConfig(self.device), load_config=LoadConfig(load_format=self.load_format,
+                                   model_loader_extra_config=self.model_loader_extra_config),
             lora_config=LoRAConfig(self.max_lora_rank, self.max_loras) if self.enable_lora else None,
             speculative_config=spec,
             structured_outputs_config=StructuredOutputsConfig(self.structured_outputs_backend,

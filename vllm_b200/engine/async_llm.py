@@ -46,6 +46,8 @@ class AsyncLLM:
         self.output_handler: Optional[asyncio.Task] = None
         self._errored_with: Optional[BaseException] = None
         self._paused = False
+        from vllm_b200.usage import usage_message
+        usage_message.report_usage(vllm_config, "OPENAI_API_SERVER")
 
     @classmethod
     def from_engine_args(cls, engine_args: EngineArgs, **kw) -> "AsyncLLM":

@@ -41,6 +41,8 @@ class LLMEngine:
         if log_stats:
             from vllm_b200.metrics import StatLoggerManager
             self.stat_logger = StatLoggerManager(vllm_config, stat_loggers)
+        from vllm_b200.usage import usage_message
+        usage_message.report_usage(vllm_config, "LLM_CLASS")
 
     @classmethod
     def from_engine_args(cls, engine_args: EngineArgs, **kw) -> "LLMEngine":

@@ -66,8 +66,13 @@ def _iter_pt(path: str) -> Iterator[tuple[str, torch.Tensor]]:
         del sd
 
 
-def iter_weights(path: str, load_format: str = "auto") -> Iterator[tuple[str, torch.Tensor]]:
+def iter_weights(path: str, load_format: str = "auto", extra: Optional[dict] = None) -> Iterator[tuple[str, torch.Tensor]]:
     has_st = bool(glob.glob(os.path.join(path, "*.safetensors")))
+    if load_format in ("streamer", "runai_streamer", "runai_streamer_sharded"):
+        from vllm_b200.model_loader.streamer import stream_safetensors
+        extra = extra or {}
+        return stream_safetensors(path, int(extra.get("concurrency", os.environ.get("VLLM_B200_STREAMER_THREADS", 16))),
+                                  extra.get("memory_limit"), pin_memory=torch.cuda.is_available())
     if load_format == "safetensors" or (load_format == "auto" and has_st):
         return _iter_safetensors(path)
     return _iter_pt(path)
@@ -108,7 +113,7 @@ def get_model(vllm_config: VllmConfig, device: torch.device,
             from vllm_b200.model_loader.sharded_state import load_sharded_state
             load_sharded_state(model, mc.model)
         else:
-            loaded = model.load_weights(_wrap(iter_weights(mc.model, fmt)))
+            loaded = model.load_weights(_wrap(iter_weights(mc.model, fmt, getattr(lc, 'model_loader_extra_config', None))))
             missing = {n for n, _ in model.named_parameters()} - set(loaded)
             missing = {m for m in missing if "lm_head" not in m}
             if missing:
