@@ -1114,3 +1114,32 @@ def test_usage_stats_record_and_opt_out(tmp_path, monkeypatch):
     assert first["tensor_parallel_size"] == 1 and first["gpu_count"] == 0 and first["uuid"] == msg.uuid
     assert lines[1]["api"] == "completions" and lines[1]["uuid"] == msg.uuid
     assert "prompt" not in json.dumps(first)            # configuration facts only, never request content
+
+
+def test_sparsemixer_routing_matches_hf():
+    """The Phi-3.5-MoE router (threshold-masked sequential top-2) equals transformers' ``sparsemixer`` in eval mode, and
+    FusedMoE uses a plugged-in router instead of softmax top-k."""
+    from transformers.models.phimoe.modeling_phimoe import sparsemixer
+    from vllm_b200.layers.moe import sparsemixer_routing
+    torch.manual_seed(0)
+    logits = torch.randn(64, 16) * 2
+    logits[0, :2] = torch.tensor([3.0, 2.999])          # near tie: both survive the first mask
+    w_ref, ids_ref = sparsemixer(logits.clone(), jitter_eps=0.01, training=False)
+    w, ids = sparsemixer_routing(0.01)(logits, 2)
+    assert torch.equal(ids.long(), ids_ref) and torch.allclose(w, w_ref, atol=1e-6)
+    from tests.utils import make_llm
+    llm = make_llm("mixtral-tiny")
+    model = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    moe = model.model.layers[0].block_sparse_moe.experts
+    x = torch.randn(5, moe.w13_weight.shape[-1])
+    rl = torch.randn(5, 4)
+    base = moe(x, rl)
+    moe.custom_routing = sparsemixer_routing(0.01)
+    other = moe(x, rl)
+    moe.custom_routing = lambda l, k: (torch.softmax(l.float(), -1).topk(k)[0] / torch.softmax(l.float(), -1).topk(k)[0].sum(-1, keepdim=True),
+                                       torch.softmax(l.float(), -1).topk(k)[1].to(torch.int32))
+    same = moe(x, rl)
+    llm.shutdown()
+    scale = base.abs().max().item() + 1e-30
+    assert (same - base).abs().max().item() / scale < 1e-4           # plug-in reproducing softmax top-k renormalised
+    assert (other - base).abs().max().item() / scale > 1e-3          # sparsemixer weights differ from it

@@ -36,6 +36,7 @@ class FusedMoE(nn.Module):
         self.renormalize = renormalize
         self.use_grouped_topk, self.n_group, self.topk_group = use_grouped_topk, n_group, topk_group
         self.scoring_func, self.routed_scaling_factor = scoring_func, routed_scaling_factor
+        self.custom_routing = None          # optional ``fn(router_logits, top_k) -> (weights fp32 [T,k], ids [T,k])``
         self.act = act
         self.reduce_results = reduce_results
         self.ep = enable_ep and self.tp_size > 1
@@ -118,6 +119,8 @@ class FusedMoE(nn.Module):
 
     # ------------------------------------------------------------ routing
     def select_experts(self, router_logits: torch.Tensor):
+        if self.custom_routing is not None:                      # model-specific router, e.g. ``sparsemixer_routing``
+            return self.custom_routing(router_logits, self.top_k)
         if self.use_grouped_topk:
             return ops.grouped_topk(router_logits, self.top_k, self.n_group, self.topk_group, self.renormalize,
                                     self.scoring_func, self.e_score_correction_bias, self.routed_scaling_factor)
@@ -294,3 +297,23 @@ def make_expert_params_mapping(gate_name: str, down_name: str, up_name: str, num
             pname = f"{prefix}.w2_weight" if shard == "w2" else f"{prefix}.w13_weight"
             out.append((pname, f"{prefix}.{e}.{ck}.weight", e, shard))
     return out
+
+
+def sparsemixer_routing(jitter_eps: float = 0.01):
+    """Phi-3.5-MoE router at inference (reference: models/phimoe.py ``phimoe_routing_function`` / ``sparsemixer``):
+    experts are picked one at a time; for each pick, logits further than ``2 * jitter_eps`` (relative) below the
+    current maximum are masked before the softmax that yields the pick's weight, and the picked expert is removed
+    from the next round.  Plugged into ``FusedMoE.custom_routing``."""
+    def route(logits: torch.Tensor, top_k: int):
+        scores = logits.float()
+        work = scores
+        ws, ids = [], []
+        for _ in range(top_k):
+            mx, idx = work.max(dim=-1, keepdim=True)
+            factor = scores.abs().clamp(min=mx)
+            masked = work.masked_fill(((mx - scores) / factor) > (2 * jitter_eps), float("-inf"))
+            ws.append(torch.softmax(masked, dim=-1).gather(-1, idx))
+            ids.append(idx)
+            work = work.scatter(-1, idx, float("-inf"))
+        return torch.cat(ws, dim=-1), torch.cat(ids, dim=-1).to(torch.int32)
+    return route
