@@ -1,16 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark (BASELINE.json): decode output tokens/s for Llama-3-8B, TP = N GPUs, a fixed batch of 64
-synthetic requests (random-init weights, synthetic prompts).
+"""Headline benchmark (BASELINE.json): decode output tokens/s for a fixed batch of 64 synthetic requests
+(1024-token prompts), Llama-3-8B at TP = N GPUs (the scaling line); ``--model llama-3-70b`` (TP8 headline),
+``--model mixtral-8x7b`` and ``--model deepseek-small`` select the other BASELINE configs.
 
-    python bench.py --gpus 1 --steps 64 --warmup 8
+    python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        bench.py --gpus N --steps K --warmup W
+        bench.py --gpus N --steps K --warmup W [--impl reference]
 
-``value``  = 64 * K / (device time of K consecutive engine decode steps, CUDA events, max over ranks).
-``e2e``    = the same metric through the public API (LLMEngine.add_request / step), wall clock with a device
-             synchronise on both sides; every step copies its inputs from pinned host memory (H2D) and reads the
-             sampled token ids back (D2H).
-``--impl reference`` runs the unmodified reference from baseline/_ref if it could be installed.
+Both arms print the SAME ``metric`` string and measure the SAME thing:
+
+``value``  ours: 64 * K / (device time of K consecutive engine decode steps, CUDA events, max over ranks).
+           reference: 64 * K / (decode wall time of K steps, see ``e2e``) — an external process cannot be
+           event-timed, so for the reference ``value`` == ``e2e.value``.
+``e2e``    BOTH arms, identical method (the reference's own latency harness, vllm/benchmarks/latency.py:34-178,
+           times whole ``LLM.generate`` calls): the whole batch is prefilled in one engine step
+           (max_num_batched_tokens = 64 * 1024), then
+               t_decode = min_r wall(LLM.generate(max_tokens = K + 1)) - min_r wall(LLM.generate(max_tokens = 1))
+           over R interleaved repetitions after a full warm-up generate; e2e = 64 * K / t_decode.  Every engine
+           step inside copies its inputs host -> device from pinned memory and reads the sampled ids back.
+
+``--impl reference`` runs the UNMODIFIED reference (baseline/_ref if the offline install worked, else the stock
+vLLM wheel of the image — DESIGN.md §0) on its DEFAULT engine: multiprocess engine core, async scheduling,
+torch.compile + CUDA graphs, its own custom all-reduce / NCCL.  Under torchrun only rank 0 drives it (it spawns
+its own TP workers, one per GPU); the other torchrun ranks stay off the GPUs and wait.
 """
 from __future__ import annotations
 
@@ -27,7 +39,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BASELINE_TOK_S = None  # BASELINE.json "published" is empty
+BASELINE_TOK_S = None  # BASELINE.json "published" is empty: no published number to divide by
+METRIC = ("decode output tokens/s (whole box): batch of 64 synthetic requests x 1024-token prompts, "
+          "K decode steps after one-step prefill, max over ranks")
+DATA = "synthetic prompts (uniform random token ids), random-init weights (dummy loader)"
+REPS = 3
+
+# HF config.json of the benchmarked architectures (random-init weights).  Kept literal here so that the reference
+# arm needs nothing from this repository.
+_LLAMA = dict(architectures=["LlamaForCausalLM"], model_type="llama", hidden_act="silu", rms_norm_eps=1e-5,
+              max_position_embeddings=8192, torch_dtype="bfloat16", tie_word_embeddings=False, bos_token_id=128000,
+              eos_token_id=128001, vocab_size=128256, rope_theta=500000.0)
+REF_CONFIGS = {
+    "llama-3-8b": dict(_LLAMA, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                       num_attention_heads=32, num_key_value_heads=8),
+    "llama-3-70b": dict(_LLAMA, hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
+                        num_attention_heads=64, num_key_value_heads=8),
+    "mixtral-8x7b": dict(architectures=["MixtralForCausalLM"], model_type="mixtral", hidden_act="silu",
+                         rms_norm_eps=1e-5, max_position_embeddings=32768, torch_dtype="bfloat16",
+                         tie_word_embeddings=False, bos_token_id=1, eos_token_id=2, vocab_size=32000,
+                         rope_theta=1000000.0, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                         num_attention_heads=32, num_key_value_heads=8, num_local_experts=8, num_experts_per_tok=2,
+                         sliding_window=None),
+}
 
 
 def _clock_sampler(stop: threading.Event, out: list) -> None:
@@ -50,36 +84,77 @@ def _clock_sampler(stop: threading.Event, out: list) -> None:
 
 
 def _summarise_clocks(lines: list, local_rank: int) -> dict:
-    sm, mx, reasons = [], 0, set()
+    """Median SM clock of the samples taken UNDER LOAD (power above idle) on this rank's GPU."""
+    rows, mx, reasons = [], 0, set()
     for ln in lines:
         f = [x.strip() for x in ln.split(",")]
         if len(f) < 8 or not f[0].isdigit() or int(f[0]) != local_rank:
             continue
         try:
-            sm.append(float(f[1]))
+            rows.append((float(f[1]), float(f[3])))
             mx = max(mx, float(f[2]))
         except ValueError:
             continue
         for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
             if v.lower().startswith("active"):
                 reasons.add(name)
-    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-            "samples": len(sm)}
+    if rows:
+        pmax = max(p for _, p in rows)
+        load = [c for c, p in rows if p >= 0.6 * pmax] or [c for c, _ in rows]
+    else:
+        load = []
+    return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+            "samples": len(rows)}
 
 
+def _prompts(B: int, S_in: int, vocab: int) -> list:
+    import torch
+    g = torch.Generator().manual_seed(1234)
+    return [{"prompt_token_ids": torch.randint(10, vocab - 10, (S_in,), generator=g).tolist()} for _ in range(B)]
+
+
+def _timed_generates(gen, K: int, reps: int, sync=None):
+    """min wall time of generate(max_tokens=1) and generate(max_tokens=K+1), interleaved; returns (t1, tK, all)."""
+    t1s, tks = [], []
+    for _ in range(reps):
+        for n, acc in ((1, t1s), (K + 1, tks)):
+            if sync:
+                sync()
+            t0 = time.perf_counter()
+            gen(n)
+            if sync:
+                sync()
+            acc.append(time.perf_counter() - t0)
+    return min(t1s), min(tks), {"generate_1_s": t1s, "generate_K1_s": tks}
+
+
+# ===================================================================================== reference arm
 def _reference_unavailable(why: str) -> None:
     if int(os.environ.get("RANK", 0)) == 0:
         print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
 
 
+def _sentinel_path() -> str:
+    return os.path.join("/tmp", f"vb_ref_done_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}")
+
+
 def run_reference(args) -> None:
-    """The reference arm: stock vLLM through its own public API (``vllm.LLM`` → ``llm_engine.add_request/step``), same
-    model architecture, batch, prompt length and step accounting as our arm; none of this repository's code is on
-    that path.  Source: ``baseline/_ref`` when the offline install of /root/reference succeeded; otherwise the stock
-    vLLM wheel that ships in the image (named in the output), otherwise ``unavailable``."""
     install_note = ("pip install of /root/reference into baseline/_ref is not possible offline: the metadata step needs "
                     "setuptools_rust (no Rust toolchain) and it pins torch==2.13 / flashinfer 0.6.17 vs torch 2.11 in "
                     "this image; see DESIGN.md")
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    sentinel = _sentinel_path()
+    timeout_s = int(os.environ.get("VLLM_B200_REFERENCE_TIMEOUT", "820"))
+    if rank != 0:
+        # the reference spawns its own worker per GPU from rank 0; the other torchrun ranks must not hold a context
+        t_end = time.time() + timeout_s + 30
+        while not os.path.exists(sentinel) and time.time() < t_end:
+            time.sleep(0.5)
+        return
+    try:
+        os.unlink(sentinel)
+    except OSError:
+        pass
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]      # nothing of ours importable from here on
     source = None
@@ -87,102 +162,113 @@ def run_reference(args) -> None:
         sys.path.insert(0, ref_dir)
         source = "baseline/_ref"
     if os.environ.get("VLLM_B200_REFERENCE_FROM_IMAGE", "1") == "0" and source is None:
-        return _reference_unavailable(install_note)
-    timeout_s = int(os.environ.get("VLLM_B200_REFERENCE_TIMEOUT", "900"))
+        _reference_unavailable(install_note)
+        open(sentinel, "w").close()
+        return
+
+    def finish(code: int = 0):
+        try:
+            open(sentinel, "w").close()
+        finally:
+            os._exit(code)
 
     def watchdog():
         time.sleep(timeout_s)
         _reference_unavailable(f"reference arm did not finish within {timeout_s}s ({install_note})")
-        os._exit(0)
+        finish()
     threading.Thread(target=watchdog, daemon=True).start()
     try:
+        # a clean, default environment for the stock engine: drop torchrun's rendezvous variables (the reference
+        # would read RANK / LOCAL_RANK / WORLD_SIZE as its own) and do not override any of its engine defaults
+        for k in list(os.environ):
+            if k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "ROLE_NAME",
+                     "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS") \
+                    or k.startswith(("TORCHELASTIC_", "TORCH_NCCL_ASYNC", "VLLM_B200_")):
+                os.environ.pop(k, None)
         os.environ.setdefault("HF_HUB_OFFLINE", "1")
-        os.environ.setdefault("VLLM_ENABLE_V1_MULTIPROCESSING", "0")       # engine core in-process: steps are timeable
         os.environ.setdefault("VLLM_LOGGING_LEVEL", "WARNING")
         os.environ.setdefault("VLLM_PLUGINS", "")                          # stock code path: no third-party plug-ins
         import tempfile
 
-        import torch
         import vllm
         from vllm import LLM, SamplingParams
         if source is None:
             source = f"vllm {vllm.__version__} wheel of the image ({install_note})"
-        rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-        presets = {   # HF config.json of the benchmarked architectures (random-init weights: load_format="dummy")
-            "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
-                               num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0),
-            "llama-3-70b": dict(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64,
-                                num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0),
-        }
-        if args.model not in presets:
-            return _reference_unavailable(f"reference arm has no config for {args.model}")
-        cfg = dict(architectures=["LlamaForCausalLM"], model_type="llama", hidden_act="silu", rms_norm_eps=1e-5,
-                   max_position_embeddings=8192, torch_dtype="bfloat16", tie_word_embeddings=False, bos_token_id=128000,
-                   eos_token_id=128001, **presets[args.model])
+        if args.model not in REF_CONFIGS:
+            _reference_unavailable(f"reference arm has no config for {args.model}")
+            finish()
+        cfg = REF_CONFIGS[args.model]
         d = tempfile.mkdtemp(prefix="ref_cfg_")
         with open(os.path.join(d, "config.json"), "w") as f:
             json.dump(cfg, f)
         B, S_in, K, W = args.batch, args.input_len, args.steps, max(args.warmup, 3)
-        out_len = W + K + 2
-        llm = LLM(model=d, load_format="dummy", skip_tokenizer_init=True, dtype="bfloat16", tensor_parallel_size=args.gpus,
-                  max_model_len=S_in + 2 * out_len + 64, max_num_seqs=max(B, 8), max_num_batched_tokens=16384,
-                  enable_prefix_caching=False, gpu_memory_utilization=0.85, generation_config="vllm",
-                  distributed_executor_backend="external_launcher" if world > 1 else None, enforce_eager=args.eager)
-        eng = llm.llm_engine
-        g = torch.Generator().manual_seed(1234)
-        sp = SamplingParams(max_tokens=out_len, temperature=0.0, ignore_eos=True, detokenize=False)
-        for i in range(B):
-            ids = torch.randint(10, cfg["vocab_size"] - 10, (S_in,), generator=g).tolist()
-            eng.add_request(f"a-{i}", {"prompt_token_ids": ids}, sp)
-        seen: dict[str, int] = {}
-        while len(seen) < B:
-            for o in eng.step():
-                seen[o.request_id] = 1
-        for _ in range(W):
-            eng.step()
+        llm = LLM(model=d, load_format="dummy", skip_tokenizer_init=True, dtype="bfloat16",
+                  tensor_parallel_size=args.gpus, max_model_len=S_in + W + K + 64, max_num_seqs=max(B, 8),
+                  max_num_batched_tokens=B * S_in, enable_prefix_caching=False, gpu_memory_utilization=0.85,
+                  generation_config="vllm", enforce_eager=args.eager, disable_log_stats=False)
+        prompts = _prompts(B, S_in, cfg["vocab_size"])
+        last = {}
+
+        def gen(n):
+            sp = SamplingParams(max_tokens=n, temperature=0.0, ignore_eos=True, detokenize=False)
+            last["outs"] = llm.generate(prompts, sp, use_tqdm=False)
+        gen(W + K + 1)                           # warm-up: one prefill + (W + K) decode steps, graphs / JIT all hot
+        gen(1)
         stop, lines = threading.Event(), []
         th = threading.Thread(target=_clock_sampler, args=(stop, lines), daemon=True)
         th.start()
-        time.sleep(0.3)
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            eng.step()
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-        ms = (time.perf_counter() - t0) * 1e3
+        time.sleep(0.2)
+        t1, tk, raw = _timed_generates(gen, K, REPS)
         stop.set()
         th.join(timeout=2)
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t[0])
-        value = B * K / (ms / 1e3)
-        if rank == 0:
-            print(json.dumps({
-                "metric": "decode output tokens/s (whole box, K engine decode steps, device-synchronised wall clock, max over ranks)",
-                "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic prompts (uniform random token ids), random-init weights (dummy loader)",
-                "config": {"model": args.model, "global_batch": B, "seq_len": S_in, "parallelism": f"tp{args.gpus}",
-                           "cuda_graphs": not args.eager},
-                "clocks": _summarise_clocks(lines, int(os.environ.get("LOCAL_RANK", 0))),
-                "e2e": {"value": value, "unit": "tokens/s", "ms_per_step": ms / K,
-                        "note": "the reference is timed through its public API only (engine.step), i.e. end to end"},
-                "impl": "reference", "reference_source": source}), flush=True)
+        # the reference's own engine-core timestamps of the last K+1 run (first → last token of the batch)
+        eng_ms = None
+        try:
+            st = [o.metrics for o in last["outs"] if getattr(o, "metrics", None) is not None]
+            if st:
+                eng_ms = (max(s.last_token_ts for s in st) - min(s.first_token_ts for s in st)) * 1e3 / K
+        except Exception:
+            eng_ms = None
+        dec_s = tk - t1
+        value = B * K / dec_s
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": dec_s * 1e3 / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": DATA,
+            "config": {"model": args.model, "global_batch": B, "seq_len": S_in, "parallelism": f"tp{args.gpus}",
+                       "cuda_graphs": not args.eager, "engine": "default (multiprocess engine core, async scheduling)",
+                       "l2": "no flush needed: every step streams far more weights+KV than the 126 MB L2"},
+            "clocks": _summarise_clocks(lines, 0),
+            "e2e": {"value": value, "unit": "tokens/s", "ms_per_step": dec_s * 1e3 / K,
+                    "method": "min wall(LLM.generate(K+1)) - min wall(LLM.generate(1)), %d reps" % REPS, **raw,
+                    "engine_core_itl_ms": eng_ms},
+            "impl": "reference", "reference_source": source}), flush=True)
+        try:
+            del llm
+        except Exception:
+            pass
     except BaseException as e:  # noqa: BLE001 - whatever goes wrong, the arm reports instead of crashing the driver
         _reference_unavailable(f"reference arm failed: {type(e).__name__}: {str(e)[:300]} ({install_note})")
-    os._exit(0)          # stock vLLM leaves non-daemon threads / process groups behind; the line above is the result
+    finish()          # stock vLLM leaves non-daemon threads / process groups behind; the line above is the result
+
+
+# ===================================================================================== our arm
+def _exposed_comm(engine, runner, args, T: int) -> dict | None:
+    """Per-call device time of the fused RowParallel kernel (GEMM + NVSwitch all-reduce + residual + RMSNorm) vs the
+    same GEMM + a local norm without any peer traffic, for the two RowParallel shapes of the model → exposed
+    communication per decode step and NVLink bytes.  Runs after the timed region."""
+    try:
+        from vllm_b200.benchmarks.comm_probe import probe_row_parallel
+        return probe_row_parallel(runner, T)
+    except Exception as e:  # noqa: BLE001 - diagnostic only
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
 
 
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3-8b")
     ap.add_argument("--batch", type=int, default=64)
@@ -190,6 +276,8 @@ def main() -> None:
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync", action="store_true", help="disable async scheduling (host waits for every step)")
+    ap.add_argument("--parallelism", default="tp", choices=["tp", "ep"],
+                    help="MoE models: ep = experts sharded over the TP group with the fused all-to-all kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -204,29 +292,29 @@ def main() -> None:
     assert world == args.gpus, f"launch with torchrun --nproc-per-node {args.gpus} (WORLD_SIZE={world})"
     torch.cuda.set_device(local_rank)
 
-    from vllm_b200 import SamplingParams
-    from vllm_b200.engine.arg_utils import EngineArgs
-    from vllm_b200.engine.llm_engine import LLMEngine
+    from vllm_b200 import LLM, SamplingParams
 
     B, S_in, K, W = args.batch, args.input_len, args.steps, args.warmup
     out_len = W + K + 2
     max_len = S_in + 2 * out_len + 64
-    ea = EngineArgs(model=args.model, load_format="dummy", dtype="bfloat16", tensor_parallel_size=args.gpus,
-                    max_model_len=max_len, max_num_seqs=max(B, 8), max_num_batched_tokens=16384,
-                    enable_prefix_caching=False, enforce_eager=args.eager,
-                    distributed_executor_backend="external_launcher" if world > 1 else "uni",
-                    cudagraph_capture_sizes=[B], disable_log_stats=True, gpu_memory_utilization=0.85,
-                    async_scheduling=not args.sync)
-    engine = LLMEngine.from_engine_args(ea, multiprocess_mode=False)
+    extra = {}
+    if args.parallelism == "ep":
+        extra["enable_expert_parallel"] = True
+    llm = LLM(args.model, load_format="dummy", dtype="bfloat16", tensor_parallel_size=args.gpus,
+              max_model_len=max_len, max_num_seqs=max(B, 8), max_num_batched_tokens=B * S_in,
+              enable_prefix_caching=False, enforce_eager=args.eager,
+              distributed_executor_backend="external_launcher" if world > 1 else "uni",
+              cudagraph_capture_sizes=[B], disable_log_stats=True, gpu_memory_utilization=0.85,
+              async_scheduling=not args.sync, multiprocess_mode=False, **extra)
+    engine = llm.llm_engine
     runner = engine.engine_core.engine_core.model_executor.worker.runner
     vocab = engine.model_config.vocab_size
+    prompts = _prompts(B, S_in, vocab)
 
     def add_batch(tag: str) -> None:
-        g = torch.Generator().manual_seed(1234)
         sp = SamplingParams(max_tokens=out_len, temperature=0.0, ignore_eos=True, detokenize=False)
-        for i in range(B):
-            ids = torch.randint(10, vocab - 10, (S_in,), generator=g).tolist()
-            engine.add_request(f"{tag}-{i}", {"prompt_token_ids": ids}, sp)
+        for i, p in enumerate(prompts):
+            engine.add_request(f"{tag}-{i}", p, sp)
 
     def barrier() -> None:
         if world > 1:
@@ -234,7 +322,6 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def prefill_until_decoding() -> None:
-        # run steps until every request of the batch has produced its first token (prefill finished)
         seen: dict[str, int] = {}
         while len(seen) < B:
             for o in engine.step():
@@ -250,7 +337,6 @@ def main() -> None:
     th.start()
     time.sleep(0.3)
     launches0 = runner.launch_count
-    h2d0, d2h0 = runner.h2d_bytes, runner.d2h_bytes
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -260,42 +346,38 @@ def main() -> None:
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = runner.launch_count - launches0
-    h2d_step = (runner.h2d_bytes - h2d0) / K
-    d2h_step = (runner.d2h_bytes - d2h0) / K
-    stop.set()
-    th.join(timeout=2)
-    clocks = _summarise_clocks(lines, local_rank)
     while engine.has_unfinished_requests():
         engine.step()
 
-    # ---------------- phase B: end to end through the public API (wall clock)
-    e2e = None
+    # ---------------- phase B: end to end through the public API, same method as the reference arm
+    e2e, e2e_s, raw = None, 0.0, {}
+    h2d_step = d2h_step = 0
     if not args.no_e2e:
-        add_batch("b")
-        prefill_until_decoding()
-        for _ in range(W):
-            engine.step()
-        barrier()
-        t0 = time.perf_counter()
-        n_tok = 0
-        for _ in range(K):
-            for o in engine.step():
-                pass
-            n_tok += B
-        barrier()
-        wall = time.perf_counter() - t0
-        e2e_ms = wall * 1e3
-        while engine.has_unfinished_requests():
-            engine.step()
+        def gen(n):
+            llm.generate(prompts, SamplingParams(max_tokens=n, temperature=0.0, ignore_eos=True, detokenize=False))
+        gen(W + K + 1)
+        gen(1)
+        h2d0, d2h0 = runner.h2d_bytes, runner.d2h_bytes
+        t1, tk, raw = _timed_generates(gen, K, REPS, sync=barrier)
+        e2e_s = tk - t1
+        n_steps = REPS * (K + 2)                          # engine steps executed by the timed generate calls
+        h2d_step = (runner.h2d_bytes - h2d0) / n_steps
+        d2h_step = (runner.d2h_bytes - d2h0) / n_steps
+    stop.set()
+    th.join(timeout=2)
+    clocks = _summarise_clocks(lines, local_rank)
+    comm = _exposed_comm(engine, runner, args, B) if world > 1 else None
+
     # ---------------- reduce over ranks (max time)
-    t = torch.tensor([dev_ms, e2e_ms if not args.no_e2e else 0.0], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_s = t.tolist()
     value = B * K / (dev_ms / 1e3)
     if not args.no_e2e:
-        e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d_step),
-               "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / K}
+        e2e = {"value": B * K / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d_step),
+               "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_s * 1e3 / K,
+               "method": "min wall(LLM.generate(K+1)) - min wall(LLM.generate(1)), %d reps" % REPS, **raw}
     if rank == 0:
         roof = None
         try:   # analytical roofline of the timed steps (weights + KV bytes, FLOPs) → achieved TB/s, MBU, MFU
@@ -308,17 +390,17 @@ def main() -> None:
                                                                 args.gpus).items()}
         except Exception:
             roof = None
+        par = f"tp{args.gpus}" + ("+ep" if args.parallelism == "ep" else "")
         print(json.dumps({
-            "metric": "decode output tokens/s (whole box, device-timed decode steps, max over ranks)",
-            "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "itl_p50_ms": dev_ms / K, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": (value / BASELINE_TOK_S) if BASELINE_TOK_S else None, "dtype": "bf16",
-            "data": "synthetic prompts (uniform random token ids), random-init weights (dummy loader)",
-            "config": {"model": args.model, "global_batch": B, "seq_len": S_in, "parallelism": f"tp{args.gpus}",
-                       "cuda_graphs": not args.eager,
-                       "l2": "no flush needed: every step streams >16 GB of weights+KV, far above the 126 MB L2"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "impl": "ours"}))
-    engine.shutdown()
+            "vs_baseline": (value / BASELINE_TOK_S) if BASELINE_TOK_S else None, "dtype": "bf16", "data": DATA,
+            "config": {"model": args.model, "global_batch": B, "seq_len": S_in, "parallelism": par,
+                       "cuda_graphs": not args.eager, "engine": "in-process engine core, async scheduling",
+                       "l2": "no flush needed: every step streams far more weights+KV than the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "fused_comm": comm, "impl": "ours"}), flush=True)
+    llm.shutdown() if hasattr(llm, "shutdown") else engine.shutdown()
     if world > 1 and dist.is_initialized():
         dist.barrier()
 

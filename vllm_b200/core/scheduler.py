@@ -274,7 +274,16 @@ class Scheduler:
                 if req.status == RequestStatus.WAITING_FOR_REMOTE_KVS:
                     if self.connector is not None and self.connector.is_recv_finished(req):
                         req.status = RequestStatus.WAITING
-                        kv.cache_blocks(req, req.num_computed_tokens)
+                        if self.connector.take_recv_failed(req):
+                            # the transfer died: its destination blocks hold garbage.  Give them back uncached and
+                            # recompute the prompt locally (reference: invalid-block handling in scheduler.py
+                            # ``_handle_invalid_blocks``); the request must not ask for the remote copy again
+                            kv.free(req)
+                            req.num_computed_tokens = 0
+                            if isinstance(req.kv_transfer_params, dict):
+                                req.kv_transfer_params["do_remote_prefill"] = False
+                        else:
+                            kv.cache_blocks(req, req.num_computed_tokens)
                     else:
                         skipped.append(self.waiting.pop())
                         continue
@@ -425,6 +434,7 @@ class Scheduler:
         if mo.logprobs is not None:
             lp_ids, lp_vals, lp_ranks = mo.logprobs.tolists()
         stopped_running: set[str] = set()
+        stopped_preempted: list[Request] = []
         lp_offsets: list[int] = []
         if lp_ids is not None:
             acc = 0
@@ -442,7 +452,8 @@ class Scheduler:
             if spec:
                 n_draft = len(spec)
                 n_acc = max(len(gen) - 1, 0)
-                if gen:
+                if gen and req.num_computed_tokens > 0:
+                    # (a request preempted while this step was in flight was reset to 0: nothing to roll back)
                     req.num_computed_tokens -= n_draft - n_acc
                 self._spec_drafts += 1
                 self._spec_draft_tokens += n_draft
@@ -455,6 +466,9 @@ class Scheduler:
                 req.num_output_placeholders = max(req.num_output_placeholders, 0)
             stopped = False
             new_ids = gen
+            # batch-queue path (async scheduling / PP): schedule N+1 may have preempted this request before the
+            # output of step N arrived — it then sits in the waiting queue, not in `running`
+            was_preempted = req.status == RequestStatus.PREEMPTED
             if gen:
                 for k, tok in enumerate(gen):
                     req.append_output_token_ids(tok)
@@ -502,7 +516,10 @@ class Scheduler:
             kv_params = None
             if stopped:
                 kv_params = self._free_request(req)
-                stopped_running.add(rid)
+                if was_preempted:
+                    stopped_preempted.append(req)
+                else:
+                    stopped_running.add(rid)
             if new_ids or pooled is not None or stopped or plp is not None:
                 outputs.setdefault(req.client_index, []).append(EngineCoreOutput(
                     request_id=rid, new_token_ids=list(new_ids), new_logprobs=new_lp,
@@ -512,6 +529,12 @@ class Scheduler:
                     kv_transfer_params=kv_params, events=req.take_events()))
         if stopped_running:
             self.running = [r for r in self.running if r.request_id not in stopped_running]
+        for r in stopped_preempted:
+            # finished while parked: it must not be rescheduled (its entry in self.requests is gone)
+            try:
+                self.waiting.remove(r)
+            except (ValueError, KeyError):
+                pass
         if mo.kv_connector_output is not None and self.connector is not None:
             self._update_from_kv_xfer(mo.kv_connector_output)
         result = {ci: EngineCoreOutputs(outputs=outs, timestamp=time.monotonic())
@@ -530,6 +553,8 @@ class Scheduler:
         return result
 
     def _update_from_kv_xfer(self, kvo) -> None:
+        for rid in getattr(kvo, "failed_recving", None) or ():
+            self.connector.mark_recv_failed(rid)
         for rid in getattr(kvo, "finished_recving", None) or ():
             self.connector.mark_recv_finished(rid)
         for rid in getattr(kvo, "finished_sending", None) or ():

@@ -25,6 +25,7 @@ class EngineArgs:
     tokenizer_mode: str = "auto"
     skip_tokenizer_init: bool = False
     trust_remote_code: bool = False
+    allowed_local_media_path: Optional[str] = None   # file:// media parts are refused unless set (then confined to it)
     dtype: str = "auto"
     seed: int = 0
     max_model_len: Optional[int] = None
@@ -101,6 +102,9 @@ class EngineArgs:
     enable_fault_tolerance: bool = False
 
     def create_engine_config(self) -> VllmConfig:
+        if self.allowed_local_media_path:
+            from vllm_b200.entrypoints.chat_utils import set_allowed_local_media_path
+            set_allowed_local_media_path(self.allowed_local_media_path)
         mc = ModelConfig(
             model=self.model, tokenizer=self.tokenizer, tokenizer_mode=self.tokenizer_mode,
             trust_remote_code=self.trust_remote_code, dtype=self.dtype, seed=self.seed,

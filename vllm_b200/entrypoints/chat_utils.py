@@ -57,6 +57,29 @@ def extract_mm_items(messages: list[dict]) -> list[Any]:
     return _flatten_content(messages)[1]
 
 
+_ALLOWED_LOCAL_MEDIA_PATH: Any = None    # set by ``--allowed-local-media-path`` / VLLM_ALLOWED_LOCAL_MEDIA_PATH
+
+
+def set_allowed_local_media_path(path: Any) -> None:
+    global _ALLOWED_LOCAL_MEDIA_PATH
+    _ALLOWED_LOCAL_MEDIA_PATH = path or None
+
+
+def resolve_local_media(url: str) -> str:
+    """``file://`` URL → real path, only inside the operator-configured directory (reference:
+    multimodal/media/connector.py ``_load_file_url``: local files are refused unless
+    ``--allowed-local-media-path`` is set, and then confined to that directory after symlink resolution)."""
+    import os
+    root = _ALLOWED_LOCAL_MEDIA_PATH or os.environ.get("VLLM_ALLOWED_LOCAL_MEDIA_PATH")
+    if not root:
+        raise ValueError("local file:// media is disabled: start the server with --allowed-local-media-path <dir>")
+    root = os.path.realpath(root)
+    path = os.path.realpath(url[len("file://"):])
+    if os.path.commonpath([root, path]) != root:
+        raise ValueError(f"file:// media must live under {root}")
+    return path
+
+
 def load_mm_item(part: dict) -> Any:
     """One OpenAI content part → a decoded media object (images: PIL.Image; tensors / arrays pass through).
     ``data:`` URLs and local ``file://`` paths are supported; remote fetches need network access and are refused
@@ -73,7 +96,7 @@ def load_mm_item(part: dict) -> Any:
         if url.startswith("data:"):
             return Image.open(io.BytesIO(base64.b64decode(url.split(",", 1)[1]))).convert("RGB")
         if url.startswith("file://"):
-            return Image.open(url[len("file://"):]).convert("RGB")
+            return Image.open(resolve_local_media(url)).convert("RGB")
         if os.environ.get("VLLM_ALLOW_REMOTE_MEDIA") == "1":
             import requests
             return Image.open(io.BytesIO(requests.get(url, timeout=10).content)).convert("RGB")
@@ -115,7 +138,7 @@ def load_video(url: str, num_frames: int = 32):
         tmp.close()
         path = tmp.name
     elif url.startswith("file://"):
-        path = url[len("file://"):]
+        path = resolve_local_media(url)
     else:
         raise ValueError("remote video URLs are disabled (use a data: URL or file://)")
     try:

@@ -25,6 +25,7 @@ from typing import Any, AsyncGenerator, Optional
 from fastapi import FastAPI, Request, WebSocket  # noqa: F401
 from fastapi.responses import JSONResponse, Response, StreamingResponse
 
+from vllm_b200 import envs
 from vllm_b200.engine.arg_utils import EngineArgs
 from vllm_b200.engine.exceptions import EngineDeadError
 from vllm_b200.entrypoints.chat_utils import render_chat
@@ -103,6 +104,12 @@ def _chat_logprobs(ctx: ServingContext, token_ids, logprobs, k: int) -> P.ChatLo
     return P.ChatLogprobs(content=content)
 
 
+_OPEN_PATHS = frozenset({"/health", "/ping", "/version", "/metrics", "/load"})
+# worker methods an operator may invoke over HTTP in dev mode (extend with VLLM_SERVER_DEV_RPC_METHODS=a,b)
+_RPC_ALLOWED = frozenset({"checkpoint_prepare", "checkpoint_restore", "reset_after_fault", "get_memory_stats",
+                          "report_device_memory", "is_sleeping", "list_loras", "update_weights", "init_weight_transfer"})
+
+
 def build_app(ctx: ServingContext):
     @asynccontextmanager
     async def lifespan(app):
@@ -113,7 +120,9 @@ def build_app(ctx: ServingContext):
 
     @app.middleware("http")
     async def auth(request: Request, call_next):
-        if ctx.api_key and request.url.path.startswith("/v1"):
+        # every route except liveness / scrape endpoints is behind the key (the reference guards /v1 only and keeps
+        # its admin routes out of production builds; here both protections apply)
+        if ctx.api_key and request.url.path not in _OPEN_PATHS and request.method != "OPTIONS":
             if request.headers.get("Authorization") != f"Bearer {ctx.api_key}":
                 return JSONResponse({"error": "Unauthorized"}, status_code=401)
         rid = request.headers.get("X-Request-Id")
@@ -1029,7 +1038,30 @@ def build_app(ctx: ServingContext):
                 "usage": {"billed_units": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"]},
                           "tokens": {"input_tokens": u["prompt_tokens"], "output_tokens": u["completion_tokens"]}}}
 
-    # -------------------------------------------------------- dev routes
+    # ---------------------------------------- runtime LoRA management (opt-in: VLLM_ALLOW_RUNTIME_LORA_UPDATING=1)
+    if envs.VLLM_ALLOW_RUNTIME_LORA_UPDATING:
+        @app.post("/v1/load_lora_adapter")
+        async def load_lora(body: dict):
+            from vllm_b200.core.request import LoRARequest
+            name, path = body["lora_name"], body["lora_path"]
+            lid = ctx.lora_ids.setdefault(name, len(ctx.lora_ids) + 1)
+            ctx.lora_requests[name] = LoRARequest(name, lid, path)
+            await ctx.engine.collective_rpc("add_lora", (), {"lora_request": ctx.lora_requests[name]})
+            return {"status": "ok", "lora_int_id": lid}
+
+        @app.post("/v1/unload_lora_adapter")
+        async def unload_lora(body: dict):
+            req = ctx.lora_requests.pop(body["lora_name"], None)
+            if req is None:
+                return JSONResponse({"error": "unknown adapter"}, status_code=404)
+            await ctx.engine.collective_rpc("remove_lora", (req.lora_int_id,))
+            return {"status": "ok"}
+
+    # -------------------------------------------------------- dev routes (opt-in: VLLM_SERVER_DEV_MODE=1, as in the
+    # reference's entrypoints/serve/*: never mounted on a production server)
+    if not envs.VLLM_SERVER_DEV_MODE:
+        return app
+
     @app.post("/start_profile")
     async def start_profile():
         await ctx.engine.start_profile()
@@ -1069,23 +1101,6 @@ def build_app(ctx: ServingContext):
         ok = await ctx.engine.handle_fault(body.get("instruction", "retry"))
         return {"ok": bool(ok)}
 
-    @app.post("/v1/load_lora_adapter")
-    async def load_lora(body: dict):
-        from vllm_b200.core.request import LoRARequest
-        name, path = body["lora_name"], body["lora_path"]
-        lid = ctx.lora_ids.setdefault(name, len(ctx.lora_ids) + 1)
-        ctx.lora_requests[name] = LoRARequest(name, lid, path)
-        await ctx.engine.collective_rpc("add_lora", (), {"lora_request": ctx.lora_requests[name]})
-        return {"status": "ok", "lora_int_id": lid}
-
-    @app.post("/v1/unload_lora_adapter")
-    async def unload_lora(body: dict):
-        req = ctx.lora_requests.pop(body["lora_name"], None)
-        if req is None:
-            return JSONResponse({"error": "unknown adapter"}, status_code=404)
-        await ctx.engine.collective_rpc("remove_lora", (req.lora_int_id,))
-        return {"status": "ok"}
-
     @app.post("/scale_elastic_ep")
     async def scale_elastic_ep(body: dict):
         try:
@@ -1106,6 +1121,9 @@ def build_app(ctx: ServingContext):
 
     @app.post("/collective_rpc")
     async def collective_rpc(body: dict):
+        method = body.get("method")
+        if method not in _RPC_ALLOWED and method not in envs.VLLM_SERVER_DEV_RPC_METHODS.split(","):
+            return _error(f"collective_rpc method {method!r} is not on the allow-list", 403, "Forbidden")
         res = await ctx.engine.collective_rpc(body["method"], tuple(body.get("args", [])), body.get("kwargs"))
         return {"results": [r if isinstance(r, (int, float, str, bool, type(None))) else repr(r) for r in (res or [])]}
 

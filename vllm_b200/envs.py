@@ -49,6 +49,11 @@ environment_variables: dict[str, Callable[[], Any]] = {
     "VLLM_HOST_IP": _str("VLLM_HOST_IP", "127.0.0.1"),
     "VLLM_PORT": _int("VLLM_PORT", 0),
     "VLLM_API_KEY": _str("VLLM_API_KEY", None),
+    # admin / debug HTTP routes (sleep, profile, cache reset, collective_rpc, checkpoint, elastic scale) are only
+    # mounted in dev mode; runtime LoRA loading is its own opt-in (both as in the reference's envs.py)
+    "VLLM_SERVER_DEV_MODE": _bool("VLLM_SERVER_DEV_MODE", False),
+    "VLLM_SERVER_DEV_RPC_METHODS": _str("VLLM_SERVER_DEV_RPC_METHODS", ""),
+    "VLLM_ALLOW_RUNTIME_LORA_UPDATING": _bool("VLLM_ALLOW_RUNTIME_LORA_UPDATING", False),
     # --- kernels / device
     "VLLM_B200_FORCE_REF_OPS": _bool("VLLM_B200_FORCE_REF_OPS", False),
     "VLLM_B200_GEMM": _str("VLLM_B200_GEMM", "auto"),  # auto|cublas|tcgen05

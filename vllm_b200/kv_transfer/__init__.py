@@ -41,6 +41,7 @@ class KVConnectorMetadata:
 class KVConnectorOutput:
     finished_sending: set[str] = field(default_factory=set)
     finished_recving: set[str] = field(default_factory=set)
+    failed_recving: set[str] = field(default_factory=set)     # transfers that ended without valid KV (⊆ finished_recving)
 
 
 class KVConnectorBase:
@@ -50,6 +51,7 @@ class KVConnectorBase:
         self.cfg = vllm_config.kv_transfer_config
         self.block_size = vllm_config.cache_config.block_size
         self._recv_done: set[str] = set()
+        self._recv_failed: set[str] = set()
 
     # ---- scheduler side
     def get_num_new_matched_tokens(self, request, num_computed_tokens: int) -> tuple[int, bool]:
@@ -69,6 +71,16 @@ class KVConnectorBase:
 
     def mark_recv_finished(self, request_id: str) -> None:
         self._recv_done.add(request_id)
+
+    def mark_recv_failed(self, request_id: str) -> None:
+        """The transfer ended but the destination blocks do not hold valid KV: the scheduler must recompute."""
+        self._recv_failed.add(request_id)
+
+    def take_recv_failed(self, request) -> bool:
+        if request.request_id in self._recv_failed:
+            self._recv_failed.discard(request.request_id)
+            return True
+        return False
 
     # ---- worker side
     def start_load_kv(self, meta: Any, kv_caches: dict[str, torch.Tensor]) -> None:
@@ -155,10 +167,42 @@ class BlockConnector(KVConnectorBase):
         self._pending_loads: dict[str, tuple[int, int]] = {}   # req → (first block index, n blocks)
         self.num_loaded_blocks = 0
         self.num_saved_blocks = 0
+        # Keys carry the identity of WHAT is stored, not only the token prefix: a namespace hashed from the model,
+        # dtypes, block size and parallel layout, plus the shard coordinates of the worker that owns the bytes —
+        # two models sharing a store, or the TP ranks of one engine, can never read each other's blocks.
+        import hashlib
+        import json
+        mc, cc, pc = vllm_config.model_config, vllm_config.cache_config, vllm_config.parallel_config
+        ident = {"model": getattr(mc, "model", None), "dtype": str(getattr(mc, "torch_dtype", getattr(mc, "dtype", None))),
+                 "kv_dtype": str(getattr(cc, "cache_dtype", None)), "block_size": self.block_size,
+                 "tp": getattr(pc, "tensor_parallel_size", 1), "pp": getattr(pc, "pipeline_parallel_size", 1),
+                 "dcp": getattr(pc, "decode_context_parallel_size", 1),
+                 "hf": getattr(mc, "hf_config", None)}
+        self._ns = hashlib.sha256(json.dumps(ident, sort_keys=True, default=str).encode()).hexdigest()[:12]
+        self._tp, self._pp = ident["tp"] or 1, ident["pp"] or 1
+        self._shard: Optional[str] = None      # resolved lazily on the worker (parallel groups exist by then)
 
-    @staticmethod
-    def _key(h) -> str:
-        return h.hex() if isinstance(h, (bytes, bytearray)) else format(int(h) & ((1 << 128) - 1), "032x")
+    def _key(self, h) -> str:
+        hx = h.hex() if isinstance(h, (bytes, bytearray)) else format(int(h) & ((1 << 128) - 1), "032x")
+        return f"{self._ns}-{hx}"
+
+    def _shards(self) -> list[str]:
+        return [f".t{t}p{p}" for p in range(self._pp) for t in range(self._tp)]
+
+    def _my_shard(self) -> str:
+        if self._shard is None:
+            t = p = 0
+            try:
+                from vllm_b200.parallel.state import get_pp_group, get_tp_group
+                t, p = max(get_tp_group().rank_in_group, 0), max(get_pp_group().rank_in_group, 0)
+            except Exception:
+                pass
+            self._shard = f".t{t}p{p}"
+        return self._shard
+
+    def _stored(self, key: str) -> bool:
+        """Scheduler side: a block counts as stored only when every shard of it is."""
+        return all(self.store.contains(key + sh) for sh in self._shards())
 
     # ---- scheduler side
     def get_num_new_matched_tokens(self, request, num_computed_tokens: int) -> tuple[int, bool]:
@@ -169,7 +213,7 @@ class BlockConnector(KVConnectorBase):
         # never cover the whole prompt: the last token must be computed to produce logits
         limit = min(len(request.block_hashes), (request.num_tokens - 1) // bs)
         n = first
-        while n < limit and self.store.contains(self._key(request.block_hashes[n])):
+        while n < limit and self._stored(self._key(request.block_hashes[n])):
             n += 1
         if n > first:
             self._pending_loads[request.request_id] = (first, n - first)
@@ -227,7 +271,7 @@ class BlockConnector(KVConnectorBase):
         for bid, key in meta.loads:
             parts = [torch.empty(kv_caches[n].shape[1:], dtype=kv_caches[n].dtype) for n in names]
             flat = torch.empty(sum(p.numel() * p.element_size() for p in parts), dtype=torch.uint8)
-            if not self.store.get(key, flat):
+            if not self.store.get(key + self._my_shard(), flat):
                 raise RuntimeError(f"KV block {key} vanished from the store")
             off = 0
             for n, p in zip(names, parts):
@@ -241,6 +285,7 @@ class BlockConnector(KVConnectorBase):
             return
         names = sorted(kv_caches)
         for bid, key in meta.saves:
+            key = key + self._my_shard()
             if self.store.contains(key):
                 continue
             flat = torch.cat([kv_caches[n][bid].contiguous().view(torch.uint8).reshape(-1).cpu() for n in names])

@@ -37,6 +37,7 @@ class P2pPullConnector(KVConnectorBase):
         self.host = c.kv_ip
         self.port = c.kv_port + c.kv_rank
         self.send_timeout = float(c.kv_connector_extra_config.get("send_timeout_s", 120.0))
+        self.pull_timeout_ms = int(c.kv_connector_extra_config.get("pull_timeout_ms", 60000))
         # scheduler side
         self._pending: dict[str, tuple[int, int]] = {}
         self._jobs: list[dict] = []
@@ -46,6 +47,7 @@ class P2pPullConnector(KVConnectorBase):
         self._lock = threading.Lock()
         self._fin_send: set[str] = set()
         self._fin_recv: set[str] = set()
+        self._fail_recv: set[str] = set()
         self._server: Optional[threading.Thread] = None
         self._stop = False
         self.num_pulled_blocks = 0
@@ -150,7 +152,8 @@ class P2pPullConnector(KVConnectorBase):
         try:
             ctx = zmq.Context.instance()
             s = ctx.socket(zmq.REQ)
-            s.setsockopt(zmq.RCVTIMEO, 60000)
+            s.setsockopt(zmq.RCVTIMEO, self.pull_timeout_ms)
+            s.setsockopt(zmq.LINGER, 0)
             s.connect(f"tcp://{job['host']}:{job['port']}")
             s.send(msgspec.msgpack.encode({"op": "pull", "block_ids": job["remote_ids"]}))
             raw = torch.frombuffer(bytearray(s.recv()), dtype=torch.uint8)
@@ -169,9 +172,11 @@ class P2pPullConnector(KVConnectorBase):
             self.num_pulled_blocks += len(job["local_ids"])
         except Exception:
             logger.exception("KV pull for %s failed", job["req_id"])
+            with self._lock:
+                self._fail_recv.add(job["req_id"])      # the blocks hold garbage: the scheduler recomputes, never caches them
         finally:
             with self._lock:
-                self._fin_recv.add(job["req_id"])       # on failure the blocks hold garbage → see invalid-block handling
+                self._fin_recv.add(job["req_id"])
 
     def start_load_kv(self, meta, kv_caches) -> None:
         if self._kv is None:
@@ -188,9 +193,10 @@ class P2pPullConnector(KVConnectorBase):
         with self._lock:
             if not self._fin_send and not self._fin_recv:
                 return None
-            out = KVConnectorOutput(set(self._fin_send), set(self._fin_recv))
+            out = KVConnectorOutput(set(self._fin_send), set(self._fin_recv), set(self._fail_recv))
             self._fin_send.clear()
             self._fin_recv.clear()
+            self._fail_recv.clear()
         return out
 
     def shutdown(self) -> None:

@@ -169,24 +169,50 @@ class RejectionSampler:
     Greedy: accept draft token i while it equals the target argmax; emit the
     first mismatch's target token (or the bonus token if all accepted).
     Random: standard accept with prob min(1, p/q) for draft-model proposals;
-    n-gram drafts have q = 1 (deterministic proposal)."""
+    n-gram drafts have q = 1 (deterministic proposal).
+
+    ``md`` is EXPANDED: one metadata row per target-logit row (request i, draft position j → row cu[i] + j, whose
+    ``output_token_ids`` already contain drafts[:j]), so that the same logits processors, grammar bitmask, penalties
+    and top-k / top-p / min-p filters as the non-speculative ``Sampler`` shape every verified position — a speculated
+    run then samples from exactly the distribution the plain run would (reference: rejection_sampler.py
+    ``apply_logits_processors`` / ``apply_sampling_constraints``)."""
+
+    def __init__(self, sampler: Optional["Sampler"] = None) -> None:
+        self.sampler = sampler or Sampler()
+
+    def process(self, logits: torch.Tensor, md: SamplingMetadata, bitmask: Optional[torch.Tensor]) -> torch.Tensor:
+        """Raw target logits → the logits the plain sampler would draw from (temperature applied on random rows)."""
+        logits = logits.float()
+        if bitmask is not None:
+            logits = apply_bitmask(logits, bitmask)
+        logits = Sampler.apply_logits_processors(logits, md)
+        for proc in self.sampler.custom:
+            if md.extra_args and any(md.extra_args) and not (md.all_greedy and proc.is_argmax_invariant()):
+                logits = proc.apply(logits, md)
+        if not md.no_penalties:
+            logits = ref.apply_penalties(logits, md.prompt_mask, md.output_counts, md.presence, md.frequency,
+                                         md.repetition)
+        if not md.all_greedy:
+            t = torch.where(md.temperature < 1e-5, torch.ones_like(md.temperature), md.temperature)
+            logits = logits / t[:, None]
+            if md.top_k is not None or md.top_p is not None or md.min_p is not None:
+                logits = ref.apply_top_k_top_p_min_p(logits, md.top_k, md.top_p, md.min_p)
+        return logits
 
     def __call__(self, target_logits: torch.Tensor, draft_ids: list[list[int]], md: SamplingMetadata,
-                 cu: list[int]) -> list[list[int]]:
+                 cu: list[int], bitmask: Optional[torch.Tensor] = None) -> list[list[int]]:
         """target_logits: [sum(k_i + 1), V] — for request i rows cu[i]:cu[i+1] are the logits
         after each of its k_i drafts' prefixes (+1 bonus)."""
         out: list[list[int]] = []
-        if md.all_greedy:
-            tgt = target_logits.argmax(dim=-1).tolist()
-        else:
-            temps = md.temperature
-            tgt = None
+        logits = self.process(target_logits, md, bitmask)
+        tgt = logits.argmax(dim=-1).tolist() if md.all_greedy else None
+        temps = md.temperature.tolist() if not md.all_greedy else None
         for i, drafts in enumerate(draft_ids):
             s = cu[i]
             acc: list[int] = []
-            if md.all_greedy or float(md.temperature[i]) < 1e-5:
+            if md.all_greedy or temps[s] < 1e-5:
                 row_t = tgt[s:s + len(drafts) + 1] if tgt is not None else \
-                    target_logits[s:s + len(drafts) + 1].argmax(-1).tolist()
+                    logits[s:s + len(drafts) + 1].argmax(-1).tolist()
                 for j, d in enumerate(drafts):
                     if row_t[j] == d:
                         acc.append(d)
@@ -194,8 +220,8 @@ class RejectionSampler:
                         break
                 acc.append(row_t[len(acc)])
             else:
-                g = md.generators.get(i)
-                probs = (target_logits[s:s + len(drafts) + 1].float() / temps[i]).softmax(-1)
+                g = md.generators.get(s)
+                probs = logits[s:s + len(drafts) + 1].softmax(-1)
                 ok = True
                 for j, d in enumerate(drafts):
                     u = torch.rand((), generator=g, device=probs.device if g is None else g.device).item()
@@ -204,8 +230,11 @@ class RejectionSampler:
                     else:
                         p = probs[j].clone()
                         p[d] = 0
-                        p = p / p.sum()
-                        acc.append(int(torch.multinomial(p, 1, generator=g).item()))
+                        tot = p.sum()
+                        if float(tot) <= 0:      # the draft was the only admissible token and lost the coin flip
+                            acc.append(d)
+                            continue
+                        acc.append(int(torch.multinomial(p / tot, 1, generator=g).item()))
                         ok = False
                         break
                 if ok:

@@ -332,30 +332,56 @@ class StructuredOutputManager:
 
     def grammar_bitmask(self, requests: dict, structured_ids: list[str], spec_tokens: dict[str, list[int]]
                         ) -> Optional[np.ndarray]:
+        """One bitmask row per verified position: request ``rid`` with k scheduled draft tokens owns k + 1 consecutive
+        rows (the mask after drafts[:j] for j = 0..k), in ``structured_ids`` order — the grammar is advanced over the
+        drafts and rolled back (reference: structured_output/__init__.py ``grammar_bitmask`` with
+        ``scheduled_spec_decode_tokens``).  Without speculation that is the familiar one row per request."""
         if not structured_ids:
             return None
         W = (self.vocab_size + 31) // 32
-        n = len(structured_ids)
+        n = sum(len(spec_tokens.get(rid) or ()) + 1 for rid in structured_ids)
         if self._bitmask is None or self._bitmask.shape[0] < n:
             self._bitmask = np.full((max(n, 8), W), -1, dtype=np.int32)
         bm = self._bitmask
-        for row, rid in enumerate(structured_ids):
-            req = requests.get(rid)
-            so = req.structured_output_request if req is not None else None
-            if so is None or not so.is_ready():
-                bm[row] = -1
-                continue
-            if so.grammar.is_terminated():
+        eos = self.vllm_config.model_config.eos_token_id
+
+        def fill(g, row):
+            if g.is_terminated():
                 # nothing may follow a complete match: only end-of-sequence is allowed (the scheduler also finishes
                 # the request as soon as its grammar terminates)
-                eos = self.vllm_config.model_config.eos_token_id
                 if eos is None:
                     bm[row] = -1
                 else:
                     bm[row] = 0
                     bm[row, eos >> 5] = np.int32(np.uint32(1 << (eos & 31)).view(np.int32))
+            else:
+                g.fill_bitmask(bm, row)
+        row = 0
+        for rid in structured_ids:
+            req = requests.get(rid)
+            so = req.structured_output_request if req is not None else None
+            drafts = list(spec_tokens.get(rid) or ())
+            if so is None or not so.is_ready():
+                bm[row:row + len(drafts) + 1] = -1
+                row += len(drafts) + 1
                 continue
-            so.grammar.fill_bitmask(bm, row)
+            g = so.grammar
+            fill(g, row)
+            row += 1
+            adv = 0
+            for d in drafts:
+                if adv >= 0 and not g.is_terminated() and g.accept_tokens(rid, [d]):
+                    adv += 1
+                    fill(g, row)
+                else:
+                    # an inadmissible draft is rejected at its own position; later positions are never reached
+                    if adv >= 0:
+                        g.rollback(adv)
+                        adv = -1
+                    bm[row] = -1
+                row += 1
+            if adv > 0:
+                g.rollback(adv)
         return bm[:n].copy()
 
     def shutdown(self) -> None:

@@ -162,7 +162,7 @@ class ModelRunner:
         self.model: Optional[torch.nn.Module] = None
         from vllm_b200.sample.sampler import load_logits_processors
         self.sampler = Sampler(load_logits_processors(vllm_config.model_config.logits_processors, vllm_config, device))
-        self.rejection_sampler = RejectionSampler()
+        self.rejection_sampler = RejectionSampler(self.sampler)
         self.kv_caches: dict[str, torch.Tensor] = {}
         self.layer_to_group: dict[str, int] = {}
         self.num_kv_groups = 1
@@ -1025,15 +1025,27 @@ class ModelRunner:
             md.allowed_token_ids_mask = m.to(dev)
         return md
 
-    def _gather_bitmask(self, so: SchedulerOutput, states: list[ReqState]) -> Optional[torch.Tensor]:
+    def _gather_bitmask(self, so: SchedulerOutput, states: list[ReqState], expand: bool = False
+                        ) -> Optional[torch.Tensor]:
+        """Grammar bitmask rows in batch order.  The scheduler lays the mask out per structured request with one row
+        per verified position (k drafts → k + 1 rows); ``expand`` returns all of them (spec verification: one row
+        per target-logit row), otherwise the first row of each request (plain sampling)."""
         bm = so.grammar_bitmask
-        idx = {rid: i for i, rid in enumerate(so.structured_output_request_ids)}
+        spec = so.scheduled_spec_decode_tokens
+        start, off = {}, 0
+        for rid in so.structured_output_request_ids:
+            start[rid] = off
+            off += len(spec.get(rid) or ()) + 1
         W = bm.shape[1]
-        full = np.full((len(states), W), -1, dtype=np.int32)
-        for j, s in enumerate(states):
-            i = idx.get(s.req_id)
+        n_rows = sum(len(spec.get(s.req_id) or ()) + 1 for s in states) if expand else len(states)
+        full = np.full((n_rows, W), -1, dtype=np.int32)
+        r = 0
+        for s in states:
+            k = (len(spec.get(s.req_id) or ()) + 1) if expand else 1
+            i = start.get(s.req_id)
             if i is not None:
-                full[j] = bm[i]
+                full[r:r + k] = bm[i:i + k]
+            r += k
         return torch.from_numpy(full).to(self.device)
 
     def _prompt_logprobs(self, hidden, states, rows, ns, cu) -> dict[str, Optional[LogprobsTensors]]:
@@ -1089,9 +1101,33 @@ class ModelRunner:
             self.step_hidden = (src, rows.copy(), cu.copy(), self.num_computed_cpu[rows].copy())
         idx = torch.tensor(idx_list, dtype=torch.int64, device=self.device)
         logits = self.model.compute_logits(hidden[idx]).float()
-        smd = self._sampling_metadata(states, rows, len(states))
+        # one metadata row per verified position: the request's sampling state as it will be AFTER drafts[:p], so the
+        # grammar mask, processors, penalties and top-k/p filters of the plain sampler apply to every position
+        import dataclasses
+        exp_states, exp_rows = [], []
+        for j, s in enumerate(states):
+            for pos in range(len(draft_lists[j]) + 1):
+                exp_states.append(s if pos == 0 else
+                                  dataclasses.replace(s, output_token_ids=s.output_token_ids + draft_lists[j][:pos]))
+                exp_rows.append(rows[j])
+        smd = self._sampling_metadata(exp_states, exp_rows, len(exp_states))
+        bitmask = self._gather_bitmask(so, states, expand=True) if so.grammar_bitmask is not None else None
         total_after = self.num_computed_cpu[rows] + ns
-        accepted = self.rejection_sampler(logits, draft_lists, smd, cu_l)
+        accepted = self.rejection_sampler(logits, draft_lists, smd, cu_l, bitmask)
+        lp_tensors = None
+        if smd.max_num_logprobs is not None:
+            sel, toks = [], []
+            for j, acc in enumerate(accepted):
+                if total_after[j] - len(draft_lists[j]) < self.num_tokens_cpu[rows[j]]:
+                    continue                      # still prefilling: nothing is emitted for this request
+                sel.extend(range(cu_l[j], cu_l[j] + len(acc)))
+                toks.extend(acc)
+            if sel:
+                si = torch.tensor(sel, dtype=torch.int64, device=self.device)
+                from vllm_b200.ops import ref as ref_ops
+                lp = ref_ops.compute_logprobs(logits[si], torch.tensor(toks, dtype=torch.int64, device=self.device),
+                                              smd.max_num_logprobs)
+                lp_tensors = LogprobsTensors(lp[0].cpu(), lp[1].cpu(), lp[2].cpu())
         req_ids, out_ids = [], []
         for j, s in enumerate(states):
             r = rows[j]
@@ -1116,7 +1152,7 @@ class ModelRunner:
                 self.spec_hidden[r] = hidden[int(cu[j + 1]) - k - 1 + len(acc) - 1]
         spec_ids = self.drafter.propose(self, rows, out_ids) if self.drafter is not None else None
         return ModelRunnerOutput(req_ids=req_ids, req_id_to_index={r: i for i, r in enumerate(req_ids)},
-                                 sampled_token_ids=out_ids, spec_token_ids=spec_ids,
+                                 sampled_token_ids=out_ids, spec_token_ids=spec_ids, logprobs=lp_tensors,
                                  forward_ms=(time.perf_counter() - t0) * 1e3)
 
     # --------------------------------------------------------- profiling
