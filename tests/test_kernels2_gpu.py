@@ -1,0 +1,412 @@
+"""Round-2 sm_100a kernels vs fp32 PyTorch references: activation quantisers and their norm / activation fusions,
+fused q/k-norm + RoPE + cache insert, cache maintenance, multi-LoRA BGMV (run on the B200 box)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vllm_b200.ops import ref  # noqa: E402
+
+
+def cu():
+    from vllm_b200.ops import cuda_ops
+    return cuda_ops()
+
+
+def close(a, b, atol=2e-2, rtol=2e-2):
+    torch.testing.assert_close(a.float(), b.float(), atol=atol, rtol=rtol)
+
+
+def deq_close(q, s, expect, rel=0.07):
+    """fp8 round trip: |q * s - x| <= rel * max(|x|, s-granularity) elementwise (e4m3 has 3 mantissa bits)."""
+    got = q.float() * s
+    err = (got - expect.float()).abs()
+    tol = rel * expect.float().abs() + 2.0 * torch.as_tensor(s).float().expand_as(got) * 2 ** -9 + 1e-6
+    assert bool((err <= tol).all()), f"max err {err.max().item()} (tol {tol.max().item()})"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T,H", [(1, 128), (7, 1024), (64, 4096), (33, 7168), (3, 16384)])
+def test_scaled_fp8_quant(dtype, T, H):
+    torch.manual_seed(0)
+    x = torch.randn(T, H, device="cuda", dtype=dtype) * 3
+    # dynamic per token: identical scales, codes equal to the reference quantiser up to rounding ties
+    q, s = cu().scaled_fp8_quant(x, per_token=True)
+    rq, rs = ref.scaled_fp8_quant(x, per_token=True)
+    close(s, rs, atol=0, rtol=1e-6)
+    assert (q.float() - rq.float()).abs().max() <= 32.0          # one e4m3 step at the top binade
+    deq_close(q, s, x)
+    # dynamic per tensor
+    q, s = cu().scaled_fp8_quant(x)
+    close(s.reshape(()), ref.scaled_fp8_quant(x)[1].reshape(()), atol=0, rtol=1e-6)
+    deq_close(q, s, x)
+    # static
+    sc = torch.tensor([0.05], device="cuda")
+    q, _ = cu().scaled_fp8_quant(x, sc)
+    assert torch.equal(q.float(), ref.scaled_fp8_quant(x, sc)[0].float())
+
+
+@pytest.mark.parametrize("group", [128, 64, 32])
+@pytest.mark.parametrize("T,H", [(5, 512), (64, 7168), (17, 2048)])
+def test_per_token_group_quant(group, T, H):
+    torch.manual_seed(1)
+    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16) * torch.rand(T, 1, device="cuda") * 4
+    rq, rs = ref.per_token_group_quant_fp8(x, group)
+    q, s = cu().per_token_group_quant_fp8(x, group)
+    close(s, rs, atol=0, rtol=1e-6)
+    assert torch.equal(q.float(), rq.float())
+    # column-major scale storage (TMA-friendly) carries the same values
+    q2, s2 = cu().per_token_group_quant_fp8(x, group, col_major=True)
+    assert s2.shape == (T, H // group) and s2.stride(0) == 1
+    close(s2, rs, atol=0, rtol=1e-6)
+    assert torch.equal(q2.float(), rq.float())
+    # UE8M0: power-of-two scales >= the exact ones, dequantisation still within fp8 accuracy
+    q3, s3 = cu().per_token_group_quant_fp8(x, group, ue8m0=True)
+    assert bool((s3 >= rs * (1 - 1e-6)).all()) and bool((torch.log2(s3) == torch.log2(s3).round()).all())
+    deq_close(q3, s3.repeat_interleave(group, 1), x)
+
+
+def test_scaled_int8_quant():
+    torch.manual_seed(2)
+    x = torch.randn(19, 4096, device="cuda", dtype=torch.float16) * 2
+    q, s = cu().scaled_int8_quant(x)
+    rq, rs = ref.scaled_int8_quant(x)
+    close(s, rs, atol=0, rtol=1e-6)
+    assert (q.int() - rq.int()).abs().max() <= 1
+    sc = torch.tensor([0.03], device="cuda")
+    q, _ = cu().scaled_int8_quant(x, sc)
+    assert (q.int() - ref.scaled_int8_quant(x, sc)[0].int()).abs().max() <= 1
+
+
+@pytest.mark.parametrize("mode", ["static", "token", "group"])
+@pytest.mark.parametrize("with_residual", [False, True])
+def test_rms_norm_quant_fusion(mode, with_residual):
+    torch.manual_seed(3)
+    T, H = 48, 4096
+    dt = torch.bfloat16
+    x = torch.randn(T, H, device="cuda", dtype=dt)
+    r = torch.randn(T, H, device="cuda", dtype=dt)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dt)
+    sc = torch.tensor([0.02], device="cuda")
+    if with_residual:
+        y, r_exp = ref.fused_add_rms_norm(x.clone(), r.clone(), w, 1e-5)
+    else:
+        y, r_exp = ref.rms_norm(x, w, 1e-5), None
+    r2 = r.clone() if with_residual else None
+    q, s = cu().rms_norm_quant(x, w, 1e-5, residual=r2, scale=sc if mode == "static" else None, mode=mode)
+    if with_residual:
+        close(r2, r_exp, atol=1e-2)
+    if mode == "static":
+        deq_close(q, sc, y.float().clamp(-448 * 0.02, 448 * 0.02), rel=0.08)
+    elif mode == "token":
+        close(s, ref.scaled_fp8_quant(y, per_token=True)[1], atol=0, rtol=2e-2)
+        deq_close(q, s, y, rel=0.08)
+    else:
+        close(s, ref.per_token_group_quant_fp8(y, 128)[1], atol=0, rtol=2e-2)
+        deq_close(q, s.repeat_interleave(128, 1), y, rel=0.08)
+
+
+@pytest.mark.parametrize("mode", ["static", "token", "group"])
+def test_silu_mul_quant_fusion(mode):
+    torch.manual_seed(4)
+    T, H = 33, 2048
+    x = torch.randn(T, 2 * H, device="cuda", dtype=torch.bfloat16)
+    y = ref.silu_and_mul(x.float())
+    sc = torch.tensor([0.01], device="cuda")
+    q, s = cu().act_mul_quant(x, "silu", scale=sc if mode == "static" else None, mode=mode)
+    if mode == "static":
+        deq_close(q, sc, y.clamp(-4.48, 4.48), rel=0.08)
+    elif mode == "token":
+        deq_close(q, s, y, rel=0.08)
+    else:
+        deq_close(q, s.repeat_interleave(128, 1), y, rel=0.08)
+
+
+def test_nvfp4_and_mxfp4_quant_roundtrip():
+    torch.manual_seed(5)
+    T, H = 40, 1024
+    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16)
+    gs = (448.0 * 6.0) / x.float().abs().max()
+    q, sf = cu().scaled_fp4_quant(x, gs.reshape(1).float())
+    deq = ref.fp4_dequant(q, sf.view(torch.float8_e4m3fn).float(), 1.0 / float(gs), block=16)
+    rel = (deq - x.float()).norm() / x.float().norm()
+    assert rel < 0.13, rel                       # e2m1: ~9-10 % relative error on gaussian data
+    # MXFP4: block 32, e8m0 scale bytes
+    q2, sf2 = cu().scaled_fp4_quant(x, mx=True)
+    sc = torch.pow(2.0, sf2.float() - 127.0)
+    deq2 = ref.fp4_dequant(q2, sc, 1.0, block=32)
+    assert (deq2 - x.float()).norm() / x.float().norm() < 0.16
+    # the swizzled scale layout holds the same bytes at the tile offsets
+    q3, sfs = cu().scaled_fp4_quant(x, gs.reshape(1).float(), swizzled=True)
+    assert torch.equal(q3, q)
+    m, k = 37, 21
+    off = ((m >> 7) * ((H // 16 + 3) // 4) + (k >> 2)) * 512 + (m & 31) * 16 + ((m >> 5) & 3) * 4 + (k & 3)
+    assert int(sfs[off]) == int(sf[m, k])
+
+
+@pytest.mark.parametrize("neox", [True, False])
+@pytest.mark.parametrize("Hq,Hkv,D,rot", [(32, 8, 128, 128), (8, 2, 128, 64), (4, 4, 64, 64), (8, 1, 256, 256)])
+def test_fused_qknorm_rope_cache(neox, Hq, Hkv, D, rot):
+    torch.manual_seed(6)
+    T, BS, NB = 29, 16, 12
+    dt = torch.bfloat16
+    from vllm_b200.layers.rotary import RotaryEmbedding
+    rope = RotaryEmbedding(D, rot, 2048, 10000.0, neox).cuda()
+    qkv = torch.randn(T, (Hq + 2 * Hkv) * D, device="cuda", dtype=dt)
+    qw = (1 + 0.1 * torch.randn(D, device="cuda")).to(dt)
+    kw = (1 + 0.1 * torch.randn(D, device="cuda")).to(dt)
+    pos = torch.randint(0, 2048, (T,), device="cuda")
+    slots = torch.randperm(NB * BS, device="cuda")[:T].long()
+    slots[5] = -1
+    q, k, v = qkv.split([Hq * D, Hkv * D, Hkv * D], dim=-1)
+    eq, ek = ref.fused_qk_norm_rope(pos, q.clone(), k.clone(), qw, kw, rope.cos_sin_cache, D, 1e-6, neox)
+    cache_ref = torch.zeros(NB, 2, Hkv, BS, D, device="cuda", dtype=dt)
+    ref.reshape_and_cache(ek.view(T, Hkv, D), v.reshape(T, Hkv, D), cache_ref, slots)
+    cache = torch.zeros_like(cache_ref)
+    assert cu().qknorm_rope_ok(D, rot, neox)
+    oq, ok = cu().fused_qk_norm_rope(pos, q, k, qw, kw, rope.cos_sin_cache, D, 1e-6, neox, v=v, kv_cache=cache,
+                                     slot_mapping=slots)
+    close(oq, eq, atol=3e-2)
+    close(ok, ek, atol=3e-2)
+    close(cache, cache_ref, atol=3e-2)
+
+
+def test_swap_copy_gather_convert():
+    torch.manual_seed(7)
+    NB, BS, Hkv, D = 24, 16, 4, 128
+    cache = torch.randn(NB, 2, Hkv, BS, D, device="cuda", dtype=torch.bfloat16)
+    host = torch.zeros(8, 2, Hkv, BS, D, dtype=torch.bfloat16).pin_memory()
+    pairs = [(3, 0), (17, 5), (9, 7)]
+    cu().swap_blocks(cache, host, pairs)                       # swap out
+    torch.cuda.synchronize()
+    for s, d in pairs:
+        assert torch.equal(host[d], cache[s].cpu())
+    dst = torch.zeros_like(cache)
+    cu().swap_blocks(host, dst, [(0, 11), (5, 2)])             # swap in
+    torch.cuda.synchronize()
+    assert torch.equal(dst[11].cpu(), host[0]) and torch.equal(dst[2].cpu(), host[5])
+    c2 = cache.clone()
+    cu().copy_blocks(c2, torch.tensor([[1, 20], [4, 21]], device="cuda"))
+    assert torch.equal(c2[20], cache[1]) and torch.equal(c2[21], cache[4]) and torch.equal(c2[5], cache[5])
+    # gather of MLA-style latent rows (bf16 and fp8 source)
+    lat = torch.randn(NB, BS, 576, device="cuda", dtype=torch.bfloat16)
+    lens = [37, 5, 64]
+    bt = torch.randperm(NB, device="cuda")[:3 * 5].int().view(3, 5)
+    cu_l = torch.tensor([0, 37, 42, 106], dtype=torch.int32, device="cuda")
+    out = torch.zeros(106, 576, device="cuda", dtype=torch.bfloat16)
+    cu().gather_cache(lat, bt, cu_l, out, max(lens))
+    exp = torch.cat([lat[bt[b].long()].reshape(-1, 576)[:n] for b, n in enumerate(lens)])
+    assert torch.equal(out, exp)
+    lat8 = (lat.float() / 0.5).clamp(-448, 448).to(torch.float8_e4m3fn)
+    out8 = torch.zeros_like(out)
+    cu().gather_cache(lat8, bt, cu_l, out8, max(lens), scale=0.5)
+    exp8 = torch.cat([lat8[bt[b].long()].reshape(-1, 576)[:n] for b, n in enumerate(lens)]).float() * 0.5
+    close(out8, exp8, atol=1e-2)
+    # convert
+    x = torch.randn(1000, 64, device="cuda", dtype=torch.bfloat16)
+    c = cu().convert_fp8(x, 0.25, True)
+    assert torch.equal(c.float(), ref.convert_fp8(x, 0.25, True).float())
+    close(cu().convert_fp8(c, 0.25, False), ref.convert_fp8(c, 0.25, False), atol=1e-2)
+
+
+@pytest.mark.parametrize("n_sub,N", [(1, 4096), (3, 6144), (2, 2 * 1408)])
+def test_lora_bgmv(n_sub, N):
+    torch.manual_seed(8)
+    T, K, r, S = 37, 2048, 16, 4
+    dt = torch.bfloat16
+    x = torch.randn(T, K, device="cuda", dtype=dt)
+    y0 = torch.randn(T, N, device="cuda", dtype=dt)
+    A = torch.randn(S, n_sub, r, K, device="cuda", dtype=dt) * 0.05
+    B = torch.randn(S, N, r, device="cuda", dtype=dt) * 0.05
+    slots = torch.randint(-1, S, (T,), device="cuda", dtype=torch.int64)
+    if n_sub == 3:
+        bounds = [4096, 5120]
+    elif n_sub == 2:
+        bounds = [1408]
+    else:
+        bounds = []
+    offs = (n_sub, *(bounds + [N] * (3 - len(bounds))))
+    y = y0.clone()
+    cu().lora_bgmv(x, y, A, B, slots, offs)
+    exp = y0.float().clone()
+    edges = [0] + bounds + [N]
+    for t in range(T):
+        s = int(slots[t])
+        if s < 0:
+            continue
+        for j in range(n_sub):
+            v = A[s, j].float() @ x[t].float()
+            exp[t, edges[j]:edges[j + 1]] += B[s, edges[j]:edges[j + 1]].float() @ v
+    close(y, exp, atol=6e-2, rtol=3e-2)
+    assert torch.equal(y[slots < 0], y0[slots < 0])
+
+
+# ------------------------------------------------------------------ SSM / linear attention over the state pool
+def _ssm_md(q_lens, ctx_lens, rows):
+    from types import SimpleNamespace
+    qsl = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    sl = torch.tensor([c + q for c, q in zip(ctx_lens, q_lens)], dtype=torch.int32, device="cuda")
+    bt = torch.tensor(rows, dtype=torch.int32, device="cuda").view(-1, 1).repeat(1, 3).contiguous()
+    return SimpleNamespace(num_reqs=len(q_lens), query_start_loc=qsl, seq_lens=sl, block_table=bt)
+
+
+@pytest.mark.parametrize("K", [2, 4])
+def test_causal_conv1d_with_cached_window(K):
+    torch.manual_seed(10)
+    C, q_lens, ctx = 384, [5, 1, 17, 1], [0, 9, 3, 0]
+    rows = [3, 7, 1, 5]
+    T = sum(q_lens)
+    x = torch.randn(T, C, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(C, K, device="cuda", dtype=torch.bfloat16) * 0.5
+    b = torch.randn(C, device="cuda", dtype=torch.bfloat16) * 0.1
+    extra = 40
+    pool = torch.randn(9, C * (K - 1) + extra, device="cuda", dtype=torch.float32)
+    pool0 = pool.clone()
+    md = _ssm_md(q_lens, ctx, rows)
+    out = cu().causal_conv1d(x, w, b, pool, md)
+    s = 0
+    for i, n in enumerate(q_lens):
+        win = pool0[rows[i], :C * (K - 1)].view(C, K - 1) if ctx[i] > 0 else torch.zeros(C, K - 1, device="cuda")
+        xin = torch.cat([win.t(), x[s:s + n].float()], 0)                   # [K-1+n, C]
+        conv = (xin.unfold(0, K, 1) * w.float()[None]).sum(-1) + b.float()
+        close(out[s:s + n], torch.nn.functional.silu(conv), atol=2e-3, rtol=2e-3)
+        close(pool[rows[i], :C * (K - 1)].view(C, K - 1), xin[-(K - 1):].t(), atol=1e-6, rtol=0)
+        assert torch.equal(pool[rows[i], C * (K - 1):], pool0[rows[i], C * (K - 1):])      # rest of the row untouched
+        s += n
+
+
+def test_selective_scan_mamba1():
+    torch.manual_seed(11)
+    di, N, q_lens, ctx, rows = 256, 16, [6, 1, 33], [0, 4, 2], [2, 0, 5]
+    T = sum(q_lens)
+    x = torch.randn(T, di, device="cuda")
+    dt = torch.nn.functional.softplus(torch.randn(T, di, device="cuda"))
+    B, Cm = torch.randn(T, N, device="cuda"), torch.randn(T, N, device="cuda")
+    A = -torch.rand(di, N, device="cuda") - 0.1
+    D = torch.randn(di, device="cuda")
+    off = 64
+    pool = torch.randn(6, off + di * N, device="cuda")
+    pool0 = pool.clone()
+    y = cu().selective_scan(x, dt, B, Cm, A, D, pool, off, _ssm_md(q_lens, ctx, rows))
+    s = 0
+    for i, n in enumerate(q_lens):
+        h = pool0[rows[i], off:].view(di, N).clone() if ctx[i] > 0 else torch.zeros(di, N, device="cuda")
+        for t in range(s, s + n):
+            h = torch.exp(dt[t][:, None] * A) * h + (dt[t] * x[t])[:, None] * B[t][None]
+            close(y[t], (h * Cm[t][None]).sum(-1) + D * x[t], atol=2e-3, rtol=2e-3)
+        close(pool[rows[i], off:].view(di, N), h, atol=2e-3, rtol=2e-3)
+        s += n
+
+
+@pytest.mark.parametrize("N,G", [(128, 1), (64, 2), (32, 4)])
+def test_ssd_scan_mamba2_matches_chunked_reference(N, G):
+    torch.manual_seed(12)
+    nh, hd, q_lens, ctx, rows = 8, 16, [70, 1, 9], [0, 11, 5], [1, 4, 2]
+    T = sum(q_lens)
+    d_inner = nh * hd
+    xbc = torch.randn(T, d_inner + 2 * G * N, device="cuda") * 0.5
+    dt_raw = torch.randn(T, nh, device="cuda")
+    dt_bias, A_log, D = torch.randn(nh, device="cuda") * 0.3, torch.randn(nh, device="cuda") * 0.3, torch.randn(nh, device="cuda")
+    off = 24
+    pool = torch.randn(6, off + nh * hd * N, device="cuda") * 0.3
+    pool0 = pool.clone()
+    y = cu().ssd_scan(xbc, dt_raw, dt_bias, A_log, D, pool, off, _ssm_md(q_lens, ctx, rows), nh, hd, G, N)
+    s = 0
+    for i, n in enumerate(q_lens):
+        h0 = pool0[rows[i], off:].view(nh, hd, N).clone() if ctx[i] > 0 else None
+        seg = xbc[s:s + n]
+        xs, Bs, Cs = seg.split([d_inner, G * N, G * N], -1)
+        dt = torch.nn.functional.softplus(dt_raw[s:s + n] + dt_bias)
+        ye, hf = ref.ssd_chunk_scan(xs.view(n, nh, hd), dt, -torch.exp(A_log), Bs.view(n, G, N), Cs.view(n, G, N), 16, h0)
+        ye = ye + D[None, :, None] * xs.view(n, nh, hd)
+        close(y[s:s + n], ye.reshape(n, d_inner), atol=5e-3, rtol=5e-3)
+        close(pool[rows[i], off:].view(nh, hd, N), hf, atol=5e-3, rtol=5e-3)
+        s += n
+
+
+def test_gdn_scan_matches_recurrence():
+    torch.manual_seed(13)
+    nv, dk, dv, q_lens, ctx, rows = 4, 64, 32, [12, 1, 5], [0, 3, 1], [0, 3, 2]
+    T = sum(q_lens)
+    q = torch.nn.functional.normalize(torch.randn(T, nv, dk, device="cuda"), dim=-1) * dk ** -0.5
+    k = torch.nn.functional.normalize(torch.randn(T, nv, dk, device="cuda"), dim=-1)
+    v = torch.randn(T, nv, dv, device="cuda")
+    g = -torch.rand(T, nv, device="cuda")
+    beta = torch.rand(T, nv, device="cuda")
+    off = 16
+    pool = torch.randn(5, off + nv * dk * dv, device="cuda") * 0.2
+    pool0 = pool.clone()
+    o = cu().gdn_scan(q, k, v, g, beta, pool, off, _ssm_md(q_lens, ctx, rows))
+    s = 0
+    for i, n in enumerate(q_lens):
+        S = pool0[rows[i], off:].view(nv, dk, dv).clone() if ctx[i] > 0 else torch.zeros(nv, dk, dv, device="cuda")
+        for t in range(s, s + n):
+            S = S * g[t].exp()[:, None, None]
+            delta = (v[t] - (S * k[t][..., None]).sum(-2)) * beta[t][:, None]
+            S = S + k[t][..., None] * delta[:, None, :]
+            close(o[t], (S * q[t][..., None]).sum(-2), atol=2e-3, rtol=2e-3)
+        close(pool[rows[i], off:].view(nv, dk, dv), S, atol=2e-3, rtol=2e-3)
+        s += n
+
+
+# ------------------------------------------------------------------ tcgen05 fp8 GEMMs (csrc/gemm_fp8.cu)
+def _fp8_block_ref(xq, xs, wq, ws):
+    K = xq.shape[1]
+    xd = xq.float() * xs.float().repeat_interleave(128, dim=1)[:, :K]
+    wd = wq.float() * ws.repeat_interleave(128, 0)[:wq.shape[0]].repeat_interleave(128, 1)[:, :K]
+    return xd @ wd.t()
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 512, 512), (16, 7168, 2048), (64, 4096, 7168), (33, 1536, 7168),
+                                   (128, 2112, 7168), (100, 576, 1024), (48, 24576, 1536),
+                                   (300, 4096, 7168), (1024, 2048, 4096)])
+def test_gemm_fp8_block_scaled(M, N, K):
+    torch.manual_seed(20)
+    x = (torch.randn(M, K, device="cuda") * (1 + torch.rand(M, 1, device="cuda") * 3)).to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda") * 0.05
+    wq, ws = ref.block_quant_weight_fp8(w, 128)
+    xq, xs = cu().per_token_group_quant_fp8(x, 128, col_major=True)
+    y = cu().gemm_fp8_block(xq, xs, wq, ws.contiguous(), torch.bfloat16)
+    exp = _fp8_block_ref(xq, xs, wq, ws)
+    close(y, exp, atol=2e-2 * exp.abs().max().item() / 8 + 1e-2, rtol=2e-2)
+    # end to end against the unquantised product: fp8 accuracy
+    full = x.float() @ w.t()
+    assert ((y.float() - full).norm() / full.norm()) < 0.06
+    # the public op (fused quantiser + GEMM, bias)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    y2 = cu().block_fp8_linear(x, wq, ws, 128, bias)
+    close(y2, exp + bias.float(), atol=2e-2 * exp.abs().max().item() / 8 + 2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 1024, 1024), (64, 6144, 4096), (128, 4096, 14336), (500, 3072, 2048)])
+@pytest.mark.parametrize("per_token,per_channel", [(True, True), (False, False), (True, False)])
+def test_gemm_fp8_scaled_mm(M, N, K, per_token, per_channel):
+    torch.manual_seed(21)
+    a = (torch.randn(M, K, device="cuda") * 2).clamp(-448, 448).to(torch.float8_e4m3fn)
+    b = (torch.randn(N, K, device="cuda") * 2).clamp(-448, 448).to(torch.float8_e4m3fn)
+    sa = torch.rand(M if per_token else 1, 1, device="cuda") * 0.02 + 0.001
+    sb = torch.rand(N if per_channel else 1, 1, device="cuda") * 0.02 + 0.001
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    y = cu().scaled_mm(a, b, sa, sb, torch.bfloat16, bias)
+    exp = ref.scaled_mm(a, b, sa, sb, torch.float32, bias)
+    close(y, exp, atol=1e-2 * exp.abs().max().item() + 1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("E,N,K,R,bn", [(8, 1024, 1024, 64, 16), (4, 4096, 7168, 200, 64), (16, 512, 2048, 37, 32)])
+def test_gemm_fp8_grouped(E, N, K, R, bn):
+    torch.manual_seed(22)
+    x = torch.randn(R, K, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(E, N, K, device="cuda") * 0.05
+    wq = torch.empty(E, N, K, device="cuda", dtype=torch.float8_e4m3fn)
+    ws = torch.empty(E, (N + 127) // 128, K // 128, device="cuda")
+    for e in range(E):
+        wq[e], ws[e] = ref.block_quant_weight_fp8(w[e], 128)
+    cuts = torch.sort(torch.randint(0, R + 1, (E - 1,))).values.tolist()
+    offs = torch.tensor([0] + cuts + [R], dtype=torch.int32, device="cuda")
+    xq, xs = cu().per_token_group_quant_fp8(x, 128, col_major=True)
+    y = cu().gemm_fp8_grouped(xq, xs, wq, ws, offs, bn)
+    o = offs.tolist()
+    for e in range(E):
+        if o[e + 1] > o[e]:
+            exp = _fp8_block_ref(xq[o[e]:o[e + 1]], xs[o[e]:o[e + 1]], wq[e], ws[e])
+            close(y[o[e]:o[e + 1]], exp, atol=2e-2 * exp.abs().max().item() / 8 + 1e-2, rtol=2e-2)

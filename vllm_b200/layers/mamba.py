@@ -23,6 +23,11 @@ from vllm_b200.layers import attention as _attn
 from vllm_b200.layers.linear import ReplicatedLinear
 
 
+def _cuda_ssm(x: torch.Tensor) -> bool:
+    from vllm_b200 import envs
+    return x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not envs.VLLM_B200_FORCE_REF_OPS
+
+
 class MambaMixer(nn.Module):
     def __init__(self, hidden: int, d_inner: int, d_state: int, d_conv: int, dt_rank: int, use_bias: bool,
                  use_conv_bias: bool, dtype, prefix: str, bcdt_norm_eps: Optional[float] = None) -> None:
@@ -95,6 +100,16 @@ class MambaMixer(nn.Module):
         if md is None or cache is None:          # profiling run: stateless pass over the whole buffer as one sequence
             y, _, _ = self._segment(x, x.new_zeros(self.d_inner, self.d_conv - 1, dtype=torch.float32),
                                     x.new_zeros(self.d_inner, self.d_state, dtype=torch.float32))
+            return self.out_proj((y * F.silu(z.float())).to(hidden.dtype))
+        if _cuda_ssm(x) and self.d_state in (8, 16, 32) and 2 <= self.d_conv <= 4:
+            # device path (csrc/ssm.cu): conv window and SSM state are advanced in place in the cache pool by two varlen
+            # kernels — same code for decode, prefill and chunked prefill; no host loop, graph capturable
+            from vllm_b200.ops import cuda_ops
+            cu = cuda_ops()
+            xa = cu.causal_conv1d(x, self.conv_weight, self.conv_bias, cache, md)
+            dt, Bm, Cm = self._ssm_params(xa.to(x.dtype))
+            y = cu.selective_scan(xa, dt, Bm, Cm, -torch.exp(self.A_log), self.D, cache,
+                                  self.d_inner * (self.d_conv - 1), md)
             return self.out_proj((y * F.silu(z.float())).to(hidden.dtype))
         cache = cache.view(cache.shape[0], -1).view(torch.float32) if cache.dtype != torch.float32 else cache
         if md.decode_only:
@@ -211,6 +226,13 @@ class Mamba2Mixer(nn.Module):
         if md is None or cache is None:                      # profiling run: one stateless sequence
             y, _, _ = self._segment(xbc, dt, torch.zeros(self.conv_dim, self.k - 1, device=dev),
                                     torch.zeros(self.nh, self.hd, self.N, device=dev))
+            return self.out_proj(self._gated_norm(y, z).to(hidden.dtype))
+        if _cuda_ssm(xbc) and self.N % 32 == 0 and self.N <= 256 and 2 <= self.k <= 4:
+            from vllm_b200.ops import cuda_ops
+            cu = cuda_ops()
+            xa = cu.causal_conv1d(xbc, self.conv_weight, self.conv_bias, cache, md)
+            y = cu.ssd_scan(xa, dt.float(), self.dt_bias, self.A_log, self.D, cache, self.conv_dim * (self.k - 1), md,
+                            self.nh, self.hd, self.G, self.N, self.dt_min, self.dt_max)
             return self.out_proj(self._gated_norm(y, z).to(hidden.dtype))
         cache = cache.view(cache.shape[0], -1).view(torch.float32) if cache.dtype != torch.float32 else cache
         out = torch.zeros(T, self.d_inner, dtype=torch.float32, device=dev)

@@ -94,6 +94,14 @@ def apply_lora(layer, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     if b is None or not table:
         return y
     x2, y2 = x.reshape(-1, x.shape[-1]), y.reshape(-1, y.shape[-1])
+    stack = getattr(layer, "lora_stack", None)
+    if stack is not None and x2.is_cuda:
+        # device path: two BGMV launches over the token → slot table (csrc/lora.cu); no host-side grouping
+        from vllm_b200.ops import cuda_ops
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        cuda_ops().lora_bgmv(x2, y2, stack["A"], stack["B"], b.token_slots, stack["offs"])
+        return y
     for slot in b.active:
         entries = table.get(slot)
         if not entries:
@@ -154,6 +162,32 @@ class LoRAModelManager:
             t = getattr(m, "lora_table", None)
             if t:
                 t.pop(slot, None)
+            st = getattr(m, "lora_stack", None)
+            if st is not None:
+                st["A"][slot].zero_()
+                st["B"][slot].zero_()
+
+    def _stack_for(self, mod) -> dict:
+        """Per-module stacked adapter weights for the BGMV kernels: A [slots, n_sub, r_max, K], B [slots, N, r_max]
+        (scaling folded into B; empty slots / sub-projections stay zero and contribute nothing)."""
+        st = getattr(mod, "lora_stack", None)
+        if st is None:
+            from vllm_b200.layers.linear import MergedColumnParallelLinear, QKVParallelLinear
+            w = mod.weight
+            N, K = w.shape[0], w.shape[1]
+            if isinstance(mod, QKVParallelLinear):
+                sizes = [mod.q_size, mod.kv_size, mod.kv_size]
+            elif isinstance(mod, MergedColumnParallelLinear):
+                sizes = [s_ // mod.tp_size for s_ in mod.output_sizes]
+            else:
+                sizes = [N]
+            r_max = (self.cfg.max_lora_rank + 7) // 8 * 8
+            offs = [sum(sizes[:i + 1]) for i in range(len(sizes) - 1)] + [N] * (4 - len(sizes))
+            st = {"A": torch.zeros(self.max_loras, len(sizes), r_max, K, dtype=self.dtype, device=self.device),
+                  "B": torch.zeros(self.max_loras, N, r_max, dtype=self.dtype, device=self.device),
+                  "offs": (len(sizes), offs[0], offs[1], offs[2]), "starts": [sum(sizes[:i]) for i in range(len(sizes))]}
+            mod.lora_stack = st
+        return st
 
     def _slice_for(self, mod, sub_idx: Optional[int], a: torch.Tensor, b: torch.Tensor):
         """(out_offset, out_len, A, B) for this TP rank."""
@@ -211,6 +245,14 @@ class LoRAModelManager:
             if not hasattr(mod, "lora_table") or mod.lora_table is None:
                 mod.lora_table = {}
             mod.lora_table.setdefault(slot, []).append(ent)
+            if self.device.type == "cuda" and getattr(mod, "weight", None) is not None and mod.weight.dim() == 2 \
+                    and mod.weight.dtype == self.dtype and mod.weight.shape[1] % 8 == 0 \
+                    and self.dtype in (torch.bfloat16, torch.float16):
+                st = self._stack_for(mod)
+                j = st["starts"].index(off) if off in st["starts"] else 0
+                r = ent[2].shape[0]
+                st["A"][slot, j, :r].copy_(ent[2])
+                st["B"][slot, off:off + n, :r].copy_(ent[3] * lora.scaling)
             n_attached += 1
         logger.info("LoRA %d → slot %d (%d target modules)", lid, slot, n_attached)
         return slot

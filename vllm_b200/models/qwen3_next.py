@@ -123,6 +123,16 @@ class GatedDeltaNet(nn.Module):
                                       torch.zeros(self.nv, self.dk, self.dv, device=dev))
             out = torch.cat([out, torch.zeros(T - out.shape[0], self.nv, self.dv, device=dev)]) if T > out.shape[0] else out
             return self.out_proj(self._gated_norm(out, z).reshape(T, -1).to(hidden.dtype))
+        from vllm_b200.layers.mamba import _cuda_ssm
+        if _cuda_ssm(qkv) and self.dk % 32 == 0 and self.dk <= 256 and 2 <= self.k <= 4:
+            # device path (csrc/ssm.cu): causal conv + gated-delta-rule scan over the cache pool, any batch shape
+            from vllm_b200.ops import cuda_ops
+            cu = cuda_ops()
+            conv = cu.causal_conv1d(qkv, self.conv_weight, None, cache, md)
+            qh, kh, vh = self._qkv_heads(conv)
+            g = -self.A_log.exp() * F.softplus(a.float() + self.dt_bias)
+            o = cu.gdn_scan(qh, kh, vh, g, b.float().sigmoid(), cache, self.conv_dim * (self.k - 1), md)
+            return self.out_proj(self._gated_norm(o, z).reshape(T, -1).to(hidden.dtype))
         cache = cache.view(cache.shape[0], -1).view(torch.float32) if cache.dtype != torch.float32 else cache
         if md.decode_only:
             Bn = md.num_reqs

@@ -163,15 +163,93 @@ def block_fp8_linear(x, wq, w_scale, block=128, bias=None):
     return ref.block_fp8_linear(x, wq, w_scale, block, bias)
 
 
-# -- ops served by the PyTorch implementations on every device (elementwise / bookkeeping; not on a hot path that a
-#    dedicated kernel would change): extra gated activations, q/k-norm + RoPE, cache maintenance, activation quantisers
+# -- quantisers, q/k-norm + RoPE, cache maintenance: CUDA kernels (csrc/quant.cu, qknorm_rope.cu, cache_ops.cu), fp32
+#    PyTorch reference on the CPU
+def scaled_fp8_quant(x, scale=None, per_token: bool = False):
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 8 == 0:
+        return cuda_ops().scaled_fp8_quant(x, scale, per_token)
+    return ref.scaled_fp8_quant(x, scale, per_token)
+
+
+def scaled_int8_quant(x, scale=None):
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 8 == 0:
+        return cuda_ops().scaled_int8_quant(x, scale)
+    return ref.scaled_int8_quant(x, scale)
+
+
+def per_token_group_quant_fp8(x, group: int = 128, col_major: bool = False, ue8m0: bool = False):
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16):
+        return cuda_ops().per_token_group_quant_fp8(x, group, col_major, ue8m0)
+    return ref.per_token_group_quant_fp8(x.reshape(-1, x.shape[-1]), group)
+
+
+def rms_norm_quant(x, weight, eps, *, residual=None, scale=None, mode: str = "static", group: int = 128,
+                   gemma: bool = False):
+    """(residual add +) RMSNorm + fp8 quant in one pass; returns (q, scale) and updates ``residual`` in place."""
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 8 == 0:
+        return cuda_ops().rms_norm_quant(x, weight, eps, residual=residual, scale=scale, mode=mode, group=group,
+                                         gemma=gemma)
+    if residual is not None:
+        y, _ = ref.fused_add_rms_norm(x, residual, weight, eps, gemma)
+    else:
+        y = ref.rms_norm(x, weight, eps, gemma)
+    if mode == "group":
+        return ref.per_token_group_quant_fp8(y.reshape(-1, y.shape[-1]), group)
+    return ref.scaled_fp8_quant(y, scale, per_token=(mode == "token"))
+
+
+def act_mul_quant(x, act: str = "silu", *, scale=None, mode: str = "static", group: int = 128):
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 16 == 0:
+        return cuda_ops().act_mul_quant(x, act, scale=scale, mode=mode, group=group)
+    y = ref.silu_and_mul(x) if act == "silu" else ref.gelu_and_mul(x, "tanh" if "tanh" in act else "none")
+    if mode == "group":
+        return ref.per_token_group_quant_fp8(y.reshape(-1, y.shape[-1]), group)
+    return ref.scaled_fp8_quant(y, scale, per_token=(mode == "token"))
+
+
+def fused_qk_norm_rope(positions, q, k, q_weight, k_weight, cos_sin_cache, head_dim, eps, is_neox=True, **kw):
+    if _use_cuda(q) and q.dtype in (torch.bfloat16, torch.float16) and cuda_ops().qknorm_rope_ok(
+            head_dim, cos_sin_cache.shape[-1] if cos_sin_cache is not None else 0, is_neox):
+        return cuda_ops().fused_qk_norm_rope(positions, q, k, q_weight, k_weight, cos_sin_cache, head_dim, eps, is_neox,
+                                             **kw)
+    q, k = ref.fused_qk_norm_rope(positions, q, k, q_weight, k_weight, cos_sin_cache, head_dim, eps, is_neox)
+    if kw.get("kv_cache") is not None:
+        v = kw["v"]
+        Hkv = k.shape[-1] // head_dim
+        reshape_and_cache(k.reshape(-1, Hkv, head_dim), v.reshape(-1, Hkv, head_dim), kw["kv_cache"],
+                          kw["slot_mapping"], vt=kw.get("vt", False))
+    return q, k
+
+
+def swap_blocks(src, dst, mapping) -> None:
+    if (src.is_cuda or dst.is_cuda) and not envs.VLLM_B200_FORCE_REF_OPS and (src.is_cuda or src.is_pinned()) \
+            and (dst.is_cuda or dst.is_pinned()) and (src[0].numel() * src.element_size()) % 16 == 0 \
+            and src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype:
+        return cuda_ops().swap_blocks(src, dst, mapping)
+    return ref.swap_blocks(src, dst, mapping if not isinstance(mapping, torch.Tensor) else mapping.tolist())
+
+
+def convert_fp8(x, scale: float = 1.0, to_fp8: bool = True):
+    if _use_cuda(x) and (x.dtype in (torch.bfloat16, torch.float16) or not to_fp8):
+        return cuda_ops().convert_fp8(x, scale, to_fp8)
+    return ref.convert_fp8(x, scale, to_fp8)
+
+
+def scaled_fp4_quant(x, global_scale=None, mx: bool = False):
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 32 == 0:
+        return cuda_ops().scaled_fp4_quant(x, global_scale, mx)
+    raise NotImplementedError("fp4 activation quantisation runs on the device only")
+
+
+def scaled_mm(a, b, scale_a, scale_b, out_dtype, bias=None):
+    """W8A8: (a · bᵀ) * scale_a * scale_b (+bias).  fp8 operands run on the tcgen05 f8f6f4 kernel."""
+    if _use_cuda(a):
+        return cuda_ops().scaled_mm(a, b, scale_a, scale_b, out_dtype, bias)
+    return ref.scaled_mm(a, b, scale_a, scale_b, out_dtype, bias)
+
+
+# -- ops served by the PyTorch implementations on every device (elementwise / bookkeeping)
 mul_and_silu = ref.mul_and_silu
 fatrelu_and_mul = ref.fatrelu_and_mul
 swigluoai_and_mul = ref.swigluoai_and_mul
-fused_qk_norm_rope = ref.fused_qk_norm_rope
-swap_blocks = ref.swap_blocks
-convert_fp8 = ref.convert_fp8
-scaled_fp8_quant = ref.scaled_fp8_quant
-scaled_int8_quant = ref.scaled_int8_quant
-scaled_mm = ref.scaled_mm
 fp4_dequant = ref.fp4_dequant

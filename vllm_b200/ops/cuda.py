@@ -552,6 +552,395 @@ def fused_moe(x, w13, w2, topk_w, topk_ids, act="silu", expert_map=None):
     return moe.fused_moe_cuda(x, w13, w2, topk_w, topk_ids, act, expert_map)
 
 
+_gemm_fp8_plan = _sig("vb_gemm_fp8_plan", _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i))
+_gemm_fp8 = _sig("vb_gemm_fp8", _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _vp)
+_gemm_fp8_grouped = _sig("vb_gemm_fp8_grouped", _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _vp)
+_fp8_plan_cache: dict[tuple, tuple] = {}
+
+
+def _fp8_plan(M: int, N: int, K: int) -> tuple:
+    key = (M, N, K)
+    p = _fp8_plan_cache.get(key)
+    if p is None:
+        swap, bn, splits = _i(), _i(), _i()
+        _gemm_fp8_plan(M, N, K, ctypes.byref(swap), ctypes.byref(bn), ctypes.byref(splits))
+        p = _fp8_plan_cache[key] = (swap.value, bn.value, splits.value)
+    return p
+
+
+def gemm_fp8_block(xq, xs, wq, ws, out_dtype=torch.bfloat16, bias=None, out=None):
+    """Block-scaled fp8 GEMM (tcgen05 kind::f8f6f4, csrc/gemm_fp8.cu).  xq [M, K] e4m3; xs [M, K/128] fp32 with
+    stride(0) == 1 (the column-major output of ``per_token_group_quant_fp8(col_major=True)``); wq [N, K] e4m3;
+    ws [ceil(N/128), K/128] fp32."""
+    M, K = xq.shape
+    N = wq.shape[0]
+    assert xs.stride(0) == 1 and ws.is_contiguous() and wq.is_contiguous() and xq.stride(1) == 1
+    swap, bn, splits = _fp8_plan(M, N, K)
+    y = out if out is not None else torch.empty((M, N), dtype=out_dtype, device=xq.device)
+    _check(_gemm_fp8(xq.data_ptr(), wq.data_ptr(), xs.data_ptr(), ws.data_ptr(), _p(bias), y.data_ptr(), M, N, K,
+                     xq.stride(0), xs.stride(1), 0, 1, 1, swap, bn, splits, _DT[y.dtype], _st()),
+           f"gemm_fp8_block(M={M},N={N},K={K})")
+    return y
+
+
+def gemm_fp8_scaled(xq, wq, scale_a, scale_b, out_dtype=torch.bfloat16, bias=None):
+    """W8A8 fp8 GEMM with per-token / per-tensor activation scales and per-channel / per-tensor weight scales
+    (the reference's ``cutlass_scaled_mm`` contract): y = (xq · wq^T) * scale_a[:, None] * scale_b[None, :]."""
+    M, K = xq.shape
+    N = wq.shape[0]
+    swap, bn, splits = _fp8_plan(M, N, K)
+    y = torch.empty((M, N), dtype=out_dtype, device=xq.device)
+    sa, sb = scale_a.reshape(-1).float().contiguous(), scale_b.reshape(-1).float().contiguous()
+    _check(_gemm_fp8(xq.data_ptr(), wq.data_ptr(), sa.data_ptr(), sb.data_ptr(), _p(bias), y.data_ptr(), M, N, K,
+                     xq.stride(0), 0, 1, int(sa.numel() > 1), int(sb.numel() > 1), swap, bn, splits, _DT[y.dtype], _st()),
+           f"gemm_fp8_scaled(M={M},N={N},K={K})")
+    return y
+
+
+def gemm_fp8_grouped(xq, xs, wq, ws, offs, bn: int, out_dtype=torch.bfloat16):
+    """Grouped (MoE) block-scaled fp8 GEMM: rows of xq sorted by expert (``offs``), wq [E, N, K], ws [E, N/128, K/128]."""
+    R, K = xq.shape
+    E, N, _ = wq.shape
+    y = torch.empty((R, N), dtype=out_dtype, device=xq.device)
+    _check(_gemm_fp8_grouped(xq.data_ptr(), wq.data_ptr(), xs.data_ptr(), ws.data_ptr(), y.data_ptr(), offs.data_ptr(), R, N,
+                             K, E, xs.stride(1), bn, _DT[y.dtype], _st()), f"gemm_fp8_grouped(R={R},N={N},K={K},E={E})")
+    return y
+
+
 def block_fp8_linear(x, wq, w_scale, block=128, bias=None):
+    """Activations quantised per (token, 128-group) on the fly, weights per 128x128 block: fused quantiser kernel +
+    tcgen05 block-scaled GEMM.  Shapes the kernel does not cover take the fp32 reference."""
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if (block == 128 and K % 128 == 0 and x2.dtype in (torch.bfloat16, torch.float16) and x2.shape[0] > 0
+            and wq.dtype == torch.float8_e4m3fn and wq.is_contiguous() and w_scale.dtype == torch.float32):
+        xq, xs = per_token_group_quant_fp8(x2, 128, col_major=True)
+        y = gemm_fp8_block(xq, xs, wq, w_scale.contiguous(), x.dtype, bias)
+        return y.view(x.shape[:-1] + (wq.shape[0],))
     from vllm_b200.ops import ref
     return ref.block_fp8_linear(x, wq, w_scale, block, bias)
+
+
+def scaled_mm(a, b, scale_a, scale_b, out_dtype, bias=None):
+    if (a.dtype == torch.float8_e4m3fn and b.dtype == torch.float8_e4m3fn and a.shape[1] % 16 == 0 and a.stride(1) == 1
+            and b.is_contiguous() and out_dtype in (torch.bfloat16, torch.float16) and (a.stride(0) % 16) == 0):
+        return gemm_fp8_scaled(a, b, scale_a, scale_b, out_dtype, bias)
+    from vllm_b200.ops import ref
+    return ref.scaled_mm(a, b, scale_a, scale_b, out_dtype, bias)
+
+
+# ------------------------------------------------------------------ LoRA (csrc/lora.cu)
+_lora_shrink = _sig("vb_lora_shrink", _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp)
+_lora_expand = _sig("vb_lora_expand", _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp)
+
+
+def lora_bgmv(x, y, A, B, token_slots, offs) -> None:
+    """y[t] += B[slot(t)] (A[slot(t)] x[t]) for every token with slot >= 0, in place.  A [S, n_sub, r, K],
+    B [S, N, r] (scaling folded in), ``offs`` = (n_sub, o1, o2, o3) sub-projection boundaries of the N outputs."""
+    T, K = x.shape
+    N, r = B.shape[1], B.shape[2]
+    n_sub, o1, o2, o3 = offs
+    v = torch.empty((T, n_sub, r), dtype=torch.float32, device=x.device)
+    _check(_lora_shrink(x.data_ptr(), x.stride(0), A.data_ptr(), token_slots.data_ptr(), v.data_ptr(), T, K, r, n_sub,
+                        _DT[x.dtype], _st()), "lora_shrink")
+    _check(_lora_expand(y.data_ptr(), y.stride(0), B.data_ptr(), token_slots.data_ptr(), v.data_ptr(), T, N, r, n_sub,
+                        o1, o2, o3, _DT[y.dtype], _st()), "lora_expand")
+
+
+# ------------------------------------------------------------------ activation quantisation (csrc/quant.cu)
+_quant_rows = _sig("vb_quant_rows", _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i,
+                   _vp)
+_absmax_scale = _sig("vb_absmax_scale", _vp, _i64, _i64, _i64, _vp, _vp, _f, _i, _i, _vp)
+_fp4_quant = _sig("vb_fp4_quant", _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp)
+_Q_FP8_STATIC, _Q_FP8_TOKEN, _Q_FP8_GROUP, _Q_INT8_TOKEN, _Q_INT8_STATIC = range(5)
+_PRE_NONE, _PRE_RMS, _PRE_ACT = range(3)
+_amax_scratch: dict[int, torch.Tensor] = {}
+
+
+def _quant_call(x2, H, pre, qm, out_dtype, *, residual=None, weight=None, scale_in=None, group=128, col_major=False,
+                ue8m0=False, gemma=False, act=0, eps=0.0, scale_ub=0.0):
+    T = x2.shape[0]
+    dev = x2.device
+    q = torch.empty((T, H), dtype=out_dtype, device=dev)
+    scale = None
+    stride = 0
+    if qm in (_Q_FP8_TOKEN, _Q_INT8_TOKEN):
+        scale = torch.empty((T, 1), dtype=torch.float32, device=dev)
+    elif qm == _Q_FP8_GROUP:
+        G = H // group
+        if col_major:
+            stride = (T + 3) // 4 * 4            # TMA-friendly leading dimension
+            scale = torch.empty((G, stride), dtype=torch.float32, device=dev)
+        else:
+            scale = torch.empty((T, G), dtype=torch.float32, device=dev)
+    _check(_quant_rows(x2.data_ptr(), x2.stride(0), _p(residual), _p(weight), q.data_ptr(), _p(scale), _p(scale_in), T, H,
+                       pre, qm, group, int(col_major), stride, int(ue8m0), int(gemma), act, eps, scale_ub, _DT[x2.dtype],
+                       _st()), "quant_rows")
+    if qm == _Q_FP8_GROUP and col_major:
+        scale = scale[:, :T].t()                 # logical [T, G] view over the column-major storage
+    return q, scale
+
+
+def _rows(x):
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    return x2
+
+
+def dynamic_scale(x: torch.Tensor, qmax: float = 448.0) -> torch.Tensor:
+    """scale[0] = max|x| / qmax on the device (pass 1 of dynamic per-tensor quantisation)."""
+    x2 = _rows(x)
+    dev = x2.device.index or 0
+    scr = _amax_scratch.get(dev)
+    if scr is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("dynamic per-tensor quantisation scratch must exist before CUDA-graph capture")
+        scr = _amax_scratch[dev] = torch.zeros(1, dtype=torch.int32, device=x2.device)
+    scale = torch.empty(1, dtype=torch.float32, device=x2.device)
+    _check(_absmax_scale(x2.data_ptr(), x2.shape[0], x2.shape[1], x2.stride(0), scr.data_ptr(), scale.data_ptr(), qmax,
+                         num_sms(), _DT[x2.dtype], _st()), "absmax_scale", 2)
+    return scale
+
+
+def scaled_fp8_quant(x, scale=None, per_token: bool = False, scale_ub: float = 0.0):
+    x2 = _rows(x)
+    H = x2.shape[1]
+    if per_token:
+        q, s = _quant_call(x2, H, _PRE_NONE, _Q_FP8_TOKEN, torch.float8_e4m3fn, scale_ub=scale_ub)
+        return q.view(x.shape), s.view(x.shape[:-1] + (1,))
+    if scale is None:
+        scale = dynamic_scale(x2)
+    q, _ = _quant_call(x2, H, _PRE_NONE, _Q_FP8_STATIC, torch.float8_e4m3fn, scale_in=scale.reshape(-1))
+    return q.view(x.shape), scale
+
+
+def scaled_int8_quant(x, scale=None):
+    x2 = _rows(x)
+    H = x2.shape[1]
+    if scale is None:
+        q, s = _quant_call(x2, H, _PRE_NONE, _Q_INT8_TOKEN, torch.int8)
+        return q.view(x.shape), s.view(x.shape[:-1] + (1,))
+    q, _ = _quant_call(x2, H, _PRE_NONE, _Q_INT8_STATIC, torch.int8, scale_in=scale.reshape(-1))
+    return q.view(x.shape), scale
+
+
+def per_token_group_quant_fp8(x, group: int = 128, col_major: bool = False, ue8m0: bool = False):
+    x2 = _rows(x)
+    H = x2.shape[1]
+    if H % group or group not in (32, 64, 128) or H % 8:
+        from vllm_b200.ops import ref
+        return ref.per_token_group_quant_fp8(x2, group)
+    return _quant_call(x2, H, _PRE_NONE, _Q_FP8_GROUP, torch.float8_e4m3fn, group=group, col_major=col_major, ue8m0=ue8m0)
+
+
+def rms_norm_quant(x, weight, eps, *, residual=None, scale=None, mode: str = "static", group: int = 128,
+                   gemma: bool = False, col_major: bool = False, ue8m0: bool = False):
+    """Fused (residual add +) RMSNorm + fp8 quantisation.  mode: static | token | group.  ``residual`` is updated in
+    place (residual += x) like fused_add_rms_norm.  Returns (q, scale)."""
+    x2 = _rows(x)
+    H = x2.shape[1]
+    qm = {"static": _Q_FP8_STATIC, "token": _Q_FP8_TOKEN, "group": _Q_FP8_GROUP}[mode]
+    if residual is not None:
+        assert residual.is_contiguous()
+    q, s = _quant_call(x2, H, _PRE_RMS, qm, torch.float8_e4m3fn, residual=residual, weight=weight, eps=eps, gemma=gemma,
+                       scale_in=None if scale is None else scale.reshape(-1), group=group, col_major=col_major,
+                       ue8m0=ue8m0)
+    return q.view(x.shape), (scale if mode == "static" else s)
+
+
+def act_mul_quant(x, act: str = "silu", *, scale=None, mode: str = "static", group: int = 128, col_major: bool = False,
+                  ue8m0: bool = False):
+    """Fused act(gate) * up + fp8 quantisation over x[..., 2H] → (q[..., H], scale)."""
+    x2 = _rows(x)
+    H = x2.shape[1] // 2
+    qm = {"static": _Q_FP8_STATIC, "token": _Q_FP8_TOKEN, "group": _Q_FP8_GROUP}[mode]
+    a = {"silu": 0, "gelu": 1, "gelu_tanh": 2, "gelu_pytorch_tanh": 2}[act]
+    q, s = _quant_call(x2, H, _PRE_ACT, qm, torch.float8_e4m3fn, act=a, scale_in=None if scale is None else scale.reshape(-1),
+                       group=group, col_major=col_major, ue8m0=ue8m0)
+    return q.view(x.shape[:-1] + (H,)), (scale if mode == "static" else s)
+
+
+def scaled_fp4_quant(x, global_scale=None, mx: bool = False, swizzled: bool = False):
+    """NVFP4 (block 16, e4m3 block scales x fp32 ``global_scale``) or MXFP4 (block 32, e8m0 scales).
+    Returns (packed uint8 [T, H/2], block scales uint8 [T, H/16 or H/32] — or the 128x4-tiled buffer if swizzled)."""
+    x2 = _rows(x)
+    T, H = x2.shape
+    blk = 32 if mx else 16
+    q = torch.empty((T, H // 2), dtype=torch.uint8, device=x2.device)
+    G = H // blk
+    if swizzled:
+        sf = torch.zeros(((T + 127) // 128) * ((G + 3) // 4) * 512, dtype=torch.uint8, device=x2.device)
+    else:
+        sf = torch.empty((T, G), dtype=torch.uint8, device=x2.device)
+    if global_scale is None and not mx:
+        global_scale = torch.ones(1, dtype=torch.float32, device=x2.device)
+    _check(_fp4_quant(x2.data_ptr(), x2.stride(0), q.data_ptr(), sf.data_ptr(), _p(global_scale), T, H, int(mx),
+                      int(swizzled), _DT[x2.dtype], _st()), "fp4_quant")
+    return q, sf
+
+
+# ------------------------------------------------------------------ q/k norm + RoPE + cache (csrc/qknorm_rope.cu)
+_qknorm_rope = _sig("vb_qknorm_rope_cache", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp,
+                    _vp, _i, _i, _i, _i, _f, _f, _f, _i, _vp)
+
+
+def qknorm_rope_ok(head_dim: int, rot: int, is_neox: bool) -> bool:
+    E = head_dim // 32
+    if head_dim % 32 or E not in (2, 4, 8, 16):
+        return False
+    if rot:
+        if is_neox:
+            half = rot // 2
+            if half % E:
+                return False
+            span = half // E
+            return span & (span - 1) == 0
+        return E % 2 == 0
+    return True
+
+
+def fused_qk_norm_rope(positions, q, k, q_weight, k_weight, cos_sin_cache, head_dim, eps, is_neox=True, *, v=None,
+                       kv_cache=None, slot_mapping=None, gemma: bool = False, k_scale: float = 1.0, v_scale: float = 1.0,
+                       vt: bool = False):
+    """In place: per-head RMSNorm(q), RMSNorm(k) → RoPE → (optionally) K/V insert into the paged cache; one launch."""
+    T = q.shape[0]
+    Hq, Hkv = q.shape[-1] // head_dim, k.shape[-1] // head_dim
+    rot = cos_sin_cache.shape[-1] if cos_sin_cache is not None else 0
+    assert q.stride(-1) == 1 and k.stride(-1) == 1
+    flags = 0
+    BS = 1
+    if kv_cache is not None:
+        flags = _kv_fp8(kv_cache) | (2 if vt else 0)
+        BS = kv_cache.shape[3]
+    _check(_qknorm_rope(_p(positions), q.data_ptr(), k.data_ptr(), _p(v), _p(q_weight), _p(k_weight), _p(cos_sin_cache),
+                        rot, T, Hq, Hkv, head_dim, q.stride(0), k.stride(0), v.stride(0) if v is not None else 0,
+                        _p(kv_cache), _p(slot_mapping), BS, int(is_neox), int(gemma), flags, eps, k_scale, v_scale,
+                        _DT[q.dtype], _st()), "qknorm_rope_cache")
+    return q, k
+
+
+# ------------------------------------------------------------------ cache maintenance (csrc/cache_ops.cu)
+_copy_blocks = _sig("vb_copy_blocks", _vp, _vp, _vp, _i, _i64, _vp)
+_gather_cache = _sig("vb_gather_cache", _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _f, _i, _i, _vp)
+_convert_fp8 = _sig("vb_convert_fp8", _vp, _vp, _i64, _f, _i, _i, _vp)
+
+
+def swap_blocks(src: torch.Tensor, dst: torch.Tensor, mapping) -> None:
+    """dst[j] = src[i] for (i, j) in mapping; whole blocks (dim 0).  Either side may be pinned host memory."""
+    if isinstance(mapping, torch.Tensor):
+        m = mapping.to(torch.int64)
+    else:
+        if not mapping:
+            return
+        m = torch.tensor(mapping, dtype=torch.int64)
+    dev = src.device if src.is_cuda else dst.device
+    m = m.to(dev, non_blocking=True).contiguous()
+    block_bytes = src[0].numel() * src.element_size()
+    assert dst[0].numel() * dst.element_size() == block_bytes and src.is_contiguous() and dst.is_contiguous()
+    assert block_bytes % 16 == 0
+    for t in (src, dst):
+        assert t.is_cuda or t.is_pinned(), "host side of swap_blocks must be pinned (mapped) memory"
+    _check(_copy_blocks(src.data_ptr(), dst.data_ptr(), m.data_ptr(), m.shape[0], block_bytes, _st()), "copy_blocks")
+
+
+def copy_blocks(cache: torch.Tensor, mapping) -> None:
+    swap_blocks(cache, cache, mapping)
+
+
+def gather_cache(cache, block_table, cu_seq_lens, out, max_tokens: int, seq_starts=None, scale: float = 1.0):
+    """Dense [total_tokens, row] copy of the cached rows of a batch (cache [blocks, BS, row], fp8 → out.dtype with
+    ``scale`` when the cache is 8-bit)."""
+    B = cu_seq_lens.numel() - 1
+    BS, row = cache.shape[1], cache.shape[2]
+    src8 = cache.element_size() == 1
+    _check(_gather_cache(cache.data_ptr(), out.data_ptr(), block_table.data_ptr(), block_table.stride(0),
+                         cu_seq_lens.data_ptr(), _p(seq_starts), B, max_tokens, BS, row, cache.stride(0), out.stride(0),
+                         scale, int(src8), _DT[out.dtype], _st()), "gather_cache")
+    return out
+
+
+def convert_fp8(x: torch.Tensor, scale: float = 1.0, to_fp8: bool = True, out_dtype=torch.bfloat16):
+    xc = x.contiguous()
+    n = xc.numel()
+    if n % 8:
+        from vllm_b200.ops import ref
+        return ref.convert_fp8(x, scale, to_fp8)
+    if to_fp8:
+        out = torch.empty(xc.shape, dtype=torch.float8_e4m3fn, device=xc.device)
+        _check(_convert_fp8(xc.data_ptr(), out.data_ptr(), n, scale, 1, num_sms(), _DT[xc.dtype], _st()), "convert_fp8")
+    else:
+        out = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
+        _check(_convert_fp8(xc.data_ptr(), out.data_ptr(), n, scale, 0, num_sms(), _DT[out_dtype], _st()), "convert_fp8")
+    return out
+
+
+# ------------------------------------------------------------------ SSM / linear attention (csrc/ssm.cu)
+_conv1d = _sig("vb_causal_conv1d", _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp)
+_sel_scan = _sig("vb_selective_scan", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i, _i, _i,
+                 _vp)
+_ssd_scan = _sig("vb_ssd_scan", _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i, _i, _i,
+                 _i, _i, _f, _f, _vp)
+_gdn_scan = _sig("vb_gdn_scan", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp)
+
+
+def _state_view(cache: torch.Tensor) -> torch.Tensor:
+    """The recurrent-state pool as [rows, floats] fp32 (one row per request)."""
+    c = cache.view(cache.shape[0], -1)
+    return c if c.dtype == torch.float32 else c.view(torch.float32)
+
+
+def causal_conv1d(x, weight, bias, cache, md, act: bool = True) -> torch.Tensor:
+    """Depthwise causal conv over each request's tokens with the (k-1)-window kept at the head of its state row.
+    x [T, C] (bf16/fp16, any row stride) → fp32 [T, C]; the window in the cache is advanced in place."""
+    T, C = x.shape
+    st = _state_view(cache)
+    out = torch.zeros((T, C), dtype=torch.float32, device=x.device)
+    bt = md.block_table
+    _check(_conv1d(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), weight.data_ptr(), _p(bias), st.data_ptr(),
+                   st.stride(0), md.query_start_loc.data_ptr(), md.seq_lens.data_ptr(), bt.data_ptr(), bt.stride(0),
+                   md.num_reqs, C, weight.shape[-1], int(act), _DT[x.dtype], _st()), "causal_conv1d")
+    return out
+
+
+def selective_scan(x, dt, B, C, A, D, cache, state_off: int, md) -> torch.Tensor:
+    """Mamba-1: fp32 x/dt [T, di], B/C [T, N], A [di, N], D [di] → y [T, di]; state rows updated in place."""
+    T, di = x.shape
+    N = B.shape[-1]
+    st = _state_view(cache)
+    y = torch.zeros((T, di), dtype=torch.float32, device=x.device)
+    bt = md.block_table
+    args = [t.contiguous() for t in (x, dt, B, C, A, D)]
+    _check(_sel_scan(*[t.data_ptr() for t in args], y.data_ptr(), st.data_ptr(), st.stride(0), state_off,
+                     md.query_start_loc.data_ptr(), md.seq_lens.data_ptr(), bt.data_ptr(), bt.stride(0), md.num_reqs, di, N,
+                     _st()), "selective_scan")
+    return y
+
+
+def ssd_scan(xbc, dt_raw, dt_bias, A_log, D, cache, state_off: int, md, nh: int, hd: int, G: int, N: int,
+             dt_min: float = 0.0, dt_max: float = float("inf")) -> torch.Tensor:
+    """Mamba-2: conv output xbc fp32 [T, nh*hd + 2*G*N], raw dt [T, nh] fp32 → y [T, nh*hd] (D skip included)."""
+    T = xbc.shape[0]
+    st = _state_view(cache)
+    y = torch.zeros((T, nh * hd), dtype=torch.float32, device=xbc.device)
+    bt = md.block_table
+    dt_max = min(dt_max, 3.0e38)
+    _check(_ssd_scan(xbc.data_ptr(), xbc.stride(0), dt_raw.data_ptr(), dt_raw.stride(0), dt_bias.data_ptr(),
+                     A_log.data_ptr(), D.data_ptr(), y.data_ptr(), st.data_ptr(), st.stride(0), state_off,
+                     md.query_start_loc.data_ptr(), md.seq_lens.data_ptr(), bt.data_ptr(), bt.stride(0), md.num_reqs, nh, hd,
+                     G, N, dt_min, dt_max, _st()), "ssd_scan")
+    return y
+
+
+def gdn_scan(q, k, v, g, beta, cache, state_off: int, md) -> torch.Tensor:
+    """Gated delta rule: fp32 q/k [T, nv, dk], v [T, nv, dv], g/beta [T, nv] → o [T, nv, dv]; state [nv, dk, dv]."""
+    T, nv, dk = q.shape
+    dv = v.shape[-1]
+    st = _state_view(cache)
+    o = torch.zeros((T, nv, dv), dtype=torch.float32, device=q.device)
+    bt = md.block_table
+    a = [t.contiguous() for t in (q, k, v, g, beta)]
+    _check(_gdn_scan(*[t.data_ptr() for t in a], o.data_ptr(), st.data_ptr(), st.stride(0), state_off,
+                     md.query_start_loc.data_ptr(), md.seq_lens.data_ptr(), bt.data_ptr(), bt.stride(0), md.num_reqs, nv, dk,
+                     dv, _st()), "gdn_scan")
+    return o
