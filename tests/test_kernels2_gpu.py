@@ -410,3 +410,30 @@ def test_gemm_fp8_grouped(E, N, K, R, bn):
         if o[e + 1] > o[e]:
             exp = _fp8_block_ref(xq[o[e]:o[e + 1]], xs[o[e]:o[e + 1]], wq[e], ws[e])
             close(y[o[e]:o[e + 1]], exp, atol=2e-2 * exp.abs().max().item() / 8 + 1e-2, rtol=2e-2)
+
+
+# ------------------------------------------------------------------ tcgen05 MLA decode (csrc/mla_decode.cu)
+@pytest.mark.parametrize("H", [16, 128, 8, 40])
+@pytest.mark.parametrize("BS,splits", [(64, 1), (64, 3), (32, 1), (128, 2)])
+def test_mla_decode_tc(H, BS, splits):
+    torch.manual_seed(30)
+    dt = torch.bfloat16
+    seq_lens = [1, 63, 64, 65, 200, 777, 1300]
+    B = len(seq_lens)
+    max_blocks = max((s + BS - 1) // BS for s in seq_lens) + 1
+    NB = B * max_blocks + 3
+    cache = (torch.randn(NB, BS, 576, device="cuda") * 0.5).to(dt)
+    bt = (torch.randperm(NB - 1, device="cuda")[:B * max_blocks].int() + 1).view(B, max_blocks).contiguous()
+    sl = torch.tensor(seq_lens, dtype=torch.int32, device="cuda")
+    qn = (torch.randn(B, H, 512, device="cuda") * 0.3).to(dt)
+    qp = (torch.randn(B, H, 64, device="cuda") * 0.3).to(dt)
+    scale = 0.07
+    out, lse = cu().mla_decode_tc(qn, qp, cache, bt, sl, scale, max(seq_lens), num_splits=splits, return_lse=True)
+    qsl = torch.arange(B + 1, dtype=torch.int32)
+    exp = ref.mla_decode_attention(qn, qp, cache, bt, sl.cpu(), qsl, scale, 512)
+    close(out, exp, atol=2e-2, rtol=3e-2)
+    # lse against a direct computation for one sequence
+    b = 4
+    lat = cache[bt[b].long()].reshape(-1, 576)[:seq_lens[b]].float()
+    att = (torch.cat([qn[b], qp[b]], -1).float() @ lat.t()) * scale
+    close(lse[b], torch.logsumexp(att, -1), atol=2e-2, rtol=1e-2)

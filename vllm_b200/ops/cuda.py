@@ -294,16 +294,71 @@ def merge_attn_states(o1, lse1, o2, lse2):
     return out, lse
 
 
+_mla_decode = _sig("vb_mla_decode", _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
+                   _i, _i, _f, _i, _vp)
+_mla_ws: dict[int, tuple] = {}
+
+
+def mla_decode_splits(B: int, H: int, max_seq_len: int) -> int:
+    forced = envs.VLLM_B200_ATTN_SPLITS
+    if forced > 0:
+        return forced
+    groups = (H + 31) // 32 if H > 16 else 1
+    ctas = max(B * groups, 1)
+    s = max(1, min(16, (num_sms() + ctas - 1) // ctas))
+    return max(1, min(s, max_seq_len // 512))       # every split should still stream >= 8 tiles
+
+
+def mla_decode_tc(q_nope_abs, q_pe, kv_cache, block_table, seq_lens, scale, max_seq_len: int, num_splits: int = 0,
+                  return_lse: bool = False):
+    """tcgen05 MLA decode (csrc/mla_decode.cu): q_nope_abs [B, H, 512], q_pe [B, H, 64], cache [blocks, BS, 576]."""
+    B, H, R = q_nope_abs.shape
+    assert R == 512 and q_pe.shape[-1] == 64 and kv_cache.shape[-1] == 576 and q_nope_abs.stride(-1) == 1 and q_pe.stride(-1) == 1
+    dev = q_nope_abs.device
+    splits = num_splits or mla_decode_splits(B, H, max_seq_len)
+    out = torch.empty((B, H, R), dtype=q_nope_abs.dtype, device=dev)
+    lse = torch.empty((B, H), dtype=torch.float32, device=dev) if return_lse else None
+    po = pl = None
+    if splits > 1:
+        key = dev.index or 0
+        need = B * H * splits
+        ws = _mla_ws.get(key)
+        if ws is None or ws[1].numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("MLA split-KV workspace must be allocated before CUDA-graph capture")
+            n = max(need, 64 * 128 * 4)
+            ws = _mla_ws[key] = (torch.empty(n * R, dtype=torch.float32, device=dev),
+                                 torch.empty(n, dtype=torch.float32, device=dev))
+        po, pl = ws
+    _check(_mla_decode(q_nope_abs.data_ptr(), q_pe.data_ptr(), kv_cache.data_ptr(), kv_cache.shape[0],
+                       block_table.data_ptr(), seq_lens.data_ptr(), out.data_ptr(), _p(po), _p(pl), _p(lse), B, H,
+                       kv_cache.shape[1], q_nope_abs.stride(0), q_nope_abs.stride(1), q_pe.stride(0), q_pe.stride(1),
+                       out.stride(0), block_table.stride(0), splits, scale, _DT[q_nope_abs.dtype], _st()),
+           f"mla_decode(B={B},H={H})", 2 if splits > 1 else 1)
+    return (out, lse) if return_lse else out
+
+
+def _mla_tc_ok(q_nope_abs, q_pe, kv_cache) -> bool:
+    return (q_nope_abs.dtype in (torch.bfloat16, torch.float16) and kv_cache.dtype == q_nope_abs.dtype
+            and q_nope_abs.shape[-1] == 512 and q_pe.shape[-1] == 64 and kv_cache.dim() == 3 and kv_cache.shape[-1] == 576
+            and kv_cache.shape[1] in (16, 32, 64, 128) and q_nope_abs.stride(-1) == 1 and q_pe.stride(-1) == 1
+            and (q_nope_abs.stride(0) * 2) % 16 == 0 and (q_nope_abs.stride(1) * 2) % 16 == 0
+            and (q_pe.stride(0) * 2) % 16 == 0 and (q_pe.stride(1) * 2) % 16 == 0 and envs.VLLM_B200_ATTN != "simt")
+
+
 def mla_attention(q_nope_abs, q_pe, kv_cache, md, scale, kv_lora_rank):
     """MLA as MQA over the latent cache (K = 576-d latent+rope, V = first 512 dims of the same rows).
 
-    Decode batches run as dense batched GEMMs over the gathered latent pages with a device-side length mask:
-    no host synchronisation, static shapes → CUDA-graph capturable.  Mixed / prefill batches use the
-    variable-length loop (eager only).  A dedicated tcgen05 MLA kernel (latent tile shared by all 128 heads
-    through TMEM) is the planned replacement for both."""
+    Decode batches run on the tcgen05 MLA kernel (csrc/mla_decode.cu: the latent tile is shared by all heads of the
+    CTA and by both matrix products, split-KV for long contexts; no host synchronisation, graph capturable).
+    Shapes it does not cover (other latent widths) use dense batched GEMMs over the gathered pages; mixed / prefill
+    batches use the variable-length reference loop (eager only)."""
     from vllm_b200.ops import ref
     if md.decode_only:
         B, H, R = q_nope_abs.shape
+        if R == kv_lora_rank and _mla_tc_ok(q_nope_abs, q_pe, kv_cache):
+            return mla_decode_tc(q_nope_abs, q_pe, kv_cache, md.block_table, md.seq_lens, scale, md.max_seq_len,
+                                 md.num_splits or 0)
         bs = kv_cache.shape[1]
         nbk = max((md.max_seq_len + bs - 1) // bs, 1)
         lat = kv_cache[md.block_table[:B, :nbk].long()].reshape(B, nbk * bs, -1)        # [B, S, 576]
