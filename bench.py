@@ -360,6 +360,20 @@ def main() -> None:
         h2d0, d2h0 = runner.h2d_bytes, runner.d2h_bytes
         t1, tk, raw = _timed_generates(gen, K, REPS, sync=barrier)
         e2e_s = tk - t1
+        # per-step wall clock of one more generate(K+1) (diagnostic: where the end-to-end time goes)
+        stamps = []
+        orig_step = engine.step
+
+        def timed_step():
+            r = orig_step()
+            stamps.append(time.perf_counter())
+            return r
+        engine.step = timed_step
+        barrier()
+        t_begin = time.perf_counter()
+        gen(K + 1)
+        engine.step = orig_step
+        raw["step_wall_ms"] = [round((b - a) * 1e3, 3) for a, b in zip([t_begin] + stamps[:-1], stamps)]
         n_steps = REPS * (K + 2)                          # engine steps executed by the timed generate calls
         h2d_step = (runner.h2d_bytes - h2d0) / n_steps
         d2h_step = (runner.d2h_bytes - d2h0) / n_steps

@@ -50,7 +50,7 @@ def test_scaled_fp8_quant(dtype, T, H):
 @pytest.mark.parametrize("T,H", [(5, 512), (64, 7168), (17, 2048)])
 def test_per_token_group_quant(group, T, H):
     torch.manual_seed(1)
-    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16) * torch.rand(T, 1, device="cuda") * 4
+    x = (torch.randn(T, H, device="cuda") * torch.rand(T, 1, device="cuda") * 4).to(torch.bfloat16)
     rq, rs = ref.per_token_group_quant_fp8(x, group)
     q, s = cu().per_token_group_quant_fp8(x, group)
     close(s, rs, atol=0, rtol=1e-6)
@@ -437,3 +437,39 @@ def test_mla_decode_tc(H, BS, splits):
     lat = cache[bt[b].long()].reshape(-1, 576)[:seq_lens[b]].float()
     att = (torch.cat([qn[b], qp[b]], -1).float() @ lat.t()) * scale
     close(lse[b], torch.logsumexp(att, -1), atol=2e-2, rtol=1e-2)
+
+
+# ------------------------------------------------------------------ persistent stream-K decode GEMM (csrc/gemm_sk.cu)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(1, 128, 512), (64, 6144, 4096), (64, 28672, 4096), (64, 4096, 14336), (17, 4096, 4096),
+                                   (128, 1280, 8192), (200, 2048, 1024), (33, 1000, 2048), (64, 128256, 4096),
+                                   (8, 12800, 256)])
+def test_gemm_stream_k(dtype, M, N, K):
+    torch.manual_seed(40)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    b = torch.randn(N, device="cuda").to(dtype)
+    exp = x.float() @ w.float().t()
+    y = cu().gemm_sk(x, w)
+    close(y, exp, atol=3e-2, rtol=2e-2)
+    close(cu().gemm_sk(x, w, b), exp + b.float(), atol=3e-2, rtol=2e-2)
+    # bit-identical run to run (fixed summation order of the stream-K partials), and no stale counters / workspace
+    for _ in range(3):
+        assert torch.equal(cu().gemm_sk(x, w), y)
+    # strided activations (a slice of a fused buffer)
+    xb = torch.zeros(M, K + 64, device="cuda", dtype=dtype)
+    xb[:, :K] = x
+    assert torch.equal(cu().gemm_sk(xb[:, :K], w), y)
+
+
+@pytest.mark.parametrize("M,I,K", [(64, 14336, 4096), (5, 1792, 1024), (128, 3584, 8192)])
+def test_gemm_stream_k_fused_silu_mul(M, I, K):
+    torch.manual_seed(41)
+    dt = torch.bfloat16
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
+    wg = (torch.randn(I, K, device="cuda") * 0.05).to(dt)
+    wu = (torch.randn(I, K, device="cuda") * 0.05).to(dt)
+    w_il = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()      # rows: gate_0, up_0, gate_1, up_1, ...
+    y = cu().gemm_sk(x, w_il, act=True)
+    g, u = x.float() @ wg.float().t(), x.float() @ wu.float().t()
+    close(y, torch.nn.functional.silu(g) * u, atol=3e-2, rtol=3e-2)

@@ -454,6 +454,48 @@ def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     return y
 
 
+_gemm_sk_plan = _sig("vb_gemm_sk_plan", _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
+                     ctypes.POINTER(_i64), ctypes.POINTER(_i))
+_gemm_sk = _sig("vb_gemm_sk", _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp, _vp, _i, _i, _vp)
+_sk_plan_cache: dict[tuple, tuple] = {}
+_sk_ws: dict[int, tuple] = {}
+
+
+def _sk_workspace(dev: torch.device) -> tuple:
+    """Stream-K partial-tile workspace + tile counters, sized once for the largest plan (SMs x 2 slots x 256 x 128 fp32)."""
+    key = dev.index or 0
+    ws = _sk_ws.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("stream-K GEMM workspace must be allocated before CUDA-graph capture")
+        ws = _sk_ws[key] = (torch.empty(num_sms() * 2 * 256 * 128, dtype=torch.float32, device=dev),
+                            torch.zeros(16384, dtype=torch.int32, device=dev))
+    return ws
+
+
+def gemm_sk(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            act: bool = False) -> torch.Tensor:
+    """Y = X W^T on the persistent stream-K tcgen05 kernel (csrc/gemm_sk.cu), M <= 256.  ``act``: W's rows are
+    interleaved (gate_i, up_i) pairs and the epilogue emits silu(gate) * up ([M, N/2])."""
+    M, K = x.shape
+    N = w.shape[0]
+    key = (M, N, K)
+    plan = _sk_plan_cache.get(key)
+    if plan is None:
+        bn, grid, per, tiles = _i(), _i(), _i(), _i()
+        wsb = _i64()
+        rc = _gemm_sk_plan(M, N, K, num_sms(), ctypes.byref(bn), ctypes.byref(grid), ctypes.byref(per), ctypes.byref(wsb),
+                           ctypes.byref(tiles))
+        assert rc == 0 and tiles.value <= 16384
+        plan = _sk_plan_cache[key] = (bn.value, grid.value, per.value)
+    bn, grid, per = plan
+    ws, counters = _sk_workspace(x.device)
+    y = out if out is not None else torch.empty((M, N // 2 if act else N), dtype=x.dtype, device=x.device)
+    _check(_gemm_sk(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(), M, N, K, x.stride(0), bn, grid, per, ws.data_ptr(),
+                    counters.data_ptr(), int(act), _DT[x.dtype], _st()), f"gemm_sk(M={M},N={N},K={K})")
+    return y
+
+
 def _tc_ok(x2: torch.Tensor, w: torch.Tensor, force: bool = False) -> bool:
     mode = envs.VLLM_B200_GEMM
     if mode == "cublas" and not force:
@@ -471,7 +513,12 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     K = x.shape[-1]
     x2 = x.reshape(-1, K)
     if x2.shape[0] > 0 and _tc_ok(x2, weight):
-        y = gemm_tc(x2, weight, bias)
+        # decode shapes: persistent stream-K kernel (every SM streams weights all the time); VLLM_B200_GEMM_SK=0 selects
+        # the tile-per-CTA / cluster split-K kernel for A/B measurements
+        if x2.shape[0] <= 256 and envs.VLLM_B200_GEMM_SK and weight.shape[0] * (K // 64) >= 64:
+            y = gemm_sk(x2, weight, bias)
+        else:
+            y = gemm_tc(x2, weight, bias)
         return y.view(x.shape[:-1] + (weight.shape[0],))
     return torch.nn.functional.linear(x, weight, bias)
 
@@ -783,7 +830,7 @@ def scaled_int8_quant(x, scale=None):
 def per_token_group_quant_fp8(x, group: int = 128, col_major: bool = False, ue8m0: bool = False):
     x2 = _rows(x)
     H = x2.shape[1]
-    if H % group or group not in (32, 64, 128) or H % 8:
+    if H % group or group not in (32, 64, 128) or H % 8 or x2.dtype not in (torch.bfloat16, torch.float16):
         from vllm_b200.ops import ref
         return ref.per_token_group_quant_fp8(x2, group)
     return _quant_call(x2, H, _PRE_NONE, _Q_FP8_GROUP, torch.float8_e4m3fn, group=group, col_major=col_major, ue8m0=ue8m0)
