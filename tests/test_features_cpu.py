@@ -1188,3 +1188,20 @@ def test_sparsemixer_routing_matches_hf():
     scale = base.abs().max().item() + 1e-30
     assert (same - base).abs().max().item() / scale < 1e-4           # plug-in reproducing softmax top-k renormalised
     assert (other - base).abs().max().item() / scale > 1e-3          # sparsemixer weights differ from it
+
+
+def test_interleaved_gate_up_weights_match_plain_layout(monkeypatch):
+    """gate|up stored as interleaved rows (the layout the fused SiLU·mul GEMM epilogue needs) is a pure re-ordering:
+    same checkpoint, same tokens as the [gate | up] layout."""
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=9))
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VLLM_B200_FUSED_ACT", flag)
+        llm = make_llm("llama-tiny", weights=w, dtype="bfloat16")
+        mlp = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model.model.layers[0].mlp
+        assert mlp.gate_up_proj.interleave == (flag == "1")
+        outs.append([o.outputs[0].token_ids for o in llm.generate(PROMPTS, sp)])
+        llm.shutdown()
+    assert outs[0] == outs[1]

@@ -34,7 +34,7 @@ struct Params {
   float* lse_out;
   int64_t out_stride;
   int bt_stride;
-  int Hq, Hkv, G, num_splits, window;
+  int Hq, Hkv, G, num_splits, window, B;
   float scale_log2;
 };
 
@@ -52,6 +52,11 @@ VB_DEVICE void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
 VB_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 VB_DEVICE void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Persistent: grid = min(work items, SMs); a work item is (kv split, kv head, sequence).  Barriers, TMEM and the zeroed
+// shared memory are set up once per CTA; the three roles walk the same item list independently, tied together only by
+// the mbarrier phases (a CTA-global tile counter), so the TMA producer runs up to STAGES tiles ahead ACROSS item
+// boundaries: the K/V stream of the next (sequence, head) is already in flight while the softmax / epilogue of the
+// current one finish.  (The one-item-per-CTA version paid ~3.5 us of setup + pipeline fill per 11 us of streaming.)
 template <typename T, int G>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fmha_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -60,11 +65,12 @@ fmha_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* k_smem = smem;                                 // STAGES x 32 KB
   unsigned char* v_smem = k_smem + STAGES * K_BYTES;            // STAGES x 32 KB
-  unsigned char* q_smem = v_smem + STAGES * V_BYTES;            // 4 KB
-  unsigned char* p_smem = q_smem + Q_BYTES;                     // 4 KB
+  unsigned char* q_smem = v_smem + STAGES * V_BYTES;            // 2 x 4 KB (double-buffered across items)
+  unsigned char* p_smem = q_smem + 2 * Q_BYTES;                 // 4 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* k_full = q_empty + 2;
   uint64_t* v_full = k_full + STAGES;
   uint64_t* kv_empty = v_full + STAGES;
   uint64_t* s_full = kv_empty + STAGES;    // [2]
@@ -73,29 +79,16 @@ fmha_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* pv_done = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
   float* wred = reinterpret_cast<float*>(tmem_slot + 2);        // [4 warps][NQ] column max / sum exchange
-  int* blk_ids = reinterpret_cast<int*>(wred + 4 * NQ);         // [2 * MAX_TILES_SMEM]
+  int* blk_ids = reinterpret_cast<int*>(wred + 4 * NQ);         // [2 * MAX_TILES_SMEM] (producer warp only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   pdl_trigger();
   pdl_wait();   // q, the new K/V rows and seq_lens come from the preceding kernels
-  const int seq_len = p.seq_lens[b];
-  const int qpos = seq_len - 1;
-  const int kv_end = seq_len;
-  const int kv_begin = p.window > 0 ? max(0, qpos - p.window + 1) : 0;
-  int tile_lo = kv_begin / TILE, tile_hi = (kv_end + TILE - 1) / TILE;
-  {
-    const int total = tile_hi - tile_lo;
-    const int per = (total + p.num_splits - 1) / p.num_splits;
-    tile_lo += split * per;
-    tile_hi = min(tile_hi, tile_lo + per);
-  }
-  const int n_tiles = max(tile_hi - tile_lo, 0);
-  const int n_pages_total = (kv_end + BS - 1) / BS;
+  const int n_items = p.num_splits * p.Hkv * p.B;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 128); }
     mbar_init(p_full, 128);
@@ -107,12 +100,8 @@ fmha_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // Q / P rows beyond the group and the partially filled last tile must be finite: zero once
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* s4 = reinterpret_cast<uint4*>(smem);
-    const int n16 = (STAGES * (K_BYTES + V_BYTES) + Q_BYTES + P_BYTES) / 16;
+    const int n16 = (STAGES * (K_BYTES + V_BYTES) + 2 * Q_BYTES + P_BYTES) / 16;
     for (int i = threadIdx.x; i < n16; i += NUM_THREADS) s4[i] = z;
-  }
-  for (int i = threadIdx.x; i < 2 * n_tiles && i < 2 * MAX_TILES_SMEM; i += NUM_THREADS) {
-    const int page = tile_lo * 2 + i;
-    blk_ids[i] = page < n_pages_total ? p.block_table[(int64_t)b * p.bt_stride + page] : -1;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -121,199 +110,249 @@ fmha_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 32;   // S^T buffers at columns 0..15 and 16..31, O^T at 32..47
 
-  if (n_tiles == 0) {
-    if (warp >= 2 && p.num_splits > 1) {
-      const int d = (warp & 3) * 32 + lane;
-      for (int g = 0; g < G; ++g) {
-        const int64_t pi = ((int64_t)b * p.Hq + (h * G + g)) * p.num_splits + split;
-        p.part_out[pi * D + d] = 0.f;
-        if (d == 0) p.part_lse[pi] = -INFINITY;
-      }
-    }
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 64);
-    return;
-  }
+  // the KV tile range of a work item (identical arithmetic in every role)
+  auto item_range = [&](int it, int& split, int& h, int& b, int& tile_lo, int& kv_begin, int& kv_end) -> int {
+    split = it % p.num_splits;
+    const int rest = it / p.num_splits;
+    h = rest % p.Hkv;
+    b = rest / p.Hkv;
+    const int seq_len = p.seq_lens[b];
+    kv_end = seq_len;
+    kv_begin = p.window > 0 ? max(0, seq_len - p.window) : 0;
+    tile_lo = kv_begin / TILE;
+    int tile_hi = (kv_end + TILE - 1) / TILE;
+    const int per = (tile_hi - tile_lo + p.num_splits - 1) / p.num_splits;
+    tile_lo += split * per;
+    tile_hi = min(tile_hi, tile_lo + per);
+    return max(tile_hi - tile_lo, 0);
+  };
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * G * 64 * 2);
-      tma_load_3d(q_smem, &tmap_q, 0, h * G, b, q_full);
-      tma_load_3d(q_smem + NQ * 128, &tmap_q, 64, h * G, b, q_full);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % STAGES;
-        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
-        int blk[2];
-        for (int u = 0; u < 2; ++u) {
-          if (j < MAX_TILES_SMEM) blk[u] = blk_ids[2 * j + u];
-          else {
-            const int page = (tile_lo + j) * 2 + u;
-            blk[u] = page < n_pages_total ? p.block_table[(int64_t)b * p.bt_stride + page] : -1;
+    // ===== TMA producer (the whole warp stages the item's block ids, lane 0 issues the copies)
+    int gt = 0, qi = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      int split, h, b, tile_lo, kv_begin, kv_end;
+      const int n_tiles = item_range(it, split, h, b, tile_lo, kv_begin, kv_end);
+      if (n_tiles == 0) continue;
+      const int n_pages_total = (kv_end + BS - 1) / BS;
+      __syncwarp();
+      for (int i = lane; i < 2 * n_tiles && i < 2 * MAX_TILES_SMEM; i += 32) {
+        const int page = tile_lo * 2 + i;
+        blk_ids[i] = page < n_pages_total ? p.block_table[(int64_t)b * p.bt_stride + page] : -1;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const int qb = qi & 1;
+        mbar_wait(&q_empty[qb], ((qi >> 1) & 1) ^ 1);
+        unsigned char* qs = q_smem + qb * Q_BYTES;
+        mbar_expect_tx(&q_full[qb], 2 * G * 64 * 2);
+        tma_load_3d(qs, &tmap_q, 0, h * G, b, &q_full[qb]);
+        tma_load_3d(qs + NQ * 128, &tmap_q, 64, h * G, b, &q_full[qb]);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int g = gt + j, s = g % STAGES;
+          mbar_wait(&kv_empty[s], ((g / STAGES) & 1) ^ 1);
+          int blk[2];
+          for (int u = 0; u < 2; ++u) {
+            if (j < MAX_TILES_SMEM) blk[u] = blk_ids[2 * j + u];
+            else {
+              const int page = (tile_lo + j) * 2 + u;
+              blk[u] = page < n_pages_total ? p.block_table[(int64_t)b * p.bt_stride + page] : -1;
+            }
+          }
+          const int n_valid = (blk[0] >= 0) + (blk[1] >= 0);
+          unsigned char* ks = k_smem + s * K_BYTES;
+          unsigned char* vs = v_smem + s * V_BYTES;
+          mbar_expect_tx(&k_full[s], n_valid * BS * D * 2);
+          mbar_expect_tx(&v_full[s], n_valid * BS * D * 2);
+          for (int u = 0; u < 2; ++u) {
+            if (blk[u] < 0) continue;
+            const int chunk = (blk[u] * 2 + 0) * p.Hkv + h;
+            tma_load_2d_hint(ks + 0 * (TILE * 128) + u * (BS * 128), &tmap_k, 0, chunk * BS, &k_full[s], L2_EVICT_FIRST);
+            tma_load_2d_hint(ks + 1 * (TILE * 128) + u * (BS * 128), &tmap_k, 64, chunk * BS, &k_full[s], L2_EVICT_FIRST);
+          }
+          for (int u = 0; u < 2; ++u) {
+            if (blk[u] < 0) continue;
+            const int chunk = (blk[u] * 2 + 1) * p.Hkv + h;
+            tma_load_2d_hint(vs + u * (D * 128), &tmap_v, 0, chunk * D, &v_full[s], L2_EVICT_FIRST);
           }
         }
-        const int n_valid = (blk[0] >= 0) + (blk[1] >= 0);
-        unsigned char* ks = k_smem + s * K_BYTES;
-        unsigned char* vs = v_smem + s * V_BYTES;
-        mbar_expect_tx(&k_full[s], n_valid * BS * D * 2);
-        mbar_expect_tx(&v_full[s], n_valid * BS * D * 2);
-        for (int u = 0; u < 2; ++u) {
-          if (blk[u] < 0) continue;
-          const int chunk = (blk[u] * 2 + 0) * p.Hkv + h;
-          tma_load_2d_hint(ks + 0 * (TILE * 128) + u * (BS * 128), &tmap_k, 0, chunk * BS, &k_full[s], L2_EVICT_FIRST);
-          tma_load_2d_hint(ks + 1 * (TILE * 128) + u * (BS * 128), &tmap_k, 64, chunk * BS, &k_full[s], L2_EVICT_FIRST);
-        }
-        for (int u = 0; u < 2; ++u) {
-          if (blk[u] < 0) continue;
-          const int chunk = (blk[u] * 2 + 1) * p.Hkv + h;
-          tma_load_2d_hint(vs + u * (D * 128), &tmap_v, 0, chunk * D, &v_full[s], L2_EVICT_FIRST);
-        }
       }
+      gt += n_tiles;
+      ++qi;
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_f16(128, NQ, DTypeOf<T>::v == DT_BF16);
-    mbar_wait(q_full, 0);
-    for (int j = 0; j <= n_tiles; ++j) {
-      if (j < n_tiles) {
-        const int s = j % STAGES, sb = j & 1;
-        mbar_wait(&k_full[s], (j / STAGES) & 1);
-        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const unsigned char* ks = k_smem + s * K_BYTES;
+    int gt = 0, qi = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      int split, h, b, tile_lo, kv_begin, kv_end;
+      const int n_tiles = item_range(it, split, h, b, tile_lo, kv_begin, kv_end);
+      if (n_tiles == 0) continue;
+      const int qb = qi & 1;
+      const unsigned char* qs = q_smem + qb * Q_BYTES;
+      mbar_wait(&q_full[qb], (qi >> 1) & 1);
+      for (int j = 0; j <= n_tiles; ++j) {
+        if (j < n_tiles) {
+          const int g = gt + j, s = g % STAGES, sb = g & 1;
+          mbar_wait(&k_full[s], (g / STAGES) & 1);
+          mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const unsigned char* ks = k_smem + s * K_BYTES;
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t da = umma_desc_sw128(ks + kb * (TILE * 128));
-            const uint64_t db = umma_desc_sw128(q_smem + kb * (NQ * 128));
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t da = umma_desc_sw128(ks + kb * (TILE * 128));
+              const uint64_t db = umma_desc_sw128(qs + kb * (NQ * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base + sb * NQ, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base + sb * NQ, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            umma_commit(&s_full[sb]);
+            if (j == n_tiles - 1) umma_commit(&q_empty[qb]);      // every QK of this item has read Q
           }
-          umma_commit(&s_full[sb]);
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      if (j > 0) {
-        const int jj = j - 1, s = jj % STAGES;
-        mbar_wait(&v_full[s], (jj / STAGES) & 1);
-        mbar_wait(p_full, jj & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const unsigned char* vs = v_smem + s * V_BYTES;
+        if (j > 0) {
+          const int jj = j - 1, g = gt + jj, s = g % STAGES;
+          mbar_wait(&v_full[s], (g / STAGES) & 1);
+          mbar_wait(p_full, g & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const unsigned char* vs = v_smem + s * V_BYTES;
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t da = umma_desc_sw128(vs + kb * (D * 128));
-            const uint64_t db = umma_desc_sw128(p_smem + kb * (NQ * 128));
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t da = umma_desc_sw128(vs + kb * (D * 128));
+              const uint64_t db = umma_desc_sw128(p_smem + kb * (NQ * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_o, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (jj | kb | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_o, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (jj | kb | k) != 0);
+            }
+            umma_commit(&kv_empty[s]);
+            umma_commit(pv_done);
           }
-          umma_commit(&kv_empty[s]);
-          umma_commit(pv_done);
+          __syncwarp();
         }
-        __syncwarp();
       }
+      gt += n_tiles;
+      ++qi;
     }
   } else {
     // ===== softmax: thread = kv token of the tile (TMEM lane); later thread = output dim
     const int qd = warp & 3;
     const int t = qd * 32 + lane;
     const uint32_t t_lane = (uint32_t)(qd * 32) << 16;
-    float m_used[G], l_thr[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) { m_used[g] = -INFINITY; l_thr[g] = 0.f; }
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t sv[16];
-      tmem_ld_32x16(tmem_base + sb * NQ + t_lane, sv);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_empty[sb]);                 // S^T is in registers: the buffer can take QK_{j+2}
-      const int kpos = (tile_lo + j) * TILE + t;
-      const bool ok = kpos < kv_end && kpos >= kv_begin;
-      float s[G], cmax[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        s[g] = ok ? __uint_as_float(sv[g]) * p.scale_log2 : -INFINITY;
-        cmax[g] = warp_max(s[g]);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) wred[qd * NQ + g] = cmax[g];
-      }
-      bar_sync_softmax();
-      float alpha[G];
-      bool rescale = false;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float mx = fmaxf(fmaxf(wred[g], wred[NQ + g]), fmaxf(wred[2 * NQ + g], wred[3 * NQ + g]));
-        alpha[g] = 1.f;
-        if (mx > m_used[g] + 8.f || (m_used[g] == -INFINITY && mx > -INFINITY)) {
-          if (m_used[g] != -INFINITY) { alpha[g] = ex2(m_used[g] - mx); rescale = true; }
-          m_used[g] = mx;
+    int gt = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      int split, h, b, tile_lo, kv_begin, kv_end;
+      const int n_tiles = item_range(it, split, h, b, tile_lo, kv_begin, kv_end);
+      if (n_tiles == 0) {
+        if (p.num_splits > 1) {
+          for (int g = 0; g < G; ++g) {
+            const int64_t pi = ((int64_t)b * p.Hq + (h * G + g)) * p.num_splits + split;
+            p.part_out[pi * D + t] = 0.f;
+            if (t == 0) p.part_lse[pi] = -INFINITY;
+          }
         }
+        continue;
       }
-      // P and O^T may only be touched once PV_{j-1} has retired
-      if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
-      if (rescale) {   // uniform across the CTA: every thread sees the same column maxima
-        uint32_t ov[16];
-        tmem_ld_32x16(tmem_o + t_lane, ov);
+      float m_used[G], l_thr[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) { m_used[g] = -INFINITY; l_thr[g] = 0.f; }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int gj = gt + j, sb = gj & 1;
+        mbar_wait(&s_full[sb], (gj >> 1) & 1);
+        tc_fence_after();
+        uint32_t sv[16];
+        tmem_ld_32x16(tmem_base + sb * NQ + t_lane, sv);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[sb]);                 // S^T is in registers: the buffer can take QK_{j+2}
+        const int kpos = (tile_lo + j) * TILE + t;
+        const bool ok = kpos < kv_end && kpos >= kv_begin;
+        float s[G], cmax[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          ov[g] = __float_as_uint(__uint_as_float(ov[g]) * alpha[g]);
-          l_thr[g] *= alpha[g];
+          s[g] = ok ? __uint_as_float(sv[g]) * p.scale_log2 : -INFINITY;
+          cmax[g] = warp_max(s[g]);
         }
-        tmem_st_32x16(tmem_o + t_lane, ov);
-        tmem_st_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) wred[qd * NQ + g] = cmax[g];
+        }
+        bar_sync_softmax();
+        float alpha[G];
+        bool rescale = false;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float mx = fmaxf(fmaxf(wred[g], wred[NQ + g]), fmaxf(wred[2 * NQ + g], wred[3 * NQ + g]));
+          alpha[g] = 1.f;
+          if (mx > m_used[g] + 8.f || (m_used[g] == -INFINITY && mx > -INFINITY)) {
+            if (m_used[g] != -INFINITY) { alpha[g] = ex2(m_used[g] - mx); rescale = true; }
+            m_used[g] = mx;
+          }
+        }
+        // P and O^T may only be touched once the previous PV (of this or of the previous item) has retired
+        if (gj > 0) { mbar_wait(pv_done, (gj - 1) & 1); tc_fence_after(); }
+        if (rescale) {   // uniform across the CTA: every thread sees the same column maxima
+          uint32_t ov[16];
+          tmem_ld_32x16(tmem_o + t_lane, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            ov[g] = __float_as_uint(__uint_as_float(ov[g]) * alpha[g]);
+            l_thr[g] *= alpha[g];
+          }
+          tmem_st_32x16(tmem_o + t_lane, ov);
+          tmem_st_wait();
+        }
+        unsigned char* pcol = p_smem + (t >> 6) * (NQ * 128) + ((t & 63) & 7) * 2;
+        const int chunk = (t & 63) >> 3;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float m_ref = (m_used[g] == -INFINITY) ? 0.f : m_used[g];
+          const float pe = ok ? ex2(s[g] - m_ref) : 0.f;
+          l_thr[g] += pe;
+          *reinterpret_cast<T*>(pcol + g * 128 + ((chunk ^ (g & 7)) << 4)) = from_f32<T>(pe);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(p_full);
+        bar_sync_softmax();                         // wred is reused by the next tile
       }
-      unsigned char* pcol = p_smem + (t >> 6) * (NQ * 128) + ((t & 63) & 7) * 2;
-      const int chunk = (t & 63) >> 3;
+      // ---- epilogue of the item: column sums over the 128 threads, then thread = output dim d
+      float l_tot[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) l_tot[g] = warp_sum(l_thr[g]);
+      if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) wred[qd * NQ + g] = l_tot[g];
+      }
+      bar_sync_softmax();
+      mbar_wait(pv_done, (gt + n_tiles - 1) & 1);
+      tc_fence_after();
+      uint32_t ov[16];
+      tmem_ld_32x16(tmem_o + t_lane, ov);
+      tmem_ld_wait();
+      tc_fence_before();
+      const int d = t;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float m_ref = (m_used[g] == -INFINITY) ? 0.f : m_used[g];
-        const float pe = ok ? ex2(s[g] - m_ref) : 0.f;
-        l_thr[g] += pe;
-        *reinterpret_cast<T*>(pcol + g * 128 + ((chunk ^ (g & 7)) << 4)) = from_f32<T>(pe);
+        const float l = wred[g] + wred[NQ + g] + wred[2 * NQ + g] + wred[3 * NQ + g];
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        const float o = __uint_as_float(ov[g]) * inv;
+        const int hq = h * G + g;
+        if (p.num_splits == 1) {
+          reinterpret_cast<T*>(p.out)[(int64_t)b * p.out_stride + (int64_t)hq * D + d] = from_f32<T>(o);
+          if (p.lse_out && d == 0)
+            p.lse_out[(int64_t)b * p.Hq + hq] = l > 0.f ? (m_used[g] + log2f(l)) * 0.6931471805599453f : -INFINITY;
+        } else {
+          const int64_t pi = ((int64_t)b * p.Hq + hq) * p.num_splits + split;
+          p.part_out[pi * D + d] = o;
+          if (d == 0) p.part_lse[pi] = l > 0.f ? m_used[g] + log2f(l) : -INFINITY;
+        }
       }
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(p_full);
-      bar_sync_softmax();                         // wred is reused by the next tile
+      bar_sync_softmax();                           // wred is reused by the next item
+      gt += n_tiles;
     }
-    // ---- epilogue: column sums over the 128 threads, then thread = output dim d
-    float l_tot[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) l_tot[g] = warp_sum(l_thr[g]);
-    if (lane == 0) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) wred[qd * NQ + g] = l_tot[g];
-    }
-    bar_sync_softmax();
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
-    tc_fence_after();
-    uint32_t ov[16];
-    tmem_ld_32x16(tmem_o + t_lane, ov);
-    tmem_ld_wait();
-    const int d = t;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float l = wred[g] + wred[NQ + g] + wred[2 * NQ + g] + wred[3 * NQ + g];
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      const float o = __uint_as_float(ov[g]) * inv;
-      const int hq = h * G + g;
-      if (p.num_splits == 1) {
-        reinterpret_cast<T*>(p.out)[(int64_t)b * p.out_stride + (int64_t)hq * D + d] = from_f32<T>(o);
-        if (p.lse_out && d == 0)
-          p.lse_out[(int64_t)b * p.Hq + hq] = l > 0.f ? (m_used[g] + log2f(l)) * 0.6931471805599453f : -INFINITY;
-      } else {
-        const int64_t pi = ((int64_t)b * p.Hq + hq) * p.num_splits + split;
-        p.part_out[pi * D + d] = o;
-        if (d == 0) p.part_lse[pi] = l > 0.f ? m_used[g] + log2f(l) : -INFINITY;
-      }
-    }
-    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
@@ -356,7 +395,7 @@ static EncodeTiledFn get_encode() {
 template <typename T, int G>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, dim3 grid,
                   cudaStream_t st) {
-  const int smem = STAGES * (K_BYTES + V_BYTES) + Q_BYTES + P_BYTES + 32 * 8 + 16 + 4 * NQ * 4 +
+  const int smem = STAGES * (K_BYTES + V_BYTES) + 2 * Q_BYTES + P_BYTES + 32 * 8 + 16 + 4 * NQ * 4 +
                    2 * MAX_TILES_SMEM * 4 + 1024;
   auto k = fmha_decode_kernel<T, G>;
   static bool a = false;
@@ -383,7 +422,7 @@ EXPORT int vb_fmha_tc_decode(const void* q, const void* kv_cache, int64_t num_bl
   Params p;
   p.block_table = block_table; p.seq_lens = seq_lens; p.out = out; p.part_out = part_out; p.part_lse = part_lse;
   p.lse_out = lse_out; p.out_stride = out_stride; p.bt_stride = bt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G;
-  p.num_splits = num_splits; p.window = window; p.scale_log2 = scale * 1.4426950408889634f;
+  p.num_splits = num_splits; p.window = window; p.scale_log2 = scale * 1.4426950408889634f; p.B = B;
   CUtensorMap tq, tk, tv;
   {
     cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Hq, (cuuint64_t)B};
@@ -412,7 +451,10 @@ EXPORT int vb_fmha_tc_decode(const void* q, const void* kv_cache, int64_t num_bl
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return -13;
   }
-  dim3 grid(num_splits, Hkv, B);
+  static int n_sms = 0;
+  if (!n_sms) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dv); }
+  const int n_items = num_splits * Hkv * B;
+  dim3 grid(n_items < n_sms ? n_items : n_sms);
   int rc = -5;
 #define VB_GO(GV)                                                                          \
   rc = bf16 ? launch<__nv_bfloat16, GV>(tq, tk, tv, p, grid, st) : launch<__half, GV>(tq, tk, tv, p, grid, st)

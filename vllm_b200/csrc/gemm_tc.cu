@@ -209,7 +209,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int c = 0; c < BN; c += CH) {
         float v[CH];
         load_chunk(c, v);
-        if (SWAP) {
+        if (SWAP && p.act) {
+          // rows interleave (gate_i, up_i): even lane holds gate, odd lane up → y[tok, i] = silu(gate) * up
+          const int n = a_tile * TM + row;
+          const int m0 = b_row0 + c;
+          const int n_out = p.N >> 1;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
+            const float g = v[j];
+            const float r = (g / (1.f + __expf(-g))) * other;
+            if ((lane & 1) == 0 && n < p.N && c + j < m_lim) y[(size_t)(m0 + j) * n_out + (n >> 1)] = from_f32<T>(r);
+          }
+        } else if (SWAP) {
           // accumulator is Y^T: row = output feature, column = token
           const int n = a_tile * TM + row;
           if (n < p.N) {
@@ -285,8 +297,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int r = 1; r < 8; ++r)
               if (r < p.splits) { acc.x += x[h][r].x; acc.y += x[h][r].y; acc.z += x[h][r].z; acc.w += x[h][r].w; }
             const int n = a_tile * TM + rq * 4;
-            T* yr = y + (size_t)(m_base + col) * p.N + n;
             float o[4] = {acc.x, acc.y, acc.z, acc.w};
+            if (p.act) {      // (gate, up) pairs are adjacent features: two outputs per unit
+              if (n + 4 <= p.N) {
+                T* ya = y + (size_t)(m_base + col) * (p.N >> 1) + (n >> 1);
+                const uint32_t pk = pack2<T>((o[0] / (1.f + __expf(-o[0]))) * o[1], (o[2] / (1.f + __expf(-o[2]))) * o[3]);
+                *reinterpret_cast<uint32_t*>(ya) = pk;
+              }
+              continue;
+            }
+            T* yr = y + (size_t)(m_base + col) * p.N + n;
             if (p.bias) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) if (n + e < p.N) o[e] += to_f32(reinterpret_cast<const T*>(p.bias)[n + e]);
@@ -418,17 +438,25 @@ EXPORT int vb_gemm_tc_plan(int M, int N, int K, int num_sms, int* swap, int* bn,
   return 0;
 }
 
+EXPORT int vb_gemm_tc2(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int64_t x_stride,
+                       int swap, int bn, int splits, float* ws, unsigned* counters, int act, int dtype, cudaStream_t st);
 EXPORT int vb_gemm_tc(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int64_t x_stride,
                       int swap, int bn, int splits, float* ws, unsigned* counters, int dtype, cudaStream_t st) {
+  return vb_gemm_tc2(x, w, bias, y, M, N, K, x_stride, swap, bn, splits, ws, counters, 0, dtype, st);
+}
+// act = 1: W rows interleave (gate_i, up_i); y is [M, N/2] = silu(gate) * up (swap-AB shapes only, N % 4 == 0, no bias)
+EXPORT int vb_gemm_tc2(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int64_t x_stride,
+                       int swap, int bn, int splits, float* ws, unsigned* counters, int act, int dtype, cudaStream_t st) {
   using namespace gemm;
   if (dtype == DT_F32 || K % 8 != 0) return -1;
+  if (act && (!swap || bias || (N & 3))) return -1;
   const bool bf16 = dtype == DT_BF16;
   CUtensorMap ta, tb;
   Params p;
   p.trace = g_trace;
   p.expert_offs = nullptr; p.n_experts = 0;
   { static int pf = -1; if (pf < 0) { const char* e = std::getenv("VLLM_B200_GEMM_PF"); pf = (e && e[0] == '1') ? 1 : 0; } p.pf = pf; }
-  p.y = y; p.bias = bias; p.ws = ws; p.counters = counters; p.M = M; p.N = N; p.K = K; p.splits = splits; p.act = 0;
+  p.y = y; p.bias = bias; p.ws = ws; p.counters = counters; p.M = M; p.N = N; p.K = K; p.splits = splits; p.act = act;
   const int kb = (K + BK - 1) / BK;
   p.k_blocks_per_split = (kb + splits - 1) / splits;
   int rc;

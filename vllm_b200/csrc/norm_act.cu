@@ -137,6 +137,26 @@ __global__ void act_and_mul_kernel(T* __restrict__ out, const T* __restrict__ x,
   }
 }
 
+// interleaved variant: x[t, 2i] = gate_i, x[t, 2i+1] = up_i (the weight layout of the fused gate_up GEMM epilogue)
+template <typename T>
+__global__ void silu_mul_interleaved_kernel(T* __restrict__ out, const T* __restrict__ x, int d, int64_t total_vec) {
+  constexpr int N = Vec16<T>::N;
+  pdl_trigger();
+  pdl_wait();
+  const int vec_per_row = d / N;                       // output vectors per row; each consumes two input vectors
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / vec_per_row;
+    const int c = (int)(i - t * vec_per_row) * N;
+    Vec16<T> a = ld16(x + t * 2 * d + 2 * c), b = ld16(x + t * 2 * d + 2 * c + N), o;
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      o.e[j] = from_f32<T>(act_fn<ACT_SILU>(to_f32(a.e[2 * j])) * to_f32(a.e[2 * j + 1]));
+      o.e[N / 2 + j] = from_f32<T>(act_fn<ACT_SILU>(to_f32(b.e[2 * j])) * to_f32(b.e[2 * j + 1]));
+    }
+    st16(out + t * d + c, o);
+  }
+}
+
 template <typename T, int ACT>
 __global__ void act_kernel(T* __restrict__ out, const T* __restrict__ x, int64_t total_vec) {
   constexpr int N = Vec16<T>::N;
@@ -215,6 +235,17 @@ EXPORT int vb_act_and_mul(void* out, const void* x, int64_t T, int d, int act, i
       case ACT_GELU: vb_launch(act_and_mul_kernel<TT, ACT_GELU>, blocks, 256, 0, st, (TT*)out, (const TT*)x, d, total); break;
       default: vb_launch(act_and_mul_kernel<TT, ACT_GELU_TANH>, blocks, 256, 0, st, (TT*)out, (const TT*)x, d, total); break;
     }
+  });
+  return (int)cudaGetLastError();
+}
+
+EXPORT int vb_silu_mul_interleaved(void* out, const void* x, int64_t T, int d, int dtype, cudaStream_t st) {
+  if (T == 0) return 0;
+  if (dtype == DT_F32 || d % 8 != 0) return -1;
+  const int64_t total = T * (d / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  DISPATCH_HALF(dtype, TT, {
+    vb_launch(silu_mul_interleaved_kernel<TT>, blocks, 256, 0, st, (TT*)out, (const TT*)x, d, total);
   });
   return (int)cudaGetLastError();
 }

@@ -57,7 +57,9 @@ environment_variables: dict[str, Callable[[], Any]] = {
     # --- kernels / device
     "VLLM_B200_FORCE_REF_OPS": _bool("VLLM_B200_FORCE_REF_OPS", False),
     "VLLM_B200_GEMM": _str("VLLM_B200_GEMM", "auto"),  # auto|cublas|tcgen05
-    "VLLM_B200_GEMM_SK": _bool("VLLM_B200_GEMM_SK", True),   # decode GEMMs on the persistent stream-K kernel
+    "VLLM_B200_FUSED_ACT": _bool("VLLM_B200_FUSED_ACT", True),   # gate|up as interleaved rows, SiLU·mul in the GEMM epilogue
+    "VLLM_B200_GEMM_SK": _bool("VLLM_B200_GEMM_SK", False),  # decode GEMMs on the persistent stream-K kernel (measured slower than the
+    # cluster split-K kernel on every decode shape: profiles/kernels_bench.md; kept for experiments)
     "VLLM_B200_ATTN_SPLITS": _int("VLLM_B200_ATTN_SPLITS", 0),
     "VLLM_B200_ATTN": _str("VLLM_B200_ATTN", "auto"),  # auto|simt (disable the tcgen05 attention kernel)
     "VLLM_B200_FUSED_AR": _bool("VLLM_B200_FUSED_AR", True),

@@ -114,11 +114,26 @@ class MergedColumnParallelLinear(ColumnParallelLinear):
     """Several column-parallel matrices fused along the output dim (gate|up)."""
 
     def __init__(self, input_size, output_sizes: list[int], bias=False, dtype=None, quant_config=None,
-                 prefix="") -> None:
+                 prefix="", interleave: bool = False) -> None:
         self.output_sizes = output_sizes
         super().__init__(input_size, sum(output_sizes), bias, False, dtype, quant_config, prefix)
+        # gate|up stored as interleaved rows (gate_0, up_0, gate_1, up_1, ...): the gated activation then pairs
+        # adjacent accumulator rows of ONE GEMM tile and fuses into the GEMM epilogue (``forward_gated_silu``)
+        self.interleave = bool(interleave and len(output_sizes) == 2 and output_sizes[0] == output_sizes[1]
+                               and not bias and type(self.quant_method) is LinearMethod
+                               and self.dtype in (torch.bfloat16, torch.float16))
+
+    def forward_gated_silu(self, x: torch.Tensor) -> torch.Tensor:
+        assert self.interleave
+        if self.lora_table:
+            return ops.silu_and_mul_interleaved(self._apply(x, None))
+        return ops.gated_silu_linear(x, self.weight)
 
     def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id=None) -> None:
+        if shard_id is not None and self.interleave and param is self.weight:
+            n = self.output_sizes[shard_id] // self.tp_size
+            param.data[shard_id::2].copy_(w.narrow(0, self.tp_rank * n, n))
+            return
         if shard_id is None:  # already fused on disk
             off = 0
             for i, sz in enumerate(self.output_sizes):

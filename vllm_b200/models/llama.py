@@ -29,17 +29,24 @@ from vllm_b200.parallel.utils import get_pp_indices
 class LlamaMLP(nn.Module):
     def __init__(self, hidden, inter, act: str, bias: bool, dtype, quant_config, prefix) -> None:
         super().__init__()
+        from vllm_b200 import envs
         self.gate_up_proj = MergedColumnParallelLinear(hidden, [inter, inter], bias, dtype, quant_config,
-                                                       f"{prefix}.gate_up_proj")
+                                                       f"{prefix}.gate_up_proj",
+                                                       interleave=(act == "silu" and envs.VLLM_B200_FUSED_ACT))
         self.down_proj = RowParallelLinear(inter, hidden, bias, dtype=dtype, quant_config=quant_config,
                                            prefix=f"{prefix}.down_proj")
         self.act = get_act_and_mul(act)
 
+    def _gated(self, x):
+        if self.gate_up_proj.interleave:
+            return self.gate_up_proj.forward_gated_silu(x)
+        return self.act(self.gate_up_proj(x))
+
     def forward(self, x):
-        return self.down_proj(self.act(self.gate_up_proj(x)))
+        return self.down_proj(self._gated(x))
 
     def forward_reduce_norm(self, x, residual, norm):
-        return self.down_proj.forward_reduce_norm(self.act(self.gate_up_proj(x)), residual, norm)
+        return self.down_proj.forward_reduce_norm(self._gated(x), residual, norm)
 
 
 class LlamaAttention(nn.Module):

@@ -57,6 +57,26 @@ def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
     return ref.silu_and_mul(x)
 
 
+def silu_and_mul_interleaved(x: torch.Tensor) -> torch.Tensor:
+    """silu(x[..., 0::2]) * x[..., 1::2]: the activation for gate_up weights stored as interleaved (gate_i, up_i) rows."""
+    if _use_cuda(x) and x.dtype in (torch.bfloat16, torch.float16) and (x.shape[-1] // 2) % 8 == 0:
+        return cuda_ops().silu_and_mul_interleaved(x)
+    return (torch.nn.functional.silu(x[..., 0::2].float()) * x[..., 1::2].float()).to(x.dtype)
+
+
+def gated_silu_linear(x: torch.Tensor, weight_il: torch.Tensor) -> torch.Tensor:
+    """silu(x Wg^T) * (x Wu^T) for a weight whose rows interleave (gate_i, up_i).  Decode batches on CUDA run ONE
+    kernel: the stream-K tcgen05 GEMM applies SiLU·mul in its epilogue (csrc/gemm_sk.cu)."""
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if _use_cuda(x):
+        cu = cuda_ops()
+        if 0 < x2.shape[0] <= 256 and cu._tc_ok(x2, weight_il) and weight_il.shape[0] % 4 == 0:
+            fn = cu.gemm_sk if envs.VLLM_B200_GEMM_SK else cu.gemm_tc
+            return fn(x2, weight_il, act=True).view(x.shape[:-1] + (weight_il.shape[0] // 2,))
+    return silu_and_mul_interleaved(linear(x, weight_il))
+
+
 def gelu_and_mul(x: torch.Tensor, approximate: str = "none") -> torch.Tensor:
     if _use_cuda(x):
         return cuda_ops().act_and_mul(x, "gelu_tanh" if approximate == "tanh" else "gelu")

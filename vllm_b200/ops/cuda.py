@@ -61,7 +61,7 @@ _topk_topp = _sig("vb_topk_topp", _vp, _i, _i, _vp, _vp, _vp, _vp)
 _row_lse = _sig("vb_row_lse", _vp, _i64, _i, _i, _vp, _i, _vp)
 _gemm_plan = _sig("vb_gemm_tc_plan", _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
                   ctypes.POINTER(_i64), ctypes.POINTER(_i))
-_gemm_tc = _sig("vb_gemm_tc", _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp, _vp, _i, _vp)
+_gemm_tc = _sig("vb_gemm_tc2", _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp, _vp, _i, _i, _vp)
 
 
 def _st() -> int:
@@ -130,6 +130,18 @@ def act_and_mul(x, act: str):
     out = torch.empty(x.shape[:-1] + (d,), dtype=x.dtype, device=x.device)
     _check(_act_and_mul(out.data_ptr(), xc.data_ptr(), xc.numel() // (2 * d), d, _ACT[act], _DT[x.dtype], _st()),
            "act_and_mul")
+    return out
+
+
+_silu_mul_il = _sig("vb_silu_mul_interleaved", _vp, _vp, _i64, _i, _i, _vp)
+
+
+def silu_and_mul_interleaved(x):
+    """x[..., 2i] = gate_i, x[..., 2i+1] = up_i → silu(gate) * up."""
+    d = x.shape[-1] // 2
+    xc = x.contiguous()
+    out = torch.empty(x.shape[:-1] + (d,), dtype=x.dtype, device=x.device)
+    _check(_silu_mul_il(out.data_ptr(), xc.data_ptr(), xc.numel() // (2 * d), d, _DT[x.dtype], _st()), "silu_mul_interleaved")
     return out
 
 
@@ -435,8 +447,9 @@ def _plan(M: int, N: int, K: int):
 
 
 def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Y = X W^T on our tcgen05 kernel. x: [M, K] (row stride free), w: [N, K] contiguous."""
+            out: Optional[torch.Tensor] = None, act: bool = False) -> torch.Tensor:
+    """Y = X W^T on our tcgen05 kernel. x: [M, K] (row stride free), w: [N, K] contiguous.  ``act`` (M <= 256): W's
+    rows interleave (gate_i, up_i) and the epilogue emits silu(gate) * up → [M, N/2]."""
     M, K = x.shape
     N = w.shape[0]
     swap, bn, splits, wsb, tiles = _plan(M, N, K)
@@ -448,9 +461,9 @@ def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
                 raise RuntimeError("GEMM split-K workspace must be allocated before CUDA-graph capture")
             g.ws = torch.empty(max(wsb // 4, 16 << 20), dtype=torch.float32, device=x.device)
             g.counters = torch.zeros(max(tiles, 4096), dtype=torch.int32, device=x.device)
-    y = out if out is not None else torch.empty((M, N), dtype=x.dtype, device=x.device)
+    y = out if out is not None else torch.empty((M, N // 2 if act else N), dtype=x.dtype, device=x.device)
     _check(_gemm_tc(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(), M, N, K, x.stride(0), swap, bn, splits,
-                    _p(g.ws), _p(g.counters), _DT[x.dtype], _st()), f"gemm_tc(M={M},N={N},K={K})")
+                    _p(g.ws), _p(g.counters), int(act), _DT[x.dtype], _st()), f"gemm_tc(M={M},N={N},K={K})")
     return y
 
 
