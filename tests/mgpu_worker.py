@@ -129,6 +129,69 @@ def test_collectives():
         print("collectives ok (multicast=%s)" % comm.use_mc, flush=True)
 
 
+def test_fused_stress():
+    """Protocol stress for csrc/gemm_ar.cu (reference strategy: tests/distributed/test_custom_all_reduce.py:33-100):
+    integer-valued operands so that every partial and every sum is exact in bf16/fp16 → the owned residual rows must be
+    BIT-identical to NCCL's; rows whose partial sums are all -0.0 (the Lamport sentinel bit pattern) and denormal-heavy
+    rows; 1000 CUDA-graph replays interleaving four token counts so the three rotating buffers and the device-side call
+    counter see every phase; both protocols (one-shot / two-shot)."""
+    from vllm_b200.parallel import state as ps
+    tp = ps.get_tp_group()
+    comm = tp.device_comm
+    rank, world = tp.rank_in_group, tp.world_size
+    dev = torch.device("cuda", torch.cuda.current_device())
+    H, K = 4096, 128
+    for dtype in (torch.bfloat16, torch.float16):
+        for mode in (1, 0):
+            comm.fused_mode = mode
+            g = torch.Generator(device=dev).manual_seed(1000 + rank)
+            w = torch.randint(-1, 2, (H, K), device=dev, generator=g).to(dtype)
+            tiny = 6e-8 if dtype == torch.float16 else 1e-21      # tiny * tiny underflows to (signed) zero in `dtype`
+            w[:, 0] = tiny
+            nw = torch.ones(H, device=dev, dtype=dtype)
+            graphs = {}
+            for T in (1, 7, 64, 128):
+                x = torch.randint(-1, 2, (T, K), device=dev, generator=g).to(dtype)
+                if T > 1:
+                    x[0] = 0.0
+                    x[0, 0] = -tiny       # every partial of row 0 rounds to -0.0 (the sentinel bit pattern): must not hang
+                    x[1] = 0.0
+                    x[1, 0] = tiny        # +0.0 / denormal-range row
+                res0 = torch.randint(-3, 4, (T, H), device=dev,
+                                     generator=torch.Generator(device=dev).manual_seed(50 + T)).to(dtype)
+                y = torch.nn.functional.linear(x.float(), w.float())
+                dist.all_reduce(y, group=tp.device_group)
+                exp_res = (y + res0.float()).to(dtype)            # exact: small integers
+                res = res0.clone()
+                out = comm.gemm_allreduce_rmsnorm(x, w, res, nw, 1e-5)   # eager call (also arms the buffers for this H)
+                check(out is not None, "fused path declined")
+                torch.cuda.synchronize()
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    res.copy_(res0)
+                    og = comm.gemm_allreduce_rmsnorm(x, w, res, nw, 1e-5)[0]
+                graphs[T] = (gph, res, og, exp_res)
+            order = torch.randint(0, 4, (1000,), generator=torch.Generator().manual_seed(77)).tolist()   # same on all ranks
+            keys = [1, 7, 64, 128]
+            for i, o in enumerate(order):
+                T = keys[o]
+                gph, res, og, exp_res = graphs[T]
+                gph.replay()
+                if i % 50 == 0 or i > 990:
+                    torch.cuda.synchronize()
+                    per = (T + world - 1) // world if mode == 1 else T
+                    r0, r1 = (rank * per, min(T, rank * per + per)) if mode == 1 else (0, T)
+                    if r1 > r0:
+                        check(torch.equal(res[r0:r1], exp_res[r0:r1]), f"replay {i}: residual rows differ (T={T}, mode={mode}, {dtype})")
+                    e = exp_res.float()
+                    e_norm = e * torch.rsqrt(e.pow(2).mean(-1, keepdim=True) + 1e-5)
+                    torch.testing.assert_close(og.float(), e_norm, atol=3e-2, rtol=2e-2)
+            torch.cuda.synchronize()
+    comm.fused_mode = 1
+    if rank == 0:
+        print("fused stress ok", flush=True)
+
+
 def test_e2e_tp(expected_path):
     import json
     from vllm_b200 import LLM, SamplingParams
@@ -160,11 +223,11 @@ if __name__ == "__main__":
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
-    if mode == "collectives":
+    if mode in ("collectives", "stress"):
         from vllm_b200.parallel import state as ps
         ps.init_distributed_environment(world, rank, local_rank, "env://")
         ps.initialize_model_parallel(tp=world)
-        test_collectives()
+        test_collectives() if mode == "collectives" else test_fused_stress()
         dist.barrier()
         ps.destroy_distributed_environment()
     elif mode == "e2e":

@@ -18,25 +18,42 @@ def _torchrun(n, *args, timeout=600):
     return r.stdout
 
 
-def test_symm_collectives_match_nccl():
-    out = _torchrun(2, "collectives")
+def _need(n):
+    import torch
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_symm_collectives_match_nccl(world):
+    _need(world)
+    out = _torchrun(world, "collectives")
     assert "collectives ok" in out
 
 
-def test_tp2_matches_tp1(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_gemm_allreduce_protocol_stress(world):
+    """Bit-exact residual rows vs NCCL on integer data, -0.0 / denormal rows, 1000 graph replays with varying T."""
+    _need(world)
+    out = _torchrun(world, "stress", timeout=900)
+    assert "fused stress ok" in out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tp_matches_tp1(tmp_path, world):
+    _need(world)
     base = str(tmp_path / "e2e.json")
     env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29612")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py"), "e2e", base], env=env,
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    _torchrun(2, "e2e", base)
-    a, b = json.load(open(base + ".tp1")), json.load(open(base + ".tp2"))
+    _torchrun(world, "e2e", base)
+    a, b = json.load(open(base + ".tp1")), json.load(open(base + f".tp{world}"))
     first_agree = 0
     diffs = []
     for ta, tb, la, lb in zip(a["tokens"], b["tokens"], a["logprobs"], b["logprobs"]):
         first_agree += ta[0] == tb[0]
         assert len(la) == len(lb)
         diffs += [abs(x - y) for x, y in zip(la, lb)]
-    # teacher-forced prompt logprobs must agree to bf16 accuracy; greedy continuations may flip near-ties later
     assert max(diffs) < 0.15 and sum(diffs) / len(diffs) < 0.03, (max(diffs), sum(diffs) / len(diffs))
     assert first_agree >= len(a["tokens"]) - 1

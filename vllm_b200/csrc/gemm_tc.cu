@@ -466,7 +466,11 @@ EXPORT int vb_gemm_tc2(const void* x, const void* w, const void* bias, void* y, 
     dim3 grid((N + TM - 1) / TM, (M + bn - 1) / bn, splits);
     static int n_sms = 0;
     if (!n_sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, d); }
-    const bool two = splits == 1 && (int)(grid.x * grid.y) > n_sms && bn <= 128;   // multi-wave → 2 CTAs / SM
+    // multi-wave → 2 CTAs / SM.  VLLM_B200_GEMM_2CTA=1 forces the half-size ring for every decode GEMM: a CTA of the NEXT
+    // kernel can then co-reside with a CTA of this one, so its launch + first-byte latency overlaps this kernel's epilogue
+    static int force_two = -1;
+    if (force_two < 0) { const char* e = std::getenv("VLLM_B200_GEMM_2CTA"); force_two = (e && e[0] == '1') ? 1 : 0; }
+    const bool two = bn <= 128 && (force_two || (splits == 1 && (int)(grid.x * grid.y) > n_sms));
 #define GO(BNV, ST, ST2)                                                                 \
     if (two) {                                                                           \
       if (bf16) return launch<__nv_bfloat16, BNV, ST2, true>(ta, tb, p, grid, st);       \

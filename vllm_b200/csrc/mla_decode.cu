@@ -11,8 +11,11 @@
 // for O, the heads are the MMA N (16 or 32 per CTA; 128-head models run 4 head groups per sequence) — and each latent
 // byte is fetched from HBM once and from shared memory by two tcgen05.mma streams, never transposed, never copied.
 //
-// A tile is 64 KV tokens (9 k-blocks of [64 tok x 64 dims] = 72 KB); two tiles are resident, so the TMA stream of tile
-// j+1 and QK_{j+1} run under the softmax and PV of tile j.  The QK MMA is issued with M = 128 (the instruction shape the
+// A tile is 64 KV tokens (9 k-blocks of [64 tok x 64 dims] = 72 KB); two tiles are resident.  Every k-block has its own
+// full / empty mbarrier: QK starts on the first k-block that lands (rope first), the rope block is released when QK
+// retires and each pair of latent blocks when the PV product of its 128 output dims retires — so the TMA stream of
+// tile j+2 starts under the PV of tile j instead of after it (ncu of the whole-tile version: softmax warps spent 70 %
+// of their time waiting for S, i.e. the load latency sat on the critical path once per tile).  The QK MMA is issued with M = 128 (the instruction shape the
 // accumulator layout is simplest for): rows 64..127 read the following k-block's bytes, land in TMEM lanes the softmax
 // never looks at, and cost nothing that matters — at 16-32 heads per CTA the kernel is bound by the latent stream
 // (1152 B per token), not by tensor-core time.
@@ -89,9 +92,9 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmap_qn, const __grid_cons
   unsigned char* p_smem = q_smem + Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + (P_BYTES < 8192 ? 8192 : P_BYTES));
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;              // [STAGES]
-  uint64_t* kv_empty = kv_full + STAGES;     // [STAGES]
-  uint64_t* s_full = kv_empty + STAGES;      // [2]
+  uint64_t* kv_full = bars + 1;              // [STAGES * NKB] one per k-block buffer
+  uint64_t* kv_empty = kv_full + STAGES * NKB;
+  uint64_t* s_full = kv_empty + STAGES * NKB;   // [2]
   uint64_t* s_empty = s_full + 2;            // [2]
   uint64_t* p_full = s_empty + 2;
   uint64_t* pv_done = p_full + 1;
@@ -121,7 +124,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmap_qn, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qn); tma_prefetch_desc(&tmap_qr); tma_prefetch_desc(&tmap_kv);
     mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < STAGES * NKB; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 128); }
     mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
@@ -171,20 +174,26 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmap_qn, const __grid_cons
       for (int kb = 0; kb < 8; ++kb) tma_load_3d(q_smem + kb * (N * 128), &tmap_qn, kb * 64, h0, b, q_full);
       tma_load_3d(q_smem + 8 * (N * 128), &tmap_qr, 0, h0, b, q_full);
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % STAGES;
+        const int st = j % STAGES;
+        const uint32_t par = ((j / STAGES) & 1) ^ 1;
         int row[8], n_valid = 0;
         for (int u = 0; u < ppt; ++u) {
           const int i = j * ppt + u;
           row[u] = i < MAX_IDS_SMEM ? blk_ids[i] : box_row(i);
           n_valid += row[u] >= 0;
         }
-        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], (uint32_t)n_valid * rows * 128 * NKB);
-        unsigned char* st = kv_smem + s * STAGE_BYTES;
-        for (int kb = 0; kb < NKB; ++kb)
+        const uint32_t bytes = (uint32_t)n_valid * rows * 128;
+        unsigned char* stp = kv_smem + st * STAGE_BYTES;
+#pragma unroll 1
+        for (int i = 0; i < NKB; ++i) {
+          const int kb = i == 0 ? NKB - 1 : i - 1;             // rope block first: QK releases it first
+          const int slot = st * NKB + kb;
+          mbar_wait(&kv_empty[slot], par);
+          mbar_expect_tx(&kv_full[slot], bytes);
           for (int u = 0; u < ppt; ++u)
             if (row[u] >= 0)
-              tma_load_2d_hint(st + kb * KB_BYTES + u * rows * 128, &tmap_kv, kb * 64, row[u], &kv_full[s], L2_EVICT_FIRST);
+              tma_load_2d_hint(stp + kb * KB_BYTES + u * rows * 128, &tmap_kv, kb * 64, row[u], &kv_full[slot], L2_EVICT_FIRST);
+        }
       }
     }
   } else if (warp == 1) {
@@ -193,44 +202,56 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmap_qn, const __grid_cons
     const uint32_t idesc_s = umma_idesc_f16(128, N, bf16);
     const uint32_t idesc_o = idesc_f16_a_mn(128, N, bf16);
     mbar_wait(q_full, 0);
+    // descriptors are built once; every MMA adds a compile-time offset (in 16-byte units) to the address field
+    const uint64_t d_kv = umma_desc_sw128(kv_smem);
+    const uint64_t d_kv_mn = umma_desc_sw128_mn(kv_smem, KB_BYTES);
+    const uint64_t d_q = umma_desc_sw128(q_smem);
+    const uint64_t d_p = umma_desc_sw128(p_smem);
     for (int j = 0; j <= n_tiles; ++j) {
       if (j < n_tiles) {
-        // ---- S^T_j = Kc · Q^T over the 9 k-blocks (M = 128: rows 64..127 are padding, see the header)
-        const int s = j % STAGES, sb = j & 1;
-        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        // ---- S^T_j = Kc · Q^T, k-block by k-block as they land (M = 128: rows 64..127 are padding, see the header)
+        const int st = j % STAGES, sb = j & 1;
+        const uint32_t par = (j / STAGES) & 1;
         mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const unsigned char* st = kv_smem + s * STAGE_BYTES;
 #pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) {
-            const uint64_t da = umma_desc_sw128(st + kb * KB_BYTES);
-            const uint64_t db = umma_desc_sw128(q_smem + kb * (N * 128));
+        for (int i = 0; i < NKB; ++i) {
+          const int kb = i == 0 ? NKB - 1 : i - 1;
+          const int slot = st * NKB + kb;
+          mbar_wait(&kv_full[slot], par);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t da = d_kv + (uint64_t)((st * STAGE_BYTES + kb * KB_BYTES) >> 4);
+            const uint64_t db = d_q + (uint64_t)((kb * (N * 128)) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base + sb * N, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, (kb | k) != 0);
+              umma_f16(tmem_base + sb * N, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, (i | k) != 0);
           }
+          __syncwarp();
+        }
+        if (lane == 0) {
           umma_commit(&s_full[sb]);
+          umma_commit(&kv_empty[st * NKB + NKB - 1]);          // the rope block is only read by QK
         }
         __syncwarp();
       }
       if (j > 0) {
-        // ---- O^T += V^T · P^T for tile j-1: four 128-dim chunks (k-blocks 2c, 2c+1 read MN-major), K = 64 tokens
-        const int jj = j - 1, s = jj % STAGES;
+        // ---- O^T += V^T · P^T for tile j-1: four 128-dim chunks (k-blocks 2c, 2c+1 read MN-major), K = 64 tokens;
+        // each chunk hands its two k-block buffers back to the producer as soon as it retires
+        const int jj = j - 1, st = jj % STAGES;
         mbar_wait(p_full, jj & 1);
         tc_fence_after();
         if (lane == 0) {
-          const unsigned char* st = kv_smem + s * STAGE_BYTES;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
             for (int kk = 0; kk < TILE / 16; ++kk) {
-              const uint64_t da = umma_desc_sw128_mn(st + (2 * c) * KB_BYTES + kk * 2048, KB_BYTES);
-              const uint64_t db = umma_desc_sw128(p_smem) + (uint64_t)(kk * 2);
-              umma_f16(tmem_o + c * N, da, db, idesc_o, (jj | kk) != 0);
+              const uint64_t da = d_kv_mn + (uint64_t)((st * STAGE_BYTES + (2 * c) * KB_BYTES + kk * 2048) >> 4);
+              umma_f16(tmem_o + c * N, da, d_p + (uint64_t)(kk * 2), idesc_o, (jj | kk) != 0);
             }
+            umma_commit(&kv_empty[st * NKB + 2 * c]);
+            umma_commit(&kv_empty[st * NKB + 2 * c + 1]);
           }
-          umma_commit(&kv_empty[s]);
           umma_commit(pv_done);
         }
         __syncwarp();
@@ -406,7 +427,7 @@ static EncodeTiledFn get_encode() {
 template <typename T, int N>
 static int launch(const CUtensorMap& tqn, const CUtensorMap& tqr, const CUtensorMap& tkv, const Params& p, dim3 grid,
                   cudaStream_t st) {
-  const int smem = STAGES * STAGE_BYTES + NKB * N * 128 + 8192 + 32 * 8 + 16 + 4 * N * 4 + MAX_IDS_SMEM * 4 + 1024;
+  const int smem = STAGES * STAGE_BYTES + NKB * N * 128 + 8192 + (2 * STAGES * NKB + 8) * 8 + 16 + 4 * N * 4 + MAX_IDS_SMEM * 4 + 1024;
   auto k = mla_decode_kernel<T, N>;
   static bool a = false;
   if (!a) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a = true; }

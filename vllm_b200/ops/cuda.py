@@ -317,7 +317,7 @@ def mla_decode_splits(B: int, H: int, max_seq_len: int) -> int:
         return forced
     groups = (H + 31) // 32 if H > 16 else 1
     ctas = max(B * groups, 1)
-    s = max(1, min(16, (num_sms() + ctas - 1) // ctas))
+    s = max(1, min(16, num_sms() // ctas))           # one CTA per SM (170 KB smem): stay inside ONE wave
     return max(1, min(s, max_seq_len // 512))       # every split should still stream >= 8 tiles
 
 
