@@ -192,6 +192,64 @@ def test_fused_stress():
         print("fused stress ok", flush=True)
 
 
+def test_fused_moe():
+    """Fused MoE tail under EP inside the TP group: every rank owns E / W experts, the w2 grouped-GEMM epilogue red.adds
+    weighted rows into the owner rank's accumulator over NVLink, the finish kernel normalises and multicasts."""
+    from vllm_b200.ops import ref
+    from vllm_b200.ops.moe import fused_moe_reduce_norm
+    from vllm_b200.parallel import state as ps
+    tp = ps.get_tp_group()
+    comm = tp.device_comm
+    rank, world = tp.rank_in_group, tp.world_size
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dt = torch.bfloat16
+    E, k, H, I = 8, 2, 2048, 1024
+    g = torch.Generator(device=dev).manual_seed(4321)          # identical on every rank
+    w13 = (torch.randn(E, 2 * I, H, device=dev, generator=g) * 0.03).to(dt)
+    w2 = (torch.randn(E, H, I, device=dev, generator=g) * 0.03).to(dt)
+    nw = (1 + 0.1 * torch.randn(H, device=dev, generator=g)).to(dt)
+    per_e = E // world
+    emap = torch.full((E,), -1, dtype=torch.int32, device=dev)
+    emap[rank * per_e:(rank + 1) * per_e] = torch.arange(per_e, dtype=torch.int32, device=dev)
+    w13_l, w2_l = w13[rank * per_e:(rank + 1) * per_e].contiguous(), w2[rank * per_e:(rank + 1) * per_e].contiguous()
+    for it, T in enumerate((64, 7, 200, 1, 64, 64)):
+        x = (torch.randn(T, H, device=dev, generator=g) * 0.5).to(dt)
+        logits = torch.randn(T, E, device=dev, generator=g)
+        res = torch.randn(T, H, device=dev, generator=g).to(dt)
+        tw, ids = ref.topk_softmax(logits, k, True)
+        exp = ref.fused_moe(x, w13, w2, tw, ids, "silu", None)
+        e_norm, e_res = ref.fused_add_rms_norm(exp.clone(), res.clone(), nw, 1e-5)
+        r2 = res.clone()
+        out = fused_moe_reduce_norm(x, w13_l, w2_l, tw.float(), ids.int(), "silu", emap, r2, nw, 1e-5, False, comm)
+        check(out is not None, "fused MoE path declined")
+        torch.testing.assert_close(out[0].float(), e_norm.float(), atol=6e-2, rtol=4e-2)
+        per = (T + world - 1) // world
+        r0, r1 = rank * per, min(T, rank * per + per)
+        if r1 > r0:
+            torch.testing.assert_close(r2[r0:r1].float(), e_res[r0:r1].float(), atol=6e-2, rtol=4e-2)
+    # CUDA-graph replay (rotating accumulators are re-zeroed by the finish kernel)
+    T = 64
+    x = (torch.randn(T, H, device=dev, generator=g) * 0.5).to(dt)
+    logits = torch.randn(T, E, device=dev, generator=g)
+    res0 = torch.randn(T, H, device=dev, generator=g).to(dt)
+    tw, ids = ref.topk_softmax(logits, k, True)
+    twf, idsi = tw.float().contiguous(), ids.int().contiguous()
+    exp = ref.fused_moe(x, w13, w2, tw, ids, "silu", None)
+    e_norm, _ = ref.fused_add_rms_norm(exp.clone(), res0.clone(), nw, 1e-5)
+    rg = res0.clone()
+    torch.cuda.synchronize()
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph):
+        rg.copy_(res0)
+        og = fused_moe_reduce_norm(x, w13_l, w2_l, twf, idsi, "silu", emap, rg, nw, 1e-5, False, comm)[0]
+    for _ in range(10):
+        gph.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(og.float(), e_norm.float(), atol=6e-2, rtol=4e-2)
+    if rank == 0:
+        print("fused moe ok", flush=True)
+
+
 def test_e2e_tp(expected_path):
     import json
     from vllm_b200 import LLM, SamplingParams
@@ -223,11 +281,11 @@ if __name__ == "__main__":
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
-    if mode in ("collectives", "stress"):
+    if mode in ("collectives", "stress", "moe"):
         from vllm_b200.parallel import state as ps
         ps.init_distributed_environment(world, rank, local_rank, "env://")
         ps.initialize_model_parallel(tp=world)
-        test_collectives() if mode == "collectives" else test_fused_stress()
+        {"collectives": test_collectives, "stress": test_fused_stress, "moe": test_fused_moe}[mode]()
         dist.barrier()
         ps.destroy_distributed_environment()
     elif mode == "e2e":

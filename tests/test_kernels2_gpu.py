@@ -495,3 +495,26 @@ def test_gemm_tc_fused_silu_mul(M, I, K):
     from vllm_b200 import ops
     close(ops.gated_silu_linear(x, w_il), torch.nn.functional.silu(g) * u, atol=3e-2, rtol=3e-2)
     close(ops.silu_and_mul_interleaved(ops.linear(x, w_il)), torch.nn.functional.silu(g) * u, atol=4e-2, rtol=3e-2)
+
+
+# ------------------------------------------------------------------ fused MoE combine + residual + norm (one GPU)
+@pytest.mark.parametrize("T,E,k,H,I", [(64, 8, 2, 4096, 1792), (7, 16, 4, 1024, 512), (200, 8, 2, 2048, 1024)])
+def test_fused_moe_reduce_norm_single_gpu(T, E, k, H, I):
+    from vllm_b200.ops.moe import fused_moe_reduce_norm
+    torch.manual_seed(50)
+    dt = torch.bfloat16
+    x = (torch.randn(T, H, device="cuda") * 0.5).to(dt)
+    w13 = (torch.randn(E, 2 * I, H, device="cuda") * 0.03).to(dt)
+    w2 = (torch.randn(E, H, I, device="cuda") * 0.03).to(dt)
+    logits = torch.randn(T, E, device="cuda")
+    tw, ids = ref.topk_softmax(logits, k, True)
+    res = torch.randn(T, H, device="cuda").to(dt)
+    nw = (1 + 0.1 * torch.randn(H, device="cuda")).to(dt)
+    exp_moe = ref.fused_moe(x, w13, w2, tw, ids, "silu", None)
+    e_norm, e_res = ref.fused_add_rms_norm(exp_moe.clone(), res.clone(), nw, 1e-5)
+    for _ in range(3):                       # the accumulator must come back zeroed
+        r2 = res.clone()
+        out = fused_moe_reduce_norm(x, w13, w2, tw.float(), ids.int(), "silu", None, r2, nw, 1e-5)
+        assert out is not None
+        close(out[0], e_norm, atol=6e-2, rtol=4e-2)
+        close(r2, e_res, atol=6e-2, rtol=4e-2)

@@ -40,6 +40,14 @@ def test_fused_gemm_allreduce_protocol_stress(world):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_moe_combine_over_nvlink(world):
+    """Expert-parallel MoE tail: grouped-GEMM epilogue red.adds into the token owner's accumulator, vs the fp32 reference."""
+    _need(world)
+    out = _torchrun(world, "moe")
+    assert "fused moe ok" in out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_tp_matches_tp1(tmp_path, world):
     _need(world)
     base = str(tmp_path / "e2e.json")

@@ -13,10 +13,13 @@
 
 namespace {
 
+// acc32_off != 0: the rows this rank owns were already summed into an fp32 accumulator at that offset of the LOCAL
+// buffer (by red.add epilogues of every rank's grouped GEMM: fused MoE combine + reduce-scatter); phase 1 reads and
+// re-zeroes it instead of reducing the staged 16-bit partials.
 template <typename T>
 __global__ void __launch_bounds__(1024) ar_rows_kernel(CommCtx c, const T* __restrict__ x, size_t in_off, size_t out_off,
                                                         T* __restrict__ residual, const T* __restrict__ norm_w,
-                                                        float eps, int T_rows, int H, int gemma) {
+                                                        float eps, int T_rows, int H, int gemma, size_t acc32_off) {
   __shared__ float red[32];
   const uint32_t e0 = c.state[0];
   const int vec_per_row = H / 8;
@@ -38,7 +41,14 @@ __global__ void __launch_bounds__(1024) ar_rows_kernel(CommCtx c, const T* __res
     const bool active = threadIdx.x < vec_per_row;
     const size_t off = ((size_t)row * H + threadIdx.x * 8) * sizeof(T);
     if (active) {
-      reduce8<T>(c, in_off + off, acc);
+      if (acc32_off) {
+        float4* a4 = reinterpret_cast<float4*>(c.local + acc32_off) + ((size_t)row * H + threadIdx.x * 8) / 4;
+        const float4 lo = a4[0], hi = a4[1];
+        a4[0] = make_float4(0.f, 0.f, 0.f, 0.f); a4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[0] = lo.x; acc[1] = lo.y; acc[2] = lo.z; acc[3] = lo.w; acc[4] = hi.x; acc[5] = hi.y; acc[6] = hi.z; acc[7] = hi.w;
+      } else {
+        reduce8<T>(c, in_off + off, acc);
+      }
       if (residual) {
         Vec16<T> rv = ld16(residual + (size_t)row * H + threadIdx.x * 8), ro;
 #pragma unroll
@@ -108,9 +118,20 @@ static CommCtx make_ctx(void* local, void* const* peers, void* mc, uint32_t* sta
 }
 
 // x may be null when the partial already lives in the symmetric buffer at in_off (e.g. written by a GEMM epilogue)
+EXPORT int vb_comm_allreduce_rows2(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
+                                   const void* x, int64_t in_off, int64_t out_off, void* residual, const void* norm_w,
+                                   float eps, int T_rows, int H, int gemma, int num_sms, int64_t acc32_off, int dtype,
+                                   cudaStream_t st);
 EXPORT int vb_comm_allreduce_rows(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
                                   const void* x, int64_t in_off, int64_t out_off, void* residual, const void* norm_w,
                                   float eps, int T_rows, int H, int gemma, int num_sms, int dtype, cudaStream_t st) {
+  return vb_comm_allreduce_rows2(local, peers, mc, state, rank, world, x, in_off, out_off, residual, norm_w, eps, T_rows, H,
+                                 gemma, num_sms, 0, dtype, st);
+}
+EXPORT int vb_comm_allreduce_rows2(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
+                                   const void* x, int64_t in_off, int64_t out_off, void* residual, const void* norm_w,
+                                   float eps, int T_rows, int H, int gemma, int num_sms, int64_t acc32_off, int dtype,
+                                   cudaStream_t st) {
   if (T_rows == 0) return 0;
   if (dtype == DT_F32 || H % 8 != 0 || H / 8 > 1024) return -1;
   CommCtx c = make_ctx(local, peers, mc, state, rank, world);
@@ -120,7 +141,7 @@ EXPORT int vb_comm_allreduce_rows(void* local, void* const* peers, void* mc, uin
   int thr = ((H / 8 + 31) / 32) * 32;
   DISPATCH_HALF(dtype, TT, {
     ar_rows_kernel<TT><<<grid, thr, 0, st>>>(c, (const TT*)x, (size_t)in_off, (size_t)out_off, (TT*)residual,
-                                              (const TT*)norm_w, eps, T_rows, H, gemma);
+                                              (const TT*)norm_w, eps, T_rows, H, gemma, (size_t)acc32_off);
   });
   return (int)cudaGetLastError();
 }

@@ -26,7 +26,9 @@ constexpr int BK = 128;           // fp8 elements per K-block = 128 B = one swiz
 constexpr int TM = 128;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_THREADS = 128;
-constexpr int SC_KB = 64;         // K-blocks of combined scales staged in shared memory per CTA
+constexpr int SC_KB_MAX = 96;
+// K-blocks of combined scales staged in shared memory per CTA (token tiles up to 64 wide: 96, wider: 64)
+VB_HOST_DEVICE constexpr int sc_kb(int bn) { return bn <= 64 ? 96 : 64; }
 
 struct Params {
   void* y;
@@ -182,7 +184,7 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int KBt = total_kb;
       // 16-byte scale loads need token offsets that are multiples of 4 (always true outside the grouped mode)
       const bool xs_vec = ((b_row0 & 3) == 0) && ((p.xs_stride & 3) == 0);
-      const bool staged = SWAP && nkb <= SC_KB;
+      const bool staged = SWAP && nkb <= sc_kb(BN);
       if (staged) {
         const int et = threadIdx.x - 64;
         for (int i = et; i < nkb * BN; i += EPI_THREADS) {
@@ -398,7 +400,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 template <typename T, int BN, int STAGES, bool SWAP, bool BLOCK>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
   using L = Smem<BN>;
-  const int smem = STAGES * L::STAGE_BYTES + (2 * STAGES + 4) * 8 + 32 + (SWAP && BLOCK ? SC_KB * BN * 4 : 0) + 1024;
+  const int smem = STAGES * L::STAGE_BYTES + (2 * STAGES + 4) * 8 + 32 + (SWAP && BLOCK ? sc_kb(BN) * BN * 4 : 0) + 1024;
   auto k = gemm_fp8_kernel<T, BN, STAGES, SWAP, BLOCK>;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
@@ -443,7 +445,7 @@ EXPORT int vb_gemm_fp8_plan(int M, int N, int K, int* swap, int* bn, int* splits
       break;
     }
     if (nt >= 56 && kb < 16) s = 1;
-    while (kb / s > SC_KB && s < 8 && (s + 1) * nt <= 132) ++s;     // staged scales cover SC_KB K-blocks per CTA
+    while ((kb + s - 1) / s > sc_kb(b) && s < 8 && (s + 1) * nt <= 132) ++s;     // staged scales cover sc_kb() K-blocks per CTA
     *swap = 1; *bn = b; *splits = s;
   } else {
     *swap = 0; *bn = 128; *splits = 1;

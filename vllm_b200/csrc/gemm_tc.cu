@@ -39,8 +39,22 @@ struct Params {
   // [expert_offs[e], expert_offs[e+1]) of X (tokens sorted by expert) with W[e] = rows [e*N, (e+1)*N) of the weight
   const int* expert_offs;
   int n_experts;
+  // grouped mode, fused MoE combine (+ cross-rank reduce-scatter): instead of storing Y, every output element is scaled
+  // by its pair's routing weight and ADDED (red.add.f32, system scope, straight over NVLink) into the fp32 accumulator
+  // row of the rank that OWNS the token (row owner = token / red_per, the same sharding the fused all-reduce kernels use
+  // for the residual stream) — top-k combine + reduce-scatter inside the GEMM epilogue, one NVLink hop, no staging
+  float* red_acc;          // this rank's accumulator [T, red_H] (also the single-GPU target)
+  float* red_peer[8];      // the same buffer on every rank of the group (red_world > 1)
+  const int* row_pair;     // sorted row → pair index i = token * k + slot
+  const float* pair_w;     // [T * k] routing weights
+  int red_k, red_H, red_world, red_per;
   long long* trace;        // debug: per-CTA clock64 stamps [cta][16] (null in production)
 };
+
+VB_DEVICE void red_add_f32(float* p, float v) { asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+VB_DEVICE void red_add_f32_sys(float* p, float v) {
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 
 template <int BN> struct SmemLayout {
   static constexpr int A_BYTES = TM * BK * 2;
@@ -209,7 +223,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int c = 0; c < BN; c += CH) {
         float v[CH];
         load_chunk(c, v);
-        if (SWAP && p.act) {
+        if (SWAP && p.red_acc) {
+          // fused combine: acc[token(row), n] += w(row) * y[row, n]   (lanes = 32 consecutive n → 128-byte bursts)
+          const int n = a_tile * TM + row;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            if (c + j < m_lim) {
+              const int pair = p.row_pair[b_row0 + c + j];
+              const float val = v[j] * p.pair_w[pair];
+              const int tok = pair / p.red_k;
+              const size_t off = (size_t)tok * p.red_H + n;
+              if (n < p.N) {
+                if (p.red_world > 1) red_add_f32_sys(p.red_peer[tok / p.red_per] + off, val);
+                else red_add_f32(p.red_acc + off, val);
+              }
+            }
+          }
+        } else if (SWAP && p.act) {
           // rows interleave (gate_i, up_i): even lane holds gate, odd lane up → y[tok, i] = silu(gate) * up
           const int n = a_tile * TM + row;
           const int m0 = b_row0 + c;
@@ -454,7 +484,7 @@ EXPORT int vb_gemm_tc2(const void* x, const void* w, const void* bias, void* y, 
   CUtensorMap ta, tb;
   Params p;
   p.trace = g_trace;
-  p.expert_offs = nullptr; p.n_experts = 0;
+  p.expert_offs = nullptr; p.n_experts = 0; p.red_acc = nullptr; p.row_pair = nullptr; p.pair_w = nullptr; p.red_k = 1; p.red_H = 0; p.red_world = 1; p.red_per = 1;
   { static int pf = -1; if (pf < 0) { const char* e = std::getenv("VLLM_B200_GEMM_PF"); pf = (e && e[0] == '1') ? 1 : 0; } p.pf = pf; }
   p.y = y; p.bias = bias; p.ws = ws; p.counters = counters; p.M = M; p.N = N; p.K = K; p.splits = splits; p.act = act;
   const int kb = (K + BK - 1) / BK;
@@ -505,8 +535,21 @@ EXPORT int vb_gemm_tc2(const void* x, const void* w, const void* bias, void* y, 
 // Grouped (MoE) GEMM: Y[r, :] = X[r, :] · W[e(r)]^T for rows sorted by expert; offs[e] .. offs[e+1] delimit expert e.
 // X: [R, K], W: [E, N, K] contiguous, Y: [R, N].  bn = token-tile width (16..128), every expert gets
 // ceil(R / bn) candidate chunks; chunks without tokens exit immediately (their weights are never read).
+EXPORT int vb_gemm_tc_grouped_red(const void* x, const void* w, void* y, const int* offs, int R, int N, int K, int E, int bn,
+                                  float* red_acc, void* const* red_peers, int64_t red_off, int red_world, int red_per,
+                                  const int* row_pair, const float* pair_w, int red_k, int red_H, int dtype,
+                                  cudaStream_t st);
 EXPORT int vb_gemm_tc_grouped(const void* x, const void* w, void* y, const int* offs, int R, int N, int K, int E, int bn,
                               int dtype, cudaStream_t st) {
+  return vb_gemm_tc_grouped_red(x, w, y, offs, R, N, K, E, bn, nullptr, nullptr, 0, 1, 1, nullptr, nullptr, 1, 0, dtype, st);
+}
+// red_acc != null: the epilogue adds w(row) * y[row, :] into acc[token(row), :] instead of storing y.  red_world > 1:
+// the accumulator lives at byte offset red_off of every rank's symmetric buffer (red_peers) and a token's row is added
+// on the rank that owns it (token / red_per).
+EXPORT int vb_gemm_tc_grouped_red(const void* x, const void* w, void* y, const int* offs, int R, int N, int K, int E, int bn,
+                                  float* red_acc, void* const* red_peers, int64_t red_off, int red_world, int red_per,
+                                  const int* row_pair, const float* pair_w, int red_k, int red_H, int dtype,
+                                  cudaStream_t st) {
   using namespace gemm;
   if (dtype == DT_F32 || K % 8 != 0 || bn > 128 || bn % 16) return -1;
   const bool bf16 = dtype == DT_BF16;
@@ -515,6 +558,10 @@ EXPORT int vb_gemm_tc_grouped(const void* x, const void* w, void* y, const int* 
   p.trace = nullptr; p.pf = 0;
   p.y = y; p.bias = nullptr; p.ws = nullptr; p.counters = nullptr; p.M = R; p.N = N; p.K = K; p.splits = 1; p.act = 0;
   p.expert_offs = offs; p.n_experts = E;
+  p.red_acc = red_acc; p.row_pair = row_pair; p.pair_w = pair_w; p.red_k = red_k; p.red_H = red_H;
+  p.red_world = red_world; p.red_per = red_per < 1 ? 1 : red_per;
+  for (int i = 0; i < 8; ++i)
+    p.red_peer[i] = (red_peers && i < red_world) ? reinterpret_cast<float*>((unsigned char*)red_peers[i] + red_off) : nullptr;
   const int kb = (K + BK - 1) / BK;
   p.k_blocks_per_split = kb;
   int rc;

@@ -67,7 +67,8 @@ __global__ void topk_softmax_kernel(const T* __restrict__ logits, float* __restr
 //   sorted_tok[p] : token of the pair placed at sorted position p;  inv[i] : sorted position of pair i (or -1)
 //   offs[e] : first sorted position of local expert e;  offs[E] = number of valid pairs
 __global__ void align_kernel(const int* __restrict__ ids, const int* __restrict__ emap, int* __restrict__ sorted_tok,
-                             int* __restrict__ inv, int* __restrict__ offs, int R, int k, int E) {
+                             int* __restrict__ inv, int* __restrict__ offs, int R, int k, int E,
+                             int* __restrict__ sorted_pair) {
   extern __shared__ int sm[];
   int* cnt = sm;            // [E]
   int* start = sm + E;      // [E + 1]
@@ -95,10 +96,76 @@ __global__ void align_kernel(const int* __restrict__ ids, const int* __restrict_
     if (e < 0) { inv[i] = -1; continue; }
     const int p = start[e] + atomicAdd(&cnt[e], 1);
     sorted_tok[p] = i / k;
+    if (sorted_pair) sorted_pair[p] = i;
     inv[i] = p;
   }
   // sorted positions past the valid pairs (padding rows of the activation buffer) point at token 0
-  for (int p = start[E] + threadIdx.x; p < R; p += blockDim.x) sorted_tok[p] = 0;
+  for (int p = start[E] + threadIdx.x; p < R; p += blockDim.x) { sorted_tok[p] = 0; if (sorted_pair) sorted_pair[p] = 0; }
+}
+
+// Tail of the fused MoE combine: acc (fp32, every rank holds the complete sum after the multimem.red epilogue of the
+// w2 grouped GEMM) + residual → new residual, RMSNorm → out; acc is zeroed for its next use.  One CTA per token.
+template <typename T, bool GEMMA>
+__global__ void __launch_bounds__(1024) moe_finish_kernel(float* __restrict__ acc, T* __restrict__ residual,
+                                                           const T* __restrict__ w, T* __restrict__ out, int H, float eps) {
+  __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
+  const int64_t row = blockIdx.x;
+  float* a = acc + row * H;
+  T* r = residual ? residual + row * H : nullptr;
+  constexpr int MAXV4 = 8;                     // float4 per thread kept in registers (H <= 1024 * 8 * 4)
+  float4 v[MAXV4];
+  float ss = 0.f;
+  const int nv = H / 4;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nv) {
+      v[i] = *reinterpret_cast<const float4*>(a + vi * 4);
+      *reinterpret_cast<float4*>(a + vi * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r) {
+        const uint2 rv = *reinterpret_cast<const uint2*>(r + vi * 4);
+        const float2 r0 = unpack2<T>(rv.x), r1 = unpack2<T>(rv.y);
+        // the stream is kept in T: round the sum through T like the unfused path
+        v[i].x = to_f32(from_f32<T>(v[i].x)) + r0.x; v[i].y = to_f32(from_f32<T>(v[i].y)) + r0.y;
+        v[i].z = to_f32(from_f32<T>(v[i].z)) + r1.x; v[i].w = to_f32(from_f32<T>(v[i].w)) + r1.y;
+        uint2 o;
+        o.x = pack2<T>(v[i].x, v[i].y); o.y = pack2<T>(v[i].z, v[i].w);
+        *reinterpret_cast<uint2*>(r + vi * 4) = o;
+        const float2 q0 = unpack2<T>(o.x), q1 = unpack2<T>(o.y);
+        v[i] = make_float4(q0.x, q0.y, q1.x, q1.y);
+      }
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  if (w == nullptr) {                          // no norm: out = combined (+ residual) in T
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      const int vi = threadIdx.x + i * blockDim.x;
+      if (vi < nv) {
+        uint2 o;
+        o.x = pack2<T>(v[i].x, v[i].y); o.y = pack2<T>(v[i].z, v[i].w);
+        *reinterpret_cast<uint2*>(out + row * H + vi * 4) = o;
+      }
+    }
+    return;
+  }
+  ss = block_sum(ss, red);
+  const float inv = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nv) {
+      const uint2 wv = *reinterpret_cast<const uint2*>(w + vi * 4);
+      float2 w0 = unpack2<T>(wv.x), w1 = unpack2<T>(wv.y);
+      if (GEMMA) { w0.x += 1.f; w0.y += 1.f; w1.x += 1.f; w1.y += 1.f; }
+      uint2 o;
+      o.x = pack2<T>(v[i].x * inv * w0.x, v[i].y * inv * w0.y);
+      o.y = pack2<T>(v[i].z * inv * w1.x, v[i].w * inv * w1.y);
+      *reinterpret_cast<uint2*>(out + row * H + vi * 4) = o;
+    }
+  }
 }
 
 // out[t, :] = sum_j w[t, j] * y[inv[t*k + j], :]   (pairs not computed on this rank contribute 0)
@@ -151,11 +218,29 @@ EXPORT int vb_moe_topk_softmax(const void* logits, float* out_w, int* out_ids, i
   return (int)cudaGetLastError();
 }
 
-EXPORT int vb_moe_align(const int* ids, const int* emap, int* sorted_tok, int* inv, int* offs, int R, int k, int E,
-                        cudaStream_t st) {
+EXPORT int vb_moe_align2(const int* ids, const int* emap, int* sorted_tok, int* inv, int* offs, int R, int k, int E,
+                         int* sorted_pair, cudaStream_t st) {
   if (E > 4096) return -1;
   vb_launch(moe::align_kernel, dim3(1), dim3(256), (size_t)(2 * E + 1) * sizeof(int), st, ids, emap, sorted_tok, inv, offs,
-            R, k, E);
+            R, k, E, sorted_pair);
+  return (int)cudaGetLastError();
+}
+EXPORT int vb_moe_align(const int* ids, const int* emap, int* sorted_tok, int* inv, int* offs, int R, int k, int E,
+                        cudaStream_t st) {
+  return vb_moe_align2(ids, emap, sorted_tok, inv, offs, R, k, E, nullptr, st);
+}
+
+// out = RMSNorm(acc + residual) (norm_w may be null: out = acc (+ residual)); residual updated in place; acc zeroed
+EXPORT int vb_moe_finish(float* acc, void* residual, const void* norm_w, void* out, int T_, int H, float eps, int gemma,
+                         int dtype, cudaStream_t st) {
+  if (T_ == 0) return 0;
+  if (dtype == DT_F32 || H % 4 || H > 1024 * 8 * 4) return -1;
+  int thr = ((H / 4 + 7) / 8 + 31) / 32 * 32;
+  thr = thr < 64 ? 64 : (thr > 1024 ? 1024 : thr);
+  DISPATCH_HALF(dtype, T, {
+    if (gemma) vb_launch(moe::moe_finish_kernel<T, true>, dim3(T_), dim3(thr), 0, st, acc, (T*)residual, (const T*)norm_w, (T*)out, H, eps);
+    else vb_launch(moe::moe_finish_kernel<T, false>, dim3(T_), dim3(thr), 0, st, acc, (T*)residual, (const T*)norm_w, (T*)out, H, eps);
+  });
   return (int)cudaGetLastError();
 }
 

@@ -147,6 +147,32 @@ class FusedMoE(nn.Module):
             out = get_tp_group().all_reduce(out)
         return out.reshape(shape)
 
+    def forward_reduce_norm(self, x: torch.Tensor, router_logits: torch.Tensor, residual: torch.Tensor, norm):
+        """(normed, residual) = norm(all_reduce(moe(x)) + residual) with the combine, the cross-rank reduction, the
+        residual add and the RMSNorm fused around the grouped GEMMs (``ops/moe.py::fused_moe_reduce_norm``): the w2
+        epilogue red.adds every weighted row into the accumulator of the rank that owns the token.  None = not covered
+        (wide EP, EPLB, fp8 experts, prefill-sized batches, CPU) → the caller uses the unfused sequence."""
+        if (not x.is_cuda or self.wide_ep or self.eplb or self.fp8_block or norm is None
+                or x.dtype not in (torch.bfloat16, torch.float16) or self.w13_weight.dtype != x.dtype):
+            return None
+        from vllm_b200 import envs
+        if envs.VLLM_B200_FORCE_REF_OPS or not envs.VLLM_B200_FUSED_MOE:
+            return None
+        comm = None
+        if self.tp_size > 1:
+            comm = get_tp_group().device_comm
+            if comm is None:
+                return None
+        from vllm_b200.ops.moe import fused_moe_reduce_norm
+        x2 = x.reshape(-1, x.shape[-1])
+        w, ids = self.select_experts(router_logits.reshape(-1, router_logits.shape[-1]))
+        out = fused_moe_reduce_norm(x2, self.w13_weight, self.w2_weight, w.to(torch.float32), ids, self.act,
+                                    self.expert_map, residual.view(-1, x.shape[-1]), norm.weight, norm.eps,
+                                    getattr(norm, "gemma", False), comm)
+        if out is None:
+            return None
+        return out[0].view(x.shape), residual
+
     # ------------------------------------------------------------ EPLB
     def _set_placement(self, phy2log: torch.Tensor) -> None:
         """(Re)builds the routing tables IN PLACE — captured CUDA graphs keep pointing at the same buffers."""

@@ -87,6 +87,10 @@ class MoeDecoderLayer(nn.Module):
         hidden, residual = self.self_attn.o_proj.forward_reduce_norm(a, residual, self.post_attention_layernorm)
         if self.dense is not None:
             return self.dense.forward_reduce_norm(hidden, residual, next_norm)
+        if next_norm is not None and self.moe.shared_expert is None:
+            fused = self.moe.experts.forward_reduce_norm(hidden, self.moe.gate(hidden), residual, next_norm)
+            if fused is not None:
+                return fused
         partial = self.moe(hidden)
         if next_norm is None:
             tp = get_tp_group()

@@ -599,7 +599,12 @@ def comm_barrier(c) -> None:
 
 # ------------------------------------------------------------------ MoE (csrc/moe.cu + grouped mode of gemm_tc.cu)
 _moe_topk = _sig("vb_moe_topk_softmax", _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp)
-_moe_align = _sig("vb_moe_align", _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp)
+_moe_align = _sig("vb_moe_align2", _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp)
+_moe_finish = _sig("vb_moe_finish", _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp)
+_gemm_grouped_red = _sig("vb_gemm_tc_grouped_red", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _i,
+                         _i, _vp)
+_comm_ar_rows2 = _sig("vb_comm_allreduce_rows2", _vp, _vp, _vp, _vp, _i, _i, _vp, _i64, _i64, _vp, _vp, _f, _i, _i, _i, _i, _i64,
+                      _i, _vp)
 _moe_combine = _sig("vb_moe_combine", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp)
 _moe_gather = _sig("vb_moe_gather", _vp, _vp, _vp, _i, _i, _i, _vp)
 _gemm_grouped = _sig("vb_gemm_tc_grouped", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp)
@@ -618,17 +623,50 @@ def topk_softmax(gating, k, renormalize, scale: float = 1.0):
     return w, ids
 
 
-def moe_align(topk_ids: torch.Tensor, num_local_experts: int, expert_map: Optional[torch.Tensor] = None):
-    """(sorted_tok [R], inv [R], offs [E+1]) for R = T*k (token, slot) pairs — all on the device."""
+def moe_align(topk_ids: torch.Tensor, num_local_experts: int, expert_map: Optional[torch.Tensor] = None,
+              with_pairs: bool = False):
+    """(sorted_tok [R], inv [R], offs [E+1]) for R = T*k (token, slot) pairs — all on the device.  ``with_pairs`` also
+    returns sorted_pair [R]: the pair index (token * k + slot) of every sorted row."""
     T, k = topk_ids.shape
     R = T * k
     dev = topk_ids.device
     sorted_tok = torch.empty(R, dtype=torch.int32, device=dev)
     inv = torch.empty(R, dtype=torch.int32, device=dev)
     offs = torch.empty(num_local_experts + 1, dtype=torch.int32, device=dev)
+    pairs = torch.empty(R, dtype=torch.int32, device=dev) if with_pairs else None
     _check(_moe_align(topk_ids.data_ptr(), _p(expert_map), sorted_tok.data_ptr(), inv.data_ptr(), offs.data_ptr(), R, k,
-                      num_local_experts, _st()), "moe_align")
-    return sorted_tok, inv, offs
+                      num_local_experts, _p(pairs), _st()), "moe_align")
+    return (sorted_tok, inv, offs, pairs) if with_pairs else (sorted_tok, inv, offs)
+
+
+def gemm_tc_grouped_combine(xs, w, offs, bn, sorted_pair, pair_w, k: int, H: int, *, acc_ptr: int = 0, comm=None,
+                            acc_off: int = 0, per: int = 1) -> None:
+    """Grouped GEMM whose epilogue adds w(row) * y[row] into the fp32 accumulator row of its token: a local buffer
+    (``acc_ptr``) on one GPU; with ``comm`` the buffer at ``acc_off`` of the symmetric heap OF THE RANK THAT OWNS THE
+    TOKEN (token // per), reached with red.add over NVLink → top-k combine + reduce-scatter inside the GEMM."""
+    R, K = xs.shape
+    E, N, _ = w.shape
+    if comm is not None:
+        rc = _gemm_grouped_red(xs.data_ptr(), w.data_ptr(), None, offs.data_ptr(), R, N, K, E, bn, comm.local_ptr + acc_off,
+                               comm.peer_arr, acc_off, comm.world, per, sorted_pair.data_ptr(), pair_w.data_ptr(), k, H,
+                               _DT[xs.dtype], _st())
+    else:
+        rc = _gemm_grouped_red(xs.data_ptr(), w.data_ptr(), None, offs.data_ptr(), R, N, K, E, bn, acc_ptr, None, 0, 1, 1,
+                               sorted_pair.data_ptr(), pair_w.data_ptr(), k, H, _DT[xs.dtype], _st())
+    _check(rc, f"gemm_tc_grouped_combine(R={R},N={N},K={K},E={E})")
+
+
+def comm_finish_rows_acc32(c, acc_off: int, out_off: int, residual, norm_w, eps, T, H, gemma, dtype) -> None:
+    """Second half of the fused MoE tail under TP/EP: barrier → every rank reads (and re-zeroes) the fp32 sums of the
+    rows it owns, adds its residual rows, normalises and multicasts the rows → barrier (csrc/comm.cu ar_rows_kernel)."""
+    _check(_comm_ar_rows2(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, None, c.off_in, out_off,
+                          _p(residual), _p(norm_w), eps, T, H, int(gemma), num_sms(), acc_off, _DT[dtype], _st()),
+           "comm_finish_rows_acc32")
+
+
+def moe_finish(acc_ptr: int, residual, norm_w, out, T: int, H: int, eps: float, gemma: bool = False) -> None:
+    _check(_moe_finish(acc_ptr, _p(residual), _p(norm_w), out.data_ptr(), T, H, eps, int(gemma), _DT[out.dtype], _st()),
+           "moe_finish")
 
 
 def moe_gather(x: torch.Tensor, sorted_tok: torch.Tensor) -> torch.Tensor:

@@ -47,6 +47,58 @@ def fused_moe_grouped(x, w13, w2, topk_w, topk_ids, act, expert_map):
     return cu.moe_combine(y, inv, topk_w.to(torch.float32).contiguous(), T)
 
 
+_local_acc: dict[int, torch.Tensor] = {}
+
+
+def fused_moe_reduce_norm(x, w13, w2, topk_w, topk_ids, act, expert_map, residual, norm_w, eps, gemma=False, comm=None):
+    """MoE block tail inside the GEMM: align → gather → grouped GEMM (w13) → act·mul → grouped GEMM (w2) whose epilogue
+    scales every output row by its routing weight and ADDS it (red.add.f32) into the fp32 accumulator row of its token —
+    on one GPU a local buffer; under TP / EP the accumulator of the rank that OWNS the token, reached straight over
+    NVLink (peer pointers of the symmetric heap): top-k combine + reduce-scatter with no staging buffer and no separate
+    combine / collective launch; a final kernel (barrier → owned rows + residual → RMSNorm → multicast → barrier, or
+    the local finish kernel on one GPU) produces the next block's input and re-zeroes the accumulator.
+    Returns (normed, residual) or None when the shape is not covered (callers fall back to combine + reduce kernels).
+    Reference semantics: fused_moe/modular_kernel.py:42-83 (prepare → experts → finalize); baseline being replaced:
+    device_communicators/all2all.py:101-150 (AgRs: all-gather + reduce-scatter around the experts)."""
+    from vllm_b200.ops import cuda as cu
+    from vllm_b200.parallel.symm import LAM_H_MAX, MOE_T_CAP
+    T, k = topk_ids.shape
+    H = x.shape[1]
+    R = T * k
+    multi = comm is not None and comm.world > 1
+    if (not _grouped_ok(x, w13, w2, R) or T > MOE_T_CAP or H > LAM_H_MAX or H % 8 or act not in ("silu", "gelu", "gelu_tanh")
+            or (residual is not None and (not residual.is_contiguous() or residual.dtype != x.dtype))
+            or (multi and (H // 8 > 1024 or norm_w is None))):
+        return None
+    E = w13.shape[0]
+    ids = topk_ids if topk_ids.dtype == torch.int32 else topk_ids.to(torch.int32)
+    sorted_tok, inv, offs, pairs = cu.moe_align(ids.contiguous(), E, expert_map, with_pairs=True)
+    xs = cu.moe_gather(x, sorted_tok)
+    avg = max(R // max(E, 1), 1)
+    bn = 16
+    while bn < 128 and bn < 2 * avg:
+        bn += 16
+    h = cu.gemm_tc_grouped(xs, w13, offs, bn)
+    a = cu.act_and_mul(h, act)
+    pw = topk_w.to(torch.float32).contiguous()
+    if multi:
+        acc_off = comm.next_moe_acc()
+        per = (T + comm.world - 1) // comm.world
+        cu.gemm_tc_grouped_combine(a, w2, offs, bn, pairs, pw, k, H, comm=comm, acc_off=acc_off, per=per)
+        out = comm.moe_finish_rows(acc_off, T, H, x.dtype, residual, norm_w, eps, gemma)
+        return out, residual
+    dev = x.device.index or 0
+    acc = _local_acc.get(dev)
+    if acc is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("MoE accumulator must be allocated before CUDA-graph capture")
+        acc = _local_acc[dev] = torch.zeros(MOE_T_CAP * LAM_H_MAX, dtype=torch.float32, device=x.device)
+    cu.gemm_tc_grouped_combine(a, w2, offs, bn, pairs, pw, k, H, acc_ptr=acc.data_ptr())
+    out = torch.empty((T, H), dtype=x.dtype, device=x.device)
+    cu.moe_finish(acc.data_ptr(), residual, norm_w, out, T, H, eps, gemma)
+    return out, residual
+
+
 def fused_moe_cuda(x, w13, w2, topk_w, topk_ids, act="silu", expert_map: Optional[torch.Tensor] = None):
     from vllm_b200 import ops
     if _grouped_ok(x, w13, w2, topk_ids.numel()):

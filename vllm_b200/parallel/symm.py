@@ -31,6 +31,7 @@ logger = init_logger(__name__)
 FLAGS_BYTES = 4096
 LAM_T_CAP = 128      # the fused GEMM+all-reduce kernel handles up to 128 tokens (decode / small mixed batches)
 LAM_H_MAX = 8192
+MOE_T_CAP = 256      # tokens covered by the fused MoE combine accumulators (decode / small mixed batches)
 _ALIGN = 1 << 16
 
 
@@ -69,12 +70,17 @@ class SymmComm:
         self.lam_stride = _round(self.world * LAM_T_CAP * LAM_H_MAX * 2)
         # two-shot mode: 3 rotating output buffers (normalised rows multicast by their owners), sentinel-armed too
         self.oring_stride = _round(LAM_T_CAP * LAM_H_MAX * 2)
-        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride + 3 * self.oring_stride
+        # fused MoE combine: 3 rotating fp32 accumulators [MOE_T_CAP, LAM_H_MAX] that the w2 grouped-GEMM epilogues of ALL
+        # ranks add into through the multicast alias (multimem.red); zeroed again by the finish kernel that reads them
+        self.moe_stride = _round(MOE_T_CAP * LAM_H_MAX * 4)
+        total = FLAGS_BYTES + 3 * region + 3 * self.lam_stride + 3 * self.oring_stride + 3 * self.moe_stride
         self.buf = self._symm.empty(total, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
         self.off_lam = FLAGS_BYTES + 3 * region
         self.off_oring = self.off_lam + 3 * self.lam_stride
-        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
+        self.off_moe = self.off_oring + 3 * self.oring_stride
+        self._moe_flip = 0
+        self.buf[self.off_lam:self.off_moe].view(torch.int16).fill_(-32768)   # sentinel = bf16/fp16 negative zero
         self.lam_H = 0
         self._armed_mode = -1
         torch.cuda.synchronize()
@@ -208,7 +214,7 @@ class SymmComm:
             raise RuntimeError("Lamport buffers must be armed for this hidden size before CUDA-graph capture")
         torch.cuda.synchronize()
         self.group.barrier()
-        self.buf[self.off_lam:].view(torch.int16).fill_(-32768)
+        self.buf[self.off_lam:self.off_moe].view(torch.int16).fill_(-32768)
         self.state[8:13].zero_()
         torch.cuda.synchronize()
         self.group.barrier()
@@ -231,6 +237,18 @@ class SymmComm:
         part.masked_fill_(mask.reshape(-1, 1), 0)
         out = self.allreduce_rows(None, T, H, weight.dtype)
         return out.view(ids.shape + (H,)).clone()
+
+    def next_moe_acc(self) -> int:
+        """Byte offset (same on every rank) of the next rotating fp32 MoE accumulator; its owned rows are all-zero."""
+        self._moe_flip = (self._moe_flip + 1) % 3
+        return self.off_moe + self._moe_flip * self.moe_stride
+
+    def moe_finish_rows(self, acc_off: int, T: int, H: int, dtype, residual, norm_w, eps: float, gemma: bool = False):
+        """Rows summed into the accumulator by the grouped-GEMM epilogues → + residual → RMSNorm → every rank."""
+        self.ensure_capacity(T * H * dtype.itemsize)
+        out_off = self._next_out()
+        self.cu.comm_finish_rows_acc32(self, acc_off, out_off, residual, norm_w, eps, T, H, gemma, dtype)
+        return self._view(out_off, (T, H), dtype)
 
     def barrier(self) -> None:
         self.cu.comm_barrier(self)
