@@ -518,3 +518,70 @@ def test_fused_moe_reduce_norm_single_gpu(T, E, k, H, I):
         assert out is not None
         close(out[0], e_norm, atol=6e-2, rtol=4e-2)
         close(r2, e_res, atol=6e-2, rtol=4e-2)
+
+
+def test_fused_moe_fp8_grouped_matches_dequantised_reference():
+    from vllm_b200.ops.moe import fused_moe_fp8_grouped
+    torch.manual_seed(60)
+    T, E, k, H, I = 48, 8, 2, 2048, 1024
+    dt = torch.bfloat16
+    x = (torch.randn(T, H, device="cuda") * 0.5).to(dt)
+    w13 = torch.randn(E, 2 * I, H, device="cuda") * 0.03
+    w2 = torch.randn(E, H, I, device="cuda") * 0.03
+    q13, s13, q2, s2 = [], [], [], []
+    for e in range(E):
+        a, b = ref.block_quant_weight_fp8(w13[e], 128); q13.append(a); s13.append(b)
+        a, b = ref.block_quant_weight_fp8(w2[e], 128); q2.append(a); s2.append(b)
+    q13, s13, q2, s2 = torch.stack(q13), torch.stack(s13), torch.stack(q2), torch.stack(s2)
+    tw, ids = ref.topk_softmax(torch.randn(T, E, device="cuda"), k, True)
+    y = fused_moe_fp8_grouped(x, q13, s13, q2, s2, tw.float(), ids.int(), None)
+    exp = ref.fused_moe(x, w13.to(dt), w2.to(dt), tw, ids, "silu", None)
+    rel = (y.float() - exp.float()).norm() / exp.float().norm()
+    assert rel < 0.08, rel
+
+
+def test_gpu_input_prep_kernels_match_numpy_expansion():
+    """prep_step / block-table diffs / append_sampled vs the host-side expansion the runner does in numpy."""
+    import numpy as np
+    torch.manual_seed(70)
+    R, L, MB, BS = 32, 512, 16, 32
+    rng = np.random.default_rng(0)
+    token_table = torch.randint(0, 30000, (R, L), dtype=torch.int32, device="cuda")
+    block_rows = torch.zeros((R, MB), dtype=torch.int32, device="cuda")
+    bt_np = rng.integers(1, 1000, (R, MB)).astype(np.int32)
+    # stage the block tables through diffs: two appends per row
+    d_row, d_start, d_cnt, d_off, flat = [], [], [], [], []
+    for r in range(R):
+        for s, n in ((0, 5), (5, MB - 5)):
+            d_row.append(r); d_start.append(s); d_cnt.append(n); d_off.append(len(flat)); flat += bt_np[r, s:s + n].tolist()
+    t = lambda a: torch.tensor(a, dtype=torch.int32, device="cuda")   # noqa: E731
+    cu().block_table_apply_diffs(block_rows, t(d_row), t(d_start), t(d_cnt), t(d_off), t(flat))
+    assert np.array_equal(block_rows.cpu().numpy(), bt_np)
+    rows = rng.permutation(R)[:20].astype(np.int32)
+    nc = rng.integers(0, 300, 20).astype(np.int32)
+    ns = rng.integers(1, 40, 20).astype(np.int32)
+    ns[3] = 1
+    T = int(ns.sum())
+    nblk = int((nc + ns).max() + BS - 1) // BS
+    input_ids = torch.zeros(T, dtype=torch.int32, device="cuda")
+    positions = torch.zeros(T, dtype=torch.int64, device="cuda")
+    qsl = torch.zeros(21, dtype=torch.int32, device="cuda")
+    seq_lens = torch.zeros(20, dtype=torch.int32, device="cuda")
+    slots = torch.zeros(T, dtype=torch.int64, device="cuda")
+    bt = torch.zeros((20, MB), dtype=torch.int32, device="cuda")
+    cu().prep_step(t(rows), t(nc), t(ns), token_table, block_rows, input_ids, positions, qsl, seq_lens, slots, bt, nblk, BS)
+    tt = token_table.cpu().numpy()
+    cum = np.concatenate([[0], np.cumsum(ns)])
+    assert np.array_equal(qsl.cpu().numpy(), cum) and np.array_equal(seq_lens.cpu().numpy(), nc + ns)
+    for b in range(20):
+        pos = nc[b] + np.arange(ns[b])
+        sl = slice(cum[b], cum[b + 1])
+        assert np.array_equal(input_ids.cpu().numpy()[sl], tt[rows[b], pos])
+        assert np.array_equal(positions.cpu().numpy()[sl], pos)
+        assert np.array_equal(slots.cpu().numpy()[sl], bt_np[rows[b], pos // BS].astype(np.int64) * BS + pos % BS)
+        assert np.array_equal(bt.cpu().numpy()[b, :nblk], bt_np[rows[b], :nblk])
+    sampled = torch.randint(0, 30000, (20,), dtype=torch.int64, device="cuda")
+    cu().append_sampled(token_table, t(rows), t(nc + ns), sampled)
+    tt2 = token_table.cpu().numpy()
+    for b in range(20):
+        assert tt2[rows[b], nc[b] + ns[b]] == int(sampled[b])

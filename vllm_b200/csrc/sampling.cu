@@ -30,7 +30,7 @@ template <typename T, bool SAMPLE>
 __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logits, int64_t row_stride, int V,
                                                        const float* __restrict__ temperature,
                                                        const int64_t* __restrict__ seeds, const int* __restrict__ step_ptr,
-                                                       int64_t* __restrict__ out) {
+                                                       int64_t* __restrict__ out, int idx_off, float4* __restrict__ cand) {
   constexpr int N = Vec16<T>::N;
   __shared__ float sv[32];
   __shared__ int si[32];
@@ -55,13 +55,14 @@ __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logi
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       float x = to_f32(v.e[j]);
-      const int idx = vi * N + j;
+      const int idx = idx_off + vi * N + j;        // global vocabulary id: the noise is indexed by it (TP-invariant)
       if (noisy) x = x * inv_t + gumbel(seed, step, (uint32_t)idx);
       best = better(best, ArgMax{x, idx});
     }
   }
-  for (int idx = nvec * N + threadIdx.x; idx < V; idx += blockDim.x) {
-    float x = to_f32(lr[idx]);
+  for (int i = nvec * N + threadIdx.x; i < V; i += blockDim.x) {
+    float x = to_f32(lr[i]);
+    const int idx = idx_off + i;
     if (noisy) x = x * inv_t + gumbel(seed, step, (uint32_t)idx);
     best = better(best, ArgMax{x, idx});
   }
@@ -81,8 +82,25 @@ __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logi
       ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
       best = better(best, other);
     }
-    if (lane == 0) out[row] = best.i == 0x7fffffff ? 0 : best.i;
+    if (lane == 0) {
+      if (cand) cand[row] = make_float4(best.v, __int_as_float(best.i), 0.f, 0.f);   // this rank's candidate
+      else out[row] = best.i == 0x7fffffff ? 0 : best.i;
+    }
   }
+}
+
+// final pick over the per-rank candidates gathered as [B, W] x (value, index): same tie-break as the single-GPU kernel
+__global__ void select_candidate_kernel(const float4* __restrict__ cands, int W, int64_t* __restrict__ out, int B) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  ArgMax best{-INFINITY, 0x7fffffff};
+  for (int r = 0; r < W; ++r) {
+    const float4 c = cands[(size_t)row * W + r];
+    best = better(best, ArgMax{c.x, __float_as_int(c.y)});
+  }
+  out[row] = best.i == 0x7fffffff ? 0 : best.i;
 }
 
 // In-place top-k / top-p / min-p masking of fp32 logits (already divided by temperature).
@@ -216,7 +234,7 @@ __global__ void __launch_bounds__(1024) row_lse_kernel(const T* __restrict__ log
 EXPORT int vb_argmax(const void* logits, int64_t row_stride, int B, int V, int64_t* out, int dtype, cudaStream_t st) {
   if (B == 0) return 0;
   DISPATCH_DTYPE(dtype, TT, {
-    sample_kernel<TT, false><<<B, 1024, 0, st>>>((const TT*)logits, row_stride, V, nullptr, nullptr, nullptr, out);
+    sample_kernel<TT, false><<<B, 1024, 0, st>>>((const TT*)logits, row_stride, V, nullptr, nullptr, nullptr, out, 0, nullptr);
   });
   return (int)cudaGetLastError();
 }
@@ -225,8 +243,26 @@ EXPORT int vb_fused_sample(const void* logits, int64_t row_stride, int B, int V,
                            const int64_t* seeds, const int* step, int64_t* out, int dtype, cudaStream_t st) {
   if (B == 0) return 0;
   DISPATCH_DTYPE(dtype, TT, {
-    vb_launch(sample_kernel<TT, true>, B, 1024, 0, st, (const TT*)logits, row_stride, V, temperature, seeds, step, out);
+    vb_launch(sample_kernel<TT, true>, B, 1024, 0, st, (const TT*)logits, row_stride, V, temperature, seeds, step, out, 0, (float4*)nullptr);
   });
+  return (int)cudaGetLastError();
+}
+
+// TP vocab shards: every rank samples over ITS shard (global ids = idx_off + local id, V = valid local rows) and emits one
+// (value, id) candidate per row; after a 16-byte-per-row all-gather vb_select_candidate picks the winner — the 2 MiB of
+// logits per rank that the full all-gather moved never leave the GPU.
+EXPORT int vb_fused_sample_cand(const void* logits, int64_t row_stride, int B, int V, const float* temperature,
+                                const int64_t* seeds, const int* step, int idx_off, void* cand, int dtype, cudaStream_t st) {
+  if (B == 0) return 0;
+  DISPATCH_DTYPE(dtype, TT, {
+    vb_launch(sample_kernel<TT, true>, B, 1024, 0, st, (const TT*)logits, row_stride, V, temperature, seeds, step,
+              (int64_t*)nullptr, idx_off, (float4*)cand);
+  });
+  return (int)cudaGetLastError();
+}
+EXPORT int vb_select_candidate(const void* cands, int W, int64_t* out, int B, cudaStream_t st) {
+  if (B == 0) return 0;
+  vb_launch(select_candidate_kernel, dim3((B + 127) / 128), dim3(128), 0, st, (const float4*)cands, W, out, B);
   return (int)cudaGetLastError();
 }
 

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from vllm_b200 import ops
+from vllm_b200 import envs, ops
 from vllm_b200.core.kv_cache_manager import FullAttentionSpec, KVCacheSpec, MLAAttentionSpec, SlidingWindowSpec
 from vllm_b200.forward_context import get_forward_context
 
@@ -57,9 +57,11 @@ class Attention(nn.Module):
                    dtype_size=dtype_size, sliding_window=self.sliding_window)
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
-                positions: Optional[torch.Tensor] = None) -> torch.Tensor:
+                positions: Optional[torch.Tensor] = None, qk_norm: Optional[tuple] = None) -> torch.Tensor:
         """q: [T, Hq*D], k/v: [T, Hkv*D] → [T, Hq*D]. If the layer has a ``rope``,
-        rotation and the KV write happen in one fused kernel."""
+        rotation and the KV write happen in one fused kernel.  ``qk_norm`` = (q_norm, k_norm) per-head RMSNorm modules
+        (Qwen3 / Gemma-3 / OLMo-2 style): on CUDA they are fused with the rotation and the cache insert into ONE launch
+        (csrc/qknorm_rope.cu), otherwise applied here before the rotation."""
         ctx = get_forward_context()
         T = q.shape[0]
         D = self.head_size
@@ -75,7 +77,29 @@ class Attention(nn.Module):
             return q.clone() if q.shape[-1] == self.num_heads * D else q
         pcp = ctx.extra.get("pcp")
         mpos = ctx.extra.get("mrope_positions") if (self.rope is not None and self.rope.mrope_section) else None
-        if mpos is not None:
+        if qk_norm is not None:
+            qn, kn = qk_norm
+            fused = (md is not None and kv_cache is not None and q.is_cuda and pcp is None and mpos is None
+                     and self.rope is not None and positions is not None and q.dtype in (torch.bfloat16, torch.float16)
+                     and kv_cache.dtype == q.dtype and getattr(qn, "gemma", False) == getattr(kn, "gemma", False)
+                     and qn.eps == kn.eps and not envs.VLLM_B200_FORCE_REF_OPS
+                     and ops.cuda_ops().qknorm_rope_ok(D, self.rope.cos_sin_cache.shape[-1], self.rope.is_neox_style))
+            if fused:
+                ops.cuda_ops().fused_qk_norm_rope(positions, q, k, qn.weight, kn.weight, self.rope.cos_sin_cache, D, qn.eps,
+                                                  self.rope.is_neox_style, v=v, kv_cache=kv_cache,
+                                                  slot_mapping=md.slot_mapping, gemma=getattr(qn, "gemma", False),
+                                                  vt=md.kv_vt)
+                positions = None            # rotation and cache insert are done: skip them below
+                skip_cache_write = True
+            else:
+                q = qn(q.reshape(T, -1, D)).reshape(T, -1)
+                k = kn(k.reshape(T, -1, D)).reshape(T, -1)
+                skip_cache_write = False
+        else:
+            skip_cache_write = False
+        if skip_cache_write:
+            pass
+        elif mpos is not None:
             # multimodal rotary ids differ per channel section for image tokens: rotate un-fused, then the ordinary
             # cache write (text-only steps take the fused path below with 1-D positions = index + per-request delta)
             q, k = self.rope.forward_mrope(mpos, q, k)

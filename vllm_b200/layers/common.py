@@ -144,6 +144,26 @@ class LogitsProcessor(nn.Module):
         self.scale = scale
         self.soft_cap = soft_cap
 
+    def sample_candidates(self, lm_head: ParallelLMHead, hidden: torch.Tensor, temperature, seeds, steps,
+                          out: torch.Tensor) -> bool:
+        """TP fast path for greedy / temperature-only sampling (no logprobs, penalties, filters): every rank runs the
+        fused sampler over ITS vocab shard and only one 16-byte (value, token id) candidate per row crosses NVLink
+        (our all-gather kernel), instead of the full logits (reference call site: logits_processor.py:118-130,171-187
+        gathers the whole vocabulary).  Returns False when not applicable (the caller takes the full-logits path)."""
+        g = get_tp_group()
+        if (lm_head.tp_size == 1 or g.device_comm is None or not hidden.is_cuda or self.soft_cap or self.scale != 1.0
+                or lm_head.bias is not None):
+            return False
+        logits = ops.linear(hidden, lm_head.weight, None)                     # [B, vocab / W] local shard
+        cu = ops.cuda_ops()
+        v_valid = min(lm_head.per_rank, self.vocab_size - lm_head.start)
+        cand = cu.fused_sample_candidates(logits, temperature, seeds, steps, lm_head.start, v_valid)
+        gathered = g.device_comm.all_gather(cand.view(torch.bfloat16), 1)     # [B, 8 * W] bf16 = [B, W, 4] fp32
+        if gathered is None:
+            return False
+        cu.select_candidates(gathered.view(torch.float32), lm_head.tp_size, out)
+        return True
+
     def forward(self, lm_head: ParallelLMHead, hidden: torch.Tensor) -> torch.Tensor:
         logits = ops.linear(hidden, lm_head.weight, lm_head.bias)
         if lm_head.tp_size > 1:

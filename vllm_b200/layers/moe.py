@@ -243,6 +243,10 @@ class FusedMoE(nn.Module):
     def _forward_fp8(self, x: torch.Tensor, topk_w: torch.Tensor, topk_ids: torch.Tensor) -> torch.Tensor:
         """Expand only the routed experts to the compute dtype and run them through the regular fused path with a
         compacted expert numbering."""
+        from vllm_b200.ops.moe import fp8_grouped_ok, fused_moe_fp8_grouped
+        if self.act == "silu" and fp8_grouped_ok(x, self.w13_weight, self.w2_weight, topk_ids.numel(), self.fp8_block):
+            return fused_moe_fp8_grouped(x, self.w13_weight, self.w13_scale, self.w2_weight, self.w2_scale, topk_w, topk_ids,
+                                         self.expert_map)
         ids = topk_ids.long()
         if self.expert_map is not None:
             ids = self.expert_map[ids].long()

@@ -94,24 +94,31 @@ class Fp8LinearMethod(LinearMethod):
         layer.weight_scale = nn.Parameter(scale.to(torch.float32), requires_grad=False)
 
     def apply(self, layer, x, bias):
-        # dynamic per-token activation quantisation, fp32 accumulation, scales applied in the epilogue
+        # dynamic per-token (or static per-tensor) activation quantisation, fp32 accumulation, scales in the epilogue
+        w_scale = layer.weight_scale
+        static = getattr(layer, "input_scale", None)
+        if (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 16 == 0
+                and layer.out_dtype in (torch.bfloat16, torch.float16)):
+            # device path: fused quantiser kernel (csrc/quant.cu) + tcgen05 kind::f8f6f4 GEMM with per-token x
+            # per-channel scales in its epilogue (csrc/gemm_fp8.cu) — no library GEMM, no fp32 round trip
+            shape = x.shape
+            x2 = x.reshape(-1, shape[-1])
+            if static is not None:
+                a_scale = static.float().max().reshape(1)
+                xq, _ = ops.scaled_fp8_quant(x2, a_scale)
+            else:
+                xq, a_scale = ops.scaled_fp8_quant(x2, per_token=True)
+            y = ops.scaled_mm(xq, layer.weight, a_scale, w_scale if self.per_channel else w_scale.reshape(-1)[:1],
+                              layer.out_dtype, bias)
+            return y.reshape(*shape[:-1], -1)
         xf = x.float()
-        if getattr(layer, "input_scale", None) is not None:
-            a_scale = layer.input_scale.float().max().expand(xf.shape[0], 1)
+        if static is not None:
+            a_scale = static.float().max().expand(xf.shape[0], 1)
         else:
             a_scale = (xf.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12) / ref.FP8_MAX)
         xq = (xf / a_scale).clamp(-ref.FP8_MAX, ref.FP8_MAX).to(torch.float8_e4m3fn)
-        w_scale = layer.weight_scale
-        if x.is_cuda and hasattr(torch, "_scaled_mm") and x.dim() == 2 and x.shape[-1] % 16 == 0 \
-                and layer.weight.shape[0] % 16 == 0:
-            # cuBLASLt fp8 GEMM (library) until the block-scaled tcgen05 kernel covers this case too
-            y = torch._scaled_mm(xq, layer.weight.t(), scale_a=a_scale.float(),
-                                 scale_b=(w_scale.reshape(1, -1) if self.per_channel
-                                          else w_scale.expand(layer.weight.shape[0]).reshape(1, -1)).float(),
-                                 out_dtype=layer.out_dtype)
-        else:
-            y = (xq.float() @ layer.weight.float().t()) * a_scale * (w_scale if self.per_channel else w_scale[0])
-            y = y.to(layer.out_dtype)
+        y = (xq.float() @ layer.weight.float().t()) * a_scale * (w_scale if self.per_channel else w_scale[0])
+        y = y.to(layer.out_dtype)
         return y if bias is None else y + bias
 
 
@@ -158,8 +165,8 @@ class Int8LinearMethod(LinearMethod):
     def apply(self, layer, x, bias):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        xq, a_scale = ref.scaled_int8_quant(x2, layer.input_scale.float().max() if getattr(layer, "input_scale", None) is not None
-                                            else None)
+        xq, a_scale = ops.scaled_int8_quant(x2, layer.input_scale.float().max().reshape(1)
+                                            if getattr(layer, "input_scale", None) is not None else None)
         if x2.is_cuda and hasattr(torch, "_int_mm") and x2.shape[0] > 16 and x2.shape[0] % 8 == 0 and x2.shape[1] % 8 == 0 \
                 and layer.weight.shape[0] % 8 == 0:
             acc = torch._int_mm(xq, layer.weight.t()).float()                 # int8 tensor-core GEMM (library)

@@ -94,9 +94,8 @@ class LlamaAttention(nn.Module):
         if self.qk_norm_full:
             q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
         elif self.qk_norm:
-            T = q.shape[0]
-            q = self.q_norm(q.reshape(T, -1, self.head_dim)).reshape(T, -1)
-            k = self.k_norm(k.reshape(T, -1, self.head_dim)).reshape(T, -1)
+            # per-head q/k RMSNorm: fused with RoPE and the KV insert on CUDA (one launch), applied by the layer otherwise
+            return self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm))
         return self.attn(q, k, v, positions)
 
 
@@ -208,6 +207,10 @@ class LlamaForCausalLM(nn.Module):
 
     def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
         return self.logits_processor(self.lm_head, hidden)
+
+    def sample_candidates(self, hidden, temperature, seeds, steps, out) -> bool:
+        """Decode-graph fast path under TP: sample per vocab shard, gather one candidate per row (layers/common.py)."""
+        return self.logits_processor.sample_candidates(self.lm_head, hidden, temperature, seeds, steps, out)
 
     # ------------------------------------------------------------ weights
     stacked = [("qkv_proj", "q_proj", "q"), ("qkv_proj", "k_proj", "k"), ("qkv_proj", "v_proj", "v"),

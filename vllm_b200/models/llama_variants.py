@@ -111,9 +111,8 @@ class VariantAttention(nn.Module):
     def forward(self, positions, x):
         q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
         if self.qk_norm in ("head", "head1p"):
-            T = q.shape[0]
-            q = self.q_norm(q.reshape(-1, self.hd)).view(T, -1)
-            k = self.k_norm(k.reshape(-1, self.hd)).view(T, -1)
+            # per-head norms ride along with RoPE + the KV insert (one fused launch on CUDA, layers/attention.py)
+            return self.o_proj(self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm)))
         elif self.qk_norm == "full":
             q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
         return self.o_proj(self.attn(q, k, v, positions))

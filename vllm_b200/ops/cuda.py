@@ -408,6 +408,27 @@ def fused_sample(logits, temperature, seeds, step, out: Optional[torch.Tensor] =
     return out
 
 
+_fused_sample_cand = _sig("vb_fused_sample_cand", _vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp)
+_select_cand = _sig("vb_select_candidate", _vp, _i, _vp, _i, _vp)
+
+
+def fused_sample_candidates(logits_local, temperature, seeds, step, idx_off: int, v_valid: int) -> torch.Tensor:
+    """Per-row best (value, global id) of this rank's vocab shard as a [B, 8] bf16-viewable 16-byte record."""
+    B = logits_local.shape[0]
+    cand = torch.empty((B, 4), dtype=torch.float32, device=logits_local.device)
+    _check(_fused_sample_cand(logits_local.data_ptr(), logits_local.stride(0), B, max(v_valid, 0), temperature.data_ptr(),
+                              seeds.data_ptr(), step.data_ptr(), idx_off, cand.data_ptr(), _DT[logits_local.dtype], _st()),
+           "fused_sample_cand")
+    return cand
+
+
+def select_candidates(cands: torch.Tensor, W: int, out: torch.Tensor) -> torch.Tensor:
+    """cands: [B, W, 4] fp32 records gathered from the W ranks → winning token id per row."""
+    B = out.shape[0]
+    _check(_select_cand(cands.data_ptr(), W, out.data_ptr(), B, _st()), "select_candidate")
+    return out
+
+
 def topk_topp_mask_(logits: torch.Tensor, top_k, top_p, min_p=None) -> torch.Tensor:
     assert logits.dtype == torch.float32 and logits.is_contiguous()
     B, V = logits.shape
@@ -903,7 +924,7 @@ def rms_norm_quant(x, weight, eps, *, residual=None, scale=None, mode: str = "st
 
 
 def act_mul_quant(x, act: str = "silu", *, scale=None, mode: str = "static", group: int = 128, col_major: bool = False,
-                  ue8m0: bool = False):
+                  ue8m0: bool = False):  # noqa: D401
     """Fused act(gate) * up + fp8 quantisation over x[..., 2H] → (q[..., H], scale)."""
     x2 = _rows(x)
     H = x2.shape[1] // 2
@@ -1097,3 +1118,29 @@ def gdn_scan(q, k, v, g, beta, cache, state_off: int, md) -> torch.Tensor:
                      md.query_start_loc.data_ptr(), md.seq_lens.data_ptr(), bt.data_ptr(), bt.stride(0), md.num_reqs, nv, dk,
                      dv, _st()), "gdn_scan")
     return o
+
+
+# ------------------------------------------------------------------ GPU-side input preparation (csrc/input_prep.cu)
+_prep_step = _sig("vb_prep_step", _vp, _vp, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp)
+_bt_diff = _sig("vb_block_table_diff", _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp)
+_append_sampled = _sig("vb_append_sampled", _vp, _i64, _vp, _vp, _vp, _i, _vp)
+
+
+def prep_step(rows, num_computed, num_sched, token_table, block_rows, input_ids, positions, qsl, seq_lens, slot_mapping,
+              block_table, nblk: int, block_size: int, pos_delta=None) -> None:
+    """Expand per-request (row, computed, scheduled) triples into the per-token step inputs on the device."""
+    nb = rows.numel()
+    _check(_prep_step(rows.data_ptr(), num_computed.data_ptr(), num_sched.data_ptr(), nb, token_table.data_ptr(),
+                      token_table.stride(0), block_rows.data_ptr(), block_rows.stride(0), input_ids.data_ptr(),
+                      positions.data_ptr(), qsl.data_ptr(), seq_lens.data_ptr(), slot_mapping.data_ptr(),
+                      block_table.data_ptr(), block_table.stride(0), nblk, block_size, _p(pos_delta), _st()), "prep_step")
+
+
+def block_table_apply_diffs(block_rows, d_row, d_start, d_cnt, d_off, ids_flat) -> None:
+    _check(_bt_diff(block_rows.data_ptr(), block_rows.stride(0), d_row.data_ptr(), d_start.data_ptr(), d_cnt.data_ptr(),
+                    d_off.data_ptr(), ids_flat.data_ptr(), d_row.numel(), _st()), "block_table_diff")
+
+
+def append_sampled(token_table, rows, pos, sampled) -> None:
+    _check(_append_sampled(token_table.data_ptr(), token_table.stride(0), rows.data_ptr(), pos.data_ptr(),
+                           sampled.data_ptr(), rows.numel(), _st()), "append_sampled")

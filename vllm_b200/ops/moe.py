@@ -47,6 +47,36 @@ def fused_moe_grouped(x, w13, w2, topk_w, topk_ids, act, expert_map):
     return cu.moe_combine(y, inv, topk_w.to(torch.float32).contiguous(), T)
 
 
+def fused_moe_fp8_grouped(x, w13q, w13_scale, w2q, w2_scale, topk_w, topk_ids, expert_map):
+    """Block-scaled fp8 experts on the device (DeepSeek-V3 checkpoints): align → gather → per-(token,128) fp8 quant →
+    grouped tcgen05 f8f6f4 GEMM (w13) → fused SiLU·mul + re-quant → grouped fp8 GEMM (w2) → weighted combine.  Weight
+    traffic stays at the fp8 size (the previous path expanded the routed experts to bf16 on every call)."""
+    from vllm_b200.ops import cuda as cu
+    T, k = topk_ids.shape
+    R = T * k
+    E = w13q.shape[0]
+    ids = topk_ids if topk_ids.dtype == torch.int32 else topk_ids.to(torch.int32)
+    sorted_tok, inv, offs = cu.moe_align(ids.contiguous(), E, expert_map)
+    xs = cu.moe_gather(x, sorted_tok)
+    avg = max(R // max(E, 1), 1)
+    bn = 16
+    while bn < 128 and bn < 2 * avg:
+        bn += 16
+    if bn in (80, 112):
+        bn += 16
+    xq, xsc = cu.per_token_group_quant_fp8(xs, 128, col_major=True)
+    h = cu.gemm_fp8_grouped(xq, xsc, w13q, w13_scale.contiguous(), offs, bn, x.dtype)
+    aq, asc = cu.act_mul_quant(h, "silu", mode="group", group=128, col_major=True)
+    y = cu.gemm_fp8_grouped(aq, asc, w2q, w2_scale.contiguous(), offs, bn, x.dtype)
+    return cu.moe_combine(y, inv, topk_w.to(torch.float32).contiguous(), T)
+
+
+def fp8_grouped_ok(x, w13q, w2q, R: int, block: int) -> bool:
+    return (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and block == 128 and R <= GROUPED_MAX_ROWS
+            and w13q.dtype == torch.float8_e4m3fn and w2q.dtype == torch.float8_e4m3fn and x.shape[1] % 128 == 0
+            and w2q.shape[2] % 128 == 0 and w13q.is_contiguous() and w2q.is_contiguous() and x.is_contiguous())
+
+
 _local_acc: dict[int, torch.Tensor] = {}
 
 

@@ -60,6 +60,9 @@ class DecodeGraph:
                              num_tokens=b)
         with set_forward_context(ctx):
             hidden = r.model(r.input_ids[:b], r.positions[:b], None)
+        fast = getattr(r.model, "sample_candidates", None)
+        if fast is not None and fast(hidden, self.temperature, self.seeds, self.steps, self.out):
+            return                      # TP: per-shard sampling + 16-byte candidate gather instead of the logits all-gather
         logits = r.model.compute_logits(hidden)
         cuda_ops().fused_sample(logits, self.temperature, self.seeds, self.steps, self.out)
 
