@@ -120,6 +120,9 @@ def _timed_generates(gen, K: int, reps: int, sync=None):
         for n, acc in ((1, t1s), (K + 1, tks)):
             if sync:
                 sync()
+            # same GPU state at the start of both kinds of call: without the pause a generate(K+1) always starts right
+            # after a 64 x 1024-token prefill burst (power-capped clocks) and a generate(1) right after light decode steps
+            time.sleep(1.0)
             t0 = time.perf_counter()
             gen(n)
             if sync:

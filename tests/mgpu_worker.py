@@ -152,6 +152,7 @@ def test_fused_stress():
             graphs = {}
             for T in (1, 7, 64, 128):
                 x = torch.randint(-1, 2, (T, K), device=dev, generator=g).to(dtype)
+                x[:, 0] = 0.0                 # only rows 0 / 1 use the tiny-scale column (keeps every other sum an exact integer)
                 if T > 1:
                     x[0] = 0.0
                     x[0, 0] = -tiny       # every partial of row 0 rounds to -0.0 (the sentinel bit pattern): must not hang

@@ -113,6 +113,32 @@ def test_moe_and_mla_models_cuda_vs_ref(model):
     assert diffs[int(0.9 * len(diffs))] < 0.15 and diffs[len(diffs) // 2] < 0.05, (diffs[len(diffs) // 2], diffs[-5:])
 
 
+@pytest.mark.parametrize("model,quant", [("deepseek-small", "fp8_block"), ("llama-small", "fp8"), ("mixtral-small", "fp8_block")])
+def test_fp8_models_run_on_own_kernels_and_track_bf16(model, quant):
+    """Online-quantised fp8 runs (block-scaled tcgen05 f8f6f4 GEMMs, fused quantisers, grouped fp8 experts, MLA kernel)
+    stay within fp8 accuracy of the bf16 run of the same weights: teacher-forced prompt logprobs."""
+    from vllm_b200 import SamplingParams
+    from vllm_b200 import LLM
+    sp = SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True, prompt_logprobs=0)
+    kw = dict(max_model_len=1024, max_num_seqs=16, max_num_batched_tokens=1024, gpu_memory_utilization=0.25,
+              load_format="dummy", model_loader_extra_config={"dummy_range": 0.05}, cudagraph_capture_sizes=[1, 2, 4, 8])
+    llm = LLM(model, **kw)                    # same seeded random weights in both runs; the second quantises them online
+    base = llm.generate(PROMPTS, sp)
+    llm.shutdown()
+    llm_q = LLM(model, quantization=quant, **kw)
+    n0 = __import__("vllm_b200.ops.cuda", fromlist=["x"]).LAUNCHES
+    out = llm_q.generate(PROMPTS, sp)
+    llm_q.shutdown()
+    assert __import__("vllm_b200.ops.cuda", fromlist=["x"]).LAUNCHES > n0
+    diffs = []
+    for a, b in zip(out, base):
+        for pa, pb in zip(a.prompt_logprobs[1:], b.prompt_logprobs[1:]):
+            (ta, la), = [(t, l.logprob) for t, l in pa.items() if l.rank is not None][:1]
+            diffs.append(abs(la - pb[ta].logprob))
+    diffs.sort()
+    assert diffs[len(diffs) // 2] < 0.12 and diffs[int(0.9 * len(diffs))] < 0.6, (diffs[len(diffs) // 2], diffs[-5:])
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()

@@ -14,6 +14,13 @@ def _torchrun(n, *args, timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py"), *args]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    if r.returncode != 0:
+        try:        # keep the ranks' output where a remote run can bring it back
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"mgpu_fail_{args[0]}_w{n}.log"), "w") as f:
+                f.write(r.stdout[-20000:] + "\n==== stderr ====\n" + r.stderr[-40000:])
+        except OSError:
+            pass
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
     return r.stdout
 

@@ -108,7 +108,8 @@ def get_model(vllm_config: VllmConfig, device: torch.device,
             from vllm_b200.model_loader.gguf import iter_gguf_weights
             model.load_weights(iter_gguf_weights(mc.model, mc.torch_dtype))
         elif fmt == "dummy" or (fmt == "auto" and not os.path.isdir(mc.model)):
-            initialize_dummy_weights(model, lc.dummy_seed)
+            rng_ = float((getattr(lc, "model_loader_extra_config", None) or {}).get("dummy_range", 1e-3))
+            initialize_dummy_weights(model, lc.dummy_seed, -rng_, rng_)
         elif fmt == "sharded_state":
             from vllm_b200.model_loader.sharded_state import load_sharded_state
             load_sharded_state(model, mc.model)
