@@ -83,7 +83,7 @@ class ParallelConfig(_ConfigBase):
     data_parallel_external_lb: bool = False
     data_parallel_hybrid_lb: bool = False
     enable_expert_parallel: bool = False
-    all2all_backend: str = "nvswitch_fused"  # nvswitch_fused|allgather_reducescatter|naive
+    all2all_backend: str = "a2a"  # a2a (token all-to-all) | allgather_reducescatter | naive   (wide EP across DP replicas)
     enable_eplb: bool = False
     eplb_window_size: int = 1000
     eplb_step_interval: int = 3000

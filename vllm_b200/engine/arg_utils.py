@@ -59,7 +59,7 @@ class EngineArgs:
     data_parallel_external_lb: bool = False
     data_parallel_hybrid_lb: bool = False
     enable_expert_parallel: bool = False
-    all2all_backend: str = "nvswitch_fused"
+    all2all_backend: str = "a2a"
     logits_processors: Optional[list[str]] = None    # "pkg.module:Class" plug-ins (comma separated on the CLI)
     enable_eplb: bool = False
     num_redundant_experts: int = 0

@@ -63,6 +63,8 @@ class LlamaAttention(nn.Module):
                                         bool(cfg.get("attention_out_bias", False)), dtype=dtype,
                                         quant_config=quant_config, prefix=f"{prefix}.o_proj")
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
+        from vllm_b200 import envs
+        self._l2_prefetch = bool(envs.VLLM_B200_L2_PREFETCH)
         self.qk_norm = bool(cfg.get("qk_norm", False))
         self.qk_norm_full = cfg.get("qk_norm") == "full"          # OLMo-2 / OLMoE: one RMSNorm over the whole projection
         if self.qk_norm_full:
@@ -90,6 +92,10 @@ class LlamaAttention(nn.Module):
 
     def forward(self, positions, hidden):
         qkv = self.qkv_proj(hidden)
+        if hidden.is_cuda and hidden.shape[0] <= 256 and self._l2_prefetch:
+            # decode: the o_proj weights stream into L2 while rope + attention run (csrc/cache_ops.cu::l2_prefetch_kernel)
+            from vllm_b200.ops import cuda_ops
+            cuda_ops().l2_prefetch_async(self.o_proj.weight)
         q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
         if self.qk_norm_full:
             q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
@@ -170,6 +176,9 @@ class LlamaModel(nn.Module):
                 aux.append(residual)
         if aux:
             fctx.extra["aux_hidden"] = torch.cat(aux, dim=-1)
+        if hidden.is_cuda:
+            from vllm_b200.ops import cuda_ops
+            cuda_ops().l2_prefetch_join()
         if self.norm is None:  # not the last PP stage: ship the un-normalised pair
             return {"hidden_states": hidden, "residual": residual}
         if get_tp_group().world_size > 1 and hidden.is_cuda:

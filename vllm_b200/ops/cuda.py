@@ -1144,3 +1144,33 @@ def block_table_apply_diffs(block_rows, d_row, d_start, d_cnt, d_off, ids_flat) 
 def append_sampled(token_table, rows, pos, sampled) -> None:
     _check(_append_sampled(token_table.data_ptr(), token_table.stride(0), rows.data_ptr(), pos.data_ptr(),
                            sampled.data_ptr(), rows.numel(), _st()), "append_sampled")
+
+
+# ------------------------------------------------------------------ L2 weight prefetch on a side stream
+_l2_prefetch = _sig("vb_l2_prefetch", _vp, _i64, _vp)
+_side_streams: dict[int, torch.cuda.Stream] = {}
+_side_dirty: dict[int, bool] = {}
+
+
+def l2_prefetch_async(t: torch.Tensor) -> None:
+    """Start pulling ``t`` into L2 on a forked stream, ordered after everything enqueued so far on the current stream
+    (so it runs concurrently with the NEXT kernel launched here).  A hint only: nothing ever waits for it except
+    ``l2_prefetch_join`` at the end of the forward pass (required to close a CUDA-graph capture)."""
+    dev = t.device.index or 0
+    side = _side_streams.get(dev)
+    if side is None:
+        if torch.cuda.is_current_stream_capturing():
+            return
+        side = _side_streams[dev] = torch.cuda.Stream(t.device)
+    cur = torch.cuda.current_stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        _check(_l2_prefetch(t.data_ptr(), t.numel() * t.element_size(), side.cuda_stream), "l2_prefetch", 0)
+    _side_dirty[dev] = True
+
+
+def l2_prefetch_join() -> None:
+    dev = torch.cuda.current_device()
+    if _side_dirty.get(dev):
+        torch.cuda.current_stream().wait_stream(_side_streams[dev])
+        _side_dirty[dev] = False

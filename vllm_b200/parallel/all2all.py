@@ -14,7 +14,8 @@ Two algorithms (``--all2all-backend``):
 
 ``--enable-dbo`` software-pipelines the token all-to-all over two micro-batches (see ``_a2a``).
 
-``a2a`` (also ``nvswitch_fused`` until the fused peer-memory kernel lands for this path)
+``a2a`` (NCCL token all-to-all between replicas; the in-replica EP path does NOT go through this module: there the
+    combine + reduce-scatter is fused into the w2 grouped-GEMM epilogue over peer memory, ``ops/moe.py::fused_moe_reduce_norm``)
     token rows travel only to the rank that owns the routed expert: counts exchange, one ``all_to_all`` of rows +
     expert ids, local grouped expert compute, the reverse ``all_to_all`` of results, weighted sum at the source.
     Inside a TP group each rank dispatches a 1/TP slice of the replica's tokens and the results are all-gathered.
