@@ -114,11 +114,15 @@ def test_moe_and_mla_models_cuda_vs_ref(model):
 
 
 @pytest.mark.parametrize("model,quant", [("deepseek-small", "fp8_block"), ("llama-small", "fp8"), ("mixtral-small", "fp8_block")])
-def test_fp8_models_run_on_own_kernels_and_track_bf16(model, quant):
+def test_fp8_models_run_on_own_kernels_and_track_bf16(model, quant, monkeypatch):
     """Online-quantised fp8 runs (block-scaled tcgen05 f8f6f4 GEMMs, fused quantisers, grouped fp8 experts, MLA kernel)
     stay within fp8 accuracy of the bf16 run of the same weights: teacher-forced prompt logprobs."""
     from vllm_b200 import SamplingParams
-    from vllm_b200 import LLM
+    from vllm_b200 import LLM, envs
+    # the bf16 run would store gate|up row-interleaved (fused GEMM epilogue) and the quantised run would not: the
+    # dummy loader fills the stored tensor, so keep both runs on the plain layout to compare the SAME weights
+    monkeypatch.setenv("VLLM_B200_FUSED_ACT", "0")
+    envs._cache.pop("VLLM_B200_FUSED_ACT", None)
     sp = SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True, prompt_logprobs=0)
     kw = dict(max_model_len=1024, max_num_seqs=16, max_num_batched_tokens=1024, gpu_memory_utilization=0.25,
               load_format="dummy", model_loader_extra_config={"dummy_range": 0.05}, cudagraph_capture_sizes=[1, 2, 4, 8])

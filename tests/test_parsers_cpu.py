@@ -81,3 +81,47 @@ def test_reasoning_streaming_splits_at_end_tag():
             r += d.get("reasoning_content", "") or ""
             c += d.get("content", "") or ""
     assert r == "step one, step two" and c == "The answer."
+
+
+def test_round2_tool_call_formats():
+    """MiniMax-M2 / dots invoke-XML, Apertus keyed JSON, Cohere actions, LFM2 marked pythonic, GigaChat-3, GPT-OSS
+    harmony commentary calls, Step-3 steptml (reference: vllm/tool_parsers/{minimax_m2,dots,apertus,cohere_command,lfm2,
+    gigachat3,gptoss,step3}_tool_parser.py)."""
+    import json
+    from vllm_b200.tool_parsers import get_tool_parser
+    cases = {
+        "minimax_m2": ('ok <minimax:tool_call><invoke name="get_weather"><parameter name="city">Paris</parameter>'
+                       '<parameter name="days">3</parameter></invoke></minimax:tool_call>', "get_weather",
+                       {"city": "Paris", "days": 3}, "ok"),
+        "dots": ('<dots_function_call><invoke name=f><parameter name=q>"a b"</parameter></invoke></dots_function_call>',
+                 "f", {"q": "a b"}, None),
+        "apertus": ('I check. <|tools_prefix|>[{"get_weather": {"city": "Paris"}}]<|tools_suffix|>', "get_weather",
+                    {"city": "Paris"}, "I check."),
+        "cohere": ('plan <|START_ACTION|>[{"tool_call_id":"0","tool_name":"f","parameters":{"a":1}}]<|END_ACTION|>', "f",
+                   {"a": 1}, "plan"),
+        "lfm2": ('<|tool_call_start|>[get_weather(location="Paris")]<|tool_call_end|>done', "get_weather",
+                 {"location": "Paris"}, "done"),
+        "gigachat3": ('thinking<|function_call|>{"name":"f","arguments":{"x":2}}', "f", {"x": 2}, "thinking"),
+        "openai": ('<|channel|>commentary to=functions.get_weather <|constrain|>json<|message|>{"city":"SF"}<|call|>',
+                   "get_weather", {"city": "SF"}, None),
+        "step3p5": ('<｜tool_calls_begin｜><｜tool_call_begin｜>function<｜tool_sep｜><steptml:invoke name="f">'
+                    '<steptml:parameter name="a">1</steptml:parameter></steptml:invoke><｜tool_call_end｜><｜tool_calls_end｜>',
+                    "f", {"a": 1}, None),
+    }
+    for name, (text, fn, args, content) in cases.items():
+        r = get_tool_parser(name)().extract(text)
+        assert len(r["tool_calls"]) == 1, name
+        c = r["tool_calls"][0]["function"]
+        assert c["name"] == fn and json.loads(c["arguments"]) == args, (name, c)
+        assert r["content"] == content, (name, r["content"])
+        # plain text passes through untouched, and streaming emits the call exactly once
+        assert get_tool_parser(name)().extract("just text")["tool_calls"] == []
+        p = get_tool_parser(name)()
+        emitted, prev = [], ""
+        for i in range(1, len(text) + 1, 7):
+            d = p.extract_streaming(prev, text[:i], text[len(prev):i])
+            prev = text[:i]
+            emitted += (d or {}).get("tool_calls", [])
+        d = p.extract_streaming(prev, text, text[len(prev):])
+        emitted += (d or {}).get("tool_calls", [])
+        assert [e["function"]["name"] for e in emitted] == [fn], (name, emitted)

@@ -319,6 +319,165 @@ class DeepSeekV31ToolParser(ToolParser):
         return text.rstrip().endswith(("<｜tool▁call▁end｜>", "<｜tool▁calls▁end｜>"))
 
 
+class InvokeXmlToolParser(ToolParser):
+    """``<invoke name="fn"><parameter name="k">v</parameter>…</invoke>`` blocks inside an outer wrapper: MiniMax-M2
+    (``<minimax:tool_call>``), dots.llm (``<dots_function_call>``), Claude-style ``<function_calls>``.  Values are JSON
+    when they parse, strings otherwise."""
+    start_markers = ("<minimax:tool_call>", "<dots_function_call>", "<function_calls>", "<invoke ")
+    _inv = re.compile(r"<invoke\s+name\s*=\s*\"?([^\">]+)\"?\s*>(.*?)</invoke>", re.S)
+    _par = re.compile(r"<parameter\s+name\s*=\s*\"?([^\">]+)\"?\s*>(.*?)</parameter>", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = []
+        for m in self._inv.finditer(text):
+            args = {}
+            for k, v in self._par.findall(m.group(2)):
+                v = v.strip()
+                try:
+                    args[k.strip()] = json.loads(v)
+                except json.JSONDecodeError:
+                    args[k.strip()] = v
+            calls.append(_call(m.group(1).strip(), args, len(calls)))
+        cut = min((text.find(x) for x in self.start_markers if x in text), default=len(text))
+        return {"tool_calls": calls, "content": (text[:cut].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("</invoke>", "</minimax:tool_call>", "</dots_function_call>", "</function_calls>"))
+
+
+class KeyedJsonToolParser(ToolParser):
+    """``<|tools_prefix|>[{"fn": {args}}, …]<|tools_suffix|>`` (Apertus): each list item maps ONE function name to its
+    argument object."""
+    start_markers = ("<|tools_prefix|>",)
+
+    def extract(self, text: str) -> dict:
+        i = text.find(self.start_markers[0])
+        if i < 0:
+            return {"tool_calls": [], "content": text}
+        body = text[i + len(self.start_markers[0]):].split("<|tools_suffix|>", 1)[0].strip()
+        calls = []
+        try:
+            for item in json.loads(body):
+                if isinstance(item, dict):
+                    for name, args in item.items():
+                        calls.append(_call(name, args, len(calls)))
+        except json.JSONDecodeError:
+            pass
+        return {"tool_calls": calls, "content": text[:i].strip() or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        return "<|tools_suffix|>" in text
+
+
+class CohereActionToolParser(ToolParser):
+    """Command-R / Command-A: ``<|START_ACTION|>[{"tool_call_id": "0", "tool_name": "fn", "parameters": {…}}]<|END_ACTION|>``
+    (older checkpoints: ``Action: ```json [...]```'' with ``tool_name`` / ``parameters``)."""
+    start_markers = ("<|START_ACTION|>", "Action: ```json")
+
+    def extract(self, text: str) -> dict:
+        cut = min((text.find(m) for m in self.start_markers if m in text), default=-1)
+        if cut < 0:
+            return {"tool_calls": [], "content": text}
+        m = next(m for m in self.start_markers if text.startswith(m, cut))
+        body = text[cut + len(m):]
+        for e in ("<|END_ACTION|>", "```"):
+            if e in body:
+                body = body.split(e, 1)[0]
+        calls = []
+        try:
+            for it in json.loads(body.strip()):
+                name = it.get("tool_name") or it.get("name")
+                if name:
+                    calls.append(_call(name, it.get("parameters", it.get("arguments", {})), len(calls)))
+        except (json.JSONDecodeError, AttributeError, TypeError):
+            pass
+        return {"tool_calls": calls, "content": text[:cut].strip() or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("<|END_ACTION|>", "```"))
+
+
+class MarkedPythonicToolParser(PythonicToolParser):
+    """Pythonic call lists inside sentinels: LFM2 (``<|tool_call_start|>[fn(a=1)]<|tool_call_end|>``)."""
+    start_markers = ("<|tool_call_start|>",)
+
+    def extract(self, text: str) -> dict:
+        i = text.find(self.start_markers[0])
+        if i < 0:
+            return {"tool_calls": [], "content": text}
+        body = text[i + len(self.start_markers[0]):].split("<|tool_call_end|>", 1)[0].strip()
+        inner = super().extract(body)
+        tail = text.split("<|tool_call_end|>", 1)[1].strip() if "<|tool_call_end|>" in text else ""
+        content = (text[:i].strip() + (" " + tail if tail else "")).strip() or None
+        return {"tool_calls": inner["tool_calls"], "content": content if inner["tool_calls"] else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return "<|tool_call_end|>" in text
+
+
+class GigaChatToolParser(ToolParser):
+    """GigaChat-3: ``function call<|role_sep|>\n{"name": …, "arguments": {…}}`` or ``<|function_call|>{…}`` (one call)."""
+    start_markers = ("<|function_call|>", "function call<|role_sep|>")
+    _rx = re.compile(r"(?:function call<\|role_sep\|>\n?|<\|function_call\|>)(.*)", re.S)
+
+    def extract(self, text: str) -> dict:
+        m = self._rx.search(text)
+        if not m:
+            return {"tool_calls": [], "content": text}
+        body = m.group(1).split("<|message_sep|>", 1)[0].strip()
+        try:
+            calls = _json_calls(json.loads(body))
+        except json.JSONDecodeError:
+            calls = []
+        return {"tool_calls": calls, "content": (text[:m.start()].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("}", "<|message_sep|>"))
+
+
+class HarmonyToolParser(ToolParser):
+    """GPT-OSS harmony format: ``<|start|>assistant<|channel|>commentary to=functions.NAME <|constrain|>json<|message|>{args}<|call|>``;
+    text of the ``final`` channel is the content (the ``analysis`` channel is handled by the reasoning parser)."""
+    start_markers = ("to=functions.",)
+    _rx = re.compile(r"to=functions\.([\w\-.]+)[^<]*(?:<\|constrain\|>\s*\w+\s*)?<\|message\|>(.*?)(?:<\|call\|>|<\|end\|>|$)", re.S)
+    _final = re.compile(r"<\|channel\|>final<\|message\|>(.*?)(?:<\|end\|>|<\|return\|>|$)", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = [_call(m.group(1), m.group(2).strip(), i) for i, m in enumerate(self._rx.finditer(text))]
+        fm = self._final.search(text)
+        content = fm.group(1).strip() if fm else (None if calls else text)
+        return {"tool_calls": calls, "content": content or None}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("<|call|>", "<|end|>", "<|return|>"))
+
+
+class Step3ToolParser(ToolParser):
+    """Step-3: ``<｜tool_calls_begin｜><｜tool_call_begin｜>function<｜tool_sep｜><steptml:invoke name="fn">
+    <steptml:parameter name="k">v</steptml:parameter></steptml:invoke><｜tool_call_end｜><｜tool_calls_end｜>``."""
+    start_markers = ("<｜tool_calls_begin｜>", "<steptml:invoke")
+    _inv = re.compile(r"<steptml:invoke\s+name=\"([^\"]+)\">(.*?)</steptml:invoke>", re.S)
+    _par = re.compile(r"<steptml:parameter\s+name=\"([^\"]+)\">(.*?)</steptml:parameter>", re.S)
+
+    def extract(self, text: str) -> dict:
+        calls = []
+        for m in self._inv.finditer(text):
+            args = {}
+            for k, v in self._par.findall(m.group(2)):
+                try:
+                    args[k] = json.loads(v)
+                except json.JSONDecodeError:
+                    args[k] = v.strip()
+            calls.append(_call(m.group(1), args, len(calls)))
+        cut = min((text.find(x) for x in self.start_markers if x in text), default=len(text))
+        return {"tool_calls": calls, "content": (text[:cut].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("</steptml:invoke>", "<｜tool_call_end｜>", "<｜tool_calls_end｜>"))
+
+
+
+
 _PARSERS: dict[str, type[ToolParser]] = {
     "hermes": HermesToolParser, "qwen": HermesToolParser, "qwen3": HermesToolParser, "nous": HermesToolParser,
     "llama3_json": Llama3JsonToolParser, "llama4_json": Llama3JsonToolParser,
@@ -336,6 +495,12 @@ _PARSERS: dict[str, type[ToolParser]] = {
     "step3": XmlParamToolParser, "glm45": Glm4MoeToolParser, "glm47": Glm4MoeToolParser,
     "kimi_k2": KimiK2ToolParser, "longcat": _marker_parser(("<longcat_tool_call>",), ("</longcat_tool_call>",)),
     "ernie45": _marker_parser(("<tool_call>",), ("</tool_call>",)), "functiongemma": PythonicToolParser, "deepseek_v31": DeepSeekV31ToolParser, "deepseek_v32": DeepSeekV31ToolParser,
+    "minimax_m2": InvokeXmlToolParser, "dots": InvokeXmlToolParser, "dots1": InvokeXmlToolParser,
+    "apertus": KeyedJsonToolParser, "cohere": CohereActionToolParser, "command_r": CohereActionToolParser,
+    "lfm2": MarkedPythonicToolParser, "gigachat3": GigaChatToolParser, "openai": HarmonyToolParser,
+    "gptoss": HarmonyToolParser, "step3p5": Step3ToolParser, "step3_xml": Step3ToolParser,
+    "hy_v3": _marker_parser(("<tool_calls>",), ("</tool_calls>",)), "ling": HermesToolParser, "ling3": HermesToolParser,
+    "granite4": HermesToolParser, "glm4_moe": Glm4MoeToolParser, "minimax_m1": _marker_parser(("<tool_calls>",), ("</tool_calls>",)),
 }
 
 
