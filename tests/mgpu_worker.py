@@ -29,7 +29,7 @@ def test_collectives():
     dev = torch.device("cuda", torch.cuda.current_device())
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     for dtype in (torch.bfloat16, torch.float16):
-        for T, H in ((1, 1024), (7, 4096), (64, 4096), (64, 8192), (300, 2048)):
+        for T, H in ((1, 1024), (7, 4096), (64, 4096), (64, 8192), (300, 2048), (700, 1024)):
             x = torch.randint(-8, 9, (T, H), device=dev, generator=g).to(dtype)
             exp = x.clone()
             dist.all_reduce(exp, group=tp.device_group)

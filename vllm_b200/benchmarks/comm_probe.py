@@ -56,6 +56,44 @@ def _time_graph(fn, iters: int, reps: int = 5) -> float:
     return best
 
 
+PHASES = ("pdl_wait", "gemm", "splitk_push", "wait_reduce_bcast", "rearm", "collect_norm")
+
+
+def trace_fused(fn, iters: int = 8) -> dict:
+    """Per-phase time line of the LAST of ``iters`` back-to-back fused calls (graph replay): the kernel's epilogue
+    stamps %globaltimer at its phase boundaries per CTA.  Returns median / max over CTAs of every phase (µs) and the
+    span from the first CTA's start to the last CTA's end."""
+    from vllm_b200.ops import cuda_ops
+    cu = cuda_ops()
+    tr = torch.zeros(160 * 8, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    cu.gemm_ar_set_trace(tr)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        tr.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+    finally:
+        cu.gemm_ar_set_trace(None)
+    t = tr.view(160, 8).cpu()
+    t = t[t[:, 0] > 0].double()
+    if t.numel() == 0:
+        return {}
+    out = {"ctas": int(t.shape[0]), "span_us": round(float(t[:, 6].max() - t[:, 0].min()) / 1e3, 2)}
+    for i, name in enumerate(PHASES):
+        d = (t[:, i + 1] - t[:, i]) / 1e3
+        out[name] = [round(float(d.median()), 2), round(float(d.max()), 2)]
+    out["start_skew_us"] = round(float(t[:, 0].max() - t[:, 0].min()) / 1e3, 2)
+    return out
+
+
 def probe_row_parallel(runner, T: int, iters: int = 16) -> dict:
     import torch.distributed as dist
 
@@ -111,6 +149,10 @@ def probe_row_parallel(runner, T: int, iters: int = 16) -> dict:
                               "exposed_us": round(t_f - t_l, 2), "nvlink_bytes_per_rank": int(link_bytes),
                               "weight_bytes": int(w_bytes), "roofline_us": round(roof_us, 2),
                               "fraction_of_roofline": round(roof_us / t_f, 3)}
+        try:
+            out["paths"][name]["trace_us_median_max"] = trace_fused(fused)
+        except Exception as e:      # diagnostic only
+            out["paths"][name]["trace_us_median_max"] = {"error": str(e)[:200]}
         exposed += (t_f - t_l) * L
     out["exposed_comm_us_per_step"] = round(exposed, 1)
     return out

@@ -84,6 +84,53 @@ __global__ void __launch_bounds__(1024) ar_rows_kernel(CommCtx c, const T* __res
   grid_rank_barrier(c, &c.state[3], &c.state[4], e0 + 2, false, true);
 }
 
+// One-shot all-reduce into a PRIVATE destination (small T: decode-size activations, embeddings): every rank pulls all
+// W replicas of every row over NVLink (all loads in flight at once), sums them in RANK ORDER — so every GPU produces
+// bit-identical rows, which a switch-side multimem.ld_reduce issued from different GPUs does not promise — and writes
+// them straight to `dst`: no broadcast phase and no copy out of the symmetric heap afterwards.
+// The trailing (non-waiting) barrier only keeps the staging region from being overwritten while a peer still reads.
+template <typename T>
+__global__ void __launch_bounds__(1024) ar_oneshot_kernel(CommCtx c, const T* __restrict__ x, size_t in_off,
+                                                           T* __restrict__ dst, int T_rows, int H) {
+  const uint32_t e0 = c.state[0];
+  const int vec_per_row = H / 8;
+  if (x != nullptr) {
+    const size_t total = (size_t)T_rows * vec_per_row;
+    uint4* st = reinterpret_cast<uint4*>(c.local + in_off);
+    const uint4* src = reinterpret_cast<const uint4*>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+      st[i] = src[i];
+  }
+  grid_rank_barrier(c, &c.state[1], &c.state[2], e0 + 1, true);
+  if (threadIdx.x < vec_per_row) {
+    for (int row = blockIdx.x; row < T_rows; row += gridDim.x) {
+      float acc[8];
+      const size_t el = (size_t)row * H + threadIdx.x * 8;
+      uint4 w[VB_MAX_RANKS];
+#pragma unroll
+      for (int p = 0; p < VB_MAX_RANKS; ++p)
+        if (p < c.world)   // .sys loads: peer lines may linger in this SM's L1 from the previous call otherwise
+          asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(w[p].x), "=r"(w[p].y), "=r"(w[p].z), "=r"(w[p].w)
+                       : "l"(c.peer[p] + in_off + el * sizeof(T)) : "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int p = 0; p < VB_MAX_RANKS; ++p)
+        if (p < c.world) {
+          const uint32_t u[4] = {w[p].x, w[p].y, w[p].z, w[p].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { float2 f = unpack2<T>(u[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
+      Vec16<T> o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.e[i] = from_f32<T>(acc[i]);
+      st16(dst + el, o);
+    }
+  }
+  grid_rank_barrier(c, &c.state[3], &c.state[4], e0 + 2, false, true);
+}
+
 // all-gather along the last dim: out[row, rank*cols + j] = x[row, j] on every rank
 template <typename T>
 __global__ void all_gather_kernel(CommCtx c, const T* __restrict__ x, size_t out_off, int rows, int cols) {
@@ -142,6 +189,20 @@ EXPORT int vb_comm_allreduce_rows2(void* local, void* const* peers, void* mc, ui
   DISPATCH_HALF(dtype, TT, {
     ar_rows_kernel<TT><<<grid, thr, 0, st>>>(c, (const TT*)x, (size_t)in_off, (size_t)out_off, (TT*)residual,
                                               (const TT*)norm_w, eps, T_rows, H, gemma, (size_t)acc32_off);
+  });
+  return (int)cudaGetLastError();
+}
+
+EXPORT int vb_comm_allreduce_oneshot(void* local, void* const* peers, void* mc, uint32_t* state, int rank, int world,
+                                     const void* x, int64_t in_off, void* dst, int T_rows, int H, int num_sms, int dtype,
+                                     cudaStream_t st) {
+  if (T_rows == 0) return 0;
+  if (dtype == DT_F32 || H % 8 != 0 || H / 8 > 1024) return -1;
+  CommCtx c = make_ctx(local, peers, mc, state, rank, world);
+  int grid = T_rows < num_sms ? T_rows : num_sms;
+  int thr = ((H / 8 + 31) / 32) * 32;
+  DISPATCH_HALF(dtype, TT, {
+    ar_oneshot_kernel<TT><<<grid, thr, 0, st>>>(c, (const TT*)x, (size_t)in_off, (TT*)dst, T_rows, H);
   });
   return (int)cudaGetLastError();
 }

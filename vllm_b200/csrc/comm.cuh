@@ -24,6 +24,28 @@ struct CommCtx {
 };
 
 
+// Bounded spin: a barrier whose peer never arrives (dead rank, SMs held elsewhere) traps after ~20 s instead of hanging
+// the GPU until the driver's watchdog (the reference's DCP kernels carry the same guard, dcp_direct_common.cuh:15).
+VB_DEVICE unsigned long long vb_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+struct SpinGuard {
+  unsigned long long t0;
+  uint32_t n;
+  VB_DEVICE SpinGuard() : t0(0), n(0) {}
+  VB_DEVICE void tick(int what) {
+    if ((++n & 0xfffffu) != 0) return;
+    const unsigned long long now = vb_gtime();
+    if (t0 == 0) { t0 = now; return; }
+    if (now - t0 > 20ull * 1000 * 1000 * 1000) {
+      printf("vllm_b200 comm: spin limit exceeded (site %d, block %d)\n", what, blockIdx.x);
+      __trap();
+    }
+  }
+};
+
 // All ranks rendezvous: executed by (at least) `world` threads of ONE block per rank.
 // Rank r publishes `target` into slot r of every peer's flag array, then waits for all slots of its own.
 VB_DEVICE void rank_barrier(const CommCtx& c, uint32_t target) {
@@ -32,7 +54,8 @@ VB_DEVICE void rank_barrier(const CommCtx& c, uint32_t target) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(c.peer[t]) + c.rank;
     st_release_sys(dst, target);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.local) + t;
-    while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {}
+    SpinGuard sg;
+    while ((int32_t)(ld_acquire_sys(mine) - target) < 0) sg.tick(0);
   }
 }
 
@@ -59,7 +82,10 @@ VB_DEVICE void grid_rank_barrier(const CommCtx& c, uint32_t* counter, uint32_t* 
       st_release_gpu(go, target);
     }
   } else if (wait_all) {
-    if (threadIdx.x == 0) while ((int32_t)(ld_acquire_gpu(go) - target) < 0) {}
+    if (threadIdx.x == 0) {
+      SpinGuard sg;
+      while ((int32_t)(ld_acquire_gpu(go) - target) < 0) sg.tick(1);
+    }
   }
   if (wait_all) __syncthreads();
 }

@@ -8,6 +8,7 @@
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 #include <cstdlib>
 
 #define VB_HOST_DEVICE __host__ __device__ __forceinline__

@@ -44,7 +44,23 @@ struct Params {
   int k_blocks_per_split, splits;
   float eps;
   int gemma;
+  unsigned long long* trace;   // optional [n_ctas][8] globaltimer stamps of the epilogue phases (benchmarks/comm_probe.py)
 };
+
+VB_DEVICE unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// A reducer that spins on data another CTA / GPU must produce cannot make progress if that producer never runs
+// (a peer died, SMs held by another stream): after SPIN_LIMIT_NS it reports and traps instead of hanging the box.
+constexpr unsigned long long SPIN_LIMIT_NS = 20ull * 1000 * 1000 * 1000;
+VB_DEVICE void spin_guard(uint32_t& n, unsigned long long t0, int what) {
+  if ((++n & 0xfffffu) == 0 && gtime() - t0 > SPIN_LIMIT_NS) {
+    printf("gemm_ar: rank-visible spin limit exceeded (phase %d, block %d,%d)\n", what, blockIdx.x, blockIdx.z);
+    __trap();
+  }
+}
 
 template <int BN> struct SmemLayout {
   static constexpr int A_BYTES = TM * BK * 2;
@@ -155,7 +171,14 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row = q * 32 + lane;                         // feature inside the tile
     const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int n_ctas = gridDim.x * gridDim.z;
+    const int cta = blockIdx.z * gridDim.x + blockIdx.x;
+    const unsigned long long t_begin = gtime();
+    uint32_t spins = 0;
+#define VB_STAMP(i) do { if (p.trace && et == 0) p.trace[cta * 8 + (i)] = gtime(); } while (0)
+    VB_STAMP(0);
     pdl_wait();
+    VB_STAMP(1);
     // device-side state (slots 8..12 of c.state; 0..7 belong to comm.cu): [8] call counter → buffer rotation,
     // [9] CTA-done counter, [10+b] rows dirtied in buffer b by its last use
     const uint32_t call = c.state[8];
@@ -164,6 +187,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     unsigned char* lam_clear = c.local + p.lam_off + (size_t)((call + 2) % 3) * p.lam_stride;
     const size_t lam_cur_off = p.lam_off + (size_t)(call % 3) * p.lam_stride;
     if (nkb > 0) { mbar_wait(tmem_full, 0); tc_fence_after(); }
+    VB_STAMP(2);
     auto load_chunk = [&](int cc, float (&v)[CH]) {
       if (nkb == 0) {
 #pragma unroll
@@ -260,9 +284,8 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
     tc_fence_before();
+    VB_STAMP(3);
     // ---- reducer: CTA `cta` owns rows cta, cta + n_ctas, ...
-    const int n_ctas = gridDim.x * gridDim.z;
-    const int cta = blockIdx.z * gridDim.x + blockIdx.x;
     const int groups = p.N / 8;                            // 16-byte groups per row
     constexpr int MAXG = 8;                                // groups per thread kept in registers (H <= 8192)
     const bool two = p.mode == 1;
@@ -299,7 +322,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int src = 0; src < VB_MAX_RANKS; ++src) {
           if (src >= c.world) break;
           const unsigned char* ptr = lam_cur + (((size_t)src * p.t_cap + t) * p.N + g * 8) * sizeof(T);
-          while (has_sentinel(w[src])) ld_relaxed_sys_v4(ptr, w[src]);
+          while (has_sentinel(w[src])) { spin_guard(spins, t_begin, 0); ld_relaxed_sys_v4(ptr, w[src]); }
 #pragma unroll
           for (int e = 0; e < 4; ++e) { float2 f = unpack2<T>(w[src][e]); acc[gi][2 * e] += f.x; acc[gi][2 * e + 1] += f.y; }
           // re-arm the same slot of the buffer used two calls from now
@@ -360,7 +383,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int src = 0; src < VB_MAX_RANKS; ++src) {
           if (src >= c.world) break;
           const unsigned char* ptr = lam_cur + (((size_t)src * p.t_cap + t) * p.N + g * 8) * sizeof(T);
-          while (has_sentinel(w[src])) ld_relaxed_sys_v4(ptr, w[src]);
+          while (has_sentinel(w[src])) { spin_guard(spins, t_begin, 1); ld_relaxed_sys_v4(ptr, w[src]); }
 #pragma unroll
           for (int e = 0; e < 4; ++e) { float2 f = unpack2<T>(w[src][e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
         }
@@ -371,6 +394,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t o[4] = {sanitize(ro.u.x), sanitize(ro.u.y), sanitize(ro.u.z), sanitize(ro.u.w)};
         bcast16(c, oring_cur + ((size_t)t * p.N + g * 8) * sizeof(T), o);
       }
+      VB_STAMP(4);
       // re-arm the buffers used two calls from now: the rows this rank owned under their previous token count
       // (input ring, all source ranks) and every row of the output ring
       {
@@ -389,6 +413,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           *reinterpret_cast<uint4*>(dst) = make_uint4(SENT32, SENT32, SENT32, SENT32);
         }
       }
+      VB_STAMP(5);
       // (B) collect + normalise: rows cta, cta + n_ctas, ...
       const unsigned char* oc = c.local + oring_cur;
       for (int t = cta; t < p.M; t += n_ctas) {
@@ -404,7 +429,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int g = et + gi * EPI_THREADS;
           if (g >= groups) break;
           const unsigned char* ptr = oc + ((size_t)t * p.N + g * 8) * sizeof(T);
-          while (has_sentinel(w[gi])) ld_relaxed_sys_v4(ptr, w[gi]);
+          while (has_sentinel(w[gi])) { spin_guard(spins, t_begin, 2); ld_relaxed_sys_v4(ptr, w[gi]); }
 #pragma unroll
           for (int e = 0; e < 4; ++e) { float2 f = unpack2<T>(w[gi][e]); ss += f.x * f.x + f.y * f.y; }
         }
@@ -430,6 +455,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
+    VB_STAMP(6);
     // ---- last CTA out advances the call counter
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
     if (et == 0) {
@@ -491,6 +517,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 
 }  // namespace gemm_ar
 
+static unsigned long long* g_trace = nullptr;
+EXPORT void vb_gemm_ar_set_trace(void* p) { g_trace = reinterpret_cast<unsigned long long*>(p); }
+
 // Plan: number of K splits so that tiles*splits <= num_sms (all CTAs must be co-resident: reducers spin on
 // data produced by other CTAs / other GPUs).
 extern "C" int vb_gemm_max_active_clusters(int c);
@@ -534,7 +563,7 @@ EXPORT int vb_gemm_ar(void* local, void* const* peers, void* mc, uint32_t* state
   p.lam_off = (size_t)lam_off; p.lam_stride = (size_t)lam_stride; p.M = M; p.N = N; p.K = K; p.splits = splits;
   const int kb = (K + BK - 1) / BK;
   p.k_blocks_per_split = (kb + splits - 1) / splits;
-  p.eps = eps; p.gemma = gemma; p.t_cap = t_cap;
+  p.eps = eps; p.gemma = gemma; p.t_cap = t_cap; p.trace = g_trace;
   p.mode = mode; p.oring_off = (size_t)oring_off; p.oring_stride = (size_t)oring_stride;
   if (M > t_cap) return -7;
   int rc;

@@ -570,6 +570,15 @@ def comm_allreduce_rows(c, x, in_off, out_off, residual, norm_w, eps, T, H, gemm
            "comm_allreduce_rows")
 
 
+_comm_ar_oneshot = _sig("vb_comm_allreduce_oneshot", _vp, _vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i, _i, _i, _i, _vp)
+
+
+def comm_allreduce_oneshot(c, x, in_off, dst, T, H) -> None:
+    """Sum over ranks of [T,H] (``x`` or what already sits in the staging region) straight into the private ``dst``."""
+    _check(_comm_ar_oneshot(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, _p(x), in_off,
+                            dst.data_ptr(), T, H, num_sms(), _DT[dst.dtype], _st()), "comm_allreduce_oneshot")
+
+
 def comm_all_gather(c, x, out_off, rows, cols) -> None:
     _check(_comm_ag(c.local_ptr, c.peer_arr, c._mc(), c.state.data_ptr(), c.rank, c.world, x.data_ptr(), out_off,
                     rows, cols, num_sms(), _DT[x.dtype], _st()), "comm_all_gather")
@@ -612,6 +621,13 @@ def gemm_ar(c, x, w, residual, norm_w, out, eps, gemma, mode=0, oring_off=0, ori
                     int(gemma),
                     _DT[x.dtype], _st()), f"gemm_ar(M={M},N={N},K={K})")
     return True
+
+
+def gemm_ar_set_trace(t: Optional[torch.Tensor]) -> None:
+    """Point the fused kernel's phase stamps ([n_ctas, 8] int64 globaltimer values) at ``t`` (None = off)."""
+    fn = _lib.vb_gemm_ar_set_trace
+    fn.argtypes, fn.restype = [_vp], None
+    fn(t.data_ptr() if t is not None else None)
 
 
 def comm_barrier(c) -> None:

@@ -31,6 +31,7 @@ logger = init_logger(__name__)
 FLAGS_BYTES = 4096
 LAM_T_CAP = 128      # the fused GEMM+all-reduce kernel handles up to 128 tokens (decode / small mixed batches)
 LAM_H_MAX = 8192
+ONESHOT_T_MAX = 512  # rows up to which a plain all-reduce is one-shot into private memory (no heap copy-out)
 MOE_T_CAP = 256      # tokens covered by the fused MoE combine accumulators (decode / small mixed batches)
 _ALIGN = 1 << 16
 
@@ -147,6 +148,13 @@ class SymmComm:
             return None
         H = x.shape[-1]
         T = x.numel() // H
+        if T <= ONESHOT_T_MAX:       # decode-size: every rank reduces all rows in the switch, straight into private memory
+            self.ensure_capacity(T * H * x.dtype.itemsize)
+            out = torch.empty_like(x)
+            self.cu.comm_allreduce_oneshot(self, x.view(T, H), self.off_in, out, T, H)
+            return out
+        # large T: two-shot (1/W of the traffic per rank); the result lands in a rotating heap region that later
+        # collectives reuse, so it is copied out once
         out = self.allreduce_rows(x.view(T, H), T, H, x.dtype)
         return out.view(x.shape).clone()
 
@@ -235,6 +243,10 @@ class SymmComm:
         local = (ids - start).masked_fill(mask, 0)
         torch.index_select(weight, 0, local.reshape(-1).to(torch.int64), out=part)
         part.masked_fill_(mask.reshape(-1, 1), 0)
+        if T <= ONESHOT_T_MAX:
+            out = torch.empty(ids.shape + (H,), dtype=weight.dtype, device=weight.device)
+            self.cu.comm_allreduce_oneshot(self, None, self.off_in, out, T, H)
+            return out
         out = self.allreduce_rows(None, T, H, weight.dtype)
         return out.view(ids.shape + (H,)).clone()
 
