@@ -171,12 +171,12 @@ def test_fused_stress():
                 with torch.cuda.graph(gph):
                     res.copy_(res0)
                     og = comm.gemm_allreduce_rmsnorm(x, w, res, nw, 1e-5)[0]
-                graphs[T] = (gph, res, og, exp_res)
+                graphs[T] = (gph, res, og, exp_res, x, res0)     # the graph reads x / res0: keep them alive
             order = torch.randint(0, 4, (1000,), generator=torch.Generator().manual_seed(77)).tolist()   # same on all ranks
             keys = [1, 7, 64, 128]
             for i, o in enumerate(order):
                 T = keys[o]
-                gph, res, og, exp_res = graphs[T]
+                gph, res, og, exp_res = graphs[T][:4]
                 gph.replay()
                 if i % 50 == 0 or i > 990:
                     torch.cuda.synchronize()

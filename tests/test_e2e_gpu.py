@@ -146,3 +146,25 @@ def test_fp8_models_run_on_own_kernels_and_track_bf16(model, quant, monkeypatch)
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize("model", ["llama-small", "bamba-tiny"])
+def test_gpu_input_prep_equals_host_prep(model, monkeypatch):
+    """Device-resident token / block tables + on-device expansion (csrc/input_prep.cu) produce exactly the tokens of the
+    host-side numpy expansion: chunked prefill, more requests than rows (queueing, row moves on completion), prefix
+    caching, CUDA-graph padding, and a hybrid model with several KV-cache groups."""
+    from vllm_b200 import SamplingParams, envs
+    prompts = [{"prompt_token_ids": [(11 * i + 5 * j) % 300 + 5 for j in range(30 + 41 * i)]} for i in range(9)]
+    prompts += prompts[:3]                                     # repeated prompts: prefix-cache hits
+    sps = [SamplingParams(max_tokens=5 + 3 * (i % 4), temperature=0.0, ignore_eos=True) for i in range(len(prompts))]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VLLM_B200_GPU_INPUT_PREP", mode)
+        envs._cache.pop("VLLM_B200_GPU_INPUT_PREP", None)
+        llm, runner = _llm(model, max_num_seqs=4, max_num_batched_tokens=64, enable_prefix_caching=(model == "llama-small"),
+                           cudagraph_capture_sizes=[1, 2, 4])
+        assert runner.gpu_prep == (mode == "1")
+        res[mode] = [o.outputs[0].token_ids for o in llm.generate(prompts, sps)]
+        llm.shutdown()
+        del runner
+    assert res["1"] == res["0"]

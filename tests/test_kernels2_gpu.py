@@ -580,6 +580,29 @@ def test_gpu_input_prep_kernels_match_numpy_expansion():
         assert np.array_equal(positions.cpu().numpy()[sl], pos)
         assert np.array_equal(slots.cpu().numpy()[sl], bt_np[rows[b], pos // BS].astype(np.int64) * BS + pos % BS)
         assert np.array_equal(bt.cpu().numpy()[b, :nblk], bt_np[rows[b], :nblk])
+    # mixed-batch bucket padding: 24 request slots, T_pad tokens — empty padding requests, inert padding tokens
+    Tp = T + 13
+    input_ids2 = torch.full((Tp,), 7, dtype=torch.int32, device="cuda")
+    positions2 = torch.full((Tp,), 7, dtype=torch.int64, device="cuda")
+    slots2 = torch.full((Tp,), 7, dtype=torch.int64, device="cuda")
+    qsl2 = torch.zeros(25, dtype=torch.int32, device="cuda")
+    sl2 = torch.zeros(24, dtype=torch.int32, device="cuda")
+    bt2 = torch.full((24, MB), 9, dtype=torch.int32, device="cuda")
+    cu().prep_step(t(rows), t(nc), t(ns), token_table, block_rows, input_ids2, positions2, qsl2, sl2, slots2, bt2, nblk, BS,
+                   pad_b=24, pad_t=Tp)
+    assert torch.equal(input_ids2[:T], input_ids) and torch.equal(slots2[:T], slots)
+    assert (input_ids2[T:] == 0).all() and (positions2[T:] == 0).all() and (slots2[T:] == -1).all()
+    assert qsl2[:21].tolist() == cum.tolist() and (qsl2[21:] == T).all() and (bt2[20:, 0] == 0).all()
+    # decode bucket padding: one-token requests on the null block
+    ns1 = np.ones(20, dtype=np.int32)
+    ids3 = torch.full((24,), 7, dtype=torch.int32, device="cuda")
+    pos3 = torch.full((24,), 7, dtype=torch.int64, device="cuda")
+    sl3 = torch.full((24,), 7, dtype=torch.int64, device="cuda")
+    qsl3 = torch.zeros(25, dtype=torch.int32, device="cuda")
+    seq3 = torch.zeros(24, dtype=torch.int32, device="cuda")
+    cu().prep_step(t(rows), t(nc), t(ns1), token_table, block_rows, ids3, pos3, qsl3, seq3, sl3, bt2, nblk, BS, pad_b=24)
+    assert qsl3.tolist() == list(range(25)) and (seq3[20:] == 1).all() and (sl3[20:] == -1).all() and (ids3[20:] == 0).all()
+    assert np.array_equal(seq3[:20].cpu().numpy(), nc + 1)
     sampled = torch.randint(0, 30000, (20,), dtype=torch.int64, device="cuda")
     cu().append_sampled(token_table, t(rows), t(nc + ns), sampled)
     tt2 = token_table.cpu().numpy()

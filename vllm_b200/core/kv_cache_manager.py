@@ -349,6 +349,8 @@ class KVCacheManager:
         self.block_hasher = make_block_hasher(self.block_size, hash_algo) if enable_caching else None
         self.prefix_cache_stats = PrefixCacheStats()
         self._empty = KVCacheBlocks(tuple([] for _ in self.managers))
+        # steady-state decode: one full-attention group → "does the last block still have room" is one comparison
+        self._single_full = len(self.managers) == 1 and type(self.managers[0]) is FullAttentionManager
 
     @property
     def usage(self) -> float:
@@ -404,6 +406,26 @@ class KVCacheManager:
         if num_new_tokens == 0 and num_new_computed_tokens == 0:
             raise ValueError("num_new_tokens must be > 0")
         rid = request.request_id
+        if self._single_full and new_computed_blocks is None and num_new_computed_tokens == 0:
+            # fast path (every decode step of every running request): nothing to allocate while the tokens fit in the
+            # blocks the request already owns; a block is (hash-)cached only when a token completes it
+            m = self.managers[0]
+            blocks = m.req_to_blocks.get(rid)
+            if blocks is not None:
+                nc = request.num_computed_tokens
+                total = nc + num_new_tokens + num_lookahead_tokens
+                if total > self.max_model_len:
+                    total = self.max_model_len
+                bs = m.block_size
+                if total <= len(blocks) * bs:
+                    if self.enable_caching and not delay_cache_blocks:
+                        final = nc + num_new_tokens
+                        nt = request.num_tokens
+                        if final > nt:
+                            final = nt
+                        if final // bs > m.num_cached.get(rid, 0):
+                            m.cache_blocks(request, final)
+                    return self._empty
         new_computed = new_computed_blocks.blocks if new_computed_blocks is not None else \
             tuple([] for _ in self.managers)
         # reclaim out-of-window blocks first so they can serve this very allocation

@@ -389,6 +389,7 @@ class Scheduler:
     def _make_cached(self, running, resumed, num_sched, spec_sched, new_blocks_of) -> CachedRequestData:
         c = CachedRequestData()
         pp = self.vllm_config.parallel_config.pipeline_parallel_size > 1
+        empty = self.kv_cache_manager.empty_blocks()
         for is_resumed, reqs in ((False, running), (True, resumed)):
             for r in reqs:
                 rid = r.request_id
@@ -402,7 +403,8 @@ class Scheduler:
                 else:
                     c.new_token_ids.append([])
                 blocks = new_blocks_of.get(rid)
-                c.new_block_ids.append(blocks.get_block_ids() if blocks is not None else None)
+                # (the shared empty result of the allocation fast path: nothing new to ship)
+                c.new_block_ids.append(blocks.get_block_ids() if blocks is not None and blocks is not empty else None)
                 c.num_computed_tokens.append(r.num_computed_tokens)
                 c.num_output_tokens.append(r.num_output_tokens)
         return c
@@ -441,13 +443,47 @@ class Scheduler:
             for g in sampled:
                 lp_offsets.append(acc)
                 acc += len(g)
+        # plain generation step (no speculation / logprobs / pooling / prompt logprobs / NaN report): the per-request
+        # work below shrinks to "append the token, check the stop conditions, emit the delta"
+        plain = (not so.scheduled_spec_decode_tokens and lp_ids is None and not mo.pooler_output
+                 and not mo.prompt_logprobs_dict and mo.spec_token_ids is None and not mo.num_nans_in_logits)
+        requests, r2i, n_samp, mml = self.requests, mo.req_id_to_index, len(sampled), self.max_model_len
         for rid, n_sched in so.num_scheduled_tokens.items():
-            req = self.requests.get(rid)
+            req = requests.get(rid)
             if req is None or req.is_finished():
                 # aborted while the step was in flight
                 continue
-            idx = mo.req_id_to_index.get(rid)
-            gen = sampled[idx] if idx is not None and idx < len(sampled) else []
+            idx = r2i.get(rid)
+            gen = sampled[idx] if idx is not None and idx < n_samp else []
+            if plain and not req.use_structured_output:
+                if not gen:
+                    continue                      # prefill chunk: nothing to report
+                if req.num_output_placeholders > 0:
+                    req.num_output_placeholders = max(req.num_output_placeholders - len(gen), 0)
+                was_preempted = req.status == RequestStatus.PREEMPTED
+                stopped, new_ids = False, gen
+                for k, tok in enumerate(gen):
+                    req.append_output_token_ids(tok)
+                    if check_stop(req, mml):
+                        stopped, new_ids = True, gen[:k + 1]
+                        break
+                kv_params = None
+                if stopped:
+                    kv_params = self._free_request(req)
+                    if was_preempted:
+                        stopped_preempted.append(req)
+                    else:
+                        stopped_running.add(rid)
+                outs = outputs.get(req.client_index)
+                if outs is None:
+                    outs = outputs[req.client_index] = []
+                nct = req.num_cached_tokens
+                outs.append(EngineCoreOutput(
+                    request_id=rid, new_token_ids=list(new_ids),
+                    finish_reason=int(req.get_finished_reason()) if stopped else None, stop_reason=req.stop_reason,
+                    num_cached_tokens=nct if nct > 0 else 0, kv_transfer_params=kv_params,
+                    events=req.take_events() if req.events else None))
+                continue
             spec = so.scheduled_spec_decode_tokens.get(rid)
             if spec:
                 n_draft = len(spec)

@@ -342,6 +342,9 @@ int dispatch_rows(int R, const AttnParams& p, dim3 grid, cudaStream_t st) {
 
 template <typename T, bool FP8>
 int dispatch_shape(int D, int BS, int R, const AttnParams& p, dim3 grid, cudaStream_t st) {
+  if (D == 128 && BS == 64) return dispatch_rows<T, 128, 64, FP8>(R, p, grid, st);   // CUDA default page size: fp8 KV
+  if (D == 64 && BS == 64) return dispatch_rows<T, 64, 64, FP8>(R, p, grid, st);     // caches, soft-cap / ALiBi / sink
+  if (D == 32 && BS == 64) return dispatch_rows<T, 32, 64, FP8>(R, p, grid, st);     // layers, draft heads
   if (D == 128 && BS == 32) return dispatch_rows<T, 128, 32, FP8>(R, p, grid, st);
   if (D == 128 && BS == 16) return dispatch_rows<T, 128, 16, FP8>(R, p, grid, st);
   if (D == 64 && BS == 32) return dispatch_rows<T, 64, 32, FP8>(R, p, grid, st);

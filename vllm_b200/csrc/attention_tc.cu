@@ -43,6 +43,8 @@ struct Params {
   int Hq, Hkv, G, TQ, num_splits;
   int window, causal;
   float scale_log2;
+  int flat_B;              // > 0: grid.x enumerates the (request, query tile) pairs of `flat_B` requests (device-side
+                           //      schedule from qsl: the launch geometry depends only on the bucket, not on the lengths)
 };
 
 VB_DEVICE void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
@@ -85,9 +87,40 @@ fmha_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   int* blk_ids = reinterpret_cast<int*>(tmem_slot + 2);   // [2 * MAX_TILES_SMEM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
+  int b = blockIdx.z;
+  const int h = blockIdx.y;
   int split = 0, qt = 0;
-  if (p.qsl) qt = blockIdx.x; else split = blockIdx.x;
+  if (p.flat_B > 0) {
+    // flat tile index → (request, tile): every warp walks the per-request tile counts 32 requests at a time (redundantly:
+    // no shared memory or barrier before the early exit)
+    int target = blockIdx.x, found_b = -1;
+    for (int base = 0; base < p.flat_B && found_b < 0; base += 32) {
+      const int r = base + lane;
+      int nt = 0;
+      if (r < p.flat_B) nt = (p.qsl[r + 1] - p.qsl[r] + p.TQ - 1) / p.TQ;
+      int inc = nt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, target < inc);
+      if (hit) {
+        const int l = __ffs(hit) - 1;
+        const int before = __shfl_sync(0xffffffffu, inc - nt, l);
+        found_b = base + l;
+        qt = target - before;
+      } else {
+        target -= __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    if (found_b < 0) return;                       // more CTAs than tiles (bucket padding)
+    b = found_b;
+  } else if (p.qsl) {
+    qt = blockIdx.x;
+  } else {
+    split = blockIdx.x;
+  }
   const int seq_len = p.seq_lens[b];
   const int q0 = p.qsl ? p.qsl[b] : b;
   const int q_len = p.qsl ? p.qsl[b + 1] - q0 : 1;
@@ -411,11 +444,26 @@ static EncodeTiledFn get_encode() {
 }  // namespace fmha
 
 // kv_cache: [nb, 2, Hkv, BS*D] with K pages [BS, D] and V pages stored transposed [D, BS].
+EXPORT int vb_fmha_tc2(const void* q, const void* kv_cache, int64_t num_blocks, const int* block_table,
+                       const int* seq_lens, const int* qsl, void* out, float* part_out, float* part_lse,
+                       float* lse_out, int B, int T_total, int max_q_len, int Hq, int Hkv, int64_t q_stride,
+                       int64_t out_stride, int bt_stride, int num_splits, int window, float scale, int causal,
+                       int flat, int dtype, cudaStream_t st);
 EXPORT int vb_fmha_tc(const void* q, const void* kv_cache, int64_t num_blocks, const int* block_table,
                       const int* seq_lens, const int* qsl, void* out, float* part_out, float* part_lse,
                       float* lse_out, int B, int T_total, int max_q_len, int Hq, int Hkv, int64_t q_stride,
                       int64_t out_stride, int bt_stride, int num_splits, int window, float scale, int causal,
                       int dtype, cudaStream_t st) {
+  return vb_fmha_tc2(q, kv_cache, num_blocks, block_table, seq_lens, qsl, out, part_out, part_lse, lse_out, B, T_total,
+                     max_q_len, Hq, Hkv, q_stride, out_stride, bt_stride, num_splits, window, scale, causal, 0, dtype, st);
+}
+// flat != 0 (varlen only): the grid is sized from (T_total, B) alone — T_total / TQ + B tiles bound every split of
+// T_total tokens over B requests — so one captured launch serves any mixed batch of that bucket.
+EXPORT int vb_fmha_tc2(const void* q, const void* kv_cache, int64_t num_blocks, const int* block_table,
+                       const int* seq_lens, const int* qsl, void* out, float* part_out, float* part_lse,
+                       float* lse_out, int B, int T_total, int max_q_len, int Hq, int Hkv, int64_t q_stride,
+                       int64_t out_stride, int bt_stride, int num_splits, int window, float scale, int causal,
+                       int flat, int dtype, cudaStream_t st) {
   using namespace fmha;
   if (B == 0) return 0;
   if (dtype == DT_F32) return -1;
@@ -430,6 +478,7 @@ EXPORT int vb_fmha_tc(const void* q, const void* kv_cache, int64_t num_blocks, c
   p.part_lse = part_lse; p.lse_out = lse_out; p.out_stride = out_stride; p.bt_stride = bt_stride; p.Hq = Hq;
   p.Hkv = Hkv; p.G = G; p.TQ = qsl ? TILE_M / G : 1; p.num_splits = qsl ? 1 : num_splits; p.window = window;
   p.causal = causal; p.scale_log2 = scale * 1.4426950408889634f;
+  p.flat_B = (flat && qsl) ? B : 0;
   CUtensorMap tq, tk, tv;
   {  // q: [T, Hq, D] with token stride q_stride; box {64, G, TQ}
     cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Hq, (cuuint64_t)T_total};
@@ -460,6 +509,7 @@ EXPORT int vb_fmha_tc(const void* q, const void* kv_cache, int64_t num_blocks, c
   }
   const int smem = Q_BYTES + P_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 32 * 8 + 16 + 2 * MAX_TILES_SMEM * 4 + 1024;
   dim3 grid = qsl ? dim3((max_q_len + p.TQ - 1) / p.TQ, Hkv, B) : dim3(p.num_splits, Hkv, B);
+  if (p.flat_B) grid = dim3(T_total / p.TQ + B, Hkv, 1);
   if (bf16) {
     auto k = fmha_kernel<__nv_bfloat16>;
     static bool a = false;

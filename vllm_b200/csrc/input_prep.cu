@@ -22,14 +22,14 @@ __global__ void __launch_bounds__(256) prep_step_kernel(
     const int* __restrict__ token_table, int64_t tt_stride, const int* __restrict__ block_rows, int64_t br_stride,
     int* __restrict__ input_ids, int64_t* __restrict__ positions, int* __restrict__ qsl, int* __restrict__ seq_lens,
     int64_t* __restrict__ slot_mapping, int* __restrict__ block_table, int64_t bt_stride, int nblk, int block_size,
-    const int64_t* __restrict__ pos_delta) {
+    const int64_t* __restrict__ pos_delta, int write_tokens, int pad_t) {
   __shared__ int s_off;
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x;
-  // exclusive prefix of num_sched[0..b)
+  // exclusive prefix of num_sched[0..min(b, nb))
   int part = 0;
-  for (int i = threadIdx.x; i < b; i += blockDim.x) part += num_sched[i];
+  for (int i = threadIdx.x; i < min(b, nb); i += blockDim.x) part += num_sched[i];
   __shared__ int red[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -44,8 +44,39 @@ __global__ void __launch_bounds__(256) prep_step_kernel(
   }
   __syncthreads();
   const int off = s_off;
+  if (b >= nb && pad_t > 0) {
+    // mixed-batch bucket: padding REQUESTS are empty (query length 0 — the flat attention schedule skips them, their
+    // "last token" index resolves to the batch's last real token), padding TOKENS [T, pad_t) sit at position 0 and
+    // write to no cache slot; the extra CTA b == gridDim.x - 1 fills the token padding
+    if (threadIdx.x == 0 && b < (int)gridDim.x - 1) {
+      if (write_tokens) { qsl[b + 1] = off; seq_lens[b] = 1; }
+      block_table[(int64_t)b * bt_stride] = 0;
+    }
+    if (b == (int)gridDim.x - 1)
+      for (int i = off + threadIdx.x; i < pad_t; i += blockDim.x) {
+        if (write_tokens) { input_ids[i] = 0; positions[i] = 0; }
+        slot_mapping[i] = -1;
+      }
+    return;
+  }
+  if (b >= nb) {
+    // padding slot of a decode bucket: one token at position 0 that writes to no cache slot and attends over one
+    // token of the null block (same convention as the host path, worker/model_runner.py `_h2d`)
+    if (threadIdx.x == 0) {
+      const int idx = off + (b - nb);
+      if (write_tokens) {
+        input_ids[idx] = 0;
+        positions[idx] = 0;
+        qsl[b + 1] = idx + 1;
+        seq_lens[b] = 1;
+      }
+      slot_mapping[idx] = -1;
+      block_table[(int64_t)b * bt_stride] = 0;
+    }
+    return;
+  }
   const int row = rows[b], nc = num_computed[b], ns = num_sched[b];
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && write_tokens) {
     qsl[b] = off;
     if (b == nb - 1) qsl[nb] = off + ns;
     seq_lens[b] = nc + ns;
@@ -55,8 +86,10 @@ __global__ void __launch_bounds__(256) prep_step_kernel(
   const int64_t delta = pos_delta ? pos_delta[b] : 0;       // M-RoPE: rotary position runs behind the sequence index
   for (int i = threadIdx.x; i < ns; i += blockDim.x) {
     const int pos = nc + i;
-    input_ids[off + i] = toks[pos];
-    positions[off + i] = (int64_t)pos + delta;
+    if (write_tokens) {
+      input_ids[off + i] = toks[pos];
+      positions[off + i] = (int64_t)pos + delta;
+    }
     slot_mapping[off + i] = (int64_t)blks[pos / block_size] * block_size + pos % block_size;
   }
   int* bt = block_table + (int64_t)b * bt_stride;
@@ -88,14 +121,46 @@ __global__ void __launch_bounds__(256) append_sampled_kernel(int* __restrict__ t
 
 }  // namespace
 
+EXPORT int vb_prep_step3(const int* rows, const int* num_computed, const int* num_sched, int nb, int pad_b, int pad_t,
+                         const int* token_table, int64_t tt_stride, const int* block_rows, int64_t br_stride, int* input_ids,
+                         int64_t* positions, int* qsl, int* seq_lens, int64_t* slot_mapping, int* block_table,
+                         int64_t bt_stride, int nblk, int block_size, const int64_t* pos_delta, int write_tokens,
+                         cudaStream_t st);
+EXPORT int vb_prep_step2(const int* rows, const int* num_computed, const int* num_sched, int nb, int pad_b,
+                         const int* token_table, int64_t tt_stride, const int* block_rows, int64_t br_stride, int* input_ids,
+                         int64_t* positions, int* qsl, int* seq_lens, int64_t* slot_mapping, int* block_table,
+                         int64_t bt_stride, int nblk, int block_size, const int64_t* pos_delta, int write_tokens,
+                         cudaStream_t st);
 EXPORT int vb_prep_step(const int* rows, const int* num_computed, const int* num_sched, int nb, const int* token_table,
                         int64_t tt_stride, const int* block_rows, int64_t br_stride, int* input_ids, int64_t* positions,
                         int* qsl, int* seq_lens, int64_t* slot_mapping, int* block_table, int64_t bt_stride, int nblk,
                         int block_size, const int64_t* pos_delta, cudaStream_t st) {
-  if (nb == 0) return 0;
-  vb_launch(prep_step_kernel, dim3(nb), dim3(256), 0, st, rows, num_computed, num_sched, nb, token_table, tt_stride,
-            block_rows, br_stride, input_ids, positions, qsl, seq_lens, slot_mapping, block_table, bt_stride, nblk, block_size,
-            pos_delta);
+  return vb_prep_step2(rows, num_computed, num_sched, nb, nb, token_table, tt_stride, block_rows, br_stride, input_ids,
+                       positions, qsl, seq_lens, slot_mapping, block_table, bt_stride, nblk, block_size, pos_delta, 1, st);
+}
+
+// pad_b >= nb: entries [nb, pad_b) are graph-bucket padding; write_tokens = 0 for the 2nd.. KV-cache group of a hybrid
+// model (only slot_mapping / block_table differ between groups)
+EXPORT int vb_prep_step2(const int* rows, const int* num_computed, const int* num_sched, int nb, int pad_b,
+                         const int* token_table, int64_t tt_stride, const int* block_rows, int64_t br_stride, int* input_ids,
+                         int64_t* positions, int* qsl, int* seq_lens, int64_t* slot_mapping, int* block_table,
+                         int64_t bt_stride, int nblk, int block_size, const int64_t* pos_delta, int write_tokens,
+                         cudaStream_t st) {
+  return vb_prep_step3(rows, num_computed, num_sched, nb, pad_b, 0, token_table, tt_stride, block_rows, br_stride, input_ids,
+                       positions, qsl, seq_lens, slot_mapping, block_table, bt_stride, nblk, block_size, pos_delta,
+                       write_tokens, st);
+}
+
+// pad_t > 0: mixed-batch bucket of pad_t tokens / pad_b requests (empty padding requests + padding tokens)
+EXPORT int vb_prep_step3(const int* rows, const int* num_computed, const int* num_sched, int nb, int pad_b, int pad_t,
+                         const int* token_table, int64_t tt_stride, const int* block_rows, int64_t br_stride, int* input_ids,
+                         int64_t* positions, int* qsl, int* seq_lens, int64_t* slot_mapping, int* block_table,
+                         int64_t bt_stride, int nblk, int block_size, const int64_t* pos_delta, int write_tokens,
+                         cudaStream_t st) {
+  if (pad_b <= 0) return 0;
+  vb_launch(prep_step_kernel, dim3(pad_t > 0 ? pad_b + 1 : pad_b), dim3(256), 0, st, rows, num_computed, num_sched, nb,
+            token_table, tt_stride, block_rows, br_stride, input_ids, positions, qsl, seq_lens, slot_mapping, block_table,
+            bt_stride, nblk, block_size, pos_delta, write_tokens, pad_t);
   return (int)cudaGetLastError();
 }
 

@@ -59,6 +59,8 @@ environment_variables: dict[str, Callable[[], Any]] = {
     "VLLM_B200_GEMM": _str("VLLM_B200_GEMM", "auto"),  # auto|cublas|tcgen05
     # decode: pull the next few-tile GEMM's weights into L2 on a side stream while the HBM-bound attention kernel runs
     "VLLM_B200_L2_PREFETCH": _bool("VLLM_B200_L2_PREFETCH", False),
+    # device-resident token / block tables + on-device expansion of the step inputs (csrc/input_prep.cu)
+    "VLLM_B200_GPU_INPUT_PREP": _bool("VLLM_B200_GPU_INPUT_PREP", True),
     "VLLM_B200_FUSED_MOE": _bool("VLLM_B200_FUSED_MOE", True),   # MoE combine + reduce in the w2 grouped-GEMM epilogue
     "VLLM_B200_FUSED_ACT": _bool("VLLM_B200_FUSED_ACT", True),   # gate|up as interleaved rows, SiLU·mul in the GEMM epilogue
     "VLLM_B200_GEMM_SK": _bool("VLLM_B200_GEMM_SK", False),  # decode GEMMs on the persistent stream-K kernel (measured slower than the

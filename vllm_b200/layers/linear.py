@@ -110,6 +110,12 @@ class ColumnParallelLinear(LinearBase):
         param.data.copy_(w)
 
 
+def _lora_enabled() -> bool:
+    from vllm_b200.config import get_current_vllm_config_or_none
+    cfg = get_current_vllm_config_or_none()
+    return cfg is not None and getattr(cfg, "lora_config", None) is not None
+
+
 class MergedColumnParallelLinear(ColumnParallelLinear):
     """Several column-parallel matrices fused along the output dim (gate|up)."""
 
@@ -119,9 +125,10 @@ class MergedColumnParallelLinear(ColumnParallelLinear):
         super().__init__(input_size, sum(output_sizes), bias, False, dtype, quant_config, prefix)
         # gate|up stored as interleaved rows (gate_0, up_0, gate_1, up_1, ...): the gated activation then pairs
         # adjacent accumulator rows of ONE GEMM tile and fuses into the GEMM epilogue (``forward_gated_silu``)
+        # (LoRA adapters address gate and up as contiguous output slices: keep the plain layout when they are enabled)
         self.interleave = bool(interleave and len(output_sizes) == 2 and output_sizes[0] == output_sizes[1]
                                and not bias and type(self.quant_method) is LinearMethod
-                               and self.dtype in (torch.bfloat16, torch.float16))
+                               and self.dtype in (torch.bfloat16, torch.float16) and not _lora_enabled())
 
     def forward_gated_silu(self, x: torch.Tensor) -> torch.Tensor:
         assert self.interleave

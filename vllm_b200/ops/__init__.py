@@ -89,15 +89,29 @@ def activation(x: torch.Tensor, name: str) -> torch.Tensor:
     return ref.ACT_FNS[name](x)
 
 
+_HALF = (torch.bfloat16, torch.float16)
+_SIMT_ATTN_SHAPES = {(128, 64), (64, 64), (32, 64), (128, 32), (128, 16), (64, 32), (64, 16), (256, 32), (32, 32), (32, 16)}
+
+
+def _rope_ok(q, cos_sin_cache, head_dim) -> bool:
+    """Shapes the vectorised RoPE / cache-write kernel covers (16-byte vectors over half-precision heads)."""
+    rot = cos_sin_cache.shape[-1]
+    return q.dtype in _HALF and head_dim % 8 == 0 and (rot // 2) % 8 == 0 and (head_dim - rot) % 8 == 0
+
+
+def cuda_attention_supported(D: int, BS: int, dtype, vt: bool) -> bool:
+    return dtype in _HALF and (vt or (D, BS) in _SIMT_ATTN_SHAPES)
+
+
 def rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox=True):
     """In place on CUDA; returns (q, k)."""
-    if _use_cuda(q):
+    if _use_cuda(q) and _rope_ok(q, cos_sin_cache, head_dim):
         return cuda_ops().rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
     return ref.rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
 
 
 def reshape_and_cache(key, value, kv_cache, slot_mapping, vt: bool = False) -> None:
-    if _use_cuda(key):
+    if _use_cuda(key) and (vt or (key.dtype in _HALF and key.shape[-1] % 8 == 0)):
         return cuda_ops().reshape_and_cache(key, value, kv_cache, slot_mapping, vt=vt)
     return ref.reshape_and_cache(key, value, kv_cache, slot_mapping)
 
@@ -105,7 +119,7 @@ def reshape_and_cache(key, value, kv_cache, slot_mapping, vt: bool = False) -> N
 def rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache, slot_mapping, vt: bool = False):
     """Fused RoPE(q,k) + paged KV write. q/k: [T, H*D] views; returns (q, k) rotated.
     ``vt``: the cache uses the tensor-core layout (V pages transposed), CUDA only."""
-    if _use_cuda(q):
+    if _use_cuda(q) and (vt or _rope_ok(q, cos_sin_cache, head_dim)):
         return cuda_ops().rope_and_cache(positions, q, k, v, cos_sin_cache, head_dim, is_neox, kv_cache,
                                          slot_mapping, vt=vt)
     q, k = ref.rotary_embedding(positions, q, k, cos_sin_cache, head_dim, is_neox)
@@ -125,7 +139,7 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
                     out: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
                     sinks: Optional[torch.Tensor] = None, chunk_size: int = 0, return_lse: bool = False):
     """``md``: AttentionMetadata (see vllm_b200.forward_context)."""
-    if _use_cuda(q):
+    if _use_cuda(q) and cuda_attention_supported(q.shape[-1], kv_cache.shape[3], q.dtype, md.kv_vt):
         return cuda_ops().paged_attention(q, kv_cache, md, scale, sliding_window, logits_soft_cap, causal, out,
                                           return_lse=return_lse, alibi_slopes=alibi_slopes, sinks=sinks,
                                           chunk_size=chunk_size)

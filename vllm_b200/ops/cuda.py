@@ -1137,19 +1137,24 @@ def gdn_scan(q, k, v, g, beta, cache, state_off: int, md) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ GPU-side input preparation (csrc/input_prep.cu)
-_prep_step = _sig("vb_prep_step", _vp, _vp, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp)
+_prep_step = _sig("vb_prep_step3", _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp,
+                  _i, _vp)
 _bt_diff = _sig("vb_block_table_diff", _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp)
 _append_sampled = _sig("vb_append_sampled", _vp, _i64, _vp, _vp, _vp, _i, _vp)
 
 
 def prep_step(rows, num_computed, num_sched, token_table, block_rows, input_ids, positions, qsl, seq_lens, slot_mapping,
-              block_table, nblk: int, block_size: int, pos_delta=None) -> None:
-    """Expand per-request (row, computed, scheduled) triples into the per-token step inputs on the device."""
+              block_table, nblk: int, block_size: int, pos_delta=None, pad_b: int = 0, write_tokens: bool = True,
+              pad_t: int = 0) -> None:
+    """Expand per-request (row, computed, scheduled) triples into the per-token step inputs on the device.  Entries
+    [nb, pad_b) are CUDA-graph bucket padding: one-token requests on the null block (decode buckets, ``pad_t`` = 0) or
+    empty requests plus padding tokens up to ``pad_t`` (mixed-batch buckets)."""
     nb = rows.numel()
-    _check(_prep_step(rows.data_ptr(), num_computed.data_ptr(), num_sched.data_ptr(), nb, token_table.data_ptr(),
-                      token_table.stride(0), block_rows.data_ptr(), block_rows.stride(0), input_ids.data_ptr(),
-                      positions.data_ptr(), qsl.data_ptr(), seq_lens.data_ptr(), slot_mapping.data_ptr(),
-                      block_table.data_ptr(), block_table.stride(0), nblk, block_size, _p(pos_delta), _st()), "prep_step")
+    _check(_prep_step(rows.data_ptr(), num_computed.data_ptr(), num_sched.data_ptr(), nb, max(pad_b, nb), pad_t,
+                      token_table.data_ptr(), token_table.stride(0), block_rows.data_ptr(), block_rows.stride(0),
+                      input_ids.data_ptr(), positions.data_ptr(), qsl.data_ptr(), seq_lens.data_ptr(),
+                      slot_mapping.data_ptr(), block_table.data_ptr(), block_table.stride(0), nblk, block_size,
+                      _p(pos_delta), int(write_tokens), _st()), "prep_step")
 
 
 def block_table_apply_diffs(block_rows, d_row, d_start, d_cnt, d_off, ids_flat) -> None:

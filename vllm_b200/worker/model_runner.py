@@ -76,6 +76,12 @@ class _Staging:
         self.fix_idx = mk(R, dtype=torch.int64)
         self.fix_rows = mk(R, dtype=torch.int64)
         self.rows = mk(R, dtype=torch.int64)
+        # GPU-side input prep: [rows | num_computed | num_scheduled | append_pos] packed for ONE H2D copy per step, and
+        # the staged block-table appends [row | start | count | offset] + their ids
+        self.meta = mk(4 * R, dtype=torch.int32)
+        self.tok_hdr = mk(4 * R, dtype=torch.int32)
+        self.diff_hdr = [mk(8 * R, dtype=torch.int32) for _ in range(G)] if pin else []
+        self.diff_ids = [mk(min(R * MB, max(1 << 20, 4 * R + MB)), dtype=torch.int32) for _ in range(G)] if pin else []
         self.event = torch.cuda.Event() if pin else None
 
     def wait(self) -> None:
@@ -233,6 +239,14 @@ class ModelRunner:
         self.capture_sizes: list[int] = []
         self._step = 0
         self.launch_count = 0   # our kernels launched (graph replays count their captured launches)
+        # device-resident request state + on-device expansion of the step inputs (csrc/input_prep.cu); decided in
+        # initialize_kv_cache
+        self.gpu_prep = False
+        self.dev_tokens: Optional[torch.Tensor] = None
+        self.dev_block_rows: list[torch.Tensor] = []
+        self._bt_diffs: list[list[tuple[str, int, list[int]]]] = []
+        self._new_rids: list[str] = []
+        self.prep_host_s = 0.0  # host seconds spent preparing + uploading step inputs (diagnostic)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -314,6 +328,34 @@ class ModelRunner:
                               for _ in range(G)]
         n_sets = 3 if self.is_cuda else 1
         self.staging = [_Staging(self.max_num_tokens, R, MB, G, self.is_cuda) for _ in range(n_sets)]
+        self._init_gpu_prep()
+
+    def _init_gpu_prep(self) -> None:
+        """Persistent device mirrors of the per-request token ids and block tables (reference:
+        v1/worker/gpu/states.py:9, block_table.py:228-330).  With them a step uploads four ints per scheduled request
+        plus the block ids that were appended since the last step; token ids, positions, slot mappings, query offsets
+        and the compact block table are expanded by ``prep_step`` on the device, and sampled ids are appended to the
+        table by ``append_sampled`` without a host round trip."""
+        from vllm_b200 import envs
+        pc = self.vllm_config.parallel_config
+        R, L = self.max_num_reqs, self.token_ids_cpu.shape[1]
+        ok = (self.is_cuda and envs.VLLM_B200_GPU_INPUT_PREP and not envs.VLLM_B200_FORCE_REF_OPS and self.dcp == 1
+              and self.pcp == 1 and not self.uses_mrope and self.num_spec_tokens == 0 and not self.is_enc_dec
+              and pc.pipeline_parallel_size == 1 and R * L * 4 <= (1 << 30))
+        self.gpu_prep = bool(ok)
+        if not ok:
+            return
+        from vllm_b200.ops import cuda_ops
+        self._cu = cuda_ops()
+        self.dev_tokens = torch.zeros(R, L, dtype=torch.int32, device=self.device)
+        self.dev_block_rows = [torch.zeros(R, self.max_blocks_per_req, dtype=torch.int32, device=self.device)
+                               for _ in range(self.num_kv_groups)]
+        self.step_meta = torch.zeros(4 * R, dtype=torch.int32, device=self.device)
+        self.tok_hdr_dev = torch.zeros(4 * R, dtype=torch.int32, device=self.device)
+        self.diff_hdr_dev = [torch.zeros(8 * R, dtype=torch.int32, device=self.device) for _ in range(self.num_kv_groups)]
+        self.diff_ids_dev = [torch.zeros(self.staging[0].diff_ids[g].numel(), dtype=torch.int32, device=self.device)
+                             for g in range(self.num_kv_groups)]
+        self._bt_diffs = [[] for _ in range(self.num_kv_groups)]
 
     # ------------------------------------------------------- batch maintenance
     def _move_row(self, src: int, dst: int) -> None:
@@ -328,6 +370,12 @@ class ModelRunner:
             self.num_blocks_cpu[g][dst] = nb
         if self.is_cuda:
             self.last_sampled[dst:dst + 1].copy_(self.last_sampled[src:src + 1])
+        if self.gpu_prep:       # stream-ordered after the append of the step that is still in flight
+            nl = int(self.num_logical_cpu[src]) + 1
+            self.dev_tokens[dst, :nl].copy_(self.dev_tokens[src, :nl])
+            for g in range(self.num_kv_groups):
+                nb = int(self.num_blocks_cpu[g][src])
+                self.dev_block_rows[g][dst, :nb].copy_(self.dev_block_rows[g][src, :nb])
 
     def _remove(self, req_id: str, park: bool = False) -> None:
         row = self.req_index.pop(req_id, None)
@@ -381,6 +429,8 @@ class ModelRunner:
             ids = block_ids[g]
             self.block_tables_cpu[g][row, :len(ids)] = ids
             self.num_blocks_cpu[g][row] = len(ids)
+        if self.gpu_prep:       # admission: the whole row travels once, with this step's uploads (_flush_gpu_state)
+            self._new_rids.append(st.req_id)
 
     def _add(self, nr) -> None:
         sp = nr.sampling_params
@@ -427,6 +477,8 @@ class ModelRunner:
                         s = self.num_blocks_cpu[g][row]
                         self.block_tables_cpu[g][row, s:s + len(ids)] = ids
                         self.num_blocks_cpu[g][row] = s + len(ids)
+                        if self.gpu_prep:     # keyed by request: a later removal in this step may still move the row
+                            self._bt_diffs[g].append((rid, int(s), ids))
 
     # ---------------------------------------------------------- input prep
     def _prepare(self, so: SchedulerOutput, stg: _Staging):
@@ -516,6 +568,117 @@ class ModelRunner:
             self.seq_lens[nb:pad_b].fill_(1)
             self.qsl[nb + 1:pad_b + 1].copy_(
                 torch.arange(T + 1, T + 1 + pad_b - nb, dtype=torch.int32, device=self.device))
+
+    # ------------------------------------------------- device-side input prep
+    def _flush_gpu_state(self, stg: _Staging) -> None:
+        """Bring the device mirrors up to date with O(1) CUDA calls: the token rows of requests admitted this step and
+        the block ids appended since the last step are packed into pinned staging, shipped with one copy each, and
+        scattered into the tables by ``block_table_apply_diffs`` (row, start, count, offset) entries."""
+        cu = self._cu
+        R = self.max_num_reqs
+        if self._new_rids:
+            rids, self._new_rids = self._new_rids, []
+            pin, cap = stg.input_ids, stg.input_ids.numel()
+            pv = pin.numpy()
+            d_row, d_cnt, d_off = [], [], []
+            off = 0
+            for rid in rids:
+                row = self.req_index.get(rid)
+                if row is None:
+                    continue
+                n = int(self.num_tokens_cpu[row])
+                for g in range(self.num_kv_groups):      # the whole block list of the row goes through the diff path
+                    k = int(self.num_blocks_cpu[g][row])
+                    if k:
+                        self._bt_diffs[g].append((rid, 0, self.block_tables_cpu[g][row, :k]))
+                if off + n <= cap and len(d_row) < R:
+                    pv[off:off + n] = self.token_ids_cpu[row, :n]
+                    d_row.append(row)
+                    d_cnt.append(n)
+                    d_off.append(off)
+                    off += n
+                else:                       # does not fit the packed upload (very long prompts): pageable row copy
+                    self.dev_tokens[row, :n].copy_(torch.from_numpy(self.token_ids_cpu[row, :n].copy()))
+                self.h2d_bytes += n * 4
+            n_e = len(d_row)
+            if n_e:
+                hv = stg.tok_hdr.numpy()
+                hv[:n_e], hv[n_e:2 * n_e], hv[2 * n_e:3 * n_e], hv[3 * n_e:4 * n_e] = d_row, 0, d_cnt, d_off
+                self.tok_hdr_dev[:4 * n_e].copy_(stg.tok_hdr[:4 * n_e], non_blocking=True)
+                # the step's own input_ids buffer doubles as device scratch: prep_step overwrites it afterwards
+                self.input_ids[:off].copy_(pin[:off], non_blocking=True)
+                th = self.tok_hdr_dev
+                cu.block_table_apply_diffs(self.dev_tokens, th[:n_e], th[n_e:2 * n_e], th[2 * n_e:3 * n_e],
+                                           th[3 * n_e:4 * n_e], self.input_ids)
+        for g in range(self.num_kv_groups):
+            diffs = self._bt_diffs[g]
+            if not diffs:
+                continue
+            iv = stg.diff_ids[g].numpy()
+            d_row, d_start, d_cnt, d_off = [], [], [], []
+            o = 0
+            for rid, start, new in diffs:
+                row = self.req_index.get(rid)
+                if row is None:
+                    continue
+                k = len(new)
+                if len(d_row) >= 2 * R or o + k > iv.shape[0]:   # staging full (pathological): upload the row
+                    tot = int(self.num_blocks_cpu[g][row])
+                    self.dev_block_rows[g][row, :tot].copy_(torch.from_numpy(self.block_tables_cpu[g][row, :tot].copy()))
+                    continue
+                d_row.append(row)
+                d_start.append(start)
+                d_cnt.append(k)
+                d_off.append(o)
+                iv[o:o + k] = new
+                o += k
+            diffs.clear()
+            n = len(d_row)
+            if n == 0:
+                continue
+            hv = stg.diff_hdr[g].numpy()
+            hv[:n], hv[n:2 * n], hv[2 * n:3 * n], hv[3 * n:4 * n] = d_row, d_start, d_cnt, d_off
+            dh, di = self.diff_hdr_dev[g], self.diff_ids_dev[g]
+            dh[:4 * n].copy_(stg.diff_hdr[g][:4 * n], non_blocking=True)
+            di[:o].copy_(stg.diff_ids[g][:o], non_blocking=True)
+            self.h2d_bytes += 16 * n + 4 * o
+            cu.block_table_apply_diffs(self.dev_block_rows[g], dh[:n], dh[n:2 * n], dh[2 * n:3 * n], dh[3 * n:4 * n], di)
+
+    def _prepare_gpu(self, so: SchedulerOutput, stg: _Staging):
+        """O(requests) host work: which rows run, how many tokens each, and the scalars the device expansion needs."""
+        B = len(self.req_ids)
+        get = so.num_scheduled_tokens.get
+        n_sched = np.fromiter((get(r, 0) for r in self.req_ids), dtype=np.int32, count=B)
+        rows = np.nonzero(n_sched)[0].astype(np.int64)
+        ns = n_sched[rows]
+        nb = len(rows)
+        T = int(ns.sum())
+        cu = np.zeros(nb + 1, dtype=np.int32)
+        np.cumsum(ns, out=cu[1:])
+        computed = self.num_computed_cpu[rows]
+        seq_lens = computed + ns
+        produces = seq_lens >= self.num_logical_cpu[rows]
+        m = stg.meta.numpy()
+        m[:nb] = rows
+        m[nb:2 * nb] = computed
+        m[2 * nb:3 * nb] = ns
+        m[3 * nb:4 * nb] = np.where(produces, seq_lens, -1)     # where the sampled id goes in the device token table
+        stg.rows[:nb] = torch.from_numpy(rows)
+        max_q = int(ns.max()) if nb else 0
+        max_s = int(seq_lens.max()) if nb else 0
+        return rows, ns, cu, T, max_q, max_s, 0
+
+    def _h2d_gpu(self, stg: _Staging, nb, T, pad_b, max_s) -> None:
+        cu = self._cu
+        self._flush_gpu_state(stg)
+        self.step_meta[:4 * nb].copy_(stg.meta[:4 * nb], non_blocking=True)
+        self.h2d_bytes += 16 * nb
+        nbk = max(cdiv(max_s, self.vblock), 1)
+        sm = self.step_meta
+        for g in range(self.num_kv_groups):
+            cu.prep_step(sm[:nb], sm[nb:2 * nb], sm[2 * nb:3 * nb], self.dev_tokens, self.dev_block_rows[g], self.input_ids,
+                         self.positions, self.qsl, self.seq_lens, self.slot_mappings[g], self.block_tables[g], nbk,
+                         self.block_size, pad_b=pad_b, write_tokens=(g == 0))
 
     def _make_metadata(self, nb, T, max_q, max_s, decode_only, cpu_qsl=None, cpu_sl=None) -> dict[int, AttentionMetadata]:
         nbk = max(cdiv(max_s, self.vblock), 1)
@@ -797,7 +960,9 @@ class ModelRunner:
                                           or self.drafter is not None or so.grammar_bitmask is not None):
             self._pending.get()
         stg = self._next_staging()
-        rows, ns, cu, T, max_q, max_s, n_fix = self._prepare(so, stg)
+        t_prep = time.perf_counter()
+        gpu_prep = self.gpu_prep and not so.scheduled_spec_decode_tokens
+        rows, ns, cu, T, max_q, max_s, n_fix = (self._prepare_gpu if gpu_prep else self._prepare)(so, stg)
         nb = len(rows)
         has_spec = bool(so.scheduled_spec_decode_tokens)
         decode_only = max_q == 1 and not has_spec
@@ -817,7 +982,11 @@ class ModelRunner:
             if graph is None:
                 pad_b = nb
         pad_t = pad_b if graph is not None else T
-        self._h2d(stg, rows, nb, T, pad_b, pad_t, max_s, n_fix)
+        if gpu_prep:
+            self._h2d_gpu(stg, nb, T, pad_b, max_s)
+        else:
+            self._h2d(stg, rows, nb, T, pad_b, pad_t, max_s, n_fix)
+        self.prep_host_s += time.perf_counter() - t_prep
         cpu_qsl = stg.qsl[:nb + 1] if not self.is_cuda else None
         cpu_sl = stg.seq_lens[:nb] if not self.is_cuda else None
         # which rows produce a token this step (prefill chunk finished / decode)
@@ -909,6 +1078,8 @@ class ModelRunner:
         if self.is_cuda:
             rows_dev = stg.rows[:nb].to(self.device, non_blocking=True)
             self.last_sampled.index_copy_(0, rows_dev, sampled)
+            if gpu_prep:        # the new ids become next step's inputs on the device (no D2H → H2D round trip)
+                self._cu.append_sampled(self.dev_tokens, self.step_meta[:nb], self.step_meta[3 * nb:4 * nb], sampled)
             stg.sampled[:nb].copy_(sampled, non_blocking=True)
             stg.event.record()
             ev = stg.event
@@ -1163,7 +1334,7 @@ class ModelRunner:
         self.input_ids[:T].zero_()
         self.positions[:T].zero_()
         hidden = self._forward(T, {})
-        if not isinstance(hidden, dict):
+        if not isinstance(hidden, dict) and not getattr(self.model, "is_pooling_model", False):
             n = min(self.max_num_reqs, T)
             logits = self.model.compute_logits(hidden[:n])
             logits.float().argmax(-1)
@@ -1171,8 +1342,23 @@ class ModelRunner:
             torch.cuda.synchronize()
 
     # -------------------------------------------------------- CUDA graphs
+    def _attention_kernels_cover_model(self) -> bool:
+        """False when some attention layer would fall back to the plain-PyTorch op (which syncs with the host)."""
+        from vllm_b200.ops import cuda_attention_supported
+        for name, cache in self.kv_caches.items():
+            layer = attention_layers().get(name)
+            if layer is None or cache.dim() != 5:
+                continue
+            if not cuda_attention_supported(cache.shape[4], cache.shape[3], self.dtype, self.kv_vt[self.layer_to_group[name]]):
+                return False
+        return True
+
     def capture_model(self) -> None:
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or getattr(self.model, "is_pooling_model", False):
+            return
+        if not self._attention_kernels_cover_model():
+            logger.warning("attention shapes outside the CUDA kernels' coverage: running eagerly on the reference ops")
+            self.use_cuda_graph = False
             return
         from vllm_b200.worker.cudagraph import DecodeGraph
         sizes = self.vllm_config.compilation_config.capture_sizes(self.max_num_reqs)
