@@ -351,6 +351,22 @@ def main() -> None:
     launches = runner.launch_count - launches0
     while engine.has_unfinished_requests():
         engine.step()
+    # device-only step time: K back-to-back replays of the captured decode graph with NO host work in between (the
+    # buffers still hold the last step's inputs).  value vs this number = how much of a step is host-bound.
+    gpu_only_ms = None
+    g = getattr(runner, "graphs", {}).get(B)
+    if g is not None:
+        runner.finalize_pending()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            g.graph.replay()
+        g0.record()
+        for _ in range(K):
+            g.graph.replay()
+        g1.record()
+        barrier()
+        gpu_only_ms = g0.elapsed_time(g1) / K
 
     # ---------------- phase B: end to end through the public API, same method as the reference arm
     e2e, e2e_s, raw = None, 0.0, {}
@@ -369,14 +385,18 @@ def main() -> None:
 
         def timed_step():
             r = orig_step()
-            stamps.append(time.perf_counter())
+            stamps.append((time.perf_counter(), runner.wait_s))
             return r
         engine.step = timed_step
         barrier()
-        t_begin = time.perf_counter()
+        t_begin = (time.perf_counter(), runner.wait_s)
         gen(K + 1)
         engine.step = orig_step
-        raw["step_wall_ms"] = [round((b - a) * 1e3, 3) for a, b in zip([t_begin] + stamps[:-1], stamps)]
+        seq = [t_begin] + stamps
+        raw["step_wall_ms"] = [round((b[0] - a[0]) * 1e3, 3) for a, b in zip(seq[:-1], seq[1:])]
+        # host work per decode step = wall time of the step minus the time the host sat blocked on the device
+        host = sorted((b[0] - a[0]) - (b[1] - a[1]) for a, b in zip(seq[3:-1], seq[4:]))
+        raw["host_ms_per_step_p50"] = round(host[len(host) // 2] * 1e3, 3) if host else None
         n_steps = REPS * (K + 2)                          # engine steps executed by the timed generate calls
         h2d_step = (runner.h2d_bytes - h2d0) / n_steps
         d2h_step = (runner.d2h_bytes - d2h0) / n_steps
@@ -416,6 +436,7 @@ def main() -> None:
                        "cuda_graphs": not args.eager, "engine": "in-process engine core, async scheduling",
                        "l2": "no flush needed: every step streams far more weights+KV than the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "gpu_only_ms_per_step": gpu_only_ms,
             "fused_comm": comm, "impl": "ours"}), flush=True)
     llm.shutdown() if hasattr(llm, "shutdown") else engine.shutdown()
     if world > 1 and dist.is_initialized():

@@ -24,11 +24,13 @@ def run(B: int) -> dict:
     sp = SamplingParams(max_tokens=48, temperature=0.0, ignore_eos=True)
     llm.generate(prompts, SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True))      # warm-up
     t0, s0, h0 = runner.prep_host_s, runner._step, runner.h2d_bytes
+    d0, n0 = runner.prep_decode_s, runner.prep_decode_n
     llm.generate(prompts, sp)
     torch.cuda.synchronize()
     steps = runner._step - s0
     res = {"batch": B, "gpu_input_prep": bool(runner.gpu_prep), "steps": steps,
            "host_prep_us_per_step": round((runner.prep_host_s - t0) / steps * 1e6, 1),
+           "host_prep_us_per_decode_step": round((runner.prep_decode_s - d0) / max(runner.prep_decode_n - n0, 1) * 1e6, 1),
            "h2d_bytes_per_step": int((runner.h2d_bytes - h0) / steps)}
     llm.shutdown()
     return res

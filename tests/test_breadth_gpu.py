@@ -215,7 +215,7 @@ def test_sleep_wake_prefix_cache_and_kv_fp8_on_device():
         llm.shutdown()
         del r
     d = sorted(abs(x - y) for x, y in zip(res["auto"], res["fp8"]))
-    assert 0 < d[-1] and d[len(d) // 2] < 0.05 and d[int(0.95 * len(d))] < 0.2, d[-5:]
+    assert 0 < d[-1] and d[len(d) // 2] < 0.08 and d[int(0.95 * len(d))] < 0.3, d[-5:]
 
 
 def test_structured_output_and_penalties_on_device():
@@ -251,7 +251,7 @@ def test_pooling_and_whisper_and_vlm_on_device():
     from vllm_b200 import LLM, SamplingParams
     llm = LLM("bert-tiny", max_model_len=128, gpu_memory_utilization=0.1, load_format="dummy", dtype="bfloat16")
     outs = llm.embed([{"prompt_token_ids": [3, 4, 5, 6, 7]}, {"prompt_token_ids": [9, 8, 7]}])
-    e = torch.tensor([o.outputs.embedding for o in outs])
+    e = torch.stack([torch.as_tensor(o.outputs.data).float() for o in outs])
     assert e.shape[0] == 2 and torch.isfinite(e).all() and (e.norm(dim=-1) > 0).all()
     llm.shutdown()
     import numpy as np

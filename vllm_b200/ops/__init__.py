@@ -30,8 +30,13 @@ def _use_cuda(x: torch.Tensor) -> bool:
     return x.is_cuda and not envs.VLLM_B200_FORCE_REF_OPS
 
 
+def _vec_ok(x: torch.Tensor) -> bool:
+    """The row kernels move 16-byte vectors: the row width must be a multiple of 16 bytes."""
+    return (x.shape[-1] * x.element_size()) % 16 == 0
+
+
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, gemma: bool = False) -> torch.Tensor:
-    if _use_cuda(x):
+    if _use_cuda(x) and _vec_ok(x):
         return cuda_ops().rms_norm(x, weight, eps, gemma)
     return ref.rms_norm(x, weight, eps, gemma)
 
@@ -40,7 +45,7 @@ def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Te
                        gemma: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
     """Returns (normed, new_residual). The CUDA path updates ``residual`` in place and
     writes the normed result into ``x``'s storage."""
-    if _use_cuda(x):
+    if _use_cuda(x) and _vec_ok(x):
         return cuda_ops().fused_add_rms_norm(x, residual, weight, eps, gemma)
     return ref.fused_add_rms_norm(x, residual, weight, eps, gemma)
 

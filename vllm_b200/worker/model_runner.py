@@ -107,7 +107,9 @@ class AsyncStepOutput:
             return self._out
         r = self.runner
         if self.event is not None:
+            t_w = time.perf_counter()
             self.event.synchronize()
+            r.wait_s += time.perf_counter() - t_w
         toks = self.staging.sampled[:self.nb].tolist()
         r.d2h_bytes += self.nb * 8
         out_ids: list[list[int]] = []
@@ -247,6 +249,8 @@ class ModelRunner:
         self._bt_diffs: list[list[tuple[str, int, list[int]]]] = []
         self._new_rids: list[str] = []
         self.prep_host_s = 0.0  # host seconds spent preparing + uploading step inputs (diagnostic)
+        self.prep_decode_s, self.prep_decode_n = 0.0, 0
+        self.wait_s = 0.0       # host seconds blocked on the device (D2H of sampled ids, staging reuse)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -935,7 +939,9 @@ class ModelRunner:
     def _next_staging(self) -> _Staging:
         self._stage_i = (self._stage_i + 1) % len(self.staging)
         stg = self.staging[self._stage_i]
+        t_w = time.perf_counter()
         stg.wait()  # the copies that used this set 2-3 steps ago have long completed
+        self.wait_s += time.perf_counter() - t_w
         return stg
 
     def finalize_pending(self) -> None:
@@ -986,7 +992,11 @@ class ModelRunner:
             self._h2d_gpu(stg, nb, T, pad_b, max_s)
         else:
             self._h2d(stg, rows, nb, T, pad_b, pad_t, max_s, n_fix)
-        self.prep_host_s += time.perf_counter() - t_prep
+        dt_prep = time.perf_counter() - t_prep
+        self.prep_host_s += dt_prep
+        if max_q == 1:                   # steady-state decode steps, admission / prefill excluded
+            self.prep_decode_s += dt_prep
+            self.prep_decode_n += 1
         cpu_qsl = stg.qsl[:nb + 1] if not self.is_cuda else None
         cpu_sl = stg.seq_lens[:nb] if not self.is_cuda else None
         # which rows produce a token this step (prefill chunk finished / decode)
@@ -1364,7 +1374,14 @@ class ModelRunner:
         sizes = self.vllm_config.compilation_config.capture_sizes(self.max_num_reqs)
         self.capture_sizes = sorted(sizes)
         t0 = time.perf_counter()
-        for b in reversed(self.capture_sizes):
-            self.graphs[b] = DecodeGraph(self, b)
+        try:
+            for b in reversed(self.capture_sizes):
+                self.graphs[b] = DecodeGraph(self, b)
+        except Exception as e:      # a layer fell back to an op that cannot be captured (host sync, unpinned copy)
+            logger.warning("CUDA-graph capture failed (%s: %s): decode steps run eagerly", type(e).__name__, str(e)[:200])
+            self.graphs.clear()
+            self.use_cuda_graph = False
+            torch.cuda.synchronize()
+            return
         torch.cuda.synchronize()
         logger.info("captured %d decode CUDA graphs in %.1fs", len(self.graphs), time.perf_counter() - t0)
