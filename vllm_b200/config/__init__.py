@@ -228,9 +228,17 @@ class CompilationConfig(_ConfigBase):
     decode step is a fixed kernel sequence captured directly.
     Modes mirror the reference's CUDAGraphMode (config/compilation.py:53-64)."""
 
-    cudagraph_mode: str = "FULL_DECODE_ONLY"  # NONE|FULL_DECODE_ONLY|FULL
+    cudagraph_mode: str = "FULL_DECODE_ONLY"  # NONE|FULL_DECODE_ONLY|FULL  (FULL: mixed prefill+decode buckets too)
     cudagraph_capture_sizes: Optional[list[int]] = None
     max_cudagraph_capture_size: int = 512
+    # token buckets of the mixed-batch graphs (mode FULL); the request bucket of each is min(tokens, max_num_seqs, 256)
+    mixed_capture_sizes: Optional[list[int]] = None
+
+    def mixed_sizes(self, max_num_batched_tokens: int) -> list[int]:
+        if self.cudagraph_mode not in ("FULL", "FULL_AND_PIECEWISE"):
+            return []
+        sizes = self.mixed_capture_sizes if self.mixed_capture_sizes is not None else [64, 128, 256, 512]
+        return sorted({s for s in sizes if s <= max_num_batched_tokens})
 
     def capture_sizes(self, max_num_seqs: int) -> list[int]:
         if self.cudagraph_capture_sizes is not None:

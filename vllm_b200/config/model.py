@@ -39,6 +39,14 @@ PRESETS: dict[str, dict[str, Any]] = {
         head_dim=128, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0,
         hidden_act="silu", bos_token_id=128000, eos_token_id=128001, torch_dtype="bfloat16",
         tie_word_embeddings=False, attention_bias=False, mlp_bias=False),
+    # one rank's share of Llama-3-8B under TP=8 (4 of 32 heads, 1 of 8 KV heads, 1/8 of the MLP and of the vocabulary):
+    # lets a single GPU run — and ncu profile — exactly the kernel shapes of a TP8 decode step, without the collectives
+    "llama-3-8b-tp8-shard": dict(
+        architectures=["LlamaForCausalLM"], model_type="llama", vocab_size=16032, hidden_size=4096,
+        intermediate_size=1792, num_hidden_layers=32, num_attention_heads=4, num_key_value_heads=1,
+        head_dim=128, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0,
+        hidden_act="silu", bos_token_id=0, eos_token_id=1, torch_dtype="bfloat16",
+        tie_word_embeddings=False, attention_bias=False, mlp_bias=False),
     "llama-3-70b": dict(
         architectures=["LlamaForCausalLM"], model_type="llama", vocab_size=128256, hidden_size=8192,
         intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64, num_key_value_heads=8,

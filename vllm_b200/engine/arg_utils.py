@@ -93,6 +93,7 @@ class EngineArgs:
     # compilation / graphs
     cudagraph_mode: str = "FULL_DECODE_ONLY"
     cudagraph_capture_sizes: Optional[list[int]] = None
+    mixed_capture_sizes: Optional[list[int]] = None
     max_cudagraph_capture_size: int = 512
     # observability
     disable_log_stats: bool = False
@@ -173,7 +174,7 @@ class EngineArgs:
                                                               reasoning_parser=self.reasoning_parser),
             observability_config=ObservabilityConfig(otlp_traces_endpoint=self.otlp_traces_endpoint),
             compilation_config=CompilationConfig(self.cudagraph_mode, self.cudagraph_capture_sizes,
-                                                 self.max_cudagraph_capture_size),
+                                                 self.max_cudagraph_capture_size, self.mixed_capture_sizes),
             kv_transfer_config=kvt, kv_events_config=kve,
             profiler_config=ProfilerConfig(self.profiler, self.torch_profiler_dir),
             fault_tolerance_config=FaultToleranceConfig(self.enable_fault_tolerance),

@@ -59,6 +59,9 @@ environment_variables: dict[str, Callable[[], Any]] = {
     "VLLM_B200_GEMM": _str("VLLM_B200_GEMM", "auto"),  # auto|cublas|tcgen05
     # decode: pull the next few-tile GEMM's weights into L2 on a side stream while the HBM-bound attention kernel runs
     "VLLM_B200_L2_PREFETCH": _bool("VLLM_B200_L2_PREFETCH", False),
+    # decode steps: pull up to this many MiB of the NEXT layer's weights into L2 on a side stream while the current layer
+    # runs (0 = off).  Pays when a layer's kernels are latency-bound and HBM is mostly idle (high TP degree, small models)
+    "VLLM_B200_LAYER_PREFETCH_MB": lambda: int(os.environ.get("VLLM_B200_LAYER_PREFETCH_MB", "0")),
     # device-resident token / block tables + on-device expansion of the step inputs (csrc/input_prep.cu)
     "VLLM_B200_GPU_INPUT_PREP": _bool("VLLM_B200_GPU_INPUT_PREP", True),
     "VLLM_B200_FUSED_MOE": _bool("VLLM_B200_FUSED_MOE", True),   # MoE combine + reduce in the w2 grouped-GEMM epilogue

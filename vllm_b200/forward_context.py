@@ -29,6 +29,9 @@ class AttentionMetadata:
     decode_only: bool = False      # every request has exactly one new token
     kv_vt: bool = False            # tensor-core cache layout: V pages stored transposed [D, block_size]
     causal: bool = True
+    # mixed-batch CUDA graphs: the varlen attention grid is sized from (tokens, requests) of the BUCKET and every CTA finds
+    # its (request, query tile) from query_start_loc on the device (csrc/attention_tc.cu flat schedule)
+    flat: bool = False
     # decode split-KV workspace (allocated once by the runner)
     workspace: Any = None
     num_splits: int = 0

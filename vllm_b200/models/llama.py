@@ -152,6 +152,31 @@ class LlamaModel(nn.Module):
     def _make_layer(self, cfg, mc, dtype, quant_config, prefix, idx):
         return LlamaDecoderLayer(cfg, mc, dtype, quant_config, prefix, idx, self.gemma)
 
+    @property
+    def _layer_ahead(self):
+        from vllm_b200 import envs
+        mb = envs.VLLM_B200_LAYER_PREFETCH_MB
+        return mb if mb > 0 else None
+
+    def _prefetch_layer(self, i: int) -> None:
+        """Start pulling layer ``i``'s weight matrices into L2 (side stream, csrc/cache_ops.cu::l2_prefetch_kernel) in the
+        order its kernels will read them, up to the configured budget."""
+        from vllm_b200 import envs
+        from vllm_b200.ops import cuda_ops
+        cu = cuda_ops()
+        budget = envs.VLLM_B200_LAYER_PREFETCH_MB << 20
+        ws = self._layer_weights.get(i) if hasattr(self, "_layer_weights") else None
+        if ws is None:
+            if not hasattr(self, "_layer_weights"):
+                self._layer_weights = {}
+            ws = self._layer_weights[i] = [p for _, p in self.layers[i].named_parameters() if p.dim() >= 2 and p.is_cuda]
+        for w in ws:
+            nbytes = w.numel() * w.element_size()
+            if nbytes > budget:
+                break
+            cu.l2_prefetch_async(w)
+            budget -= nbytes
+
     def embed_input_ids(self, input_ids: torch.Tensor) -> torch.Tensor:
         h = self.embed_tokens(input_ids)
         return h * self.embed_scale if self.embed_scale != 1.0 else h
@@ -169,8 +194,11 @@ class LlamaModel(nn.Module):
         fctx = get_forward_context_or_none()
         taps = fctx.extra.get("aux_layers") if fctx is not None else None     # EAGLE-3: residual streams of a few layers
         aux = [] if taps else None
+        ahead = self._layer_ahead if hidden.is_cuda and hidden.shape[0] <= 256 else None
         for i, layer in enumerate(self.layers):
             nxt = self.layers[i + 1].input_layernorm if i + 1 < n else self.norm
+            if ahead is not None and i + 1 < n:
+                self._prefetch_layer(i + 1)
             hidden, residual = layer(positions, hidden, residual, nxt)
             if aux is not None and (self.start + i) in taps:
                 aux.append(residual)

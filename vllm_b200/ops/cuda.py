@@ -50,8 +50,8 @@ _paged_attention = _sig("vb_paged_attention", _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                         _i64, _i64, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp)
 _paged_attention_ex = _sig("vb_paged_attention_ex", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                            _i64, _i64, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp, _vp, _i, _vp)
-_fmha_tc = _sig("vb_fmha_tc", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i,
-                _i, _i, _f, _i, _i, _vp)
+_fmha_tc = _sig("vb_fmha_tc2", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i,
+                _i, _i, _f, _i, _i, _i, _vp)
 _fmha_tc_decode = _sig("vb_fmha_tc_decode", _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i,
                        _i, _i, _f, _i, _vp)
 _merge_states = _sig("vb_merge_attn_states", _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp)
@@ -248,7 +248,8 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
     T, Hq, D = q.shape
     Hkv, BS = kv_cache.shape[2], kv_cache.shape[3]
     if out is None:
-        out = torch.empty((T, Hq, D), dtype=q.dtype, device=q.device)
+        # (bucket padding rows are written by no CTA: keep them finite for the row-wise layers that follow)
+        out = (torch.zeros if md.flat else torch.empty)((T, Hq, D), dtype=q.dtype, device=q.device)
     lse = torch.empty((T, Hq), dtype=torch.float32, device=q.device) if return_lse else None
     bt = md.block_table
     if md.kv_vt:
@@ -272,7 +273,7 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
                       None if decode else md.query_start_loc.data_ptr(), out.data_ptr(),
                       _p(ws.part_out) if ws else None, _p(ws.part_lse) if ws else None, _p(lse), md.num_reqs, T,
                       md.max_query_len, Hq, Hkv, q.stride(0), out.stride(0), bt.stride(0), splits,
-                      sliding_window or 0, scale, int(causal), _DT[q.dtype], _st())
+                      sliding_window or 0, scale, int(causal), int(md.flat and not decode), _DT[q.dtype], _st())
         _check(rc, f"fmha_tc(G={Hq // Hkv})", 2 if splits > 1 else 1)
         return (out, lse) if return_lse else out
     if alibi_slopes is not None:

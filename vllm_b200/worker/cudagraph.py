@@ -72,4 +72,66 @@ class DecodeGraph:
         self.seeds.copy_(stg.seeds[:b], non_blocking=True)
         self.steps.copy_(stg.steps[:b], non_blocking=True)
         self.graph.replay()
+        self.replays = getattr(self, "replays", 0) + 1
         return self.out
+
+
+class MixedGraph(DecodeGraph):
+    """Full-step graph for a MIXED batch (prefill chunks + decodes) of at most ``t`` tokens in at most ``b`` requests.
+
+    Reference: vllm/v1/cudagraph_dispatcher.py (padded buckets keyed by token count), config/compilation.py:53-64
+    (FULL / FULL_AND_PIECEWISE).  The reference captures the token-wise pieces and leaves attention eager; here the
+    whole step is one graph because nothing in it depends on the batch composition on the host side: the input expansion
+    runs on the device (csrc/input_prep.cu: empty padding requests, inert padding tokens), the varlen attention kernel
+    derives its (request, query tile) schedule from ``query_start_loc`` on the device (``AttentionMetadata.flat``), and
+    the rows that feed the LM head are gathered with device-side indices."""
+
+    def __init__(self, runner, t: int, b: int) -> None:
+        self.t = t
+        self.runner = runner
+        self.b = b
+        dev = runner.device
+        self.temperature = torch.zeros(b, dtype=torch.float32, device=dev)
+        self.seeds = torch.zeros(b, dtype=torch.int64, device=dev)
+        self.steps = torch.zeros(b, dtype=torch.int32, device=dev)
+        self.out = torch.zeros(b, dtype=torch.int64, device=dev)
+        # placeholder inputs for warm-up / capture: one request of t tokens at positions 0..t-1 writing nowhere
+        runner.input_ids[:t].zero_()
+        runner.positions[:t].copy_(torch.arange(t, dtype=torch.int64, device=dev))
+        runner.seq_lens[:b].fill_(1)
+        runner.seq_lens[:1].fill_(t)
+        runner.qsl[:b + 1].fill_(t)
+        runner.qsl[:1].zero_()
+        for g in range(runner.num_kv_groups):
+            runner.slot_mappings[g][:t].fill_(-1)
+            runner.block_tables[g][:b].zero_()
+        self.md = runner._make_metadata(b, t, t, runner.max_model_len, False)
+        for m in self.md.values():
+            m.flat = True
+        self.graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if runner.graph_pool is None:
+            runner.graph_pool = torch.cuda.graph_pool_handle()
+        n0 = cuda_ops().LAUNCHES
+        with torch.cuda.graph(self.graph, pool=runner.graph_pool):
+            self._body()
+        self.num_launches = cuda_ops().LAUNCHES - n0
+
+    def _body(self) -> None:
+        r, b, t = self.runner, self.b, self.t
+        ctx = ForwardContext(attn_metadata=self.md, kv_caches=r.kv_caches, layer_to_group=r.layer_to_group, num_tokens=t)
+        with set_forward_context(ctx):
+            hidden = r.model(r.input_ids[:t], r.positions[:t], None)
+        # last scheduled token of every request (empty padding requests resolve to the batch's last real token)
+        last = hidden.index_select(0, (r.qsl[1:b + 1] - 1).clamp_min(0).to(torch.int64))
+        fast = getattr(r.model, "sample_candidates", None)
+        if fast is not None and fast(last, self.temperature, self.seeds, self.steps, self.out):
+            return
+        logits = r.model.compute_logits(last)
+        cuda_ops().fused_sample(logits, self.temperature, self.seeds, self.steps, self.out)

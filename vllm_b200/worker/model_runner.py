@@ -235,6 +235,7 @@ class ModelRunner:
         self._stage_i = 0
         self._pending: Optional[AsyncStepOutput] = None
         self.graphs: dict[int, Any] = {}
+        self.mixed_graphs: dict[int, Any] = {}     # token bucket → MixedGraph (cudagraph_mode FULL)
         self.graph_pool = None
         self.use_cuda_graph = (self.is_cuda and not self.mc.enforce_eager
                                and vllm_config.compilation_config.cudagraph_mode != "NONE" and self.pcp == 1)
@@ -672,7 +673,7 @@ class ModelRunner:
         max_s = int(seq_lens.max()) if nb else 0
         return rows, ns, cu, T, max_q, max_s, 0
 
-    def _h2d_gpu(self, stg: _Staging, nb, T, pad_b, max_s) -> None:
+    def _h2d_gpu(self, stg: _Staging, nb, T, pad_b, max_s, pad_t: int = 0) -> None:
         cu = self._cu
         self._flush_gpu_state(stg)
         self.step_meta[:4 * nb].copy_(stg.meta[:4 * nb], non_blocking=True)
@@ -682,7 +683,7 @@ class ModelRunner:
         for g in range(self.num_kv_groups):
             cu.prep_step(sm[:nb], sm[nb:2 * nb], sm[2 * nb:3 * nb], self.dev_tokens, self.dev_block_rows[g], self.input_ids,
                          self.positions, self.qsl, self.seq_lens, self.slot_mappings[g], self.block_tables[g], nbk,
-                         self.block_size, pad_b=pad_b, write_tokens=(g == 0))
+                         self.block_size, pad_b=pad_b, write_tokens=(g == 0), pad_t=pad_t)
 
     def _make_metadata(self, nb, T, max_q, max_s, decode_only, cpu_qsl=None, cpu_sl=None) -> dict[int, AttentionMetadata]:
         nbk = max(cdiv(max_s, self.vblock), 1)
@@ -988,8 +989,20 @@ class ModelRunner:
             if graph is None:
                 pad_b = nb
         pad_t = pad_b if graph is not None else T
+        mixed = None
+        if (graph is None and not decode_only and self.mixed_graphs and gpu_prep and simple and no_filter and not kv_meta
+                and lora_batch is None and not has_spec):
+            for tb in sorted(self.mixed_graphs):
+                if tb >= T:
+                    if nb <= self.mixed_graphs[tb].b:
+                        mixed = self.mixed_graphs[tb]
+                    break
+            if mixed is not None and any(self.states[self.req_ids[r]].mm_features for r in rows):
+                mixed = None
+        if mixed is not None:
+            graph, pad_b, pad_t = mixed, mixed.b, mixed.t
         if gpu_prep:
-            self._h2d_gpu(stg, nb, T, pad_b, max_s)
+            self._h2d_gpu(stg, nb, T, pad_b, max_s, pad_t if mixed is not None else 0)
         else:
             self._h2d(stg, rows, nb, T, pad_b, pad_t, max_s, n_fix)
         dt_prep = time.perf_counter() - t_prep
@@ -1371,7 +1384,7 @@ class ModelRunner:
             self.use_cuda_graph = False
             return
         from vllm_b200.worker.cudagraph import DecodeGraph
-        sizes = self.vllm_config.compilation_config.capture_sizes(self.max_num_reqs)
+        sizes = [b for b in self.vllm_config.compilation_config.capture_sizes(self.max_num_reqs) if b <= self.max_num_reqs]
         self.capture_sizes = sorted(sizes)
         t0 = time.perf_counter()
         try:
@@ -1385,3 +1398,24 @@ class ModelRunner:
             return
         torch.cuda.synchronize()
         logger.info("captured %d decode CUDA graphs in %.1fs", len(self.graphs), time.perf_counter() - t0)
+        self._capture_mixed()
+
+    def _capture_mixed(self) -> None:
+        """Mixed prefill+decode buckets (cudagraph_mode FULL): needs the device-side input expansion and the tensor-core
+        attention layout on every KV group (the flat varlen schedule lives in that kernel)."""
+        sizes = self.vllm_config.compilation_config.mixed_sizes(self.max_num_tokens)
+        if not sizes or not self.gpu_prep or not all(self.kv_vt) or self.has_mm or self.drafter is not None:
+            return
+        from vllm_b200.worker.cudagraph import MixedGraph
+        t0 = time.perf_counter()
+        try:
+            for t in reversed(sizes):
+                self.mixed_graphs[t] = MixedGraph(self, t, min(t, self.max_num_reqs, 256))
+        except Exception as e:
+            logger.warning("mixed-batch CUDA-graph capture failed (%s: %s): mixed steps run eagerly", type(e).__name__,
+                           str(e)[:200])
+            self.mixed_graphs.clear()
+        torch.cuda.synchronize()
+        if self.mixed_graphs:
+            logger.info("captured %d mixed-batch CUDA graphs %s in %.1fs", len(self.mixed_graphs),
+                        sorted(self.mixed_graphs), time.perf_counter() - t0)
