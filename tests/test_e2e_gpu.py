@@ -113,7 +113,8 @@ def test_moe_and_mla_models_cuda_vs_ref(model):
     assert diffs[int(0.9 * len(diffs))] < 0.15 and diffs[len(diffs) // 2] < 0.05, (diffs[len(diffs) // 2], diffs[-5:])
 
 
-@pytest.mark.parametrize("model,quant", [("deepseek-small", "fp8_block"), ("llama-small", "fp8"), ("mixtral-small", "fp8_block")])
+@pytest.mark.parametrize("model,quant", [("deepseek-small", "fp8_block"), ("llama-small", "fp8"), ("mixtral-small", "fp8_block"),
+                                         ("llama-small", "nvfp4"), ("llama-small", "mxfp4")])
 def test_fp8_models_run_on_own_kernels_and_track_bf16(model, quant, monkeypatch):
     """Online-quantised fp8 runs (block-scaled tcgen05 f8f6f4 GEMMs, fused quantisers, grouped fp8 experts, MLA kernel)
     stay within fp8 accuracy of the bf16 run of the same weights: teacher-forced prompt logprobs."""
@@ -140,7 +141,8 @@ def test_fp8_models_run_on_own_kernels_and_track_bf16(model, quant, monkeypatch)
             (ta, la), = [(t, l.logprob) for t, l in pa.items() if l.rank is not None][:1]
             diffs.append(abs(la - pb[ta].logprob))
     diffs.sort()
-    assert diffs[len(diffs) // 2] < 0.12 and diffs[int(0.9 * len(diffs))] < 0.6, (diffs[len(diffs) // 2], diffs[-5:])
+    tol = (0.12, 0.6) if "fp8" in quant else (0.5, 1.5)          # 4-bit weights: coarser, still tracking
+    assert diffs[len(diffs) // 2] < tol[0] and diffs[int(0.9 * len(diffs))] < tol[1], (diffs[len(diffs) // 2], diffs[-5:])
 
 
 def test_smoke_entry():

@@ -608,3 +608,32 @@ def test_gpu_input_prep_kernels_match_numpy_expansion():
     tt2 = token_table.cpu().numpy()
     for b in range(20):
         assert tt2[rows[b], nc[b] + ns[b]] == int(sampled[b])
+
+
+@pytest.mark.parametrize("fmt", ["nvfp4", "mxfp4"])
+@pytest.mark.parametrize("M,N,K", [(1, 256, 512), (7, 384, 1024), (64, 6144, 4096), (64, 4096, 14336), (128, 1000, 2048)])
+def test_w4a16_fp4_gemm(fmt, M, N, K):
+    """Weight-only FP4 decode GEMM (csrc/gemm_w4.cu: bulk-copied tile-major codes, PRMT expansion, tcgen05 kind::f16) vs
+    x @ dequant(W)^T in fp32.  Every product of an e2m1 code and its block scale is exact in bf16, so the only
+    difference to the reference is fp32 accumulation order."""
+    torch.manual_seed(80 + M)
+    dt = torch.bfloat16
+    w = torch.randn(N, K, device="cuda") * 0.05
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
+    bias = (torch.randn(N, device="cuda") * 0.1).to(dt) if N % 3 == 0 else None
+    if fmt == "nvfp4":
+        codes, sc, g = ref.fp4_quant(w, 16)
+        wd = ref.fp4_dequant(codes, sc, g, 16)
+    else:
+        codes, sc = ref.mxfp4_quant(w)
+        g = 1.0
+        wd = ref.mxfp4_dequant(codes, sc)
+    tiled = cu().pack_w4_tiles(codes, sc, fmt)
+    y = cu().gemm_w4(x, tiled, N, g, fmt, bias)
+    exp = x.float() @ wd.t() + (bias.float() if bias is not None else 0.0)
+    err = (y.float() - exp).abs().max().item()
+    assert err <= 2e-2 * exp.abs().max().item() + 1e-3, (err, exp.abs().max().item())
+    # fp16 activations take the fp16 expansion tables
+    if fmt == "nvfp4" and M == 7:
+        y16 = cu().gemm_w4(x.half(), tiled, N, g, fmt, bias.half() if bias is not None else None)
+        assert (y16.float() - exp).abs().max().item() <= 2e-2 * exp.abs().max().item() + 1e-2

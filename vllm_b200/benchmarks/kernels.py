@@ -22,8 +22,10 @@ _FLUSH = None
 def _flush():
     global _FLUSH
     if _FLUSH is None:
-        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    _FLUSH.add_(1)
+        _FLUSH = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
+    # READ a buffer twice the size of L2: the victims are replaced by clean lines.  (A write-based flush leaves 126 MB of
+    # dirty lines whose write-back is then charged to the kernel under test: measured +40 % on TMA first-byte latency.)
+    _FLUSH.view(torch.int64).sum()
 
 
 def timeit(fn, iters: int = 20, warmup: int = 5) -> float:
@@ -79,6 +81,35 @@ def bench_gemm(rows: list) -> None:
         t_cb = timeit(lambda: torch.matmul(x, w.t()))
         tb = N * K * 2 / t_sk / 1e6
         rows.append(f"| qkv M={M} {N} x {K} | {t_sk:.1f} | {t_tc:.1f} | {t_cb:.1f} | {tb:.2f} | {tb * 1e3 / peak:.0%} |")
+
+
+def bench_w4(rows: list) -> None:
+    """Weight-only FP4 decode GEMM (csrc/gemm_w4.cu) against the bf16 kernel on the same shapes."""
+    from vllm_b200.ops import cuda as cu
+    from vllm_b200.ops import ref
+    shapes = [("8B qkv", 6144, 4096), ("8B o", 4096, 4096), ("8B gate_up", 28672, 4096), ("8B down", 4096, 14336),
+              ("lm_head", 128256, 4096), ("70B/TP8 gate_up", 7168, 8192), ("70B/TP8 down", 8192, 3584)]
+    peak = hbm_gbs()
+    rows.append("\n## weight-only FP4 (W4A16) decode GEMM, M = 64 tokens (µs, L2 flushed)\n")
+    rows.append("| shape (N x K) | bf16 tile kernel | NVFP4 (e4m3 / 16) | MXFP4 (e8m0 / 32) | NVFP4 TB/s of packed bytes | of measured HBM | speed-up vs bf16 |")
+    rows.append("|---|---|---|---|---|---|---|")
+    for name, N, K in shapes:
+        x = torch.randn(64, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02
+        t_bf = timeit(lambda: cu.gemm_tc(x, w))
+        # quantise in row chunks (the reference quantiser materialises an [R, C, 8] distance tensor)
+        parts = [ref.fp4_quant(w[i:i + 4096].float(), 16) for i in range(0, N, 4096)]
+        g = max(p_[2] for p_ in parts)
+        codes = torch.cat([p_[0] for p_ in parts]); sc = torch.cat([p_[1] for p_ in parts])
+        tiled = cu.pack_w4_tiles(codes, sc, "nvfp4")
+        t_nv = timeit(lambda: cu.gemm_w4(x, tiled, N, g, "nvfp4"))
+        parts = [ref.mxfp4_quant(w[i:i + 4096].float()) for i in range(0, N, 4096)]
+        tiled_mx = cu.pack_w4_tiles(torch.cat([p_[0] for p_ in parts]), torch.cat([p_[1] for p_ in parts]), "mxfp4")
+        t_mx = timeit(lambda: cu.gemm_w4(x, tiled_mx, N, 1.0, "mxfp4"))
+        tb = tiled.numel() / t_nv / 1e6
+        rows.append(f"| {name} {N} x {K} | {t_bf:.1f} | {t_nv:.1f} | {t_mx:.1f} | {tb:.2f} | {tb * 1e3 / peak:.0%} | {t_bf / t_nv:.2f}x |")
+        del w, codes, sc, tiled, tiled_mx, parts
+        torch.cuda.empty_cache()
 
 
 def bench_fp8(rows: list) -> None:
@@ -227,10 +258,10 @@ def bench_quant(rows: list) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/kernels_bench.md")
-    ap.add_argument("--only", default="gemm,fp8,attn,mla,quant")
+    ap.add_argument("--only", default="gemm,w4,fp8,attn,mla,quant")
     args = ap.parse_args()
     rows = [f"# Kernel micro-benchmarks on {torch.cuda.get_device_name()} (measured HBM copy {hbm_gbs():.0f} GB/s)"]
-    for name, fn in (("gemm", bench_gemm), ("fp8", bench_fp8), ("attn", bench_attn), ("mla", bench_mla),
+    for name, fn in (("gemm", bench_gemm), ("w4", bench_w4), ("fp8", bench_fp8), ("attn", bench_attn), ("mla", bench_mla),
                      ("quant", bench_quant)):
         if name in args.only.split(","):
             try:

@@ -198,7 +198,7 @@ class BlockFloatLinearMethod(LinearMethod):
     (reference: quantization/ online modes nvfp4 / mxfp8, modelopt.py, mxfp8 utils)."""
 
     def __init__(self, fmt: str) -> None:
-        assert fmt in ("nvfp4", "mxfp8")
+        assert fmt in ("nvfp4", "mxfp8", "mxfp4")
         self.fmt = fmt
 
     def create_weights(self, layer, in_per_rank, out_per_rank, dtype) -> None:
@@ -218,6 +218,15 @@ class BlockFloatLinearMethod(LinearMethod):
             layer.weight_packed = nn.Parameter(packed, requires_grad=False)
             layer.weight_scale = nn.Parameter(bscale, requires_grad=False)
             layer.weight_global_scale = float(gscale)
+        elif self.fmt == "mxfp4":
+            K = w.shape[1]
+            pad = (-K) % 32
+            if pad:
+                w = torch.nn.functional.pad(w, (0, pad))
+            packed, sc = ref.mxfp4_quant(w)
+            layer.weight_packed = nn.Parameter(packed, requires_grad=False)
+            layer.weight_scale = nn.Parameter(sc, requires_grad=False)
+            layer.weight_global_scale = 1.0
         else:
             K = w.shape[1]
             pad = (-K) % 32
@@ -229,11 +238,20 @@ class BlockFloatLinearMethod(LinearMethod):
             layer.weight_packed = nn.Parameter(q.reshape(w.shape[0], -1), requires_grad=False)
             layer.weight_scale = nn.Parameter((e + 127).to(torch.uint8), requires_grad=False)          # e8m0
         layer.in_features = K
+        layer.out_features = w.shape[0]
         layer.weight = nn.Parameter(torch.empty(0, dtype=layer.out_dtype), requires_grad=False)       # drop the bf16 copy
+        # decode path: tile-major copy of the codes + block scales for the W4A16 tcgen05 kernel (csrc/gemm_w4.cu), which
+        # streams the 4-bit weights and expands them in shared memory (prefill keeps the expanded-weight GEMM)
+        layer.weight_tiled = None
+        if self.fmt in ("nvfp4", "mxfp4") and layer.weight_packed.is_cuda and layer.weight_packed.shape[1] * 2 % 64 == 0:
+            from vllm_b200.ops import cuda_ops
+            layer.weight_tiled = cuda_ops().pack_w4_tiles(layer.weight_packed, layer.weight_scale, self.fmt)
 
     def _expand(self, layer) -> torch.Tensor:
         if self.fmt == "nvfp4":
             w = ref.fp4_dequant(layer.weight_packed, layer.weight_scale, layer.weight_global_scale, 16)
+        elif self.fmt == "mxfp4":
+            w = ref.mxfp4_dequant(layer.weight_packed, layer.weight_scale)
         else:
             q = layer.weight_packed.float()
             sc = torch.exp2(layer.weight_scale.float() - 127.0).repeat_interleave(32, dim=1)
@@ -243,6 +261,14 @@ class BlockFloatLinearMethod(LinearMethod):
     def apply(self, layer, x, bias):
         if getattr(layer, "weight_packed", None) is None:
             return ops.linear(x, layer.weight, bias)
+        tiled = getattr(layer, "weight_tiled", None)
+        if tiled is not None and not ops.envs.VLLM_B200_FORCE_REF_OPS:
+            x2 = x.reshape(-1, x.shape[-1])
+            Kp = layer.weight_packed.shape[1] * 2
+            cu = ops.cuda_ops()
+            if x2.shape[1] == Kp and cu.gemm_w4_ok(x2, Kp):
+                y = cu.gemm_w4(x2, tiled, layer.out_features, layer.weight_global_scale, self.fmt, bias)
+                return y.view(*x.shape[:-1], layer.out_features)
         return ops.linear(x, self._expand(layer), bias)
 
 
@@ -271,7 +297,7 @@ def _compressed_tensors_scheme(hq: dict) -> dict:
 
 QUANTIZATION_METHODS = ("fp8", "fp8_block", "fbgemm_fp8", "modelopt", "deepseek_v3_fp8", "awq", "gptq", "awq_marlin",
                         "gptq_marlin", "nvfp4", "modelopt_fp4", "int8", "w8a8", "compressed-tensors", "compressed_tensors",
-                        "bitsandbytes", "mxfp8", "nvfp4_online")
+                        "bitsandbytes", "mxfp8", "nvfp4_online", "mxfp4")
 
 
 def get_quant_config(model_config) -> Optional[QuantConfig]:
@@ -290,8 +316,8 @@ def get_quant_config(model_config) -> Optional[QuantConfig]:
         return Fp8Config(online=not hq, per_channel=(q == "fbgemm_fp8" or hq.get("strategy") == "channel"))
     if q in ("int8", "w8a8"):
         return Int8Config(online=not hq)
-    if q == "mxfp8" or (q in ("nvfp4", "nvfp4_online") and not hq):
-        return BlockFloatConfig("mxfp8" if q == "mxfp8" else "nvfp4")         # online: quantise the loaded bf16 weights
+    if q in ("mxfp8", "mxfp4") or (q in ("nvfp4", "nvfp4_online") and not hq):
+        return BlockFloatConfig(q if q in ("mxfp8", "mxfp4") else "nvfp4")    # online: quantise the loaded bf16 weights
     if q in ("compressed-tensors", "compressed_tensors"):
         sc = _compressed_tensors_scheme(hq)
         ignored = tuple(i.replace("re:", "") for i in (hq.get("ignore") or ["lm_head"])) + ("gate.",)

@@ -1168,6 +1168,46 @@ def append_sampled(token_table, rows, pos, sampled) -> None:
                            sampled.data_ptr(), rows.numel(), _st()), "append_sampled")
 
 
+# ------------------------------------------------------------------ weight-only FP4 decode GEMM (csrc/gemm_w4.cu)
+_gemm_w4 = _sig("vb_gemm_w4", _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _i, _i, _vp)
+W4_MAX_TOKENS = 128
+
+
+def pack_w4_tiles(codes: torch.Tensor, scales: torch.Tensor, fmt: str) -> torch.Tensor:
+    """Tile-major operand layout of the W4A16 kernel.  ``codes``: uint8 [N, K/2] (two e2m1 codes per byte, low nibble
+    first); ``scales``: one byte per 16 (``nvfp4``: e4m3) or 32 (``mxfp4``: e8m0) columns, [N, K/16] or [N, K/32].
+    Returns uint8 [ceil(N/128), K/64, 4096 + 128 * {4, 2}]: every (128-row tile, 64-column block) is one contiguous
+    record = the codes of its 128 rows followed by their scales."""
+    N, K2 = codes.shape
+    K = K2 * 2
+    assert K % 64 == 0, "W4 kernel: K must be a multiple of 64"
+    spb = 4 if fmt == "nvfp4" else 2                 # scale bytes per row per 64-column block
+    sc = scales.view(torch.uint8) if scales.dtype != torch.uint8 else scales
+    assert sc.shape == (N, K // 64 * spb), (sc.shape, N, K)
+    Np = (N + 127) // 128 * 128
+    if Np != N:
+        codes = torch.nn.functional.pad(codes, (0, 0, 0, Np - N))
+        sc = torch.nn.functional.pad(sc, (0, 0, 0, Np - N))
+    c = codes.view(Np // 128, 128, K // 64, 32).permute(0, 2, 1, 3).reshape(Np // 128, K // 64, 4096)
+    s = sc.reshape(Np // 128, 128, K // 64, spb).permute(0, 2, 1, 3).reshape(Np // 128, K // 64, 128 * spb)
+    return torch.cat([c, s], dim=-1).contiguous()
+
+
+def gemm_w4(x: torch.Tensor, tiled: torch.Tensor, N: int, gscale: float, fmt: str, bias: Optional[torch.Tensor] = None
+            ) -> torch.Tensor:
+    """Y = X · dequant(W)^T for FP4 weights in the tile-major layout of ``pack_w4_tiles`` (M <= 128 tokens)."""
+    M, K = x.shape
+    y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    _check(_gemm_w4(x.data_ptr(), tiled.data_ptr(), _p(bias), y.data_ptr(), M, N, K, x.stride(0), float(gscale),
+                    0 if fmt == "nvfp4" else 1, _DT[x.dtype], _st()), f"gemm_w4(M={M},N={N},K={K},{fmt})")
+    return y
+
+
+def gemm_w4_ok(x: torch.Tensor, K: int) -> bool:
+    return (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 2 and 0 < x.shape[0] <= W4_MAX_TOKENS
+            and K % 64 == 0 and x.stride(1) == 1 and (x.stride(0) * 2) % 16 == 0)
+
+
 # ------------------------------------------------------------------ L2 weight prefetch on a side stream
 _l2_prefetch = _sig("vb_l2_prefetch", _vp, _i64, _vp)
 _side_streams: dict[int, torch.cuda.Stream] = {}

@@ -457,6 +457,24 @@ def fp4_dequant(packed: torch.Tensor, block_scale: torch.Tensor, global_scale, b
     return vals * sc * float(global_scale)
 
 
+def mxfp4_quant(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """OCP MXFP4: e2m1 codes (two per byte, low nibble first) with one power-of-two e8m0 scale per 32 values
+    (the GPT-OSS expert format).  Returns (packed uint8 [R, C/2], scales uint8 [R, C/32])."""
+    wf = w.float()
+    R, C = wf.shape
+    g = wf.reshape(R, C // 32, 32)
+    e = torch.ceil(torch.log2(g.abs().amax(-1).clamp_min(2.0 ** -120) / 6.0)).clamp(-126, 127)
+    x = g / torch.exp2(e)[..., None]
+    lut = torch.tensor(E2M1_VALUES, dtype=torch.float32, device=w.device)
+    idx = (x.abs()[..., None] - lut).abs().argmin(-1)
+    code = (idx + 8 * (x < 0).long()).reshape(R, C).to(torch.uint8)
+    return (code[:, 0::2] | (code[:, 1::2] << 4)).contiguous(), (e + 127).to(torch.uint8)
+
+
+def mxfp4_dequant(packed: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    return fp4_dequant(packed, torch.exp2(scales.float() - 127.0), 1.0, 32)
+
+
 def fp4_quant(w: torch.Tensor, block: int = 16) -> tuple[torch.Tensor, torch.Tensor, float]:
     """Reference NVFP4 quantiser: per-16 block scale (stored fp8 e4m3) + global fp32 scale → packed nibbles."""
     wf = w.float()
@@ -466,7 +484,7 @@ def fp4_quant(w: torch.Tensor, block: int = 16) -> tuple[torch.Tensor, torch.Ten
     gscale = float(amax.max() / (6.0 * FP8_MAX)) or 1.0
     bscale = (amax / 6.0 / gscale).clamp_min(1e-12).to(torch.float8_e4m3fn)
     x = g / (bscale.float()[..., None] * gscale)
-    lut = torch.tensor(E2M1_VALUES, dtype=torch.float32)
+    lut = torch.tensor(E2M1_VALUES, dtype=torch.float32, device=w.device)
     idx = (x.abs()[..., None] - lut).abs().argmin(-1)
     code = (idx + 8 * (x < 0).long()).reshape(R, C).to(torch.uint8)
     return (code[:, 0::2] | (code[:, 1::2] << 4)).contiguous(), bscale, gscale
