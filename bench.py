@@ -131,6 +131,12 @@ def _timed_generates(gen, K: int, reps: int, sync=None):
     return min(t1s), min(tks), {"generate_1_s": t1s, "generate_K1_s": tks}
 
 
+def _prefill_tok_s(t1: float, B: int, S_in: int) -> float:
+    """Second metric: prompt tokens per second of the whole call LLM.generate(max_tokens=1) — one-step prefill of B x S_in
+    tokens through the public API, tokenised prompts in, first token out (includes scheduling, H2D, sampling, D2H)."""
+    return B * S_in / t1
+
+
 # ===================================================================================== reference arm
 def _reference_unavailable(why: str) -> None:
     if int(os.environ.get("RANK", 0)) == 0:
@@ -244,7 +250,7 @@ def run_reference(args) -> None:
             "clocks": _summarise_clocks(lines, 0),
             "e2e": {"value": value, "unit": "tokens/s", "ms_per_step": dec_s * 1e3 / K,
                     "method": "min wall(LLM.generate(K+1)) - min wall(LLM.generate(1)), %d reps" % REPS, **raw,
-                    "engine_core_itl_ms": eng_ms},
+                    "engine_core_itl_ms": eng_ms, "prefill_tokens_per_s": _prefill_tok_s(t1, B, S_in)},
             "impl": "reference", "reference_source": source}), flush=True)
         try:
             del llm
@@ -414,7 +420,8 @@ def main() -> None:
     if not args.no_e2e:
         e2e = {"value": B * K / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d_step),
                "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_s * 1e3 / K,
-               "method": "min wall(LLM.generate(K+1)) - min wall(LLM.generate(1)), %d reps" % REPS, **raw}
+               "method": "min wall(LLM.generate(K+1)) - min wall(LLM.generate(1)), %d reps" % REPS, **raw,
+               "prefill_tokens_per_s": _prefill_tok_s(t1, B, S_in)}
     if rank == 0:
         roof = None
         try:   # analytical roofline of the timed steps (weights + KV bytes, FLOPs) → achieved TB/s, MBU, MFU
