@@ -337,14 +337,14 @@ def main() -> None:
                 seen[o.request_id] = len(o.outputs[0].token_ids)
 
     # ---------------- phase A: device-timed decode steps
-    add_batch("a")
-    prefill_until_decoding()
-    for _ in range(W):
-        engine.step()
     stop, lines = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, lines), daemon=True)
     th.start()
-    time.sleep(0.3)
+    time.sleep(0.3)                 # (the sampler is running before any timed work: no idle gap between warm-up and timing —
+    add_batch("a")                  #  an idle GPU drops its clocks and the first timed steps would pay the ramp)
+    prefill_until_decoding()
+    for _ in range(W):
+        engine.step()
     launches0 = runner.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
