@@ -304,7 +304,8 @@ def main() -> None:
     from vllm_b200 import LLM, SamplingParams
 
     B, S_in, K, W = args.batch, args.input_len, args.steps, args.warmup
-    out_len = W + K + 2
+    SETTLE = 16                      # untimed decode steps between the prefill cool-down pause and the W warm-up steps
+    out_len = W + K + 2 + SETTLE
     max_len = S_in + 2 * out_len + 64
     extra = {}
     if args.parallelism == "ep":
@@ -340,10 +341,15 @@ def main() -> None:
     stop, lines = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, lines), daemon=True)
     th.start()
-    time.sleep(0.3)                 # (the sampler is running before any timed work: no idle gap between warm-up and timing —
-    add_batch("a")                  #  an idle GPU drops its clocks and the first timed steps would pay the ramp)
+    time.sleep(0.3)
+    add_batch("a")
     prefill_until_decoding()
-    for _ in range(W):
+    # The one-step 64 x 1024-token prefill runs at the power cap and leaves the clocks capped for ~100 ms; an idle GPU
+    # on the other hand drops its clocks and pays a ramp.  So: pause AFTER the prefill (cap window expires), then SETTLE
+    # untimed decode steps (clocks back up), then the W warm-up steps, then — with no idle gap — the K timed steps.
+    torch.cuda.synchronize()
+    time.sleep(1.0)
+    for _ in range(SETTLE + W):
         engine.step()
     launches0 = runner.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
