@@ -304,7 +304,7 @@ def main() -> None:
     from vllm_b200 import LLM, SamplingParams
 
     B, S_in, K, W = args.batch, args.input_len, args.steps, args.warmup
-    SETTLE = 16                      # untimed decode steps between the prefill cool-down pause and the W warm-up steps
+    SETTLE = 24                      # untimed decode steps between the prefill and the W warm-up steps (see phase A)
     out_len = W + K + 2 + SETTLE
     max_len = S_in + 2 * out_len + 64
     extra = {}
@@ -344,11 +344,11 @@ def main() -> None:
     time.sleep(0.3)
     add_batch("a")
     prefill_until_decoding()
-    # The one-step 64 x 1024-token prefill runs at the power cap and leaves the clocks capped for ~100 ms; an idle GPU
-    # on the other hand drops its clocks and pays a ramp.  So: pause AFTER the prefill (cap window expires), then SETTLE
-    # untimed decode steps (clocks back up), then the W warm-up steps, then — with no idle gap — the K timed steps.
-    torch.cuda.synchronize()
-    time.sleep(1.0)
+    # The one-step 64 x 1024-token prefill runs at the power cap and leaves the clocks capped for ~100 ms afterwards
+    # (measured: ~15 decode steps at 6.7 instead of 5.4 ms on one GPU); an IDLE pause instead lets the clocks drop and the
+    # timed steps pay the ramp (measured: +0.3 ms per step at TP4 / TP8).  So the GPU is kept busy: SETTLE untimed decode
+    # steps (a fixed count: every rank must run the same steps, the collectives are inside them), then the W warm-up
+    # steps, then — no gap — the K timed steps.
     for _ in range(SETTLE + W):
         engine.step()
     launches0 = runner.launch_count
@@ -435,7 +435,7 @@ def main() -> None:
             from vllm_b200.metrics.perf import model_step_cost, utilisation
             hf = get_preset_hf_config(args.model)
             if hf is not None:
-                ctx = S_in + W + K // 2
+                ctx = S_in + SETTLE + W + K // 2
                 roof = {k: round(v, 4) for k, v in utilisation(model_step_cost(hf, B, [ctx] * B), dev_ms / K / 1e3,
                                                                 args.gpus).items()}
         except Exception:
