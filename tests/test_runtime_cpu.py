@@ -418,3 +418,29 @@ def test_ray_executor_with_stub_cluster():
     # without ray installed the backend fails with an actionable message
     with pytest.raises(ImportError, match="ray executor needs"):
         make_llm("llama-tiny", distributed_executor_backend="ray")
+
+
+def test_out_of_band_tensor_frames_roundtrip_and_alias():
+    """engine/serial.py multi-frame codec: large tensors / arrays leave the msgpack body and travel as their own frames that
+    ALIAS the source storage (zero copy on the sending side); small ones stay inline; typed decoding of engine messages."""
+    import numpy as np
+    import torch
+    from vllm_b200.core.request import EngineCoreRequest
+    from vllm_b200.engine.serial import (OOBDecoder, OOBEncoder, decode_request_frames, encode_request_frames)
+    from vllm_b200.sampling_params import SamplingParams
+    enc, dec = OOBEncoder(), OOBDecoder()
+    big, small = torch.randn(64, 128).bfloat16(), torch.arange(5)
+    msg = {"big": big, "small": small, "arr": np.arange(1000, dtype=np.float32).reshape(10, 100), "nest": [1, {"t": torch.randn(300)}]}
+    frames = enc.encode(msg)
+    assert len(frames) == 4 and len(frames[1]) == big.numel() * 2                # body + three out-of-band buffers
+    big.view(torch.int16)[0, 0] = 1234                                          # the frame is a view of the tensor
+    assert bytes(frames[1][:2]) == (1234).to_bytes(2, "little")
+    out = dec.decode([bytes(f) for f in frames])
+    assert torch.equal(out["big"], big) and torch.equal(out["small"], small) and np.array_equal(out["arr"], msg["arr"])
+    assert torch.equal(out["nest"][1]["t"], msg["nest"][1]["t"])
+    r = EngineCoreRequest(request_id="r1", prompt_token_ids=[1, 2, 3], sampling_params=SamplingParams(max_tokens=3),
+                          prompt_embeds=torch.randn(3, 64))
+    fr = encode_request_frames(r)
+    assert len(fr) == 2
+    back = decode_request_frames([bytes(f) for f in fr])
+    assert back.request_id == "r1" and torch.equal(back.prompt_embeds, r.prompt_embeds)

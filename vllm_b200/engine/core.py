@@ -230,7 +230,7 @@ class EngineCoreProc(EngineCore):
 
     # ---- IO threads
     def _input_loop(self) -> None:
-        from vllm_b200.engine.serial import decode_any, decode_request
+        from vllm_b200.engine.serial import decode_any, decode_request_frames
         import zmq
         poller = zmq.Poller()
         for s in self._in_socks:
@@ -239,17 +239,17 @@ class EngineCoreProc(EngineCore):
             try:
                 ready = poller.poll(500) if len(self._in_socks) > 1 else [(self._in_sock, zmq.POLLIN)]
                 for sock, _ in ready:
-                    frames = sock.recv_multipart()
-                    kind = frames[0]
-                    if kind == REQ_ADD:
-                        self.input_queue.put((kind, decode_request(frames[1])))
+                    frames = sock.recv_multipart(copy=False)
+                    kind = frames[0].bytes
+                    if kind == REQ_ADD:        # frame 1 = msgpack head, frames 2.. = out-of-band tensor storage (zero copy)
+                        self.input_queue.put((kind, decode_request_frames(frames[1:])))
                     else:
-                        self.input_queue.put((kind, decode_any(frames[1]) if len(frames) > 1 else None))
+                        self.input_queue.put((kind, decode_any(frames[1].bytes) if len(frames) > 1 else None))
             except Exception:
                 break
 
     def _output_loop(self) -> None:
-        from vllm_b200.engine.serial import encode_outputs
+        from vllm_b200.engine.serial import encode_outputs_frames
         while True:
             item = self.output_queue.get()
             if item is None:
@@ -259,7 +259,7 @@ class EngineCoreProc(EngineCore):
                     s.send(item)
                 continue
             ci = item[0] if 0 <= item[0] < len(self._out_socks) else 0
-            self._out_socks[ci].send(encode_outputs(item))
+            self._out_socks[ci].send_multipart(encode_outputs_frames(item), copy=False)
 
     # ---- busy loop
     def run_busy_loop(self) -> None:

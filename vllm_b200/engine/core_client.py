@@ -24,7 +24,7 @@ from vllm_b200.core.request import EngineCoreOutputs, EngineCoreRequest
 from vllm_b200.engine.core import (ENGINE_CORE_DEAD, REQ_ABORT, REQ_ADD, REQ_SHUTDOWN, REQ_UTILITY, EngineCore,
                                    EngineCoreProc)
 from vllm_b200.engine.exceptions import EngineDeadError
-from vllm_b200.engine.serial import decode_outputs, encode_any, encode_request
+from vllm_b200.engine.serial import decode_outputs_frames, encode_any, encode_request_frames
 from vllm_b200.logger import init_logger
 from vllm_b200.utils import get_open_zmq_ipc_path
 
@@ -225,14 +225,14 @@ class SyncMPClient(MPClient):
                         self.outputs_queue.put(EngineDeadError())
                         return
                     continue
-                msg = self.output_socket.recv()
+                frames = self.output_socket.recv_multipart(copy=False)
             except zmq.ZMQError:
                 return
-            if msg == ENGINE_CORE_DEAD:
+            if len(frames) == 1 and frames[0].bytes == ENGINE_CORE_DEAD:
                 self.res.engine_dead = True
                 self.outputs_queue.put(EngineDeadError())
                 return
-            _, outs = decode_outputs(msg)
+            _, outs = decode_outputs_frames(frames)
             if outs.utility_output is not None:
                 cid, err, result = outs.utility_output
                 self.utility_results[cid] = (err, result)
@@ -254,7 +254,7 @@ class SyncMPClient(MPClient):
     def add_request(self, r: EngineCoreRequest) -> None:
         self._check_alive()
         r.client_index = self.client_index
-        self.input_socket.send_multipart([self.engine_ids[0], REQ_ADD, encode_request(r)])
+        self.input_socket.send_multipart([self.engine_ids[0], REQ_ADD, *encode_request_frames(r)], copy=False)
 
     def abort_requests(self, ids: list[str]) -> None:
         if ids and not self.res.engine_dead:
@@ -306,12 +306,12 @@ class AsyncMPClient(MPClient):
                             f.set_exception(EngineDeadError())
                     return
                 continue
-            msg = await self.output_socket.recv()
-            if msg == ENGINE_CORE_DEAD:
+            frames = await self.output_socket.recv_multipart(copy=False)
+            if len(frames) == 1 and frames[0].bytes == ENGINE_CORE_DEAD:
                 self.res.engine_dead = True
                 await self.outputs_queue.put(EngineDeadError())
                 return
-            _, outs = decode_outputs(msg)
+            _, outs = decode_outputs_frames(frames)
             self._on_outputs(outs)
             if outs.utility_output is not None:
                 cid, err, result = outs.utility_output
@@ -343,7 +343,7 @@ class AsyncMPClient(MPClient):
         self._check_alive()
         r.client_index = self.client_index
         eid = self._pick_engine(r)
-        await self.input_socket.send_multipart([eid, REQ_ADD, encode_request(r)])
+        await self.input_socket.send_multipart([eid, REQ_ADD, *encode_request_frames(r)], copy=False)
 
     async def abort_requests_async(self, ids: list[str]) -> None:
         if ids and not self.res.engine_dead:
