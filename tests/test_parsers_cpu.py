@@ -125,3 +125,44 @@ def test_round2_tool_call_formats():
         d = p.extract_streaming(prev, text, text[len(prev):])
         emitted += (d or {}).get("tool_calls", [])
         assert [e["function"]["name"] for e in emitted] == [fn], (name, emitted)
+
+
+def test_builtin_chat_templates_and_resolution(tmp_path):
+    """Named / per-family chat templates (entrypoints/chat_templates.py): exact wire text of the common dialects, system
+    message folding where the dialect has no system role, resolution of --chat-template by name / file / source."""
+    from vllm_b200.entrypoints.chat_templates import TEMPLATES, builtin_for_model_type, resolve_chat_template
+    from vllm_b200.entrypoints.chat_utils import render_chat
+
+    class Tok:                       # no template of its own, no HF machinery: the jinja path renders
+        chat_template = None
+
+    msgs = [{"role": "system", "content": "Be brief."}, {"role": "user", "content": "Hi"},
+            {"role": "assistant", "content": "Hello."}, {"role": "user", "content": [{"type": "text", "text": "Bye"}]}]
+    r = lambda name, **kw: render_chat(Tok(), msgs, name, **kw)        # noqa: E731
+    assert r("chatml") == ("<|im_start|>system\nBe brief.<|im_end|>\n<|im_start|>user\nHi<|im_end|>\n<|im_start|>assistant\n"
+                           "Hello.<|im_end|>\n<|im_start|>user\nBye<|im_end|>\n<|im_start|>assistant\n")
+    assert r("llama-3").startswith("<|begin_of_text|><|start_header_id|>system<|end_header_id|>\n\nBe brief.<|eot_id|>")
+    assert r("llama-3").endswith("<|start_header_id|>user<|end_header_id|>\n\nBye<|eot_id|><|start_header_id|>assistant<|end_header_id|>\n\n")
+    assert r("llama-2") == "<s>[INST] <<SYS>>\nBe brief.\n<</SYS>>\n\nHi [/INST] Hello. </s><s>[INST] Bye [/INST]"
+    assert r("mistral") == "<s>[INST] Be brief.\n\nHi [/INST]Hello.</s>[INST] Bye [/INST]"
+    assert r("gemma") == ("<bos><start_of_turn>user\nBe brief.\n\nHi<end_of_turn>\n<start_of_turn>model\nHello.<end_of_turn>\n"
+                          "<start_of_turn>user\nBye<end_of_turn>\n<start_of_turn>model\n")
+    assert r("phi-3").endswith("<|user|>\nBye<|end|>\n<|assistant|>\n")
+    assert r("deepseek") == "<｜begin▁of▁sentence｜>Be brief.<｜User｜>Hi<｜Assistant｜>Hello.<｜end▁of▁sentence｜><｜User｜>Bye<｜Assistant｜>"
+    assert r("command-r").endswith("<|START_OF_TURN_TOKEN|><|USER_TOKEN|>Bye<|END_OF_TURN_TOKEN|><|START_OF_TURN_TOKEN|><|CHATBOT_TOKEN|>")
+    assert r("vicuna").startswith("Be brief. USER: Hi ASSISTANT: Hello.</s> USER: Bye ASSISTANT:")
+    assert r("alpaca").endswith("### Instruction:\nBye\n\n### Response:\n")
+    assert r("chatml", add_generation_prompt=False).endswith("Bye<|im_end|>\n")
+    # family fallback when the tokenizer has no template; 32k-vocabulary Llama speaks [INST]
+    t = Tok()
+    t.model_type = "qwen3"
+    assert render_chat(t, msgs[1:2]) == "<|im_start|>user\nHi<|im_end|>\n<|im_start|>assistant\n"
+    assert builtin_for_model_type("llama", 128256) is TEMPLATES["llama-3"] and builtin_for_model_type("llama", 32000) is TEMPLATES["llama-2"]
+    assert builtin_for_model_type("no_such_family") is None
+    # --chat-template: name, file, source, error
+    f = tmp_path / "t.jinja"
+    f.write_text("{{ messages[0]['content'] }}!")
+    assert resolve_chat_template("ChatML") is TEMPLATES["chatml"] and resolve_chat_template(str(f)).endswith("}}!")
+    assert resolve_chat_template("{{ 1 }}") == "{{ 1 }}" and resolve_chat_template(None) is None
+    with pytest.raises(ValueError):
+        resolve_chat_template("nonexistent-template")

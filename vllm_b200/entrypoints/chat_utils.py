@@ -32,8 +32,17 @@ def _flatten_content(messages: list[dict]) -> tuple[list[dict], list[Any]]:
 def render_chat(tokenizer, messages: list[dict], chat_template: Optional[str] = None,
                 add_generation_prompt: bool = True, continue_final_message: bool = False,
                 tools: Optional[list[dict]] = None, **kwargs: Any) -> str:
+    """Resolution order: explicit template (request / ``--chat-template``: built-in name, file or jinja source) → the
+    tokenizer's own template → the built-in template of the model family (``model_type`` kwarg or tokenizer attribute)
+    → a neutral role-tag format."""
+    from vllm_b200.entrypoints.chat_templates import TEMPLATES, builtin_for_model_type
     msgs, _ = _flatten_content(messages)
+    model_type = kwargs.pop("model_type", None) or getattr(tokenizer, "model_type", None)
+    if chat_template and chat_template.lower() in TEMPLATES:
+        chat_template = TEMPLATES[chat_template.lower()]
     tmpl = chat_template or getattr(tokenizer, "chat_template", None)
+    if tmpl is None and not (hasattr(tokenizer, "apply_chat_template") and not hasattr(tokenizer, "backend_tokenizer")):
+        tmpl = builtin_for_model_type(model_type, getattr(tokenizer, "vocab_size", None))
     if tmpl is None and hasattr(tokenizer, "apply_chat_template") and not hasattr(tokenizer, "backend_tokenizer"):
         text = tokenizer.apply_chat_template(msgs, add_generation_prompt=add_generation_prompt, tokenize=False)
     elif tmpl is not None and hasattr(tokenizer, "backend_tokenizer"):

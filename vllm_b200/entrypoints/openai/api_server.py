@@ -1214,10 +1214,12 @@ async def run_server(args: argparse.Namespace) -> None:
         args.model = args.model_tag
     ea = EngineArgs.from_cli_args(args)
     engine = AsyncLLM.from_engine_args(ea)
-    template = None
-    if args.chat_template:
-        with open(args.chat_template) as f:
-            template = f.read()
+    from vllm_b200.entrypoints.chat_templates import resolve_chat_template
+    template = resolve_chat_template(args.chat_template)        # built-in name, file, or jinja source
+    try:
+        engine.tokenizer.model_type = engine.model_config.hf_config.get("model_type")    # family fallback template
+    except Exception:
+        pass
     ctx = ServingContext(engine, ea.served_model_name or ea.model, engine.model_config.max_model_len, engine.tokenizer,
                          api_key=args.api_key, tool_parser=args.tool_call_parser,
                          reasoning_parser=ea.reasoning_parser or None, enable_auto_tools=args.enable_auto_tool_choice,

@@ -109,5 +109,10 @@ def get_tokenizer(name: Optional[str], tokenizer_mode: str = "auto", trust_remot
 def init_tokenizer_from_config(model_config):
     if model_config.skip_tokenizer_init:
         return None
-    return get_tokenizer(model_config.tokenizer, model_config.tokenizer_mode, model_config.trust_remote_code,
-                         vocab_size=model_config.vocab_size, eos_token_id=model_config.eos_token_id)
+    tok = get_tokenizer(model_config.tokenizer, model_config.tokenizer_mode, model_config.trust_remote_code,
+                        vocab_size=model_config.vocab_size, eos_token_id=model_config.eos_token_id)
+    try:        # lets chat rendering fall back to the model family's built-in template (entrypoints/chat_templates.py)
+        tok.model_type = model_config.hf_config.get("model_type")
+    except Exception:
+        pass
+    return tok
