@@ -311,6 +311,25 @@ def test_native_frontend_text_prompts_with_tiktoken_tokenizer(tmp_path):
         assert by_text["choices"][0]["token_ids"] == by_ids["choices"][0]["token_ids"]
         out_ids = [i for i in by_text["choices"][0]["token_ids"] if i < 267]
         assert by_text["choices"][0]["text"] == tok.enc.decode(out_ids, errors="replace")
+        # chat completions on the C++ tier: messages rendered in the daemon's dialect (neutral role tags here), tokenised
+        # natively, answered as chat.completion / chat.completion.chunk objects
+        msgs = [{"role": "system", "content": "hello"}, {"role": "user", "content": [{"type": "text", "text": "the world"}]}]
+        rendered = "<|system|>\nhello\n<|user|>\nthe world\n<|assistant|>\n"
+        chat = requests.post(url + "/v1/chat/completions", json={"messages": msgs, "max_tokens": 6, "temperature": 0}, timeout=120).json()
+        same = requests.post(url + "/v1/completions", json={"prompt": rendered, "max_tokens": 6, "temperature": 0,
+                                                            "add_special_tokens": False}, timeout=120).json()
+        assert chat["object"] == "chat.completion" and chat["id"].startswith("chatcmpl-")
+        assert chat["choices"][0]["message"] == {"role": "assistant", "content": same["choices"][0]["text"]}
+        assert chat["usage"]["prompt_tokens"] == same["usage"]["prompt_tokens"] == len(tok.encode(rendered))
+        with requests.post(url + "/v1/chat/completions", json={"messages": msgs, "max_tokens": 6, "temperature": 0, "stream": True},
+                           stream=True, timeout=120) as r:
+            r.encoding = "utf-8"
+            chunks = [json.loads(l[6:]) for l in r.iter_lines(decode_unicode=True) if l.startswith("data: {")]
+        assert chunks and chunks[0]["object"] == "chat.completion.chunk" and chunks[0]["choices"][0]["delta"].get("role") == "assistant"
+        assert "".join(c["choices"][0]["delta"].get("content", "") for c in chunks) == same["choices"][0]["text"]
+        assert chunks[-1]["choices"][0]["finish_reason"] == "length"
+        bad = requests.post(url + "/v1/chat/completions", json={"messages": [{"role": "user", "content": [{"type": "image_url"}]}]}, timeout=30)
+        assert bad.status_code == 400 and "Python API server" in bad.json()["error"]["message"]
     finally:
         proc.terminate()
         try:

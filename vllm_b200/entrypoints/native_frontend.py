@@ -200,7 +200,7 @@ def write_vocab_table(tok, vocab_size: int, path: str) -> None:
 
 def spawn_frontd(*, host: str, port: int, in_addr: str, out_addr: str, model: str, max_model_len: int,
                  eos_token_id: Optional[int], vocab_path: Optional[str], num_engines: int = 1,
-                 api_key: Optional[str] = None) -> subprocess.Popen:
+                 api_key: Optional[str] = None, chat_template: Optional[str] = None) -> subprocess.Popen:
     from vllm_b200.native import build_frontd
     cmd = [build_frontd(), "--host", host, "--port", str(port), "--in-addr", in_addr, "--out-addr", out_addr,
            "--model", model, "--max-model-len", str(max_model_len), "--libzmq", find_libzmq(),
@@ -211,7 +211,19 @@ def spawn_frontd(*, host: str, port: int, in_addr: str, out_addr: str, model: st
         cmd += ["--vocab", vocab_path]
     if api_key:
         cmd += ["--api-key", api_key]
+    if chat_template:
+        cmd += ["--chat-template", chat_template]
     return subprocess.Popen(cmd)
+
+
+def _daemon_dialect(spec: Optional[str], model_type: Optional[str]) -> Optional[str]:
+    """The chat dialect the C++ daemon renders natively (chatml / llama-3 / neutral role tags): the operator's
+    ``--chat-template`` if it names one of them, else the model family's default when that is one of them."""
+    native = {"chatml": "chatml", "llama-3": "llama-3", "llama3": "llama-3", "plain": "plain"}
+    if spec and spec.lower() in native:
+        return native[spec.lower()]
+    fam = {"qwen2": "chatml", "qwen3": "chatml", "qwen2_moe": "chatml", "qwen3_moe": "chatml", "smollm3": "chatml"}
+    return fam.get(model_type or "")
 
 
 def run_native_server(args) -> None:
@@ -235,7 +247,8 @@ def run_native_server(args) -> None:
     fd = spawn_frontd(host=args.host if args.host != "0.0.0.0" else "0.0.0.0", port=args.port, in_addr=in_addr,
                       out_addr=out_addr, model=ea.served_model_name or ea.model,
                       max_model_len=cfg.model_config.max_model_len, eos_token_id=cfg.model_config.eos_token_id,
-                      vocab_path=vocab_path, num_engines=n, api_key=args.api_key)
+                      vocab_path=vocab_path, num_engines=n, api_key=args.api_key,
+                      chat_template=_daemon_dialect(getattr(args, "chat_template", None), cfg.model_config.hf_config.get("model_type")))
     time.sleep(0.2)                                    # the daemon binds before the engines connect (ipc:// needs it)
     procs = _launch_engines(cfg, in_addr, out_addr, n, log_stats=not ea.disable_log_stats)
     stop = {"v": False}

@@ -84,7 +84,7 @@ bool recv_multipart(void* sock, std::vector<std::string>& frames) {
 
 // ------------------------------------------------------------------------------------------------ configuration
 struct Config {
-  std::string host = "127.0.0.1", in_addr, out_addr, model = "model", vocab_path, libzmq, api_key;
+  std::string host = "127.0.0.1", in_addr, out_addr, model = "model", vocab_path, libzmq, api_key, chat_template = "plain";
   int port = 8000, num_engines = 1;
   int64_t max_model_len = 8192, eos = -1;
 };
@@ -147,6 +147,7 @@ struct Req {
   std::string rid, model, pending, text;   // pending: bytes not yet on a UTF-8 boundary
   uint64_t conn_id = 0;
   bool stream = false, token_api = false, detok = true, include_stop = false, skip_special = true, done = false, include_usage = false;
+  bool chat = false, sent_role = false;     // /v1/chat/completions: chat.completion(.chunk) objects, role in the first delta
   std::vector<int64_t> out_ids;
   std::vector<std::string> stops;
   size_t n_prompt = 0, sent_text = 0, sent_ids = 0, hold = 0;
@@ -211,6 +212,64 @@ struct Server {
 
   // ---------------------------------------------------------------- response formatting
   static const char* finish_name(int64_t f) { return f == 0 ? "stop" : f == 1 ? "length" : "abort"; }
+
+  // chat.completion / chat.completion.chunk (reference: entrypoints/openai/chat_completion/protocol.py)
+  std::string chat_json(Req& r, const std::string& text, const char* finish, bool chunk, bool usage, bool no_choices = false) {
+    std::string o = "{\"id\":";
+    wire::json_escape(o, r.rid);
+    o += chunk ? ",\"object\":\"chat.completion.chunk\"" : ",\"object\":\"chat.completion\"";
+    o += ",\"created\":" + std::to_string(r.created) + ",\"model\":";
+    wire::json_escape(o, r.model);
+    o += ",\"choices\":[";
+    if (!no_choices) {
+      o += chunk ? "{\"index\":0,\"delta\":{" : "{\"index\":0,\"message\":{";
+      bool role = !chunk || !r.sent_role;
+      if (role) { o += "\"role\":\"assistant\""; r.sent_role = true; }
+      if (!chunk || !text.empty()) { o += role ? ",\"content\":" : "\"content\":"; wire::json_escape(o, text); }
+      o += "},\"logprobs\":null,\"finish_reason\":";
+      if (finish) { o.push_back('"'); o += finish; o.push_back('"'); } else o += "null";
+      o += "}";
+    }
+    o += "]";
+    if (usage) {
+      o += ",\"usage\":{\"prompt_tokens\":" + std::to_string(r.n_prompt) + ",\"completion_tokens\":" + std::to_string(r.out_ids.size()) +
+           ",\"total_tokens\":" + std::to_string(r.n_prompt + r.out_ids.size()) + "}";
+    }
+    o += "}";
+    return o;
+  }
+
+  // messages → prompt text in one of the built-in dialects (the Python server's entrypoints/chat_templates.py has the full
+  // set and jinja; the daemon covers the two most common wire formats plus neutral role tags).  Returns false with `err`.
+  bool render_chat(const Val& messages, bool add_generation_prompt, std::string& out, std::string& err) const {
+    if (messages.t != Val::ARR || messages.a.empty()) { err = "`messages` must be a non-empty array"; return false; }
+    const std::string& d = cfg.chat_template;
+    if (d == "llama-3" || d == "llama3") out += "<|begin_of_text|>";
+    for (auto& m : messages.a) {
+      const Val* role = m.get("role");
+      const Val* content = m.get("content");
+      if (!role || role->t != Val::STR) { err = "every message needs a string `role`"; return false; }
+      std::string text;
+      if (content && content->t == Val::STR) text = content->s;
+      else if (content && content->t == Val::ARR) {
+        for (auto& part : content->a) {
+          const Val* ty = part.get("type");
+          const Val* tx = part.get("text");
+          if (ty && ty->t == Val::STR && ty->s == "text" && tx && tx->t == Val::STR) { if (!text.empty()) text += "\n"; text += tx->s; }
+          else { err = "the native front-end renders text content only; send multimodal messages to the Python API server"; return false; }
+        }
+      } else if (content && content->t != Val::NIL) { err = "`content` must be a string or an array of parts"; return false; }
+      if (d == "chatml") out += "<|im_start|>" + role->s + "\n" + text + "<|im_end|>\n";
+      else if (d == "llama-3" || d == "llama3") out += "<|start_header_id|>" + role->s + "<|end_header_id|>\n\n" + text + "<|eot_id|>";
+      else out += "<|" + role->s + "|>\n" + text + "\n";
+    }
+    if (add_generation_prompt) {
+      if (d == "chatml") out += "<|im_start|>assistant\n";
+      else if (d == "llama-3" || d == "llama3") out += "<|start_header_id|>assistant<|end_header_id|>\n\n";
+      else out += "<|assistant|>\n";
+    }
+    return true;
+  }
 
   std::string completion_json(const Req& r, const std::string& text, const char* finish, bool chunk, bool usage,
                               bool no_choices = false) {
@@ -319,18 +378,20 @@ struct Server {
         if (upto > r.sent_text || finished) {
           std::string delta = upto > r.sent_text ? r.text.substr(r.sent_text, upto - r.sent_text) : std::string();
           if (upto > r.sent_text) r.sent_text = upto;
-          if (!delta.empty() || finished) data = sse_chunk(completion_json(r, delta, finish, true, false));
+          if (!delta.empty() || finished)
+            data = sse_chunk(r.chat ? chat_json(r, delta, finish, true, false) : completion_json(r, delta, finish, true, false));
         }
       }
       if (finished) {
         if (r.include_usage && !r.token_api) {
-          data += sse_chunk(completion_json(r, "", nullptr, true, true, true));
+          data += sse_chunk(r.chat ? chat_json(r, "", nullptr, true, true, true) : completion_json(r, "", nullptr, true, true, true));
         }
         data += sse_chunk("[DONE]") + "0\r\n\r\n";
       }
       if (!data.empty()) outbox.push_back({r.conn_id, std::move(data), finished, false});
     } else if (finished) {
-      std::string body = r.token_api ? token_json(r, 0, finish, true) : completion_json(r, r.text, finish, false, true);
+      std::string body = r.token_api ? token_json(r, 0, finish, true)
+                         : r.chat ? chat_json(r, r.text, finish, false, true) : completion_json(r, r.text, finish, false, true);
       outbox.push_back({r.conn_id, http_response(200, "OK", body), true, false});
     }
     if (finished) {
@@ -411,13 +472,15 @@ struct Server {
     for (auto k : keys) if (const Val* v = src.get(k)) if (v->t != Val::NIL) dst.emplace_back(k, *v);
   }
 
-  void handle_generate(Conn& c, const Val& body, bool token_api) {
+  void handle_generate(Conn& c, const Val& body, bool token_api, const std::string* chat_prompt = nullptr) {
     std::vector<int64_t> prompt;
-    const Val* p = token_api ? body.get("token_ids") : body.get("prompt");
+    Val chat_val;
+    if (chat_prompt) { chat_val.t = Val::STR; chat_val.s = *chat_prompt; }
+    const Val* p = chat_prompt ? &chat_val : token_api ? body.get("token_ids") : body.get("prompt");
     if (token_api && !p) p = body.get("prompt_token_ids");
     if (p && p->t == Val::ARR && p->a.size() == 1 && (p->a[0].t == Val::ARR || p->a[0].t == Val::STR)) p = &p->a[0];
     if (p && p->t == Val::STR && vocab.enc.ready) {              // text prompt: native BPE encoder
-      bool bos = true;
+      bool bos = chat_prompt == nullptr;                    // chat dialects spell their own begin-of-text marker
       if (const Val* v = body.get("add_special_tokens")) bos = v->truthy();
       for (auto t : vocab.enc.encode(p->s, bos)) prompt.push_back(t);
       if (prompt.empty()) { reply(c, 400, "Bad Request", error_json("the prompt is empty", "BadRequestError", 400)); return; }
@@ -444,6 +507,7 @@ struct Server {
     r->rid = std::string(token_api ? "gen-" : "cmpl-") + std::to_string(getpid()) + "-" + std::to_string(next_req++);
     if (const Val* v = body.get("request_id")) if (v->t == Val::STR) r->rid = "gen-" + v->s;
     r->conn_id = c.id; r->token_api = token_api; r->n_prompt = prompt.size(); r->created = int64_t(now_s());
+    if (chat_prompt) { r->chat = true; r->rid = "chatcmpl-" + std::to_string(getpid()) + "-" + std::to_string(next_req - 1); }
     r->model = cfg.model;
     if (const Val* v = body.get("stream")) r->stream = v->truthy();
     if (const Val* v = body.get("stream_options")) if (const Val* u = v->get("include_usage")) r->include_usage = u->truthy();
@@ -540,6 +604,20 @@ struct Server {
         reply(c, 200, "OK", o); return;
       }
       reply(c, 404, "Not Found", error_json("no such route", "NotFoundError", 404)); return;
+    }
+    if (method == "POST" && path == "/v1/chat/completions") {
+      Val v;
+      try { wire::JsonReader jr(body); v = jr.read(); } catch (const std::exception& e) { reply(c, 400, "Bad Request", error_json(e.what(), "BadRequestError", 400)); return; }
+      if (v.t != Val::MAP) { reply(c, 400, "Bad Request", error_json("body must be a JSON object", "BadRequestError", 400)); return; }
+      if (!vocab.enc.ready) { reply(c, 400, "Bad Request", error_json("chat completions need the native tokenizer (start the daemon with --vocab)", "BadRequestError", 400)); return; }
+      if (v.get("tools") || v.get("response_format")) { reply(c, 400, "Bad Request", error_json("tool calling / structured output are served by the Python API server", "BadRequestError", 400)); return; }
+      const Val* msgs = v.get("messages");
+      bool gen = true;
+      if (const Val* g = v.get("add_generation_prompt")) gen = g->truthy();
+      std::string prompt, err;
+      if (!msgs || !render_chat(*msgs, gen, prompt, err)) { reply(c, 400, "Bad Request", error_json(err.empty() ? "`messages` is required" : err, "BadRequestError", 400)); return; }
+      handle_generate(c, v, false, &prompt);
+      return;
     }
     if (method == "POST" && (path == "/v1/completions" || path == "/inference/v1/generate" || path == "/detokenize" || path == "/tokenize")) {
       Val v;
@@ -705,6 +783,7 @@ int main(int argc, char** argv) {
     if (k == "--host") s.cfg.host = v; else if (k == "--port") s.cfg.port = atoi(v.c_str());
     else if (k == "--in-addr") s.cfg.in_addr = v; else if (k == "--out-addr") s.cfg.out_addr = v;
     else if (k == "--model") s.cfg.model = v; else if (k == "--vocab") s.cfg.vocab_path = v;
+    else if (k == "--chat-template") s.cfg.chat_template = v;
     else if (k == "--libzmq") s.cfg.libzmq = v; else if (k == "--api-key") s.cfg.api_key = v;
     else if (k == "--num-engines") s.cfg.num_engines = atoi(v.c_str());
     else if (k == "--max-model-len") s.cfg.max_model_len = atoll(v.c_str());
