@@ -150,6 +150,33 @@ def test_deepseek_tp2_with_decode_context_parallel(dcp):
     assert got == ref
 
 
+def test_gqa_decode_context_parallel_on_replicated_kv_heads():
+    """DCP for an ordinary (non-MLA) cache: an MQA model at TP=2 replicates its single KV head on both ranks; with dcp=2
+    the two replicas shard the cache by position instead (half the slots per block on each rank), gather each other's
+    query heads, and merge partial attention by log-sum-exp — same tokens as TP=1, chunked prefill included."""
+    from tests.utils import llama_full_weights, make_llm
+    from vllm_b200 import SamplingParams
+    from vllm_b200.config import get_preset_hf_config
+    ov = {"num_key_value_heads": 1}
+    cfg = dict(get_preset_hf_config("llama-tiny"), **ov)
+    w = list(llama_full_weights(cfg, seed=4, scale=0.08))
+    prompts = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41, 8]}, {"prompt_token_ids": list(range(10, 47))}]
+    sp = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True)
+    llm = make_llm("llama-tiny", weights=w, hf_overrides=ov)
+    ref = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    llm.shutdown()
+    llm = make_llm("llama-tiny", hf_overrides=ov, tensor_parallel_size=2, decode_context_parallel_size=2,
+                   distributed_executor_backend="mp", block_size=16, max_num_batched_tokens=16)
+    ex = llm.llm_engine.engine_core.engine_core.model_executor
+    ex.collective_rpc("load_model", kwargs={"weights": w})
+    got = [o.outputs[0].token_ids for o in llm.generate(prompts, sp)]
+    specs = ex.collective_rpc("get_kv_cache_specs")
+    s0 = next(iter(specs[0].values()))
+    llm.shutdown()
+    assert s0.dcp == 2 and s0.block_size == 32 and s0.phys_block_size == 16
+    assert got == ref
+
+
 def test_mixtral_expert_parallel_tp2():
     """--enable-expert-parallel: each of the 2 ranks owns 2 whole experts (expert map), combine = all-reduce."""
     from tests.utils import make_hf_model, make_llm

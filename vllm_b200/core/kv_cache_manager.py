@@ -42,10 +42,16 @@ class FullAttentionSpec(KVCacheSpec):
     head_size: int = 128
     dtype_size: int = 2
     sliding_window: Optional[int] = None  # informational when hybrid manager is disabled
+    dcp: int = 1      # decode-context-parallel degree: ``block_size`` counts sequence positions, of which this rank
+                      # stores every dcp-th (the ranks of a DCP group hold replicas of the same KV heads)
+
+    @property
+    def phys_block_size(self) -> int:
+        return self.block_size // self.dcp
 
     @property
     def page_size_bytes(self) -> int:
-        return 2 * self.block_size * self.num_kv_heads * self.head_size * self.dtype_size
+        return 2 * self.phys_block_size * self.num_kv_heads * self.head_size * self.dtype_size
 
 
 @dataclass(frozen=True)

@@ -52,9 +52,70 @@ class Attention(nn.Module):
         _LAYER_REGISTRY[prefix] = self
 
     def get_kv_cache_spec(self, block_size: int, dtype_size: int) -> KVCacheSpec:
+        from vllm_b200.parallel.state import get_dcp_group
+        d = get_dcp_group().world_size
+        if d > 1:
+            if self.sliding_window or self.alibi_slopes is not None or self.sinks is not None or self.chunk_size:
+                raise NotImplementedError("decode context parallelism covers full causal attention (no sliding window / "
+                                          "ALiBi / sinks / chunked-local layers)")
+            return FullAttentionSpec(block_size=block_size * d, num_kv_heads=self.num_kv_heads, head_size=self.head_size,
+                                     dtype_size=dtype_size, dcp=d)
         cls = SlidingWindowSpec if self.sliding_window else FullAttentionSpec
         return cls(block_size=block_size, num_kv_heads=self.num_kv_heads, head_size=self.head_size,
                    dtype_size=dtype_size, sliding_window=self.sliding_window)
+
+    def _forward_dcp(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positions, md, kv_cache) -> torch.Tensor:
+        """Decode context parallelism for GQA / MQA caches (reference: config/parallel.py:342-388, v1/attention/ops/dcp.py:
+        241-338).  It applies where tensor parallelism REPLICATES KV heads (tp > num_kv_heads): the d ranks that hold
+        replicas of the same heads stop storing the same tokens d times and shard the cache by position instead (token p
+        lives on rank p % d), so the group holds d x more context.  Per step: the ranks all-gather their query heads, each
+        attends over its shard of the *previous* context for all of them, the partial results are merged by their
+        log-sum-exp across the group; the tokens of the current step are attended locally (their K / V were just computed
+        on every rank)."""
+        from vllm_b200.ops import ref
+        from vllm_b200.parallel.state import get_dcp_group
+        g = get_dcp_group()
+        d, r = g.world_size, g.rank_in_group
+        T, D, h, hkv = q.shape[0], self.head_size, self.num_heads, self.num_kv_heads
+        if self.rope is not None and positions is not None:
+            q, k = self.rope(positions, q, k)
+        k3, v3 = k.reshape(T, hkv, D), v.reshape(T, hkv, D)
+        ops.reshape_and_cache(k3, v3, kv_cache, md.slot_mapping)               # positions owned elsewhere carry slot -1
+        q3 = q.reshape(T, h, D)
+        # gathered query heads: [T, d, hkv, h/hkv, D] → regrouped so that the heads of one KV head stay contiguous
+        q_all = g.all_gather(q3.reshape(T, 1, hkv, h // hkv, D).contiguous(), dim=1)
+        q_all = q_all.permute(0, 2, 1, 3, 4).reshape(T, d * h, D)
+        qsl = (md.query_start_loc_cpu if md.query_start_loc_cpu is not None else md.query_start_loc.cpu()).tolist()
+        sls = (md.seq_lens_cpu if md.seq_lens_cpu is not None else md.seq_lens.cpu()).tolist()
+        bs = kv_cache.shape[3]
+        o_ctx = torch.zeros(T, d * h, D, dtype=torch.float32, device=q.device)
+        lse_ctx = torch.full((T, d * h), float("-inf"), dtype=torch.float32, device=q.device)
+        o_new = torch.zeros(T, h, D, dtype=torch.float32, device=q.device)
+        lse_new = torch.full((T, h), float("-inf"), dtype=torch.float32, device=q.device)
+        for i in range(md.num_reqs):
+            s, e = qsl[i], qsl[i + 1]
+            if e <= s:
+                continue
+            ctx = sls[i] - (e - s)                                             # positions before this step's tokens
+            n_loc = (ctx - r + d - 1) // d if ctx > r else 0                   # ... of which this rank stores n_loc
+            if n_loc > 0:
+                nb = (n_loc + bs - 1) // bs
+                blk = kv_cache[md.block_table[i, :nb].long()]                  # [nb, 2, hkv, bs, D]
+                kc = blk[:, 0].permute(0, 2, 1, 3).reshape(nb * bs, hkv, D)[:n_loc]
+                vc = blk[:, 1].permute(0, 2, 1, 3).reshape(nb * bs, hkv, D)[:n_loc]
+                o_ctx[s:e], lse_ctx[s:e] = ref.partial_attention(q_all[s:e], kc, vc, self.scale, None, self.logits_soft_cap)
+            o_new[s:e], lse_new[s:e] = ref.partial_attention(q3[s:e], k3[s:e], v3[s:e], self.scale, 0, self.logits_soft_cap)
+        # merge the context partials of the d ranks (softmax-weighted by their lse), keep this rank's heads
+        lse_all = g.all_gather(lse_ctx[..., None].contiguous(), dim=-1)       # [T, d*h, d]
+        lse_tot = torch.logsumexp(lse_all, dim=-1)
+        w = torch.exp(lse_ctx - lse_tot).nan_to_num(0.0)                      # ranks without context contribute 0
+        o_all = g.all_reduce((o_ctx * w[..., None]).contiguous())
+        mine = o_all.reshape(T, hkv, d, h // hkv, D)[:, :, r].reshape(T, h, D)
+        lse_c = lse_tot.reshape(T, hkv, d, h // hkv)[:, :, r].reshape(T, h)
+        m = torch.maximum(lse_c, lse_new)
+        wc, wn = torch.exp(lse_c - m).nan_to_num(0.0), torch.exp(lse_new - m)
+        out = (mine * wc[..., None] + o_new * wn[..., None]) / (wc + wn)[..., None]
+        return out.to(q.dtype).reshape(T, h * D)
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                 positions: Optional[torch.Tensor] = None, qk_norm: Optional[tuple] = None) -> torch.Tensor:
@@ -75,6 +136,13 @@ class Attention(nn.Module):
             if self.rope is not None and positions is not None:
                 q, k = self.rope(positions, q, k)
             return q.clone() if q.shape[-1] == self.num_heads * D else q
+        from vllm_b200.parallel.state import get_dcp_group
+        if get_dcp_group().world_size > 1:
+            if qk_norm is not None:
+                qn, kn = qk_norm
+                q = qn(q.reshape(T, -1, D)).reshape(T, -1)
+                k = kn(k.reshape(T, -1, D)).reshape(T, -1)
+            return self._forward_dcp(q, k, v, positions, md, kv_cache)
         pcp = ctx.extra.get("pcp")
         mpos = ctx.extra.get("mrope_positions") if (self.rope is not None and self.rope.mrope_section) else None
         if qk_norm is not None:

@@ -274,6 +274,31 @@ def mla_partial_attention(q_abs: torch.Tensor, q_pe: torch.Tensor, lat: torch.Te
     return torch.einsum("qhk,kr->qhr", p, kc), lse
 
 
+def partial_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float,
+                      causal_offset: Optional[int] = None, soft_cap: float = 0.0) -> tuple[torch.Tensor, torch.Tensor]:
+    """Attention of q [q, H, D] over k / v [n, Hkv, D] (H a multiple of Hkv, GQA) without normalising across calls:
+    returns (out [q, H, D] fp32, lse [q, H]) so that partial results over disjoint key sets merge exactly.
+    ``causal_offset``: query i may see keys 0..causal_offset+i (None = all keys).  n = 0 gives (0, -inf)."""
+    Q, H, D = q.shape
+    n, Hkv = k.shape[0], k.shape[1]
+    if n == 0:
+        return (torch.zeros(Q, H, D, dtype=torch.float32, device=q.device),
+                torch.full((Q, H), float("-inf"), dtype=torch.float32, device=q.device))
+    g = H // Hkv
+    kf = k.float().repeat_interleave(g, dim=1)
+    vf = v.float().repeat_interleave(g, dim=1)
+    att = torch.einsum("qhd,khd->qhk", q.float(), kf) * scale
+    if soft_cap:
+        att = soft_cap * torch.tanh(att / soft_cap)
+    if causal_offset is not None:
+        qi = torch.arange(Q, device=att.device)[:, None, None]
+        kj = torch.arange(n, device=att.device)[None, None, :]
+        att = att.masked_fill(kj > qi + causal_offset, float("-inf"))
+    lse = torch.logsumexp(att, dim=-1)
+    p = torch.exp(att - lse[..., None])
+    return torch.einsum("qhk,khd->qhd", p, vf), lse
+
+
 # -------------------------------------------------------------- sampling
 def apply_penalties(logits: torch.Tensor, prompt_mask: torch.Tensor, output_counts: torch.Tensor,
                     presence: torch.Tensor, frequency: torch.Tensor, repetition: torch.Tensor) -> torch.Tensor:

@@ -290,8 +290,18 @@ class ModelRunner:
         if self.dcp > 1:
             from vllm_b200.parallel.state import get_dcp_group
             self.dcp_rank = max(get_dcp_group().rank_in_group, 0)
-            if not all(isinstance(g.spec, MLAAttentionSpec) for g in cfg.kv_cache_groups):
-                raise NotImplementedError("decode context parallelism is implemented for MLA (latent-cache) models")
+            hf = self.mc.hf_config
+            total_kv = hf.get("num_key_value_heads") or hf.get("num_attention_heads") or 1
+            tp = self.vllm_config.parallel_config.tensor_parallel_size
+            if any(not isinstance(g.spec, MLAAttentionSpec) for g in cfg.kv_cache_groups) and \
+                    (tp % total_kv != 0 or (tp // total_kv) % self.dcp != 0):
+                raise ValueError(f"decode context parallelism shards the positions of REPLICATED KV heads: it needs "
+                                 f"tensor_parallel_size / num_key_value_heads ({tp} / {total_kv}) to be a multiple of "
+                                 f"decode_context_parallel_size ({self.dcp})")
+            if not all(isinstance(g.spec, MLAAttentionSpec) or getattr(g.spec, "dcp", 1) == self.dcp
+                       for g in cfg.kv_cache_groups):
+                raise NotImplementedError("decode context parallelism covers MLA latent caches and full-attention GQA / MQA "
+                                          "caches (no sliding-window or state-space groups)")
             if self.use_cuda_graph:
                 logger.warning("decode context parallelism runs eagerly (per-request merge on the host)")
                 self.use_cuda_graph = False
@@ -305,7 +315,7 @@ class ModelRunner:
             self.kv_vt.append(bool(
                 self.is_cuda and not envs.VLLM_B200_FORCE_REF_OPS and envs.VLLM_B200_ATTN != "simt"
                 and not isinstance(s, MLAAttentionSpec) and getattr(s, "head_size", 0) == 128
-                and s.block_size == 64 and kvd in (torch.bfloat16, torch.float16)
+                and s.block_size == 64 and getattr(s, "dcp", 1) == 1 and kvd in (torch.bfloat16, torch.float16)
                 and self.dtype in (torch.bfloat16, torch.float16)
                 # features only the generic kernel implements keep the whole group on the standard layout
                 and all(not getattr(attention_layers().get(n), "logits_soft_cap", 0.0)
@@ -321,7 +331,7 @@ class ModelRunner:
                 if isinstance(s, MLAAttentionSpec):
                     shape = (cfg.num_blocks, s.phys_block_size, s.head_size)
                 else:
-                    shape = (cfg.num_blocks, 2, s.num_kv_heads, s.block_size, s.head_size)
+                    shape = (cfg.num_blocks, 2, s.num_kv_heads, getattr(s, "phys_block_size", s.block_size), s.head_size)
                 self.kv_caches[name] = torch.zeros(shape, dtype=kvd, device=self.device)
         if self.kv_connector is not None and hasattr(self.kv_connector, "register_kv_caches"):
             self.kv_connector.register_kv_caches(self.kv_caches)
