@@ -166,3 +166,36 @@ def test_builtin_chat_templates_and_resolution(tmp_path):
     assert resolve_chat_template("{{ 1 }}") == "{{ 1 }}" and resolve_chat_template(None) is None
     with pytest.raises(ValueError):
         resolve_chat_template("nonexistent-template")
+
+
+def test_round2_reasoning_formats():
+    """Tag dialects added in round 2: custom tags, three-token markers with a pre-filled opener, newline-trimmed end tag,
+    self-addressed channel framing; batch and streaming agree."""
+    def run(name, text, chunks=None):
+        p = get_reasoning_parser(name)()
+        r, c = p.extract(text)
+        ps = get_reasoning_parser(name)()
+        rs, cs, cur = "", "", ""
+        for d in (chunks or [text[i:i + 5] for i in range(0, len(text), 5)]):
+            prev, cur = cur, cur + d
+            out = ps.extract_streaming(prev, cur, d)
+            if out:
+                rs += out.get("reasoning_content") or ""
+                cs += out.get("content") or ""
+        return (r, c), (rs.strip() or None, cs.strip() or None)
+
+    (r, c), (rs, cs) = run("minimax_m3", "<mm:think>plan the answer</mm:think>The answer is 4.")
+    assert (r, c) == ("plan the answer", "The answer is 4.") and (rs, cs) == (r, c)
+    (r, c), (rs, cs) = run("kimi_k3", " weigh options <|close|>think<|sep|>Pick B.")           # opener was the generation prefix
+    assert (r, c) == ("weigh options", "Pick B.") and (rs, cs) == (r, c)
+    (r, c), _ = run("kimi_k3", "<|open|>think<|sep|>x<|close|>think<|sep|>y")
+    assert (r, c) == ("x", "y")
+    (r, c), (rs, cs) = run("step3p5", "<think>two lines\nof thought\n</think>\nDone.")
+    assert (r, c) == ("two lines\nof thought", "Done.") and rs == r and cs == c
+    (r, c), _ = run("muse_glimmer", "to=self<|message|>check units<|eom|><|start|>assistant<|message|>12 km<|eot|>")
+    assert (r, c) == ("check units", "12 km")
+    (r, c), _ = run("muse_glimmer", "<|start|>assistant<|message|>plain reply<|eot|>")
+    assert (r, c) == (None, "plain reply")
+    for name in ("deepseek_v4", "glm47_moe", "hy_v3", "ling3", "inkling", "poolside_v1", "gptoss"):
+        assert name in list_reasoning_parsers()
+    assert get_reasoning_parser("hy_v3")().extract("<think>a</think>b") == ("a", "b")

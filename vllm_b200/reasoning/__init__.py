@@ -119,6 +119,53 @@ class GptOssReasoningParser(ReasoningParser):
         return (r.strip() or None) if r else None, c
 
 
+class TrimmedThinkParser(ReasoningParser):
+    """``<think>…</think>`` where the model tends to put a newline right before and right after the end tag
+    (Step-3.5 style): those two newlines belong to neither stream."""
+
+    def extract(self, text: str):
+        r, c = super().extract(text)
+        return (r.strip("\n") or None) if r else r, (c.lstrip("\n") or None) if c else c
+
+    def extract_streaming(self, prev, cur, delta):
+        out = super().extract_streaming(prev, cur, delta)
+        if out and out.get("done") and out.get("reasoning_content"):
+            out["reasoning_content"] = out["reasoning_content"].rstrip("\n") or None
+            if out["reasoning_content"] is None:
+                out.pop("reasoning_content")
+        return out
+
+
+class SelfChannelReasoningParser(ReasoningParser):
+    """Channel-framed output where the chain of thought is addressed to the model itself:
+    ``to=self<|message|>…reasoning…<|eom|>`` followed by the user-facing message
+    (``<|start|>assistant<|message|>…<|eot|>``); all framing markers are dropped from both streams."""
+    start, end = "to=self<|message|>", "<|eom|>"
+    start_optional = False
+    _MARKERS = ("<|start|>assistant", "<|message|>", "<|eom|>", "<|eot|>", "<|start|>")
+
+    def _clean(self, c):
+        if not c:
+            return None
+        for m in self._MARKERS:
+            c = c.replace(m, "")
+        return c.strip() or None
+
+    def extract(self, text: str):
+        if self.start not in text:
+            return None, self._clean(text)
+        body = text.split(self.start, 1)[1]
+        r, _, rest = body.partition(self.end)
+        return (r.strip() or None), self._clean(rest)
+
+
+class Kimi3ReasoningParser(ReasoningParser):
+    """Three-token markers: ``<|open|>think<|sep|> reasoning <|close|>think<|sep|>``; the opening marker may have been fed
+    as the generation prefix, so output can begin inside the block."""
+    start, end = "<|open|>think<|sep|>", "<|close|>think<|sep|>"
+    start_optional = True
+
+
 class IdentityReasoningParser(ReasoningParser):
     def extract(self, text: str):
         return None, text
@@ -136,7 +183,13 @@ _PARSERS = {
     "seed_oss": _tag_parser("<seed:think>", "</seed:think>"), "kimi": _tag_parser("◁think▷", "◁/think▷"),
     "cohere_command": _tag_parser("<|START_THINKING|>", "<|END_THINKING|>", False),
     "gemma4": _tag_parser("<|think|>", "<|/think|>", False),
-    "gpt_oss": GptOssReasoningParser, "openai_gptoss": GptOssReasoningParser, "identity": IdentityReasoningParser,
+    "gpt_oss": GptOssReasoningParser, "openai_gptoss": GptOssReasoningParser, "gptoss": GptOssReasoningParser,
+    "identity": IdentityReasoningParser,
+    # further <think> dialects of the reference's registry
+    "deepseek_v4": ReasoningParser, "glm47_moe": ReasoningParser, "hy_v3": ReasoningParser, "ling3": ReasoningParser,
+    "inkling": ReasoningParser, "poolside_v1": ReasoningParser, "step3p5": TrimmedThinkParser,
+    "minimax_m3": _tag_parser("<mm:think>", "</mm:think>"), "kimi_k3": Kimi3ReasoningParser,
+    "muse_glimmer": SelfChannelReasoningParser,
 }
 
 
