@@ -314,11 +314,32 @@ PRESETS: dict[str, dict[str, Any]] = {
         rms_norm_eps=1e-5, hidden_act="silu", max_position_embeddings=512, sliding_window=None,
         layer_types=["full_attention", "full_attention", "full_attention"],
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
-    "olmo-tiny": dict(      # not implemented natively → exercises the Transformers back-end
+    "apertus-tiny": dict(   # not implemented natively → exercises the Transformers back-end
+        architectures=["ApertusForCausalLM"], model_type="apertus", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, hidden_act="xielu",
+        rms_norm_eps=1e-5, rope_theta=10000.0, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
+        tie_word_embeddings=False),
+    "hunyuan-dense-tiny": dict(   # Transformers back-end as well (q/k norms after the rotation)
+        architectures=["HunYuanDenseV1ForCausalLM"], model_type="hunyuan_v1_dense", vocab_size=512, hidden_size=64,
+        intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
+        max_position_embeddings=256, hidden_act="silu", rms_norm_eps=1e-5, rope_theta=10000.0, use_qk_norm=True,
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "ministral-tiny": dict(
+        architectures=["MinistralForCausalLM"], model_type="ministral", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        sliding_window=16, layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"],
+        rms_norm_eps=1e-5, rope_theta=10000.0, hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32",
+        tie_word_embeddings=False),
+    "glm-tiny": dict(
+        architectures=["GlmForCausalLM"], model_type="glm", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        partial_rotary_factor=0.5, attention_bias=True, rms_norm_eps=1e-5, rope_theta=10000.0, hidden_act="silu",
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "olmo-tiny": dict(
         architectures=["OlmoForCausalLM"], model_type="olmo", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
-        rope_theta=10000.0, hidden_act="silu", bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
-        tie_word_embeddings=False),
+        rope_theta=10000.0, hidden_act="silu", clip_qkv=2.0, bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=False),
     "stablelm-tiny": dict(
         architectures=["StableLmForCausalLM"], model_type="stablelm", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
@@ -515,15 +536,18 @@ class ModelConfig:
 
     @property
     def hidden_size(self) -> int:
-        return int(self.hf_config.get("hidden_size", self.hf_config.get("n_embd", 0)))
+        c = self.hf_config
+        return int(c.get("hidden_size") or c.get("n_embd") or c.get("d_model") or 0)
 
     @property
     def num_layers(self) -> int:
-        return int(self.hf_config.get("num_hidden_layers", self.hf_config.get("n_layer", 0)))
+        c = self.hf_config
+        return int(c.get("num_hidden_layers") or c.get("n_layer") or c.get("num_layers") or c.get("n_layers") or 0)
 
     @property
     def num_attention_heads(self) -> int:
-        return int(self.hf_config.get("num_attention_heads", self.hf_config.get("n_head", 0)))
+        c = self.hf_config
+        return int(c.get("num_attention_heads") or c.get("n_head") or c.get("num_heads") or c.get("n_heads") or 0)
 
     @property
     def num_kv_heads(self) -> int:

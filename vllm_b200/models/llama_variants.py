@@ -42,6 +42,17 @@ class _LN1P(nn.Module):
                                               self.eps).to(x.dtype)
 
 
+class _LNPlain(nn.Module):
+    """LayerNorm without learnable scale or shift (OLMo-1)."""
+
+    def __init__(self, eps) -> None:
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x):
+        return torch.nn.functional.layer_norm(x.float(), (x.shape[-1],), None, None, self.eps).to(x.dtype)
+
+
 class _Identity(nn.Module):
     def forward(self, x, residual=None):
         return x if residual is None else (x + residual, x + residual)
@@ -58,6 +69,8 @@ def _norm(kind: str, H: int, eps: float, dtype) -> nn.Module:
         return LayerNorm(H, eps, False, dtype)
     if kind == "ln1p":
         return _LN1P(H, eps, dtype)
+    if kind == "ln_plain":
+        return _LNPlain(eps)
     if kind == "none":
         return _Identity()
     raise ValueError(kind)
@@ -88,6 +101,7 @@ class VariantAttention(nn.Module):
         self.o_proj = RowParallelLinear(nh * hd, H, o["o_bias"], dtype=dtype, prefix=f"{prefix}.o_proj")
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
         eps = o["eps"]
+        self.clip_qkv = o.get("clip_qkv")                             # clamp the projections to ±clip (OLMo-1)
         self.qk_norm = o["qk_norm"]                                   # None | "head" | "head1p" | "full"
         if self.qk_norm in ("head", "head1p"):
             self.q_norm, self.k_norm = RMSNorm(hd, eps, dtype, self.qk_norm == "head1p"), RMSNorm(hd, eps, dtype, self.qk_norm == "head1p")
@@ -109,7 +123,10 @@ class VariantAttention(nn.Module):
                               logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0, prefix=f"{prefix}.attn", rope=rope)
 
     def forward(self, positions, x):
-        q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        qkv = self.qkv_proj(x)
+        if self.clip_qkv:
+            qkv = qkv.clamp(-self.clip_qkv, self.clip_qkv)
+        q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
         if self.qk_norm in ("head", "head1p"):
             # per-head norms ride along with RoPE + the KV insert (one fused launch on CUDA, layers/attention.py)
             return self.o_proj(self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm)))
@@ -155,7 +172,7 @@ class VariantLayer(nn.Module):
 _DEFAULTS = dict(norm="rms", structure="pre", eps=1e-6, qkv_bias=False, o_bias=False, mlp_bias=False, gated_mlp=True,
                  act="silu", qk_norm=None, neox=True, scale=None, residual_multiplier=1.0, sliding=lambda i: False,
                  embed_scale=1.0, logit_scale=1.0, lm_head_bias=False, final_norm_name="model.norm",
-                 use_rope=lambda i, sliding: True)
+                 use_rope=lambda i, sliding: True, clip_qkv=None)
 
 
 class VariantModel(LlamaModel):
@@ -336,4 +353,40 @@ class Ernie4_5ForCausalLM(VariantForCausalLM):
         c.setdefault("tie_word_embeddings", True)
         return dict(eps=c.get("rms_norm_eps", 1e-5), neox=False, qkv_bias=bool(c.get("use_bias")), o_bias=bool(c.get("use_bias")),
                     mlp_bias=bool(c.get("use_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class OlmoForCausalLM(VariantForCausalLM):
+    """OLMo-1: Llama block with parameter-free LayerNorms and optional clamping of the q/k/v projections
+    (reference: models/olmo.py)."""
+    def options(self, c):
+        return dict(norm="ln_plain", eps=1e-5, clip_qkv=c.get("clip_qkv"), qkv_bias=bool(c.get("attention_bias")),
+                    o_bias=bool(c.get("attention_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class StableLmForCausalLM(VariantForCausalLM):
+    """StableLM-2 / StableLM-3B: LayerNorm (with bias), partial rotary, optional q/k/v biases, optional parallel residual
+    (reference: models/stablelm.py).  Per-head q/k LayerNorm (stablelm-2-12b) is not implemented."""
+    def options(self, c):
+        if c.get("qk_layernorm"):
+            raise NotImplementedError("StableLM with per-head q/k LayerNorm (stablelm-2-12b)")
+        return dict(norm="ln", eps=c.get("layer_norm_eps", 1e-5), qkv_bias=bool(c.get("use_qkv_bias")),
+                    structure="parallel" if c.get("use_parallel_residual") else "pre")
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class MinistralForCausalLM(VariantForCausalLM):
+    """Mistral block with per-layer sliding-window / full attention (``layer_types``) (reference: models/mistral.py family)."""
+    def options(self, c):
+        types = c.get("layer_types")
+        return dict(eps=c.get("rms_norm_eps", 1e-6), sliding=(lambda i: types[i] == "sliding_attention") if types else (lambda i: bool(c.get("sliding_window"))))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class GlmForCausalLM(VariantForCausalLM):
+    """GLM-4-9B (HF ``glm``): pre-norm Llama block, biased q/k/v, half-width interleaved rotary, fused gate_up tensor
+    (reference: models/glm.py)."""
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-5), qkv_bias=bool(c.get("attention_bias", True)), neox=False)
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]

@@ -36,6 +36,11 @@ _MODELS: dict[str, tuple[str, str]] = {
     "ArceeForCausalLM": ("llama_variants", "ArceeForCausalLM"),
     "HeliumForCausalLM": ("llama_variants", "HeliumForCausalLM"),
     "Ernie4_5ForCausalLM": ("llama_variants", "Ernie4_5ForCausalLM"),
+    "OlmoForCausalLM": ("llama_variants", "OlmoForCausalLM"),
+    "StableLmForCausalLM": ("llama_variants", "StableLmForCausalLM"),
+    "StableLMEpochForCausalLM": ("llama_variants", "StableLmForCausalLM"),
+    "MinistralForCausalLM": ("llama_variants", "MinistralForCausalLM"),
+    "GlmForCausalLM": ("llama_variants", "GlmForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
