@@ -324,6 +324,12 @@ PRESETS: dict[str, dict[str, Any]] = {
         intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
         max_position_embeddings=256, hidden_act="silu", rms_norm_eps=1e-5, rope_theta=10000.0, use_qk_norm=True,
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "phimoe-tiny": dict(
+        architectures=["PhimoeForCausalLM"], model_type="phimoe", vocab_size=512, hidden_size=64, intermediate_size=96,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2,
+        max_position_embeddings=256, rms_norm_eps=1e-5, rope_theta=10000.0, hidden_act="silu", attention_bias=True,
+        lm_head_bias=True, router_jitter_noise=0.01, input_jitter_noise=0.0, sliding_window=None,
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "ministral-tiny": dict(
         architectures=["MinistralForCausalLM"], model_type="ministral", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,

@@ -141,7 +141,18 @@ class VariantLayer(nn.Module):
         H, eps = cfg["hidden_size"], o["eps"]
         self.o = o
         self.self_attn = VariantAttention(cfg, mc, dtype, f"{prefix}.self_attn", idx, o)
-        if o["gated_mlp"]:
+        self.moe_partial = False
+        if o.get("moe"):
+            # sparse block (router + fused experts); returns this rank's PARTIAL sum, reduced in forward()
+            from vllm_b200.models.mixtral import SparseMoeBlock
+            m = o["moe"]
+            self.mlp = SparseMoeBlock(cfg, dtype, quant_config, f"{prefix}.mlp", m.get("enable_ep", False),
+                                      n_experts=m["n_experts"], top_k=m["top_k"], inter=cfg["intermediate_size"],
+                                      renormalize=m.get("renormalize", False))
+            if m.get("routing") is not None:
+                self.mlp.experts.custom_routing = m["routing"]
+            self.moe_partial = True
+        elif o["gated_mlp"]:
             self.mlp = LlamaMLP(H, cfg["intermediate_size"], o["act"], o["mlp_bias"], dtype, quant_config, f"{prefix}.mlp")
         else:
             self.mlp = _PlainMLP(H, cfg["intermediate_size"], o["act"], o["mlp_bias"], dtype, f"{prefix}.mlp")
@@ -163,6 +174,8 @@ class VariantLayer(nn.Module):
                 a = self.post_attn_norm(a)
             x = x + a * self.rm
             m = self.mlp(self.pre_mlp_norm(x) if st in ("pre", "sandwich") else x)
+            if self.moe_partial and get_tp_group().world_size > 1:
+                m = get_tp_group().all_reduce(m)
             if st in ("post", "sandwich"):
                 m = self.post_mlp_norm(m)
             x = x + m * self.rm
@@ -390,3 +403,28 @@ class GlmForCausalLM(VariantForCausalLM):
     def options(self, c):
         return dict(eps=c.get("rms_norm_eps", 1e-5), qkv_bias=bool(c.get("attention_bias", True)), neox=False)
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class PhimoeForCausalLM(VariantForCausalLM):
+    """Phi-3.5-MoE: LayerNorm (with bias) block, biased attention projections, 16 experts / top-2 with the *sparsemixer*
+    router (experts picked one at a time, weights from a softmax over the logits within a jitter band of the running
+    maximum), biased LM head (reference: models/phimoe.py)."""
+    expert_names = {"w1": ("w13_weight", "w1"), "w3": ("w13_weight", "w3"), "w2": ("w2_weight", "w2")}
+    expert_container = "mlp.experts"
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".block_sparse_moe.", ".mlp."), (".mlp.router.", ".mlp.gate.")]
+
+    def options(self, c):
+        from vllm_b200.layers.moe import sparsemixer_routing
+        return dict(norm="ln", eps=c.get("rms_norm_eps", 1e-5), qkv_bias=bool(c.get("attention_bias", True)),
+                    o_bias=bool(c.get("attention_bias", True)), lm_head_bias=bool(c.get("lm_head_bias", True)),
+                    moe=dict(n_experts=c["num_local_experts"], top_k=c["num_experts_per_tok"], renormalize=False,
+                             routing=sparsemixer_routing(float(c.get("router_jitter_noise", 0.01)))))
+
+
+def _mix_in_expert_loader():
+    # the per-expert / fused expert tensor loader lives with the Mixtral family; the variant block only renames
+    from vllm_b200.models.mixtral import MixtralForCausalLM
+    PhimoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+
+
+_mix_in_expert_loader()

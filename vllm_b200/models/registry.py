@@ -41,6 +41,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "StableLMEpochForCausalLM": ("llama_variants", "StableLmForCausalLM"),
     "MinistralForCausalLM": ("llama_variants", "MinistralForCausalLM"),
     "GlmForCausalLM": ("llama_variants", "GlmForCausalLM"),
+    "PhimoeForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
+    "PhiMoEForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
