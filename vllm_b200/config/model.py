@@ -133,6 +133,11 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,
         layer_norm_epsilon=1e-5, intermediate_size=128, bos_token_id=0, eos_token_id=0, pad_token_id=0,
         torch_dtype="float32", tie_word_embeddings=True, max_position_embeddings=1024),
+    "falconmamba-tiny": dict(
+        architectures=["FalconMambaForCausalLM"], model_type="falcon_mamba", vocab_size=512, hidden_size=64, state_size=8,
+        num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,
+        layer_norm_epsilon=1e-5, mixer_rms_eps=1e-6, intermediate_size=128, bos_token_id=0, eos_token_id=0, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=True, max_position_embeddings=1024),
     "phi3-tiny": dict(
         architectures=["Phi3ForCausalLM"], model_type="phi3", vocab_size=512, hidden_size=128, intermediate_size=256,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=1024,
@@ -319,7 +324,7 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, hidden_act="xielu",
         rms_norm_eps=1e-5, rope_theta=10000.0, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
         tie_word_embeddings=False),
-    "hunyuan-dense-tiny": dict(   # Transformers back-end as well (q/k norms after the rotation)
+    "hunyuan-dense-tiny": dict(   # q/k norms after the rotation
         architectures=["HunYuanDenseV1ForCausalLM"], model_type="hunyuan_v1_dense", vocab_size=512, hidden_size=64,
         intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
         max_position_embeddings=256, hidden_act="silu", rms_norm_eps=1e-5, rope_theta=10000.0, use_qk_norm=True,

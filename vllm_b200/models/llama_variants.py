@@ -103,7 +103,7 @@ class VariantAttention(nn.Module):
         eps = o["eps"]
         self.clip_qkv = o.get("clip_qkv")                             # clamp the projections to ±clip (OLMo-1)
         self.qk_norm = o["qk_norm"]                                   # None | "head" | "head1p" | "full"
-        if self.qk_norm in ("head", "head1p"):
+        if self.qk_norm in ("head", "head1p", "head_post_rope"):
             self.q_norm, self.k_norm = RMSNorm(hd, eps, dtype, self.qk_norm == "head1p"), RMSNorm(hd, eps, dtype, self.qk_norm == "head1p")
         elif self.qk_norm == "full":
             assert get_tp_group().world_size == 1, "whole-projection q/k norms need the unsharded projection"
@@ -132,6 +132,14 @@ class VariantAttention(nn.Module):
             return self.o_proj(self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm)))
         elif self.qk_norm == "full":
             q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
+        elif self.qk_norm == "head_post_rope":
+            # HunYuan: the per-head norms act on the ROTATED q / k — rotate here, norm, hand over without positions
+            T = q.shape[0]
+            if self.attn.rope is not None:
+                q, k = self.attn.rope(positions, q.contiguous(), k.contiguous())
+            q = self.q_norm(q.reshape(T, -1, self.hd)).reshape(T, -1)
+            k = self.k_norm(k.reshape(T, -1, self.hd)).reshape(T, -1)
+            return self.o_proj(self.attn(q, k, v, None))
         return self.o_proj(self.attn(q, k, v, positions))
 
 
@@ -403,6 +411,15 @@ class GlmForCausalLM(VariantForCausalLM):
     def options(self, c):
         return dict(eps=c.get("rms_norm_eps", 1e-5), qkv_bias=bool(c.get("attention_bias", True)), neox=False)
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class HunYuanDenseV1ForCausalLM(VariantForCausalLM):
+    """HunYuan dense: Llama block whose per-head q / k RMSNorms are applied AFTER the rotary embedding
+    (reference: models/hunyuan_v1.py)."""
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-5), qk_norm="head_post_rope" if c.get("use_qk_norm", True) else None,
+                    qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")), mlp_bias=bool(c.get("mlp_bias")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".query_layernorm.", ".q_norm."), (".key_layernorm.", ".k_norm.")]
 
 
 class PhimoeForCausalLM(VariantForCausalLM):

@@ -25,9 +25,12 @@ class MambaBlock(nn.Module):
         dtr = cfg.get("time_step_rank", "auto")
         dtr = math.ceil(H / 16) if dtr == "auto" else int(dtr)
         self.norm = RMSNorm(H, cfg.get("layer_norm_epsilon", 1e-5), dtype)
+        # FalconMamba: weight-free RMS normalisation of dt / B / C (the norm modules keep their all-ones weights: the
+        # checkpoint has none) — reference: models/falcon_mamba config ``mixer_rms_eps``
+        bcdt = float(cfg["mixer_rms_eps"]) if cfg.get("model_type") == "falcon_mamba" and cfg.get("mixer_rms_eps") else None
         self.mixer = MambaMixer(H, di, cfg.get("state_size", 16), cfg.get("conv_kernel", 4), dtr,
                                 bool(cfg.get("use_bias", False)), bool(cfg.get("use_conv_bias", True)), dtype,
-                                f"{prefix}.mixer")
+                                f"{prefix}.mixer", bcdt_norm_eps=bcdt)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return x + self.mixer(self.norm(x))

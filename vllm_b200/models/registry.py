@@ -41,6 +41,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "StableLMEpochForCausalLM": ("llama_variants", "StableLmForCausalLM"),
     "MinistralForCausalLM": ("llama_variants", "MinistralForCausalLM"),
     "GlmForCausalLM": ("llama_variants", "GlmForCausalLM"),
+    "HunYuanDenseV1ForCausalLM": ("llama_variants", "HunYuanDenseV1ForCausalLM"),
     "PhimoeForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "PhiMoEForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
@@ -61,6 +62,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3MoeForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
     "GptOssForCausalLM": ("gpt_oss", "GptOssForCausalLM"),
     "MambaForCausalLM": ("mamba", "MambaForCausalLM"),
+    "FalconMambaForCausalLM": ("mamba", "MambaForCausalLM"),
     "Qwen3NextForCausalLM": ("qwen3_next", "Qwen3NextForCausalLM"),
     "Mamba2ForCausalLM": ("mamba2", "Mamba2ForCausalLM"),
     "BambaForCausalLM": ("mamba2", "BambaForCausalLM"),
