@@ -133,6 +133,16 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,
         layer_norm_epsilon=1e-5, intermediate_size=128, bos_token_id=0, eos_token_id=0, pad_token_id=0,
         torch_dtype="float32", tie_word_embeddings=True, max_position_embeddings=1024),
+    "biogpt-tiny": dict(
+        architectures=["BioGptForCausalLM"], model_type="biogpt", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, max_position_embeddings=256, hidden_act="gelu", layer_norm_eps=1e-5,
+        scale_embedding=True, bos_token_id=0, eos_token_id=2, pad_token_id=1, torch_dtype="float32",
+        tie_word_embeddings=True, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, activation_dropout=0.0),
+    "xglm-tiny": dict(
+        architectures=["XGLMForCausalLM"], model_type="xglm", vocab_size=512, d_model=64, ffn_dim=128, num_layers=2,
+        attention_heads=4, max_position_embeddings=256, activation_function="gelu", scale_embedding=True,
+        bos_token_id=0, eos_token_id=2, pad_token_id=1, decoder_start_token_id=2, torch_dtype="float32",
+        tie_word_embeddings=True, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layerdrop=0.0),
     "falconmamba-tiny": dict(
         architectures=["FalconMambaForCausalLM"], model_type="falcon_mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

@@ -71,11 +71,14 @@ class OPTForCausalLM(nn.Module):
             self.lm_head.tie_weights(self.embed_tokens)
         self.logits_processor = LogitsProcessor(cfg["vocab_size"])
 
+    embed_scale = 1.0
+
     def embed_input_ids(self, ids):
-        return self.embed_tokens(ids)
+        h = self.embed_tokens(ids)
+        return h * self.embed_scale if self.embed_scale != 1.0 else h
 
     def forward(self, input_ids, positions, intermediate_tensors=None, inputs_embeds=None):
-        h = inputs_embeds if inputs_embeds is not None else self.embed_tokens(input_ids)
+        h = inputs_embeds if inputs_embeds is not None else self.embed_input_ids(input_ids)
         if self.project_in is not None:
             h = self.project_in(h)
         h = h + self.embed_positions(positions + 2)
@@ -95,7 +98,9 @@ class OPTForCausalLM(nn.Module):
         modules = dict(self.named_modules())
         loaded = set()
         for name, w in weights:
-            name = name.replace("model.decoder.", "").replace("decoder.", "")
+            name = self._rename(name)
+            if name is None:
+                continue
             if name.startswith("lm_head") and self.cfg.get("tie_word_embeddings", True):
                 continue
             name = name.replace("self_attn.out_proj", "out_proj")
@@ -113,6 +118,77 @@ class OPTForCausalLM(nn.Module):
                 params[name].data.copy_(w)
             loaded.add(name)
         return loaded
+
+
+    def _rename(self, name: str):
+        return name.replace("model.decoder.", "").replace("decoder.", "")
+
+
+def _as_opt_config(cfg: dict, *, ffn: str, act: str) -> dict:
+    cfg.setdefault("ffn_dim", cfg.get(ffn))
+    cfg.setdefault("activation_function", cfg.get(act, "gelu"))
+    cfg.setdefault("do_layer_norm_before", True)
+    cfg.setdefault("enable_bias", True)
+    return cfg
+
+
+class BioGptForCausalLM(OPTForCausalLM):
+    """BioGPT: the OPT block (pre-LayerNorm, learned positions with offset 2) with sqrt(H)-scaled embeddings and GELU
+    (reference: models via the Transformers back-end; HF ``modeling_biogpt``)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = _as_opt_config(vllm_config.model_config.hf_config, ffn="intermediate_size", act="hidden_act")
+        super().__init__(vllm_config, prefix)
+        self.embed_scale = float(cfg["hidden_size"]) ** 0.5 if cfg.get("scale_embedding", True) else 1.0
+
+    def _rename(self, name: str):
+        name = name.replace("biogpt.", "")
+        if name.startswith("layer_norm."):
+            name = "final_layer_norm." + name[len("layer_norm."):]
+        return name.replace("output_projection.", "lm_head.")
+
+
+class _FixedTable(nn.Module):
+    def __init__(self, table: torch.Tensor) -> None:
+        super().__init__()
+        self.register_buffer("table", table, persistent=False)
+
+    def forward(self, idx: torch.Tensor) -> torch.Tensor:
+        return self.table[idx]
+
+
+class XGLMForCausalLM(OPTForCausalLM):
+    """XGLM: the OPT block with sqrt(H)-scaled embeddings and fixed sinusoidal positions (offset 2)
+    (HF ``modeling_xglm``; fairseq-style table: [sin | cos] halves, padding row zero)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        import math
+        cfg = _as_opt_config(vllm_config.model_config.hf_config, ffn="ffn_dim", act="activation_function")
+        cfg.setdefault("hidden_size", cfg.get("d_model"))
+        cfg.setdefault("num_attention_heads", cfg.get("attention_heads"))
+        cfg.setdefault("num_hidden_layers", cfg.get("num_layers"))
+        super().__init__(vllm_config, prefix)
+        H = cfg["hidden_size"]
+        self.embed_scale = math.sqrt(H) if cfg.get("scale_embedding", True) else 1.0
+        n = cfg["max_position_embeddings"] + 2
+        half = H // 2
+        freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+        ang = torch.arange(n, dtype=torch.float32)[:, None] * freq[None]
+        table = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
+        if H % 2:
+            table = torch.cat([table, torch.zeros(n, 1)], dim=1)
+        pad = cfg.get("pad_token_id")
+        if pad is not None and pad < n:
+            table[pad] = 0
+        self.embed_positions = _FixedTable(table.to(vllm_config.model_config.torch_dtype))   # a buffer: not a weight
+
+    def _rename(self, name: str):
+        if "embed_positions" in name:
+            return None                      # the table is a function of the position, not a checkpoint tensor
+        name = name.replace("model.", "", 1) if name.startswith("model.") else name
+        if name.startswith("layer_norm."):
+            name = "final_layer_norm." + name[len("layer_norm."):]
+        return name
 
 
 class GPT2Block(nn.Module):

@@ -54,6 +54,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "FalconForCausalLM": ("gpt_neox", "FalconForCausalLM"),
     "RWForCausalLM": ("gpt_neox", "FalconForCausalLM"),
     "OPTForCausalLM": ("opt", "OPTForCausalLM"),
+    "BioGptForCausalLM": ("opt", "BioGptForCausalLM"),
+    "XGLMForCausalLM": ("opt", "XGLMForCausalLM"),
     "GPT2LMHeadModel": ("opt", "GPT2LMHeadModel"),
     "GPTBigCodeForCausalLM": ("opt", "GPTBigCodeForCausalLM"),
     "MixtralForCausalLM": ("mixtral", "MixtralForCausalLM"),
