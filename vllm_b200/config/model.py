@@ -143,6 +143,13 @@ PRESETS: dict[str, dict[str, Any]] = {
         attention_heads=4, max_position_embeddings=256, activation_function="gelu", scale_embedding=True,
         bos_token_id=0, eos_token_id=2, pad_token_id=1, decoder_start_token_id=2, torch_dtype="float32",
         tie_word_embeddings=True, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layerdrop=0.0),
+    "vaultgemma-tiny": dict(
+        architectures=["VaultGemmaForCausalLM"], model_type="vaultgemma", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        sliding_window=16, layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"],
+        query_pre_attn_scalar=16, attn_logit_softcapping=50.0, final_logit_softcapping=30.0,
+        hidden_activation="gelu_pytorch_tanh", rms_norm_eps=1e-6, rope_theta=10000.0, bos_token_id=2, eos_token_id=1,
+        pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
     "falconmamba-tiny": dict(
         architectures=["FalconMambaForCausalLM"], model_type="falcon_mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

@@ -413,6 +413,19 @@ class GlmForCausalLM(VariantForCausalLM):
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
 
 
+class VaultGemmaForCausalLM(VariantForCausalLM):
+    """VaultGemma: the Gemma-2 recipe (scaled embeddings, (1+w) RMSNorm, tanh-GELU gated MLP, attention / logit soft caps,
+    alternating sliding-window layers) with pre-norms only (HF ``modeling_vaultgemma``)."""
+    def options(self, c):
+        c.setdefault("tie_word_embeddings", True)
+        types = c.get("layer_types")
+        return dict(norm="rms1p", eps=c.get("rms_norm_eps", 1e-6), act=c.get("hidden_activation", "gelu_pytorch_tanh"),
+                    scale=float(c.get("query_pre_attn_scalar", 256)) ** -0.5, embed_scale=float(c["hidden_size"]) ** 0.5,
+                    qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")),
+                    sliding=(lambda i: types[i] == "sliding_attention") if types else (lambda i: i % 2 == 0))
+    renames = [(".pre_feedforward_layernorm.", ".pre_mlp_norm.")]
+
+
 class HunYuanDenseV1ForCausalLM(VariantForCausalLM):
     """HunYuan dense: Llama block whose per-head q / k RMSNorms are applied AFTER the rotary embedding
     (reference: models/hunyuan_v1.py)."""

@@ -42,6 +42,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "MinistralForCausalLM": ("llama_variants", "MinistralForCausalLM"),
     "GlmForCausalLM": ("llama_variants", "GlmForCausalLM"),
     "HunYuanDenseV1ForCausalLM": ("llama_variants", "HunYuanDenseV1ForCausalLM"),
+    "VaultGemmaForCausalLM": ("llama_variants", "VaultGemmaForCausalLM"),
     "PhimoeForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "PhiMoEForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
