@@ -143,6 +143,12 @@ PRESETS: dict[str, dict[str, Any]] = {
         attention_heads=4, max_position_embeddings=256, activation_function="gelu", scale_embedding=True,
         bos_token_id=0, eos_token_id=2, pad_token_id=1, decoder_start_token_id=2, torch_dtype="float32",
         tie_word_embeddings=True, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layerdrop=0.0),
+    "ernie45moe-tiny": dict(
+        architectures=["Ernie4_5_MoeForCausalLM"], model_type="ernie4_5_moe", vocab_size=512, hidden_size=64,
+        intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, moe_num_experts=4, moe_k=2,
+        moe_intermediate_size=48, moe_num_shared_experts=1, moe_layer_start_index=1, moe_layer_interval=1,
+        moe_layer_end_index=2, max_position_embeddings=256, rms_norm_eps=1e-5, rope_theta=10000.0, hidden_act="silu",
+        use_bias=False, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
     "vaultgemma-tiny": dict(
         architectures=["VaultGemmaForCausalLM"], model_type="vaultgemma", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,

@@ -277,6 +277,35 @@ class Glm4MoeForCausalLM(DeepseekV3ForCausalLM):
         super().__init__(vllm_config, prefix)
 
 
+class Ernie4_5_MoeForCausalLM(Glm4MoeForCausalLM):
+    """ERNIE-4.5 MoE (text): GQA attention with interleaved rotary + softmax router whose top-k SELECTION adds a learned
+    correction bias while the mixing weights stay the unbiased, renormalised probabilities; shared experts; leading dense
+    layers (reference: models/ernie45_moe.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("n_routed_experts", cfg.get("moe_num_experts"))
+        cfg.setdefault("num_experts_per_tok", cfg.get("moe_k", 2))
+        cfg.setdefault("n_shared_experts", cfg.get("moe_num_shared_experts", 0))
+        cfg.setdefault("first_k_dense_replace", cfg.get("moe_layer_start_index", 0))
+        cfg.setdefault("scoring_func", "softmax")
+        cfg.setdefault("norm_topk_prob", True)
+        cfg.setdefault("partial_rotary_factor", 1.0)
+        cfg.setdefault("rope_interleaved", True)
+        cfg.setdefault("attention_bias", bool(cfg.get("use_bias", False)))
+        cfg.setdefault("tie_word_embeddings", True)
+        super().__init__(vllm_config, prefix)
+
+    def load_weights(self, weights):
+        def mapped():
+            for name, w in weights:
+                if name.endswith(".mlp.gate.moe_statics.e_score_correction_bias"):
+                    yield name.replace(".moe_statics.", "."), w.reshape(-1)
+                else:
+                    yield name, w
+        return super().load_weights(mapped())
+
+
 class Dots1ForCausalLM(Glm4MoeForCausalLM):
     """dots.llm1: the same composition (GQA attention with per-head q/k norms + DeepSeek-V3 style MoE), full rotary
     (reference: models/dots1.py)."""

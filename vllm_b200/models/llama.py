@@ -78,8 +78,8 @@ class LlamaAttention(nn.Module):
             self.k_norm = RMSNorm(self.head_dim, eps, dtype)
         rot = int(self.head_dim * cfg.get("partial_rotary_factor", 1.0))
         rope = get_rope(self.head_dim, rot, mc.max_model_len if mc.max_model_len > 0 else
-                        cfg.get("max_position_embeddings", 8192), cfg.get("rope_theta", 10000.0), True,
-                        cfg.get("rope_scaling"))
+                        cfg.get("max_position_embeddings", 8192), cfg.get("rope_theta", 10000.0),
+                        not cfg.get("rope_interleaved", False), cfg.get("rope_scaling"))
         sw = cfg.get("sliding_window")
         if sw is not None and cfg.get("max_window_layers") is not None and layer_idx < cfg["max_window_layers"]:
             sw = None  # qwen2: only upper layers use SWA

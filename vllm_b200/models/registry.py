@@ -87,6 +87,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Llama4ForCausalLM": ("llama4", "Llama4ForCausalLM"),
     "Dots1ForCausalLM": ("deepseek", "Dots1ForCausalLM"),
     "Glm4MoeForCausalLM": ("deepseek", "Glm4MoeForCausalLM"),
+    "Ernie4_5_MoeForCausalLM": ("deepseek", "Ernie4_5_MoeForCausalLM"),
     "DeepseekV3ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
 }
 
