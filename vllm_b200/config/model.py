@@ -143,6 +143,11 @@ PRESETS: dict[str, dict[str, Any]] = {
         attention_heads=4, max_position_embeddings=256, activation_function="gelu", scale_embedding=True,
         bos_token_id=0, eos_token_id=2, pad_token_id=1, decoder_start_token_id=2, torch_dtype="float32",
         tie_word_embeddings=True, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layerdrop=0.0),
+    "hunyuan-moe-tiny": dict(
+        architectures=["HunYuanMoEV1ForCausalLM"], model_type="hunyuan_v1_moe", vocab_size=512, hidden_size=64,
+        intermediate_size=96, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, num_experts=4,
+        moe_topk=2, max_position_embeddings=256, hidden_act="silu", rms_norm_eps=1e-5, rope_theta=10000.0, use_qk_norm=True,
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "ernie45moe-tiny": dict(
         architectures=["Ernie4_5_MoeForCausalLM"], model_type="ernie4_5_moe", vocab_size=512, hidden_size=64,
         intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, moe_num_experts=4, moe_k=2,

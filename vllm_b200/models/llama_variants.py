@@ -155,8 +155,8 @@ class VariantLayer(nn.Module):
             from vllm_b200.models.mixtral import SparseMoeBlock
             m = o["moe"]
             self.mlp = SparseMoeBlock(cfg, dtype, quant_config, f"{prefix}.mlp", m.get("enable_ep", False),
-                                      n_experts=m["n_experts"], top_k=m["top_k"], inter=cfg["intermediate_size"],
-                                      renormalize=m.get("renormalize", False))
+                                      n_experts=m["n_experts"], top_k=m["top_k"], inter=m.get("inter") or cfg["intermediate_size"],
+                                      renormalize=m.get("renormalize", False), shared_inter=m.get("shared_inter", 0))
             if m.get("routing") is not None:
                 self.mlp.experts.custom_routing = m["routing"]
             self.moe_partial = True
@@ -451,10 +451,29 @@ class PhimoeForCausalLM(VariantForCausalLM):
                              routing=sparsemixer_routing(float(c.get("router_jitter_noise", 0.01)))))
 
 
+class HunYuanMoEV1ForCausalLM(VariantForCausalLM):
+    """HunYuan MoE (A13B family): the HunYuan attention (per-head q / k norms after the rotation), softmax top-k router with
+    renormalised weights, and an always-on shared MLP next to the routed experts (reference: models/hunyuan_v1.py)."""
+    expert_names = {"w1": ("w13_weight", "w1"), "w3": ("w13_weight", "w3"), "w2": ("w2_weight", "w2")}
+    expert_container = "mlp.experts"
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".query_layernorm.", ".q_norm."), (".key_layernorm.", ".k_norm."),
+               (".mlp.gate.wg.", ".mlp.gate."), (".mlp.shared_mlp.", ".mlp.shared_expert.")]
+
+    def options(self, c):
+        ne, tk = c["num_experts"], c.get("moe_topk", 1)
+        if not isinstance(ne, int) or not isinstance(tk, int):
+            raise NotImplementedError("HunYuan MoE with per-layer expert counts")
+        return dict(eps=c.get("rms_norm_eps", 1e-5), qk_norm="head_post_rope" if c.get("use_qk_norm", True) else None,
+                    qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")),
+                    moe=dict(n_experts=ne, top_k=tk, renormalize=True, inter=c.get("moe_intermediate_size") or c["intermediate_size"],
+                             shared_inter=c["intermediate_size"] if c.get("use_mixed_mlp_moe", True) else 0))
+
+
 def _mix_in_expert_loader():
     # the per-expert / fused expert tensor loader lives with the Mixtral family; the variant block only renames
     from vllm_b200.models.mixtral import MixtralForCausalLM
     PhimoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+    HunYuanMoEV1ForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
 
 
 _mix_in_expert_loader()

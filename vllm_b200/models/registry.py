@@ -43,6 +43,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "GlmForCausalLM": ("llama_variants", "GlmForCausalLM"),
     "HunYuanDenseV1ForCausalLM": ("llama_variants", "HunYuanDenseV1ForCausalLM"),
     "VaultGemmaForCausalLM": ("llama_variants", "VaultGemmaForCausalLM"),
+    "HunYuanMoEV1ForCausalLM": ("llama_variants", "HunYuanMoEV1ForCausalLM"),
     "PhimoeForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "PhiMoEForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
