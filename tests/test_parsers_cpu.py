@@ -199,3 +199,27 @@ def test_round2_reasoning_formats():
     for name in ("deepseek_v4", "glm47_moe", "hy_v3", "ling3", "inkling", "poolside_v1", "gptoss"):
         assert name in list_reasoning_parsers()
     assert get_reasoning_parser("hy_v3")().extract("<think>a</think>b") == ("a", "b")
+
+
+def test_channel_and_function_xml_tool_formats():
+    """Kimi-K3 channel markup (typed arguments, escaped attributes, response channel → content) and the
+    ``<function name=…><param name=…>`` XML dialect; registry aliases of the remaining reference names."""
+    p = get_tool_parser("kimi_k3")()
+    text = ('<|open|>response<|sep|>Let me run that.<|close|>response<|sep|><|open|>tools<|sep|>'
+            '<|open|>call tool="python" index="1"<|sep|><|open|>argument key="code" type="string"<|sep|>print("a<b")<|close|>argument<|sep|>'
+            '<|open|>argument key="opts" type="object"<|sep|>{"n": 3}<|close|>argument<|sep|><|close|>call<|sep|>'
+            '<|open|>call tool="say &quot;hi&quot;" index="2"<|sep|><|open|>argument key="times" type="number"<|sep|>2<|close|>argument<|sep|><|close|>call<|sep|>'
+            '<|close|>tools<|sep|>')
+    out = p.extract(text)
+    assert out["content"] == "Let me run that." and len(out["tool_calls"]) == 2
+    c0, c1 = out["tool_calls"]
+    assert c0["function"]["name"] == "python" and json.loads(c0["function"]["arguments"]) == {"code": 'print("a<b")', "opts": {"n": 3}}
+    assert c1["function"]["name"] == 'say "hi"' and json.loads(c1["function"]["arguments"]) == {"times": 2}
+    assert p.extract("<|open|>response<|sep|>just text<|close|>response<|sep|>") == {"tool_calls": [], "content": "just text"}
+    q = get_tool_parser("minicpm5")()
+    out = q.extract('Checking.<function name="get_weather"><param name="city">Paris</param><param name="days">3</param></function>'
+                    "<function name='noop'></function>")
+    assert out["content"] == "Checking." and [c["function"]["name"] for c in out["tool_calls"]] == ["get_weather", "noop"]
+    assert json.loads(out["tool_calls"][0]["function"]["arguments"]) == {"city": "Paris", "days": 3}
+    for name in ("cohere_command3", "cohere_command4", "deepseek_v4", "poolside_v1", "inkling", "mimo"):
+        assert name in list_tool_parsers()

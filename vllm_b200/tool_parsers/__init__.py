@@ -478,6 +478,81 @@ class Step3ToolParser(ToolParser):
 
 
 
+class ChannelCallToolParser(ToolParser):
+    """Kimi-K3 channel markup: the reply lives in ``<|open|>response<|sep|>…<|close|>response<|sep|>``, tool calls in a
+    sibling ``tools`` channel::
+
+        <|open|>tools<|sep|><|open|>call tool="NAME" index="1"<|sep|>
+          <|open|>argument key="k" type="string"<|sep|>raw text<|close|>argument<|sep|>
+          <|open|>argument key="n" type="number"<|sep|>3<|close|>argument<|sep|>
+        <|close|>call<|sep|><|close|>tools<|sep|>
+
+    ``type="string"`` values are taken verbatim, every other type is JSON-decoded; attribute values are entity-escaped
+    (``&quot;``, ``&amp;``)."""
+    start_markers = ("<|open|>tools<|sep|>", "<|open|>call ")
+    _call_re = re.compile(r"<\|open\|>call\s+([^<]*?)<\|sep\|>(.*?)<\|close\|>call<\|sep\|>", re.S)
+    _arg_re = re.compile(r"<\|open\|>argument\s+([^<]*?)<\|sep\|>(.*?)<\|close\|>argument<\|sep\|>", re.S)
+    _attr_re = re.compile(r"(\w+)\s*=\s*\"([^\"]*)\"")
+    _resp_re = re.compile(r"<\|open\|>response<\|sep\|>(.*?)(?:<\|close\|>response<\|sep\|>|$)", re.S)
+
+    @classmethod
+    def _attrs(cls, s: str) -> dict:
+        return {k: v.replace("&quot;", '"').replace("&amp;", "&") for k, v in cls._attr_re.findall(s)}
+
+    def extract(self, text: str) -> dict:
+        calls = []
+        for m in self._call_re.finditer(text):
+            head = self._attrs(m.group(1))
+            args = {}
+            for am in self._arg_re.finditer(m.group(2)):
+                a = self._attrs(am.group(1))
+                raw = am.group(2)
+                if a.get("type", "string") == "string":
+                    args[a.get("key", "")] = raw
+                else:
+                    try:
+                        args[a.get("key", "")] = json.loads(raw)
+                    except json.JSONDecodeError:
+                        args[a.get("key", "")] = raw.strip()
+            calls.append(_call(head.get("tool", ""), args, len(calls)))
+        rm = self._resp_re.search(text)
+        if rm:
+            content = rm.group(1).strip() or None
+        else:
+            cut = min((text.find(x) for x in self.start_markers if x in text), default=len(text))
+            content = text[:cut].strip() or None
+        return {"tool_calls": calls, "content": content if (calls or rm) else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith(("<|close|>call<|sep|>", "<|close|>tools<|sep|>"))
+
+
+class FunctionParamXmlToolParser(ToolParser):
+    """``<function name="fn"><param name="k">v</param>…</function>`` blocks (MiniCPM-5 XML dialect); values are JSON when
+    they parse, strings otherwise; tokenizer space / newline glyphs (``Ġ`` / ``Ċ``) left in undecoded text are normalised."""
+    start_markers = ("<function name=", "<function ")
+    _fn = re.compile(r"<function\s+name\s*=\s*['\"]([^'\"]+)['\"][^>]*>(.*?)</function>", re.S)
+    _par = re.compile(r"<param\s+name\s*=\s*['\"]([^'\"]+)['\"]\s*>(.*?)</param>", re.S)
+
+    def extract(self, text: str) -> dict:
+        text = text.replace("\u0120", " ").replace("\u010a", "\n")
+        calls = []
+        for m in self._fn.finditer(text):
+            args = {}
+            for k, v in self._par.findall(m.group(2)):
+                v = v.strip()
+                try:
+                    args[k] = json.loads(v)
+                except json.JSONDecodeError:
+                    args[k] = v
+            calls.append(_call(m.group(1), args, len(calls)))
+        cut = min((text.find(x) for x in self.start_markers if x in text), default=len(text))
+        return {"tool_calls": calls, "content": (text[:cut].strip() or None) if calls else text}
+
+    def _looks_complete(self, text: str) -> bool:
+        return text.rstrip().endswith("</function>")
+
+
 _PARSERS: dict[str, type[ToolParser]] = {
     "hermes": HermesToolParser, "qwen": HermesToolParser, "qwen3": HermesToolParser, "nous": HermesToolParser,
     "llama3_json": Llama3JsonToolParser, "llama4_json": Llama3JsonToolParser,
@@ -500,6 +575,9 @@ _PARSERS: dict[str, type[ToolParser]] = {
     "lfm2": MarkedPythonicToolParser, "gigachat3": GigaChatToolParser, "openai": HarmonyToolParser,
     "gptoss": HarmonyToolParser, "step3p5": Step3ToolParser, "step3_xml": Step3ToolParser,
     "hy_v3": _marker_parser(("<tool_calls>",), ("</tool_calls>",)), "ling": HermesToolParser, "ling3": HermesToolParser,
+    "kimi_k3": ChannelCallToolParser, "minicpm5": FunctionParamXmlToolParser,
+    "cohere_command3": CohereActionToolParser, "cohere_command4": CohereActionToolParser,
+    "deepseek_v4": DeepSeekV31ToolParser, "poolside_v1": HermesToolParser, "inkling": HermesToolParser, "mimo": HermesToolParser,
     "granite4": HermesToolParser, "glm4_moe": Glm4MoeToolParser, "minimax_m1": _marker_parser(("<tool_calls>",), ("</tool_calls>",)),
 }
 
