@@ -96,6 +96,7 @@ class ParallelConfig(_ConfigBase):
     disable_custom_all_reduce: bool = False
     distributed_executor_backend: Optional[str] = None  # uni|mp|external_launcher
     worker_cls: str = "auto"
+    worker_extension_cls: str = ""
     max_parallel_loading_workers: Optional[int] = None
     enable_elastic_ep: bool = False
     rank: int = 0

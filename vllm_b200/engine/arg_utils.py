@@ -70,6 +70,8 @@ class EngineArgs:
     dcp_comm_backend: str = "ag_rs"
     disable_custom_all_reduce: bool = False
     distributed_executor_backend: Optional[str] = None
+    worker_cls: str = "auto"                 # qualified class name replacing the built-in worker
+    worker_extension_cls: str = ""           # qualified class whose methods are mixed into the worker (collective_rpc targets)
     enable_elastic_ep: bool = False
     # scheduler
     max_num_batched_tokens: Optional[int] = None
@@ -143,6 +145,7 @@ class EngineArgs:
             prefill_context_parallel_size=self.prefill_context_parallel_size,
             dcp_comm_backend=self.dcp_comm_backend, disable_custom_all_reduce=self.disable_custom_all_reduce,
             distributed_executor_backend=self.distributed_executor_backend,
+            worker_cls=self.worker_cls, worker_extension_cls=self.worker_extension_cls,
             enable_elastic_ep=self.enable_elastic_ep)
         # usage defaults sized for 180 GB HBM3e (reference picks 16384/8192 on big-HBM parts)
         mnbt = self.max_num_batched_tokens or 16384

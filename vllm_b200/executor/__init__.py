@@ -127,8 +127,8 @@ class UniProcExecutor(Executor):
     """Single worker inside the engine-core process (TP=PP=1)."""
 
     def _init_executor(self) -> None:
-        from vllm_b200.worker.worker import Worker
-        self.worker = Worker(self.vllm_config, local_rank=0, rank=0)
+        from vllm_b200.worker import resolve_worker_class
+        self.worker = resolve_worker_class(self.vllm_config)(self.vllm_config, local_rank=0, rank=0)
         self.worker.init_device()
         self.worker.load_model()
 
@@ -160,10 +160,10 @@ class ExternalLauncherExecutor(UniProcExecutor):
     ranks take identical decisions (reference: uniproc_executor.py:161)."""
 
     def _init_executor(self) -> None:
-        from vllm_b200.worker.worker import Worker
+        from vllm_b200.worker import resolve_worker_class
         rank = int(os.environ.get("RANK", 0))
         local_rank = int(os.environ.get("LOCAL_RANK", rank))
-        self.worker = Worker(self.vllm_config, local_rank=local_rank, rank=rank,
+        self.worker = resolve_worker_class(self.vllm_config)(self.vllm_config, local_rank=local_rank, rank=rank,
                              distributed_init_method="env://")
         self.worker.init_device()
         self.worker.load_model()

@@ -63,8 +63,8 @@ def _worker_main(vllm_config: VllmConfig, rank: int, local_rank: int, init_metho
 
     worker = None
     try:
-        from vllm_b200.worker.worker import Worker
-        worker = Worker(vllm_config, local_rank=local_rank, rank=rank, distributed_init_method=init_method,
+        from vllm_b200.worker import resolve_worker_class
+        worker = resolve_worker_class(vllm_config)(vllm_config, local_rank=local_rank, rank=rank, distributed_init_method=init_method,
                         is_driver_worker=rank == 0)
         worker.init_device()
         worker.load_model()

@@ -47,9 +47,9 @@ class RayWorkerActor:
         return ip, gpus
 
     def init_worker(self, rank: int, local_rank: int, init_method: str) -> None:
-        from vllm_b200.worker.worker import Worker
+        from vllm_b200.worker import resolve_worker_class
         # Ray narrows CUDA_VISIBLE_DEVICES to the actor's GPU: the device index inside the actor is 0
-        self.worker = Worker(self.vllm_config, local_rank=local_rank, rank=rank, distributed_init_method=init_method,
+        self.worker = resolve_worker_class(self.vllm_config)(self.vllm_config, local_rank=local_rank, rank=rank, distributed_init_method=init_method,
                              is_driver_worker=(rank == 0))
         self.worker.init_device()
         self.worker.load_model()
