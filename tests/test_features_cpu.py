@@ -1205,3 +1205,55 @@ def test_interleaved_gate_up_weights_match_plain_layout(monkeypatch):
         outs.append([o.outputs[0].token_ids for o in llm.generate(PROMPTS, sp)])
         llm.shutdown()
     assert outs[0] == outs[1]
+
+
+def test_batch_invariant_policy_and_generation(monkeypatch):
+    """VLLM_BATCH_INVARIANT (reference: tests/v1/determinism/test_batch_invariance.py): the dispatch policy stops
+    looking at the batch (no split-K / split-KV, rank-ordered collectives, no atomic MoE combine), and a prompt
+    generates the same tokens and logprobs alone, first in a batch, and last in a batch of unrelated prompts."""
+    import os
+    from tests.utils import make_llm
+    from vllm_b200 import SamplingParams, envs
+    from vllm_b200.ops import cuda as cu
+    from vllm_b200.utils import batch_invariant as bi
+    monkeypatch.setattr(cu, "num_sms", lambda: 148)
+    assert cu.decode_splits(4, 8, 32768, 64) > 1 and cu.mla_decode_splits(2, 128, 16384) > 1
+    cu._plan_cache.clear()
+    base = cu._plan(16, 4096, 4096)
+    monkeypatch.setenv("VLLM_BATCH_INVARIANT", "1")
+    envs._cache.clear()
+    saved = {k: os.environ.get(k) for k in bi._NCCL}
+    try:
+        assert cu.batch_invariant() and bi.apply_env_overrides()
+        assert os.environ["NCCL_ALGO"] == "allreduce:tree" and os.environ["NCCL_NVLS_ENABLE"] == "0"
+        assert cu.decode_splits(4, 8, 32768, 64) == 1 and cu.mla_decode_splits(2, 128, 16384) == 1
+        cu._plan_cache.clear()
+        for M in (1, 16, 64, 256, 257, 4096):
+            assert cu._plan(M, 4096, 4096)[2] == 1
+        assert base[0] == 1          # (sanity: the default plan for 16 rows is the swap-AB decode kernel)
+        cu._plan_cache.clear()
+        llm = make_llm("llama-tiny", max_num_seqs=16)
+        sp = SamplingParams(max_tokens=12, temperature=0.0, ignore_eos=True, logprobs=3)
+        needle = {"prompt_token_ids": [11, 45, 7, 300, 21, 9, 77]}
+        others = [{"prompt_token_ids": [(13 * i + 5 * j) % 500 + 3 for j in range(4 + 3 * i)]} for i in range(7)]
+
+        def run(prompts, idx):
+            o = llm.generate(prompts, sp)[idx].outputs[0]
+            return list(o.token_ids), [lp[t].logprob for lp, t in zip(o.logprobs, o.token_ids)]
+        alone = run([needle], 0)
+        first = run([needle] + others, 0)
+        last = run(others + [needle], len(others))
+        llm.shutdown()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        os.environ.pop("CUBLAS_WORKSPACE_CONFIG", None)
+        monkeypatch.delenv("VLLM_BATCH_INVARIANT")
+        envs._cache.clear()
+        cu._plan_cache.clear()
+    assert alone[0] == first[0] == last[0]
+    for a, b in ((alone[1], first[1]), (alone[1], last[1])):
+        assert max(abs(x - y) for x, y in zip(a, b)) < 1e-5

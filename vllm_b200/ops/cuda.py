@@ -228,7 +228,22 @@ def _get_attn_ws(B: int, Hq: int, D: int, splits: int, device) -> AttnWorkspace:
     return ws
 
 
+def batch_invariant() -> bool:
+    """``VLLM_BATCH_INVARIANT=1``: every dispatch decision that changes a row's floating-point reduction order is
+    made from that row's own shape only — never from how many other rows share the launch.  Concretely: no split-K in
+    the decode GEMMs (the split factor is otherwise chosen per (N, K) but switches off above 256 rows), no split-KV in
+    decode attention (the split count depends on batch × heads), decode-only batches run the same varlen attention
+    kernel as mixed batches, collectives reduce in rank order at every size (no in-switch multimem reduction, no
+    Lamport fused GEMM + all-reduce), and the MoE combine does not use ``red.add`` epilogues (atomic arrival order).
+    Reference: vllm/model_executor/layers/batch_invariant.py (``VLLM_BATCH_INVARIANT`` swaps in fixed-reduction-order
+    matmul / softmax / rms-norm kernels, fixes the attention split size and pins NCCL to one algorithm :1105-1180),
+    tests/v1/determinism/test_batch_invariance.py."""
+    return bool(envs.VLLM_BATCH_INVARIANT)
+
+
 def decode_splits(B: int, Hkv: int, max_seq_len: int, block_size: int) -> int:
+    if batch_invariant():
+        return 1
     forced = envs.VLLM_B200_ATTN_SPLITS
     if forced > 0:
         return forced
@@ -256,7 +271,8 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
         # tcgen05 kernel over the tensor-core cache layout
         assert D == 128 and BS == 64 and not logits_soft_cap and alibi_slopes is None and sinks is None and not chunk_size, \
             "tensor-core attention: D=128, 64-token pages, no soft-cap / ALiBi / sinks / chunked-local mask"
-        decode = md.decode_only
+        # batch-invariant mode: a decode row takes the varlen kernel it would take inside a mixed batch
+        decode = md.decode_only and not (batch_invariant() and md.query_start_loc is not None)
         splits = (md.num_splits or decode_splits(md.num_reqs, Hkv, md.max_seq_len, 128)) if decode else 1
         ws = _get_attn_ws(md.num_reqs, Hq, D, splits, q.device) if splits > 1 else None
         G = Hq // Hkv
@@ -280,8 +296,10 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
         alibi_slopes = alibi_slopes.to(device=q.device, dtype=torch.float32).contiguous()
     if sinks is not None:
         sinks = sinks.to(device=q.device, dtype=torch.float32).contiguous()
-    if md.decode_only:
+    n_launch = 1
+    if md.decode_only and not (batch_invariant() and md.query_start_loc is not None):
         splits = md.num_splits or decode_splits(md.num_reqs, Hkv, md.max_seq_len, BS)
+        n_launch = 2 if splits > 1 else 1
         ws = _get_attn_ws(md.num_reqs, Hq, D, splits, q.device) if splits > 1 else None
         rc = _paged_attention_ex(q.data_ptr(), kv_cache.data_ptr(), bt.data_ptr(), md.seq_lens.data_ptr(), None,
                                  out.data_ptr(), _p(ws.part_out) if ws else None, _p(ws.part_lse) if ws else None,
@@ -294,7 +312,7 @@ def paged_attention(q, kv_cache, md, scale, sliding_window=None, logits_soft_cap
                                  md.max_query_len, Hq, Hkv, D, BS, q.stride(0), out.stride(0), bt.stride(0), 1,
                                  sliding_window or 0, scale, logits_soft_cap, kv_scale, int(causal),
                                  _kv_fp8(kv_cache), _DT[q.dtype], _p(alibi_slopes), _p(sinks), int(chunk_size or 0), _st())
-    _check(rc, f"paged_attention(D={D}, BS={BS}, G={Hq // Hkv})", 2 if (md.decode_only and splits > 1) else 1)
+    _check(rc, f"paged_attention(D={D}, BS={BS}, G={Hq // Hkv})", n_launch)
     return (out, lse) if return_lse else out
 
 
@@ -313,6 +331,8 @@ _mla_ws: dict[int, tuple] = {}
 
 
 def mla_decode_splits(B: int, H: int, max_seq_len: int) -> int:
+    if batch_invariant():
+        return 1
     forced = envs.VLLM_B200_ATTN_SPLITS
     if forced > 0:
         return forced
@@ -463,7 +483,7 @@ def _plan(M: int, N: int, K: int):
         wsb = _i64()
         _gemm_plan(M, N, K, num_sms(), ctypes.byref(swap), ctypes.byref(bn), ctypes.byref(splits), ctypes.byref(wsb),
                    ctypes.byref(tiles))
-        p = (swap.value, bn.value, splits.value, wsb.value, tiles.value)
+        p = (swap.value, bn.value, 1 if batch_invariant() else splits.value, wsb.value, tiles.value)
         _plan_cache[key] = p
     return p
 
@@ -755,7 +775,7 @@ def _fp8_plan(M: int, N: int, K: int) -> tuple:
     if p is None:
         swap, bn, splits = _i(), _i(), _i()
         _gemm_fp8_plan(M, N, K, ctypes.byref(swap), ctypes.byref(bn), ctypes.byref(splits))
-        p = _fp8_plan_cache[key] = (swap.value, bn.value, splits.value)
+        p = _fp8_plan_cache[key] = (swap.value, bn.value, 1 if batch_invariant() else splits.value)
     return p
 
 

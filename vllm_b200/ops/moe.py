@@ -96,6 +96,8 @@ def fused_moe_reduce_norm(x, w13, w2, topk_w, topk_ids, act, expert_map, residua
     H = x.shape[1]
     R = T * k
     multi = comm is not None and comm.world > 1
+    if cu.batch_invariant():          # red.add epilogues sum a token's k expert rows in arrival order
+        return None
     if (not _grouped_ok(x, w13, w2, R) or T > MOE_T_CAP or H > LAM_H_MAX or H % 8 or act not in ("silu", "gelu", "gelu_tanh")
             or (residual is not None and (not residual.is_contiguous() or residual.dtype != x.dtype))
             or (multi and (H // 8 > 1024 or norm_w is None))):

@@ -59,6 +59,11 @@ class SymmComm:
         self.use_mc = bool(self.mc_ptr) and envs.VLLM_B200_AR_BACKEND in ("auto", "nvls")
         if envs.VLLM_B200_AR_BACKEND == "p2p":
             self.use_mc = False
+        # VLLM_BATCH_INVARIANT: every reduction is the rank-ordered one-shot kernel, whatever the row count — the
+        # in-switch multimem reduction and the Lamport fused GEMM + all-reduce pick their order / GEMM split by size
+        self.batch_invariant = bool(envs.VLLM_BATCH_INVARIANT)
+        if self.batch_invariant:
+            self.use_mc = False
         m = envs.VLLM_B200_FUSED_AR_MODE
         self.fused_mode = 0 if m == "oneshot" else 1
         logger.info("SymmComm[%s] rank %d/%d: %d MiB regions, multicast=%s", group.name, self.rank, self.world,
@@ -148,7 +153,7 @@ class SymmComm:
             return None
         H = x.shape[-1]
         T = x.numel() // H
-        if T <= ONESHOT_T_MAX:       # decode-size: every rank reduces all rows in the switch, straight into private memory
+        if T <= ONESHOT_T_MAX or self.batch_invariant:       # decode-size: every rank reduces all rows in the switch, straight into private memory
             self.ensure_capacity(T * H * x.dtype.itemsize)
             out = torch.empty_like(x)
             self.cu.comm_allreduce_oneshot(self, x.view(T, H), self.off_in, out, T, H)
@@ -172,7 +177,7 @@ class SymmComm:
     def gemm_allreduce_rmsnorm(self, x: torch.Tensor, w: torch.Tensor, residual: torch.Tensor,
                                norm_w: torch.Tensor, eps: float, gemma: bool = False):
         """(normed, residual) = RMSNorm(all_reduce(x @ w.T) + residual)."""
-        if not envs.VLLM_B200_FUSED_AR or x.dtype not in (torch.bfloat16, torch.float16):
+        if not envs.VLLM_B200_FUSED_AR or x.dtype not in (torch.bfloat16, torch.float16) or self.batch_invariant:
             return None
         K = x.shape[-1]
         x2 = x.reshape(-1, K)
@@ -206,7 +211,7 @@ class SymmComm:
                              gemma: bool = False):
         """Same contract as ``gemm_allreduce_rmsnorm`` for a partial sum that is already computed."""
         H = partial.shape[-1]
-        if (partial.dtype not in (torch.bfloat16, torch.float16) or H % 8 or H // 8 > 1024
+        if (self.batch_invariant or partial.dtype not in (torch.bfloat16, torch.float16) or H % 8 or H // 8 > 1024
                 or not residual.is_contiguous() or residual.dtype != partial.dtype):
             return None
         p2 = partial.reshape(-1, H)
@@ -243,7 +248,7 @@ class SymmComm:
         local = (ids - start).masked_fill(mask, 0)
         torch.index_select(weight, 0, local.reshape(-1).to(torch.int64), out=part)
         part.masked_fill_(mask.reshape(-1, 1), 0)
-        if T <= ONESHOT_T_MAX:
+        if T <= ONESHOT_T_MAX or self.batch_invariant:
             out = torch.empty(ids.shape + (H,), dtype=weight.dtype, device=weight.device)
             self.cu.comm_allreduce_oneshot(self, None, self.off_in, out, T, H)
             return out

@@ -41,6 +41,9 @@ class Worker:
     # ----------------------------------------------------------------- init
     def init_device(self) -> None:
         pc = self.vllm_config.parallel_config
+        from vllm_b200.utils.batch_invariant import apply_env_overrides
+        if apply_env_overrides():
+            logger.info("batch-invariant mode: fixed-order reductions (no split-K / split-KV / in-switch reduce)")
         dev_type = self.vllm_config.device_config.resolve()
         if dev_type == "cuda":
             # DP rank d owns GPUs [d*world, (d+1)*world) of the node
