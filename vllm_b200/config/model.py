@@ -347,11 +347,36 @@ PRESETS: dict[str, dict[str, Any]] = {
         rms_norm_eps=1e-5, hidden_act="silu", max_position_embeddings=512, sliding_window=None,
         layer_types=["full_attention", "full_attention", "full_attention"],
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
-    "apertus-tiny": dict(   # not implemented natively → exercises the Transformers back-end
+    "apertus-tiny": dict(
         architectures=["ApertusForCausalLM"], model_type="apertus", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, hidden_act="xielu",
-        rms_norm_eps=1e-5, rope_theta=10000.0, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
+        rms_norm_eps=1e-5, rope_theta=10000.0, rope_parameters=dict(rope_type="default", rope_theta=10000.0), bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
         tie_word_embeddings=False),
+    "cwm-tiny": dict(
+        architectures=["CwmForCausalLM"], model_type="cwm", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256, sliding_window=16,
+        layer_types=["full_attention", "sliding_attention", "sliding_attention", "full_attention"], hidden_act="silu",
+        rms_norm_eps=1e-5, rope_theta=10000.0,
+        rope_parameters=dict(rope_type="llama3", rope_theta=10000.0, factor=4.0, original_max_position_embeddings=64,
+                             low_freq_factor=1.0, high_freq_factor=4.0), bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
+        tie_word_embeddings=False),
+    "jais2-tiny": dict(
+        architectures=["Jais2ForCausalLM"], model_type="jais2", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        hidden_act="relu2", layer_norm_eps=1e-5, attention_bias=True, mlp_bias=True, rope_theta=10000.0, bos_token_id=1,
+        eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "ministral3-tiny": dict(
+        architectures=["Ministral3ForCausalLM"], model_type="ministral3", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        sliding_window=None, hidden_act="silu", rms_norm_eps=1e-5, bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        rope_parameters=dict(rope_type="yarn", rope_theta=10000.0, factor=4.0, original_max_position_embeddings=16,
+                             beta_fast=32.0, beta_slow=1.0, mscale=1.0, mscale_all_dim=1.0, llama_4_scaling_beta=0.1),
+        torch_dtype="float32", tie_word_embeddings=False),
+    "flexolmo-tiny": dict(
+        architectures=["FlexOlmoForCausalLM"], model_type="flex_olmo", vocab_size=512, hidden_size=64, intermediate_size=96,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, num_experts=4,
+        num_experts_per_tok=2, norm_topk_prob=False, hidden_act="silu", rms_norm_eps=1e-6, rope_theta=10000.0,
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "hunyuan-dense-tiny": dict(   # q/k norms after the rotation
         architectures=["HunYuanDenseV1ForCausalLM"], model_type="hunyuan_v1_dense", vocab_size=512, hidden_size=64,
         intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16,

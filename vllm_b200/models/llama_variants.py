@@ -76,17 +76,40 @@ def _norm(kind: str, H: int, eps: float, dtype) -> nn.Module:
     raise ValueError(kind)
 
 
+class _XIELU(nn.Module):
+    """xIELU (arXiv:2411.13010; Apertus): x > 0 → a_p x² + β x, else a_n (expm1(min(x, ε)) − x) + β x, with
+    a_p = softplus(alpha_p), a_n = β + softplus(alpha_n) learned per layer."""
+
+    def __init__(self, dtype) -> None:
+        super().__init__()
+        self.alpha_p = nn.Parameter(torch.zeros(1, dtype=dtype), requires_grad=False)
+        self.alpha_n = nn.Parameter(torch.zeros(1, dtype=dtype), requires_grad=False)
+        self.beta = nn.Parameter(torch.full((), 0.5, dtype=dtype), requires_grad=False)
+        self.eps = nn.Parameter(torch.full((), -1e-6, dtype=dtype), requires_grad=False)
+
+    def forward(self, x):
+        ap = torch.nn.functional.softplus(self.alpha_p)
+        an = self.beta + torch.nn.functional.softplus(self.alpha_n)
+        return torch.where(x > 0, ap * x * x + self.beta * x, (torch.expm1(torch.min(x, self.eps)) - x) * an + self.beta * x)
+
+
 class _PlainMLP(nn.Module):
     def __init__(self, H, I, act, bias, dtype, prefix) -> None:
         super().__init__()
         # (names differ from the gated MLP's on purpose: the Llama loader fuses ``up_proj`` into ``gate_up_proj``)
         self.fc_in = ColumnParallelLinear(H, I, bias, dtype=dtype, prefix=f"{prefix}.fc_in")
         self.fc_out = RowParallelLinear(I, H, bias, dtype=dtype, prefix=f"{prefix}.fc_out")
-        self.act = Activation(act) if act != "relu2" else None
+        if act == "xielu":
+            self.act_fn = _XIELU(dtype)
+        self.act = Activation(act) if act not in ("relu2", "xielu") else None
+        self.kind = act
 
     def forward(self, x):
         h = self.fc_in(x)
-        h = torch.relu(h).square() if self.act is None else self.act(h)
+        if self.kind == "xielu":
+            h = self.act_fn(h)
+        else:
+            h = torch.relu(h).square() if self.act is None else self.act(h)
         return self.fc_out(h)
 
 
@@ -102,6 +125,7 @@ class VariantAttention(nn.Module):
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
         eps = o["eps"]
         self.clip_qkv = o.get("clip_qkv")                             # clamp the projections to ±clip (OLMo-1)
+        self.q_pos_scale = o.get("q_pos_scale")                       # (beta, original_max_pos): Llama-4 style length scaling
         self.qk_norm = o["qk_norm"]                                   # None | "head" | "head1p" | "full"
         if self.qk_norm in ("head", "head1p", "head_post_rope"):
             self.q_norm, self.k_norm = RMSNorm(hd, eps, dtype, self.qk_norm == "head1p"), RMSNorm(hd, eps, dtype, self.qk_norm == "head1p")
@@ -127,6 +151,11 @@ class VariantAttention(nn.Module):
         if self.clip_qkv:
             qkv = qkv.clamp(-self.clip_qkv, self.clip_qkv)
         q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        if self.q_pos_scale:
+            # q · (1 + β log(1 + ⌊pos / L₀⌋)): a per-token scalar, so it commutes with the rotation applied later
+            beta, L0 = self.q_pos_scale
+            s = 1.0 + beta * torch.log1p(torch.floor(positions.to(torch.float32) / L0))
+            q = (q * s.unsqueeze(-1).to(q.dtype))
         if self.qk_norm in ("head", "head1p"):
             # per-head norms ride along with RoPE + the KV insert (one fused launch on CUDA, layers/attention.py)
             return self.o_proj(self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm)))
@@ -469,11 +498,66 @@ class HunYuanMoEV1ForCausalLM(VariantForCausalLM):
                              shared_inter=c["intermediate_size"] if c.get("use_mixed_mlp_moe", True) else 0))
 
 
+class ApertusForCausalLM(VariantForCausalLM):
+    """Apertus: per-head q / k RMSNorm, plain (non-gated) MLP with the learnable xIELU activation
+    (reference: models/apertus.py)."""
+    def options(self, c):
+        return dict(eps=c.get("rms_norm_eps", 1e-5), qk_norm="head", gated_mlp=False, act=c.get("hidden_act", "xielu"),
+                    qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")), mlp_bias=bool(c.get("mlp_bias")))
+    renames = [(".attention_layernorm.", ".input_layernorm."), (".feedforward_layernorm.", ".pre_mlp_norm."),
+               (".mlp.up_proj.", ".mlp.fc_in."), (".mlp.down_proj.", ".mlp.fc_out.")]
+
+
+class CwmForCausalLM(VariantForCausalLM):
+    """Code World Model: the Llama-3 block with sliding-window and full-attention layers interleaved by ``layer_types``
+    (reference: models/cwm.py)."""
+    def options(self, c):
+        types = c.get("layer_types")
+        return dict(eps=c.get("rms_norm_eps", 1e-5), mlp_bias=bool(c.get("mlp_bias")),
+                    sliding=(lambda i: types[i] == "sliding_attention") if types else (lambda i: False))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class Jais2ForCausalLM(VariantForCausalLM):
+    """Jais-2: LayerNorm (with bias), biased projections, plain squared-ReLU MLP (reference: models/jais2.py)."""
+    def options(self, c):
+        return dict(norm="ln", eps=c.get("layer_norm_eps", 1e-5), gated_mlp=False, act=c.get("hidden_act", "relu2"),
+                    qkv_bias=bool(c.get("attention_bias", True)), o_bias=bool(c.get("attention_bias", True)),
+                    mlp_bias=bool(c.get("mlp_bias", True)))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".mlp.up_proj.", ".mlp.fc_in."), (".mlp.down_proj.", ".mlp.fc_out.")]
+
+
+class Ministral3ForCausalLM(VariantForCausalLM):
+    """Ministral-3 / Mistral-Large-3 text block: Mistral with YaRN rotary and the Llama-4 length-dependent query scale
+    ``1 + β log(1 + ⌊pos / L₀⌋)`` (reference: models/mistral.py ``Ministral3``, HF ``modeling_ministral3``)."""
+    def options(self, c):
+        rp = c.get("rope_parameters") or c.get("rope_scaling") or {}
+        beta = rp.get("llama_4_scaling_beta")
+        L0 = rp.get("original_max_position_embeddings") or c.get("max_position_embeddings", 8192)
+        return dict(eps=c.get("rms_norm_eps", 1e-5), q_pos_scale=(float(beta), float(L0)) if beta else None,
+                    sliding=lambda i: bool(c.get("sliding_window")))
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+class FlexOlmoForCausalLM(VariantForCausalLM):
+    """FlexOlmo: the OLMo-2 block (sub-layer output norms, whole-projection q / k norms) around a softmax top-k expert
+    layer (reference: models/flex_olmo.py)."""
+    expert_names = {"w1": ("w13_weight", "w1"), "w3": ("w13_weight", "w3"), "w2": ("w2_weight", "w2")}
+    expert_container = "mlp.experts"
+    renames = [(".post_attention_layernorm.", ".post_attn_norm."), (".post_feedforward_layernorm.", ".post_mlp_norm.")]
+
+    def options(self, c):
+        return dict(structure="post", eps=c.get("rms_norm_eps", 1e-6), qk_norm="full", qkv_bias=bool(c.get("attention_bias")),
+                    o_bias=bool(c.get("attention_bias")),
+                    moe=dict(n_experts=c["num_experts"], top_k=c["num_experts_per_tok"], renormalize=bool(c.get("norm_topk_prob", False))))
+
+
 def _mix_in_expert_loader():
     # the per-expert / fused expert tensor loader lives with the Mixtral family; the variant block only renames
     from vllm_b200.models.mixtral import MixtralForCausalLM
     PhimoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     HunYuanMoEV1ForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+    FlexOlmoForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
 
 
 _mix_in_expert_loader()

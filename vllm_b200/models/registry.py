@@ -46,6 +46,12 @@ _MODELS: dict[str, tuple[str, str]] = {
     "HunYuanMoEV1ForCausalLM": ("llama_variants", "HunYuanMoEV1ForCausalLM"),
     "PhimoeForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
     "PhiMoEForCausalLM": ("llama_variants", "PhimoeForCausalLM"),
+    "ApertusForCausalLM": ("llama_variants", "ApertusForCausalLM"),
+    "CwmForCausalLM": ("llama_variants", "CwmForCausalLM"),
+    "Jais2ForCausalLM": ("llama_variants", "Jais2ForCausalLM"),
+    "Ministral3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
+    "MistralLarge3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
+    "FlexOlmoForCausalLM": ("llama_variants", "FlexOlmoForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
