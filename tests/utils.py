@@ -16,6 +16,11 @@ def make_hf_model(preset: str, seed: int = 0, dtype=torch.float32):
     hf_cfg = transformers.AutoConfig.for_model(mt, **kw)
     torch.manual_seed(seed)
     model = getattr(transformers, arch)(hf_cfg).to(dtype).eval()
+    # router selection biases are zero-initialised buffers: give them values so the biased top-k is actually exercised
+    g = torch.Generator().manual_seed(seed + 1)
+    for name, buf in model.named_buffers():
+        if name.endswith("e_score_correction_bias"):
+            buf.copy_((torch.rand(buf.shape, generator=g) - 0.5) * 0.2)
     return model
 
 

@@ -377,6 +377,26 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, num_experts=4,
         num_experts_per_tok=2, norm_topk_prob=False, hidden_act="silu", rms_norm_eps=1e-6, rope_theta=10000.0,
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "minimaxm2-tiny": dict(
+        architectures=["MiniMaxM2ForCausalLM"], model_type="minimax_m2", vocab_size=512, hidden_size=64, intermediate_size=96,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        num_local_experts=4, num_experts_per_tok=2, hidden_act="silu", rms_norm_eps=1e-6,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=0.5), bos_token_id=1, eos_token_id=2,
+        pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "exaonemoe-tiny": dict(
+        architectures=["ExaoneMoeForCausalLM"], model_type="exaone_moe", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        sliding_window=16, sliding_window_pattern=2, first_k_dense_replace=1, moe_intermediate_size=32, num_experts=8,
+        num_experts_per_tok=2, num_shared_experts=1, norm_topk_prob=True, routed_scaling_factor=2.5, n_group=2, topk_group=1,
+        hidden_act="silu", rms_norm_eps=1e-5, rope_parameters=dict(rope_type="default", rope_theta=10000.0), bos_token_id=1,
+        eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "solaropen-tiny": dict(
+        architectures=["SolarOpenForCausalLM"], model_type="solar_open", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256, moe_intermediate_size=32,
+        num_experts_per_tok=2, n_shared_experts=1, n_routed_experts=8, routed_scaling_factor=1.5, n_group=2, topk_group=1,
+        norm_topk_prob=True, hidden_act="silu", rms_norm_eps=1e-5, attention_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=1.0), bos_token_id=1, eos_token_id=2,
+        pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "hunyuan-dense-tiny": dict(   # q/k norms after the rotation
         architectures=["HunYuanDenseV1ForCausalLM"], model_type="hunyuan_v1_dense", vocab_size=512, hidden_size=64,
         intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16,

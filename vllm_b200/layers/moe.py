@@ -292,8 +292,12 @@ class FusedMoE(nn.Module):
             off = 0 if shard_id == "w1" else Ib
             param.data[le, off:off + Ib].copy_(w[r0:r0 + Ib])
 
-    def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id: str, expert_id: int) -> None:
+    def weight_loader(self, param: nn.Parameter, w: torch.Tensor, shard_id: Optional[str] = None,
+                      expert_id: Optional[int] = None) -> None:
         """shard_id: 'w1' (gate), 'w3' (up), 'w2' (down); ``w`` is the checkpoint's full tensor."""
+        if expert_id is None:                          # router-side tensors (selection bias): replicated, whole
+            param.data.copy_(w.reshape(param.shape))
+            return
         if self.eplb:                                  # every local physical slot that holds this logical expert
             I = self.inter_per_rank
             for p_ in (self.phy2log[self.e_start:self.e_end] == expert_id).nonzero().flatten().tolist():

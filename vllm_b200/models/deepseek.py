@@ -306,6 +306,18 @@ class Ernie4_5_MoeForCausalLM(Glm4MoeForCausalLM):
         return super().load_weights(mapped())
 
 
+class SolarOpenForCausalLM(Glm4MoeForCausalLM):
+    """Solar-Open: the GLM-4.5 MoE composition with every layer sparse, no q / k norms and full-width rotary by default
+    (reference: models/solar_open.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("first_k_dense_replace", 0)
+        cfg.setdefault("intermediate_size", cfg["moe_intermediate_size"])
+        cfg.setdefault("partial_rotary_factor", (cfg.get("rope_parameters") or {}).get("partial_rotary_factor", 1.0))
+        super().__init__(vllm_config, prefix)
+
+
 class Dots1ForCausalLM(Glm4MoeForCausalLM):
     """dots.llm1: the same composition (GQA attention with per-head q/k norms + DeepSeek-V3 style MoE), full rotary
     (reference: models/dots1.py)."""

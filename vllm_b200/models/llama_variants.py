@@ -179,13 +179,16 @@ class VariantLayer(nn.Module):
         self.o = o
         self.self_attn = VariantAttention(cfg, mc, dtype, f"{prefix}.self_attn", idx, o)
         self.moe_partial = False
-        if o.get("moe"):
+        m = o.get("moe")
+        if callable(m):                      # per-layer choice: leading dense layers, alternating sparse steps
+            m = m(idx)
+        if m:
             # sparse block (router + fused experts); returns this rank's PARTIAL sum, reduced in forward()
             from vllm_b200.models.mixtral import SparseMoeBlock
-            m = o["moe"]
             self.mlp = SparseMoeBlock(cfg, dtype, quant_config, f"{prefix}.mlp", m.get("enable_ep", False),
                                       n_experts=m["n_experts"], top_k=m["top_k"], inter=m.get("inter") or cfg["intermediate_size"],
-                                      renormalize=m.get("renormalize", False), shared_inter=m.get("shared_inter", 0))
+                                      renormalize=m.get("renormalize", False), shared_inter=m.get("shared_inter", 0),
+                                      moe_kw=m.get("kw"))
             if m.get("routing") is not None:
                 self.mlp.experts.custom_routing = m["routing"]
             self.moe_partial = True
@@ -552,12 +555,59 @@ class FlexOlmoForCausalLM(VariantForCausalLM):
                     moe=dict(n_experts=c["num_experts"], top_k=c["num_experts_per_tok"], renormalize=bool(c.get("norm_topk_prob", False))))
 
 
+_EXPERTS_ANY = {"w1": ("w13_weight", "w1"), "w3": ("w13_weight", "w3"), "w2": ("w2_weight", "w2"),
+                "gate_proj": ("w13_weight", "w1"), "up_proj": ("w13_weight", "w3"), "down_proj": ("w2_weight", "w2")}
+_BIAS_RENAMES = [(".mlp.gate.e_score_correction_bias", ".mlp.experts.e_score_correction_bias"),
+                 (".mlp.e_score_correction_bias", ".mlp.experts.e_score_correction_bias")]
+
+
+class MiniMaxM2ForCausalLM(VariantForCausalLM):
+    """MiniMax-M2: whole-projection q / k RMSNorm, partial rotary, every layer sparse — sigmoid scores, selection with a
+    learned correction bias, mixing weights renormalised over the chosen experts (reference: models/minimax_m2.py)."""
+    expert_names = _EXPERTS_ANY
+    expert_container = "mlp.experts"
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".block_sparse_moe.", ".mlp.")] + _BIAS_RENAMES
+
+    def options(self, c):
+        rp = c.get("rope_parameters") or {}
+        if "partial_rotary_factor" not in c and "rotary_dim" in c:
+            c["partial_rotary_factor"] = c["rotary_dim"] / (c.get("head_dim") or c["hidden_size"] // c["num_attention_heads"])
+        c.setdefault("partial_rotary_factor", rp.get("partial_rotary_factor", 1.0))
+        return dict(eps=c.get("rms_norm_eps", 1e-6), qk_norm="full" if c.get("use_qk_norm", True) else None,
+                    moe=dict(n_experts=c["num_local_experts"], top_k=c["num_experts_per_tok"], renormalize=True,
+                             kw=dict(use_grouped_topk=True, n_group=1, topk_group=1, scoring_func="sigmoid", e_score_bias=True)))
+
+
+class ExaoneMoeForCausalLM(VariantForCausalLM):
+    """EXAONE MoE (K-EXAONE): pre-norm block, per-head q / k RMSNorm, sliding-window layers with rotary and global layers
+    without, leading dense layers then DeepSeek-V3 style experts (sigmoid scores + correction bias, grouped top-k, shared
+    expert, routed scaling) (reference: models/exaone_moe.py)."""
+    expert_names = _EXPERTS_ANY
+    expert_container = "mlp.experts"
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".mlp.shared_experts.", ".mlp.shared_expert.")] + _BIAS_RENAMES
+
+    def options(self, c):
+        hybrid = bool(c.get("sliding_window"))
+        sl = _types_sliding(c) if hybrid else (lambda i: False)
+        kinds = c.get("mlp_layer_types")
+        dense_k = c.get("first_k_dense_replace", 1)
+        moe = dict(n_experts=c["num_experts"], top_k=c["num_experts_per_tok"], renormalize=bool(c.get("norm_topk_prob", True)),
+                   inter=c["moe_intermediate_size"], shared_inter=c["moe_intermediate_size"] * int(c.get("num_shared_experts", 0)),
+                   kw=dict(use_grouped_topk=True, n_group=c.get("n_group") or 1, topk_group=c.get("topk_group") or 1,
+                           scoring_func="sigmoid", e_score_bias=True, routed_scaling_factor=float(c.get("routed_scaling_factor", 1.0))))
+        return dict(eps=c.get("rms_norm_eps", 1e-5), qk_norm="head", sliding=sl,
+                    use_rope=(lambda i, sliding: sliding) if hybrid else (lambda i, sliding: True),
+                    moe=lambda i: moe if (kinds[i] == "sparse" if kinds else i >= dense_k) else None)
+
+
 def _mix_in_expert_loader():
     # the per-expert / fused expert tensor loader lives with the Mixtral family; the variant block only renames
     from vllm_b200.models.mixtral import MixtralForCausalLM
     PhimoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     HunYuanMoEV1ForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     FlexOlmoForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+    MiniMaxM2ForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+    ExaoneMoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
 
 
 _mix_in_expert_loader()

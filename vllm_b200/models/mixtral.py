@@ -25,13 +25,14 @@ class SparseMoeBlock(nn.Module):
 
     def __init__(self, cfg: dict, dtype, quant_config, prefix: str, enable_ep: bool, *, gate_name: str = "gate",
                  n_experts: int, top_k: int, inter: int, renormalize: bool, shared_inter: int = 0,
-                 shared_gate: bool = False) -> None:
+                 shared_gate: bool = False, moe_kw: Optional[dict] = None) -> None:
         super().__init__()
         hidden = cfg["hidden_size"]
         self.gate = ReplicatedLinear(hidden, n_experts, False, dtype, None, f"{prefix}.{gate_name}")
+        # moe_kw: router flavour (sigmoid scores, selection bias, grouped top-k, routed scaling) — FusedMoE keywords
         self.experts = FusedMoE(n_experts, top_k, hidden, inter, dtype, renormalize=renormalize,
                                 act=cfg.get("hidden_act", "silu"), enable_ep=enable_ep, reduce_results=False,
-                                prefix=f"{prefix}.experts")
+                                prefix=f"{prefix}.experts", **(moe_kw or {}))
         self.shared_expert = None
         self.shared_expert_gate = None
         if shared_inter > 0:

@@ -52,6 +52,9 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Ministral3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
     "MistralLarge3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
     "FlexOlmoForCausalLM": ("llama_variants", "FlexOlmoForCausalLM"),
+    "MiniMaxM2ForCausalLM": ("llama_variants", "MiniMaxM2ForCausalLM"),
+    "ExaoneMoeForCausalLM": ("llama_variants", "ExaoneMoeForCausalLM"),
+    "SolarOpenForCausalLM": ("deepseek", "SolarOpenForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
