@@ -21,6 +21,9 @@ def make_hf_model(preset: str, seed: int = 0, dtype=torch.float32):
     for name, buf in model.named_buffers():
         if name.endswith("e_score_correction_bias"):
             buf.copy_((torch.rand(buf.shape, generator=g) - 0.5) * 0.2)
+    for name, prm in model.named_parameters():
+        if name.endswith(".expert_bias"):
+            prm.data.copy_((torch.rand(prm.shape, generator=g) - 0.5) * 0.2)
     return model
 
 

@@ -377,6 +377,21 @@ PRESETS: dict[str, dict[str, Any]] = {
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, num_experts=4,
         num_experts_per_tok=2, norm_topk_prob=False, hidden_act="silu", rms_norm_eps=1e-6, rope_theta=10000.0,
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "glm4moelite-tiny": dict(
+        architectures=["Glm4MoeLiteForCausalLM"], model_type="glm4_moe_lite", vocab_size=512, hidden_size=64,
+        intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=4,
+        n_shared_experts=1, n_routed_experts=8, routed_scaling_factor=1.8, kv_lora_rank=32, q_lora_rank=48, qk_rope_head_dim=8,
+        v_head_dim=16, qk_nope_head_dim=16, n_group=1, topk_group=1, num_experts_per_tok=2, norm_topk_prob=True,
+        hidden_act="silu", max_position_embeddings=256, rms_norm_eps=1e-5, rope_interleave=True,
+        mlp_layer_types=["dense", "sparse", "sparse"], rope_parameters=dict(rope_type="default", rope_theta=10000.0),
+        bos_token_id=0, eos_token_id=1, torch_dtype="float32", tie_word_embeddings=False),
+    "afmoe-tiny": dict(
+        architectures=["AfmoeForCausalLM"], model_type="afmoe", vocab_size=512, hidden_size=64, intermediate_size=128,
+        moe_intermediate_size=32, num_hidden_layers=4, num_dense_layers=1, num_attention_heads=4, num_key_value_heads=2,
+        head_dim=16, max_position_embeddings=256, num_experts=8, num_experts_per_tok=2, num_shared_experts=1, route_scale=1.5,
+        global_attn_every_n_layers=2, sliding_window=16, mup_enabled=True, hidden_act="silu", rms_norm_eps=1e-5,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0), bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=False),
     "minimaxm2-tiny": dict(
         architectures=["MiniMaxM2ForCausalLM"], model_type="minimax_m2", vocab_size=512, hidden_size=64, intermediate_size=96,
         num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,

@@ -235,6 +235,23 @@ class DeepseekV3ForCausalLM(LlamaForCausalLM):
 
 
 # ------------------------------------------------------------------------------------------------ GLM-4.5 / 4.6 (MoE)
+class Glm4MoeLiteForCausalLM(DeepseekV3ForCausalLM):
+    """GLM-4.7-Flash ("MoE lite"): the DeepSeek-V3 block — MLA with interleaved rotary, sigmoid router with selection bias,
+    shared expert, leading dense layers given by ``mlp_layer_types`` (reference: models/glm4_moe_lite.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("topk_method", "noaux_tc")
+        cfg.setdefault("scoring_func", "sigmoid")
+        kinds = cfg.get("mlp_layer_types")
+        if kinds and "first_k_dense_replace" not in cfg:
+            cfg["first_k_dense_replace"] = next((i for i, k in enumerate(kinds) if k == "sparse"), len(kinds))
+        cfg.setdefault("first_k_dense_replace", 1)
+        rp = cfg.get("rope_parameters") or {}
+        cfg.setdefault("rope_theta", rp.get("rope_theta", 10000.0))
+        super().__init__(vllm_config, prefix)
+
+
 class Glm4MoeDecoderLayer(DeepseekDecoderLayer):
     """DeepSeek-V3 style MoE block (sigmoid scores + correction bias, grouped top-k, shared experts, leading dense
     layers) around ordinary GQA attention with partial rotary and optional per-head q/k norms

@@ -126,6 +126,9 @@ class VariantAttention(nn.Module):
         eps = o["eps"]
         self.clip_qkv = o.get("clip_qkv")                             # clamp the projections to ±clip (OLMo-1)
         self.q_pos_scale = o.get("q_pos_scale")                       # (beta, original_max_pos): Llama-4 style length scaling
+        self.out_gate = None
+        if o.get("attn_gate"):                                        # attention output · sigmoid(W_g x), element-wise
+            self.out_gate = ColumnParallelLinear(H, nh * hd, False, dtype=dtype, prefix=f"{prefix}.out_gate")
         self.qk_norm = o["qk_norm"]                                   # None | "head" | "head1p" | "full"
         if self.qk_norm in ("head", "head1p", "head_post_rope"):
             self.q_norm, self.k_norm = RMSNorm(hd, eps, dtype, self.qk_norm == "head1p"), RMSNorm(hd, eps, dtype, self.qk_norm == "head1p")
@@ -147,6 +150,12 @@ class VariantAttention(nn.Module):
                               logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0, prefix=f"{prefix}.attn", rope=rope)
 
     def forward(self, positions, x):
+        a = self._attend(positions, x)
+        if self.out_gate is not None:
+            a = a * torch.sigmoid(self.out_gate(x))
+        return self.o_proj(a)
+
+    def _attend(self, positions, x):
         qkv = self.qkv_proj(x)
         if self.clip_qkv:
             qkv = qkv.clamp(-self.clip_qkv, self.clip_qkv)
@@ -158,7 +167,7 @@ class VariantAttention(nn.Module):
             q = (q * s.unsqueeze(-1).to(q.dtype))
         if self.qk_norm in ("head", "head1p"):
             # per-head norms ride along with RoPE + the KV insert (one fused launch on CUDA, layers/attention.py)
-            return self.o_proj(self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm)))
+            return self.attn(q, k, v, positions, qk_norm=(self.q_norm, self.k_norm))
         elif self.qk_norm == "full":
             q, k = self.q_norm(q.contiguous()), self.k_norm(k.contiguous())
         elif self.qk_norm == "head_post_rope":
@@ -168,8 +177,8 @@ class VariantAttention(nn.Module):
                 q, k = self.attn.rope(positions, q.contiguous(), k.contiguous())
             q = self.q_norm(q.reshape(T, -1, self.hd)).reshape(T, -1)
             k = self.k_norm(k.reshape(T, -1, self.hd)).reshape(T, -1)
-            return self.o_proj(self.attn(q, k, v, None))
-        return self.o_proj(self.attn(q, k, v, positions))
+            return self.attn(q, k, v, None)
+        return self.attn(q, k, v, positions)
 
 
 class VariantLayer(nn.Module):
@@ -600,6 +609,32 @@ class ExaoneMoeForCausalLM(VariantForCausalLM):
                     moe=lambda i: moe if (kinds[i] == "sparse" if kinds else i >= dense_k) else None)
 
 
+class AfmoeForCausalLM(VariantForCausalLM):
+    """Arcee AFMoE (Trinity): sandwich norms, per-head q / k RMSNorm, sigmoid-gated attention output, sliding-window
+    layers with rotary and global layers without, leading dense layers then sigmoid-routed experts with a selection bias,
+    renormalised and scaled mixing weights and shared experts; optional muP embedding scale (reference: models/afmoe.py)."""
+    expert_names = _EXPERTS_ANY
+    expert_container = "mlp.experts"
+    renames = [(".post_attention_layernorm.", ".post_attn_norm."), (".pre_mlp_layernorm.", ".pre_mlp_norm."),
+               (".post_mlp_layernorm.", ".post_mlp_norm."), (".self_attn.gate_proj.", ".self_attn.out_gate."),
+               (".mlp.router.gate.", ".mlp.gate."), (".mlp.expert_bias", ".mlp.experts.e_score_correction_bias"),
+               (".mlp.shared_experts.", ".mlp.shared_expert.")]
+
+    def options(self, c):
+        types = c.get("layer_types")
+        every = c.get("global_attn_every_n_layers") or 4
+        sl = (lambda i: types[i] == "sliding_attention") if types else (lambda i: (i + 1) % every != 0)
+        dense_k = c.get("num_dense_layers") or 0
+        moe = dict(n_experts=c["num_experts"], top_k=c["num_experts_per_tok"], renormalize=True, inter=c["moe_intermediate_size"],
+                   shared_inter=c["moe_intermediate_size"] * int(c.get("num_shared_experts") or 0),
+                   kw=dict(use_grouped_topk=True, n_group=1, topk_group=1, scoring_func="sigmoid", e_score_bias=True,
+                           routed_scaling_factor=float(c.get("route_scale") or 1.0)))
+        return dict(structure="sandwich", eps=c.get("rms_norm_eps", 1e-5), qk_norm="head", attn_gate=True, sliding=sl,
+                    use_rope=lambda i, sliding: sliding, qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")),
+                    embed_scale=float(c["hidden_size"]) ** 0.5 if c.get("mup_enabled") else 1.0,
+                    moe=lambda i: moe if i >= dense_k else None)
+
+
 def _mix_in_expert_loader():
     # the per-expert / fused expert tensor loader lives with the Mixtral family; the variant block only renames
     from vllm_b200.models.mixtral import MixtralForCausalLM
@@ -608,6 +643,7 @@ def _mix_in_expert_loader():
     FlexOlmoForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     MiniMaxM2ForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     ExaoneMoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+    AfmoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
 
 
 _mix_in_expert_loader()

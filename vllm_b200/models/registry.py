@@ -52,6 +52,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Ministral3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
     "MistralLarge3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
     "FlexOlmoForCausalLM": ("llama_variants", "FlexOlmoForCausalLM"),
+    "Glm4MoeLiteForCausalLM": ("deepseek", "Glm4MoeLiteForCausalLM"),
+    "AfmoeForCausalLM": ("llama_variants", "AfmoeForCausalLM"),
     "MiniMaxM2ForCausalLM": ("llama_variants", "MiniMaxM2ForCausalLM"),
     "ExaoneMoeForCausalLM": ("llama_variants", "ExaoneMoeForCausalLM"),
     "SolarOpenForCausalLM": ("deepseek", "SolarOpenForCausalLM"),
