@@ -357,3 +357,33 @@ def test_modernbert_embeddings_match_hf():
         ref = torch.nn.functional.normalize(ref, dim=-1)
         torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_dbrx_matches_hf():
+    """DBRX against transformers.  transformers >= 5 keeps each expert matrix transposed relative to the released
+    checkpoints ([D, I] slabs under swapped config names); the test converts to the released [E·I, D] layout, which is
+    what the loader accepts."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("dbrx-tiny")
+    D, I, E = cfg["d_model"], cfg["ffn_config"]["ffn_hidden_size"], cfg["ffn_config"]["moe_num_experts"]
+    ffn = dict(cfg["ffn_config"], ffn_hidden_size=D, hidden_size=I)
+    hf_cfg = transformers.DbrxConfig(d_model=D, n_heads=cfg["n_heads"], n_layers=cfg["n_layers"], max_seq_len=cfg["max_seq_len"],
+                                     vocab_size=cfg["vocab_size"], attn_config=cfg["attn_config"], ffn_config=ffn,
+                                     tie_word_embeddings=False)
+    torch.manual_seed(0)
+    hf = transformers.DbrxForCausalLM(hf_cfg).float().eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():      # (the default init leaves the expert slabs near zero)
+            if ".experts.mlp." in n or "Wqkv" in n:
+                p.copy_(torch.randn_like(p) * 0.3)
+    sd = {}
+    for k, v in hf.state_dict().items():
+        if ".experts.mlp." in k:
+            v = v.view(E, D, I).transpose(1, 2).reshape(E * I, D).contiguous()
+        sd[k] = v
+    llm = make_llm("dbrx-tiny", weights=sd.items())
+    sp = SamplingParams(max_tokens=10, temperature=0.0, ignore_eos=True)
+    outs = llm.generate([{"prompt_token_ids": p} for p in PROMPTS], sp)
+    for p, o in zip(PROMPTS, outs):
+        assert o.outputs[0].token_ids == hf_greedy(hf, p, 10)

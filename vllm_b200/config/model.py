@@ -385,6 +385,12 @@ PRESETS: dict[str, dict[str, Any]] = {
         hidden_act="silu", max_position_embeddings=256, rms_norm_eps=1e-5, rope_interleave=True,
         mlp_layer_types=["dense", "sparse", "sparse"], rope_parameters=dict(rope_type="default", rope_theta=10000.0),
         bos_token_id=0, eos_token_id=1, torch_dtype="float32", tie_word_embeddings=False),
+    "dbrx-tiny": dict(
+        architectures=["DbrxForCausalLM"], model_type="dbrx", vocab_size=512, d_model=64, n_heads=4, n_layers=2, max_seq_len=256,
+        attn_config=dict(kv_n_heads=2, clip_qkv=0.5, rope_theta=10000.0),
+        ffn_config=dict(ffn_hidden_size=96, moe_num_experts=4, moe_top_k=2, moe_normalize_expert_weights=1.0,
+                        ffn_act_fn=dict(name="silu")),
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "afmoe-tiny": dict(
         architectures=["AfmoeForCausalLM"], model_type="afmoe", vocab_size=512, hidden_size=64, intermediate_size=128,
         moe_intermediate_size=32, num_hidden_layers=4, num_dense_layers=1, num_attention_heads=4, num_key_value_heads=2,
@@ -538,6 +544,26 @@ def get_preset_hf_config(name: str) -> Optional[dict[str, Any]]:
     return dict(cfg) if cfg is not None else None
 
 
+def _flatten_nested_config(c: dict) -> None:
+    """Families whose config.json nests or renames the fields the engine sizes the KV cache from."""
+    if c.get("model_type") == "dbrx":
+        a, f = c.get("attn_config") or {}, c.get("ffn_config") or {}
+        c.setdefault("hidden_size", c.get("d_model"))
+        c.setdefault("num_attention_heads", c.get("n_heads"))
+        c.setdefault("num_hidden_layers", c.get("n_layers"))
+        c.setdefault("max_position_embeddings", c.get("max_seq_len", 2048))
+        c.setdefault("num_key_value_heads", a.get("kv_n_heads") or c.get("n_heads"))
+        c.setdefault("rope_theta", a.get("rope_theta", 10000.0))
+        c.setdefault("clip_qkv", a.get("clip_qkv"))
+        c.setdefault("num_local_experts", f.get("moe_num_experts", 1))
+        c.setdefault("num_experts_per_tok", f.get("moe_top_k", 1))
+        c.setdefault("hidden_act", (f.get("ffn_act_fn") or {}).get("name", "silu"))
+        if "intermediate_size" not in c:
+            # released checkpoints: ffn_hidden_size is the expert width; transformers >= 5 swaps the two field names
+            fh, hs = f.get("ffn_hidden_size"), f.get("hidden_size")
+            c["intermediate_size"] = hs if (hs and fh == c.get("d_model") and hs != fh) else fh
+
+
 @dataclass
 class ModelConfig:
     model: str = "opt-tiny"
@@ -568,6 +594,7 @@ class ModelConfig:
             tc = self.hf_config.pop("text_config")
             self.hf_config = {**tc, **self.hf_config}
         self.hf_config.update(self.hf_overrides)
+        _flatten_nested_config(self.hf_config)
         if self.tokenizer is None:
             self.tokenizer = self.model
         if self.served_model_name is None:

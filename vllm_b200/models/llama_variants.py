@@ -609,6 +609,50 @@ class ExaoneMoeForCausalLM(VariantForCausalLM):
                     moe=lambda i: moe if (kinds[i] == "sparse" if kinds else i >= dense_k) else None)
 
 
+class DbrxForCausalLM(VariantForCausalLM):
+    """DBRX: bias-free LayerNorms, fused and clamped Wqkv, 16 experts / top-4 with the mixing weights normalised by their
+    p-norm; experts stored as three [E·I, D] tensors (reference: models/dbrx.py)."""
+    expert_names = _EXPERTS_ANY
+    expert_container = "mlp.experts"
+
+    def options(self, c):
+        f = c.get("ffn_config") or {}
+        p = f.get("moe_normalize_expert_weights", 1.0)
+        if p not in (None, 1, 1.0):
+            raise NotImplementedError(f"DBRX with moe_normalize_expert_weights={p} (only the 1-norm / none)")
+        return dict(norm="ln_nobias", eps=1e-5, clip_qkv=c.get("clip_qkv"), act=c.get("hidden_act", "silu"),
+                    moe=dict(n_experts=c["num_local_experts"], top_k=c["num_experts_per_tok"], renormalize=p is not None))
+
+    def load_weights(self, weights):
+        c = self.cfg
+        nh, nkv = c["num_attention_heads"], c["num_key_value_heads"]
+        hd = c["hidden_size"] // nh
+        E, I, D = c["num_local_experts"], c["intermediate_size"], c["hidden_size"]
+
+        def mapped():
+            for name, w in weights:
+                name = (name.replace("transformer.wte.", "model.embed_tokens.").replace("transformer.norm_f.", "model.norm.")
+                        .replace("transformer.blocks.", "model.layers.").replace(".norm_attn_norm.norm_1.", ".input_layernorm.")
+                        .replace(".norm_attn_norm.norm_2.", ".pre_mlp_norm.").replace(".norm_attn_norm.attn.", ".self_attn.")
+                        .replace(".out_proj.", ".o_proj.").replace(".ffn.router.layer.", ".mlp.gate.").replace(".ffn.", ".mlp."))
+                if ".self_attn.Wqkv." in name:
+                    q, k, v = w.split([nh * hd, nkv * hd, nkv * hd], dim=0)
+                    for part, t in (("q_proj", q), ("k_proj", k), ("v_proj", v)):
+                        yield name.replace("Wqkv", part), t
+                elif ".mlp.experts.mlp." in name:
+                    kind = name.rsplit(".", 1)[1]                        # w1 (gate) | v1 (up) | w2 (down, stored [I, D])
+                    base = name[: name.index(".mlp.experts.")] + ".mlp.experts."
+                    w3 = w.reshape(E, I, D)
+                    for e in range(E):
+                        if kind == "w2":
+                            yield f"{base}{e}.down_proj.weight", w3[e].t()
+                        else:
+                            yield f"{base}{e}.{'gate_proj' if kind == 'w1' else 'up_proj'}.weight", w3[e]
+                else:
+                    yield name, w
+        return super().load_weights(mapped())
+
+
 class AfmoeForCausalLM(VariantForCausalLM):
     """Arcee AFMoE (Trinity): sandwich norms, per-head q / k RMSNorm, sigmoid-gated attention output, sliding-window
     layers with rotary and global layers without, leading dense layers then sigmoid-routed experts with a selection bias,
@@ -644,6 +688,7 @@ def _mix_in_expert_loader():
     MiniMaxM2ForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     ExaoneMoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
     AfmoeForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
+    DbrxForCausalLM.__bases__ = (VariantForCausalLM, MixtralForCausalLM)
 
 
 _mix_in_expert_loader()

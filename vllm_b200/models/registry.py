@@ -53,6 +53,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "MistralLarge3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
     "FlexOlmoForCausalLM": ("llama_variants", "FlexOlmoForCausalLM"),
     "Glm4MoeLiteForCausalLM": ("deepseek", "Glm4MoeLiteForCausalLM"),
+    "DbrxForCausalLM": ("llama_variants", "DbrxForCausalLM"),
     "AfmoeForCausalLM": ("llama_variants", "AfmoeForCausalLM"),
     "MiniMaxM2ForCausalLM": ("llama_variants", "MiniMaxM2ForCausalLM"),
     "ExaoneMoeForCausalLM": ("llama_variants", "ExaoneMoeForCausalLM"),
