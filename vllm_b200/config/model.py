@@ -237,6 +237,23 @@ PRESETS: dict[str, dict[str, Any]] = {
         mamba_chunk_size=16, mamba_conv_bias=True, mamba_proj_bias=False, rms_norm_eps=1e-5, hidden_act="silu",
         max_position_embeddings=512, rope_theta=10000.0, partial_rotary_factor=1.0, attention_bias=False,
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "qwen35-tiny": dict(
+        architectures=["Qwen3_5ForCausalLM"], model_type="qwen3_5_text", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,
+        linear_num_key_heads=2, linear_key_head_dim=16, linear_value_head_dim=16, linear_conv_kernel_dim=4,
+        layer_types=["linear_attention", "full_attention", "linear_attention", "full_attention"], rms_norm_eps=1e-6,
+        hidden_act="silu", max_position_embeddings=512, attention_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=0.25), bos_token_id=1,
+        eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "qwen35moe-tiny": dict(
+        architectures=["Qwen3_5MoeForCausalLM"], model_type="qwen3_5_moe_text", vocab_size=512, hidden_size=64,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,
+        linear_num_key_heads=2, linear_key_head_dim=16, linear_value_head_dim=16, linear_conv_kernel_dim=4,
+        layer_types=["linear_attention", "full_attention", "linear_attention", "full_attention"],
+        num_experts=4, num_experts_per_tok=2, moe_intermediate_size=32, shared_expert_intermediate_size=32, rms_norm_eps=1e-6,
+        hidden_act="silu", max_position_embeddings=512, attention_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=0.25), bos_token_id=1,
+        eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "qwen3next-tiny": dict(
         architectures=["Qwen3NextForCausalLM"], model_type="qwen3_next", vocab_size=512, hidden_size=64,
         intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16,

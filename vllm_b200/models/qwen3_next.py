@@ -265,3 +265,45 @@ class Qwen3NextForCausalLM(Qwen2MoeForCausalLM):
                 continue
             rest.append((name, w))
         return loaded | super().load_weights(rest)
+
+
+class Qwen3_5ForCausalLM(Qwen3NextForCausalLM):
+    """Qwen3.5 text decoder (dense and MoE): the Qwen3-Next hybrid with the gated-delta-net input projection stored as four
+    plain tensors (q|k|v, z, b, a) instead of the per-key-head interleaved pair; the loader re-interleaves them into the
+    layout the mixer splits (reference: models/qwen3_5.py).  Text positions only: the three M-RoPE axes coincide."""
+
+    def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
+        c = self.cfg
+        nk, nv = c["linear_num_key_heads"], c["linear_num_value_heads"]
+        dk, dv, r = c["linear_key_head_dim"], c["linear_value_head_dim"], c["linear_num_value_heads"] // c["linear_num_key_heads"]
+        pending: dict[str, dict[str, torch.Tensor]] = {}
+
+        def mapped():
+            for name, w in weights:
+                name = name.replace("model.language_model.", "model.")
+                if name.startswith(("model.visual.", "visual.", "mtp.")):
+                    continue
+                hit = next((k for k in ("in_proj_qkv", "in_proj_z", "in_proj_b", "in_proj_a") if f".linear_attn.{k}.weight" in name), None)
+                if hit is None:
+                    yield name, w
+                    continue
+                base = name[: name.index(".linear_attn.")] + ".linear_attn."
+                got = pending.setdefault(base, {})
+                got[hit] = w
+                if len(got) < 4:
+                    continue
+                q, k, v = got["in_proj_qkv"].split([nk * dk, nk * dk, nv * dv], dim=0)
+                z, b, a = got["in_proj_z"], got["in_proj_b"], got["in_proj_a"]
+                H = q.shape[1]
+                qkvz = torch.cat([q.view(nk, dk, H), k.view(nk, dk, H), v.view(nk, r * dv, H), z.view(nk, r * dv, H)], dim=1)
+                ba = torch.cat([b.view(nk, r, H), a.view(nk, r, H)], dim=1)
+                del pending[base]
+                yield base + "in_proj_qkvz.weight", qkvz.reshape(-1, H)
+                yield base + "in_proj_ba.weight", ba.reshape(-1, H)
+        out = super().load_weights(mapped())
+        assert not pending, f"incomplete gated-delta-net projections for {sorted(pending)}"
+        return out
+
+
+class Qwen3_5MoeForCausalLM(Qwen3_5ForCausalLM):
+    pass

@@ -80,6 +80,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "MambaForCausalLM": ("mamba", "MambaForCausalLM"),
     "FalconMambaForCausalLM": ("mamba", "MambaForCausalLM"),
     "Qwen3NextForCausalLM": ("qwen3_next", "Qwen3NextForCausalLM"),
+    "Qwen3_5ForCausalLM": ("qwen3_next", "Qwen3_5ForCausalLM"),
+    "Qwen3_5MoeForCausalLM": ("qwen3_next", "Qwen3_5MoeForCausalLM"),
     "Mamba2ForCausalLM": ("mamba2", "Mamba2ForCausalLM"),
     "BambaForCausalLM": ("mamba2", "BambaForCausalLM"),
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
