@@ -237,6 +237,24 @@ PRESETS: dict[str, dict[str, Any]] = {
         mamba_chunk_size=16, mamba_conv_bias=True, mamba_proj_bias=False, rms_norm_eps=1e-5, hidden_act="silu",
         max_position_embeddings=512, rope_theta=10000.0, partial_rotary_factor=1.0, attention_bias=False,
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "nemotronh-tiny": dict(
+        architectures=["NemotronHForCausalLM"], model_type="nemotron_h", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, layers_block_type=["mamba", "moe", "attention", "moe"], num_attention_heads=4, num_key_value_heads=2,
+        head_dim=16, mamba_num_heads=4, mamba_head_dim=16, ssm_state_size=16, n_groups=2, conv_kernel=4, chunk_size=32,
+        use_conv_bias=True, use_bias=False, mlp_bias=False, mlp_hidden_act="relu2", mamba_hidden_act="silu",
+        n_routed_experts=8, num_experts_per_tok=2, moe_intermediate_size=32, moe_shared_expert_intermediate_size=48,
+        moe_latent_size=None, n_group=2, topk_group=1, norm_topk_prob=True, routed_scaling_factor=1.5, layer_norm_epsilon=1e-5,
+        max_position_embeddings=256, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
+        tie_word_embeddings=False),
+    "nemotronh-latent-tiny": dict(
+        architectures=["NemotronHForCausalLM"], model_type="nemotron_h", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=3, layers_block_type=["mamba", "attention", "moe"], num_attention_heads=4, num_key_value_heads=4,
+        head_dim=16, mamba_num_heads=8, mamba_head_dim=8, ssm_state_size=16, n_groups=1, conv_kernel=4, chunk_size=32,
+        use_conv_bias=True, use_bias=True, mlp_bias=True, mlp_hidden_act="relu2", mamba_hidden_act="silu",
+        n_routed_experts=4, num_experts_per_tok=2, moe_intermediate_size=32, moe_shared_expert_intermediate_size=48,
+        moe_latent_size=32, n_group=1, topk_group=1, norm_topk_prob=False, routed_scaling_factor=1.0, layer_norm_epsilon=1e-5,
+        max_position_embeddings=256, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
+        tie_word_embeddings=False),
     "qwen35-tiny": dict(
         architectures=["Qwen3_5ForCausalLM"], model_type="qwen3_5_text", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,

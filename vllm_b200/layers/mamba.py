@@ -161,9 +161,11 @@ class Mamba2Mixer(nn.Module):
 
     def __init__(self, hidden: int, num_heads: int, head_dim: int, d_state: int, d_conv: int, n_groups: int,
                  use_bias: bool, use_conv_bias: bool, chunk_size: int, eps: float, dtype, prefix: str,
-                 time_step_limit: tuple[float, float] = (0.0, float("inf")), norm_before_gate: bool = False) -> None:
+                 time_step_limit: tuple[float, float] = (0.0, float("inf")), norm_before_gate: bool = False,
+                 norm_groups: int = 1) -> None:
         super().__init__()
         self.nh, self.hd, self.N, self.k, self.G = num_heads, head_dim, d_state, d_conv, n_groups
+        self.norm_groups = norm_groups        # gated RMSNorm statistics per group of channels (Nemotron-H, Zamba-2, Falcon-H1)
         self.d_inner = num_heads * head_dim
         self.conv_dim = self.d_inner + 2 * n_groups * d_state
         self.chunk = chunk_size
@@ -198,7 +200,11 @@ class Mamba2Mixer(nn.Module):
 
     def _gated_norm(self, y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
         y = y.float() * F.silu(z.float())
-        y = y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + self.norm_eps)
+        if self.norm_groups > 1:
+            g = y.view(*y.shape[:-1], self.norm_groups, -1)
+            y = (g * torch.rsqrt(g.pow(2).mean(-1, keepdim=True) + self.norm_eps)).view(y.shape)
+        else:
+            y = y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + self.norm_eps)
         return (self.norm_weight.float() * y)
 
     def _segment(self, xbc: torch.Tensor, dt: torch.Tensor, conv_state: torch.Tensor, h: torch.Tensor):

@@ -82,6 +82,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3NextForCausalLM": ("qwen3_next", "Qwen3NextForCausalLM"),
     "Qwen3_5ForCausalLM": ("qwen3_next", "Qwen3_5ForCausalLM"),
     "Qwen3_5MoeForCausalLM": ("qwen3_next", "Qwen3_5MoeForCausalLM"),
+    "NemotronHForCausalLM": ("nemotron_h", "NemotronHForCausalLM"),
+    "NemotronHPuzzleForCausalLM": ("nemotron_h", "NemotronHForCausalLM"),
     "Mamba2ForCausalLM": ("mamba2", "Mamba2ForCausalLM"),
     "BambaForCausalLM": ("mamba2", "BambaForCausalLM"),
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
