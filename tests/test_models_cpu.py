@@ -22,7 +22,8 @@ PROMPTS = [[5, 17, 99, 3, 250, 41], [7, 7, 7, 301, 12], list(range(10, 60))]
                                     "apertus-tiny", "hunyuan-dense-tiny", "phimoe-tiny", "falconmamba-tiny", "biogpt-tiny", "xglm-tiny", "vaultgemma-tiny", "ernie45moe-tiny", "hunyuan-moe-tiny",
                                     "cwm-tiny", "jais2-tiny", "ministral3-tiny", "flexolmo-tiny",
                                     "minimaxm2-tiny", "exaonemoe-tiny", "solaropen-tiny", "afmoe-tiny", "glm4moelite-tiny",
-                                    "qwen35-tiny", "qwen35moe-tiny", "nemotronh-tiny", "nemotronh-latent-tiny"])
+                                    "qwen35-tiny", "qwen35moe-tiny", "nemotronh-tiny", "nemotronh-latent-tiny",
+                                    "falconh1-tiny", "falconh1-nonorm-tiny"])
 def test_greedy_matches_hf(preset):
     hf = make_hf_model(preset)
     llm = make_llm(preset, weights=hf.state_dict().items())

@@ -255,6 +255,26 @@ PRESETS: dict[str, dict[str, Any]] = {
         moe_latent_size=32, n_group=1, topk_group=1, norm_topk_prob=False, routed_scaling_factor=1.0, layer_norm_epsilon=1e-5,
         max_position_embeddings=256, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32",
         tie_word_embeddings=False),
+    "falconh1-tiny": dict(
+        architectures=["FalconH1ForCausalLM"], model_type="falcon_h1", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        mamba_d_ssm=64, mamba_n_heads=4, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=16, mamba_d_conv=4, mamba_chunk_size=32,
+        mamba_conv_bias=True, mamba_proj_bias=False, mamba_norm_before_gate=True, mamba_rms_norm=True, projectors_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0), lm_head_multiplier=0.7, embedding_multiplier=3.0,
+        mlp_multipliers=[0.9, 1.2], key_multiplier=0.8, attention_out_multiplier=0.6, attention_in_multiplier=1.3,
+        ssm_multipliers=[0.5, 1.5, 0.7, 1.1, 0.9], ssm_in_multiplier=1.4, ssm_out_multiplier=0.5, attention_bias=False,
+        mlp_bias=False, hidden_act="silu", rms_norm_eps=1e-5, bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=False),
+    "falconh1-nonorm-tiny": dict(
+        architectures=["FalconH1ForCausalLM"], model_type="falcon_h1", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16, max_position_embeddings=256,
+        mamba_d_ssm=64, mamba_n_heads=4, mamba_d_head=16, mamba_n_groups=1, mamba_d_state=16, mamba_d_conv=4, mamba_chunk_size=32,
+        mamba_conv_bias=True, mamba_proj_bias=True, mamba_rms_norm=False, projectors_bias=True,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0), lm_head_multiplier=1.0, embedding_multiplier=1.0,
+        mlp_multipliers=[1.1, 0.8], key_multiplier=1.2, attention_out_multiplier=0.9, attention_in_multiplier=1.0,
+        ssm_multipliers=[1.0, 0.8, 1.2, 1.0, 1.1], ssm_in_multiplier=1.0, ssm_out_multiplier=1.3, attention_bias=True,
+        mlp_bias=True, hidden_act="silu", rms_norm_eps=1e-5, bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=True),
     "qwen35-tiny": dict(
         architectures=["Qwen3_5ForCausalLM"], model_type="qwen3_5_text", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,

@@ -166,6 +166,8 @@ class Mamba2Mixer(nn.Module):
         super().__init__()
         self.nh, self.hd, self.N, self.k, self.G = num_heads, head_dim, d_state, d_conv, n_groups
         self.norm_groups = norm_groups        # gated RMSNorm statistics per group of channels (Nemotron-H, Zamba-2, Falcon-H1)
+        # gate placement: False → norm(y · silu(z)) (Mamba-2 default), True → norm(y) · silu(z), None → y · silu(z), no norm
+        self.norm_before_gate = norm_before_gate
         self.d_inner = num_heads * head_dim
         self.conv_dim = self.d_inner + 2 * n_groups * d_state
         self.chunk = chunk_size
@@ -199,13 +201,16 @@ class Mamba2Mixer(nn.Module):
         return dt.clamp(self.dt_min, self.dt_max) if (self.dt_min > 0 or self.dt_max != float("inf")) else dt
 
     def _gated_norm(self, y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
-        y = y.float() * F.silu(z.float())
+        if self.norm_before_gate is None:
+            return y.float() * F.silu(z.float())
+        y = y.float() if self.norm_before_gate else y.float() * F.silu(z.float())
         if self.norm_groups > 1:
             g = y.view(*y.shape[:-1], self.norm_groups, -1)
             y = (g * torch.rsqrt(g.pow(2).mean(-1, keepdim=True) + self.norm_eps)).view(y.shape)
         else:
             y = y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + self.norm_eps)
-        return (self.norm_weight.float() * y)
+        y = self.norm_weight.float() * y
+        return y * F.silu(z.float()) if self.norm_before_gate else y
 
     def _segment(self, xbc: torch.Tensor, dt: torch.Tensor, conv_state: torch.Tensor, h: torch.Tensor):
         """ONE request: xbc [q, conv_dim], dt [q, nh] raw → (y [q, d_inner] fp32, conv_state, h)."""

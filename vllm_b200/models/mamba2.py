@@ -115,6 +115,7 @@ class BambaLayer(nn.Module):
 
 
 class BambaForCausalLM(nn.Module):
+    layer_cls = BambaLayer
     stacked = [("qkv_proj", "q_proj", "q"), ("qkv_proj", "k_proj", "k"), ("qkv_proj", "v_proj", "v"),
                ("gate_up_proj", "gate_proj", 0), ("gate_up_proj", "up_proj", 1)]
 
@@ -126,7 +127,7 @@ class BambaForCausalLM(nn.Module):
         self.cfg = cfg
         H = cfg["hidden_size"]
         self.embed_tokens = VocabParallelEmbedding(cfg["vocab_size"], H, dtype)
-        self.layers = nn.ModuleList([BambaLayer(cfg, mc, dtype, f"{prefix}model.layers.{i}", i)
+        self.layers = nn.ModuleList([self.layer_cls(cfg, mc, dtype, f"{prefix}model.layers.{i}", i)
                                      for i in range(cfg["num_hidden_layers"])])
         self.final_layernorm = RMSNorm(H, cfg.get("rms_norm_eps", 1e-5), dtype)
         self.lm_head = ParallelLMHead(cfg["vocab_size"], H, dtype=dtype)

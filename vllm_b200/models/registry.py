@@ -84,6 +84,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3_5MoeForCausalLM": ("qwen3_next", "Qwen3_5MoeForCausalLM"),
     "NemotronHForCausalLM": ("nemotron_h", "NemotronHForCausalLM"),
     "NemotronHPuzzleForCausalLM": ("nemotron_h", "NemotronHForCausalLM"),
+    "FalconH1ForCausalLM": ("falcon_h1", "FalconH1ForCausalLM"),
     "Mamba2ForCausalLM": ("mamba2", "Mamba2ForCausalLM"),
     "BambaForCausalLM": ("mamba2", "BambaForCausalLM"),
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
