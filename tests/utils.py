@@ -19,7 +19,7 @@ def make_hf_model(preset: str, seed: int = 0, dtype=torch.float32):
     # router selection biases are zero-initialised buffers: give them values so the biased top-k is actually exercised
     g = torch.Generator().manual_seed(seed + 1)
     for name, buf in model.named_buffers():
-        if name.endswith("e_score_correction_bias"):
+        if name.endswith("e_score_correction_bias") or name.endswith(".expert_bias"):
             buf.copy_((torch.rand(buf.shape, generator=g) - 0.5) * 0.2)
     for name, prm in model.named_parameters():
         if name.endswith(".expert_bias"):

@@ -275,6 +275,19 @@ PRESETS: dict[str, dict[str, Any]] = {
         ssm_multipliers=[1.0, 0.8, 1.2, 1.0, 1.1], ssm_in_multiplier=1.0, ssm_out_multiplier=1.3, attention_bias=True,
         mlp_bias=True, hidden_act="silu", rms_norm_eps=1e-5, bos_token_id=1, eos_token_id=2, pad_token_id=0,
         torch_dtype="float32", tie_word_embeddings=True),
+    "lfm2-tiny": dict(
+        architectures=["Lfm2ForCausalLM"], model_type="lfm2", vocab_size=512, hidden_size=64, intermediate_size=192,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256, norm_eps=1e-5,
+        conv_bias=False, conv_L_cache=3, block_multiple_of=32, block_ffn_dim_multiplier=1.0, block_auto_adjust_ff_dim=True,
+        layer_types=["conv", "conv", "full_attention", "conv"], rope_parameters=dict(rope_type="default", rope_theta=10000.0),
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=True),
+    "lfm2moe-tiny": dict(
+        architectures=["Lfm2MoeForCausalLM"], model_type="lfm2_moe", vocab_size=512, hidden_size=64, intermediate_size=128,
+        moe_intermediate_size=32, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
+        norm_eps=1e-5, conv_bias=True, conv_L_cache=4, num_dense_layers=1, num_experts_per_tok=2, num_experts=8, use_expert_bias=True,
+        routed_scaling_factor=1.5, norm_topk_prob=True, layer_types=["conv", "full_attention", "conv", "full_attention"],
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0), bos_token_id=1, eos_token_id=2, pad_token_id=0,
+        torch_dtype="float32", tie_word_embeddings=True),
     "qwen35-tiny": dict(
         architectures=["Qwen3_5ForCausalLM"], model_type="qwen3_5_text", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,

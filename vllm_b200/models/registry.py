@@ -85,6 +85,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "NemotronHForCausalLM": ("nemotron_h", "NemotronHForCausalLM"),
     "NemotronHPuzzleForCausalLM": ("nemotron_h", "NemotronHForCausalLM"),
     "FalconH1ForCausalLM": ("falcon_h1", "FalconH1ForCausalLM"),
+    "Lfm2ForCausalLM": ("lfm2", "Lfm2ForCausalLM"),
+    "Lfm2MoeForCausalLM": ("lfm2", "Lfm2MoeForCausalLM"),
     "Mamba2ForCausalLM": ("mamba2", "Mamba2ForCausalLM"),
     "BambaForCausalLM": ("mamba2", "BambaForCausalLM"),
     "JambaForCausalLM": ("jamba", "JambaForCausalLM"),
