@@ -389,3 +389,102 @@ def test_dbrx_matches_hf():
     outs = llm.generate([{"prompt_token_ids": p} for p in PROMPTS], sp)
     for p, o in zip(PROMPTS, outs):
         assert o.outputs[0].token_ids == hf_greedy(hf, p, 10)
+
+
+def _gen(preset, weights, overrides=None, n=8):
+    llm = make_llm(preset, weights=weights, **({"hf_overrides": overrides} if overrides else {}))
+    sp = SamplingParams(max_tokens=n, temperature=0.0, ignore_eos=True, logprobs=1)
+    outs = llm.generate([{"prompt_token_ids": p} for p in PROMPTS], sp)
+    llm.shutdown()
+    return [(list(o.outputs[0].token_ids), [lp[t].logprob for lp, t in zip(o.outputs[0].logprobs, o.outputs[0].token_ids)])
+            for o in outs]
+
+
+def _same(a, b, tol=1e-4):
+    for (ta, la), (tb, lb) in zip(a, b):
+        assert ta == tb
+        assert max(abs(x - y) for x, y in zip(la, lb)) < tol
+
+
+def test_llama_aliases_match_llama_on_converted_checkpoints():
+    """InternLM2 (packed wqkv, w1/w3/w2), EXAONE-3 (GPT-style names), InternLM3 / IQuest-Coder / TeleChat3 (aliases), MiMo
+    (Qwen2 + ignored MTP heads): the same weights under each family's checkpoint naming give the Llama outputs."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    w = dict(llama_full_weights(cfg, seed=3))
+    ref = _gen("llama-tiny", list(w.items()))
+    nh, nkv = cfg["num_attention_heads"], cfg.get("num_key_value_heads") or cfg["num_attention_heads"]
+    hd, g = cfg["hidden_size"] // nh, nh // nkv
+
+    # ---- InternLM2
+    il = {}
+    for k, v in w.items():
+        if ".self_attn.q_proj." in k:
+            q, kk, vv = v, w[k.replace("q_proj", "k_proj")], w[k.replace("q_proj", "v_proj")]
+            H = q.shape[1]
+            packed = torch.cat([q.view(nkv, g, hd, H), kk.view(nkv, 1, hd, H), vv.view(nkv, 1, hd, H)], dim=1)
+            il[k.replace(".self_attn.q_proj.", ".attention.wqkv.")] = packed.reshape(-1, H)
+        elif ".self_attn.k_proj." in k or ".self_attn.v_proj." in k:
+            continue
+        else:
+            k2 = (k.replace("model.embed_tokens.", "model.tok_embeddings.").replace("lm_head.weight", "output.weight")
+                  .replace(".input_layernorm.", ".attention_norm.").replace(".post_attention_layernorm.", ".ffn_norm.")
+                  .replace(".self_attn.o_proj.", ".attention.wo.").replace(".mlp.gate_proj.", ".feed_forward.w1.")
+                  .replace(".mlp.up_proj.", ".feed_forward.w3.").replace(".mlp.down_proj.", ".feed_forward.w2."))
+            il[k2] = v
+    _same(ref, _gen("llama-tiny", list(il.items()), {"architectures": ["InternLM2ForCausalLM"]}))
+
+    # ---- EXAONE-3
+    ex = {}
+    for k, v in w.items():
+        k2 = (k.replace("model.embed_tokens.", "transformer.wte.").replace("model.norm.", "transformer.ln_f.")
+              .replace("model.layers.", "transformer.h.").replace(".self_attn.o_proj.", ".attn.attention.out_proj.")
+              .replace(".self_attn.", ".attn.attention.").replace(".input_layernorm.", ".ln_1.")
+              .replace(".post_attention_layernorm.", ".ln_2.").replace(".mlp.gate_proj.", ".mlp.c_fc_0.")
+              .replace(".mlp.up_proj.", ".mlp.c_fc_1.").replace(".mlp.down_proj.", ".mlp.c_proj."))
+        ex[k2] = v
+    ov = {"architectures": ["ExaoneForCausalLM"], "num_layers": cfg["num_hidden_layers"], "layer_norm_epsilon": cfg.get("rms_norm_eps", 1e-5),
+          "activation_function": "silu"}
+    _same(ref, _gen("llama-tiny", list(ex.items()), ov))
+
+    # ---- plain aliases
+    for arch in ("InternLM3ForCausalLM", "IQuestCoderForCausalLM", "TeleChat3ForCausalLM", "TransformersForCausalLM"):
+        _same(ref, _gen("llama-tiny", list(w.items()), {"architectures": [arch]}), tol=2e-4)
+
+
+def test_mup_llamas_match_granite_parameterisation():
+    """MiniCPM's scale_emb / scale_depth / dim_model_base and TeleFLM's input / output multipliers are the Granite
+    multipliers under other names: identical weights, identical outputs."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    import math
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=5))
+    L, H = cfg["num_hidden_layers"], cfg["hidden_size"]
+    hd = H // cfg["num_attention_heads"]
+    gr = {"architectures": ["GraniteForCausalLM"], "embedding_multiplier": 6.0, "residual_multiplier": 1.4 / math.sqrt(L),
+          "logits_scaling": H / 32.0, "attention_multiplier": hd ** -0.5}
+    mc = {"architectures": ["MiniCPMForCausalLM"], "scale_emb": 6.0, "scale_depth": 1.4, "dim_model_base": 32}
+    _same(_gen("llama-tiny", w, gr), _gen("llama-tiny", w, mc))
+    gr2 = {"architectures": ["GraniteForCausalLM"], "embedding_multiplier": 3.0, "residual_multiplier": 1.0, "logits_scaling": 4.0,
+           "attention_multiplier": hd ** -0.5}
+    tf = {"architectures": ["TeleFLMForCausalLM"], "use_mup": True, "input_mult": 3.0, "output_mult": 2.0, "mup_scale_factor": 8.0}
+    _same(_gen("llama-tiny", w, gr2), _gen("llama-tiny", w, tf))
+    # MiMo: Qwen2 with extra multi-token-prediction tensors in the checkpoint
+    q = _gen("llama-tiny", w, {"architectures": ["Qwen2ForCausalLM"], "attention_bias": False})
+    extra = w + [("model.mtp_layers.0.input_layernorm.weight", torch.ones(H))]
+    _same(q, _gen("llama-tiny", extra, {"architectures": ["MiMoForCausalLM"], "attention_bias": False}))
+
+
+def test_deepseek_v1_moe_and_orion_run():
+    """Families without a transformers implementation to compare against: DeepSeek-MoE v1 (softmax router, shared experts,
+    full rotary) must equal the GLM-4.5 composition configured the same way; Orion (LayerNorm Llama) must generate."""
+    from vllm_b200.config import get_preset_hf_config
+    base = {"use_qk_norm": False, "partial_rotary_factor": 1.0, "scoring_func": "softmax", "topk_method": "greedy",
+            "norm_topk_prob": False, "n_group": 1, "topk_group": 1}
+    a = _gen("dots1-tiny", None, dict(base, architectures=["Glm4MoeForCausalLM"]))
+    b = _gen("dots1-tiny", None, {"architectures": ["DeepseekForCausalLM"], "use_qk_norm": False, "n_group": 1, "topk_group": 1})
+    _same(a, b)
+    o = _gen("llama-tiny", None, {"architectures": ["OrionForCausalLM"]})
+    assert all(len(t) == 8 for t, _ in o)

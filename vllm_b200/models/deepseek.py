@@ -323,6 +323,20 @@ class Ernie4_5_MoeForCausalLM(Glm4MoeForCausalLM):
         return super().load_weights(mapped())
 
 
+class DeepseekForCausalLM(Glm4MoeForCausalLM):
+    """DeepSeek-MoE (v1, 16B): Llama attention with full rotary, softmax router without bias or groups, shared experts,
+    leading dense layer (reference: models/deepseek_v2.py ``DeepseekForCausalLM``)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("topk_method", "greedy")
+        cfg.setdefault("scoring_func", "softmax")
+        cfg.setdefault("partial_rotary_factor", 1.0)
+        cfg.setdefault("norm_topk_prob", False)
+        cfg.setdefault("first_k_dense_replace", 1)
+        super().__init__(vllm_config, prefix)
+
+
 class SolarOpenForCausalLM(Glm4MoeForCausalLM):
     """Solar-Open: the GLM-4.5 MoE composition with every layer sparse, no q / k norms and full-width rotary by default
     (reference: models/solar_open.py)."""

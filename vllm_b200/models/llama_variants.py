@@ -287,7 +287,9 @@ class VariantForCausalLM(LlamaForCausalLM):
 
 class GraniteForCausalLM(VariantForCausalLM):
     def options(self, c):
-        return dict(eps=c.get("rms_norm_eps", 1e-6), scale=float(c.get("attention_multiplier", 1.0)), qkv_bias=bool(c.get("attention_bias")),
+        types = c.get("layer_types")
+        return dict(sliding=(lambda i: types[i] == "sliding_attention") if types and c.get("sliding_window") else (lambda i: False),
+                    eps=c.get("rms_norm_eps", 1e-6), scale=float(c.get("attention_multiplier", 1.0)), qkv_bias=bool(c.get("attention_bias")),
                     o_bias=bool(c.get("attention_bias")), mlp_bias=bool(c.get("mlp_bias")), residual_multiplier=c.get("residual_multiplier", 1.0),
                     embed_scale=float(c.get("embedding_multiplier", 1.0)), logit_scale=1.0 / float(c.get("logits_scaling", 1.0)))
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]

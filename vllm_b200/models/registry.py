@@ -58,6 +58,20 @@ _MODELS: dict[str, tuple[str, str]] = {
     "MiniMaxM2ForCausalLM": ("llama_variants", "MiniMaxM2ForCausalLM"),
     "ExaoneMoeForCausalLM": ("llama_variants", "ExaoneMoeForCausalLM"),
     "SolarOpenForCausalLM": ("deepseek", "SolarOpenForCausalLM"),
+    "InternLM2ForCausalLM": ("llama_aliases", "InternLM2ForCausalLM"),
+    "InternLM3ForCausalLM": ("llama_aliases", "InternLM3ForCausalLM"),
+    "IQuestCoderForCausalLM": ("llama", "LlamaForCausalLM"),
+    "TeleChat3ForCausalLM": ("llama", "LlamaForCausalLM"),
+    "ExaoneForCausalLM": ("llama_aliases", "ExaoneForCausalLM"),
+    "MiMoForCausalLM": ("llama_aliases", "MiMoForCausalLM"),
+    "MiniCPMForCausalLM": ("llama_aliases", "MiniCPMForCausalLM"),
+    "TeleFLMForCausalLM": ("llama_aliases", "TeleFLMForCausalLM"),
+    "OrionForCausalLM": ("llama_aliases", "OrionForCausalLM"),
+    "GraniteSWAForCausalLM": ("llama_variants", "GraniteForCausalLM"),
+    "DeepseekForCausalLM": ("deepseek", "DeepseekForCausalLM"),
+    "TransformersForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
+    "TransformersMoEForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
+    "RobertaForMaskedLM": ("bert", "RobertaModel"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
