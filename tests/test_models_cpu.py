@@ -488,3 +488,100 @@ def test_deepseek_v1_moe_and_orion_run():
     _same(a, b)
     o = _gen("llama-tiny", None, {"architectures": ["OrionForCausalLM"]})
     assert all(len(t) == 8 for t, _ in o)
+
+
+def _hf_from_preset(preset, cls_name, model_type=None, **extra):
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config(preset)
+    kw = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type", "torch_dtype")}
+    kw.update(extra)
+    hf_cfg = transformers.AutoConfig.for_model(model_type or cfg["model_type"], **kw)
+    torch.manual_seed(0)
+    return getattr(transformers, cls_name)(hf_cfg).float().eval()
+
+
+def _pooling_llm(preset, arch, hf, **ov):
+    llm = make_llm(preset, hf_overrides=dict(architectures=[arch], **ov), runner="pooling", enable_prefix_caching=False)
+    m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    m.load_weights(hf.state_dict().items())
+    return llm, m
+
+
+def test_classification_heads_match_hf():
+    """Sequence and token classification heads of the encoder families and a decoder with an irregular base name:
+    RoBERTa (dense-tanh-out_proj on <s>), BERT token classifier, ModernBERT prediction head (CLS and per token), GPT-2
+    last-token classifier — probabilities equal to transformers."""
+    prompts = [[3, 17, 99, 250, 41, 7], list(range(10, 45))]
+    # RoBERTa: position ids start at padding_idx + 1 → compare with explicit position ids
+    hf = _hf_from_preset("bert-tiny", "RobertaForSequenceClassification", "roberta", num_labels=3, pad_token_id=1,
+                         max_position_embeddings=258)
+    llm, m = _pooling_llm("bert-tiny", "RobertaForSequenceClassification", hf, num_labels=3, model_type="roberta",
+                          max_position_embeddings=258)
+    assert type(m).__name__ == "RobertaForSequenceClassification"
+    for p, o in zip(prompts, llm.classify([{"prompt_token_ids": p} for p in prompts])):
+        with torch.no_grad():
+            ref = hf(torch.tensor([p]), position_ids=torch.arange(2, 2 + len(p))[None]).logits[0].softmax(-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()
+    # BERT token classification
+    hf = _hf_from_preset("bert-tiny", "BertForTokenClassification", num_labels=5)
+    llm, m = _pooling_llm("bert-tiny", "BertForTokenClassification", hf, num_labels=5)
+    outs = llm.encode([{"prompt_token_ids": p} for p in prompts], pooling_task="token_classify")
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = hf(torch.tensor([p])).logits[0].softmax(-1)
+        got = torch.as_tensor(o.outputs.data).float()
+        assert got.shape == (len(p), 5)
+        torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()
+    # ModernBERT sequence + token heads
+    for cls, task in (("ModernBertForSequenceClassification", "classify"), ("ModernBertForTokenClassification", "token_classify")):
+        hf = _hf_from_preset("modernbert-tiny", cls, num_labels=4, classifier_bias=True)
+        llm, m = _pooling_llm("modernbert-tiny", cls, hf, num_labels=4, classifier_bias=True)
+        outs = llm.encode([{"prompt_token_ids": p} for p in prompts], pooling_task=task)
+        for p, o in zip(prompts, outs):
+            with torch.no_grad():
+                ref = hf(torch.tensor([p])).logits[0].softmax(-1)
+            torch.testing.assert_close(torch.as_tensor(o.outputs.data).float().reshape(ref.shape), ref, atol=3e-4, rtol=1e-3)
+        llm.shutdown()
+    # GPT-2 (causal base class is GPT2LMHeadModel, not GPT2ForCausalLM)
+    hf = _hf_from_preset("gpt2-tiny", "GPT2ForSequenceClassification", num_labels=3, pad_token_id=0)
+    llm, m = _pooling_llm("gpt2-tiny", "GPT2ForSequenceClassification", hf, num_labels=3)
+    for p, o in zip(prompts, llm.classify([{"prompt_token_ids": p} for p in prompts])):
+        with torch.no_grad():
+            ref = hf(torch.tensor([p])).logits[0].softmax(-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()
+
+
+def test_reward_model_heads():
+    """Per-token reward heads: Qwen2 PRM (Linear-ReLU-Linear → 2 classes per position) and the InternLM2 ``v_head``."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    H = cfg["hidden_size"]
+    w = list(llama_full_weights(cfg, seed=2))
+    g = torch.Generator().manual_seed(0)
+    head = {"score.0.weight": torch.randn(H, H, generator=g) * 0.1, "score.0.bias": torch.randn(H, generator=g) * 0.1,
+            "score.2.weight": torch.randn(2, H, generator=g) * 0.1, "score.2.bias": torch.randn(2, generator=g) * 0.1}
+    prompts = [[5, 17, 99, 3, 250, 41]]
+    llm = make_llm("llama-tiny", hf_overrides={"architectures": ["Qwen2ForProcessRewardModel"], "attention_bias": False},
+                   runner="pooling")
+    m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    m.load_weights(w + list(head.items()))
+    out = llm.encode([{"prompt_token_ids": p} for p in prompts], pooling_task="token_classify")[0]
+    got = torch.as_tensor(out.outputs.data).float()
+    llm.shutdown()
+    # reference: hidden states of the embedding adapter of the same weights, head applied by hand
+    llm = make_llm("llama-tiny", hf_overrides={"architectures": ["Qwen2Model"], "attention_bias": False}, runner="pooling")
+    llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model.load_weights(w)
+    from vllm_b200 import PoolingParams
+    hid = torch.as_tensor(llm.encode([{"prompt_token_ids": prompts[0]}], PoolingParams(task="token_embed", normalize=False))[0].outputs.data).float()
+    llm.shutdown()
+    ref = (torch.relu(hid @ head["score.0.weight"].t() + head["score.0.bias"]) @ head["score.2.weight"].t() + head["score.2.bias"]).softmax(-1)
+    assert got.shape == (6, 2)
+    torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-3)
+    from vllm_b200.models.registry import resolve_model_cls
+    assert resolve_model_cls("InternLM2ForRewardModel").__name__ == "InternLM2RewardModel"
+    assert resolve_model_cls("Gemma3TextModel").__name__.startswith("Gemma3")

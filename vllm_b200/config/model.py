@@ -705,8 +705,7 @@ class ModelConfig:
     # -- accessors --------------------------------------------------------
     @property
     def is_encoder_only(self) -> bool:
-        return self.architecture in ("BertModel", "BertForMaskedLM", "BertForSequenceClassification", "RobertaModel",
-                                     "XLMRobertaModel")
+        return self.architecture.startswith(("Bert", "Roberta", "XLMRoberta"))
 
     @property
     def architecture(self) -> str:

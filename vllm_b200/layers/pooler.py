@@ -7,6 +7,8 @@ import torch
 def pool_hidden(hidden: torch.Tensor, params, model=None) -> torch.Tensor:
     """hidden: [n_tokens, H] of ONE request."""
     kind = (params.pooling_type or getattr(model, "default_pooling", "LAST")).upper()
+    if params.task in ("token_classify", "token_embed"):
+        kind = "ALL"
     h = hidden.float()
     if kind == "LAST":
         out = h[-1]
@@ -18,7 +20,7 @@ def pool_hidden(hidden: torch.Tensor, params, model=None) -> torch.Tensor:
         out = h
     else:
         raise ValueError(f"unknown pooling type {kind}")
-    if params.task == "classify" and model is not None and hasattr(model, "score"):
+    if params.task in ("classify", "token_classify") and model is not None and hasattr(model, "score"):
         out = model.score(out.to(hidden.dtype)).float().softmax(-1)
     if params.dimensions:
         out = out[..., :params.dimensions]

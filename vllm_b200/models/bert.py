@@ -148,3 +148,46 @@ class BertForSequenceClassification(BertModel):
     def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
         vllm_config.model_config.hf_config["_classifier"] = True
         super().__init__(vllm_config, prefix)
+
+
+class RobertaForSequenceClassification(RobertaModel):
+    """RoBERTa / XLM-R classification head: dense → tanh → out_proj on the ``<s>`` state (no BERT pooler)
+    (reference: models/roberta.py ``RobertaClassificationHead``)."""
+    default_pooling = "CLS"
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg, dtype = self.cfg, vllm_config.model_config.torch_dtype
+        n = int(cfg.get("num_labels") or len(cfg.get("id2label") or {}) or 1)
+        self.cls_dense = nn.Linear(cfg["hidden_size"], cfg["hidden_size"], dtype=dtype)
+        self.cls_out = nn.Linear(cfg["hidden_size"], n, dtype=dtype)
+
+    def score(self, pooled: torch.Tensor) -> torch.Tensor:
+        return self.cls_out(torch.tanh(self.cls_dense(pooled)))
+
+    def load_weights(self, weights):
+        return super().load_weights((n.replace("classifier.dense.", "cls_dense.").replace("classifier.out_proj.", "cls_out."), w)
+                                    for n, w in weights)
+
+
+class BertForTokenClassification(BertModel):
+    """One label distribution per token: linear classifier on every position (``LLM.encode(..., pooling_task=
+    "token_classify")``) (reference: models/bert.py ``BertForTokenClassification``)."""
+    default_pooling = "ALL"
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg = self.cfg
+        n = int(cfg.get("num_labels") or len(cfg.get("id2label") or {}) or 2)
+        self.tok_classifier = nn.Linear(cfg["hidden_size"], n, dtype=vllm_config.model_config.torch_dtype)
+
+    def score(self, hidden: torch.Tensor) -> torch.Tensor:
+        return self.tok_classifier(hidden)
+
+    def load_weights(self, weights):
+        return super().load_weights((("tok_classifier." + n[len("classifier."):]) if n.startswith("classifier.") else n, w)
+                                    for n, w in weights)
+
+
+class RobertaForTokenClassification(BertForTokenClassification):
+    pos_offset = 2

@@ -100,3 +100,33 @@ class ModernBertModel(nn.Module):
             loader(params[name], w, None) if loader is not None else params[name].data.copy_(w)
             loaded.add(name)
         return loaded
+
+
+class ModernBertForSequenceClassification(ModernBertModel):
+    """Prediction head (dense → activation → LayerNorm) on the [CLS] / mean-pooled state, then a linear classifier
+    (reference: models/modernbert.py)."""
+    per_token = False
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg, dtype = self.cfg, vllm_config.model_config.torch_dtype
+        H = cfg["hidden_size"]
+        n = int(cfg.get("num_labels") or len(cfg.get("id2label") or {}) or 2)
+        self.head_dense = nn.Linear(H, H, bias=bool(cfg.get("classifier_bias", False)), dtype=dtype)
+        self.head_norm = LayerNorm(H, cfg.get("norm_eps", 1e-5), bool(cfg.get("norm_bias", False)), dtype)
+        self.classifier = nn.Linear(H, n, dtype=dtype)
+        from vllm_b200.layers.common import Activation
+        self.head_act = Activation(cfg.get("classifier_activation", "gelu"))
+        if self.per_token:
+            self.default_pooling = "ALL"
+
+    def score(self, pooled: torch.Tensor) -> torch.Tensor:
+        x = self.head_norm(self.head_act(self.head_dense(pooled)))
+        return self.classifier(x)
+
+    def load_weights(self, weights):
+        return super().load_weights((n.replace("head.dense.", "head_dense.").replace("head.norm.", "head_norm."), w) for n, w in weights)
+
+
+class ModernBertForTokenClassification(ModernBertForSequenceClassification):
+    per_token = True

@@ -72,6 +72,13 @@ _MODELS: dict[str, tuple[str, str]] = {
     "TransformersForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "TransformersMoEForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "RobertaForMaskedLM": ("bert", "RobertaModel"),
+    "RobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
+    "XLMRobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
+    "BertForTokenClassification": ("bert", "BertForTokenClassification"),
+    "RobertaForTokenClassification": ("bert", "RobertaForTokenClassification"),
+    "XLMRobertaForTokenClassification": ("bert", "RobertaForTokenClassification"),
+    "ModernBertForSequenceClassification": ("modernbert", "ModernBertForSequenceClassification"),
+    "ModernBertForTokenClassification": ("modernbert", "ModernBertForTokenClassification"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
@@ -135,11 +142,21 @@ def supported_archs() -> list[str]:
     return sorted(_MODELS)
 
 
+# bases whose causal-LM class is not called ``<X>ForCausalLM``
+_IRREGULAR_BASE = {"GPT2ForCausalLM": "GPT2LMHeadModel", "Gemma3TextForCausalLM": "Gemma3ForCausalLM"}
+_REWARD = {"Qwen2ForRewardModel": ("Qwen2ForCausalLM", dict(n_out=1, mlp=True)),
+           "Qwen2ForProcessRewardModel": ("Qwen2ForCausalLM", dict(n_out=2, mlp=True)),
+           "InternLM2ForRewardModel": ("InternLM2ForCausalLM", dict(n_out=1, mlp=False, head_name="v_head"))}
+
+
 def _adapter_for(arch: str):
     """``XForSequenceClassification`` / ``XForRewardModel`` / bare ``XModel`` of a registered ``XForCausalLM``."""
+    if arch in _REWARD:
+        return _REWARD[arch][0], "reward"
     for suffix, kind in (("ForSequenceClassification", "cls"), ("ForRewardModel", "cls"), ("Model", "embed")):
         if arch.endswith(suffix):
             base = arch[: -len(suffix)] + "ForCausalLM"
+            base = _IRREGULAR_BASE.get(base, base)
             if base in _MODELS:
                 return base, kind
     return None
@@ -149,6 +166,8 @@ def resolve_model_cls(arch: str) -> Type[nn.Module]:
     if arch not in _MODELS and _adapter_for(arch):
         from vllm_b200.models import adapters
         base, kind = _adapter_for(arch)
+        if kind == "reward":
+            return adapters.as_reward_model(resolve_model_cls(base), **_REWARD[arch][1])
         fn = adapters.as_seq_cls_model if kind == "cls" else adapters.as_embedding_model
         return fn(resolve_model_cls(base))
     if arch not in _MODELS:
