@@ -585,3 +585,33 @@ def test_reward_model_heads():
     from vllm_b200.models.registry import resolve_model_cls
     assert resolve_model_cls("InternLM2ForRewardModel").__name__ == "InternLM2RewardModel"
     assert resolve_model_cls("Gemma3TextModel").__name__.startswith("Gemma3")
+
+
+def _vlm_text_cfg(cfg, drop):
+    return {k: v for k, v in cfg.items() if k not in drop}
+
+
+def test_smolvlm_matches_hf_with_image():
+    """SigLIP tower + pixel-shuffle connector + Llama decoder == HF SmolVLMForConditionalGeneration (greedy), and the same
+    weights under the Idefics3 architecture name."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("smolvlm-tiny")
+    text = _vlm_text_cfg(cfg, ("architectures", "model_type", "vision_config", "image_token_id", "scale_factor", "torch_dtype"))
+    hf_cfg = transformers.SmolVLMConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="llama", **text),
+                                        scale_factor=2, image_token_id=511, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    hf = transformers.SmolVLMForConditionalGeneration(hf_cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    ids = [5, 17, 511, 99, 3, 250]                       # one <image> placeholder → (32/8)^2 / 4 = 4 tokens
+    exp_ids = [5, 17] + [511] * 4 + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None, None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    for arch in ("SmolVLMForConditionalGeneration", "Idefics3ForConditionalGeneration"):
+        llm = make_llm("smolvlm-tiny", weights=hf.state_dict().items(), hf_overrides={"architectures": [arch]})
+        out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}, {"prompt_token_ids": [7, 8, 9, 10]}], sp)
+        assert out[0].outputs[0].token_ids == ref
+        llm.shutdown()

@@ -128,6 +128,13 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "smolvlm-tiny": dict(
+        architectures=["SmolVLMForConditionalGeneration"], model_type="smolvlm", image_token_id=511, scale_factor=2,
+        vision_config=dict(model_type="smolvlm_vision", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=32, patch_size=8, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

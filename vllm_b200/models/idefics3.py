@@ -1,0 +1,108 @@
+"""Idefics3 / SmolVLM: SigLIP vision tower → pixel-shuffle connector (s×s neighbouring patches concatenated channel-wise,
+then one bias-free linear) → Llama decoder.
+
+Reference parity: vllm/model_executor/models/idefics3.py, smolvlm.py, siglip.py (``SiglipVisionModel``), HF
+``modeling_smolvlm`` (``SmolVLMConnector.pixel_shuffle``).  One image → one ``image_size``-square tile (the front-end
+resizes; sub-image splitting of the HF processor is a preprocessing choice, each extra tile is just another image here).
+The tower is replicated on every TP rank, like the CLIP tower of LLaVA.
+"""
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+import torch.nn as nn
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.models.llama import LlamaForCausalLM
+from vllm_b200.models.llava import CLIPLayer
+
+
+class SiglipVisionTower(nn.Module):
+    """SigLIP ViT: biased patch convolution, learned positions for the patch grid (no class token), pre-norm encoder
+    layers with tanh-GELU MLPs, final LayerNorm."""
+
+    def __init__(self, vc: dict, dtype) -> None:
+        super().__init__()
+        H, P, S = vc["hidden_size"], vc["patch_size"], vc["image_size"]
+        self.patch_embedding = nn.Conv2d(vc.get("num_channels", 3), H, P, P, bias=True, dtype=dtype)
+        self.position_embedding = nn.Embedding((S // P) ** 2, H, dtype=dtype)
+        eps = vc.get("layer_norm_eps", 1e-6)
+        self.layers = nn.ModuleList([CLIPLayer(H, vc["intermediate_size"], vc["num_attention_heads"], eps,
+                                               vc.get("hidden_act", "gelu_pytorch_tanh"), dtype)
+                                     for _ in range(vc["num_hidden_layers"])])
+        self.post_layernorm = nn.LayerNorm(H, eps, dtype=dtype)
+
+    def forward(self, pixels: torch.Tensor) -> torch.Tensor:
+        x = self.patch_embedding(pixels.to(self.patch_embedding.weight.dtype)).flatten(2).transpose(1, 2)
+        x = x + self.position_embedding.weight[None, : x.shape[1]]
+        for layer in self.layers:
+            x = layer(x)
+        return self.post_layernorm(x)
+
+    @staticmethod
+    def rename(n: str) -> str:
+        return (n.replace("embeddings.", "").replace("encoder.layers.", "layers.").replace("self_attn.", "").replace("mlp.", ""))
+
+
+def pixel_shuffle(x: torch.Tensor, s: int) -> torch.Tensor:
+    """[B, N, C] on a √N × √N grid → [B, N / s², C · s²]: each s×s block of patches becomes one token."""
+    B, N, C = x.shape
+    h = w = int(N ** 0.5)
+    x = x.view(B, h, w // s, C * s).permute(0, 2, 1, 3)
+    x = x.reshape(B, w // s, h // s, C * s * s).permute(0, 2, 1, 3)
+    return x.reshape(B, N // (s * s), C * s * s)
+
+
+class Idefics3ForConditionalGeneration(nn.Module):
+    supports_multimodal = True
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__()
+        mc = vllm_config.model_config
+        cfg, dtype = mc.hf_config, mc.torch_dtype
+        self.cfg = cfg
+        self.image_token = cfg.get("image_token_id", cfg.get("image_token_index"))
+        self.scale = int(cfg.get("scale_factor", 2))
+        vc = cfg["vision_config"]
+        self.vision_model = SiglipVisionTower(vc, dtype)
+        self.proj = nn.Linear(vc["hidden_size"] * self.scale ** 2, cfg["hidden_size"], bias=False, dtype=dtype)
+        self.language_model = LlamaForCausalLM(vllm_config, prefix=f"{prefix}language_model.")
+
+    @torch.inference_mode()
+    def embed_multimodal(self, pixels: torch.Tensor) -> torch.Tensor:
+        return self.proj(pixel_shuffle(self.vision_model(pixels), self.scale))
+
+    def embed_input_ids(self, input_ids: torch.Tensor) -> torch.Tensor:
+        return self.language_model.embed_input_ids(input_ids)
+
+    def forward(self, input_ids, positions, intermediate_tensors=None, inputs_embeds=None):
+        return self.language_model(input_ids, positions, intermediate_tensors, inputs_embeds)
+
+    def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
+        return self.language_model.compute_logits(hidden)
+
+    def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
+        own = dict(self.named_parameters())
+        text: list[tuple[str, torch.Tensor]] = []
+        loaded: set[str] = set()
+        for name, w in weights:
+            n = name[len("model."):] if name.startswith("model.") else name
+            if n.startswith("text_model."):
+                text.append(("model." + n[len("text_model."):], w))
+            elif n.startswith("lm_head."):
+                text.append((n, w))
+            elif n.startswith("vision_model."):
+                t = "vision_model." + SiglipVisionTower.rename(n[len("vision_model."):])
+                if t in own:
+                    own[t].data.copy_(w)
+                    loaded.add(t)
+            elif n.startswith("connector.modality_projection.proj."):
+                own["proj." + n.rsplit(".", 1)[1]].data.copy_(w)
+                loaded.add("proj.weight")
+        loaded |= {"language_model." + x for x in self.language_model.load_weights(text)}
+        return loaded
+
+
+class SmolVLMForConditionalGeneration(Idefics3ForConditionalGeneration):
+    pass

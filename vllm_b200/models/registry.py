@@ -116,6 +116,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "WhisperForConditionalGeneration": ("whisper", "WhisperForConditionalGeneration"),
     "Qwen2_5_VLForConditionalGeneration": ("qwen2_vl", "Qwen2_5_VLForConditionalGeneration"),
     "Qwen2VLForConditionalGeneration": ("qwen2_vl", "Qwen2VLForConditionalGeneration"),
+    "Idefics3ForConditionalGeneration": ("idefics3", "Idefics3ForConditionalGeneration"),
+    "SmolVLMForConditionalGeneration": ("idefics3", "SmolVLMForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

@@ -59,6 +59,12 @@ class MultiModalProcessor:
         self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
         n = (self.image_size // self.patch) ** 2
         self.tokens_per_image = n if cfg.get("vision_feature_select_strategy", "default") == "default" else n + 1
+        if cfg.get("scale_factor"):                         # pixel-shuffle connectors (Idefics3 / SmolVLM): s x s patches per token
+            self.tokens_per_image = n // int(cfg["scale_factor"]) ** 2
+        elif cfg.get("downsample_ratio"):                   # InternVL: ratio 0.5 → 4 patches per token
+            self.tokens_per_image = int(n * float(cfg["downsample_ratio"]) ** 2)
+        elif cfg.get("mm_tokens_per_image"):                # pooled projector with a fixed output length (Gemma-3)
+            self.tokens_per_image = int(cfg["mm_tokens_per_image"])
         self.cache: "OrderedDict[str, torch.Tensor]" = OrderedDict()   # processing cache (hash → pixels)
         self.cache_items = 256
 
