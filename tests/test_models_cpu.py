@@ -615,3 +615,30 @@ def test_smolvlm_matches_hf_with_image():
         out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}, {"prompt_token_ids": [7, 8, 9, 10]}], sp)
         assert out[0].outputs[0].token_ids == ref
         llm.shutdown()
+
+
+def test_gemma3_multimodal_matches_hf_with_image():
+    """SigLIP tower → pooled, normed, projected image tokens → Gemma-3 decoder == HF Gemma3ForConditionalGeneration (greedy;
+    HF without ``token_type_ids`` uses the causal mask as well)."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("gemma3mm-tiny")
+    text = _vlm_text_cfg(cfg, ("architectures", "model_type", "vision_config", "image_token_index", "mm_tokens_per_image", "torch_dtype"))
+    hf_cfg = transformers.Gemma3Config(vision_config=cfg["vision_config"], text_config=dict(model_type="gemma3_text", **text),
+                                       mm_tokens_per_image=4, image_token_index=511, boi_token_index=509, eoi_token_index=510)
+    torch.manual_seed(0)
+    hf = transformers.Gemma3ForConditionalGeneration(hf_cfg).eval()
+    with torch.no_grad():
+        hf.model.multi_modal_projector.mm_input_projection_weight.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    ids = [5, 17, 511, 99, 3, 250]
+    exp_ids = [5, 17] + [511] * 4 + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("gemma3mm-tiny", weights=hf.state_dict().items())
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}], sp)
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

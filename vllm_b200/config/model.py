@@ -135,6 +135,18 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "gemma3mm-tiny": dict(
+        architectures=["Gemma3ForConditionalGeneration"], model_type="gemma3", image_token_index=511, mm_tokens_per_image=4,
+        vision_config=dict(model_type="siglip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=32, patch_size=8, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6,
+                           vision_use_head=False),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+        max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", head_dim=16,
+        rms_norm_eps=1e-6, hidden_activation="gelu_pytorch_tanh", query_pre_attn_scalar=16, sliding_window=16,
+        layer_types=["sliding_attention", "full_attention"],
+        rope_parameters=dict(sliding_attention=dict(rope_type="default", rope_theta=10000.0),
+                             full_attention=dict(rope_type="default", rope_theta=1000000.0)),
+        tie_word_embeddings=True),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

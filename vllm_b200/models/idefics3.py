@@ -54,8 +54,14 @@ def pixel_shuffle(x: torch.Tensor, s: int) -> torch.Tensor:
     return x.reshape(B, N // (s * s), C * s * s)
 
 
-class Idefics3ForConditionalGeneration(nn.Module):
+class SiglipVLM(nn.Module):
+    """SigLIP tower + a family-specific projector + a registered text decoder; subclasses fill in ``_build_projector`` /
+    ``_project`` and the checkpoint prefixes."""
     supports_multimodal = True
+    text_cls = LlamaForCausalLM
+    text_prefixes = ("text_model.", "language_model.")
+    vision_prefixes = ("vision_model.", "vision_tower.vision_model.")
+    projector_prefixes = ("connector.", "multi_modal_projector.")
 
     def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
         super().__init__()
@@ -63,15 +69,22 @@ class Idefics3ForConditionalGeneration(nn.Module):
         cfg, dtype = mc.hf_config, mc.torch_dtype
         self.cfg = cfg
         self.image_token = cfg.get("image_token_id", cfg.get("image_token_index"))
-        self.scale = int(cfg.get("scale_factor", 2))
-        vc = cfg["vision_config"]
-        self.vision_model = SiglipVisionTower(vc, dtype)
-        self.proj = nn.Linear(vc["hidden_size"] * self.scale ** 2, cfg["hidden_size"], bias=False, dtype=dtype)
-        self.language_model = LlamaForCausalLM(vllm_config, prefix=f"{prefix}language_model.")
+        self.vision_model = SiglipVisionTower(cfg["vision_config"], dtype)
+        self._build_projector(cfg, dtype)
+        self.language_model = self.text_cls(vllm_config, prefix=f"{prefix}language_model.")
+
+    def _build_projector(self, cfg, dtype) -> None:
+        raise NotImplementedError
+
+    def _project(self, feats: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _projector_name(self, n: str) -> str:
+        return n
 
     @torch.inference_mode()
     def embed_multimodal(self, pixels: torch.Tensor) -> torch.Tensor:
-        return self.proj(pixel_shuffle(self.vision_model(pixels), self.scale))
+        return self._project(self.vision_model(pixels))
 
     def embed_input_ids(self, input_ids: torch.Tensor) -> torch.Tensor:
         return self.language_model.embed_input_ids(input_ids)
@@ -88,21 +101,66 @@ class Idefics3ForConditionalGeneration(nn.Module):
         loaded: set[str] = set()
         for name, w in weights:
             n = name[len("model."):] if name.startswith("model.") else name
-            if n.startswith("text_model."):
-                text.append(("model." + n[len("text_model."):], w))
+            tp = next((p for p in self.text_prefixes if n.startswith(p)), None)
+            vp = next((p for p in self.vision_prefixes if n.startswith(p)), None)
+            pp = next((p for p in self.projector_prefixes if n.startswith(p)), None)
+            if tp is not None:
+                rest = n[len(tp):]
+                rest = rest[len("model."):] if rest.startswith("model.") else rest
+                text.append((rest if rest.startswith("lm_head") else "model." + rest, w))
             elif n.startswith("lm_head."):
                 text.append((n, w))
-            elif n.startswith("vision_model."):
-                t = "vision_model." + SiglipVisionTower.rename(n[len("vision_model."):])
+            elif vp is not None:
+                t = "vision_model." + SiglipVisionTower.rename(n[len(vp):])
                 if t in own:
                     own[t].data.copy_(w)
                     loaded.add(t)
-            elif n.startswith("connector.modality_projection.proj."):
-                own["proj." + n.rsplit(".", 1)[1]].data.copy_(w)
-                loaded.add("proj.weight")
+            elif pp is not None:
+                t = self._projector_name(n[len(pp):])
+                if t in own:
+                    own[t].data.copy_(w)
+                    loaded.add(t)
         loaded |= {"language_model." + x for x in self.language_model.load_weights(text)}
         return loaded
 
 
+class Idefics3ForConditionalGeneration(SiglipVLM):
+    def _build_projector(self, cfg, dtype) -> None:
+        self.scale = int(cfg.get("scale_factor", 2))
+        self.proj = nn.Linear(cfg["vision_config"]["hidden_size"] * self.scale ** 2, cfg["hidden_size"], bias=False, dtype=dtype)
+
+    def _project(self, feats):
+        return self.proj(pixel_shuffle(feats, self.scale))
+
+    def _projector_name(self, n):
+        return n.replace("modality_projection.proj.", "proj.")
+
+
 class SmolVLMForConditionalGeneration(Idefics3ForConditionalGeneration):
     pass
+
+
+class Gemma3ForConditionalGeneration(SiglipVLM):
+    """Gemma-3 vision-language: SigLIP tower → average-pool the patch grid down to ``mm_tokens_per_image`` → (1+w) RMSNorm →
+    one projection matrix → Gemma-3 decoder (reference: models/gemma3_mm.py).  Image positions attend causally here; the
+    bidirectional image-block mask of the HF implementation (``token_type_ids``) is not applied."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        from vllm_b200.models.llama_variants import Gemma3ForCausalLM
+        self.text_cls = Gemma3ForCausalLM
+        super().__init__(vllm_config, prefix)
+
+    def _build_projector(self, cfg, dtype) -> None:
+        from vllm_b200.layers.common import RMSNorm
+        vc = cfg["vision_config"]
+        self.mm_input_projection_weight = nn.Parameter(torch.zeros(vc["hidden_size"], cfg["hidden_size"], dtype=dtype), requires_grad=False)
+        self.mm_soft_emb_norm = RMSNorm(vc["hidden_size"], vc.get("layer_norm_eps", 1e-6), dtype, True)
+        self.side = vc["image_size"] // vc["patch_size"]
+        self.kernel = self.side // int(int(cfg.get("mm_tokens_per_image", 256)) ** 0.5)
+
+    def _project(self, feats):
+        B, _, C = feats.shape
+        x = feats.transpose(1, 2).reshape(B, C, self.side, self.side)
+        x = torch.nn.functional.avg_pool2d(x, self.kernel, self.kernel).flatten(2).transpose(1, 2)
+        x = self.mm_soft_emb_norm(x.reshape(-1, C)).view(B, -1, C)
+        return torch.matmul(x, self.mm_input_projection_weight)

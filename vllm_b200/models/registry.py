@@ -118,6 +118,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen2VLForConditionalGeneration": ("qwen2_vl", "Qwen2VLForConditionalGeneration"),
     "Idefics3ForConditionalGeneration": ("idefics3", "Idefics3ForConditionalGeneration"),
     "SmolVLMForConditionalGeneration": ("idefics3", "SmolVLMForConditionalGeneration"),
+    "Gemma3ForConditionalGeneration": ("idefics3", "Gemma3ForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),
