@@ -642,3 +642,34 @@ def test_gemma3_multimodal_matches_hf_with_image():
     out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}], sp)
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_cohere_vision_models_match_hf_with_image():
+    """Command-A Vision and Aya Vision: SigLIP → pixel shuffle → SwiGLU projector (with / without the leading LayerNorm,
+    post-norm / pre-norm tower features) → Cohere-2 decoder, against transformers."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("cohere2vision-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_id", "downsample_factor", "alignment_intermediate_size", "torch_dtype")
+    text = dict(model_type="cohere2", **_vlm_text_cfg(cfg, drop))
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    ids = [5, 17, 511, 99, 3, 250]
+    exp_ids = [5, 17] + [511] * 4 + [99, 3, 250]
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    for arch, cfg_cls, kw in (("Cohere2VisionForConditionalGeneration", "Cohere2VisionConfig", {}),
+                              ("AyaVisionForConditionalGeneration", "AyaVisionConfig",
+                               dict(vision_feature_layer=-1, vision_feature_select_strategy="full", adapter_layer_norm_eps=1e-6))):
+        hf_cfg = getattr(transformers, cfg_cls)(vision_config=cfg["vision_config"], text_config=text, downsample_factor=2,
+                                                alignment_intermediate_size=96, image_token_id=511, **kw)
+        if arch.startswith("Aya"):
+            hf_cfg.image_token_index = 511
+        torch.manual_seed(0)
+        hf = getattr(transformers, arch)(hf_cfg).eval()
+        with torch.no_grad():
+            ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], max_new_tokens=8, do_sample=False,
+                              pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+        llm = make_llm("cohere2vision-tiny", weights=hf.state_dict().items(), hf_overrides={"architectures": [arch]})
+        out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}], sp)
+        assert out[0].outputs[0].token_ids == ref, arch
+        llm.shutdown()

@@ -147,6 +147,17 @@ PRESETS: dict[str, dict[str, Any]] = {
         rope_parameters=dict(sliding_attention=dict(rope_type="default", rope_theta=10000.0),
                              full_attention=dict(rope_type="default", rope_theta=1000000.0)),
         tie_word_embeddings=True),
+    "cohere2vision-tiny": dict(
+        architectures=["Cohere2VisionForConditionalGeneration"], model_type="cohere2_vision", image_token_id=511, downsample_factor=2,
+        alignment_intermediate_size=96,
+        vision_config=dict(model_type="siglip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=32, patch_size=8, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6,
+                           vision_use_head=False),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2,
+        max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0,
+        hidden_act="silu", head_dim=16, layer_norm_eps=1e-5, logit_scale=0.25,
+        layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"], sliding_window=16,
+        tie_word_embeddings=True),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

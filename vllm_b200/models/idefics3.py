@@ -33,12 +33,12 @@ class SiglipVisionTower(nn.Module):
                                      for _ in range(vc["num_hidden_layers"])])
         self.post_layernorm = nn.LayerNorm(H, eps, dtype=dtype)
 
-    def forward(self, pixels: torch.Tensor) -> torch.Tensor:
+    def forward(self, pixels: torch.Tensor, final_norm: bool = True) -> torch.Tensor:
         x = self.patch_embedding(pixels.to(self.patch_embedding.weight.dtype)).flatten(2).transpose(1, 2)
         x = x + self.position_embedding.weight[None, : x.shape[1]]
         for layer in self.layers:
             x = layer(x)
-        return self.post_layernorm(x)
+        return self.post_layernorm(x) if final_norm else x
 
     @staticmethod
     def rename(n: str) -> str:
@@ -49,7 +49,7 @@ def pixel_shuffle(x: torch.Tensor, s: int) -> torch.Tensor:
     """[B, N, C] on a √N × √N grid → [B, N / s², C · s²]: each s×s block of patches becomes one token."""
     B, N, C = x.shape
     h = w = int(N ** 0.5)
-    x = x.view(B, h, w // s, C * s).permute(0, 2, 1, 3)
+    x = x.reshape(B, h, w // s, C * s).permute(0, 2, 1, 3)
     x = x.reshape(B, w // s, h // s, C * s * s).permute(0, 2, 1, 3)
     return x.reshape(B, N // (s * s), C * s * s)
 
@@ -164,3 +164,43 @@ class Gemma3ForConditionalGeneration(SiglipVLM):
         x = torch.nn.functional.avg_pool2d(x, self.kernel, self.kernel).flatten(2).transpose(1, 2)
         x = self.mm_soft_emb_norm(x.reshape(-1, C)).view(B, -1, C)
         return torch.matmul(x, self.mm_input_projection_weight)
+
+
+
+class Cohere2VisionForConditionalGeneration(SiglipVLM):
+    """Command-A Vision: SigLIP tower → pixel shuffle (f×f patches per token) → SwiGLU projector → Cohere-2 decoder
+    (reference: models/cohere2_vision.py)."""
+    final_norm = True
+    pre_ln = False
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        from vllm_b200.models.llama_variants import Cohere2ForCausalLM
+        self.text_cls = Cohere2ForCausalLM
+        super().__init__(vllm_config, prefix)
+
+    def _build_projector(self, cfg, dtype) -> None:
+        self.f = int(cfg.get("downsample_factor", 2))
+        Hin = cfg["vision_config"]["hidden_size"] * self.f ** 2
+        mid = int(cfg.get("alignment_intermediate_size") or cfg["hidden_size"])
+        if self.pre_ln:
+            self.layernorm = nn.LayerNorm(Hin, cfg.get("adapter_layer_norm_eps", 1e-6), dtype=dtype)
+        self.linear_1 = nn.Linear(Hin, mid, dtype=dtype)
+        self.linear_2 = nn.Linear(mid // 2, cfg["hidden_size"], dtype=dtype)
+
+    @torch.inference_mode()
+    def embed_multimodal(self, pixels: torch.Tensor) -> torch.Tensor:
+        return self._project(self.vision_model(pixels, final_norm=self.final_norm))
+
+    def _project(self, feats):
+        x = pixel_shuffle(feats, self.f)
+        if self.pre_ln:
+            x = self.layernorm(x)
+        x, gate = self.linear_1(x).chunk(2, dim=-1)
+        return self.linear_2(torch.nn.functional.silu(gate) * x)
+
+
+class AyaVisionForConditionalGeneration(Cohere2VisionForConditionalGeneration):
+    """Aya Vision: the same connector with a LayerNorm in front, fed from the last encoder layer BEFORE the tower's final
+    LayerNorm (``vision_feature_layer = -1``) (reference: models/aya_vision.py)."""
+    final_norm = False
+    pre_ln = True

@@ -119,6 +119,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Idefics3ForConditionalGeneration": ("idefics3", "Idefics3ForConditionalGeneration"),
     "SmolVLMForConditionalGeneration": ("idefics3", "SmolVLMForConditionalGeneration"),
     "Gemma3ForConditionalGeneration": ("idefics3", "Gemma3ForConditionalGeneration"),
+    "Cohere2VisionForConditionalGeneration": ("idefics3", "Cohere2VisionForConditionalGeneration"),
+    "AyaVisionForConditionalGeneration": ("idefics3", "AyaVisionForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

@@ -59,7 +59,9 @@ class MultiModalProcessor:
         self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
         n = (self.image_size // self.patch) ** 2
         self.tokens_per_image = n if cfg.get("vision_feature_select_strategy", "default") == "default" else n + 1
-        if cfg.get("scale_factor"):                         # pixel-shuffle connectors (Idefics3 / SmolVLM): s x s patches per token
+        if cfg.get("downsample_factor"):                    # Aya Vision / Command-A Vision
+            self.tokens_per_image = n // int(cfg["downsample_factor"]) ** 2
+        elif cfg.get("scale_factor"):                         # pixel-shuffle connectors (Idefics3 / SmolVLM): s x s patches per token
             self.tokens_per_image = n // int(cfg["scale_factor"]) ** 2
         elif cfg.get("downsample_ratio"):                   # InternVL: ratio 0.5 → 4 patches per token
             self.tokens_per_image = int(n * float(cfg["downsample_ratio"]) ** 2)
