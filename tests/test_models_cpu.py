@@ -673,3 +673,29 @@ def test_cohere_vision_models_match_hf_with_image():
         out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}], sp)
         assert out[0].outputs[0].token_ids == ref, arch
         llm.shutdown()
+
+
+def test_internvl_matches_hf_with_image():
+    """InternViT (class token, layer scales, q/k RMSNorm) → pixel shuffle → LN-MLP projector → Qwen2 decoder == HF
+    InternVLForConditionalGeneration (greedy)."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("internvl-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_id", "downsample_ratio", "vision_feature_layer",
+            "vision_feature_select_strategy", "projector_hidden_act", "text_model_type", "torch_dtype")
+    hf_cfg = transformers.InternVLConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="qwen2", **_vlm_text_cfg(cfg, drop)),
+                                         image_token_id=511, downsample_ratio=0.5)
+    torch.manual_seed(0)
+    hf = transformers.InternVLForConditionalGeneration(hf_cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    ids = [5, 17, 511, 99, 3, 250]
+    exp_ids = [5, 17] + [511] * 4 + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("internvl-tiny", weights=hf.state_dict().items())
+    out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

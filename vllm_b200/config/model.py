@@ -158,6 +158,16 @@ PRESETS: dict[str, dict[str, Any]] = {
         hidden_act="silu", head_dim=16, layer_norm_eps=1e-5, logit_scale=0.25,
         layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"], sliding_window=16,
         tie_word_embeddings=True),
+    "internvl-tiny": dict(
+        architectures=["InternVLForConditionalGeneration"], model_type="internvl", image_token_id=511, downsample_ratio=0.5,
+        vision_feature_layer=-1, vision_feature_select_strategy="default", projector_hidden_act="gelu", text_model_type="qwen2",
+        vision_config=dict(model_type="internvl_vision", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=[32, 32], patch_size=[8, 8], use_qk_norm=True, norm_type="layer_norm",
+                           attention_bias=True, layer_norm_eps=1e-6, hidden_act="gelu", use_mean_pooling=True,
+                           use_absolute_position_embeddings=True, layer_scale_init_value=0.5),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,
@@ -691,6 +701,8 @@ class ModelConfig:
             # vision-language checkpoints nest the decoder's fields: lift them to the top level (top-level wins)
             tc = self.hf_config.pop("text_config")
             self.hf_config = {**tc, **self.hf_config}
+            if tc.get("model_type"):
+                self.hf_config.setdefault("text_model_type", tc["model_type"])
         self.hf_config.update(self.hf_overrides)
         _flatten_nested_config(self.hf_config)
         if self.tokenizer is None:

@@ -121,6 +121,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Gemma3ForConditionalGeneration": ("idefics3", "Gemma3ForConditionalGeneration"),
     "Cohere2VisionForConditionalGeneration": ("idefics3", "Cohere2VisionForConditionalGeneration"),
     "AyaVisionForConditionalGeneration": ("idefics3", "AyaVisionForConditionalGeneration"),
+    "InternVLForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
+    "InternS1ForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),
@@ -136,6 +138,17 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Ernie4_5_MoeForCausalLM": ("deepseek", "Ernie4_5_MoeForCausalLM"),
     "DeepseekV3ForCausalLM": ("deepseek", "DeepseekV3ForCausalLM"),
 }
+
+
+_TEXT_BY_TYPE = {"llama": "LlamaForCausalLM", "mistral": "MistralForCausalLM", "qwen2": "Qwen2ForCausalLM", "qwen3": "Qwen3ForCausalLM",
+                 "gemma": "GemmaForCausalLM", "gemma2": "Gemma2ForCausalLM", "gemma3_text": "Gemma3ForCausalLM", "phi3": "Phi3ForCausalLM",
+                 "cohere2": "Cohere2ForCausalLM", "internlm2": "InternLM2ForCausalLM", "qwen3_moe": "Qwen3MoeForCausalLM",
+                 "granite": "GraniteForCausalLM", "gpt_oss": "GptOssForCausalLM", "olmo2": "Olmo2ForCausalLM"}
+
+
+def text_decoder_cls(cfg: dict, default: str = "LlamaForCausalLM") -> Type[nn.Module]:
+    """The decoder class behind a composite (vision / audio + text) checkpoint, from its ``text_config.model_type``."""
+    return resolve_model_cls(_TEXT_BY_TYPE.get(cfg.get("text_model_type") or "", default))
 
 
 def register_model(arch: str, module: str, cls: str) -> None:

@@ -56,6 +56,10 @@ class MultiModalProcessor:
         vc = cfg["vision_config"]
         self.image_size = vc.get("image_size", 336)
         self.patch = vc.get("patch_size", 14)
+        if isinstance(self.image_size, (list, tuple)):
+            self.image_size = self.image_size[0]
+        if isinstance(self.patch, (list, tuple)):
+            self.patch = self.patch[0]
         self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
         n = (self.image_size // self.patch) ** 2
         self.tokens_per_image = n if cfg.get("vision_feature_select_strategy", "default") == "default" else n + 1
