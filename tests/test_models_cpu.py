@@ -699,3 +699,53 @@ def test_internvl_matches_hf_with_image():
                        SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_audio_language_models_match_hf():
+    """Qwen2-Audio (masked, pooled Whisper tower + linear projector; a full window and a clip shorter than the window) and
+    Voxtral (tower + frame-group GELU projector) against transformers, greedy, with precomputed log-mel inputs."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    g = torch.Generator().manual_seed(1)
+    # ---- Qwen2-Audio
+    cfg = get_preset_hf_config("qwen2audio-tiny")
+    drop = ("architectures", "model_type", "audio_config", "audio_token_index", "text_model_type", "torch_dtype")
+    hf_cfg = transformers.Qwen2AudioConfig(audio_config=cfg["audio_config"], text_config=dict(model_type="qwen2", **_vlm_text_cfg(cfg, drop)),
+                                           audio_token_index=511)
+    torch.manual_seed(0)
+    hf = transformers.Qwen2AudioForConditionalGeneration(hf_cfg).eval()
+    llm = make_llm("qwen2audio-tiny", weights=hf.state_dict().items())
+    for valid in (48, 30):
+        mel = torch.randn(16, 48, generator=g)
+        mel[:, valid:] = -1.0
+        n = ((valid - 1) // 2 + 1 - 2) // 2 + 1
+        ids = [5, 17, 511, 99, 3, 250]
+        exp_ids = [5, 17] + [511] * n + [99, 3, 250]
+        fam = torch.zeros(1, 48, dtype=torch.long)
+        fam[:, :valid] = 1
+        with torch.no_grad():
+            ref = hf.generate(input_ids=torch.tensor([exp_ids]), input_features=mel[None], feature_attention_mask=fam,
+                              attention_mask=torch.ones(1, len(exp_ids), dtype=torch.long), max_new_tokens=8, do_sample=False,
+                              pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+        out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"audio": mel[:, :valid]}}], sp)
+        assert out[0].outputs[0].token_ids == ref, valid
+    llm.shutdown()
+    # ---- Voxtral
+    cfg = get_preset_hf_config("voxtral-tiny")
+    drop = ("architectures", "model_type", "audio_config", "audio_token_id", "text_model_type", "projector_hidden_act", "torch_dtype")
+    hf_cfg = transformers.VoxtralConfig(audio_config=cfg["audio_config"], text_config=dict(model_type="llama", **_vlm_text_cfg(cfg, drop)),
+                                        audio_token_id=511)
+    torch.manual_seed(0)
+    hf = transformers.VoxtralForConditionalGeneration(hf_cfg).eval()
+    mel = torch.randn(16, 48, generator=g)
+    n = 24 * 32 // 64
+    ids = [5, 17, 511, 99, 3, 250]
+    exp_ids = [5, 17] + [511] * n + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), input_features=mel[None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("voxtral-tiny", weights=hf.state_dict().items())
+    out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"audio": mel}}], sp)
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

@@ -168,6 +168,21 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "qwen2audio-tiny": dict(
+        architectures=["Qwen2AudioForConditionalGeneration"], model_type="qwen2_audio", audio_token_index=511, text_model_type="qwen2",
+        audio_config=dict(model_type="qwen2_audio_encoder", num_mel_bins=16, d_model=32, encoder_layers=2, encoder_attention_heads=2,
+                          encoder_ffn_dim=64, max_source_positions=24, activation_function="gelu", scale_embedding=False),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "voxtral-tiny": dict(
+        architectures=["VoxtralForConditionalGeneration"], model_type="voxtral", audio_token_id=511, text_model_type="llama",
+        projector_hidden_act="gelu",
+        audio_config=dict(model_type="voxtral_encoder", vocab_size=512, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                          num_attention_heads=2, num_mel_bins=16, max_source_positions=24, head_dim=16),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, head_dim=16, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

@@ -31,12 +31,12 @@ class InputProcessor:
         self.mm_processor = None
         # sender half of the multimodal input cache (one engine core only: with DP the target engine is picked later)
         self.mm_sender = None
-        if (self.mc.hf_config.get("vision_config") is not None or self.mc.hf_config.get("is_encoder_decoder")) \
-                and vllm_config.parallel_config.data_parallel_size == 1:
+        from vllm_b200.multimodal import MULTIMODAL_REGISTRY
+        has_mm = MULTIMODAL_REGISTRY.supports_multimodal(self.mc)
+        if (has_mm or self.mc.hf_config.get("is_encoder_decoder")) and vllm_config.parallel_config.data_parallel_size == 1:
             from vllm_b200.multimodal.cache import SenderShadow
             self.mm_sender = SenderShadow(int(os.environ.get("VLLM_B200_MM_CACHE_ITEMS", "256")))
-        if self.mc.hf_config.get("vision_config") is not None:
-            from vllm_b200.multimodal import MULTIMODAL_REGISTRY
+        if has_mm:
             self.mm_processor = MULTIMODAL_REGISTRY.create_processor(self.mc)
 
     def process_inputs(self, request_id: str, prompt: PromptType,

@@ -123,6 +123,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "AyaVisionForConditionalGeneration": ("idefics3", "AyaVisionForConditionalGeneration"),
     "InternVLForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
     "InternS1ForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
+    "Qwen2AudioForConditionalGeneration": ("audio_lm", "Qwen2AudioForConditionalGeneration"),
+    "VoxtralForConditionalGeneration": ("audio_lm", "VoxtralForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

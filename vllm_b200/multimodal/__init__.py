@@ -139,10 +139,14 @@ class _Registry:
                 and model_config.architecture not in self.processors):
             from vllm_b200.multimodal.qwen_vl import Qwen2VLProcessor
             self.processors[model_config.architecture] = Qwen2VLProcessor
+        if model_config.hf_config.get("audio_config") is not None and model_config.architecture not in self.processors:
+            from vllm_b200.models.audio_lm import AudioLMProcessor
+            self.processors[model_config.architecture] = AudioLMProcessor
         return self.processors.get(model_config.architecture, MultiModalProcessor)(model_config)
 
     def supports_multimodal(self, model_config) -> bool:
-        return model_config.hf_config.get("vision_config") is not None
+        c = model_config.hf_config
+        return c.get("vision_config") is not None or (c.get("audio_config") is not None and not c.get("is_encoder_decoder"))
 
 
 MULTIMODAL_REGISTRY = _Registry()

@@ -196,7 +196,8 @@ class ModelRunner:
         if ecp:
             from vllm_b200.ec_transfer import ECSharedStorageConnector
             self.ec_connector = ECSharedStorageConnector(ecp, os.environ.get("VLLM_B200_EC_ROLE", "ec_both"))
-        self.has_mm = vllm_config.model_config.hf_config.get("vision_config") is not None
+        from vllm_b200.multimodal import MULTIMODAL_REGISTRY
+        self.has_mm = MULTIMODAL_REGISTRY.supports_multimodal(vllm_config.model_config)
         self.uses_mrope = vllm_config.model_config.hf_config.get("model_type") in ("qwen2_vl", "qwen2_5_vl")
         self.kv_connector = None
         ktc = vllm_config.kv_transfer_config
