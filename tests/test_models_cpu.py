@@ -749,3 +749,33 @@ def test_audio_language_models_match_hf():
     out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"audio": mel}}], sp)
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_mistral3_matches_hf_with_image():
+    """Pixtral tower (2-D rotary) → norm → learned 2×2 patch merger → projector → Mistral decoder == HF
+    Mistral3ForConditionalGeneration, with the [IMG]…[IMG_BREAK]…[IMG_END] row layout produced by the processor."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("mistral3-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "spatial_merge_size", "multimodal_projector_bias",
+            "projector_hidden_act", "vision_feature_layer", "text_model_type", "torch_dtype")
+    hf_cfg = transformers.Mistral3Config(vision_config=cfg["vision_config"], text_config=dict(model_type="mistral", **_vlm_text_cfg(cfg, drop)),
+                                         image_token_index=10, spatial_merge_size=2, multimodal_projector_bias=False, vision_feature_layer=-1)
+    torch.manual_seed(0)
+    hf = transformers.Mistral3ForConditionalGeneration(hf_cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    ids = [5, 17, 10, 99, 3, 250]
+    rows = []
+    for r in range(4):                                     # 32 / 4 / 2 = 4 merged patches per side
+        rows += [10] * 4 + [13 if r == 3 else 12]
+    exp_ids = [5, 17] + rows + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], image_sizes=torch.tensor([[32, 32]]),
+                          max_new_tokens=8, do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("mistral3-tiny", weights=hf.state_dict().items())
+    out = llm.generate([{"prompt_token_ids": ids, "multi_modal_data": {"image": img}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    assert out[0].prompt_token_ids == exp_ids
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

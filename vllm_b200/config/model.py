@@ -183,6 +183,14 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, head_dim=16, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "mistral3-tiny": dict(
+        architectures=["Mistral3ForConditionalGeneration"], model_type="mistral3", image_token_index=10, spatial_merge_size=2,
+        multimodal_projector_bias=False, projector_hidden_act="gelu", vision_feature_layer=-1, text_model_type="mistral",
+        vision_config=dict(model_type="pixtral", hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2,
+                           head_dim=16, image_size=32, patch_size=4, hidden_act="silu", rope_theta=10000.0),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, head_dim=16, max_position_embeddings=256, rms_norm_eps=1e-5, rope_theta=10000.0, sliding_window=None,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

@@ -125,6 +125,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "InternS1ForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
     "Qwen2AudioForConditionalGeneration": ("audio_lm", "Qwen2AudioForConditionalGeneration"),
     "VoxtralForConditionalGeneration": ("audio_lm", "VoxtralForConditionalGeneration"),
+    "Mistral3ForConditionalGeneration": ("mistral3", "Mistral3ForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

@@ -945,7 +945,8 @@ class ModelRunner:
                 if self.ec_connector is not None:
                     self.ec_connector.save(f["hash"], enc)
             dst0 = int(cu[j]) + (lo - start)
-            emb[dst0:dst0 + (hi - lo)] = enc[lo - f["offset"]:hi - f["offset"]]
+            e0 = int(f.get("enc_offset", 0))                 # records that cover one slice of a shared encoder output
+            emb[dst0:dst0 + (hi - lo)] = enc[e0 + lo - f["offset"]:e0 + hi - f["offset"]]
         return emb
 
     def _next_staging(self) -> _Staging:
