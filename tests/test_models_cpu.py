@@ -23,7 +23,7 @@ PROMPTS = [[5, 17, 99, 3, 250, 41], [7, 7, 7, 301, 12], list(range(10, 60))]
                                     "cwm-tiny", "jais2-tiny", "ministral3-tiny", "flexolmo-tiny",
                                     "minimaxm2-tiny", "exaonemoe-tiny", "solaropen-tiny", "afmoe-tiny", "glm4moelite-tiny",
                                     "qwen35-tiny", "qwen35moe-tiny", "nemotronh-tiny", "nemotronh-latent-tiny",
-                                    "falconh1-tiny", "falconh1-nonorm-tiny", "lfm2-tiny", "lfm2moe-tiny"])
+                                    "falconh1-tiny", "falconh1-nonorm-tiny", "lfm2-tiny", "lfm2moe-tiny", "olmohybrid-tiny"])
 def test_greedy_matches_hf(preset):
     hf = make_hf_model(preset)
     llm = make_llm(preset, weights=hf.state_dict().items())

@@ -351,6 +351,13 @@ PRESETS: dict[str, dict[str, Any]] = {
         routed_scaling_factor=1.5, norm_topk_prob=True, layer_types=["conv", "full_attention", "conv", "full_attention"],
         rope_parameters=dict(rope_type="default", rope_theta=10000.0), bos_token_id=1, eos_token_id=2, pad_token_id=0,
         torch_dtype="float32", tie_word_embeddings=True),
+    "olmohybrid-tiny": dict(
+        architectures=["OlmoHybridForCausalLM"], model_type="olmo_hybrid", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
+        layer_types=["linear_attention", "full_attention", "linear_attention", "full_attention"], linear_num_key_heads=2,
+        linear_num_value_heads=4, linear_key_head_dim=16, linear_value_head_dim=16, linear_conv_kernel_dim=4,
+        linear_allow_neg_eigval=True, rms_norm_eps=1e-6, hidden_act="silu", rope_parameters=dict(rope_type="default", rope_theta=10000.0),
+        pad_token_id=0, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "qwen35-tiny": dict(
         architectures=["Qwen3_5ForCausalLM"], model_type="qwen3_5_text", vocab_size=512, hidden_size=64, intermediate_size=128,
         num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,

@@ -44,6 +44,7 @@ class GatedDeltaNet(nn.Module):
         self.k = cfg.get("linear_conv_kernel_dim", 4)
         self.conv_dim = 2 * self.key_dim + self.value_dim
         self.eps = cfg.get("rms_norm_eps", 1e-6)
+        self.beta_scale = 1.0                 # OLMo-hybrid lets the write strength reach 2 (negative eigenvalues of the update)
         self.in_proj_qkvz = ReplicatedLinear(H, 2 * self.key_dim + 2 * self.value_dim, False, dtype, None, f"{prefix}.in_proj_qkvz")
         self.in_proj_ba = ReplicatedLinear(H, 2 * self.nv, False, dtype, None, f"{prefix}.in_proj_ba")
         self.conv_weight = nn.Parameter(torch.empty(self.conv_dim, self.k, dtype=dtype), requires_grad=False)
@@ -100,7 +101,7 @@ class GatedDeltaNet(nn.Module):
         xin = torch.cat([conv_state.t().to(qkv.dtype), qkv], dim=0)
         conv = F.silu((xin.float().unfold(0, self.k, 1) * self.conv_weight.float()[None]).sum(-1))
         q, k, v = self._qkv_heads(conv)
-        beta = b.float().sigmoid()
+        beta = b.float().sigmoid() * self.beta_scale
         g = -self.A_log.exp() * F.softplus(a.float() + self.dt_bias)
         out = torch.empty(n, self.nv, self.dv, dtype=torch.float32, device=qkv.device)
         S = S[None]
@@ -131,7 +132,7 @@ class GatedDeltaNet(nn.Module):
             conv = cu.causal_conv1d(qkv, self.conv_weight, None, cache, md)
             qh, kh, vh = self._qkv_heads(conv)
             g = -self.A_log.exp() * F.softplus(a.float() + self.dt_bias)
-            o = cu.gdn_scan(qh, kh, vh, g, b.float().sigmoid(), cache, self.conv_dim * (self.k - 1), md)
+            o = cu.gdn_scan(qh, kh, vh, g, b.float().sigmoid() * self.beta_scale, cache, self.conv_dim * (self.k - 1), md)
             return self.out_proj(self._gated_norm(o, z).reshape(T, -1).to(hidden.dtype))
         cache = cache.view(cache.shape[0], -1).view(torch.float32) if cache.dtype != torch.float32 else cache
         if md.decode_only:
@@ -142,7 +143,7 @@ class GatedDeltaNet(nn.Module):
             conv = F.silu((xin * self.conv_weight.float()[None]).sum(-1))
             qh, kh, vh = self._qkv_heads(conv)
             g = -self.A_log.exp() * F.softplus(a[:Bn].float() + self.dt_bias)
-            S, o = self._step(S, qh, kh, vh, g, b[:Bn].float().sigmoid())
+            S, o = self._step(S, qh, kh, vh, g, b[:Bn].float().sigmoid() * self.beta_scale)
             cache[slots] = torch.cat([xin[:, :, 1:].reshape(Bn, -1), S.reshape(Bn, -1)], dim=-1)
             out[:Bn] = o
         else:
