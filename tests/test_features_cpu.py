@@ -1257,3 +1257,85 @@ def test_batch_invariant_policy_and_generation(monkeypatch):
     assert alone[0] == first[0] == last[0]
     for a, b in ((alone[1], first[1]), (alone[1], last[1])):
         assert max(abs(x - y) for x, y in zip(a, b)) < 1e-5
+
+
+@pytest.mark.parametrize("preset", ["deepseek-tiny", "glm4moe-tiny", "qwen3next-tiny", "gemma3-tiny"])
+def test_mtp_head_uses_the_targets_own_layer_kind(preset):
+    """Multi-token prediction on families whose prediction block is NOT a Llama layer: the head builds one more layer
+    through the target's layer factory (MLA + experts, q/k-normed GQA + experts, gated attention, sandwich-norm Gemma),
+    keeps its own KV arena in the right layout (latent cache for MLA), drafts, and stays lossless."""
+    llm = make_llm(preset)
+    ref = _greedy(llm)
+    llm.shutdown()
+    llm = make_llm(preset, speculative_config=dict(method="mtp", num_speculative_tokens=2))
+    runner = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner
+    head = runner.drafter.head
+    assert head.native_layer
+    kind = type(head.layers[0]).__name__
+    assert kind != "LlamaDecoderLayer", kind
+    got = _greedy(llm)
+    sched = llm.llm_engine.engine_core.engine_core.scheduler
+    llm.shutdown()
+    assert got == ref
+    assert sched._spec_draft_tokens > 0
+
+
+def test_mtp_weights_are_picked_out_of_the_target_checkpoint():
+    """DeepSeek-V3 style naming (``model.layers.<L>.{enorm,hnorm,eh_proj,shared_head.norm,self_attn…,mlp.experts…}``), the
+    Qwen3-Next ``mtp.*`` naming and MiMo's ``model.mtp_layers.0.*``: every tensor lands in the head."""
+    import torch
+    from vllm_b200.spec_decode.eagle import EagleHead
+    llm = make_llm("glm4moe-tiny", speculative_config=dict(method="mtp", num_speculative_tokens=1))
+    head: EagleHead = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.drafter.head
+    L = 3
+    g = torch.Generator().manual_seed(0)
+    src = {}
+    for n, p in head.named_parameters():
+        t = torch.randn(p.shape, generator=g).to(p.dtype)
+        if n.startswith("layers.0."):
+            rest = n[len("layers.0."):]
+            if rest.endswith("experts.w13_weight"):
+                I = t.shape[1] // 2
+                for e in range(t.shape[0]):
+                    src[f"model.layers.{L}.{rest[:-len('w13_weight')]}{e}.gate_proj.weight"] = t[e, :I]
+                    src[f"model.layers.{L}.{rest[:-len('w13_weight')]}{e}.up_proj.weight"] = t[e, I:]
+            elif rest.endswith("experts.w2_weight"):
+                for e in range(t.shape[0]):
+                    src[f"model.layers.{L}.{rest[:-len('w2_weight')]}{e}.down_proj.weight"] = t[e]
+            elif rest.endswith("experts.e_score_correction_bias"):
+                src[f"model.layers.{L}.mlp.gate.e_score_correction_bias"] = t
+            elif ".qkv_proj." in rest:
+                q, k, v = t.split([head.layers[0].self_attn.q_size, head.layers[0].self_attn.kv_size, head.layers[0].self_attn.kv_size], dim=0)
+                for part, tt in (("q_proj", q), ("k_proj", k), ("v_proj", v)):
+                    src[f"model.layers.{L}.{rest.replace('qkv_proj', part)}"] = tt
+            elif ".gate_up_proj." in rest:
+                a, b = t.chunk(2, dim=0)
+                src[f"model.layers.{L}.{rest.replace('gate_up_proj', 'gate_proj')}"] = a
+                src[f"model.layers.{L}.{rest.replace('gate_up_proj', 'up_proj')}"] = b
+            else:
+                src[f"model.layers.{L}.{rest}"] = t
+        else:
+            name = {"fc.weight": "eh_proj.weight", "norm.weight": "shared_head.norm.weight"}.get(n, n)
+            src[f"model.layers.{L}.{name}"] = t
+    src[f"model.layers.{L}.shared_head.head.weight"] = torch.zeros(4, 4)          # shared with the target: ignored
+    src["model.layers.0.input_layernorm.weight"] = torch.zeros(4)                  # not part of the block: ignored
+    want = {n: p.detach().clone() for n, p in head.named_parameters()}
+    n = head.load_mtp_weights(src.items(), L)
+    assert n >= len(src) - 2 - 1
+    # round trip: reconstruct what was fed and compare with what the head now holds
+    for name, p in head.named_parameters():
+        assert not torch.equal(p, want[name]) or p.numel() <= 1, name
+    llm.shutdown()
+    # the other two naming schemes resolve to the same targets
+    picked = []
+    orig = EagleHead.load_weights
+    try:
+        EagleHead.load_weights = lambda self, ws: picked.extend(n for n, _ in ws) or 0
+        head.load_mtp_weights([("mtp.fc.weight", 0), ("mtp.pre_fc_norm_hidden.weight", 0), ("mtp.pre_fc_norm_embedding.weight", 0),
+                               ("mtp.norm.weight", 0), ("mtp.layers.0.self_attn.q_proj.weight", 0),
+                               ("model.mtp_layers.0.token_layernorm.weight", 0), ("model.mtp_layers.0.input_proj.weight", 0),
+                               ("model.mtp_layers.0.final_layernorm.weight", 0), ("model.mtp_layers.0.mlp.down_proj.weight", 0)], 99)
+    finally:
+        EagleHead.load_weights = orig
+    assert picked == ["fc.weight", "hnorm.weight", "enorm.weight", "norm.weight", "layers.0.self_attn.q_proj.weight",
+                      "enorm.weight", "fc.weight", "norm.weight", "layers.0.mlp.down_proj.weight"]

@@ -29,7 +29,7 @@ logger = init_logger(__name__)
 
 
 class EagleHead(nn.Module):
-    def __init__(self, cfg: dict, mc, dtype, mtp: bool, prefix: str = "eagle.") -> None:
+    def __init__(self, cfg: dict, mc, dtype, mtp: bool, prefix: str = "eagle.", layer_factory=None) -> None:
         super().__init__()
         H = cfg["hidden_size"]
         eps = cfg.get("rms_norm_eps", 1e-6)
@@ -37,7 +37,12 @@ class EagleHead(nn.Module):
         self.enorm = RMSNorm(H, eps, dtype) if mtp else None
         self.hnorm = RMSNorm(H, eps, dtype) if mtp else None
         self.fc = nn.Linear(2 * H, H, bias=False, dtype=dtype)
-        self.layers = nn.ModuleList([LlamaDecoderLayer(cfg, mc, dtype, None, f"{prefix}layers.0", 0)])
+        # MTP heads are one more decoder layer OF THE TARGET'S OWN KIND (MLA + experts for DeepSeek-V3, q/k-normed GQA +
+        # experts for GLM-4.5, …): the target model's layer factory builds it; EAGLE heads are a Llama layer
+        layer = layer_factory(f"{prefix}layers.0") if layer_factory is not None else \
+            LlamaDecoderLayer(cfg, mc, dtype, None, f"{prefix}layers.0", 0)
+        self.layers = nn.ModuleList([layer])
+        self.native_layer = layer_factory is not None
         self.norm = RMSNorm(H, eps, dtype)
 
     def forward(self, emb: torch.Tensor, hidden: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
@@ -51,12 +56,49 @@ class EagleHead(nn.Module):
     stacked = [("qkv_proj", "q_proj", "q"), ("qkv_proj", "k_proj", "k"), ("qkv_proj", "v_proj", "v"),
                ("gate_up_proj", "gate_proj", 0), ("gate_up_proj", "up_proj", 1)]
 
+    # checkpoint names of the MTP block inside a TARGET checkpoint → ours (DeepSeek-V3 / GLM-4.5 / ERNIE: extra decoder
+    # layer index L; Qwen3-Next: ``mtp.*``; MiMo: ``model.mtp_layers.0.*``)
+    _MTP_RENAMES = [("eh_proj.", "fc."), ("shared_head.norm.", "norm."), ("pre_fc_norm_embedding.", "enorm."),
+                    ("pre_fc_norm_hidden.", "hnorm."), ("token_layernorm.", "enorm."), ("hidden_layernorm.", "hnorm."),
+                    ("input_proj.", "fc."), ("final_layernorm.", "norm."), ("mtp_block.", "layers.0.")]
+    _EXPERT = {"gate_proj": ("w13_weight", "w1"), "up_proj": ("w13_weight", "w3"), "down_proj": ("w2_weight", "w2"),
+               "w1": ("w13_weight", "w1"), "w3": ("w13_weight", "w3"), "w2": ("w2_weight", "w2")}
+
+    def load_mtp_weights(self, weights: Iterable[tuple[str, torch.Tensor]], num_layers: int) -> int:
+        """Pick the multi-token-prediction tensors out of the target's checkpoint stream and load them."""
+        pres = (f"model.layers.{num_layers}.", "mtp.layers.0.", "mtp.", "model.mtp_layers.0.", "model.mtp.layers.0.", "model.mtp.")
+        top = ("enorm.", "hnorm.", "fc.", "norm.")
+
+        def picked():
+            for name, w in weights:
+                pre = next((p for p in pres if name.startswith(p)), None)
+                if pre is None:
+                    continue
+                rest = name[len(pre):]
+                if rest.startswith(("embed_tokens.", "shared_head.head.")):        # shared with the target
+                    continue
+                for a, b in self._MTP_RENAMES:
+                    if rest.startswith(a):
+                        rest = b + rest[len(a):]
+                yield (rest if rest.startswith(top) or rest.startswith("layers.0.") else "layers.0." + rest), w
+        return self.load_weights(picked())
+
     def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> int:
         params = dict(self.named_parameters())
         modules = dict(self.named_modules())
         n = 0
         for name, w in weights:
             name = name.removeprefix("model.")
+            if ".mlp.experts." in name and name.split(".mlp.experts.")[1].split(".")[0].isdigit():
+                head, tail = name.split(".mlp.experts.", 1)
+                e, which = tail.split(".")[0], tail.split(".")[1]
+                suffix, shard = self._EXPERT[which]
+                pn = f"{head}.mlp.experts.{suffix}"
+                if pn in params:
+                    modules[f"{head}.mlp.experts"].weight_loader(params[pn], w, shard, int(e))
+                    n += 1
+                continue
+            name = name.replace(".mlp.gate.e_score_correction_bias", ".mlp.experts.e_score_correction_bias")
             target, shard = name, None
             for fused, part, sid in self.stacked:
                 if f".{part}." in name:
@@ -148,7 +190,8 @@ class EagleDrafter:
                     self.aux_layers = tuple(sorted({min(2, L - 1), L // 2, max(L - 3, 0)}))     # low / mid / high taps
                     self.head = Eagle3Head(mc.hf_config, mc, mc.torch_dtype, len(self.aux_layers))
                 else:
-                    self.head = EagleHead(mc.hf_config, mc, mc.torch_dtype, mtp=sc.method == "mtp")
+                    self.head = EagleHead(mc.hf_config, mc, mc.torch_dtype, mtp=sc.method == "mtp",
+                                          layer_factory=self._native_layer_factory(runner, mc) if sc.method == "mtp" else None)
         finally:
             torch.set_default_dtype(old)
         reg = attn_mod.attention_layers()
@@ -161,19 +204,49 @@ class EagleDrafter:
             from vllm_b200.model_loader import iter_weights
             logger.info("EAGLE head: loaded %d tensors from %s", self.head.load_weights(iter_weights(sc.model, "auto")),
                         sc.model)
+        elif sc.method == "mtp" and os.path.isdir(mc.model):
+            # the prediction block ships inside the target checkpoint
+            from vllm_b200.model_loader import iter_weights
+            got = self.head.load_mtp_weights(iter_weights(mc.model, "auto"), mc.hf_config["num_hidden_layers"])
+            logger.info("MTP head (%s layer): loaded %d tensors from the target checkpoint",
+                        "native" if self.head.native_layer else "Llama", got)
         self.head.eval()
         self.bs = vllm_config.cache_config.block_size
         R = runner.max_num_reqs
         self.blocks_per_row = cdiv(runner.max_model_len + self.k + 1, self.bs)
         self.kv = {}
+        from vllm_b200.core.kv_cache_manager import MambaSpec, MLAAttentionSpec
         for name, layer in self.layers.items():
-            self.kv[name] = torch.zeros((R * self.blocks_per_row, 2, layer.num_kv_heads, self.bs, layer.head_size),
-                                        dtype=mc.torch_dtype, device=self.device)
+            spec = layer.get_kv_cache_spec(self.bs, mc.torch_dtype.itemsize) if hasattr(layer, "get_kv_cache_spec") else None
+            if isinstance(spec, MambaSpec):
+                raise NotImplementedError("multi-token-prediction blocks with recurrent (state-space / delta-net) mixers")
+            shape = ((R * self.blocks_per_row, self.bs, layer.head_size) if isinstance(spec, MLAAttentionSpec) else
+                     (R * self.blocks_per_row, 2, layer.num_kv_heads, self.bs, layer.head_size))
+            self.kv[name] = torch.zeros(shape, dtype=mc.torch_dtype, device=self.device)
         self.block_table = torch.arange(R * self.blocks_per_row, dtype=torch.int32, device=self.device).view(R, -1)
         self.layer_to_group = {n: 0 for n in self.layers}
         self.row_req: dict[int, str] = {}          # arena row → request id it currently serves
         self.base = np.zeros(R, dtype=np.int64)    # first position the head saw for that request (prefix-cache hits)
         self.filled = np.zeros(R, dtype=np.int64)  # positions < filled have valid head KV
+
+    @staticmethod
+    def _native_layer_factory(runner, mc):
+        """A builder for one more decoder layer of the target's own kind (index = num_hidden_layers), or None when the
+        target model does not expose its layer factory (then the head falls back to a Llama layer)."""
+        inner = getattr(runner.model, "model", None)
+        if inner is None and hasattr(runner.model, "language_model"):
+            inner = getattr(runner.model.language_model, "model", None)
+        make = getattr(inner, "_make_layer", None)
+        if make is None:
+            return None
+        cfg = mc.hf_config
+        L = cfg["num_hidden_layers"]
+        # per-layer lists are indexed by the layer id: give index L the kind the checkpoints use for the prediction block
+        for key, fill in (("layer_types", "full_attention"), ("mlp_layer_types", "sparse"), ("no_rope_layers", 1)):
+            v = cfg.get(key)
+            if isinstance(v, list) and len(v) == L:
+                v.append(fill)
+        return lambda prefix: make(cfg, mc, mc.torch_dtype, None, prefix, L)
 
     def _run(self, emb, hidden, pos, md, last_idx):
         ctx = ForwardContext(attn_metadata={0: md}, kv_caches=self.kv, layer_to_group=self.layer_to_group,
