@@ -1339,3 +1339,22 @@ def test_mtp_weights_are_picked_out_of_the_target_checkpoint():
         EagleHead.load_weights = orig
     assert picked == ["fc.weight", "hnorm.weight", "enorm.weight", "norm.weight", "layers.0.self_attn.q_proj.weight",
                       "enorm.weight", "fc.weight", "norm.weight", "layers.0.mlp.down_proj.weight"]
+
+
+def test_speculative_method_is_inferred_from_the_draft_architecture(tmp_path):
+    import json
+    from vllm_b200.config import SpeculativeConfig
+    from vllm_b200.spec_decode import DRAFT_ARCHS, infer_method
+    assert SpeculativeConfig(method="auto").method == "ngram"
+    assert SpeculativeConfig(method="auto", model="llama-tiny").method == "draft_model"
+    for arch, want in (("EagleLlamaForCausalLM", "eagle"), ("Eagle3Qwen3ForCausalLM", "eagle3"), ("DeepSeekMTPModel", "mtp"),
+                       ("Glm4MoeMTPModel", "mtp"), ("MedusaModel", "medusa"), ("LlamaForCausalLM", "draft_model")):
+        d = tmp_path / arch
+        d.mkdir()
+        (d / "config.json").write_text(json.dumps({"architectures": [arch]}))
+        assert infer_method(str(d)) == want, arch
+    d = tmp_path / "yuhuili-EAGLE3-x"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps({"architectures": ["LlamaForCausalLM"]}))
+    assert infer_method(str(d)) == "eagle3"
+    assert len(DRAFT_ARCHS) > 40

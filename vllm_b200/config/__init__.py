@@ -194,7 +194,7 @@ class LoRAConfig(_ConfigBase):
 class SpeculativeConfig(_ConfigBase):
     """Reference: vllm/config/speculative.py."""
 
-    method: str = "ngram"  # ngram|eagle|eagle3|mtp|medusa|draft_model|suffix
+    method: str = "ngram"  # ngram|eagle|eagle3|mtp|medusa|draft_model|suffix|auto (from the draft checkpoint's architecture)
     num_speculative_tokens: int = 4
     model: Optional[str] = None
     prompt_lookup_max: int = 5
@@ -205,6 +205,11 @@ class SpeculativeConfig(_ConfigBase):
     # (EMA; shrink when drafts are mostly rejected, grow back when they are accepted) between 1 and num_speculative_tokens
     dynamic_k: bool = False
     dynamic_k_ema: float = 0.5
+
+    def __post_init__(self) -> None:
+        if self.method in ("auto", None, ""):
+            from vllm_b200.spec_decode import infer_method
+            self.method = infer_method(self.model)
 
 
 @dataclass

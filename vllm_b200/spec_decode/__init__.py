@@ -117,6 +117,53 @@ class SuffixDrafter:
         return out
 
 
+# Draft / prediction-head architectures as they appear in checkpoints' config.json → proposer that serves them
+# (reference: vllm/model_executor/models/registry.py ``_SPECULATIVE_DECODING_MODELS``, config/speculative.py method inference)
+DRAFT_ARCHS: dict[str, str] = {
+    **{a: "eagle" for a in ("EagleLlamaForCausalLM", "EagleLlama4ForCausalLM", "EagleMistralForCausalLM", "EagleMiniCPMForCausalLM",
+                            "EagleCohereForCausalLM", "EagleMistralLarge3ForCausalLM", "EagleDeepSeekMTPModel")},
+    **{a: "eagle3" for a in ("Eagle3LlamaForCausalLM", "LlamaForCausalLMEagle3", "Eagle3Qwen3ForCausalLM", "Eagle3Qwen2_5vlForCausalLM",
+                             "Eagle3Qwen3vlForCausalLM", "Eagle3MiniMaxM2ForCausalLM", "Eagle3DeepseekV2ForCausalLM",
+                             "Eagle3DeepseekV3ForCausalLM", "PeagleLlamaForCausalLM", "PeagleQwen3ForCausalLM", "PEagleDraftModel")},
+    **{a: "mtp" for a in ("DeepSeekMTPModel", "DeepseekV32MTPModel", "Glm4MoeMTPModel", "Glm4MoeLiteMTPModel", "GlmOcrMTPModel",
+                          "MiMoMTPModel", "MiMoV2MTPModel", "ErnieMTPModel", "Qwen3NextMTP", "Qwen3_5MTP", "Qwen3_5MoeMTP",
+                          "ExaoneMoeMTP", "Exaone4_5_MTP", "NemotronHMTPModel", "LongCatFlashMTPModel", "OpenPanguMTPModel",
+                          "Step3p5MTP", "BailingMoeV25MTPModel", "BailingMoeV3MTPModel", "HYV3MTPModel", "KimiK3MTPModel",
+                          "Gemma4MTPModel", "InklingMTPModel", "Dots3NoteMTPModel", "MiniMaxM3MTP", "MiMoV2OmniMTPModel",
+                          "InternS2MobiusMTP", "DeepSeekV4MTPModel")},
+    "MedusaModel": "medusa",
+}
+
+
+def infer_method(draft: Optional[str]) -> str:
+    """``method="auto"``: no draft checkpoint → n-gram lookup; a draft whose config names a known head architecture → that
+    head's proposer; any other causal LM → an independent draft model."""
+    if not draft:
+        return "ngram"
+    import json
+    import os
+    cfg = None
+    p = os.path.join(draft, "config.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            cfg = json.load(f)
+    else:
+        from vllm_b200.config import get_preset_hf_config
+        cfg = get_preset_hf_config(draft)
+    archs = (cfg or {}).get("architectures") or []
+    for a in archs:
+        if a in DRAFT_ARCHS:
+            return DRAFT_ARCHS[a]
+    low = " ".join(archs).lower() + " " + os.path.basename(str(draft)).lower()
+    if "eagle3" in low:
+        return "eagle3"
+    if "eagle" in low:
+        return "eagle"
+    if "medusa" in low:
+        return "medusa"
+    return "draft_model"
+
+
 def make_drafter(vllm_config, runner) -> Optional[object]:
     sc = vllm_config.speculative_config
     if sc is None:
