@@ -779,3 +779,52 @@ def test_mistral3_matches_hf_with_image():
     assert out[0].prompt_token_ids == exp_ids
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_llava_next_anyres_matches_hf():
+    """Any-resolution LLaVA-NeXT: a wide image on a 1×2 tile grid (padding rows cropped, newline token per feature row) and
+    the same model on a square single-canvas image, against transformers; plus the built-in tiler's token count."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = dict(get_preset_hf_config("llava-tiny"))
+    pins = [[28, 28], [28, 56], [56, 28], [56, 56]]
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "vision_feature_layer",
+            "vision_feature_select_strategy", "projector_hidden_act", "torch_dtype")
+    hf_cfg = transformers.LlavaNextConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="llama", **_vlm_text_cfg(cfg, drop)),
+                                          image_token_index=511, vision_feature_layer=-2, vision_feature_select_strategy="default",
+                                          projector_hidden_act="gelu", image_grid_pinpoints=pins)
+    torch.manual_seed(0)
+    hf = transformers.LlavaNextForConditionalGeneration(hf_cfg).eval()
+    with torch.no_grad():
+        hf.model.image_newline.normal_(0, 0.5)
+    llm = make_llm("llava-tiny", weights=hf.state_dict().items(),
+                   hf_overrides={"architectures": ["LlavaNextForConditionalGeneration"], "image_grid_pinpoints": pins})
+    proc = llm.llm_engine.processor.mm_processor if hasattr(llm.llm_engine, "processor") else None
+    g = torch.Generator().manual_seed(1)
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    for size, n_tiles in (((20, 50), 3), ((40, 44), 5)):
+        tiles = torch.randn(n_tiles, 3, 28, 28, generator=g)
+        with torch.no_grad():
+            feats = hf.get_image_features(pixel_values=tiles[None], image_sizes=torch.tensor([size]),
+                                          vision_feature_layer=-2, vision_feature_select_strategy="default").pooler_output
+        n = feats[0].shape[0] if isinstance(feats, (list, tuple)) else feats.shape[0]
+        exp_ids = [5, 17] + [511] * n + [99, 3, 250]
+        with torch.no_grad():
+            ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=tiles[None], image_sizes=torch.tensor([size]),
+                              max_new_tokens=8, do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+        out = llm.generate([{"prompt_token_ids": [5, 17, 511, 99, 3, 250],
+                             "multi_modal_data": {"image": {"tiles": tiles, "image_size": size}}}], sp)
+        assert len(out[0].prompt_token_ids) == len(exp_ids), (size, n)
+        assert out[0].outputs[0].token_ids == ref, size
+    # the built-in tiler: raw HWC uint8 image → canvas fit + tiles, token count consistent with the packer
+    from vllm_b200.models.llava_next import LlavaNextProcessor
+    import numpy as np
+    mc = llm.llm_engine.vllm_config.model_config
+    p = LlavaNextProcessor(mc)
+    img = (np.random.RandomState(0).rand(20, 50, 3) * 255).astype(np.uint8)
+    ids, feats = p.process([5, 511, 7], {"image": img})
+    assert feats[0]["data"].shape == (3, 3, 28, 28) and feats[0]["image_size"] == (20, 50)
+    assert len(ids) == 2 + feats[0]["length"]
+    out = llm.generate([{"prompt_token_ids": [5, 511, 7], "multi_modal_data": {"image": img}}], sp)
+    assert len(out[0].outputs[0].token_ids) == 8
+    llm.shutdown()

@@ -90,7 +90,10 @@ class LlavaForConditionalGeneration(nn.Module):
         self.linear_2 = nn.Linear(Ht, Ht, dtype=dtype)
         self.proj_act = _act(cfg.get("projector_hidden_act", "gelu"))
         # the text stack reads the flattened text fields of the same config
-        self.language_model = LlamaForCausalLM(vllm_config, prefix=f"{prefix}language_model.")
+        from vllm_b200.models.registry import text_decoder_cls
+        if cfg.get("text_model_type") == "qwen2":
+            cfg.setdefault("attention_bias", True)
+        self.language_model = text_decoder_cls(cfg, "LlamaForCausalLM")(vllm_config, prefix=f"{prefix}language_model.")
 
     # ---------------------------------------------------------------- multimodal
     @torch.inference_mode()

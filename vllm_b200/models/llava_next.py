@@ -1,0 +1,155 @@
+"""LLaVA-NeXT (LLaVA-1.6): any-resolution input — the image is fitted into the best of a few tile grids, cut into
+``image_size`` tiles, every tile and a down-scaled copy of the whole image go through the CLIP tower + projector; the
+tile features are laid back out as one big feature map, the padding the fit introduced is cropped away, a learned
+``image_newline`` vector closes every feature row, and [whole-image tokens | rows] replace the placeholder.
+
+Reference parity: vllm/model_executor/models/llava_next.py, HF ``modeling_llava_next`` (``pack_image_features``,
+``unpad_image``, ``select_best_resolution``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from vllm_b200.config import VllmConfig
+from vllm_b200.models.llava import LlavaForConditionalGeneration
+
+
+def select_best_resolution(size: tuple[int, int], candidates: list) -> tuple[int, int]:
+    """(height, width) of the candidate canvas that keeps the most image pixels, ties broken by least padding."""
+    oh, ow = size
+    best, best_eff, best_waste = None, 0, float("inf")
+    for h, w in candidates:
+        s = min(w / ow, h / oh)
+        eff = min(int(ow * s) * int(oh * s), ow * oh)
+        waste = w * h - eff
+        if eff > best_eff or (eff == best_eff and waste < best_waste):
+            best, best_eff, best_waste = (h, w), eff, waste
+    return best
+
+
+def unpadded_grid(cur_h: int, cur_w: int, orig: tuple[int, int]) -> tuple[int, int, int, int]:
+    """Rows / columns of the feature map that hold image content: (row0, row1, col0, col1)."""
+    oh, ow = orig
+    if ow / oh > cur_w / cur_h:
+        new_h = int(round(oh * (cur_w / ow), 7))
+        pad = (cur_h - new_h) // 2
+        return pad, cur_h - pad, 0, cur_w
+    new_w = int(round(ow * (cur_h / oh), 7))
+    pad = (cur_w - new_w) // 2
+    return 0, cur_h, pad, cur_w - pad
+
+
+class LlavaNextForConditionalGeneration(LlavaForConditionalGeneration):
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg = self.cfg
+        self.image_newline = nn.Parameter(torch.zeros(cfg["hidden_size"], dtype=vllm_config.model_config.torch_dtype), requires_grad=False)
+        vc = cfg["vision_config"]
+        self.side = vc["image_size"] // vc["patch_size"]
+        self.tile = vc["image_size"]
+        self.pinpoints = [tuple(p) for p in cfg.get("image_grid_pinpoints") or [(self.tile, self.tile)]]
+
+    @torch.inference_mode()
+    def embed_multimodal_item(self, f: dict) -> torch.Tensor:
+        tiles = torch.as_tensor(f["data"]).to(self.image_newline.device)
+        feats = self.embed_multimodal(tiles)                              # [T, side², H]
+        if feats.shape[0] == 1:
+            return torch.cat([feats[0], self.image_newline[None].to(feats.dtype)], dim=0)
+        base, rest = feats[0], feats[1:]
+        bh, bw = select_best_resolution(tuple(f["image_size"]), self.pinpoints)
+        gh, gw = bh // self.tile, bw // self.tile
+        s = self.side
+        fmap = rest.view(gh, gw, s, s, -1).permute(4, 0, 2, 1, 3).reshape(-1, gh * s, gw * s)     # [H, rows, cols]
+        r0, r1, c0, c1 = unpadded_grid(gh * s, gw * s, tuple(f["image_size"]))
+        fmap = fmap[:, r0:r1, c0:c1]
+        nl = self.image_newline.to(fmap.dtype)[:, None, None].expand(-1, fmap.shape[1], 1)
+        rows = torch.cat([fmap, nl], dim=-1).flatten(1, 2).t()
+        return torch.cat([base, rows], dim=0)
+
+    def load_weights(self, weights):
+        rest = []
+        loaded = set()
+        for n, w in weights:
+            if n.endswith("image_newline"):
+                self.image_newline.data.copy_(w)
+                loaded.add("image_newline")
+            else:
+                rest.append((n, w))
+        return super().load_weights(rest) | loaded
+
+
+class LlavaNextProcessor:
+    """Image → fitted canvas → tiles (+ the whole image at tile size first); ``{"tiles": [T,3,S,S], "image_size": (H, W)}``
+    is accepted as-is (what an external HF processor returns as ``pixel_values`` / ``image_sizes``)."""
+
+    def __init__(self, model_config) -> None:
+        cfg = model_config.hf_config
+        vc = cfg["vision_config"]
+        self.tile, self.side = vc["image_size"], vc["image_size"] // vc["patch_size"]
+        self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
+        self.pinpoints = [tuple(p) for p in cfg.get("image_grid_pinpoints") or [(self.tile, self.tile)]]
+        self.default = cfg.get("vision_feature_select_strategy", "default") == "default"
+
+    def num_tokens(self, size: tuple[int, int], n_tiles: int) -> int:
+        base = self.side ** 2 + (0 if self.default else 1)
+        if n_tiles == 1:
+            return base + 1
+        bh, bw = select_best_resolution(size, self.pinpoints)
+        r0, r1, c0, c1 = unpadded_grid(bh // self.tile * self.side, bw // self.tile * self.side, size)
+        return base + (r1 - r0) * (c1 - c0 + 1)
+
+    def _tiles(self, img: Any) -> tuple[torch.Tensor, tuple[int, int]]:
+        from vllm_b200.multimodal import CLIP_MEAN, CLIP_STD
+        import numpy as np
+        if isinstance(img, dict):
+            return torch.as_tensor(img["tiles"]).float(), tuple(int(v) for v in img["image_size"])
+        if hasattr(img, "convert"):
+            img = np.array(img.convert("RGB"))
+        t = torch.as_tensor(np.asarray(img)) if not isinstance(img, torch.Tensor) else img
+        normalised = t.is_floating_point() and t.dim() == 3 and t.shape[0] == 3
+        if t.dim() == 3 and t.shape[-1] == 3 and not normalised:
+            t = t.permute(2, 0, 1)
+        t = t.float() / (255.0 if not normalised and t.max() > 1.5 else 1.0)
+        oh, ow = t.shape[1:]
+        bh, bw = select_best_resolution((oh, ow), self.pinpoints)
+        s = min(bw / ow, bh / oh)
+        nh, nw = min(math.ceil(oh * s), bh), min(math.ceil(ow * s), bw)
+        fit = F.interpolate(t[None], size=(nh, nw), mode="bicubic", align_corners=False)[0]
+        canvas = torch.zeros(3, bh, bw)
+        y0, x0 = (bh - nh) // 2, (bw - nw) // 2
+        canvas[:, y0:y0 + nh, x0:x0 + nw] = fit
+        tiles = [F.interpolate(t[None], size=(self.tile, self.tile), mode="bicubic", align_corners=False)[0]]
+        for y in range(0, bh, self.tile):
+            for x in range(0, bw, self.tile):
+                tiles.append(canvas[:, y:y + self.tile, x:x + self.tile])
+        px = torch.stack(tiles)
+        if not normalised:
+            px = (px.clamp(0, 1) - torch.tensor(CLIP_MEAN)[None, :, None, None]) / torch.tensor(CLIP_STD)[None, :, None, None]
+        return px, (oh, ow)
+
+    def process(self, ids: list[int], mm_data: dict[str, Any]) -> tuple[list[int], list[dict[str, Any]]]:
+        from vllm_b200.multimodal import hash_item
+        images = mm_data.get("image")
+        if images is None:
+            return ids, []
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        slots = [i for i, t in enumerate(ids) if t == self.image_token]
+        if len(slots) != len(images):
+            raise ValueError(f"{len(images)} images but {len(slots)} image placeholders in the prompt")
+        out, feats, prev = [], [], 0
+        for slot, img in zip(slots, images):
+            px, size = self._tiles(img)
+            n = self.num_tokens(size, px.shape[0])
+            out.extend(ids[prev:slot])
+            feats.append({"modality": "image", "hash": hash_item(px.numpy()), "offset": len(out), "length": n, "data": px,
+                          "image_size": size})
+            out.extend([self.image_token] * n)
+            prev = slot + 1
+        out.extend(ids[prev:])
+        return out, feats

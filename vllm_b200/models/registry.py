@@ -127,6 +127,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen2AudioForConditionalGeneration": ("audio_lm", "Qwen2AudioForConditionalGeneration"),
     "VoxtralForConditionalGeneration": ("audio_lm", "VoxtralForConditionalGeneration"),
     "Mistral3ForConditionalGeneration": ("mistral3", "Mistral3ForConditionalGeneration"),
+    "LlavaNextForConditionalGeneration": ("llava_next", "LlavaNextForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

@@ -142,6 +142,9 @@ class _Registry:
         if model_config.architecture in ("Mistral3ForConditionalGeneration",) and model_config.architecture not in self.processors:
             from vllm_b200.models.mistral3 import PixtralLayoutProcessor
             self.processors[model_config.architecture] = PixtralLayoutProcessor
+        if model_config.architecture == "LlavaNextForConditionalGeneration" and model_config.architecture not in self.processors:
+            from vllm_b200.models.llava_next import LlavaNextProcessor
+            self.processors[model_config.architecture] = LlavaNextProcessor
         if model_config.hf_config.get("audio_config") is not None and model_config.architecture not in self.processors:
             from vllm_b200.models.audio_lm import AudioLMProcessor
             self.processors[model_config.architecture] = AudioLMProcessor
