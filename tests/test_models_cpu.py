@@ -828,3 +828,16 @@ def test_llava_next_anyres_matches_hf():
     out = llm.generate([{"prompt_token_ids": [5, 511, 7], "multi_modal_data": {"image": img}}], sp)
     assert len(out[0].outputs[0].token_ids) == 8
     llm.shutdown()
+
+
+def test_nomic_bert_embeddings_match_hf():
+    """Rotary, SwiGLU, post-norm encoder: mean-pooled, normalised embeddings == HF NomicBertModel."""
+    hf = make_hf_model("nomicbert-tiny")
+    llm = make_llm("nomicbert-tiny", weights=hf.state_dict().items())
+    prompts = [[3, 17, 99, 250, 41, 7], list(range(10, 45))]
+    outs = llm.embed([{"prompt_token_ids": p} for p in prompts])
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = torch.nn.functional.normalize(hf(torch.tensor([p])).last_hidden_state[0].mean(0), dim=-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()

@@ -608,6 +608,10 @@ PRESETS: dict[str, dict[str, Any]] = {
         max_source_positions=1500, max_target_positions=128, max_position_embeddings=128,
         activation_function="gelu", scale_embedding=False, pad_token_id=0, bos_token_id=1, eos_token_id=2,
         decoder_start_token_id=1, torch_dtype="float32", tie_word_embeddings=True, is_encoder_decoder=True),
+    "nomicbert-tiny": dict(
+        architectures=["NomicBertModel"], model_type="nomic_bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
+        num_attention_heads=4, head_dim=16, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2, hidden_act="silu",
+        layer_norm_eps=1e-12, rope_parameters=dict(rope_type="default", rope_theta=1000.0), torch_dtype="float32", pad_token_id=0),
     "bert-tiny": dict(
         architectures=["BertModel"], model_type="bert", vocab_size=512, hidden_size=64, num_hidden_layers=2,
         num_attention_heads=4, intermediate_size=128, max_position_embeddings=256, type_vocab_size=2,
@@ -777,7 +781,7 @@ class ModelConfig:
     # -- accessors --------------------------------------------------------
     @property
     def is_encoder_only(self) -> bool:
-        return self.architecture.startswith(("Bert", "Roberta", "XLMRoberta"))
+        return self.architecture.startswith(("Bert", "Roberta", "XLMRoberta", "NomicBert"))
 
     @property
     def architecture(self) -> str:

@@ -72,6 +72,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "TransformersForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "TransformersMoEForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "RobertaForMaskedLM": ("bert", "RobertaModel"),
+    "NomicBertModel": ("nomic_bert", "NomicBertModel"),
     "RobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
     "XLMRobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
     "BertForTokenClassification": ("bert", "BertForTokenClassification"),
