@@ -841,3 +841,33 @@ def test_nomic_bert_embeddings_match_hf():
             ref = torch.nn.functional.normalize(hf(torch.tensor([p])).last_hidden_state[0].mean(0), dim=-1)
         torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_colbert_and_splade_heads_on_bert():
+    """Late-interaction (per-token projected, normalised vectors) and SPLADE (max over tokens of log(1+relu(MLM logits)))
+    heads against the same computation done by hand on transformers' BERT states / masked-LM logits."""
+    import transformers
+    prompts = [[3, 17, 99, 250, 41, 7], list(range(10, 30))]
+    hf = _hf_from_preset("bert-tiny", "BertForMaskedLM")
+    sd = dict(hf.state_dict())
+    g = torch.Generator().manual_seed(0)
+    lin = torch.randn(24, 64, generator=g) * 0.2
+    llm, m = _pooling_llm("bert-tiny", "HF_ColBERT", hf, colbert_dim=24)
+    m.load_weights([("linear.weight", lin)])
+    outs = llm.encode([{"prompt_token_ids": p} for p in prompts], pooling_task="token_embed")
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            h = hf.bert(torch.tensor([p])).last_hidden_state[0]
+        ref = torch.nn.functional.normalize(h @ lin.t(), dim=-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=3e-4, rtol=1e-3)
+    llm.shutdown()
+    llm, m = _pooling_llm("bert-tiny", "BertSpladeSparseEmbeddingModel", hf)
+    from vllm_b200 import PoolingParams
+    outs = llm.encode([{"prompt_token_ids": p} for p in prompts], PoolingParams(task="embed", normalize=False))
+    for p, o in zip(prompts, outs):
+        with torch.no_grad():
+            ref = torch.log1p(torch.relu(hf(torch.tensor([p])).logits[0])).amax(0)
+        got = torch.as_tensor(o.outputs.data).float()
+        assert got.shape == (512,)
+        torch.testing.assert_close(got, ref, atol=3e-4, rtol=1e-3)
+    llm.shutdown()

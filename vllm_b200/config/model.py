@@ -781,7 +781,7 @@ class ModelConfig:
     # -- accessors --------------------------------------------------------
     @property
     def is_encoder_only(self) -> bool:
-        return self.architecture.startswith(("Bert", "Roberta", "XLMRoberta", "NomicBert"))
+        return self.architecture.startswith(("Bert", "Roberta", "XLMRoberta", "NomicBert", "HF_ColBERT", "ColBERTJinaRoberta"))
 
     @property
     def architecture(self) -> str:

@@ -20,6 +20,8 @@ def pool_hidden(hidden: torch.Tensor, params, model=None) -> torch.Tensor:
         out = h
     else:
         raise ValueError(f"unknown pooling type {kind}")
+    if params.task in ("embed", "token_embed") and model is not None and hasattr(model, "project_embedding"):
+        out = model.project_embedding(out.to(hidden.dtype), per_token=(kind == "ALL")).float()   # ColBERT / sparse heads
     if params.task in ("classify", "token_classify") and model is not None and hasattr(model, "score"):
         out = model.score(out.to(hidden.dtype)).float().softmax(-1)
     if params.dimensions:

@@ -123,7 +123,7 @@ class BertModel(nn.Module):
                         break
             if name not in params:
                 continue
-            mod = modules[name.rsplit(".", 1)[0]]
+            mod = modules[name.rsplit(".", 1)[0] if "." in name else ""]
             loader = getattr(mod, "weight_loader", None)
             if loader is not None:
                 loader(params[name], w, shard)
@@ -191,3 +191,72 @@ class BertForTokenClassification(BertModel):
 
 class RobertaForTokenClassification(BertForTokenClassification):
     pos_offset = 2
+
+
+class _LateInteraction:
+    """ColBERT-style late interaction: every token state goes through a bias-free linear map to a small dimension and is
+    L2-normalised; queries and documents are scored by MaxSim outside the engine (``LLM.encode(..., pooling_task=
+    "token_embed")``) (reference: models/colbert.py / bert.py ``HF_ColBERT``)."""
+
+    def _init_colbert(self, cfg, dtype) -> None:
+        dim = int(cfg.get("colbert_dim") or cfg.get("dim") or 128)
+        self.colbert_linear = nn.Linear(cfg["hidden_size"], dim, bias=False, dtype=dtype)
+
+    def project_embedding(self, x: torch.Tensor, per_token: bool) -> torch.Tensor:
+        return self.colbert_linear(x) if per_token else x
+
+    @staticmethod
+    def _colbert_names(weights):
+        for n, w in weights:
+            if n in ("linear.weight", "colbert_linear.weight"):
+                yield "colbert_linear.weight", w
+            else:
+                yield n, w
+
+
+class HF_ColBERT(_LateInteraction, BertModel):
+    default_pooling = "ALL"
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        BertModel.__init__(self, vllm_config, prefix)
+        self._init_colbert(self.cfg, vllm_config.model_config.torch_dtype)
+
+    def load_weights(self, weights):
+        return BertModel.load_weights(self, self._colbert_names(weights))
+
+
+class ColBERTJinaRobertaModel(HF_ColBERT):
+    pos_offset = 2
+
+
+class BertSpladeSparseEmbeddingModel(BertModel):
+    """SPLADE: masked-LM logits per token → log(1 + relu) → max over the sequence = one sparse |V|-dimensional lexical
+    vector (reference: models/bert.py ``BertSpladeSparseEmbeddingModel``)."""
+    default_pooling = "ALL"
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg, dtype = self.cfg, vllm_config.model_config.torch_dtype
+        H = cfg["hidden_size"]
+        self.mlm_dense = nn.Linear(H, H, dtype=dtype)
+        self.mlm_ln = nn.LayerNorm(H, cfg.get("layer_norm_eps", 1e-12), dtype=dtype)
+        self.mlm_bias = nn.Parameter(torch.zeros(cfg["vocab_size"], dtype=dtype), requires_grad=False)
+        self.mlm_decoder = None            # tied to the word embeddings unless the checkpoint carries its own matrix
+
+    def project_embedding(self, x: torch.Tensor, per_token: bool) -> torch.Tensor:
+        h = self.mlm_ln(torch.nn.functional.gelu(self.mlm_dense(x)))
+        w = self.mlm_decoder if self.mlm_decoder is not None else self.embeddings.word_embeddings.weight
+        logits = h @ w.t() + self.mlm_bias
+        return torch.log1p(torch.relu(logits)).amax(dim=0) if per_token else torch.log1p(torch.relu(logits))
+
+    def load_weights(self, weights):
+        def ren():
+            for n, w in weights:
+                n = (n.replace("cls.predictions.transform.dense.", "mlm_dense.").replace("cls.predictions.transform.LayerNorm.", "mlm_ln.")
+                     .replace("cls.predictions.bias", "mlm_bias").replace("cls.predictions.decoder.bias", "mlm_bias"))
+                if n == "cls.predictions.decoder.weight":
+                    if w.data_ptr() != 0 and not torch.equal(w, self.embeddings.word_embeddings.weight.to(w.dtype)):
+                        self.mlm_decoder = nn.Parameter(w.clone().to(self.mlm_bias.dtype), requires_grad=False)
+                    continue
+                yield n, w
+        return super().load_weights(ren())

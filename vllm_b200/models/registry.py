@@ -73,6 +73,9 @@ _MODELS: dict[str, tuple[str, str]] = {
     "TransformersMoEForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "RobertaForMaskedLM": ("bert", "RobertaModel"),
     "NomicBertModel": ("nomic_bert", "NomicBertModel"),
+    "HF_ColBERT": ("bert", "HF_ColBERT"),
+    "ColBERTJinaRobertaModel": ("bert", "ColBERTJinaRobertaModel"),
+    "BertSpladeSparseEmbeddingModel": ("bert", "BertSpladeSparseEmbeddingModel"),
     "RobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
     "XLMRobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
     "BertForTokenClassification": ("bert", "BertForTokenClassification"),
