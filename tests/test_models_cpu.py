@@ -871,3 +871,51 @@ def test_colbert_and_splade_heads_on_bert():
         assert got.shape == (512,)
         torch.testing.assert_close(got, ref, atol=3e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_bidirectional_llama_embeddings_match_hf():
+    """A decoder checkpoint served as a bidirectional encoder (``LlamaBidirectionalModel``, mean pooling): equals
+    transformers' LlamaModel run with an all-ones 4-D mask; the Voyage variant adds its linear head."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    kw = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type", "torch_dtype")}
+    hf_cfg = transformers.AutoConfig.for_model("llama", **kw)
+    torch.manual_seed(1)
+    base = transformers.LlamaModel(hf_cfg).float().eval()
+    prompts = [[5, 17, 99, 3, 250, 41], list(range(10, 45))]
+
+    def hf_states(p):
+        n = len(p)
+        with torch.no_grad():
+            return base(torch.tensor([p]), attention_mask=torch.zeros(1, 1, n, n)).last_hidden_state[0]
+    llm = make_llm("llama-tiny", hf_overrides={"architectures": ["LlamaBidirectionalModel"], "pooling": "avg"}, runner="pooling")
+    assert llm.llm_engine.vllm_config.model_config.is_encoder_only
+    llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model.load_weights(base.state_dict().items())
+    for p, o in zip(prompts, llm.embed([{"prompt_token_ids": p} for p in prompts])):
+        ref = torch.nn.functional.normalize(hf_states(p).mean(0), dim=-1)
+        torch.testing.assert_close(torch.as_tensor(o.outputs.data).float(), ref, atol=2e-4, rtol=1e-3)
+    llm.shutdown()
+
+
+def test_bge_m3_three_views():
+    """Dense / multi-vector / lexical outputs of BGE-M3 from one XLM-R encoder, against the heads applied by hand to
+    transformers' hidden states."""
+    hf = _hf_from_preset("bert-tiny", "XLMRobertaModel", "xlm-roberta", pad_token_id=1, max_position_embeddings=258)
+    g = torch.Generator().manual_seed(0)
+    heads = {"sparse_linear.weight": torch.randn(1, 64, generator=g) * 0.3, "sparse_linear.bias": torch.randn(1, generator=g) * 0.1,
+             "colbert_linear.weight": torch.randn(64, 64, generator=g) * 0.2, "colbert_linear.bias": torch.randn(64, generator=g) * 0.1}
+    llm, m = _pooling_llm("bert-tiny", "BgeM3EmbeddingModel", hf, model_type="xlm-roberta", max_position_embeddings=258)
+    m.load_weights(heads.items())
+    p = [3, 17, 99, 250, 41, 7, 12]
+    with torch.no_grad():
+        h = hf(torch.tensor([p]), position_ids=torch.arange(2, 2 + len(p))[None]).last_hidden_state[0]
+    dense = torch.as_tensor(llm.embed([{"prompt_token_ids": p}])[0].outputs.data).float()
+    torch.testing.assert_close(dense, torch.nn.functional.normalize(h[0], dim=-1), atol=3e-4, rtol=1e-3)
+    multi = torch.as_tensor(llm.encode([{"prompt_token_ids": p}], pooling_task="token_embed")[0].outputs.data).float()
+    ref = torch.nn.functional.normalize(h[1:] @ heads["colbert_linear.weight"].t() + heads["colbert_linear.bias"], dim=-1)
+    torch.testing.assert_close(multi, ref, atol=3e-4, rtol=1e-3)
+    lex = torch.as_tensor(llm.encode([{"prompt_token_ids": p}], pooling_task="token_classify")[0].outputs.data).float()
+    ref = torch.relu(h @ heads["sparse_linear.weight"].t() + heads["sparse_linear.bias"]).squeeze(-1)
+    torch.testing.assert_close(lex, ref, atol=3e-4, rtol=1e-3)
+    llm.shutdown()

@@ -781,7 +781,8 @@ class ModelConfig:
     # -- accessors --------------------------------------------------------
     @property
     def is_encoder_only(self) -> bool:
-        return self.architecture.startswith(("Bert", "Roberta", "XLMRoberta", "NomicBert", "HF_ColBERT", "ColBERTJinaRoberta"))
+        return (self.architecture.startswith(("Bert", "Roberta", "XLMRoberta", "NomicBert", "HF_ColBERT", "ColBERTJinaRoberta", "BgeM3"))
+                or "Bidirectional" in self.architecture or self.hf_config.get("is_causal") is False)
 
     @property
     def architecture(self) -> str:

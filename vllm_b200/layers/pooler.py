@@ -23,7 +23,9 @@ def pool_hidden(hidden: torch.Tensor, params, model=None) -> torch.Tensor:
     if params.task in ("embed", "token_embed") and model is not None and hasattr(model, "project_embedding"):
         out = model.project_embedding(out.to(hidden.dtype), per_token=(kind == "ALL")).float()   # ColBERT / sparse heads
     if params.task in ("classify", "token_classify") and model is not None and hasattr(model, "score"):
-        out = model.score(out.to(hidden.dtype)).float().softmax(-1)
+        out = model.score(out.to(hidden.dtype)).float()
+        if not getattr(model, "raw_scores", False):
+            out = out.softmax(-1)
     if params.dimensions:
         out = out[..., :params.dimensions]
     if params.normalize and params.task in ("embed", "token_embed"):

@@ -260,3 +260,24 @@ class BertSpladeSparseEmbeddingModel(BertModel):
                     continue
                 yield n, w
         return super().load_weights(ren())
+
+
+class BgeM3EmbeddingModel(RobertaModel):
+    """BGE-M3: one XLM-R encoder, three retrieval views — dense ([CLS], ``embed``), multi-vector (``colbert_linear`` on every
+    token after [CLS], ``token_embed``) and lexical (``relu(sparse_linear)`` weight per token, ``token_classify``)
+    (reference: models/roberta.py ``BgeM3EmbeddingModel``)."""
+    default_pooling = "CLS"
+    raw_scores = True
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg, dtype = self.cfg, vllm_config.model_config.torch_dtype
+        H = cfg["hidden_size"]
+        self.sparse_linear = nn.Linear(H, 1, dtype=dtype)
+        self.colbert_linear = nn.Linear(H, int(cfg.get("colbert_dim") or H), dtype=dtype)
+
+    def project_embedding(self, x: torch.Tensor, per_token: bool) -> torch.Tensor:
+        return self.colbert_linear(x[1:]) if per_token else x
+
+    def score(self, hidden: torch.Tensor) -> torch.Tensor:
+        return torch.relu(self.sparse_linear(hidden)).squeeze(-1)

@@ -88,7 +88,7 @@ class LlamaAttention(nn.Module):
         self.attn = Attention(self.qkv_proj.num_heads, self.head_dim, self.head_dim ** -0.5,
                               self.qkv_proj.num_kv_heads, sliding_window=sw,
                               logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0,
-                              prefix=f"{prefix}.attn", rope=rope)
+                              prefix=f"{prefix}.attn", rope=rope, causal=bool(cfg.get("is_causal", True)))
 
     def forward(self, positions, hidden):
         qkv = self.qkv_proj(hidden)

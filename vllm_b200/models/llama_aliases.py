@@ -120,3 +120,72 @@ class OrionForCausalLM(VariantForCausalLM):
     def options(self, c):
         return dict(norm="ln", eps=c.get("rms_norm_eps", 1e-5), qkv_bias=bool(c.get("attention_bias")), o_bias=bool(c.get("attention_bias")))
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
+
+
+# ---- decoders run as bidirectional encoders (embedding / reranking checkpoints trained without the causal mask) ----------
+_POOL = {"avg": "MEAN", "mean": "MEAN", "cls": "CLS", "last": "LAST"}
+
+
+def _bidirectional(base):
+    from vllm_b200.models import adapters
+
+    class Bidirectional(adapters.as_embedding_model(base)):           # type: ignore[misc, valid-type]
+        """``is_causal = False`` on every attention layer; the whole sequence is one prefill pass (the engine disables
+        chunked prefill and prefix reuse for these, like for the BERT family); pooling from ``config.pooling``
+        (reference: models/config.py ``LlamaBidirectionalConfig``)."""
+
+        def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+            cfg = vllm_config.model_config.hf_config
+            cfg["is_causal"] = False
+            super().__init__(vllm_config, prefix)
+            self.default_pooling = _POOL.get(str(cfg.get("pooling", "avg")).lower(), "MEAN")
+    return Bidirectional
+
+
+LlamaBidirectionalModel = _bidirectional(LlamaForCausalLM)
+LlamaBidirectionalModel.__name__ = "LlamaBidirectionalModel"
+
+
+class LlamaBidirectionalForSequenceClassification(LlamaForCausalLM):
+    pass
+
+
+def _make_bidir_cls():
+    from vllm_b200.models import adapters
+    base = adapters.as_seq_cls_model(LlamaForCausalLM)
+
+    class Cls(base):                                                   # type: ignore[misc, valid-type]
+        def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+            cfg = vllm_config.model_config.hf_config
+            cfg["is_causal"] = False
+            super().__init__(vllm_config, prefix)
+            self.default_pooling = _POOL.get(str(cfg.get("pooling", "avg")).lower(), "MEAN")
+    Cls.__name__ = "LlamaBidirectionalForSequenceClassification"
+    return Cls
+
+
+LlamaBidirectionalForSequenceClassification = _make_bidir_cls()
+
+
+class VoyageQwen3BidirectionalEmbedModel(_bidirectional(__import__("vllm_b200.models.llama", fromlist=["Qwen3ForCausalLM"]).Qwen3ForCausalLM)):
+    """voyage-4 family: bidirectional Qwen3 with a bias-free linear embedding head (``linear.weight``: hidden → num_labels)
+    applied to the pooled state (reference: models/voyage.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg = self.cfg
+        n = int(cfg.get("num_labels") or cfg["hidden_size"])
+        self.voyage_linear = torch.nn.Linear(cfg["hidden_size"], n, bias=False, dtype=vllm_config.model_config.torch_dtype)
+        self.default_pooling = _POOL.get(str(cfg.get("pooling", "avg")).lower(), "MEAN")
+
+    def project_embedding(self, x, per_token: bool):
+        return self.voyage_linear(x)
+
+    def load_weights(self, weights):
+        rest = []
+        for n, w in weights:
+            if n == "linear.weight":
+                self.voyage_linear.weight.data.copy_(w)
+            else:
+                rest.append((n, w))
+        return super().load_weights(rest) | {"voyage_linear.weight"}

@@ -73,6 +73,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "TransformersMoEForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "RobertaForMaskedLM": ("bert", "RobertaModel"),
     "NomicBertModel": ("nomic_bert", "NomicBertModel"),
+    "BgeM3EmbeddingModel": ("bert", "BgeM3EmbeddingModel"),
     "HF_ColBERT": ("bert", "HF_ColBERT"),
     "ColBERTJinaRobertaModel": ("bert", "ColBERTJinaRobertaModel"),
     "BertSpladeSparseEmbeddingModel": ("bert", "BertSpladeSparseEmbeddingModel"),
@@ -83,6 +84,9 @@ _MODELS: dict[str, tuple[str, str]] = {
     "XLMRobertaForTokenClassification": ("bert", "RobertaForTokenClassification"),
     "ModernBertForSequenceClassification": ("modernbert", "ModernBertForSequenceClassification"),
     "ModernBertForTokenClassification": ("modernbert", "ModernBertForTokenClassification"),
+    "LlamaBidirectionalModel": ("llama_aliases", "LlamaBidirectionalModel"),
+    "LlamaBidirectionalForSequenceClassification": ("llama_aliases", "LlamaBidirectionalForSequenceClassification"),
+    "VoyageQwen3BidirectionalEmbedModel": ("llama_aliases", "VoyageQwen3BidirectionalEmbedModel"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
