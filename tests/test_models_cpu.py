@@ -919,3 +919,29 @@ def test_bge_m3_three_views():
     ref = torch.relu(h @ heads["sparse_linear.weight"].t() + heads["sparse_linear.bias"]).squeeze(-1)
     torch.testing.assert_close(lex, ref, atol=3e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_nemotron_nas_blocks():
+    """DeciLM / Nemotron-NAS: with uniform block configs the model IS the Llama it was searched from (same weights, same
+    outputs); with a searched layout (different KV-head counts per layer, a layer without attention, a layer without MLP)
+    it builds exactly the parameters the checkpoint has, serves from per-layer-sized KV caches, and generates."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=4))
+    uniform = [{"attention": {"n_heads_in_group": 2, "no_op": False}, "ffn": {"intermediate_size": 256, "no_op": False}}] * 2
+    _same(_gen("llama-tiny", w), _gen("llama-tiny", w, {"architectures": ["DeciLMForCausalLM"], "block_configs": uniform}))
+    searched = [{"attention": {"n_heads_in_group": 1, "no_op": False}, "ffn": {"ffn_mult": 1.0, "no_op": False}},
+                {"attention": {"no_op": True}, "ffn": {"intermediate_size": 128, "no_op": False}},
+                {"attention": {"n_heads_in_group": 4, "no_op": False}, "ffn": {"no_op": True}},
+                {"attention": {"no_op": True}, "ffn": {"no_op": True}}]
+    llm = make_llm("llama-tiny", hf_overrides={"architectures": ["DeciLMForCausalLM"], "block_configs": searched, "num_hidden_layers": 4})
+    m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    names = {n for n, _ in m.named_parameters()}
+    assert "model.layers.1.post_attention_layernorm.weight" in names and not any(n.startswith("model.layers.1.self_attn") for n in names)
+    assert not any(n.startswith("model.layers.2.mlp") for n in names) and not any(n.startswith("model.layers.3.") for n in names)
+    assert m.model.layers[0].self_attn.qkv_proj.num_kv_heads == 4 and m.model.layers[2].self_attn.qkv_proj.num_kv_heads == 1
+    assert m.model.layers[0].mlp.gate_up_proj.weight.shape[0] == 2 * 256            # round_up(int(2 * 1.0 * 128 / 3), 256)
+    out = llm.generate([{"prompt_token_ids": p} for p in PROMPTS], SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True))
+    assert all(len(o.outputs[0].token_ids) == 6 for o in out)
+    llm.shutdown()

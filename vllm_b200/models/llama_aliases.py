@@ -189,3 +189,55 @@ class VoyageQwen3BidirectionalEmbedModel(_bidirectional(__import__("vllm_b200.mo
             else:
                 rest.append((n, w))
         return super().load_weights(rest) | {"voyage_linear.weight"}
+
+
+# ---- Nemotron-NAS / DeciLM: a Llama whose layers were searched individually ----------------------------------------------
+def _round_up(n: int, m: int) -> int:
+    return n if n % m == 0 else n + m - n % m
+
+
+class _NasLayer(torch.nn.Module):
+    """One searched block: attention with its own KV-head count (or none at all), gated MLP with its own width (or none).
+    The residual stream is explicit — the fused add-norm path assumes both halves exist."""
+
+    def __init__(self, cfg, mc, dtype, quant_config, prefix, idx) -> None:
+        super().__init__()
+        from vllm_b200.layers.common import RMSNorm
+        from vllm_b200.models.llama import LlamaAttention, LlamaMLP
+        from vllm_b200.models.llama_variants import _Identity
+        b = cfg["block_configs"][idx]
+        a, f = b.get("attention") or {}, b.get("ffn") or {}
+        if a.get("replace_with_linear") or f.get("replace_with_linear"):
+            raise NotImplementedError("Nemotron-NAS blocks replaced by a single linear layer")
+        H, eps = cfg["hidden_size"], cfg.get("rms_norm_eps", 1e-5)
+        self.no_attn, self.no_ffn = bool(a.get("no_op")), bool(f.get("no_op"))
+        if not self.no_ffn:
+            I = f.get("intermediate_size") or _round_up(int(2 * float(f["ffn_mult"]) * H / 3), 256)
+            self.post_attention_layernorm = RMSNorm(H, eps, dtype)
+            self.mlp = LlamaMLP(H, int(I), cfg.get("hidden_act", "silu"), bool(cfg.get("mlp_bias", False)), dtype, quant_config, f"{prefix}.mlp")
+        if not self.no_attn:
+            sub = dict(cfg, num_key_value_heads=cfg["num_attention_heads"] // int(a["n_heads_in_group"]))
+            self.self_attn = LlamaAttention(sub, mc, dtype, quant_config, f"{prefix}.self_attn", idx)
+            self.input_layernorm = RMSNorm(H, eps, dtype)
+        else:      # the first norm of the block is whatever comes first in it (LlamaModel applies it before calling the block)
+            self.input_layernorm = self.post_attention_layernorm if not self.no_ffn else _Identity()
+
+    def forward(self, positions, hidden, residual, next_norm):
+        x, h = residual, hidden
+        if not self.no_attn:
+            x = x + self.self_attn.o_proj(self.self_attn(positions, h))
+            h = self.post_attention_layernorm(x) if not self.no_ffn else None
+        if not self.no_ffn:
+            x = x + self.mlp(h)
+        return (next_norm(x) if next_norm is not None else x), x
+
+
+class _NasModel(__import__("vllm_b200.models.llama", fromlist=["LlamaModel"]).LlamaModel):
+    def _make_layer(self, cfg, mc, dtype, quant_config, prefix, idx):
+        return _NasLayer(cfg, mc, dtype, quant_config, prefix, idx)
+
+
+class DeciLMForCausalLM(LlamaForCausalLM):
+    """Llama-3.1-Nemotron-51B / Llama-3.3-Nemotron-Super-49B / Ultra-253B: ``block_configs`` gives every layer its own
+    KV-head count and MLP width, and lets it drop the attention or the MLP altogether (reference: models/nemotron_nas.py)."""
+    model_cls = _NasModel

@@ -87,6 +87,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "LlamaBidirectionalModel": ("llama_aliases", "LlamaBidirectionalModel"),
     "LlamaBidirectionalForSequenceClassification": ("llama_aliases", "LlamaBidirectionalForSequenceClassification"),
     "VoyageQwen3BidirectionalEmbedModel": ("llama_aliases", "VoyageQwen3BidirectionalEmbedModel"),
+    "DeciLMForCausalLM": ("llama_aliases", "DeciLMForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
     "Starcoder2ForCausalLM": ("gpt_neox", "Starcoder2ForCausalLM"),
