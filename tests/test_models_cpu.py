@@ -945,3 +945,44 @@ def test_nemotron_nas_blocks():
     out = llm.generate([{"prompt_token_ids": p} for p in PROMPTS], SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True))
     assert all(len(o.outputs[0].token_ids) == 6 for o in out)
     llm.shutdown()
+
+
+def test_qwen3_vl_matches_hf():
+    """Qwen3-VL: resampled position table + 2-D rotary ViT, DeepStack features added after the first decoder layers,
+    interleaved M-RoPE, q/k-normed decoder — greedy continuation equals transformers for image+text and text-only prompts."""
+    import numpy as np
+    import transformers
+    from PIL import Image
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("qwen3vl-tiny")
+    text_keys = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "head_dim",
+                 "num_key_value_heads", "max_position_embeddings", "rms_norm_eps", "hidden_act", "tie_word_embeddings", "attention_bias")
+    tc = {k: cfg[k] for k in text_keys}
+    tc["rope_parameters"] = dict(cfg["rope_parameters"])
+    hf_cfg = transformers.Qwen3VLConfig(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500, video_token_id=501,
+                                        vision_start_token_id=502, vision_end_token_id=503, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    hf = transformers.Qwen3VLForConditionalGeneration(hf_cfg).float().eval()
+    rng = np.random.default_rng(0)
+    img = Image.fromarray(rng.integers(0, 255, (64, 96, 3), dtype=np.uint8))
+    ip = transformers.Qwen2VLImageProcessor(patch_size=16, merge_size=2, image_mean=[0.5] * 3, image_std=[0.5] * 3,
+                                            size={"shortest_edge": 32 * 32, "longest_edge": 16 * 16 * 4 * 4096})
+    px = ip(images=[img], return_tensors="pt")
+    n_img = int(px["image_grid_thw"][0].prod()) // 4
+    pre, post = [5, 17, 99, 502], [503, 3, 250, 41, 7]
+    ids_hf = pre + [500] * n_img + post
+    with torch.no_grad():
+        ref_img = hf.generate(input_ids=torch.tensor([ids_hf]), attention_mask=torch.ones(1, len(ids_hf), dtype=torch.long),
+                              pixel_values=px["pixel_values"], image_grid_thw=px["image_grid_thw"],
+                              mm_token_type_ids=torch.tensor([[1 if t == 500 else 0 for t in ids_hf]]), max_new_tokens=8,
+                              do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(ids_hf):].tolist()
+    text_prompt = [5, 17, 99, 3, 250, 41, 5, 17, 99, 3]
+    ref_txt = hf_greedy(hf, text_prompt, 8)
+    llm = make_llm("qwen3vl-tiny", weights=hf.state_dict().items(), enable_prefix_caching=False, hf_overrides={"min_pixels": 32 * 32})
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    outs = llm.generate([{"prompt_token_ids": pre + [500] + post, "multi_modal_data": {"image": img}},
+                         {"prompt_token_ids": text_prompt}], sp)
+    llm.shutdown()
+    assert len(outs[0].prompt_token_ids) == len(ids_hf)
+    assert outs[0].outputs[0].token_ids == ref_img, (outs[0].outputs[0].token_ids, ref_img)
+    assert outs[1].outputs[0].token_ids == ref_txt

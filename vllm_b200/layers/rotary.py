@@ -112,7 +112,16 @@ class RotaryEmbedding(nn.Module):
         cs = self.cos_sin_cache[positions.long()]                              # [3, T, rot]
         cos3, sin3 = cs[..., :half], cs[..., half:]
         sec = list(self.mrope_section)
-        idx = torch.cat([torch.full((n,), i % 3, dtype=torch.long) for i, n in enumerate(sec)]).to(q.device)[:half]
+        if self.rope_scaling.get("mrope_interleaved"):
+            # Qwen3-VL: frequency j belongs to axis j % 3 (t, h, w, t, h, w, …) while that axis still has channels left,
+            # the tail falls back to the temporal axis
+            j = torch.arange(half)
+            idx = torch.zeros(half, dtype=torch.long)
+            for ax in (1, 2):
+                idx[(j % 3 == ax) & (j < 3 * sec[ax])] = ax
+            idx = idx.to(q.device)
+        else:
+            idx = torch.cat([torch.full((n,), i % 3, dtype=torch.long) for i, n in enumerate(sec)]).to(q.device)[:half]
         ar = torch.arange(half, device=q.device)
         cos = cos3[idx, :, ar].t()                                              # [T, half]
         sin = sin3[idx, :, ar].t()

@@ -194,12 +194,19 @@ class LlamaModel(nn.Module):
         fctx = get_forward_context_or_none()
         taps = fctx.extra.get("aux_layers") if fctx is not None else None     # EAGLE-3: residual streams of a few layers
         aux = [] if taps else None
+        deep = fctx.extra.get("deepstack") if fctx is not None else None
+        H = residual.shape[-1]
         ahead = self._layer_ahead if hidden.is_cuda and hidden.shape[0] <= 256 else None
         for i, layer in enumerate(self.layers):
             nxt = self.layers[i + 1].input_layernorm if i + 1 < n else self.norm
             if ahead is not None and i + 1 < n:
                 self._prefetch_layer(i + 1)
             hidden, residual = layer(positions, hidden, residual, nxt)
+            if deep is not None and (self.start + i) * H < deep.shape[1]:
+                # DeepStack (Qwen3-VL): the i-th level of vision features is added to the stream after decoder layer i (zero
+                # rows at text positions); the fused add-norm already produced ``hidden`` → redo the norm on the new stream
+                residual = residual + deep[:, (self.start + i) * H:(self.start + i + 1) * H].to(residual.dtype)
+                hidden = nxt(residual)
             if aux is not None and (self.start + i) in taps:
                 aux.append(residual)
         if aux:

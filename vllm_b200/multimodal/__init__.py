@@ -135,7 +135,8 @@ class _Registry:
         self.processors[arch] = cls
 
     def create_processor(self, model_config):
-        if (model_config.architecture in ("Qwen2VLForConditionalGeneration", "Qwen2_5_VLForConditionalGeneration")
+        if (model_config.architecture in ("Qwen2VLForConditionalGeneration", "Qwen2_5_VLForConditionalGeneration",
+                                          "Qwen3VLForConditionalGeneration", "Qwen3VLMoeForConditionalGeneration")
                 and model_config.architecture not in self.processors):
             from vllm_b200.multimodal.qwen_vl import Qwen2VLProcessor
             self.processors[model_config.architecture] = Qwen2VLProcessor

@@ -30,7 +30,7 @@ def smart_resize(h: int, w: int, factor: int = 28, min_pixels: int = 56 * 56, ma
 
 
 def image_to_patches(img: Any, patch: int = 14, merge: int = 2, temporal: int = 2, min_pixels: int = 56 * 56,
-                     max_pixels: int = 14 * 14 * 4 * 1280) -> tuple[torch.Tensor, tuple[int, int, int]]:
+                     max_pixels: int = 14 * 14 * 4 * 1280, mean=CLIP_MEAN, std=CLIP_STD) -> tuple[torch.Tensor, tuple[int, int, int]]:
     """→ (patches [grid_h*grid_w, 3*temporal*patch*patch] in merge-block order, (1, grid_h, grid_w))."""
     if hasattr(img, "convert"):                                # PIL
         img = img.convert("RGB")
@@ -49,7 +49,7 @@ def image_to_patches(img: Any, patch: int = 14, merge: int = 2, temporal: int = 
         hb, wb = smart_resize(h, w, patch * merge, min_pixels, max_pixels)
         if (hb, wb) != (h, w):
             arr = torch.nn.functional.interpolate(arr[None], size=(hb, wb), mode="bicubic", align_corners=False)[0].clamp(0, 255)
-    x = (arr / 255.0 - torch.tensor(CLIP_MEAN)[:, None, None]) / torch.tensor(CLIP_STD)[:, None, None]
+    x = (arr / 255.0 - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]
     gh, gw = hb // patch, wb // patch
     x = x[None].repeat(temporal, 1, 1, 1)                                         # a still image fills the temporal patch
     x = x.reshape(1, temporal, 3, gh // merge, merge, patch, gw // merge, merge, patch)
@@ -126,6 +126,10 @@ class Qwen2VLProcessor:
         self.tokens_per_second = vc.get("tokens_per_second", 0)           # Qwen2.5-VL only
         self.min_pixels = cfg.get("min_pixels", 56 * 56)
         self.max_pixels = cfg.get("max_pixels", 14 * 14 * 4 * 1280)
+        q3 = str(cfg.get("model_type", "")).startswith("qwen3_vl")
+        self.mean, self.std = ((0.5,) * 3, (0.5,) * 3) if q3 else (CLIP_MEAN, CLIP_STD)
+        if q3:
+            self.min_pixels, self.max_pixels = cfg.get("min_pixels", 65536), cfg.get("max_pixels", 16 * 16 * 4 * 4096)
         self.cache: "OrderedDict[str, Any]" = OrderedDict()
 
     def process(self, ids: list[int], mm_data: dict[str, Any]) -> tuple[list[int], list[dict[str, Any]]]:
@@ -153,7 +157,8 @@ class Qwen2VLProcessor:
         ii = vi = 0
         for slot, tok in enumerate(ids):
             if tok == self.image_token:
-                px, grid = image_to_patches(images[ii], self.patch, self.merge, self.temporal, self.min_pixels, self.max_pixels)
+                px, grid = image_to_patches(images[ii], self.patch, self.merge, self.temporal, self.min_pixels, self.max_pixels,
+                                            self.mean, self.std)
                 ii += 1
                 modality, scale = "image", 1.0
             elif tok == self.video_token:

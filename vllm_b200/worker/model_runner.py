@@ -198,7 +198,8 @@ class ModelRunner:
             self.ec_connector = ECSharedStorageConnector(ecp, os.environ.get("VLLM_B200_EC_ROLE", "ec_both"))
         from vllm_b200.multimodal import MULTIMODAL_REGISTRY
         self.has_mm = MULTIMODAL_REGISTRY.supports_multimodal(vllm_config.model_config)
-        self.uses_mrope = vllm_config.model_config.hf_config.get("model_type") in ("qwen2_vl", "qwen2_5_vl")
+        self.uses_mrope = vllm_config.model_config.hf_config.get("model_type") in ("qwen2_vl", "qwen2_5_vl", "qwen3_vl", "qwen3_vl_moe")
+        self._deepstack, self._deepstack_live = None, False
         self.kv_connector = None
         ktc = vllm_config.kv_transfer_config
         if ktc is not None and ktc.kv_connector:
@@ -925,6 +926,7 @@ class ModelRunner:
             from vllm_b200.multimodal import EncoderCache
             self.encoder_cache = EncoderCache()
         emb = self.model.embed_input_ids(self.input_ids[:T]).clone()
+        self._deepstack_live = False
         for j, f, lo, hi, start in todo:
             enc = self.encoder_cache.get(f["hash"])
             if enc is None and self.ec_connector is not None:          # another instance may have encoded it
@@ -946,7 +948,17 @@ class ModelRunner:
                     self.ec_connector.save(f["hash"], enc)
             dst0 = int(cu[j]) + (lo - start)
             e0 = int(f.get("enc_offset", 0))                 # records that cover one slice of a shared encoder output
-            emb[dst0:dst0 + (hi - lo)] = enc[e0 + lo - f["offset"]:e0 + hi - f["offset"]]
+            rows_ = enc[e0 + lo - f["offset"]:e0 + hi - f["offset"]]
+            Hd = emb.shape[-1]
+            emb[dst0:dst0 + (hi - lo)] = rows_[:, :Hd]
+            if rows_.shape[-1] > Hd:                         # towers that also emit per-layer features (DeepStack)
+                if self._deepstack is None or self._deepstack.shape != (T, rows_.shape[-1] - Hd):
+                    self._deepstack = torch.zeros(T, rows_.shape[-1] - Hd, dtype=emb.dtype, device=emb.device)
+                    self._deepstack_live = True
+                elif not self._deepstack_live:
+                    self._deepstack.zero_()
+                    self._deepstack_live = True
+                self._deepstack[dst0:dst0 + (hi - lo)] = rows_[:, Hd:]
         return emb
 
     def _next_staging(self) -> _Staging:
@@ -1060,6 +1072,8 @@ class ModelRunner:
                     mpos = self._mrope_positions(states, rows, ns, cu, T)
                     if mpos is not None:
                         extra = dict(extra or {}, mrope_positions=mpos)
+                if mm_emb is not None and self._deepstack_live:
+                    extra = dict(extra or {}, deepstack=self._deepstack)
             pcp_last = None
             if self.pcp > 1:
                 if (lora_batch is not None or mm_emb is not None or extra or has_spec or self.drafter is not None
