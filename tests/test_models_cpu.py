@@ -947,22 +947,28 @@ def test_nemotron_nas_blocks():
     llm.shutdown()
 
 
-def test_qwen3_vl_matches_hf():
+@pytest.mark.parametrize("moe", [False, True])
+def test_qwen3_vl_matches_hf(moe):
     """Qwen3-VL: resampled position table + 2-D rotary ViT, DeepStack features added after the first decoder layers,
     interleaved M-RoPE, q/k-normed decoder — greedy continuation equals transformers for image+text and text-only prompts."""
     import numpy as np
     import transformers
     from PIL import Image
     from vllm_b200.config import get_preset_hf_config
-    cfg = get_preset_hf_config("qwen3vl-tiny")
+    preset = "qwen3vlmoe-tiny" if moe else "qwen3vl-tiny"
+    cfg = get_preset_hf_config(preset)
     text_keys = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "head_dim",
                  "num_key_value_heads", "max_position_embeddings", "rms_norm_eps", "hidden_act", "tie_word_embeddings", "attention_bias")
+    if moe:
+        text_keys += ("moe_intermediate_size", "num_experts", "num_experts_per_tok", "norm_topk_prob", "decoder_sparse_step", "mlp_only_layers")
     tc = {k: cfg[k] for k in text_keys}
     tc["rope_parameters"] = dict(cfg["rope_parameters"])
-    hf_cfg = transformers.Qwen3VLConfig(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500, video_token_id=501,
+    CfgCls = transformers.Qwen3VLMoeConfig if moe else transformers.Qwen3VLConfig
+    ModelCls = transformers.Qwen3VLMoeForConditionalGeneration if moe else transformers.Qwen3VLForConditionalGeneration
+    hf_cfg = CfgCls(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500, video_token_id=501,
                                         vision_start_token_id=502, vision_end_token_id=503, tie_word_embeddings=False)
     torch.manual_seed(0)
-    hf = transformers.Qwen3VLForConditionalGeneration(hf_cfg).float().eval()
+    hf = ModelCls(hf_cfg).float().eval()
     rng = np.random.default_rng(0)
     img = Image.fromarray(rng.integers(0, 255, (64, 96, 3), dtype=np.uint8))
     ip = transformers.Qwen2VLImageProcessor(patch_size=16, merge_size=2, image_mean=[0.5] * 3, image_std=[0.5] * 3,
@@ -978,7 +984,7 @@ def test_qwen3_vl_matches_hf():
                               do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(ids_hf):].tolist()
     text_prompt = [5, 17, 99, 3, 250, 41, 5, 17, 99, 3]
     ref_txt = hf_greedy(hf, text_prompt, 8)
-    llm = make_llm("qwen3vl-tiny", weights=hf.state_dict().items(), enable_prefix_caching=False, hf_overrides={"min_pixels": 32 * 32})
+    llm = make_llm(preset, weights=hf.state_dict().items(), enable_prefix_caching=False, hf_overrides={"min_pixels": 32 * 32})
     sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
     outs = llm.generate([{"prompt_token_ids": pre + [500] + post, "multi_modal_data": {"image": img}},
                          {"prompt_token_ids": text_prompt}], sp)

@@ -113,7 +113,7 @@ class Qwen3VisionTransformer(nn.Module):
         return torch.cat([self.merger(x)] + deep, dim=-1)
 
 
-class Qwen3VLForConditionalGeneration(Qwen3ForCausalLM):
+class _Qwen3VLMixin:
     uses_mrope = True
 
     def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
@@ -151,3 +151,16 @@ class Qwen3VLForConditionalGeneration(Qwen3ForCausalLM):
                 name = "model." + name[len("model.language_model."):]
             rest.append((name, w))
         return loaded | super().load_weights(rest)
+
+
+class Qwen3VLForConditionalGeneration(_Qwen3VLMixin, Qwen3ForCausalLM):
+    pass
+
+
+def _moe_base():
+    from vllm_b200.models.mixtral import Qwen3MoeForCausalLM
+    return Qwen3MoeForCausalLM
+
+
+class Qwen3VLMoeForConditionalGeneration(_Qwen3VLMixin, _moe_base()):
+    """The same tower and DeepStack path in front of the Qwen3-MoE decoder (reference: models/qwen3_vl_moe.py)."""
