@@ -992,3 +992,39 @@ def test_qwen3_vl_matches_hf(moe):
     assert len(outs[0].prompt_token_ids) == len(ids_hf)
     assert outs[0].outputs[0].token_ids == ref_img, (outs[0].outputs[0].token_ids, ref_img)
     assert outs[1].outputs[0].token_ids == ref_txt
+
+
+def test_llava_onevision_matches_hf():
+    """LLaVA-OneVision: SigLIP tiles, unpadded feature map, down-sampling once the map exceeds ``anyres_max_N`` tiles' worth
+    of patches, newline column, Qwen2 decoder — for a 1×3 canvas (shrunk) and a 2×2 canvas, against transformers."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llavaov-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "vision_feature_layer", "vision_feature_select_strategy",
+            "projector_hidden_act", "vision_aspect_ratio", "image_grid_pinpoints", "multimodal_projector_bias", "text_model_type", "torch_dtype")
+    hf_cfg = transformers.LlavaOnevisionConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="qwen2", **_vlm_text_cfg(cfg, drop)),
+                                               image_token_index=511, vision_feature_layer=-1, vision_feature_select_strategy="full",
+                                               vision_aspect_ratio="anyres_max_2", image_grid_pinpoints=cfg["image_grid_pinpoints"],
+                                               multimodal_projector_bias=True, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    hf = transformers.LlavaOnevisionForConditionalGeneration(hf_cfg).eval()
+    with torch.no_grad():
+        hf.model.image_newline.normal_(0, 0.5)
+    llm = make_llm("llavaov-tiny", weights=hf.state_dict().items())
+    g = torch.Generator().manual_seed(1)
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    for size, n_tiles in (((30, 95), 4), ((60, 64), 5)):
+        tiles = torch.randn(n_tiles, 3, 32, 32, generator=g)
+        with torch.no_grad():
+            feats = hf.get_image_features(pixel_values=tiles[None], image_sizes=torch.tensor([size]), vision_feature_layer=-1,
+                                          vision_feature_select_strategy="full").pooler_output
+        n = feats[0].shape[0] if isinstance(feats, (list, tuple)) else feats.shape[0]
+        exp_ids = [5, 17] + [511] * n + [99, 3, 250]
+        with torch.no_grad():
+            ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=tiles[None], image_sizes=torch.tensor([size]),
+                              max_new_tokens=8, do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+        out = llm.generate([{"prompt_token_ids": [5, 17, 511, 99, 3, 250],
+                             "multi_modal_data": {"image": {"tiles": tiles, "image_size": size}}}], sp)
+        assert len(out[0].prompt_token_ids) == len(exp_ids), (size, n, len(out[0].prompt_token_ids) - 5)
+        assert out[0].outputs[0].token_ids == ref, size
+    llm.shutdown()

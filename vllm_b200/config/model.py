@@ -191,6 +191,17 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, head_dim=16, max_position_embeddings=256, rms_norm_eps=1e-5, rope_theta=10000.0, sliding_window=None,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "llavaov-tiny": dict(
+        architectures=["LlavaOnevisionForConditionalGeneration"], model_type="llava_onevision", image_token_index=511,
+        vision_feature_layer=-1, vision_feature_select_strategy="full", projector_hidden_act="gelu", vision_aspect_ratio="anyres_max_2",
+        image_grid_pinpoints=[[32, 32], [32, 64], [64, 32], [64, 64], [32, 96], [96, 32]], multimodal_projector_bias=True,
+        text_model_type="qwen2",
+        vision_config=dict(model_type="siglip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=32, patch_size=8, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6,
+                           vision_use_head=False),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,

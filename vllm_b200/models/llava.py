@@ -84,16 +84,22 @@ class LlavaForConditionalGeneration(nn.Module):
         dtype = mc.torch_dtype
         self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
         self.select = cfg.get("vision_feature_select_strategy", "default")
-        self.vision_tower = CLIPVisionTower(cfg["vision_config"], dtype, cfg.get("vision_feature_layer", -2))
+        self.vision_tower = self._build_tower(cfg, dtype)
         Hv, Ht = cfg["vision_config"]["hidden_size"], cfg["hidden_size"]
-        self.linear_1 = nn.Linear(Hv, Ht, dtype=dtype)
-        self.linear_2 = nn.Linear(Ht, Ht, dtype=dtype)
+        pb = bool(cfg.get("multimodal_projector_bias", True))
+        self.linear_1 = nn.Linear(Hv, Ht, bias=pb, dtype=dtype)
+        self.linear_2 = nn.Linear(Ht, Ht, bias=pb, dtype=dtype)
         self.proj_act = _act(cfg.get("projector_hidden_act", "gelu"))
         # the text stack reads the flattened text fields of the same config
         from vllm_b200.models.registry import text_decoder_cls
         if cfg.get("text_model_type") == "qwen2":
             cfg.setdefault("attention_bias", True)
         self.language_model = text_decoder_cls(cfg, "LlamaForCausalLM")(vllm_config, prefix=f"{prefix}language_model.")
+
+    def _build_tower(self, cfg, dtype) -> nn.Module:
+        return CLIPVisionTower(cfg["vision_config"], dtype, cfg.get("vision_feature_layer", -2))
+
+    _tower_rename = None           # subclasses with another tower family: checkpoint name → tower parameter name
 
     # ---------------------------------------------------------------- multimodal
     @torch.inference_mode()
@@ -127,8 +133,11 @@ class LlavaForConditionalGeneration(nn.Module):
             elif n.startswith("lm_head."):
                 text.append((n, w))
             elif n.startswith("vision_tower."):
-                t = (n.replace("vision_tower.vision_model.", "vision_tower.").replace("embeddings.", "")
-                     .replace("encoder.layers.", "layers.").replace("self_attn.", "").replace("mlp.", ""))
+                if self._tower_rename is not None:
+                    t = "vision_tower." + self._tower_rename(n[len("vision_tower."):].removeprefix("vision_model."))
+                else:
+                    t = (n.replace("vision_tower.vision_model.", "vision_tower.").replace("embeddings.", "")
+                         .replace("encoder.layers.", "layers.").replace("self_attn.", "").replace("mlp.", ""))
                 if t in own:
                     own[t].data.copy_(w)
                     loaded.add(t)

@@ -66,10 +66,13 @@ class LlavaNextForConditionalGeneration(LlavaForConditionalGeneration):
         s = self.side
         fmap = rest.view(gh, gw, s, s, -1).permute(4, 0, 2, 1, 3).reshape(-1, gh * s, gw * s)     # [H, rows, cols]
         r0, r1, c0, c1 = unpadded_grid(gh * s, gw * s, tuple(f["image_size"]))
-        fmap = fmap[:, r0:r1, c0:c1]
+        fmap = self._limit(fmap[:, r0:r1, c0:c1])
         nl = self.image_newline.to(fmap.dtype)[:, None, None].expand(-1, fmap.shape[1], 1)
         rows = torch.cat([fmap, nl], dim=-1).flatten(1, 2).t()
         return torch.cat([base, rows], dim=0)
+
+    def _limit(self, fmap: torch.Tensor) -> torch.Tensor:
+        return fmap
 
     def load_weights(self, weights):
         rest = []
@@ -95,13 +98,21 @@ class LlavaNextProcessor:
         self.pinpoints = [tuple(p) for p in cfg.get("image_grid_pinpoints") or [(self.tile, self.tile)]]
         self.default = cfg.get("vision_feature_select_strategy", "default") == "default"
 
+    has_cls = True
+    max_tiles = 0                       # > 0: feature maps larger than this many tiles' worth of patches are down-sampled
+
     def num_tokens(self, size: tuple[int, int], n_tiles: int) -> int:
-        base = self.side ** 2 + (0 if self.default else 1)
+        base = self.side ** 2 + (1 if self.has_cls and not self.default else 0)
         if n_tiles == 1:
             return base + 1
         bh, bw = select_best_resolution(size, self.pinpoints)
         r0, r1, c0, c1 = unpadded_grid(bh // self.tile * self.side, bw // self.tile * self.side, size)
-        return base + (r1 - r0) * (c1 - c0 + 1)
+        r, c = r1 - r0, c1 - c0
+        if self.max_tiles:
+            ratio = math.sqrt(r * c / (self.max_tiles * self.side ** 2))
+            if ratio > 1.1:
+                r, c = int(r // ratio), int(c // ratio)
+        return base + r * (c + 1)
 
     def _tiles(self, img: Any) -> tuple[torch.Tensor, tuple[int, int]]:
         from vllm_b200.multimodal import CLIP_MEAN, CLIP_STD
@@ -153,3 +164,46 @@ class LlavaNextProcessor:
             prev = slot + 1
         out.extend(ids[prev:])
         return out, feats
+
+
+class LlavaOnevisionForConditionalGeneration(LlavaNextForConditionalGeneration):
+    """LLaVA-OneVision: the any-resolution scheme over a SigLIP tower (no class token, features taken before the tower's
+    final norm), biased projector, Qwen2 decoder, and a cap on visual tokens — feature maps worth more than
+    ``anyres_max_N`` tiles are bilinearly shrunk before the newline column is added (reference: models/llava_onevision.py)."""
+
+    def _build_tower(self, cfg, dtype):
+        from vllm_b200.models.idefics3 import SiglipVisionTower
+        tower = SiglipVisionTower(cfg["vision_config"], dtype)
+        inner = tower.forward
+        tower.forward = lambda pixels: inner(pixels, final_norm=False)      # vision_feature_layer = -1: last encoder layer
+        return tower
+
+    @staticmethod
+    def _tower_rename(n: str) -> str:
+        from vllm_b200.models.idefics3 import SiglipVisionTower
+        return SiglipVisionTower.rename(n)
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg["vision_feature_select_strategy"] = "full"
+        super().__init__(vllm_config, prefix)
+        ar = str(cfg.get("vision_aspect_ratio", "anyres_max_9"))
+        self.max_tiles = int(ar.rsplit("_", 1)[1]) if ar.startswith("anyres_max_") else 0
+
+    def _limit(self, fmap):
+        if not self.max_tiles:
+            return fmap
+        _, r, c = fmap.shape
+        ratio = math.sqrt(r * c / (self.max_tiles * self.side ** 2))
+        if ratio > 1.1:
+            fmap = F.interpolate(fmap[None], [int(r // ratio), int(c // ratio)], mode="bilinear")[0]
+        return fmap
+
+
+class LlavaOnevisionProcessor(LlavaNextProcessor):
+    has_cls = False
+
+    def __init__(self, model_config) -> None:
+        super().__init__(model_config)
+        ar = str(model_config.hf_config.get("vision_aspect_ratio", "anyres_max_9"))
+        self.max_tiles = int(ar.rsplit("_", 1)[1]) if ar.startswith("anyres_max_") else 0

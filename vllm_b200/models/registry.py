@@ -139,6 +139,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "LlavaNextForConditionalGeneration": ("llava_next", "LlavaNextForConditionalGeneration"),
     "Qwen3VLForConditionalGeneration": ("qwen3_vl", "Qwen3VLForConditionalGeneration"),
     "Qwen3VLMoeForConditionalGeneration": ("qwen3_vl", "Qwen3VLMoeForConditionalGeneration"),
+    "LlavaOnevisionForConditionalGeneration": ("llava_next", "LlavaOnevisionForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

@@ -146,6 +146,9 @@ class _Registry:
         if model_config.architecture == "LlavaNextForConditionalGeneration" and model_config.architecture not in self.processors:
             from vllm_b200.models.llava_next import LlavaNextProcessor
             self.processors[model_config.architecture] = LlavaNextProcessor
+        if model_config.architecture == "LlavaOnevisionForConditionalGeneration" and model_config.architecture not in self.processors:
+            from vllm_b200.models.llava_next import LlavaOnevisionProcessor
+            self.processors[model_config.architecture] = LlavaOnevisionProcessor
         if model_config.hf_config.get("audio_config") is not None and model_config.architecture not in self.processors:
             from vllm_b200.models.audio_lm import AudioLMProcessor
             self.processors[model_config.architecture] = AudioLMProcessor
