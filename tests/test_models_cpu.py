@@ -1028,3 +1028,31 @@ def test_llava_onevision_matches_hf():
         assert len(out[0].prompt_token_ids) == len(exp_ids), (size, n, len(out[0].prompt_token_ids) - 5)
         assert out[0].outputs[0].token_ids == ref, size
     llm.shutdown()
+
+
+def test_paligemma_prefix_lm_matches_hf():
+    """PaliGemma: image + prompt attend bidirectionally (prefix-LM), continuation is causal — greedy output equals
+    transformers given ``token_type_ids`` that mark the whole prompt as prefix; the engine keeps the prompt in one pass."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("paligemma-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "text_model_type", "projection_dim", "torch_dtype", "hidden_act")
+    hf_cfg = transformers.PaliGemmaConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="gemma", **_vlm_text_cfg(cfg, drop)),
+                                          image_token_index=511, projection_dim=64, hidden_size=64)
+    torch.manual_seed(0)
+    hf = transformers.PaliGemmaForConditionalGeneration(hf_cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    exp_ids = [511] * 4 + [2, 17, 99, 3, 250]                      # image tokens first, then <bos> + prompt
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], token_type_ids=torch.zeros(1, len(exp_ids), dtype=torch.long),
+                          attention_mask=torch.ones(1, len(exp_ids), dtype=torch.long), max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("paligemma-tiny", weights=hf.state_dict().items())
+    vc = llm.llm_engine.vllm_config
+    assert not vc.scheduler_config.enable_chunked_prefill and not vc.cache_config.enable_prefix_caching
+    out = llm.generate([{"prompt_token_ids": [511, 2, 17, 99, 3, 250], "multi_modal_data": {"image": img}},
+                        {"prompt_token_ids": [511, 2, 9, 9, 41], "multi_modal_data": {"image": img}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

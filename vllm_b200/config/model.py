@@ -202,6 +202,16 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-6, rope_theta=10000.0,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "paligemma-tiny": dict(
+        architectures=["PaliGemmaForConditionalGeneration"], model_type="paligemma", image_token_index=511, text_model_type="gemma",
+        projection_dim=64,
+        vision_config=dict(model_type="siglip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=32, patch_size=16, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6,
+                           vision_use_head=False, projection_dim=64),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=1,
+        head_dim=16, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0, hidden_act="gelu_pytorch_tanh",
+        hidden_activation="gelu_pytorch_tanh", bos_token_id=2, eos_token_id=1, pad_token_id=0, torch_dtype="float32",
+        tie_word_embeddings=True),
     "mamba-tiny": dict(
         architectures=["MambaForCausalLM"], model_type="mamba", vocab_size=512, hidden_size=64, state_size=8,
         num_hidden_layers=2, expand=2, conv_kernel=4, time_step_rank=4, use_bias=False, use_conv_bias=True,
@@ -814,7 +824,13 @@ class ModelConfig:
     @property
     def is_encoder_only(self) -> bool:
         return (self.architecture.startswith(("Bert", "Roberta", "XLMRoberta", "NomicBert", "HF_ColBERT", "ColBERTJinaRoberta", "BgeM3"))
-                or "Bidirectional" in self.architecture or self.hf_config.get("is_causal") is False)
+                or "Bidirectional" in self.architecture
+                or (self.hf_config.get("is_causal") is False and not self.prefix_lm))
+
+    @property
+    def prefix_lm(self) -> bool:
+        """Generative models whose PROMPT attends bidirectionally (PaliGemma): the prompt must be one prefill pass."""
+        return self.architecture.startswith("PaliGemma")
 
     @property
     def architecture(self) -> str:

@@ -157,6 +157,10 @@ class EngineArgs:
             mc.runner = "pooling"
             chunked = False
             cc.enable_prefix_caching = False
+        if mc.prefix_lm:
+            # prefix-LM attention: image + prompt see each other in full, which only holds if they are prefilled together
+            chunked = False
+            cc.enable_prefix_caching = False
         if not chunked:
             mnbt = max(mnbt, mml)
         sc = SchedulerConfig(

@@ -31,7 +31,8 @@ class Gemma2Attention(nn.Module):
         rope = get_rope(hd, hd, max_pos, cfg.get("rope_theta", 10000.0), True, None)
         self.attn = Attention(self.qkv_proj.num_heads, hd, float(cfg.get("query_pre_attn_scalar", hd)) ** -0.5,
                               self.qkv_proj.num_kv_heads, sliding_window=cfg.get("sliding_window") if sliding else None,
-                              logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0, prefix=f"{prefix}.attn", rope=rope)
+                              logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0, prefix=f"{prefix}.attn", rope=rope,
+                              causal=bool(cfg.get("is_causal", True)))
 
     def forward(self, positions, hidden):
         q, k, v = self.qkv_proj(hidden).split([self.q_size, self.kv_size, self.kv_size], dim=-1)

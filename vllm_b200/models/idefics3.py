@@ -204,3 +204,27 @@ class AyaVisionForConditionalGeneration(Cohere2VisionForConditionalGeneration):
     LayerNorm (``vision_feature_layer = -1``) (reference: models/aya_vision.py)."""
     final_norm = False
     pre_ln = True
+
+
+class PaliGemmaForConditionalGeneration(SiglipVLM):
+    """PaliGemma / PaliGemma-2: SigLIP tower → one linear projection → Gemma (or Gemma-2) decoder run as a PREFIX-LM: image
+    and prompt tokens attend to each other in both directions, generated tokens causally.  The attention layers are built
+    non-causal; a decode step has one query at the end of its sequence, for which that is the causal result, and the
+    engine keeps the prompt in a single prefill pass (no chunked prefill, no prefix reuse — ``ModelConfig.prefix_lm``).
+    The ``1/sqrt(hidden)`` HF applies to the projected image features only cancels Gemma's embedding scale, which here
+    never touches spliced features (reference: models/paligemma.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        from vllm_b200.models.registry import text_decoder_cls
+        cfg = vllm_config.model_config.hf_config
+        cfg["is_causal"] = False
+        cfg.setdefault("tie_word_embeddings", True)
+        cfg["model_type"] = cfg.get("text_model_type") or "gemma"          # the decoder keys its Gemma-isms on this
+        self.text_cls = text_decoder_cls(cfg, "GemmaForCausalLM")
+        super().__init__(vllm_config, prefix)
+
+    def _build_projector(self, cfg, dtype) -> None:
+        self.linear = nn.Linear(cfg["vision_config"]["hidden_size"], cfg["hidden_size"], dtype=dtype)
+
+    def _project(self, feats):
+        return self.linear(feats)

@@ -140,6 +140,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3VLForConditionalGeneration": ("qwen3_vl", "Qwen3VLForConditionalGeneration"),
     "Qwen3VLMoeForConditionalGeneration": ("qwen3_vl", "Qwen3VLMoeForConditionalGeneration"),
     "LlavaOnevisionForConditionalGeneration": ("llava_next", "LlavaOnevisionForConditionalGeneration"),
+    "PaliGemmaForConditionalGeneration": ("idefics3", "PaliGemmaForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),
