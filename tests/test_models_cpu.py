@@ -1056,3 +1056,21 @@ def test_paligemma_prefix_lm_matches_hf():
                        SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_hyperclovax_is_granite_with_optional_output_norms():
+    """HyperCLOVA X without post-norms equals Granite (logits_scaling multiplies instead of divides); with ``use_post_norm`` it
+    is the sandwich block: identity-initialised output norms leave unit-norm'd sub-layer outputs, so the two differ."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=6))
+    hd = cfg["hidden_size"] // cfg["num_attention_heads"]
+    common = {"embedding_multiplier": 4.0, "residual_multiplier": 0.5, "attention_multiplier": hd ** -0.5}
+    a = _gen("llama-tiny", w, dict(common, architectures=["GraniteForCausalLM"], logits_scaling=4.0))
+    b = _gen("llama-tiny", w, dict(common, architectures=["HyperCLOVAXForCausalLM"], logits_scaling=0.25))
+    _same(a, b)
+    c = _gen("llama-tiny", w, dict(common, architectures=["HyperCLOVAXForCausalLM"], logits_scaling=0.25, use_post_norm=True))
+    assert [t for t, _ in c] != [t for t, _ in b]
+    from vllm_b200.models.registry import resolve_model_cls
+    assert resolve_model_cls("Rnj1ForCausalLM").__name__ == "Gemma3ForCausalLM"

@@ -23,7 +23,7 @@ from vllm_b200.parallel.state import get_tp_group
 
 
 class _Attn(nn.Module):
-    def __init__(self, cfg, mc, dtype, prefix) -> None:
+    def __init__(self, cfg, mc, dtype, prefix, sliding: bool = False) -> None:
         super().__init__()
         H, nh = cfg["hidden_size"], cfg["num_attention_heads"]
         nkv = cfg.get("num_key_value_heads") or nh
@@ -38,7 +38,8 @@ class _Attn(nn.Module):
             max_pos = mc.max_model_len if mc.max_model_len > 0 else cfg.get("max_position_embeddings", 8192)
             rope = get_rope(hd, hd, max_pos, rp.get("rope_theta", cfg.get("rope_theta", 10000.0)), True, cfg.get("rope_scaling"))
         self.attn = Attention(self.qkv_proj.num_heads, hd, float(cfg.get("attention_multiplier") or hd ** -0.5),
-                              self.qkv_proj.num_kv_heads, prefix=f"{prefix}.attn", rope=rope)
+                              self.qkv_proj.num_kv_heads, prefix=f"{prefix}.attn", rope=rope,
+                              sliding_window=cfg.get("sliding_window") if sliding else None)
 
     def forward(self, positions, x):
         q, k, v = self.qkv_proj(x).split(self.sizes, dim=-1)
@@ -70,7 +71,8 @@ class GraniteMoeLayer(nn.Module):
                                      bool(cfg.get("mamba_proj_bias", False)), bool(cfg.get("mamba_conv_bias", True)),
                                      cfg.get("mamba_chunk_size", 256), eps, dtype, f"{prefix}.mamba")
         else:
-            self.self_attn = _Attn(cfg, mc, dtype, f"{prefix}.self_attn")
+            # Granite-SWA checkpoints mark some attention layers as sliding-window in ``layer_types``
+            self.self_attn = _Attn(cfg, mc, dtype, f"{prefix}.self_attn", sliding=bool(types) and types[idx] == "sliding_attention")
         E = cfg.get("num_local_experts") or 0
         self.router = self.experts = None
         if E > 0:

@@ -85,6 +85,9 @@ class LlamaAttention(nn.Module):
             sw = None  # qwen2: only upper layers use SWA
         if cfg.get("use_sliding_window") is False:
             sw = None
+        types = cfg.get("layer_types")
+        if sw is not None and isinstance(types, list) and layer_idx < len(types) and types[layer_idx] in ("full_attention", "sliding_attention"):
+            sw = sw if types[layer_idx] == "sliding_attention" else None       # per-layer windows (Mellum, Qwen3 SWA variants)
         self.attn = Attention(self.qkv_proj.num_heads, self.head_dim, self.head_dim ** -0.5,
                               self.qkv_proj.num_kv_heads, sliding_window=sw,
                               logits_soft_cap=cfg.get("attn_logit_softcapping") or 0.0,

@@ -295,6 +295,19 @@ class GraniteForCausalLM(VariantForCausalLM):
     renames = [(".post_attention_layernorm.", ".pre_mlp_norm.")]
 
 
+class HyperCLOVAXForCausalLM(GraniteForCausalLM):
+    """HyperCLOVA X (SEED / THINK text decoders): the Granite muP parameterisation (embedding, attention, residual multipliers;
+    ``logits_scaling`` here MULTIPLIES the logits) with optional extra norms on the sub-layer outputs (``use_post_norm``)
+    (reference: models/hyperclovax.py)."""
+    def options(self, c):
+        o = super().options(c)
+        o["logit_scale"] = float(c.get("logit_scale", 1.0)) * float(c.get("logits_scaling", 1.0))
+        if c.get("use_post_norm"):
+            o["structure"] = "sandwich"
+        return o
+    renames = [(".post_attention_layernorm.", ".pre_mlp_norm."), (".post_norm1.", ".post_attn_norm."), (".post_norm2.", ".post_mlp_norm.")]
+
+
 class Olmo2ForCausalLM(VariantForCausalLM):
     def options(self, c):
         return dict(structure="post", eps=c.get("rms_norm_eps", 1e-5), qk_norm="full", qkv_bias=bool(c.get("attention_bias")),

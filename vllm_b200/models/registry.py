@@ -68,6 +68,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "TeleFLMForCausalLM": ("llama_aliases", "TeleFLMForCausalLM"),
     "OrionForCausalLM": ("llama_aliases", "OrionForCausalLM"),
     "GraniteSWAForCausalLM": ("llama_variants", "GraniteForCausalLM"),
+    "GraniteMoeSWAForCausalLM": ("granite_moe", "GraniteMoeForCausalLM"),
     "DeepseekForCausalLM": ("deepseek", "DeepseekForCausalLM"),
     "TransformersForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
     "TransformersMoEForCausalLM": ("transformers_backend", "TransformersForCausalLM"),
@@ -87,6 +88,9 @@ _MODELS: dict[str, tuple[str, str]] = {
     "LlamaBidirectionalModel": ("llama_aliases", "LlamaBidirectionalModel"),
     "LlamaBidirectionalForSequenceClassification": ("llama_aliases", "LlamaBidirectionalForSequenceClassification"),
     "VoyageQwen3BidirectionalEmbedModel": ("llama_aliases", "VoyageQwen3BidirectionalEmbedModel"),
+    "HyperCLOVAXForCausalLM": ("llama_variants", "HyperCLOVAXForCausalLM"),
+    "Rnj1ForCausalLM": ("llama_variants", "Gemma3ForCausalLM"),
+    "MellumForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
     "DeciLMForCausalLM": ("llama_aliases", "DeciLMForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
