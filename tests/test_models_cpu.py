@@ -1074,3 +1074,31 @@ def test_hyperclovax_is_granite_with_optional_output_norms():
     assert [t for t, _ in c] != [t for t, _ in b]
     from vllm_b200.models.registry import resolve_model_cls
     assert resolve_model_cls("Rnj1ForCausalLM").__name__ == "Gemma3ForCausalLM"
+
+
+def test_ultravox_projector_and_splice():
+    """Ultravox (no transformers implementation): the tower is the Whisper encoder already checked against transformers, so
+    the test pins the projector (frame stacking with tail padding, RMSNorm → linear → SwiGLU → RMSNorm → linear) and the
+    token count against a hand computation, and runs the spliced model end to end."""
+    llm = make_llm("ultravox-tiny")
+    m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in m.multi_modal_projector.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.2 if p.dim() > 1 else 1.0) + (0.0 if p.dim() > 1 else 1.0))
+    x = torch.randn(10, 32, generator=g)                            # 10 encoder frames, stack 4 → 3 tokens (2 padded rows)
+    P = m.multi_modal_projector
+
+    def rms(v, w):
+        return v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    st = torch.cat([x, torch.zeros(2, 32)]).view(3, 128)
+    h = rms(st, P["ln_pre"].weight) @ P["linear_1"].weight.t()
+    a, b = h.chunk(2, dim=-1)
+    ref = rms(a * torch.nn.functional.silu(b), P["ln_mid"].weight) @ P["linear_2"].weight.t()
+    torch.testing.assert_close(m._project(x), ref, atol=1e-5, rtol=1e-4)
+    assert type(m).num_tokens({}, 37, 4) == 5 and type(m).num_tokens({}, 1, 4) == 1      # ceil(((37-1)//2+1) / 4)
+    mel = torch.randn(16, 37, generator=g)
+    out = llm.generate([{"prompt_token_ids": [5, 17, 511, 99], "multi_modal_data": {"audio": mel}}],
+                       SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True))
+    assert len(out[0].prompt_token_ids) == 3 + 5 and len(out[0].outputs[0].token_ids) == 4
+    llm.shutdown()

@@ -175,6 +175,14 @@ PRESETS: dict[str, dict[str, Any]] = {
         vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
         num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
         hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
+    "ultravox-tiny": dict(
+        architectures=["UltravoxModel"], model_type="ultravox", audio_token_index=511, text_model_type="llama", stack_factor=4,
+        projector_act="swiglu", projector_ln_mid=True, projector_hidden_size=96,
+        audio_config=dict(model_type="whisper", num_mel_bins=16, d_model=32, encoder_layers=2, encoder_attention_heads=2,
+                          encoder_ffn_dim=64, max_source_positions=24),
+        vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, rope_theta=10000.0,
+        hidden_act="silu", bos_token_id=1, eos_token_id=2, torch_dtype="float32", tie_word_embeddings=False),
     "voxtral-tiny": dict(
         architectures=["VoxtralForConditionalGeneration"], model_type="voxtral", audio_token_id=511, text_model_type="llama",
         projector_hidden_act="gelu",
@@ -773,6 +781,9 @@ class ModelConfig:
     def __post_init__(self) -> None:
         if not self.hf_config:
             self.hf_config = self._load_hf_config()
+        if self.hf_config.get("model_type") == "ultravox" and "projector_hidden_size" not in self.hf_config:
+            # Ultravox's top-level ``hidden_size`` is the projector width, not the decoder's
+            self.hf_config["projector_hidden_size"] = self.hf_config.pop("hidden_size", 4096)
         if isinstance(self.hf_config.get("text_config"), dict):
             # vision-language checkpoints nest the decoder's fields: lift them to the top level (top-level wins)
             tc = self.hf_config.pop("text_config")

@@ -166,6 +166,56 @@ class VoxtralForConditionalGeneration(_AudioLM):
         return windows * ac["max_source_positions"] * (ac.get("hidden_size") or ac["d_model"]) // ac["intermediate_size"]
 
 
+class UltravoxModel(_AudioLM):
+    """Ultravox: Whisper encoder (padding masked) → 8 consecutive frames stacked per token → RMSNorm → linear → SwiGLU →
+    (RMSNorm) → linear → (RMSNorm) → Llama-family decoder; v0.5+ checkpoints norm in the middle, earlier ones at the end
+    (reference: models/ultravox.py ``UltravoxFeedForwardProjector``)."""
+
+    def _build_projector(self, cfg, dtype) -> None:
+        from vllm_b200.layers.common import RMSNorm
+        ac = cfg["audio_config"]
+        self.stack = int(cfg.get("stack_factor", 8))
+        d_in = (ac.get("d_model") or ac["hidden_size"]) * self.stack
+        mid = int(cfg.get("projector_hidden_size", cfg["hidden_size"]))
+        self.swiglu = cfg.get("projector_act", "swiglu") == "swiglu"
+        d_mid = mid // 2 if self.swiglu else mid
+        ln_mid = bool(cfg.get("projector_ln_mid", False))
+        mods = {"ln_pre": RMSNorm(d_in, 1e-6, dtype), "linear_1": nn.Linear(d_in, mid, bias=False, dtype=dtype),
+                "linear_2": nn.Linear(d_mid, cfg["hidden_size"], bias=False, dtype=dtype)}
+        mods["ln_mid" if ln_mid else "ln_post"] = RMSNorm(d_mid if ln_mid else cfg["hidden_size"], 1e-6, dtype)
+        self.multi_modal_projector = nn.ModuleDict(mods)
+        self.act_name = cfg.get("projector_act", "swiglu")
+
+    def _project(self, x):
+        p = self.multi_modal_projector
+        T, C = x.shape
+        pad = (-T) % self.stack
+        x = F.pad(x, (0, 0, 0, pad)).view((T + pad) // self.stack, C * self.stack)
+        h = p["linear_1"](p["ln_pre"](x))
+        if self.swiglu:
+            a, b = h.chunk(2, dim=-1)
+            h = a * F.silu(b)
+        else:
+            h = F.gelu(h)
+        if "ln_mid" in p:
+            h = p["ln_mid"](h)
+        h = p["linear_2"](h)
+        return p["ln_post"](h) if "ln_post" in p else h
+
+    @torch.inference_mode()
+    def embed_multimodal_item(self, f: dict) -> torch.Tensor:
+        mel = torch.as_tensor(f["data"])
+        valid = f.get("valid_frames")
+        x = self.audio_tower(mel, valid)
+        if valid is not None:
+            x = x[: (valid - 1) // 2 + 1]
+        return self._project(x)[: f["length"]]
+
+    @staticmethod
+    def num_tokens(ac: dict, valid_frames: int, stack: int = 8) -> int:
+        return max(1, -(-((valid_frames - 1) // 2 + 1) // stack))
+
+
 class AudioLMProcessor:
     """``multi_modal_data={"audio": clip | [clips]}``: clip = waveform array / (array, sr) / path / bytes, or a precomputed
     log-mel ``[n_mels, frames]`` tensor.  Pads to whole tower windows, records the valid frame count, expands the placeholder."""
@@ -178,6 +228,7 @@ class AudioLMProcessor:
         self.model_cls = resolve_model_cls(model_config.architecture)
         self.window = 2 * self.ac["max_source_positions"]
         self.multi_window = model_config.architecture.startswith("Voxtral")
+        self.stack = int(cfg.get("stack_factor", 8)) if model_config.architecture.startswith("Ultravox") else 0
 
     def _mel(self, clip: Any) -> tuple[torch.Tensor, int]:
         if isinstance(clip, torch.Tensor) and clip.dim() == 2:
@@ -209,7 +260,7 @@ class AudioLMProcessor:
         out, feats, prev = [], [], 0
         for slot, clip in zip(slots, clips):
             mel, valid = self._mel(clip)
-            n = int(self.model_cls.num_tokens(self.ac, valid))
+            n = int(self.model_cls.num_tokens(self.ac, valid, self.stack) if self.stack else self.model_cls.num_tokens(self.ac, valid))
             out.extend(ids[prev:slot])
             feats.append({"modality": "audio", "hash": hash_item(np.ascontiguousarray(mel.numpy())), "offset": len(out), "length": n,
                           "data": mel, "valid_frames": valid})

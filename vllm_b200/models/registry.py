@@ -138,6 +138,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "InternVLForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
     "InternS1ForConditionalGeneration": ("internvl", "InternVLForConditionalGeneration"),
     "Qwen2AudioForConditionalGeneration": ("audio_lm", "Qwen2AudioForConditionalGeneration"),
+    "UltravoxModel": ("audio_lm", "UltravoxModel"),
     "VoxtralForConditionalGeneration": ("audio_lm", "VoxtralForConditionalGeneration"),
     "Mistral3ForConditionalGeneration": ("mistral3", "Mistral3ForConditionalGeneration"),
     "LlavaNextForConditionalGeneration": ("llava_next", "LlavaNextForConditionalGeneration"),
