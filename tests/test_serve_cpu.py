@@ -336,3 +336,29 @@ def test_native_frontend_text_prompts_with_tiktoken_tokenizer(tmp_path):
             proc.wait(timeout=30)
         except subprocess.TimeoutExpired:
             proc.kill()
+
+
+def test_render_server_and_mm_processor_bench():
+    """``launch render``: templating / tokenisation / detokenisation with no engine (TestClient over the same app the CLI
+    serves); ``bench mm_processor``: the front-end processor benchmark runs for an image and an audio model."""
+    from fastapi.testclient import TestClient
+    from vllm_b200.entrypoints.render_server import build_render_app
+    c = TestClient(build_render_app("llama-tiny", chat_template="chatml"))
+    assert c.get("/health").status_code == 200
+    r = c.post("/render", json={"messages": [{"role": "user", "content": "hi there"}]}).json()
+    assert r["prompt"].startswith("<|im_start|>user\nhi there<|im_end|>") and r["prompt"].endswith("<|im_start|>assistant\n")
+    assert r["count"] == len(r["token_ids"]) > 0
+    back = c.post("/derender", json={"token_ids": r["token_ids"], "skip_special_tokens": False}).json()["text"]
+    assert "hi there" in back
+    t = c.post("/tokenize", json={"prompt": "abc def", "return_token_strs": True}).json()
+    assert t["count"] == len(t["tokens"]) == len(t["token_strs"])
+    assert c.post("/detokenize", json={"tokens": t["tokens"]}).json()["prompt"].endswith("abc def")
+    assert c.get("/v1/models").json()["data"][0]["id"] == "llama-tiny"
+    from vllm_b200.entrypoints.cli import _bench_parser
+    from vllm_b200 import benchmarks as B
+    a = _bench_parser().parse_args(["mm_processor", "--model", "llava-tiny", "--num-items", "6", "--image-size", "40x60", "--unique", "2"])
+    res = B.bench_mm_processor(a)
+    assert res["modality"] == "image" and res["items"] == 6 and res["items_per_s"] > 0 and res["placeholder_tokens_per_item"] == 4
+    a = _bench_parser().parse_args(["mm_processor", "--model", "qwen2audio-tiny", "--num-items", "3", "--audio-seconds", "0.2"])
+    res = B.bench_mm_processor(a)
+    assert res["modality"] == "audio" and res["placeholder_tokens_per_item"] >= 1

@@ -240,6 +240,44 @@ def bench_serve(args) -> dict[str, Any]:
     return asyncio.run(bench_serve_async(args))
 
 
+# ------------------------------------------------------------------ bench mm_processor
+def bench_mm_processor(args) -> dict[str, Any]:
+    """Front-end multimodal preprocessing throughput with no engine: synthetic images (or audio clips) through the model's
+    processor — resize / tiling / patching / log-mel, placeholder expansion, content hashing (reference:
+    benchmarks/mm_processor.py)."""
+    import numpy as np
+    from vllm_b200.config.model import ModelConfig
+    from vllm_b200.multimodal import MULTIMODAL_REGISTRY
+    mc = ModelConfig(model=args.model, hf_overrides=getattr(args, "hf_overrides", None) or {})
+    if not MULTIMODAL_REGISTRY.supports_multimodal(mc):
+        raise SystemExit(f"{args.model} has no multimodal processor")
+    proc = MULTIMODAL_REGISTRY.create_processor(mc)
+    cfg = mc.hf_config
+    audio = cfg.get("audio_config") is not None and cfg.get("vision_config") is None
+    tok = cfg.get("audio_token_index", cfg.get("audio_token_id")) if audio else cfg.get("image_token_index", cfg.get("image_token_id"))
+    rng = np.random.default_rng(0)
+    n, uniq = args.num_items, (args.unique or args.num_items)
+    if audio:
+        items = [rng.standard_normal(int(16000 * args.audio_seconds)).astype(np.float32) * 0.1 for _ in range(uniq)]
+        key = "audio"
+    else:
+        h, w = (int(x) for x in args.image_size.lower().split("x"))
+        items = [rng.integers(0, 255, (h, w, 3), dtype=np.uint8) for _ in range(uniq)]
+        key = "image"
+    lat, toks = [], 0
+    t0 = time.perf_counter()
+    for i in range(n):
+        t = time.perf_counter()
+        ids, feats = proc.process([1, tok, 2], {key: items[i % uniq]})
+        lat.append(time.perf_counter() - t)
+        toks += len(ids) - 2
+    total = time.perf_counter() - t0
+    lat.sort()
+    return {"model": args.model, "modality": key, "items": n, "unique_items": uniq, "items_per_s": n / total,
+            "placeholder_tokens_per_item": toks / n, "latency_ms": {"mean": 1e3 * sum(lat) / n, "p50": 1e3 * lat[n // 2],
+                                                                  "p99": 1e3 * lat[min(n - 1, int(n * 0.99))]}}
+
+
 # ------------------------------------------------------------------ bench startup
 def bench_startup(args) -> dict[str, Any]:
     """Cold engine start → first token (reference: benchmarks/startup.py)."""

@@ -63,6 +63,14 @@ def _bench_parser() -> argparse.ArgumentParser:
     sw.add_argument("--max-concurrencies", default="none", help="comma-separated concurrency caps")
     sw.add_argument("--slo-ttft-ms", type=float, default=None)
     sw.add_argument("--slo-tpot-ms", type=float, default=None)
+    mm = sub.add_parser("mm_processor", **common)
+    mm.add_argument("--model", required=True)
+    mm.add_argument("--num-items", type=int, default=64)
+    mm.add_argument("--image-size", default="448x448", help="HxW of the synthetic images")
+    mm.add_argument("--audio-seconds", type=float, default=10.0)
+    mm.add_argument("--unique", type=int, default=0, help="number of distinct items (0 = all distinct; fewer exercises the cache)")
+    mm.add_argument("--hf-overrides", type=json.loads, default=None)
+    mm.add_argument("--output-json", default=None)
     st = sub.add_parser("startup", **common)
     st.add_argument("--output-json", default=None)
     EngineArgs.add_cli_args(st)
@@ -73,7 +81,7 @@ def _cmd_bench(argv: list[str]) -> None:
     from vllm_b200 import benchmarks as B
     args = _bench_parser().parse_args(argv)
     fn = {"latency": B.bench_latency, "throughput": B.bench_throughput, "serve": B.bench_serve,
-          "startup": B.bench_startup, "sweep": B.bench_sweep}[args.bench]
+          "startup": B.bench_startup, "sweep": B.bench_sweep, "mm_processor": B.bench_mm_processor}[args.bench]
     res = fn(args)
     print(json.dumps(res, indent=2))
     if getattr(args, "output_json", None):
@@ -152,7 +160,20 @@ def _cmd_collect_env(argv: list[str]) -> None:
     print(collect_env())
 
 
+def _cmd_launch(argv: list[str]) -> None:
+    """``launch <component>``: individual serving components (reference: cli/launch.py)."""
+    if not argv or argv[0] in ("-h", "--help"):
+        print("usage: vllm_b200 launch {render} ...")
+        return
+    comp = argv.pop(0)
+    if comp != "render":
+        raise SystemExit(f"unknown component {comp!r}; expected one of ['render']")
+    from vllm_b200.entrypoints.render_server import main as render_main
+    render_main(argv)
+
+
 COMMANDS = {
+    "launch": _cmd_launch,
     "serve": _cmd_serve, "bench": _cmd_bench, "chat": lambda a: _client(a, True),
     "complete": lambda a: _client(a, False), "run-batch": _cmd_run_batch, "collect-env": _cmd_collect_env,
 }
