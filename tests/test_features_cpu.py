@@ -714,7 +714,7 @@ def test_gguf_checkpoint_roundtrip(tmp_path):
         assert np.allclose(got6[b], y, atol=1e-5)
 
 
-@pytest.mark.parametrize("backend", ["xgrammar", "guidance"])
+@pytest.mark.parametrize("backend", ["xgrammar", "guidance", "outlines", "lm-format-enforcer"])
 def test_structured_output_library_backends(backend):
     """xgrammar / llguidance matchers behind the same bitmask interface, driven with a real (programmatically built)
     byte-level BPE tokenizer: every token of a valid document is allowed in turn, an invalid one is masked, the

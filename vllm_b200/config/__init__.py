@@ -214,7 +214,7 @@ class SpeculativeConfig(_ConfigBase):
 
 @dataclass
 class StructuredOutputsConfig(_ConfigBase):
-    backend: str = "auto"  # auto|xgrammar|regex_fsm
+    backend: str = "auto"  # auto|xgrammar|guidance|outlines|lm-format-enforcer|regex_fsm
     disable_fallback: bool = False
     reasoning_parser: str = ""
 

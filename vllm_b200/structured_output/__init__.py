@@ -218,6 +218,98 @@ class GuidanceGrammar(Grammar):
         return bool(self.m.is_stopped())
 
 
+class OutlinesGrammar(Grammar):
+    """outlines-core ``Guide`` over a regex ``Index`` (reference: v1/structured_output/backend_outlines.py): JSON schemas are
+    lowered to a regex by the library, the index is a token-level DFA, the allowed set is written straight into our row."""
+
+    def __init__(self, guide, vocab_size: int) -> None:
+        self.g, self.vocab_size = guide, vocab_size
+        self.n_accepted = 0
+        self._done = False
+
+    def fill_bitmask(self, bitmask: np.ndarray, row: int) -> None:
+        r = bitmask[row]
+        r[:] = 0
+        self.g.write_mask_into(r.ctypes.data, r.size, 4)
+
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool:
+        for t in tokens:
+            if self.g.is_finished() and self._done:
+                return True
+            if int(t) not in set(self.g.get_tokens()):
+                return False
+            try:
+                self.g.advance(int(t))
+            except Exception:
+                return False
+            self.n_accepted += 1
+        return True
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        n = 0
+        for t in tokens:
+            if int(t) not in set(self.g.get_tokens()):
+                break
+            self.g.advance(int(t))
+            n += 1
+        if n:
+            self.g.rollback_state(n)
+        return list(tokens[:n])
+
+    def rollback(self, n: int) -> None:
+        if n > 0:
+            self.g.rollback_state(n)
+            self.n_accepted -= n
+
+    def is_terminated(self) -> bool:
+        # finished states may still allow more text (e.g. ``a+``): terminate only when nothing but EOS can follow
+        return bool(self.g.is_finished()) and len(self.g.get_tokens()) <= 1
+
+
+class LMFormatEnforcerGrammar(Grammar):
+    """lm-format-enforcer ``TokenEnforcer`` (reference: v1/structured_output/backend_lm_format_enforcer.py): a character-
+    level parser (JSON schema / regex / choices) walked over the token prefix tree; stateless per call, so the grammar
+    keeps the token history and rollback is a truncation."""
+
+    def __init__(self, enforcer, vocab_size: int, eos: Optional[int]) -> None:
+        self.e, self.vocab_size, self.eos = enforcer, vocab_size, eos
+        self.hist: list[int] = []
+
+    def _allowed(self, hist=None) -> list[int]:
+        a = self.e.get_allowed_tokens(list(self.hist if hist is None else hist))
+        return list(getattr(a, "allowed_tokens", a))
+
+    def fill_bitmask(self, bitmask: np.ndarray, row: int) -> None:
+        r = bitmask[row]
+        r[:] = 0
+        ids = np.asarray([t for t in self._allowed() if t < self.vocab_size], dtype=np.int64)
+        np.bitwise_or.at(r.view(np.uint32), ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
+
+    def accept_tokens(self, request_id: str, tokens: list[int]) -> bool:
+        for t in tokens:
+            if int(t) not in self._allowed():
+                return False
+            self.hist.append(int(t))
+        return True
+
+    def validate_tokens(self, tokens: list[int]) -> list[int]:
+        h, n = list(self.hist), 0
+        for t in tokens:
+            if int(t) not in self._allowed(h):
+                break
+            h.append(int(t))
+            n += 1
+        return list(tokens[:n])
+
+    def rollback(self, n: int) -> None:
+        if n > 0:
+            del self.hist[-n:]
+
+    def is_terminated(self) -> bool:
+        a = self._allowed()
+        return bool(self.hist) and (self.hist[-1] == self.eos or (len(a) == 1 and a[0] == self.eos))
+
+
 class StructuredOutputRequest:
     def __init__(self, params: StructuredOutputsParams, fut: Future) -> None:
         self.params = params
@@ -265,6 +357,10 @@ class StructuredOutputManager:
         eos = self.vllm_config.model_config.eos_token_id
         if self.backend == "guidance" and hasattr(tok, "backend_tokenizer"):
             return self._compile_guidance(kind, p, tok)
+        if self.backend == "outlines":
+            return self._compile_outlines(kind, p, tok, eos)
+        if self.backend in ("lm-format-enforcer", "lm_format_enforcer"):
+            return self._compile_lmfe(kind, p, tok, eos)
         use_xgr = self.backend in ("auto", "xgrammar") and hasattr(tok, "backend_tokenizer")
         if use_xgr:
             try:
@@ -306,6 +402,46 @@ class StructuredOutputManager:
         else:
             raise ValueError(kind)
         return XGrammarGrammar(xgr.GrammarMatcher(g, max_rollback_tokens=64), self.vocab_size)
+
+    def _regex_for(self, kind: str, p: StructuredOutputsParams) -> str:
+        if kind == "regex":
+            return p.regex
+        if kind == "choice":
+            return "(" + "|".join(re.escape(c) for c in p.choice) + ")"
+        if kind in ("json", "json_object"):
+            import outlines_core.json_schema as ojs
+            schema = p.json if kind == "json" else {"type": "object"}
+            return ojs.build_regex_from_schema(schema if isinstance(schema, str) else json.dumps(schema))
+        raise ValueError(f"the outlines back-end compiles regex, JSON-schema and choice constraints, not {kind!r}")
+
+    def _compile_outlines(self, kind: str, p: StructuredOutputsParams, tok, eos) -> Grammar:
+        from outlines_core import Guide, Index, Vocabulary
+        if getattr(self, "_outlines_vocab", None) is None:
+            by_text: dict[str, list[int]] = {}
+            for i, t in enumerate(_vocab_texts(tok, self.vocab_size)):
+                if t and i != eos:
+                    by_text.setdefault(t, []).append(i)
+            self._outlines_vocab = Vocabulary(int(eos if eos is not None else 0), by_text)
+        return OutlinesGrammar(Guide(Index(self._regex_for(kind, p), self._outlines_vocab)), self.vocab_size)
+
+    def _compile_lmfe(self, kind: str, p: StructuredOutputsParams, tok, eos) -> Grammar:
+        import lmformatenforcer as lmfe
+        if getattr(self, "_lmfe_data", None) is None:
+            texts = _vocab_texts(tok, self.vocab_size)
+            regular = [(i, t, t.startswith(" ")) for i, t in enumerate(texts) if t and i != eos]
+            self._lmfe_data = lmfe.TokenEnforcerTokenizerData(regular, lambda ids: tok.decode(list(ids)), int(eos if eos is not None else 0),
+                                                               False, self.vocab_size)
+        if kind == "json":
+            parser = lmfe.JsonSchemaParser(json.loads(p.json) if isinstance(p.json, str) else p.json)
+        elif kind == "json_object":
+            parser = lmfe.JsonSchemaParser(None)
+        elif kind == "regex":
+            parser = lmfe.RegexParser(p.regex)
+        elif kind == "choice":
+            parser = lmfe.UnionParser([lmfe.StringParser(c) for c in p.choice])
+        else:
+            raise ValueError(f"lm-format-enforcer compiles JSON-schema, regex and choice constraints, not {kind!r}")
+        return LMFormatEnforcerGrammar(lmfe.TokenEnforcer(self._lmfe_data, parser), self.vocab_size, eos)
 
     def _compile_guidance(self, kind: str, p: StructuredOutputsParams, tok) -> Grammar:
         import llguidance
