@@ -1118,11 +1118,16 @@ def test_streaming_safetensors_loader(tmp_path):
     sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
     p = [{"prompt_token_ids": [5, 17, 99, 3, 250, 41]}]
     outs = {}
-    for fmt in ("safetensors", "streamer"):
-        llm = make_llm(str(m), load_format=fmt, model_loader_extra_config={"concurrency": 4} if fmt == "streamer" else None)
+    for fmt in ("safetensors", "streamer", "fastsafetensors"):
+        llm = make_llm(str(m), load_format=fmt, model_loader_extra_config={"concurrency": 4} if fmt != "safetensors" else None)
         outs[fmt] = llm.generate(p, sp)[0].outputs[0].token_ids
         llm.shutdown()
-    assert outs["streamer"] == outs["safetensors"]
+    assert outs["streamer"] == outs["safetensors"] == outs["fastsafetensors"]
+    # the fastsafetensors iterator returns every tensor of a multi-file checkpoint
+    from vllm_b200.model_loader import iter_weights
+    got = {k: v.clone() for k, v in iter_weights(str(d), "fastsafetensors", {"files_per_batch": 2})}
+    assert set(got) == set(ref)
+    assert torch.equal(got["w.big"], ref["w.big"]) and torch.equal(got["v.x"], ref["v.x"])
 
 
 def test_usage_stats_record_and_opt_out(tmp_path, monkeypatch):

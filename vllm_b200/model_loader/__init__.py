@@ -66,8 +66,36 @@ def _iter_pt(path: str) -> Iterator[tuple[str, torch.Tensor]]:
         del sd
 
 
+def _iter_fastsafetensors(path: str, extra: Optional[dict]) -> Iterator[tuple[str, torch.Tensor]]:
+    """``--load-format fastsafetensors``: the fastsafetensors library reads whole files into a device-side buffer with many
+    threads (GPUDirect Storage when the box has it: ``{"gds": true}`` in ``--model-loader-extra-config``) and hands out
+    tensor views; the buffer of a file is released after its tensors were consumed, so each yielded tensor is copied into
+    the parameter by the caller before the next file is opened (reference: model_loader/weight_utils.py
+    ``fastsafetensors_weights_iterator``)."""
+    from fastsafetensors import SafeTensorsFileLoader, SingleGroup
+    extra = extra or {}
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+    per = max(1, int(extra.get("files_per_batch", 1)))
+    for i in range(0, len(files), per):
+        ld = SafeTensorsFileLoader(SingleGroup(), dev, nogds=not bool(extra.get("gds", False)), debug_log=False,
+                                   max_threads=int(extra.get("concurrency", 16)))
+        try:
+            ld.add_filenames({0: files[i:i + per]})
+            fb = ld.copy_files_to_device()
+            try:
+                for k in list(fb.key_to_rank_lidx.keys()):
+                    yield k, fb.get_tensor(k)
+            finally:
+                fb.close()
+        finally:
+            ld.close()
+
+
 def iter_weights(path: str, load_format: str = "auto", extra: Optional[dict] = None) -> Iterator[tuple[str, torch.Tensor]]:
     has_st = bool(glob.glob(os.path.join(path, "*.safetensors")))
+    if load_format == "fastsafetensors":
+        return _iter_fastsafetensors(path, extra)
     if load_format in ("streamer", "runai_streamer", "runai_streamer_sharded"):
         from vllm_b200.model_loader.streamer import stream_safetensors
         extra = extra or {}
