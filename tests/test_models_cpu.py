@@ -1102,3 +1102,26 @@ def test_ultravox_projector_and_splice():
                        SamplingParams(max_tokens=4, temperature=0.0, ignore_eos=True))
     assert len(out[0].prompt_token_ids) == 3 + 5 and len(out[0].outputs[0].token_ids) == 4
     llm.shutdown()
+
+
+def test_glm_moe_dsa_dense_path_matches_hf_within_index_topk():
+    """GLM-5 / DeepSeek-V3.2 (sparse-attention indexer): while the context fits in ``index_topk`` the indexer selects every
+    token, so our dense MLA path must equal transformers (eager attention: its sdpa path drops the causal mask when the
+    mask argument is absent).  Indexer tensors in the checkpoint are skipped; V3.2 keeps DeepSeek's interleaved rotary."""
+    hf = make_hf_model("glmmoedsa-tiny")
+    hf.config._attn_implementation = "eager"
+    for layer in hf.model.layers:
+        layer.self_attn.config._attn_implementation = "eager"
+    sd = hf.state_dict()
+    assert any(".indexer." in k for k in sd)
+    llm = make_llm("glmmoedsa-tiny", weights=sd.items())
+    sp = SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True)
+    for p, o in zip(PROMPTS, llm.generate([{"prompt_token_ids": p} for p in PROMPTS], sp)):
+        assert o.outputs[0].token_ids == hf_greedy(hf, p, 8)
+    m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    assert m.model.layers[0].self_attn.rope.is_neox_style
+    llm.shutdown()
+    llm = make_llm("glmmoedsa-tiny", hf_overrides={"architectures": ["DeepseekV32ForCausalLM"]})
+    m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
+    assert not m.model.layers[0].self_attn.rope.is_neox_style
+    llm.shutdown()

@@ -579,6 +579,14 @@ PRESETS: dict[str, dict[str, Any]] = {
         ffn_config=dict(ffn_hidden_size=96, moe_num_experts=4, moe_top_k=2, moe_normalize_expert_weights=1.0,
                         ffn_act_fn=dict(name="silu")),
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "glmmoedsa-tiny": dict(
+        architectures=["GlmMoeDsaForCausalLM"], model_type="glm_moe_dsa", vocab_size=512, hidden_size=64,
+        intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=4,
+        n_shared_experts=1, n_routed_experts=8, routed_scaling_factor=1.8, kv_lora_rank=32, q_lora_rank=48, qk_rope_head_dim=8,
+        v_head_dim=16, qk_nope_head_dim=16, n_group=1, topk_group=1, num_experts_per_tok=2, norm_topk_prob=True,
+        hidden_act="silu", max_position_embeddings=256, rms_norm_eps=1e-5, mlp_layer_types=["dense", "sparse", "sparse"],
+        index_topk=256, index_head_dim=16, index_n_heads=2, rope_parameters=dict(rope_type="default", rope_theta=10000.0),
+        bos_token_id=0, eos_token_id=1, torch_dtype="float32", tie_word_embeddings=False),
     "afmoe-tiny": dict(
         architectures=["AfmoeForCausalLM"], model_type="afmoe", vocab_size=512, hidden_size=64, intermediate_size=128,
         moe_intermediate_size=32, num_hidden_layers=4, num_dense_layers=1, num_attention_heads=4, num_key_value_heads=2,

@@ -58,7 +58,9 @@ class DeepseekMLA(nn.Module):
                                         prefix=f"{prefix}.o_proj")
         rs = cfg.get("rope_scaling")
         max_pos = mc.max_model_len if mc.max_model_len > 0 else cfg.get("max_position_embeddings", 4096)
-        self.rope = get_rope(self.rope_dim, self.rope_dim, max_pos, cfg.get("rope_theta", 10000.0), False, rs)
+        # DeepSeek checkpoints rotate (even, odd) pairs; GLM-5's MLA rotates the two halves (``rope_interleave: false``)
+        self.rope = get_rope(self.rope_dim, self.rope_dim, max_pos, cfg.get("rope_theta", 10000.0),
+                             not bool(cfg.get("rope_interleave", True)), rs)
         scale = self.q_head ** -0.5
         if rs and rs.get("mscale_all_dim"):
             m = yarn_mscale(rs["factor"], rs["mscale_all_dim"])
@@ -250,6 +252,35 @@ class Glm4MoeLiteForCausalLM(DeepseekV3ForCausalLM):
         rp = cfg.get("rope_parameters") or {}
         cfg.setdefault("rope_theta", rp.get("rope_theta", 10000.0))
         super().__init__(vllm_config, prefix)
+
+
+class GlmMoeDsaForCausalLM(Glm4MoeLiteForCausalLM):
+    """GLM-5 / DeepSeek-V3.2 family: the MLA + MoE block with a *lightning indexer* that restricts every query to its
+    ``index_topk`` (2048) highest-scoring cached tokens.  PARTIAL: the indexer is not run — attention is dense over the whole
+    context, which is exactly the sparse model's output while the context is at most ``index_topk`` tokens (the indexer then
+    selects everything) and a superset of its attention pattern beyond; the indexer tensors of the checkpoint are skipped.
+    Reference: models/deepseek_v2.py (``DeepseekV32ForCausalLM``, ``Indexer``), v1/attention/backends/mla/indexer.py."""
+
+    rope_interleave_default = False
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        vllm_config.model_config.hf_config.setdefault("rope_interleave", self.rope_interleave_default)
+        super().__init__(vllm_config, prefix)
+        cfg = vllm_config.model_config
+        topk = int(cfg.hf_config.get("index_topk") or 2048)
+        if cfg.max_model_len > topk:
+            from vllm_b200.logger import init_logger
+            init_logger(__name__).warning(
+                "sparse-attention indexer not applied: contexts beyond index_topk=%d tokens are attended densely "
+                "(max_model_len=%d)", topk, cfg.max_model_len)
+
+    def load_weights(self, weights):
+        return super().load_weights((n, w) for n, w in weights if ".indexer." not in n)
+
+
+class DeepseekV32ForCausalLM(GlmMoeDsaForCausalLM):
+    """DeepSeek-V3.2-Exp: same partial support; its MLA keeps DeepSeek's interleaved rotary."""
+    rope_interleave_default = True
 
 
 class Glm4MoeDecoderLayer(DeepseekDecoderLayer):

@@ -53,6 +53,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "MistralLarge3ForCausalLM": ("llama_variants", "Ministral3ForCausalLM"),
     "FlexOlmoForCausalLM": ("llama_variants", "FlexOlmoForCausalLM"),
     "Glm4MoeLiteForCausalLM": ("deepseek", "Glm4MoeLiteForCausalLM"),
+    "GlmMoeDsaForCausalLM": ("deepseek", "GlmMoeDsaForCausalLM"),
+    "DeepseekV32ForCausalLM": ("deepseek", "DeepseekV32ForCausalLM"),
     "DbrxForCausalLM": ("llama_variants", "DbrxForCausalLM"),
     "AfmoeForCausalLM": ("llama_variants", "AfmoeForCausalLM"),
     "MiniMaxM2ForCausalLM": ("llama_variants", "MiniMaxM2ForCausalLM"),
