@@ -1125,3 +1125,34 @@ def test_glm_moe_dsa_dense_path_matches_hf_within_index_topk():
     m = llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model
     assert not m.model.layers[0].self_attn.rope.is_neox_style
     llm.shutdown()
+
+
+def test_transformers_backend_pooling_and_modernbert_colbert():
+    """``TransformersEmbeddingModel`` (the pooling adapter over the Transformers back-end) gives the same last-token
+    embedding as the native ``LlamaModel`` adapter on the same weights; ColBERT-ModernBERT applies its projection per token."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    kw = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type", "torch_dtype")}
+    torch.manual_seed(1)
+    base = transformers.LlamaModel(transformers.AutoConfig.for_model("llama", **kw)).float().eval()
+    prompts = [[5, 17, 99, 3, 250, 41], list(range(10, 45))]
+    outs = {}
+    for arch in ("LlamaModel", "TransformersEmbeddingModel"):
+        llm = make_llm("llama-tiny", hf_overrides={"architectures": [arch]}, runner="pooling")
+        llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model.load_weights(base.state_dict().items())
+        outs[arch] = [torch.as_tensor(o.outputs.data).float() for o in llm.embed([{"prompt_token_ids": p} for p in prompts])]
+        llm.shutdown()
+    for a, b in zip(outs["LlamaModel"], outs["TransformersEmbeddingModel"]):
+        torch.testing.assert_close(a, b, atol=3e-4, rtol=1e-3)
+    hf = make_hf_model("modernbert-tiny")
+    g = torch.Generator().manual_seed(0)
+    lin = torch.randn(16, 64, generator=g) * 0.2
+    llm, m = _pooling_llm("modernbert-tiny", "ColBERTModernBertModel", hf, colbert_dim=16)
+    m.load_weights([("linear.weight", lin)])
+    p = [3, 17, 99, 250, 41, 7]
+    got = torch.as_tensor(llm.encode([{"prompt_token_ids": p}], pooling_task="token_embed")[0].outputs.data).float()
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(hf(torch.tensor([p])).last_hidden_state[0] @ lin.t(), dim=-1)
+    torch.testing.assert_close(got, ref, atol=3e-4, rtol=1e-3)
+    llm.shutdown()

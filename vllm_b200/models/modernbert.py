@@ -130,3 +130,22 @@ class ModernBertForSequenceClassification(ModernBertModel):
 
 class ModernBertForTokenClassification(ModernBertForSequenceClassification):
     per_token = True
+
+
+class ColBERTModernBertModel(ModernBertModel):
+    """ModernBERT late-interaction retriever (answerai-colbert, GTE-ModernColBERT): every token state → bias-free linear →
+    L2 norm (reference: models/colbert.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg = self.cfg
+        self.default_pooling = "ALL"
+        self.colbert_linear = nn.Linear(cfg["hidden_size"], int(cfg.get("colbert_dim") or cfg.get("dim") or 128), bias=False,
+                                        dtype=vllm_config.model_config.torch_dtype)
+
+    def project_embedding(self, x: torch.Tensor, per_token: bool) -> torch.Tensor:
+        return self.colbert_linear(x) if per_token else x
+
+    def load_weights(self, weights):
+        return super().load_weights((("colbert_linear.weight" if n in ("linear.weight", "colbert_linear.weight", "1.linear.weight") else n), w)
+                                    for n, w in weights)

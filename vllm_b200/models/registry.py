@@ -78,6 +78,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "NomicBertModel": ("nomic_bert", "NomicBertModel"),
     "BgeM3EmbeddingModel": ("bert", "BgeM3EmbeddingModel"),
     "HF_ColBERT": ("bert", "HF_ColBERT"),
+    "ColBERTModernBertModel": ("modernbert", "ColBERTModernBertModel"),
     "ColBERTJinaRobertaModel": ("bert", "ColBERTJinaRobertaModel"),
     "BertSpladeSparseEmbeddingModel": ("bert", "BertSpladeSparseEmbeddingModel"),
     "RobertaForSequenceClassification": ("bert", "RobertaForSequenceClassification"),
@@ -186,7 +187,11 @@ def supported_archs() -> list[str]:
 
 
 # bases whose causal-LM class is not called ``<X>ForCausalLM``
-_IRREGULAR_BASE = {"GPT2ForCausalLM": "GPT2LMHeadModel", "Gemma3TextForCausalLM": "Gemma3ForCausalLM"}
+_IRREGULAR_BASE = {"GPT2ForCausalLM": "GPT2LMHeadModel", "Gemma3TextForCausalLM": "Gemma3ForCausalLM",
+                   # pooling checkpoints routed to the Transformers back-end by name (``--model-impl transformers``)
+                   "TransformersEmbeddingForCausalLM": "TransformersForCausalLM",
+                   "TransformersMoEEmbeddingForCausalLM": "TransformersForCausalLM",
+                   "TransformersMoEForCausalLM": "TransformersForCausalLM"}
 _REWARD = {"Qwen2ForRewardModel": ("Qwen2ForCausalLM", dict(n_out=1, mlp=True)),
            "Qwen2ForProcessRewardModel": ("Qwen2ForCausalLM", dict(n_out=2, mlp=True)),
            "InternLM2ForRewardModel": ("InternLM2ForCausalLM", dict(n_out=1, mlp=False, head_name="v_head"))}
