@@ -1156,3 +1156,38 @@ def test_transformers_backend_pooling_and_modernbert_colbert():
         ref = torch.nn.functional.normalize(hf(torch.tensor([p])).last_hidden_state[0] @ lin.t(), dim=-1)
     torch.testing.assert_close(got, ref, atol=3e-4, rtol=1e-3)
     llm.shutdown()
+
+
+def test_qwen3_5_vl_matches_hf():
+    """Qwen3.5-VL: Qwen3-VL tower (no DeepStack) + gated-delta-net hybrid decoder with interleaved, partial M-RoPE on its
+    attention layers — greedy continuation for an image prompt equals transformers."""
+    import numpy as np
+    import transformers
+    from PIL import Image
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("qwen35vl-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_id", "video_token_id", "vision_start_token_id",
+            "vision_end_token_id", "torch_dtype")
+    tc = {k: v for k, v in cfg.items() if k not in drop}
+    hf_cfg = transformers.Qwen3_5Config(text_config=tc, vision_config=cfg["vision_config"], image_token_id=500, video_token_id=501,
+                                        vision_start_token_id=502, vision_end_token_id=503, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    hf = transformers.Qwen3_5ForConditionalGeneration(hf_cfg).float().eval()
+    rng = np.random.default_rng(0)
+    img = Image.fromarray(rng.integers(0, 255, (64, 96, 3), dtype=np.uint8))
+    ip = transformers.Qwen2VLImageProcessor(patch_size=16, merge_size=2, image_mean=[0.5] * 3, image_std=[0.5] * 3,
+                                            size={"shortest_edge": 32 * 32, "longest_edge": 16 * 16 * 4 * 4096})
+    px = ip(images=[img], return_tensors="pt")
+    n_img = int(px["image_grid_thw"][0].prod()) // 4
+    pre, post = [5, 17, 99, 502], [503, 3, 250, 41, 7]
+    ids_hf = pre + [500] * n_img + post
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([ids_hf]), attention_mask=torch.ones(1, len(ids_hf), dtype=torch.long),
+                          pixel_values=px["pixel_values"], image_grid_thw=px["image_grid_thw"],
+                          mm_token_type_ids=torch.tensor([[1 if t == 500 else 0 for t in ids_hf]]), max_new_tokens=8,
+                          do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(ids_hf):].tolist()
+    llm = make_llm("qwen35vl-tiny", weights=hf.state_dict().items(), enable_prefix_caching=False, hf_overrides={"min_pixels": 32 * 32})
+    out = llm.generate([{"prompt_token_ids": pre + [500] + post, "multi_modal_data": {"image": img}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    llm.shutdown()
+    assert out[0].outputs[0].token_ids == ref, (out[0].outputs[0].token_ids, ref)

@@ -489,6 +489,19 @@ PRESETS: dict[str, dict[str, Any]] = {
                            num_heads=2, in_channels=3, patch_size=16, spatial_merge_size=2, temporal_patch_size=2,
                            num_position_embeddings=36, deepstack_visual_indexes=[0]),
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "qwen35vl-tiny": dict(
+        architectures=["Qwen3_5ForConditionalGeneration"], model_type="qwen3_5", vocab_size=512, hidden_size=64, intermediate_size=128,
+        num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, linear_num_value_heads=4,
+        linear_num_key_heads=2, linear_key_head_dim=16, linear_value_head_dim=16, linear_conv_kernel_dim=4,
+        layer_types=["linear_attention", "full_attention", "linear_attention", "full_attention"], rms_norm_eps=1e-6,
+        hidden_act="silu", max_position_embeddings=512, attention_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=0.5, mrope_section=[2, 1, 1],
+                             mrope_interleaved=True),
+        image_token_id=500, video_token_id=501, vision_start_token_id=502, vision_end_token_id=503,
+        vision_config=dict(depth=2, hidden_size=32, out_hidden_size=64, intermediate_size=48, hidden_act="gelu_pytorch_tanh",
+                           num_heads=2, in_channels=3, patch_size=16, spatial_merge_size=2, temporal_patch_size=2,
+                           num_position_embeddings=36, deepstack_visual_indexes=[]),
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "smollm3-tiny": dict(architectures=["SmolLM3ForCausalLM"], model_type="smollm3", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", rms_norm_eps=1e-6,
         no_rope_layers=[1, 1, 1, 0], no_rope_layer_interval=4, tie_word_embeddings=True),
     "cohere2-tiny": dict(architectures=["Cohere2ForCausalLM"], model_type="cohere2", vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=512, bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", rope_theta=10000.0, hidden_act="silu", head_dim=16, layer_norm_eps=1e-5,

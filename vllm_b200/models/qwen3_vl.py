@@ -150,6 +150,8 @@ class _Qwen3VLMixin:
             if name.startswith("model.language_model."):
                 name = "model." + name[len("model.language_model."):]
             rest.append((name, w))
+        if isinstance(self, _VisualOnly):
+            return loaded
         return loaded | super().load_weights(rest)
 
 
@@ -164,3 +166,34 @@ def _moe_base():
 
 class Qwen3VLMoeForConditionalGeneration(_Qwen3VLMixin, _moe_base()):
     """The same tower and DeepStack path in front of the Qwen3-MoE decoder (reference: models/qwen3_vl_moe.py)."""
+
+
+def _q35_base():
+    from vllm_b200.models.qwen3_next import Qwen3_5ForCausalLM
+    return Qwen3_5ForCausalLM
+
+
+class Qwen3_5ForConditionalGeneration(_Qwen3VLMixin, _q35_base()):
+    """Qwen3.5 vision-language (dense and MoE): the Qwen3-VL tower without DeepStack in front of the gated-delta-net hybrid
+    decoder; the full-attention layers rotate with interleaved M-RoPE (reference: models/qwen3_5.py)."""
+
+    def load_weights(self, weights):
+        vis, rest = [], []
+        for n, w in weights:
+            (vis if n.startswith(("model.visual.", "visual.")) else rest).append((n, w))
+        loaded = _Qwen3VLMixin.load_weights(_VisualOnly(self), vis)
+        return loaded | _q35_base().load_weights(self, rest)
+
+
+class _VisualOnly:
+    """Runs the mixin's visual-weight loop against a model without touching its decoder loader."""
+
+    def __init__(self, model) -> None:
+        self.visual = model.visual
+
+    def __getattr__(self, name):
+        raise AttributeError(name)
+
+
+class Qwen3_5MoeForConditionalGeneration(Qwen3_5ForConditionalGeneration):
+    pass

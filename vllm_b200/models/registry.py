@@ -149,6 +149,8 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3VLMoeForConditionalGeneration": ("qwen3_vl", "Qwen3VLMoeForConditionalGeneration"),
     "LlavaOnevisionForConditionalGeneration": ("llava_next", "LlavaOnevisionForConditionalGeneration"),
     "PaliGemmaForConditionalGeneration": ("idefics3", "PaliGemmaForConditionalGeneration"),
+    "Qwen3_5ForConditionalGeneration": ("qwen3_vl", "Qwen3_5ForConditionalGeneration"),
+    "Qwen3_5MoeForConditionalGeneration": ("qwen3_vl", "Qwen3_5MoeForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

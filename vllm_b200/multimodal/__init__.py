@@ -136,7 +136,8 @@ class _Registry:
 
     def create_processor(self, model_config):
         if (model_config.architecture in ("Qwen2VLForConditionalGeneration", "Qwen2_5_VLForConditionalGeneration",
-                                          "Qwen3VLForConditionalGeneration", "Qwen3VLMoeForConditionalGeneration")
+                                          "Qwen3VLForConditionalGeneration", "Qwen3VLMoeForConditionalGeneration",
+                                          "Qwen3_5ForConditionalGeneration", "Qwen3_5MoeForConditionalGeneration")
                 and model_config.architecture not in self.processors):
             from vllm_b200.multimodal.qwen_vl import Qwen2VLProcessor
             self.processors[model_config.architecture] = Qwen2VLProcessor

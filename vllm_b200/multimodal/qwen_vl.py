@@ -126,7 +126,7 @@ class Qwen2VLProcessor:
         self.tokens_per_second = vc.get("tokens_per_second", 0)           # Qwen2.5-VL only
         self.min_pixels = cfg.get("min_pixels", 56 * 56)
         self.max_pixels = cfg.get("max_pixels", 14 * 14 * 4 * 1280)
-        q3 = str(cfg.get("model_type", "")).startswith("qwen3_vl")
+        q3 = str(cfg.get("model_type", "")).startswith(("qwen3_vl", "qwen3_5"))
         self.mean, self.std = ((0.5,) * 3, (0.5,) * 3) if q3 else (CLIP_MEAN, CLIP_STD)
         if q3:
             self.min_pixels, self.max_pixels = cfg.get("min_pixels", 65536), cfg.get("max_pixels", 16 * 16 * 4 * 4096)

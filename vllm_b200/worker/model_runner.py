@@ -198,7 +198,7 @@ class ModelRunner:
             self.ec_connector = ECSharedStorageConnector(ecp, os.environ.get("VLLM_B200_EC_ROLE", "ec_both"))
         from vllm_b200.multimodal import MULTIMODAL_REGISTRY
         self.has_mm = MULTIMODAL_REGISTRY.supports_multimodal(vllm_config.model_config)
-        self.uses_mrope = vllm_config.model_config.hf_config.get("model_type") in ("qwen2_vl", "qwen2_5_vl", "qwen3_vl", "qwen3_vl_moe")
+        self.uses_mrope = vllm_config.model_config.hf_config.get("model_type") in ("qwen2_vl", "qwen2_5_vl", "qwen3_vl", "qwen3_vl_moe", "qwen3_5", "qwen3_5_moe")
         self._deepstack, self._deepstack_live = None, False
         self.kv_connector = None
         ktc = vllm_config.kv_transfer_config
