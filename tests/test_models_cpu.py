@@ -1191,3 +1191,35 @@ def test_qwen3_5_vl_matches_hf():
                        SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
     llm.shutdown()
     assert out[0].outputs[0].token_ids == ref, (out[0].outputs[0].token_ids, ref)
+
+
+def test_llava_next_video_matches_hf():
+    """LLaVA-NeXT-Video: per-frame tower features, stride-2 average pooling, projector, frames concatenated over the video
+    placeholder — greedy continuation equals transformers for a 3-frame clip."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = dict(get_preset_hf_config("llava-tiny"))
+    pins = [[28, 28], [28, 56], [56, 28]]
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "vision_feature_layer",
+            "vision_feature_select_strategy", "projector_hidden_act", "torch_dtype")
+    hf_cfg = transformers.LlavaNextVideoConfig(vision_config=cfg["vision_config"], text_config=dict(model_type="llama", **_vlm_text_cfg(cfg, drop)),
+                                               image_token_index=511, video_token_index=510, vision_feature_layer=-2,
+                                               vision_feature_select_strategy="default", projector_hidden_act="gelu",
+                                               image_grid_pinpoints=pins, spatial_pool_mode="average", spatial_pool_stride=2)
+    torch.manual_seed(0)
+    hf = transformers.LlavaNextVideoForConditionalGeneration(hf_cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    frames = torch.randn(3, 3, 28, 28, generator=g)
+    n = 3 * 1                                              # (28 / 14 / 2)^2 = 1 token per frame
+    exp_ids = [5, 17] + [510] * n + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values_videos=frames[None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("llava-tiny", weights=hf.state_dict().items(),
+                   hf_overrides={"architectures": ["LlavaNextVideoForConditionalGeneration"], "image_grid_pinpoints": pins,
+                                 "video_token_index": 510, "spatial_pool_stride": 2, "spatial_pool_mode": "average"})
+    out = llm.generate([{"prompt_token_ids": [5, 17, 510, 99, 3, 250], "multi_modal_data": {"video": frames}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    assert out[0].prompt_token_ids == exp_ids
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

@@ -207,3 +207,75 @@ class LlavaOnevisionProcessor(LlavaNextProcessor):
         super().__init__(model_config)
         ar = str(model_config.hf_config.get("vision_aspect_ratio", "anyres_max_9"))
         self.max_tiles = int(ar.rsplit("_", 1)[1]) if ar.startswith("anyres_max_") else 0
+
+
+class LlavaNextVideoForConditionalGeneration(LlavaNextForConditionalGeneration):
+    """LLaVA-NeXT-Video: images as in LLaVA-NeXT; a video is a stack of frames, each through the tower, spatially pooled
+    (stride-s average / max) and projected, the frames' tokens concatenated over the ``<video>`` placeholder
+    (reference: models/llava_next_video.py)."""
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        super().__init__(vllm_config, prefix)
+        cfg = self.cfg
+        self.video_token = cfg.get("video_token_index", cfg.get("video_token_id"))
+        self.pool_stride = int(cfg.get("spatial_pool_stride", 2))
+        self.pool_mode = cfg.get("spatial_pool_mode", "average")
+        if self.pool_mode not in ("average", "max"):
+            raise NotImplementedError(f"spatial_pool_mode={self.pool_mode!r}")
+
+    @torch.inference_mode()
+    def embed_multimodal_item(self, f: dict) -> torch.Tensor:
+        if f.get("modality") != "video":
+            return super().embed_multimodal_item(f)
+        frames = torch.as_tensor(f["data"]).to(self.image_newline.device)
+        x = self.vision_tower(frames)
+        if self.select == "default":
+            x = x[:, 1:]
+        F_, N, C = x.shape
+        s = int(N ** 0.5)
+        g = x.view(F_, s, s, C).permute(0, 3, 1, 2)
+        g = (F.avg_pool2d if self.pool_mode == "average" else F.max_pool2d)(g, self.pool_stride, self.pool_stride)
+        x = g.flatten(2).transpose(1, 2)
+        return self.linear_2(self.proj_act(self.linear_1(x))).reshape(-1, self.linear_2.out_features)
+
+    def load_weights(self, weights):
+        return super().load_weights((n, w) for n, w in weights if "vision_resampler" not in n)
+
+
+class LlavaNextVideoProcessor(LlavaNextProcessor):
+    def __init__(self, model_config) -> None:
+        super().__init__(model_config)
+        cfg = model_config.hf_config
+        self.video_token = cfg.get("video_token_index", cfg.get("video_token_id"))
+        self.stride = int(cfg.get("spatial_pool_stride", 2))
+
+    def process(self, ids, mm_data):
+        from vllm_b200.multimodal import hash_item, preprocess_image
+        import numpy as np
+        ids, feats = super().process(ids, mm_data)
+        vids = mm_data.get("video")
+        if vids is None:
+            return ids, feats
+        if isinstance(vids, torch.Tensor) and vids.dim() == 4 or isinstance(vids, np.ndarray) and vids.ndim == 4:
+            vids = [vids]
+        elif isinstance(vids, (list, tuple)) and vids and not (isinstance(vids[0], (torch.Tensor, np.ndarray)) and np.asarray(vids[0]).ndim == 4):
+            vids = [vids]
+        slots = [i for i, t in enumerate(ids) if t == self.video_token]
+        if len(slots) != len(vids):
+            raise ValueError(f"{len(vids)} videos but {len(slots)} video placeholders in the prompt")
+        per = (self.side // self.stride) ** 2
+        out, shift, prev = [], 0, 0
+        new_feats = []
+        for slot, v in zip(slots, vids):
+            frames = torch.stack([preprocess_image(fr, self.tile) for fr in v])
+            out.extend(ids[prev:slot])
+            n = frames.shape[0] * per
+            new_feats.append({"modality": "video", "hash": hash_item(frames.numpy()), "offset": len(out), "length": n, "data": frames})
+            out.extend([self.video_token] * n)
+            prev = slot + 1
+        out.extend(ids[prev:])
+        # image records sit at offsets of the pre-expansion prompt: shift those that come after an expanded video slot
+        for f in feats:
+            moved = sum(nf["length"] - 1 for nf, sl in zip(new_feats, slots) if sl < f["offset"])
+            f["offset"] += moved
+        return out, sorted(feats + new_feats, key=lambda r: r["offset"])

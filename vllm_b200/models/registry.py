@@ -151,6 +151,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "PaliGemmaForConditionalGeneration": ("idefics3", "PaliGemmaForConditionalGeneration"),
     "Qwen3_5ForConditionalGeneration": ("qwen3_vl", "Qwen3_5ForConditionalGeneration"),
     "Qwen3_5MoeForConditionalGeneration": ("qwen3_vl", "Qwen3_5MoeForConditionalGeneration"),
+    "LlavaNextVideoForConditionalGeneration": ("llava_next", "LlavaNextVideoForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

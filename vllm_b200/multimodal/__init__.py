@@ -147,6 +147,9 @@ class _Registry:
         if model_config.architecture == "LlavaNextForConditionalGeneration" and model_config.architecture not in self.processors:
             from vllm_b200.models.llava_next import LlavaNextProcessor
             self.processors[model_config.architecture] = LlavaNextProcessor
+        if model_config.architecture == "LlavaNextVideoForConditionalGeneration" and model_config.architecture not in self.processors:
+            from vllm_b200.models.llava_next import LlavaNextVideoProcessor
+            self.processors[model_config.architecture] = LlavaNextVideoProcessor
         if model_config.architecture == "LlavaOnevisionForConditionalGeneration" and model_config.architecture not in self.processors:
             from vllm_b200.models.llava_next import LlavaOnevisionProcessor
             self.processors[model_config.architecture] = LlavaOnevisionProcessor
