@@ -1223,3 +1223,19 @@ def test_llava_next_video_matches_hf():
     assert out[0].prompt_token_ids == exp_ids
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_minicpm3_is_dense_mla_with_mup_scalars():
+    """MiniCPM3 (no transformers implementation): with neutral scalars (scale_emb 1, scale_depth √L, dim_model_base = hidden)
+    it must equal the dense DeepSeek MLA decoder with rotate-half rotary on the same weights; non-neutral scalars change
+    the output."""
+    import math
+    base = {"n_routed_experts": None, "first_k_dense_replace": 99, "rope_interleave": False}
+    a = _gen("deepseek-tiny", None, dict(base, architectures=["DeepseekV3ForCausalLM"]))
+    neutral = {"architectures": ["MiniCPM3ForCausalLM"], "n_routed_experts": None, "scale_emb": 1.0, "scale_depth": math.sqrt(3),
+               "dim_model_base": 128}
+    b = _gen("deepseek-tiny", None, neutral)
+    _same(a, b)
+    c = _gen("deepseek-tiny", None, dict(neutral, scale_emb=12.0, scale_depth=1.4, dim_model_base=32))
+    # (tiny dummy weights keep the argmax; the scalars must show in the log-probabilities)
+    assert max(abs(x - y) for (_, lc), (_, lb) in zip(c, b) for x, y in zip(lc, lb)) > 1e-4

@@ -237,6 +237,52 @@ class DeepseekV3ForCausalLM(LlamaForCausalLM):
 
 
 # ------------------------------------------------------------------------------------------------ GLM-4.5 / 4.6 (MoE)
+class _MiniCPM3Layer(nn.Module):
+    """MLA attention + dense gated MLP with the muP residual scale ``scale_depth / sqrt(num_layers)`` on both branches
+    (explicit residual stream: the fused add-norm path has no place for the multiplier)."""
+
+    def __init__(self, cfg, mc, dtype, quant_config, prefix: str, layer_idx: int, enable_ep: bool) -> None:
+        super().__init__()
+        import math
+        eps = cfg.get("rms_norm_eps", 1e-6)
+        self.self_attn = DeepseekMLA(cfg, mc, dtype, quant_config, f"{prefix}.self_attn")
+        self.input_layernorm = RMSNorm(cfg["hidden_size"], eps, dtype)
+        self.post_attention_layernorm = RMSNorm(cfg["hidden_size"], eps, dtype)
+        self.mlp = LlamaMLP(cfg["hidden_size"], cfg["intermediate_size"], cfg.get("hidden_act", "silu"), False, dtype, quant_config,
+                            f"{prefix}.mlp")
+        self.rm = float(cfg.get("scale_depth", 1.0)) / math.sqrt(cfg["num_hidden_layers"])
+
+    def forward(self, positions, hidden, residual, next_norm: Optional[nn.Module]):
+        x = residual + self.self_attn.o_proj(self.self_attn(positions, hidden)) * self.rm
+        x = x + self.mlp(self.post_attention_layernorm(x)) * self.rm
+        return (next_norm(x) if next_norm is not None else x), x
+
+
+class _MiniCPM3Model(DeepseekModel):
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "model", quant_config=None) -> None:
+        super().__init__(vllm_config, prefix, quant_config)
+        self.embed_scale = float(self.cfg.get("scale_emb", 1.0))
+
+    def _make_layer(self, cfg, mc, dtype, quant_config, prefix, idx):
+        return _MiniCPM3Layer(cfg, mc, dtype, quant_config, prefix, idx, self._enable_ep)
+
+
+class MiniCPM3ForCausalLM(DeepseekV3ForCausalLM):
+    """MiniCPM3-4B: multi-head latent attention (rotate-half rotary, LongRoPE) in a dense decoder with the MiniCPM muP
+    scalars — scaled embeddings, residual branches × ``scale_depth / sqrt(L)``, logits ÷ ``hidden / dim_model_base``
+    (reference: models/minicpm3.py)."""
+    model_cls = _MiniCPM3Model
+
+    def __init__(self, vllm_config: VllmConfig, prefix: str = "") -> None:
+        cfg = vllm_config.model_config.hf_config
+        cfg.setdefault("rope_interleave", False)
+        cfg.pop("n_routed_experts", None)
+        super().__init__(vllm_config, prefix)
+        if self.is_last:
+            from vllm_b200.layers.common import LogitsProcessor
+            self.logits_processor = LogitsProcessor(cfg["vocab_size"], scale=float(cfg.get("dim_model_base", cfg["hidden_size"])) / cfg["hidden_size"])
+
+
 class Glm4MoeLiteForCausalLM(DeepseekV3ForCausalLM):
     """GLM-4.7-Flash ("MoE lite"): the DeepSeek-V3 block — MLA with interleaved rotary, sigmoid router with selection bias,
     shared expert, leading dense layers given by ``mlp_layer_types`` (reference: models/glm4_moe_lite.py)."""

@@ -66,6 +66,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "TeleChat3ForCausalLM": ("llama", "LlamaForCausalLM"),
     "ExaoneForCausalLM": ("llama_aliases", "ExaoneForCausalLM"),
     "MiMoForCausalLM": ("llama_aliases", "MiMoForCausalLM"),
+    "MiniCPM3ForCausalLM": ("deepseek", "MiniCPM3ForCausalLM"),
     "MiniCPMForCausalLM": ("llama_aliases", "MiniCPMForCausalLM"),
     "TeleFLMForCausalLM": ("llama_aliases", "TeleFLMForCausalLM"),
     "OrionForCausalLM": ("llama_aliases", "OrionForCausalLM"),
