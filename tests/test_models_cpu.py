@@ -1239,3 +1239,28 @@ def test_minicpm3_is_dense_mla_with_mup_scalars():
     c = _gen("deepseek-tiny", None, dict(neutral, scale_emb=12.0, scale_depth=1.4, dim_model_base=32))
     # (tiny dummy weights keep the argmax; the scalars must show in the log-probabilities)
     assert max(abs(x - y) for (_, lc), (_, lb) in zip(c, b) for x, y in zip(lc, lb)) > 1e-4
+
+
+def test_llama4_vision_matches_hf():
+    """Llama-4 multimodal: unfolded-patch ViT with 2-D rotary pairs, pixel-shuffle adapter, projector, Llama-4 MoE decoder
+    (chunked attention, NoPE layers) — greedy continuation with an image equals transformers."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama4mm-tiny")
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "torch_dtype")
+    hf_cfg = transformers.Llama4Config(vision_config=cfg["vision_config"], text_config=_vlm_text_cfg(cfg, drop), image_token_index=511,
+                                       boi_token_index=509, eoi_token_index=510)
+    torch.manual_seed(0)
+    hf = transformers.Llama4ForConditionalGeneration(hf_cfg).float().eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    exp_ids = [5, 17] + [511] * 4 + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], max_new_tokens=8, do_sample=False,
+                          pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("llama4mm-tiny", weights=hf.state_dict().items())
+    out = llm.generate([{"prompt_token_ids": [5, 17, 511, 99, 3, 250], "multi_modal_data": {"image": img}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    assert out[0].prompt_token_ids == exp_ids
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

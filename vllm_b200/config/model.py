@@ -458,6 +458,18 @@ PRESETS: dict[str, dict[str, Any]] = {
         rope_parameters=dict(rope_type="default", rope_theta=10000.0),
         layer_types=["chunked_attention", "chunked_attention", "chunked_attention", "full_attention"],
         bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
+    "llama4mm-tiny": dict(architectures=["Llama4ForConditionalGeneration"], model_type="llama4", image_token_index=511,
+        vision_config=dict(model_type="llama4_vision_model", hidden_size=32, intermediate_size=128, num_hidden_layers=2,
+                           num_attention_heads=2, image_size=32, patch_size=8, num_channels=3, vision_output_dim=48,
+                           pixel_shuffle_ratio=0.5, projector_input_dim=48, projector_output_dim=48,
+                           rope_parameters=dict(rope_type="default", rope_theta=10000.0)),
+        vocab_size=512, hidden_size=64, intermediate_size=32, intermediate_size_mlp=128, num_hidden_layers=4, num_attention_heads=4,
+        num_key_value_heads=2, head_dim=16, num_local_experts=4, num_experts_per_tok=1, interleave_moe_layer_step=2, moe_layers=[1, 3],
+        no_rope_layers=[1, 1, 1, 0], attention_chunk_size=16, attn_temperature_tuning=True, floor_scale=8, attn_scale=0.1,
+        use_qk_norm=True, rms_norm_eps=1e-5, hidden_act="silu", max_position_embeddings=512, attention_bias=False,
+        rope_parameters=dict(rope_type="default", rope_theta=10000.0),
+        layer_types=["chunked_attention", "chunked_attention", "chunked_attention", "full_attention"],
+        bos_token_id=1, eos_token_id=2, pad_token_id=0, torch_dtype="float32", tie_word_embeddings=False),
     "qwen25vl-tiny": dict(
         architectures=["Qwen2_5_VLForConditionalGeneration"], model_type="qwen2_5_vl", vocab_size=512, hidden_size=64,
         intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,

@@ -153,6 +153,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "Qwen3_5ForConditionalGeneration": ("qwen3_vl", "Qwen3_5ForConditionalGeneration"),
     "Qwen3_5MoeForConditionalGeneration": ("qwen3_vl", "Qwen3_5MoeForConditionalGeneration"),
     "LlavaNextVideoForConditionalGeneration": ("llava_next", "LlavaNextVideoForConditionalGeneration"),
+    "Llama4ForConditionalGeneration": ("llama4_mm", "Llama4ForConditionalGeneration"),
     "LlavaForConditionalGeneration": ("llava", "LlavaForConditionalGeneration"),
     "ModernBertModel": ("modernbert", "ModernBertModel"),
     "ModernBertForMaskedLM": ("modernbert", "ModernBertModel"),

@@ -63,7 +63,9 @@ class MultiModalProcessor:
         self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
         n = (self.image_size // self.patch) ** 2
         self.tokens_per_image = n if cfg.get("vision_feature_select_strategy", "default") == "default" else n + 1
-        if cfg.get("downsample_factor"):                    # Aya Vision / Command-A Vision
+        if vc.get("pixel_shuffle_ratio"):                   # Llama-4: ratio 0.5 → 2 x 2 patches per token
+            self.tokens_per_image = int(n * float(vc["pixel_shuffle_ratio"]) ** 2)
+        elif cfg.get("downsample_factor"):                    # Aya Vision / Command-A Vision
             self.tokens_per_image = n // int(cfg["downsample_factor"]) ** 2
         elif cfg.get("scale_factor"):                         # pixel-shuffle connectors (Idefics3 / SmolVLM): s x s patches per token
             self.tokens_per_image = n // int(cfg["scale_factor"]) ** 2
