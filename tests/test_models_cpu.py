@@ -1264,3 +1264,36 @@ def test_llama4_vision_matches_hf():
     assert out[0].prompt_token_ids == exp_ids
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_llava_with_pixtral_tower_matches_hf():
+    """pixtral-12b in the HF layout = LLaVA with a Pixtral tower: 2-D rotary ViT, all patch tokens, row-break image layout —
+    greedy continuation equals transformers' LlavaForConditionalGeneration."""
+    import transformers
+    from vllm_b200.config import get_preset_hf_config
+    cfg = dict(get_preset_hf_config("llava-tiny"))
+    vc = dict(model_type="pixtral", hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, head_dim=16,
+              image_size=32, patch_size=8, hidden_act="silu", rope_theta=10000.0)
+    drop = ("architectures", "model_type", "vision_config", "image_token_index", "vision_feature_layer",
+            "vision_feature_select_strategy", "projector_hidden_act", "torch_dtype")
+    hf_cfg = transformers.LlavaConfig(vision_config=vc, text_config=dict(model_type="llama", **_vlm_text_cfg(cfg, drop)), image_token_index=10,
+                                      vision_feature_layer=-1, vision_feature_select_strategy="full", projector_hidden_act="gelu")
+    torch.manual_seed(0)
+    hf = transformers.LlavaForConditionalGeneration(hf_cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, 32, 32, generator=g)
+    rows = []
+    for r in range(4):
+        rows += [10] * 4 + [13 if r == 3 else 12]
+    exp_ids = [5, 17] + rows + [99, 3, 250]
+    with torch.no_grad():
+        ref = hf.generate(input_ids=torch.tensor([exp_ids]), pixel_values=img[None], image_sizes=torch.tensor([[32, 32]]),
+                          max_new_tokens=8, do_sample=False, pad_token_id=0, eos_token_id=None)[0, len(exp_ids):].tolist()
+    llm = make_llm("llava-tiny", weights=hf.state_dict().items(),
+                   hf_overrides={"vision_config": vc, "image_token_index": 10, "vision_feature_layer": -1,
+                                 "vision_feature_select_strategy": "full"})
+    out = llm.generate([{"prompt_token_ids": [5, 17, 10, 99, 3, 250], "multi_modal_data": {"image": img}}],
+                       SamplingParams(max_tokens=8, temperature=0.0, ignore_eos=True))
+    assert out[0].prompt_token_ids == exp_ids
+    assert out[0].outputs[0].token_ids == ref
+    llm.shutdown()

@@ -83,8 +83,8 @@ class LlavaForConditionalGeneration(nn.Module):
         self.cfg = cfg
         dtype = mc.torch_dtype
         self.image_token = cfg.get("image_token_index", cfg.get("image_token_id"))
-        self.select = cfg.get("vision_feature_select_strategy", "default")
         self.vision_tower = self._build_tower(cfg, dtype)
+        self.select = cfg.get("vision_feature_select_strategy", "default")
         Hv, Ht = cfg["vision_config"]["hidden_size"], cfg["hidden_size"]
         pb = bool(cfg.get("multimodal_projector_bias", True))
         self.linear_1 = nn.Linear(Hv, Ht, bias=pb, dtype=dtype)
@@ -97,6 +97,16 @@ class LlavaForConditionalGeneration(nn.Module):
         self.language_model = text_decoder_cls(cfg, "LlamaForCausalLM")(vllm_config, prefix=f"{prefix}language_model.")
 
     def _build_tower(self, cfg, dtype) -> nn.Module:
+        if cfg["vision_config"].get("model_type") == "pixtral":
+            # pixtral-12b in the HF layout: Pixtral tower (2-D rotary, no class token) behind the LLaVA projector
+            from vllm_b200.models.mistral3 import PixtralTower
+            tower = PixtralTower(cfg["vision_config"], dtype)
+            inner = tower.forward
+            tower.forward = lambda pixels: torch.stack([inner(px)[0] for px in pixels])
+            self._tower_rename = lambda n: (n.replace("transformer.layers.", "layers.").replace(".attention.", ".")
+                                            .replace(".feed_forward.", "."))
+            cfg["vision_feature_select_strategy"] = "full"
+            return tower
         return CLIPVisionTower(cfg["vision_config"], dtype, cfg.get("vision_feature_layer", -2))
 
     _tower_rename = None           # subclasses with another tower family: checkpoint name → tower parameter name

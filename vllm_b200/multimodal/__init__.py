@@ -146,6 +146,11 @@ class _Registry:
         if model_config.architecture in ("Mistral3ForConditionalGeneration",) and model_config.architecture not in self.processors:
             from vllm_b200.models.mistral3 import PixtralLayoutProcessor
             self.processors[model_config.architecture] = PixtralLayoutProcessor
+        if (model_config.architecture == "LlavaForConditionalGeneration"
+                and (model_config.hf_config.get("vision_config") or {}).get("model_type") == "pixtral"):
+            from vllm_b200.models.mistral3 import PixtralLayoutProcessor
+            model_config.hf_config.setdefault("spatial_merge_size", 1)
+            return PixtralLayoutProcessor(model_config)
         if model_config.architecture == "LlavaNextForConditionalGeneration" and model_config.architecture not in self.processors:
             from vllm_b200.models.llava_next import LlavaNextProcessor
             self.processors[model_config.architecture] = LlavaNextProcessor
