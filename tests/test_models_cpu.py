@@ -1297,3 +1297,19 @@ def test_llava_with_pixtral_tower_matches_hf():
     assert out[0].prompt_token_ids == exp_ids
     assert out[0].outputs[0].token_ids == ref
     llm.shutdown()
+
+
+def test_solar_block_skip_connections():
+    """Solar (depth-up-scaled Llama with block skip connections): blend weight 0 is the plain Llama; a non-zero weight must
+    equal a by-hand blend — checked through the invariant that blending a layer's input with ITSELF (save and mix at the
+    same layer) is the identity, and that mixing an earlier stream changes the output."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=8))
+    ref = _gen("llama-tiny", w)
+    solar = {"architectures": ["SolarForCausalLM"], "bskcn_1": [0], "bskcn_2": [], "bskcn_3": [1], "bskcn_4": []}
+    _same(ref, _gen("llama-tiny", w, dict(solar, bskcn_tv=[0.9, 0.0])))                 # inference weight 0 → plain Llama
+    _same(ref, _gen("llama-tiny", w, dict(solar, bskcn_3=[0], bskcn_tv=[0.9, 0.4])))     # stream blended with itself
+    mixed = _gen("llama-tiny", w, dict(solar, bskcn_tv=[0.9, 0.4]))
+    assert max(abs(x - y) for (_, a), (_, b) in zip(mixed, ref) for x, y in zip(a, b)) > 1e-4

@@ -180,6 +180,20 @@ class LlamaModel(nn.Module):
             cu.l2_prefetch_async(w)
             budget -= nbytes
 
+    @property
+    def _block_skips(self):
+        got = self.__dict__.get("_block_skips_cache", 0)
+        if got != 0:
+            return got
+        c = self.cfg
+        out = None
+        if c.get("bskcn_1") or c.get("bskcn_2"):
+            tv = c.get("bskcn_tv") or [0.0, 0.0]
+            out = {"save": [set(c.get("bskcn_1") or ()), set(c.get("bskcn_2") or ())],
+                   "mix": [set(c.get("bskcn_3") or ()), set(c.get("bskcn_4") or ())], "tv": float(tv[1] if len(tv) > 1 else tv[0])}
+        self.__dict__["_block_skips_cache"] = out
+        return out
+
     def embed_input_ids(self, input_ids: torch.Tensor) -> torch.Tensor:
         h = self.embed_tokens(input_ids)
         return h * self.embed_scale if self.embed_scale != 1.0 else h
@@ -200,7 +214,20 @@ class LlamaModel(nn.Module):
         deep = fctx.extra.get("deepstack") if fctx is not None else None
         H = residual.shape[-1]
         ahead = self._layer_ahead if hidden.is_cuda and hidden.shape[0] <= 256 else None
+        skip = self._block_skips
+        saved: dict[int, torch.Tensor] = {}
         for i, layer in enumerate(self.layers):
+            if skip is not None:
+                # Solar "block skip connections": the stream entering a few early layers is blended (weight tv) into the stream
+                # entering later ones; the fused add-norm already normalised the un-blended stream → redo this layer's input norm
+                li = self.start + i
+                for k, src in enumerate(skip["save"]):
+                    if li in src:
+                        saved[k] = residual
+                for k, dst in enumerate(skip["mix"]):
+                    if li in dst and k in saved:
+                        residual = saved[k] * skip["tv"] + residual * (1.0 - skip["tv"])
+                        hidden = layer.input_layernorm(residual)
             nxt = self.layers[i + 1].input_layernorm if i + 1 < n else self.norm
             if ahead is not None and i + 1 < n:
                 self._prefetch_layer(i + 1)

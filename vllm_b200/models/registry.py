@@ -95,6 +95,7 @@ _MODELS: dict[str, tuple[str, str]] = {
     "HyperCLOVAXForCausalLM": ("llama_variants", "HyperCLOVAXForCausalLM"),
     "Rnj1ForCausalLM": ("llama_variants", "Gemma3ForCausalLM"),
     "MellumForCausalLM": ("mixtral", "Qwen3MoeForCausalLM"),
+    "SolarForCausalLM": ("llama", "LlamaForCausalLM"),
     "DeciLMForCausalLM": ("llama_aliases", "DeciLMForCausalLM"),
     "Gemma2ForCausalLM": ("gemma2", "Gemma2ForCausalLM"),
     "GPTNeoXForCausalLM": ("gpt_neox", "GPTNeoXForCausalLM"),
