@@ -1313,3 +1313,25 @@ def test_solar_block_skip_connections():
     _same(ref, _gen("llama-tiny", w, dict(solar, bskcn_3=[0], bskcn_tv=[0.9, 0.4])))     # stream blended with itself
     mixed = _gen("llama-tiny", w, dict(solar, bskcn_tv=[0.9, 0.4]))
     assert max(abs(x - y) for (_, a), (_, b) in zip(mixed, ref) for x, y in zip(a, b)) > 1e-4
+
+
+def test_model_impl_selects_backend():
+    """--model-impl: ``transformers`` serves a natively supported architecture through the HF back-end (same tokens), the
+    native-only setting refuses an architecture that only the back-end could run."""
+    from tests.utils import llama_full_weights
+    from vllm_b200.config import get_preset_hf_config
+    from vllm_b200.models.registry import resolve_model_cls
+    cfg = get_preset_hf_config("llama-tiny")
+    w = list(llama_full_weights(cfg, seed=9))
+    sp = SamplingParams(max_tokens=6, temperature=0.0, ignore_eos=True)
+    outs = {}
+    for impl in ("auto", "transformers"):
+        llm = make_llm("llama-tiny", weights=w, model_impl=impl)
+        name = type(llm.llm_engine.engine_core.engine_core.model_executor.worker.runner.model).__name__
+        assert name == ("TransformersForCausalLM" if impl == "transformers" else "LlamaForCausalLM")
+        outs[impl] = [o.outputs[0].token_ids for o in llm.generate([{"prompt_token_ids": p} for p in PROMPTS], sp)]
+        llm.shutdown()
+    assert outs["auto"] == outs["transformers"]
+    with pytest.raises(ValueError, match="no native implementation"):
+        resolve_model_cls("PersimmonForCausalLM", "vllm_b200")
+    assert resolve_model_cls("PersimmonForCausalLM").__name__ == "TransformersForCausalLM"

@@ -805,6 +805,7 @@ class ModelConfig:
     served_model_name: Optional[str] = None
     hf_overrides: dict[str, Any] = field(default_factory=dict)
     runner: str = "generate"  # generate|pooling
+    model_impl: str = "auto"  # auto|vllm_b200|transformers (reference: ``--model-impl``)
     skip_tokenizer_init: bool = False
     generation_config: str = "auto"
     logits_processors: Optional[list[str]] = None

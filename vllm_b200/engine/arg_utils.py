@@ -35,6 +35,7 @@ class EngineArgs:
     served_model_name: Optional[str] = None
     hf_overrides: Optional[dict[str, Any]] = None
     runner: str = "generate"
+    model_impl: str = "auto"              # auto | vllm_b200 (native classes only) | transformers (force the HF back-end)
     load_format: str = "auto"
     model_loader_extra_config: Optional[dict[str, Any]] = None
     device: str = "auto"
@@ -114,7 +115,7 @@ class EngineArgs:
             max_model_len=self.max_model_len or 0, quantization=self.quantization,
             enforce_eager=self.enforce_eager, max_logprobs=self.max_logprobs,
             served_model_name=self.served_model_name, hf_overrides=self.hf_overrides or {},
-            runner=self.runner, skip_tokenizer_init=self.skip_tokenizer_init,
+            runner=self.runner, model_impl=self.model_impl, skip_tokenizer_init=self.skip_tokenizer_init,
             logits_processors=[str(x) for x in self.logits_processors] if self.logits_processors else None)
         block_size = self.block_size
         if block_size is None:

@@ -109,7 +109,7 @@ def iter_weights(path: str, load_format: str = "auto", extra: Optional[dict] = N
 def get_model(vllm_config: VllmConfig, device: torch.device,
               weights: Optional[Iterable[tuple[str, torch.Tensor]]] = None, prefix: str = "") -> nn.Module:
     mc, lc = vllm_config.model_config, vllm_config.load_config
-    cls = resolve_model_cls(mc.architecture)
+    cls = resolve_model_cls(mc.architecture, getattr(mc, "model_impl", "auto"))
     t0 = time.perf_counter()
     old = torch.get_default_dtype()
     torch.set_default_dtype(mc.torch_dtype)

@@ -216,7 +216,19 @@ def _adapter_for(arch: str):
     return None
 
 
-def resolve_model_cls(arch: str) -> Type[nn.Module]:
+def resolve_model_cls(arch: str, impl: str = "auto") -> Type[nn.Module]:
+    """``impl``: ``auto`` — native class, else the Transformers back-end for causal LMs transformers implements;
+    ``vllm_b200`` (alias ``vllm``) — native classes only; ``transformers`` — always the back-end (reference: ``--model-impl``)."""
+    if impl == "transformers":
+        from vllm_b200.models import adapters
+        from vllm_b200.models.transformers_backend import TransformersForCausalLM
+        if arch.endswith("ForSequenceClassification") or arch.endswith("ForRewardModel"):
+            return adapters.as_seq_cls_model(TransformersForCausalLM)
+        if arch.endswith("Model") and not arch.endswith("LMHeadModel"):
+            return adapters.as_embedding_model(TransformersForCausalLM)
+        return TransformersForCausalLM
+    if impl in ("vllm", "vllm_b200") and arch not in _MODELS and not _adapter_for(arch):
+        raise ValueError(f"architecture {arch!r} has no native implementation (--model-impl {impl}); supported: {supported_archs()}")
     if arch not in _MODELS and _adapter_for(arch):
         from vllm_b200.models import adapters
         base, kind = _adapter_for(arch)
