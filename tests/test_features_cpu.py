@@ -1363,3 +1363,28 @@ def test_speculative_method_is_inferred_from_the_draft_architecture(tmp_path):
     (d / "config.json").write_text(json.dumps({"architectures": ["LlamaForCausalLM"]}))
     assert infer_method(str(d)) == "eagle3"
     assert len(DRAFT_ARCHS) > 40
+
+
+def test_reference_style_engine_flags():
+    """--spec-method / --spec-tokens shorthand, --limit-mm-per-prompt, --disable-sliding-window, multi-node fields and the
+    compatibility-only flags parse and take effect."""
+    import argparse
+    from vllm_b200.engine.arg_utils import EngineArgs
+    ap = EngineArgs.add_cli_args(argparse.ArgumentParser())
+    ns = ap.parse_args(["--model", "llama-tiny", "--spec-method", "ngram", "--spec-tokens", "3", "--revision", "main", "--hf-token", "x",
+                        "--nnodes", "2", "--node-rank", "1", "--master-addr", "10.0.0.1", "--limit-mm-per-prompt", '{"image": 1}',
+                        "--no-enable-sleep-mode"])
+    ea = EngineArgs.from_cli_args(ns)
+    cfg = ea.create_engine_config()
+    assert cfg.speculative_config.method == "ngram" and cfg.speculative_config.num_speculative_tokens == 3
+    assert cfg.parallel_config.nnodes == 2 and cfg.parallel_config.node_rank == 1 and cfg.parallel_config.master_addr == "10.0.0.1"
+    assert cfg.model_config.hf_config["limit_mm_per_prompt"] == {"image": 1}
+    cfg = EngineArgs(model="ministral-tiny", disable_sliding_window=True, device="cpu").create_engine_config()
+    assert cfg.model_config.hf_config["sliding_window"] is None and cfg.model_config.max_model_len == 16
+    llm = make_llm("llava-tiny", limit_mm_per_prompt={"image": 1})
+    img = torch.randn(3, 28, 28)
+    with pytest.raises(ValueError, match="at most 1 image"):
+        llm.generate([{"prompt_token_ids": [5, 511, 511, 9], "multi_modal_data": {"image": [img, img]}}], SamplingParams(max_tokens=2))
+    out = llm.generate([{"prompt_token_ids": [5, 511, 9], "multi_modal_data": {"image": [img]}}], SamplingParams(max_tokens=2))
+    assert len(out[0].outputs[0].token_ids) == 2
+    llm.shutdown()

@@ -9,6 +9,7 @@ from __future__ import annotations
 import argparse
 import dataclasses
 import json
+import os
 from dataclasses import dataclass, field
 from typing import Any, Optional, Union, get_args, get_origin
 
@@ -104,11 +105,52 @@ class EngineArgs:
     profiler: Optional[str] = None
     torch_profiler_dir: Optional[str] = None
     enable_fault_tolerance: bool = False
+    # ---- reference flags with a direct meaning here ------------------------------------------------------------------
+    spec_method: Optional[str] = None                 # shorthand for --speculative-config {"method": …, "model": …, "num_speculative_tokens": …}
+    spec_model: Optional[str] = None
+    spec_tokens: Optional[int] = None
+    limit_mm_per_prompt: Optional[dict[str, Any]] = None     # {"image": 4, "audio": 0, …}: items allowed per request
+    disable_sliding_window: bool = False              # run sliding-window models as full attention, capped at the window
+    disable_cascade_attn: bool = False
+    hf_config_path: Optional[str] = None              # directory whose config.json overrides the model's own
+    nnodes: int = 1
+    node_rank: int = 0
+    master_addr: str = "127.0.0.1"
+    master_port: int = 29501
+    # ---- accepted for command-line compatibility; always-on or not applicable in an offline box ---------------------------
+    revision: Optional[str] = None                    # (hub revisions: models are local directories or presets here)
+    code_revision: Optional[str] = None
+    tokenizer_revision: Optional[str] = None
+    hf_token: Optional[str] = None
+    download_dir: Optional[str] = None
+    use_tqdm_on_load: bool = True
+    enable_sleep_mode: bool = True                    # sleep / wake_up are always available
+    enable_prompt_embeds: bool = True                 # prompt_embeds inputs are always accepted
+    enable_mm_embeds: bool = True
 
     def create_engine_config(self) -> VllmConfig:
         if self.allowed_local_media_path:
             from vllm_b200.entrypoints.chat_utils import set_allowed_local_media_path
             set_allowed_local_media_path(self.allowed_local_media_path)
+        hf_over = dict(self.hf_overrides or {})
+        if self.hf_config_path:
+            import json as _json
+            with open(os.path.join(self.hf_config_path, "config.json")) as f:
+                hf_over = {**_json.load(f), **hf_over}
+        if self.limit_mm_per_prompt:
+            hf_over["limit_mm_per_prompt"] = {str(k): (v.get("count") if isinstance(v, dict) else v)
+                                              for k, v in dict(self.limit_mm_per_prompt).items()}
+        self.hf_overrides = hf_over
+        if self.spec_method or self.spec_model or self.spec_tokens:
+            sc = dict(self.speculative_config or {})
+            sc.setdefault("method", self.spec_method or ("auto" if self.spec_model else "ngram"))
+            if self.spec_model:
+                sc.setdefault("model", self.spec_model)
+            if self.spec_tokens:
+                sc.setdefault("num_speculative_tokens", int(self.spec_tokens))
+            self.speculative_config = sc
+        if self.disable_cascade_attn:
+            os.environ["VLLM_B200_CASCADE_MIN_REQS"] = str(1 << 30)
         mc = ModelConfig(
             model=self.model, tokenizer=self.tokenizer, tokenizer_mode=self.tokenizer_mode,
             trust_remote_code=self.trust_remote_code, dtype=self.dtype, seed=self.seed,
@@ -117,6 +159,12 @@ class EngineArgs:
             served_model_name=self.served_model_name, hf_overrides=self.hf_overrides or {},
             runner=self.runner, model_impl=self.model_impl, skip_tokenizer_init=self.skip_tokenizer_init,
             logits_processors=[str(x) for x in self.logits_processors] if self.logits_processors else None)
+        if self.disable_sliding_window and mc.hf_config.get("sliding_window"):
+            # reference semantics (config/model.py ``disable_sliding_window``): full attention, context capped at the window
+            w = int(mc.hf_config["sliding_window"])
+            mc.hf_config["sliding_window"] = None
+            mc.hf_config["use_sliding_window"] = False
+            mc.max_model_len = min(mc.max_model_len, w) if mc.max_model_len > 0 else w
         block_size = self.block_size
         if block_size is None:
             # 64-token pages are the tcgen05 kernels' TMA box; models that run on the generic kernel (other head sizes,
@@ -132,6 +180,7 @@ class EngineArgs:
             prefix_caching_hash_algo=self.prefix_caching_hash_algo,
             kv_cache_memory_bytes=self.kv_cache_memory_bytes, cpu_offload_gb=self.cpu_offload_gb)
         pc = ParallelConfig(
+            nnodes=self.nnodes, node_rank=self.node_rank, master_addr=self.master_addr,
             tensor_parallel_size=self.tensor_parallel_size, pipeline_parallel_size=self.pipeline_parallel_size,
             data_parallel_size=self.data_parallel_size, data_parallel_rank=self.data_parallel_rank or 0,
             data_parallel_size_local=self.data_parallel_size_local,

@@ -106,6 +106,12 @@ class InputProcessor:
                 "shorten it or raise --max-model-len")
         mm_features = None
         if extras.get("multi_modal_data") and self.mm_processor is not None:
+            lim = self.mc.hf_config.get("limit_mm_per_prompt") or {}
+            for kind, items in extras["multi_modal_data"].items():
+                cap = lim.get(kind)
+                n = len(items) if isinstance(items, (list, tuple)) else (0 if items is None else 1)
+                if cap is not None and n > int(cap):
+                    raise ValueError(f"at most {cap} {kind} item(s) per prompt are allowed (--limit-mm-per-prompt), got {n}")
             ids, mm_features = self.mm_processor.process(ids, extras["multi_modal_data"])
         if embeds_feature is not None:
             mm_features = (mm_features or []) + [embeds_feature]
